@@ -1,0 +1,431 @@
+// engine.cu — per-GPU execution context behind the C ABI (include/gofr_b200.h).
+//
+// Stands where net/http's conn.serve → router.ServeHTTP sits in the reference (pkg/gofr/httpServer.go:29-33): the
+// caller hands over a batch of parsed requests and gets the response bytes back.  Two entry styles:
+//   gofr_serve_device   — everything already in HBM; one fused launch on the caller's stream;
+//   gofr_batch_submit/_wait — host buffers; the batch is cut into chunks that flow through a 3-deep
+//                         H2D → kernel → D2H pipeline on the engine's own streams (copy engines overlap the kernel).
+// There is no CPU fallback: without a CUDA device engine creation fails with GOFR_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <time.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "../../include/gofr_b200.h"
+#include "engine_internal.h"
+#include "table_format.h"
+
+static thread_local char g_err[512];
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return GOFR_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+using namespace gofr;
+
+namespace {
+
+constexpr int kSlots = 3;  // pipeline depth of the host-batch path
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    // device buffers (grown on demand)
+    void* d_desc = nullptr; void* d_ids = nullptr; uint8_t* d_arena = nullptr; uint8_t* d_out = nullptr;
+    uint32_t* d_off = nullptr; uint32_t* d_meta = nullptr;
+    unsigned long long* d_state = nullptr; uint32_t* d_flag = nullptr;
+    size_t cap_n = 0, cap_arena = 0, cap_out = 0, cap_tiles = 0;
+    // pinned staging for the tiny per-chunk read-backs
+    uint32_t* h_tail = nullptr;  // [0] = chunk total bytes, [1] = overflow flag
+};
+
+}  // namespace
+
+struct gofr_engine {
+    int device = 0;
+    int sm_count = 0;
+    ImageHeader hdr;
+    uint8_t* d_image = nullptr;
+    uint32_t image_bytes = 0;
+    // launch geometry
+    uint32_t in_cap = 0, out_stage_cap = 0, smem_bytes = 0;
+    int grid = 0, blocks_per_sm = 0;
+    uint32_t epoch = 0;
+    // resident path scratch
+    unsigned long long* d_state = nullptr;
+    size_t state_tiles = 0;
+    uint32_t* d_flag = nullptr;
+    // host path
+    Slot slots[kSlots];
+    uint32_t chunk = 65536;
+    std::mutex mu;
+    uint64_t launches = 0;
+    // kernel timing (events on the launch stream)
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
+    bool timing_on = true;
+    double timed_ms = 0;
+    uint64_t timed_launches = 0;
+    // tickets
+    struct Pending { gofr_resp_batch* out; int rc; bool open; };
+    std::vector<Pending> pending;
+};
+
+static int configure_geometry(gofr_engine* e, uint32_t in_per_req, uint32_t out_per_req) {
+    e->in_cap = (kServeThreads * in_per_req + 127u) & ~127u;
+    e->out_stage_cap = (kServeThreads * out_per_req + 127u) & ~127u;
+    e->smem_bytes = serve_smem_bytes(e->hdr.hot_bytes, e->in_cap, e->out_stage_cap);
+    if (e->smem_bytes > 227 * 1024) { set_last_error("tile geometry needs %u bytes of shared memory", e->smem_bytes); return GOFR_ERR_CAPACITY; }
+    int g = serve_max_grid(e->smem_bytes, e->device, &e->blocks_per_sm);
+    if (g <= 0) { set_last_error("serve kernel cannot be resident with %u bytes of shared memory", e->smem_bytes); return GOFR_ERR_CUDA; }
+    e->grid = g;
+    return GOFR_OK;
+}
+
+extern "C" {
+
+int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
+    if (!out || !t) return GOFR_ERR_INVALID;
+    const std::vector<uint8_t>& img = gofr_table_image(t);
+    if (img.empty()) return GOFR_ERR_NOT_SEALED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_last_error("no CUDA device: gofr_b200 has no CPU path");
+        return GOFR_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) return GOFR_ERR_INVALID;
+    CUDA_TRY(cudaSetDevice(device));
+    gofr_engine* e = new gofr_engine();
+    e->device = device;
+    memcpy(&e->hdr, img.data(), sizeof(ImageHeader));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    e->sm_count = prop.multiProcessorCount;
+    e->image_bytes = (uint32_t)img.size();
+    CUDA_TRY(cudaMalloc(&e->d_image, img.size() + 64));
+    CUDA_TRY(cudaMemcpy(e->d_image, img.data(), img.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&e->d_flag, 64));
+    CUDA_TRY(cudaMemset(e->d_flag, 0, 64));
+    // default tile geometry: sized from the table's largest fixed response, clamped so that ≥ 2 CTAs fit per SM
+    uint32_t out_per = std::min<uint32_t>(std::max<uint32_t>(e->hdr.max_fixed_len + 224, 320), 640);
+    int rc = configure_geometry(e, 256, out_per);
+    if (rc != GOFR_OK) { delete e; return rc; }
+    for (auto& s : e->slots) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        CUDA_TRY(cudaMallocHost(&s.h_tail, 64));
+    }
+    *out = e;
+    return GOFR_OK;
+}
+
+void gofr_engine_destroy(gofr_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (auto& s : e->slots) {
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.done) cudaEventDestroy(s.done);
+        cudaFree(s.d_desc); cudaFree(s.d_ids); cudaFree(s.d_arena); cudaFree(s.d_out); cudaFree(s.d_off); cudaFree(s.d_meta);
+        cudaFree(s.d_state); cudaFree(s.d_flag);
+        if (s.h_tail) cudaFreeHost(s.h_tail);
+    }
+    for (auto& ev : e->timing) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    cudaFree(e->d_image); cudaFree(e->d_state); cudaFree(e->d_flag);
+    delete e;
+}
+
+int gofr_engine_set_tile(gofr_engine* e, uint32_t in_bytes_per_req, uint32_t out_bytes_per_req) {
+    if (!e || !in_bytes_per_req || !out_bytes_per_req) return GOFR_ERR_INVALID;
+    std::lock_guard<std::mutex> g(e->mu);
+    return configure_geometry(e, in_bytes_per_req, out_bytes_per_req);
+}
+
+int gofr_engine_set_chunk(gofr_engine* e, uint32_t requests_per_chunk) {
+    if (!e || requests_per_chunk == 0) return GOFR_ERR_INVALID;
+    e->chunk = requests_per_chunk;
+    return GOFR_OK;
+}
+
+}  // extern "C"
+
+// one fused launch; `state`/`flag` are scratch owned by the caller of this helper
+static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, const uint8_t* d_arena, uint32_t n,
+                      const char* date29, uint8_t* d_out, uint64_t out_cap, uint32_t* d_off, uint32_t* d_meta,
+                      unsigned long long* d_state, uint32_t* d_flag, cudaStream_t stream) {
+    ServeParams p;
+    memset(&p, 0, sizeof p);
+    p.desc = d_desc; p.ids = d_ids; p.arena = d_arena; p.n = n;
+    p.n_tiles = (n + kServeThreads - 1) / kServeThreads;
+    p.image = e->d_image; p.hot_bytes = e->hdr.hot_bytes;
+    e->epoch = (e->epoch + 1) & 0xFFFFFu;
+    if (e->epoch == 0) e->epoch = 1;  // state words are zero-initialised: epoch 0 never matches
+    p.epoch = e->epoch;
+    p.out = d_out; p.out_cap = out_cap; p.out_off = d_off; p.meta = d_meta;
+    p.tile_state = d_state; p.overflow = d_flag;
+    p.in_cap = e->in_cap; p.out_stage_cap = e->out_stage_cap;
+    memcpy(p.date, date29, 29);
+    int grid = (int)std::min<uint32_t>((uint32_t)e->grid, p.n_tiles);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (e->timing_on) {
+        CUDA_TRY(cudaEventCreate(&ev0));
+        CUDA_TRY(cudaEventCreate(&ev1));
+        CUDA_TRY(cudaEventRecord(ev0, stream));
+    }
+    int rc = launch_serve(p, grid, e->smem_bytes, stream);
+    if (rc != 0) { set_last_error("serve kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
+    if (e->timing_on) {
+        CUDA_TRY(cudaEventRecord(ev1, stream));
+        e->timing.emplace_back(ev0, ev1);
+    }
+    e->launches++;
+    return GOFR_OK;
+}
+
+extern "C" {
+
+int gofr_serve_device(gofr_engine* e, const gofr_req_desc* d_desc, const uint8_t* d_trace_ids, const uint8_t* d_arena,
+                      uint32_t n, const char* date29, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off,
+                      uint32_t* d_meta, void* stream) {
+    if (!e || !date29 || (n && (!d_desc || !d_trace_ids || !d_out || !d_out_off || !d_meta))) return GOFR_ERR_INVALID;
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) {
+        CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st));
+        return GOFR_OK;
+    }
+    size_t tiles = (n + kServeThreads - 1) / kServeThreads;
+    if (tiles > e->state_tiles) {
+        // grow the look-back scratch; stream-ordered w.r.t. earlier launches because cudaFree synchronises
+        cudaFree(e->d_state);
+        e->d_state = nullptr;
+        CUDA_TRY(cudaMalloc(&e->d_state, tiles * 8));
+        CUDA_TRY(cudaMemset(e->d_state, 0, tiles * 8));
+        e->state_tiles = tiles;
+    }
+    return launch_one(e, d_desc, d_trace_ids, d_arena, n, date29, d_out, out_cap, d_out_off, d_meta, e->d_state, e->d_flag, st);
+}
+
+int gofr_engine_overflowed(gofr_engine* e, int* flag_out, int reset) {
+    if (!e || !flag_out) return GOFR_ERR_INVALID;
+    uint32_t f = 0;
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaMemcpy(&f, e->d_flag, 4, cudaMemcpyDeviceToHost));
+    if (reset && f) CUDA_TRY(cudaMemset(e->d_flag, 0, 4));
+    *flag_out = (int)f;
+    return GOFR_OK;
+}
+
+uint64_t gofr_engine_launch_count(const gofr_engine* e) { return e ? e->launches : 0; }
+
+int gofr_engine_kernel_time_ms(gofr_engine* e, double* total_ms, uint64_t* launches, int reset) {
+    if (!e) return GOFR_ERR_INVALID;
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    for (auto& ev : e->timing) {
+        CUDA_TRY(cudaEventSynchronize(ev.second));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        e->timed_ms += ms;
+        e->timed_launches++;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    e->timing.clear();
+    if (total_ms) *total_ms = e->timed_ms;
+    if (launches) *launches = e->timed_launches;
+    if (reset) { e->timed_ms = 0; e->timed_launches = 0; }
+    return GOFR_OK;
+}
+
+int gofr_engine_set_timing(gofr_engine* e, int on) {
+    if (!e) return GOFR_ERR_INVALID;
+    e->timing_on = on != 0;
+    return GOFR_OK;
+}
+
+int gofr_engine_geometry(const gofr_engine* e, uint32_t* grid, uint32_t* blocks_per_sm, uint32_t* smem_bytes,
+                         uint32_t* sm_count) {
+    if (!e) return GOFR_ERR_INVALID;
+    if (grid) *grid = (uint32_t)e->grid;
+    if (blocks_per_sm) *blocks_per_sm = (uint32_t)e->blocks_per_sm;
+    if (smem_bytes) *smem_bytes = e->smem_bytes;
+    if (sm_count) *sm_count = (uint32_t)e->sm_count;
+    return GOFR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-batch path
+// ---------------------------------------------------------------------------------------------------------------
+
+static int grow(void** p, size_t* cap, size_t need, size_t slack) {
+    if (need <= *cap) return GOFR_OK;
+    cudaFree(*p);
+    *p = nullptr;
+    size_t c = need + need / 4 + slack;
+    cudaError_t er = cudaMalloc(p, c);
+    if (er != cudaSuccess) { set_last_error("cudaMalloc(%zu) failed: %s", c, cudaGetErrorString(er)); *cap = 0; return GOFR_ERR_NOMEM; }
+    *cap = c;
+    return GOFR_OK;
+}
+
+// A chunk = contiguous request range [lo, hi) and the arena byte range it covers.
+struct ChunkPlan { uint32_t lo, hi; uint32_t arena_lo, arena_hi; };
+
+int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch* out, gofr_ticket* ticket) {
+    if (!e || !in || !out || !ticket) return GOFR_ERR_INVALID;
+    if (in->n && (!in->desc || !in->trace_ids || !out->out || !out->out_off || !out->meta)) return GOFR_ERR_INVALID;
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    out->out_bytes = 0;
+    const uint32_t n = in->n;
+    int final_rc = GOFR_OK;
+    if (n == 0) { out->out_off[0] = 0; }
+
+    // plan chunks (contiguous request ranges; each chunk's arena range is [first.off, last.end))
+    std::vector<ChunkPlan> plan;
+    for (uint32_t lo = 0; lo < n; lo += e->chunk) {
+        uint32_t hi = std::min<uint32_t>(n, lo + e->chunk);
+        uint32_t alo = 0xFFFFFFFFu, ahi = 0;
+        // descriptors are normally monotonic; scan the ends cheaply (first/last) and verify with min/max
+        for (uint32_t i = lo; i < hi; i++) {
+            const gofr_req_desc& d = in->desc[i];
+            uint32_t dend = ((d.arena_off + d.path_len + d.query_len + 3u) & ~3u) + d.data_len;
+            alo = std::min(alo, d.arena_off);
+            ahi = std::max(ahi, dend);
+        }
+        alo &= ~15u;
+        ahi = (ahi + 15u) & ~15u;
+        if ((uint64_t)ahi > ((in->arena_bytes + 15u) & ~(uint64_t)15u)) { set_last_error("descriptor %u..%u points outside the arena", lo, hi); return GOFR_ERR_INVALID; }
+        plan.push_back({lo, hi, alo, ahi});
+    }
+
+    // ---- straightforward 3-slot software pipeline ----
+    auto ensure = [&](Slot& s, uint32_t cn, size_t abytes, size_t ocap) -> int {
+        int rc;
+        if (cn > s.cap_n) {
+            cudaFree(s.d_desc); cudaFree(s.d_ids); cudaFree(s.d_off); cudaFree(s.d_meta); cudaFree(s.d_state);
+            s.d_desc = s.d_ids = nullptr; s.d_off = s.d_meta = nullptr; s.d_state = nullptr;
+            size_t c = (size_t)cn + cn / 4 + 256;
+            size_t tiles = (c + kServeThreads - 1) / kServeThreads;
+            if (cudaMalloc(&s.d_desc, c * 16) != cudaSuccess || cudaMalloc(&s.d_ids, c * 16) != cudaSuccess ||
+                cudaMalloc(&s.d_off, (c + 1) * 4) != cudaSuccess || cudaMalloc(&s.d_meta, c * 4) != cudaSuccess ||
+                cudaMalloc(&s.d_state, tiles * 8) != cudaSuccess) { set_last_error("cudaMalloc failed for a %zu-request chunk", c); s.cap_n = 0; return GOFR_ERR_NOMEM; }
+            if (cudaMemset(s.d_state, 0, tiles * 8) != cudaSuccess) return GOFR_ERR_CUDA;
+            s.cap_n = c;
+        }
+        if (!s.d_flag) { if (cudaMalloc(&s.d_flag, 64) != cudaSuccess || cudaMemset(s.d_flag, 0, 64) != cudaSuccess) return GOFR_ERR_NOMEM; }
+        if ((rc = grow((void**)&s.d_arena, &s.cap_arena, abytes, 256))) return rc;
+        if ((rc = grow((void**)&s.d_out, &s.cap_out, ocap, 256))) return rc;
+        return GOFR_OK;
+    };
+
+    size_t issued = 0, finished = 0;
+    uint64_t write_pos = 0;
+    const size_t nchunks = plan.size();
+    // issue order == completion order == chunk order; out offsets are rebased on the host as chunks complete
+    while (finished < nchunks) {
+        // keep up to kSlots chunks in flight
+        while (issued < nchunks && issued - finished < (size_t)kSlots) {
+            int si = (int)(issued % kSlots);
+            Slot& s = e->slots[si];
+            const ChunkPlan& c = plan[issued];
+            uint32_t cn = c.hi - c.lo;
+            size_t abytes = (size_t)c.arena_hi - c.arena_lo;
+            size_t ocap = std::min<size_t>((size_t)cn * (e->hdr.max_fixed_len + 64) + 6 * abytes + 4096, 0xFFFFFFF0ull);
+            int rc = ensure(s, cn, abytes, ocap);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(s.d_desc, in->desc + c.lo, (size_t)cn * 16, cudaMemcpyHostToDevice, s.stream));
+            CUDA_TRY(cudaMemcpyAsync(s.d_ids, in->trace_ids + (size_t)c.lo * 16, (size_t)cn * 16, cudaMemcpyHostToDevice, s.stream));
+            if (abytes) {
+                size_t avail = in->arena_bytes > c.arena_lo ? (size_t)in->arena_bytes - c.arena_lo : 0;
+                CUDA_TRY(cudaMemcpyAsync(s.d_arena, in->arena + c.arena_lo, std::min(abytes, avail), cudaMemcpyHostToDevice, s.stream));
+            }
+            // descriptors keep absolute arena offsets: pass a rebased arena pointer
+            rc = launch_one(e, s.d_desc, s.d_ids, s.d_arena - c.arena_lo, cn, in->date, s.d_out, s.cap_out, s.d_off, s.d_meta,
+                            s.d_state, s.d_flag, s.stream);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(out->out_off + c.lo, s.d_off, (size_t)cn * 4, cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(cudaMemcpyAsync(out->meta + c.lo, s.d_meta, (size_t)cn * 4, cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(cudaMemcpyAsync(&s.h_tail[0], s.d_off + cn, 4, cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(cudaMemcpyAsync(&s.h_tail[1], s.d_flag, 4, cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(cudaEventRecord(s.done, s.stream));
+            issued++;
+        }
+        // retire the oldest chunk: learn its size, then pull exactly that many bytes
+        int si = (int)(finished % kSlots);
+        Slot& s = e->slots[si];
+        const ChunkPlan& c = plan[finished];
+        CUDA_TRY(cudaEventSynchronize(s.done));
+        uint32_t total = s.h_tail[0];
+        if (s.h_tail[1]) { CUDA_TRY(cudaMemsetAsync(s.d_flag, 0, 4, s.stream)); final_rc = GOFR_ERR_CAPACITY; set_last_error("device output buffer too small for chunk %zu", finished); total = 0; }
+        if (write_pos + total > out->out_cap) { final_rc = GOFR_ERR_CAPACITY; set_last_error("output capacity %llu too small", (unsigned long long)out->out_cap); total = 0; }
+        if (total) CUDA_TRY(cudaMemcpyAsync(out->out + write_pos, s.d_out, total, cudaMemcpyDeviceToHost, s.stream));
+        // rebase this chunk's offsets while the copy runs
+        if (write_pos) for (uint32_t i = c.lo; i < c.hi; i++) out->out_off[i] += (uint32_t)write_pos;
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        write_pos += total;
+        finished++;
+    }
+    out->out_off[n] = (uint32_t)write_pos;
+    out->out_bytes = write_pos;
+    e->pending.push_back({out, final_rc, true});
+    *ticket = e->pending.size();
+    return GOFR_OK;
+}
+
+int gofr_batch_wait(gofr_engine* e, gofr_ticket ticket) {
+    if (!e || ticket == 0) return GOFR_ERR_INVALID;
+    std::lock_guard<std::mutex> g(e->mu);
+    if (ticket > e->pending.size() || !e->pending[ticket - 1].open) return GOFR_ERR_INVALID;
+    e->pending[ticket - 1].open = false;
+    return e->pending[ticket - 1].rc;
+}
+
+void* gofr_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { set_last_error("cudaMallocHost(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void gofr_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+const char* gofr_last_error(void) { return g_err; }
+uint32_t gofr_abi_version(void) { return GOFR_ABI_VERSION; }
+
+void gofr_format_http_date(int64_t unix_seconds, char out29[29]) {
+    static const char* days[] = {"Sun", "Mon", "Tue", "Wed", "Thu", "Fri", "Sat"};
+    static const char* mons[] = {"Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec"};
+    time_t tt = (time_t)unix_seconds;
+    struct tm g;
+    gmtime_r(&tt, &g);
+    char tmp[48];
+    snprintf(tmp, sizeof tmp, "%s, %02d %s %04d %02d:%02d:%02d GMT", days[g.tm_wday], g.tm_mday, mons[g.tm_mon],
+             g.tm_year + 1900, g.tm_hour, g.tm_min, g.tm_sec);
+    memcpy(out29, tmp, 29);
+}
+
+int gofr_grpc_hello_device(gofr_engine* e, const uint8_t* d_in, const uint32_t* d_in_off, uint32_t n, uint8_t* d_out,
+                           uint64_t out_cap, uint32_t* d_out_off, uint32_t* d_meta, void* stream) {
+    (void)e; (void)d_in; (void)d_in_off; (void)n; (void)d_out; (void)out_cap; (void)d_out_off; (void)d_meta; (void)stream;
+    set_last_error("gofr_grpc_hello_device: not built yet");
+    return GOFR_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

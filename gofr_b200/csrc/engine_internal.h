@@ -1,0 +1,58 @@
+// engine_internal.h — declarations shared by the host-side translation units of libgofr_b200.
+#pragma once
+#include <stdint.h>
+
+#include <vector>
+
+struct gofr_table;
+
+void set_last_error(const char* fmt, ...);
+const std::vector<uint8_t>& gofr_table_image(const gofr_table* t);
+
+namespace gofr {
+
+// Launch parameters of the fused serve kernel (serve_kernel.cu).
+struct ServeParams {
+    const void* desc;        // gofr_req_desc[n]
+    const void* ids;         // uint8[n][16]
+    const uint8_t* arena;
+    uint32_t n;
+    uint32_t n_tiles;
+    const uint8_t* image;    // sealed table in HBM
+    uint32_t hot_bytes;
+    uint32_t epoch;          // look-back generation (state words from older launches read as "not ready")
+    uint8_t* out;
+    uint64_t out_cap;
+    uint32_t* out_off;       // n + 1
+    uint32_t* meta;          // n
+    unsigned long long* tile_state;  // n_tiles
+    uint32_t* overflow;      // set to 1 if out_cap was too small
+    uint32_t in_cap;         // shared-memory staging capacity for request bytes (multiple of 16)
+    uint32_t out_stage_cap;  // shared-memory staging capacity for response bytes (multiple of 16)
+    uint32_t date[8];        // 29-byte IMF-fixdate, zero padded
+};
+
+constexpr int kServeThreads = 128;  // requests per tile = threads per CTA
+
+// Returns dynamic shared memory bytes needed for (hot_bytes, in_cap, out_stage_cap).
+uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap, uint32_t out_stage_cap);
+// cudaError_t as int
+int launch_serve(const ServeParams& p, int grid, uint32_t smem_bytes, void* stream);
+int serve_max_grid(uint32_t smem_bytes, int device, int* blocks_per_sm);
+
+struct GrpcParams {
+    const uint8_t* in;
+    const uint32_t* in_off;
+    uint32_t n;
+    uint32_t n_tiles;
+    uint32_t epoch;
+    uint8_t* out;
+    uint64_t out_cap;
+    uint32_t* out_off;
+    uint32_t* meta;
+    unsigned long long* tile_state;
+    uint32_t* overflow;
+};
+int launch_grpc_hello(const GrpcParams& p, int grid, void* stream);
+
+}  // namespace gofr

@@ -1,0 +1,824 @@
+// serve_device.cuh — per-request device logic of the fused serve kernel.
+//
+// One thread owns one request.  Everything here is straight-line integer/byte work on generic pointers (the tile's
+// request bytes live in shared memory when they fit the staging buffer, in HBM otherwise; the response is written into
+// a shared-memory staging tile, or straight to HBM when a tile is too large).  Three stages per request:
+//   route_request()  — mux cleanPath + Router.Match (gorilla/mux v1.8.1 semantics; pkg/gofr/http/router.go:14,30-33),
+//                      CORS OPTIONS predicate (middleware/cors.go:10-13), handler kind → response program
+//   run_prog<false>  — size pass: exact byte length of header block and body
+//   run_prog<true>   — emit pass: writes the bytes through the word-stream Writer
+// The functions are __host__ __device__ so tests/emu can run the very same code on the CPU per request (test
+// infrastructure only; the product has no CPU path).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/gofr_b200.h"
+#include "table_format.h"
+
+#if defined(__CUDACC__)
+#define GOFR_HD __host__ __device__ __forceinline__
+#define GOFR_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define GOFR_HD inline
+#define GOFR_HD_NOINLINE
+#endif
+
+namespace gofr {
+
+// ---------------------------------------------------------------------------------------------------------------
+// bit helpers
+// ---------------------------------------------------------------------------------------------------------------
+
+// (hi:lo << sh) >> 32, sh in [0,31]
+GOFR_HD uint32_t fsl(uint32_t lo, uint32_t hi, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, sh);
+#else
+    return sh ? (hi << sh) | (lo >> (32 - sh)) : hi;
+#endif
+}
+// low 32 bits of (hi:lo >> sh), sh in [0,31]
+GOFR_HD uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+GOFR_HD int clz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)v);
+#else
+    return v ? __builtin_clzll(v) : 64;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// word-stream writer: appends bytes at an arbitrary byte address using aligned 32-bit stores.
+// `pend` holds the nb (0..3) not-yet-stored bytes in its TOP bytes; a full-word append is one funnel shift + one
+// store.  The first word of a response may be shared with the previous response's tail (packed output), so its
+// leading `head` bytes are never written: that word is stored byte-wise.
+// ---------------------------------------------------------------------------------------------------------------
+struct Writer {
+    uint32_t* wp;
+    uint32_t pend;
+    uint32_t nb;
+    uint32_t head;
+
+    GOFR_HD void init(uint8_t* dst) {
+        uintptr_t a = (uintptr_t)dst;
+        wp = (uint32_t*)(a & ~(uintptr_t)3);
+        nb = (uint32_t)(a & 3);
+        head = nb;
+        pend = 0;
+    }
+    GOFR_HD void store_word(uint32_t x) {
+        if (head) {
+            uint8_t* b = (uint8_t*)wp;
+            for (uint32_t k = head; k < 4; k++) b[k] = (uint8_t)(x >> (8 * k));
+            head = 0;
+        } else {
+            *wp = x;
+        }
+        wp++;
+    }
+    GOFR_HD void put4(uint32_t v) {
+        store_word(fsl(pend, v, nb * 8));
+        pend = v;
+    }
+    // k in 1..3; bytes of v above k are ignored
+    GOFR_HD void putk(uint32_t v, uint32_t k) {
+        uint32_t c = fsl(pend, v, nb * 8);
+        uint32_t t = nb + k;
+        if (t >= 4) {
+            store_word(c);
+            pend = v << (8 * (4 - k));
+            nb = t - 4;
+        } else {
+            pend = c << (8 * (4 - t));
+            nb = t;
+        }
+    }
+    GOFR_HD void put(uint32_t v, uint32_t k) {
+        if (k == 4) put4(v);
+        else if (k) putk(v, k);
+    }
+    GOFR_HD void put1(uint32_t c) { putk(c, 1); }
+    GOFR_HD void finish() {
+        if (nb) {
+            uint32_t c = pend >> (8 * (4 - nb));
+            uint8_t* b = (uint8_t*)wp;
+            for (uint32_t k = head; k < nb; k++) b[k] = (uint8_t)(c >> (8 * k));
+        }
+    }
+};
+
+// Copy len bytes from an aligned word array (literal pool): src is 4-byte aligned and padded.
+GOFR_HD void emit_words(Writer& w, const uint32_t* src, uint32_t len) {
+    uint32_t nw = len >> 2;
+    for (uint32_t i = 0; i < nw; i++) w.put4(src[i]);
+    uint32_t r = len & 3;
+    if (r) w.putk(src[nw], r);
+}
+
+// Copy len bytes from an arbitrary byte address.  Only words that contain at least one source byte are read.
+GOFR_HD void emit_bytes(Writer& w, const uint8_t* p, uint32_t len) {
+    if (!len) return;
+    uintptr_t a = (uintptr_t)p;
+    const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
+    uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t cur = *q;
+    uint32_t have = 4 - (uint32_t)(a & 3);  // source bytes available in cur
+    while (len >= 4) {
+        uint32_t nxt = (sh != 0 || len > 4) ? q[1] : 0;
+        w.put4(fsr(cur, nxt, sh));
+        cur = nxt;
+        q++;
+        len -= 4;
+    }
+    if (len) {
+        uint32_t nxt = len > have ? q[1] : 0;
+        w.putk(fsr(cur, nxt, sh), len);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// encoding/json string contents (Go 1.21, escapeHTML on)
+// ---------------------------------------------------------------------------------------------------------------
+
+// 0x80 in every byte lane that needs the slow path: < 0x20, >= 0x80, or one of " & < > backslash
+GOFR_HD uint32_t json_special_mask(uint32_t x) {
+    uint32_t y = x & 0x7F7F7F7Fu;
+    uint32_t ge20 = y + 0x60606060u;                          // bit7 set iff y >= 0x20
+    uint32_t qa = ((y | 0x04040404u) ^ 0x26262626u) + 0x7F7F7F7Fu;  // bit7 clear iff y in {0x22 '"', 0x26 '&'}
+    uint32_t lg = ((y | 0x02020202u) ^ 0x3E3E3E3Eu) + 0x7F7F7F7Fu;  // bit7 clear iff y in {0x3C '<', 0x3E '>'}
+    uint32_t bs = (y ^ 0x5C5C5C5Cu) + 0x7F7F7F7Fu;                  // bit7 clear iff y == 0x5C
+    return (~(ge20 & qa & lg & bs) | x) & 0x80808080u;
+}
+
+// true if [p, p+len) contains a byte that encoding/json does not copy verbatim
+GOFR_HD bool json_needs_escape(const uint8_t* p, uint32_t len) {
+    if (!len) return false;
+    uintptr_t a = (uintptr_t)p;
+    const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
+    uint32_t lead = (uint32_t)(a & 3);
+    uint32_t bad = 0;
+    // first (possibly partial) word: neutralise bytes before p
+    uint32_t x = *q;
+    uint32_t total = lead + len;  // bytes from q to end
+    if (lead) x = (x & (0xFFFFFFFFu << (8 * lead))) | (0x61616161u >> (8 * (4 - lead)));
+    uint32_t nwords = (total + 3) >> 2;
+    for (uint32_t i = 0; i < nwords; i++) {
+        if (i) x = q[i];
+        if (i == nwords - 1 && (total & 3)) {
+            uint32_t keep = total & 3;
+            x = (x & (0xFFFFFFFFu >> (8 * (4 - keep)))) | (0x61616161u << (8 * keep));
+        }
+        bad |= json_special_mask(x);
+    }
+    return bad != 0;
+}
+
+// Go utf8.DecodeRune acceptance on a plain byte range: length of the well-formed sequence at p (2..4) or 0.
+GOFR_HD uint32_t utf8_len_at(const uint8_t* p, uint32_t n) {
+    uint32_t a = p[0];
+    uint32_t len = (a >= 0xC2 && a <= 0xDF) ? 2u : (a >= 0xE0 && a <= 0xEF) ? 3u : (a >= 0xF0 && a <= 0xF4) ? 4u : 0u;
+    if (!len || n < len) return 0;
+    uint32_t lo = a == 0xE0 ? 0xA0u : a == 0xF0 ? 0x90u : 0x80u;
+    uint32_t hi = a == 0xED ? 0x9Fu : a == 0xF4 ? 0x8Fu : 0xBFu;
+    uint32_t b = p[1];
+    if (b < lo || b > hi) return 0;
+    for (uint32_t k = 2; k < len; k++)
+        if ((p[k] & 0xC0) != 0x80) return 0;
+    return len;
+}
+
+GOFR_HD uint32_t hex_lc(uint32_t v) { return v < 10 ? '0' + v : 'a' + v - 10; }
+
+// Slow path: escape [p, p+len) rune by rune.  EMIT=false only counts.
+template <bool EMIT>
+GOFR_HD uint32_t json_escape_slow(Writer* w, const uint8_t* p, uint32_t len) {
+    uint32_t out = 0;
+    for (uint32_t i = 0; i < len;) {
+        uint32_t c = p[i];
+        if (c < 0x80) {
+            if (c >= 0x20 && c != '"' && c != '\\' && c != '<' && c != '>' && c != '&') {
+                if (EMIT) w->put1(c);
+                out += 1;
+            } else if (c == '"' || c == '\\' || c == '\n' || c == '\r' || c == '\t') {
+                uint32_t e = c == '\n' ? 'n' : c == '\r' ? 'r' : c == '\t' ? 't' : c;
+                if (EMIT) w->putk('\\' | e << 8, 2);
+                out += 2;
+            } else {
+                if (EMIT) { w->put4('\\' | 'u' << 8 | '0' << 16 | '0' << 24); w->putk(hex_lc(c >> 4) | hex_lc(c & 15) << 8, 2); }
+                out += 6;
+            }
+            i++;
+            continue;
+        }
+        uint32_t L = utf8_len_at(p + i, len - i);
+        if (L == 0) {
+            if (EMIT) { w->put4('\\' | 'u' << 8 | 'f' << 16 | 'f' << 24); w->putk('f' | 'd' << 8, 2); }
+            out += 6;
+            i++;
+        } else if (L == 3 && c == 0xE2 && p[i + 1] == 0x80 && (p[i + 2] == 0xA8 || p[i + 2] == 0xA9)) {
+            if (EMIT) { w->put4('\\' | 'u' << 8 | '2' << 16 | '0' << 24); w->putk('2' | (p[i + 2] == 0xA8 ? '8' : '9') << 8, 2); }
+            out += 6;
+            i += 3;
+        } else {
+            if (EMIT) for (uint32_t k = 0; k < L; k++) w->put1(p[i + k]);
+            out += L;
+            i += L;
+        }
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// integers (strconv.AppendInt base 10)
+// ---------------------------------------------------------------------------------------------------------------
+
+GOFR_HD uint32_t ndigits_u32_lt1e8(uint32_t v) {
+    return v < 10000u ? (v < 100u ? (v < 10u ? 1u : 2u) : (v < 1000u ? 3u : 4u))
+                      : (v < 1000000u ? (v < 100000u ? 5u : 6u) : (v < 10000000u ? 7u : 8u));
+}
+GOFR_HD uint32_t ndigits_u64(uint64_t v) {
+    if (v < 100000000ull) return ndigits_u32_lt1e8((uint32_t)v);
+    if (v < 10000000000000000ull) return 8 + ndigits_u32_lt1e8((uint32_t)(v / 100000000ull));
+    return 16 + ndigits_u32_lt1e8((uint32_t)(v / 10000000000000000ull));
+}
+
+// four decimal digits of q (< 10000) as ASCII, most significant digit in the lowest byte
+GOFR_HD uint32_t ascii4(uint32_t q) {
+    uint32_t hi = q / 100, lo = q - hi * 100;
+    uint32_t a = hi / 10, b = hi - a * 10, c = lo / 10, d = lo - c * 10;
+    return (a | b << 8 | c << 16 | d << 24) + 0x30303030u;
+}
+
+template <bool EMIT>
+GOFR_HD uint32_t emit_i64(Writer* w, int64_t sv) {
+    uint64_t v = sv < 0 ? (uint64_t)0 - (uint64_t)sv : (uint64_t)sv;
+    uint32_t nd = ndigits_u64(v);
+    uint32_t total = nd + (sv < 0 ? 1u : 0u);
+    if (!EMIT) return total;
+    if (sv < 0) w->put1('-');
+    // zero-padded 20 digits as five words W[0..4], W[0] most significant
+    uint32_t W[5];
+    uint64_t top = v / 10000000000000000ull;           // < 1845
+    uint64_t rest = v - top * 10000000000000000ull;    // < 1e16
+    uint32_t mid = (uint32_t)(rest / 100000000ull), low = (uint32_t)(rest - (uint64_t)mid * 100000000ull);
+    W[0] = ascii4((uint32_t)top);
+    uint32_t mh = mid / 10000, ml = mid - mh * 10000, lh = low / 10000, ll = low - lh * 10000;
+    W[1] = ascii4(mh); W[2] = ascii4(ml); W[3] = ascii4(lh); W[4] = ascii4(ll);
+    uint32_t skip = 20 - nd;  // leading zeros to drop
+    uint32_t wi = skip >> 2, part = 4 - (skip & 3);
+#pragma unroll
+    for (uint32_t k = 0; k < 5; k++) {
+        if (k == wi) { if (part == 4) w->put4(W[k]); else w->putk(W[k] >> (8 * (4 - part)), part); }
+        else if (k > wi) w->put4(W[k]);
+    }
+    return total;
+}
+
+template <bool EMIT>
+GOFR_HD uint32_t emit_u32(Writer* w, uint32_t v) {
+    uint32_t nd = v < 10 ? 1 : v < 100 ? 2 : v < 1000 ? 3 : v < 10000 ? 4 : v < 100000 ? 5 : v < 1000000 ? 6
+                : v < 10000000 ? 7 : v < 100000000 ? 8 : v < 1000000000 ? 9 : 10;
+    if (!EMIT) return nd;
+    uint32_t hi = v / 100000000u, rest = v - hi * 100000000u;
+    uint32_t W[3] = {ascii4(hi), ascii4(rest / 10000), ascii4(rest % 10000)};
+    uint32_t skip = 12 - nd, wi = skip >> 2, part = 4 - (skip & 3);
+#pragma unroll
+    for (uint32_t k = 0; k < 3; k++) {
+        if (k == wi) { if (part == 4) w->put4(W[k]); else w->putk(W[k] >> (8 * (4 - part)), part); }
+        else if (k > wi) w->put4(W[k]);
+    }
+    return nd;
+}
+
+// 4 id bytes → 8 lower-case hex chars (two words), byte order preserved
+GOFR_HD void hex8(uint32_t x, uint32_t& w0, uint32_t& w1) {
+    // nibble spread: byte b → (b >> 4) in one lane, (b & 15) in the next
+    uint32_t b0 = x & 0xFF, b1 = (x >> 8) & 0xFF, b2 = (x >> 16) & 0xFF, b3 = x >> 24;
+    uint32_t n0 = (b0 >> 4) | (b0 & 15) << 8 | (b1 >> 4) << 16 | (b1 & 15) << 24;
+    uint32_t n1 = (b2 >> 4) | (b2 & 15) << 8 | (b3 >> 4) << 16 | (b3 & 15) << 24;
+    // digit → '0'+d, or 'a'+d-10 when d > 9: add 39 where (d + 6) carries into bit 4
+    uint32_t c0 = ((n0 + 0x06060606u) >> 4) & 0x01010101u, c1 = ((n1 + 0x06060606u) >> 4) & 0x01010101u;
+    w0 = n0 + 0x30303030u + c0 * 39u;
+    w1 = n1 + 0x30303030u + c1 * 39u;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// table view (pointers into the shared-memory copy of the image)
+// ---------------------------------------------------------------------------------------------------------------
+struct TableView {
+    const uint8_t* base;  // hot part (shared memory on the device)
+    const uint8_t* cold;  // file blobs (HBM)
+    const ImageHeader* hdr;
+    const RouteRec* routes;
+    const PieceRec* pieces;
+    const ProgRec* progs;
+    const Op* ops;
+    const SchemaRec* schemas;
+    const uint8_t* lits;  // literal pool; every *_off of a literal is relative to it
+
+    GOFR_HD void bind(const uint8_t* hot, const uint8_t* image_global) {
+        base = hot;
+        hdr = (const ImageHeader*)hot;
+        routes = (const RouteRec*)(hot + hdr->routes_off);
+        pieces = (const PieceRec*)(hot + hdr->pieces_off);
+        progs = (const ProgRec*)(hot + hdr->progs_off);
+        ops = (const Op*)(hot + hdr->ops_off);
+        schemas = (const SchemaRec*)(hot + hdr->schemas_off);
+        lits = hot + hdr->lits_off;
+        cold = image_global + hdr->cold_off;
+    }
+    GOFR_HD const uint32_t* lit_words(uint32_t off) const { return (const uint32_t*)(lits + off); }
+    GOFR_HD const uint8_t* lit_bytes(uint32_t off) const { return lits + off; }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-request context
+// ---------------------------------------------------------------------------------------------------------------
+struct ReqCtx {
+    const uint8_t* path;
+    const uint8_t* query;
+    const uint8_t* data;
+    uint32_t path_len, query_len, data_len;
+    uint32_t method, flags;
+    uint32_t id[4];
+    uint32_t prog;       // program index, 0xFFFF = nothing to emit (GOFR_H_HOST)
+    uint32_t route;      // matched route or GOFR_ROUTE_NONE
+    uint32_t status;
+    uint32_t pv_off, pv_len, pv_flags;  // query value span; flags bit0 found&non-empty, bit1 needs decode/escape
+    uint32_t body_len, total_len;
+    uint32_t slow_mask;  // bit k: k-th OP_STR of the program needs the slow escape path
+    uint32_t def_off, def_len;  // OP_PARAM default (pre-escaped literal)
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// mux cleanPath
+// ---------------------------------------------------------------------------------------------------------------
+
+// cleanPath(p) == p  ⇔  p starts with '/', has no empty / "." / ".." segment (a single trailing slash is kept)
+GOFR_HD bool path_is_clean(const uint8_t* p, uint32_t n) {
+    if (n == 0 || p[0] != '/') return false;
+    uint32_t i = 1;
+    while (i < n) {
+        uint32_t j = i;
+        while (j < n && p[j] != '/') j++;
+        uint32_t len = j - i;
+        if (len == 0) return false;
+        if (p[i] == '.' && (len == 1 || (len == 2 && p[i + 1] == '.'))) return false;
+        i = j + 1;
+    }
+    return true;
+}
+
+GOFR_HD bool url_path_keep(uint32_t c) {
+    return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c == '-' || c == '_' ||
+           c == '.' || c == '~' || c == '$' || c == '&' || c == '+' || c == ',' || c == '/' || c == ':' || c == ';' ||
+           c == '=' || c == '@';
+}
+GOFR_HD uint32_t hex_uc(uint32_t v) { return v < 10 ? '0' + v : 'A' + v - 10; }
+
+template <bool EMIT>
+GOFR_HD uint32_t put_url_escaped(Writer* w, uint32_t c) {
+    if (url_path_keep(c)) { if (EMIT) w->put1(c); return 1; }
+    if (EMIT) w->putk('%' | hex_uc(c >> 4) << 8 | hex_uc(c & 15) << 16, 3);
+    return 3;
+}
+
+// Location of the 301: url.String() with Path = cleanPath(path) → escape(path, encodePath) + "?" + RawQuery.
+// path.Clean's stack is replayed per segment: a normal segment survives iff no later ".." pops it.  Quadratic in the
+// segment count, but only requests that are being redirected come here.
+template <bool EMIT>
+GOFR_HD uint32_t emit_location(Writer* w, const ReqCtx& c) {
+    const uint8_t* p = c.path;
+    uint32_t n = c.path_len;
+    uint32_t out = 0;
+    if (EMIT) w->put1('/');
+    out += 1;
+    uint32_t i = (n && p[0] == '/') ? 1 : 0;  // mux prepends '/' when missing
+    bool any = false;
+    while (i < n) {
+        uint32_t j = i;
+        while (j < n && p[j] != '/') j++;
+        uint32_t len = j - i;
+        bool dot = len == 1 && p[i] == '.';
+        bool dotdot = len == 2 && p[i] == '.' && p[i + 1] == '.';
+        if (len && !dot && !dotdot) {
+            // survives?
+            int depth = 1;
+            uint32_t a = j < n ? j + 1 : n;
+            while (a < n && depth > 0) {
+                uint32_t b = a;
+                while (b < n && p[b] != '/') b++;
+                uint32_t l2 = b - a;
+                if (l2 == 2 && p[a] == '.' && p[a + 1] == '.') depth--;
+                else if (l2 && !(l2 == 1 && p[a] == '.')) depth++;
+                a = b < n ? b + 1 : n;
+            }
+            if (depth > 0) {
+                if (any) { if (EMIT) w->put1('/'); out += 1; }
+                for (uint32_t k = i; k < j; k++) out += put_url_escaped<EMIT>(w, p[k]);
+                any = true;
+            }
+        }
+        i = j < n ? j + 1 : n;
+    }
+    // "put the trailing slash back if necessary": original ends in '/' and the cleaned path is not "/"
+    if (n && p[n - 1] == '/' && any) { if (EMIT) w->put1('/'); out += 1; }
+    if (c.query_len || (c.flags & GOFR_REQ_FORCE_QUERY)) {
+        if (EMIT) { w->put1('?'); emit_bytes(*w, c.query, c.query_len); }
+        out += 1 + c.query_len;
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// route matching
+// ---------------------------------------------------------------------------------------------------------------
+
+GOFR_HD bool cls_has(const uint32_t* cls, uint32_t c) { return (cls[c >> 5] >> (c & 31)) & 1u; }
+
+GOFR_HD bool bytes_equal(const uint8_t* a, const uint8_t* b, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++)
+        if (a[i] != b[i]) return false;
+    return true;
+}
+
+// both 4-byte aligned
+GOFR_HD bool words_equal(const uint32_t* a, const uint32_t* b, uint32_t n) {
+    uint32_t nw = n >> 2, diff = 0;
+    for (uint32_t i = 0; i < nw; i++) diff |= a[i] ^ b[i];
+    uint32_t r = n & 3;
+    if (r) diff |= (a[nw] ^ b[nw]) & (0xFFFFFFFFu >> (8 * (4 - r)));
+    return diff == 0;
+}
+
+// Anchored leftmost-first match of lit0 var0 lit1 var1 ... litN [$]: greedy variables with backtracking — what Go's
+// regexp reports for the regexp mux builds from a path template.
+GOFR_HD bool template_match(const TableView& tv, const RouteRec& R, const uint8_t* p, uint32_t n) {
+    const PieceRec* pc = tv.pieces + R.first_piece;
+    uint32_t np = R.n_pieces;
+    bool prefix = R.flags & RF_PREFIX;
+    uint32_t start[kMaxVars + 1], take[kMaxVars + 1];
+    uint32_t k = 0, pos = 0;
+    for (;;) {
+        // literal k at pos
+        bool ok = n - pos >= pc[k].lit_len && bytes_equal(p + pos, tv.lit_bytes(pc[k].lit_off), pc[k].lit_len);
+        if (ok) {
+            pos += pc[k].lit_len;
+            if (!pc[k].has_var) {
+                if (prefix || pos == n) return true;
+                ok = false;
+            } else {
+                uint32_t run = 0;
+                while (pos + run < n && cls_has(pc[k].cls, p[pos + run])) run++;
+                if (run >= pc[k].min_rep) {
+                    start[k] = pos;
+                    take[k] = run;
+                    pos += run;
+                    k++;
+                    if (k >= np) return prefix || pos == n;  // defensive: templates always end with a literal piece
+                    continue;
+                }
+                ok = false;
+            }
+        }
+        // backtrack: shorten the most recent variable that can still give a byte back
+        for (;;) {
+            if (k == 0) return false;
+            k--;
+            if (take[k] > pc[k].min_rep) {
+                take[k]--;
+                pos = start[k] + take[k];
+                k++;
+                break;
+            }
+        }
+    }
+}
+
+GOFR_HD bool route_path_ok(const TableView& tv, const RouteRec& R, const uint8_t* p, uint32_t n) {
+    if (R.flags & RF_LITERAL) {
+        if (n != R.lit_len) return false;
+        if (((uintptr_t)p & 3) == 0) return words_equal((const uint32_t*)p, tv.lit_words(R.lit_off), n);
+        return bytes_equal(p, tv.lit_bytes(R.lit_off), n);
+    }
+    return template_match(tv, R, p, n);
+}
+
+// Router.Match over routes in registration order with mux v1.8.1's ErrMethodMismatch bookkeeping.
+// Returns route index, or -1 (no route: 404) / -2 (405).
+GOFR_HD int mux_match(const TableView& tv, uint32_t method, const uint8_t* p, uint32_t n) {
+    bool mismatch = false;
+    uint32_t nr = tv.hdr->n_routes;
+    for (uint32_t r = 0; r < nr; r++) {
+        const RouteRec& R = tv.routes[r];
+        if (R.flags & RF_DEAD) continue;
+        bool has_m = R.method != GOFR_M_ANY;
+        bool m_ok = !has_m || (R.method == method && method != GOFR_M_OTHER);
+        // evaluation order inside Route.Match: method matcher, then path matcher; any matcher that succeeds clears
+        // a stale ErrMethodMismatch; a failing path matcher returns without touching it
+        if (has_m && m_ok) mismatch = false;
+        bool p_ok = route_path_ok(tv, R, p, n);
+        if (!p_ok) continue;
+        mismatch = false;
+        if (!m_ok) { mismatch = true; continue; }
+        return (int)r;
+    }
+    return mismatch ? -2 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// query parameter: req.URL.Query().Get(key)  (pkg/gofr/http/request.go:28-30 → url.ParseQuery)
+// ---------------------------------------------------------------------------------------------------------------
+
+GOFR_HD int hexval(uint32_t c) {
+    if (c >= '0' && c <= '9') return (int)c - '0';
+    if (c >= 'a' && c <= 'f') return (int)c - 'a' + 10;
+    if (c >= 'A' && c <= 'F') return (int)c - 'A' + 10;
+    return -1;
+}
+
+// does QueryUnescape(raw[0..n)) succeed and equal key?   (an invalid %-escape drops the pair)
+GOFR_HD bool query_key_equals(const uint8_t* raw, uint32_t n, const uint8_t* key, uint32_t kn) {
+    uint32_t j = 0;
+    bool eq = true;
+    for (uint32_t i = 0; i < n;) {
+        uint32_t c = raw[i];
+        if (c == '%') {
+            if (i + 2 >= n) return false;
+            int h = hexval(raw[i + 1]), l = hexval(raw[i + 2]);
+            if (h < 0 || l < 0) return false;
+            c = (uint32_t)(h << 4 | l);
+            i += 3;
+        } else {
+            if (c == '+') c = ' ';
+            i++;
+        }
+        if (j >= kn || key[j] != c) eq = false;
+        j++;
+    }
+    return eq && j == kn;
+}
+
+// bit0: all %-escapes valid; bit1: contains '%' or '+' or a byte encoding/json would not copy verbatim
+GOFR_HD uint32_t query_value_scan(const uint8_t* v, uint32_t n) {
+    uint32_t special = 0;
+    for (uint32_t i = 0; i < n;) {
+        uint32_t c = v[i];
+        if (c == '%') {
+            if (i + 2 >= n || hexval(v[i + 1]) < 0 || hexval(v[i + 2]) < 0) return 0;
+            special = 2;
+            i += 3;
+            continue;
+        }
+        if (c == '+' || c < 0x20 || c >= 0x80 || c == '"' || c == '\\' || c == '<' || c == '>' || c == '&') special = 2;
+        i++;
+    }
+    return 1 | special;
+}
+
+GOFR_HD void find_param(ReqCtx& c, const uint8_t* key, uint32_t kn) {
+    const uint8_t* q = c.query;
+    uint32_t qn = c.query_len;
+    c.pv_flags = 0;
+    c.pv_off = c.pv_len = 0;
+    uint32_t i = 0;
+    while (i < qn) {
+        uint32_t j = i, eq = 0xFFFFFFFFu;
+        bool semi = false;
+        while (j < qn && q[j] != '&') {
+            uint32_t ch = q[j];
+            if (ch == ';') semi = true;
+            if (ch == '=' && eq == 0xFFFFFFFFu) eq = j;
+            j++;
+        }
+        uint32_t ps = i, pe = j;
+        i = j < qn ? j + 1 : j;
+        if (semi || pe == ps) continue;
+        uint32_t kend = eq == 0xFFFFFFFFu ? pe : eq;
+        if (!query_key_equals(q + ps, kend - ps, key, kn)) continue;
+        uint32_t vs = eq == 0xFFFFFFFFu ? pe : eq + 1;
+        uint32_t f = query_value_scan(q + vs, pe - vs);
+        if (!(f & 1)) continue;
+        // first successfully parsed pair for this key decides; an empty value makes the handler use its default
+        if (pe > vs) { c.pv_off = vs; c.pv_len = pe - vs; c.pv_flags = 1 | (f & 2); }
+        return;
+    }
+}
+
+// QueryUnescape + encoding/json escape of the value, rune by rune over the DECODED bytes
+template <bool EMIT>
+GOFR_HD uint32_t emit_param_slow(Writer* w, const uint8_t* v, uint32_t n) {
+    uint32_t out = 0;
+    uint32_t i = 0;
+    // decode one byte at raw position i → (byte, next position)
+    auto dec = [&](uint32_t at, uint32_t& next) -> uint32_t {
+        uint32_t c = v[at];
+        if (c == '%') { next = at + 3; return (uint32_t)(hexval(v[at + 1]) << 4 | hexval(v[at + 2])); }
+        next = at + 1;
+        return c == '+' ? ' ' : c;
+    };
+    while (i < n) {
+        uint32_t nx;
+        uint32_t c = dec(i, nx);
+        if (c < 0x80) {
+            uint8_t one = (uint8_t)c;
+            out += json_escape_slow<EMIT>(w, &one, 1);
+            i = nx;
+            continue;
+        }
+        // gather up to 4 decoded bytes to validate the UTF-8 sequence
+        uint8_t buf[4];
+        uint32_t pos[5];
+        uint32_t cnt = 0, at = i;
+        while (cnt < 4 && at < n) { uint32_t nn; buf[cnt] = (uint8_t)dec(at, nn); pos[cnt] = at; at = nn; cnt++; }
+        pos[cnt] = at;
+        uint32_t L = utf8_len_at(buf, cnt);
+        if (L == 0) { out += json_escape_slow<EMIT>(w, buf, 1); i = pos[1]; }
+        else { out += json_escape_slow<EMIT>(w, buf, L); i = pos[L]; }
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stage 1: route + handler kind → program
+// ---------------------------------------------------------------------------------------------------------------
+GOFR_HD void route_request(const TableView& tv, ReqCtx& c) {
+    const ImageHeader& H = *tv.hdr;
+    bool head = c.method == GOFR_M_HEAD;
+    c.route = GOFR_ROUTE_NONE;
+    c.pv_flags = 0;
+    c.slow_mask = 0;
+    c.def_off = c.def_len = 0;
+    if (!path_is_clean(c.path, c.path_len)) {  // mux redirects before routing and before any middleware
+        c.prog = head ? H.prog_301_head : H.prog_301;
+        return;
+    }
+    int m = mux_match(tv, c.method, c.path, c.path_len);
+    if (m == -2) { c.prog = head ? H.prog_405_head : H.prog_405; return; }
+    if (m == -1) { c.prog = H.prog_404; return; }
+    c.route = (uint32_t)m;
+    const RouteRec& R = tv.routes[m];
+    if (c.method == GOFR_M_OPTIONS) { c.prog = H.prog_options; return; }  // middleware/cors.go:10-13
+    c.prog = R.prog_ok;
+    if (R.hkind == GOFR_H_PARAM_FORMAT) {
+        find_param(c, tv.lit_bytes(R.key_off), R.key_len);
+        c.def_off = R.def_off;
+        c.def_len = R.def_len;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stages 2+3: interpret the response program.  EMIT=false: compute c.body_len / c.total_len / c.slow_mask and
+// validate the row (returns false → caller switches to the panic program).  EMIT=true: write the bytes.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool EMIT>
+GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w, const uint32_t* date_words) {
+    const ProgRec& P = tv.progs[c.prog];
+    const Op* ops = tv.ops + P.first_op;
+    bool head = c.method == GOFR_M_HEAD;
+    const uint32_t* row = (const uint32_t*)c.data;
+    uint32_t row_words = c.data_len >> 2;
+    uint32_t str_cursor = 0;  // byte offset of the next string in the row's string area
+    uint32_t str_base = 0;
+    if (P.flags & PF_NEEDS_ROW) {
+        const SchemaRec& S = tv.schemas[tv.routes[c.route].schema];
+        str_base = (uint32_t)S.fixed_words * 4;
+        if (!EMIT && str_base > c.data_len) return false;
+    }
+    uint32_t hdr_dyn = 0, body_dyn = 0, str_idx = 0;
+    bool first = true, skip = false;
+    for (uint32_t oi = 0; oi < P.n_ops; oi++) {
+        const Op& o = ops[oi];
+        bool body = o.flags & OPF_BODY;
+        if (EMIT && head && body) break;  // chunkWriter eats the body of a HEAD response; body ops come last
+        uint32_t produced = 0;
+        bool governed = o.flags & OPF_VALUE_OF_KEY;
+        switch (o.code) {
+            case OP_LIT:
+                if (governed) {
+                    if (!skip) { if (EMIT) emit_words(*w, tv.lit_words(o.off), o.len); produced = o.len; }
+                } else if (EMIT) emit_words(*w, tv.lit_words(o.off), o.len);
+                break;
+            case OP_HEXID:
+                if (EMIT) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { uint32_t a, b; hex8(c.id[k], a, b); w->put4(a); w->put4(b); }
+                }
+                break;
+            case OP_DATE:
+                if (EMIT) {
+#pragma unroll
+                    for (int k = 0; k < 7; k++) w->put4(date_words[k]);
+                    w->putk(date_words[7], 1);
+                }
+                break;
+            case OP_CLEN:
+                if (EMIT) emit_u32<true>(w, c.body_len);
+                break;  // sized after the loop
+            case OP_KEY: {
+                (void)row_words;
+                bool empty = false;
+                if (o.flags & OPF_OMITEMPTY) {
+                    uint32_t wv = row[o.aux];
+                    if (o.kind == GOFR_F_INT64 || o.kind == 5) empty = (wv | row[o.aux + 1]) == 0;
+                    else empty = wv == 0;
+                }
+                skip = empty;
+                if (!empty) {
+                    if (!first) { if (EMIT) w->put1(','); produced += 1; }
+                    first = false;
+                    if (EMIT) emit_words(*w, tv.lit_words(o.off), o.len);
+                    produced += o.len;
+                }
+                break;
+            }
+            case OP_I64: {
+                int64_t v = (int64_t)((uint64_t)row[o.off] | (uint64_t)row[o.off + 1] << 32);
+                if (!(governed && skip)) produced = emit_i64<EMIT>(w, v);
+                break;
+            }
+            case OP_I32:
+                if (!(governed && skip)) produced = emit_i64<EMIT>(w, (int64_t)(int32_t)row[o.off]);
+                break;
+            case OP_BOOL:
+                if (!(governed && skip)) {
+                    bool t = row[o.off] != 0;
+                    if (EMIT) { if (t) w->put4('t' | 'r' << 8 | 'u' << 16 | 'e' << 24); else { w->put4('f' | 'a' << 8 | 'l' << 16 | 's' << 24); w->put1('e'); } }
+                    produced = t ? 4 : 5;
+                }
+                break;
+            case OP_STR: {
+                uint32_t len = row[o.off];
+                if (!EMIT && (str_base + str_cursor + (uint64_t)len > c.data_len)) return false;
+                const uint8_t* s = c.data + str_base + str_cursor;
+                str_cursor += len;
+                uint32_t bit = 1u << (str_idx & 31);
+                str_idx++;
+                if (governed && skip) break;
+                if (!EMIT) {
+                    if (json_needs_escape(s, len)) { c.slow_mask |= bit; produced = json_escape_slow<false>(nullptr, s, len); }
+                    else produced = len;
+                } else {
+                    if (c.slow_mask & bit) json_escape_slow<true>(w, s, len);
+                    else emit_bytes(*w, s, len);
+                }
+                break;
+            }
+            case OP_PARAM:
+                if (c.pv_flags & 1) {
+                    const uint8_t* v = c.query + c.pv_off;
+                    if (c.pv_flags & 2) produced = emit_param_slow<EMIT>(w, v, c.pv_len);
+                    else { if (EMIT) emit_bytes(*w, v, c.pv_len); produced = c.pv_len; }
+                } else {
+                    if (EMIT) emit_words(*w, tv.lit_words(c.def_off), c.def_len);
+                    produced = c.def_len;
+                }
+                break;
+            case OP_LOCATION: produced = emit_location<EMIT>(w, c); break;
+            case OP_BLOB:
+                if (EMIT) emit_bytes(*w, tv.cold + o.off, o.len);
+                break;
+            default: break;  // OP_ERRMSG is handled by the Bind stage (bind_device.cuh)
+        }
+        if (body) body_dyn += produced; else hdr_dyn += produced;
+    }
+    if (!EMIT) {
+        c.body_len = P.body_fixed + body_dyn;
+        uint32_t hl = P.hdr_fixed + hdr_dyn;
+        if (P.flags & PF_HAS_CLEN) hl += emit_u32<false>(nullptr, c.body_len);
+        c.total_len = hl + (head ? 0 : c.body_len);
+        c.status = P.status;
+    }
+    return true;
+}
+
+// Full size stage for one request: route, size; a malformed handler-result row is answered like a handler panic.
+GOFR_HD void size_request(const TableView& tv, ReqCtx& c) {
+    route_request(tv, c);
+    if (c.prog == 0xFFFF) {  // GOFR_H_HOST: nothing to emit, status 0 = pending on the host
+        c.body_len = c.total_len = 0;
+        c.status = 0;
+        return;
+    }
+    if (!run_prog<false>(tv, c, nullptr, nullptr)) {
+        c.prog = tv.hdr->prog_panic;
+        c.slow_mask = 0;
+        run_prog<false>(tv, c, nullptr, nullptr);
+    }
+}
+
+GOFR_HD void emit_request(const TableView& tv, ReqCtx& c, uint8_t* dst, const uint32_t* date_words) {
+    if (c.total_len == 0) return;
+    Writer w;
+    w.init(dst);
+    run_prog<true>(tv, c, &w, date_words);
+    w.finish();
+}
+
+}  // namespace gofr

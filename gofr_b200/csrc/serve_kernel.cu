@@ -1,0 +1,299 @@
+// serve_kernel.cu — the fused, persistent serve kernel for sm_100a.
+//
+// One launch replaces, for a whole batch, what the reference does per request on a goroutine:
+// mux.Router.ServeHTTP → Tracer/Logging/CORS → handler.ServeHTTP → Responder.Respond → net/http framing
+// (pkg/gofr/http/router.go:14, middleware/*.go, pkg/gofr/handler.go:32-36, pkg/gofr/http/responder.go:19-41).
+//
+// Execution model (HBM-bound integer/byte work; no tensor cores):
+//   * grid = co-resident CTAs only (SMs × occupancy); CTA b walks tiles b, b+grid, … of 128 requests, one thread per
+//     request;
+//   * the tile's descriptors and trace ids are read with coalesced 16-byte loads; its contiguous arena byte range is
+//     pulled into shared memory with ONE TMA bulk copy (cp.async.bulk.shared::cluster.global + mbarrier) when it
+//     fits, so all per-request byte walking hits shared memory, not HBM;
+//   * responses are packed back-to-back in request order: sizes are scanned inside the CTA and chained across CTAs
+//     with a decoupled look-back (single pass — inputs are read from HBM exactly once);
+//   * each thread writes its response into a shared-memory staging tile with aligned 32-bit stores through a
+//     funnel-shift word stream (serve_device.cuh); the tile leaves for HBM as ONE TMA bulk store
+//     (cp.async.bulk.global.shared::cta) plus ≤30 edge bytes, so HBM sees only full-line writes.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "engine_internal.h"
+#include "serve_device.cuh"
+
+namespace gofr {
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// global → shared bulk copy (TMA, 1-D): dst/src 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_global, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst_smem)),
+                 "l"(src_global), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+// shared → global bulk store (TMA, 1-D)
+__device__ __forceinline__ void bulk_s2g(void* dst_global, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(smem_addr(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// decoupled look-back over tile totals.  state = epoch(20) | flag(2) | value(42); flag 1 = tile total, 2 = inclusive
+// prefix.  Words written by earlier launches carry an older epoch and read as "not ready".
+// ---------------------------------------------------------------------------------------------------------------
+constexpr unsigned long long kValMask = (1ull << 42) - 1;
+__device__ __forceinline__ unsigned long long pack_state(uint32_t epoch, uint32_t flag, unsigned long long v) {
+    return ((unsigned long long)(epoch & 0xFFFFFu) << 44) | ((unsigned long long)flag << 42) | (v & kValMask);
+}
+
+// Called by warp 0.  Returns the exclusive prefix of `tile` (valid in every lane).
+__device__ __forceinline__ unsigned long long lookback(unsigned long long* state, uint32_t epoch, uint32_t tile,
+                                                       unsigned long long total, uint32_t lane) {
+    if (lane == 0) st_state(&state[tile], pack_state(epoch, tile == 0 ? 2 : 1, total));
+    unsigned long long excl = 0;
+    if (tile > 0) {
+        long long base = (long long)tile - 1;
+        for (;;) {
+            long long t = base - (long long)lane;
+            unsigned long long s = t >= 0 ? ld_state(&state[t]) : pack_state(epoch, 2, 0);
+            uint32_t flag = (uint32_t)(s >> 42) & 3u;
+            bool ready = (uint32_t)(s >> 44) == (epoch & 0xFFFFFu) && flag != 0;
+            uint32_t not_ready = __ballot_sync(0xFFFFFFFFu, !ready);
+            uint32_t is_p = __ballot_sync(0xFFFFFFFFu, ready && flag == 2);
+            uint32_t upto = is_p ? (uint32_t)__ffs((int)is_p) - 1 : 31u;  // lanes 0..upto contribute
+            uint32_t need = upto == 31 ? 0xFFFFFFFFu : ((1u << (upto + 1)) - 1);
+            if (not_ready & need) { __nanosleep(40); continue; }
+            unsigned long long v = (lane <= upto) ? (s & kValMask) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            excl += v;
+            if (is_p) break;
+            base -= 32;
+        }
+        if (lane == 0) st_state(&state[tile], pack_state(epoch, 2, excl + total));
+    }
+    return excl;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int T = kServeThreads;
+constexpr int NW = T / 32;
+
+struct TileShared {
+    uint64_t bar;  // mbarrier for the arena bulk load
+    uint32_t warp_sum[NW];
+    uint32_t warp_lo[NW], warp_hi[NW];
+    unsigned long long tile_base;
+    uint32_t tile_total;
+    uint32_t in_lo, in_hi;
+    uint32_t date[8];
+};
+
+__global__ void __launch_bounds__(T) serve_kernel(const ServeParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ TileShared sh;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* tbl = smem;
+    uint8_t* in_stage = smem + ((p.hot_bytes + 127u) & ~127u);
+    uint8_t* out_stage = in_stage + p.in_cap + 128;
+
+    // table → shared memory (once per CTA)
+    {
+        const uint4* src = (const uint4*)p.image;
+        uint4* dst = (uint4*)tbl;
+        for (uint32_t i = tid; i < p.hot_bytes / 16; i += T) dst[i] = src[i];
+        if (tid < 8) sh.date[tid] = p.date[tid];
+        if (tid == 0) {
+            mbar_init(&sh.bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    __syncthreads();
+    TableView tv;
+    tv.bind(tbl, p.image);
+
+    uint32_t parity = 0;
+    bool store_pending = false;
+
+    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const uint32_t i = tile * T + tid;
+        const bool valid = i < p.n;
+        uint4 d = make_uint4(0, 0, 0, 0), id = make_uint4(0, 0, 0, 0);
+        if (valid) {
+            d = __ldg((const uint4*)p.desc + i);
+            id = __ldg((const uint4*)p.ids + i);
+        }
+        const uint32_t arena_off = d.x, path_len = d.y & 0xFFFFu, query_len = d.y >> 16, data_len = d.z;
+        const uint32_t data_off = (arena_off + path_len + query_len + 3u) & ~3u;
+        const uint32_t end = data_off + data_len;
+
+        // ---- the tile's arena byte range ----
+        uint32_t lo = valid ? arena_off : 0xFFFFFFFFu, hi = valid ? end : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+        }
+        if (lane == 0) { sh.warp_lo[warp] = lo; sh.warp_hi[warp] = hi; }
+        __syncthreads();  // also: every thread is done reading the previous tile's in_stage
+        if (tid == 0) {
+            uint32_t l = sh.warp_lo[0], h = sh.warp_hi[0];
+#pragma unroll
+            for (int w = 1; w < NW; w++) { l = min(l, sh.warp_lo[w]); h = max(h, sh.warp_hi[w]); }
+            l &= ~15u;
+            h = (h + 15u) & ~15u;
+            sh.in_lo = l;
+            sh.in_hi = h;
+            if (h > l && h - l <= p.in_cap) {
+                mbar_expect_tx(&sh.bar, h - l);
+                bulk_g2s(in_stage, p.arena + l, h - l, &sh.bar);
+            }
+        }
+        __syncthreads();
+        const uint32_t in_lo = sh.in_lo, in_hi = sh.in_hi;
+        const bool in_staged = in_hi > in_lo && in_hi - in_lo <= p.in_cap;
+        const uint8_t* abase = p.arena;
+        if (in_staged) {
+            mbar_wait(&sh.bar, parity);
+            parity ^= 1;
+            abase = in_stage - in_lo;  // abase + arena_off lands in the staged copy
+        }
+
+        // ---- stage 1+2: route, size ----
+        ReqCtx c;
+        c.path = abase + arena_off;
+        c.query = c.path + path_len;
+        c.data = abase + data_off;
+        c.path_len = path_len; c.query_len = query_len; c.data_len = data_len;
+        c.method = d.w & 0xFFu;
+        c.flags = (d.w >> 8) & 0xFFu;
+        c.id[0] = id.x; c.id[1] = id.y; c.id[2] = id.z; c.id[3] = id.w;
+        c.total_len = 0; c.body_len = 0; c.status = 0; c.route = GOFR_ROUTE_NONE; c.prog = 0xFFFF;
+        if (valid) size_request(tv, c);
+
+        // ---- block scan of response sizes ----
+        uint32_t incl = c.total_len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (uint32_t)o) incl += v;
+        }
+        if (lane == 31) sh.warp_sum[warp] = incl;
+        __syncthreads();
+        uint32_t warp_excl = 0, tile_total = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            uint32_t s = sh.warp_sum[w];
+            if ((uint32_t)w < warp) warp_excl += s;
+            tile_total += s;
+        }
+        const uint32_t excl = warp_excl + incl - c.total_len;
+
+        // ---- chain tiles (warp 0), and make sure the previous bulk store has drained the staging tile ----
+        if (warp == 0) {
+            unsigned long long base = lookback(p.tile_state, p.epoch, tile, tile_total, lane);
+            if (lane == 0) {
+                sh.tile_base = base;
+                if (store_pending) bulk_wait_read();
+            }
+        }
+        __syncthreads();
+        const unsigned long long tile_base = sh.tile_base;
+        const bool fits = tile_base + tile_total <= p.out_cap && tile_base + tile_total <= 0xFFFFFFFFull;
+        if (!fits && tid == 0) atomicExch(p.overflow, 1u);
+        if (valid) {
+            p.out_off[i] = (uint32_t)(tile_base + excl);
+            p.meta[i] = c.status | (c.route << 16);
+            if (i == p.n - 1) p.out_off[p.n] = (uint32_t)(tile_base + excl + c.total_len);
+        }
+
+        // ---- stage 3: emit ----
+        const uint32_t mis = (uint32_t)tile_base & 15u;
+        const bool out_staged = tile_total + 16u <= p.out_stage_cap;
+        if (fits && valid && c.total_len) {
+            uint8_t* dst = out_staged ? out_stage + mis + excl : p.out + tile_base + excl;
+            emit_request(tv, c, dst, sh.date);
+        }
+        if (fits && out_staged && tile_total) {
+            fence_proxy_async();  // my generic-proxy writes → visible to the TMA engine
+            __syncthreads();
+            const unsigned long long g0 = tile_base, g1 = tile_base + tile_total;
+            const unsigned long long a0 = (g0 + 15ull) & ~15ull, a1 = g1 & ~15ull;
+            if (tid == 0 && a1 > a0) {
+                bulk_s2g(p.out + a0, out_stage + mis + (uint32_t)(a0 - g0), (uint32_t)(a1 - a0));
+                bulk_commit();
+            }
+            store_pending = true;  // uniform; only thread 0 waits on it
+            // edges: up to 15 bytes before a0 and after a1
+            const unsigned long long head_end = a0 < g1 ? a0 : g1;
+            if (tid < 16) {
+                unsigned long long g = g0 + tid;
+                if (g < head_end) p.out[g] = out_stage[mis + tid];
+            } else if (tid < 32 && a1 >= a0) {
+                unsigned long long g = a1 + (tid - 16);
+                if (g >= head_end && g < g1) p.out[g] = out_stage[mis + (uint32_t)(g - g0)];
+            }
+        }
+        // the next iteration's first __syncthreads orders these shared-memory reads before any overwrite
+    }
+    if (tid == 0) bulk_wait_all();
+}
+
+uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap, uint32_t out_stage_cap) {
+    return ((hot_bytes + 127u) & ~127u) + in_cap + 128 + out_stage_cap + 64;
+}
+
+int serve_max_grid(uint32_t smem_bytes, int device, int* blocks_per_sm) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(serve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, serve_kernel, T, smem_bytes) != cudaSuccess) return -1;
+    if (blocks_per_sm) *blocks_per_sm = nb;
+    return nb * prop.multiProcessorCount;
+}
+
+int launch_serve(const ServeParams& p, int grid, uint32_t smem_bytes, void* stream) {
+    serve_kernel<<<grid, T, smem_bytes, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace gofr

@@ -1,0 +1,883 @@
+// table_build.cpp — host side of the route table: registration → sealed image.
+//
+// Mirrors the registration half of the reference: Router.Add (pkg/gofr/http/router.go:30-33) appends
+// [methodMatcher, pathRegexp] routes in call order; App.Run (pkg/gofr/gofr.go:102-107) appends health, favicon and
+// the PathPrefix("/") catch-all; after Run nothing mutates the table.  gofr_table_seal "compiles" every route into a
+// response program (table_format.h) so the device never interprets Go semantics at request time: status line, the
+// sorted header block net/http 1.21 writes, the envelope of Responder.Respond (pkg/gofr/http/responder.go:19-41) and
+// the struct keys of encoding/json are all folded into literals; only per-request values remain as ops.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gofr_b200.h"
+#include "engine_internal.h"
+#include "table_format.h"
+
+namespace gofr {
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------------
+
+// encoding/json string escaping with escapeHTML=true, Go 1.21 (no \b \f short forms).  Driven by a class table so it
+// shares no structure with the test oracle.  Returns the escaped contents WITHOUT the surrounding quotes.
+static const uint8_t* escape_class_table() {
+    // 0 = copy, 1 = \uXXXX, 2 = backslash + char, 3 = \n, 4 = \r, 5 = \t, 6 = multi-byte lead / invalid
+    static uint8_t t[256];
+    static bool init = false;
+    if (!init) {
+        for (int c = 0; c < 256; c++) t[c] = c < 0x20 ? 1 : (c >= 0x80 ? 6 : 0);
+        t['"'] = 2; t['\\'] = 2; t['\n'] = 3; t['\r'] = 4; t['\t'] = 5;
+        t['<'] = 1; t['>'] = 1; t['&'] = 1;
+        init = true;
+    }
+    return t;
+}
+
+// length of the well-formed UTF-8 sequence starting at s (Go utf8 acceptance), 0 if ill-formed
+static int utf8_seq_len(const uint8_t* s, size_t n) {
+    uint8_t a = s[0];
+    int len = a >= 0xC2 && a <= 0xDF ? 2 : a >= 0xE0 && a <= 0xEF ? 3 : a >= 0xF0 && a <= 0xF4 ? 4 : 0;
+    if (!len || n < (size_t)len) return 0;
+    uint8_t lo = a == 0xE0 ? 0xA0 : a == 0xF0 ? 0x90 : 0x80;
+    uint8_t hi = a == 0xED ? 0x9F : a == 0xF4 ? 0x8F : 0xBF;
+    if (s[1] < lo || s[1] > hi) return 0;
+    for (int k = 2; k < len; k++)
+        if ((s[k] & 0xC0) != 0x80) return 0;
+    return len;
+}
+
+std::string json_escape_go(const std::string& in) {
+    static const char* hex = "0123456789abcdef";
+    const uint8_t* cls = escape_class_table();
+    std::string out;
+    out.reserve(in.size() + 8);
+    const uint8_t* s = (const uint8_t*)in.data();
+    size_t n = in.size();
+    for (size_t i = 0; i < n;) {
+        uint8_t c = s[i];
+        switch (cls[c]) {
+            case 0: out.push_back((char)c); i++; break;
+            case 1: out += "\\u00"; out.push_back(hex[c >> 4]); out.push_back(hex[c & 15]); i++; break;
+            case 2: out.push_back('\\'); out.push_back((char)c); i++; break;
+            case 3: out += "\\n"; i++; break;
+            case 4: out += "\\r"; i++; break;
+            case 5: out += "\\t"; i++; break;
+            default: {
+                int L = utf8_seq_len(s + i, n - i);
+                if (L == 0) { out += "\\ufffd"; i++; break; }
+                if (L == 3 && s[i] == 0xE2 && s[i + 1] == 0x80 && (s[i + 2] == 0xA8 || s[i + 2] == 0xA9)) {
+                    out += s[i + 2] == 0xA8 ? "\\u2028" : "\\u2029";
+                } else {
+                    out.append((const char*)s + i, (size_t)L);
+                }
+                i += (size_t)L;
+            }
+        }
+    }
+    return out;
+}
+
+static bool valid_utf8(const std::string& s) {
+    const uint8_t* p = (const uint8_t*)s.data();
+    for (size_t i = 0; i < s.size();) {
+        if (p[i] < 0x80) { i++; continue; }
+        int L = utf8_seq_len(p + i, s.size() - i);
+        if (!L) return false;
+        i += (size_t)L;
+    }
+    return true;
+}
+
+static const char* status_text(int code) {
+    switch (code) {
+        case 200: return "OK";
+        case 301: return "Moved Permanently";
+        case 404: return "Not Found";
+        case 405: return "Method Not Allowed";
+        case 500: return "Internal Server Error";
+    }
+    return "";
+}
+
+// http.DetectContentType for static file blobs (seal time).  Signature list restated from net/http's sniffing
+// algorithm; covers the formats a static asset route serves.
+static std::string sniff_content_type(const std::string& blob) {
+    std::string d = blob.substr(0, 512);
+    auto starts = [&](const char* sig, size_t n) { return d.size() >= n && memcmp(d.data(), sig, n) == 0; };
+    size_t ws = 0;
+    while (ws < d.size() && strchr("\t\n\x0c\r ", d[ws]) && d[ws]) ws++;
+    static const char* html[] = {"<!DOCTYPE HTML", "<HTML", "<HEAD", "<SCRIPT", "<IFRAME", "<H1", "<DIV", "<FONT", "<TABLE",
+                                 "<A", "<STYLE", "<TITLE", "<B", "<BODY", "<BR", "<P", "<!--"};
+    for (const char* sig : html) {
+        size_t L = strlen(sig);
+        if (d.size() - ws < L + 1) continue;
+        bool ok = true;
+        for (size_t q = 0; q < L && ok; q++) {
+            uint8_t c = (uint8_t)d[ws + q], s = (uint8_t)sig[q];
+            if (s >= 'A' && s <= 'Z') c &= 0xDF;
+            ok = c == s;
+        }
+        if (ok && (d[ws + L] == ' ' || d[ws + L] == '>')) return "text/html; charset=utf-8";
+    }
+    if (d.size() - ws >= 5 && memcmp(d.data() + ws, "<?xml", 5) == 0) return "text/xml; charset=utf-8";
+    if (starts("%PDF-", 5)) return "application/pdf";
+    if (starts("%!PS-Adobe-", 11)) return "application/postscript";
+    if (d.size() >= 4 && (uint8_t)d[0] == 0xFE && (uint8_t)d[1] == 0xFF) return "text/plain; charset=utf-16be";
+    if (d.size() >= 4 && (uint8_t)d[0] == 0xFF && (uint8_t)d[1] == 0xFE) return "text/plain; charset=utf-16le";
+    if (d.size() >= 4 && (uint8_t)d[0] == 0xEF && (uint8_t)d[1] == 0xBB && (uint8_t)d[2] == 0xBF) return "text/plain; charset=utf-8";
+    if (starts("\x00\x00\x01\x00", 4) || starts("\x00\x00\x02\x00", 4)) return "image/x-icon";
+    if (starts("BM", 2)) return "image/bmp";
+    if (starts("GIF87a", 6) || starts("GIF89a", 6)) return "image/gif";
+    if (d.size() >= 14 && starts("RIFF", 4) && memcmp(d.data() + 8, "WEBPVP", 6) == 0) return "image/webp";
+    if (starts("\x89PNG\x0D\x0A\x1A\x0A", 8)) return "image/png";
+    if (starts("\xFF\xD8\xFF", 3)) return "image/jpeg";
+    if (starts("\x1F\x8B\x08", 3)) return "application/x-gzip";
+    if (starts("PK\x03\x04", 4)) return "application/zip";
+    for (unsigned char c : d)
+        if (c <= 0x08 || c == 0x0B || (c >= 0x0E && c <= 0x1A) || (c >= 0x1C && c <= 0x1F)) return "application/octet-stream";
+    return "text/plain; charset=utf-8";
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// builder state
+// ---------------------------------------------------------------------------------------------------------------
+
+struct Piece {
+    std::string lit;
+    bool has_var = false;
+    uint32_t cls[8] = {0};
+    int min_rep = 1;
+};
+
+struct RouteDef {
+    uint32_t method;
+    std::string pattern;
+    bool prefix = false, dead = false;
+    std::vector<Piece> pieces;
+    uint32_t hkind = 0, schema_id = 0;
+    std::string s[4];
+    std::string blob;
+};
+
+struct FieldDef {
+    std::string go_name, json_name;
+    uint8_t kind;
+    bool omitempty;
+};
+struct SchemaDef {
+    uint32_t id;
+    std::string go_type;
+    std::vector<FieldDef> fields;
+};
+
+// symbolic op before literal-pool assignment
+struct SOp {
+    uint8_t code;
+    uint8_t arg = 0, flags = 0, kind = 0;
+    uint32_t aux = 0, off = 0;
+    std::string lit;  // OP_LIT / OP_KEY
+    bool body = false;
+};
+
+struct Prog {
+    int status = 200;
+    std::vector<SOp> ops;
+};
+
+}  // namespace gofr
+
+using namespace gofr;
+
+struct gofr_table {
+    uint32_t frame_mode = 0;
+    bool sealed = false;
+    bool has_catchall = false;
+    std::vector<RouteDef> routes;
+    std::vector<SchemaDef> schemas;
+    std::vector<uint8_t> image;
+};
+
+namespace gofr {
+
+static void cls_set(uint32_t* c, int b) { c[b >> 5] |= 1u << (b & 31); }
+static void cls_range(uint32_t* c, int a, int b) { for (int x = a; x <= b; x++) cls_set(c, x); }
+
+// {name:regexp}: accept  X+ / X*  with X a bracket class, \d, \w or '.'
+static int parse_var_regexp(const std::string& re, Piece& pc) {
+    memset(pc.cls, 0, sizeof pc.cls);
+    size_t n = re.size(), i = 0;
+    if (n < 2) return GOFR_ERR_UNSUPPORTED;
+    auto add_esc = [&](int e) {
+        if (e == 'd') cls_range(pc.cls, '0', '9');
+        else if (e == 'w') { cls_range(pc.cls, '0', '9'); cls_range(pc.cls, 'a', 'z'); cls_range(pc.cls, 'A', 'Z'); cls_set(pc.cls, '_'); }
+        else cls_set(pc.cls, e);
+    };
+    if (re[0] == '[') {
+        bool neg = false, first = true;
+        i = 1;
+        if (i < n && re[i] == '^') { neg = true; i++; }
+        while (i < n && (re[i] != ']' || first)) {
+            int a = (uint8_t)re[i];
+            if (a == '\\') {
+                if (i + 1 >= n) return GOFR_ERR_UNSUPPORTED;
+                int e = (uint8_t)re[i + 1];
+                if (e == 'd' || e == 'w') { add_esc(e); i += 2; first = false; continue; }
+                a = e;
+                i++;
+            }
+            if (a >= 0x80) return GOFR_ERR_UNSUPPORTED;
+            if (i + 2 < n && re[i + 1] == '-' && re[i + 2] != ']') {
+                int b = (uint8_t)re[i + 2];
+                if (b == '\\') { if (i + 3 >= n) return GOFR_ERR_UNSUPPORTED; b = (uint8_t)re[i + 3]; i++; }
+                if (b >= 0x80 || b < a) return GOFR_ERR_UNSUPPORTED;
+                cls_range(pc.cls, a, b);
+                i += 3;
+            } else { cls_set(pc.cls, a); i++; }
+            first = false;
+        }
+        if (i >= n) return GOFR_ERR_UNSUPPORTED;
+        i++;
+        if (neg) for (auto& w : pc.cls) w = ~w;
+    } else if (re[0] == '\\') {
+        if (re[1] != 'd' && re[1] != 'w') return GOFR_ERR_UNSUPPORTED;
+        add_esc(re[1]);
+        i = 2;
+    } else if (re[0] == '.') {
+        for (auto& w : pc.cls) w = 0xFFFFFFFFu;
+        pc.cls[0] &= ~(1u << '\n');
+        i = 1;
+    } else return GOFR_ERR_UNSUPPORTED;
+    if (i != n - 1) return GOFR_ERR_UNSUPPORTED;
+    if (re[i] == '+') pc.min_rep = 1;
+    else if (re[i] == '*') pc.min_rep = 0;
+    else return GOFR_ERR_UNSUPPORTED;
+    return GOFR_OK;
+}
+
+// mux newRouteRegexp: literal text between top-level {...}; returns GOFR_OK, GOFR_ERR_UNSUPPORTED, or -1 for a
+// template mux itself rejects (the route then exists but never matches).
+static int parse_template(const std::string& tpl, std::vector<Piece>& out) {
+    size_t n = tpl.size(), i = 0;
+    for (;;) {
+        size_t j = i;
+        while (j < n && tpl[j] != '{' && tpl[j] != '}') j++;
+        if (j < n && tpl[j] == '}') return -1;
+        Piece pc;
+        pc.lit = tpl.substr(i, j - i);
+        if (j >= n) { out.push_back(pc); break; }
+        int depth = 0;
+        size_t k = j;
+        for (; k < n; k++) {
+            if (tpl[k] == '{') depth++;
+            else if (tpl[k] == '}' && --depth == 0) break;
+        }
+        if (k >= n) return -1;
+        std::string body = tpl.substr(j + 1, k - j - 1);
+        size_t colon = body.find(':');
+        std::string name = colon == std::string::npos ? body : body.substr(0, colon);
+        if (name.empty()) return -1;
+        pc.has_var = true;
+        if (colon == std::string::npos) {
+            for (auto& w : pc.cls) w = 0xFFFFFFFFu;
+            pc.cls['/' >> 5] &= ~(1u << ('/' & 31));
+            pc.min_rep = 1;
+        } else {
+            std::string re = body.substr(colon + 1);
+            if (re.empty()) return -1;
+            int rc = parse_var_regexp(re, pc);
+            if (rc != GOFR_OK) return rc;
+        }
+        out.push_back(pc);
+        i = k + 1;
+        if ((int)out.size() > kMaxVars) return GOFR_ERR_UNSUPPORTED;
+    }
+    return GOFR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// program construction
+// ---------------------------------------------------------------------------------------------------------------
+
+struct HeaderKV { std::string k, v; bool hexid = false; };
+
+enum BodyKind { BODY_NONE, BODY_JSON, BODY_FILE, BODY_PLAIN404, BODY_PANIC };
+
+static SOp lit(const std::string& s, bool body) { SOp o; o.code = OP_LIT; o.lit = s; o.body = body; return o; }
+static SOp op(uint8_t code, bool body) { SOp o; o.code = code; o.body = body; return o; }
+
+// The header block net/http 1.21 writes (chunkWriter.writeHeader + Header.WriteSubset + extraHeader.Write).
+//   handler headers sorted by key; then Date, Content-Length, Content-Type (sniffed only if the handler's snapshot has
+//   none and the body is non-empty).  `with_mw`: the Tracer/Logging/CORS chain ran (a route matched).
+static void build_header(Prog& p, uint32_t frame_mode, int status, bool with_mw, BodyKind bk, bool head_no_body,
+                         const std::string& file_ct_given, const std::string& file_ct_sniffed, bool location) {
+    if (frame_mode == GOFR_FRAME_BODY) return;
+    std::vector<HeaderKV> h;
+    if (with_mw) {
+        HeaderKV id; id.k = "X-Correlation-Id"; id.hexid = true;  // Header.Set canonicalises X-Correlation-ID
+        h.push_back(id);
+        h.push_back({"Access-Control-Allow-Origin", "*"});
+        h.push_back({"Access-Control-Allow-Methods", "POST, GET, OPTIONS, PUT, DELETE"});
+    }
+    bool have_type = false;
+    if (bk == BODY_PLAIN404) {  // http.Error sets both before WriteHeader
+        h.push_back({"Content-Type", "text/plain; charset=utf-8"});
+        h.push_back({"X-Content-Type-Options", "nosniff"});
+        have_type = true;
+    }
+    if (frame_mode == GOFR_FRAME_INTENDED) {
+        // what the tests read from the live recorder map: the late Header().Set is visible
+        if (bk == BODY_JSON) { h.push_back({"Content-Type", "application/json"}); have_type = true; }
+        if (bk == BODY_FILE) { h.push_back({"Content-Type", file_ct_given}); have_type = true; }
+    }
+    std::sort(h.begin(), h.end(), [](const HeaderKV& a, const HeaderKV& b) { return a.k < b.k; });
+    std::string acc = std::string("HTTP/1.1 ") + std::to_string(status) + " " + status_text(status) + "\r\n";
+    if (location) {
+        // Location sorts among the handler headers; a 301 carries no others
+        acc += "Location: ";
+        p.ops.push_back(lit(acc, false));
+        p.ops.push_back(op(OP_LOCATION, false));
+        acc = "\r\n";
+    }
+    for (auto& kv : h) {
+        acc += kv.k + ": ";
+        if (kv.hexid) {
+            p.ops.push_back(lit(acc, false));
+            p.ops.push_back(op(OP_HEXID, false));
+            acc.clear();
+        } else acc += kv.v;
+        acc += "\r\n";
+    }
+    acc += "Date: ";
+    p.ops.push_back(lit(acc, false));
+    p.ops.push_back(op(OP_DATE, false));
+    acc = "\r\n";
+    bool body_nonempty = bk != BODY_NONE;
+    if (!head_no_body) {
+        acc += "Content-Length: ";
+        if (body_nonempty) {
+            p.ops.push_back(lit(acc, false));
+            p.ops.push_back(op(OP_CLEN, false));
+            acc = "\r\n";
+        } else acc += "0\r\n";
+    }
+    if (!have_type && body_nonempty) {
+        acc += "Content-Type: ";
+        acc += bk == BODY_FILE ? file_ct_sniffed : "text/plain; charset=utf-8";  // JSON text never sniffs as anything else
+        acc += "\r\n";
+    }
+    acc += "\r\n";
+    p.ops.push_back(lit(acc, false));
+}
+
+// struct → JSON object ops.  Schemas without omitempty collapse to literals around value ops.
+static void build_struct_ops(Prog& p, const SchemaDef& sc) {
+    bool dynamic = false;
+    for (auto& f : sc.fields) dynamic |= f.omitempty;
+    std::string acc = "{";
+    uint16_t word = 0, str_ord = 0;
+    bool first = true;
+    for (auto& f : sc.fields) {
+        std::string key = "\"" + json_escape_go(f.json_name) + "\":";
+        uint16_t w = word;
+        word += (f.kind == GOFR_F_INT64 || f.kind == 5) ? 2 : 1;
+        SOp v;
+        v.body = true;
+        v.off = w;
+        switch (f.kind) {
+            case GOFR_F_INT64: case 5: v.code = OP_I64; break;
+            case GOFR_F_INT32: v.code = OP_I32; break;
+            case GOFR_F_BOOL: v.code = OP_BOOL; break;
+            default: v.code = OP_STR; v.arg = (uint8_t)str_ord++; break;
+        }
+        if (!dynamic) {
+            if (!first) acc += ",";
+            acc += key;
+            if (f.kind == GOFR_F_STRING) acc += "\"";
+            p.ops.push_back(lit(acc, true));
+            p.ops.push_back(v);
+            acc = f.kind == GOFR_F_STRING ? "\"" : "";
+        } else {
+            if (!acc.empty()) { p.ops.push_back(lit(acc, true)); acc.clear(); }
+            SOp k;
+            k.code = OP_KEY; k.body = true; k.kind = f.kind; k.off = w; k.lit = key;
+            k.flags = f.omitempty ? OPF_OMITEMPTY : 0;
+            if (f.kind == GOFR_F_STRING) k.lit += "\"";
+            p.ops.push_back(k);
+            v.flags |= OPF_VALUE_OF_KEY;
+            p.ops.push_back(v);
+            if (f.kind == GOFR_F_STRING) { SOp q = lit("\"", true); q.flags |= OPF_VALUE_OF_KEY; p.ops.push_back(q); }
+        }
+        first = false;
+    }
+    acc += "}";
+    p.ops.push_back(lit(acc, true));
+}
+
+struct Builder {
+    gofr_table* t;
+    std::vector<Prog> progs;
+    std::string err;
+
+    int add(Prog p) { progs.push_back(std::move(p)); return (int)progs.size() - 1; }
+
+    // Responder.Respond envelope: {"error":{"message":...},"data":...}\n  (error first; both omitempty)
+    int json_prog(int status, const std::vector<SOp>& body_ops) {
+        Prog p;
+        p.status = status;
+        build_header(p, t->frame_mode, status, true, BODY_JSON, false, "", "", false);
+        for (auto o : body_ops) { o.body = true; p.ops.push_back(o); }
+        return add(std::move(p));
+    }
+};
+
+}  // namespace gofr
+
+// ---------------------------------------------------------------------------------------------------------------
+// image assembly
+// ---------------------------------------------------------------------------------------------------------------
+
+namespace gofr {
+
+struct Pool {
+    std::vector<uint8_t>& img;
+    std::map<std::string, uint32_t> seen;
+    explicit Pool(std::vector<uint8_t>& i) : img(i) {}
+    uint32_t put(const std::string& s) {  // 4-byte aligned, padded with zeros to a word boundary (+4 slack)
+        auto it = seen.find(s);
+        if (it != seen.end()) return it->second;
+        while (img.size() % 4) img.push_back(0);
+        uint32_t off = (uint32_t)img.size();
+        img.insert(img.end(), s.begin(), s.end());
+        while (img.size() % 4) img.push_back(0);
+        for (int k = 0; k < 4; k++) img.push_back(0);
+        seen[s] = off;
+        return off;
+    }
+};
+
+static void merge_literals(std::vector<SOp>& ops) {
+    std::vector<SOp> out;
+    for (auto& o : ops) {
+        if (o.code == OP_LIT && o.lit.empty()) continue;
+        if (o.code == OP_LIT && !out.empty() && out.back().code == OP_LIT && out.back().body == o.body &&
+            out.back().flags == o.flags) {
+            out.back().lit += o.lit;
+        } else out.push_back(o);
+    }
+    ops.swap(out);
+}
+
+static const char* go_kind_name(uint8_t k) {
+    switch (k) {
+        case GOFR_F_INT64: return "int64";
+        case GOFR_F_INT32: return "int32";
+        case GOFR_F_BOOL: return "bool";
+        case GOFR_F_STRING: return "string";
+        case 5: return "int";
+    }
+    return "?";
+}
+
+static std::string fold_lower(const std::string& s) {
+    std::string r = s;
+    for (auto& c : r) if (c >= 'A' && c <= 'Z') c = (char)(c + 32);
+    return r;
+}
+
+int seal_table(gofr_table* t) {
+    Builder b{t, {}, {}};
+    uint32_t fm = t->frame_mode;
+
+    // ---- fixed programs (mux / middleware outcomes that exist for every table) ----
+    auto simple = [&](int status, bool with_mw, BodyKind bk, bool head_no_body, bool location, const std::string& body) {
+        Prog p;
+        p.status = status;
+        build_header(p, fm, status, with_mw, bk, head_no_body, "", "", location);
+        if (!body.empty()) p.ops.push_back(lit(body, true));
+        return b.add(std::move(p));
+    };
+    int p301 = simple(301, false, BODY_NONE, false, true, "");
+    int p301h = simple(301, false, BODY_NONE, true, true, "");
+    int p404 = simple(404, false, BODY_PLAIN404, false, false, "404 page not found\n");  // http.NotFoundHandler
+    int p405 = simple(405, false, BODY_NONE, false, false, "");                           // mux methodNotAllowedHandler
+    int p405h = simple(405, false, BODY_NONE, true, false, "");
+    int popt = simple(200, true, BODY_NONE, false, false, "");                            // CORS short-circuit
+    int ppanic = simple(500, true, BODY_PANIC, false, false,
+                        "{\"code\":500,\"message\":\"Some unexpected error has occurred\",\"status\":\"ERROR\"}\n");
+
+    // ---- per-route programs ----
+    std::vector<int> prog_ok(t->routes.size(), 0xFFFF), prog_err(t->routes.size(), 0xFFFF);
+    for (size_t ri = 0; ri < t->routes.size(); ri++) {
+        RouteDef& r = t->routes[ri];
+        const SchemaDef* sc = nullptr;
+        if (r.hkind == GOFR_H_ROW || r.hkind == GOFR_H_BIND_ECHO) {
+            for (auto& s : t->schemas) if (s.id == r.schema_id) sc = &s;
+            if (!sc) { set_last_error("route %s: unknown schema %u", r.pattern.c_str(), r.schema_id); return GOFR_ERR_INVALID; }
+        }
+        switch (r.hkind) {
+            case GOFR_H_HOST: break;
+            case GOFR_H_STATIC_STRING:
+                prog_ok[ri] = b.json_prog(200, {lit("{\"data\":\"" + json_escape_go(r.s[0]) + "\"}\n", true)});
+                break;
+            case GOFR_H_STATIC_ERROR:
+                prog_ok[ri] = b.json_prog(500, {lit("{\"error\":{\"message\":\"" + json_escape_go(r.s[0]) + "\"}}\n", true)});
+                break;
+            case GOFR_H_NIL: prog_ok[ri] = b.json_prog(200, {lit("{}\n", true)}); break;
+            case GOFR_H_HEALTH: prog_ok[ri] = b.json_prog(200, {lit("{\"data\":{}}\n", true)}); break;
+            case GOFR_H_MISSING_FILE:
+                prog_ok[ri] = b.json_prog(404, {lit("{\"error\":{\"message\":\"http: no such file\"}}\n", true)});
+                break;
+            case GOFR_H_PANIC: prog_ok[ri] = ppanic; break;
+            case GOFR_H_PARAM_FORMAT: {
+                if (!valid_utf8(r.s[2]) || !valid_utf8(r.s[3])) {
+                    set_last_error("route %s: format prefix/suffix must be valid UTF-8", r.pattern.c_str());
+                    return GOFR_ERR_UNSUPPORTED;
+                }
+                prog_ok[ri] = b.json_prog(200, {lit("{\"data\":\"" + json_escape_go(r.s[2]), true), op(OP_PARAM, true),
+                                                lit(json_escape_go(r.s[3]) + "\"}\n", true)});
+                break;
+            }
+            case GOFR_H_ROW:
+            case GOFR_H_BIND_ECHO: {
+                Prog p;
+                p.status = 200;
+                build_header(p, fm, 200, true, BODY_JSON, false, "", "", false);
+                p.ops.push_back(lit("{\"data\":", true));
+                build_struct_ops(p, *sc);
+                p.ops.push_back(lit("}\n", true));
+                prog_ok[ri] = b.add(std::move(p));
+                if (r.hkind == GOFR_H_BIND_ECHO)
+                    prog_err[ri] = b.json_prog(500, {lit("{\"error\":{\"message\":\"", true), op(OP_ERRMSG, true),
+                                                     lit("\"}}\n", true)});
+                break;
+            }
+            case GOFR_H_FILE: {
+                Prog p;
+                p.status = 200;
+                if (r.blob.empty()) {
+                    // Write(nil) after WriteHeader: empty body → "Content-Length: 0" and nothing to sniff; the
+                    // recorder's live map (INTENDED) still shows the type the handler set.
+                    build_header(p, fm, 200, true, fm == GOFR_FRAME_INTENDED ? BODY_FILE : BODY_NONE, false, r.s[0], "", false);
+                } else {
+                    build_header(p, fm, 200, true, BODY_FILE, false, r.s[0], sniff_content_type(r.blob), false);
+                    SOp bo = op(OP_BLOB, true);
+                    bo.lit = r.blob;
+                    p.ops.push_back(bo);
+                }
+                prog_ok[ri] = b.add(std::move(p));
+                break;
+            }
+            default: set_last_error("route %s: unknown handler kind %u", r.pattern.c_str(), r.hkind); return GOFR_ERR_INVALID;
+        }
+    }
+
+    // ---- lay out the image ----
+    std::vector<uint8_t>& img = t->image;
+    img.clear();
+    img.resize(sizeof(ImageHeader), 0);
+    ImageHeader H;
+    memset(&H, 0, sizeof H);
+    H.magic = kMagic; H.version = kImageVersion; H.frame_mode = fm;
+    H.n_routes = (uint32_t)t->routes.size();
+    H.prog_301 = (uint16_t)p301; H.prog_301_head = (uint16_t)p301h; H.prog_404 = (uint16_t)p404; H.prog_405 = (uint16_t)p405;
+    H.prog_405_head = (uint16_t)p405h; H.prog_options = (uint16_t)popt; H.prog_panic = (uint16_t)ppanic;
+    H.has_catchall = t->has_catchall;
+
+    auto align16 = [&]() { while (img.size() % 16) img.push_back(0); };
+    std::vector<RouteRec> routes(t->routes.size());
+    std::vector<PieceRec> pieces;
+    // We build sections into separate byte vectors, then concatenate.
+    std::vector<uint8_t> lits;
+    Pool pool(lits);
+    std::vector<uint8_t> cold;
+
+    for (size_t ri = 0; ri < t->routes.size(); ri++) {
+        RouteDef& r = t->routes[ri];
+        RouteRec& R = routes[ri];
+        memset(&R, 0, sizeof R);
+        R.method = (uint8_t)r.method;
+        R.flags = (r.prefix ? RF_PREFIX : 0) | (r.dead ? RF_DEAD : 0);
+        R.hkind = (uint8_t)r.hkind;
+        R.first_piece = (uint16_t)pieces.size();
+        R.n_pieces = (uint8_t)r.pieces.size();
+        R.prog_ok = (uint16_t)prog_ok[ri];
+        R.prog_err = (uint16_t)prog_err[ri];
+        if (!r.dead && !r.prefix && r.pieces.size() == 1 && !r.pieces[0].has_var) {
+            R.flags |= RF_LITERAL;
+            R.lit_off = pool.put(r.pattern);
+            R.lit_len = (uint16_t)r.pattern.size();
+        }
+        for (auto& pc : r.pieces) {
+            PieceRec P;
+            memset(&P, 0, sizeof P);
+            P.lit_off = pool.put(pc.lit);
+            P.lit_len = (uint16_t)pc.lit.size();
+            P.has_var = pc.has_var;
+            P.min_rep = (uint8_t)pc.min_rep;
+            memcpy(P.cls, pc.cls, sizeof P.cls);
+            pieces.push_back(P);
+        }
+        if (r.hkind == GOFR_H_PARAM_FORMAT) {
+            R.key_off = pool.put(r.s[0]);
+            R.key_len = (uint16_t)r.s[0].size();
+            std::string d = json_escape_go(r.s[1]);
+            R.def_off = pool.put(d);
+            R.def_len = (uint16_t)d.size();
+        }
+        if (r.hkind == GOFR_H_ROW || r.hkind == GOFR_H_BIND_ECHO)
+            for (size_t si = 0; si < t->schemas.size(); si++)
+                if (t->schemas[si].id == r.schema_id) R.schema = (uint16_t)si;
+    }
+
+    std::vector<ProgRec> progs(b.progs.size());
+    std::vector<Op> ops;
+    uint32_t max_fixed = 0;
+    for (size_t pi = 0; pi < b.progs.size(); pi++) {
+        Prog& p = b.progs[pi];
+        merge_literals(p.ops);
+        ProgRec& P = progs[pi];
+        memset(&P, 0, sizeof P);
+        P.first_op = (uint16_t)ops.size();
+        P.n_ops = (uint16_t)p.ops.size();
+        P.status = (uint16_t)p.status;
+        for (auto& so : p.ops) {
+            Op o;
+            memset(&o, 0, sizeof o);
+            o.code = so.code; o.arg = so.arg; o.kind = so.kind;
+            o.flags = so.flags | (so.body ? OPF_BODY : 0);
+            o.off = so.off; o.aux = so.aux;
+            uint32_t fixed = 0;
+            switch (so.code) {
+                case OP_LIT:
+                    o.off = pool.put(so.lit);
+                    o.len = (uint32_t)so.lit.size();
+                    if (!(so.flags & OPF_VALUE_OF_KEY)) fixed = o.len; else P.flags |= PF_DYNAMIC;
+                    break;
+                case OP_KEY:
+                    o.aux = so.off;  // row word of the governed field
+                    o.off = pool.put(so.lit);
+                    o.len = (uint32_t)so.lit.size();
+                    P.flags |= PF_DYNAMIC | PF_NEEDS_ROW;
+                    break;
+                case OP_HEXID: fixed = 32; break;
+                case OP_DATE: fixed = 29; break;
+                case OP_CLEN: P.flags |= PF_HAS_CLEN; break;
+                case OP_BLOB:
+                    while (cold.size() % 16) cold.push_back(0);
+                    o.off = (uint32_t)cold.size();
+                    o.len = (uint32_t)so.lit.size();
+                    cold.insert(cold.end(), so.lit.begin(), so.lit.end());
+                    fixed = o.len;
+                    break;
+                case OP_I64: case OP_I32: case OP_BOOL: case OP_STR: P.flags |= PF_DYNAMIC | PF_NEEDS_ROW; break;
+                default: P.flags |= PF_DYNAMIC; break;
+            }
+            if (so.body) P.body_fixed += fixed; else P.hdr_fixed += fixed;
+            ops.push_back(o);
+        }
+        max_fixed = std::max(max_fixed, P.hdr_fixed + P.body_fixed);
+    }
+
+    std::vector<uint8_t> schema_bytes;
+    std::vector<SchemaRec> srecs(t->schemas.size());
+    std::vector<std::vector<FieldRec>> frecs(t->schemas.size());
+    for (size_t si = 0; si < t->schemas.size(); si++) {
+        SchemaDef& s = t->schemas[si];
+        SchemaRec& S = srecs[si];
+        memset(&S, 0, sizeof S);
+        S.n_fields = (uint16_t)s.fields.size();
+        S.type_off = pool.put(s.go_type + std::string(1, '\0'));
+        uint16_t word = 0, so = 0;
+        for (auto& f : s.fields) {
+            FieldRec F;
+            memset(&F, 0, sizeof F);
+            F.kind = f.kind; F.omitempty = f.omitempty; F.word = word;
+            word += (f.kind == GOFR_F_INT64 || f.kind == 5) ? 2 : 1;
+            F.name_len = (uint16_t)f.json_name.size();
+            F.name_off = pool.put(f.json_name);
+            F.fold_off = pool.put(fold_lower(f.json_name));
+            if (f.kind == GOFR_F_STRING) F.str_ord = so++;
+            std::string tn = go_kind_name(f.kind);
+            F.type_off = pool.put(tn);
+            F.type_len = (uint16_t)tn.size();
+            frecs[si].push_back(F);
+        }
+        S.fixed_words = word;
+        S.n_strings = so;
+    }
+
+    H.n_pieces = (uint32_t)pieces.size();
+    H.n_progs = (uint32_t)progs.size();
+    H.n_ops = (uint32_t)ops.size();
+    H.n_schemas = (uint32_t)srecs.size();
+    H.max_fixed_len = max_fixed;
+
+    auto append = [&](const void* p, size_t n) {
+        align16();
+        uint32_t off = (uint32_t)img.size();
+        img.insert(img.end(), (const uint8_t*)p, (const uint8_t*)p + n);
+        return off;
+    };
+    H.routes_off = append(routes.data(), routes.size() * sizeof(RouteRec));
+    H.pieces_off = append(pieces.data(), pieces.size() * sizeof(PieceRec));
+    H.progs_off = append(progs.data(), progs.size() * sizeof(ProgRec));
+    H.ops_off = append(ops.data(), ops.size() * sizeof(Op));
+    // schemas: SchemaRec[n] then each field table
+    align16();
+    H.schemas_off = (uint32_t)img.size();
+    size_t srec_pos = img.size();
+    img.resize(img.size() + srecs.size() * sizeof(SchemaRec));
+    for (size_t si = 0; si < srecs.size(); si++) {
+        srecs[si].fields_off = append(frecs[si].data(), frecs[si].size() * sizeof(FieldRec));
+        memcpy(img.data() + srec_pos + si * sizeof(SchemaRec), &srecs[si], sizeof(SchemaRec));
+    }
+    H.lits_off = append(lits.data(), lits.size());
+    align16();
+    H.hot_bytes = (uint32_t)img.size();
+    H.cold_off = append(cold.data(), cold.size());
+    align16();
+    H.total_bytes = (uint32_t)img.size();
+    memcpy(img.data(), &H, sizeof H);
+    if (H.hot_bytes > kMaxHotBytes) {
+        set_last_error("sealed table needs %u bytes of shared memory (limit %u)", H.hot_bytes, kMaxHotBytes);
+        return GOFR_ERR_CAPACITY;
+    }
+    t->sealed = true;
+    return GOFR_OK;
+}
+
+}  // namespace gofr
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int gofr_table_create(gofr_table** out, uint32_t frame_mode) {
+    if (!out || frame_mode > GOFR_FRAME_BODY) return GOFR_ERR_INVALID;
+    *out = new gofr_table();
+    (*out)->frame_mode = frame_mode;
+    return GOFR_OK;
+}
+
+void gofr_table_destroy(gofr_table* t) { delete t; }
+
+int gofr_table_add_schema(gofr_table* t, uint32_t schema_id, const char* go_type_name, const gofr_field_desc* fields,
+                          uint32_t n_fields) {
+    if (!t || !fields || n_fields == 0 || n_fields > (uint32_t)kMaxFields) return GOFR_ERR_INVALID;
+    if (t->sealed) return GOFR_ERR_SEALED;
+    SchemaDef s;
+    s.id = schema_id;
+    s.go_type = go_type_name ? go_type_name : "";
+    for (uint32_t i = 0; i < n_fields; i++) {
+        FieldDef f;
+        f.go_name = fields[i].go_name ? fields[i].go_name : "";
+        f.json_name = fields[i].json_name && fields[i].json_name[0] ? fields[i].json_name : f.go_name;
+        f.kind = fields[i].kind;
+        f.omitempty = fields[i].omitempty != 0;
+        if (f.kind < GOFR_F_INT64 || f.kind > 5) { set_last_error("schema %u: unsupported field kind %u", schema_id, f.kind); return GOFR_ERR_UNSUPPORTED; }
+        s.fields.push_back(f);
+    }
+    t->schemas.push_back(s);
+    return GOFR_OK;
+}
+
+int gofr_table_add_route(gofr_table* t, uint32_t method, const char* pattern, uint32_t pattern_len,
+                         const gofr_handler_desc* h, uint32_t* route_id_out) {
+    if (!t || !pattern || !h) return GOFR_ERR_INVALID;
+    if (t->sealed) return GOFR_ERR_SEALED;
+    if (method > GOFR_M_OTHER && method != GOFR_M_ANY) return GOFR_ERR_INVALID;
+    RouteDef r;
+    r.method = method;
+    r.pattern.assign(pattern, pattern_len);
+    r.prefix = method == GOFR_M_ANY;
+    r.hkind = h->kind;
+    r.schema_id = h->schema_id;
+    const char* ss[4] = {h->s0, h->s1, h->s2, h->s3};
+    uint32_t sl[4] = {h->s0_len, h->s1_len, h->s2_len, h->s3_len};
+    for (int k = 0; k < 4; k++) if (ss[k]) r.s[k].assign(ss[k], sl[k]);
+    if (h->blob) r.blob.assign((const char*)h->blob, h->blob_len);
+    int rc = parse_template(r.pattern, r.pieces);
+    if (rc == GOFR_ERR_UNSUPPORTED) { set_last_error("pattern %s: unsupported variable regexp", r.pattern.c_str()); return rc; }
+    // mux: "path must start with a slash" / malformed braces → route.err → the route never matches
+    if (rc == -1 || r.pattern.empty() || r.pattern[0] != '/') { r.dead = true; r.pieces.clear(); r.pieces.push_back(Piece()); }
+    if (route_id_out) *route_id_out = (uint32_t)t->routes.size();
+    t->routes.push_back(std::move(r));
+    return GOFR_OK;
+}
+
+int gofr_table_add_default_routes(gofr_table* t, const uint8_t* favicon, uint32_t favicon_len) {
+    if (!t) return GOFR_ERR_INVALID;
+    if (t->sealed) return GOFR_ERR_SEALED;
+    gofr_handler_desc h;
+    memset(&h, 0, sizeof h);
+    h.kind = GOFR_H_HEALTH;
+    int rc = gofr_table_add_route(t, GOFR_M_GET, "/.well-known/health", 19, &h, nullptr);
+    if (rc) return rc;
+    h.kind = GOFR_H_FILE; h.s0 = "image/x-icon"; h.s0_len = 12; h.blob = favicon; h.blob_len = favicon_len;
+    rc = gofr_table_add_route(t, GOFR_M_GET, "/favicon.ico", 12, &h, nullptr);
+    if (rc) return rc;
+    memset(&h, 0, sizeof h);
+    h.kind = GOFR_H_MISSING_FILE;
+    rc = gofr_table_add_route(t, GOFR_M_ANY, "/", 1, &h, nullptr);
+    if (rc) return rc;
+    t->has_catchall = true;
+    return GOFR_OK;
+}
+
+int gofr_table_seal(gofr_table* t) {
+    if (!t) return GOFR_ERR_INVALID;
+    if (t->sealed) return GOFR_ERR_SEALED;
+    return seal_table(t);
+}
+
+int gofr_table_serialize(const gofr_table* t, uint8_t* buf, uint64_t* len_inout) {
+    if (!t || !len_inout) return GOFR_ERR_INVALID;
+    if (!t->sealed) return GOFR_ERR_NOT_SEALED;
+    uint64_t need = t->image.size();
+    if (!buf) { *len_inout = need; return GOFR_OK; }
+    if (*len_inout < need) { *len_inout = need; return GOFR_ERR_CAPACITY; }
+    memcpy(buf, t->image.data(), need);
+    *len_inout = need;
+    return GOFR_OK;
+}
+
+int gofr_table_deserialize(gofr_table** out, const uint8_t* buf, uint64_t len) {
+    if (!out || !buf || len < sizeof(ImageHeader)) return GOFR_ERR_INVALID;
+    ImageHeader H;
+    memcpy(&H, buf, sizeof H);
+    if (H.magic != kMagic || H.version != kImageVersion || H.total_bytes != len || H.hot_bytes > kMaxHotBytes) {
+        set_last_error("not a sealed gofr table image (magic/version/length mismatch)");
+        return GOFR_ERR_INVALID;
+    }
+    gofr_table* t = new gofr_table();
+    t->frame_mode = H.frame_mode;
+    t->has_catchall = H.has_catchall != 0;
+    t->image.assign(buf, buf + len);
+    t->sealed = true;
+    *out = t;
+    return GOFR_OK;
+}
+
+uint32_t gofr_table_route_count(const gofr_table* t) {
+    if (!t) return 0;
+    if (!t->image.empty()) { ImageHeader H; memcpy(&H, t->image.data(), sizeof H); return H.n_routes; }
+    return (uint32_t)t->routes.size();
+}
+
+uint32_t gofr_table_max_response_bytes(const gofr_table* t, uint32_t max_data_len) {
+    if (!t || t->image.empty()) return 0;
+    ImageHeader H;
+    memcpy(&H, t->image.data(), sizeof H);
+    // fixed part + Content-Length digits + every data byte escaped six-fold (\u00XX) + Location (3x path + query)
+    return H.max_fixed_len + 16 + 6 * max_data_len + 3 * 65535 + 65535 + 2;
+}
+
+}  // extern "C"
+
+const std::vector<uint8_t>& gofr_table_image(const gofr_table* t) { return t->image; }

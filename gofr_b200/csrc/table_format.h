@@ -1,0 +1,144 @@
+// table_format.h — binary layout of the sealed route/schema table ("image").
+//
+// The image is position independent (offsets from its base), so the same bytes are (a) broadcast from rank 0 to all
+// ranks, (b) copied once to HBM, and (c) copied by every CTA into shared memory at kernel start (the "hot" part).
+// It is the compiled form of what the reference keeps as a []*mux.Route plus closures
+// (pkg/gofr/http/router.go:30-33, pkg/gofr/gofr.go:171-177): routes in registration order (= match priority), each
+// pointing at a response *program* — a list of ops the serve kernel interprets to produce the exact bytes that
+// handler + Responder.Respond + encoding/json + net/http framing produce in the reference.
+#pragma once
+#include <stdint.h>
+
+namespace gofr {
+
+constexpr uint32_t kMagic = 0x52464F47u;  // "GOFR"
+constexpr uint32_t kImageVersion = 3;
+constexpr uint32_t kMaxHotBytes = 40 * 1024;  // shared-memory budget for the table
+constexpr int kMaxVars = 8;                   // variables per route template
+constexpr int kMaxFields = 32;                // struct fields per schema
+
+struct ImageHeader {  // 96 B
+    uint32_t magic, version;
+    uint32_t frame_mode;
+    uint32_t n_routes, n_pieces, n_progs, n_ops, n_schemas;
+    uint32_t routes_off, pieces_off, progs_off, ops_off, schemas_off, lits_off;
+    uint32_t hot_bytes;    // [0, hot_bytes) is copied to shared memory
+    uint32_t cold_off;     // file blobs: read from global memory only
+    uint32_t total_bytes;
+    uint16_t prog_301, prog_301_head, prog_404, prog_405, prog_405_head, prog_options, prog_panic, pad0;
+    uint32_t max_fixed_len;  // largest fixed (literal) part of any program, for capacity estimates
+    uint32_t has_catchall;
+    uint32_t reserved[1];
+};
+static_assert(sizeof(ImageHeader) == 96, "ImageHeader layout");
+
+enum RouteFlags : uint8_t {
+    RF_PREFIX = 1,   // PathPrefix: regexp has no trailing '$'
+    RF_DEAD = 2,     // mux route.err != nil: never matches
+    RF_LITERAL = 4,  // no variables: one word-wise compare
+};
+
+struct RouteRec {  // 32 B
+    uint8_t method;  // GOFR_M_* or 255
+    uint8_t flags;
+    uint8_t n_pieces;
+    uint8_t hkind;  // GOFR_H_*
+    uint16_t first_piece;
+    uint16_t schema;    // index into schemas
+    uint16_t prog_ok;   // program of the normal outcome (0xFFFF: none — GOFR_H_HOST)
+    uint16_t prog_err;  // GOFR_H_BIND_ECHO: the 500 program
+    uint32_t lit_off;   // RF_LITERAL: the whole pattern, 4-byte aligned in the literal pool
+    uint16_t lit_len;
+    uint16_t key_len;   // GOFR_H_PARAM_FORMAT: query key
+    uint32_t key_off;
+    uint32_t def_off;   // default value, already JSON-escaped
+    uint16_t def_len;
+    uint16_t pad;
+};
+static_assert(sizeof(RouteRec) == 32, "RouteRec layout");
+
+struct PieceRec {  // 48 B: literal, then (optionally) a variable = class repeated >= min_rep times, greedy
+    uint32_t lit_off;
+    uint16_t lit_len;
+    uint8_t has_var;
+    uint8_t min_rep;
+    uint32_t cls[8];  // 256-bit membership
+    uint32_t pad[2];
+};
+static_assert(sizeof(PieceRec) == 48, "PieceRec layout");
+
+enum OpCode : uint8_t {
+    OP_LIT = 0,     // literal bytes lits[off .. off+len)
+    OP_HEXID = 1,   // 32 lower-case hex chars of the request's trace id   (middleware/logger.go:46-47)
+    OP_DATE = 2,    // the batch's 29-byte IMF-fixdate
+    OP_CLEN = 3,    // decimal length of the body                           (net/http Content-Length)
+    OP_I64 = 4,     // strconv.AppendInt of a row field; off = word index in the row
+    OP_I32 = 5,
+    OP_BOOL = 6,    // true / false
+    OP_STR = 7,     // encoding/json-escaped string contents (quotes live in the neighbouring literals);
+                    // off = word index of its length, arg = ordinal among the string fields
+    OP_PARAM = 8,   // escaped query value of the route's key, or the default  (request.go:28-30)
+    OP_LOCATION = 9,  // url.String() of the cleaned URL                        (mux 301)
+    OP_ERRMSG = 10,   // escaped err.Error() of a failed Bind                   (responder.go:43-57)
+    OP_BLOB = 11,     // raw bytes from the cold section                        (response.File)
+    OP_KEY = 12,      // struct member key with dynamic comma / omitempty: emits [","] + lits[off..off+len) unless the
+                      // field (arg) is empty and flagged; used only for schemas that have an omitempty field
+};
+
+enum OpFlags : uint8_t {
+    OPF_BODY = 1,       // op belongs to the response body (counts toward Content-Length; dropped for HEAD)
+    OPF_OMITEMPTY = 2,  // OP_KEY: skip key and value when the field is the zero value
+    OPF_VALUE_OF_KEY = 4,  // value op governed by the preceding OP_KEY
+};
+
+struct Op {  // 16 B (one LDS.128)
+    uint8_t code;
+    uint8_t arg;
+    uint8_t flags;
+    uint8_t kind;  // field kind for OP_KEY emptiness test
+    uint32_t len;
+    uint32_t off;
+    uint32_t aux;
+};
+static_assert(sizeof(Op) == 16, "Op layout");
+
+struct ProgRec {  // 16 B
+    uint16_t first_op;
+    uint16_t n_ops;
+    uint16_t status;     // HTTP status code
+    uint16_t flags;      // PF_*
+    uint32_t hdr_fixed;  // sum of the fixed-length header ops (LIT, HEXID, DATE)
+    uint32_t body_fixed; // sum of the fixed-length body ops
+};
+static_assert(sizeof(ProgRec) == 16, "ProgRec layout");
+
+enum ProgFlags : uint16_t {
+    PF_HAS_CLEN = 1,
+    PF_DYNAMIC = 2,   // has at least one variable-length op besides CLEN
+    PF_NEEDS_ROW = 4,
+};
+
+struct SchemaRec {  // 16 B + per-field table
+    uint16_t n_fields;
+    uint16_t n_strings;
+    uint16_t fixed_words;  // words in the fixed part of a row
+    uint16_t pad;
+    uint32_t fields_off;  // FieldRec[n_fields]
+    uint32_t type_off;    // reflect.Type.String(), for Bind error text
+};
+
+struct FieldRec {  // 24 B
+    uint8_t kind;  // GOFR_F_*
+    uint8_t omitempty;
+    uint16_t word;      // word index in the row
+    uint16_t name_len;  // JSON key name (for Bind)
+    uint16_t str_ord;   // ordinal among string fields
+    uint32_t name_off;
+    uint32_t fold_off;  // simple-folded (lower-cased) name
+    uint16_t type_len;  // Go type name for error text ("int64", "string", ...)
+    uint16_t pad;
+    uint32_t type_off;
+};
+static_assert(sizeof(FieldRec) == 24, "FieldRec layout");
+
+}  // namespace gofr

@@ -1,0 +1,188 @@
+"""Plain-data description of a route table and of request batches (host side).
+
+The numeric constants are the ones in include/gofr_b200.h.  A `TableSpec` is what `gofr.New()` + `app.GET(...)` calls
+accumulate before `app.Run()` (pkg/gofr/gofr.go:152-177, :102-107); a `RequestBatch` is the SoA staging layout the
+C ABI consumes (desc[n], trace_id[n][16], arena).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+# methods
+M_GET, M_HEAD, M_POST, M_PUT, M_PATCH, M_DELETE, M_CONNECT, M_OPTIONS, M_TRACE = range(9)
+M_OTHER = 15
+M_ANY = 255
+METHOD_BY_NAME = {"GET": M_GET, "HEAD": M_HEAD, "POST": M_POST, "PUT": M_PUT, "PATCH": M_PATCH, "DELETE": M_DELETE,
+                  "CONNECT": M_CONNECT, "OPTIONS": M_OPTIONS, "TRACE": M_TRACE}
+
+# frame modes
+FRAME_WIRE, FRAME_INTENDED, FRAME_BODY = 0, 1, 2
+
+# handler kinds
+(H_HOST, H_STATIC_STRING, H_STATIC_ERROR, H_NIL, H_PARAM_FORMAT, H_ROW, H_BIND_ECHO, H_HEALTH, H_MISSING_FILE, H_FILE,
+ H_PANIC) = range(11)
+
+# field kinds
+F_INT64, F_INT32, F_BOOL, F_STRING, F_INT = 1, 2, 3, 4, 5
+
+REQ_FORCE_QUERY = 1
+ROUTE_NONE = 0xFFFF
+
+DESC_DTYPE = np.dtype([("arena_off", "<u4"), ("path_len", "<u2"), ("query_len", "<u2"), ("data_len", "<u4"),
+                       ("method", "u1"), ("flags", "u1"), ("aux", "<u2")])
+assert DESC_DTYPE.itemsize == 16
+
+
+def method_code(name: str) -> int:
+    """mux's methodMatcher compares exact strings: anything but the canonical upper-case names is OTHER."""
+    return METHOD_BY_NAME.get(name, M_OTHER)
+
+
+@dataclass
+class Field:
+    go_name: str
+    kind: int
+    json_name: str = ""
+    omitempty: bool = False
+
+    @property
+    def name(self) -> str:
+        return self.json_name or self.go_name
+
+
+@dataclass
+class Schema:
+    id: int
+    go_type: str  # reflect.Type.String(), e.g. "main.Person"
+    fields: List[Field]
+
+    def fixed_bytes(self) -> int:
+        return sum(8 if f.kind in (F_INT64, F_INT) else 4 for f in self.fields)
+
+    def encode_row(self, values: Sequence) -> bytes:
+        """Handler-result row: one LE u32 word per field (INT64/INT two), then the string bytes in order."""
+        words = bytearray()
+        tail = bytearray()
+        for f, v in zip(self.fields, values):
+            if f.kind in (F_INT64, F_INT):
+                words += int(v).to_bytes(8, "little", signed=True)
+            elif f.kind == F_INT32:
+                words += int(v).to_bytes(4, "little", signed=True)
+            elif f.kind == F_BOOL:
+                words += (1 if v else 0).to_bytes(4, "little")
+            elif f.kind == F_STRING:
+                b = v.encode("utf-8", "surrogateescape") if isinstance(v, str) else bytes(v)
+                words += len(b).to_bytes(4, "little")
+                tail += b
+            else:
+                raise ValueError(f"bad field kind {f.kind}")
+        return bytes(words + tail)
+
+
+@dataclass
+class Route:
+    method: int
+    pattern: str
+    kind: int
+    schema_id: int = 0
+    s0: bytes = b""
+    s1: bytes = b""
+    s2: bytes = b""
+    s3: bytes = b""
+    blob: bytes = b""
+
+
+@dataclass
+class TableSpec:
+    frame_mode: int = FRAME_WIRE
+    schemas: List[Schema] = field(default_factory=list)
+    routes: List[Route] = field(default_factory=list)
+    default_routes: bool = True  # what App.Run() appends (gofr.go:102-107)
+    favicon: bytes = b"\x89PNG\r\n\x1a\n" + bytes(range(48))  # stand-in blob with the PNG signature of the embedded one
+
+    def schema(self, sid: int) -> Schema:
+        for s in self.schemas:
+            if s.id == sid:
+                return s
+        raise KeyError(sid)
+
+
+@dataclass
+class Req:
+    method: int
+    path: bytes
+    query: bytes = b""
+    data: bytes = b""
+    flags: int = 0
+    trace_id: Optional[bytes] = None
+
+
+class RequestBatch:
+    """desc[n] / trace_ids[n,16] / arena — contiguous numpy arrays in the ABI layout."""
+
+    def __init__(self, desc: np.ndarray, trace_ids: np.ndarray, arena: np.ndarray):
+        assert desc.dtype == DESC_DTYPE and trace_ids.dtype == np.uint8 and arena.dtype == np.uint8
+        assert trace_ids.shape == (len(desc), 16)
+        self.desc = np.ascontiguousarray(desc)
+        self.trace_ids = np.ascontiguousarray(trace_ids)
+        self.arena = np.ascontiguousarray(arena)
+
+    @property
+    def n(self) -> int:
+        return len(self.desc)
+
+    def slice(self, lo: int, hi: int) -> "RequestBatch":
+        """A contiguous shard [lo, hi) that shares the arena (offsets stay absolute)."""
+        return RequestBatch(self.desc[lo:hi].copy(), self.trace_ids[lo:hi].copy(), self.arena)
+
+    def input_bytes(self) -> int:
+        """Bytes the serve kernel must read: descriptors + trace ids + the arena bytes the descriptors cover."""
+        return self.n * 32 + int(self.arena_span())
+
+    def arena_span(self) -> int:
+        if self.n == 0:
+            return 0
+        d = self.desc
+        start = int(d["arena_off"][0])
+        last = d[-1]
+        end = ((int(last["arena_off"]) + int(last["path_len"]) + int(last["query_len"]) + 3) & ~3) + int(last["data_len"])
+        return end - start
+
+    @staticmethod
+    def pack(reqs: Sequence[Req], seed: int = 0x60F2B200) -> "RequestBatch":
+        n = len(reqs)
+        desc = np.zeros(n, dtype=DESC_DTYPE)
+        ids = np.zeros((n, 16), dtype=np.uint8)
+        arena = bytearray()
+        rng = np.random.default_rng(seed)
+        rnd = rng.integers(0, 256, size=(n, 16), dtype=np.uint8)
+        for i, r in enumerate(reqs):
+            while len(arena) % 4:
+                arena.append(0)
+            off = len(arena)
+            arena += r.path
+            arena += r.query
+            while len(arena) % 4:
+                arena.append(0)
+            arena += r.data
+            desc[i] = (off, len(r.path), len(r.query), len(r.data), r.method, r.flags, 0)
+            ids[i] = np.frombuffer(r.trace_id, dtype=np.uint8) if r.trace_id is not None else rnd[i]
+        while len(arena) % 16:
+            arena.append(0)
+        return RequestBatch(desc, ids, np.frombuffer(bytes(arena), dtype=np.uint8).copy())
+
+
+def http_date(unix_seconds: int) -> bytes:
+    """net/http appendTime: IMF-fixdate, always 29 bytes."""
+    import time
+    t = time.gmtime(unix_seconds)
+    days = ["Mon", "Tue", "Wed", "Thu", "Fri", "Sat", "Sun"]
+    months = ["Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec"]
+    s = "%s, %02d %s %04d %02d:%02d:%02d GMT" % (days[t.tm_wday], t.tm_mday, months[t.tm_mon - 1], t.tm_year,
+                                                  t.tm_hour, t.tm_min, t.tm_sec)
+    b = s.encode()
+    assert len(b) == 29
+    return b

@@ -1,0 +1,233 @@
+/*
+ * gofr_b200.h — C ABI of the B200-native GoFr request hot path.
+ *
+ * This is the drop-in boundary.  The reference (JigarJoshi04/gofr) has no FFI of its own: its seams
+ * are in-process Go interfaces.  Each entry point below names the reference interface it stands in for, so a Go shim
+ * (go/gofrb200/) binds them one-to-one over cgo:
+ *
+ *   reference interface (file:line)                              replaced by
+ *   ------------------------------------------------------------ ---------------------------------------------
+ *   http.NewRouter                pkg/gofr/http/router.go:17-28    gofr_table_create
+ *   Router.Add / App.add          pkg/gofr/http/router.go:30-33,   gofr_table_add_route
+ *                                 pkg/gofr/gofr.go:171-177
+ *   App.Run default routes        pkg/gofr/gofr.go:102-107         gofr_table_add_default_routes
+ *   (route table frozen at Run)   pkg/gofr/gofr.go:90-126          gofr_table_seal / _serialize / _deserialize
+ *   mux.Router.ServeHTTP → middleware chain → handler.ServeHTTP → Responder.Respond → net/http framing
+ *                                 pkg/gofr/http/router.go:14,
+ *                                 pkg/gofr/http/middleware/{tracer,logger,cors}.go,
+ *                                 pkg/gofr/handler.go:32-36,
+ *                                 pkg/gofr/http/responder.go:19-41 gofr_serve_device / gofr_batch_submit+wait
+ *   Request.Param / Bind          pkg/gofr/http/request.go:28-47   (fused into the serve kernel per handler kind)
+ *   _Hello_SayHello_Handler       examples/grpc-server/grpc/
+ *                                 hello_grpc.pb.go:73-89           gofr_grpc_hello_device
+ *
+ * Conventions (mirroring the reference's "log and continue", responder.go:29,40): plain C types only, integer status
+ * codes, never abort; per-request outcomes are reported in the response meta column; the table is immutable after
+ * seal (the reference never mutates routes after Run()); no callbacks into the caller from CUDA threads (cgo-safe).
+ * Values that are non-deterministic in the reference are INPUTS here: the 16-byte OTel trace id per request
+ * (middleware/logger.go:46-47) and the IMF-fixdate `Date` string per batch (net/http).
+ */
+#ifndef GOFR_B200_H
+#define GOFR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GOFR_ABI_VERSION 1
+
+/* ---- status codes (returned by every entry point) ---- */
+enum {
+    GOFR_OK = 0,
+    GOFR_ERR_INVALID = 1,      /* bad argument */
+    GOFR_ERR_UNSUPPORTED = 2,  /* e.g. a {var:regexp} outside the supported class, a float field */
+    GOFR_ERR_NOMEM = 3,
+    GOFR_ERR_CUDA = 4,         /* a CUDA runtime call failed; gofr_last_error() has the text */
+    GOFR_ERR_SEALED = 5,       /* mutation after seal */
+    GOFR_ERR_NOT_SEALED = 6,
+    GOFR_ERR_CAPACITY = 7,     /* batch / arena / output larger than the engine was created for */
+    GOFR_ERR_NO_DEVICE = 8     /* no CUDA device: the product path has no CPU fallback, by design */
+};
+
+/* ---- request methods.  mux's methodMatcher compares exact upper-case strings; the shim maps the exact strings
+ *      below and sends everything else (including lower-case spellings) as GOFR_M_OTHER, which matches no
+ *      method-restricted route. ---- */
+enum {
+    GOFR_M_GET = 0, GOFR_M_HEAD = 1, GOFR_M_POST = 2, GOFR_M_PUT = 3, GOFR_M_PATCH = 4, GOFR_M_DELETE = 5,
+    GOFR_M_CONNECT = 6, GOFR_M_OPTIONS = 7, GOFR_M_TRACE = 8, GOFR_M_OTHER = 15,
+    GOFR_M_ANY = 255 /* registration only: no method matcher (PathPrefix("/") catch-all, gofr.go:104) */
+};
+
+/* ---- framing modes ---- */
+enum {
+    GOFR_FRAME_WIRE = 0,     /* what net/http 1.21 puts on the socket: Responder sets Content-type AFTER WriteHeader
+                                (responder.go:21 vs :39) so the type is sniffed: text/plain; charset=utf-8 */
+    GOFR_FRAME_INTENDED = 1, /* what the reference's tests observe through the live recorder map
+                                (responder_test.go:28, gofr_test.go:104): Content-Type: application/json */
+    GOFR_FRAME_BODY = 2      /* response body only (unambiguous in both modes) */
+};
+
+/* ---- declarative handler kinds.  User handlers are arbitrary Go closures (handler.go:12) and cannot run on the
+ *      GPU; the kinds below are the closures the reference's examples/tests use, expressed as data so the whole
+ *      request can be served by one fused kernel.  GOFR_H_HOST is the general case: the GPU routes, the host runs
+ *      the closure, the GPU encodes (two launches). ---- */
+enum {
+    GOFR_H_HOST = 0,          /* arbitrary closure on the host; serve emits nothing and reports route_id */
+    GOFR_H_STATIC_STRING = 1, /* return s0, nil                       gofr_test.go:62-64 */
+    GOFR_H_STATIC_ERROR = 2,  /* return nil, errors.New(s0)           examples/http-server/main.go:41-43 */
+    GOFR_H_NIL = 3,           /* return nil, nil                      handler_test.go:29 */
+    GOFR_H_PARAM_FORMAT = 4,  /* v := c.Param(s0); if v == "" { v = s1 }; return s2 + v + s3, nil
+                                 examples/http-server/main.go:31-39, gofr_test.go:80-82 */
+    GOFR_H_ROW = 5,           /* return <struct of schema>, nil; field values arrive in the request's data section */
+    GOFR_H_BIND_ECHO = 6,     /* var v T; if err := c.Bind(&v); err != nil { return nil, err }; return v, nil */
+    GOFR_H_HEALTH = 7,        /* healthHandler with no datasources: map{} handler.go:38-40, container.go:26-38 */
+    GOFR_H_MISSING_FILE = 8,  /* catchAllHandler: return nil, http.ErrMissingFile      handler.go:51-53 */
+    GOFR_H_FILE = 9,          /* return response.File{Content: blob, ContentType: s0}   handler.go:42-49 */
+    GOFR_H_PANIC = 10         /* handler panics; middleware.panicRecovery answers       middleware/logger.go:91-114 */
+};
+
+/* ---- struct field kinds for response / Bind schemas ---- */
+enum {
+    GOFR_F_INT64 = 1,
+    GOFR_F_INT32 = 2,
+    GOFR_F_BOOL = 3,
+    GOFR_F_STRING = 4,
+    GOFR_F_INT = 5     /* Go int (64-bit); only the type name in Bind error text differs from INT64 */
+};
+
+typedef struct gofr_field_desc {
+    const char* go_name;   /* Go field name (case-insensitive Bind fallback, error text) */
+    const char* json_name; /* `json:"..."` name; NULL/"" = go_name */
+    uint8_t kind;          /* GOFR_F_* */
+    uint8_t omitempty;
+    uint8_t reserved[6];
+} gofr_field_desc;
+
+typedef struct gofr_handler_desc {
+    uint32_t kind;        /* GOFR_H_* */
+    uint32_t schema_id;   /* GOFR_H_ROW, GOFR_H_BIND_ECHO */
+    const char* s0; uint32_t s0_len;
+    const char* s1; uint32_t s1_len;
+    const char* s2; uint32_t s2_len;
+    const char* s3; uint32_t s3_len;
+    const uint8_t* blob; uint32_t blob_len; /* GOFR_H_FILE */
+} gofr_handler_desc;
+
+/* ---- request batch (host or device memory, SoA): desc[n], trace_id[n][16], arena[arena_bytes] ----
+ * A request's variable bytes are contiguous in the arena:
+ *   [ URL.Path (decoded) | URL.RawQuery | pad to 4 | data section ]
+ * arena_off must be a multiple of 4.  The data section is the request body for GOFR_H_BIND_ECHO routes and the
+ * handler-result row for GOFR_H_ROW routes.  Row format: one little-endian 32-bit word per field in schema order
+ * (INT64: two words lo,hi; INT32: one; BOOL: one, 0/1; STRING: one, the byte length) followed by the string bytes
+ * of all STRING fields concatenated in schema order. */
+typedef struct gofr_req_desc {
+    uint32_t arena_off;
+    uint16_t path_len;
+    uint16_t query_len;
+    uint32_t data_len;
+    uint8_t method; /* GOFR_M_* */
+    uint8_t flags;  /* GOFR_REQ_* */
+    uint16_t aux;
+} gofr_req_desc;
+
+#define GOFR_REQ_FORCE_QUERY 0x01u /* url.URL.ForceQuery: target ended in a bare '?' (only visible in a 301 Location) */
+
+/* ---- response batch: out[out_off[i] .. out_off[i+1]) are request i's bytes, packed in request order;
+ *      meta[i] = status (low 16 bits) | route_id << 16 (0xFFFF = no user route; status 0 = GOFR_H_HOST pending) ---- */
+#define GOFR_META_STATUS(m) ((uint32_t)(m) & 0xFFFFu)
+#define GOFR_META_ROUTE(m) ((uint32_t)(m) >> 16)
+#define GOFR_ROUTE_NONE 0xFFFFu
+
+typedef struct gofr_table gofr_table;
+typedef struct gofr_engine gofr_engine;
+typedef uint64_t gofr_ticket;
+
+/* ================= route table (startup, single thread) ================= */
+int gofr_table_create(gofr_table** out, uint32_t frame_mode);
+void gofr_table_destroy(gofr_table*);
+int gofr_table_add_schema(gofr_table*, uint32_t schema_id, const char* go_type_name, const gofr_field_desc* fields,
+                          uint32_t n_fields);
+/* Call order is match priority (mux scans routes in registration order).  Patterns: literals, {name} (= [^/]+) and
+ * {name:[class]+} / {name:[class]*} with a bracket class or \d / \w / .   Other regexps → GOFR_ERR_UNSUPPORTED. */
+int gofr_table_add_route(gofr_table*, uint32_t method, const char* pattern, uint32_t pattern_len,
+                         const gofr_handler_desc* handler, uint32_t* route_id_out);
+/* GET /.well-known/health, GET /favicon.ico, PathPrefix("/") catch-all — appended after the user routes, as
+ * App.Run does.  Without this call the table behaves like the router before Run() (gofr_test.go:85-95): mux's own
+ * plain-text 404 / empty 405 answer unmatched requests and no middleware runs for them. */
+int gofr_table_add_default_routes(gofr_table*, const uint8_t* favicon, uint32_t favicon_len);
+int gofr_table_seal(gofr_table*);
+/* The sealed image is position independent: rank 0 seals and serializes, the bytes are broadcast (NCCL), every
+ * other rank deserializes.  *len_inout: capacity in, size out (call with buf NULL to query). */
+int gofr_table_serialize(const gofr_table*, uint8_t* buf, uint64_t* len_inout);
+int gofr_table_deserialize(gofr_table** out, const uint8_t* buf, uint64_t len);
+uint32_t gofr_table_route_count(const gofr_table*);
+uint32_t gofr_table_max_response_bytes(const gofr_table*, uint32_t max_data_len);
+
+/* ================= engine (one per GPU / process) ================= */
+int gofr_engine_create(gofr_engine** out, const gofr_table* sealed, int device);
+void gofr_engine_destroy(gofr_engine*);
+
+/* Device-resident batch: every pointer is device memory, `stream` is a cudaStream_t (NULL = default stream).
+ * One fused launch: route match + middleware predicates + handler kind + JSON encode + HTTP framing.
+ * date is the 29-byte IMF-fixdate for this batch (host memory).  d_total receives the packed size (= out_off[n]). */
+int gofr_serve_device(gofr_engine*, const gofr_req_desc* d_desc, const uint8_t* d_trace_ids, const uint8_t* d_arena,
+                      uint32_t n, const char* date29, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off,
+                      uint32_t* d_meta, void* stream);
+
+/* Host batch: pinned (gofr_alloc_pinned) or pageable caller-owned buffers; the engine pipelines
+ * H2D → kernel → D2H in chunks over its own streams.  submit is thread-safe; wait blocks the caller. */
+typedef struct gofr_req_batch {
+    const gofr_req_desc* desc;
+    const uint8_t* trace_ids;
+    const uint8_t* arena;
+    uint64_t arena_bytes;
+    uint32_t n;
+    char date[29];
+    uint8_t pad[3];
+} gofr_req_batch;
+
+typedef struct gofr_resp_batch {
+    uint8_t* out;       /* capacity out_cap */
+    uint64_t out_cap;
+    uint32_t* out_off;  /* n+1 */
+    uint32_t* meta;     /* n */
+    uint64_t out_bytes; /* filled by wait */
+} gofr_resp_batch;
+
+int gofr_batch_submit(gofr_engine*, const gofr_req_batch* in, gofr_resp_batch* out, gofr_ticket* ticket);
+int gofr_batch_wait(gofr_engine*, gofr_ticket ticket);
+int gofr_engine_set_chunk(gofr_engine*, uint32_t requests_per_chunk);
+/* Tile geometry: shared-memory staging budget per request (bytes).  Tiles whose request bytes / response bytes exceed
+ * the budget are still served correctly, straight from / to HBM. */
+int gofr_engine_set_tile(gofr_engine*, uint32_t in_bytes_per_req, uint32_t out_bytes_per_req);
+int gofr_engine_geometry(const gofr_engine*, uint32_t* grid, uint32_t* blocks_per_sm, uint32_t* smem_bytes,
+                         uint32_t* sm_count);
+/* gofr_serve_device reports an undersized d_out through this flag (the launch itself is asynchronous). */
+int gofr_engine_overflowed(gofr_engine*, int* flag_out, int reset);
+int gofr_engine_set_timing(gofr_engine*, int on);
+
+void* gofr_alloc_pinned(size_t bytes);
+void gofr_free_pinned(void*);
+
+/* gRPC unary Hello (config 5): length-prefixed HelloRequest frames in, length-prefixed HelloResponse frames out,
+ * packed; frame i of the input starts at in_off[i].  meta[i] = 0 ok, else a GOFR_GRPC_* error (frame emitted empty). */
+enum { GOFR_GRPC_OK = 0, GOFR_GRPC_COMPRESSED = 1, GOFR_GRPC_BAD_LENGTH = 2, GOFR_GRPC_BAD_PROTO = 3, GOFR_GRPC_BAD_UTF8 = 4 };
+int gofr_grpc_hello_device(gofr_engine*, const uint8_t* d_in, const uint32_t* d_in_off, uint32_t n, uint8_t* d_out,
+                           uint64_t out_cap, uint32_t* d_out_off, uint32_t* d_meta, void* stream);
+
+/* number of kernels launched by this engine so far (bench.py reports it as gpu_launches) */
+uint64_t gofr_engine_launch_count(const gofr_engine*);
+/* duration in ms of the serve kernels launched since the last reset, measured with CUDA events on the launch stream */
+int gofr_engine_kernel_time_ms(gofr_engine*, double* total_ms, uint64_t* launches, int reset);
+
+const char* gofr_last_error(void);
+uint32_t gofr_abi_version(void);
+void gofr_format_http_date(int64_t unix_seconds, char out29[29]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOFR_B200_H */

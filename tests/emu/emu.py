@@ -1,0 +1,51 @@
+"""TEST INFRASTRUCTURE ONLY: CPU execution of the kernel's per-request device code (see emu_serve.cpp)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+LIB = os.path.join(HERE, "libgofr_emu.so")
+_lib = None
+
+
+def _build():
+    srcs = [os.path.join(HERE, "emu_serve.cpp"), os.path.join(ROOT, "gofr_b200", "csrc", "serve_device.cuh"),
+            os.path.join(ROOT, "gofr_b200", "csrc", "bind_device.cuh"),
+            os.path.join(ROOT, "gofr_b200", "csrc", "table_format.h")]
+    srcs = [s for s in srcs if os.path.exists(s)]
+    if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
+        return
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
+                           "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-static-libubsan",
+                           "-o", LIB, os.path.join(HERE, "emu_serve.cpp")])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _build()
+        _lib = C.CDLL(LIB)
+        _lib.emu_serve.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p,
+                                   C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
+    return _lib
+
+
+def serve(image: bytes, batch, date: bytes, out_cap: int | None = None, misalign: int = 0):
+    n = batch.n
+    if out_cap is None:
+        out_cap = max(4096, n * 700 + int(batch.arena.size) * 6) + 64 + len(image) * max(1, n // 8)
+    img = np.frombuffer(image, dtype=np.uint8).copy()
+    out = np.full(out_cap, 0xEE, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    meta = np.zeros(n, dtype=np.uint32)
+    rc = lib().emu_serve(img.ctypes.data, len(image), batch.desc.ctypes.data, batch.trace_ids.ctypes.data,
+                         batch.arena.ctypes.data, n, date, out.ctypes.data, out_cap, off.ctypes.data, meta.ctypes.data,
+                         misalign)
+    if rc != 0:
+        raise RuntimeError("emu output capacity too small")
+    return out, off, meta

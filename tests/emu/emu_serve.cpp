@@ -1,0 +1,53 @@
+// emu_serve.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// Runs the serve kernel's per-request code (gofr_b200/csrc/serve_device.cuh, the very same __host__ __device__
+// functions the CUDA kernel calls) on the CPU, one request after another, packing the output the way the kernel does.
+// Purpose: this container has no GPU, so kernel *logic* bugs (routing, sizing, the funnel-shift word writer) are caught
+// here against the oracle; tile staging, the block scan and the look-back only exist in serve_kernel.cu and are
+// covered by the `-m gpu` tests.  Nothing in the product links or loads this file.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../gofr_b200/csrc/serve_device.cuh"
+
+using namespace gofr;
+
+extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t* desc, const uint8_t* ids,
+                         const uint8_t* arena, uint32_t n, const char* date29, uint8_t* out, uint64_t out_cap,
+                         uint32_t* out_off, uint32_t* meta, uint32_t start_misalign) {
+    (void)image_len;
+    // the kernel works on a 16-byte aligned shared-memory copy of the hot part
+    ImageHeader H;
+    memcpy(&H, image, sizeof H);
+    std::vector<uint32_t> hot((H.hot_bytes + 3) / 4 + 4);
+    memcpy(hot.data(), image, H.hot_bytes);
+    TableView tv;
+    tv.bind((const uint8_t*)hot.data(), image);
+    uint32_t date[8] = {0};
+    memcpy(date, date29, 29);
+    uint64_t pos = start_misalign;  // lets the test exercise every head alignment
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t d[4];
+        memcpy(d, desc + (size_t)i * 16, 16);
+        ReqCtx c;
+        uint32_t arena_off = d[0], path_len = d[1] & 0xFFFF, query_len = d[1] >> 16, data_len = d[2];
+        uint32_t data_off = (arena_off + path_len + query_len + 3u) & ~3u;
+        c.path = arena + arena_off;
+        c.query = c.path + path_len;
+        c.data = arena + data_off;
+        c.path_len = path_len; c.query_len = query_len; c.data_len = data_len;
+        c.method = d[3] & 0xFF;
+        c.flags = (d[3] >> 8) & 0xFF;
+        memcpy(c.id, ids + (size_t)i * 16, 16);
+        c.total_len = c.body_len = 0; c.status = 0; c.route = GOFR_ROUTE_NONE; c.prog = 0xFFFF;
+        size_request(tv, c);
+        out_off[i] = (uint32_t)pos;
+        meta[i] = c.status | (c.route << 16);
+        if (pos + c.total_len > out_cap) return -1;
+        emit_request(tv, c, out + pos, date);
+        pos += c.total_len;
+    }
+    out_off[n] = (uint32_t)pos;
+    return 0;
+}

@@ -1,0 +1,167 @@
+"""ctypes binding of the CPU oracle (oracle/libgofr_oracle.so) — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Tuple
+
+import numpy as np
+
+from gofr_b200 import spec as S
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB_PATH = os.path.join(_ROOT, "oracle", "libgofr_oracle.so")
+_lib = None
+
+
+def build() -> None:
+    srcs = ["gofr_oracle.c", "orc_bind.c", "orc_grpc.c", "gofr_oracle.h", "orc_internal.h"]
+    odir = os.path.join(_ROOT, "oracle")
+    if os.path.exists(_LIB_PATH):
+        so_m = os.path.getmtime(_LIB_PATH)
+        if all(os.path.getmtime(os.path.join(odir, s)) <= so_m for s in srcs):
+            return
+    subprocess.check_call(["make", "-C", odir, "-s", "CC=gcc"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.orc_table_new.restype = C.c_void_p
+        L.orc_table_new.argtypes = [C.c_int]
+        L.orc_table_free.argtypes = [C.c_void_p]
+        L.orc_add_schema.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_char_p),
+                                     C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_add_route.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int] + \
+            [C.c_char_p, C.c_int] * 4 + [C.c_char_p, C.c_int]
+        L.orc_add_default_routes.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.orc_serve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_void_p,
+                                C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_grpc_hello.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                     C.c_int]
+        for name in ("orc_json_string", "orc_clean_path", "orc_escape_path"):
+            getattr(L, name).argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+        L.orc_json_int.argtypes = [C.c_int64, C.c_char_p, C.c_int]
+        L.orc_query_get.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+        L.orc_match.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+        L.orc_bind.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+        L.orc_rpclog_string.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_char_p, C.c_char_p, C.c_int]
+        L.orc_format_http_date.argtypes = [C.c_int64, C.c_char_p]
+        _lib = L
+    return _lib
+
+
+def _buf_call(fn, *args, cap=1 << 16) -> bytes:
+    out = C.create_string_buffer(cap)
+    n = fn(*args, out, cap)
+    if n < 0:
+        raise RuntimeError(f"oracle call failed: {n}")
+    return out.raw[:n]
+
+
+def json_string(s: bytes) -> bytes:
+    return _buf_call(lib().orc_json_string, s, len(s), cap=len(s) * 6 + 16)
+
+
+def json_int(v: int) -> bytes:
+    return _buf_call(lib().orc_json_int, v)
+
+
+def clean_path(p: bytes) -> bytes:
+    return _buf_call(lib().orc_clean_path, p, len(p), cap=len(p) + 16)
+
+
+def escape_path(p: bytes) -> bytes:
+    return _buf_call(lib().orc_escape_path, p, len(p), cap=len(p) * 3 + 16)
+
+
+def query_get(q: bytes, key: bytes) -> bytes:
+    return _buf_call(lib().orc_query_get, q, len(q), key, len(key), cap=len(q) + 16)
+
+
+def rpclog_string(id_: str, start: str, rt: int, method: str) -> bytes:
+    return _buf_call(lib().orc_rpclog_string, id_.encode(), start.encode(), rt, method.encode())
+
+
+def http_date(unix_seconds: int) -> bytes:
+    out = C.create_string_buffer(29)
+    lib().orc_format_http_date(unix_seconds, out)
+    return out.raw[:29]
+
+
+class OracleTable:
+    def __init__(self, spec: S.TableSpec):
+        L = lib()
+        self._t = L.orc_table_new(spec.frame_mode)
+        self.spec = spec
+        for sc in spec.schemas:
+            n = len(sc.fields)
+            go = (C.c_char_p * n)(*[f.go_name.encode() for f in sc.fields])
+            js = (C.c_char_p * n)(*[f.json_name.encode() for f in sc.fields])
+            kinds = (C.c_int * n)(*[f.kind for f in sc.fields])
+            oe = (C.c_int * n)(*[1 if f.omitempty else 0 for f in sc.fields])
+            L.orc_add_schema(self._t, sc.id, sc.go_type.encode(), n, go, js, kinds, oe)
+        self.route_ids = []
+        for r in spec.routes:
+            p = r.pattern.encode()
+            rid = L.orc_add_route(self._t, r.method, p, len(p), r.kind, r.schema_id, r.s0, len(r.s0), r.s1, len(r.s1),
+                                  r.s2, len(r.s2), r.s3, len(r.s3), r.blob, len(r.blob))
+            if rid < 0:
+                raise ValueError(f"oracle refused route {r.pattern!r}")
+            self.route_ids.append(rid)
+        if spec.default_routes:
+            L.orc_add_default_routes(self._t, spec.favicon, len(spec.favicon))
+
+    def __del__(self):
+        try:
+            lib().orc_table_free(self._t)
+        except Exception:
+            pass
+
+    def match(self, method: int, path: bytes) -> int:
+        return lib().orc_match(self._t, method, path, len(path))
+
+    def bind(self, schema_id: int, body: bytes):
+        out = C.create_string_buffer(len(body) * 4 + 4096)
+        n = lib().orc_bind(self._t, schema_id, body, len(body), out, len(out))
+        if n >= 0:
+            return True, out.raw[:n]
+        return False, out.raw[:-n]
+
+    def serve(self, batch: S.RequestBatch, date: bytes, out_cap: int | None = None,
+              nthreads: int = 1) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        n = batch.n
+        if out_cap is None:
+            out_cap = max(4096, n * 640 + int(batch.arena.size) * 6 + len(self.spec.favicon) * n // 4)
+        out = np.zeros(out_cap, dtype=np.uint8)
+        off = np.zeros(n + 1, dtype=np.uint32)
+        meta = np.zeros(n, dtype=np.uint32)
+        rc = lib().orc_serve(self._t, batch.desc.ctypes.data, batch.trace_ids.ctypes.data, batch.arena.ctypes.data, n,
+                             date, out.ctypes.data, out_cap, off.ctypes.data, meta.ctypes.data, nthreads)
+        if rc != 0:
+            raise RuntimeError("oracle output capacity too small")
+        return out, off, meta
+
+
+def responses(out: np.ndarray, off: np.ndarray):
+    b = out.tobytes()
+    return [b[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)]
+
+
+def grpc_hello(frames: np.ndarray, in_off: np.ndarray, nthreads: int = 1):
+    n = len(in_off) - 1
+    cap = int(frames.size) + 32 * n + 64
+    out = np.zeros(cap, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    meta = np.zeros(n, dtype=np.uint32)
+    rc = lib().orc_grpc_hello(frames.ctypes.data, in_off.ctypes.data, n, out.ctypes.data, cap, off.ctypes.data,
+                              meta.ctypes.data, nthreads)
+    if rc != 0:
+        raise RuntimeError("oracle output capacity too small")
+    return out, off, meta
