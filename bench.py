@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — requests/s of the GoFr request hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference path, host cores
+
+A "step" is one pass of the hot path over one batch of synthetic requests.  Workload at every N: BASELINE config 2 —
+16-route GET table, 256-byte JSON struct body, 1 Mi requests per GPU (weak scaling: each rank serves its own
+contiguous shard of the request stream; no data-path collective, the sealed route table is broadcast once with NCCL).
+  value  : whole-job requests/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e    : the same through the host-buffer call a user makes (gofr_batch_submit/_wait): pinned host buffers,
+           H2D and D2H inside the timed region
+  roofline: algorithmic bytes of one launch / its mean CUDA-event duration, against the measured HBM copy peak
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from gofr_b200 import spec as S  # noqa: E402
+from gofr_b200 import synth  # noqa: E402
+
+METRIC = "requests_per_sec_256B_json_body"
+UNIT = "req/s"
+DATE_UNIX = 1789974595
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nm, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args):
+    """The reference arm: the CPU restatement of the reference's Go path (oracle/, kind "port" — no Go toolchain
+    exists in this image, so the reference itself cannot be built) on all host cores, same workload and metric."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    from tests import oracle as O
+    cores = os.cpu_count() or 1
+    n = args.ref_requests
+    spec = synth.config2_spec(S.FRAME_WIRE)
+    batch = synth.config2_batch(n)
+    table = O.OracleTable(spec)
+    date = S.http_date(DATE_UNIX)
+    cap = n * 640 + 4096
+    out = np.zeros(cap, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    meta = np.zeros(n, dtype=np.uint32)
+
+    def step():
+        rc = O.lib().orc_serve(table._t, batch.desc.ctypes.data, batch.trace_ids.ctypes.data, batch.arena.ctypes.data,
+                               n, date, out.ctypes.data, cap, off.ctypes.data, meta.ctypes.data, cores)
+        assert rc == 0
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"{n} requests per step of the config-2 stream, {cores} pthreads, in-memory (no sockets, no logging)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(n, args.gpus, "cpu"),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n, gpus, where):
+    return {"workload": "BASELINE config 2: 16-route GET table, 256B JSON struct body (521B full HTTP/1.1 response, "
+                        "wire framing), %d requests per %s" % (n, "GPU" if where == "gpu" else "step"),
+            "requests_per_gpu": n, "frame_mode": "wire", "routes": 16, "parallelism": f"dp{gpus} (requests sharded, no data-path collective)",
+            "l2": "inputs+outputs per step (~0.8 GB) exceed the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--requests", type=int, default=1 << 20, help="requests per GPU per step")
+    ap.add_argument("--ref-requests", type=int, default=1 << 18, help="requests per step of the CPU reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=1 << 19, help="requests in the cpu_baseline sample")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer measurement (default: --steps)")
+    ap.add_argument("--chunk", type=int, default=65536)
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from gofr_b200.engine import Engine, pin_batch, pinned_array
+    from gofr_b200.table import Table
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: gofr_b200 has no CPU path"}))
+        return 2
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- route table: sealed on rank 0, broadcast as bytes over NCCL, deserialised everywhere ----
+    if rank == 0:
+        image = Table(synth.config2_spec(S.FRAME_WIRE)).serialize()
+        ln = torch.tensor([len(image)], dtype=torch.int64, device=dev)
+    else:
+        image, ln = b"", torch.zeros(1, dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(ln, 0)
+        buf = torch.frombuffer(bytearray(image), dtype=torch.uint8).to(dev) if rank == 0 else torch.empty(int(ln.item()), dtype=torch.uint8, device=dev)
+        dist.broadcast(buf, 0)
+        image = buf.cpu().numpy().tobytes()
+    table = Table(image=image)
+    eng = Engine(table, local)
+    eng.set_chunk(args.chunk)
+
+    n = args.requests
+    date = S.http_date(DATE_UNIX)
+    batch = synth.config2_batch(n, start=rank * n)  # this rank's shard of the stream
+    out_bytes = n * synth.C2_WIRE_BYTES
+    db = eng.upload(batch)
+    resp = eng.alloc_responses(n, out_bytes + 4096)
+    # algorithmic bytes of one launch: every input byte read once, every output byte written once
+    algo_bytes = batch.input_bytes() + out_bytes + 4 * (n + 1) + 4 * n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident measurement (`value`, roofline) ----
+    for _ in range(args.warmup):
+        eng.serve_device(db, date, resp)
+    barrier()
+    assert not eng.overflowed()
+    eng.kernel_time_ms(reset=True)
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        eng.serve_device(db, date, resp)
+    ev1.record()
+    barrier()
+    ms = reduce_max(ev0.elapsed_time(ev1))
+    clocks = sampler.stop()
+    kernel_ms, kernel_launches = eng.kernel_time_ms(reset=True)
+    launches = eng.launch_count() - launches0
+    value = n * world * args.steps / (ms / 1e3)
+    per_launch_ms = kernel_ms / max(kernel_launches, 1)
+    achieved = algo_bytes / (per_launch_ms / 1e3) / 1e9
+    peak, peak_src = hbm_peak()
+
+    # spot check inside the bench: sizes are what the workload says
+    off = resp.out_off.cpu().numpy().view(np.uint32)
+    assert int(off[n]) == out_bytes, "unexpected response size"
+
+    # ---- end-to-end measurement: host buffers through gofr_batch_submit/_wait ----
+    e2e = None
+    if not args.no_e2e:
+        hb = pin_batch(batch)
+        h_out = pinned_array(out_bytes + 4096)
+        h_off = pinned_array(4 * (n + 1), np.uint32)
+        h_meta = pinned_array(4 * n, np.uint32)
+        ksteps = args.e2e_steps or args.steps
+        for _ in range(args.warmup):
+            got = eng.serve_host(hb, date, h_out, h_off, h_meta)
+        assert got == out_bytes
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            eng.serve_host(hb, date, h_out, h_off, h_meta)
+        barrier()
+        dt = reduce_max(time.perf_counter() - t0)
+        h2d = n * 32 + int(batch.arena_span())
+        d2h = out_bytes + 4 * n + 4 * n + 8 * ((n + args.chunk - 1) // args.chunk)
+        e2e = {"value": n * world * ksteps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt / ksteps * 1e3, "steps": ksteps, "chunk_requests": args.chunk,
+               "timing": "wall clock around the synchronous host-buffer calls, max over ranks"}
+        # the last host result must match the resident one byte for byte
+        dev_out = resp.out[:out_bytes].cpu().numpy()
+        assert np.array_equal(h_out[:out_bytes], dev_out), "host path and resident path disagree"
+
+    # ---- CPU baseline beside it (rank 0, bounded sample of the same stream) ----
+    cpu = None
+    if rank == 0:
+        from tests import oracle as O
+        cores = os.cpu_count() or 1
+        m = min(args.cpu_sample, n)
+        sb = synth.config2_batch(m)
+        ot = O.OracleTable(synth.config2_spec(S.FRAME_WIRE))
+        cap = m * 640 + 4096
+        o = np.zeros(cap, dtype=np.uint8)
+        f = np.zeros(m + 1, dtype=np.uint32)
+        mt = np.zeros(m, dtype=np.uint32)
+        reps = 4
+        O.lib().orc_serve(ot._t, sb.desc.ctypes.data, sb.trace_ids.ctypes.data, sb.arena.ctypes.data, m, date,
+                          o.ctypes.data, cap, f.ctypes.data, mt.ctypes.data, cores)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            O.lib().orc_serve(ot._t, sb.desc.ctypes.data, sb.trace_ids.ctypes.data, sb.arena.ctypes.data, m, date,
+                              o.ctypes.data, cap, f.ctypes.data, mt.ctypes.data, cores)
+        dtc = time.perf_counter() - t0
+        cpu = {"value": m * reps / dtc, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{reps} passes over the first {m} requests of the same stream, {cores} pthreads, in-memory"}
+        # the sample doubles as a parity check of the bench's own output
+        o1, f1, _ = ot.serve(sb.slice(0, 4096), date)
+        g = resp.out[:4096 * synth.C2_WIRE_BYTES].cpu().numpy()
+        assert np.array_equal(g, o1[:4096 * synth.C2_WIRE_BYTES]), "bench output differs from the oracle"
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic", "config": workload_config(n, world, "gpu"),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                             "algorithmic_bytes_per_request": algo_bytes / n, "kernel_ms_per_launch": per_launch_ms,
+                             "kernel": "gofr::serve_kernel"},
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "geometry": eng.geometry()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

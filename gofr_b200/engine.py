@@ -1,0 +1,152 @@
+"""Per-GPU engine: thin wrapper over gofr_engine_* (include/gofr_b200.h).
+
+torch is plumbing only: it owns device buffers and the CUDA stream whose raw handle is passed through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _abi
+from . import spec as S
+from .table import Table
+
+
+@dataclass
+class DeviceBatch:
+    """A request batch resident in HBM (torch uint8 tensors)."""
+    desc: "torch.Tensor"
+    trace_ids: "torch.Tensor"
+    arena: "torch.Tensor"
+    n: int
+    input_bytes: int
+
+
+@dataclass
+class DeviceResponses:
+    out: "torch.Tensor"       # uint8[out_cap]
+    out_off: "torch.Tensor"   # int32 view of uint32[n+1]
+    meta: "torch.Tensor"      # int32 view of uint32[n]
+    n: int
+
+    def to_host(self):
+        import torch
+        off = self.out_off.cpu().numpy().view(np.uint32)
+        meta = self.meta.cpu().numpy().view(np.uint32)
+        total = int(off[self.n])
+        out = self.out[:total].cpu().numpy()
+        return out, off, meta
+
+
+class Engine:
+    def __init__(self, table: Table, device: int = 0):
+        L = _abi.lib()
+        self._e = C.c_void_p()
+        self.table = table
+        self.device = device
+        _abi.check(L.gofr_engine_create(C.byref(self._e), table.handle, device), "gofr_engine_create")
+
+    def close(self):
+        if self._e:
+            _abi.lib().gofr_engine_destroy(self._e)
+            self._e = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration ----
+    def set_tile(self, in_bytes_per_req: int, out_bytes_per_req: int):
+        _abi.check(_abi.lib().gofr_engine_set_tile(self._e, in_bytes_per_req, out_bytes_per_req), "gofr_engine_set_tile")
+
+    def set_chunk(self, n: int):
+        _abi.check(_abi.lib().gofr_engine_set_chunk(self._e, n), "gofr_engine_set_chunk")
+
+    def set_timing(self, on: bool):
+        _abi.check(_abi.lib().gofr_engine_set_timing(self._e, 1 if on else 0), "gofr_engine_set_timing")
+
+    def geometry(self):
+        g, b, s, m = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _abi.check(_abi.lib().gofr_engine_geometry(self._e, C.byref(g), C.byref(b), C.byref(s), C.byref(m)),
+                   "gofr_engine_geometry")
+        return {"grid": g.value, "blocks_per_sm": b.value, "smem_bytes": s.value, "sm_count": m.value}
+
+    def launch_count(self) -> int:
+        return int(_abi.lib().gofr_engine_launch_count(self._e))
+
+    def kernel_time_ms(self, reset: bool = False):
+        ms, n = C.c_double(), C.c_uint64()
+        _abi.check(_abi.lib().gofr_engine_kernel_time_ms(self._e, C.byref(ms), C.byref(n), 1 if reset else 0),
+                   "gofr_engine_kernel_time_ms")
+        return ms.value, n.value
+
+    def overflowed(self, reset: bool = True) -> bool:
+        f = C.c_int()
+        _abi.check(_abi.lib().gofr_engine_overflowed(self._e, C.byref(f), 1 if reset else 0), "gofr_engine_overflowed")
+        return bool(f.value)
+
+    # ---- device-resident path ----
+    def upload(self, batch: S.RequestBatch) -> DeviceBatch:
+        import torch
+        dev = torch.device("cuda", self.device)
+        desc = torch.from_numpy(batch.desc.view(np.uint8).reshape(-1).copy()).to(dev)
+        ids = torch.from_numpy(batch.trace_ids.reshape(-1).copy()).to(dev)
+        pad = (-batch.arena.size) % 16 + 16
+        arena = torch.from_numpy(np.concatenate([batch.arena, np.zeros(pad, dtype=np.uint8)])).to(dev)
+        return DeviceBatch(desc, ids, arena, batch.n, batch.input_bytes())
+
+    def alloc_responses(self, n: int, out_cap: int) -> DeviceResponses:
+        import torch
+        dev = torch.device("cuda", self.device)
+        out = torch.empty(out_cap + 64, dtype=torch.uint8, device=dev)
+        off = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        meta = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+        return DeviceResponses(out, off, meta, n)
+
+    def serve_device(self, b: DeviceBatch, date: bytes, resp: DeviceResponses, stream=None) -> None:
+        """One fused launch on torch's current stream (or `stream`).  Asynchronous."""
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        assert len(date) == 29
+        _abi.check(_abi.lib().gofr_serve_device(self._e, b.desc.data_ptr(), b.trace_ids.data_ptr(), b.arena.data_ptr(),
+                                                b.n, date, resp.out.data_ptr(), resp.out.numel() - 64,
+                                                resp.out_off.data_ptr(), resp.meta.data_ptr(), st.cuda_stream),
+                   "gofr_serve_device")
+
+    # ---- host path (the call a user makes): host buffers in, host buffers out ----
+    def serve_host(self, batch: S.RequestBatch, date: bytes, out: np.ndarray, out_off: np.ndarray, meta: np.ndarray) -> int:
+        L = _abi.lib()
+        rb = _abi.ReqBatch(desc=batch.desc.ctypes.data, trace_ids=batch.trace_ids.ctypes.data,
+                           arena=batch.arena.ctypes.data, arena_bytes=batch.arena.size, n=batch.n, date=date)
+        ob = _abi.RespBatch(out=out.ctypes.data, out_cap=out.size, out_off=out_off.ctypes.data, meta=meta.ctypes.data,
+                            out_bytes=0)
+        t = C.c_uint64()
+        _abi.check(L.gofr_batch_submit(self._e, C.byref(rb), C.byref(ob), C.byref(t)), "gofr_batch_submit")
+        _abi.check(L.gofr_batch_wait(self._e, t.value), "gofr_batch_wait")
+        return int(ob.out_bytes)
+
+
+def pinned_array(nbytes: int, dtype=np.uint8) -> np.ndarray:
+    """numpy view over cudaMallocHost memory (gofr_alloc_pinned).  The memory lives until process exit."""
+    L = _abi.lib()
+    p = L.gofr_alloc_pinned(max(nbytes, 1))
+    if not p:
+        raise MemoryError(L.gofr_last_error().decode())
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p)
+    a = np.frombuffer(buf, dtype=np.uint8)[:nbytes]
+    return a.view(dtype)
+
+
+def pin_batch(batch: S.RequestBatch) -> S.RequestBatch:
+    d = pinned_array(batch.desc.nbytes).view(S.DESC_DTYPE)
+    d[:] = batch.desc
+    i = pinned_array(batch.trace_ids.nbytes).reshape(-1, 16)
+    i[:] = batch.trace_ids
+    a = pinned_array(batch.arena.nbytes)
+    a[:] = batch.arena
+    return S.RequestBatch(d, i, a)

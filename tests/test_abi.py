@@ -1,0 +1,72 @@
+"""Host-side checks that need no GPU: the C-ABI library builds, loads and exports every declared symbol; tables seal,
+serialize and deserialize; errors are reported as codes."""
+import ctypes as C
+import re
+import os
+
+import numpy as np
+import pytest
+
+from gofr_b200 import _abi
+from gofr_b200 import spec as S
+from gofr_b200 import synth
+from gofr_b200.table import Table
+from tests.conftest import has_gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _abi.lib()
+    header = open(os.path.join(ROOT, "include", "gofr_b200.h")).read()
+    declared = set(re.findall(r"\b(gofr_[a-z0-9_]+)\s*\(", header))
+    declared -= {"gofr_table", "gofr_engine"}
+    assert declared, "no declarations found"
+    assert declared == set(_abi.DECLARED_SYMBOLS)
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/gofr_b200.h but not exported"
+    assert L.gofr_abi_version() == 1
+
+
+def test_no_torch_types_in_header():
+    header = open(os.path.join(ROOT, "include", "gofr_b200.h")).read()
+    assert "torch" not in header and "at::" not in header
+
+
+def test_table_seal_serialize_roundtrip():
+    t = Table(synth.config4_spec())
+    img = t.serialize()
+    assert t.route_count() == 64 + 3
+    t2 = Table(image=img)
+    assert t2.serialize() == img and t2.route_count() == 67
+
+
+def test_table_errors_are_codes():
+    L = _abi.lib()
+    with pytest.raises(_abi.GofrError) as e:
+        Table(S.TableSpec(routes=[S.Route(S.M_GET, "/x/{id:(a|b)}", S.H_NIL)]))
+    assert e.value.code == 2  # GOFR_ERR_UNSUPPORTED
+    with pytest.raises(_abi.GofrError) as e:
+        Table(S.TableSpec(routes=[S.Route(S.M_GET, "/x", S.H_ROW, schema_id=99)]))
+    assert e.value.code == 1
+    t = Table(synth.config1_spec())
+    h = _abi.HandlerDesc(kind=S.H_NIL)
+    assert L.gofr_table_add_route(t.handle, 0, b"/late", 5, C.byref(h), None) == 5  # GOFR_ERR_SEALED
+    with pytest.raises(_abi.GofrError):
+        Table(image=b"\x00" * 200)
+
+
+def test_http_date_helper():
+    out = C.create_string_buffer(29)
+    _abi.lib().gofr_format_http_date(1789974595, out)
+    assert out.raw == b"Mon, 21 Sep 2026 07:09:55 GMT"
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-device behaviour")
+def test_engine_fails_loudly_without_a_gpu():
+    """There is no CPU fallback: creating an engine without a CUDA device is an error, not a slow path."""
+    t = Table(synth.config1_spec())
+    e = C.c_void_p()
+    rc = _abi.lib().gofr_engine_create(C.byref(e), t.handle, 0)
+    assert rc == 8  # GOFR_ERR_NO_DEVICE
+    assert b"no CPU path" in _abi.lib().gofr_last_error()
