@@ -122,9 +122,9 @@ int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
     CUDA_TRY(cudaMemcpy(e->d_image, img.data(), img.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&e->d_flag, 64));
     CUDA_TRY(cudaMemset(e->d_flag, 0, 64));
-    // default tile geometry: sized from the table's largest fixed response, clamped so that ≥ 2 CTAs fit per SM
-    uint32_t out_per = std::min<uint32_t>(std::max<uint32_t>(e->hdr.max_fixed_len + 224, 320), 640);
-    int rc = configure_geometry(e, 256, out_per);
+    // default tile geometry: 256 bytes of request data per request are staged in shared memory (larger tiles are
+    // read from HBM directly)
+    int rc = configure_geometry(e, 256, 0);
     if (rc != GOFR_OK) { delete e; return rc; }
     for (auto& s : e->slots) {
         CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -152,7 +152,7 @@ void gofr_engine_destroy(gofr_engine* e) {
 }
 
 int gofr_engine_set_tile(gofr_engine* e, uint32_t in_bytes_per_req, uint32_t out_bytes_per_req) {
-    if (!e || !in_bytes_per_req || !out_bytes_per_req) return GOFR_ERR_INVALID;
+    if (!e || !in_bytes_per_req) return GOFR_ERR_INVALID;
     std::lock_guard<std::mutex> g(e->mu);
     return configure_geometry(e, in_bytes_per_req, out_bytes_per_req);
 }

@@ -11,6 +11,7 @@
 // infrastructure only; the product has no CPU path).
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/gofr_b200.h"
 #include "table_format.h"
@@ -54,33 +55,79 @@ GOFR_HD int clz64(uint64_t v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// word-stream writer: appends bytes at an arbitrary byte address using aligned 32-bit stores.
-// `pend` holds the nb (0..3) not-yet-stored bytes in its TOP bytes; a full-word append is one funnel shift + one
-// store.  The first word of a response may be shared with the previous response's tail (packed output), so its
-// leading `head` bytes are never written: that word is stored byte-wise.
+// word-stream writer: appends bytes at an arbitrary byte address of the packed output and leaves for HBM in aligned
+// 16-byte chunks.
+//   * sub-word: `pend` holds the nb (0..3) not-yet-complete bytes in its TOP bytes; appending a full word is one
+//     funnel shift;
+//   * completed words go into an 8-word ring in shared memory (word-major, stride = CTA size: a warp's accesses are
+//     conflict-free); every 4th word one 16-byte chunk is complete and is stored with a single st.global.cs.v4.
+//     The flush happens on the WORD COUNT, not on the address phase, so lanes that run the same program flush
+//     in the same instruction (no divergence even though their chunk phases differ);
+//   * the first and last chunk of a response are shared with its neighbours in the packed stream: only the bytes
+//     that belong to this response are written there (word / byte stores).
 // ---------------------------------------------------------------------------------------------------------------
-struct Writer {
-    uint32_t* wp;
-    uint32_t pend;
-    uint32_t nb;
-    uint32_t head;
+#if defined(__CUDA_ARCH__)
+#define GOFR_RING_STRIDE_BYTES 512u  /* kServeThreads words */
+#else
+#define GOFR_RING_STRIDE_BYTES 4u
+#endif
 
-    GOFR_HD void init(uint8_t* dst) {
+struct Writer {
+    uint8_t* chunk0;   // 16-byte aligned address of the chunk that holds the first byte
+    uint8_t* ring;     // this thread's column of the ring
+    uint32_t roff;     // byte offset of the next ring slot (k * stride)
+    uint32_t pend, nb;
+    uint32_t cnt;      // words completed so far
+    uint32_t flushed;  // chunks stored so far
+    uint32_t lead;     // bytes of chunk 0 that belong to the previous response (0..15)
+
+    GOFR_HD void init(uint8_t* dst, uint32_t* ring_col) {
         uintptr_t a = (uintptr_t)dst;
-        wp = (uint32_t*)(a & ~(uintptr_t)3);
-        nb = (uint32_t)(a & 3);
-        head = nb;
+        chunk0 = (uint8_t*)(a & ~(uintptr_t)15);
+        lead = (uint32_t)(a & 15);
+        nb = lead & 3;
+        ring = (uint8_t*)ring_col;
+        roff = (lead >> 2) * GOFR_RING_STRIDE_BYTES;
         pend = 0;
+        cnt = 0;
+        flushed = 0;
+    }
+    GOFR_HD uint32_t ring_word(uint32_t k) const { return *(const uint32_t*)(ring + k * GOFR_RING_STRIDE_BYTES); }
+
+    // write bytes [lo, hi) of the 16-byte chunk at addr from v[0..3]
+    GOFR_HD static void store_partial(uint8_t* addr, const uint32_t v[4], uint32_t lo, uint32_t hi) {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) {
+            uint32_t b0 = 4 * j, b1 = b0 + 4;
+            if (b1 <= lo || b0 >= hi) continue;
+            if (b0 >= lo && b1 <= hi) {
+                ((uint32_t*)addr)[j] = v[j];
+            } else {
+                uint32_t s = b0 > lo ? b0 : lo, e = b1 < hi ? b1 : hi;
+                for (uint32_t b = s; b < e; b++) addr[b] = (uint8_t)(v[j] >> (8 * (b - b0)));
+            }
+        }
+    }
+    GOFR_HD void flush_chunk() {
+        uint32_t base = (flushed & 1) * 4;
+        uint32_t v[4] = {ring_word(base), ring_word(base + 1), ring_word(base + 2), ring_word(base + 3)};
+        uint8_t* addr = chunk0 + 16u * flushed;
+        if (flushed == 0 && lead) {
+            store_partial(addr, v, lead, 16);
+        } else {
+#if defined(__CUDA_ARCH__)
+            __stcs((uint4*)addr, make_uint4(v[0], v[1], v[2], v[3]));
+#else
+            memcpy(addr, v, 16);
+#endif
+        }
+        flushed++;
     }
     GOFR_HD void store_word(uint32_t x) {
-        if (head) {
-            uint8_t* b = (uint8_t*)wp;
-            for (uint32_t k = head; k < 4; k++) b[k] = (uint8_t)(x >> (8 * k));
-            head = 0;
-        } else {
-            *wp = x;
-        }
-        wp++;
+        *(uint32_t*)(ring + roff) = x;
+        roff = (roff + GOFR_RING_STRIDE_BYTES) & (8 * GOFR_RING_STRIDE_BYTES - 1);
+        cnt++;
+        if ((cnt & 3) == 0) flush_chunk();
     }
     GOFR_HD void put4(uint32_t v) {
         store_word(fsl(pend, v, nb * 8));
@@ -105,10 +152,18 @@ struct Writer {
     }
     GOFR_HD void put1(uint32_t c) { putk(c, 1); }
     GOFR_HD void finish() {
-        if (nb) {
-            uint32_t c = pend >> (8 * (4 - nb));
-            uint8_t* b = (uint8_t*)wp;
-            for (uint32_t k = head; k < nb; k++) b[k] = (uint8_t)(c >> (8 * k));
+        // words in the stream (including the phantom words of `lead`) minus the flushed ones: 0..6
+        uint32_t rem = (lead >> 2) + cnt - 4 * flushed;
+        if (rem >= 4) { flush_chunk(); rem -= 4; }
+        if (rem || nb) {
+            uint32_t base = (flushed & 1) * 4;
+            uint32_t v[4];
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) v[j] = j < rem ? ring_word(base + j) : 0u;
+            uint32_t tail = nb ? pend >> (8 * (4 - nb)) : 0u;
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) if (j == rem) v[j] = tail;
+            store_partial(chunk0 + 16u * flushed, v, flushed == 0 ? lead : 0u, 4 * rem + nb);
         }
     }
 };
@@ -321,6 +376,9 @@ struct TableView {
     const Op* ops;
     const SchemaRec* schemas;
     const uint8_t* lits;  // literal pool; every *_off of a literal is relative to it
+    const uint16_t* hash_tab;
+    const uint16_t* tmpl_list;
+    const uint16_t* last_method;
 
     GOFR_HD void bind(const uint8_t* hot, const uint8_t* image_global) {
         base = hot;
@@ -331,6 +389,9 @@ struct TableView {
         ops = (const Op*)(hot + hdr->ops_off);
         schemas = (const SchemaRec*)(hot + hdr->schemas_off);
         lits = hot + hdr->lits_off;
+        hash_tab = (const uint16_t*)(hot + hdr->hash_off);
+        tmpl_list = (const uint16_t*)(hot + hdr->tmpl_off);
+        last_method = (const uint16_t*)(hot + hdr->last_method_off);
         cold = image_global + hdr->cold_off;
     }
     GOFR_HD const uint32_t* lit_words(uint32_t off) const { return (const uint32_t*)(lits + off); }
@@ -511,8 +572,8 @@ GOFR_HD bool route_path_ok(const TableView& tv, const RouteRec& R, const uint8_t
 }
 
 // Router.Match over routes in registration order with mux v1.8.1's ErrMethodMismatch bookkeeping.
-// Returns route index, or -1 (no route: 404) / -2 (405).
-GOFR_HD int mux_match(const TableView& tv, uint32_t method, const uint8_t* p, uint32_t n) {
+// Returns route index, or -1 (no route: 404) / -2 (405).  Reference formulation: every route is evaluated.
+GOFR_HD int mux_match_linear(const TableView& tv, uint32_t method, const uint8_t* p, uint32_t n) {
     bool mismatch = false;
     uint32_t nr = tv.hdr->n_routes;
     for (uint32_t r = 0; r < nr; r++) {
@@ -530,6 +591,42 @@ GOFR_HD int mux_match(const TableView& tv, uint32_t method, const uint8_t* p, ui
         return (int)r;
     }
     return mismatch ? -2 : -1;
+}
+
+// Same result, evaluating only the routes whose path matcher can succeed: the literal routes in hash(path)'s bucket
+// and the template / prefix routes, merged in registration order.  Skipped routes have a failing path matcher, so
+// their only possible effect is a succeeding METHOD matcher clearing a stale ErrMethodMismatch; that is recovered at
+// the end from last_method[] (index of the last live route registered for the request's method).
+GOFR_HD int mux_match(const TableView& tv, uint32_t method, const uint8_t* p, uint32_t n) {
+    if (((uintptr_t)p & 3) != 0) return mux_match_linear(tv, method, p, n);
+    const uint32_t* pw = (const uint32_t*)p;
+    uint32_t h = n, nw = n >> 2, r4 = n & 3;
+    for (uint32_t i = 0; i < nw; i++) h = path_hash_step(h, pw[i]);
+    if (r4) h = path_hash_step(h, pw[nw] & (0xFFFFFFFFu >> (8 * (4 - r4))));
+    uint32_t lit = n ? tv.hash_tab[h >> (32 - tv.hdr->hash_bits)] : 0xFFFFu;
+    uint32_t ti = 0, nt = tv.hdr->n_tmpl;
+    int a_last = -1;
+    for (;;) {
+        uint32_t t = ti < nt ? tv.tmpl_list[ti] : 0xFFFFu;
+        uint32_t r = lit < t ? lit : t;
+        if (r == 0xFFFFu) break;
+        const RouteRec& R = tv.routes[r];
+        bool p_ok;
+        if (r == lit) {
+            lit = R.next_lit;
+            p_ok = n == R.lit_len && words_equal(pw, tv.lit_words(R.lit_off), n);
+        } else {
+            ti++;
+            p_ok = template_match(tv, R, p, n);
+        }
+        if (!p_ok) continue;
+        bool m_ok = R.method == GOFR_M_ANY || (R.method == method && method != GOFR_M_OTHER);
+        if (m_ok) return (int)r;
+        a_last = (int)r;
+    }
+    if (a_last < 0) return -1;
+    int lm = method < 16 && method != GOFR_M_OTHER ? (int)tv.last_method[method] - 1 : -1;
+    return lm > a_last ? -1 : -2;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -678,7 +775,7 @@ GOFR_HD void route_request(const TableView& tv, ReqCtx& c) {
 // validate the row (returns false → caller switches to the panic program).  EMIT=true: write the bytes.
 // ---------------------------------------------------------------------------------------------------------------
 template <bool EMIT>
-GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w, const uint32_t* date_words) {
+GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
     const ProgRec& P = tv.progs[c.prog];
     const Op* ops = tv.ops + P.first_op;
     bool head = c.method == GOFR_M_HEAD;
@@ -709,13 +806,6 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w, const uint32_t*
                 if (EMIT) {
 #pragma unroll
                     for (int k = 0; k < 4; k++) { uint32_t a, b; hex8(c.id[k], a, b); w->put4(a); w->put4(b); }
-                }
-                break;
-            case OP_DATE:
-                if (EMIT) {
-#pragma unroll
-                    for (int k = 0; k < 7; k++) w->put4(date_words[k]);
-                    w->putk(date_words[7], 1);
                 }
                 break;
             case OP_CLEN:
@@ -806,19 +896,28 @@ GOFR_HD void size_request(const TableView& tv, ReqCtx& c) {
         c.status = 0;
         return;
     }
-    if (!run_prog<false>(tv, c, nullptr, nullptr)) {
+    if (!run_prog<false>(tv, c, nullptr)) {
         c.prog = tv.hdr->prog_panic;
         c.slow_mask = 0;
-        run_prog<false>(tv, c, nullptr, nullptr);
+        run_prog<false>(tv, c, nullptr);
     }
 }
 
-GOFR_HD void emit_request(const TableView& tv, ReqCtx& c, uint8_t* dst, const uint32_t* date_words) {
+GOFR_HD void emit_request(const TableView& tv, ReqCtx& c, uint8_t* dst, uint32_t* ring_col) {
     if (c.total_len == 0) return;
     Writer w;
-    w.init(dst);
-    run_prog<true>(tv, c, &w, date_words);
+    w.init(dst, ring_col);
+    run_prog<true>(tv, c, &w);
     w.finish();
+}
+
+// Patch the batch's Date into a private copy of the table's hot part (the kernel does this on its shared-memory
+// copy right after loading it; `idx`/`step` spread the work over the CTA).
+GOFR_HD void patch_dates(uint8_t* hot, const uint8_t* date29, uint32_t idx, uint32_t step) {
+    const ImageHeader* H = (const ImageHeader*)hot;
+    const uint32_t* fix = (const uint32_t*)(hot + H->fixups_off);
+    uint8_t* lits = hot + H->lits_off;
+    for (uint32_t k = idx; k < H->n_fixups * 29u; k += step) lits[fix[k / 29u] + k % 29u] = date29[k % 29u];
 }
 
 }  // namespace gofr

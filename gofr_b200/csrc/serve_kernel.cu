@@ -2,7 +2,7 @@
 //
 // One launch replaces, for a whole batch, what the reference does per request on a goroutine:
 // mux.Router.ServeHTTP → Tracer/Logging/CORS → handler.ServeHTTP → Responder.Respond → net/http framing
-// (pkg/gofr/http/router.go:14, middleware/*.go, pkg/gofr/handler.go:32-36, pkg/gofr/http/responder.go:19-41).
+// (pkg/gofr/http/router.go:14, middleware/{tracer,logger,cors}.go, pkg/gofr/handler.go:32-36, pkg/gofr/http/responder.go:19-41).
 //
 // Execution model (HBM-bound integer/byte work; no tensor cores):
 //   * grid = co-resident CTAs only (SMs × occupancy); CTA b walks tiles b, b+grid, … of 128 requests, one thread per
@@ -12,9 +12,10 @@
 //     fits, so all per-request byte walking hits shared memory, not HBM;
 //   * responses are packed back-to-back in request order: sizes are scanned inside the CTA and chained across CTAs
 //     with a decoupled look-back (single pass — inputs are read from HBM exactly once);
-//   * each thread writes its response into a shared-memory staging tile with aligned 32-bit stores through a
-//     funnel-shift word stream (serve_device.cuh); the tile leaves for HBM as ONE TMA bulk store
-//     (cp.async.bulk.global.shared::cta) plus ≤30 edge bytes, so HBM sees only full-line writes.
+//   * each thread streams its response through a funnel-shift word writer (serve_device.cuh) whose completed words
+//     collect in a conflict-free shared-memory ring and leave for HBM as aligned 16-byte st.global.cs.v4 chunks;
+//     L2 merges the two halves of each sector, so HBM sees full-sector writes.  No output tile lives in shared
+//     memory, which keeps 5 CTAs (20 warps) resident per SM for this latency-bound byte work.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -52,17 +53,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_global,
                  "l"(src_global), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
-// shared → global bulk store (TMA, 1-D)
-__device__ __forceinline__ void bulk_s2g(void* dst_global, const void* src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(smem_addr(src_smem)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 __device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -121,37 +111,35 @@ struct TileShared {
     uint32_t warp_sum[NW];
     uint32_t warp_lo[NW], warp_hi[NW];
     unsigned long long tile_base;
-    uint32_t tile_total;
     uint32_t in_lo, in_hi;
-    uint32_t date[8];
+    uint32_t ring[8 * T];  // word-major output ring of the Writer (serve_device.cuh)
 };
 
 __global__ void __launch_bounds__(T) serve_kernel(const ServeParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ TileShared sh;
+    __shared__ __align__(16) TileShared sh;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint8_t* tbl = smem;
     uint8_t* in_stage = smem + ((p.hot_bytes + 127u) & ~127u);
-    uint8_t* out_stage = in_stage + p.in_cap + 128;
 
-    // table → shared memory (once per CTA)
+    // table → shared memory (once per CTA), then the batch's Date is patched into the literal pool
     {
         const uint4* src = (const uint4*)p.image;
         uint4* dst = (uint4*)tbl;
         for (uint32_t i = tid; i < p.hot_bytes / 16; i += T) dst[i] = src[i];
-        if (tid < 8) sh.date[tid] = p.date[tid];
         if (tid == 0) {
             mbar_init(&sh.bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
     __syncthreads();
+    patch_dates(tbl, (const uint8_t*)p.date, tid, T);
+    __syncthreads();
     TableView tv;
     tv.bind(tbl, p.image);
 
     uint32_t parity = 0;
-    bool store_pending = false;
 
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const uint32_t i = tile * T + tid;
@@ -227,13 +215,10 @@ __global__ void __launch_bounds__(T) serve_kernel(const ServeParams p) {
         }
         const uint32_t excl = warp_excl + incl - c.total_len;
 
-        // ---- chain tiles (warp 0), and make sure the previous bulk store has drained the staging tile ----
+        // ---- chain tiles (warp 0) ----
         if (warp == 0) {
             unsigned long long base = lookback(p.tile_state, p.epoch, tile, tile_total, lane);
-            if (lane == 0) {
-                sh.tile_base = base;
-                if (store_pending) bulk_wait_read();
-            }
+            if (lane == 0) sh.tile_base = base;
         }
         __syncthreads();
         const unsigned long long tile_base = sh.tile_base;
@@ -245,40 +230,15 @@ __global__ void __launch_bounds__(T) serve_kernel(const ServeParams p) {
             if (i == p.n - 1) p.out_off[p.n] = (uint32_t)(tile_base + excl + c.total_len);
         }
 
-        // ---- stage 3: emit ----
-        const uint32_t mis = (uint32_t)tile_base & 15u;
-        const bool out_staged = tile_total + 16u <= p.out_stage_cap;
-        if (fits && valid && c.total_len) {
-            uint8_t* dst = out_staged ? out_stage + mis + excl : p.out + tile_base + excl;
-            emit_request(tv, c, dst, sh.date);
-        }
-        if (fits && out_staged && tile_total) {
-            fence_proxy_async();  // my generic-proxy writes → visible to the TMA engine
-            __syncthreads();
-            const unsigned long long g0 = tile_base, g1 = tile_base + tile_total;
-            const unsigned long long a0 = (g0 + 15ull) & ~15ull, a1 = g1 & ~15ull;
-            if (tid == 0 && a1 > a0) {
-                bulk_s2g(p.out + a0, out_stage + mis + (uint32_t)(a0 - g0), (uint32_t)(a1 - a0));
-                bulk_commit();
-            }
-            store_pending = true;  // uniform; only thread 0 waits on it
-            // edges: up to 15 bytes before a0 and after a1
-            const unsigned long long head_end = a0 < g1 ? a0 : g1;
-            if (tid < 16) {
-                unsigned long long g = g0 + tid;
-                if (g < head_end) p.out[g] = out_stage[mis + tid];
-            } else if (tid < 32 && a1 >= a0) {
-                unsigned long long g = a1 + (tid - 16);
-                if (g >= head_end && g < g1) p.out[g] = out_stage[mis + (uint32_t)(g - g0)];
-            }
-        }
-        // the next iteration's first __syncthreads orders these shared-memory reads before any overwrite
+        // ---- stage 3: emit straight to HBM in 16-byte chunks ----
+        if (fits && valid && c.total_len) emit_request(tv, c, p.out + tile_base + excl, &sh.ring[tid]);
+        // the next iteration's first __syncthreads orders this tile's shared-memory reads before any overwrite
     }
-    if (tid == 0) bulk_wait_all();
 }
 
 uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap, uint32_t out_stage_cap) {
-    return ((hot_bytes + 127u) & ~127u) + in_cap + 128 + out_stage_cap + 64;
+    (void)out_stage_cap;
+    return ((hot_bytes + 127u) & ~127u) + in_cap + 64;
 }
 
 int serve_max_grid(uint32_t smem_bytes, int device, int* blocks_per_sm) {

@@ -181,6 +181,7 @@ struct SOp {
     uint32_t aux = 0, off = 0;
     std::string lit;  // OP_LIT / OP_KEY
     bool body = false;
+    std::vector<uint32_t> date_pos;  // offsets inside `lit` of 29-byte Date placeholders
 };
 
 struct Prog {
@@ -352,8 +353,12 @@ static void build_header(Prog& p, uint32_t frame_mode, int status, bool with_mw,
         acc += "\r\n";
     }
     acc += "Date: ";
-    p.ops.push_back(lit(acc, false));
-    p.ops.push_back(op(OP_DATE, false));
+    {
+        // the batch's Date is patched into the shared-memory copy of the literal pool at kernel start (fixup)
+        SOp d = lit(acc + std::string(29, '\0'), false);
+        d.date_pos.push_back((uint32_t)acc.size());
+        p.ops.push_back(d);
+    }
     acc = "\r\n";
     bool body_nonempty = bk != BODY_NONE;
     if (!head_no_body) {
@@ -446,15 +451,16 @@ struct Pool {
     std::vector<uint8_t>& img;
     std::map<std::string, uint32_t> seen;
     explicit Pool(std::vector<uint8_t>& i) : img(i) {}
-    uint32_t put(const std::string& s) {  // 4-byte aligned, padded with zeros to a word boundary (+4 slack)
-        auto it = seen.find(s);
+    uint32_t put(const std::string& s, bool dated = false) {  // 4-byte aligned, zero padded to a word (+4 slack)
+        std::string key = (dated ? "D" : "L") + s;
+        auto it = seen.find(key);
         if (it != seen.end()) return it->second;
         while (img.size() % 4) img.push_back(0);
         uint32_t off = (uint32_t)img.size();
         img.insert(img.end(), s.begin(), s.end());
         while (img.size() % 4) img.push_back(0);
         for (int k = 0; k < 4; k++) img.push_back(0);
-        seen[s] = off;
+        seen[key] = off;
         return off;
     }
 };
@@ -465,6 +471,7 @@ static void merge_literals(std::vector<SOp>& ops) {
         if (o.code == OP_LIT && o.lit.empty()) continue;
         if (o.code == OP_LIT && !out.empty() && out.back().code == OP_LIT && out.back().body == o.body &&
             out.back().flags == o.flags) {
+            for (uint32_t dp : o.date_pos) out.back().date_pos.push_back(dp + (uint32_t)out.back().lit.size());
             out.back().lit += o.lit;
         } else out.push_back(o);
     }
@@ -633,8 +640,36 @@ int seal_table(gofr_table* t) {
                 if (t->schemas[si].id == r.schema_id) R.schema = (uint16_t)si;
     }
 
+    // ---- literal-route dispatch structures ----
+    uint32_t n_lit = 0;
+    for (auto& R : routes) n_lit += (R.flags & RF_LITERAL) ? 1 : 0;
+    uint32_t hash_bits = 4;
+    while ((1u << hash_bits) < 4 * n_lit && hash_bits < 11) hash_bits++;
+    std::vector<uint16_t> hash_tab(1u << hash_bits, 0xFFFF), tmpl_list, last_method(16, 0);
+    {
+        std::vector<uint16_t> tail(1u << hash_bits, 0xFFFF);
+        for (size_t ri = 0; ri < routes.size(); ri++) {
+            RouteRec& R = routes[ri];
+            R.next_lit = 0xFFFF;
+            if (R.flags & RF_DEAD) continue;
+            if (R.method < 16) last_method[R.method] = (uint16_t)(ri + 1);
+            if (!(R.flags & RF_LITERAL)) { tmpl_list.push_back((uint16_t)ri); continue; }
+            const std::string& pat = t->routes[ri].pattern;
+            uint32_t h = (uint32_t)pat.size();
+            for (size_t i = 0; i < pat.size(); i += 4) {
+                uint32_t w = 0;
+                for (size_t k = 0; k < 4 && i + k < pat.size(); k++) w |= (uint32_t)(uint8_t)pat[i + k] << (8 * k);
+                h = path_hash_step(h, w);
+            }
+            uint32_t slot = h >> (32 - hash_bits);
+            if (tail[slot] == 0xFFFF) hash_tab[slot] = (uint16_t)ri; else routes[tail[slot]].next_lit = (uint16_t)ri;
+            tail[slot] = (uint16_t)ri;
+        }
+    }
+
     std::vector<ProgRec> progs(b.progs.size());
     std::vector<Op> ops;
+    std::vector<uint32_t> fixups;
     uint32_t max_fixed = 0;
     for (size_t pi = 0; pi < b.progs.size(); pi++) {
         Prog& p = b.progs[pi];
@@ -653,8 +688,9 @@ int seal_table(gofr_table* t) {
             uint32_t fixed = 0;
             switch (so.code) {
                 case OP_LIT:
-                    o.off = pool.put(so.lit);
+                    o.off = pool.put(so.lit, !so.date_pos.empty());
                     o.len = (uint32_t)so.lit.size();
+                    for (uint32_t dp : so.date_pos) fixups.push_back(o.off + dp);
                     if (!(so.flags & OPF_VALUE_OF_KEY)) fixed = o.len; else P.flags |= PF_DYNAMIC;
                     break;
                 case OP_KEY:
@@ -664,7 +700,6 @@ int seal_table(gofr_table* t) {
                     P.flags |= PF_DYNAMIC | PF_NEEDS_ROW;
                     break;
                 case OP_HEXID: fixed = 32; break;
-                case OP_DATE: fixed = 29; break;
                 case OP_CLEN: P.flags |= PF_HAS_CLEN; break;
                 case OP_BLOB:
                     while (cold.size() % 16) cold.push_back(0);
@@ -726,6 +761,13 @@ int seal_table(gofr_table* t) {
     H.pieces_off = append(pieces.data(), pieces.size() * sizeof(PieceRec));
     H.progs_off = append(progs.data(), progs.size() * sizeof(ProgRec));
     H.ops_off = append(ops.data(), ops.size() * sizeof(Op));
+    H.hash_off = append(hash_tab.data(), hash_tab.size() * 2);
+    H.hash_bits = hash_bits;
+    H.tmpl_off = append(tmpl_list.data(), tmpl_list.size() * 2);
+    H.n_tmpl = (uint32_t)tmpl_list.size();
+    H.last_method_off = append(last_method.data(), last_method.size() * 2);
+    H.fixups_off = append(fixups.data(), fixups.size() * 4);
+    H.n_fixups = (uint32_t)fixups.size();
     // schemas: SchemaRec[n] then each field table
     align16();
     H.schemas_off = (uint32_t)img.size();

@@ -12,12 +12,12 @@
 namespace gofr {
 
 constexpr uint32_t kMagic = 0x52464F47u;  // "GOFR"
-constexpr uint32_t kImageVersion = 3;
+constexpr uint32_t kImageVersion = 4;
 constexpr uint32_t kMaxHotBytes = 40 * 1024;  // shared-memory budget for the table
 constexpr int kMaxVars = 8;                   // variables per route template
 constexpr int kMaxFields = 32;                // struct fields per schema
 
-struct ImageHeader {  // 96 B
+struct ImageHeader {  // 128 B
     uint32_t magic, version;
     uint32_t frame_mode;
     uint32_t n_routes, n_pieces, n_progs, n_ops, n_schemas;
@@ -28,9 +28,17 @@ struct ImageHeader {  // 96 B
     uint16_t prog_301, prog_301_head, prog_404, prog_405, prog_405_head, prog_options, prog_panic, pad0;
     uint32_t max_fixed_len;  // largest fixed (literal) part of any program, for capacity estimates
     uint32_t has_catchall;
-    uint32_t reserved[1];
+    // literal-route dispatch: hash(path) → first literal route of a chain (RouteRec.next_lit), in registration order
+    uint32_t hash_off;       // uint16[1 << hash_bits], 0xFFFF = empty
+    uint32_t hash_bits;
+    uint32_t tmpl_off;       // uint16[n_tmpl]: live routes that are not plain literals (templates, prefixes), in order
+    uint32_t n_tmpl;
+    uint32_t last_method_off;  // uint16[16]: 1 + index of the last live route registered for that method, 0 = none
+    uint32_t fixups_off;     // uint32[n_fixups]: literal-pool offsets of 29-byte Date placeholders
+    uint32_t n_fixups;
+    uint32_t reserved[2];
 };
-static_assert(sizeof(ImageHeader) == 96, "ImageHeader layout");
+static_assert(sizeof(ImageHeader) == 128, "ImageHeader layout");
 
 enum RouteFlags : uint8_t {
     RF_PREFIX = 1,   // PathPrefix: regexp has no trailing '$'
@@ -53,7 +61,7 @@ struct RouteRec {  // 32 B
     uint32_t key_off;
     uint32_t def_off;   // default value, already JSON-escaped
     uint16_t def_len;
-    uint16_t pad;
+    uint16_t next_lit;  // next literal route in the same hash bucket (registration order), 0xFFFF = end
 };
 static_assert(sizeof(RouteRec) == 32, "RouteRec layout");
 
@@ -70,7 +78,7 @@ static_assert(sizeof(PieceRec) == 48, "PieceRec layout");
 enum OpCode : uint8_t {
     OP_LIT = 0,     // literal bytes lits[off .. off+len)
     OP_HEXID = 1,   // 32 lower-case hex chars of the request's trace id   (middleware/logger.go:46-47)
-    OP_DATE = 2,    // the batch's 29-byte IMF-fixdate
+    OP_DATE = 2,    // (builder only) the batch's 29-byte IMF-fixdate: sealed as a literal placeholder + fixup
     OP_CLEN = 3,    // decimal length of the body                           (net/http Content-Length)
     OP_I64 = 4,     // strconv.AppendInt of a row field; off = word index in the row
     OP_I32 = 5,
@@ -140,5 +148,12 @@ struct FieldRec {  // 24 B
     uint32_t type_off;
 };
 static_assert(sizeof(FieldRec) == 24, "FieldRec layout");
+
+// Hash of a path for the literal-route table: word-wise FNV-style over the 4-byte aligned, zero-padded path.
+// The device computes it from the request bytes, the builder from the pattern; both use this function.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t path_hash_step(uint32_t h, uint32_t w) { return (h ^ w) * 0x9E3779B1u; }
 
 }  // namespace gofr

@@ -46,6 +46,8 @@ def serve(image: bytes, batch, date: bytes, out_cap: int | None = None, misalign
     rc = lib().emu_serve(img.ctypes.data, len(image), batch.desc.ctypes.data, batch.trace_ids.ctypes.data,
                          batch.arena.ctypes.data, n, date, out.ctypes.data, out_cap, off.ctypes.data, meta.ctypes.data,
                          misalign)
+    if rc == -2:
+        raise AssertionError("hashed and linear route matchers disagree")
     if rc != 0:
         raise RuntimeError("emu output capacity too small")
     return out, off, meta

@@ -22,10 +22,10 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
     memcpy(&H, image, sizeof H);
     std::vector<uint32_t> hot((H.hot_bytes + 3) / 4 + 4);
     memcpy(hot.data(), image, H.hot_bytes);
+    patch_dates((uint8_t*)hot.data(), (const uint8_t*)date29, 0, 1);
     TableView tv;
     tv.bind((const uint8_t*)hot.data(), image);
-    uint32_t date[8] = {0};
-    memcpy(date, date29, 29);
+    uint32_t ring[8];
     uint64_t pos = start_misalign;  // lets the test exercise every head alignment
     for (uint32_t i = 0; i < n; i++) {
         uint32_t d[4];
@@ -42,10 +42,14 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
         memcpy(c.id, ids + (size_t)i * 16, 16);
         c.total_len = c.body_len = 0; c.status = 0; c.route = GOFR_ROUTE_NONE; c.prog = 0xFFFF;
         size_request(tv, c);
+        if (c.prog != 0xFFFF && path_is_clean(c.path, c.path_len)) {  // both matchers must always agree
+            int a = mux_match(tv, c.method, c.path, c.path_len), b = mux_match_linear(tv, c.method, c.path, c.path_len);
+            if (a != b) return -2;
+        }
         out_off[i] = (uint32_t)pos;
         meta[i] = c.status | (c.route << 16);
         if (pos + c.total_len > out_cap) return -1;
-        emit_request(tv, c, out + pos, date);
+        emit_request(tv, c, out + pos, ring);
         pos += c.total_len;
     }
     out_off[n] = (uint32_t)pos;

@@ -58,6 +58,7 @@ def _check(spec, batch, eng=None, host=False, chunk=None):
 
 
 def test_native_library_is_the_one_running(torch_cuda):
+    _abi.lib()
     assert os.path.exists(_abi.lib_path())
     with open("/proc/self/maps") as f:
         assert "libgofr_b200.so" in f.read()
