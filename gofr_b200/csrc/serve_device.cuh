@@ -55,16 +55,18 @@ GOFR_HD int clz64(uint64_t v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// word-stream writer: appends bytes at an arbitrary byte address of the packed output and leaves for HBM in aligned
-// 16-byte chunks.
-//   * sub-word: `pend` holds the nb (0..3) not-yet-complete bytes in its TOP bytes; appending a full word is one
-//     funnel shift;
-//   * completed words go into an 8-word ring in shared memory (word-major, stride = CTA size: a warp's accesses are
-//     conflict-free); every 4th word one 16-byte chunk is complete and is stored with a single st.global.cs.v4.
-//     The flush happens on the WORD COUNT, not on the address phase, so lanes that run the same program flush
-//     in the same instruction (no divergence even though their chunk phases differ);
-//   * the first and last chunk of a response are shared with its neighbours in the packed stream: only the bytes
-//     that belong to this response are written there (word / byte stores).
+// output writer: appends bytes at an arbitrary byte address of the packed output; HBM only ever sees aligned 16-byte
+// st.global.cs.v4 stores (plus the few edge bytes a response shares with its neighbours in the packed stream).
+//
+//   bulk path  (copy): once the destination sits on a 16-byte boundary, a chunk is built in registers from five
+//     consecutive source words — shared memory addresses words for free, so only the BYTE misalignment between source
+//     and destination needs work: 4 loads + 4 funnel shifts + 1 vector store per 16 bytes.  Literals, string fields,
+//     query values and file blobs all go this way.
+//   word path  (put4/putk): seams between ops, integers, hex ids.  `pend` holds the nb (0..3) incomplete bytes in
+//     its TOP bytes (appending a full word = one funnel shift); complete words collect in a 4-word ring in shared
+//     memory (word-major, stride = CTA size → conflict-free) and leave as one chunk when the 4th arrives.
+//   edges: the first chunk's leading `lead` bytes and the last chunk's tail belong to neighbouring responses written
+//     by other threads; only this response's bytes are stored there.
 // ---------------------------------------------------------------------------------------------------------------
 #if defined(__CUDA_ARCH__)
 #define GOFR_RING_STRIDE_BYTES 512u  /* kServeThreads words */
@@ -72,28 +74,42 @@ GOFR_HD int clz64(uint64_t v) {
 #define GOFR_RING_STRIDE_BYTES 4u
 #endif
 
+// load k (1..4) bytes at an arbitrary address as the low bytes of a word; reads only words that hold source bytes
+GOFR_HD uint32_t load_bytes(const uint8_t* p, uint32_t k) {
+    uintptr_t a = (uintptr_t)p;
+    const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
+    uint32_t o = (uint32_t)(a & 3);
+    uint32_t w0 = q[0];
+    uint32_t w1 = o + k > 4 ? q[1] : 0u;
+    return fsr(w0, w1, o * 8);
+}
+
 struct Writer {
-    uint8_t* chunk0;   // 16-byte aligned address of the chunk that holds the first byte
-    uint8_t* ring;     // this thread's column of the ring
-    uint32_t roff;     // byte offset of the next ring slot (k * stride)
+    uint8_t* chunk;  // 16-byte aligned address of the chunk being filled
+    uint8_t* ring;   // this thread's column of the 4-word ring
+    uint32_t a;      // complete words in the current chunk (0..3)
     uint32_t pend, nb;
-    uint32_t cnt;      // words completed so far
-    uint32_t flushed;  // chunks stored so far
-    uint32_t lead;     // bytes of chunk 0 that belong to the previous response (0..15)
+    uint32_t lead;   // bytes at the start of the current chunk owned by the previous response (first chunk only)
 
     GOFR_HD void init(uint8_t* dst, uint32_t* ring_col) {
-        uintptr_t a = (uintptr_t)dst;
-        chunk0 = (uint8_t*)(a & ~(uintptr_t)15);
-        lead = (uint32_t)(a & 15);
+        uintptr_t x = (uintptr_t)dst;
+        chunk = (uint8_t*)(x & ~(uintptr_t)15);
+        lead = (uint32_t)(x & 15);
+        a = lead >> 2;
         nb = lead & 3;
         ring = (uint8_t*)ring_col;
-        roff = (lead >> 2) * GOFR_RING_STRIDE_BYTES;
         pend = 0;
-        cnt = 0;
-        flushed = 0;
     }
     GOFR_HD uint32_t ring_word(uint32_t k) const { return *(const uint32_t*)(ring + k * GOFR_RING_STRIDE_BYTES); }
 
+    GOFR_HD static void store16(uint8_t* addr, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+#if defined(__CUDA_ARCH__)
+        __stcs((uint4*)addr, make_uint4(v0, v1, v2, v3));
+#else
+        uint32_t v[4] = {v0, v1, v2, v3};
+        memcpy(addr, v, 16);
+#endif
+    }
     // write bytes [lo, hi) of the 16-byte chunk at addr from v[0..3]
     GOFR_HD static void store_partial(uint8_t* addr, const uint32_t v[4], uint32_t lo, uint32_t hi) {
 #pragma unroll
@@ -108,26 +124,17 @@ struct Writer {
             }
         }
     }
-    GOFR_HD void flush_chunk() {
-        uint32_t base = (flushed & 1) * 4;
-        uint32_t v[4] = {ring_word(base), ring_word(base + 1), ring_word(base + 2), ring_word(base + 3)};
-        uint8_t* addr = chunk0 + 16u * flushed;
-        if (flushed == 0 && lead) {
-            store_partial(addr, v, lead, 16);
-        } else {
-#if defined(__CUDA_ARCH__)
-            __stcs((uint4*)addr, make_uint4(v[0], v[1], v[2], v[3]));
-#else
-            memcpy(addr, v, 16);
-#endif
-        }
-        flushed++;
+    GOFR_HD void flush() {
+        uint32_t v[4] = {ring_word(0), ring_word(1), ring_word(2), ring_word(3)};
+        if (lead) { store_partial(chunk, v, lead, 16); lead = 0; }
+        else store16(chunk, v[0], v[1], v[2], v[3]);
+        chunk += 16;
+        a = 0;
     }
     GOFR_HD void store_word(uint32_t x) {
-        *(uint32_t*)(ring + roff) = x;
-        roff = (roff + GOFR_RING_STRIDE_BYTES) & (8 * GOFR_RING_STRIDE_BYTES - 1);
-        cnt++;
-        if ((cnt & 3) == 0) flush_chunk();
+        *(uint32_t*)(ring + a * GOFR_RING_STRIDE_BYTES) = x;
+        a++;
+        if (a == 4) flush();
     }
     GOFR_HD void put4(uint32_t v) {
         store_word(fsl(pend, v, nb * 8));
@@ -151,51 +158,60 @@ struct Writer {
         else if (k) putk(v, k);
     }
     GOFR_HD void put1(uint32_t c) { putk(c, 1); }
+
+    // Append len bytes from src (any address space, any alignment).  Every source must be readable up to the end of
+    // the aligned word that follows its last byte (literal pool, staged arena and blobs are padded accordingly).
+    GOFR_HD void copy(const uint8_t* src, uint32_t len) {
+        // seam: bring the destination to a 16-byte boundary through the word path
+        if (nb && len) {
+            uint32_t k = 4 - nb < len ? 4 - nb : len;
+            putk(load_bytes(src, k), k);
+            src += k;
+            len -= k;
+        }
+        while (a && len >= 4) {  // nb == 0 here whenever len >= 4 remains
+            put4(load_bytes(src, 4));
+            src += 4;
+            len -= 4;
+        }
+        if (len >= 16) {  // a == 0 and nb == 0: destination aligned
+            uintptr_t x = (uintptr_t)src;
+            const uint32_t* q = (const uint32_t*)(x & ~(uintptr_t)3);
+            uint32_t sh = (uint32_t)(x & 3) * 8;
+            uint32_t w0 = q[0];
+            do {
+                uint32_t w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+                store16(chunk, fsr(w0, w1, sh), fsr(w1, w2, sh), fsr(w2, w3, sh), fsr(w3, w4, sh));
+                w0 = w4;
+                q += 4;
+                chunk += 16;
+                len -= 16;
+            } while (len >= 16);
+            src = (const uint8_t*)q + (sh >> 3);
+        }
+        while (len >= 4) {
+            put4(load_bytes(src, 4));
+            src += 4;
+            len -= 4;
+        }
+        if (len) putk(load_bytes(src, len), len);
+    }
     GOFR_HD void finish() {
-        // words in the stream (including the phantom words of `lead`) minus the flushed ones: 0..6
-        uint32_t rem = (lead >> 2) + cnt - 4 * flushed;
-        if (rem >= 4) { flush_chunk(); rem -= 4; }
-        if (rem || nb) {
-            uint32_t base = (flushed & 1) * 4;
+        if (a || nb) {
             uint32_t v[4];
 #pragma unroll
-            for (uint32_t j = 0; j < 4; j++) v[j] = j < rem ? ring_word(base + j) : 0u;
+            for (uint32_t j = 0; j < 4; j++) v[j] = j < a ? ring_word(j) : 0u;
             uint32_t tail = nb ? pend >> (8 * (4 - nb)) : 0u;
 #pragma unroll
-            for (uint32_t j = 0; j < 4; j++) if (j == rem) v[j] = tail;
-            store_partial(chunk0 + 16u * flushed, v, flushed == 0 ? lead : 0u, 4 * rem + nb);
+            for (uint32_t j = 0; j < 4; j++) if (j == a) v[j] = tail;
+            store_partial(chunk, v, lead, 4 * a + nb);
         }
     }
 };
 
-// Copy len bytes from an aligned word array (literal pool): src is 4-byte aligned and padded.
-GOFR_HD void emit_words(Writer& w, const uint32_t* src, uint32_t len) {
-    uint32_t nw = len >> 2;
-    for (uint32_t i = 0; i < nw; i++) w.put4(src[i]);
-    uint32_t r = len & 3;
-    if (r) w.putk(src[nw], r);
-}
-
-// Copy len bytes from an arbitrary byte address.  Only words that contain at least one source byte are read.
-GOFR_HD void emit_bytes(Writer& w, const uint8_t* p, uint32_t len) {
-    if (!len) return;
-    uintptr_t a = (uintptr_t)p;
-    const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
-    uint32_t sh = (uint32_t)(a & 3) * 8;
-    uint32_t cur = *q;
-    uint32_t have = 4 - (uint32_t)(a & 3);  // source bytes available in cur
-    while (len >= 4) {
-        uint32_t nxt = (sh != 0 || len > 4) ? q[1] : 0;
-        w.put4(fsr(cur, nxt, sh));
-        cur = nxt;
-        q++;
-        len -= 4;
-    }
-    if (len) {
-        uint32_t nxt = len > have ? q[1] : 0;
-        w.putk(fsr(cur, nxt, sh), len);
-    }
-}
+// Copy len bytes from the literal pool (4-byte aligned, zero padded) / from an arbitrary byte address.
+GOFR_HD void emit_words(Writer& w, const uint32_t* src, uint32_t len) { w.copy((const uint8_t*)src, len); }
+GOFR_HD void emit_bytes(Writer& w, const uint8_t* p, uint32_t len) { w.copy(p, len); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // encoding/json string contents (Go 1.21, escapeHTML on)
@@ -217,21 +233,21 @@ GOFR_HD bool json_needs_escape(const uint8_t* p, uint32_t len) {
     uintptr_t a = (uintptr_t)p;
     const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
     uint32_t lead = (uint32_t)(a & 3);
-    uint32_t bad = 0;
-    // first (possibly partial) word: neutralise bytes before p
-    uint32_t x = *q;
-    uint32_t total = lead + len;  // bytes from q to end
+    uint32_t total = lead + len;           // bytes from q to the end of the string
+    uint32_t last = (total - 1) >> 2;      // index of the word holding the last byte
+    uint32_t keep = total & 3;             // valid bytes in that word (0 = all four)
+    // bytes outside the string are replaced by 'a' so they can never flag
+    uint32_t x = q[0];
     if (lead) x = (x & (0xFFFFFFFFu << (8 * lead))) | (0x61616161u >> (8 * (4 - lead)));
-    uint32_t nwords = (total + 3) >> 2;
-    for (uint32_t i = 0; i < nwords; i++) {
-        if (i) x = q[i];
-        if (i == nwords - 1 && (total & 3)) {
-            uint32_t keep = total & 3;
-            x = (x & (0xFFFFFFFFu >> (8 * (4 - keep)))) | (0x61616161u << (8 * keep));
-        }
-        bad |= json_special_mask(x);
+    if (last == 0) {
+        if (keep) x = (x & (0xFFFFFFFFu >> (8 * (4 - keep)))) | (0x61616161u << (8 * keep));
+        return json_special_mask(x) != 0;
     }
-    return bad != 0;
+    uint32_t bad = json_special_mask(x);
+    for (uint32_t i = 1; i < last; i++) bad |= json_special_mask(q[i]);
+    x = q[last];
+    if (keep) x = (x & (0xFFFFFFFFu >> (8 * (4 - keep)))) | (0x61616161u << (8 * keep));
+    return (bad | json_special_mask(x)) != 0;
 }
 
 // Go utf8.DecodeRune acceptance on a plain byte range: length of the well-formed sequence at p (2..4) or 0.

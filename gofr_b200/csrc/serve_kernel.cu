@@ -112,7 +112,7 @@ struct TileShared {
     uint32_t warp_lo[NW], warp_hi[NW];
     unsigned long long tile_base;
     uint32_t in_lo, in_hi;
-    uint32_t ring[8 * T];  // word-major output ring of the Writer (serve_device.cuh)
+    uint32_t ring[4 * T];  // word-major pending-chunk ring of the Writer (serve_device.cuh)
 };
 
 __global__ void __launch_bounds__(T) serve_kernel(const ServeParams p) {
