@@ -159,42 +159,94 @@ struct Writer {
     }
     GOFR_HD void put1(uint32_t c) { putk(c, 1); }
 
-    // Append len bytes from src (any address space, any alignment).  Every source must be readable up to the end of
-    // the aligned word that follows its last byte (literal pool, staged arena and blobs are padded accordingly).
+    // Append len bytes from src (any address space, any alignment) — seamless and phase agnostic.
+    // View the pending bytes of the current chunk (pb = 4a + nb) as a prefix of the source: in "source coordinates"
+    // the chunk starts at z = src - pb, so chunk c word j is simply the unaligned source word at z + 16c + 4j: one
+    // funnel shift of two aligned loads, for EVERY lane regardless of its destination phase.  Only chunk 0 mixes in
+    // the pending words (ring) and the pending sub-word bytes; whatever does not fill a chunk becomes the new
+    // pending state.  All lanes run the same code; trip counts differ by at most one chunk.
+    // Sources must be readable up to the end of the aligned word following their last byte (literal pool, staged
+    // arena and blobs are padded accordingly); no byte before the source is ever read.
     GOFR_HD void copy(const uint8_t* src, uint32_t len) {
-        // seam: bring the destination to a 16-byte boundary through the word path
-        if (nb && len) {
-            uint32_t k = 4 - nb < len ? 4 - nb : len;
-            putk(load_bytes(src, k), k);
-            src += k;
-            len -= k;
+        if (!len) return;
+        const uint32_t pb = 4 * a + nb;
+        const uintptr_t z = (uintptr_t)src - pb;
+        const uint32_t zo = (uint32_t)(z & 3), sh = zo * 8;
+        const uint32_t* Z = (const uint32_t*)(z - zo);
+        uint32_t remaining = pb + len;                      // bytes from the chunk's byte 0 to the end of the data
+        const uint32_t first_i = (pb + zo) >> 2;            // first / last aligned word that holds source bytes
+        const uint32_t last_i = (pb + zo + len - 1) >> 2;
+        // ---- chunk 0: pending words + pending bytes + source ----
+        uint32_t s0 = first_i == 0 ? Z[0] : 0u;
+        uint32_t s1 = (first_i <= 1 && 1 <= last_i) ? Z[1] : 0u;
+        uint32_t s2 = (first_i <= 2 && 2 <= last_i) ? Z[2] : 0u;
+        uint32_t s3 = (first_i <= 3 && 3 <= last_i) ? Z[3] : 0u;
+        uint32_t s4 = 4 <= last_i ? Z[4] : 0u;
+        uint32_t v0 = fsr(s0, s1, sh), v1 = fsr(s1, s2, sh), v2 = fsr(s2, s3, sh), v3 = fsr(s3, s4, sh);
+        {
+            const uint32_t keep = 0xFFFFFFFFu << (8 * nb);
+            const uint32_t plo = nb ? pend >> (8 * (4 - nb)) : 0u;
+            if (a == 0) v0 = (v0 & keep) | plo;
+            else if (a == 1) v1 = (v1 & keep) | plo;
+            else if (a == 2) v2 = (v2 & keep) | plo;
+            else v3 = (v3 & keep) | plo;
         }
-        while (a && len >= 4) {  // nb == 0 here whenever len >= 4 remains
-            put4(load_bytes(src, 4));
-            src += 4;
-            len -= 4;
+        if (remaining < 16) {
+            // nothing completes: extend the pending state
+            const uint32_t na = remaining >> 2, nn = remaining & 3;
+            if (a <= 0 && 0 < na) *(uint32_t*)(ring) = v0;
+            if (a <= 1 && 1 < na) *(uint32_t*)(ring + GOFR_RING_STRIDE_BYTES) = v1;
+            if (a <= 2 && 2 < na) *(uint32_t*)(ring + 2 * GOFR_RING_STRIDE_BYTES) = v2;
+            const uint32_t part = na == 0 ? v0 : na == 1 ? v1 : na == 2 ? v2 : v3;
+            pend = nn ? part << (8 * (4 - nn)) : 0u;
+            a = na;
+            nb = nn;
+            return;
         }
-        if (len >= 16) {  // a == 0 and nb == 0: destination aligned
-            uintptr_t x = (uintptr_t)src;
-            const uint32_t* q = (const uint32_t*)(x & ~(uintptr_t)3);
-            uint32_t sh = (uint32_t)(x & 3) * 8;
-            uint32_t w0 = q[0];
-            do {
-                uint32_t w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
-                store16(chunk, fsr(w0, w1, sh), fsr(w1, w2, sh), fsr(w2, w3, sh), fsr(w3, w4, sh));
-                w0 = w4;
-                q += 4;
-                chunk += 16;
-                len -= 16;
-            } while (len >= 16);
-            src = (const uint8_t*)q + (sh >> 3);
+        if (a > 0) v0 = ring_word(0);
+        if (a > 1) v1 = ring_word(1);
+        if (a > 2) v2 = ring_word(2);
+        if (lead) {
+            const uint32_t vv[4] = {v0, v1, v2, v3};
+            store_partial(chunk, vv, lead, 16);
+            lead = 0;
+        } else {
+            store16(chunk, v0, v1, v2, v3);
         }
-        while (len >= 4) {
-            put4(load_bytes(src, 4));
-            src += 4;
-            len -= 4;
+        chunk += 16;
+        remaining -= 16;
+        Z += 4;
+        uint32_t zi = 4;  // index of Z[0] relative to the first aligned word
+        // ---- full chunks straight from the source ----
+        while (remaining >= 16) {
+            s0 = s4;
+            s1 = Z[1]; s2 = Z[2]; s3 = Z[3]; s4 = Z[4];
+            store16(chunk, fsr(s0, s1, sh), fsr(s1, s2, sh), fsr(s2, s3, sh), fsr(s3, s4, sh));
+            chunk += 16;
+            remaining -= 16;
+            Z += 4;
+            zi += 4;
         }
-        if (len) putk(load_bytes(src, len), len);
+        // ---- tail: the new pending state ----
+        {
+            const uint32_t na = remaining >> 2, nn = remaining & 3;
+            const uint32_t li = last_i >= zi ? last_i - zi : 0u;  // last word (relative to Z) that holds source bytes
+            s0 = s4;
+            s1 = (remaining && 1 <= li) ? Z[1] : 0u;
+            s2 = (remaining && 2 <= li) ? Z[2] : 0u;
+            s3 = (remaining && 3 <= li) ? Z[3] : 0u;
+            v0 = fsr(s0, s1, sh); v1 = fsr(s1, s2, sh); v2 = fsr(s2, s3, sh);
+            // word 3 can only be partial here (remaining < 16)
+            uint32_t s4b = (remaining && 4 <= li) ? Z[4] : 0u;
+            v3 = fsr(s3, s4b, sh);
+            if (0 < na) *(uint32_t*)(ring) = v0;
+            if (1 < na) *(uint32_t*)(ring + GOFR_RING_STRIDE_BYTES) = v1;
+            if (2 < na) *(uint32_t*)(ring + 2 * GOFR_RING_STRIDE_BYTES) = v2;
+            const uint32_t part = na == 0 ? v0 : na == 1 ? v1 : na == 2 ? v2 : v3;
+            pend = nn ? part << (8 * (4 - nn)) : 0u;
+            a = na;
+            nb = nn;
+        }
     }
     GOFR_HD void finish() {
         if (a || nb) {
