@@ -69,7 +69,7 @@ GOFR_HD int clz64(uint64_t v) {
 //     by other threads; only this response's bytes are stored there.
 // ---------------------------------------------------------------------------------------------------------------
 #if defined(__CUDA_ARCH__)
-#define GOFR_RING_STRIDE_BYTES 512u  /* kServeThreads words */
+#define GOFR_RING_STRIDE_BYTES 512u  /* kServeThreads words: word-major ring, 16 words per thread */
 #else
 #define GOFR_RING_STRIDE_BYTES 4u
 #endif
@@ -86,8 +86,9 @@ GOFR_HD uint32_t load_bytes(const uint8_t* p, uint32_t k) {
 
 struct Writer {
     uint8_t* chunk;  // 16-byte aligned address of the chunk being filled
-    uint8_t* ring;   // this thread's column of the 4-word ring
-    uint32_t a;      // complete words in the current chunk (0..3)
+    uint8_t* ring;   // this thread's column of the 16-word ring
+    uint32_t r0;     // ring index (0..15) of the current chunk's word 0
+    uint32_t a;      // complete words waiting in the ring (word path may run ahead of the flush: up to 12)
     uint32_t pend, nb;
     uint32_t lead;   // bytes at the start of the current chunk owned by the previous response (first chunk only)
 
@@ -98,9 +99,10 @@ struct Writer {
         a = lead >> 2;
         nb = lead & 3;
         ring = (uint8_t*)ring_col;
+        r0 = 0;
         pend = 0;
     }
-    GOFR_HD uint32_t ring_word(uint32_t k) const { return *(const uint32_t*)(ring + k * GOFR_RING_STRIDE_BYTES); }
+    GOFR_HD uint32_t* slot(uint32_t k) const { return (uint32_t*)(ring + ((r0 + k) & 15u) * GOFR_RING_STRIDE_BYTES); }
 
     GOFR_HD static void store16(uint8_t* addr, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
 #if defined(__CUDA_ARCH__)
@@ -124,17 +126,28 @@ struct Writer {
             }
         }
     }
-    GOFR_HD void flush() {
-        uint32_t v[4] = {ring_word(0), ring_word(1), ring_word(2), ring_word(3)};
-        if (lead) { store_partial(chunk, v, lead, 16); lead = 0; }
-        else store16(chunk, v[0], v[1], v[2], v[3]);
+    GOFR_HD void emit_chunk(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+        if (lead) {
+            const uint32_t vv[4] = {v0, v1, v2, v3};
+            store_partial(chunk, vv, lead, 16);
+            lead = 0;
+        } else {
+            store16(chunk, v0, v1, v2, v3);
+        }
         chunk += 16;
-        a = 0;
+    }
+    // store every complete chunk waiting in the ring (called once per op, not per word)
+    GOFR_HD void drain() {
+        while (a >= 4) {
+            emit_chunk(*slot(0), *slot(1), *slot(2), *slot(3));
+            r0 = (r0 + 4) & 15u;
+            a -= 4;
+        }
     }
     GOFR_HD void store_word(uint32_t x) {
-        *(uint32_t*)(ring + a * GOFR_RING_STRIDE_BYTES) = x;
+        *slot(a) = x;
         a++;
-        if (a == 4) flush();
+        if (a >= 12) drain();  // long word-path runs (escaped strings, redirects) must not lap the ring
     }
     GOFR_HD void put4(uint32_t v) {
         store_word(fsl(pend, v, nb * 8));
@@ -159,29 +172,39 @@ struct Writer {
     }
     GOFR_HD void put1(uint32_t c) { putk(c, 1); }
 
+    // short data through the word path (at most 15 bytes per call: the ring has room for 12 words past a chunk)
+    GOFR_HD void copy_small(const uint8_t* src, uint32_t len) {
+        while (len >= 4) {
+            put4(load_bytes(src, 4));
+            src += 4;
+            len -= 4;
+        }
+        if (len) putk(load_bytes(src, len), len);
+    }
+
     // Append len bytes from src (any address space, any alignment) — seamless and phase agnostic.
     // View the pending bytes of the current chunk (pb = 4a + nb) as a prefix of the source: in "source coordinates"
     // the chunk starts at z = src - pb, so chunk c word j is simply the unaligned source word at z + 16c + 4j: one
     // funnel shift of two aligned loads, for EVERY lane regardless of its destination phase.  Only chunk 0 mixes in
-    // the pending words (ring) and the pending sub-word bytes; whatever does not fill a chunk becomes the new
-    // pending state.  All lanes run the same code; trip counts differ by at most one chunk.
+    // the pending ring words and the pending sub-word bytes; the < 16 bytes left after the last full chunk go through
+    // the word path.  All lanes run the same code; trip counts differ by at most one chunk.
     // Sources must be readable up to the end of the aligned word following their last byte (literal pool, staged
     // arena and blobs are padded accordingly); no byte before the source is ever read.
     GOFR_HD void copy(const uint8_t* src, uint32_t len) {
-        if (!len) return;
+        drain();
         const uint32_t pb = 4 * a + nb;
+        if (pb + len < 16) { copy_small(src, len); return; }
         const uintptr_t z = (uintptr_t)src - pb;
         const uint32_t zo = (uint32_t)(z & 3), sh = zo * 8;
         const uint32_t* Z = (const uint32_t*)(z - zo);
-        uint32_t remaining = pb + len;                      // bytes from the chunk's byte 0 to the end of the data
-        const uint32_t first_i = (pb + zo) >> 2;            // first / last aligned word that holds source bytes
-        const uint32_t last_i = (pb + zo + len - 1) >> 2;
+        uint32_t remaining = pb + len - 16;                 // bytes after chunk 0
+        const uint32_t first_i = (pb + zo) >> 2;            // first aligned word that holds source bytes (0..4)
         // ---- chunk 0: pending words + pending bytes + source ----
         uint32_t s0 = first_i == 0 ? Z[0] : 0u;
-        uint32_t s1 = (first_i <= 1 && 1 <= last_i) ? Z[1] : 0u;
-        uint32_t s2 = (first_i <= 2 && 2 <= last_i) ? Z[2] : 0u;
-        uint32_t s3 = (first_i <= 3 && 3 <= last_i) ? Z[3] : 0u;
-        uint32_t s4 = 4 <= last_i ? Z[4] : 0u;
+        uint32_t s1 = first_i <= 1 ? Z[1] : 0u;
+        uint32_t s2 = first_i <= 2 ? Z[2] : 0u;
+        uint32_t s3 = first_i <= 3 ? Z[3] : 0u;
+        uint32_t s4 = Z[4];
         uint32_t v0 = fsr(s0, s1, sh), v1 = fsr(s1, s2, sh), v2 = fsr(s2, s3, sh), v3 = fsr(s3, s4, sh);
         {
             const uint32_t keep = 0xFFFFFFFFu << (8 * nb);
@@ -191,32 +214,11 @@ struct Writer {
             else if (a == 2) v2 = (v2 & keep) | plo;
             else v3 = (v3 & keep) | plo;
         }
-        if (remaining < 16) {
-            // nothing completes: extend the pending state
-            const uint32_t na = remaining >> 2, nn = remaining & 3;
-            if (a <= 0 && 0 < na) *(uint32_t*)(ring) = v0;
-            if (a <= 1 && 1 < na) *(uint32_t*)(ring + GOFR_RING_STRIDE_BYTES) = v1;
-            if (a <= 2 && 2 < na) *(uint32_t*)(ring + 2 * GOFR_RING_STRIDE_BYTES) = v2;
-            const uint32_t part = na == 0 ? v0 : na == 1 ? v1 : na == 2 ? v2 : v3;
-            pend = nn ? part << (8 * (4 - nn)) : 0u;
-            a = na;
-            nb = nn;
-            return;
-        }
-        if (a > 0) v0 = ring_word(0);
-        if (a > 1) v1 = ring_word(1);
-        if (a > 2) v2 = ring_word(2);
-        if (lead) {
-            const uint32_t vv[4] = {v0, v1, v2, v3};
-            store_partial(chunk, vv, lead, 16);
-            lead = 0;
-        } else {
-            store16(chunk, v0, v1, v2, v3);
-        }
-        chunk += 16;
-        remaining -= 16;
+        if (a > 0) v0 = *slot(0);
+        if (a > 1) v1 = *slot(1);
+        if (a > 2) v2 = *slot(2);
+        emit_chunk(v0, v1, v2, v3);
         Z += 4;
-        uint32_t zi = 4;  // index of Z[0] relative to the first aligned word
         // ---- full chunks straight from the source ----
         while (remaining >= 16) {
             s0 = s4;
@@ -225,34 +227,20 @@ struct Writer {
             chunk += 16;
             remaining -= 16;
             Z += 4;
-            zi += 4;
         }
-        // ---- tail: the new pending state ----
-        {
-            const uint32_t na = remaining >> 2, nn = remaining & 3;
-            const uint32_t li = last_i >= zi ? last_i - zi : 0u;  // last word (relative to Z) that holds source bytes
-            s0 = s4;
-            s1 = (remaining && 1 <= li) ? Z[1] : 0u;
-            s2 = (remaining && 2 <= li) ? Z[2] : 0u;
-            s3 = (remaining && 3 <= li) ? Z[3] : 0u;
-            v0 = fsr(s0, s1, sh); v1 = fsr(s1, s2, sh); v2 = fsr(s2, s3, sh);
-            // word 3 can only be partial here (remaining < 16)
-            uint32_t s4b = (remaining && 4 <= li) ? Z[4] : 0u;
-            v3 = fsr(s3, s4b, sh);
-            if (0 < na) *(uint32_t*)(ring) = v0;
-            if (1 < na) *(uint32_t*)(ring + GOFR_RING_STRIDE_BYTES) = v1;
-            if (2 < na) *(uint32_t*)(ring + 2 * GOFR_RING_STRIDE_BYTES) = v2;
-            const uint32_t part = na == 0 ? v0 : na == 1 ? v1 : na == 2 ? v2 : v3;
-            pend = nn ? part << (8 * (4 - nn)) : 0u;
-            a = na;
-            nb = nn;
-        }
+        // ---- tail (< 16 bytes): word path from a fresh chunk ----
+        a = 0;
+        nb = 0;
+        r0 = 0;
+        pend = 0;
+        copy_small((const uint8_t*)Z + zo, remaining);
     }
     GOFR_HD void finish() {
+        drain();
         if (a || nb) {
             uint32_t v[4];
 #pragma unroll
-            for (uint32_t j = 0; j < 4; j++) v[j] = j < a ? ring_word(j) : 0u;
+            for (uint32_t j = 0; j < 4; j++) v[j] = j < a ? *slot(j) : 0u;
             uint32_t tail = nb ? pend >> (8 * (4 - nb)) : 0u;
 #pragma unroll
             for (uint32_t j = 0; j < 4; j++) if (j == a) v[j] = tail;

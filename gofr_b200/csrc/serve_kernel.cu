@@ -112,10 +112,10 @@ struct TileShared {
     uint32_t warp_lo[NW], warp_hi[NW];
     unsigned long long tile_base;
     uint32_t in_lo, in_hi;
-    uint32_t ring[4 * T];  // word-major pending-chunk ring of the Writer (serve_device.cuh)
+    uint32_t ring[16 * T];  // word-major ring of the Writer's word path (serve_device.cuh)
 };
 
-__global__ void __launch_bounds__(T) serve_kernel(const ServeParams p) {
+__global__ void __launch_bounds__(T, 4) serve_kernel(const ServeParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(16) TileShared sh;
 
