@@ -122,9 +122,14 @@ int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
     CUDA_TRY(cudaMemcpy(e->d_image, img.data(), img.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&e->d_flag, 64));
     CUDA_TRY(cudaMemset(e->d_flag, 0, 64));
-    // default tile geometry: 256 bytes of request data per request are staged in shared memory (larger tiles are
-    // read from HBM directly)
-    int rc = configure_geometry(e, 256, 0);
+    // default tile geometry: stage as many request bytes per request in shared memory as still lets 4 CTAs share an
+    // SM (the kernel is latency bound: residency matters more than staging every tile); larger tiles are read from
+    // HBM directly.
+    uint32_t per_cta = 227u * 1024u / 4u - 1024u /*reserved*/ - 16640u /*static: staging buffer + tile state*/;
+    uint32_t hot = (e->hdr.hot_bytes + 127u) & ~127u;
+    uint32_t in_per = per_cta > hot + 64u * kServeThreads ? ((per_cta - hot - 64u) / kServeThreads) & ~15u : 64u;
+    if (in_per > 256u) in_per = 256u;
+    int rc = configure_geometry(e, in_per, 0);
     if (rc != GOFR_OK) { delete e; return rc; }
     for (auto& s : e->slots) {
         CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));

@@ -58,21 +58,25 @@ GOFR_HD int clz64(uint64_t v) {
 // output writer: appends bytes at an arbitrary byte address of the packed output; HBM only ever sees aligned 16-byte
 // st.global.cs.v4 stores (plus the few edge bytes a response shares with its neighbours in the packed stream).
 //
-//   bulk path  (copy): once the destination sits on a 16-byte boundary, a chunk is built in registers from five
-//     consecutive source words — shared memory addresses words for free, so only the BYTE misalignment between source
-//     and destination needs work: 4 loads + 4 funnel shifts + 1 vector store per 16 bytes.  Literals, string fields,
-//     query values and file blobs all go this way.
-//   word path  (put4/putk): seams between ops, integers, hex ids.  `pend` holds the nb (0..3) incomplete bytes in
-//     its TOP bytes (appending a full word = one funnel shift); complete words collect in a 4-word ring in shared
-//     memory (word-major, stride = CTA size → conflict-free) and leave as one chunk when the 4th arrives.
-//   edges: the first chunk's leading `lead` bytes and the last chunk's tail belong to neighbouring responses written
-//     by other threads; only this response's bytes are stored there.
+// Each thread owns a 32-word staging buffer in shared memory, laid out word-major (word k of thread t at
+// [k * CTA + t]): whatever word index a lane is at, its bank is its lane id, so accesses never conflict.  The buffer is
+// DESTINATION-ALIGNED: word 0 is the first word of the 16-byte chunk at `chunk`.
+//   produce: bytes are appended as whole words.  `pend` holds the nb (0..3) incomplete bytes in its TOP bytes, so
+//            appending a word is one funnel shift + one STS + a pointer bump — no branches, no per-word flush test,
+//            and the same code for every lane whatever its phase.  A memory source is streamed with the pending
+//            bytes treated as a prefix of the source ("virtual source"): one aligned load + one funnel shift per
+//            output word regardless of source and destination alignment.
+//   flush:   decoupled from producing — between ops, when at least 16 words wait, whole chunks leave as
+//            4 conflict-free LDS + one st.global.cs.v4; no shifting is needed because the buffer is already aligned.
+//   edges:   the first chunk's leading `lead` bytes and the last chunk's tail belong to neighbouring responses
+//            written by other threads; only this response's bytes are stored there.
 // ---------------------------------------------------------------------------------------------------------------
 #if defined(__CUDA_ARCH__)
-#define GOFR_RING_STRIDE_BYTES 512u  /* kServeThreads words: word-major ring, 16 words per thread */
+#define GOFR_RING_STRIDE_BYTES 512u  /* kServeThreads words: word-major staging, 32 words per thread */
 #else
 #define GOFR_RING_STRIDE_BYTES 4u
 #endif
+#define GOFR_STAGE_WORDS 32u
 
 // load k (1..4) bytes at an arbitrary address as the low bytes of a word; reads only words that hold source bytes
 GOFR_HD uint32_t load_bytes(const uint8_t* p, uint32_t k) {
@@ -85,24 +89,24 @@ GOFR_HD uint32_t load_bytes(const uint8_t* p, uint32_t k) {
 }
 
 struct Writer {
-    uint8_t* chunk;  // 16-byte aligned address of the chunk being filled
-    uint8_t* ring;   // this thread's column of the 16-word ring
-    uint32_t r0;     // ring index (0..15) of the current chunk's word 0
-    uint32_t a;      // complete words waiting in the ring (word path may run ahead of the flush: up to 12)
+    uint8_t* chunk;  // 16-byte aligned global address that staging word 0 maps to
+    uint8_t* base;   // this thread's column of the staging buffer
+    uint8_t* wp;     // base + wl * stride: where the next complete word goes
+    uint32_t wl;     // complete words staged (0 .. GOFR_STAGE_WORDS)
     uint32_t pend, nb;
-    uint32_t lead;   // bytes at the start of the current chunk owned by the previous response (first chunk only)
+    uint32_t lead;   // bytes at the start of the first chunk owned by the previous response
 
-    GOFR_HD void init(uint8_t* dst, uint32_t* ring_col) {
+    GOFR_HD void init(uint8_t* dst, uint32_t* col) {
         uintptr_t x = (uintptr_t)dst;
         chunk = (uint8_t*)(x & ~(uintptr_t)15);
         lead = (uint32_t)(x & 15);
-        a = lead >> 2;
+        wl = lead >> 2;  // phantom words of the neighbour: never stored
         nb = lead & 3;
-        ring = (uint8_t*)ring_col;
-        r0 = 0;
+        base = (uint8_t*)col;
+        wp = base + wl * GOFR_RING_STRIDE_BYTES;
         pend = 0;
     }
-    GOFR_HD uint32_t* slot(uint32_t k) const { return (uint32_t*)(ring + ((r0 + k) & 15u) * GOFR_RING_STRIDE_BYTES); }
+    GOFR_HD uint32_t word(uint32_t k) const { return *(const uint32_t*)(base + k * GOFR_RING_STRIDE_BYTES); }
 
     GOFR_HD static void store16(uint8_t* addr, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
 #if defined(__CUDA_ARCH__)
@@ -126,28 +130,41 @@ struct Writer {
             }
         }
     }
-    GOFR_HD void emit_chunk(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
-        if (lead) {
-            const uint32_t vv[4] = {v0, v1, v2, v3};
+    // store every complete chunk, move the (< 4) left-over words to the front
+    GOFR_HD void flush() {
+        uint32_t n = wl >> 2;
+        const uint8_t* rp = base;
+        if (n && lead) {  // first chunk of the response: skip the neighbour's bytes
+            const uint32_t vv[4] = {word(0), word(1), word(2), word(3)};
             store_partial(chunk, vv, lead, 16);
             lead = 0;
-        } else {
-            store16(chunk, v0, v1, v2, v3);
+            chunk += 16;
+            rp += 4 * GOFR_RING_STRIDE_BYTES;
+            n--;
         }
-        chunk += 16;
+        for (; n; n--) {
+            store16(chunk, *(const uint32_t*)rp, *(const uint32_t*)(rp + GOFR_RING_STRIDE_BYTES),
+                    *(const uint32_t*)(rp + 2 * GOFR_RING_STRIDE_BYTES), *(const uint32_t*)(rp + 3 * GOFR_RING_STRIDE_BYTES));
+            chunk += 16;
+            rp += 4 * GOFR_RING_STRIDE_BYTES;
+        }
+        uint32_t r = wl & 3;
+        if (wl >= 4) {
+            if (r > 0) *(uint32_t*)base = *(const uint32_t*)rp;
+            if (r > 1) *(uint32_t*)(base + GOFR_RING_STRIDE_BYTES) = *(const uint32_t*)(rp + GOFR_RING_STRIDE_BYTES);
+            if (r > 2) *(uint32_t*)(base + 2 * GOFR_RING_STRIDE_BYTES) = *(const uint32_t*)(rp + 2 * GOFR_RING_STRIDE_BYTES);
+        }
+        wl = r;
+        wp = base + r * GOFR_RING_STRIDE_BYTES;
     }
-    // store every complete chunk waiting in the ring (called once per op, not per word)
-    GOFR_HD void drain() {
-        while (a >= 4) {
-            emit_chunk(*slot(0), *slot(1), *slot(2), *slot(3));
-            r0 = (r0 + 4) & 15u;
-            a -= 4;
-        }
+    // make room for n more words (n <= 28)
+    GOFR_HD void reserve(uint32_t n) {
+        if (wl + n > GOFR_STAGE_WORDS) flush();
     }
     GOFR_HD void store_word(uint32_t x) {
-        *slot(a) = x;
-        a++;
-        if (a >= 12) drain();  // long word-path runs (escaped strings, redirects) must not lap the ring
+        *(uint32_t*)wp = x;
+        wp += GOFR_RING_STRIDE_BYTES;
+        wl++;
     }
     GOFR_HD void put4(uint32_t v) {
         store_word(fsl(pend, v, nb * 8));
@@ -170,81 +187,70 @@ struct Writer {
         if (k == 4) put4(v);
         else if (k) putk(v, k);
     }
-    GOFR_HD void put1(uint32_t c) { putk(c, 1); }
-
-    // short data through the word path (at most 15 bytes per call: the ring has room for 12 words past a chunk)
-    GOFR_HD void copy_small(const uint8_t* src, uint32_t len) {
-        while (len >= 4) {
-            put4(load_bytes(src, 4));
-            src += 4;
-            len -= 4;
-        }
-        if (len) putk(load_bytes(src, len), len);
+    // single bytes from slow paths: room is checked here because those loops are unbounded
+    GOFR_HD void put1(uint32_t c) {
+        if (wl >= GOFR_STAGE_WORDS - 2) flush();
+        putk(c, 1);
     }
 
-    // Append len bytes from src (any address space, any alignment) — seamless and phase agnostic.
-    // View the pending bytes of the current chunk (pb = 4a + nb) as a prefix of the source: in "source coordinates"
-    // the chunk starts at z = src - pb, so chunk c word j is simply the unaligned source word at z + 16c + 4j: one
-    // funnel shift of two aligned loads, for EVERY lane regardless of its destination phase.  Only chunk 0 mixes in
-    // the pending ring words and the pending sub-word bytes; the < 16 bytes left after the last full chunk go through
-    // the word path.  All lanes run the same code; trip counts differ by at most one chunk.
+    // Append len bytes from memory (any address space, any alignment).  With y = src - nb the stream
+    // "pending bytes ++ source" is word-aligned with the destination, so output word k is the unaligned word at
+    // y + 4k: one aligned load (the previous one is carried) and one funnel shift.  Only word 0 mixes in `pend`.
     // Sources must be readable up to the end of the aligned word following their last byte (literal pool, staged
     // arena and blobs are padded accordingly); no byte before the source is ever read.
     GOFR_HD void copy(const uint8_t* src, uint32_t len) {
-        drain();
-        const uint32_t pb = 4 * a + nb;
-        if (pb + len < 16) { copy_small(src, len); return; }
-        const uintptr_t z = (uintptr_t)src - pb;
-        const uint32_t zo = (uint32_t)(z & 3), sh = zo * 8;
-        const uint32_t* Z = (const uint32_t*)(z - zo);
-        uint32_t remaining = pb + len - 16;                 // bytes after chunk 0
-        const uint32_t first_i = (pb + zo) >> 2;            // first aligned word that holds source bytes (0..4)
-        // ---- chunk 0: pending words + pending bytes + source ----
-        uint32_t s0 = first_i == 0 ? Z[0] : 0u;
-        uint32_t s1 = first_i <= 1 ? Z[1] : 0u;
-        uint32_t s2 = first_i <= 2 ? Z[2] : 0u;
-        uint32_t s3 = first_i <= 3 ? Z[3] : 0u;
-        uint32_t s4 = Z[4];
-        uint32_t v0 = fsr(s0, s1, sh), v1 = fsr(s1, s2, sh), v2 = fsr(s2, s3, sh), v3 = fsr(s3, s4, sh);
-        {
-            const uint32_t keep = 0xFFFFFFFFu << (8 * nb);
-            const uint32_t plo = nb ? pend >> (8 * (4 - nb)) : 0u;
-            if (a == 0) v0 = (v0 & keep) | plo;
-            else if (a == 1) v1 = (v1 & keep) | plo;
-            else if (a == 2) v2 = (v2 & keep) | plo;
-            else v3 = (v3 & keep) | plo;
+        if (!len) return;
+        const uintptr_t y = (uintptr_t)src - nb;
+        const uint32_t yo = (uint32_t)(y & 3), sh = yo * 8;
+        const uint32_t* Y = (const uint32_t*)(y - yo);
+        const uint32_t total = nb + len;
+        uint32_t nwords = total >> 2;
+        const uint32_t nn = total & 3;
+        // Y[0] holds source bytes iff the source starts inside it
+        uint32_t cur = (yo + nb < 4) ? Y[0] : 0u;
+        uint32_t nxt = (yo + total > 4) ? Y[1] : 0u;  // second word needed only if the data reaches it
+        uint32_t w0 = fsr(cur, nxt, sh);
+        if (nb) w0 = (w0 & (0xFFFFFFFFu << (8 * nb))) | (pend >> (8 * (4 - nb)));
+        if (nwords == 0) {  // still inside the same word
+            pend = w0 << (8 * (4 - nn));
+            nb = nn;
+            return;
         }
-        if (a > 0) v0 = *slot(0);
-        if (a > 1) v1 = *slot(1);
-        if (a > 2) v2 = *slot(2);
-        emit_chunk(v0, v1, v2, v3);
-        Z += 4;
-        // ---- full chunks straight from the source ----
-        while (remaining >= 16) {
-            s0 = s4;
-            s1 = Z[1]; s2 = Z[2]; s3 = Z[3]; s4 = Z[4];
-            store16(chunk, fsr(s0, s1, sh), fsr(s1, s2, sh), fsr(s2, s3, sh), fsr(s3, s4, sh));
-            chunk += 16;
-            remaining -= 16;
-            Z += 4;
+        uint32_t blk = nwords < 16 ? nwords : 16;
+        reserve(blk);
+        store_word(w0);
+        cur = nxt;
+        Y += 2;  // Y now points at the NEXT word to load
+        nwords -= blk;
+        blk--;
+        for (;;) {
+            for (; blk; blk--) {
+                nxt = *Y++;
+                store_word(fsr(cur, nxt, sh));
+                cur = nxt;
+            }
+            if (!nwords) break;
+            blk = nwords < 16 ? nwords : 16;
+            reserve(blk);
+            nwords -= blk;
         }
-        // ---- tail (< 16 bytes): word path from a fresh chunk ----
-        a = 0;
-        nb = 0;
-        r0 = 0;
-        pend = 0;
-        copy_small((const uint8_t*)Z + zo, remaining);
+        if (nn) {
+            // the partial last word: its bytes may or may not spill into the next aligned word
+            nxt = (yo + nn > 4) ? *Y : 0u;
+            pend = fsr(cur, nxt, sh) << (8 * (4 - nn));
+        }
+        nb = nn;
     }
     GOFR_HD void finish() {
-        drain();
-        if (a || nb) {
+        flush();
+        if (wl || nb) {
             uint32_t v[4];
 #pragma unroll
-            for (uint32_t j = 0; j < 4; j++) v[j] = j < a ? *slot(j) : 0u;
+            for (uint32_t j = 0; j < 4; j++) v[j] = j < wl ? word(j) : 0u;
             uint32_t tail = nb ? pend >> (8 * (4 - nb)) : 0u;
 #pragma unroll
-            for (uint32_t j = 0; j < 4; j++) if (j == a) v[j] = tail;
-            store_partial(chunk, v, lead, 4 * a + nb);
+            for (uint32_t j = 0; j < 4; j++) if (j == wl) v[j] = tail;
+            store_partial(chunk, v, lead, 4 * wl + nb);
         }
     }
 };
@@ -311,6 +317,7 @@ template <bool EMIT>
 GOFR_HD uint32_t json_escape_slow(Writer* w, const uint8_t* p, uint32_t len) {
     uint32_t out = 0;
     for (uint32_t i = 0; i < len;) {
+        if (EMIT) w->reserve(4);
         uint32_t c = p[i];
         if (c < 0x80) {
             if (c >= 0x20 && c != '"' && c != '\\' && c != '<' && c != '>' && c != '&') {
@@ -502,7 +509,7 @@ GOFR_HD uint32_t hex_uc(uint32_t v) { return v < 10 ? '0' + v : 'A' + v - 10; }
 template <bool EMIT>
 GOFR_HD uint32_t put_url_escaped(Writer* w, uint32_t c) {
     if (url_path_keep(c)) { if (EMIT) w->put1(c); return 1; }
-    if (EMIT) w->putk('%' | hex_uc(c >> 4) << 8 | hex_uc(c & 15) << 16, 3);
+    if (EMIT) { w->reserve(2); w->putk('%' | hex_uc(c >> 4) << 8 | hex_uc(c & 15) << 16, 3); }
     return 3;
 }
 
@@ -850,6 +857,7 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
         const Op& o = ops[oi];
         bool body = o.flags & OPF_BODY;
         if (EMIT && head && body) break;  // chunkWriter eats the body of a HEAD response; body ops come last
+        if (EMIT && w->wl >= 16) w->flush();  // every non-copy op appends at most 16 words
         uint32_t produced = 0;
         bool governed = o.flags & OPF_VALUE_OF_KEY;
         switch (o.code) {

@@ -112,7 +112,7 @@ struct TileShared {
     uint32_t warp_lo[NW], warp_hi[NW];
     unsigned long long tile_base;
     uint32_t in_lo, in_hi;
-    uint32_t ring[16 * T];  // word-major ring of the Writer's word path (serve_device.cuh)
+    uint32_t ring[32 * T];  // word-major staging buffer of the Writer (serve_device.cuh)
 };
 
 __global__ void __launch_bounds__(T, 4) serve_kernel(const ServeParams p) {

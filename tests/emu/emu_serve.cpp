@@ -25,7 +25,7 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
     patch_dates((uint8_t*)hot.data(), (const uint8_t*)date29, 0, 1);
     TableView tv;
     tv.bind((const uint8_t*)hot.data(), image);
-    uint32_t ring[16];
+    uint32_t ring[32];
     uint64_t pos = start_misalign;  // lets the test exercise every head alignment
     for (uint32_t i = 0; i < n; i++) {
         uint32_t d[4];
