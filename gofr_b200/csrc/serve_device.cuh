@@ -21,7 +21,8 @@
 #define GOFR_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define GOFR_HD inline
-#define GOFR_HD_NOINLINE
+#define GOFR_HD_NOINLINE inline
+struct uint4 { uint32_t x, y, z, w; };  // host build (tests/emu) only
 #endif
 
 namespace gofr {
@@ -51,6 +52,16 @@ GOFR_HD int clz64(uint64_t v) {
     return __clzll((long long)v);
 #else
     return v ? __builtin_clzll(v) : 64;
+#endif
+}
+
+// true if the predicate holds for ANY currently active lane: used so that lanes whose phases differ still take
+// flush decisions together (flushing early is harmless, flushing at different times runs the flush code repeatedly)
+GOFR_HD bool warp_any(bool p) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(__activemask(), p);
+#else
+    return p;
 #endif
 }
 
@@ -116,17 +127,17 @@ struct Writer {
         memcpy(addr, v, 16);
 #endif
     }
-    // write bytes [lo, hi) of the 16-byte chunk at addr from v[0..3]
+    // write bytes [lo, hi) of the 16-byte chunk at addr from v[0..3]: whole words where possible, else single bytes
     GOFR_HD static void store_partial(uint8_t* addr, const uint32_t v[4], uint32_t lo, uint32_t hi) {
 #pragma unroll
         for (uint32_t j = 0; j < 4; j++) {
-            uint32_t b0 = 4 * j, b1 = b0 + 4;
-            if (b1 <= lo || b0 >= hi) continue;
-            if (b0 >= lo && b1 <= hi) {
+            const uint32_t b0 = 4 * j;
+            if (b0 >= lo && b0 + 4 <= hi) {
                 ((uint32_t*)addr)[j] = v[j];
-            } else {
-                uint32_t s = b0 > lo ? b0 : lo, e = b1 < hi ? b1 : hi;
-                for (uint32_t b = s; b < e; b++) addr[b] = (uint8_t)(v[j] >> (8 * (b - b0)));
+            } else if (b0 + 4 > lo && b0 < hi) {
+#pragma unroll
+                for (uint32_t b = 0; b < 4; b++)
+                    if (b0 + b >= lo && b0 + b < hi) addr[b0 + b] = (uint8_t)(v[j] >> (8 * b));
             }
         }
     }
@@ -159,7 +170,7 @@ struct Writer {
     }
     // make room for n more words (n <= 28)
     GOFR_HD void reserve(uint32_t n) {
-        if (wl + n > GOFR_STAGE_WORDS) flush();
+        if (warp_any(wl + n > GOFR_STAGE_WORDS)) flush();
     }
     GOFR_HD void store_word(uint32_t x) {
         *(uint32_t*)wp = x;
@@ -189,7 +200,7 @@ struct Writer {
     }
     // single bytes from slow paths: room is checked here because those loops are unbounded
     GOFR_HD void put1(uint32_t c) {
-        if (wl >= GOFR_STAGE_WORDS - 2) flush();
+        if (warp_any(wl >= GOFR_STAGE_WORDS - 2)) flush();
         putk(c, 1);
     }
 
@@ -216,23 +227,31 @@ struct Writer {
             nb = nn;
             return;
         }
-        uint32_t blk = nwords < 16 ? nwords : 16;
-        reserve(blk);
+        reserve(4);
         store_word(w0);
         cur = nxt;
         Y += 2;  // Y now points at the NEXT word to load
-        nwords -= blk;
-        blk--;
-        for (;;) {
-            for (; blk; blk--) {
+        nwords--;
+        while (nwords >= 4) {  // four words per trip: immediate offsets, one room check, one pointer bump each
+            reserve(4);
+            const uint32_t n0 = Y[0], n1 = Y[1], n2 = Y[2], n3 = Y[3];
+            *(uint32_t*)wp = fsr(cur, n0, sh);
+            *(uint32_t*)(wp + GOFR_RING_STRIDE_BYTES) = fsr(n0, n1, sh);
+            *(uint32_t*)(wp + 2 * GOFR_RING_STRIDE_BYTES) = fsr(n1, n2, sh);
+            *(uint32_t*)(wp + 3 * GOFR_RING_STRIDE_BYTES) = fsr(n2, n3, sh);
+            cur = n3;
+            Y += 4;
+            wp += 4 * GOFR_RING_STRIDE_BYTES;
+            wl += 4;
+            nwords -= 4;
+        }
+        if (nwords) {
+            reserve(3);
+            for (; nwords; nwords--) {
                 nxt = *Y++;
                 store_word(fsr(cur, nxt, sh));
                 cur = nxt;
             }
-            if (!nwords) break;
-            blk = nwords < 16 ? nwords : 16;
-            reserve(blk);
-            nwords -= blk;
         }
         if (nn) {
             // the partial last word: its bytes may or may not spill into the next aligned word
@@ -312,9 +331,10 @@ GOFR_HD uint32_t utf8_len_at(const uint8_t* p, uint32_t n) {
 
 GOFR_HD uint32_t hex_lc(uint32_t v) { return v < 10 ? '0' + v : 'a' + v - 10; }
 
-// Slow path: escape [p, p+len) rune by rune.  EMIT=false only counts.
+// Slow path: escape [p, p+len) rune by rune.  EMIT=false only counts.  Kept out of line: it is rare and large, and
+// the kernel is instruction-cache sensitive.
 template <bool EMIT>
-GOFR_HD uint32_t json_escape_slow(Writer* w, const uint8_t* p, uint32_t len) {
+GOFR_HD_NOINLINE uint32_t json_escape_slow(Writer* w, const uint8_t* p, uint32_t len) {
     uint32_t out = 0;
     for (uint32_t i = 0; i < len;) {
         if (EMIT) w->reserve(4);
@@ -517,7 +537,7 @@ GOFR_HD uint32_t put_url_escaped(Writer* w, uint32_t c) {
 // path.Clean's stack is replayed per segment: a normal segment survives iff no later ".." pops it.  Quadratic in the
 // segment count, but only requests that are being redirected come here.
 template <bool EMIT>
-GOFR_HD uint32_t emit_location(Writer* w, const ReqCtx& c) {
+GOFR_HD_NOINLINE uint32_t emit_location(Writer* w, const ReqCtx& c) {
     const uint8_t* p = c.path;
     uint32_t n = c.path_len;
     uint32_t out = 0;
@@ -583,7 +603,7 @@ GOFR_HD bool words_equal(const uint32_t* a, const uint32_t* b, uint32_t n) {
 
 // Anchored leftmost-first match of lit0 var0 lit1 var1 ... litN [$]: greedy variables with backtracking — what Go's
 // regexp reports for the regexp mux builds from a path template.
-GOFR_HD bool template_match(const TableView& tv, const RouteRec& R, const uint8_t* p, uint32_t n) {
+GOFR_HD_NOINLINE bool template_match(const TableView& tv, const RouteRec& R, const uint8_t* p, uint32_t n) {
     const PieceRec* pc = tv.pieces + R.first_piece;
     uint32_t np = R.n_pieces;
     bool prefix = R.flags & RF_PREFIX;
@@ -636,7 +656,7 @@ GOFR_HD bool route_path_ok(const TableView& tv, const RouteRec& R, const uint8_t
 
 // Router.Match over routes in registration order with mux v1.8.1's ErrMethodMismatch bookkeeping.
 // Returns route index, or -1 (no route: 404) / -2 (405).  Reference formulation: every route is evaluated.
-GOFR_HD int mux_match_linear(const TableView& tv, uint32_t method, const uint8_t* p, uint32_t n) {
+GOFR_HD_NOINLINE int mux_match_linear(const TableView& tv, uint32_t method, const uint8_t* p, uint32_t n) {
     bool mismatch = false;
     uint32_t nr = tv.hdr->n_routes;
     for (uint32_t r = 0; r < nr; r++) {
@@ -742,7 +762,7 @@ GOFR_HD uint32_t query_value_scan(const uint8_t* v, uint32_t n) {
     return 1 | special;
 }
 
-GOFR_HD void find_param(ReqCtx& c, const uint8_t* key, uint32_t kn) {
+GOFR_HD_NOINLINE void find_param(ReqCtx& c, const uint8_t* key, uint32_t kn) {
     const uint8_t* q = c.query;
     uint32_t qn = c.query_len;
     c.pv_flags = 0;
@@ -773,7 +793,7 @@ GOFR_HD void find_param(ReqCtx& c, const uint8_t* key, uint32_t kn) {
 
 // QueryUnescape + encoding/json escape of the value, rune by rune over the DECODED bytes
 template <bool EMIT>
-GOFR_HD uint32_t emit_param_slow(Writer* w, const uint8_t* v, uint32_t n) {
+GOFR_HD_NOINLINE uint32_t emit_param_slow(Writer* w, const uint8_t* v, uint32_t n) {
     uint32_t out = 0;
     uint32_t i = 0;
     // decode one byte at raw position i → (byte, next position)
@@ -837,13 +857,16 @@ GOFR_HD void route_request(const TableView& tv, ReqCtx& c) {
 // stages 2+3: interpret the response program.  EMIT=false: compute c.body_len / c.total_len / c.slow_mask and
 // validate the row (returns false → caller switches to the panic program).  EMIT=true: write the bytes.
 // ---------------------------------------------------------------------------------------------------------------
+// Out-of-line slow paths work on a copy of the Writer so that the hot Writer never has its address taken (it stays in
+// registers); the copy lives in local memory only while the rare path runs.
+#define GOFR_SLOW_CALL(w, expr) do { Writer t_ = *(w); Writer* tw = &t_; (void)tw; expr; *(w) = t_; } while (0)
+
 template <bool EMIT>
 GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
     const ProgRec& P = tv.progs[c.prog];
     const Op* ops = tv.ops + P.first_op;
-    bool head = c.method == GOFR_M_HEAD;
+    const bool head = c.method == GOFR_M_HEAD;
     const uint32_t* row = (const uint32_t*)c.data;
-    uint32_t row_words = c.data_len >> 2;
     uint32_t str_cursor = 0;  // byte offset of the next string in the row's string area
     uint32_t str_base = 0;
     if (P.flags & PF_NEEDS_ROW) {
@@ -851,95 +874,96 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
         str_base = (uint32_t)S.fixed_words * 4;
         if (!EMIT && str_base > c.data_len) return false;
     }
-    uint32_t hdr_dyn = 0, body_dyn = 0, str_idx = 0;
+    uint32_t hdr_dyn = 0, body_dyn = 0, str_bit = 1;
     bool first = true, skip = false;
     for (uint32_t oi = 0; oi < P.n_ops; oi++) {
-        const Op& o = ops[oi];
-        bool body = o.flags & OPF_BODY;
+        const uint4 raw = *(const uint4*)(ops + oi);  // one 16-byte load per op
+        const uint32_t code = raw.x & 0xFFu, oflags = (raw.x >> 16) & 0xFFu, okind = raw.x >> 24;
+        const uint32_t olen = raw.y, ooff = raw.z, oaux = raw.w;
+        const bool body = oflags & OPF_BODY;
         if (EMIT && head && body) break;  // chunkWriter eats the body of a HEAD response; body ops come last
-        if (EMIT && w->wl >= 16) w->flush();  // every non-copy op appends at most 16 words
+        if (EMIT && warp_any(w->wl >= 16)) w->flush();  // every non-copy op appends at most 16 words
+        const bool governed = oflags & OPF_VALUE_OF_KEY;
         uint32_t produced = 0;
-        bool governed = o.flags & OPF_VALUE_OF_KEY;
-        switch (o.code) {
-            case OP_LIT:
-                if (governed) {
-                    if (!skip) { if (EMIT) emit_words(*w, tv.lit_words(o.off), o.len); produced = o.len; }
-                } else if (EMIT) emit_words(*w, tv.lit_words(o.off), o.len);
-                break;
-            case OP_HEXID:
-                if (EMIT) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) { uint32_t a, b; hex8(c.id[k], a, b); w->put4(a); w->put4(b); }
-                }
-                break;
-            case OP_CLEN:
-                if (EMIT) emit_u32<true>(w, c.body_len);
-                break;  // sized after the loop
-            case OP_KEY: {
-                (void)row_words;
-                bool empty = false;
-                if (o.flags & OPF_OMITEMPTY) {
-                    uint32_t wv = row[o.aux];
-                    if (o.kind == GOFR_F_INT64 || o.kind == 5) empty = (wv | row[o.aux + 1]) == 0;
-                    else empty = wv == 0;
-                }
-                skip = empty;
-                if (!empty) {
-                    if (!first) { if (EMIT) w->put1(','); produced += 1; }
-                    first = false;
-                    if (EMIT) emit_words(*w, tv.lit_words(o.off), o.len);
-                    produced += o.len;
-                }
-                break;
+        const uint8_t* csrc = nullptr;  // ops that append memory verbatim meet at the single copy() below
+        uint32_t clen = 0;
+        if (code == OP_LIT) {
+            if (!(governed && skip)) {
+                csrc = tv.lit_bytes(ooff);
+                clen = olen;
+                if (governed) produced = olen;  // ungoverned literals are pre-summed in hdr_fixed / body_fixed
             }
-            case OP_I64: {
-                int64_t v = (int64_t)((uint64_t)row[o.off] | (uint64_t)row[o.off + 1] << 32);
-                if (!(governed && skip)) produced = emit_i64<EMIT>(w, v);
-                break;
-            }
-            case OP_I32:
-                if (!(governed && skip)) produced = emit_i64<EMIT>(w, (int64_t)(int32_t)row[o.off]);
-                break;
-            case OP_BOOL:
-                if (!(governed && skip)) {
-                    bool t = row[o.off] != 0;
-                    if (EMIT) { if (t) w->put4('t' | 'r' << 8 | 'u' << 16 | 'e' << 24); else { w->put4('f' | 'a' << 8 | 'l' << 16 | 's' << 24); w->put1('e'); } }
-                    produced = t ? 4 : 5;
-                }
-                break;
-            case OP_STR: {
-                uint32_t len = row[o.off];
-                if (!EMIT && (str_base + str_cursor + (uint64_t)len > c.data_len)) return false;
-                const uint8_t* s = c.data + str_base + str_cursor;
-                str_cursor += len;
-                uint32_t bit = 1u << (str_idx & 31);
-                str_idx++;
-                if (governed && skip) break;
+        } else if (code == OP_STR) {
+            const uint32_t len = row[ooff];
+            if (!EMIT && (str_base + str_cursor + (uint64_t)len > c.data_len)) return false;
+            const uint8_t* sp = c.data + str_base + str_cursor;
+            str_cursor += len;
+            const uint32_t bit = str_bit;
+            str_bit <<= 1;
+            if (!(governed && skip)) {
                 if (!EMIT) {
-                    if (json_needs_escape(s, len)) { c.slow_mask |= bit; produced = json_escape_slow<false>(nullptr, s, len); }
+                    if (json_needs_escape(sp, len)) { c.slow_mask |= bit; produced = json_escape_slow<false>(nullptr, sp, len); }
                     else produced = len;
+                } else if (c.slow_mask & bit) {
+                    GOFR_SLOW_CALL(w, json_escape_slow<true>(tw, sp, len));
                 } else {
-                    if (c.slow_mask & bit) json_escape_slow<true>(w, s, len);
-                    else emit_bytes(*w, s, len);
+                    csrc = sp;
+                    clen = len;
                 }
-                break;
             }
-            case OP_PARAM:
-                if (c.pv_flags & 1) {
-                    const uint8_t* v = c.query + c.pv_off;
-                    if (c.pv_flags & 2) produced = emit_param_slow<EMIT>(w, v, c.pv_len);
-                    else { if (EMIT) emit_bytes(*w, v, c.pv_len); produced = c.pv_len; }
-                } else {
-                    if (EMIT) emit_words(*w, tv.lit_words(c.def_off), c.def_len);
-                    produced = c.def_len;
-                }
-                break;
-            case OP_LOCATION: produced = emit_location<EMIT>(w, c); break;
-            case OP_BLOB:
-                if (EMIT) emit_bytes(*w, tv.cold + o.off, o.len);
-                break;
-            default: break;  // OP_ERRMSG is handled by the Bind stage (bind_device.cuh)
+        } else if (code == OP_I64 || code == OP_I32) {
+            if (!(governed && skip)) {
+                const int64_t v = code == OP_I64 ? (int64_t)((uint64_t)row[ooff] | (uint64_t)row[ooff + 1] << 32)
+                                                 : (int64_t)(int32_t)row[ooff];
+                produced = emit_i64<EMIT>(w, v);
+            }
+        } else if (code == OP_BOOL) {
+            if (!(governed && skip)) {
+                const bool t = row[ooff] != 0;
+                if (EMIT) { if (t) w->put4('t' | 'r' << 8 | 'u' << 16 | 'e' << 24); else { w->put4('f' | 'a' << 8 | 'l' << 16 | 's' << 24); w->put1('e'); } }
+                produced = t ? 4 : 5;
+            }
+        } else if (code == OP_HEXID) {
+            if (EMIT) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) { uint32_t a, b; hex8(c.id[k], a, b); w->put4(a); w->put4(b); }
+            }
+        } else if (code == OP_CLEN) {
+            if (EMIT) emit_u32<true>(w, c.body_len);  // sized after the loop
+        } else if (code == OP_KEY) {
+            bool empty = false;
+            if (oflags & OPF_OMITEMPTY) {
+                const uint32_t wv = row[oaux];
+                empty = (okind == GOFR_F_INT64 || okind == GOFR_F_INT) ? (wv | row[oaux + 1]) == 0 : wv == 0;
+            }
+            skip = empty;
+            if (!empty) {
+                if (!first) { if (EMIT) w->put1(','); produced += 1; }
+                first = false;
+                csrc = tv.lit_bytes(ooff);
+                clen = olen;
+                produced += olen;
+            }
+        } else if (code == OP_PARAM) {
+            if (c.pv_flags & 1) {
+                const uint8_t* v = c.query + c.pv_off;
+                if (c.pv_flags & 2) {
+                    if (EMIT) GOFR_SLOW_CALL(w, emit_param_slow<true>(tw, v, c.pv_len));
+                    else produced = emit_param_slow<false>(nullptr, v, c.pv_len);
+                } else { csrc = v; clen = c.pv_len; produced = c.pv_len; }
+            } else {
+                csrc = tv.lit_bytes(c.def_off);
+                clen = c.def_len;
+                produced = c.def_len;
+            }
+        } else if (code == OP_LOCATION) {
+            if (EMIT) GOFR_SLOW_CALL(w, emit_location<true>(tw, c));
+            else produced = emit_location<false>(nullptr, c);
+        } else if (code == OP_BLOB) {
+            csrc = tv.cold + ooff;
+            clen = olen;
         }
+        if (EMIT && clen) w->copy(csrc, clen);
         if (body) body_dyn += produced; else hdr_dyn += produced;
     }
     if (!EMIT) {
