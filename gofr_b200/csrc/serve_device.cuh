@@ -89,6 +89,52 @@ GOFR_HD bool warp_any(bool p) {
 #endif
 #define GOFR_STAGE_WORDS 32u
 
+// ---- explicit address spaces -------------------------------------------------------------------------------------
+// The staging buffer, the table's literal pool and (for staged tiles) the request bytes all live in shared memory.
+// Going through generic pointers costs 64-bit address arithmetic, window checks and the slower LD.E/ST.E path, so on
+// the device they are addressed with 32-bit shared-memory addresses and ld/st.shared; on the host (tests/emu) the
+// same code runs on plain pointers.
+#if defined(__CUDA_ARCH__)
+typedef uint32_t saddr_t;
+GOFR_HD saddr_t to_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// staging buffer accesses are read-after-write on the same addresses: keep them ordered
+GOFR_HD void stg_st(saddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+GOFR_HD uint32_t stg_ld(saddr_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+// sources are read-only while a response is being written: let the compiler schedule these freely
+GOFR_HD uint32_t src_ld(saddr_t a) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+GOFR_HD uint32_t salign(saddr_t a) { return a & 3u; }
+#else
+typedef const uint8_t* saddr_t;
+GOFR_HD saddr_t to_saddr(const void* p) { return (const uint8_t*)p; }
+GOFR_HD void stg_st(saddr_t a, uint32_t v) { *(uint32_t*)a = v; }
+GOFR_HD uint32_t stg_ld(saddr_t a) { return *(const uint32_t*)a; }
+GOFR_HD uint32_t src_ld(saddr_t a) { return *(const uint32_t*)a; }
+GOFR_HD uint32_t salign(saddr_t a) { return (uint32_t)((uintptr_t)a & 3u); }
+#endif
+
+// memory policy of a copy source: SH = shared-memory address, otherwise a generic pointer
+template <bool SH> struct SrcMem;
+template <> struct SrcMem<true> {
+    typedef saddr_t A;
+    GOFR_HD static A from(const uint8_t* p) { return to_saddr(p); }
+    GOFR_HD static uint32_t ld(A a) { return src_ld(a); }
+    GOFR_HD static uint32_t low2(A a) { return salign(a); }
+};
+template <> struct SrcMem<false> {
+    typedef const uint8_t* A;
+    GOFR_HD static A from(const uint8_t* p) { return p; }
+    GOFR_HD static uint32_t ld(A a) { return *(const uint32_t*)a; }
+    GOFR_HD static uint32_t low2(A a) { return (uint32_t)((uintptr_t)a & 3u); }
+};
+
 // load k (1..4) bytes at an arbitrary address as the low bytes of a word; reads only words that hold source bytes
 GOFR_HD uint32_t load_bytes(const uint8_t* p, uint32_t k) {
     uintptr_t a = (uintptr_t)p;
@@ -101,8 +147,8 @@ GOFR_HD uint32_t load_bytes(const uint8_t* p, uint32_t k) {
 
 struct Writer {
     uint8_t* chunk;  // 16-byte aligned global address that staging word 0 maps to
-    uint8_t* base;   // this thread's column of the staging buffer
-    uint8_t* wp;     // base + wl * stride: where the next complete word goes
+    saddr_t base;    // this thread's column of the staging buffer
+    saddr_t wp;      // base + wl * stride: where the next complete word goes
     uint32_t wl;     // complete words staged (0 .. GOFR_STAGE_WORDS)
     uint32_t pend, nb;
     uint32_t lead;   // bytes at the start of the first chunk owned by the previous response
@@ -113,11 +159,11 @@ struct Writer {
         lead = (uint32_t)(x & 15);
         wl = lead >> 2;  // phantom words of the neighbour: never stored
         nb = lead & 3;
-        base = (uint8_t*)col;
+        base = to_saddr(col);
         wp = base + wl * GOFR_RING_STRIDE_BYTES;
         pend = 0;
     }
-    GOFR_HD uint32_t word(uint32_t k) const { return *(const uint32_t*)(base + k * GOFR_RING_STRIDE_BYTES); }
+    GOFR_HD uint32_t word(uint32_t k) const { return stg_ld(base + k * GOFR_RING_STRIDE_BYTES); }
 
     GOFR_HD static void store16(uint8_t* addr, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
 #if defined(__CUDA_ARCH__)
@@ -144,7 +190,7 @@ struct Writer {
     // store every complete chunk, move the (< 4) left-over words to the front
     GOFR_HD void flush() {
         uint32_t n = wl >> 2;
-        const uint8_t* rp = base;
+        saddr_t rp = base;
         if (n && lead) {  // first chunk of the response: skip the neighbour's bytes
             const uint32_t vv[4] = {word(0), word(1), word(2), word(3)};
             store_partial(chunk, vv, lead, 16);
@@ -154,26 +200,26 @@ struct Writer {
             n--;
         }
         for (; n; n--) {
-            store16(chunk, *(const uint32_t*)rp, *(const uint32_t*)(rp + GOFR_RING_STRIDE_BYTES),
-                    *(const uint32_t*)(rp + 2 * GOFR_RING_STRIDE_BYTES), *(const uint32_t*)(rp + 3 * GOFR_RING_STRIDE_BYTES));
+            store16(chunk, stg_ld(rp), stg_ld(rp + GOFR_RING_STRIDE_BYTES), stg_ld(rp + 2 * GOFR_RING_STRIDE_BYTES),
+                    stg_ld(rp + 3 * GOFR_RING_STRIDE_BYTES));
             chunk += 16;
             rp += 4 * GOFR_RING_STRIDE_BYTES;
         }
         uint32_t r = wl & 3;
         if (wl >= 4) {
-            if (r > 0) *(uint32_t*)base = *(const uint32_t*)rp;
-            if (r > 1) *(uint32_t*)(base + GOFR_RING_STRIDE_BYTES) = *(const uint32_t*)(rp + GOFR_RING_STRIDE_BYTES);
-            if (r > 2) *(uint32_t*)(base + 2 * GOFR_RING_STRIDE_BYTES) = *(const uint32_t*)(rp + 2 * GOFR_RING_STRIDE_BYTES);
+            if (r > 0) stg_st(base, stg_ld(rp));
+            if (r > 1) stg_st(base + GOFR_RING_STRIDE_BYTES, stg_ld(rp + GOFR_RING_STRIDE_BYTES));
+            if (r > 2) stg_st(base + 2 * GOFR_RING_STRIDE_BYTES, stg_ld(rp + 2 * GOFR_RING_STRIDE_BYTES));
         }
         wl = r;
         wp = base + r * GOFR_RING_STRIDE_BYTES;
     }
-    // make room for n more words (n <= 28)
+    // make room for n more words (n <= 28); the decision is taken together by all active lanes
     GOFR_HD void reserve(uint32_t n) {
         if (warp_any(wl + n > GOFR_STAGE_WORDS)) flush();
     }
     GOFR_HD void store_word(uint32_t x) {
-        *(uint32_t*)wp = x;
+        stg_st(wp, x);
         wp += GOFR_RING_STRIDE_BYTES;
         wl++;
     }
@@ -204,22 +250,23 @@ struct Writer {
         putk(c, 1);
     }
 
-    // Append len bytes from memory (any address space, any alignment).  With y = src - nb the stream
-    // "pending bytes ++ source" is word-aligned with the destination, so output word k is the unaligned word at
-    // y + 4k: one aligned load (the previous one is carried) and one funnel shift.  Only word 0 mixes in `pend`.
+    // Append len bytes from memory (any alignment).  With y = src - nb the stream "pending bytes ++ source" is
+    // word-aligned with the destination, so output word k is the unaligned word at y + 4k: one aligned load (the
+    // previous one is carried) and one funnel shift.  Only word 0 mixes in `pend`.
     // Sources must be readable up to the end of the aligned word following their last byte (literal pool, staged
     // arena and blobs are padded accordingly); no byte before the source is ever read.
-    GOFR_HD void copy(const uint8_t* src, uint32_t len) {
+    template <bool SH>
+    GOFR_HD void copy(typename SrcMem<SH>::A src, uint32_t len) {
+        typedef SrcMem<SH> M;
         if (!len) return;
-        const uintptr_t y = (uintptr_t)src - nb;
-        const uint32_t yo = (uint32_t)(y & 3), sh = yo * 8;
-        const uint32_t* Y = (const uint32_t*)(y - yo);
+        const uint32_t yo = (M::low2(src) - nb) & 3u, sh = yo * 8;
+        typename M::A Y = src - nb - yo;  // aligned word that holds stream byte 0
         const uint32_t total = nb + len;
         uint32_t nwords = total >> 2;
         const uint32_t nn = total & 3;
         // Y[0] holds source bytes iff the source starts inside it
-        uint32_t cur = (yo + nb < 4) ? Y[0] : 0u;
-        uint32_t nxt = (yo + total > 4) ? Y[1] : 0u;  // second word needed only if the data reaches it
+        uint32_t cur = (yo + nb < 4) ? M::ld(Y) : 0u;
+        uint32_t nxt = (yo + total > 4) ? M::ld(Y + 4) : 0u;  // second word needed only if the data reaches it
         uint32_t w0 = fsr(cur, nxt, sh);
         if (nb) w0 = (w0 & (0xFFFFFFFFu << (8 * nb))) | (pend >> (8 * (4 - nb)));
         if (nwords == 0) {  // still inside the same word
@@ -230,17 +277,17 @@ struct Writer {
         reserve(4);
         store_word(w0);
         cur = nxt;
-        Y += 2;  // Y now points at the NEXT word to load
+        Y += 8;  // Y now points at the NEXT word to load
         nwords--;
         while (nwords >= 4) {  // four words per trip: immediate offsets, one room check, one pointer bump each
             reserve(4);
-            const uint32_t n0 = Y[0], n1 = Y[1], n2 = Y[2], n3 = Y[3];
-            *(uint32_t*)wp = fsr(cur, n0, sh);
-            *(uint32_t*)(wp + GOFR_RING_STRIDE_BYTES) = fsr(n0, n1, sh);
-            *(uint32_t*)(wp + 2 * GOFR_RING_STRIDE_BYTES) = fsr(n1, n2, sh);
-            *(uint32_t*)(wp + 3 * GOFR_RING_STRIDE_BYTES) = fsr(n2, n3, sh);
+            const uint32_t n0 = M::ld(Y), n1 = M::ld(Y + 4), n2 = M::ld(Y + 8), n3 = M::ld(Y + 12);
+            stg_st(wp, fsr(cur, n0, sh));
+            stg_st(wp + GOFR_RING_STRIDE_BYTES, fsr(n0, n1, sh));
+            stg_st(wp + 2 * GOFR_RING_STRIDE_BYTES, fsr(n1, n2, sh));
+            stg_st(wp + 3 * GOFR_RING_STRIDE_BYTES, fsr(n2, n3, sh));
             cur = n3;
-            Y += 4;
+            Y += 16;
             wp += 4 * GOFR_RING_STRIDE_BYTES;
             wl += 4;
             nwords -= 4;
@@ -248,14 +295,15 @@ struct Writer {
         if (nwords) {
             reserve(3);
             for (; nwords; nwords--) {
-                nxt = *Y++;
+                nxt = M::ld(Y);
+                Y += 4;
                 store_word(fsr(cur, nxt, sh));
                 cur = nxt;
             }
         }
         if (nn) {
             // the partial last word: its bytes may or may not spill into the next aligned word
-            nxt = (yo + nn > 4) ? *Y : 0u;
+            nxt = (yo + nn > 4) ? M::ld(Y) : 0u;
             pend = fsr(cur, nxt, sh) << (8 * (4 - nn));
         }
         nb = nn;
@@ -274,9 +322,8 @@ struct Writer {
     }
 };
 
-// Copy len bytes from the literal pool (4-byte aligned, zero padded) / from an arbitrary byte address.
-GOFR_HD void emit_words(Writer& w, const uint32_t* src, uint32_t len) { w.copy((const uint8_t*)src, len); }
-GOFR_HD void emit_bytes(Writer& w, const uint8_t* p, uint32_t len) { w.copy(p, len); }
+// generic-pointer copy: out-of-line slow paths, file blobs, tiles too large for the shared-memory staging
+GOFR_HD_NOINLINE void emit_bytes(Writer& w, const uint8_t* p, uint32_t len) { w.copy<false>(p, len); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // encoding/json string contents (Go 1.21, escapeHTML on)
@@ -293,24 +340,25 @@ GOFR_HD uint32_t json_special_mask(uint32_t x) {
 }
 
 // true if [p, p+len) contains a byte that encoding/json does not copy verbatim
-GOFR_HD bool json_needs_escape(const uint8_t* p, uint32_t len) {
+template <bool SH>
+GOFR_HD bool json_needs_escape(typename SrcMem<SH>::A p, uint32_t len) {
+    typedef SrcMem<SH> M;
     if (!len) return false;
-    uintptr_t a = (uintptr_t)p;
-    const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
-    uint32_t lead = (uint32_t)(a & 3);
-    uint32_t total = lead + len;           // bytes from q to the end of the string
-    uint32_t last = (total - 1) >> 2;      // index of the word holding the last byte
-    uint32_t keep = total & 3;             // valid bytes in that word (0 = all four)
+    const uint32_t lead = M::low2(p);
+    typename M::A q = p - lead;
+    const uint32_t total = lead + len;      // bytes from q to the end of the string
+    const uint32_t last = (total - 1) >> 2; // index of the word holding the last byte
+    const uint32_t keep = total & 3;        // valid bytes in that word (0 = all four)
     // bytes outside the string are replaced by 'a' so they can never flag
-    uint32_t x = q[0];
+    uint32_t x = M::ld(q);
     if (lead) x = (x & (0xFFFFFFFFu << (8 * lead))) | (0x61616161u >> (8 * (4 - lead)));
     if (last == 0) {
         if (keep) x = (x & (0xFFFFFFFFu >> (8 * (4 - keep)))) | (0x61616161u << (8 * keep));
         return json_special_mask(x) != 0;
     }
     uint32_t bad = json_special_mask(x);
-    for (uint32_t i = 1; i < last; i++) bad |= json_special_mask(q[i]);
-    x = q[last];
+    for (uint32_t i = 1; i < last; i++) bad |= json_special_mask(M::ld(q + 4 * i));
+    x = M::ld(q + 4 * last);
     if (keep) x = (x & (0xFFFFFFFFu >> (8 * (4 - keep)))) | (0x61616161u << (8 * keep));
     return (bad | json_special_mask(x)) != 0;
 }
@@ -496,6 +544,7 @@ struct ReqCtx {
     uint32_t status;
     uint32_t pv_off, pv_len, pv_flags;  // query value span; flags bit0 found&non-empty, bit1 needs decode/escape
     uint32_t body_len, total_len;
+    uint32_t staged;     // request bytes live in shared memory (tile staged by TMA)
     uint32_t slow_mask;  // bit k: k-th OP_STR of the program needs the slow escape path
     uint32_t def_off, def_len;  // OP_PARAM default (pre-escaped literal)
 };
@@ -887,6 +936,7 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
         uint32_t produced = 0;
         const uint8_t* csrc = nullptr;  // ops that append memory verbatim meet at the single copy() below
         uint32_t clen = 0;
+        bool cshared = true;            // literals live in the shared-memory copy of the table
         if (code == OP_LIT) {
             if (!(governed && skip)) {
                 csrc = tv.lit_bytes(ooff);
@@ -902,13 +952,15 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
             str_bit <<= 1;
             if (!(governed && skip)) {
                 if (!EMIT) {
-                    if (json_needs_escape(sp, len)) { c.slow_mask |= bit; produced = json_escape_slow<false>(nullptr, sp, len); }
+                    const bool esc = c.staged ? json_needs_escape<true>(SrcMem<true>::from(sp), len) : json_needs_escape<false>(sp, len);
+                    if (esc) { c.slow_mask |= bit; produced = json_escape_slow<false>(nullptr, sp, len); }
                     else produced = len;
                 } else if (c.slow_mask & bit) {
                     GOFR_SLOW_CALL(w, json_escape_slow<true>(tw, sp, len));
                 } else {
                     csrc = sp;
                     clen = len;
+                    cshared = c.staged;
                 }
             }
         } else if (code == OP_I64 || code == OP_I32) {
@@ -950,7 +1002,7 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
                 if (c.pv_flags & 2) {
                     if (EMIT) GOFR_SLOW_CALL(w, emit_param_slow<true>(tw, v, c.pv_len));
                     else produced = emit_param_slow<false>(nullptr, v, c.pv_len);
-                } else { csrc = v; clen = c.pv_len; produced = c.pv_len; }
+                } else { csrc = v; clen = c.pv_len; produced = c.pv_len; cshared = c.staged; }
             } else {
                 csrc = tv.lit_bytes(c.def_off);
                 clen = c.def_len;
@@ -962,8 +1014,12 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
         } else if (code == OP_BLOB) {
             csrc = tv.cold + ooff;
             clen = olen;
+            cshared = false;
         }
-        if (EMIT && clen) w->copy(csrc, clen);
+        if (EMIT && clen) {
+            if (cshared) w->copy<true>(SrcMem<true>::from(csrc), clen);
+            else GOFR_SLOW_CALL(w, emit_bytes(*tw, csrc, clen));
+        }
         if (body) body_dyn += produced; else hdr_dyn += produced;
     }
     if (!EMIT) {

@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(T, 4) serve_kernel(const ServeParams p) {
         c.flags = (d.w >> 8) & 0xFFu;
         c.id[0] = id.x; c.id[1] = id.y; c.id[2] = id.z; c.id[3] = id.w;
         c.total_len = 0; c.body_len = 0; c.status = 0; c.route = GOFR_ROUTE_NONE; c.prog = 0xFFFF;
+        c.staged = in_staged ? 1u : 0u;
         if (valid) size_request(tv, c);
 
         // ---- block scan of response sizes ----

@@ -41,6 +41,7 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
         c.flags = (d[3] >> 8) & 0xFF;
         memcpy(c.id, ids + (size_t)i * 16, 16);
         c.total_len = c.body_len = 0; c.status = 0; c.route = GOFR_ROUTE_NONE; c.prog = 0xFFFF;
+        c.staged = (i & 1);  // alternate so both source policies are exercised
         size_request(tv, c);
         if (c.prog != 0xFFFF && path_is_clean(c.path, c.path_len)) {  // both matchers must always agree
             int a = mux_match(tv, c.method, c.path, c.path_len), b = mux_match_linear(tv, c.method, c.path, c.path_len);
