@@ -586,7 +586,7 @@ GOFR_HD uint32_t put_url_escaped(Writer* w, uint32_t c) {
 // path.Clean's stack is replayed per segment: a normal segment survives iff no later ".." pops it.  Quadratic in the
 // segment count, but only requests that are being redirected come here.
 template <bool EMIT>
-GOFR_HD_NOINLINE uint32_t emit_location(Writer* w, const ReqCtx& c) {
+GOFR_HD_NOINLINE uint32_t emit_location(Writer* w, const ReqCtx c) {
     const uint8_t* p = c.path;
     uint32_t n = c.path_len;
     uint32_t out = 0;
@@ -652,7 +652,7 @@ GOFR_HD bool words_equal(const uint32_t* a, const uint32_t* b, uint32_t n) {
 
 // Anchored leftmost-first match of lit0 var0 lit1 var1 ... litN [$]: greedy variables with backtracking — what Go's
 // regexp reports for the regexp mux builds from a path template.
-GOFR_HD_NOINLINE bool template_match(const TableView& tv, const RouteRec& R, const uint8_t* p, uint32_t n) {
+GOFR_HD_NOINLINE bool template_match(const TableView tv, const RouteRec R, const uint8_t* p, uint32_t n) {
     const PieceRec* pc = tv.pieces + R.first_piece;
     uint32_t np = R.n_pieces;
     bool prefix = R.flags & RF_PREFIX;
@@ -705,7 +705,7 @@ GOFR_HD bool route_path_ok(const TableView& tv, const RouteRec& R, const uint8_t
 
 // Router.Match over routes in registration order with mux v1.8.1's ErrMethodMismatch bookkeeping.
 // Returns route index, or -1 (no route: 404) / -2 (405).  Reference formulation: every route is evaluated.
-GOFR_HD_NOINLINE int mux_match_linear(const TableView& tv, uint32_t method, const uint8_t* p, uint32_t n) {
+GOFR_HD_NOINLINE int mux_match_linear(const TableView tv, uint32_t method, const uint8_t* p, uint32_t n) {
     bool mismatch = false;
     uint32_t nr = tv.hdr->n_routes;
     for (uint32_t r = 0; r < nr; r++) {
@@ -811,11 +811,9 @@ GOFR_HD uint32_t query_value_scan(const uint8_t* v, uint32_t n) {
     return 1 | special;
 }
 
-GOFR_HD_NOINLINE void find_param(ReqCtx& c, const uint8_t* key, uint32_t kn) {
-    const uint8_t* q = c.query;
-    uint32_t qn = c.query_len;
-    c.pv_flags = 0;
-    c.pv_off = c.pv_len = 0;
+struct ParamSpan { uint32_t off, len, flags; };
+GOFR_HD_NOINLINE ParamSpan find_param(const uint8_t* q, uint32_t qn, const uint8_t* key, uint32_t kn) {
+    ParamSpan r = {0, 0, 0};
     uint32_t i = 0;
     while (i < qn) {
         uint32_t j = i, eq = 0xFFFFFFFFu;
@@ -835,9 +833,10 @@ GOFR_HD_NOINLINE void find_param(ReqCtx& c, const uint8_t* key, uint32_t kn) {
         uint32_t f = query_value_scan(q + vs, pe - vs);
         if (!(f & 1)) continue;
         // first successfully parsed pair for this key decides; an empty value makes the handler use its default
-        if (pe > vs) { c.pv_off = vs; c.pv_len = pe - vs; c.pv_flags = 1 | (f & 2); }
-        return;
+        if (pe > vs) { r.off = vs; r.len = pe - vs; r.flags = 1 | (f & 2); }
+        return r;
     }
+    return r;
 }
 
 // QueryUnescape + encoding/json escape of the value, rune by rune over the DECODED bytes
@@ -896,7 +895,8 @@ GOFR_HD void route_request(const TableView& tv, ReqCtx& c) {
     if (c.method == GOFR_M_OPTIONS) { c.prog = H.prog_options; return; }  // middleware/cors.go:10-13
     c.prog = R.prog_ok;
     if (R.hkind == GOFR_H_PARAM_FORMAT) {
-        find_param(c, tv.lit_bytes(R.key_off), R.key_len);
+        const ParamSpan ps = find_param(c.query, c.query_len, tv.lit_bytes(R.key_off), R.key_len);
+        c.pv_off = ps.off; c.pv_len = ps.len; c.pv_flags = ps.flags;
         c.def_off = R.def_off;
         c.def_len = R.def_len;
     }
@@ -912,8 +912,10 @@ GOFR_HD void route_request(const TableView& tv, ReqCtx& c) {
 
 template <bool EMIT>
 GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
-    const ProgRec& P = tv.progs[c.prog];
+    const ProgRec P = tv.progs[c.prog];  // by value: the staging stores below must not force re-reads of the table
     const Op* ops = tv.ops + P.first_op;
+    const uint32_t n_ops = P.n_ops;
+    const uint8_t* const lits = tv.lits;
     const bool head = c.method == GOFR_M_HEAD;
     const uint32_t* row = (const uint32_t*)c.data;
     uint32_t str_cursor = 0;  // byte offset of the next string in the row's string area
@@ -925,7 +927,7 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
     }
     uint32_t hdr_dyn = 0, body_dyn = 0, str_bit = 1;
     bool first = true, skip = false;
-    for (uint32_t oi = 0; oi < P.n_ops; oi++) {
+    for (uint32_t oi = 0; oi < n_ops; oi++) {
         const uint4 raw = *(const uint4*)(ops + oi);  // one 16-byte load per op
         const uint32_t code = raw.x & 0xFFu, oflags = (raw.x >> 16) & 0xFFu, okind = raw.x >> 24;
         const uint32_t olen = raw.y, ooff = raw.z, oaux = raw.w;
@@ -939,7 +941,7 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
         bool cshared = true;            // literals live in the shared-memory copy of the table
         if (code == OP_LIT) {
             if (!(governed && skip)) {
-                csrc = tv.lit_bytes(ooff);
+                csrc = lits + ooff;
                 clen = olen;
                 if (governed) produced = olen;  // ungoverned literals are pre-summed in hdr_fixed / body_fixed
             }
@@ -992,7 +994,7 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
             if (!empty) {
                 if (!first) { if (EMIT) w->put1(','); produced += 1; }
                 first = false;
-                csrc = tv.lit_bytes(ooff);
+                csrc = lits + ooff;
                 clen = olen;
                 produced += olen;
             }
@@ -1004,7 +1006,7 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
                     else produced = emit_param_slow<false>(nullptr, v, c.pv_len);
                 } else { csrc = v; clen = c.pv_len; produced = c.pv_len; cshared = c.staged; }
             } else {
-                csrc = tv.lit_bytes(c.def_off);
+                csrc = lits + c.def_off;
                 clen = c.def_len;
                 produced = c.def_len;
             }
