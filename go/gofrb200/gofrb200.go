@@ -1,0 +1,162 @@
+// Package gofrb200 binds libgofr_b200.so (include/gofr_b200.h) over cgo.
+//
+// UNVERIFIED SOURCE: there is no Go toolchain in the build image or on the GPU box, so this file has never been
+// compiled.  It shows the exact binding a GoFr maintainer would add; every C call is one declared in
+// include/gofr_b200.h.  The C++/Python harnesses in this repository exercise the same ABI.
+//
+// How it plugs into GoFr (reference paths):
+//   - App.add (pkg/gofr/gofr.go:171-177) additionally calls Table.AddRoute with the declarative handler kind (or
+//     HHost for an arbitrary closure);
+//   - App.Run (pkg/gofr/gofr.go:90-126) calls Table.AddDefaultRoutes, Table.Seal and NewEngine instead of
+//     httpServer.Run, and starts a Batcher that collects parsed requests from the connection goroutines;
+//   - the Batcher hands batches to Engine.Serve and fans the response bytes back to the connections.
+package gofrb200
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../gofr_b200 -lgofr_b200 -Wl,-rpath,${SRCDIR}/../../gofr_b200
+#include <stdlib.h>
+#include "gofr_b200.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"time"
+	"unsafe"
+)
+
+// Method codes: mux compares exact upper-case method strings, everything else is MOther.
+const (
+	MGet = iota
+	MHead
+	MPost
+	MPut
+	MPatch
+	MDelete
+	MConnect
+	MOptions
+	MTrace
+	MOther = 15
+)
+
+var methodCodes = map[string]uint8{"GET": MGet, "HEAD": MHead, "POST": MPost, "PUT": MPut, "PATCH": MPatch,
+	"DELETE": MDelete, "CONNECT": MConnect, "OPTIONS": MOptions, "TRACE": MTrace}
+
+func MethodCode(m string) uint8 {
+	if c, ok := methodCodes[m]; ok {
+		return c
+	}
+	return MOther
+}
+
+func check(rc C.int, where string) error {
+	if rc == 0 {
+		return nil
+	}
+	return fmt.Errorf("%s: gofr error %d: %s", where, int(rc), C.GoString(C.gofr_last_error()))
+}
+
+// Table mirrors the route slice of mux.Router: routes in registration order, frozen by Seal.
+type Table struct{ t *C.gofr_table }
+
+func NewTable(frameMode uint32) (*Table, error) {
+	var t *C.gofr_table
+	if err := check(C.gofr_table_create(&t, C.uint32_t(frameMode)), "gofr_table_create"); err != nil {
+		return nil, err
+	}
+	return &Table{t}, nil
+}
+
+// Handler is the declarative description of a gofr.Handler closure (GOFR_H_* in the header).
+type Handler struct {
+	Kind     uint32
+	SchemaID uint32
+	S0, S1   string
+	S2, S3   string
+	Blob     []byte
+}
+
+func (t *Table) AddRoute(method string, pattern string, h Handler) (uint32, error) {
+	var d C.gofr_handler_desc
+	d.kind = C.uint32_t(h.Kind)
+	d.schema_id = C.uint32_t(h.SchemaID)
+	cs := func(s string) (*C.char, C.uint32_t) { return C.CString(s), C.uint32_t(len(s)) }
+	d.s0, d.s0_len = cs(h.S0)
+	d.s1, d.s1_len = cs(h.S1)
+	d.s2, d.s2_len = cs(h.S2)
+	d.s3, d.s3_len = cs(h.S3)
+	defer func() {
+		C.free(unsafe.Pointer(d.s0)); C.free(unsafe.Pointer(d.s1)); C.free(unsafe.Pointer(d.s2)); C.free(unsafe.Pointer(d.s3))
+	}()
+	if len(h.Blob) > 0 {
+		d.blob = (*C.uint8_t)(unsafe.Pointer(&h.Blob[0]))
+		d.blob_len = C.uint32_t(len(h.Blob))
+	}
+	p := C.CString(pattern)
+	defer C.free(unsafe.Pointer(p))
+	var id C.uint32_t
+	m := C.uint32_t(MethodCode(method))
+	err := check(C.gofr_table_add_route(t.t, m, p, C.uint32_t(len(pattern)), &d, &id), "gofr_table_add_route")
+	return uint32(id), err
+}
+
+func (t *Table) AddDefaultRoutes(favicon []byte) error {
+	var p *C.uint8_t
+	if len(favicon) > 0 {
+		p = (*C.uint8_t)(unsafe.Pointer(&favicon[0]))
+	}
+	return check(C.gofr_table_add_default_routes(t.t, p, C.uint32_t(len(favicon))), "gofr_table_add_default_routes")
+}
+
+func (t *Table) Seal() error { return check(C.gofr_table_seal(t.t), "gofr_table_seal") }
+
+// Engine is one GPU.
+type Engine struct{ e *C.gofr_engine }
+
+func NewEngine(t *Table, device int) (*Engine, error) {
+	var e *C.gofr_engine
+	if err := check(C.gofr_engine_create(&e, t.t, C.int(device)), "gofr_engine_create"); err != nil {
+		return nil, err
+	}
+	return &Engine{e}, nil
+}
+
+// Batch is the pinned SoA staging area one batch of parsed requests is appended to by the connection goroutines.
+type Batch struct {
+	Desc     []C.gofr_req_desc // n
+	TraceIDs []byte            // n*16
+	Arena    []byte
+}
+
+// Serve runs one batch through the GPU.  out/off/meta are caller-owned (ideally from gofr_alloc_pinned).
+func (e *Engine) Serve(b *Batch, now time.Time, out []byte, off, meta []uint32) (int, error) {
+	n := len(b.Desc)
+	if n == 0 {
+		return 0, nil
+	}
+	if len(off) < n+1 || len(meta) < n {
+		return 0, errors.New("gofrb200: off/meta too small")
+	}
+	var in C.gofr_req_batch
+	in.desc = &b.Desc[0]
+	in.trace_ids = (*C.uint8_t)(unsafe.Pointer(&b.TraceIDs[0]))
+	in.arena = (*C.uint8_t)(unsafe.Pointer(&b.Arena[0]))
+	in.arena_bytes = C.uint64_t(len(b.Arena))
+	in.n = C.uint32_t(n)
+	C.gofr_format_http_date(C.int64_t(now.Unix()), &in.date[0])
+	var o C.gofr_resp_batch
+	o.out = (*C.uint8_t)(unsafe.Pointer(&out[0]))
+	o.out_cap = C.uint64_t(len(out))
+	o.out_off = (*C.uint32_t)(unsafe.Pointer(&off[0]))
+	o.meta = (*C.uint32_t)(unsafe.Pointer(&meta[0]))
+	var ticket C.gofr_ticket
+	if err := check(C.gofr_batch_submit(e.e, &in, &o, &ticket), "gofr_batch_submit"); err != nil {
+		return 0, err
+	}
+	if err := check(C.gofr_batch_wait(e.e, ticket), "gofr_batch_wait"); err != nil {
+		return 0, err
+	}
+	return int(o.out_bytes), nil
+}
