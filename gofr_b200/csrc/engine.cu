@@ -50,7 +50,7 @@ struct Slot {
     // device buffers (grown on demand)
     void* d_desc = nullptr; void* d_ids = nullptr; uint8_t* d_arena = nullptr; uint8_t* d_out = nullptr;
     uint32_t* d_off = nullptr; uint32_t* d_meta = nullptr;
-    unsigned long long* d_state = nullptr; uint32_t* d_flag = nullptr;
+    unsigned long long* d_state = nullptr; uint32_t* d_flag = nullptr; uint32_t* d_bind = nullptr;
     size_t cap_n = 0, cap_arena = 0, cap_out = 0, cap_tiles = 0;
     // pinned staging for the tiny per-chunk read-backs
     uint32_t* h_tail = nullptr;  // [0] = chunk total bytes, [1] = overflow flag
@@ -66,12 +66,14 @@ struct gofr_engine {
     uint32_t image_bytes = 0;
     // launch geometry
     uint32_t in_cap = 0, out_stage_cap = 0, smem_bytes = 0;
-    int grid = 0, blocks_per_sm = 0;
+    int grid = 0, blocks_per_sm = 0, grpc_grid = 0;
     uint32_t epoch = 0;
     // resident path scratch
     unsigned long long* d_state = nullptr;
     size_t state_tiles = 0;
     uint32_t* d_flag = nullptr;
+    uint32_t* d_bind = nullptr;  // Bind scratch of the resident path
+    size_t bind_cap = 0;
     // host path
     Slot slots[kSlots];
     uint32_t chunk = 65536;
@@ -148,11 +150,11 @@ void gofr_engine_destroy(gofr_engine* e) {
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.done) cudaEventDestroy(s.done);
         cudaFree(s.d_desc); cudaFree(s.d_ids); cudaFree(s.d_arena); cudaFree(s.d_out); cudaFree(s.d_off); cudaFree(s.d_meta);
-        cudaFree(s.d_state); cudaFree(s.d_flag);
+        cudaFree(s.d_state); cudaFree(s.d_flag); cudaFree(s.d_bind);
         if (s.h_tail) cudaFreeHost(s.h_tail);
     }
     for (auto& ev : e->timing) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-    cudaFree(e->d_image); cudaFree(e->d_state); cudaFree(e->d_flag);
+    cudaFree(e->d_image); cudaFree(e->d_state); cudaFree(e->d_flag); cudaFree(e->d_bind);
     delete e;
 }
 
@@ -173,7 +175,7 @@ int gofr_engine_set_chunk(gofr_engine* e, uint32_t requests_per_chunk) {
 // one fused launch; `state`/`flag` are scratch owned by the caller of this helper
 static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, const uint8_t* d_arena, uint32_t n,
                       const char* date29, uint8_t* d_out, uint64_t out_cap, uint32_t* d_off, uint32_t* d_meta,
-                      unsigned long long* d_state, uint32_t* d_flag, cudaStream_t stream) {
+                      unsigned long long* d_state, uint32_t* d_flag, uint32_t* d_bind, cudaStream_t stream) {
     ServeParams p;
     memset(&p, 0, sizeof p);
     p.desc = d_desc; p.ids = d_ids; p.arena = d_arena; p.n = n;
@@ -185,6 +187,7 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
     p.out = d_out; p.out_cap = out_cap; p.out_off = d_off; p.meta = d_meta;
     p.tile_state = d_state; p.overflow = d_flag;
     p.in_cap = e->in_cap; p.out_stage_cap = e->out_stage_cap;
+    p.bind_scratch = d_bind; p.bind_row_words = e->hdr.bind_row_words;
     memcpy(p.date, date29, 29);
     int grid = (int)std::min<uint32_t>((uint32_t)e->grid, p.n_tiles);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -225,7 +228,17 @@ int gofr_serve_device(gofr_engine* e, const gofr_req_desc* d_desc, const uint8_t
         CUDA_TRY(cudaMemset(e->d_state, 0, tiles * 8));
         e->state_tiles = tiles;
     }
-    return launch_one(e, d_desc, d_trace_ids, d_arena, n, date29, d_out, out_cap, d_out_off, d_meta, e->d_state, e->d_flag, st);
+    if (e->hdr.bind_row_words) {
+        size_t need = (size_t)n * e->hdr.bind_row_words * 4;
+        if (need > e->bind_cap) {
+            cudaFree(e->d_bind);
+            e->d_bind = nullptr;
+            CUDA_TRY(cudaMalloc(&e->d_bind, need + need / 4 + 256));
+            e->bind_cap = need + need / 4;
+        }
+    }
+    return launch_one(e, d_desc, d_trace_ids, d_arena, n, date29, d_out, out_cap, d_out_off, d_meta, e->d_state, e->d_flag,
+                      e->d_bind, st);
 }
 
 int gofr_engine_overflowed(gofr_engine* e, int* flag_out, int reset) {
@@ -326,14 +339,15 @@ int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch*
     auto ensure = [&](Slot& s, uint32_t cn, size_t abytes, size_t ocap) -> int {
         int rc;
         if (cn > s.cap_n) {
-            cudaFree(s.d_desc); cudaFree(s.d_ids); cudaFree(s.d_off); cudaFree(s.d_meta); cudaFree(s.d_state);
-            s.d_desc = s.d_ids = nullptr; s.d_off = s.d_meta = nullptr; s.d_state = nullptr;
+            cudaFree(s.d_desc); cudaFree(s.d_ids); cudaFree(s.d_off); cudaFree(s.d_meta); cudaFree(s.d_state); cudaFree(s.d_bind);
+            s.d_desc = s.d_ids = nullptr; s.d_off = s.d_meta = nullptr; s.d_state = nullptr; s.d_bind = nullptr;
             size_t c = (size_t)cn + cn / 4 + 256;
             size_t tiles = (c + kServeThreads - 1) / kServeThreads;
             if (cudaMalloc(&s.d_desc, c * 16) != cudaSuccess || cudaMalloc(&s.d_ids, c * 16) != cudaSuccess ||
                 cudaMalloc(&s.d_off, (c + 1) * 4) != cudaSuccess || cudaMalloc(&s.d_meta, c * 4) != cudaSuccess ||
                 cudaMalloc(&s.d_state, tiles * 8) != cudaSuccess) { set_last_error("cudaMalloc failed for a %zu-request chunk", c); s.cap_n = 0; return GOFR_ERR_NOMEM; }
             if (cudaMemset(s.d_state, 0, tiles * 8) != cudaSuccess) return GOFR_ERR_CUDA;
+            if (e->hdr.bind_row_words && cudaMalloc(&s.d_bind, c * e->hdr.bind_row_words * 4 + 256) != cudaSuccess) { set_last_error("cudaMalloc failed for Bind scratch"); s.cap_n = 0; return GOFR_ERR_NOMEM; }
             s.cap_n = c;
         }
         if (!s.d_flag) { if (cudaMalloc(&s.d_flag, 64) != cudaSuccess || cudaMemset(s.d_flag, 0, 64) != cudaSuccess) return GOFR_ERR_NOMEM; }
@@ -365,7 +379,7 @@ int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch*
             }
             // descriptors keep absolute arena offsets: pass a rebased arena pointer
             rc = launch_one(e, s.d_desc, s.d_ids, s.d_arena - c.arena_lo, cn, in->date, s.d_out, s.cap_out, s.d_off, s.d_meta,
-                            s.d_state, s.d_flag, s.stream);
+                            s.d_state, s.d_flag, s.d_bind, s.stream);
             if (rc) return rc;
             CUDA_TRY(cudaMemcpyAsync(out->out_off + c.lo, s.d_off, (size_t)cn * 4, cudaMemcpyDeviceToHost, s.stream));
             CUDA_TRY(cudaMemcpyAsync(out->meta + c.lo, s.d_meta, (size_t)cn * 4, cudaMemcpyDeviceToHost, s.stream));
@@ -428,9 +442,42 @@ void gofr_format_http_date(int64_t unix_seconds, char out29[29]) {
 
 int gofr_grpc_hello_device(gofr_engine* e, const uint8_t* d_in, const uint32_t* d_in_off, uint32_t n, uint8_t* d_out,
                            uint64_t out_cap, uint32_t* d_out_off, uint32_t* d_meta, void* stream) {
-    (void)e; (void)d_in; (void)d_in_off; (void)n; (void)d_out; (void)out_cap; (void)d_out_off; (void)d_meta; (void)stream;
-    set_last_error("gofr_grpc_hello_device: not built yet");
-    return GOFR_ERR_UNSUPPORTED;
+    if (!e || (n && (!d_in || !d_in_off || !d_out || !d_out_off || !d_meta))) return GOFR_ERR_INVALID;
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st)); return GOFR_OK; }
+    size_t tiles = (n + kServeThreads - 1) / kServeThreads;
+    if (tiles > e->state_tiles) {
+        cudaFree(e->d_state);
+        e->d_state = nullptr;
+        CUDA_TRY(cudaMalloc(&e->d_state, tiles * 8));
+        CUDA_TRY(cudaMemset(e->d_state, 0, tiles * 8));
+        e->state_tiles = tiles;
+    }
+    if (e->grpc_grid <= 0) {
+        e->grpc_grid = grpc_max_grid(e->device);
+        if (e->grpc_grid <= 0) { set_last_error("grpc kernel cannot be resident"); return GOFR_ERR_CUDA; }
+    }
+    GrpcParams p;
+    memset(&p, 0, sizeof p);
+    p.in = d_in; p.in_off = d_in_off; p.n = n; p.n_tiles = (uint32_t)tiles;
+    e->epoch = (e->epoch + 1) & 0xFFFFFu;
+    if (e->epoch == 0) e->epoch = 1;
+    p.epoch = e->epoch;
+    p.out = d_out; p.out_cap = out_cap; p.out_off = d_out_off; p.meta = d_meta;
+    p.tile_state = e->d_state; p.overflow = e->d_flag;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (e->timing_on) {
+        CUDA_TRY(cudaEventCreate(&ev0));
+        CUDA_TRY(cudaEventCreate(&ev1));
+        CUDA_TRY(cudaEventRecord(ev0, st));
+    }
+    int rc = launch_grpc_hello(p, (int)std::min<size_t>((size_t)e->grpc_grid, tiles), st);
+    if (rc != 0) { set_last_error("grpc kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
+    if (e->timing_on) { CUDA_TRY(cudaEventRecord(ev1, st)); e->timing.emplace_back(ev0, ev1); }
+    e->launches++;
+    return GOFR_OK;
 }
 
 }  // extern "C"

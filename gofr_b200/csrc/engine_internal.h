@@ -30,6 +30,8 @@ struct ServeParams {
     uint32_t in_cap;         // shared-memory staging capacity for request bytes (multiple of 16)
     uint32_t out_stage_cap;  // shared-memory staging capacity for response bytes (multiple of 16)
     uint32_t date[8];        // 29-byte IMF-fixdate, zero padded
+    uint32_t* bind_scratch;  // n * bind_row_words words (tables with GOFR_H_BIND_ECHO routes), else null
+    uint32_t bind_row_words;
 };
 
 constexpr int kServeThreads = 128;  // requests per tile = threads per CTA
@@ -54,5 +56,6 @@ struct GrpcParams {
     uint32_t* overflow;
 };
 int launch_grpc_hello(const GrpcParams& p, int grid, void* stream);
+int grpc_max_grid(int device);
 
 }  // namespace gofr

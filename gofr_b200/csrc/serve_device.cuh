@@ -18,7 +18,7 @@
 
 #if defined(__CUDACC__)
 #define GOFR_HD __host__ __device__ __forceinline__
-#define GOFR_HD_NOINLINE __host__ __device__ __noinline__
+#define GOFR_HD_NOINLINE inline __host__ __device__ __noinline__
 #else
 #define GOFR_HD inline
 #define GOFR_HD_NOINLINE inline
@@ -545,6 +545,7 @@ struct ReqCtx {
     uint32_t pv_off, pv_len, pv_flags;  // query value span; flags bit0 found&non-empty, bit1 needs decode/escape
     uint32_t body_len, total_len;
     uint32_t staged;     // request bytes live in shared memory (tile staged by TMA)
+    uint32_t* brow;      // this request's Bind scratch row (HBM), see bind_device.cuh
     uint32_t slow_mask;  // bit k: k-th OP_STR of the program needs the slow escape path
     uint32_t def_off, def_len;  // OP_PARAM default (pre-escaped literal)
 };
@@ -873,6 +874,12 @@ GOFR_HD_NOINLINE uint32_t emit_param_slow(Writer* w, const uint8_t* v, uint32_t 
     return out;
 }
 
+// Bind (bind_device.cuh)
+GOFR_HD_NOINLINE bool bind_request(const TableView tv, uint32_t schema_idx, const uint8_t* body, uint32_t n, uint32_t* row);
+template <bool EMIT> GOFR_HD_NOINLINE uint32_t bind_string_slow(Writer* w, const uint8_t* s, uint32_t len);
+template <bool EMIT>
+GOFR_HD_NOINLINE uint32_t emit_bind_error(Writer* w, const TableView tv, uint32_t schema_idx, const uint8_t* body, const uint32_t* row);
+
 // ---------------------------------------------------------------------------------------------------------------
 // stage 1: route + handler kind → program
 // ---------------------------------------------------------------------------------------------------------------
@@ -899,6 +906,13 @@ GOFR_HD void route_request(const TableView& tv, ReqCtx& c) {
         c.pv_off = ps.off; c.pv_len = ps.len; c.pv_flags = ps.flags;
         c.def_off = R.def_off;
         c.def_len = R.def_len;
+    } else if (R.hkind == GOFR_H_BIND_ECHO) {
+        // var v T; if err := c.Bind(&v); err != nil { return nil, err }; return v, nil
+        if (!bind_request(tv, R.schema, c.data, c.data_len, c.brow)) {
+            // bodies nested deeper than the device scanner's 64-level stack are handed to the host like a
+            // GOFR_H_HOST route (status 0) rather than answered differently from encoding/json (limit 10000)
+            c.prog = c.brow[0] == 4u /* BE_DEPTH */ ? 0xFFFFu : R.prog_err;
+        }
     }
 }
 
@@ -917,10 +931,10 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
     const uint32_t n_ops = P.n_ops;
     const uint8_t* const lits = tv.lits;
     const bool head = c.method == GOFR_M_HEAD;
-    const uint32_t* row = (const uint32_t*)c.data;
+    const uint32_t* row = (P.flags & PF_BIND) ? c.brow : (const uint32_t*)c.data;
     uint32_t str_cursor = 0;  // byte offset of the next string in the row's string area
     uint32_t str_base = 0;
-    if (P.flags & PF_NEEDS_ROW) {
+    if ((P.flags & PF_NEEDS_ROW) && !(P.flags & PF_BIND)) {
         const SchemaRec& S = tv.schemas[tv.routes[c.route].schema];
         str_base = (uint32_t)S.fixed_words * 4;
         if (!EMIT && str_base > c.data_len) return false;
@@ -965,6 +979,19 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
                     cshared = c.staged;
                 }
             }
+        } else if (code == OP_BSTR) {
+            const uint32_t boff = row[ooff], lenw = row[ooff + 1], len = lenw & 0x7FFFFFFFu;
+            if (!(governed && skip)) {
+                const uint8_t* sp = c.data + boff;
+                if (lenw >> 31) {  // JSON escapes / non-ASCII in the request: decode and re-encode rune by rune
+                    if (EMIT) GOFR_SLOW_CALL(w, bind_string_slow<true>(tw, sp, len));
+                    else produced = bind_string_slow<false>(nullptr, sp, len);
+                } else { csrc = sp; clen = len; produced = len; cshared = c.staged; }
+            }
+        } else if (code == OP_ERRMSG) {
+            const uint32_t sidx = tv.routes[c.route].schema;
+            if (EMIT) GOFR_SLOW_CALL(w, emit_bind_error<true>(tw, tv, sidx, c.data, c.brow));
+            else produced = emit_bind_error<false>(nullptr, tv, sidx, c.data, c.brow);
         } else if (code == OP_I64 || code == OP_I32) {
             if (!(governed && skip)) {
                 const int64_t v = code == OP_I64 ? (int64_t)((uint64_t)row[ooff] | (uint64_t)row[ooff + 1] << 32)
@@ -988,7 +1015,9 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
             bool empty = false;
             if (oflags & OPF_OMITEMPTY) {
                 const uint32_t wv = row[oaux];
-                empty = (okind == GOFR_F_INT64 || okind == GOFR_F_INT) ? (wv | row[oaux + 1]) == 0 : wv == 0;
+                if (okind == GOFR_F_INT64 || okind == GOFR_F_INT) empty = (wv | row[oaux + 1]) == 0;
+                else if (okind == GOFR_F_STRING && (P.flags & PF_BIND)) empty = (row[oaux + 1] & 0x7FFFFFFFu) == 0;
+                else empty = wv == 0;
             }
             skip = empty;
             if (!empty) {
@@ -1067,3 +1096,5 @@ GOFR_HD void patch_dates(uint8_t* hot, const uint8_t* date29, uint32_t idx, uint
 }
 
 }  // namespace gofr
+
+#include "bind_device.cuh"

@@ -186,6 +186,7 @@ struct SOp {
 
 struct Prog {
     int status = 200;
+    bool bind = false;
     std::vector<SOp> ops;
 };
 
@@ -379,7 +380,7 @@ static void build_header(Prog& p, uint32_t frame_mode, int status, bool with_mw,
 }
 
 // struct → JSON object ops.  Schemas without omitempty collapse to literals around value ops.
-static void build_struct_ops(Prog& p, const SchemaDef& sc) {
+static void build_struct_ops(Prog& p, const SchemaDef& sc, bool bind_layout = false) {
     bool dynamic = false;
     for (auto& f : sc.fields) dynamic |= f.omitempty;
     std::string acc = "{";
@@ -388,7 +389,10 @@ static void build_struct_ops(Prog& p, const SchemaDef& sc) {
     for (auto& f : sc.fields) {
         std::string key = "\"" + json_escape_go(f.json_name) + "\":";
         uint16_t w = word;
-        word += (f.kind == GOFR_F_INT64 || f.kind == 5) ? 2 : 1;
+        if (bind_layout) {  // span row (bind_device.cuh): 8 header words, strings are (offset, length) pairs
+            w = (uint16_t)(8 + word);
+            word += (f.kind == GOFR_F_INT32 || f.kind == GOFR_F_BOOL) ? 1 : 2;
+        } else word += (f.kind == GOFR_F_INT64 || f.kind == 5) ? 2 : 1;
         SOp v;
         v.body = true;
         v.off = w;
@@ -396,7 +400,7 @@ static void build_struct_ops(Prog& p, const SchemaDef& sc) {
             case GOFR_F_INT64: case 5: v.code = OP_I64; break;
             case GOFR_F_INT32: v.code = OP_I32; break;
             case GOFR_F_BOOL: v.code = OP_BOOL; break;
-            default: v.code = OP_STR; v.arg = (uint8_t)str_ord++; break;
+            default: v.code = bind_layout ? OP_BSTR : OP_STR; v.arg = (uint8_t)str_ord++; break;
         }
         if (!dynamic) {
             if (!first) acc += ",";
@@ -427,12 +431,28 @@ struct Builder {
     std::vector<Prog> progs;
     std::string err;
 
-    int add(Prog p) { progs.push_back(std::move(p)); return (int)progs.size() - 1; }
+    std::map<std::string, int> prog_ids;
+    // identical programs (e.g. sixteen routes returning the same struct type) are stored once
+    int add(Prog p) {
+        std::string sig = std::to_string(p.status) + (p.bind ? "B" : "R");
+        for (auto& o : p.ops) {
+            sig += "|" + std::to_string(o.code) + "," + std::to_string(o.arg) + "," + std::to_string(o.flags) + "," +
+                   std::to_string(o.kind) + "," + std::to_string(o.off) + "," + std::to_string(o.aux) + "," +
+                   (o.body ? "b" : "h") + std::to_string(o.lit.size()) + ":" + o.lit;
+            for (uint32_t d : o.date_pos) sig += "@" + std::to_string(d);
+        }
+        auto it = prog_ids.find(sig);
+        if (it != prog_ids.end()) return it->second;
+        progs.push_back(std::move(p));
+        prog_ids[sig] = (int)progs.size() - 1;
+        return (int)progs.size() - 1;
+    }
 
     // Responder.Respond envelope: {"error":{"message":...},"data":...}\n  (error first; both omitempty)
-    int json_prog(int status, const std::vector<SOp>& body_ops) {
+    int json_prog(int status, const std::vector<SOp>& body_ops, bool bind = false) {
         Prog p;
         p.status = status;
+        p.bind = bind;
         build_header(p, t->frame_mode, status, true, BODY_JSON, false, "", "", false);
         for (auto o : body_ops) { o.body = true; p.ops.push_back(o); }
         return add(std::move(p));
@@ -554,12 +574,13 @@ int seal_table(gofr_table* t) {
                 p.status = 200;
                 build_header(p, fm, 200, true, BODY_JSON, false, "", "", false);
                 p.ops.push_back(lit("{\"data\":", true));
-                build_struct_ops(p, *sc);
+                build_struct_ops(p, *sc, r.hkind == GOFR_H_BIND_ECHO);
                 p.ops.push_back(lit("}\n", true));
+                p.bind = r.hkind == GOFR_H_BIND_ECHO;
                 prog_ok[ri] = b.add(std::move(p));
                 if (r.hkind == GOFR_H_BIND_ECHO)
                     prog_err[ri] = b.json_prog(500, {lit("{\"error\":{\"message\":\"", true), op(OP_ERRMSG, true),
-                                                     lit("\"}}\n", true)});
+                                                     lit("\"}}\n", true)}, true);
                 break;
             }
             case GOFR_H_FILE: {
@@ -679,6 +700,7 @@ int seal_table(gofr_table* t) {
         P.first_op = (uint16_t)ops.size();
         P.n_ops = (uint16_t)p.ops.size();
         P.status = (uint16_t)p.status;
+        if (p.bind) P.flags |= PF_BIND;
         for (auto& so : p.ops) {
             Op o;
             memset(&o, 0, sizeof o);
@@ -708,7 +730,7 @@ int seal_table(gofr_table* t) {
                     cold.insert(cold.end(), so.lit.begin(), so.lit.end());
                     fixed = o.len;
                     break;
-                case OP_I64: case OP_I32: case OP_BOOL: case OP_STR: P.flags |= PF_DYNAMIC | PF_NEEDS_ROW; break;
+                case OP_I64: case OP_I32: case OP_BOOL: case OP_STR: case OP_BSTR: P.flags |= PF_DYNAMIC | PF_NEEDS_ROW; break;
                 default: P.flags |= PF_DYNAMIC; break;
             }
             if (so.body) P.body_fixed += fixed; else P.hdr_fixed += fixed;
@@ -749,6 +771,12 @@ int seal_table(gofr_table* t) {
     H.n_progs = (uint32_t)progs.size();
     H.n_ops = (uint32_t)ops.size();
     H.n_schemas = (uint32_t)srecs.size();
+    for (size_t ri = 0; ri < t->routes.size(); ri++) {
+        if (t->routes[ri].hkind != GOFR_H_BIND_ECHO) continue;
+        uint32_t words = 8;
+        for (auto& f : t->schemas[routes[ri].schema].fields) words += (f.kind == GOFR_F_INT32 || f.kind == GOFR_F_BOOL) ? 1 : 2;
+        H.bind_row_words = std::max(H.bind_row_words, words);
+    }
     H.max_fixed_len = max_fixed;
 
     auto append = [&](const void* p, size_t n) {

@@ -12,7 +12,7 @@
 namespace gofr {
 
 constexpr uint32_t kMagic = 0x52464F47u;  // "GOFR"
-constexpr uint32_t kImageVersion = 4;
+constexpr uint32_t kImageVersion = 5;
 constexpr uint32_t kMaxHotBytes = 40 * 1024;  // shared-memory budget for the table
 constexpr int kMaxVars = 8;                   // variables per route template
 constexpr int kMaxFields = 32;                // struct fields per schema
@@ -36,7 +36,8 @@ struct ImageHeader {  // 128 B
     uint32_t last_method_off;  // uint16[16]: 1 + index of the last live route registered for that method, 0 = none
     uint32_t fixups_off;     // uint32[n_fixups]: literal-pool offsets of 29-byte Date placeholders
     uint32_t n_fixups;
-    uint32_t reserved[2];
+    uint32_t bind_row_words;  // words of per-request Bind scratch (0: no GOFR_H_BIND_ECHO route)
+    uint32_t reserved[1];
 };
 static_assert(sizeof(ImageHeader) == 128, "ImageHeader layout");
 
@@ -89,6 +90,7 @@ enum OpCode : uint8_t {
     OP_LOCATION = 9,  // url.String() of the cleaned URL                        (mux 301)
     OP_ERRMSG = 10,   // escaped err.Error() of a failed Bind                   (responder.go:43-57)
     OP_BLOB = 11,     // raw bytes from the cold section                        (response.File)
+    OP_BSTR = 13,     // string field of a Bind span row: off = word index of (offset into the body, length | escaped<<31)
     OP_KEY = 12,      // struct member key with dynamic comma / omitempty: emits [","] + lits[off..off+len) unless the
                       // field (arg) is empty and flagged; used only for schemas that have an omitempty field
 };
@@ -124,6 +126,7 @@ enum ProgFlags : uint16_t {
     PF_HAS_CLEN = 1,
     PF_DYNAMIC = 2,   // has at least one variable-length op besides CLEN
     PF_NEEDS_ROW = 4,
+    PF_BIND = 8,      // the row is the Bind span row in scratch (bind_device.cuh), not the request's data section
 };
 
 struct SchemaRec {  // 16 B + per-field table

@@ -242,3 +242,51 @@ def config5_frames(n: int, start: int = 0, seed: int = SEED) -> Tuple[np.ndarray
         m = name_len > k
         buf[base[m] + 7 + k] = names[m, k]
     return buf, off
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# config 3: POST /echo — ctx.Bind() into a 5-field struct, echoed back
+# ---------------------------------------------------------------------------------------------------------------
+C3_SCHEMA = S.Schema(3, "main.Person", [
+    S.Field("ID", S.F_INT64, "id"), S.Field("Name", S.F_STRING, "name"), S.Field("Email", S.F_STRING, "email"),
+    S.Field("Active", S.F_BOOL, "active"), S.Field("Age", S.F_INT32, "age")])
+
+
+def config3_spec(frame_mode: int = S.FRAME_WIRE) -> S.TableSpec:
+    return S.TableSpec(frame_mode=frame_mode, schemas=[C3_SCHEMA],
+                       routes=[S.Route(S.M_POST, "/echo", S.H_BIND_ECHO, schema_id=3)])
+
+
+def config3_batch(n: int = 65536, start: int = 0, seed: int = SEED, variant_every: int = 100) -> S.RequestBatch:
+    """Compact JSON bodies with the keys in declaration order; every `variant_every`-th request is a variant:
+    reordered / case-folded / unknown keys, whitespace, escapes, or an invalid body (→ 500 with Go's error text)."""
+    idx = np.arange(start, start + n, dtype=np.uint64)
+    r = rand_u64(seed, idx, 31)
+    strs = _ALNUM[rand_bytes(seed, idx, 32, 40) % 62]
+    variants = [
+        lambda i, nm, em: b'{ "name" : "%s" , "ID" : %d , "zzz" : {"a":[1,2,{"b":null}]} , "EMAIL":"%s","active":true }' % (nm, i, em),
+        lambda i, nm, em: b'{"id":%d,"name":"a\\"b\\\\c\\u00e9\\ud83d\\ude00\\n<%s>","email":"\xc3\xa9%s","active":false,"age":-7}' % (i, nm, em),
+        lambda i, nm, em: b'{"id":"%d","name":"%s"}' % (i, nm),
+        lambda i, nm, em: b'{"id":%d,"name":"%s","age":3000000000}' % (i, nm),
+        lambda i, nm, em: b'{"id":%d,"name":"%s"' % (i, nm),
+        lambda i, nm, em: b'{"id":%d,,"name":"%s"}' % (i, nm),
+        lambda i, nm, em: b'[%d]' % i,
+        lambda i, nm, em: b'null',
+        lambda i, nm, em: b'{"id":1.5e3,"name":"%s","active":"yes"}' % nm,
+        lambda i, nm, em: b'',
+    ]
+    reqs: List[S.Req] = []
+    for k in range(n):
+        x = int(r[k])
+        ident = x % 10 ** 12
+        nm = strs[k, :8 + x % 12].tobytes()
+        em = strs[k, 20:20 + 10 + (x >> 8) % 10].tobytes()
+        if variant_every and (start + k) % variant_every == variant_every - 1:
+            body = variants[((start + k) // variant_every) % len(variants)](ident, nm, em)
+        else:
+            body = b'{"id":%d,"name":"%s","email":"%s@example.com","active":%s,"age":%d}' % (
+                ident, nm, em, b"true" if (x >> 20) & 1 else b"false", (x >> 24) % 120)
+        reqs.append(S.Req(S.M_POST, b"/echo", b"", body))
+    b = S.RequestBatch.pack(reqs)
+    b.trace_ids[:] = trace_ids(seed, idx)
+    return b

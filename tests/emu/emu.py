@@ -16,6 +16,7 @@ _lib = None
 def _build():
     srcs = [os.path.join(HERE, "emu_serve.cpp"), os.path.join(ROOT, "gofr_b200", "csrc", "serve_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "bind_device.cuh"),
+            os.path.join(ROOT, "gofr_b200", "csrc", "grpc_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "table_format.h")]
     srcs = [s for s in srcs if os.path.exists(s)]
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
@@ -32,7 +33,22 @@ def lib():
         _lib = C.CDLL(LIB)
         _lib.emu_serve.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p,
                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
+        _lib.emu_grpc_hello.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
+                                        C.c_void_p, C.c_uint32]
     return _lib
+
+
+def grpc_hello(frames, in_off, misalign: int = 0):
+    n = len(in_off) - 1
+    cap = int(frames.size) + 40 * n + 64
+    out = np.full(cap, 0xEE, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    meta = np.zeros(n, dtype=np.uint32)
+    rc = lib().emu_grpc_hello(frames.ctypes.data, in_off.ctypes.data, n, out.ctypes.data, cap, off.ctypes.data,
+                              meta.ctypes.data, misalign)
+    if rc != 0:
+        raise RuntimeError("emu output capacity too small")
+    return out, off, meta
 
 
 def serve(image: bytes, batch, date: bytes, out_cap: int | None = None, misalign: int = 0):

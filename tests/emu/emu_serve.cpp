@@ -26,6 +26,7 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
     TableView tv;
     tv.bind((const uint8_t*)hot.data(), image);
     uint32_t ring[32];
+    std::vector<uint32_t> bind_scratch((size_t)H.bind_row_words + 8);
     uint64_t pos = start_misalign;  // lets the test exercise every head alignment
     for (uint32_t i = 0; i < n; i++) {
         uint32_t d[4];
@@ -42,6 +43,7 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
         memcpy(c.id, ids + (size_t)i * 16, 16);
         c.total_len = c.body_len = 0; c.status = 0; c.route = GOFR_ROUTE_NONE; c.prog = 0xFFFF;
         c.staged = (i & 1);  // alternate so both source policies are exercised
+        c.brow = bind_scratch.data();
         size_request(tv, c);
         if (c.prog != 0xFFFF && path_is_clean(c.path, c.path_len)) {  // both matchers must always agree
             int a = mux_match(tv, c.method, c.path, c.path_len), b = mux_match_linear(tv, c.method, c.path, c.path_len);
@@ -52,6 +54,26 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
         if (pos + c.total_len > out_cap) return -1;
         emit_request(tv, c, out + pos, ring);
         pos += c.total_len;
+    }
+    out_off[n] = (uint32_t)pos;
+    return 0;
+}
+
+// ---- gRPC Hello (config 5): the same grpc_device.cuh code the CUDA kernel runs ----
+#include "../../gofr_b200/csrc/grpc_device.cuh"
+
+extern "C" int emu_grpc_hello(const uint8_t* in, const uint32_t* in_off, uint32_t n, uint8_t* out, uint64_t out_cap,
+                              uint32_t* out_off, uint32_t* meta, uint32_t start_misalign) {
+    uint32_t stage[32];
+    uint64_t pos = start_misalign;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint8_t* f = in + in_off[i];
+        HelloReq r = hello_parse(f, in_off[i + 1] - in_off[i]);
+        out_off[i] = (uint32_t)pos;
+        meta[i] = r.status;
+        if (pos + r.out_len > out_cap) return -1;
+        hello_emit(f, r, out + pos, stage);
+        pos += r.out_len;
     }
     out_off[n] = (uint32_t)pos;
     return 0;

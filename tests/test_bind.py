@@ -1,0 +1,116 @@
+"""Config 3 — Request.Bind + echo.  CPU: the kernel's device code (tests/emu) vs the oracle on the known-answer lists of
+test_oracle_golden.py, the synthetic config-3 stream and random JSON-ish bodies.  GPU (-m gpu): the CUDA kernel."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from gofr_b200 import spec as S
+from gofr_b200 import synth
+from gofr_b200.table import Table
+from tests import oracle as O
+from tests.emu import emu
+from tests.test_oracle_golden import BIND_ERR_KAT, BIND_OK_KAT, BIND_SCHEMA
+
+DATE = S.http_date(1789974595)
+KAT_SPEC = S.TableSpec(schemas=[BIND_SCHEMA], routes=[S.Route(S.M_POST, "/echo", S.H_BIND_ECHO, schema_id=7)])
+OE_SCHEMA = S.Schema(8, "pkg.Opt", [S.Field("A", S.F_STRING, "a", True), S.Field("B", S.F_INT, "b", True),
+                                    S.Field("C", S.F_BOOL, "c", True), S.Field("D", S.F_STRING, "d")])
+
+
+def _cmp(spec, bodies, mis=1, frame=S.FRAME_WIRE):
+    spec.frame_mode = frame
+    batch = S.RequestBatch.pack([S.Req(S.M_POST, b"/echo", b"", b) for b in bodies])
+    o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
+    o2, f2, m2 = emu.serve(Table(spec).serialize(), batch, DATE, misalign=mis)
+    for i, (a, b) in enumerate(zip(O.responses(o1, f1), O.responses(o2, f2))):
+        assert a == b, (bodies[i], a, b)
+    assert (m1 == m2).all()
+    return O.responses(o1, f1), m1
+
+
+@pytest.mark.parametrize("mis", [0, 1, 2, 3])
+def test_emu_known_answer_bodies(mis):
+    bodies = [b for b, _ in BIND_ERR_KAT] + [b for b, _ in BIND_OK_KAT]
+    res, meta = _cmp(KAT_SPEC, bodies, mis, S.FRAME_BODY)
+    for (body, want), r, m in zip(BIND_ERR_KAT, res, meta):
+        assert (m & 0xFFFF) == 500
+        assert r == b'{"error":{"message":' + O.json_string(want) + b"}}\n"
+    for r, m in zip(res[len(BIND_ERR_KAT):], meta[len(BIND_ERR_KAT):]):
+        assert (m & 0xFFFF) == 200 and r.startswith(b'{"data":{"id":')
+
+
+def test_emu_error_characters():
+    """quoteChar over every byte value, in the contexts where the scanner reports it."""
+    bodies = [bytes([c]) for c in range(256)] + [b'{"name":"' + bytes([c]) + b'"}' for c in range(0x20)] + \
+             [b'{"name":"\\' + bytes([c]) + b'"}' for c in range(0x20, 0x80)] + [b'{"id":1' + bytes([c]) + b"}" for c in range(256)]
+    _cmp(KAT_SPEC, bodies, 2)
+
+
+def test_emu_omitempty_and_nesting():
+    spec = S.TableSpec(schemas=[OE_SCHEMA], routes=[S.Route(S.M_POST, "/echo", S.H_BIND_ECHO, schema_id=8)])
+    bodies = [b"{}", b'{"a":"","b":0,"c":false,"d":""}', b'{"a":"x","b":-5,"c":true,"d":"y"}', b'{"A":"\\u0041","D":"<&>"}',
+              b'{"x":' + b"[" * 63 + b"]" * 63 + b"}", b'{"d":{"a":{"a":{"a":1}}},"a":"q"}',
+              b'{"b":9223372036854775807}', b'{"b":9223372036854775808}', b'{"b":-9223372036854775808}', b'{"b":-9223372036854775809}',
+              b'{"b":1e2}', b'{"b":12.0}', b'{"b":-0}', b' \t\r\n{ "d" : "v" } \n', b'{"d":"v"} x', b'{"\\u0064":"esc-key"}']
+    for mis in range(4):
+        _cmp(spec, bodies, mis)
+
+
+def test_deep_nesting_is_deferred_to_the_host():
+    """> 64 levels: the device does not decide (status 0, nothing emitted); the oracle shows what Go answers."""
+    spec = S.TableSpec(schemas=[OE_SCHEMA], routes=[S.Route(S.M_POST, "/echo", S.H_BIND_ECHO, schema_id=8)])
+    deep = b'{"x":' + b"[" * 70 + b"]" * 70 + b',"d":"ok"}'
+    batch = S.RequestBatch.pack([S.Req(S.M_POST, b"/echo", b"", deep), S.Req(S.M_POST, b"/echo", b"", b'{"d":"ok"}')])
+    o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
+    o2, f2, m2 = emu.serve(Table(spec).serialize(), batch, DATE)
+    r1, r2 = O.responses(o1, f1), O.responses(o2, f2)
+    assert (m1[0] & 0xFFFF) == 200 and (m2[0] & 0xFFFF) == 0 and r2[0] == b"" and (m2[0] >> 16) == 0
+    assert r1[1] == r2[1] and m1[1] == m2[1]
+
+
+@pytest.mark.parametrize("mode", [S.FRAME_WIRE, S.FRAME_BODY])
+def test_emu_config3_stream(mode):
+    _cmp_batch = synth.config3_batch(6000, variant_every=7)
+    spec = synth.config3_spec(mode)
+    o1, f1, m1 = O.OracleTable(spec).serve(_cmp_batch, DATE)
+    o2, f2, m2 = emu.serve(Table(spec).serialize(), _cmp_batch, DATE, misalign=3)
+    assert O.responses(o1, f1) == O.responses(o2, f2) and (m1 == m2).all()
+    assert {int(m) & 0xFFFF for m in m1} == {200, 500}
+
+
+_json_atoms = st.sampled_from([b'{', b'}', b'[', b']', b':', b',', b'"', b'\\', b'u', b'00e9', b'd83d', b'"id"', b'"name"', b'"ok"',
+                               b'"n"', b'1', b'-', b'0', b'.5', b'e9', b'true', b'false', b'null', b' ', b'\n', b'x', b'\xc3\xa9',
+                               b'\xff', b'<', b'"a\\nb"', b'123456789012345678901', b'"\\ud800"', b'NaMe', b'\\u212a'])
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.lists(st.lists(_json_atoms, min_size=0, max_size=14).map(b"".join), min_size=1, max_size=8), st.integers(0, 3))
+def test_emu_random_bodies(bodies, mis):
+    _cmp(KAT_SPEC, bodies, mis)
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.tuples(st.integers(-2 ** 63, 2 ** 63 - 1), st.text(max_size=12), st.booleans(), st.integers(-2 ** 31, 2 ** 31 - 1)),
+                min_size=1, max_size=6), st.integers(0, 3))
+def test_emu_valid_json_roundtrip(rows, mis):
+    """Bodies produced by a real JSON encoder (python json): bind + echo must reproduce the values."""
+    import json
+    bodies = [json.dumps({"id": i, "name": s, "ok": b, "n": n}).encode() for i, s, b, n in rows]
+    res, meta = _cmp(KAT_SPEC, bodies, mis, S.FRAME_BODY)
+    for (i, s, b, n), r in zip(rows, res):
+        assert json.loads(r)["data"] == {"id": i, "name": s, "ok": b, "n": n}
+
+
+@pytest.mark.gpu
+def test_gpu_config3_full_size():
+    from tests.test_gpu_parity import _check
+    _check(synth.config3_spec(), synth.config3_batch(65536))
+
+
+@pytest.mark.gpu
+def test_gpu_bind_edge_cases_and_host_path():
+    from tests.test_gpu_parity import _check
+    bodies = ([b for b, _ in BIND_ERR_KAT] + [b for b, _ in BIND_OK_KAT]) * 30
+    batch = S.RequestBatch.pack([S.Req(S.M_POST, b"/echo", b"", b) for b in bodies])
+    _check(KAT_SPEC, batch)
+    _check(synth.config3_spec(), synth.config3_batch(20000, variant_every=5), host=True, chunk=3000)
