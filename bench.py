@@ -183,16 +183,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- route table: sealed on rank 0, broadcast as bytes over NCCL, deserialised everywhere ----
-    if rank == 0:
-        image = Table(synth.config2_spec(S.FRAME_WIRE)).serialize()
-        ln = torch.tensor([len(image)], dtype=torch.int64, device=dev)
-    else:
-        image, ln = b"", torch.zeros(1, dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.broadcast(ln, 0)
-        buf = torch.frombuffer(bytearray(image), dtype=torch.uint8).to(dev) if rank == 0 else torch.empty(int(ln.item()), dtype=torch.uint8, device=dev)
-        dist.broadcast(buf, 0)
-        image = buf.cpu().numpy().tobytes()
+    from gofr_b200 import dist as gd
+    image = Table(synth.config2_spec(S.FRAME_WIRE)).serialize() if rank == 0 else None
+    image = gd.broadcast_table_image(image, rank, dev)
     table = Table(image=image)
     eng = Engine(table, local)
     eng.set_chunk(args.chunk)
