@@ -47,6 +47,8 @@ constexpr int kSlots = 3;  // pipeline depth of the host-batch path
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_served = nullptr, ev_egress = nullptr;  // streaming path
+    bool egress_pending = false;
     // device buffers (grown on demand)
     void* d_desc = nullptr; void* d_ids = nullptr; uint8_t* d_arena = nullptr; uint8_t* d_out = nullptr;
     uint32_t* d_off = nullptr; uint32_t* d_meta = nullptr;
@@ -76,6 +78,10 @@ struct gofr_engine {
     size_t bind_cap = 0;
     // host path
     Slot slots[kSlots];
+    cudaStream_t st_h2d = nullptr, st_compute = nullptr, st_egress = nullptr;
+    unsigned long long* d_chain = nullptr;  // packed position of the batch in flight
+    ChunkInfo* d_info = nullptr;            // one per slot
+    unsigned long long* h_status = nullptr; // pinned: [0] total bytes, [1] overflow
     uint32_t chunk = 65536;
     std::mutex mu;
     uint64_t launches = 0;
@@ -137,7 +143,16 @@ int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
         CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         CUDA_TRY(cudaMallocHost(&s.h_tail, 64));
+        CUDA_TRY(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&s.ev_served, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&s.ev_egress, cudaEventDisableTiming));
     }
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->st_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->st_compute, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->st_egress, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&e->d_chain, 64));
+    CUDA_TRY(cudaMalloc(&e->d_info, sizeof(ChunkInfo) * kSlots));
+    CUDA_TRY(cudaMallocHost(&e->h_status, 64));
     *out = e;
     return GOFR_OK;
 }
@@ -149,11 +164,19 @@ void gofr_engine_destroy(gofr_engine* e) {
     for (auto& s : e->slots) {
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_served) cudaEventDestroy(s.ev_served);
+        if (s.ev_egress) cudaEventDestroy(s.ev_egress);
         cudaFree(s.d_desc); cudaFree(s.d_ids); cudaFree(s.d_arena); cudaFree(s.d_out); cudaFree(s.d_off); cudaFree(s.d_meta);
         cudaFree(s.d_state); cudaFree(s.d_flag); cudaFree(s.d_bind);
         if (s.h_tail) cudaFreeHost(s.h_tail);
     }
     for (auto& ev : e->timing) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    if (e->st_h2d) cudaStreamDestroy(e->st_h2d);
+    if (e->st_compute) cudaStreamDestroy(e->st_compute);
+    if (e->st_egress) cudaStreamDestroy(e->st_egress);
+    cudaFree(e->d_chain); cudaFree(e->d_info);
+    if (e->h_status) cudaFreeHost(e->h_status);
     cudaFree(e->d_image); cudaFree(e->d_state); cudaFree(e->d_flag); cudaFree(e->d_bind);
     delete e;
 }
@@ -175,7 +198,8 @@ int gofr_engine_set_chunk(gofr_engine* e, uint32_t requests_per_chunk) {
 // one fused launch; `state`/`flag` are scratch owned by the caller of this helper
 static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, const uint8_t* d_arena, uint32_t n,
                       const char* date29, uint8_t* d_out, uint64_t out_cap, uint32_t* d_off, uint32_t* d_meta,
-                      unsigned long long* d_state, uint32_t* d_flag, uint32_t* d_bind, cudaStream_t stream) {
+                      unsigned long long* d_state, uint32_t* d_flag, uint32_t* d_bind, cudaStream_t stream,
+                      const unsigned long long* chain_pos = nullptr) {
     ServeParams p;
     memset(&p, 0, sizeof p);
     p.desc = d_desc; p.ids = d_ids; p.arena = d_arena; p.n = n;
@@ -188,6 +212,7 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
     p.tile_state = d_state; p.overflow = d_flag;
     p.in_cap = e->in_cap; p.out_stage_cap = e->out_stage_cap;
     p.bind_scratch = d_bind; p.bind_row_words = e->hdr.bind_row_words;
+    p.chain_pos = chain_pos;
     memcpy(p.date, date29, 29);
     int grid = (int)std::min<uint32_t>((uint32_t)e->grid, p.n_tiles);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -333,6 +358,87 @@ int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch*
         ahi = (ahi + 15u) & ~15u;
         if ((uint64_t)ahi > ((in->arena_bytes + 15u) & ~(uint64_t)15u)) { set_last_error("descriptor %u..%u points outside the arena", lo, hi); return GOFR_ERR_INVALID; }
         plan.push_back({lo, hi, alo, ahi});
+    }
+
+    // ---- streaming path: caller buffers are pinned → egress is device driven, the host never blocks mid-batch ----
+    auto device_visible = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+    };
+    if (n && device_visible(out->out) && device_visible(out->out_off) && device_visible(out->meta)) {
+        auto ensure_s = [&](Slot& s, uint32_t cn, size_t abytes, size_t ocap) -> int {
+            if (cn > s.cap_n) {
+                cudaFree(s.d_desc); cudaFree(s.d_ids); cudaFree(s.d_off); cudaFree(s.d_meta); cudaFree(s.d_state); cudaFree(s.d_bind);
+                s.d_desc = s.d_ids = nullptr; s.d_off = s.d_meta = nullptr; s.d_state = nullptr; s.d_bind = nullptr;
+                size_t c = (size_t)cn + cn / 4 + 256;
+                size_t tiles = (c + kServeThreads - 1) / kServeThreads;
+                if (cudaMalloc(&s.d_desc, c * 16) != cudaSuccess || cudaMalloc(&s.d_ids, c * 16) != cudaSuccess ||
+                    cudaMalloc(&s.d_off, (c + 1) * 4) != cudaSuccess || cudaMalloc(&s.d_meta, c * 4) != cudaSuccess ||
+                    cudaMalloc(&s.d_state, tiles * 8) != cudaSuccess) { set_last_error("cudaMalloc failed for a %zu-request chunk", c); s.cap_n = 0; return GOFR_ERR_NOMEM; }
+                if (cudaMemset(s.d_state, 0, tiles * 8) != cudaSuccess) return GOFR_ERR_CUDA;
+                if (e->hdr.bind_row_words && cudaMalloc(&s.d_bind, c * e->hdr.bind_row_words * 4 + 256) != cudaSuccess) { s.cap_n = 0; return GOFR_ERR_NOMEM; }
+                s.cap_n = c;
+            }
+            if (!s.d_flag) { if (cudaMalloc(&s.d_flag, 64) != cudaSuccess || cudaMemset(s.d_flag, 0, 64) != cudaSuccess) return GOFR_ERR_NOMEM; }
+            int rc;
+            if ((rc = grow((void**)&s.d_arena, &s.cap_arena, abytes, 256))) return rc;
+            if ((rc = grow((void**)&s.d_out, &s.cap_out, ocap, 256))) return rc;
+            return GOFR_OK;
+        };
+        // growing buffers frees memory: make sure nothing from an earlier batch is still using them
+        CUDA_TRY(cudaMemsetAsync(e->d_chain, 0, 8, e->st_compute));
+        e->h_status[0] = 0; e->h_status[1] = 0;
+        for (size_t ci = 0; ci < plan.size(); ci++) {
+            Slot& s = e->slots[ci % kSlots];
+            const ChunkPlan& c = plan[ci];
+            uint32_t cn = c.hi - c.lo;
+            size_t abytes = (size_t)c.arena_hi - c.arena_lo;
+            size_t ocap = std::min<size_t>((size_t)cn * (e->hdr.max_fixed_len + 64) + 6 * abytes + 4096, 0xFFFFFFF0ull);
+            if (s.egress_pending) {
+                // the slot's previous chunk must have left before its buffers are overwritten: a stream-side wait,
+                // unless the buffers have to grow (cudaFree needs the host to be sure)
+                const bool grows = cn > s.cap_n || abytes > s.cap_arena || ocap > s.cap_out;
+                if (grows) CUDA_TRY(cudaEventSynchronize(s.ev_egress));
+                else CUDA_TRY(cudaStreamWaitEvent(e->st_h2d, s.ev_egress, 0));
+                s.egress_pending = false;
+            }
+            int rc = ensure_s(s, cn, abytes, ocap);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(s.d_desc, in->desc + c.lo, (size_t)cn * 16, cudaMemcpyHostToDevice, e->st_h2d));
+            CUDA_TRY(cudaMemcpyAsync(s.d_ids, in->trace_ids + (size_t)c.lo * 16, (size_t)cn * 16, cudaMemcpyHostToDevice, e->st_h2d));
+            if (abytes) {
+                size_t avail = in->arena_bytes > c.arena_lo ? (size_t)in->arena_bytes - c.arena_lo : 0;
+                CUDA_TRY(cudaMemcpyAsync(s.d_arena, in->arena + c.arena_lo, std::min(abytes, avail), cudaMemcpyHostToDevice, e->st_h2d));
+            }
+            CUDA_TRY(cudaEventRecord(s.ev_h2d, e->st_h2d));
+            CUDA_TRY(cudaStreamWaitEvent(e->st_compute, s.ev_h2d, 0));
+            rc = launch_one(e, s.d_desc, s.d_ids, s.d_arena - c.arena_lo, cn, in->date, s.d_out, s.cap_out, s.d_off, s.d_meta,
+                            s.d_state, s.d_flag, s.d_bind, e->st_compute, e->d_chain);
+            if (rc) return rc;
+            if (launch_advance(e->d_chain, s.d_off, cn, s.d_flag, e->d_info + (ci % kSlots), out->out_cap, e->st_compute) != 0) {
+                set_last_error("advance kernel launch failed"); return GOFR_ERR_CUDA;
+            }
+            CUDA_TRY(cudaEventRecord(s.ev_served, e->st_compute));
+            CUDA_TRY(cudaStreamWaitEvent(e->st_egress, s.ev_served, 0));
+            if (launch_egress(e->d_info + (ci % kSlots), s.d_out, s.d_off, s.d_meta, cn, out->out, out->out_off + c.lo,
+                              out->meta + c.lo, e->h_status, e->sm_count / 4 > 0 ? e->sm_count / 4 : 1, e->st_egress) != 0) {
+                set_last_error("egress kernel launch failed"); return GOFR_ERR_CUDA;
+            }
+            CUDA_TRY(cudaEventRecord(s.ev_egress, e->st_egress));
+            s.egress_pending = true;
+            e->launches += 2;
+        }
+        CUDA_TRY(cudaMemcpyAsync((void*)&e->h_status[0], e->d_chain, 8, cudaMemcpyDeviceToHost, e->st_egress));
+        CUDA_TRY(cudaStreamSynchronize(e->st_egress));
+        for (auto& s : e->slots) s.egress_pending = false;
+        uint64_t total = e->h_status[0];
+        if (e->h_status[1]) { final_rc = GOFR_ERR_CAPACITY; set_last_error("output capacity too small (device chunk buffer or caller buffer)"); }
+        out->out_off[n] = (uint32_t)total;
+        out->out_bytes = total;
+        e->pending.push_back({out, final_rc, true});
+        *ticket = e->pending.size();
+        return GOFR_OK;
     }
 
     // ---- straightforward 3-slot software pipeline ----

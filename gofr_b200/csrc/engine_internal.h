@@ -32,6 +32,7 @@ struct ServeParams {
     uint32_t date[8];        // 29-byte IMF-fixdate, zero padded
     uint32_t* bind_scratch;  // n * bind_row_words words (tables with GOFR_H_BIND_ECHO routes), else null
     uint32_t bind_row_words;
+    const unsigned long long* chain_pos;  // host-batch path: packed position of the whole batch so far (else null)
 };
 
 constexpr int kServeThreads = 128;  // requests per tile = threads per CTA
@@ -41,6 +42,19 @@ uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap, uint32_t out_stag
 // cudaError_t as int
 int launch_serve(const ServeParams& p, int grid, uint32_t smem_bytes, void* stream);
 int serve_max_grid(uint32_t smem_bytes, int device, int* blocks_per_sm);
+
+// egress of the host-batch path (egress_kernel.cu)
+struct ChunkInfo {
+    unsigned long long host_base;  // where this chunk starts in the caller's output buffer
+    uint32_t base0;                // = host_base & 15: offset of the chunk inside its device buffer
+    uint32_t total;
+    uint32_t overflow;
+    uint32_t pad;
+};
+int launch_advance(unsigned long long* chain_pos, const uint32_t* d_off, uint32_t n, uint32_t* d_overflow, ChunkInfo* info,
+                   unsigned long long host_cap, void* stream);
+int launch_egress(const ChunkInfo* info, const uint8_t* d_out, const uint32_t* d_off, const uint32_t* d_meta, uint32_t n,
+                  uint8_t* h_out, uint32_t* h_off, uint32_t* h_meta, unsigned long long* h_status, int grid, void* stream);
 
 struct GrpcParams {
     const uint8_t* in;

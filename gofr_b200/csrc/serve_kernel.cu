@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(T, 4) serve_kernel(const ServeParams p) {
     tv.bind(tbl, p.image);
 
     uint32_t parity = 0;
+    const unsigned long long chain0 = p.chain_pos ? (*p.chain_pos & 15ull) : 0ull;
 
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const uint32_t i = tile * T + tid;
@@ -148,7 +149,8 @@ __global__ void __launch_bounds__(T, 4) serve_kernel(const ServeParams p) {
             if (lane == 0) sh.tile_base = base;
         }
         __syncthreads();
-        const unsigned long long tile_base = sh.tile_base;
+        // host-batch path: the chunk starts at the same offset mod 16 as its destination in the caller's buffer
+        const unsigned long long tile_base = sh.tile_base + chain0;
         const bool fits = tile_base + tile_total <= p.out_cap && tile_base + tile_total <= 0xFFFFFFFFull;
         if (!fits && tid == 0) atomicExch(p.overflow, 1u);
         if (valid) {
