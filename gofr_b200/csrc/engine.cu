@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
@@ -82,6 +83,7 @@ struct gofr_engine {
     unsigned long long* d_chain = nullptr;  // packed position of the batch in flight
     ChunkInfo* d_info = nullptr;            // one per slot
     unsigned long long* h_status = nullptr; // pinned: [0] total bytes, [1] overflow
+    int egress_grid = 37;
     uint32_t chunk = 65536;
     std::mutex mu;
     uint64_t launches = 0;
@@ -153,6 +155,8 @@ int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
     CUDA_TRY(cudaMalloc(&e->d_chain, 64));
     CUDA_TRY(cudaMalloc(&e->d_info, sizeof(ChunkInfo) * kSlots));
     CUDA_TRY(cudaMallocHost(&e->h_status, 64));
+    e->egress_grid = e->sm_count / 4 > 0 ? e->sm_count / 4 : 1;
+    if (const char* g = getenv("GOFR_EGRESS_GRID")) { int v = atoi(g); if (v > 0) e->egress_grid = v; }
     *out = e;
     return GOFR_OK;
 }
@@ -342,23 +346,30 @@ int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch*
     int final_rc = GOFR_OK;
     if (n == 0) { out->out_off[0] = 0; }
 
-    // plan chunks (contiguous request ranges; each chunk's arena range is [first.off, last.end))
-    std::vector<ChunkPlan> plan;
-    for (uint32_t lo = 0; lo < n; lo += e->chunk) {
-        uint32_t hi = std::min<uint32_t>(n, lo + e->chunk);
+    // Chunks are contiguous request ranges; a chunk's arena range is the min/max over its descriptors.  The scan is done
+    // lazily, right before a chunk is enqueued, so it overlaps with the GPU work of the chunks already in flight
+    // (scanning all descriptors up front costs milliseconds of pure latency on a 1 Mi-request batch).
+    const size_t nchunks_total = n ? (n + e->chunk - 1) / e->chunk : 0;
+    std::vector<ChunkPlan> plan(nchunks_total);
+    std::vector<char> planned(nchunks_total, 0);
+    auto plan_chunk = [&](size_t ci) -> int {
+        if (planned[ci]) return GOFR_OK;
+        uint32_t lo = (uint32_t)(ci * e->chunk), hi = std::min<uint32_t>(n, lo + e->chunk);
         uint32_t alo = 0xFFFFFFFFu, ahi = 0;
-        // descriptors are normally monotonic; scan the ends cheaply (first/last) and verify with min/max
+        const gofr_req_desc* dd = in->desc;
         for (uint32_t i = lo; i < hi; i++) {
-            const gofr_req_desc& d = in->desc[i];
-            uint32_t dend = ((d.arena_off + d.path_len + d.query_len + 3u) & ~3u) + d.data_len;
-            alo = std::min(alo, d.arena_off);
-            ahi = std::max(ahi, dend);
+            uint32_t a = dd[i].arena_off;
+            uint32_t dend = ((a + dd[i].path_len + dd[i].query_len + 3u) & ~3u) + dd[i].data_len;
+            alo = a < alo ? a : alo;
+            ahi = dend > ahi ? dend : ahi;
         }
         alo &= ~15u;
         ahi = (ahi + 15u) & ~15u;
         if ((uint64_t)ahi > ((in->arena_bytes + 15u) & ~(uint64_t)15u)) { set_last_error("descriptor %u..%u points outside the arena", lo, hi); return GOFR_ERR_INVALID; }
-        plan.push_back({lo, hi, alo, ahi});
-    }
+        plan[ci] = {lo, hi, alo, ahi};
+        planned[ci] = 1;
+        return GOFR_OK;
+    };
 
     // ---- streaming path: caller buffers are pinned → egress is device driven, the host never blocks mid-batch ----
     auto device_visible = [](const void* p) {
@@ -366,7 +377,7 @@ int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch*
         if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
         return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
     };
-    if (n && device_visible(out->out) && device_visible(out->out_off) && device_visible(out->meta)) {
+    if (n && !getenv("GOFR_LEGACY_EGRESS") && device_visible(out->out) && device_visible(out->out_off) && device_visible(out->meta)) {
         auto ensure_s = [&](Slot& s, uint32_t cn, size_t abytes, size_t ocap) -> int {
             if (cn > s.cap_n) {
                 cudaFree(s.d_desc); cudaFree(s.d_ids); cudaFree(s.d_off); cudaFree(s.d_meta); cudaFree(s.d_state); cudaFree(s.d_bind);
@@ -391,6 +402,7 @@ int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch*
         e->h_status[0] = 0; e->h_status[1] = 0;
         for (size_t ci = 0; ci < plan.size(); ci++) {
             Slot& s = e->slots[ci % kSlots];
+            { int prc = plan_chunk(ci); if (prc) return prc; }
             const ChunkPlan& c = plan[ci];
             uint32_t cn = c.hi - c.lo;
             size_t abytes = (size_t)c.arena_hi - c.arena_lo;
@@ -422,7 +434,7 @@ int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch*
             CUDA_TRY(cudaEventRecord(s.ev_served, e->st_compute));
             CUDA_TRY(cudaStreamWaitEvent(e->st_egress, s.ev_served, 0));
             if (launch_egress(e->d_info + (ci % kSlots), s.d_out, s.d_off, s.d_meta, cn, out->out, out->out_off + c.lo,
-                              out->meta + c.lo, e->h_status, e->sm_count / 4 > 0 ? e->sm_count / 4 : 1, e->st_egress) != 0) {
+                              out->meta + c.lo, e->h_status, e->egress_grid, e->st_egress) != 0) {
                 set_last_error("egress kernel launch failed"); return GOFR_ERR_CUDA;
             }
             CUDA_TRY(cudaEventRecord(s.ev_egress, e->st_egress));
@@ -471,6 +483,7 @@ int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch*
         while (issued < nchunks && issued - finished < (size_t)kSlots) {
             int si = (int)(issued % kSlots);
             Slot& s = e->slots[si];
+            { int prc = plan_chunk(issued); if (prc) return prc; }
             const ChunkPlan& c = plan[issued];
             uint32_t cn = c.hi - c.lo;
             size_t abytes = (size_t)c.arena_hi - c.arena_lo;

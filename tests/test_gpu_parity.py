@@ -26,7 +26,7 @@ def _engine(spec):
     return Engine(Table(spec), 0)
 
 
-def _check(spec, batch, eng=None, host=False, chunk=None):
+def _check(spec, batch, eng=None, host=False, chunk=None, pinned=True):
     import torch
     ot = O.OracleTable(spec)
     o1, f1, m1 = ot.serve(batch, DATE)
@@ -35,9 +35,16 @@ def _check(spec, batch, eng=None, host=False, chunk=None):
     if host:
         if chunk:
             eng.set_chunk(chunk)
-        out = np.zeros(total + 64, dtype=np.uint8)
-        off = np.zeros(batch.n + 1, dtype=np.uint32)
-        meta = np.zeros(batch.n, dtype=np.uint32)
+        if pinned:  # device-driven egress straight into pinned buffers
+            from gofr_b200.engine import pin_batch, pinned_array
+            batch = pin_batch(batch)
+            out = pinned_array(total + 64)
+            off = pinned_array(4 * (batch.n + 1), np.uint32)
+            meta = pinned_array(4 * max(batch.n, 1), np.uint32)[:batch.n]
+        else:       # pageable buffers: exact-size cudaMemcpy pipeline
+            out = np.zeros(total + 64, dtype=np.uint8)
+            off = np.zeros(batch.n + 1, dtype=np.uint32)
+            meta = np.zeros(batch.n, dtype=np.uint32)
         nbytes = eng.serve_host(batch, DATE, out, off, meta)
         assert nbytes == total
     else:
@@ -131,9 +138,25 @@ def test_repeated_launches_reuse_lookback_state(torch_cuda):
         _check(spec, synth.config2_batch(n, start=n), eng=eng)
 
 
+@pytest.mark.parametrize("pinned", [True, False])
 @pytest.mark.parametrize("chunk", [1000, 4096, 65536])
-def test_host_path_chunked_pipeline(torch_cuda, chunk):
-    _check(synth.config2_spec(), synth.config2_batch(20000), host=True, chunk=chunk)
+def test_host_path_chunked_pipeline(torch_cuda, chunk, pinned):
+    _check(synth.config2_spec(), synth.config2_batch(20000), host=True, chunk=chunk, pinned=pinned)
+
+
+def test_host_path_output_capacity(torch_cuda):
+    """A caller buffer that is too small is reported as GOFR_ERR_CAPACITY, not overrun."""
+    from gofr_b200 import _abi
+    from gofr_b200.engine import Engine, pin_batch, pinned_array
+    eng = Engine(Table(synth.config2_spec()), 0)
+    eng.set_chunk(1000)
+    b = pin_batch(synth.config2_batch(5000))
+    out = pinned_array(2000 * synth.C2_WIRE_BYTES)
+    off = pinned_array(4 * 5001, np.uint32)
+    meta = pinned_array(4 * 5000, np.uint32)
+    with pytest.raises(_abi.GofrError) as e:
+        eng.serve_host(b, DATE, out, off, meta)
+    assert e.value.code == 7
 
 
 def test_host_path_mixed(torch_cuda):
