@@ -927,8 +927,9 @@ GOFR_HD void route_request(const TableView& tv, ReqCtx& c) {
 template <bool EMIT>
 GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
     const ProgRec P = tv.progs[c.prog];  // by value: the staging stores below must not force re-reads of the table
-    const Op* ops = tv.ops + P.first_op;
-    const uint32_t n_ops = P.n_ops;
+    // the size pass visits only the ops whose length depends on the request
+    const Op* ops = tv.ops + (EMIT ? P.first_op : P.first_dyn);
+    const uint32_t n_ops = EMIT ? P.n_ops : P.n_dyn;
     const uint8_t* const lits = tv.lits;
     const bool head = c.method == GOFR_M_HEAD;
     const uint32_t* row = (P.flags & PF_BIND) ? c.brow : (const uint32_t*)c.data;
@@ -947,12 +948,14 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
         const uint32_t olen = raw.y, ooff = raw.z, oaux = raw.w;
         const bool body = oflags & OPF_BODY;
         if (EMIT && head && body) break;  // chunkWriter eats the body of a HEAD response; body ops come last
-        if (EMIT && warp_any(w->wl >= 16)) w->flush();  // every non-copy op appends at most 16 words
         const bool governed = oflags & OPF_VALUE_OF_KEY;
         uint32_t produced = 0;
         const uint8_t* csrc = nullptr;  // ops that append memory verbatim meet at the single copy() below
         uint32_t clen = 0;
         bool cshared = true;            // literals live in the shared-memory copy of the table
+        if (EMIT && code != OP_LIT && code != OP_KEY && code != OP_BLOB && olen)
+            w->copy<true>(SrcMem<true>::from(lits + oaux), olen);  // literal prefix folded into this value op
+        if (EMIT && warp_any(w->wl >= 16)) w->flush();  // every non-copy action appends at most 16 words
         if (code == OP_LIT) {
             if (!(governed && skip)) {
                 csrc = lits + ooff;

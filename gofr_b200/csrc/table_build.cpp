@@ -498,6 +498,26 @@ static void merge_literals(std::vector<SOp>& ops) {
     ops.swap(out);
 }
 
+// LIT followed by a value op of the same part (header/body) → the literal becomes the value op's prefix
+static bool op_takes_prefix(uint8_t code) {
+    return code == OP_HEXID || code == OP_CLEN || code == OP_I64 || code == OP_I32 || code == OP_BOOL || code == OP_STR ||
+           code == OP_BSTR || code == OP_PARAM || code == OP_LOCATION || code == OP_ERRMSG;
+}
+static void fold_prefixes(std::vector<SOp>& ops) {
+    std::vector<SOp> out;
+    for (size_t i = 0; i < ops.size(); i++) {
+        if (ops[i].code == OP_LIT && ops[i].flags == 0 && i + 1 < ops.size() && op_takes_prefix(ops[i + 1].code) &&
+            ops[i + 1].flags == 0 && ops[i + 1].body == ops[i].body && ops[i + 1].lit.empty()) {
+            SOp v = ops[i + 1];
+            v.lit = ops[i].lit;            // prefix bytes
+            v.date_pos = ops[i].date_pos;
+            out.push_back(v);
+            i++;
+        } else out.push_back(ops[i]);
+    }
+    ops.swap(out);
+}
+
 static const char* go_kind_name(uint8_t k) {
     switch (k) {
         case GOFR_F_INT64: return "int64";
@@ -695,6 +715,7 @@ int seal_table(gofr_table* t) {
     for (size_t pi = 0; pi < b.progs.size(); pi++) {
         Prog& p = b.progs[pi];
         merge_literals(p.ops);
+        fold_prefixes(p.ops);
         ProgRec& P = progs[pi];
         memset(&P, 0, sizeof P);
         P.first_op = (uint16_t)ops.size();
@@ -723,6 +744,7 @@ int seal_table(gofr_table* t) {
                     break;
                 case OP_HEXID: fixed = 32; break;
                 case OP_CLEN: P.flags |= PF_HAS_CLEN; break;
+                case OP_I64: case OP_I32: case OP_BOOL: case OP_STR: case OP_BSTR: P.flags |= PF_DYNAMIC | PF_NEEDS_ROW; break;
                 case OP_BLOB:
                     while (cold.size() % 16) cold.push_back(0);
                     o.off = (uint32_t)cold.size();
@@ -730,13 +752,32 @@ int seal_table(gofr_table* t) {
                     cold.insert(cold.end(), so.lit.begin(), so.lit.end());
                     fixed = o.len;
                     break;
-                case OP_I64: case OP_I32: case OP_BOOL: case OP_STR: case OP_BSTR: P.flags |= PF_DYNAMIC | PF_NEEDS_ROW; break;
                 default: P.flags |= PF_DYNAMIC; break;
+            }
+            if (op_takes_prefix(so.code) && !so.lit.empty()) {  // folded literal prefix
+                o.aux = pool.put(so.lit, !so.date_pos.empty());
+                o.len = (uint32_t)so.lit.size();
+                for (uint32_t dp : so.date_pos) fixups.push_back(o.aux + dp);
+                fixed += o.len;
             }
             if (so.body) P.body_fixed += fixed; else P.hdr_fixed += fixed;
             ops.push_back(o);
         }
         max_fixed = std::max(max_fixed, P.hdr_fixed + P.body_fixed);
+    }
+
+    // the size pass only needs the ops whose length depends on the request (everything else is pre-summed)
+    for (size_t pi = 0; pi < progs.size(); pi++) {
+        ProgRec& P = progs[pi];
+        P.first_dyn = (uint16_t)ops.size();
+        std::vector<Op> dyn;
+        for (uint32_t k = 0; k < P.n_ops; k++) {
+            const Op& o = ops[P.first_op + k];
+            bool fixed_len = (o.code == OP_LIT && !(o.flags & OPF_VALUE_OF_KEY)) || o.code == OP_HEXID || o.code == OP_CLEN || o.code == OP_BLOB;
+            if (!fixed_len) dyn.push_back(o);
+        }
+        P.n_dyn = (uint16_t)dyn.size();
+        ops.insert(ops.end(), dyn.begin(), dyn.end());
     }
 
     std::vector<uint8_t> schema_bytes;

@@ -12,7 +12,7 @@
 namespace gofr {
 
 constexpr uint32_t kMagic = 0x52464F47u;  // "GOFR"
-constexpr uint32_t kImageVersion = 5;
+constexpr uint32_t kImageVersion = 6;
 constexpr uint32_t kMaxHotBytes = 40 * 1024;  // shared-memory budget for the table
 constexpr int kMaxVars = 8;                   // variables per route template
 constexpr int kMaxFields = 32;                // struct fields per schema
@@ -95,6 +95,9 @@ enum OpCode : uint8_t {
                       // field (arg) is empty and flagged; used only for schemas that have an omitempty field
 };
 
+// Value ops (everything except OP_LIT / OP_KEY / OP_BLOB) can carry a literal PREFIX: lits[aux .. aux+len) is emitted
+// right before the op's own bytes (the builder folds `"name":"`-style literals into the field op that follows, which
+// halves the interpreter's trip count).  The prefix is part of the program's fixed byte count.
 enum OpFlags : uint8_t {
     OPF_BODY = 1,       // op belongs to the response body (counts toward Content-Length; dropped for HEAD)
     OPF_OMITEMPTY = 2,  // OP_KEY: skip key and value when the field is the zero value
@@ -112,15 +115,18 @@ struct Op {  // 16 B (one LDS.128)
 };
 static_assert(sizeof(Op) == 16, "Op layout");
 
-struct ProgRec {  // 16 B
+struct ProgRec {  // 32 B
     uint16_t first_op;
     uint16_t n_ops;
     uint16_t status;     // HTTP status code
     uint16_t flags;      // PF_*
-    uint32_t hdr_fixed;  // sum of the fixed-length header ops (LIT, HEXID, DATE)
-    uint32_t body_fixed; // sum of the fixed-length body ops
+    uint32_t hdr_fixed;  // sum of the fixed-length header bytes (literals, HEXID)
+    uint32_t body_fixed; // sum of the fixed-length body bytes
+    uint16_t first_dyn;  // the ops whose length depends on the request, in order: all the size pass has to visit
+    uint16_t n_dyn;
+    uint32_t pad[3];
 };
-static_assert(sizeof(ProgRec) == 16, "ProgRec layout");
+static_assert(sizeof(ProgRec) == 32, "ProgRec layout");
 
 enum ProgFlags : uint16_t {
     PF_HAS_CLEN = 1,
