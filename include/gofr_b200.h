@@ -172,7 +172,9 @@ void gofr_engine_destroy(gofr_engine*);
 
 /* Device-resident batch: every pointer is device memory, `stream` is a cudaStream_t (NULL = default stream).
  * One fused launch: route match + middleware predicates + handler kind + JSON encode + HTTP framing.
- * date is the 29-byte IMF-fixdate for this batch (host memory).  d_total receives the packed size (= out_off[n]). */
+ * date is the 29-byte IMF-fixdate for this batch (host memory).  out_off[n] receives the packed size.
+ * d_arena must be 16-byte aligned and its allocation must extend at least 16 bytes past the last request byte; d_out must be
+ * 16-byte aligned.  Launches on one engine must be stream-ordered with respect to each other (they share scratch). */
 int gofr_serve_device(gofr_engine*, const gofr_req_desc* d_desc, const uint8_t* d_trace_ids, const uint8_t* d_arena,
                       uint32_t n, const char* date29, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off,
                       uint32_t* d_meta, void* stream);
