@@ -54,50 +54,33 @@ __device__ __forceinline__ unsigned long long pack_state(uint32_t epoch, uint32_
 }
 
 // Called by warp 0.  Returns the exclusive prefix of `tile` (valid in every lane).
-// Each round trip inspects 128 predecessors (4 per lane, loads issued together) — the in-flight window is several
-// hundred tiles deep when all CTAs run in phase, and every round trip costs an L2 latency.
 __device__ __forceinline__ unsigned long long lookback(unsigned long long* state, uint32_t epoch, uint32_t tile,
                                                        unsigned long long total, uint32_t lane) {
     if (lane == 0) st_state(&state[tile], pack_state(epoch, tile == 0 ? 2 : 1, total));
     unsigned long long excl = 0;
     if (tile > 0) {
-        long long base = (long long)tile - 1;  // lane l, slot k looks at tile base - (k * 32 + l)
+        long long base = (long long)tile - 1;
         for (;;) {
-            unsigned long long s[4];
+            long long t = base - (long long)lane;
+            unsigned long long s = t >= 0 ? ld_state(&state[t]) : pack_state(epoch, 2, 0);
+            uint32_t flag = (uint32_t)(s >> 42) & 3u;
+            bool ready = (uint32_t)(s >> 44) == (epoch & 0xFFFFFu) && flag != 0;
+            uint32_t not_ready = __ballot_sync(0xFFFFFFFFu, !ready);
+            uint32_t is_p = __ballot_sync(0xFFFFFFFFu, ready && flag == 2);
+            uint32_t upto = is_p ? (uint32_t)__ffs((int)is_p) - 1 : 31u;  // lanes 0..upto contribute
+            uint32_t need = upto == 31 ? 0xFFFFFFFFu : ((1u << (upto + 1)) - 1);
+            if (not_ready & need) { __nanosleep(40); continue; }
+            unsigned long long v = (lane <= upto) ? (s & kValMask) : 0ull;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                long long t = base - (long long)(k * 32 + lane);
-                s[k] = t >= 0 ? ld_state(&state[t]) : pack_state(epoch, 2, 0);
-            }
-            bool done = false, retry = false;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (done || retry) continue;
-                uint32_t flag = (uint32_t)(s[k] >> 42) & 3u;
-                bool ready = (uint32_t)(s[k] >> 44) == (epoch & 0xFFFFFu) && flag != 0;
-                uint32_t not_ready = __ballot_sync(0xFFFFFFFFu, !ready);
-                uint32_t is_p = __ballot_sync(0xFFFFFFFFu, ready && flag == 2);
-                uint32_t upto = is_p ? (uint32_t)__ffs((int)is_p) - 1 : 31u;  // lanes 0..upto contribute
-                uint32_t need = upto == 31 ? 0xFFFFFFFFu : ((1u << (upto + 1)) - 1);
-                if (not_ready & need) {
-                    // keep what the earlier slots of this round trip contributed; resume from this slot
-                    base -= 32 * k;
-                    retry = true;
-                    continue;
-                }
-                unsigned long long v = (lane <= upto) ? (s[k] & kValMask) : 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-                excl += v;
-                if (is_p) done = true;
-            }
-            if (done) break;
-            if (retry) { __nanosleep(32); continue; }
-            base -= 128;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            excl += v;
+            if (is_p) break;
+            base -= 32;
         }
         if (lane == 0) st_state(&state[tile], pack_state(epoch, 2, excl + total));
     }
     return excl;
 }
+
 
 }  // namespace gofr
