@@ -325,7 +325,7 @@ GOFR_HD bool bd_parse_int(const uint8_t* s, uint32_t n, int64_t* out) {
 
 // d.object / d.literalStore into the span row.  `row` has BR_FIELDS + bind-layout words, zero-initialised here.
 GOFR_HD_NOINLINE void bind_decode(const TableView tv, uint32_t schema_idx, const uint8_t* s, uint32_t n, uint32_t* row) {
-    const SchemaRec S = tv.schemas[schema_idx];
+    const SchemaRec S = tv.schemas()[schema_idx];
     const FieldRec* F = (const FieldRec*)(tv.base + S.fields_off);
     // bind layout: word offsets
     uint32_t nwords = 0;
@@ -358,9 +358,9 @@ GOFR_HD_NOINLINE void bind_decode(const TableView tv, uint32_t schema_idx, const
         // exact name first, then fold, both in declaration order
         uint32_t fi = 0xFFFFFFFFu;
         for (uint32_t k = 0; k < S.n_fields && fi == 0xFFFFFFFFu; k++)
-            if (bd_key_matches(s, ks, kend, tv.lits + F[k].name_off, F[k].name_len, false)) fi = k;
+            if (bd_key_matches(s, ks, kend, tv.lits() + F[k].name_off, F[k].name_len, false)) fi = k;
         for (uint32_t k = 0; k < S.n_fields && fi == 0xFFFFFFFFu; k++)
-            if (bd_key_matches(s, ks, kend, tv.lits + F[k].name_off, F[k].name_len, true)) fi = k;
+            if (bd_key_matches(s, ks, kend, tv.lits() + F[k].name_off, F[k].name_len, true)) fi = k;
         uint32_t vs = i, ve = bd_skip_value(s, n, i);
         i = ve;
         if (fi != 0xFFFFFFFFu) {
@@ -477,14 +477,14 @@ GOFR_HD_NOINLINE uint32_t emit_bind_error(Writer* w, const TableView tv, uint32_
         return out;
     }
     // UnmarshalTypeError
-    const SchemaRec S = tv.schemas[schema_idx];
+    const SchemaRec S = tv.schemas()[schema_idx];
     const FieldRec* F = (const FieldRec*)(tv.base + S.fields_off);
     out += be_puts<EMIT>(w, "json: cannot unmarshal ");
     const uint32_t v = row[BR_VALUE];
     out += be_puts<EMIT>(w, v == BV_STRING ? "string" : v == BV_BOOL ? "bool" : v == BV_OBJECT ? "object" : v == BV_ARRAY ? "array"
                                                        : v == BV_NUMBER ? "number" : "number ");
     if (v == BV_NUMBER_LIT) out += be_put<EMIT>(w, body + row[BR_LIT_OFF], row[BR_LIT_LEN]);
-    const uint8_t* ty = tv.lits + S.type_off;  // NUL-terminated reflect.Type.String()
+    const uint8_t* ty = tv.lits() + S.type_off;  // NUL-terminated reflect.Type.String()
     uint32_t tl = 0, dot = 0xFFFFFFFFu;
     while (ty[tl]) { if (ty[tl] == '.') dot = tl; tl++; }
     const uint32_t fi = row[BR_FIELD];
@@ -496,9 +496,9 @@ GOFR_HD_NOINLINE uint32_t emit_bind_error(Writer* w, const TableView tv, uint32_
         uint32_t ns = dot == 0xFFFFFFFFu ? 0 : dot + 1;  // reflect.Type.Name()
         out += be_put<EMIT>(w, ty + ns, tl - ns);
         out += be_puts<EMIT>(w, ".");
-        out += be_put<EMIT>(w, tv.lits + F[fi].name_off, F[fi].name_len);
+        out += be_put<EMIT>(w, tv.lits() + F[fi].name_off, F[fi].name_len);
         out += be_puts<EMIT>(w, " of type ");
-        out += be_put<EMIT>(w, tv.lits + F[fi].type_off, F[fi].type_len);
+        out += be_put<EMIT>(w, tv.lits() + F[fi].type_off, F[fi].type_len);
     }
     return out;
 }

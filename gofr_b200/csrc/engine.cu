@@ -136,10 +136,10 @@ int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
     CUDA_TRY(cudaMemset(e->d_flag, 0, 64));
     CUDA_TRY(cudaMalloc(&e->d_ticket, 64));
     CUDA_TRY(cudaMemset(e->d_ticket, 0, 64));
-    // default tile geometry: stage as many request bytes per request in shared memory as still lets 4 CTAs share an
+    // default tile geometry: stage as many request bytes per request in shared memory as still lets 5 CTAs share an
     // SM (the kernel is latency bound: residency matters more than staging every tile); larger tiles are read from
     // HBM directly.
-    uint32_t per_cta = 227u * 1024u / 4u - 1024u /*reserved*/ - 16640u /*static: staging buffer + tile state*/;
+    uint32_t per_cta = 227u * 1024u / 5u - 1024u /*reserved*/ - 8448u /*static: staging buffer + tile state*/;
     uint32_t hot = (e->hdr.hot_bytes + 127u) & ~127u;
     uint32_t in_per = per_cta > hot + 64u * kServeThreads ? ((per_cta - hot - 64u) / kServeThreads) & ~15u : 64u;
     if (in_per > 256u) in_per = 256u;
@@ -223,6 +223,7 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
     p.in_cap = e->in_cap; p.out_stage_cap = e->out_stage_cap;
     p.bind_scratch = d_bind; p.bind_row_words = e->hdr.bind_row_words;
     p.chain_pos = chain_pos;
+    if (getenv("GOFR_DEBUG_NO_LOOKBACK")) p.debug_flags |= 1u;  // diagnostic only
     // every CTA takes tickets until it draws one past the end: n_tiles + grid tickets per launch
     p.ticket = e->d_ticket + lane_id; p.ticket_base = e->ticket_base[lane_id];
     memcpy(p.date, date29, 29);

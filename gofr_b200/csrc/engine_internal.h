@@ -35,6 +35,7 @@ struct ServeParams {
     const unsigned long long* chain_pos;  // host-batch path: packed position of the whole batch so far (else null)
     uint32_t* ticket;        // tile ticket counter (never reset: ticket_base is its value before this launch)
     uint32_t ticket_base;
+    uint32_t debug_flags;    // bit0: skip the look-back (tile_base = tile * tile_total; only valid for fixed-size responses)
 };
 
 constexpr int kServeThreads = 128;  // requests per tile = threads per CTA

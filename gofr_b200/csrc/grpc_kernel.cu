@@ -21,7 +21,7 @@ struct GrpcShared {
     uint64_t bar;
     uint32_t warp_sum[GNW];
     unsigned long long tile_base;
-    uint32_t stage[32 * GT];
+    uint32_t stage[GOFR_STAGE_WORDS * GT];
     __align__(16) uint8_t in[kGrpcStage + 32];
 };
 

@@ -83,11 +83,11 @@ GOFR_HD bool warp_any(bool p) {
 //            written by other threads; only this response's bytes are stored there.
 // ---------------------------------------------------------------------------------------------------------------
 #if defined(__CUDA_ARCH__)
-#define GOFR_RING_STRIDE_BYTES 512u  /* kServeThreads words: word-major staging, 32 words per thread */
+#define GOFR_RING_STRIDE_BYTES 512u  /* kServeThreads words: word-major staging, GOFR_STAGE_WORDS words per thread */
 #else
 #define GOFR_RING_STRIDE_BYTES 4u
 #endif
-#define GOFR_STAGE_WORDS 32u
+#define GOFR_STAGE_WORDS 16u
 
 // ---- explicit address spaces -------------------------------------------------------------------------------------
 // The staging buffer, the table's literal pool and (for staged tiles) the request bytes all live in shared memory.
@@ -498,56 +498,68 @@ GOFR_HD void hex8(uint32_t x, uint32_t& w0, uint32_t& w1) {
 // table view (pointers into the shared-memory copy of the image)
 // ---------------------------------------------------------------------------------------------------------------
 struct TableView {
+    // Only two pointers are carried (the tile loop is register bound): every section is located through the header's
+    // offsets when it is needed — a shared-memory load each, issued rarely.
     const uint8_t* base;  // hot part (shared memory on the device)
     const uint8_t* cold;  // file blobs (HBM)
-    const ImageHeader* hdr;
-    const RouteRec* routes;
-    const PieceRec* pieces;
-    const ProgRec* progs;
-    const Op* ops;
-    const SchemaRec* schemas;
-    const uint8_t* lits;  // literal pool; every *_off of a literal is relative to it
-    const uint16_t* hash_tab;
-    const uint16_t* tmpl_list;
-    const uint16_t* last_method;
 
     GOFR_HD void bind(const uint8_t* hot, const uint8_t* image_global) {
         base = hot;
-        hdr = (const ImageHeader*)hot;
-        routes = (const RouteRec*)(hot + hdr->routes_off);
-        pieces = (const PieceRec*)(hot + hdr->pieces_off);
-        progs = (const ProgRec*)(hot + hdr->progs_off);
-        ops = (const Op*)(hot + hdr->ops_off);
-        schemas = (const SchemaRec*)(hot + hdr->schemas_off);
-        lits = hot + hdr->lits_off;
-        hash_tab = (const uint16_t*)(hot + hdr->hash_off);
-        tmpl_list = (const uint16_t*)(hot + hdr->tmpl_off);
-        last_method = (const uint16_t*)(hot + hdr->last_method_off);
-        cold = image_global + hdr->cold_off;
+        cold = image_global + ((const ImageHeader*)hot)->cold_off;
     }
-    GOFR_HD const uint32_t* lit_words(uint32_t off) const { return (const uint32_t*)(lits + off); }
-    GOFR_HD const uint8_t* lit_bytes(uint32_t off) const { return lits + off; }
+    GOFR_HD const ImageHeader* hdr() const { return (const ImageHeader*)base; }
+    GOFR_HD const RouteRec* routes() const { return (const RouteRec*)(base + hdr()->routes_off); }
+    GOFR_HD const PieceRec* pieces() const { return (const PieceRec*)(base + hdr()->pieces_off); }
+    GOFR_HD const ProgRec* progs() const { return (const ProgRec*)(base + hdr()->progs_off); }
+    GOFR_HD const Op* ops() const { return (const Op*)(base + hdr()->ops_off); }
+    GOFR_HD const SchemaRec* schemas() const { return (const SchemaRec*)(base + hdr()->schemas_off); }
+    GOFR_HD const uint8_t* lits() const { return base + hdr()->lits_off; }
+    GOFR_HD const uint16_t* hash_tab() const { return (const uint16_t*)(base + hdr()->hash_off); }
+    GOFR_HD const uint16_t* tmpl_list() const { return (const uint16_t*)(base + hdr()->tmpl_off); }
+    GOFR_HD const uint16_t* last_method() const { return (const uint16_t*)(base + hdr()->last_method_off); }
+    GOFR_HD const uint32_t* lit_words(uint32_t off) const { return (const uint32_t*)(lits() + off); }
+    GOFR_HD const uint8_t* lit_bytes(uint32_t off) const { return lits() + off; }
+};
+
+// Per-launch arrays a request reaches through its index (kernel parameters: they live in uniform registers)
+struct BatchRefs {
+    const uint8_t* ids;        // trace ids, 16 bytes per request
+    uint32_t* bind_scratch;    // Bind span rows (bind_device.cuh), bind_row_words words per request
+    uint32_t bind_row_words;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
 // per-request context
 // ---------------------------------------------------------------------------------------------------------------
 struct ReqCtx {
-    const uint8_t* path;
-    const uint8_t* query;
-    const uint8_t* data;
-    uint32_t path_len, query_len, data_len;
-    uint32_t method, flags;
-    uint32_t id[4];
-    uint32_t prog;       // program index, 0xFFFF = nothing to emit (GOFR_H_HOST)
-    uint32_t route;      // matched route or GOFR_ROUTE_NONE
-    uint32_t status;
+    const uint8_t* path;   // URL.Path; the query follows it, the data section starts at path + data_off
+    uint32_t path_len, query_len, data_len, data_off;
+    uint32_t mflags;       // method | flags << 8 | staged << 16  (staged: request bytes live in shared memory)
+    uint32_t index;        // request index in the batch (trace id, Bind scratch row)
+    uint32_t prog;         // program index, 0xFFFF = nothing to emit (GOFR_H_HOST)
+    uint32_t route;        // matched route or GOFR_ROUTE_NONE
     uint32_t pv_off, pv_len, pv_flags;  // query value span; flags bit0 found&non-empty, bit1 needs decode/escape
     uint32_t body_len, total_len;
-    uint32_t staged;     // request bytes live in shared memory (tile staged by TMA)
-    uint32_t* brow;      // this request's Bind scratch row (HBM), see bind_device.cuh
-    uint32_t slow_mask;  // bit k: k-th OP_STR of the program needs the slow escape path
+    uint32_t slow_mask;    // bit k: k-th OP_STR of the program needs the slow escape path
     uint32_t def_off, def_len;  // OP_PARAM default (pre-escaped literal)
+
+    GOFR_HD const uint8_t* query() const { return path + path_len; }
+    GOFR_HD const uint8_t* data() const { return path + data_off; }
+    GOFR_HD uint32_t method() const { return mflags & 0xFFu; }
+    GOFR_HD uint32_t flags() const { return (mflags >> 8) & 0xFFu; }
+    GOFR_HD bool staged() const { return (mflags >> 16) & 1u; }
+    GOFR_HD void set(const uint8_t* arena_base, uint32_t arena_off, uint32_t pl, uint32_t ql, uint32_t dl, uint32_t method_,
+                     uint32_t flags_, bool staged_, uint32_t idx) {
+        path = arena_base + arena_off;
+        path_len = pl; query_len = ql; data_len = dl;
+        data_off = ((arena_off + pl + ql + 3u) & ~3u) - arena_off;
+        mflags = method_ | flags_ << 8 | (staged_ ? 1u << 16 : 0u);
+        index = idx;
+        prog = 0xFFFF; route = GOFR_ROUTE_NONE;
+        pv_off = pv_len = pv_flags = 0;
+        body_len = total_len = 0; slow_mask = 0; def_off = def_len = 0;
+    }
+    GOFR_HD uint32_t* brow(const BatchRefs& br) const { return br.bind_scratch + (size_t)index * br.bind_row_words; }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -623,8 +635,8 @@ GOFR_HD_NOINLINE uint32_t emit_location(Writer* w, const ReqCtx c) {
     }
     // "put the trailing slash back if necessary": original ends in '/' and the cleaned path is not "/"
     if (n && p[n - 1] == '/' && any) { if (EMIT) w->put1('/'); out += 1; }
-    if (c.query_len || (c.flags & GOFR_REQ_FORCE_QUERY)) {
-        if (EMIT) { w->put1('?'); emit_bytes(*w, c.query, c.query_len); }
+    if (c.query_len || (c.flags() & GOFR_REQ_FORCE_QUERY)) {
+        if (EMIT) { w->put1('?'); emit_bytes(*w, c.query(), c.query_len); }
         out += 1 + c.query_len;
     }
     return out;
@@ -654,7 +666,7 @@ GOFR_HD bool words_equal(const uint32_t* a, const uint32_t* b, uint32_t n) {
 // Anchored leftmost-first match of lit0 var0 lit1 var1 ... litN [$]: greedy variables with backtracking — what Go's
 // regexp reports for the regexp mux builds from a path template.
 GOFR_HD_NOINLINE bool template_match(const TableView tv, const RouteRec R, const uint8_t* p, uint32_t n) {
-    const PieceRec* pc = tv.pieces + R.first_piece;
+    const PieceRec* pc = tv.pieces() + R.first_piece;
     uint32_t np = R.n_pieces;
     bool prefix = R.flags & RF_PREFIX;
     uint32_t start[kMaxVars + 1], take[kMaxVars + 1];
@@ -708,9 +720,9 @@ GOFR_HD bool route_path_ok(const TableView& tv, const RouteRec& R, const uint8_t
 // Returns route index, or -1 (no route: 404) / -2 (405).  Reference formulation: every route is evaluated.
 GOFR_HD_NOINLINE int mux_match_linear(const TableView tv, uint32_t method, const uint8_t* p, uint32_t n) {
     bool mismatch = false;
-    uint32_t nr = tv.hdr->n_routes;
+    uint32_t nr = tv.hdr()->n_routes;
     for (uint32_t r = 0; r < nr; r++) {
-        const RouteRec& R = tv.routes[r];
+        const RouteRec& R = tv.routes()[r];
         if (R.flags & RF_DEAD) continue;
         bool has_m = R.method != GOFR_M_ANY;
         bool m_ok = !has_m || (R.method == method && method != GOFR_M_OTHER);
@@ -736,14 +748,14 @@ GOFR_HD int mux_match(const TableView& tv, uint32_t method, const uint8_t* p, ui
     uint32_t h = n, nw = n >> 2, r4 = n & 3;
     for (uint32_t i = 0; i < nw; i++) h = path_hash_step(h, pw[i]);
     if (r4) h = path_hash_step(h, pw[nw] & (0xFFFFFFFFu >> (8 * (4 - r4))));
-    uint32_t lit = n ? tv.hash_tab[h >> (32 - tv.hdr->hash_bits)] : 0xFFFFu;
-    uint32_t ti = 0, nt = tv.hdr->n_tmpl;
+    uint32_t lit = n ? tv.hash_tab()[h >> (32 - tv.hdr()->hash_bits)] : 0xFFFFu;
+    uint32_t ti = 0, nt = tv.hdr()->n_tmpl;
     int a_last = -1;
     for (;;) {
-        uint32_t t = ti < nt ? tv.tmpl_list[ti] : 0xFFFFu;
+        uint32_t t = ti < nt ? tv.tmpl_list()[ti] : 0xFFFFu;
         uint32_t r = lit < t ? lit : t;
         if (r == 0xFFFFu) break;
-        const RouteRec& R = tv.routes[r];
+        const RouteRec& R = tv.routes()[r];
         bool p_ok;
         if (r == lit) {
             lit = R.next_lit;
@@ -758,7 +770,7 @@ GOFR_HD int mux_match(const TableView& tv, uint32_t method, const uint8_t* p, ui
         a_last = (int)r;
     }
     if (a_last < 0) return -1;
-    int lm = method < 16 && method != GOFR_M_OTHER ? (int)tv.last_method[method] - 1 : -1;
+    int lm = method < 16 && method != GOFR_M_OTHER ? (int)tv.last_method()[method] - 1 : -1;
     return lm > a_last ? -1 : -2;
 }
 
@@ -883,35 +895,32 @@ GOFR_HD_NOINLINE uint32_t emit_bind_error(Writer* w, const TableView tv, uint32_
 // ---------------------------------------------------------------------------------------------------------------
 // stage 1: route + handler kind → program
 // ---------------------------------------------------------------------------------------------------------------
-GOFR_HD void route_request(const TableView& tv, ReqCtx& c) {
-    const ImageHeader& H = *tv.hdr;
-    bool head = c.method == GOFR_M_HEAD;
-    c.route = GOFR_ROUTE_NONE;
-    c.pv_flags = 0;
-    c.slow_mask = 0;
-    c.def_off = c.def_len = 0;
+GOFR_HD void route_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
+    const ImageHeader& H = *tv.hdr();
+    bool head = c.method() == GOFR_M_HEAD;
     if (!path_is_clean(c.path, c.path_len)) {  // mux redirects before routing and before any middleware
         c.prog = head ? H.prog_301_head : H.prog_301;
         return;
     }
-    int m = mux_match(tv, c.method, c.path, c.path_len);
+    int m = mux_match(tv, c.method(), c.path, c.path_len);
     if (m == -2) { c.prog = head ? H.prog_405_head : H.prog_405; return; }
     if (m == -1) { c.prog = H.prog_404; return; }
     c.route = (uint32_t)m;
-    const RouteRec& R = tv.routes[m];
-    if (c.method == GOFR_M_OPTIONS) { c.prog = H.prog_options; return; }  // middleware/cors.go:10-13
+    const RouteRec& R = tv.routes()[m];
+    if (c.method() == GOFR_M_OPTIONS) { c.prog = H.prog_options; return; }  // middleware/cors.go:10-13
     c.prog = R.prog_ok;
     if (R.hkind == GOFR_H_PARAM_FORMAT) {
-        const ParamSpan ps = find_param(c.query, c.query_len, tv.lit_bytes(R.key_off), R.key_len);
+        const ParamSpan ps = find_param(c.query(), c.query_len, tv.lit_bytes(R.key_off), R.key_len);
         c.pv_off = ps.off; c.pv_len = ps.len; c.pv_flags = ps.flags;
         c.def_off = R.def_off;
         c.def_len = R.def_len;
     } else if (R.hkind == GOFR_H_BIND_ECHO) {
         // var v T; if err := c.Bind(&v); err != nil { return nil, err }; return v, nil
-        if (!bind_request(tv, R.schema, c.data, c.data_len, c.brow)) {
+        uint32_t* brow = c.brow(br);
+        if (!bind_request(tv, R.schema, c.data(), c.data_len, brow)) {
             // bodies nested deeper than the device scanner's 64-level stack are handed to the host like a
             // GOFR_H_HOST route (status 0) rather than answered differently from encoding/json (limit 10000)
-            c.prog = c.brow[0] == 4u /* BE_DEPTH */ ? 0xFFFFu : R.prog_err;
+            c.prog = brow[0] == 4u /* BE_DEPTH */ ? 0xFFFFu : R.prog_err;
         }
     }
 }
@@ -925,18 +934,18 @@ GOFR_HD void route_request(const TableView& tv, ReqCtx& c) {
 #define GOFR_SLOW_CALL(w, expr) do { Writer t_ = *(w); Writer* tw = &t_; (void)tw; expr; *(w) = t_; } while (0)
 
 template <bool EMIT>
-GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
-    const ProgRec P = tv.progs[c.prog];  // by value: the staging stores below must not force re-reads of the table
+GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Writer* w) {
+    const ProgRec P = tv.progs()[c.prog];  // by value: the staging stores below must not force re-reads of the table
     // the size pass visits only the ops whose length depends on the request
-    const Op* ops = tv.ops + (EMIT ? P.first_op : P.first_dyn);
+    const Op* ops = tv.ops() + (EMIT ? P.first_op : P.first_dyn);
     const uint32_t n_ops = EMIT ? P.n_ops : P.n_dyn;
-    const uint8_t* const lits = tv.lits;
-    const bool head = c.method == GOFR_M_HEAD;
-    const uint32_t* row = (P.flags & PF_BIND) ? c.brow : (const uint32_t*)c.data;
+    const uint8_t* const lits = tv.lits();
+    const bool head = c.method() == GOFR_M_HEAD;
+    const uint32_t* row = (P.flags & PF_BIND) ? c.brow(br) : (const uint32_t*)c.data();
     uint32_t str_cursor = 0;  // byte offset of the next string in the row's string area
     uint32_t str_base = 0;
     if ((P.flags & PF_NEEDS_ROW) && !(P.flags & PF_BIND)) {
-        const SchemaRec& S = tv.schemas[tv.routes[c.route].schema];
+        const SchemaRec& S = tv.schemas()[tv.routes()[c.route].schema];
         str_base = (uint32_t)S.fixed_words * 4;
         if (!EMIT && str_base > c.data_len) return false;
     }
@@ -955,7 +964,7 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
         bool cshared = true;            // literals live in the shared-memory copy of the table
         if (EMIT && code != OP_LIT && code != OP_KEY && code != OP_BLOB && olen)
             w->copy<true>(SrcMem<true>::from(lits + oaux), olen);  // literal prefix folded into this value op
-        if (EMIT && warp_any(w->wl >= 16)) w->flush();  // every non-copy action appends at most 16 words
+        if (EMIT && warp_any(w->wl >= GOFR_STAGE_WORDS - 8)) w->flush();  // every non-copy action appends at most 8 words
         if (code == OP_LIT) {
             if (!(governed && skip)) {
                 csrc = lits + ooff;
@@ -965,13 +974,13 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
         } else if (code == OP_STR) {
             const uint32_t len = row[ooff];
             if (!EMIT && (str_base + str_cursor + (uint64_t)len > c.data_len)) return false;
-            const uint8_t* sp = c.data + str_base + str_cursor;
+            const uint8_t* sp = c.data() + str_base + str_cursor;
             str_cursor += len;
             const uint32_t bit = str_bit;
             str_bit <<= 1;
             if (!(governed && skip)) {
                 if (!EMIT) {
-                    const bool esc = c.staged ? json_needs_escape<true>(SrcMem<true>::from(sp), len) : json_needs_escape<false>(sp, len);
+                    const bool esc = c.staged() ? json_needs_escape<true>(SrcMem<true>::from(sp), len) : json_needs_escape<false>(sp, len);
                     if (esc) { c.slow_mask |= bit; produced = json_escape_slow<false>(nullptr, sp, len); }
                     else produced = len;
                 } else if (c.slow_mask & bit) {
@@ -979,22 +988,22 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
                 } else {
                     csrc = sp;
                     clen = len;
-                    cshared = c.staged;
+                    cshared = c.staged();
                 }
             }
         } else if (code == OP_BSTR) {
             const uint32_t boff = row[ooff], lenw = row[ooff + 1], len = lenw & 0x7FFFFFFFu;
             if (!(governed && skip)) {
-                const uint8_t* sp = c.data + boff;
+                const uint8_t* sp = c.data() + boff;
                 if (lenw >> 31) {  // JSON escapes / non-ASCII in the request: decode and re-encode rune by rune
                     if (EMIT) GOFR_SLOW_CALL(w, bind_string_slow<true>(tw, sp, len));
                     else produced = bind_string_slow<false>(nullptr, sp, len);
-                } else { csrc = sp; clen = len; produced = len; cshared = c.staged; }
+                } else { csrc = sp; clen = len; produced = len; cshared = c.staged(); }
             }
         } else if (code == OP_ERRMSG) {
-            const uint32_t sidx = tv.routes[c.route].schema;
-            if (EMIT) GOFR_SLOW_CALL(w, emit_bind_error<true>(tw, tv, sidx, c.data, c.brow));
-            else produced = emit_bind_error<false>(nullptr, tv, sidx, c.data, c.brow);
+            const uint32_t sidx = tv.routes()[c.route].schema;
+            if (EMIT) GOFR_SLOW_CALL(w, emit_bind_error<true>(tw, tv, sidx, c.data(), c.brow(br)));
+            else produced = emit_bind_error<false>(nullptr, tv, sidx, c.data(), c.brow(br));
         } else if (code == OP_I64 || code == OP_I32) {
             if (!(governed && skip)) {
                 const int64_t v = code == OP_I64 ? (int64_t)((uint64_t)row[ooff] | (uint64_t)row[ooff + 1] << 32)
@@ -1010,7 +1019,8 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
         } else if (code == OP_HEXID) {
             if (EMIT) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) { uint32_t a, b; hex8(c.id[k], a, b); w->put4(a); w->put4(b); }
+                const uint32_t* idw = (const uint32_t*)(br.ids + (size_t)c.index * 16);  // loaded here, not carried
+                for (int k = 0; k < 4; k++) { uint32_t a, b; hex8(idw[k], a, b); w->put4(a); w->put4(b); }
             }
         } else if (code == OP_CLEN) {
             if (EMIT) emit_u32<true>(w, c.body_len);  // sized after the loop
@@ -1032,11 +1042,11 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
             }
         } else if (code == OP_PARAM) {
             if (c.pv_flags & 1) {
-                const uint8_t* v = c.query + c.pv_off;
+                const uint8_t* v = c.query() + c.pv_off;
                 if (c.pv_flags & 2) {
                     if (EMIT) GOFR_SLOW_CALL(w, emit_param_slow<true>(tw, v, c.pv_len));
                     else produced = emit_param_slow<false>(nullptr, v, c.pv_len);
-                } else { csrc = v; clen = c.pv_len; produced = c.pv_len; cshared = c.staged; }
+                } else { csrc = v; clen = c.pv_len; produced = c.pv_len; cshared = c.staged(); }
             } else {
                 csrc = lits + c.def_off;
                 clen = c.def_len;
@@ -1061,31 +1071,32 @@ GOFR_HD bool run_prog(const TableView& tv, ReqCtx& c, Writer* w) {
         uint32_t hl = P.hdr_fixed + hdr_dyn;
         if (P.flags & PF_HAS_CLEN) hl += emit_u32<false>(nullptr, c.body_len);
         c.total_len = hl + (head ? 0 : c.body_len);
-        c.status = P.status;
     }
     return true;
 }
 
 // Full size stage for one request: route, size; a malformed handler-result row is answered like a handler panic.
-GOFR_HD void size_request(const TableView& tv, ReqCtx& c) {
-    route_request(tv, c);
+GOFR_HD void size_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
+    route_request(tv, br, c);
     if (c.prog == 0xFFFF) {  // GOFR_H_HOST: nothing to emit, status 0 = pending on the host
         c.body_len = c.total_len = 0;
-        c.status = 0;
         return;
     }
-    if (!run_prog<false>(tv, c, nullptr)) {
-        c.prog = tv.hdr->prog_panic;
+    if (!run_prog<false>(tv, br, c, nullptr)) {
+        c.prog = tv.hdr()->prog_panic;
         c.slow_mask = 0;
-        run_prog<false>(tv, c, nullptr);
+        run_prog<false>(tv, br, c, nullptr);
     }
 }
 
-GOFR_HD void emit_request(const TableView& tv, ReqCtx& c, uint8_t* dst, uint32_t* ring_col) {
+// HTTP status of a sized request (0: GOFR_H_HOST, the closure runs on the host)
+GOFR_HD uint32_t request_status(const TableView& tv, const ReqCtx& c) { return c.prog == 0xFFFF ? 0u : tv.progs()[c.prog].status; }
+
+GOFR_HD void emit_request(const TableView& tv, const BatchRefs& br, ReqCtx& c, uint8_t* dst, uint32_t* ring_col) {
     if (c.total_len == 0) return;
     Writer w;
     w.init(dst, ring_col);
-    run_prog<true>(tv, c, &w);
+    run_prog<true>(tv, br, c, &w);
     w.finish();
 }
 

@@ -37,10 +37,10 @@ struct TileShared {
     uint32_t warp_lo[NW], warp_hi[NW];
     unsigned long long tile_base;
     uint32_t in_lo, in_hi;
-    uint32_t ring[32 * T];  // word-major staging buffer of the Writer (serve_device.cuh)
+    uint32_t ring[GOFR_STAGE_WORDS * T];  // word-major staging buffer of the Writer (serve_device.cuh)
 };
 
-__global__ void __launch_bounds__(T, 4) serve_kernel(const ServeParams p) {
+__global__ void __launch_bounds__(T, 5) serve_kernel(const ServeParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(16) TileShared sh;
 
@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(T, 4) serve_kernel(const ServeParams p) {
     __syncthreads();
     TableView tv;
     tv.bind(tbl, p.image);
+    BatchRefs br;
+    br.ids = (const uint8_t*)p.ids; br.bind_scratch = p.bind_scratch; br.bind_row_words = p.bind_row_words;
 
     uint32_t parity = 0;
     const unsigned long long chain0 = p.chain_pos ? (*p.chain_pos & 15ull) : 0ull;
@@ -73,11 +75,8 @@ __global__ void __launch_bounds__(T, 4) serve_kernel(const ServeParams p) {
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const uint32_t i = tile * T + tid;
         const bool valid = i < p.n;
-        uint4 d = make_uint4(0, 0, 0, 0), id = make_uint4(0, 0, 0, 0);
-        if (valid) {
-            d = __ldg((const uint4*)p.desc + i);
-            id = __ldg((const uint4*)p.ids + i);
-        }
+        uint4 d = make_uint4(0, 0, 0, 0);
+        if (valid) d = __ldg((const uint4*)p.desc + i);
         const uint32_t arena_off = d.x, path_len = d.y & 0xFFFFu, query_len = d.y >> 16, data_len = d.z;
         const uint32_t data_off = (arena_off + path_len + query_len + 3u) & ~3u;
         const uint32_t end = data_off + data_len;
@@ -116,17 +115,8 @@ __global__ void __launch_bounds__(T, 4) serve_kernel(const ServeParams p) {
 
         // ---- stage 1+2: route, size ----
         ReqCtx c;
-        c.path = abase + arena_off;
-        c.query = c.path + path_len;
-        c.data = abase + data_off;
-        c.path_len = path_len; c.query_len = query_len; c.data_len = data_len;
-        c.method = d.w & 0xFFu;
-        c.flags = (d.w >> 8) & 0xFFu;
-        c.id[0] = id.x; c.id[1] = id.y; c.id[2] = id.z; c.id[3] = id.w;
-        c.total_len = 0; c.body_len = 0; c.status = 0; c.route = GOFR_ROUTE_NONE; c.prog = 0xFFFF;
-        c.staged = in_staged ? 1u : 0u;
-        c.brow = p.bind_scratch + (size_t)i * p.bind_row_words;
-        if (valid) size_request(tv, c);
+        c.set(abase, arena_off, path_len, query_len, data_len, d.w & 0xFFu, (d.w >> 8) & 0xFFu, in_staged, i);
+        if (valid) size_request(tv, br, c);
 
         // ---- block scan of response sizes ----
         uint32_t incl = c.total_len;
@@ -148,7 +138,8 @@ __global__ void __launch_bounds__(T, 4) serve_kernel(const ServeParams p) {
 
         // ---- chain tiles (warp 0) ----
         if (warp == 0) {
-            unsigned long long base = lookback(p.tile_state, p.epoch, tile, tile_total, lane);
+            unsigned long long base = (p.debug_flags & 1u) ? (unsigned long long)tile * tile_total
+                                                           : lookback(p.tile_state, p.epoch, tile, tile_total, lane);
             if (lane == 0) sh.tile_base = base;
         }
         __syncthreads();
@@ -158,12 +149,12 @@ __global__ void __launch_bounds__(T, 4) serve_kernel(const ServeParams p) {
         if (!fits && tid == 0) atomicExch(p.overflow, 1u);
         if (valid) {
             p.out_off[i] = (uint32_t)(tile_base + excl);
-            p.meta[i] = c.status | (c.route << 16);
+            p.meta[i] = request_status(tv, c) | (c.route << 16);
             if (i == p.n - 1) p.out_off[p.n] = (uint32_t)(tile_base + excl + c.total_len);
         }
 
         // ---- stage 3: emit straight to HBM in 16-byte chunks ----
-        if (fits && valid && c.total_len) emit_request(tv, c, p.out + tile_base + excl, &sh.ring[tid]);
+        if (fits && valid && c.total_len) emit_request(tv, br, c, p.out + tile_base + excl, &sh.ring[tid]);
         // the next iteration's first __syncthreads orders this tile's shared-memory reads before any overwrite
     }
 }

@@ -25,34 +25,28 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
     patch_dates((uint8_t*)hot.data(), (const uint8_t*)date29, 0, 1);
     TableView tv;
     tv.bind((const uint8_t*)hot.data(), image);
-    uint32_t ring[32];
+    uint32_t ring[GOFR_STAGE_WORDS];
     std::vector<uint32_t> bind_scratch((size_t)H.bind_row_words + 8);
+    BatchRefs br;
+    br.bind_scratch = bind_scratch.data(); br.bind_row_words = H.bind_row_words; br.ids = ids;
     uint64_t pos = start_misalign;  // lets the test exercise every head alignment
     for (uint32_t i = 0; i < n; i++) {
         uint32_t d[4];
         memcpy(d, desc + (size_t)i * 16, 16);
         ReqCtx c;
         uint32_t arena_off = d[0], path_len = d[1] & 0xFFFF, query_len = d[1] >> 16, data_len = d[2];
-        uint32_t data_off = (arena_off + path_len + query_len + 3u) & ~3u;
-        c.path = arena + arena_off;
-        c.query = c.path + path_len;
-        c.data = arena + data_off;
-        c.path_len = path_len; c.query_len = query_len; c.data_len = data_len;
-        c.method = d[3] & 0xFF;
-        c.flags = (d[3] >> 8) & 0xFF;
-        memcpy(c.id, ids + (size_t)i * 16, 16);
-        c.total_len = c.body_len = 0; c.status = 0; c.route = GOFR_ROUTE_NONE; c.prog = 0xFFFF;
-        c.staged = (i & 1);  // alternate so both source policies are exercised
-        c.brow = bind_scratch.data();
-        size_request(tv, c);
+        // alternate the "staged" flag so both source policies of the Writer are exercised
+        c.set(arena, arena_off, path_len, query_len, data_len, d[3] & 0xFF, (d[3] >> 8) & 0xFF, (i & 1) != 0, 0);
+        br.ids = ids + (size_t)i * 16;  // index 0 of a one-request view
+        size_request(tv, br, c);
         if (c.prog != 0xFFFF && path_is_clean(c.path, c.path_len)) {  // both matchers must always agree
-            int a = mux_match(tv, c.method, c.path, c.path_len), b = mux_match_linear(tv, c.method, c.path, c.path_len);
+            int a = mux_match(tv, c.method(), c.path, c.path_len), b = mux_match_linear(tv, c.method(), c.path, c.path_len);
             if (a != b) return -2;
         }
         out_off[i] = (uint32_t)pos;
-        meta[i] = c.status | (c.route << 16);
+        meta[i] = request_status(tv, c) | (c.route << 16);
         if (pos + c.total_len > out_cap) return -1;
-        emit_request(tv, c, out + pos, ring);
+        emit_request(tv, br, c, out + pos, ring);
         pos += c.total_len;
     }
     out_off[n] = (uint32_t)pos;
@@ -64,7 +58,7 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
 
 extern "C" int emu_grpc_hello(const uint8_t* in, const uint32_t* in_off, uint32_t n, uint8_t* out, uint64_t out_cap,
                               uint32_t* out_off, uint32_t* meta, uint32_t start_misalign) {
-    uint32_t stage[32];
+    uint32_t stage[GOFR_STAGE_WORDS];
     uint64_t pos = start_misalign;
     for (uint32_t i = 0; i < n; i++) {
         const uint8_t* f = in + in_off[i];
