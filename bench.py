@@ -46,6 +46,21 @@ def hbm_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one serve_kernel launch on this exact workload (1 Mi requests),
+    from the committed `ncu --set full` capture (profiles/r01/serve_kernel_final_1M_key_metrics.txt)."""
+    try:
+        tot = 0.0
+        with open(os.path.join(ROOT, "profiles", "r01", "serve_kernel_final_1M_key_metrics.txt")) as f:
+            for ln in f:
+                p = ln.split()
+                if p and p[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(p[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[p[1]]
+        return tot or None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks and throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -150,6 +165,68 @@ def workload_config(n, gpus, where):
             "l2": "inputs+outputs per step (~0.8 GB) exceed the 126 MB L2"}
 
 
+def run_secondary(args):
+    """Resident-only measurements of the other BASELINE configs (1 GPU): kernel time per launch and requests/s."""
+    import torch
+    from gofr_b200 import _abi
+    from gofr_b200.engine import Engine
+    from gofr_b200.table import Table
+    from tests import oracle as O
+    date = S.http_date(DATE_UNIX)
+    w = args.workload
+    n = {"config3": 65536, "config4": 262144, "config5": 1 << 20}[w] if args.requests == (1 << 20) and w != "config5" else args.requests
+    if w == "config5":
+        frames, off = synth.config5_frames(n)
+        eng = Engine(Table(synth.config1_spec()), 0)
+        d_in = torch.from_numpy(np.concatenate([frames, np.zeros(64, np.uint8)])).cuda()
+        d_off = torch.from_numpy(off.view(np.int32)).cuda()
+        cap = int(frames.size) + 40 * n
+        d_out = torch.zeros(cap + 64, dtype=torch.uint8, device="cuda")
+        d_ooff = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+        d_meta = torch.zeros(n, dtype=torch.int32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+
+        def step():
+            _abi.check(_abi.lib().gofr_grpc_hello_device(eng._e, d_in.data_ptr(), d_off.data_ptr(), n, d_out.data_ptr(), cap,
+                                                         d_ooff.data_ptr(), d_meta.data_ptr(), st), "grpc")
+        in_bytes = int(off[n]) + 4 * (n + 1)
+        get_out = lambda: int(d_ooff[n].item())
+    else:
+        spec, batch = {"config3": (synth.config3_spec(), lambda: synth.config3_batch(n)),
+                       "config4": (synth.config4_spec(), lambda: synth.config4_batch(n))}[w]
+        batch = batch()
+        eng = Engine(Table(spec), 0)
+        db = eng.upload(batch)
+        o1, f1, _ = O.OracleTable(spec).serve(batch, date)
+        resp = eng.alloc_responses(n, int(f1[n]) + 4096)
+
+        def step():
+            eng.serve_device(db, date, resp)
+        in_bytes = batch.input_bytes()
+        get_out = lambda: int(resp.out_off[n].item())
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    eng.kernel_time_ms(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    kms, kl = eng.kernel_time_ms(reset=True)
+    out_bytes = get_out()
+    algo = in_bytes + out_bytes + 8 * n
+    peak, src = hbm_peak()
+    print(json.dumps({"metric": "requests_per_sec", "workload": w, "value": n / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": ms, "requests": n, "out_bytes": out_bytes, "data": "synthetic",
+                      "roofline": {"bound": "hbm", "achieved": algo / (kms / kl / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": algo / (kms / kl / 1e3) / 1e9 / peak, "algorithmic_bytes_per_request": algo / n,
+                                   "kernel_ms_per_launch": kms / kl}}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -162,6 +239,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer measurement (default: --steps)")
     ap.add_argument("--chunk", type=int, default=65536)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"],
+                    help="config2 is the BASELINE metric line; the others are secondary measurements (resident only)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -174,6 +253,8 @@ def main():
     from gofr_b200.table import Table
 
     rank, world, local = dist_env()
+    if args.workload != "config2":
+        return run_secondary(args)
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device: gofr_b200 has no CPU path"}))
         return 2
@@ -298,7 +379,7 @@ def main():
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic", "config": workload_config(n, world, "gpu"),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                             "traffic": profiled_traffic() if n == (1 << 20) else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                              "algorithmic_bytes_per_request": algo_bytes / n, "kernel_ms_per_launch": per_launch_ms,
                              "kernel": "gofr::serve_kernel"},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
