@@ -97,11 +97,13 @@ GOFR_HD bool warp_any(bool p) {
 #if defined(__CUDA_ARCH__)
 typedef uint32_t saddr_t;
 GOFR_HD saddr_t to_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-// staging buffer accesses are read-after-write on the same addresses: keep them ordered
-GOFR_HD void stg_st(saddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// Staging buffer accesses are read-after-write on the same addresses: `volatile` keeps them ordered among themselves.
+// No "memory" clobber: nothing else ever touches the staging buffer, and a clobber would force every table value to be
+// re-read after each store and forbid overlapping the next loads with these stores.
+GOFR_HD void stg_st(saddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
 GOFR_HD uint32_t stg_ld(saddr_t a) {
     uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 // sources are read-only while a response is being written: let the compiler schedule these freely
