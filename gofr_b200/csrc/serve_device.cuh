@@ -667,7 +667,9 @@ GOFR_HD bool words_equal(const uint32_t* a, const uint32_t* b, uint32_t n) {
 
 // Anchored leftmost-first match of lit0 var0 lit1 var1 ... litN [$]: greedy variables with backtracking — what Go's
 // regexp reports for the regexp mux builds from a path template.
-GOFR_HD_NOINLINE bool template_match(const TableView tv, const RouteRec R, const uint8_t* p, uint32_t n) {
+// want_var >= 0: also report the span captured by that piece's variable (mux.Vars) in span_out[0..1] = (offset, length)
+GOFR_HD_NOINLINE bool template_match(const TableView tv, const RouteRec R, const uint8_t* p, uint32_t n, int want_var = -1,
+                                     uint32_t* span_out = nullptr) {
     const PieceRec* pc = tv.pieces() + R.first_piece;
     uint32_t np = R.n_pieces;
     bool prefix = R.flags & RF_PREFIX;
@@ -679,7 +681,10 @@ GOFR_HD_NOINLINE bool template_match(const TableView tv, const RouteRec R, const
         if (ok) {
             pos += pc[k].lit_len;
             if (!pc[k].has_var) {
-                if (prefix || pos == n) return true;
+                if (prefix || pos == n) {
+                    if (want_var >= 0) { span_out[0] = start[want_var]; span_out[1] = take[want_var]; }
+                    return true;
+                }
                 ok = false;
             } else {
                 uint32_t run = 0;
@@ -916,6 +921,16 @@ GOFR_HD void route_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) 
         c.pv_off = ps.off; c.pv_len = ps.len; c.pv_flags = ps.flags;
         c.def_off = R.def_off;
         c.def_len = R.def_len;
+    } else if (R.hkind == GOFR_H_PATHPARAM_FORMAT) {
+        // v := c.PathParam(name): the variable's span from the match (pkg/gofr/http/request.go:36-38)
+        uint32_t sp[2] = {0, 0};
+        if (R.key_len != 0xFFFF && template_match(tv, R, c.path, c.path_len, (int)R.key_len, sp) && sp[1]) {
+            c.pv_off = sp[0];
+            c.pv_len = sp[1];
+            c.pv_flags = 1u | 4u | (json_needs_escape<false>(c.path + sp[0], sp[1]) ? 2u : 0u);  // bit2: source is the path
+        }
+        c.def_off = R.def_off;
+        c.def_len = 0;
     } else if (R.hkind == GOFR_H_BIND_ECHO) {
         // var v T; if err := c.Bind(&v); err != nil { return nil, err }; return v, nil
         uint32_t* brow = c.brow(br);
@@ -1044,9 +1059,13 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
             }
         } else if (code == OP_PARAM) {
             if (c.pv_flags & 1) {
-                const uint8_t* v = c.query() + c.pv_off;
+                const bool from_path = c.pv_flags & 4;  // PathParam: already decoded, no query unescaping
+                const uint8_t* v = (from_path ? c.path : c.query()) + c.pv_off;
                 if (c.pv_flags & 2) {
-                    if (EMIT) GOFR_SLOW_CALL(w, emit_param_slow<true>(tw, v, c.pv_len));
+                    if (from_path) {
+                        if (EMIT) GOFR_SLOW_CALL(w, json_escape_slow<true>(tw, v, c.pv_len));
+                        else produced = json_escape_slow<false>(nullptr, v, c.pv_len);
+                    } else if (EMIT) GOFR_SLOW_CALL(w, emit_param_slow<true>(tw, v, c.pv_len));
                     else produced = emit_param_slow<false>(nullptr, v, c.pv_len);
                 } else { csrc = v; clen = c.pv_len; produced = c.pv_len; cshared = c.staged(); }
             } else {

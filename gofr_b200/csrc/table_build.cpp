@@ -148,6 +148,7 @@ static std::string sniff_content_type(const std::string& blob) {
 
 struct Piece {
     std::string lit;
+    std::string name;  // variable name (mux.Vars key)
     bool has_var = false;
     uint32_t cls[8] = {0};
     int min_rep = 1;
@@ -283,6 +284,8 @@ static int parse_template(const std::string& tpl, std::vector<Piece>& out) {
         std::string name = colon == std::string::npos ? body : body.substr(0, colon);
         if (name.empty()) return -1;
         pc.has_var = true;
+        pc.name = name;
+        for (auto& prev : out) if (prev.has_var && prev.name == name) return -1;  // mux: duplicated route variable
         if (colon == std::string::npos) {
             for (auto& w : pc.cls) w = 0xFFFFFFFFu;
             pc.cls['/' >> 5] &= ~(1u << ('/' & 31));
@@ -579,6 +582,7 @@ int seal_table(gofr_table* t) {
                 prog_ok[ri] = b.json_prog(404, {lit("{\"error\":{\"message\":\"http: no such file\"}}\n", true)});
                 break;
             case GOFR_H_PANIC: prog_ok[ri] = ppanic; break;
+            case GOFR_H_PATHPARAM_FORMAT:
             case GOFR_H_PARAM_FORMAT: {
                 if (!valid_utf8(r.s[2]) || !valid_utf8(r.s[3])) {
                     set_last_error("route %s: format prefix/suffix must be valid UTF-8", r.pattern.c_str());
@@ -668,6 +672,14 @@ int seal_table(gofr_table* t) {
             P.min_rep = (uint8_t)pc.min_rep;
             memcpy(P.cls, pc.cls, sizeof P.cls);
             pieces.push_back(P);
+        }
+        if (r.hkind == GOFR_H_PATHPARAM_FORMAT) {
+            // mux.Vars(r)[s0]: resolved to the piece index of the variable; an unknown name always yields ""
+            R.key_len = 0xFFFF;
+            for (size_t k = 0; k < r.pieces.size(); k++)
+                if (r.pieces[k].has_var && r.pieces[k].name == r.s[0]) R.key_len = (uint16_t)k;
+            R.def_off = pool.put("");
+            R.def_len = 0;
         }
         if (r.hkind == GOFR_H_PARAM_FORMAT) {
             R.key_off = pool.put(r.s[0]);

@@ -23,7 +23,7 @@ FRAME_WIRE, FRAME_INTENDED, FRAME_BODY = 0, 1, 2
 
 # handler kinds
 (H_HOST, H_STATIC_STRING, H_STATIC_ERROR, H_NIL, H_PARAM_FORMAT, H_ROW, H_BIND_ECHO, H_HEALTH, H_MISSING_FILE, H_FILE,
- H_PANIC) = range(11)
+ H_PANIC, H_PATHPARAM_FORMAT) = range(12)
 
 # field kinds
 F_INT64, F_INT32, F_BOOL, F_STRING, F_INT = 1, 2, 3, 4, 5

@@ -86,7 +86,8 @@ enum {
     GOFR_H_HEALTH = 7,        /* healthHandler with no datasources: map{} handler.go:38-40, container.go:26-38 */
     GOFR_H_MISSING_FILE = 8,  /* catchAllHandler: return nil, http.ErrMissingFile      handler.go:51-53 */
     GOFR_H_FILE = 9,          /* return response.File{Content: blob, ContentType: s0}   handler.go:42-49 */
-    GOFR_H_PANIC = 10         /* handler panics; middleware.panicRecovery answers       middleware/logger.go:91-114 */
+    GOFR_H_PANIC = 10,        /* handler panics; middleware.panicRecovery answers       middleware/logger.go:91-114 */
+    GOFR_H_PATHPARAM_FORMAT = 11 /* v := c.PathParam(s0); return s2 + v + s3, nil          pkg/gofr/http/request.go:36-38 */
 };
 
 /* ---- struct field kinds for response / Bind schemas ---- */

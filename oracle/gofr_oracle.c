@@ -32,7 +32,7 @@ enum { M_ANY = 255 };
 enum { FRAME_WIRE = 0, FRAME_INTENDED = 1, FRAME_BODY = 2 };
 enum {
     H_HOST = 0, H_STATIC_STRING = 1, H_STATIC_ERROR = 2, H_NIL = 3, H_PARAM_FORMAT = 4, H_ROW = 5, H_BIND_ECHO = 6,
-    H_HEALTH = 7, H_MISSING_FILE = 8, H_FILE = 9, H_PANIC = 10
+    H_HEALTH = 7, H_MISSING_FILE = 8, H_FILE = 9, H_PANIC = 10, H_PATHPARAM_FORMAT = 11
 };
 
 /* one piece of a mux path template: a literal followed (optionally) by a variable */
@@ -40,6 +40,7 @@ typedef struct {
     uint8_t* lit;
     int lit_len;
     int has_var;
+    char* name;      /* variable name (mux.Vars key) */
     uint8_t cls[32]; /* 256-bit membership of the variable's character class */
     int min_rep;     /* 1 for '+', 0 for '*' */
 } tpl_piece;
@@ -88,7 +89,7 @@ void orc_table_free(orc_table* t) {
     if (!t) return;
     for (int i = 0; i < t->n_routes; i++) {
         orc_route* r = &t->routes[i];
-        for (int k = 0; k < r->n_pieces; k++) free(r->pieces[k].lit);
+        for (int k = 0; k < r->n_pieces; k++) { free(r->pieces[k].lit); free(r->pieces[k].name); }
         free(r->pieces);
         for (int k = 0; k < 4; k++) free(r->s[k]);
         free(r->blob);
@@ -224,6 +225,10 @@ static int parse_template(orc_route* r, const char* tpl, int n) {
         int name_len = colon < 0 ? bl : colon;
         if (name_len == 0) return -2; /* mux: missing name → route error */
         pc->has_var = 1;
+        pc->name = (char*)calloc((size_t)name_len + 1, 1);
+        memcpy(pc->name, body, (size_t)name_len);
+        for (int q = 0; q + 1 < r->n_pieces; q++) /* mux: "duplicated route variable" → route error */
+            if (r->pieces[q].has_var && strcmp(r->pieces[q].name, pc->name) == 0) return -2;
         if (colon < 0) {
             memset(pc->cls, 0xFF, 32);
             pc->cls['/' >> 3] &= (uint8_t)~(1u << ('/' & 7));
@@ -484,7 +489,8 @@ static void query_get(const uint8_t* q, size_t qn, const uint8_t* key, size_t kn
 
 /* Anchored leftmost-first match of lit0 (var0 lit1 (var1 ...)) [$]: greedy variables with backtracking, which is
  * what Go's regexp reports for this shape. */
-static int tpl_match_from(const orc_route* r, int k, const uint8_t* p, size_t n, size_t pos) {
+typedef struct { size_t off, len; } var_span;
+static int tpl_match_from(const orc_route* r, int k, const uint8_t* p, size_t n, size_t pos, var_span* spans) {
     const tpl_piece* pc = &r->pieces[k];
     if (n - pos < (size_t)pc->lit_len || memcmp(p + pos, pc->lit, (size_t)pc->lit_len) != 0) return 0;
     pos += (size_t)pc->lit_len;
@@ -493,8 +499,10 @@ static int tpl_match_from(const orc_route* r, int k, const uint8_t* p, size_t n,
     while (pos + run < n && cls_has(pc->cls, p[pos + run])) run++;
     for (size_t take = run;; take--) {
         if (take >= (size_t)pc->min_rep) {
-            if (k + 1 < r->n_pieces) { if (tpl_match_from(r, k + 1, p, n, pos + take)) return 1; }
-            else if (r->prefix || pos + take == n) return 1;
+            int ok = 0;
+            if (k + 1 < r->n_pieces) ok = tpl_match_from(r, k + 1, p, n, pos + take, spans);
+            else ok = r->prefix || pos + take == n;
+            if (ok) { if (spans) { spans[k].off = pos; spans[k].len = take; } return 1; }
         }
         if (take == 0) break;
     }
@@ -504,7 +512,7 @@ static int tpl_match_from(const orc_route* r, int k, const uint8_t* p, size_t n,
 static int path_matches(const orc_route* r, const uint8_t* p, size_t n) {
     if (r->n_pieces == 0) return 0;
     /* a template ending in a variable has a trailing empty literal piece; one ending in a literal has has_var=0 */
-    return tpl_match_from(r, 0, p, n, 0);
+    return tpl_match_from(r, 0, p, n, 0, NULL);
 }
 
 enum { MATCH_404 = -1, MATCH_405 = -2, MATCH_301 = -3 };
@@ -884,6 +892,20 @@ static void serve_one(const orc_table* t, const req_desc* d, const uint8_t* id16
                 ob_put(&tmp2, r->s[2], (size_t)r->sl[2]);
                 if (tmp.n == 0) ob_put(&tmp2, r->s[1], (size_t)r->sl[1]);
                 else ob_put(&tmp2, tmp.p, tmp.n);
+                ob_put(&tmp2, r->s[3], (size_t)r->sl[3]);
+                hr.data_kind = 1; hr.str = tmp2.p; hr.str_len = tmp2.n;
+                break;
+            }
+            case H_PATHPARAM_FORMAT: {
+                /* v := c.PathParam(s0) — mux.Vars(r)[s0], "" when the route has no such variable (request.go:36-38) */
+                var_span spans[64];
+                memset(spans, 0, sizeof spans);
+                tpl_match_from(r, 0, path, pn, 0, spans);
+                ob_put(&tmp2, r->s[2], (size_t)r->sl[2]);
+                for (int k = 0; k < r->n_pieces; k++)
+                    if (r->pieces[k].has_var && strlen(r->pieces[k].name) == (size_t)r->sl[0] &&
+                        memcmp(r->pieces[k].name, r->s[0], (size_t)r->sl[0]) == 0)
+                        ob_put(&tmp2, path + spans[k].off, spans[k].len);
                 ob_put(&tmp2, r->s[3], (size_t)r->sl[3]);
                 hr.data_kind = 1; hr.str = tmp2.p; hr.str_len = tmp2.n;
                 break;

@@ -138,3 +138,24 @@ def test_random_paths_property(paths):
     spec = S.TableSpec(routes=[S.Route(S.M_GET, "/a", S.H_NIL), S.Route(S.M_GET, "/a/{x}", S.H_NIL),
                                S.Route(S.M_GET, "/{y}/b/", S.H_NIL)])
     _compare(spec, S.RequestBatch.pack([S.Req(S.M_GET, p.encode()) for p in paths]), 1)
+
+
+def test_path_params():
+    """Request.PathParam (pkg/gofr/http/request.go:36-38): spans captured by mux's template regexp, leftmost-first."""
+    spec = S.TableSpec(routes=[
+        S.Route(S.M_GET, "/users/{id}", S.H_PATHPARAM_FORMAT, s0=b"id", s2=b"user ", s3=b"!"),
+        S.Route(S.M_GET, "/f/{name}.json", S.H_PATHPARAM_FORMAT, s0=b"name", s2=b"", s3=b""),
+        S.Route(S.M_GET, "/x/{a}-{b}/y", S.H_PATHPARAM_FORMAT, s0=b"b", s2=b"b=", s3=b""),
+        S.Route(S.M_GET, "/x2/{a}-{b}/y", S.H_PATHPARAM_FORMAT, s0=b"a", s2=b"a=", s3=b""),
+        S.Route(S.M_GET, "/w/{rest:.*}", S.H_PATHPARAM_FORMAT, s0=b"rest", s2=b"[", s3=b"]"),
+        S.Route(S.M_GET, "/n/{id:[0-9]+}/p", S.H_PATHPARAM_FORMAT, s0=b"nosuch", s2=b"<", s3=b">"),
+        S.Route(S.M_GET, "/d/{v}/{v}", S.H_PATHPARAM_FORMAT, s0=b"v", s2=b"", s3=b""),   # duplicated variable: dead route
+    ])
+    paths = [b"/users/42", b"/users/a\"b<c", b"/users/\xc3\xa9", b"/users/\xff", b"/users/", b"/f/x.json", b"/f/a.json.json",
+             b"/x/1-2-3/y", b"/x2/1-2-3/y", b"/x/-/y", b"/w/", b"/w/a/b/c", b"/n/77/p", b"/d/1/1", b"/users/a b", b"/users/" + b"z" * 300]
+    for mis in range(4):
+        r = _compare(spec, S.RequestBatch.pack([S.Req(S.M_GET, p) for p in paths]), mis)
+    assert r[0].endswith(b'{"data":"user 42!"}\n') and r[6].endswith(b'{"data":"a.json"}\n')
+    assert r[7].endswith(b'{"data":"b=3"}\n') and r[8].endswith(b'{"data":"a=1-2"}\n')   # greedy first variable
+    assert r[11].endswith(b'{"data":"[a/b/c]"}\n') and r[12].endswith(b'{"data":"\\u003c\\u003e"}\n')
+    assert b" 404 " in r[13][:20]

@@ -202,3 +202,12 @@ def test_shards_concatenate_to_the_unsharded_result(torch_cuda):
         out, off, _ = resp.to_host()
         parts.append(out[:int(off[sh.n])])
     assert np.array_equal(np.concatenate(parts), o1[:int(f1[-1])])
+
+
+def test_path_params(torch_cuda):
+    spec = S.TableSpec(routes=[
+        S.Route(S.M_GET, "/users/{id}", S.H_PATHPARAM_FORMAT, s0=b"id", s2=b"user ", s3=b"!"),
+        S.Route(S.M_GET, "/x/{a}-{b}/y", S.H_PATHPARAM_FORMAT, s0=b"b", s2=b"b=", s3=b""),
+        S.Route(S.M_GET, "/w/{rest:.*}", S.H_PATHPARAM_FORMAT, s0=b"rest", s2=b"[", s3=b"]")])
+    paths = [b"/users/42", b"/users/a\"b<c", b"/users/\xc3\xa9", b"/users/\xff", b"/x/1-2-3/y", b"/w/a/b/c", b"/w/", b"/nope"]
+    _check(spec, S.RequestBatch.pack([S.Req(S.M_GET, paths[i % len(paths)]) for i in range(5000)]))
