@@ -85,7 +85,7 @@ def lib():
     L.gofr_batch_submit.argtypes = [vp, C.POINTER(ReqBatch), C.POINTER(RespBatch), C.POINTER(u64)]
     L.gofr_batch_wait.argtypes = [vp, u64]
     L.gofr_engine_set_chunk.argtypes = [vp, u32]
-    L.gofr_engine_set_tile.argtypes = [vp, u32, u32]
+    L.gofr_engine_set_tile.argtypes = [vp, u32]
     L.gofr_engine_set_timing.argtypes = [vp, i32]
     L.gofr_engine_overflowed.argtypes = [vp, C.POINTER(i32), i32]
     L.gofr_engine_geometry.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]

@@ -68,7 +68,7 @@ struct gofr_engine {
     uint8_t* d_image = nullptr;
     uint32_t image_bytes = 0;
     // launch geometry
-    uint32_t in_cap = 0, out_stage_cap = 0, smem_bytes = 0;
+    uint32_t in_cap = 0, smem_bytes = 0;
     int grid = 0, blocks_per_sm = 0, grpc_grid = 0;
     uint32_t epoch = 0;
     // resident path scratch
@@ -95,14 +95,14 @@ struct gofr_engine {
     double timed_ms = 0;
     uint64_t timed_launches = 0;
     // tickets
-    struct Pending { gofr_resp_batch* out; int rc; bool open; };
-    std::vector<Pending> pending;
+    // tickets of finished submits whose result has not been collected yet (submit completes the batch; wait reports)
+    std::vector<std::pair<gofr_ticket, int>> done_tickets;
+    gofr_ticket next_ticket = 1;
 };
 
-static int configure_geometry(gofr_engine* e, uint32_t in_per_req, uint32_t out_per_req) {
+static int configure_geometry(gofr_engine* e, uint32_t in_per_req) {
     e->in_cap = (kServeThreads * in_per_req + 127u) & ~127u;
-    e->out_stage_cap = (kServeThreads * out_per_req + 127u) & ~127u;
-    e->smem_bytes = serve_smem_bytes(e->hdr.hot_bytes, e->in_cap, e->out_stage_cap);
+    e->smem_bytes = serve_smem_bytes(e->hdr.hot_bytes, e->in_cap);
     if (e->smem_bytes > 227 * 1024) { set_last_error("tile geometry needs %u bytes of shared memory", e->smem_bytes); return GOFR_ERR_CAPACITY; }
     int g = serve_max_grid(e->smem_bytes, e->device, &e->blocks_per_sm);
     if (g <= 0) { set_last_error("serve kernel cannot be resident with %u bytes of shared memory", e->smem_bytes); return GOFR_ERR_CUDA; }
@@ -143,7 +143,7 @@ int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
     uint32_t hot = (e->hdr.hot_bytes + 127u) & ~127u;
     uint32_t in_per = per_cta > hot + 64u * kServeThreads ? ((per_cta - hot - 64u) / kServeThreads) & ~15u : 64u;
     if (in_per > 256u) in_per = 256u;
-    int rc = configure_geometry(e, in_per, 0);
+    int rc = configure_geometry(e, in_per);
     if (rc != GOFR_OK) { delete e; return rc; }
     for (auto& s : e->slots) {
         CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -190,10 +190,10 @@ void gofr_engine_destroy(gofr_engine* e) {
     delete e;
 }
 
-int gofr_engine_set_tile(gofr_engine* e, uint32_t in_bytes_per_req, uint32_t out_bytes_per_req) {
+int gofr_engine_set_tile(gofr_engine* e, uint32_t in_bytes_per_req) {
     if (!e || !in_bytes_per_req) return GOFR_ERR_INVALID;
     std::lock_guard<std::mutex> g(e->mu);
-    return configure_geometry(e, in_bytes_per_req, out_bytes_per_req);
+    return configure_geometry(e, in_bytes_per_req);
 }
 
 int gofr_engine_set_chunk(gofr_engine* e, uint32_t requests_per_chunk) {
@@ -220,7 +220,7 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
     p.epoch = e->epoch;
     p.out = d_out; p.out_cap = out_cap; p.out_off = d_off; p.meta = d_meta;
     p.tile_state = d_state; p.overflow = d_flag;
-    p.in_cap = e->in_cap; p.out_stage_cap = e->out_stage_cap;
+    p.in_cap = e->in_cap;
     p.bind_scratch = d_bind; p.bind_row_words = e->hdr.bind_row_words;
     p.chain_pos = chain_pos;
     if (getenv("GOFR_DEBUG_NO_LOOKBACK")) p.debug_flags |= 1u;  // diagnostic only
@@ -458,8 +458,8 @@ int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch*
         if (e->h_status[1]) { final_rc = GOFR_ERR_CAPACITY; set_last_error("output capacity too small (device chunk buffer or caller buffer)"); }
         out->out_off[n] = (uint32_t)total;
         out->out_bytes = total;
-        e->pending.push_back({out, final_rc, true});
-        *ticket = e->pending.size();
+        *ticket = e->next_ticket++;
+        e->done_tickets.emplace_back(*ticket, final_rc);
         return GOFR_OK;
     }
 
@@ -534,17 +534,21 @@ int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch*
     }
     out->out_off[n] = (uint32_t)write_pos;
     out->out_bytes = write_pos;
-    e->pending.push_back({out, final_rc, true});
-    *ticket = e->pending.size();
+    *ticket = e->next_ticket++;
+    e->done_tickets.emplace_back(*ticket, final_rc);
     return GOFR_OK;
 }
 
 int gofr_batch_wait(gofr_engine* e, gofr_ticket ticket) {
     if (!e || ticket == 0) return GOFR_ERR_INVALID;
     std::lock_guard<std::mutex> g(e->mu);
-    if (ticket > e->pending.size() || !e->pending[ticket - 1].open) return GOFR_ERR_INVALID;
-    e->pending[ticket - 1].open = false;
-    return e->pending[ticket - 1].rc;
+    for (size_t k = 0; k < e->done_tickets.size(); k++) {
+        if (e->done_tickets[k].first != ticket) continue;
+        int rc = e->done_tickets[k].second;
+        e->done_tickets.erase(e->done_tickets.begin() + (long)k);
+        return rc;
+    }
+    return GOFR_ERR_INVALID;  // unknown ticket, or already waited for
 }
 
 void* gofr_alloc_pinned(size_t bytes) {

@@ -28,7 +28,6 @@ struct ServeParams {
     unsigned long long* tile_state;  // n_tiles
     uint32_t* overflow;      // set to 1 if out_cap was too small
     uint32_t in_cap;         // shared-memory staging capacity for request bytes (multiple of 16)
-    uint32_t out_stage_cap;  // shared-memory staging capacity for response bytes (multiple of 16)
     uint32_t date[8];        // 29-byte IMF-fixdate, zero padded
     uint32_t* bind_scratch;  // n * bind_row_words words (tables with GOFR_H_BIND_ECHO routes), else null
     uint32_t bind_row_words;
@@ -40,8 +39,8 @@ struct ServeParams {
 
 constexpr int kServeThreads = 128;  // requests per tile = threads per CTA
 
-// Returns dynamic shared memory bytes needed for (hot_bytes, in_cap, out_stage_cap).
-uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap, uint32_t out_stage_cap);
+// Returns dynamic shared memory bytes needed for the table's hot part plus the request-byte staging area.
+uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap);
 // cudaError_t as int
 int launch_serve(const ServeParams& p, int grid, uint32_t smem_bytes, void* stream);
 int serve_max_grid(uint32_t smem_bytes, int device, int* blocks_per_sm);

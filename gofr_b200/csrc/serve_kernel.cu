@@ -159,8 +159,7 @@ __global__ void __launch_bounds__(T, 5) serve_kernel(const ServeParams p) {
     }
 }
 
-uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap, uint32_t out_stage_cap) {
-    (void)out_stage_cap;
+uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap) {
     return ((hot_bytes + 127u) & ~127u) + in_cap + 64;
 }
 

@@ -61,8 +61,8 @@ class Engine:
             pass
 
     # ---- configuration ----
-    def set_tile(self, in_bytes_per_req: int, out_bytes_per_req: int):
-        _abi.check(_abi.lib().gofr_engine_set_tile(self._e, in_bytes_per_req, out_bytes_per_req), "gofr_engine_set_tile")
+    def set_tile(self, in_bytes_per_req: int):
+        _abi.check(_abi.lib().gofr_engine_set_tile(self._e, in_bytes_per_req), "gofr_engine_set_tile")
 
     def set_chunk(self, n: int):
         _abi.check(_abi.lib().gofr_engine_set_chunk(self._e, n), "gofr_engine_set_chunk")

@@ -200,12 +200,15 @@ typedef struct gofr_resp_batch {
     uint64_t out_bytes; /* filled by wait */
 } gofr_resp_batch;
 
+/* submit is thread-safe (submits are serialised inside the engine) and currently runs the batch to completion before it
+ * returns; wait(ticket) reports that batch's status exactly once.  With pinned caller buffers egress is device driven
+ * (no host stall per chunk); pageable buffers fall back to an exact-size cudaMemcpy pipeline. */
 int gofr_batch_submit(gofr_engine*, const gofr_req_batch* in, gofr_resp_batch* out, gofr_ticket* ticket);
 int gofr_batch_wait(gofr_engine*, gofr_ticket ticket);
 int gofr_engine_set_chunk(gofr_engine*, uint32_t requests_per_chunk);
-/* Tile geometry: shared-memory staging budget per request (bytes).  Tiles whose request bytes / response bytes exceed
- * the budget are still served correctly, straight from / to HBM. */
-int gofr_engine_set_tile(gofr_engine*, uint32_t in_bytes_per_req, uint32_t out_bytes_per_req);
+/* Tile geometry: shared-memory staging budget for request bytes, per request.  Tiles whose request bytes exceed the
+ * budget are still served correctly, straight from HBM. */
+int gofr_engine_set_tile(gofr_engine*, uint32_t in_bytes_per_req);
 int gofr_engine_geometry(const gofr_engine*, uint32_t* grid, uint32_t* blocks_per_sm, uint32_t* smem_bytes,
                          uint32_t* sm_count);
 /* gofr_serve_device reports an undersized d_out through this flag (the launch itself is asynchronous). */
