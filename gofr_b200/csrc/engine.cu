@@ -75,8 +75,6 @@ struct gofr_engine {
     unsigned long long* d_state = nullptr;
     size_t state_tiles = 0;
     uint32_t* d_flag = nullptr;
-    uint32_t* d_ticket = nullptr;  // tile ticket counter shared by every serve launch of this engine (stream ordered use)
-    uint32_t ticket_base[2] = {0, 0};
     uint32_t* d_bind = nullptr;  // Bind scratch of the resident path
     size_t bind_cap = 0;
     // host path
@@ -134,8 +132,6 @@ int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
     CUDA_TRY(cudaMemcpy(e->d_image, img.data(), img.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&e->d_flag, 64));
     CUDA_TRY(cudaMemset(e->d_flag, 0, 64));
-    CUDA_TRY(cudaMalloc(&e->d_ticket, 64));
-    CUDA_TRY(cudaMemset(e->d_ticket, 0, 64));
     // default tile geometry: stage as many request bytes per request in shared memory as still lets 5 CTAs share an
     // SM (the kernel is latency bound: residency matters more than staging every tile); larger tiles are read from
     // HBM directly.
@@ -185,7 +181,6 @@ void gofr_engine_destroy(gofr_engine* e) {
     if (e->st_egress) cudaStreamDestroy(e->st_egress);
     cudaFree(e->d_chain); cudaFree(e->d_info);
     if (e->h_status) cudaFreeHost(e->h_status);
-    cudaFree(e->d_ticket);
     cudaFree(e->d_image); cudaFree(e->d_state); cudaFree(e->d_flag); cudaFree(e->d_bind);
     delete e;
 }
@@ -209,7 +204,6 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
                       const char* date29, uint8_t* d_out, uint64_t out_cap, uint32_t* d_off, uint32_t* d_meta,
                       unsigned long long* d_state, uint32_t* d_flag, uint32_t* d_bind, cudaStream_t stream,
                       const unsigned long long* chain_pos = nullptr) {
-    const int lane_id = chain_pos ? 1 : 0;  // host-batch launches and resident launches may overlap: separate counters
     ServeParams p;
     memset(&p, 0, sizeof p);
     p.desc = d_desc; p.ids = d_ids; p.arena = d_arena; p.n = n;
@@ -224,11 +218,8 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
     p.bind_scratch = d_bind; p.bind_row_words = e->hdr.bind_row_words;
     p.chain_pos = chain_pos;
     if (getenv("GOFR_DEBUG_NO_LOOKBACK")) p.debug_flags |= 1u;  // diagnostic only
-    // every CTA takes tickets until it draws one past the end: n_tiles + grid tickets per launch
-    p.ticket = e->d_ticket + lane_id; p.ticket_base = e->ticket_base[lane_id];
     memcpy(p.date, date29, 29);
     int grid = (int)std::min<uint32_t>((uint32_t)e->grid, p.n_tiles);
-    e->ticket_base[lane_id] += p.n_tiles + (uint32_t)grid;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (e->timing_on) {
         CUDA_TRY(cudaEventCreate(&ev0));

@@ -32,8 +32,6 @@ struct ServeParams {
     uint32_t* bind_scratch;  // n * bind_row_words words (tables with GOFR_H_BIND_ECHO routes), else null
     uint32_t bind_row_words;
     const unsigned long long* chain_pos;  // host-batch path: packed position of the whole batch so far (else null)
-    uint32_t* ticket;        // tile ticket counter (never reset: ticket_base is its value before this launch)
-    uint32_t ticket_base;
     uint32_t debug_flags;    // bit0: skip the look-back (tile_base = tile * tile_total; only valid for fixed-size responses)
 };
 
