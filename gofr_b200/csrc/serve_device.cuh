@@ -83,7 +83,9 @@ GOFR_HD bool warp_any(bool p) {
 //            written by other threads; only this response's bytes are stored there.
 // ---------------------------------------------------------------------------------------------------------------
 #if defined(__CUDA_ARCH__)
-#define GOFR_RING_STRIDE_BYTES 512u  /* kServeThreads words: word-major staging, GOFR_STAGE_WORDS words per thread */
+#ifndef GOFR_RING_STRIDE_BYTES
+#define GOFR_RING_STRIDE_BYTES 512u  /* word-major staging: one word of every thread that shares the buffer per row */
+#endif
 #else
 #define GOFR_RING_STRIDE_BYTES 4u
 #endif
@@ -112,12 +114,18 @@ GOFR_HD uint32_t src_ld(saddr_t a) {
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+GOFR_HD uint32_t stg_ld8(saddr_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
 GOFR_HD uint32_t salign(saddr_t a) { return a & 3u; }
 #else
 typedef const uint8_t* saddr_t;
 GOFR_HD saddr_t to_saddr(const void* p) { return (const uint8_t*)p; }
 GOFR_HD void stg_st(saddr_t a, uint32_t v) { *(uint32_t*)a = v; }
 GOFR_HD uint32_t stg_ld(saddr_t a) { return *(const uint32_t*)a; }
+GOFR_HD uint32_t stg_ld8(saddr_t a) { return *a; }
 GOFR_HD uint32_t src_ld(saddr_t a) { return *(const uint32_t*)a; }
 GOFR_HD uint32_t salign(saddr_t a) { return (uint32_t)((uintptr_t)a & 3u); }
 #endif
@@ -175,27 +183,23 @@ struct Writer {
         memcpy(addr, v, 16);
 #endif
     }
-    // write bytes [lo, hi) of the 16-byte chunk at addr from v[0..3]: whole words where possible, else single bytes
-    GOFR_HD static void store_partial(uint8_t* addr, const uint32_t v[4], uint32_t lo, uint32_t hi) {
-#pragma unroll
-        for (uint32_t j = 0; j < 4; j++) {
-            const uint32_t b0 = 4 * j;
-            if (b0 >= lo && b0 + 4 <= hi) {
-                ((uint32_t*)addr)[j] = v[j];
-            } else if (b0 + 4 > lo && b0 < hi) {
-#pragma unroll
-                for (uint32_t b = 0; b < 4; b++)
-                    if (b0 + b >= lo && b0 + b < hi) addr[b0 + b] = (uint8_t)(v[j] >> (8 * b));
-            }
-        }
+    // Write bytes [lo, hi) of the 16-byte chunk at addr from the four staging words at rp: whole words where possible,
+    // else single bytes.  Runs twice per response at most (first and last chunk), so it is a loop, not unrolled code.
+    GOFR_HD static void store_partial(uint8_t* addr, saddr_t rp, uint32_t lo, uint32_t hi) {
+        uint32_t b = lo;
+#pragma unroll 1
+        for (; b < hi && (b & 3u); b++) addr[b] = (uint8_t)stg_ld8(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES + (b & 3u));
+#pragma unroll 1
+        for (; b + 4 <= hi; b += 4) *(uint32_t*)(addr + b) = stg_ld(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES);
+#pragma unroll 1
+        for (; b < hi; b++) addr[b] = (uint8_t)stg_ld8(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES + (b & 3u));
     }
     // store every complete chunk, move the (< 4) left-over words to the front
     GOFR_HD void flush() {
         uint32_t n = wl >> 2;
         saddr_t rp = base;
         if (n && lead) {  // first chunk of the response: skip the neighbour's bytes
-            const uint32_t vv[4] = {word(0), word(1), word(2), word(3)};
-            store_partial(chunk, vv, lead, 16);
+            store_partial(chunk, rp, lead, 16);
             lead = 0;
             chunk += 16;
             rp += 4 * GOFR_RING_STRIDE_BYTES;
@@ -247,10 +251,10 @@ struct Writer {
         else if (k) putk(v, k);
     }
     // single bytes from slow paths: room is checked here because those loops are unbounded
-    GOFR_HD void put1(uint32_t c) {
-        if (warp_any(wl >= GOFR_STAGE_WORDS - 2)) flush();
-        putk(c, 1);
-    }
+    GOFR_HD void put1(uint32_t c);
+    GOFR_HD void reserve_out(uint32_t n);
+    // one byte from the hot path, where the caller has already made room
+    GOFR_HD void putc(uint32_t c) { putk(c, 1); }
 
     // Append len bytes from memory (any alignment).  With y = src - nb the stream "pending bytes ++ source" is
     // word-aligned with the destination, so output word k is the unaligned word at y + 4k: one aligned load (the
@@ -276,32 +280,36 @@ struct Writer {
             nb = nn;
             return;
         }
-        reserve(4);
+        reserve(8);  // at most 8 words staged from here on: the head below adds <= 4, a short copy <= 7
         store_word(w0);
         cur = nxt;
         Y += 8;  // Y now points at the NEXT word to load
         nwords--;
-        while (nwords >= 4) {  // four words per trip: immediate offsets, one room check, one pointer bump each
-            reserve(4);
-            const uint32_t n0 = M::ld(Y), n1 = M::ld(Y + 4), n2 = M::ld(Y + 8), n3 = M::ld(Y + 12);
-            stg_st(wp, fsr(cur, n0, sh));
-            stg_st(wp + GOFR_RING_STRIDE_BYTES, fsr(n0, n1, sh));
-            stg_st(wp + 2 * GOFR_RING_STRIDE_BYTES, fsr(n1, n2, sh));
-            stg_st(wp + 3 * GOFR_RING_STRIDE_BYTES, fsr(n2, n3, sh));
-            cur = n3;
-            Y += 16;
-            wp += 4 * GOFR_RING_STRIDE_BYTES;
-            wl += 4;
-            nwords -= 4;
-        }
-        if (nwords) {
-            reserve(3);
-            for (; nwords; nwords--) {
+        if (nwords >= 8) {
+            // Long copy.  Head: complete the chunk under construction (<= 3 more words), store it; from then on the
+            // staging buffer is empty and whole chunks go from registers straight to HBM.
+            while (wl & 3u) {
                 nxt = M::ld(Y);
                 Y += 4;
                 store_word(fsr(cur, nxt, sh));
                 cur = nxt;
+                nwords--;
             }
+            flush();  // wl is a multiple of 4: nothing is left behind
+            while (nwords >= 4) {
+                const uint32_t n0 = M::ld(Y), n1 = M::ld(Y + 4), n2 = M::ld(Y + 8), n3 = M::ld(Y + 12);
+                store16(chunk, fsr(cur, n0, sh), fsr(n0, n1, sh), fsr(n1, n2, sh), fsr(n2, n3, sh));
+                chunk += 16;
+                cur = n3;
+                Y += 16;
+                nwords -= 4;
+            }
+        }
+        for (; nwords; nwords--) {  // <= 7 words
+            nxt = M::ld(Y);
+            Y += 4;
+            store_word(fsr(cur, nxt, sh));
+            cur = nxt;
         }
         if (nn) {
             // the partial last word: its bytes may or may not spill into the next aligned word
@@ -312,17 +320,24 @@ struct Writer {
     }
     GOFR_HD void finish() {
         flush();
-        if (wl || nb) {
-            uint32_t v[4];
-#pragma unroll
-            for (uint32_t j = 0; j < 4; j++) v[j] = j < wl ? word(j) : 0u;
-            uint32_t tail = nb ? pend >> (8 * (4 - nb)) : 0u;
-#pragma unroll
-            for (uint32_t j = 0; j < 4; j++) if (j == wl) v[j] = tail;
-            store_partial(chunk, v, lead, 4 * wl + nb);
+        if (wl || nb) {  // the last, partial chunk; wl <= 3 after the flush
+            if (nb) stg_st(wp, pend >> (8 * (4 - nb)));
+            store_partial(chunk, base, lead, 4 * wl + nb);
         }
     }
 };
+
+// The slow paths (rune-by-rune escapes, Location, Bind errors) share one out-of-line flush: they already work on a
+// local-memory copy of the Writer, and inlining the flush into every byte loop made the kernel's code several times
+// larger than its instruction cache.
+GOFR_HD_NOINLINE void flush_out(Writer* w) { w->flush(); }
+GOFR_HD void Writer::reserve_out(uint32_t n) {
+    if (warp_any(wl + n > GOFR_STAGE_WORDS)) flush_out(this);
+}
+GOFR_HD void Writer::put1(uint32_t c) {
+    if (warp_any(wl >= GOFR_STAGE_WORDS - 2)) flush_out(this);
+    putk(c, 1);
+}
 
 // generic-pointer copy: out-of-line slow paths, file blobs, tiles too large for the shared-memory staging
 GOFR_HD_NOINLINE void emit_bytes(Writer& w, const uint8_t* p, uint32_t len) { w.copy<false>(p, len); }
@@ -387,7 +402,7 @@ template <bool EMIT>
 GOFR_HD_NOINLINE uint32_t json_escape_slow(Writer* w, const uint8_t* p, uint32_t len) {
     uint32_t out = 0;
     for (uint32_t i = 0; i < len;) {
-        if (EMIT) w->reserve(4);
+        if (EMIT) w->reserve_out(4);
         uint32_t c = p[i];
         if (c < 0x80) {
             if (c >= 0x20 && c != '"' && c != '\\' && c != '<' && c != '>' && c != '&') {
@@ -449,7 +464,7 @@ GOFR_HD uint32_t emit_i64(Writer* w, int64_t sv) {
     uint32_t nd = ndigits_u64(v);
     uint32_t total = nd + (sv < 0 ? 1u : 0u);
     if (!EMIT) return total;
-    if (sv < 0) w->put1('-');
+    if (sv < 0) w->putc('-');
     // zero-padded 20 digits as five words W[0..4], W[0] most significant
     uint32_t W[5];
     uint64_t top = v / 10000000000000000ull;           // < 1845
@@ -593,7 +608,7 @@ GOFR_HD uint32_t hex_uc(uint32_t v) { return v < 10 ? '0' + v : 'A' + v - 10; }
 template <bool EMIT>
 GOFR_HD uint32_t put_url_escaped(Writer* w, uint32_t c) {
     if (url_path_keep(c)) { if (EMIT) w->put1(c); return 1; }
-    if (EMIT) { w->reserve(2); w->putk('%' | hex_uc(c >> 4) << 8 | hex_uc(c & 15) << 16, 3); }
+    if (EMIT) { w->reserve_out(2); w->putk('%' | hex_uc(c >> 4) << 8 | hex_uc(c & 15) << 16, 3); }
     return 3;
 }
 
@@ -955,9 +970,10 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
     const ProgRec P = tv.progs()[c.prog];  // by value: the staging stores below must not force re-reads of the table
     // the size pass visits only the ops whose length depends on the request
     const Op* ops = tv.ops() + (EMIT ? P.first_op : P.first_dyn);
-    const uint32_t n_ops = EMIT ? P.n_ops : P.n_dyn;
-    const uint8_t* const lits = tv.lits();
     const bool head = c.method() == GOFR_M_HEAD;
+    // chunkWriter eats the body of a HEAD response; body ops come last, so a HEAD emit simply stops before them
+    const uint32_t n_ops = EMIT ? (head ? P.n_hdr_ops : P.n_ops) : P.n_dyn;
+    const uint8_t* const lits = tv.lits();
     const uint32_t* row = (P.flags & PF_BIND) ? c.brow(br) : (const uint32_t*)c.data();
     uint32_t str_cursor = 0;  // byte offset of the next string in the row's string area
     uint32_t str_base = 0;
@@ -973,14 +989,20 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
         const uint32_t code = raw.x & 0xFFu, oflags = (raw.x >> 16) & 0xFFu, okind = raw.x >> 24;
         const uint32_t olen = raw.y, ooff = raw.z, oaux = raw.w;
         const bool body = oflags & OPF_BODY;
-        if (EMIT && head && body) break;  // chunkWriter eats the body of a HEAD response; body ops come last
         const bool governed = oflags & OPF_VALUE_OF_KEY;
         uint32_t produced = 0;
-        const uint8_t* csrc = nullptr;  // ops that append memory verbatim meet at the single copy() below
-        uint32_t clen = 0;
-        bool cshared = true;            // literals live in the shared-memory copy of the table
-        if (EMIT && code != OP_LIT && code != OP_KEY && code != OP_BLOB && olen)
-            w->copy<true>(SrcMem<true>::from(lits + oaux), olen);  // literal prefix folded into this value op
+        // Everything that appends memory verbatim meets at the single copy() at the bottom of the two-step loop:
+        // step 0 is the literal prefix folded into a value op (emit pass only), step 1 the op itself.
+        const bool has_prefix = EMIT && code != OP_LIT && code != OP_KEY && code != OP_BLOB && olen;
+        const uint8_t* csrc = lits + oaux;
+        uint32_t clen = has_prefix ? olen : 0u;
+        bool cshared = true;  // literals live in the shared-memory copy of the table
+#pragma unroll 1
+        for (uint32_t step = EMIT ? 0u : 1u; step < 2; step++) {
+        if (step == 1) {
+        csrc = nullptr;
+        clen = 0;
+        cshared = true;
         if (EMIT && warp_any(w->wl >= GOFR_STAGE_WORDS - 8)) w->flush();  // every non-copy action appends at most 8 words
         if (code == OP_LIT) {
             if (!(governed && skip)) {
@@ -1030,13 +1052,14 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
         } else if (code == OP_BOOL) {
             if (!(governed && skip)) {
                 const bool t = row[ooff] != 0;
-                if (EMIT) { if (t) w->put4('t' | 'r' << 8 | 'u' << 16 | 'e' << 24); else { w->put4('f' | 'a' << 8 | 'l' << 16 | 's' << 24); w->put1('e'); } }
+                if (EMIT) { if (t) w->put4('t' | 'r' << 8 | 'u' << 16 | 'e' << 24); else { w->put4('f' | 'a' << 8 | 'l' << 16 | 's' << 24); w->putc('e'); } }
                 produced = t ? 4 : 5;
             }
         } else if (code == OP_HEXID) {
             if (EMIT) {
+                const uint4 id = *(const uint4*)(br.ids + (size_t)c.index * 16);  // loaded here, not carried
+                const uint32_t idw[4] = {id.x, id.y, id.z, id.w};
 #pragma unroll
-                const uint32_t* idw = (const uint32_t*)(br.ids + (size_t)c.index * 16);  // loaded here, not carried
                 for (int k = 0; k < 4; k++) { uint32_t a, b; hex8(idw[k], a, b); w->put4(a); w->put4(b); }
             }
         } else if (code == OP_CLEN) {
@@ -1051,7 +1074,7 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
             }
             skip = empty;
             if (!empty) {
-                if (!first) { if (EMIT) w->put1(','); produced += 1; }
+                if (!first) { if (EMIT) w->putc(','); produced += 1; }
                 first = false;
                 csrc = lits + ooff;
                 clen = olen;
@@ -1081,10 +1104,12 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
             clen = olen;
             cshared = false;
         }
+        }  // step == 1
         if (EMIT && clen) {
             if (cshared) w->copy<true>(SrcMem<true>::from(csrc), clen);
             else GOFR_SLOW_CALL(w, emit_bytes(*tw, csrc, clen));
         }
+        }  // steps
         if (body) body_dyn += produced; else hdr_dyn += produced;
     }
     if (!EMIT) {

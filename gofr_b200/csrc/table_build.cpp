@@ -789,6 +789,9 @@ int seal_table(gofr_table* t) {
             if (!fixed_len) dyn.push_back(o);
         }
         P.n_dyn = (uint16_t)dyn.size();
+        uint16_t nh = 0;
+        while (nh < P.n_ops && !(ops[P.first_op + nh].flags & OPF_BODY)) nh++;
+        P.n_hdr_ops = nh;
         ops.insert(ops.end(), dyn.begin(), dyn.end());
     }
 

@@ -12,7 +12,7 @@
 namespace gofr {
 
 constexpr uint32_t kMagic = 0x52464F47u;  // "GOFR"
-constexpr uint32_t kImageVersion = 6;
+constexpr uint32_t kImageVersion = 7;
 constexpr uint32_t kMaxHotBytes = 40 * 1024;  // shared-memory budget for the table
 constexpr int kMaxVars = 8;                   // variables per route template
 constexpr int kMaxFields = 32;                // struct fields per schema
@@ -124,7 +124,9 @@ struct ProgRec {  // 32 B
     uint32_t body_fixed; // sum of the fixed-length body bytes
     uint16_t first_dyn;  // the ops whose length depends on the request, in order: all the size pass has to visit
     uint16_t n_dyn;
-    uint32_t pad[3];
+    uint16_t n_hdr_ops;  // ops before the first body op (body ops come last): all a HEAD response emits
+    uint16_t pad0;
+    uint32_t pad[2];
 };
 static_assert(sizeof(ProgRec) == 32, "ProgRec layout");
 
