@@ -174,8 +174,29 @@ def run_secondary(args):
     from tests import oracle as O
     date = S.http_date(DATE_UNIX)
     w = args.workload
-    n = {"config3": 65536, "config4": 262144, "config5": 1 << 20}[w] if args.requests == (1 << 20) and w != "config5" else args.requests
-    if w == "config5":
+    n = {"config3": 65536, "config4": 262144, "config5": 1 << 20, "reqlog": 1 << 18}[w] if args.requests == (1 << 20) and w != "config5" else args.requests
+    cpu = None
+    if w == "reqlog":
+        # the RequestLog line of middleware.Logging for the config-2 stream
+        lb = synth.reqlog_batch(n)
+        eng = Engine(Table(synth.config1_spec()), 0)
+        d_desc = torch.from_numpy(lb.desc.view(np.uint8).reshape(-1).copy()).cuda()
+        d_ids = torch.from_numpy(lb.trace_ids.reshape(-1).copy()).cuda()
+        d_arena = torch.from_numpy(np.concatenate([lb.arena, np.zeros(48, np.uint8)])).cuda()
+        cap = 400 * n + 6 * int(lb.arena.size)
+        d_out = torch.zeros(cap + 64, dtype=torch.uint8, device="cuda")
+        d_ooff = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+
+        def step():
+            eng.request_log_resident(d_desc, d_ids, d_arena, n, d_out, cap, d_ooff)
+        in_bytes = lb.input_bytes() - 8 * n  # the generic "+ 8 * n" below counts offsets + meta; here only 4-byte offsets leave
+        in_bytes += 4 * n
+        get_out = lambda: int(d_ooff[n].item())
+        t0 = time.perf_counter()
+        O.request_log(lb)
+        cpu = {"value": n / (time.perf_counter() - t0), "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"one pass over the same {n} records, scalar C restatement (oracle/orc_reqlog.c)"}
+    elif w == "config5":
         frames, off = synth.config5_frames(n)
         eng = Engine(Table(synth.config1_spec()), 0)
         d_in = torch.from_numpy(np.concatenate([frames, np.zeros(64, np.uint8)])).cuda()
@@ -223,7 +244,8 @@ def run_secondary(args):
                       "warmup": args.warmup, "ms_per_step": ms, "requests": n, "out_bytes": out_bytes, "data": "synthetic",
                       "roofline": {"bound": "hbm", "achieved": algo / (kms / kl / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                    "frac": algo / (kms / kl / 1e3) / 1e9 / peak, "algorithmic_bytes_per_request": algo / n,
-                                   "kernel_ms_per_launch": kms / kl}}))
+                                   "kernel_ms_per_launch": kms / kl},
+                      **({"cpu_baseline": cpu} if cpu else {})}))
     return 0
 
 
@@ -239,7 +261,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer measurement (default: --steps)")
     ap.add_argument("--chunk", type=int, default=65536)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"],
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5", "reqlog"],
                     help="config2 is the BASELINE metric line; the others are secondary measurements (resident only)")
     args = ap.parse_args()
     if args.warmup < 3:

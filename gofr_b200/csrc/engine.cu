@@ -69,7 +69,7 @@ struct gofr_engine {
     uint32_t image_bytes = 0;
     // launch geometry
     uint32_t in_cap = 0, smem_bytes = 0;
-    int grid = 0, blocks_per_sm = 0, grpc_grid = 0;
+    int grid = 0, blocks_per_sm = 0, grpc_grid = 0, reqlog_grid = 0;
     uint32_t epoch = 0;
     // resident path scratch
     unsigned long long* d_state = nullptr;
@@ -599,6 +599,46 @@ int gofr_grpc_hello_device(gofr_engine* e, const uint8_t* d_in, const uint32_t* 
     }
     int rc = launch_grpc_hello(p, (int)std::min<size_t>((size_t)e->grpc_grid, tiles), st);
     if (rc != 0) { set_last_error("grpc kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
+    if (e->timing_on) { CUDA_TRY(cudaEventRecord(ev1, st)); e->timing.emplace_back(ev0, ev1); }
+    e->launches++;
+    return GOFR_OK;
+}
+
+int gofr_requestlog_device(gofr_engine* e, const gofr_log_desc* d_desc, const uint8_t* d_trace_ids, const uint8_t* d_arena,
+                           uint32_t n, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off, void* stream) {
+    if (!e || (n && (!d_desc || !d_trace_ids || !d_arena || !d_out || !d_out_off))) return GOFR_ERR_INVALID;
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st)); return GOFR_OK; }
+    size_t tiles = (n + kServeThreads - 1) / kServeThreads;
+    if (tiles > e->state_tiles) {
+        cudaFree(e->d_state);
+        e->d_state = nullptr;
+        CUDA_TRY(cudaMalloc(&e->d_state, tiles * 8));
+        CUDA_TRY(cudaMemset(e->d_state, 0, tiles * 8));
+        e->state_tiles = tiles;
+    }
+    if (e->reqlog_grid <= 0) {
+        e->reqlog_grid = reqlog_max_grid(e->device);
+        if (e->reqlog_grid <= 0) { set_last_error("request-log kernel cannot be resident"); return GOFR_ERR_CUDA; }
+    }
+    LogParams p;
+    memset(&p, 0, sizeof p);
+    p.desc = d_desc; p.ids = d_trace_ids; p.arena = d_arena; p.n = n; p.n_tiles = (uint32_t)tiles;
+    e->epoch = (e->epoch + 1) & 0xFFFFFu;
+    if (e->epoch == 0) e->epoch = 1;
+    p.epoch = e->epoch;
+    p.out = d_out; p.out_cap = out_cap; p.out_off = d_out_off;
+    p.tile_state = e->d_state; p.overflow = e->d_flag;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (e->timing_on) {
+        CUDA_TRY(cudaEventCreate(&ev0));
+        CUDA_TRY(cudaEventCreate(&ev1));
+        CUDA_TRY(cudaEventRecord(ev0, st));
+    }
+    int rc = launch_reqlog(p, (int)std::min<size_t>((size_t)e->reqlog_grid, tiles), st);
+    if (rc != 0) { set_last_error("request-log kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
     if (e->timing_on) { CUDA_TRY(cudaEventRecord(ev1, st)); e->timing.emplace_back(ev0, ev1); }
     e->launches++;
     return GOFR_OK;

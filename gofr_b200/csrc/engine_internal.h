@@ -70,6 +70,22 @@ struct GrpcParams {
     uint32_t* overflow;
 };
 int launch_grpc_hello(const GrpcParams& p, int grid, void* stream);
+
+struct LogParams {
+    const void* desc;   // gofr_log_desc[n]
+    const void* ids;    // n * 16 trace id bytes
+    const uint8_t* arena;
+    uint32_t n;
+    uint32_t n_tiles;
+    uint32_t epoch;
+    uint8_t* out;
+    uint64_t out_cap;
+    uint32_t* out_off;
+    unsigned long long* tile_state;
+    uint32_t* overflow;
+};
+int launch_reqlog(const LogParams& p, int grid, void* stream);
+int reqlog_max_grid(int device);
 int grpc_max_grid(int device);
 
 }  // namespace gofr

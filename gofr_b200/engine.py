@@ -118,6 +118,29 @@ class Engine:
                                                 resp.out_off.data_ptr(), resp.meta.data_ptr(), st.cuda_stream),
                    "gofr_serve_device")
 
+    # ---- RequestLog lines (middleware.Logging → logger.Log), device resident ----
+    def request_log_device(self, batch: S.LogBatch, out_cap: Optional[int] = None, stream=None):
+        """Uploads a LogBatch, runs gofr_requestlog_device, returns (out, out_off) torch tensors (uint8, int32 view)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        n = batch.n
+        d_desc = torch.from_numpy(batch.desc.view(np.uint8).reshape(-1).copy()).to(dev)
+        d_ids = torch.from_numpy(batch.trace_ids.reshape(-1).copy()).to(dev)
+        d_arena = torch.from_numpy(np.concatenate([batch.arena, np.zeros(48, dtype=np.uint8)])).to(dev)
+        if out_cap is None:
+            out_cap = 400 * n + 6 * int(batch.arena.size) + 64
+        d_out = torch.empty(out_cap + 64, dtype=torch.uint8, device=dev)
+        d_off = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        self.request_log_resident(d_desc, d_ids, d_arena, n, d_out, out_cap, d_off, stream)
+        return d_out, d_off
+
+    def request_log_resident(self, d_desc, d_ids, d_arena, n: int, d_out, out_cap: int, d_off, stream=None) -> None:
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        _abi.check(_abi.lib().gofr_requestlog_device(self._e, d_desc.data_ptr(), d_ids.data_ptr(), d_arena.data_ptr(), n,
+                                                     d_out.data_ptr(), out_cap, d_off.data_ptr(), st.cuda_stream),
+                   "gofr_requestlog_device")
+
     # ---- host path (the call a user makes): host buffers in, host buffers out ----
     def serve_host(self, batch: S.RequestBatch, date: bytes, out: np.ndarray, out_off: np.ndarray, meta: np.ndarray) -> int:
         L = _abi.lib()

@@ -175,6 +175,61 @@ class RequestBatch:
         return RequestBatch(desc, ids, np.frombuffer(bytes(arena), dtype=np.uint8).copy())
 
 
+# gofr_log_desc (include/gofr_b200.h): one RequestLog record (middleware/logger.go:24-33,41-70)
+LOG_DESC_DTYPE = np.dtype([("start_unix_ns", "<i8"), ("elapsed_ns", "<i8"), ("log_unix_ns", "<i8"), ("arena_off", "<u4"),
+                           ("method_len", "<u2"), ("ua_len", "<u2"), ("xff_len", "<u2"), ("remote_len", "<u2"),
+                           ("uri_len", "<u2"), ("status", "<u2"), ("tz_offset_s", "<i4"), ("reserved", "<u4")])
+assert LOG_DESC_DTYPE.itemsize == 48
+
+
+@dataclass
+class LogRec:
+    """What middleware.Logging reads from the clock and the request for one log line."""
+    start_unix_ns: int
+    elapsed_ns: int
+    log_unix_ns: int
+    method: bytes = b"GET"
+    user_agent: bytes = b""
+    xff: bytes = b""          # first X-Forwarded-For header value ("" if absent)
+    remote_addr: bytes = b""
+    uri: bytes = b"/"
+    status: int = 200
+    tz_offset_s: int = 0
+    trace_id: Optional[bytes] = None
+
+
+class LogBatch:
+    """desc[n] (gofr_log_desc) / trace_ids[n,16] / arena (method|user_agent|xff|remote_addr|uri per record)."""
+
+    def __init__(self, desc: np.ndarray, trace_ids: np.ndarray, arena: np.ndarray):
+        assert desc.dtype == LOG_DESC_DTYPE and trace_ids.dtype == np.uint8 and arena.dtype == np.uint8
+        assert trace_ids.shape == (len(desc), 16)
+        self.desc = np.ascontiguousarray(desc)
+        self.trace_ids = np.ascontiguousarray(trace_ids)
+        self.arena = np.ascontiguousarray(arena)
+
+    @property
+    def n(self) -> int:
+        return len(self.desc)
+
+    def input_bytes(self) -> int:
+        return self.n * (48 + 16) + int(self.arena.size)
+
+    @staticmethod
+    def pack(recs: Sequence[LogRec], seed: int = 0x60F2B200) -> "LogBatch":
+        n = len(recs)
+        desc = np.zeros(n, dtype=LOG_DESC_DTYPE)
+        ids = np.zeros((n, 16), dtype=np.uint8)
+        rnd = np.random.default_rng(seed).integers(0, 256, size=(n, 16), dtype=np.uint8)
+        arena = bytearray()
+        for i, r in enumerate(recs):
+            desc[i] = (r.start_unix_ns, r.elapsed_ns, r.log_unix_ns, len(arena), len(r.method), len(r.user_agent),
+                       len(r.xff), len(r.remote_addr), len(r.uri), r.status, r.tz_offset_s, 0)
+            arena += r.method + r.user_agent + r.xff + r.remote_addr + r.uri
+            ids[i] = np.frombuffer(r.trace_id, dtype=np.uint8) if r.trace_id is not None else rnd[i]
+        return LogBatch(desc, ids, np.frombuffer(bytes(arena), dtype=np.uint8).copy())
+
+
 def http_date(unix_seconds: int) -> bytes:
     """net/http appendTime: IMF-fixdate, always 29 bytes."""
     import time

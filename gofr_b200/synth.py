@@ -290,3 +290,63 @@ def config3_batch(n: int = 65536, start: int = 0, seed: int = SEED, variant_ever
     b = S.RequestBatch.pack(reqs)
     b.trace_ids[:] = trace_ids(seed, idx)
     return b
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# RequestLog lines: what middleware.Logging would log for the config-2 stream
+# ---------------------------------------------------------------------------------------------------------------
+_UAS = [b"Go-http-client/1.1", b"curl/8.4.0", b"Mozilla/5.0 (X11; Linux x86_64) AppleWebKit/537.36 (KHTML, like Gecko)",
+        b"k6/0.47.0 (https://k6.io/)", b""]
+
+
+def reqlog_batch(n: int, start: int = 0, seed: int = SEED, n_routes: int = 16, hostile_every: int = 0,
+                 tz_offset_s: int = 0) -> S.LogBatch:
+    """Log records of requests [start, start+n) of the config-2 stream.  hostile_every=k makes every k-th record carry
+    strings that need JSON escaping, Unicode spaces around the forwarded address, zero fields (omitempty), odd clocks."""
+    idx = np.arange(start, start + n, dtype=np.uint64)
+    r = rand_u64(seed, idx, 11)
+    r2 = rand_u64(seed, idx, 12)
+    t0 = 1_700_000_000_000_000_000
+    recs = []
+    for k in range(n):
+        i = int(idx[k])
+        a, b = int(r[k]), int(r2[k])
+        start_ns = t0 + i * 977 + (a % 1000) * 1000  # µs resolution is common; some records get full ns below
+        if a % 7 == 0:
+            start_ns += b % 1000
+        if a % 31 == 0:
+            start_ns -= start_ns % 1_000_000_000  # whole second: no fraction at all
+        elapsed = 20_000 + (b >> 8) % 3_000_000
+        route = a % n_routes
+        rec = S.LogRec(start_ns, elapsed, start_ns + elapsed + 1500, b"GET", _UAS[(a >> 8) % len(_UAS)],
+                       b"" if (a >> 16) % 3 else b"10.%d.%d.%d, 35.191.0.%d" % ((a >> 20) % 256, (a >> 28) % 256, (a >> 36) % 256, b % 256),
+                       b"192.168.%d.%d:%d" % ((b >> 16) % 256, (b >> 24) % 256, 1024 + (b >> 32) % 60000),
+                       b"/api/v1/r%02d" % route, 200, tz_offset_s)
+        if hostile_every and i % hostile_every == 0:
+            v = (i // hostile_every) % 8
+            if v == 0:
+                rec.user_agent = b'agent "quoted" <b>&amp;\\ \x01\x7f \xe2\x80\xa8 \xff\xfe'
+            elif v == 1:
+                rec.xff = b" \t\xc2\xa0 203.0.113.9\xe2\x80\x83\xe3\x80\x80 , 10.0.0.1"
+            elif v == 2:
+                rec.xff, rec.remote_addr = b",10.0.0.1", b"\xc2\x85[::1]:8080\xe1\x9a\x80\r\n"
+            elif v == 3:
+                rec.elapsed_ns, rec.status, rec.user_agent, rec.method = 999, 0, b"", b""
+            elif v == 4:
+                rec.uri = b"/search?q=<script>&x=\xc3\xa9%20\"y\""
+                rec.method = b"M-SEARCH"
+            elif v == 5:
+                rec.start_unix_ns, rec.tz_offset_s, rec.status = -1, -(3 * 3600 + 30 * 60), 404
+                rec.log_unix_ns = 1
+            elif v == 6:
+                rec.xff, rec.remote_addr = b"  \xe2\x80\x8a ", b""
+                rec.tz_offset_s = 5 * 3600 + 45 * 60 + 30
+            else:
+                rec.start_unix_ns = 4_102_444_799_999_999_990  # 2099-12-31T23:59:59.99999999
+                rec.log_unix_ns = rec.start_unix_ns + 10
+                rec.elapsed_ns = -2_000_500
+                rec.tz_offset_s = 14 * 3600
+        recs.append(rec)
+    b = S.LogBatch.pack(recs)
+    b.trace_ids[:] = trace_ids(seed, idx)
+    return b

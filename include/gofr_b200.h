@@ -20,6 +20,9 @@
  *   Request.Param / Bind          pkg/gofr/http/request.go:28-47   (fused into the serve kernel per handler kind)
  *   _Hello_SayHello_Handler       examples/grpc-server/grpc/
  *                                 hello_grpc.pb.go:73-89           gofr_grpc_hello_device
+ *   middleware.Logging's RequestLog line → logger.Log
+ *                                 pkg/gofr/http/middleware/logger.go:24-33,41-84,
+ *                                 pkg/gofr/logging/logger.go:37-74 gofr_requestlog_device
  *
  * Conventions (mirroring the reference's "log and continue", responder.go:29,40): plain C types only, integer status
  * codes, never abort; per-request outcomes are reported in the response meta column; the table is immutable after
@@ -223,6 +226,29 @@ void gofr_free_pinned(void*);
 enum { GOFR_GRPC_OK = 0, GOFR_GRPC_COMPRESSED = 1, GOFR_GRPC_BAD_LENGTH = 2, GOFR_GRPC_BAD_PROTO = 3, GOFR_GRPC_BAD_UTF8 = 4 };
 int gofr_grpc_hello_device(gofr_engine*, const uint8_t* d_in, const uint32_t* d_in_off, uint32_t n, uint8_t* d_out,
                            uint64_t out_cap, uint32_t* d_out_off, uint32_t* d_meta, void* stream);
+
+/* The JSON line middleware.Logging hands to logger.Log after every request (non-terminal writer:
+ * json.NewEncoder(out).Encode(logEntry{Level: INFO, Time: time.Now(), Message: RequestLog{...}})):
+ *   {"Level":"INFO","time":"<RFC 3339 nano>","message":{"id":"<32 hex>","start_time":"...","response_time":<µs>,
+ *    "method":"..","user_agent":"..","ip":"..","uri":"..","response":<status>}}\n
+ * with `omitempty` on every message field (logger.go:24-33).  What the reference reads from the clock and from the
+ * request is an INPUT per record: the three clock readings, the local zone offset, and five byte strings laid back to
+ * back in the arena in this order: req.Method | req.UserAgent() | first X-Forwarded-For header value | req.RemoteAddr |
+ * req.RequestURI.  getIPAddress (first comma-separated element, else RemoteAddr, strings.TrimSpace) runs on the device.
+ * Lines are packed: line i = d_out[d_out_off[i] .. d_out_off[i+1]).  The arena needs 32 readable bytes after the last
+ * record byte.  trace ids: the same 16 bytes per request gofr_serve_device takes. */
+typedef struct gofr_log_desc { /* 48 bytes */
+    int64_t start_unix_ns;   /* start := time.Now()                        logger.go:44 */
+    int64_t elapsed_ns;      /* time.Since(start)                          logger.go:53 */
+    int64_t log_unix_ns;     /* time.Now() in logger.logf                  logging/logger.go:55 */
+    uint32_t arena_off;
+    uint16_t method_len, ua_len, xff_len, remote_len, uri_len;
+    uint16_t status;         /* StatusResponseWriter.status (0: WriteHeader never ran → field omitted) */
+    int32_t tz_offset_s;     /* offset of time.Local at that instant, seconds east of UTC */
+    uint32_t reserved;
+} gofr_log_desc;
+int gofr_requestlog_device(gofr_engine*, const gofr_log_desc* d_desc, const uint8_t* d_trace_ids, const uint8_t* d_arena,
+                           uint32_t n, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off, void* stream);
 
 /* number of kernels launched by this engine so far (bench.py reports it as gpu_launches) */
 uint64_t gofr_engine_launch_count(const gofr_engine*);

@@ -62,6 +62,10 @@ int orc_bind(const orc_table*, int schema_id, const uint8_t* body, int n, uint8_
 /* RPCLog.String() (pkg/gofr/grpc/log.go:15-25): the reference's only byte-exact encoding/json golden. */
 int orc_rpclog_string(const char* id, const char* start_time, int64_t response_time, const char* method, uint8_t* out,
                       int cap);
+/* The JSON line middleware.Logging → logger.Log writes per request (orc_reqlog.c; logger.go:41-70, logging/logger.go:37-74).
+ * desc: n records of 48 bytes in the layout of gofr_log_desc (include/gofr_b200.h); lines are packed back to back. */
+int orc_request_log(const void* desc, const uint8_t* ids, const uint8_t* arena, uint32_t n, uint8_t* out, uint64_t out_cap,
+                    uint32_t* out_off);
 void orc_format_http_date(int64_t unix_seconds, char out29[29]);
 
 #ifdef __cplusplus

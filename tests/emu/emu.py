@@ -17,6 +17,7 @@ def _build():
     srcs = [os.path.join(HERE, "emu_serve.cpp"), os.path.join(ROOT, "gofr_b200", "csrc", "serve_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "bind_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "grpc_device.cuh"),
+            os.path.join(ROOT, "gofr_b200", "csrc", "reqlog_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "table_format.h")]
     srcs = [s for s in srcs if os.path.exists(s)]
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
@@ -35,7 +36,23 @@ def lib():
                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
         _lib.emu_grpc_hello.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                         C.c_void_p, C.c_uint32]
+        _lib.emu_reqlog.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
+                                    C.c_uint32]
     return _lib
+
+
+def request_log(batch, misalign: int = 0):
+    """batch: gofr_b200.spec.LogBatch.  Returns (out, out_off)."""
+    n = batch.n
+    cap = 400 * n + 6 * int(batch.arena.size) + 64
+    out = np.full(cap, 0xEE, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    arena = np.concatenate([batch.arena, np.zeros(32, dtype=np.uint8)])
+    rc = lib().emu_reqlog(batch.desc.ctypes.data, batch.trace_ids.ctypes.data, arena.ctypes.data, n, out.ctypes.data,
+                          cap, off.ctypes.data, misalign)
+    if rc != 0:
+        raise RuntimeError("emu output capacity too small")
+    return out, off
 
 
 def grpc_hello(frames, in_off, misalign: int = 0):

@@ -53,6 +53,31 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
     return 0;
 }
 
+// ---- RequestLog line: the same reqlog_device.cuh code the CUDA kernel runs ----
+#include "../../gofr_b200/csrc/reqlog_device.cuh"
+
+extern "C" int emu_reqlog(const uint8_t* desc, const uint8_t* ids, const uint8_t* arena, uint32_t n, uint8_t* out,
+                          uint64_t out_cap, uint32_t* out_off, uint32_t start_misalign) {
+    uint32_t stage[GOFR_STAGE_WORDS];
+    uint64_t pos = start_misalign;
+    for (uint32_t i = 0; i < n; i++) {
+        LogDesc d;
+        memcpy(&d, desc + (size_t)i * sizeof(LogDesc), sizeof d);
+        uint32_t id[4];
+        memcpy(id, ids + (size_t)i * 16, 16);
+        LogCtx c;
+        c.ip_off = c.ip_len = c.esc_mask = c.total_len = 0;
+        const bool staged = (i & 1) != 0;  // exercise both source policies of the Writer
+        reqlog_size(d, arena + d.arena_off, staged, c);
+        out_off[i] = (uint32_t)pos;
+        if (pos + c.total_len > out_cap) return -1;
+        reqlog_emit(d, arena + d.arena_off, staged, id, c, out + pos, stage);
+        pos += c.total_len;
+    }
+    out_off[n] = (uint32_t)pos;
+    return 0;
+}
+
 // ---- gRPC Hello (config 5): the same grpc_device.cuh code the CUDA kernel runs ----
 #include "../../gofr_b200/csrc/grpc_device.cuh"
 

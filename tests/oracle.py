@@ -43,6 +43,7 @@ def lib():
         L.orc_add_default_routes.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.orc_serve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_void_p,
                                 C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_request_log.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
         L.orc_grpc_hello.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                      C.c_int]
         for name in ("orc_json_string", "orc_clean_path", "orc_escape_path"):
@@ -152,6 +153,20 @@ class OracleTable:
 def responses(out: np.ndarray, off: np.ndarray):
     b = out.tobytes()
     return [b[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)]
+
+
+def request_log(batch):
+    """batch: gofr_b200.spec.LogBatch → (out, out_off): the packed RequestLog lines (orc_reqlog.c)."""
+    n = batch.n
+    cap = 400 * n + 6 * int(batch.arena.size) + 64
+    out = np.zeros(cap, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    arena = batch.arena if batch.arena.size else np.zeros(1, dtype=np.uint8)
+    rc = lib().orc_request_log(batch.desc.ctypes.data, batch.trace_ids.ctypes.data, arena.ctypes.data, n,
+                               out.ctypes.data, cap, off.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("oracle output capacity too small")
+    return out, off
 
 
 def grpc_hello(frames: np.ndarray, in_off: np.ndarray, nthreads: int = 1):
