@@ -18,7 +18,7 @@ struct LogDesc {  // = gofr_log_desc (include/gofr_b200.h), 48 bytes
     uint32_t arena_off;
     uint16_t method_len, ua_len, xff_len, remote_len, uri_len, status;
     int32_t tz_offset_s;
-    uint32_t reserved;
+    uint32_t kind;  // 0: RequestLog (HTTP middleware), 1: RPCLog (gRPC LoggingInterceptor, pkg/gofr/grpc/log.go:15-50)
 };
 static_assert(sizeof(LogDesc) == 48, "LogDesc layout");
 
@@ -182,10 +182,97 @@ GOFR_HD uint32_t log_string(Writer* w, const char (&key)[N], const uint8_t* s, u
     return (N - 1) + body + 1;
 }
 
+// info.FullMethod inside RPCLog inside the log entry: escaped by json.Marshal(RPCLog), then once more because the
+// marshalled document is logged as a string (grpc/log.go:22-25,43: logger.Infof("%s", l)).  Rune by rune; rare.
+template <bool EMIT>
+GOFR_HD_NOINLINE uint32_t rpc_method_slow(Writer* w, const uint8_t* p, uint32_t len) {
+    uint32_t out = 0;
+    for (uint32_t i = 0; i < len;) {
+        if (EMIT) w->reserve_out(4);
+        const uint32_t c = p[i];
+        uint32_t L = 1, u = 0;  // u != 0: the rune leaves as \\uXXXX with these four hex digits (as a word)
+        if (c < 0x80) {
+            if (c == '"' || c == '\\') {  // escaped twice: three backslashes and a quote, or four backslashes
+                if (EMIT) w->put4('\\' | '\\' << 8 | '\\' << 16 | c << 24);
+                out += 4; i++; continue;
+            }
+            if (c == '\n' || c == '\r' || c == '\t') {
+                if (EMIT) w->putk('\\' | '\\' << 8 | (c == '\n' ? 'n' : c == '\r' ? 'r' : 't') << 16, 3);
+                out += 3; i++; continue;
+            }
+            if (c >= 0x20 && c != '<' && c != '>' && c != '&') {
+                if (EMIT) w->put1(c);
+                out += 1; i++; continue;
+            }
+            u = '0' | '0' << 8 | hex_lc(c >> 4) << 16 | hex_lc(c & 15) << 24;
+        } else {
+            L = utf8_len_at(p + i, len - i);
+            if (L == 0) { L = 1; u = 'f' | 'f' << 8 | 'f' << 16 | 'd' << 24; }
+            else if (L == 3 && c == 0xE2 && p[i + 1] == 0x80 && (p[i + 2] == 0xA8 || p[i + 2] == 0xA9))
+                u = '2' | '0' << 8 | '2' << 16 | (p[i + 2] == 0xA8 ? '8' : '9') << 24;
+        }
+        if (u) {
+            if (EMIT) { w->putk('\\' | '\\' << 8 | 'u' << 16, 3); w->put4(u); }
+            out += 7;
+        } else {
+            if (EMIT) for (uint32_t k = 0; k < L; k++) w->put1(p[i + k]);
+            out += L;
+        }
+        i += L;
+    }
+    return out;
+}
+
+// The gRPC interceptor's line: {"Level":"INFO","time":"…","message":"{\\"id\\":\\"…\\",\\"startTime\\":\\"…\\",
+// \\"responseTime\\":N,\\"method\\":\\"…\\"}"}\n  (RPCLog has no omitempty; every inner quote is escaped by the outer encoder)
+// a literal of at most 32 bytes: emitted (EMIT) or just counted
+template <bool EMIT, uint32_t N>
+GOFR_HD uint32_t lit(Writer* w, const char (&s)[N]) {
+    static_assert(N - 1 <= 32, "one reserve(8) covers the literal");
+    if (EMIT) { w->reserve(8); put_lit(w, s); }
+    return N - 1;
+}
+
+template <bool EMIT>
+GOFR_HD void rpclog_run(const LogDesc& d, const uint8_t* rec, bool staged, const uint32_t id[4], LogCtx& c, Writer* w) {
+    uint32_t len = 0;
+    if (!EMIT) { c.esc_mask = 0; c.ip_off = c.ip_len = 0; }
+    len += lit<EMIT>(w, "{\"Level\":\"INFO\",\"time\":\"");
+    if (EMIT) w->reserve(9);
+    len += emit_time<EMIT>(w, d.log_ns, d.tz_offset_s, true);
+    len += lit<EMIT>(w, "\",\"message\":\"{\\\"id\\\":\\\"");
+    if (EMIT) {
+        w->reserve(8);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { uint32_t a, b; hex8(id[k], a, b); w->put4(a); w->put4(b); }
+    }
+    len += 32;
+    len += lit<EMIT>(w, "\\\",\\\"startTime\\\":\\\"");
+    if (EMIT) w->reserve(9);
+    len += emit_time<EMIT>(w, d.start_ns, d.tz_offset_s, false);
+    len += lit<EMIT>(w, "\\\",\\\"responseTime\\\":");
+    if (EMIT) w->reserve(8);
+    len += emit_i64<EMIT>(w, d.elapsed_ns / 1000);  // time.Since(start).Microseconds()
+    len += lit<EMIT>(w, ",\\\"method\\\":\\\"");
+    const uint32_t n = d.method_len;
+    if (n) {
+        if (!EMIT) {
+            const bool esc = staged ? json_needs_escape<true>(SrcMem<true>::from(rec), n) : json_needs_escape<false>(rec, n);
+            if (esc) { c.esc_mask |= 1u; len += rpc_method_slow<false>(nullptr, rec, n); }
+            else len += n;
+        } else if (c.esc_mask & 1u) GOFR_SLOW_CALL(w, rpc_method_slow<true>(tw, rec, n));
+        else if (staged) w->copy<true>(SrcMem<true>::from(rec), n);
+        else GOFR_SLOW_CALL(w, emit_bytes(*tw, rec, n));
+    }
+    len += lit<EMIT>(w, "\\\"}\"}\n");
+    if (!EMIT) c.total_len = len;
+}
+
 // One record.  EMIT=false: fills c (ip span, escape bits, total_len).  EMIT=true: writes the line through w.
 // rec = first arena byte of the record (method | user_agent | x_forwarded_for | remote_addr | request_uri).
 template <bool EMIT>
 GOFR_HD void reqlog_run(const LogDesc& d, const uint8_t* rec, bool staged, const uint32_t id[4], LogCtx& c, Writer* w) {
+    if (d.kind == 1) { rpclog_run<EMIT>(d, rec, staged, id, c, w); return; }
     uint32_t len = 0;
     if (!EMIT) { c.esc_mask = 0; reqlog_ip(rec, d, &c.ip_off, &c.ip_len); }
     if (EMIT) { w->reserve(8); put_lit(w, "{\"Level\":\"INFO\",\"time\":\""); w->reserve(9); }

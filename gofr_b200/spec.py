@@ -175,10 +175,12 @@ class RequestBatch:
         return RequestBatch(desc, ids, np.frombuffer(bytes(arena), dtype=np.uint8).copy())
 
 
+LOG_REQUEST, LOG_RPC = 0, 1
+
 # gofr_log_desc (include/gofr_b200.h): one RequestLog record (middleware/logger.go:24-33,41-70)
 LOG_DESC_DTYPE = np.dtype([("start_unix_ns", "<i8"), ("elapsed_ns", "<i8"), ("log_unix_ns", "<i8"), ("arena_off", "<u4"),
                            ("method_len", "<u2"), ("ua_len", "<u2"), ("xff_len", "<u2"), ("remote_len", "<u2"),
-                           ("uri_len", "<u2"), ("status", "<u2"), ("tz_offset_s", "<i4"), ("reserved", "<u4")])
+                           ("uri_len", "<u2"), ("status", "<u2"), ("tz_offset_s", "<i4"), ("kind", "<u4")])
 assert LOG_DESC_DTYPE.itemsize == 48
 
 
@@ -196,6 +198,7 @@ class LogRec:
     status: int = 200
     tz_offset_s: int = 0
     trace_id: Optional[bytes] = None
+    kind: int = 0             # LOG_REQUEST, or LOG_RPC (the gRPC interceptor's RPCLog line; method = info.FullMethod)
 
 
 class LogBatch:
@@ -224,7 +227,7 @@ class LogBatch:
         arena = bytearray()
         for i, r in enumerate(recs):
             desc[i] = (r.start_unix_ns, r.elapsed_ns, r.log_unix_ns, len(arena), len(r.method), len(r.user_agent),
-                       len(r.xff), len(r.remote_addr), len(r.uri), r.status, r.tz_offset_s, 0)
+                       len(r.xff), len(r.remote_addr), len(r.uri), r.status, r.tz_offset_s, r.kind)
             arena += r.method + r.user_agent + r.xff + r.remote_addr + r.uri
             ids[i] = np.frombuffer(r.trace_id, dtype=np.uint8) if r.trace_id is not None else rnd[i]
         return LogBatch(desc, ids, np.frombuffer(bytes(arena), dtype=np.uint8).copy())

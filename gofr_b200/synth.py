@@ -300,7 +300,7 @@ _UAS = [b"Go-http-client/1.1", b"curl/8.4.0", b"Mozilla/5.0 (X11; Linux x86_64) 
 
 
 def reqlog_batch(n: int, start: int = 0, seed: int = SEED, n_routes: int = 16, hostile_every: int = 0,
-                 tz_offset_s: int = 0) -> S.LogBatch:
+                 tz_offset_s: int = 0, rpc_every: int = 0) -> S.LogBatch:
     """Log records of requests [start, start+n) of the config-2 stream.  hostile_every=k makes every k-th record carry
     strings that need JSON escaping, Unicode spaces around the forwarded address, zero fields (omitempty), odd clocks."""
     idx = np.arange(start, start + n, dtype=np.uint64)
@@ -346,6 +346,12 @@ def reqlog_batch(n: int, start: int = 0, seed: int = SEED, n_routes: int = 16, h
                 rec.log_unix_ns = rec.start_unix_ns + 10
                 rec.elapsed_ns = -2_000_500
                 rec.tz_offset_s = 14 * 3600
+        if rpc_every and i % rpc_every == 0:  # the gRPC interceptor's RPCLog line for the same clock readings
+            rec.kind = S.LOG_RPC
+            if not (hostile_every and i % hostile_every == 0):
+                rec.method = b"/Hello/SayHello"
+            elif rec.method == b"GET":
+                rec.method = b'/pkg.Svc/Do"it"\\<now>&\xe2\x80\xa9\n\x02\xff\xc3\xa9'
         recs.append(rec)
     b = S.LogBatch.pack(recs)
     b.trace_ids[:] = trace_ids(seed, idx)

@@ -237,6 +237,10 @@ int gofr_grpc_hello_device(gofr_engine*, const uint8_t* d_in, const uint32_t* d_
  * req.RequestURI.  getIPAddress (first comma-separated element, else RemoteAddr, strings.TrimSpace) runs on the device.
  * Lines are packed: line i = d_out[d_out_off[i] .. d_out_off[i+1]).  The arena needs 32 readable bytes after the last
  * record byte.  trace ids: the same 16 bytes per request gofr_serve_device takes. */
+/* kind GOFR_LOG_RPC is the gRPC LoggingInterceptor's line instead (pkg/gofr/grpc/log.go:15-50): logger.Infof("%s",
+ * RPCLog{id, startTime, responseTime, method}) — the message is the STRING json.Marshal(RPCLog), escaped once more by
+ * the outer encoder; `method` carries info.FullMethod, the other four strings are ignored. */
+enum { GOFR_LOG_REQUEST = 0, GOFR_LOG_RPC = 1 };
 typedef struct gofr_log_desc { /* 48 bytes */
     int64_t start_unix_ns;   /* start := time.Now()                        logger.go:44 */
     int64_t elapsed_ns;      /* time.Since(start)                          logger.go:53 */
@@ -245,7 +249,7 @@ typedef struct gofr_log_desc { /* 48 bytes */
     uint16_t method_len, ua_len, xff_len, remote_len, uri_len;
     uint16_t status;         /* StatusResponseWriter.status (0: WriteHeader never ran → field omitted) */
     int32_t tz_offset_s;     /* offset of time.Local at that instant, seconds east of UTC */
-    uint32_t reserved;
+    uint32_t kind;           /* GOFR_LOG_REQUEST or GOFR_LOG_RPC */
 } gofr_log_desc;
 int gofr_requestlog_device(gofr_engine*, const gofr_log_desc* d_desc, const uint8_t* d_trace_ids, const uint8_t* d_arena,
                            uint32_t n, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off, void* stream);

@@ -6,6 +6,9 @@
  *   getIPAddress                  pkg/gofr/http/middleware/logger.go:72-84   (first X-Forwarded-For element, else RemoteAddr; TrimSpace)
  *   logger.logf / logEntry        pkg/gofr/logging/logger.go:37-41,43-74     (non-terminal: json.NewEncoder(out).Encode(entry))
  *   Level.MarshalJSON             pkg/gofr/logging/level.go:64-70            ("INFO" for logger.Log)
+ * kind 1 is the gRPC interceptor's line instead:
+ *   RPCLog / String / LoggingInterceptor   pkg/gofr/grpc/log.go:15-25,27-50   logger.Infof("%s", l): the message is the
+ *   STRING json.Marshal(RPCLog) — so the inner document is JSON-escaped once more by the outer encoder.
  * and of the standard-library pieces those call: time.Time.MarshalJSON (RFC 3339 with nanoseconds, trailing zeros
  * of the fraction removed, "Z" for a zero offset), Time.Format("2006-01-02T15:04:05.999999999-07:00") (same fraction
  * rule, always a numeric offset), strings.Split / strings.TrimSpace (Unicode White_Space), encoding/json string
@@ -22,7 +25,7 @@ typedef struct {
     uint16_t method_len, ua_len, xff_len, remote_len, uri_len;
     uint16_t status;        /* StatusResponseWriter.status (0 = WriteHeader never called) */
     int32_t tz_offset_s;    /* offset of time.Local at that instant, seconds east of UTC */
-    uint32_t reserved;
+    uint32_t kind;          /* 0: RequestLog (HTTP middleware), 1: RPCLog (gRPC LoggingInterceptor) */
 } orc_log_desc;
 
 /* days since 1970-01-01 → proleptic Gregorian civil date (what time.Time.Date computes) */
@@ -131,14 +134,41 @@ int orc_request_log(const void* desc_v, const uint8_t* ids, const uint8_t* arena
         b.n = 0;
         ob_puts(&b, "{\"Level\":\"INFO\",\"time\":\"");
         fmt_time(&b, d->log_unix_ns, d->tz_offset_s, 1);
-        ob_puts(&b, "\",\"message\":{");
-        int first = 1;
         /* reqID := ...TraceID().String(): 32 lower-case hex digits, never empty */
         char hex[32];
         for (int k = 0; k < 16; k++) {
             hex[2 * k] = "0123456789abcdef"[ids[(size_t)i * 16 + k] >> 4];
             hex[2 * k + 1] = "0123456789abcdef"[ids[(size_t)i * 16 + k] & 15];
         }
+        if (d->kind == 1) {
+            /* grpc/log.go:35-44: l.String() = json.Marshal(RPCLog) (no omitempty), logged with Infof("%s", l):
+             * entry.Message is that string, encoded as a JSON string by the outer json.Encoder */
+            obuf in, st;
+            ob_init(&in);
+            ob_init(&st);
+            fmt_time(&st, d->start_unix_ns, d->tz_offset_s, 0);
+            ob_puts(&in, "{\"id\":");
+            orc_enc_string(&in, (const uint8_t*)hex, 32);
+            ob_puts(&in, ",\"startTime\":");
+            orc_enc_string(&in, st.p, st.n);
+            ob_puts(&in, ",\"responseTime\":");
+            orc_enc_int(&in, d->elapsed_ns / 1000); /* time.Since(start).Microseconds() */
+            ob_puts(&in, ",\"method\":");
+            orc_enc_string(&in, method, d->method_len); /* info.FullMethod */
+            ob_putc(&in, '}');
+            ob_puts(&b, "\",\"message\":");
+            orc_enc_string(&b, in.p, in.n);
+            ob_puts(&b, "}\n");
+            ob_free(&in);
+            ob_free(&st);
+            out_off[i] = (uint32_t)pos;
+            if (pos + b.n > out_cap) { ob_free(&b); return -1; }
+            memcpy(out + pos, b.p, b.n);
+            pos += b.n;
+            continue;
+        }
+        ob_puts(&b, "\",\"message\":{");
+        int first = 1;
         key_str(&b, &first, "id", (const uint8_t*)hex, 32);
         obuf st;
         ob_init(&st);

@@ -108,10 +108,35 @@ def test_json_round_trip_of_strings():
         assert m.get("response", 0) == int(d["status"])
 
 
+# ---- the gRPC interceptor's line (pkg/gofr/grpc/log.go:15-50): message = the STRING json.Marshal(RPCLog) ----
+def test_rpclog_inner_document_matches_reference_golden():
+    # grpc/log_test.go:21-31 pins RPCLog.String(); here the same document must come back out of the outer string
+    rec = S.LogRec(1_577_880_732_000_000_000, 0, 1_577_880_732_000_000_000, method=b"GET", kind=S.LOG_RPC,
+                   trace_id=bytes.fromhex("b00ff8de800911ec8f6502bfe7568078"))
+    out, off = O.request_log(S.LogBatch.pack([rec]))
+    entry = json.loads(_lines(out, off)[0])
+    assert entry["Level"] == "INFO" and isinstance(entry["message"], str)
+    assert entry["message"] == ('{"id":"b00ff8de800911ec8f6502bfe7568078","startTime":"2020-01-01T12:12:12+00:00",'
+                                '"responseTime":0,"method":"GET"}')
+    want = O.rpclog_string("b00ff8de800911ec8f6502bfe7568078", "2020-01-01T12:12:12+00:00", 0, "GET")
+    assert entry["message"].encode() == want
+
+
+def test_rpclog_double_escaping():
+    m = b'/a"b\\<>&\n\x01\xff\xe2\x80\xa8\xc3\xa9'
+    rec = S.LogRec(1_700_000_000_000_000_001, 5_999, 1_700_000_000_000_007_000, method=m, kind=S.LOG_RPC, tz_offset_s=3600)
+    out, off = O.request_log(S.LogBatch.pack([rec]))
+    line = _lines(out, off)[0]
+    inner = json.loads(json.loads(line)["message"])
+    assert inner["method"] == m.decode("utf-8", "replace") and inner["responseTime"] == 5
+    assert inner["startTime"] == "2023-11-14T23:13:20.000000001+01:00"
+    assert b'\\\\u003c' in line and b'\\\\\\"' in line  # \\u003c and \\\" on the wire
+
+
 # ---- the kernel's per-record code on the CPU ----
 @pytest.mark.parametrize("mis", [0, 1, 7, 15])
 def test_emu_matches_oracle(mis):
-    b = synth.reqlog_batch(700, hostile_every=2, tz_offset_s=19800)
+    b = synth.reqlog_batch(700, hostile_every=2, tz_offset_s=19800, rpc_every=3)
     o1, f1 = O.request_log(b)
     o2, f2 = emu.request_log(b, mis)
     assert np.array_equal(f1 + mis, f2)
@@ -149,7 +174,7 @@ def eng():
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,hostile", [(1, 0), (127, 1), (1000, 2), (4097, 5), (200_000, 97)])
 def test_gpu_matches_oracle(eng, n, hostile):
-    b = synth.reqlog_batch(n, hostile_every=hostile, tz_offset_s=-12600 if n % 2 else 0)
+    b = synth.reqlog_batch(n, hostile_every=hostile, tz_offset_s=-12600 if n % 2 else 0, rpc_every=3 if n > 100 else 0)
     o1, f1 = O.request_log(b)
     o2, f2 = _gpu_lines(eng, b)
     assert np.array_equal(f1, f2)
