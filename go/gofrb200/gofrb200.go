@@ -160,3 +160,37 @@ func (e *Engine) Serve(b *Batch, now time.Time, out []byte, off, meta []uint32) 
 	}
 	return int(o.out_bytes), nil
 }
+
+// LogRecord is what middleware.Logging's deferred function reads from the clock and the request
+// (pkg/gofr/http/middleware/logger.go:49-63); Append packs it as one gofr_log_desc plus its strings.
+type LogBatch struct {
+	Desc     []C.gofr_log_desc
+	TraceIDs []byte // 16 bytes per record
+	Arena    []byte // method | user_agent | x_forwarded_for | remote_addr | request_uri per record
+}
+
+func (b *LogBatch) Append(start time.Time, elapsed time.Duration, now time.Time, traceID [16]byte, method, userAgent, xff,
+	remoteAddr, requestURI string, status int) {
+	_, off := start.Zone()
+	var d C.gofr_log_desc
+	d.start_unix_ns = C.int64_t(start.UnixNano())
+	d.elapsed_ns = C.int64_t(elapsed.Nanoseconds())
+	d.log_unix_ns = C.int64_t(now.UnixNano())
+	d.arena_off = C.uint32_t(len(b.Arena))
+	d.method_len, d.ua_len, d.xff_len = C.uint16_t(len(method)), C.uint16_t(len(userAgent)), C.uint16_t(len(xff))
+	d.remote_len, d.uri_len = C.uint16_t(len(remoteAddr)), C.uint16_t(len(requestURI))
+	d.status = C.uint16_t(status)
+	d.tz_offset_s = C.int32_t(off)
+	d.kind = C.GOFR_LOG_REQUEST
+	b.Desc = append(b.Desc, d)
+	b.TraceIDs = append(b.TraceIDs, traceID[:]...)
+	b.Arena = append(append(append(append(append(b.Arena, method...), userAgent...), xff...), remoteAddr...), requestURI...)
+}
+
+// RequestLogDevice runs gofr_requestlog_device on buffers that already live in device memory (the batcher uploads the
+// LogBatch next to the request batch); lines come back packed, line i = out[off[i]:off[i+1]].
+func (e *Engine) RequestLogDevice(dDesc, dTraceIDs, dArena unsafe.Pointer, n int, dOut unsafe.Pointer, outCap uint64,
+	dOff unsafe.Pointer, stream unsafe.Pointer) error {
+	return check(C.gofr_requestlog_device(e.e, (*C.gofr_log_desc)(dDesc), (*C.uint8_t)(dTraceIDs), (*C.uint8_t)(dArena),
+		C.uint32_t(n), (*C.uint8_t)(dOut), C.uint64_t(outCap), (*C.uint32_t)(dOff), stream), "gofr_requestlog_device")
+}
