@@ -604,6 +604,22 @@ int gofr_grpc_hello_device(gofr_engine* e, const uint8_t* d_in, const uint32_t* 
     return GOFR_OK;
 }
 
+int gofr_route_device(gofr_engine* e, const gofr_req_desc* d_desc, const uint8_t* d_arena, uint32_t n, uint32_t* d_meta,
+                      uint32_t* d_vars, void* stream) {
+    if (!e || (n && (!d_desc || !d_arena || !d_meta || !d_vars))) return GOFR_ERR_INVALID;
+    if (n == 0) return GOFR_OK;
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    RouteParams p;
+    memset(&p, 0, sizeof p);
+    p.desc = d_desc; p.arena = d_arena; p.n = n; p.image = e->d_image; p.hot_bytes = e->hdr.hot_bytes;
+    p.meta = d_meta; p.vars = d_vars;
+    int rc = launch_route(p, e->sm_count, stream);
+    if (rc != 0) { set_last_error("route kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
+    e->launches++;
+    return GOFR_OK;
+}
+
 int gofr_requestlog_device(gofr_engine* e, const gofr_log_desc* d_desc, const uint8_t* d_trace_ids, const uint8_t* d_arena,
                            uint32_t n, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off, void* stream) {
     if (!e || (n && (!d_desc || !d_trace_ids || !d_arena || !d_out || !d_out_off))) return GOFR_ERR_INVALID;

@@ -71,6 +71,17 @@ struct GrpcParams {
 };
 int launch_grpc_hello(const GrpcParams& p, int grid, void* stream);
 
+struct RouteParams {
+    const void* desc;
+    const uint8_t* arena;
+    uint32_t n;
+    const uint8_t* image;
+    uint32_t hot_bytes;
+    uint32_t* meta;   // n: status | route << 16
+    uint32_t* vars;   // n * kMaxVars: off | len << 16
+};
+int launch_route(const RouteParams& p, int sm_count, void* stream);
+
 struct LogParams {
     const void* desc;   // gofr_log_desc[n]
     const void* ids;    // n * 16 trace id bytes

@@ -682,7 +682,8 @@ GOFR_HD bool words_equal(const uint32_t* a, const uint32_t* b, uint32_t n) {
 
 // Anchored leftmost-first match of lit0 var0 lit1 var1 ... litN [$]: greedy variables with backtracking — what Go's
 // regexp reports for the regexp mux builds from a path template.
-// want_var >= 0: also report the span captured by that piece's variable (mux.Vars) in span_out[0..1] = (offset, length)
+// want_var >= 0: also report the span captured by that piece's variable (mux.Vars) in span_out[0..1] = (offset, length);
+// want_var == -2: report every variable, span_out[2k], span_out[2k+1] for the k-th one (template order)
 GOFR_HD_NOINLINE bool template_match(const TableView tv, const RouteRec R, const uint8_t* p, uint32_t n, int want_var = -1,
                                      uint32_t* span_out = nullptr) {
     const PieceRec* pc = tv.pieces() + R.first_piece;
@@ -698,6 +699,8 @@ GOFR_HD_NOINLINE bool template_match(const TableView tv, const RouteRec R, const
             if (!pc[k].has_var) {
                 if (prefix || pos == n) {
                     if (want_var >= 0) { span_out[0] = start[want_var]; span_out[1] = take[want_var]; }
+                    if (want_var == -2)
+                        for (uint32_t j = 0; j < k; j++) { span_out[2 * j] = start[j]; span_out[2 * j + 1] = take[j]; }
                     return true;
                 }
                 ok = false;
@@ -955,6 +958,28 @@ GOFR_HD void route_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) 
             c.prog = brow[0] == 4u /* BE_DEPTH */ ? 0xFFFFu : R.prog_err;
         }
     }
+}
+
+// Routing only (gofr_route_device): what the router and the middlewares decide before any handler runs.
+// Returns 301 (cleanPath redirect), 404 / 405 (mux's own handlers), 200 (CORS answers OPTIONS itself,
+// middleware/cors.go:10-13) or 0 = "the handler of *route runs"; vars[k] = off | len << 16 of the k-th path variable
+// (mux.Vars in template order), 0xFFFFFFFF for unused slots.
+GOFR_HD uint32_t route_only(const TableView& tv, uint32_t method, const uint8_t* path, uint32_t n, uint32_t* route,
+                            uint32_t vars[kMaxVars]) {
+    *route = GOFR_ROUTE_NONE;
+    for (int k = 0; k < kMaxVars; k++) vars[k] = 0xFFFFFFFFu;
+    if (!path_is_clean(path, n)) return 301;
+    const int m = mux_match(tv, method, path, n);
+    if (m == -2) return 405;
+    if (m == -1) return 404;
+    *route = (uint32_t)m;
+    const RouteRec R = tv.routes()[m];
+    if (!(R.flags & RF_LITERAL) && R.n_pieces > 1) {
+        uint32_t sp[2 * kMaxVars + 2];
+        template_match(tv, R, path, n, -2, sp);
+        for (uint32_t k = 0; k + 1 < R.n_pieces && k < (uint32_t)kMaxVars; k++) vars[k] = sp[2 * k] | sp[2 * k + 1] << 16;
+    }
+    return method == GOFR_M_OPTIONS ? 200u : 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -118,6 +118,18 @@ class Engine:
                                                 resp.out_off.data_ptr(), resp.meta.data_ptr(), st.cuda_stream),
                    "gofr_serve_device")
 
+    # ---- routing only: stage 1 of the split API for closures that stay on the host ----
+    def route_device(self, b: DeviceBatch, stream=None):
+        """gofr_route_device → (meta int32[n] = status | route << 16, vars int32[n, 8] = off | len << 16)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        meta = torch.zeros(max(b.n, 1), dtype=torch.int32, device=dev)
+        vars_ = torch.zeros((max(b.n, 1), 8), dtype=torch.int32, device=dev)
+        _abi.check(_abi.lib().gofr_route_device(self._e, b.desc.data_ptr(), b.arena.data_ptr(), b.n, meta.data_ptr(),
+                                                vars_.data_ptr(), st.cuda_stream), "gofr_route_device")
+        return meta[:b.n], vars_[:b.n]
+
     # ---- RequestLog lines (middleware.Logging → logger.Log), device resident ----
     def request_log_device(self, batch: S.LogBatch, out_cap: Optional[int] = None, stream=None):
         """Uploads a LogBatch, runs gofr_requestlog_device, returns (out, out_off) torch tensors (uint8, int32 view)."""

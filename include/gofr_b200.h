@@ -20,6 +20,8 @@
  *   Request.Param / Bind          pkg/gofr/http/request.go:28-47   (fused into the serve kernel per handler kind)
  *   _Hello_SayHello_Handler       examples/grpc-server/grpc/
  *                                 hello_grpc.pb.go:73-89           gofr_grpc_hello_device
+ *   Router.Match + mux.Vars (routing only, closures on the host)
+ *                                 pkg/gofr/http/router.go:14,30-33 gofr_route_device
  *   middleware.Logging's RequestLog line → logger.Log
  *                                 pkg/gofr/http/middleware/logger.go:24-33,41-84,
  *                                 pkg/gofr/logging/logger.go:37-74 gofr_requestlog_device
@@ -226,6 +228,20 @@ void gofr_free_pinned(void*);
 enum { GOFR_GRPC_OK = 0, GOFR_GRPC_COMPRESSED = 1, GOFR_GRPC_BAD_LENGTH = 2, GOFR_GRPC_BAD_PROTO = 3, GOFR_GRPC_BAD_UTF8 = 4 };
 int gofr_grpc_hello_device(gofr_engine*, const uint8_t* d_in, const uint32_t* d_in_off, uint32_t n, uint8_t* d_out,
                            uint64_t out_cap, uint32_t* d_out_off, uint32_t* d_meta, void* stream);
+
+/* Stage 1 of the split API for routes whose closure stays on the host (GOFR_H_HOST): everything mux.Router.ServeHTTP
+ * and the middleware chain decide before handler.ServeHTTP runs (pkg/gofr/http/router.go:14,30-33;
+ * middleware/cors.go:10-13; pkg/gofr/handler.go:32-36), for a whole batch resident in HBM.
+ *   d_meta[i] = status | route_id << 16, status: 301 cleanPath redirect, 404 / 405 mux's own handlers (route_id =
+ *               GOFR_ROUTE_NONE), 200 OPTIONS answered by the CORS middleware, 0 = the handler of route_id runs;
+ *   d_vars[i * GOFR_MAX_PATH_VARS + k] = offset | length << 16 of the k-th path variable inside the request's path
+ *               (mux.Vars in template order — what Request.PathParam reads, pkg/gofr/http/request.go:36-38);
+ *               0xFFFFFFFF for unused slots.
+ * The host then runs the closures and hands their results to gofr_serve_device / gofr_batch_submit (same table: the
+ * route is registered with the handler kind that describes its result, e.g. GOFR_H_ROW). */
+#define GOFR_MAX_PATH_VARS 8
+int gofr_route_device(gofr_engine*, const gofr_req_desc* d_desc, const uint8_t* d_arena, uint32_t n, uint32_t* d_meta,
+                      uint32_t* d_vars, void* stream);
 
 /* The JSON line middleware.Logging hands to logger.Log after every request (non-terminal writer:
  * json.NewEncoder(out).Encode(logEntry{Level: INFO, Time: time.Now(), Message: RequestLog{...}})):

@@ -555,6 +555,37 @@ int orc_match(const orc_table* t, int method, const uint8_t* path, int path_len)
     return mux_match(t, method, path, (size_t)path_len);
 }
 
+/* Routing only: what Router.ServeHTTP and the middleware chain decide before the handler runs (router.go:14,30-33;
+ * cors.go:10-13), plus the spans mux.Vars would hold.  meta = status | route << 16 with status 301 / 404 / 405 /
+ * 200 (OPTIONS) / 0 (handler runs); vars[k] = off | len << 16 of the k-th variable, 0xFFFFFFFF unused. */
+int orc_route_batch(const orc_table* t, const void* desc_v, const uint8_t* arena, uint32_t n, uint32_t* meta, uint32_t* vars,
+              int max_vars) {
+    const uint8_t* desc = (const uint8_t*)desc_v;
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t d[4];
+        memcpy(d, desc + (size_t)i * 16, 16);
+        const uint8_t* path = arena + d[0];
+        size_t pn = d[1] & 0xFFFFu;
+        int method = (int)(d[3] & 0xFFu);
+        for (int k = 0; k < max_vars; k++) vars[(size_t)i * (size_t)max_vars + (size_t)k] = 0xFFFFFFFFu;
+        int m = orc_match(t, method, path, (int)pn);
+        if (m < 0) {
+            meta[i] = (uint32_t)(m == MATCH_301 ? 301 : m == MATCH_405 ? 405 : 404) | 0xFFFFu << 16;
+            continue;
+        }
+        const orc_route* r = &t->routes[m];
+        var_span spans[64];
+        memset(spans, 0, sizeof spans);
+        tpl_match_from(r, 0, path, pn, 0, spans);
+        int nv = 0;
+        for (int k = 0; k < r->n_pieces && nv < max_vars; k++)
+            if (r->pieces[k].has_var)
+                vars[(size_t)i * (size_t)max_vars + (size_t)nv++] = (uint32_t)spans[k].off | (uint32_t)spans[k].len << 16;
+        meta[i] = (method == 7 /* OPTIONS */ ? 200u : 0u) | (uint32_t)m << 16;
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------------------ */
 /* http.ResponseWriter model + net/http 1.21 framing                                                            */
 /* ------------------------------------------------------------------------------------------------------------ */

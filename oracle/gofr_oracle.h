@@ -62,6 +62,9 @@ int orc_bind(const orc_table*, int schema_id, const uint8_t* body, int n, uint8_
 /* RPCLog.String() (pkg/gofr/grpc/log.go:15-25): the reference's only byte-exact encoding/json golden. */
 int orc_rpclog_string(const char* id, const char* start_time, int64_t response_time, const char* method, uint8_t* out,
                       int cap);
+/* Router.Match + mux.Vars for a batch (the oracle of gofr_route_device); desc = gofr_req_desc[n]. */
+int orc_route_batch(const orc_table*, const void* desc, const uint8_t* arena, uint32_t n, uint32_t* meta, uint32_t* vars,
+              int max_vars);
 /* The JSON line middleware.Logging → logger.Log writes per request (orc_reqlog.c; logger.go:41-70, logging/logger.go:37-74).
  * desc: n records of 48 bytes in the layout of gofr_log_desc (include/gofr_b200.h); lines are packed back to back. */
 int orc_request_log(const void* desc, const uint8_t* ids, const uint8_t* arena, uint32_t n, uint8_t* out, uint64_t out_cap,

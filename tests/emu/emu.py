@@ -36,9 +36,20 @@ def lib():
                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
         _lib.emu_grpc_hello.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                         C.c_void_p, C.c_uint32]
+        _lib.emu_route.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.emu_reqlog.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                     C.c_uint32]
     return _lib
+
+
+def route(image: bytes, batch):
+    n = batch.n
+    img = np.frombuffer(image, dtype=np.uint8).copy()
+    meta = np.zeros(n, dtype=np.uint32)
+    vars_ = np.zeros((n, 8), dtype=np.uint32)
+    lib().emu_route(img.ctypes.data, batch.desc.ctypes.data, batch.arena.ctypes.data, n, meta.ctypes.data,
+                    vars_.ctypes.data)
+    return meta, vars_
 
 
 def request_log(batch, misalign: int = 0):

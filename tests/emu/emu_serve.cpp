@@ -53,6 +53,25 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
     return 0;
 }
 
+// ---- routing only (gofr_route_device): serve_device.cuh's route_only on the CPU ----
+extern "C" int emu_route(const uint8_t* image, const uint8_t* desc, const uint8_t* arena, uint32_t n, uint32_t* meta,
+                         uint32_t* vars) {
+    ImageHeader H;
+    memcpy(&H, image, sizeof H);
+    std::vector<uint32_t> hot((H.hot_bytes + 3) / 4 + 4);
+    memcpy(hot.data(), image, H.hot_bytes);
+    TableView tv;
+    tv.bind((const uint8_t*)hot.data(), image);
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t d[4];
+        memcpy(d, desc + (size_t)i * 16, 16);
+        uint32_t route;
+        const uint32_t status = route_only(tv, d[3] & 0xFF, arena + d[0], d[1] & 0xFFFF, &route, vars + (size_t)i * kMaxVars);
+        meta[i] = status | route << 16;
+    }
+    return 0;
+}
+
 // ---- RequestLog line: the same reqlog_device.cuh code the CUDA kernel runs ----
 #include "../../gofr_b200/csrc/reqlog_device.cuh"
 

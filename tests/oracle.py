@@ -43,6 +43,7 @@ def lib():
         L.orc_add_default_routes.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.orc_serve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_void_p,
                                 C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_route_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_request_log.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
         L.orc_grpc_hello.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                      C.c_int]
@@ -148,6 +149,19 @@ class OracleTable:
         if rc != 0:
             raise RuntimeError("oracle output capacity too small")
         return out, off, meta
+
+
+MAX_PATH_VARS = 8
+
+
+def route(table: "OracleTable", batch) -> Tuple[np.ndarray, np.ndarray]:
+    """Router.Match + mux.Vars for every request: (meta[n], vars[n, 8])."""
+    n = batch.n
+    meta = np.zeros(n, dtype=np.uint32)
+    vars_ = np.zeros((n, MAX_PATH_VARS), dtype=np.uint32)
+    lib().orc_route_batch(table._t, batch.desc.ctypes.data, batch.arena.ctypes.data, n, meta.ctypes.data, vars_.ctypes.data,
+                    MAX_PATH_VARS)
+    return meta, vars_
 
 
 def responses(out: np.ndarray, off: np.ndarray):

@@ -1,0 +1,116 @@
+"""Routing only (gofr_route_device): Router.Match + mux.Vars + the middleware decisions taken before a handler runs
+(pkg/gofr/http/router.go:14,30-33; middleware/cors.go:10-13; pkg/gofr/http/request.go:36-38) — stage 1 of the split
+API for closures that stay on the host."""
+import numpy as np
+import pytest
+
+from gofr_b200 import spec as S
+from gofr_b200 import synth
+from gofr_b200.table import Table
+from tests import oracle as O
+from tests.emu import emu
+
+
+def _multi_var_spec() -> S.TableSpec:
+    host = lambda m, p: S.Route(m, p, S.H_HOST)
+    return S.TableSpec(default_routes=False, routes=[
+        host(S.M_GET, "/users/{id}"),
+        host(S.M_GET, "/users/{id}/posts/{post:[0-9]+}"),
+        host(S.M_POST, "/users/{id}"),
+        host(S.M_GET, "/files/{dir}/{name}.{ext}"),
+        host(S.M_GET, "/v{major:[0-9]+}.{minor:[0-9]+}/ping"),
+        host(S.M_GET, "/static"),
+        host(S.M_GET, "/a/{x}{y:[0-9]+}"),          # adjacent variables: leftmost-first with backtracking
+        host(S.M_DELETE, "/users/{id}"),
+    ])
+
+
+def _multi_var_batch() -> S.RequestBatch:
+    R = S.Req
+    reqs = [R(S.M_GET, b"/users/42"), R(S.M_GET, b"/users/42/posts/7"), R(S.M_GET, b"/users/42/posts/x7"),
+            R(S.M_POST, b"/users/abc"), R(S.M_PUT, b"/users/abc"), R(S.M_GET, b"/files/etc/passwd.txt"),
+            R(S.M_GET, b"/files/a/b.c.d"), R(S.M_GET, b"/v12.345/ping"), R(S.M_GET, b"/v.1/ping"), R(S.M_GET, b"/static"),
+            R(S.M_OPTIONS, b"/static"), R(S.M_OPTIONS, b"/users/9"), R(S.M_GET, b"/a/bc123"), R(S.M_GET, b"/a/123"),
+            R(S.M_GET, b"/a/1"), R(S.M_GET, b"//users/1"), R(S.M_GET, b"/users/"), R(S.M_GET, b"/nope"),
+            R(S.M_DELETE, b"/users/%C3%A9"), R(S.M_HEAD, b"/users/1"), R(S.M_OTHER, b"/static"), R(S.M_GET, b"/users/../x")]
+    return S.RequestBatch.pack(reqs)
+
+
+def test_oracle_spans_by_hand():
+    spec, b = _multi_var_spec(), _multi_var_batch()
+    meta, vars_ = O.route(O.OracleTable(spec), b)
+    span = lambda i, k: (int(vars_[i, k]) & 0xFFFF, int(vars_[i, k]) >> 16)
+    path = lambda i: bytes(b.arena[int(b.desc[i]["arena_off"]):][:int(b.desc[i]["path_len"])])
+    get = lambda i, k: path(i)[span(i, k)[0]:][:span(i, k)[1]]
+    assert meta[0] == 0 | 0 << 16 and get(0, 0) == b"42" and vars_[0, 1] == 0xFFFFFFFF
+    assert meta[1] == 0 | 1 << 16 and (get(1, 0), get(1, 1)) == (b"42", b"7")
+    assert meta[2] & 0xFFFF == 404
+    assert meta[3] == 0 | 2 << 16 and get(3, 0) == b"abc"
+    assert meta[4] & 0xFFFF == 405                       # PUT: no Run() catch-all here → mux's own 405
+    assert (get(5, 0), get(5, 1), get(5, 2)) == (b"etc", b"passwd", b"txt")
+    assert (get(6, 0), get(6, 1), get(6, 2)) == (b"a", b"b.c", b"d")   # greedy {name}, shortest {ext}
+    assert (get(7, 0), get(7, 1)) == (b"12", b"345")
+    assert meta[8] & 0xFFFF == 404
+    # OPTIONS only matches routes registered for it (app.GET → Methods("GET")): without Run()'s catch-all mux answers
+    # 405 before any middleware; with it the catch-all matches and CORS answers 200 (test_options_with_catch_all)
+    assert meta[10] & 0xFFFF == 405 and meta[11] & 0xFFFF == 405
+    assert (get(12, 0), get(12, 1)) == (b"bc12", b"3")   # {x} greedy, gives back one byte for {y:[0-9]+}
+    assert (get(13, 0), get(13, 1)) == (b"12", b"3")
+    assert meta[14] & 0xFFFF == 404                      # "1" cannot feed both variables
+    assert meta[15] & 0xFFFF == 301 and meta[21] & 0xFFFF == 301
+    assert meta[19] & 0xFFFF == 405 and meta[20] & 0xFFFF == 405
+
+
+def test_options_with_catch_all():
+    spec = _multi_var_spec()
+    spec.default_routes = True
+    b = S.RequestBatch.pack([S.Req(S.M_OPTIONS, b"/static"), S.Req(S.M_OPTIONS, b"/users/9"), S.Req(S.M_PUT, b"/static")])
+    meta, vars_ = O.route(O.OracleTable(spec), b)
+    catch_all = len(spec.routes) + 2  # health, favicon, then PathPrefix("/") (gofr.go:102-107)
+    assert meta[0] == 200 | catch_all << 16 and meta[1] == 200 | catch_all << 16
+    assert meta[2] == 0 | catch_all << 16          # the catch-all's handler answers 404 itself
+    assert (vars_ == 0xFFFFFFFF).all()
+
+
+@pytest.mark.parametrize("which", ["multi", "config4", "config1"])
+def test_emu_matches_oracle(which):
+    if which == "multi":
+        spec, b = _multi_var_spec(), _multi_var_batch()
+    elif which == "config4":
+        spec, b = synth.config4_spec(), synth.config4_batch(6000)
+    else:
+        spec, b = synth.config1_spec(), synth.config1_batch(300)
+    m1, v1 = O.route(O.OracleTable(spec), b)
+    t = Table(spec)
+    m2, v2 = emu.route(t.serialize(), b)
+    assert np.array_equal(m1, m2)
+    assert np.array_equal(v1, v2)
+
+
+def test_route_agrees_with_serve_meta():
+    # the serve path's meta column carries the same route ids; statuses agree wherever the router itself answers
+    spec, b = synth.config4_spec(), synth.config4_batch(4000)
+    ot = O.OracleTable(spec)
+    m1, _ = O.route(ot, b)
+    _, _, meta = ot.serve(b, S.http_date(1_700_000_000))
+    router_answers = (m1 & 0xFFFF) != 0
+    assert np.array_equal(m1[router_answers], meta[router_answers])
+    assert np.array_equal(m1 >> 16, meta >> 16)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which,n", [("multi", 0), ("config4", 262144), ("config2", 100000)])
+def test_gpu_matches_oracle(which, n):
+    from gofr_b200.engine import Engine
+    if which == "multi":
+        spec, b = _multi_var_spec(), _multi_var_batch()
+    elif which == "config4":
+        spec, b = synth.config4_spec(), synth.config4_batch(n)
+    else:
+        spec, b = synth.config2_spec(), synth.config2_batch(n)
+    m1, v1 = O.route(O.OracleTable(spec), b)
+    eng = Engine(Table(spec), 0)
+    meta, vars_ = eng.route_device(eng.upload(b))
+    assert np.array_equal(m1, meta.cpu().numpy().view(np.uint32))
+    assert np.array_equal(v1, vars_.cpu().numpy().view(np.uint32))
+    eng.close()
