@@ -949,6 +949,14 @@ GOFR_HD void route_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) 
         }
         c.def_off = R.def_off;
         c.def_len = 0;
+    } else if (R.hkind == GOFR_H_RESULT) {
+        // the closure ran on the host; its outcome word selects what Responder.Respond does (responder.go:19-62)
+        const uint32_t outcome = c.data_len >= 4 ? *(const uint32_t*)c.data() : 0xFFFFFFFFu;
+        if (outcome > GOFR_RESULT_MISSING) { c.prog = H.prog_panic; return; }  // malformed record from the host shim
+        c.data_off += 4;
+        c.data_len -= 4;
+        c.prog = outcome == GOFR_RESULT_DATA ? R.prog_ok : outcome == GOFR_RESULT_ERROR ? R.prog_err
+               : outcome == GOFR_RESULT_NIL ? R.key_len : R.def_len;
     } else if (R.hkind == GOFR_H_BIND_ECHO) {
         // var v T; if err := c.Bind(&v); err != nil { return nil, err }; return v, nil
         uint32_t* brow = c.brow(br);
@@ -1003,8 +1011,7 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
     uint32_t str_cursor = 0;  // byte offset of the next string in the row's string area
     uint32_t str_base = 0;
     if ((P.flags & PF_NEEDS_ROW) && !(P.flags & PF_BIND)) {
-        const SchemaRec& S = tv.schemas()[tv.routes()[c.route].schema];
-        str_base = (uint32_t)S.fixed_words * 4;
+        str_base = P.row_words ? (uint32_t)P.row_words * 4 : (uint32_t)tv.schemas()[tv.routes()[c.route].schema].fixed_words * 4;
         if (!EMIT && str_base > c.data_len) return false;
     }
     uint32_t hdr_dyn = 0, body_dyn = 0, str_bit = 1;

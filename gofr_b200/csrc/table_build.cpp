@@ -188,6 +188,7 @@ struct SOp {
 struct Prog {
     int status = 200;
     bool bind = false;
+    int row_words = 0;  // see ProgRec::row_words
     std::vector<SOp> ops;
 };
 
@@ -437,7 +438,7 @@ struct Builder {
     std::map<std::string, int> prog_ids;
     // identical programs (e.g. sixteen routes returning the same struct type) are stored once
     int add(Prog p) {
-        std::string sig = std::to_string(p.status) + (p.bind ? "B" : "R");
+        std::string sig = std::to_string(p.status) + (p.bind ? "B" : "R") + std::to_string(p.row_words);
         for (auto& o : p.ops) {
             sig += "|" + std::to_string(o.code) + "," + std::to_string(o.arg) + "," + std::to_string(o.flags) + "," +
                    std::to_string(o.kind) + "," + std::to_string(o.off) + "," + std::to_string(o.aux) + "," +
@@ -561,10 +562,11 @@ int seal_table(gofr_table* t) {
 
     // ---- per-route programs ----
     std::vector<int> prog_ok(t->routes.size(), 0xFFFF), prog_err(t->routes.size(), 0xFFFF);
+    std::vector<int> prog_err404(t->routes.size(), 0xFFFF), prog_nil(t->routes.size(), 0xFFFF);
     for (size_t ri = 0; ri < t->routes.size(); ri++) {
         RouteDef& r = t->routes[ri];
         const SchemaDef* sc = nullptr;
-        if (r.hkind == GOFR_H_ROW || r.hkind == GOFR_H_BIND_ECHO) {
+        if (r.hkind == GOFR_H_ROW || r.hkind == GOFR_H_BIND_ECHO || r.hkind == GOFR_H_RESULT) {
             for (auto& s : t->schemas) if (s.id == r.schema_id) sc = &s;
             if (!sc) { set_last_error("route %s: unknown schema %u", r.pattern.c_str(), r.schema_id); return GOFR_ERR_INVALID; }
         }
@@ -605,6 +607,30 @@ int seal_table(gofr_table* t) {
                 if (r.hkind == GOFR_H_BIND_ECHO)
                     prog_err[ri] = b.json_prog(500, {lit("{\"error\":{\"message\":\"", true), op(OP_ERRMSG, true),
                                                      lit("\"}}\n", true)}, true);
+                break;
+            }
+            case GOFR_H_RESULT: {
+                // Responder.Respond on a (data, err) the host closure produced (responder.go:19-62)
+                Prog p;
+                p.status = 200;
+                build_header(p, fm, 200, true, BODY_JSON, false, "", "", false);
+                p.ops.push_back(lit("{\"data\":", true));
+                build_struct_ops(p, *sc, false);
+                p.ops.push_back(lit("}\n", true));
+                prog_ok[ri] = b.add(std::move(p));
+                for (int which = 0; which < 2; which++) {  // 500, and 404 for errors.Is(err, http.ErrMissingFile)
+                    Prog e;
+                    e.status = which ? 404 : 500;
+                    build_header(e, fm, e.status, true, BODY_JSON, false, "", "", false);
+                    e.ops.push_back(lit("{\"error\":{\"message\":\"", true));
+                    SOp m = op(OP_STR, true);
+                    m.off = 0;  // row word 0 = len(err.Error()), the bytes follow
+                    e.ops.push_back(m);
+                    e.ops.push_back(lit("\"}}\n", true));
+                    e.row_words = 1;
+                    (which ? prog_err404 : prog_err)[ri] = b.add(std::move(e));
+                }
+                prog_nil[ri] = b.json_prog(200, {lit("{}\n", true)});
                 break;
             }
             case GOFR_H_FILE: {
@@ -688,7 +714,11 @@ int seal_table(gofr_table* t) {
             R.def_off = pool.put(d);
             R.def_len = (uint16_t)d.size();
         }
-        if (r.hkind == GOFR_H_ROW || r.hkind == GOFR_H_BIND_ECHO)
+        if (r.hkind == GOFR_H_RESULT) {  // the two spare 16-bit fields carry the other outcomes' programs
+            R.key_len = (uint16_t)prog_nil[ri];
+            R.def_len = (uint16_t)prog_err404[ri];
+        }
+        if (r.hkind == GOFR_H_ROW || r.hkind == GOFR_H_BIND_ECHO || r.hkind == GOFR_H_RESULT)
             for (size_t si = 0; si < t->schemas.size(); si++)
                 if (t->schemas[si].id == r.schema_id) R.schema = (uint16_t)si;
     }
@@ -733,6 +763,7 @@ int seal_table(gofr_table* t) {
         P.first_op = (uint16_t)ops.size();
         P.n_ops = (uint16_t)p.ops.size();
         P.status = (uint16_t)p.status;
+        P.row_words = (uint16_t)p.row_words;
         if (p.bind) P.flags |= PF_BIND;
         for (auto& so : p.ops) {
             Op o;

@@ -12,7 +12,7 @@
 namespace gofr {
 
 constexpr uint32_t kMagic = 0x52464F47u;  // "GOFR"
-constexpr uint32_t kImageVersion = 7;
+constexpr uint32_t kImageVersion = 8;
 constexpr uint32_t kMaxHotBytes = 40 * 1024;  // shared-memory budget for the table
 constexpr int kMaxVars = 8;                   // variables per route template
 constexpr int kMaxFields = 32;                // struct fields per schema
@@ -125,7 +125,7 @@ struct ProgRec {  // 32 B
     uint16_t first_dyn;  // the ops whose length depends on the request, in order: all the size pass has to visit
     uint16_t n_dyn;
     uint16_t n_hdr_ops;  // ops before the first body op (body ops come last): all a HEAD response emits
-    uint16_t pad0;
+    uint16_t row_words;  // nonzero: the row's fixed part is this many words whatever the route's schema (GOFR_H_RESULT errors)
     uint32_t pad[2];
 };
 static_assert(sizeof(ProgRec) == 32, "ProgRec layout");

@@ -92,8 +92,16 @@ enum {
     GOFR_H_MISSING_FILE = 8,  /* catchAllHandler: return nil, http.ErrMissingFile      handler.go:51-53 */
     GOFR_H_FILE = 9,          /* return response.File{Content: blob, ContentType: s0}   handler.go:42-49 */
     GOFR_H_PANIC = 10,        /* handler panics; middleware.panicRecovery answers       middleware/logger.go:91-114 */
-    GOFR_H_PATHPARAM_FORMAT = 11 /* v := c.PathParam(s0); return s2 + v + s3, nil          pkg/gofr/http/request.go:36-38 */
+    GOFR_H_PATHPARAM_FORMAT = 11, /* v := c.PathParam(s0); return s2 + v + s3, nil         pkg/gofr/http/request.go:36-38 */
+    GOFR_H_RESULT = 12        /* stage 2 of the split API: the closure already ran on the host (after gofr_route_device);
+                                 its (data, err) arrives in the request's data section and Responder.Respond runs here
+                                 (pkg/gofr/http/responder.go:19-62).  Data section: one LE u32 outcome word, then
+                                   GOFR_RESULT_DATA     a row of the route's schema (as for GOFR_H_ROW)      → 200 {"data":{…}}
+                                   GOFR_RESULT_ERROR    u32 length + err.Error() bytes                      → 500 {"error":{"message":…}}
+                                   GOFR_RESULT_NIL      nothing                                             → 200 {}
+                                   GOFR_RESULT_MISSING  u32 length + message; errors.Is(err, http.ErrMissingFile) → 404 */
 };
+enum { GOFR_RESULT_DATA = 0, GOFR_RESULT_ERROR = 1, GOFR_RESULT_NIL = 2, GOFR_RESULT_MISSING = 3 };
 
 /* ---- struct field kinds for response / Bind schemas ---- */
 enum {

@@ -32,7 +32,7 @@ enum { M_ANY = 255 };
 enum { FRAME_WIRE = 0, FRAME_INTENDED = 1, FRAME_BODY = 2 };
 enum {
     H_HOST = 0, H_STATIC_STRING = 1, H_STATIC_ERROR = 2, H_NIL = 3, H_PARAM_FORMAT = 4, H_ROW = 5, H_BIND_ECHO = 6,
-    H_HEALTH = 7, H_MISSING_FILE = 8, H_FILE = 9, H_PANIC = 10, H_PATHPARAM_FORMAT = 11
+    H_HEALTH = 7, H_MISSING_FILE = 8, H_FILE = 9, H_PANIC = 10, H_PATHPARAM_FORMAT = 11, H_RESULT = 12
 };
 
 /* one piece of a mux path template: a literal followed (optionally) by a variable */
@@ -947,6 +947,26 @@ static void serve_one(const orc_table* t, const req_desc* d, const uint8_t* id16
                     /* malformed row from the host shim: not a reference behaviour; both sides answer as a panic */
                     hr.data_kind = -1;
                 } else { hr.data_kind = 2; hr.sc = sc; hr.vals = vals; }
+                break;
+            }
+            case H_RESULT: {
+                /* stage 2 of the split API: the closure's (data, err) arrives in the data section and
+                 * Responder.Respond runs on it (responder.go:19-62) */
+                const orc_schema* sc = find_schema(t, r->schema_id);
+                uint32_t outcome = 0xFFFFFFFFu;
+                if (dn >= 4) memcpy(&outcome, data, 4);
+                const uint8_t* rest = data + 4;
+                size_t rn = dn >= 4 ? dn - 4 : 0;
+                if (outcome == 0) {
+                    if (!sc || decode_row(sc, rest, rn, vals) != 0) hr.data_kind = -1;
+                    else { hr.data_kind = 2; hr.sc = sc; hr.vals = vals; }
+                } else if (outcome == 1 || outcome == 3) {
+                    uint32_t len = 0;
+                    if (rn >= 4) memcpy(&len, rest, 4);
+                    if (rn < 4 || (uint64_t)len + 4 > rn) { hr.data_kind = -1; break; }
+                    hr.has_err = 1; hr.err_msg = rest + 4; hr.err_len = len;
+                    hr.err_is_missing_file = outcome == 3;
+                } else if (outcome != 2) hr.data_kind = -1;
                 break;
             }
             case H_BIND_ECHO: {
