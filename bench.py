@@ -48,7 +48,7 @@ def hbm_peak():
 
 def profiled_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one serve_kernel launch on this exact workload (1 Mi requests),
-    from the committed `ncu --set full` capture (profiles/r01/serve_kernel_final_1M_key_metrics.txt)."""
+    from the committed `ncu --set full` capture (profiles/r01/serve_kernel_v11_1M_key_metrics.txt)."""
     try:
         tot = 0.0
         with open(os.path.join(ROOT, "profiles", "r01", "serve_kernel_final_1M_key_metrics.txt")) as f:

@@ -115,14 +115,15 @@ GOFR_HD void hello_emit(const uint8_t* f, const HelloReq r, uint8_t* dst, uint32
     for (uint32_t v = ml;;) {  // varint(len(message))
         uint32_t b = v & 0x7F;
         v >>= 7;
-        w.put1(v ? b | 0x80 : b);
+        w.putc(v ? b | 0x80 : b);  // at most 21 bytes precede the name: the staging buffer cannot fill up
         if (!v) break;
     }
     w.put4('H' | 'e' << 8 | 'l' << 16 | 'l' << 24);
     w.putk('o' | ' ' << 8, 2);
     if (r.name_len) w.copy<false>(f + r.name_off, r.name_len);
-    else { w.put4('W' | 'o' << 8 | 'r' << 16 | 'l' << 24); w.put1('d'); }
-    w.put1('!');
+    else { w.put4('W' | 'o' << 8 | 'r' << 16 | 'l' << 24); w.putc('d'); }
+    w.reserve(2);
+    w.putc('!');
     w.finish();
 }
 
