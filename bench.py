@@ -51,7 +51,7 @@ def profiled_traffic():
     from the committed `ncu --set full` capture (profiles/r01/serve_kernel_v11_1M_key_metrics.txt)."""
     try:
         tot = 0.0
-        with open(os.path.join(ROOT, "profiles", "r01", "serve_kernel_final_1M_key_metrics.txt")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01", "serve_kernel_v11_1M_key_metrics.txt")) as f:
             for ln in f:
                 p = ln.split()
                 if p and p[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
