@@ -114,3 +114,50 @@ def test_gpu_matches_oracle(which, n):
     assert np.array_equal(m1, meta.cpu().numpy().view(np.uint32))
     assert np.array_equal(v1, vars_.cpu().numpy().view(np.uint32))
     eng.close()
+
+
+# ---- random route tables × random paths: the device matcher (hash dispatch + iterative backtracking) against the
+# oracle's literal restatement of mux (recursive leftmost-first), including variable spans ----
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_seg = st.sampled_from(["a", "b", "ab", "users", "v1", "x.y", "1", "22", "a-b", "_"])
+_var = st.sampled_from(["{id}", "{n:[0-9]+}", "{w:[a-z]+}", "{s:[a-z0-9.]*}", "{id}.{ext}", "{a}{b:[0-9]+}", "p{q}", "{d:\\d+}x"])
+_piece = st.one_of(_seg, _var)
+_pattern = st.lists(_piece, min_size=0, max_size=4).map(lambda ps: "/" + "/".join(ps))
+_method = st.sampled_from([S.M_GET, S.M_GET, S.M_POST, S.M_DELETE, S.M_ANY])
+
+
+def _rename_vars(pattern: str, k: int) -> str:
+    # mux refuses duplicate variable names inside one route; keep names unique per route
+    out, i, c = "", 0, 0
+    while i < len(pattern):
+        if pattern[i] == "{":
+            j = pattern.index("}", i)
+            body = pattern[i + 1:j]
+            name, sep, rest = body.partition(":")
+            out += "{%s%d_%d%s%s}" % (name, k, c, sep, rest)
+            c += 1
+            i = j + 1
+        else:
+            out += pattern[i]
+            i += 1
+    return out
+
+
+@settings(max_examples=250, deadline=None)
+@given(st.lists(st.tuples(_method, _pattern), min_size=1, max_size=10), st.booleans(),
+       st.lists(st.tuples(st.sampled_from([S.M_GET, S.M_POST, S.M_DELETE, S.M_OPTIONS, S.M_HEAD, S.M_OTHER]),
+                          st.lists(st.sampled_from(["a", "b", "ab", "users", "v1", "x.y", "1", "22", "a-b", "_", "42", "abc9",
+                                                    "p7", "3x", "q.tar.gz", "", ".", ".."]), min_size=0, max_size=4)),
+                min_size=1, max_size=24))
+def test_random_tables_property(routes, defaults, reqs):
+    spec = S.TableSpec(default_routes=defaults,
+                       routes=[S.Route(m, _rename_vars(p, k), S.H_HOST) for k, (m, p) in enumerate(routes)])
+    batch = S.RequestBatch.pack([S.Req(m, ("/" + "/".join(segs)).encode()) for m, segs in reqs])
+    m1, v1 = O.route(O.OracleTable(spec), batch)
+    m2, v2 = emu.route(Table(spec).serialize(), batch)
+    assert np.array_equal(m1, m2), (spec.routes, reqs)
+    assert np.array_equal(v1, v2), (spec.routes, reqs)
+    # and the full serve path reports the same route ids (H_HOST routes come back with status 0)
+    _, _, m3 = emu.serve(Table(spec).serialize(), batch, S.http_date(1_700_000_000))
+    assert np.array_equal(m1 >> 16, m3 >> 16)
