@@ -261,6 +261,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer measurement (default: --steps)")
     ap.add_argument("--chunk", type=int, default=65536)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--layout", default="packed", choices=["packed", "slots"],
+                    help="resident measurement: packed offsets (gofr_serve_device) or one 528-byte slot per response "
+                         "(gofr_serve_device_slots)")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5", "reqlog"],
                     help="config2 is the BASELINE metric line; the others are secondary measurements (resident only)")
     args = ap.parse_args()
@@ -315,8 +318,19 @@ def main():
         return float(t.item())
 
     # ---- resident measurement (`value`, roofline) ----
+    slot = (synth.C2_WIRE_BYTES + 15) & ~15
+    if args.layout == "slots":
+        s_out = torch.empty(n * slot, dtype=torch.uint8, device=dev)
+        s_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        s_meta = torch.zeros(n, dtype=torch.int32, device=dev)
+
+        def serve_resident():
+            eng.serve_device_slots(db, date, slot, out=s_out, out_len=s_len, meta=s_meta)
+    else:
+        def serve_resident():
+            eng.serve_device(db, date, resp)
     for _ in range(args.warmup):
-        eng.serve_device(db, date, resp)
+        serve_resident()
     barrier()
     assert not eng.overflowed()
     eng.kernel_time_ms(reset=True)
@@ -327,7 +341,7 @@ def main():
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        eng.serve_device(db, date, resp)
+        serve_resident()
     ev1.record()
     barrier()
     ms = reduce_max(ev0.elapsed_time(ev1))
@@ -340,6 +354,14 @@ def main():
     peak, peak_src = hbm_peak()
 
     # spot check inside the bench: sizes are what the workload says
+    if args.layout == "slots":
+        assert bool((s_len == synth.C2_WIRE_BYTES).all()), "unexpected response size"
+        eng.serve_device(db, date, resp)  # the packed result the checks below compare against
+        torch.cuda.synchronize()
+        k = 4096
+        a = s_out[:k * slot].view(k, slot)[:, :synth.C2_WIRE_BYTES].reshape(-1)
+        assert bool((a == resp.out[:k * synth.C2_WIRE_BYTES]).all()), "slot layout and packed layout disagree"
+        eng.kernel_time_ms(reset=True)
     off = resp.out_off.cpu().numpy().view(np.uint32)
     assert int(off[n]) == out_bytes, "unexpected response size"
 
@@ -399,7 +421,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8", "data": "synthetic", "config": workload_config(n, world, "gpu"),
+                "dtype": "u8", "data": "synthetic", "config": dict(workload_config(n, world, "gpu"), resident_layout=args.layout),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": profiled_traffic() if n == (1 << 20) else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                              "algorithmic_bytes_per_request": algo_bytes / n, "kernel_ms_per_launch": per_launch_ms,

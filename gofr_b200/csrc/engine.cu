@@ -203,7 +203,7 @@ int gofr_engine_set_chunk(gofr_engine* e, uint32_t requests_per_chunk) {
 static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, const uint8_t* d_arena, uint32_t n,
                       const char* date29, uint8_t* d_out, uint64_t out_cap, uint32_t* d_off, uint32_t* d_meta,
                       unsigned long long* d_state, uint32_t* d_flag, uint32_t* d_bind, cudaStream_t stream,
-                      const unsigned long long* chain_pos = nullptr) {
+                      const unsigned long long* chain_pos = nullptr, uint32_t slot_bytes = 0) {
     ServeParams p;
     memset(&p, 0, sizeof p);
     p.desc = d_desc; p.ids = d_ids; p.arena = d_arena; p.n = n;
@@ -217,6 +217,7 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
     p.in_cap = e->in_cap;
     p.bind_scratch = d_bind; p.bind_row_words = e->hdr.bind_row_words;
     p.chain_pos = chain_pos;
+    p.slot_bytes = slot_bytes;
     if (getenv("GOFR_DEBUG_NO_LOOKBACK")) p.debug_flags |= 1u;  // diagnostic only
     memcpy(p.date, date29, 29);
     int grid = (int)std::min<uint32_t>((uint32_t)e->grid, p.n_tiles);
@@ -269,6 +270,31 @@ int gofr_serve_device(gofr_engine* e, const gofr_req_desc* d_desc, const uint8_t
     }
     return launch_one(e, d_desc, d_trace_ids, d_arena, n, date29, d_out, out_cap, d_out_off, d_meta, e->d_state, e->d_flag,
                       e->d_bind, st);
+}
+
+int gofr_serve_device_slots(gofr_engine* e, const gofr_req_desc* d_desc, const uint8_t* d_trace_ids, const uint8_t* d_arena,
+                            uint32_t n, const char* date29, uint8_t* d_out, uint32_t slot_bytes, uint32_t* d_out_len,
+                            uint32_t* d_meta, void* stream) {
+    if (!e || !date29 || (n && (!d_desc || !d_trace_ids || !d_out || !d_out_len || !d_meta))) return GOFR_ERR_INVALID;
+    if (slot_bytes == 0 || (slot_bytes & 15u) || ((uintptr_t)d_out & 15u)) {
+        set_last_error("slot_bytes must be a positive multiple of 16 and d_out 16-byte aligned");
+        return GOFR_ERR_INVALID;
+    }
+    if (n == 0) return GOFR_OK;
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (e->hdr.bind_row_words) {
+        size_t need = (size_t)n * e->hdr.bind_row_words * 4;
+        if (need > e->bind_cap) {
+            cudaFree(e->d_bind);
+            e->d_bind = nullptr;
+            CUDA_TRY(cudaMalloc(&e->d_bind, need + need / 4 + 256));
+            e->bind_cap = need + need / 4;
+        }
+    }
+    // no look-back scratch: slots make the tiles independent of each other
+    return launch_one(e, d_desc, d_trace_ids, d_arena, n, date29, d_out, (uint64_t)n * slot_bytes, d_out_len, d_meta, nullptr,
+                      e->d_flag, e->d_bind, (cudaStream_t)stream, nullptr, slot_bytes);
 }
 
 int gofr_engine_overflowed(gofr_engine* e, int* flag_out, int reset) {

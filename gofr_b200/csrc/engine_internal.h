@@ -32,6 +32,8 @@ struct ServeParams {
     uint32_t* bind_scratch;  // n * bind_row_words words (tables with GOFR_H_BIND_ECHO routes), else null
     uint32_t bind_row_words;
     const unsigned long long* chain_pos;  // host-batch path: packed position of the whole batch so far (else null)
+    uint32_t slot_bytes;     // 0: packed output (out_off = offsets, n + 1 entries); else response i lives in the slot
+                             // out + i * slot_bytes (multiple of 16) and out_off[i] receives its length
     uint32_t debug_flags;    // bit0: skip the look-back (tile_base = tile * tile_total; only valid for fixed-size responses)
 };
 

@@ -318,6 +318,18 @@ struct Writer {
         }
         nb = nn;
     }
+    // Slot layout (gofr_serve_device_slots): the response owns its 16-byte aligned slot, so the last chunk is stored
+    // whole, zero padded — no byte stores, nothing of a neighbour to preserve.
+    GOFR_HD void finish_padded() {
+        flush();
+        if (wl || nb) {
+            const uint32_t tail = nb ? pend >> (8 * (4 - nb)) : 0u;
+            uint32_t v[4];
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) v[j] = j < wl ? word(j) : (j == wl ? tail : 0u);
+            store16(chunk, v[0], v[1], v[2], v[3]);
+        }
+    }
     GOFR_HD void finish() {
         flush();
         if (wl || nb) {  // the last, partial chunk; wl <= 3 after the flush
@@ -1170,12 +1182,13 @@ GOFR_HD void size_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
 // HTTP status of a sized request (0: GOFR_H_HOST, the closure runs on the host)
 GOFR_HD uint32_t request_status(const TableView& tv, const ReqCtx& c) { return c.prog == 0xFFFF ? 0u : tv.progs()[c.prog].status; }
 
+template <bool SLOTS = false>
 GOFR_HD void emit_request(const TableView& tv, const BatchRefs& br, ReqCtx& c, uint8_t* dst, uint32_t* ring_col) {
     if (c.total_len == 0) return;
     Writer w;
     w.init(dst, ring_col);
     run_prog<true>(tv, br, c, &w);
-    w.finish();
+    if (SLOTS) w.finish_padded(); else w.finish();
 }
 
 // Patch the batch's Date into a private copy of the table's hot part (the kernel does this on its shared-memory

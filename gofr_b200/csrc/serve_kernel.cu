@@ -40,7 +40,8 @@ struct TileShared {
     uint32_t ring[GOFR_STAGE_WORDS * T];  // word-major staging buffer of the Writer (serve_device.cuh)
 };
 
-__global__ void __launch_bounds__(T, 5) serve_kernel(const ServeParams p) {
+template <bool SLOTS>
+__device__ __forceinline__ void serve_body(const ServeParams& p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(16) TileShared sh;
 
@@ -118,6 +119,17 @@ __global__ void __launch_bounds__(T, 5) serve_kernel(const ServeParams p) {
         c.set(abase, arena_off, path_len, query_len, data_len, d.w & 0xFFu, (d.w >> 8) & 0xFFu, in_staged, i);
         if (valid) size_request(tv, br, c);
 
+        if (SLOTS) {
+            // Slot layout: response i owns out + i * slot_bytes.  No scan, no look-back, no dependence between tiles —
+            // and every response starts 16-byte aligned.
+            const bool fits = c.total_len <= p.slot_bytes;
+            if (valid) {
+                p.out_off[i] = c.total_len;  // the length column; > slot_bytes tells the host the slot was too small
+                p.meta[i] = request_status(tv, c) | (c.route << 16);
+                if (fits && c.total_len) emit_request<true>(tv, br, c, p.out + (size_t)i * p.slot_bytes, &sh.ring[tid]);
+            }
+            continue;
+        }
         // ---- block scan of response sizes ----
         uint32_t incl = c.total_len;
 #pragma unroll
@@ -159,6 +171,9 @@ __global__ void __launch_bounds__(T, 5) serve_kernel(const ServeParams p) {
     }
 }
 
+__global__ void __launch_bounds__(T, 5) serve_kernel(const ServeParams p) { serve_body<false>(p); }
+__global__ void __launch_bounds__(T, 5) serve_slots_kernel(const ServeParams p) { serve_body<true>(p); }
+
 uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap) {
     return ((hot_bytes + 127u) & ~127u) + in_cap + 64;
 }
@@ -167,14 +182,18 @@ int serve_max_grid(uint32_t smem_bytes, int device, int* blocks_per_sm) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(serve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
-    int nb = 0;
+    if (cudaFuncSetAttribute(serve_slots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
+    int nb = 0, nb2 = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, serve_kernel, T, smem_bytes) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, serve_slots_kernel, T, smem_bytes) != cudaSuccess) return -1;
+    if (nb2 < nb) nb = nb2;
     if (blocks_per_sm) *blocks_per_sm = nb;
     return nb * prop.multiProcessorCount;
 }
 
 int launch_serve(const ServeParams& p, int grid, uint32_t smem_bytes, void* stream) {
-    serve_kernel<<<grid, T, smem_bytes, (cudaStream_t)stream>>>(p);
+    if (p.slot_bytes) serve_slots_kernel<<<grid, T, smem_bytes, (cudaStream_t)stream>>>(p);
+    else serve_kernel<<<grid, T, smem_bytes, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }
 

@@ -153,6 +153,24 @@ class Engine:
                                                      d_out.data_ptr(), out_cap, d_off.data_ptr(), st.cuda_stream),
                    "gofr_requestlog_device")
 
+    def serve_device_slots(self, b: DeviceBatch, date: bytes, slot_bytes: int, out=None, out_len=None, meta=None, stream=None):
+        """gofr_serve_device_slots: response i at out[i * slot_bytes:], its length in out_len[i].  Returns
+        (out uint8[n * slot_bytes], out_len int32[n], meta int32[n]); pass the buffers to reuse / pre-fill them."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        if out is None:
+            out = torch.empty(max(b.n, 1) * slot_bytes, dtype=torch.uint8, device=dev)
+        if out_len is None:
+            out_len = torch.zeros(max(b.n, 1), dtype=torch.int32, device=dev)
+        if meta is None:
+            meta = torch.zeros(max(b.n, 1), dtype=torch.int32, device=dev)
+        assert len(date) == 29
+        _abi.check(_abi.lib().gofr_serve_device_slots(self._e, b.desc.data_ptr(), b.trace_ids.data_ptr(), b.arena.data_ptr(),
+                                                      b.n, date, out.data_ptr(), slot_bytes, out_len.data_ptr(),
+                                                      meta.data_ptr(), st.cuda_stream), "gofr_serve_device_slots")
+        return out, out_len[:b.n], meta[:b.n]
+
     # ---- host path (the call a user makes): host buffers in, host buffers out ----
     def serve_host(self, batch: S.RequestBatch, date: bytes, out: np.ndarray, out_off: np.ndarray, meta: np.ndarray) -> int:
         L = _abi.lib()

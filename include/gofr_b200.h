@@ -16,7 +16,7 @@
  *                                 pkg/gofr/http/router.go:14,
  *                                 pkg/gofr/http/middleware/{tracer,logger,cors}.go,
  *                                 pkg/gofr/handler.go:32-36,
- *                                 pkg/gofr/http/responder.go:19-41 gofr_serve_device / gofr_batch_submit+wait
+ *                                 pkg/gofr/http/responder.go:19-41 gofr_serve_device[_slots] / gofr_batch_submit+wait
  *   Request.Param / Bind          pkg/gofr/http/request.go:28-47   (fused into the serve kernel per handler kind)
  *   _Hello_SayHello_Handler       examples/grpc-server/grpc/
  *                                 hello_grpc.pb.go:73-89           gofr_grpc_hello_device
@@ -192,6 +192,16 @@ void gofr_engine_destroy(gofr_engine*);
 int gofr_serve_device(gofr_engine*, const gofr_req_desc* d_desc, const uint8_t* d_trace_ids, const uint8_t* d_arena,
                       uint32_t n, const char* date29, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off,
                       uint32_t* d_meta, void* stream);
+
+/* The same launch with a SLOT layout instead of packed offsets: response i is written at d_out + i * slot_bytes
+ * (slot_bytes a multiple of 16, d_out 16-byte aligned) and d_out_len[i] receives its length; the bytes between the end
+ * of a response and the next 16-byte boundary are zeroed, the rest of the slot is left untouched.  A response longer
+ * than the slot is not written: d_out_len[i] > slot_bytes tells the caller to serve that request through the packed
+ * call.  Slots remove the only dependence between requests (the running output offset): no scan, no look-back between
+ * tiles, and every response starts aligned — this is the layout a ring of pinned response buffers wants anyway. */
+int gofr_serve_device_slots(gofr_engine*, const gofr_req_desc* d_desc, const uint8_t* d_trace_ids, const uint8_t* d_arena,
+                            uint32_t n, const char* date29, uint8_t* d_out, uint32_t slot_bytes, uint32_t* d_out_len,
+                            uint32_t* d_meta, void* stream);
 
 /* Host batch: pinned (gofr_alloc_pinned) or pageable caller-owned buffers; the engine pipelines
  * H2D → kernel → D2H in chunks over its own streams.  submit is thread-safe; wait blocks the caller. */

@@ -1,0 +1,86 @@
+"""gofr_serve_device_slots: the same responses as the packed call, one 16-byte aligned slot per request."""
+import numpy as np
+import pytest
+
+from gofr_b200 import spec as S
+from gofr_b200 import synth
+from gofr_b200.table import Table
+from tests import oracle as O
+
+DATE = S.http_date(1_700_000_000)
+
+
+def _check(eng, spec, batch, slot):
+    import torch
+    o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
+    n = batch.n
+    canary = torch.full((n * slot,), 0xEE, dtype=torch.uint8, device="cuda")
+    out, out_len, meta = eng.serve_device_slots(eng.upload(batch), DATE, slot, out=canary)
+    out = out.cpu().numpy().reshape(n, slot)
+    ln = out_len.cpu().numpy().view(np.uint32)
+    assert np.array_equal(meta.cpu().numpy().view(np.uint32), m1)
+    want_len = np.diff(f1.astype(np.int64)).astype(np.uint32)
+    assert np.array_equal(ln, want_len)
+    ob = o1.tobytes()
+    for i in range(n):
+        L = int(ln[i])
+        if L > slot:                                    # too long for the slot: reported, nothing written
+            assert (out[i] == 0xEE).all()
+            continue
+        assert out[i, :L].tobytes() == ob[int(f1[i]):int(f1[i]) + L], i
+        pad = (-L) % 16
+        assert (out[i, L:L + pad] == 0).all() and (out[i, L + pad:] == 0xEE).all(), i
+    return ln
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [S.FRAME_WIRE, S.FRAME_INTENDED, S.FRAME_BODY])
+def test_config2_slots(torch_cuda, mode):
+    from gofr_b200.engine import Engine
+    spec = synth.config2_spec(mode)
+    eng = Engine(Table(spec), 0)
+    _check(eng, spec, synth.config2_batch(5000, escape_every=7), 640)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_mixed_traffic_and_short_slots(torch_cuda):
+    from gofr_b200.engine import Engine
+    spec = synth.config4_spec()
+    eng = Engine(Table(spec), 0)
+    ln = _check(eng, spec, synth.config4_batch(20000), 352)   # about half of the responses are longer than 352 bytes
+    assert (ln > 352).sum() > 1000 and (ln <= 352).sum() > 1000
+    _check(eng, spec, synth.config4_batch(3000), 4096)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_bind_and_results_in_slots(torch_cuda):
+    from gofr_b200.engine import Engine
+    spec = synth.config3_spec()
+    eng = Engine(Table(spec), 0)
+    _check(eng, spec, synth.config3_batch(4096), 1024)
+    eng.close()
+    from tests.test_result import _spec, _batch
+    eng = Engine(Table(_spec()), 0)
+    _check(eng, _spec(), _batch(), 768)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_slot_argument_checks(torch_cuda):
+    from gofr_b200 import _abi
+    from gofr_b200.engine import Engine
+    spec = synth.config1_spec()
+    eng = Engine(Table(spec), 0)
+    b = eng.upload(synth.config1_batch(10))
+    with pytest.raises(_abi.GofrError):
+        eng.serve_device_slots(b, DATE, 500)            # not a multiple of 16
+    eng.close()
