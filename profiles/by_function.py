@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Aggregates an ncu SASS source page by device function (serve_device.cuh) using nvdisasm line info.
 usage: by_function.py src.csv kernel.sass [device_header]"""
-import bisect, collections, csv, re, sys
+import bisect, collections, csv, os, re, sys
 src_csv, sass_file = sys.argv[1], sys.argv[2]
 header = sys.argv[3] if len(sys.argv) > 3 else "gofr_b200/csrc/serve_device.cuh"
 addr_line, cur, in_k = {}, None, False
@@ -9,8 +9,8 @@ for ln in open(sass_file, errors="replace"):
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2))); continue
-    if ".text." in ln and "_kernel" in ln:
-        in_k = True
+    if ".text." in ln:
+        in_k = os.environ.get("KERNEL", "serve_kernel") in ln
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
     if m and in_k:
         addr_line[int(m.group(1), 16)] = cur

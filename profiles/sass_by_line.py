@@ -4,7 +4,7 @@ same cubin, and aggregates executed instructions / stall samples per CUDA source
 
 usage: sass_by_line.py src.csv kernel.sass [top_n]
 """
-import csv
+import os, csv
 import collections
 import re
 import sys
@@ -21,8 +21,8 @@ for ln in open(sass_file, errors="replace"):
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2)))
         continue
-    if ".text." in ln and "serve_kernel" in ln:
-        in_kernel = True
+    if ".text." in ln:
+        in_kernel = os.environ.get("KERNEL", "serve_kernel") in ln
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
     if m and in_kernel:
         addr_line[int(m.group(1), 16)] = cur

@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Per source line: samples of one stall reason (ncu source page).  usage: stall_by_line.py src.csv kernel.sass stall_long_sb [top]"""
-import sys, re, csv, collections
+import os, sys, re, csv, collections
 src_csv, sass_file, col = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
 addr_line = {}; cur = None; in_k = False; text = {}
 for ln in open(sass_file, errors="replace"):
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m: cur = (m.group(1).split("/")[-1], int(m.group(2))); continue
-    if ".text." in ln and "serve_kernel" in ln: in_k = True
+    if ".text." in ln: in_k = os.environ.get("KERNEL", "serve_kernel") in ln
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
     if m and in_k: addr_line[int(m.group(1), 16)] = cur; text[int(m.group(1), 16)] = m.group(2)
 rows = list(csv.reader(open(src_csv)))
