@@ -36,10 +36,27 @@ def lib():
                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
         _lib.emu_grpc_hello.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                         C.c_void_p, C.c_uint32]
+        _lib.emu_serve_slots.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p,
+                                         C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.emu_route.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.emu_reqlog.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                     C.c_uint32]
     return _lib
+
+
+def serve_slots(image: bytes, batch, date: bytes, slot_bytes: int):
+    """Slot layout on the CPU: (out uint8[n, slot_bytes] pre-filled with 0xEE, out_len, meta)."""
+    n = batch.n
+    img = np.frombuffer(image, dtype=np.uint8).copy()
+    base = np.full(n * slot_bytes + 64, 0xEE, dtype=np.uint8)
+    shift = (-base.ctypes.data) % 16          # slots are 16-byte aligned, like cudaMalloc'ed memory
+    out = base[shift:shift + n * slot_bytes]
+    ln = np.zeros(n, dtype=np.uint32)
+    meta = np.zeros(n, dtype=np.uint32)
+    arena = np.concatenate([batch.arena, np.zeros(32, dtype=np.uint8)])
+    lib().emu_serve_slots(img.ctypes.data, len(image), batch.desc.ctypes.data, batch.trace_ids.ctypes.data, arena.ctypes.data,
+                          n, date, out.ctypes.data, slot_bytes, ln.ctypes.data, meta.ctypes.data)
+    return out.reshape(n, slot_bytes), ln, meta
 
 
 def route(image: bytes, batch):

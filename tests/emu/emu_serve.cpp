@@ -53,6 +53,36 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
     return 0;
 }
 
+// ---- slot layout (gofr_serve_device_slots): same per-request code, emit_request<true> + finish_padded ----
+extern "C" int emu_serve_slots(const uint8_t* image, uint64_t image_len, const uint8_t* desc, const uint8_t* ids,
+                               const uint8_t* arena, uint32_t n, const char* date29, uint8_t* out, uint32_t slot_bytes,
+                               uint32_t* out_len, uint32_t* meta) {
+    (void)image_len;
+    ImageHeader H;
+    memcpy(&H, image, sizeof H);
+    std::vector<uint32_t> hot((H.hot_bytes + 3) / 4 + 4);
+    memcpy(hot.data(), image, H.hot_bytes);
+    patch_dates((uint8_t*)hot.data(), (const uint8_t*)date29, 0, 1);
+    TableView tv;
+    tv.bind((const uint8_t*)hot.data(), image);
+    uint32_t ring[GOFR_STAGE_WORDS];
+    std::vector<uint32_t> bind_scratch((size_t)H.bind_row_words + 8);
+    BatchRefs br;
+    br.bind_scratch = bind_scratch.data(); br.bind_row_words = H.bind_row_words; br.ids = ids;
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t d[4];
+        memcpy(d, desc + (size_t)i * 16, 16);
+        ReqCtx c;
+        c.set(arena, d[0], d[1] & 0xFFFF, d[1] >> 16, d[2], d[3] & 0xFF, (d[3] >> 8) & 0xFF, (i & 1) != 0, 0);
+        br.ids = ids + (size_t)i * 16;
+        size_request(tv, br, c);
+        out_len[i] = c.total_len;
+        meta[i] = request_status(tv, c) | (c.route << 16);
+        if (c.total_len && c.total_len <= slot_bytes) emit_request<true>(tv, br, c, out + (size_t)i * slot_bytes, ring);
+    }
+    return 0;
+}
+
 // ---- routing only (gofr_route_device): serve_device.cuh's route_only on the CPU ----
 extern "C" int emu_route(const uint8_t* image, const uint8_t* desc, const uint8_t* arena, uint32_t n, uint32_t* meta,
                          uint32_t* vars) {

@@ -33,6 +33,33 @@ def _check(eng, spec, batch, slot):
     return ln
 
 
+def _check_slots(out, ln, meta, spec, batch, slot):
+    o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
+    assert np.array_equal(meta, m1)
+    assert np.array_equal(ln, np.diff(f1.astype(np.int64)).astype(np.uint32))
+    ob = o1.tobytes()
+    for i in range(batch.n):
+        L = int(ln[i])
+        if L > slot:
+            assert (out[i] == 0xEE).all()
+            continue
+        assert out[i, :L].tobytes() == ob[int(f1[i]):int(f1[i]) + L], i
+        pad = (-L) % 16
+        assert (out[i, L:L + pad] == 0).all() and (out[i, L + pad:] == 0xEE).all(), i
+
+
+@pytest.mark.parametrize("which,slot", [("config1", 320), ("config2", 528), ("config2", 544), ("config4", 352), ("config3", 1024)])
+def test_emu_slots_match_oracle(which, slot):
+    """the slot-layout emit path (emit_request<true>, Writer::finish_padded) on the CPU"""
+    from tests.emu import emu
+    spec, batch = {"config1": (synth.config1_spec(), synth.config1_batch(200)),
+                   "config2": (synth.config2_spec(), synth.config2_batch(300, escape_every=5)),
+                   "config3": (synth.config3_spec(), synth.config3_batch(300)),
+                   "config4": (synth.config4_spec(), synth.config4_batch(1500))}[which]
+    out, ln, meta = emu.serve_slots(Table(spec).serialize(), batch, DATE, slot)
+    _check_slots(out, ln, meta, spec, batch, slot)
+
+
 @pytest.fixture(scope="module")
 def torch_cuda():
     import torch
