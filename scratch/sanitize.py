@@ -1,0 +1,46 @@
+"""Small instances of every C-ABI entry point, for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from gofr_b200 import spec as S, synth, _abi
+from gofr_b200.engine import Engine, pin_batch, pinned_array
+from gofr_b200.table import Table
+
+date = S.http_date(1_700_000_000)
+for name, spec, batch in (("config2", synth.config2_spec(), synth.config2_batch(700, escape_every=9)),
+                          ("config3", synth.config3_spec(), synth.config3_batch(500)),
+                          ("config4", synth.config4_spec(), synth.config4_batch(900))):
+    eng = Engine(Table(spec), 0)
+    db = eng.upload(batch)
+    resp = eng.alloc_responses(batch.n, batch.n * 1200 + 4096)
+    eng.serve_device(db, date, resp)
+    eng.serve_device_slots(db, date, 1024)
+    eng.route_device(db)
+    eng.set_chunk(256)
+    hb = pin_batch(batch)
+    out = pinned_array(batch.n * 1200 + 4096)
+    off = pinned_array(4 * (batch.n + 1), np.uint32)
+    meta = pinned_array(4 * batch.n, np.uint32)
+    got = eng.serve_host(hb, date, out, off, meta)
+    out2 = np.zeros(batch.n * 1200 + 4096, dtype=np.uint8)   # pageable buffers: the cudaMemcpy pipeline
+    off2 = np.zeros(batch.n + 1, dtype=np.uint32)
+    meta2 = np.zeros(batch.n, dtype=np.uint32)
+    got2 = eng.serve_host(batch, date, out2, off2, meta2)
+    torch.cuda.synchronize()
+    assert got == got2 and np.array_equal(out[:got], out2[:got])
+    print(name, "ok", got)
+    eng.close()
+eng = Engine(Table(synth.config1_spec()), 0)
+eng.request_log_device(synth.reqlog_batch(600, hostile_every=3, rpc_every=4))
+frames, off = synth.config5_frames(1000)
+d_in = torch.from_numpy(np.concatenate([frames, np.zeros(64, np.uint8)])).cuda()
+d_off = torch.from_numpy(off.view(np.int32)).cuda()
+cap = int(frames.size) + 40 * 1000
+d_out = torch.zeros(cap + 64, dtype=torch.uint8, device="cuda")
+d_ooff = torch.zeros(1001, dtype=torch.int32, device="cuda")
+d_meta = torch.zeros(1000, dtype=torch.int32, device="cuda")
+_abi.check(_abi.lib().gofr_grpc_hello_device(eng._e, d_in.data_ptr(), d_off.data_ptr(), 1000, d_out.data_ptr(), cap,
+                                             d_ooff.data_ptr(), d_meta.data_ptr(), torch.cuda.current_stream().cuda_stream), "grpc")
+torch.cuda.synchronize()
+print("reqlog + grpc ok")
