@@ -222,10 +222,20 @@ def run_secondary(args):
         o1, f1, _ = O.OracleTable(spec).serve(batch, date)
         resp = eng.alloc_responses(n, int(f1[n]) + 4096)
 
-        def step():
-            eng.serve_device(db, date, resp)
+        if args.layout == "slots":
+            slot = 1024
+            s_out = torch.empty(n * slot, dtype=torch.uint8, device="cuda")
+            s_len = torch.zeros(n, dtype=torch.int32, device="cuda")
+            s_meta = torch.zeros(n, dtype=torch.int32, device="cuda")
+
+            def step():
+                eng.serve_device_slots(db, date, slot, out=s_out, out_len=s_len, meta=s_meta)
+            get_out = lambda: int(s_len.sum().item())
+        else:
+            def step():
+                eng.serve_device(db, date, resp)
+            get_out = lambda: int(resp.out_off[n].item())
         in_bytes = batch.input_bytes()
-        get_out = lambda: int(resp.out_off[n].item())
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -241,7 +251,7 @@ def run_secondary(args):
     out_bytes = get_out()
     algo = in_bytes + out_bytes + 8 * n
     peak, src = hbm_peak()
-    print(json.dumps({"metric": "requests_per_sec", "workload": w, "value": n / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+    print(json.dumps({"metric": "requests_per_sec", "workload": w, "layout": args.layout if w in ("config3", "config4") else None, "value": n / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": ms, "requests": n, "out_bytes": out_bytes, "data": "synthetic",
                       "roofline": {"bound": "hbm", "achieved": algo / (kms / kl / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                    "frac": algo / (kms / kl / 1e3) / 1e9 / peak, "algorithmic_bytes_per_request": algo / n,

@@ -545,6 +545,7 @@ struct TableView {
     GOFR_HD const uint8_t* lits() const { return base + hdr()->lits_off; }
     GOFR_HD const uint16_t* hash_tab() const { return (const uint16_t*)(base + hdr()->hash_off); }
     GOFR_HD const uint16_t* tmpl_list() const { return (const uint16_t*)(base + hdr()->tmpl_off); }
+    GOFR_HD const uint32_t* tmpl_keys() const { return (const uint32_t*)(base + hdr()->tmplkey_off); }
     GOFR_HD const uint16_t* last_method() const { return (const uint16_t*)(base + hdr()->last_method_off); }
     GOFR_HD const uint32_t* lit_words(uint32_t off) const { return (const uint32_t*)(lits() + off); }
     GOFR_HD const uint8_t* lit_bytes(uint32_t off) const { return lits() + off; }
@@ -787,6 +788,9 @@ GOFR_HD int mux_match(const TableView& tv, uint32_t method, const uint8_t* p, ui
     if (r4) h = path_hash_step(h, pw[nw] & (0xFFFFFFFFu >> (8 * (4 - r4))));
     uint32_t lit = n ? tv.hash_tab()[h >> (32 - tv.hdr()->hash_bits)] : 0xFFFFu;
     uint32_t ti = 0, nt = tv.hdr()->n_tmpl;
+    // the path's first eight bytes, zero beyond its end: a template whose leading literal bytes differ cannot match
+    const uint32_t w0 = n >= 4 ? pw[0] : (n ? pw[0] & (0xFFFFFFFFu >> (8 * (4 - n))) : 0u);
+    const uint32_t w1 = n >= 8 ? pw[1] : (n > 4 ? pw[1] & (0xFFFFFFFFu >> (8 * (8 - n))) : 0u);
     int a_last = -1;
     for (;;) {
         uint32_t t = ti < nt ? tv.tmpl_list()[ti] : 0xFFFFu;
@@ -798,8 +802,9 @@ GOFR_HD int mux_match(const TableView& tv, uint32_t method, const uint8_t* p, ui
             lit = R.next_lit;
             p_ok = n == R.lit_len && words_equal(pw, tv.lit_words(R.lit_off), n);
         } else {
+            const uint32_t* key = tv.tmpl_keys() + 4 * ti;
             ti++;
-            p_ok = template_match(tv, R, p, n);
+            p_ok = (((w0 ^ key[0]) & key[2]) | ((w1 ^ key[1]) & key[3])) == 0 && template_match(tv, R, p, n);
         }
         if (!p_ok) continue;
         bool m_ok = R.method == GOFR_M_ANY || (R.method == method && method != GOFR_M_OTHER);
@@ -1166,8 +1171,8 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
 }
 
 // Full size stage for one request: route, size; a malformed handler-result row is answered like a handler panic.
-GOFR_HD void size_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
-    route_request(tv, br, c);
+// sizes a routed request (route_request has run)
+GOFR_HD void size_routed(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
     if (c.prog == 0xFFFF) {  // GOFR_H_HOST: nothing to emit, status 0 = pending on the host
         c.body_len = c.total_len = 0;
         return;
@@ -1177,6 +1182,11 @@ GOFR_HD void size_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
         c.slow_mask = 0;
         run_prog<false>(tv, br, c, nullptr);
     }
+}
+
+GOFR_HD void size_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
+    route_request(tv, br, c);
+    size_routed(tv, br, c);
 }
 
 // HTTP status of a sized request (0: GOFR_H_HOST, the closure runs on the host)

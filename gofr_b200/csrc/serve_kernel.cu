@@ -35,6 +35,7 @@ struct TileShared {
     uint64_t bar;  // mbarrier for the arena bulk load
     uint32_t warp_sum[NW];
     uint32_t warp_lo[NW], warp_hi[NW];
+    uint32_t warp_cls[NW];  // slot layout: program shape class of each warp's lane 0
     unsigned long long tile_base;
     uint32_t in_lo, in_hi;
     uint32_t ring[GOFR_STAGE_WORDS * T];  // word-major staging buffer of the Writer (serve_device.cuh)
@@ -114,22 +115,64 @@ __device__ __forceinline__ void serve_body(const ServeParams& p) {
             abase = in_stage - in_lo;  // abase + arena_off lands in the staged copy
         }
 
-        // ---- stage 1+2: route, size ----
+        // ---- stage 1: route ----
         ReqCtx c;
-        c.set(abase, arena_off, path_len, query_len, data_len, d.w & 0xFFu, (d.w >> 8) & 0xFFu, in_staged, i);
-        if (valid) size_request(tv, br, c);
+        c.set(abase, arena_off, path_len, query_len, data_len, d.w & 0xFFu, (d.w >> 8) & 0xFFu, in_staged, valid ? i : 0xFFFFFFFFu);
+        if (valid) route_request(tv, br, c);
 
         if (SLOTS) {
             // Slot layout: response i owns out + i * slot_bytes.  No scan, no look-back, no dependence between tiles —
-            // and every response starts 16-byte aligned.
-            const bool fits = c.total_len <= p.slot_bytes;
-            if (valid) {
-                p.out_off[i] = c.total_len;  // the length column; > slot_bytes tells the host the slot was too small
-                p.meta[i] = request_status(tv, c) | (c.route << 16);
-                if (fits && c.total_len) emit_request<true>(tv, br, c, p.out + (size_t)i * p.slot_bytes, &sh.ring[tid]);
+            // and every response starts 16-byte aligned.  Nothing ties a request to a particular thread either, so a
+            // tile with mixed traffic is first regrouped by program shape: lanes of a warp then walk the same op
+            // sequence instead of serialising over every shape present (the interpreter's only divergence).
+            uint32_t cls = 31u;  // idle lanes sort last
+            if (valid) cls = c.prog == 0xFFFF ? 0u : tv.progs()[c.prog].shape_class;
+            const uint32_t cls0 = __shfl_sync(0xFFFFFFFFu, cls, 0);
+            if (lane == 0) sh.warp_cls[warp] = cls0;
+            bool mixed = __syncthreads_or(cls != cls0);
+#pragma unroll
+            for (int w = 1; w < NW; w++) mixed |= sh.warp_cls[w] != sh.warp_cls[0];
+            if (mixed) {
+                uint32_t* hist = sh.ring;  // the staging ring is idle until the first response is written
+                if (tid < 32) hist[tid] = 0;
+                __syncthreads();
+                const uint32_t rank = atomicAdd(&hist[cls], 1u);
+                __syncthreads();
+                if (warp == 0) {
+                    const uint32_t v = hist[lane];
+                    uint32_t incl = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                        if (lane >= (uint32_t)o) incl += u;
+                    }
+                    hist[lane] = incl - v;
+                }
+                __syncthreads();
+                const uint32_t pos = hist[cls] + rank;
+                __syncthreads();
+                uint32_t* x = sh.ring + pos;  // word-major exchange record of the request now owned by thread `pos`
+                x[0 * T] = (uint32_t)(c.path - abase); x[1 * T] = c.path_len | c.query_len << 16; x[2 * T] = c.data_len;
+                x[3 * T] = c.data_off; x[4 * T] = c.mflags; x[5 * T] = c.index; x[6 * T] = c.prog | c.route << 16;
+                x[7 * T] = c.pv_off; x[8 * T] = c.pv_len; x[9 * T] = c.pv_flags; x[10 * T] = c.def_off; x[11 * T] = c.def_len;
+                __syncthreads();
+                const uint32_t* y = sh.ring + tid;
+                c.path = abase + y[0 * T]; c.path_len = y[1 * T] & 0xFFFFu; c.query_len = y[1 * T] >> 16; c.data_len = y[2 * T];
+                c.data_off = y[3 * T]; c.mflags = y[4 * T]; c.index = y[5 * T]; c.prog = y[6 * T] & 0xFFFFu; c.route = y[6 * T] >> 16;
+                c.pv_off = y[7 * T]; c.pv_len = y[8 * T]; c.pv_flags = y[9 * T]; c.def_off = y[10 * T]; c.def_len = y[11 * T];
+                __syncthreads();  // the ring is free again before any Writer stages into it
+            }
+            const uint32_t r = c.index;  // the request this thread serves now
+            if (r != 0xFFFFFFFFu) {
+                size_routed(tv, br, c);
+                p.out_off[r] = c.total_len;  // the length column; > slot_bytes tells the host the slot was too small
+                p.meta[r] = request_status(tv, c) | (c.route << 16);
+                if (c.total_len <= p.slot_bytes && c.total_len)
+                    emit_request<true>(tv, br, c, p.out + (size_t)r * p.slot_bytes, &sh.ring[tid]);
             }
             continue;
         }
+        if (valid) size_routed(tv, br, c);
         // ---- block scan of response sizes ----
         uint32_t incl = c.total_len;
 #pragma unroll

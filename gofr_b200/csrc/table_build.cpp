@@ -809,6 +809,23 @@ int seal_table(gofr_table* t) {
         max_fixed = std::max(max_fixed, P.hdr_fixed + P.body_fixed);
     }
 
+    // shape classes: same op-code / flag sequence → same control flow in the interpreter
+    {
+        std::map<std::string, int> classes;
+        for (size_t pi = 0; pi < progs.size(); pi++) {
+            ProgRec& P = progs[pi];
+            std::string sig = std::to_string(P.flags & (PF_BIND | PF_NEEDS_ROW));
+            for (uint32_t k = 0; k < P.n_ops; k++) {
+                const Op& o = ops[P.first_op + k];
+                sig += "|" + std::to_string(o.code) + "," + std::to_string(o.flags) + "," + std::to_string(o.kind) + (o.len ? "p" : "");
+            }
+            auto it = classes.find(sig);
+            int id = it != classes.end() ? it->second : (int)classes.size() + 1;
+            if (it == classes.end()) classes[sig] = id;
+            P.shape_class = (uint8_t)(id > 30 ? 30 : id);
+        }
+    }
+
     // the size pass only needs the ops whose length depends on the request (everything else is pre-summed)
     for (size_t pi = 0; pi < progs.size(); pi++) {
         ProgRec& P = progs[pi];
@@ -880,6 +897,19 @@ int seal_table(gofr_table* t) {
     H.hash_bits = hash_bits;
     H.tmpl_off = append(tmpl_list.data(), tmpl_list.size() * 2);
     H.n_tmpl = (uint32_t)tmpl_list.size();
+    {
+        std::vector<uint32_t> keys(tmpl_list.size() * 4, 0u);
+        for (size_t ti = 0; ti < tmpl_list.size(); ti++) {
+            const RouteDef& r = t->routes[tmpl_list[ti]];
+            const std::string& l0 = r.pieces.empty() ? std::string() : r.pieces[0].lit;
+            uint8_t kb[8] = {0}, mb[8] = {0};
+            for (size_t k = 0; k < l0.size() && k < 8; k++) { kb[k] = (uint8_t)l0[k]; mb[k] = 0xFF; }
+            memcpy(&keys[ti * 4], kb, 8);
+            memcpy(&keys[ti * 4 + 2], mb, 8);
+        }
+        if (keys.empty()) keys.resize(4, 0u);
+        H.tmplkey_off = append(keys.data(), keys.size() * 4);
+    }
     H.last_method_off = append(last_method.data(), last_method.size() * 2);
     H.fixups_off = append(fixups.data(), fixups.size() * 4);
     H.n_fixups = (uint32_t)fixups.size();

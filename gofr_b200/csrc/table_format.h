@@ -12,7 +12,7 @@
 namespace gofr {
 
 constexpr uint32_t kMagic = 0x52464F47u;  // "GOFR"
-constexpr uint32_t kImageVersion = 8;
+constexpr uint32_t kImageVersion = 10;
 constexpr uint32_t kMaxHotBytes = 40 * 1024;  // shared-memory budget for the table
 constexpr int kMaxVars = 8;                   // variables per route template
 constexpr int kMaxFields = 32;                // struct fields per schema
@@ -37,7 +37,8 @@ struct ImageHeader {  // 128 B
     uint32_t fixups_off;     // uint32[n_fixups]: literal-pool offsets of 29-byte Date placeholders
     uint32_t n_fixups;
     uint32_t bind_row_words;  // words of per-request Bind scratch (0: no GOFR_H_BIND_ECHO route)
-    uint32_t reserved[1];
+    uint32_t tmplkey_off;    // uint32[4][n_tmpl]: {key0, key1, mask0, mask1} — the first <= 8 literal bytes of each template;
+                             // a path whose first bytes differ cannot match it (checked inline before template_match)
 };
 static_assert(sizeof(ImageHeader) == 128, "ImageHeader layout");
 
@@ -126,7 +127,10 @@ struct ProgRec {  // 32 B
     uint16_t n_dyn;
     uint16_t n_hdr_ops;  // ops before the first body op (body ops come last): all a HEAD response emits
     uint16_t row_words;  // nonzero: the row's fixed part is this many words whatever the route's schema (GOFR_H_RESULT errors)
-    uint32_t pad[2];
+    uint8_t shape_class;  // 1..30: programs with the same op-code sequence (same control flow in run_prog) share a class;
+                          // the kernel groups a tile's requests by class so that warps run few distinct programs
+    uint8_t pad1[3];
+    uint32_t pad[1];
 };
 static_assert(sizeof(ProgRec) == 32, "ProgRec layout");
 
