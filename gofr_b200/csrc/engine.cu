@@ -99,7 +99,7 @@ struct gofr_engine {
 };
 
 static int configure_geometry(gofr_engine* e, uint32_t in_per_req) {
-    e->in_cap = (kServeThreads * in_per_req + 127u) & ~127u;
+    e->in_cap = (kServeT * in_per_req + 127u) & ~127u;
     e->smem_bytes = serve_smem_bytes(e->hdr.hot_bytes, e->in_cap);
     if (e->smem_bytes > 227 * 1024) { set_last_error("tile geometry needs %u bytes of shared memory", e->smem_bytes); return GOFR_ERR_CAPACITY; }
     int g = serve_max_grid(e->smem_bytes, e->device, &e->blocks_per_sm);
@@ -135,9 +135,9 @@ int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
     // default tile geometry: stage as many request bytes per request in shared memory as still lets 5 CTAs share an
     // SM (the kernel is latency bound: residency matters more than staging every tile); larger tiles are read from
     // HBM directly.
-    uint32_t per_cta = 227u * 1024u / 5u - 1024u /*reserved*/ - 8448u /*static: staging buffer + tile state*/;
+    uint32_t per_cta = 227u * 1024u / (uint32_t)kServeCtas - 1024u /*reserved*/ - (64u * kServeT + 256u) /*static: staging buffer + tile state*/;
     uint32_t hot = (e->hdr.hot_bytes + 127u) & ~127u;
-    uint32_t in_per = per_cta > hot + 64u * kServeThreads ? ((per_cta - hot - 64u) / kServeThreads) & ~15u : 64u;
+    uint32_t in_per = per_cta > hot + 64u * kServeT ? ((per_cta - hot - 64u) / kServeT) & ~15u : 64u;
     if (in_per > 256u) in_per = 256u;
     int rc = configure_geometry(e, in_per);
     if (rc != GOFR_OK) { delete e; return rc; }
@@ -207,7 +207,7 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
     ServeParams p;
     memset(&p, 0, sizeof p);
     p.desc = d_desc; p.ids = d_ids; p.arena = d_arena; p.n = n;
-    p.n_tiles = (n + kServeThreads - 1) / kServeThreads;
+    p.n_tiles = (n + kServeT - 1) / kServeT;
     p.image = e->d_image; p.hot_bytes = e->hdr.hot_bytes;
     e->epoch = (e->epoch + 1) & 0xFFFFFu;
     if (e->epoch == 0) e->epoch = 1;  // state words are zero-initialised: epoch 0 never matches
@@ -250,7 +250,7 @@ int gofr_serve_device(gofr_engine* e, const gofr_req_desc* d_desc, const uint8_t
         CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st));
         return GOFR_OK;
     }
-    size_t tiles = (n + kServeThreads - 1) / kServeThreads;
+    size_t tiles = (n + 63) / 64;  // enough for any tile size in use (serve: kServeT, gRPC / log: 128)
     if (tiles > e->state_tiles) {
         // grow the look-back scratch; stream-ordered w.r.t. earlier launches because cudaFree synchronises
         cudaFree(e->d_state);
@@ -410,7 +410,7 @@ int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch*
                 cudaFree(s.d_desc); cudaFree(s.d_ids); cudaFree(s.d_off); cudaFree(s.d_meta); cudaFree(s.d_state); cudaFree(s.d_bind);
                 s.d_desc = s.d_ids = nullptr; s.d_off = s.d_meta = nullptr; s.d_state = nullptr; s.d_bind = nullptr;
                 size_t c = (size_t)cn + cn / 4 + 256;
-                size_t tiles = (c + kServeThreads - 1) / kServeThreads;
+                size_t tiles = (c + 63) / 64;
                 if (cudaMalloc(&s.d_desc, c * 16) != cudaSuccess || cudaMalloc(&s.d_ids, c * 16) != cudaSuccess ||
                     cudaMalloc(&s.d_off, (c + 1) * 4) != cudaSuccess || cudaMalloc(&s.d_meta, c * 4) != cudaSuccess ||
                     cudaMalloc(&s.d_state, tiles * 8) != cudaSuccess) { set_last_error("cudaMalloc failed for a %zu-request chunk", c); s.cap_n = 0; return GOFR_ERR_NOMEM; }
@@ -487,7 +487,7 @@ int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch*
             cudaFree(s.d_desc); cudaFree(s.d_ids); cudaFree(s.d_off); cudaFree(s.d_meta); cudaFree(s.d_state); cudaFree(s.d_bind);
             s.d_desc = s.d_ids = nullptr; s.d_off = s.d_meta = nullptr; s.d_state = nullptr; s.d_bind = nullptr;
             size_t c = (size_t)cn + cn / 4 + 256;
-            size_t tiles = (c + kServeThreads - 1) / kServeThreads;
+            size_t tiles = (c + 63) / 64;
             if (cudaMalloc(&s.d_desc, c * 16) != cudaSuccess || cudaMalloc(&s.d_ids, c * 16) != cudaSuccess ||
                 cudaMalloc(&s.d_off, (c + 1) * 4) != cudaSuccess || cudaMalloc(&s.d_meta, c * 4) != cudaSuccess ||
                 cudaMalloc(&s.d_state, tiles * 8) != cudaSuccess) { set_last_error("cudaMalloc failed for a %zu-request chunk", c); s.cap_n = 0; return GOFR_ERR_NOMEM; }

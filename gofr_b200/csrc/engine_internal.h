@@ -37,7 +37,15 @@ struct ServeParams {
     uint32_t debug_flags;    // bit0: skip the look-back (tile_base = tile * tile_total; only valid for fixed-size responses)
 };
 
-constexpr int kServeThreads = 128;  // requests per tile = threads per CTA
+constexpr int kServeThreads = 128;  // gRPC / request-log kernels: requests per tile = threads per CTA
+#ifndef GOFR_SERVE_T
+#define GOFR_SERVE_T 128
+#endif
+#ifndef GOFR_SERVE_CTAS
+#define GOFR_SERVE_CTAS 5
+#endif
+constexpr int kServeT = GOFR_SERVE_T;        // serve kernel: requests per tile = threads per CTA
+constexpr int kServeCtas = GOFR_SERVE_CTAS;  // serve kernel: CTAs per SM the register and shared-memory budgets aim at
 
 // Returns dynamic shared memory bytes needed for the table's hot part plus the request-byte staging area.
 uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap);

@@ -28,7 +28,7 @@ namespace gofr {
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int T = kServeThreads;
+constexpr int T = kServeT;
 constexpr int NW = T / 32;
 
 struct TileShared {
@@ -214,8 +214,8 @@ __device__ __forceinline__ void serve_body(const ServeParams& p) {
     }
 }
 
-__global__ void __launch_bounds__(T, 5) serve_kernel(const ServeParams p) { serve_body<false>(p); }
-__global__ void __launch_bounds__(T, 5) serve_slots_kernel(const ServeParams p) { serve_body<true>(p); }
+__global__ void __launch_bounds__(T, kServeCtas) serve_kernel(const ServeParams p) { serve_body<false>(p); }
+__global__ void __launch_bounds__(T, kServeCtas) serve_slots_kernel(const ServeParams p) { serve_body<true>(p); }
 
 uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap) {
     return ((hot_bytes + 127u) & ~127u) + in_cap + 64;
