@@ -545,6 +545,7 @@ struct TableView {
     GOFR_HD const uint8_t* lits() const { return base + hdr()->lits_off; }
     GOFR_HD const uint16_t* hash_tab() const { return (const uint16_t*)(base + hdr()->hash_off); }
     GOFR_HD const uint16_t* tmpl_list() const { return (const uint16_t*)(base + hdr()->tmpl_off); }
+    GOFR_HD const uint16_t* thash_tab() const { return (const uint16_t*)(base + hdr()->thash_off); }
     GOFR_HD const uint32_t* tmpl_keys() const { return (const uint32_t*)(base + hdr()->tmplkey_off); }
     GOFR_HD const uint16_t* last_method() const { return (const uint16_t*)(base + hdr()->last_method_off); }
     GOFR_HD const uint32_t* lit_words(uint32_t off) const { return (const uint32_t*)(lits() + off); }
@@ -791,20 +792,27 @@ GOFR_HD int mux_match(const TableView& tv, uint32_t method, const uint8_t* p, ui
     // the path's first eight bytes, zero beyond its end: a template whose leading literal bytes differ cannot match
     const uint32_t w0 = n >= 4 ? pw[0] : (n ? pw[0] & (0xFFFFFFFFu >> (8 * (4 - n))) : 0u);
     const uint32_t w1 = n >= 8 ? pw[1] : (n > 4 ? pw[1] & (0xFFFFFFFFu >> (8 * (8 - n))) : 0u);
+    // templates with a leading literal of >= 8 bytes hang off a hash of those bytes
+    uint32_t key = n >= 8 ? tv.thash_tab()[path_hash_step(path_hash_step(8u, w0), w1) >> (32 - tv.hdr()->thash_bits)] : 0xFFFFu;
     int a_last = -1;
     for (;;) {
-        uint32_t t = ti < nt ? tv.tmpl_list()[ti] : 0xFFFFu;
+        // three sources, each in registration order: the literal chain, the keyed-template chain, the short templates
+        const uint32_t t = ti < nt ? tv.tmpl_list()[ti] : 0xFFFFu;
         uint32_t r = lit < t ? lit : t;
+        r = key < r ? key : r;
         if (r == 0xFFFFu) break;
         const RouteRec& R = tv.routes()[r];
         bool p_ok;
         if (r == lit) {
             lit = R.next_lit;
             p_ok = n == R.lit_len && words_equal(pw, tv.lit_words(R.lit_off), n);
+        } else if (r == key) {
+            key = R.next_lit;
+            p_ok = template_match(tv, R, p, n);  // a different template of the same bucket fails on its first literal
         } else {
-            const uint32_t* key = tv.tmpl_keys() + 4 * ti;
+            const uint32_t* k4 = tv.tmpl_keys() + 4 * ti;
             ti++;
-            p_ok = (((w0 ^ key[0]) & key[2]) | ((w1 ^ key[1]) & key[3])) == 0 && template_match(tv, R, p, n);
+            p_ok = (((w0 ^ k4[0]) & k4[2]) | ((w1 ^ k4[1]) & k4[3])) == 0 && template_match(tv, R, p, n);
         }
         if (!p_ok) continue;
         bool m_ok = R.method == GOFR_M_ANY || (R.method == method && method != GOFR_M_OTHER);

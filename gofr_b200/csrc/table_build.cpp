@@ -729,14 +729,30 @@ int seal_table(gofr_table* t) {
     uint32_t hash_bits = 4;
     while ((1u << hash_bits) < 4 * n_lit && hash_bits < 11) hash_bits++;
     std::vector<uint16_t> hash_tab(1u << hash_bits, 0xFFFF), tmpl_list, last_method(16, 0);
+    // templates whose leading literal has at least 8 bytes are keyed by those bytes
+    uint32_t n_keyed = 0;
+    for (size_t ri = 0; ri < routes.size(); ri++)
+        if (!(routes[ri].flags & (RF_DEAD | RF_LITERAL)) && !t->routes[ri].pieces.empty() && t->routes[ri].pieces[0].lit.size() >= 8) n_keyed++;
+    uint32_t thash_bits = 4;
+    while ((1u << thash_bits) < 4 * n_keyed && thash_bits < 11) thash_bits++;
+    std::vector<uint16_t> thash_tab(1u << thash_bits, 0xFFFF);
     {
-        std::vector<uint16_t> tail(1u << hash_bits, 0xFFFF);
+        std::vector<uint16_t> tail(1u << hash_bits, 0xFFFF), ttail(1u << thash_bits, 0xFFFF);
         for (size_t ri = 0; ri < routes.size(); ri++) {
             RouteRec& R = routes[ri];
             R.next_lit = 0xFFFF;
             if (R.flags & RF_DEAD) continue;
             if (R.method < 16) last_method[R.method] = (uint16_t)(ri + 1);
-            if (!(R.flags & RF_LITERAL)) { tmpl_list.push_back((uint16_t)ri); continue; }
+            if (!(R.flags & RF_LITERAL)) {
+                const std::string& l0 = t->routes[ri].pieces.empty() ? std::string() : t->routes[ri].pieces[0].lit;
+                if (l0.size() < 8) { tmpl_list.push_back((uint16_t)ri); continue; }
+                uint32_t w0 = 0, w1 = 0;
+                for (int k = 0; k < 4; k++) { w0 |= (uint32_t)(uint8_t)l0[k] << (8 * k); w1 |= (uint32_t)(uint8_t)l0[4 + k] << (8 * k); }
+                uint32_t slot = path_hash_step(path_hash_step(8u, w0), w1) >> (32 - thash_bits);
+                if (ttail[slot] == 0xFFFF) thash_tab[slot] = (uint16_t)ri; else routes[ttail[slot]].next_lit = (uint16_t)ri;
+                ttail[slot] = (uint16_t)ri;
+                continue;
+            }
             const std::string& pat = t->routes[ri].pattern;
             uint32_t h = (uint32_t)pat.size();
             for (size_t i = 0; i < pat.size(); i += 4) {
@@ -895,6 +911,8 @@ int seal_table(gofr_table* t) {
     H.ops_off = append(ops.data(), ops.size() * sizeof(Op));
     H.hash_off = append(hash_tab.data(), hash_tab.size() * 2);
     H.hash_bits = hash_bits;
+    H.thash_off = append(thash_tab.data(), thash_tab.size() * 2);
+    H.thash_bits = thash_bits;
     H.tmpl_off = append(tmpl_list.data(), tmpl_list.size() * 2);
     H.n_tmpl = (uint32_t)tmpl_list.size();
     {

@@ -12,12 +12,12 @@
 namespace gofr {
 
 constexpr uint32_t kMagic = 0x52464F47u;  // "GOFR"
-constexpr uint32_t kImageVersion = 10;
+constexpr uint32_t kImageVersion = 11;
 constexpr uint32_t kMaxHotBytes = 40 * 1024;  // shared-memory budget for the table
 constexpr int kMaxVars = 8;                   // variables per route template
 constexpr int kMaxFields = 32;                // struct fields per schema
 
-struct ImageHeader {  // 128 B
+struct ImageHeader {  // 144 B
     uint32_t magic, version;
     uint32_t frame_mode;
     uint32_t n_routes, n_pieces, n_progs, n_ops, n_schemas;
@@ -39,8 +39,13 @@ struct ImageHeader {  // 128 B
     uint32_t bind_row_words;  // words of per-request Bind scratch (0: no GOFR_H_BIND_ECHO route)
     uint32_t tmplkey_off;    // uint32[4][n_tmpl]: {key0, key1, mask0, mask1} — the first <= 8 literal bytes of each template;
                              // a path whose first bytes differ cannot match it (checked inline before template_match)
+    // keyed template dispatch: templates whose leading literal is >= 8 bytes are reached through a hash of those 8
+    // bytes (chained through RouteRec.next_lit in registration order); tmpl_off lists only the others
+    uint32_t thash_off;      // uint16[1 << thash_bits], 0xFFFF = empty
+    uint32_t thash_bits;
+    uint32_t reserved2[2];
 };
-static_assert(sizeof(ImageHeader) == 128, "ImageHeader layout");
+static_assert(sizeof(ImageHeader) == 144, "ImageHeader layout");
 
 enum RouteFlags : uint8_t {
     RF_PREFIX = 1,   // PathPrefix: regexp has no trailing '$'
@@ -63,7 +68,8 @@ struct RouteRec {  // 32 B
     uint32_t key_off;
     uint32_t def_off;   // default value, already JSON-escaped
     uint16_t def_len;
-    uint16_t next_lit;  // next literal route in the same hash bucket (registration order), 0xFFFF = end
+    uint16_t next_lit;  // next route in the same hash bucket (literal routes: hash of the path; keyed templates: hash of
+                        // their first 8 literal bytes), registration order, 0xFFFF = end
 };
 static_assert(sizeof(RouteRec) == 32, "RouteRec layout");
 

@@ -61,6 +61,28 @@ def test_oracle_spans_by_hand():
     assert meta[19] & 0xFFFF == 405 and meta[20] & 0xFFFF == 405
 
 
+def test_keyed_templates_same_prefix_keep_registration_order():
+    host = lambda m, p: S.Route(m, p, S.H_HOST)
+    spec = S.TableSpec(default_routes=False, routes=[
+        host(S.M_GET, "/apiserver/{a}"),            # 0: leading literal "/apiserver/" (>= 8 bytes → keyed)
+        host(S.M_GET, "/apiserver/fixed"),          # 1: literal, shadowed by 0 for GET
+        host(S.M_POST, "/apiserver/fixed"),         # 2
+        host(S.M_GET, "/apiservice/{b}/x"),         # 3: same first 8 bytes as 0 → same bucket
+        host(S.M_GET, "/apiserv{c}"),               # 4: leading literal exactly 8 bytes
+        host(S.M_GET, "/api/{d}"),                  # 5: short leading literal → linear list
+    ])
+    R = S.Req
+    b = S.RequestBatch.pack([R(S.M_GET, b"/apiserver/fixed"), R(S.M_POST, b"/apiserver/fixed"), R(S.M_GET, b"/apiservice/q/x"),
+                             R(S.M_GET, b"/apiservX"), R(S.M_GET, b"/apiserv"), R(S.M_GET, b"/api/z"), R(S.M_GET, b"/apiserver/"),
+                             R(S.M_DELETE, b"/apiserver/1"), R(S.M_GET, b"/apiservice/q/y"), R(S.M_GET, b"/apiserverX")])
+    m1, v1 = O.route(O.OracleTable(spec), b)
+    assert [int(x) >> 16 for x in m1[:6]] == [0, 2, 3, 4, 0xFFFF, 5]
+    assert m1[6] & 0xFFFF == 404          # {a} must not be empty, {c} = [^/]+ cannot swallow the slash
+    assert m1[7] & 0xFFFF == 405 and m1[8] & 0xFFFF == 404 and m1[9] >> 16 == 4
+    m2, v2 = emu.route(Table(spec).serialize(), b)
+    assert np.array_equal(m1, m2) and np.array_equal(v1, v2)
+
+
 def test_options_with_catch_all():
     spec = _multi_var_spec()
     spec.default_routes = True
@@ -120,7 +142,8 @@ def test_gpu_matches_oracle(which, n):
 # oracle's literal restatement of mux (recursive leftmost-first), including variable spans ----
 from hypothesis import given, settings, strategies as st  # noqa: E402
 
-_seg = st.sampled_from(["a", "b", "ab", "users", "v1", "x.y", "1", "22", "a-b", "_"])
+_seg = st.sampled_from(["a", "b", "ab", "users", "v1", "x.y", "1", "22", "a-b", "_", "apiservice", "apiserver", "api"])  # the long ones
+# give templates a leading literal of >= 8 bytes (keyed dispatch), two of them with the same first 8 bytes
 _var = st.sampled_from(["{id}", "{n:[0-9]+}", "{w:[a-z]+}", "{s:[a-z0-9.]*}", "{id}.{ext}", "{a}{b:[0-9]+}", "p{q}", "{d:\\d+}x"])
 _piece = st.one_of(_seg, _var)
 _pattern = st.lists(_piece, min_size=0, max_size=4).map(lambda ps: "/" + "/".join(ps))
@@ -147,7 +170,7 @@ def _rename_vars(pattern: str, k: int) -> str:
 @settings(max_examples=250, deadline=None)
 @given(st.lists(st.tuples(_method, _pattern), min_size=1, max_size=10), st.booleans(),
        st.lists(st.tuples(st.sampled_from([S.M_GET, S.M_POST, S.M_DELETE, S.M_OPTIONS, S.M_HEAD, S.M_OTHER]),
-                          st.lists(st.sampled_from(["a", "b", "ab", "users", "v1", "x.y", "1", "22", "a-b", "_", "42", "abc9",
+                          st.lists(st.sampled_from(["a", "b", "ab", "users", "v1", "x.y", "1", "22", "a-b", "_", "42", "abc9", "apiservice", "apiserver", "api", "apiserv",
                                                     "p7", "3x", "q.tar.gz", "", ".", ".."]), min_size=0, max_size=4)),
                 min_size=1, max_size=24))
 def test_random_tables_property(routes, defaults, reqs):
