@@ -1023,8 +1023,11 @@ GOFR_HD uint32_t route_only(const TableView& tv, uint32_t method, const uint8_t*
 // registers); the copy lives in local memory only while the rare path runs.
 #define GOFR_SLOW_CALL(w, expr) do { Writer t_ = *(w); Writer* tw = &t_; (void)tw; expr; *(w) = t_; } while (0)
 
-template <bool EMIT>
-GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Writer* w) {
+// STATIC_N > 0: the program's ops are compile-time constants (static_ops, STATIC_N of them): the op loop is unrolled
+// and every decision that depends only on the program folds away — what a table-specific build of the kernel runs for
+// its hot programs.  STATIC_N == 0: the interpreter, ops fetched from the table in shared memory.
+template <bool EMIT, int STATIC_N = 0>
+GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Writer* w, const uint4* static_ops = nullptr) {
     const ProgRec P = tv.progs()[c.prog];  // by value: the staging stores below must not force re-reads of the table
     // the size pass visits only the ops whose length depends on the request
     const Op* ops = tv.ops() + (EMIT ? P.first_op : P.first_dyn);
@@ -1041,8 +1044,7 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
     }
     uint32_t hdr_dyn = 0, body_dyn = 0, str_bit = 1;
     bool first = true, skip = false;
-    for (uint32_t oi = 0; oi < n_ops; oi++) {
-        const uint4 raw = *(const uint4*)(ops + oi);  // one 16-byte load per op
+    auto do_op = [&](const uint4 raw) -> bool {
         const uint32_t code = raw.x & 0xFFu, oflags = (raw.x >> 16) & 0xFFu, okind = raw.x >> 24;
         const uint32_t olen = raw.y, ooff = raw.z, oaux = raw.w;
         const bool body = oflags & OPF_BODY;
@@ -1168,6 +1170,16 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
         }
         }  // steps
         if (body) body_dyn += produced; else hdr_dyn += produced;
+        return true;
+    };
+    if (STATIC_N > 0) {
+#pragma unroll
+        for (int oi = 0; oi < STATIC_N; oi++)
+            if (!do_op(static_ops[oi])) return false;
+    } else {
+#pragma unroll 1
+        for (uint32_t oi = 0; oi < n_ops; oi++)
+            if (!do_op(*(const uint4*)(ops + oi))) return false;  // one 16-byte load per op
     }
     if (!EMIT) {
         c.body_len = P.body_fixed + body_dyn;
@@ -1179,13 +1191,26 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
 }
 
 // Full size stage for one request: route, size; a malformed handler-result row is answered like a handler panic.
+#if defined(GOFR_STATIC_PROG)
+#include GOFR_STATIC_PROG  /* experiment: one program of one table as compile-time constants */
+#if defined(__CUDA_ARCH__)
+#define GOFR_IS_STATIC(c) ((c).prog == GOFR_STATIC_PROG_ID && (c).method() != GOFR_M_HEAD)
+#endif
+#endif
+
 // sizes a routed request (route_request has run)
 GOFR_HD void size_routed(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
     if (c.prog == 0xFFFF) {  // GOFR_H_HOST: nothing to emit, status 0 = pending on the host
         c.body_len = c.total_len = 0;
         return;
     }
-    if (!run_prog<false>(tv, br, c, nullptr)) {
+    bool ok;
+#ifdef GOFR_IS_STATIC
+    if (GOFR_IS_STATIC(c)) ok = run_prog<false, GOFR_STATIC_N_DYN>(tv, br, c, nullptr, kStaticDyn);
+    else
+#endif
+    ok = run_prog<false>(tv, br, c, nullptr);
+    if (!ok) {
         c.prog = tv.hdr()->prog_panic;
         c.slow_mask = 0;
         run_prog<false>(tv, br, c, nullptr);
@@ -1205,6 +1230,10 @@ GOFR_HD void emit_request(const TableView& tv, const BatchRefs& br, ReqCtx& c, u
     if (c.total_len == 0) return;
     Writer w;
     w.init(dst, ring_col);
+#ifdef GOFR_IS_STATIC
+    if (GOFR_IS_STATIC(c)) run_prog<true, GOFR_STATIC_N_EMIT>(tv, br, c, &w, kStaticEmit);
+    else
+#endif
     run_prog<true>(tv, br, c, &w);
     if (SLOTS) w.finish_padded(); else w.finish();
 }
