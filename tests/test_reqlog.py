@@ -183,6 +183,23 @@ def test_gpu_matches_oracle(eng, n, hostile):
 
 
 @pytest.mark.gpu
+def test_gpu_long_strings_unstaged_tiles(eng):
+    """records whose strings exceed the kernel's 24 KB staging budget per tile are read straight from HBM"""
+    recs = []
+    for k in range(700):
+        ua = (b"Mozilla/5.0 <" + b"x" * (300 + k % 200) + b"> \xe2\x80\xa8" + b"\xff" * (k % 3))
+        recs.append(S.LogRec(1_700_000_000_000_000_000 + k * 1_000_003, 1000 + k, 1_700_000_000_500_000_000 + k,
+                             method=b"POST", user_agent=ua, xff=b" " * (k % 5) + b"10.0.%d.%d , 1.1.1.1" % (k % 256, k // 256),
+                             remote_addr=b"[2001:db8::%x]:443" % k, uri=b"/upload/" + b"a" * (k % 300) + b"?q=\"%d\"" % k,
+                             status=200 + k % 300, tz_offset_s=(k % 27 - 13) * 1800, kind=S.LOG_RPC if k % 11 == 0 else S.LOG_REQUEST))
+    b = S.LogBatch.pack(recs)
+    o1, f1 = O.request_log(b)
+    o2, f2 = _gpu_lines(eng, b)
+    assert np.array_equal(f1, f2)
+    assert o1[:f1[-1]].tobytes() == o2.tobytes()
+
+
+@pytest.mark.gpu
 def test_gpu_empty_and_overflow(eng):
     d_out, d_off = eng.request_log_device(S.LogBatch.pack([]))
     assert d_off.cpu().numpy().tolist() == [0]

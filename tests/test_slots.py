@@ -102,6 +102,15 @@ def test_bind_and_results_in_slots(torch_cuda):
 
 
 @pytest.mark.gpu
+def test_tiny_slots_write_nothing(torch_cuda):
+    from gofr_b200.engine import Engine
+    spec = synth.config1_spec()
+    eng = Engine(Table(spec), 0)
+    _check(eng, spec, synth.config1_batch(300), 16)     # every response is longer than 16 bytes: lengths only
+    eng.close()
+
+
+@pytest.mark.gpu
 def test_slot_argument_checks(torch_cuda):
     from gofr_b200 import _abi
     from gofr_b200.engine import Engine
