@@ -384,11 +384,11 @@ static void build_header(Prog& p, uint32_t frame_mode, int status, bool with_mw,
 }
 
 // struct → JSON object ops.  Schemas without omitempty collapse to literals around value ops.
-static void build_struct_ops(Prog& p, const SchemaDef& sc, bool bind_layout = false) {
+static void build_struct_ops(Prog& p, const SchemaDef& sc, bool bind_layout = false, uint16_t word_base = 0) {
     bool dynamic = false;
     for (auto& f : sc.fields) dynamic |= f.omitempty;
     std::string acc = "{";
-    uint16_t word = 0, str_ord = 0;
+    uint16_t word = word_base, str_ord = word_base ? 1 : 0;
     bool first = true;
     for (auto& f : sc.fields) {
         std::string key = "\"" + json_escape_go(f.json_name) + "\":";
@@ -562,7 +562,7 @@ int seal_table(gofr_table* t) {
 
     // ---- per-route programs ----
     std::vector<int> prog_ok(t->routes.size(), 0xFFFF), prog_err(t->routes.size(), 0xFFFF);
-    std::vector<int> prog_err404(t->routes.size(), 0xFFFF), prog_nil(t->routes.size(), 0xFFFF);
+    std::vector<int> prog_err404(t->routes.size(), 0xFFFF), prog_nil(t->routes.size(), 0xFFFF), prog_both(t->routes.size(), 0xFFFF);
     for (size_t ri = 0; ri < t->routes.size(); ri++) {
         RouteDef& r = t->routes[ri];
         const SchemaDef* sc = nullptr;
@@ -631,6 +631,22 @@ int seal_table(gofr_table* t) {
                     (which ? prog_err404 : prog_err)[ri] = b.add(std::move(e));
                 }
                 prog_nil[ri] = b.json_prog(200, {lit("{}\n", true)});
+                {   // (data, err) both non-nil: response{Error, Data} with both members (responder.go:59-62)
+                    Prog e;
+                    e.status = 500;
+                    build_header(e, fm, 500, true, BODY_JSON, false, "", "", false);
+                    e.ops.push_back(lit("{\"error\":{\"message\":\"", true));
+                    SOp m = op(OP_STR, true);
+                    m.off = 0;
+                    e.ops.push_back(m);
+                    e.ops.push_back(lit("\"},\"data\":", true));
+                    build_struct_ops(e, *sc, false, 1);
+                    e.ops.push_back(lit("}\n", true));
+                    uint32_t fw = 1;
+                    for (auto& f : sc->fields) fw += (f.kind == GOFR_F_INT64 || f.kind == 5) ? 2 : 1;
+                    e.row_words = (int)fw;
+                    prog_both[ri] = b.add(std::move(e));
+                }
                 break;
             }
             case GOFR_H_FILE: {
@@ -717,6 +733,7 @@ int seal_table(gofr_table* t) {
         if (r.hkind == GOFR_H_RESULT) {  // the two spare 16-bit fields carry the other outcomes' programs
             R.key_len = (uint16_t)prog_nil[ri];
             R.def_len = (uint16_t)prog_err404[ri];
+            R.key_off = (uint32_t)prog_both[ri];
         }
         if (r.hkind == GOFR_H_ROW || r.hkind == GOFR_H_BIND_ECHO || r.hkind == GOFR_H_RESULT)
             for (size_t si = 0; si < t->schemas.size(); si++)

@@ -24,7 +24,7 @@ FRAME_WIRE, FRAME_INTENDED, FRAME_BODY = 0, 1, 2
 # handler kinds
 (H_HOST, H_STATIC_STRING, H_STATIC_ERROR, H_NIL, H_PARAM_FORMAT, H_ROW, H_BIND_ECHO, H_HEALTH, H_MISSING_FILE, H_FILE,
  H_PANIC, H_PATHPARAM_FORMAT, H_RESULT) = range(13)
-RESULT_DATA, RESULT_ERROR, RESULT_NIL, RESULT_MISSING = range(4)
+RESULT_DATA, RESULT_ERROR, RESULT_NIL, RESULT_MISSING, RESULT_BOTH = range(5)
 
 
 def result_record(outcome: int, payload: bytes = b"") -> bytes:
@@ -32,6 +32,14 @@ def result_record(outcome: int, payload: bytes = b"") -> bytes:
     if outcome in (RESULT_ERROR, RESULT_MISSING):
         payload = len(payload).to_bytes(4, "little") + payload
     return outcome.to_bytes(4, "little") + payload
+
+
+def result_both(schema: "Schema", values: Sequence, message: bytes) -> bytes:
+    """RESULT_BOTH record: (data, err) both non-nil — message length word + the row's fixed words, then the message
+    bytes + the row's string bytes."""
+    row = schema.encode_row(values)
+    fixed = schema.fixed_bytes()
+    return (RESULT_BOTH.to_bytes(4, "little") + len(message).to_bytes(4, "little") + row[:fixed] + message + row[fixed:])
 
 # field kinds
 F_INT64, F_INT32, F_BOOL, F_STRING, F_INT = 1, 2, 3, 4, 5

@@ -99,9 +99,12 @@ enum {
                                    GOFR_RESULT_DATA     a row of the route's schema (as for GOFR_H_ROW)      → 200 {"data":{…}}
                                    GOFR_RESULT_ERROR    u32 length + err.Error() bytes                      → 500 {"error":{"message":…}}
                                    GOFR_RESULT_NIL      nothing                                             → 200 {}
-                                   GOFR_RESULT_MISSING  u32 length + message; errors.Is(err, http.ErrMissingFile) → 404 */
+                                   GOFR_RESULT_MISSING  u32 length + message; errors.Is(err, http.ErrMissingFile) → 404
+                                   GOFR_RESULT_BOTH     (data, err) both non-nil: one row whose first field is the message
+                                                        string followed by the schema's fields (length word + fixed
+                                                        words, then message bytes + string bytes) → 500 {"error":…,"data":…} */
 };
-enum { GOFR_RESULT_DATA = 0, GOFR_RESULT_ERROR = 1, GOFR_RESULT_NIL = 2, GOFR_RESULT_MISSING = 3 };
+enum { GOFR_RESULT_DATA = 0, GOFR_RESULT_ERROR = 1, GOFR_RESULT_NIL = 2, GOFR_RESULT_MISSING = 3, GOFR_RESULT_BOTH = 4 };
 
 /* ---- struct field kinds for response / Bind schemas ---- */
 enum {

@@ -966,6 +966,24 @@ static void serve_one(const orc_table* t, const req_desc* d, const uint8_t* id16
                     if (rn < 4 || (uint64_t)len + 4 > rn) { hr.data_kind = -1; break; }
                     hr.has_err = 1; hr.err_msg = rest + 4; hr.err_len = len;
                     hr.err_is_missing_file = outcome == 3;
+                } else if (outcome == 4) {
+                    /* (data, err): one row = [message length word][schema fixed words][message bytes][string bytes] */
+                    size_t fixed = 4;
+                    if (sc) for (int i = 0; i < sc->n_fields; i++) fixed += (sc->f[i].kind == F_INT64 || sc->f[i].kind == F_INT) ? 8 : 4;
+                    uint32_t mlen = 0;
+                    if (rn >= 4) memcpy(&mlen, rest, 4);
+                    if (!sc || rn < fixed || fixed + (uint64_t)mlen > rn) { hr.data_kind = -1; break; }
+                    /* the struct's words follow the length word, its strings follow the message bytes: present them to
+                     * decode_row as an ordinary row */
+                    uint8_t* tmp_row = (uint8_t*)malloc(rn);
+                    memcpy(tmp_row, rest + 4, fixed - 4);
+                    memcpy(tmp_row + fixed - 4, rest + fixed + mlen, rn - fixed - mlen);
+                    if (decode_row(sc, tmp_row, rn - 4 - mlen, vals) != 0) { free(tmp_row); hr.data_kind = -1; break; }
+                    ob_put(&tmp2, tmp_row, rn - 4 - mlen);
+                    free(tmp_row);
+                    decode_row(sc, tmp2.p, tmp2.n, vals); /* vals must point into memory that outlives this block */
+                    hr.has_err = 1; hr.err_msg = rest + fixed; hr.err_len = mlen;
+                    hr.data_kind = 2; hr.sc = sc; hr.vals = vals;
                 } else if (outcome != 2) hr.data_kind = -1;
                 break;
             }

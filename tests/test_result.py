@@ -40,7 +40,10 @@ def _batch() -> S.RequestBatch:
             R(S.M_GET, b"/items/7", data=b""),
             R(S.M_GET, b"/items/8", data=rec(S.RESULT_DATA, row[:6])),      # truncated row
             R(S.M_GET, b"/items/10", data=rec(S.RESULT_ERROR, b"")),
-            R(S.M_OPTIONS, b"/items/1", data=rec(S.RESULT_NIL))]
+            R(S.M_OPTIONS, b"/items/1", data=rec(S.RESULT_NIL)),
+            R(S.M_GET, b"/items/11", data=S.result_both(ITEM, ["A-2", -7, ""], b'partial: 2 of 3 "shards" <down>')),
+            R(S.M_GET, b"/profile", data=S.result_both(synth.C2_SCHEMA, [5, "n", "e", False, -1], b"")),
+            R(S.M_GET, b"/items/12", data=S.result_both(ITEM, ["A", 1, "n"], b"msg")[:14])]   # truncated → panic
     return S.RequestBatch.pack(reqs)
 
 
@@ -58,6 +61,11 @@ def test_oracle_bodies():
     assert st[8] == st[9] == st[10] == st[11] == 500 and b"Some unexpected error" in r[8]
     assert r[12] == b'{"error":{"message":""}}\n' and st[12] == 500
     assert st[13] == 200 and r[13] == b""          # CORS answers OPTIONS (catch-all matches), handler never runs
+    # (data, err) both non-nil: response{Error, Data} carries both members, status from the error (responder.go:19-62)
+    assert r[14] == (b'{"error":{"message":"partial: 2 of 3 \\"shards\\" \\u003cdown\\u003e"},'
+                     b'"data":{"sku":"A-2","qty":-7}}\n') and st[14] == 500
+    assert r[15] == b'{"error":{"message":""},"data":{"id":5,"name":"n","email":"e","active":false,"count":-1}}\n'
+    assert st[16] == 500 and b"Some unexpected error" in r[16]
 
 
 @pytest.mark.parametrize("frame", [S.FRAME_WIRE, S.FRAME_INTENDED, S.FRAME_BODY])
