@@ -194,3 +194,21 @@ func (e *Engine) RequestLogDevice(dDesc, dTraceIDs, dArena unsafe.Pointer, n int
 	return check(C.gofr_requestlog_device(e.e, (*C.gofr_log_desc)(dDesc), (*C.uint8_t)(dTraceIDs), (*C.uint8_t)(dArena),
 		C.uint32_t(n), (*C.uint8_t)(dOut), C.uint64_t(outCap), (*C.uint32_t)(dOff), stream), "gofr_requestlog_device")
 }
+
+// RouteDevice is stage 1 of the split API for closures that stay in Go: routing decisions and mux.Vars spans for a
+// batch resident in device memory (gofr_route_device).  meta[i] = status | route << 16; status 0 = run handler `route`.
+func (e *Engine) RouteDevice(dDesc, dArena unsafe.Pointer, n int, dMeta, dVars unsafe.Pointer, stream unsafe.Pointer) error {
+	return check(C.gofr_route_device(e.e, (*C.gofr_req_desc)(dDesc), (*C.uint8_t)(dArena), C.uint32_t(n), (*C.uint32_t)(dMeta),
+		(*C.uint32_t)(dVars), stream), "gofr_route_device")
+}
+
+// ServeDeviceSlots writes response i into its own slotBytes-sized, 16-byte aligned slot of dOut and its length into
+// dOutLen[i] (gofr_serve_device_slots): the layout a ring of fixed-size response buffers maps onto directly.
+func (e *Engine) ServeDeviceSlots(dDesc, dTraceIDs, dArena unsafe.Pointer, n int, now time.Time, dOut unsafe.Pointer,
+	slotBytes uint32, dOutLen, dMeta unsafe.Pointer, stream unsafe.Pointer) error {
+	var date [29]C.char
+	C.gofr_format_http_date(C.int64_t(now.Unix()), &date[0])
+	return check(C.gofr_serve_device_slots(e.e, (*C.gofr_req_desc)(dDesc), (*C.uint8_t)(dTraceIDs), (*C.uint8_t)(dArena),
+		C.uint32_t(n), &date[0], (*C.uint8_t)(dOut), C.uint32_t(slotBytes), (*C.uint32_t)(dOutLen), (*C.uint32_t)(dMeta), stream),
+		"gofr_serve_device_slots")
+}
