@@ -272,6 +272,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer measurement (default: --steps)")
     ap.add_argument("--chunk", type=int, default=65536)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-layout", default="slots", choices=["packed", "slots"],
+                    help="end-to-end measurement: gofr_batch_submit (packed offsets, device-driven egress) or "
+                         "gofr_batch_submit_slots (one slot per response, plain async copies)")
     ap.add_argument("--layout", default="slots", choices=["packed", "slots"],
                     help="resident measurement: packed offsets (gofr_serve_device) or one 528-byte slot per response "
                          "(gofr_serve_device_slots)")
@@ -397,27 +400,49 @@ def main():
     e2e = None
     if not args.no_e2e:
         hb = pin_batch(batch)
-        h_out = pinned_array(out_bytes + 4096)
-        h_off = pinned_array(4 * (n + 1), np.uint32)
-        h_meta = pinned_array(4 * n, np.uint32)
         ksteps = args.e2e_steps or args.steps
-        for _ in range(args.warmup):
-            got = eng.serve_host(hb, date, h_out, h_off, h_meta)
-        assert got == out_bytes
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(ksteps):
-            eng.serve_host(hb, date, h_out, h_off, h_meta)
-        barrier()
-        dt = reduce_max(time.perf_counter() - t0)
         h2d = n * 32 + int(batch.arena_span())
-        d2h = out_bytes + 4 * n + 4 * n + 8 * ((n + args.chunk - 1) // args.chunk)
+        if args.e2e_layout == "slots":
+            h_out = pinned_array(n * slot)
+            h_len = pinned_array(4 * n, np.uint32)
+            h_meta = pinned_array(4 * n, np.uint32)
+            for _ in range(args.warmup):
+                eng.serve_host_slots(hb, date, slot, h_out, h_len, h_meta)
+            assert bool((h_len == synth.C2_WIRE_BYTES).all())
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ksteps):
+                eng.serve_host_slots(hb, date, slot, h_out, h_len, h_meta)
+            barrier()
+            dt = reduce_max(time.perf_counter() - t0)
+            d2h = n * slot + 4 * n + 4 * n
+            # the last host result must match the resident (packed) one byte for byte, response by response
+            k = 8192
+            dev_out = resp.out[:k * synth.C2_WIRE_BYTES].cpu().numpy().reshape(k, synth.C2_WIRE_BYTES)
+            assert np.array_equal(h_out[:k * slot].reshape(k, slot)[:, :synth.C2_WIRE_BYTES], dev_out), "host path and resident path disagree"
+            tail = h_out.reshape(n, slot)[-k:, :synth.C2_WIRE_BYTES]
+            dev_tail = resp.out[(n - k) * synth.C2_WIRE_BYTES:n * synth.C2_WIRE_BYTES].cpu().numpy().reshape(k, synth.C2_WIRE_BYTES)
+            assert np.array_equal(tail, dev_tail), "host path and resident path disagree"
+        else:
+            h_out = pinned_array(out_bytes + 4096)
+            h_off = pinned_array(4 * (n + 1), np.uint32)
+            h_meta = pinned_array(4 * n, np.uint32)
+            for _ in range(args.warmup):
+                got = eng.serve_host(hb, date, h_out, h_off, h_meta)
+            assert got == out_bytes
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ksteps):
+                eng.serve_host(hb, date, h_out, h_off, h_meta)
+            barrier()
+            dt = reduce_max(time.perf_counter() - t0)
+            d2h = out_bytes + 4 * n + 4 * n + 8 * ((n + args.chunk - 1) // args.chunk)
+            # the last host result must match the resident one byte for byte
+            dev_out = resp.out[:out_bytes].cpu().numpy()
+            assert np.array_equal(h_out[:out_bytes], dev_out), "host path and resident path disagree"
         e2e = {"value": n * world * ksteps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": dt / ksteps * 1e3, "steps": ksteps, "chunk_requests": args.chunk,
+               "ms_per_step": dt / ksteps * 1e3, "steps": ksteps, "chunk_requests": args.chunk, "layout": args.e2e_layout,
                "timing": "wall clock around the synchronous host-buffer calls, max over ranks"}
-        # the last host result must match the resident one byte for byte
-        dev_out = resp.out[:out_bytes].cpu().numpy()
-        assert np.array_equal(h_out[:out_bytes], dev_out), "host path and resident path disagree"
 
     # ---- CPU baseline beside it (rank 0, bounded sample of the same stream) ----
     cpu = None
@@ -449,7 +474,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8", "data": "synthetic", "config": dict(workload_config(n, world, "gpu"), resident_layout=("slots: response i in its own 528-byte slot (gofr_serve_device_slots)" if args.layout == "slots" else "packed offsets (gofr_serve_device)"), e2e_layout="packed offsets (gofr_batch_submit)"),
+                "dtype": "u8", "data": "synthetic", "config": dict(workload_config(n, world, "gpu"), resident_layout=("slots: response i in its own 528-byte slot (gofr_serve_device_slots)" if args.layout == "slots" else "packed offsets (gofr_serve_device)"), e2e_layout=("slots (gofr_batch_submit_slots)" if args.e2e_layout == "slots" else "packed offsets (gofr_batch_submit)")),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": profiled_traffic(args.layout) if n == (1 << 20) else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                              "algorithmic_bytes_per_request": algo_bytes / n, "kernel_ms_per_launch": per_launch_ms,

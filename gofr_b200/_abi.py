@@ -31,6 +31,11 @@ class ReqBatch(C.Structure):
                 ("n", C.c_uint32), ("date", C.c_char * 29), ("pad", C.c_uint8 * 3)]
 
 
+class SlotBatch(C.Structure):
+    _fields_ = [("out", C.c_void_p), ("slot_bytes", C.c_uint32), ("reserved", C.c_uint32), ("out_len", C.c_void_p),
+                ("meta", C.c_void_p)]
+
+
 class RespBatch(C.Structure):
     _fields_ = [("out", C.c_void_p), ("out_cap", C.c_uint64), ("out_off", C.c_void_p), ("meta", C.c_void_p),
                 ("out_bytes", C.c_uint64)]
@@ -85,6 +90,7 @@ def lib():
     L.gofr_serve_device_slots.argtypes = [vp, vp, vp, vp, u32, C.c_char_p, vp, u32, vp, vp, vp]
     L.gofr_batch_submit.argtypes = [vp, C.POINTER(ReqBatch), C.POINTER(RespBatch), C.POINTER(u64)]
     L.gofr_batch_wait.argtypes = [vp, u64]
+    L.gofr_batch_submit_slots.argtypes = [vp, C.POINTER(ReqBatch), C.POINTER(SlotBatch), C.POINTER(u64)]
     L.gofr_engine_set_chunk.argtypes = [vp, u32]
     L.gofr_engine_set_tile.argtypes = [vp, u32]
     L.gofr_engine_set_timing.argtypes = [vp, i32]
@@ -113,7 +119,7 @@ DECLARED_SYMBOLS = [
     "gofr_table_create", "gofr_table_destroy", "gofr_table_add_schema", "gofr_table_add_route",
     "gofr_table_add_default_routes", "gofr_table_seal", "gofr_table_serialize", "gofr_table_deserialize",
     "gofr_table_route_count", "gofr_table_max_response_bytes", "gofr_engine_create", "gofr_engine_destroy",
-    "gofr_serve_device", "gofr_serve_device_slots", "gofr_batch_submit", "gofr_batch_wait", "gofr_engine_set_chunk", "gofr_engine_set_tile",
+    "gofr_serve_device", "gofr_serve_device_slots", "gofr_batch_submit", "gofr_batch_wait", "gofr_batch_submit_slots", "gofr_engine_set_chunk", "gofr_engine_set_tile",
     "gofr_engine_set_timing", "gofr_engine_overflowed", "gofr_engine_geometry", "gofr_alloc_pinned", "gofr_free_pinned",
     "gofr_grpc_hello_device", "gofr_requestlog_device", "gofr_route_device", "gofr_engine_launch_count", "gofr_engine_kernel_time_ms", "gofr_last_error",
     "gofr_abi_version", "gofr_format_http_date",

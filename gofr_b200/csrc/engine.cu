@@ -556,6 +556,79 @@ int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch*
     return GOFR_OK;
 }
 
+int gofr_batch_submit_slots(gofr_engine* e, const gofr_req_batch* in, gofr_slot_batch* out, gofr_ticket* ticket) {
+    if (!e || !in || !out || !ticket) return GOFR_ERR_INVALID;
+    if (in->n && (!in->desc || !in->trace_ids || !out->out || !out->out_len || !out->meta)) return GOFR_ERR_INVALID;
+    if (out->slot_bytes == 0 || (out->slot_bytes & 15u)) { set_last_error("slot_bytes must be a positive multiple of 16"); return GOFR_ERR_INVALID; }
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    const uint32_t n = in->n, slot = out->slot_bytes;
+    int final_rc = GOFR_OK;
+    const size_t nchunks = n ? (n + e->chunk - 1) / e->chunk : 0;
+    for (size_t ci = 0; ci < nchunks; ci++) {
+        Slot& s = e->slots[ci % kSlots];
+        // the chunk's request range and the arena bytes it covers (scanned right before the chunk is enqueued)
+        const uint32_t lo = (uint32_t)(ci * e->chunk), hi = std::min<uint32_t>(n, lo + e->chunk), cn = hi - lo;
+        uint32_t alo = 0xFFFFFFFFu, ahi = 0;
+        for (uint32_t i = lo; i < hi; i++) {
+            const gofr_req_desc& d = in->desc[i];
+            const uint32_t dend = ((d.arena_off + d.path_len + d.query_len + 3u) & ~3u) + d.data_len;
+            alo = d.arena_off < alo ? d.arena_off : alo;
+            ahi = dend > ahi ? dend : ahi;
+        }
+        alo &= ~15u;
+        ahi = (ahi + 15u) & ~15u;
+        if ((uint64_t)ahi > ((in->arena_bytes + 15u) & ~(uint64_t)15u)) { set_last_error("descriptor %u..%u points outside the arena", lo, hi); return GOFR_ERR_INVALID; }
+        const size_t abytes = (size_t)ahi - alo, obytes = (size_t)cn * slot;
+        if (s.egress_pending) {  // the slot's previous chunk must have left before its buffers are reused
+            const bool grows = cn > s.cap_n || abytes > s.cap_arena || obytes > s.cap_out;
+            if (grows) CUDA_TRY(cudaEventSynchronize(s.ev_egress));
+            else CUDA_TRY(cudaStreamWaitEvent(e->st_h2d, s.ev_egress, 0));
+            s.egress_pending = false;
+        }
+        if (cn > s.cap_n) {
+            cudaFree(s.d_desc); cudaFree(s.d_ids); cudaFree(s.d_off); cudaFree(s.d_meta); cudaFree(s.d_state); cudaFree(s.d_bind);
+            s.d_desc = s.d_ids = nullptr; s.d_off = s.d_meta = nullptr; s.d_state = nullptr; s.d_bind = nullptr;
+            const size_t c = (size_t)cn + cn / 4 + 256, tiles = (c + 63) / 64;
+            if (cudaMalloc(&s.d_desc, c * 16) != cudaSuccess || cudaMalloc(&s.d_ids, c * 16) != cudaSuccess ||
+                cudaMalloc(&s.d_off, (c + 1) * 4) != cudaSuccess || cudaMalloc(&s.d_meta, c * 4) != cudaSuccess ||
+                cudaMalloc(&s.d_state, tiles * 8) != cudaSuccess) { set_last_error("cudaMalloc failed for a %zu-request chunk", c); s.cap_n = 0; return GOFR_ERR_NOMEM; }
+            if (cudaMemset(s.d_state, 0, tiles * 8) != cudaSuccess) return GOFR_ERR_CUDA;
+            if (e->hdr.bind_row_words && cudaMalloc(&s.d_bind, c * e->hdr.bind_row_words * 4 + 256) != cudaSuccess) { s.cap_n = 0; return GOFR_ERR_NOMEM; }
+            s.cap_n = c;
+        }
+        if (!s.d_flag) { if (cudaMalloc(&s.d_flag, 64) != cudaSuccess || cudaMemset(s.d_flag, 0, 64) != cudaSuccess) return GOFR_ERR_NOMEM; }
+        int rc;
+        if ((rc = grow((void**)&s.d_arena, &s.cap_arena, abytes, 256))) return rc;
+        if ((rc = grow((void**)&s.d_out, &s.cap_out, obytes, 256))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(s.d_desc, in->desc + lo, (size_t)cn * 16, cudaMemcpyHostToDevice, e->st_h2d));
+        CUDA_TRY(cudaMemcpyAsync(s.d_ids, in->trace_ids + (size_t)lo * 16, (size_t)cn * 16, cudaMemcpyHostToDevice, e->st_h2d));
+        if (abytes) {
+            const size_t avail = in->arena_bytes > alo ? (size_t)in->arena_bytes - alo : 0;
+            CUDA_TRY(cudaMemcpyAsync(s.d_arena, in->arena + alo, std::min(abytes, avail), cudaMemcpyHostToDevice, e->st_h2d));
+        }
+        CUDA_TRY(cudaEventRecord(s.ev_h2d, e->st_h2d));
+        CUDA_TRY(cudaStreamWaitEvent(e->st_compute, s.ev_h2d, 0));
+        rc = launch_one(e, s.d_desc, s.d_ids, s.d_arena - alo, cn, in->date, s.d_out, obytes, s.d_off, s.d_meta, s.d_state, s.d_flag,
+                        s.d_bind, e->st_compute, nullptr, slot);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(s.ev_served, e->st_compute));
+        CUDA_TRY(cudaStreamWaitEvent(e->st_egress, s.ev_served, 0));
+        CUDA_TRY(cudaMemcpyAsync(out->out + (size_t)lo * slot, s.d_out, obytes, cudaMemcpyDeviceToHost, e->st_egress));
+        CUDA_TRY(cudaMemcpyAsync(out->out_len + lo, s.d_off, (size_t)cn * 4, cudaMemcpyDeviceToHost, e->st_egress));
+        CUDA_TRY(cudaMemcpyAsync(out->meta + lo, s.d_meta, (size_t)cn * 4, cudaMemcpyDeviceToHost, e->st_egress));
+        CUDA_TRY(cudaEventRecord(s.ev_egress, e->st_egress));
+        s.egress_pending = true;
+    }
+    if (nchunks) {
+        CUDA_TRY(cudaStreamSynchronize(e->st_egress));
+        for (auto& s : e->slots) s.egress_pending = false;
+    }
+    *ticket = e->next_ticket++;
+    e->done_tickets.emplace_back(*ticket, final_rc);
+    return GOFR_OK;
+}
+
 int gofr_batch_wait(gofr_engine* e, gofr_ticket ticket) {
     if (!e || ticket == 0) return GOFR_ERR_INVALID;
     std::lock_guard<std::mutex> g(e->mu);

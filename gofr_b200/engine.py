@@ -184,6 +184,21 @@ class Engine:
         return int(ob.out_bytes)
 
 
+def _serve_host_slots(self, batch: S.RequestBatch, date: bytes, slot_bytes: int, out: np.ndarray, out_len: np.ndarray,
+                      meta: np.ndarray) -> None:
+    """gofr_batch_submit_slots + wait: host buffers in, response i in out[i * slot_bytes:], its length in out_len[i]."""
+    L = _abi.lib()
+    rb = _abi.ReqBatch(desc=batch.desc.ctypes.data, trace_ids=batch.trace_ids.ctypes.data, arena=batch.arena.ctypes.data,
+                       arena_bytes=batch.arena.size, n=batch.n, date=date)
+    sb = _abi.SlotBatch(out=out.ctypes.data, slot_bytes=slot_bytes, reserved=0, out_len=out_len.ctypes.data, meta=meta.ctypes.data)
+    t = C.c_uint64()
+    _abi.check(L.gofr_batch_submit_slots(self._e, C.byref(rb), C.byref(sb), C.byref(t)), "gofr_batch_submit_slots")
+    _abi.check(L.gofr_batch_wait(self._e, t.value), "gofr_batch_wait")
+
+
+Engine.serve_host_slots = _serve_host_slots
+
+
 def pinned_array(nbytes: int, dtype=np.uint8) -> np.ndarray:
     """numpy view over cudaMallocHost memory (gofr_alloc_pinned).  The memory lives until process exit."""
     L = _abi.lib()

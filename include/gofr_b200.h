@@ -231,6 +231,20 @@ typedef struct gofr_resp_batch {
  * (no host stall per chunk); pageable buffers fall back to an exact-size cudaMemcpy pipeline. */
 int gofr_batch_submit(gofr_engine*, const gofr_req_batch* in, gofr_resp_batch* out, gofr_ticket* ticket);
 int gofr_batch_wait(gofr_engine*, gofr_ticket ticket);
+
+/* Host batch with the slot layout: response i lands in out + i * slot_bytes (a ring of fixed-size response buffers),
+ * its length in out_len[i] (> slot_bytes: not written, serve that request through the packed call).  Chunk sizes are
+ * known on the host, so the results leave with plain asynchronous copies — no device-side packing, no egress kernel.
+ * slot_bytes: a positive multiple of 16; out: 16-byte aligned, n * slot_bytes bytes.  Whole slots are copied back: the
+ * bytes of a slot behind its (zero-padded) response are unspecified. */
+typedef struct gofr_slot_batch {
+    uint8_t* out;
+    uint32_t slot_bytes;
+    uint32_t reserved;
+    uint32_t* out_len; /* n */
+    uint32_t* meta;    /* n */
+} gofr_slot_batch;
+int gofr_batch_submit_slots(gofr_engine*, const gofr_req_batch* in, gofr_slot_batch* out, gofr_ticket* ticket);
 int gofr_engine_set_chunk(gofr_engine*, uint32_t requests_per_chunk);
 /* Tile geometry: shared-memory staging budget for request bytes, per request.  Tiles whose request bytes exceed the
  * budget are still served correctly, straight from HBM. */

@@ -33,7 +33,8 @@ def _check(eng, spec, batch, slot):
     return ln
 
 
-def _check_slots(out, ln, meta, spec, batch, slot):
+def _check_slots(out, ln, meta, spec, batch, slot, untouched=True):
+    """untouched=False: the host path copies whole slots back, so bytes behind a response are unspecified there"""
     o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
     assert np.array_equal(meta, m1)
     assert np.array_equal(ln, np.diff(f1.astype(np.int64)).astype(np.uint32))
@@ -41,11 +42,11 @@ def _check_slots(out, ln, meta, spec, batch, slot):
     for i in range(batch.n):
         L = int(ln[i])
         if L > slot:
-            assert (out[i] == 0xEE).all()
+            assert not untouched or (out[i] == 0xEE).all()
             continue
         assert out[i, :L].tobytes() == ob[int(f1[i]):int(f1[i]) + L], i
         pad = (-L) % 16
-        assert (out[i, L:L + pad] == 0).all() and (out[i, L + pad:] == 0xEE).all(), i
+        assert (out[i, L:L + pad] == 0).all() and (not untouched or (out[i, L + pad:] == 0xEE).all()), i
 
 
 @pytest.mark.parametrize("which,slot", [("config1", 320), ("config2", 528), ("config2", 544), ("config4", 352), ("config3", 1024)])
@@ -98,6 +99,36 @@ def test_bind_and_results_in_slots(torch_cuda):
     from tests.test_result import _spec, _batch
     eng = Engine(Table(_spec()), 0)
     _check(eng, _spec(), _batch(), 768)
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_batch_slots(torch_cuda, pinned):
+    """gofr_batch_submit_slots: host buffers in, slots out, chunked over the engine's three device slots"""
+    from gofr_b200.engine import Engine, pin_batch, pinned_array
+    spec = synth.config4_spec()
+    batch = synth.config4_batch(5000)
+    eng = Engine(Table(spec), 0)
+    eng.set_chunk(700)                                  # 8 chunks, the last one short
+    slot, n = 512, batch.n
+    if pinned:
+        hb = pin_batch(batch)
+        out, ln, meta = pinned_array(n * slot), pinned_array(4 * n, np.uint32), pinned_array(4 * n, np.uint32)
+    else:
+        hb = batch
+        out, ln, meta = np.zeros(n * slot, np.uint8), np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    for rep in range(2):                                # buffers are reused across batches
+        out[:] = 0xEE
+        eng.serve_host_slots(hb, DATE, slot, out, ln, meta)
+        _check_slots(out.reshape(n, slot), ln, meta, spec, batch, slot, untouched=False)
+    # and it alternates with the packed host path on the same engine
+    po, pf, pm = np.zeros(n * 700, np.uint8), np.zeros(n + 1, np.uint32), np.zeros(n, np.uint32)
+    got = eng.serve_host(batch, DATE, po, pf, pm)
+    o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
+    assert got == int(f1[-1]) and po[:got].tobytes() == o1[:got].tobytes()
+    eng.serve_host_slots(hb, DATE, slot, out, ln, meta)
+    _check_slots(out.reshape(n, slot), ln, meta, spec, batch, slot, untouched=False)
     eng.close()
 
 
