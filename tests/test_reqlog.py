@@ -154,6 +154,28 @@ def test_emu_empty_and_single():
     assert o1[:f1[-1]].tobytes() == o2[3:f2[-1]].tobytes()
 
 
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_bytes = st.one_of(st.binary(max_size=24), st.text(alphabet=' \t,"\\<&>\u00a0\u2028\u3000\u0085abc:[]1.', max_size=16).map(lambda t: t.encode()),
+                   st.sampled_from([b"", b" ", b",", b"\xc2", b"\xe2\x80", b"\xe2\x80\xa8", b" \xe3\x80\x80x\xe1\x9a\x80 "]))
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.tuples(_bytes, _bytes, _bytes, _bytes, _bytes, st.integers(-(2 ** 62), 2 ** 62), st.integers(-10 ** 12, 10 ** 12),
+                          st.integers(0, 999), st.integers(-50400, 50400), st.booleans()), min_size=1, max_size=6),
+       st.integers(0, 15))
+def test_emu_random_records_property(recs, mis):
+    batch = S.LogBatch.pack([S.LogRec(t, el, t + 7, method=m, user_agent=ua, xff=x, remote_addr=ra, uri=u, status=stt, tz_offset_s=tz,
+                                      kind=S.LOG_RPC if rpc else S.LOG_REQUEST)
+                             for (m, ua, x, ra, u, t, el, stt, tz, rpc) in recs])
+    o1, f1 = O.request_log(batch)
+    o2, f2 = emu.request_log(batch, mis)
+    assert np.array_equal(f1 + mis, f2)
+    assert o1[:f1[-1]].tobytes() == o2[mis:f2[-1]].tobytes()
+    for line in _lines(o1, f1):
+        json.loads(line)  # every line is valid JSON whatever the input bytes
+
+
 # ---- GPU ----
 def _gpu_lines(eng, b):
     d_out, d_off = eng.request_log_device(b)
