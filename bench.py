@@ -181,6 +181,7 @@ def run_secondary(args):
         # the RequestLog line of middleware.Logging for the config-2 stream
         lb = synth.reqlog_batch(n)
         eng = Engine(Table(synth.config1_spec()), 0)
+        eng.set_timing(True)
         d_desc = torch.from_numpy(lb.desc.view(np.uint8).reshape(-1).copy()).cuda()
         d_ids = torch.from_numpy(lb.trace_ids.reshape(-1).copy()).cuda()
         d_arena = torch.from_numpy(np.concatenate([lb.arena, np.zeros(48, np.uint8)])).cuda()
@@ -200,6 +201,7 @@ def run_secondary(args):
     elif w == "config5":
         frames, off = synth.config5_frames(n)
         eng = Engine(Table(synth.config1_spec()), 0)
+        eng.set_timing(True)
         d_in = torch.from_numpy(np.concatenate([frames, np.zeros(64, np.uint8)])).cuda()
         d_off = torch.from_numpy(off.view(np.int32)).cuda()
         cap = int(frames.size) + 40 * n
@@ -218,6 +220,7 @@ def run_secondary(args):
                        "config4": (synth.config4_spec(), lambda: synth.config4_batch(n))}[w]
         batch = batch()
         eng = Engine(Table(spec), 0)
+        eng.set_timing(True)
         db = eng.upload(batch)
         o1, f1, _ = O.OracleTable(spec).serve(batch, date)
         resp = eng.alloc_responses(n, int(f1[n]) + 4096)
@@ -309,6 +312,7 @@ def main():
     table = Table(image=image)
     eng = Engine(table, local)
     eng.set_chunk(args.chunk)
+    eng.set_timing(True)  # CUDA events around every kernel launch of this engine (roofline.achieved)
 
     n = args.requests
     date = S.http_date(DATE_UNIX)

@@ -89,7 +89,8 @@ struct gofr_engine {
     uint64_t launches = 0;
     // kernel timing (events on the launch stream)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
-    bool timing_on = true;
+    bool timing_on = false;  // off by default: each timed launch costs two event objects (gofr_engine_set_timing)
+    uint32_t debug_flags = 0;  // GOFR_DEBUG_* environment switches, read once at creation
     double timed_ms = 0;
     uint64_t timed_launches = 0;
     // tickets
@@ -155,6 +156,7 @@ int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
     CUDA_TRY(cudaMalloc(&e->d_chain, 64));
     CUDA_TRY(cudaMalloc(&e->d_info, sizeof(ChunkInfo) * kSlots));
     CUDA_TRY(cudaMallocHost(&e->h_status, 64));
+    if (getenv("GOFR_DEBUG_NO_LOOKBACK")) e->debug_flags |= 1u;  // diagnostic only: offsets are wrong unless every response has the same size
     e->egress_grid = e->sm_count / 4 > 0 ? e->sm_count / 4 : 1;
     if (const char* g = getenv("GOFR_EGRESS_GRID")) { int v = atoi(g); if (v > 0) e->egress_grid = v; }
     *out = e;
@@ -199,6 +201,23 @@ int gofr_engine_set_chunk(gofr_engine* e, uint32_t requests_per_chunk) {
 
 }  // extern "C"
 
+// Called with the engine lock held before a timed launch: keeps the list of pending event pairs bounded when the
+// caller never asks for the timings (finished pairs are folded into the totals; unfinished ones wait their turn).
+static void fold_timing(gofr_engine* e) {
+    if (e->timing.size() < 256) return;
+    size_t k = 0;
+    for (auto& ev : e->timing) {
+        if (cudaEventQuery(ev.second) == cudaSuccess) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) { e->timed_ms += ms; e->timed_launches++; }
+            cudaEventDestroy(ev.first);
+            cudaEventDestroy(ev.second);
+        } else e->timing[k++] = ev;
+    }
+    e->timing.resize(k);
+    cudaGetLastError();  // cudaEventQuery reports cudaErrorNotReady through the sticky-free last-error slot
+}
+
 // one fused launch; `state`/`flag` are scratch owned by the caller of this helper
 static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, const uint8_t* d_arena, uint32_t n,
                       const char* date29, uint8_t* d_out, uint64_t out_cap, uint32_t* d_off, uint32_t* d_meta,
@@ -218,11 +237,12 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
     p.bind_scratch = d_bind; p.bind_row_words = e->hdr.bind_row_words;
     p.chain_pos = chain_pos;
     p.slot_bytes = slot_bytes;
-    if (getenv("GOFR_DEBUG_NO_LOOKBACK")) p.debug_flags |= 1u;  // diagnostic only
+    p.debug_flags = e->debug_flags;
     memcpy(p.date, date29, 29);
     int grid = (int)std::min<uint32_t>((uint32_t)e->grid, p.n_tiles);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (e->timing_on) {
+        fold_timing(e);
         CUDA_TRY(cudaEventCreate(&ev0));
         CUDA_TRY(cudaEventCreate(&ev1));
         CUDA_TRY(cudaEventRecord(ev0, stream));
@@ -692,6 +712,7 @@ int gofr_grpc_hello_device(gofr_engine* e, const uint8_t* d_in, const uint32_t* 
     p.tile_state = e->d_state; p.overflow = e->d_flag;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (e->timing_on) {
+        fold_timing(e);
         CUDA_TRY(cudaEventCreate(&ev0));
         CUDA_TRY(cudaEventCreate(&ev1));
         CUDA_TRY(cudaEventRecord(ev0, st));
@@ -748,6 +769,7 @@ int gofr_requestlog_device(gofr_engine* e, const gofr_log_desc* d_desc, const ui
     p.tile_state = e->d_state; p.overflow = e->d_flag;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (e->timing_on) {
+        fold_timing(e);
         CUDA_TRY(cudaEventCreate(&ev0));
         CUDA_TRY(cudaEventCreate(&ev1));
         CUDA_TRY(cudaEventRecord(ev0, st));

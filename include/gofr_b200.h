@@ -307,7 +307,8 @@ int gofr_requestlog_device(gofr_engine*, const gofr_log_desc* d_desc, const uint
 
 /* number of kernels launched by this engine so far (bench.py reports it as gpu_launches) */
 uint64_t gofr_engine_launch_count(const gofr_engine*);
-/* duration in ms of the serve kernels launched since the last reset, measured with CUDA events on the launch stream */
+/* duration in ms of the kernels launched since the last reset, measured with CUDA events on the launch stream.
+ * Timing is OFF by default (each timed launch costs two event objects): gofr_engine_set_timing(e, 1) first. */
 int gofr_engine_kernel_time_ms(gofr_engine*, double* total_ms, uint64_t* launches, int reset);
 
 const char* gofr_last_error(void);
