@@ -1,0 +1,71 @@
+"""Third-party cross-checks of the oracle's building blocks against Python's standard library, on the input subsets
+where the Python and Go behaviours are known to coincide (the differences are handled explicitly below).  The oracle is
+a restatement written for this repo; these tests tie it to independently written code."""
+import json
+import posixpath
+import urllib.parse
+
+from hypothesis import given, settings, strategies as st
+
+from tests import oracle as O
+
+
+def _go_json_string_from_python(s: str) -> bytes:
+    """encoding/json (Go 1.21, HTML escaping on) derived from json.dumps: differences are <, >, &, U+2028/9 and the
+    short escapes \\b \\f, which Go writes as \\u0008 / \\u000c."""
+    out = json.dumps(s, ensure_ascii=False)
+    out = out.replace("\\b", "\\u0008").replace("\\f", "\\u000c")
+    out = out.replace("<", "\\u003c").replace(">", "\\u003e").replace("&", "\\u0026")
+    out = out.replace("\u2028", "\\u2028").replace("\u2029", "\\u2029")
+    return out.encode("utf-8")
+
+
+@settings(max_examples=400, deadline=None)
+@given(st.text(alphabet=st.characters(blacklist_categories=("Cs",)), max_size=40))
+def test_json_string_against_json_dumps(s):
+    # json.dumps writes "\\b" for a backspace: a literal backslash followed by b cannot appear otherwise (a backslash in
+    # the input is always doubled), so the textual replacement above is exact
+    if "\\" in s:
+        s = s.replace("\\", "/")  # keep the replacement trick unambiguous
+    assert O.json_string(s.encode("utf-8")) == _go_json_string_from_python(s)
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(-(2 ** 63), 2 ** 63 - 1))
+def test_json_int_against_str(v):
+    assert O.json_int(v) == str(v).encode()
+
+
+def _mux_clean_path_from_python(p: str) -> str:
+    """mux cleanPath (mux.go): "" → "/", ensure a leading "/", path.Clean, keep one trailing slash."""
+    if p == "":
+        return "/"
+    if p[0] != "/":
+        p = "/" + p
+    np_ = posixpath.normpath(p)
+    if np_.startswith("//"):          # POSIX keeps exactly two leading slashes; Go's path.Clean does not
+        np_ = "/" + np_.lstrip("/")
+    if p.endswith("/") and np_ != "/":
+        np_ += "/"
+    return np_
+
+
+@settings(max_examples=400, deadline=None)
+@given(st.text(alphabet="/.ab-", max_size=20))
+def test_clean_path_against_posixpath(p):
+    assert O.clean_path(p.encode()) == _mux_clean_path_from_python(p).encode()
+
+
+@settings(max_examples=400, deadline=None)
+@given(st.lists(st.tuples(st.text(alphabet="abk =+%2Fe", max_size=6), st.text(alphabet="abv +%41z&", max_size=8)), max_size=5),
+       st.sampled_from(["a", "k", "ab", "", "k k"]))
+def test_query_get_against_urllib(pairs, key):
+    """url.ParseQuery vs urllib.parse.parse_qsl on queries without ';' and with well-formed escapes only (Go drops a pair
+    with a malformed escape, urllib passes it through; Go rejects ';', older Pythons split on it)."""
+    q = "&".join(urllib.parse.quote_plus(k, safe="") + "=" + urllib.parse.quote_plus(v, safe="") for k, v in pairs)
+    want = ""
+    for k, v in urllib.parse.parse_qsl(q, keep_blank_values=True):
+        if k == key:
+            want = v
+            break
+    assert O.query_get(q.encode(), key.encode()) == want.encode()
