@@ -69,3 +69,35 @@ def test_query_get_against_urllib(pairs, key):
             want = v
             break
     assert O.query_get(q.encode(), key.encode()) == want.encode()
+
+
+# ---- json.Unmarshal's syntax check (the scanner the Bind path restates) against Python's json module ----
+from gofr_b200 import spec as S  # noqa: E402
+from gofr_b200 import synth  # noqa: E402
+
+_atoms = st.sampled_from([b"{", b"}", b"[", b"]", b":", b",", b'"a"', b'"id"', b'"\\u0041"', b'"\\x"', b'"\\ud83d\\ude00"', b'"\\ud83d"',
+                          b"1", b"-1", b"01", b"1.5", b"1e5", b"1E+2", b"-", b"1.", b".5", b"true", b"false", b"null", b"nul", b"tru",
+                          b" ", b"\n", b"\t", b'"', b"\\", b"\x01", b'"\x01"', b"0", b"-0", b"1e", b"{}", b"[]", b'"name":"x"', b"e", b"+1"])
+
+
+def _python_accepts(body: bytes) -> bool:
+    def no_constants(name):
+        raise ValueError(name)  # NaN / Infinity are not JSON; Go rejects them
+    try:
+        json.loads(body.decode("utf-8"), parse_constant=no_constants)
+        return True
+    except (ValueError, RecursionError):
+        return False
+
+
+@settings(max_examples=600, deadline=None)
+@given(st.lists(_atoms, min_size=0, max_size=10).map(b"".join))
+def test_unmarshal_syntax_check_against_python_json(body):
+    """Go's json.Unmarshal first checks the whole input for validity and reports a SyntaxError ("invalid character …",
+    "unexpected end of JSON input") before storing anything; well-formed input can at most produce an
+    UnmarshalTypeError.  Python's json.loads must agree on which inputs are well formed."""
+    ot = O.OracleTable(synth.config3_spec())
+    sid = synth.config3_spec().schemas[0].id
+    ok, msg = ot.bind(sid, body)
+    syntax_error = (not ok) and (msg.startswith(b"invalid character") or msg.startswith(b"unexpected end of JSON input"))
+    assert syntax_error == (not _python_accepts(body)), (body, ok, msg)
