@@ -175,7 +175,7 @@ def run_secondary(args):
     from tests import oracle as O
     date = S.http_date(DATE_UNIX)
     w = args.workload
-    n = {"config3": 65536, "config4": 262144, "config5": 1 << 20, "reqlog": 1 << 18}[w] if args.requests == (1 << 20) and w != "config5" else args.requests
+    n = {"config3": 65536, "config4": 262144, "config5": 1 << 20, "reqlog": 1 << 18, "http": 1 << 20}[w] if args.requests == (1 << 20) and w != "config5" else args.requests
     cpu = None
     if w == "reqlog":
         # the RequestLog line of middleware.Logging for the config-2 stream
@@ -198,6 +198,34 @@ def run_secondary(args):
         O.request_log(lb)
         cpu = {"value": n / (time.perf_counter() - t0), "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"one pass over the same {n} records, scalar C restatement (oracle/orc_reqlog.c)"}
+    elif w == "http":
+        # raw HTTP/1.1 request messages of the config-2 stream → descriptors + arena
+        n = args.requests if args.requests != (1 << 20) else (1 << 20)
+        raw, off = synth.http_messages(n)
+        eng = Engine(Table(synth.config1_spec()), 0)
+        eng.set_timing(True)
+        d_raw = torch.from_numpy(np.concatenate([raw, np.zeros(32, np.uint8)])).cuda()
+        d_off = torch.from_numpy(off.view(np.int32)).cuda()
+        d_desc = torch.zeros(n * 16, dtype=torch.uint8, device="cuda")
+        d_arena = torch.zeros(int(raw.size) + 48, dtype=torch.uint8, device="cuda")
+        d_status = torch.zeros(n, dtype=torch.int32, device="cuda")
+        d_spans = torch.zeros((n, 6), dtype=torch.int64, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+
+        def step():
+            _abi.check(_abi.lib().gofr_http_parse_device(eng._e, d_raw.data_ptr(), d_off.data_ptr(), n, d_desc.data_ptr(),
+                                                         d_arena.data_ptr(), d_status.data_ptr(), d_spans.data_ptr(), st), "http")
+        step()
+        torch.cuda.synchronize()
+        dd = d_desc.cpu().numpy().view(S.DESC_DTYPE)
+        assert int((d_status != 0).sum().item()) == 0
+        written = int(((dd["path_len"].astype(np.int64) + dd["query_len"] + 3) & ~3).sum() + dd["data_len"].astype(np.int64).sum())
+        in_bytes = int(raw.size) + 4 * (n + 1) + 16 * n + 4 * n + 48 * n - 8 * n  # the generic "+ 8 * n" is added below
+        get_out = lambda: written
+        t0 = time.perf_counter()
+        O.http_parse(raw, off)
+        cpu = {"value": n / (time.perf_counter() - t0), "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"one pass over the same {n} messages, scalar C restatement (oracle/orc_http.c)"}
     elif w == "config5":
         frames, off = synth.config5_frames(n)
         eng = Engine(Table(synth.config1_spec()), 0)
@@ -281,7 +309,7 @@ def main():
     ap.add_argument("--layout", default="slots", choices=["packed", "slots"],
                     help="resident measurement: packed offsets (gofr_serve_device) or one 528-byte slot per response "
                          "(gofr_serve_device_slots)")
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5", "reqlog"],
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5", "reqlog", "http"],
                     help="config2 is the BASELINE metric line; the others are secondary measurements (resident only)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -69,7 +69,7 @@ struct gofr_engine {
     uint32_t image_bytes = 0;
     // launch geometry
     uint32_t in_cap = 0, smem_bytes = 0;
-    int grid = 0, blocks_per_sm = 0, grpc_grid = 0, reqlog_grid = 0;
+    int grid = 0, blocks_per_sm = 0, grpc_grid = 0, reqlog_grid = 0, http_grid = 0;
     uint32_t epoch = 0;
     // resident path scratch
     unsigned long long* d_state = nullptr;
@@ -736,6 +736,35 @@ int gofr_route_device(gofr_engine* e, const gofr_req_desc* d_desc, const uint8_t
     p.meta = d_meta; p.vars = d_vars;
     int rc = launch_route(p, e->sm_count, stream);
     if (rc != 0) { set_last_error("route kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
+    e->launches++;
+    return GOFR_OK;
+}
+
+int gofr_http_parse_device(gofr_engine* e, const uint8_t* d_raw, const uint32_t* d_raw_off, uint32_t n, gofr_req_desc* d_desc,
+                           uint8_t* d_arena, uint32_t* d_status, uint64_t* d_spans, void* stream) {
+    if (!e || (n && (!d_raw || !d_raw_off || !d_desc || !d_arena || !d_status || !d_spans))) return GOFR_ERR_INVALID;
+    if (n == 0) return GOFR_OK;
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (e->http_grid <= 0) {
+        e->http_grid = http_max_grid(e->device);
+        if (e->http_grid <= 0) { set_last_error("http kernel cannot be resident"); return GOFR_ERR_CUDA; }
+    }
+    HttpParams p;
+    memset(&p, 0, sizeof p);
+    p.raw = d_raw; p.raw_off = d_raw_off; p.n = n; p.n_tiles = (n + kServeThreads - 1) / kServeThreads;
+    p.desc = d_desc; p.arena = d_arena; p.status = d_status; p.spans = (unsigned long long*)d_spans;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (e->timing_on) {
+        fold_timing(e);
+        CUDA_TRY(cudaEventCreate(&ev0));
+        CUDA_TRY(cudaEventCreate(&ev1));
+        CUDA_TRY(cudaEventRecord(ev0, st));
+    }
+    int rc = launch_http_parse(p, (int)std::min<uint32_t>((uint32_t)e->http_grid, p.n_tiles), st);
+    if (rc != 0) { set_last_error("http kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
+    if (e->timing_on) { CUDA_TRY(cudaEventRecord(ev1, st)); e->timing.emplace_back(ev0, ev1); }
     e->launches++;
     return GOFR_OK;
 }

@@ -92,6 +92,19 @@ struct RouteParams {
 };
 int launch_route(const RouteParams& p, int sm_count, void* stream);
 
+struct HttpParams {
+    const uint8_t* raw;
+    const uint32_t* raw_off;  // n + 1
+    uint32_t n;
+    uint32_t n_tiles;
+    void* desc;               // gofr_req_desc[n]
+    uint8_t* arena;           // as large as raw (+16)
+    uint32_t* status;         // n
+    unsigned long long* spans;  // n * GOFR_HTTP_SPANS
+};
+int launch_http_parse(const HttpParams& p, int grid, void* stream);
+int http_max_grid(int device);
+
 struct LogParams {
     const void* desc;   // gofr_log_desc[n]
     const void* ids;    // n * 16 trace id bytes

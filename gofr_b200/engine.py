@@ -130,6 +130,25 @@ class Engine:
                                                 vars_.data_ptr(), st.cuda_stream), "gofr_route_device")
         return meta[:b.n], vars_[:b.n]
 
+    # ---- HTTP/1.1 request heads → request descriptors (the step in front of the router) ----
+    def http_parse_device(self, raw: np.ndarray, raw_off: np.ndarray, stream=None):
+        """gofr_http_parse_device on host arrays (uploaded here).  Returns torch tensors (desc uint8[n*16], arena uint8,
+        status int32[n], spans int64[n, 6]) — desc/arena can be fed to the serve calls as they are."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        n = len(raw_off) - 1
+        d_raw = torch.from_numpy(np.concatenate([raw, np.zeros(32, dtype=np.uint8)])).to(dev)
+        d_off = torch.from_numpy(raw_off.astype(np.uint32).view(np.int32)).to(dev)
+        desc = torch.zeros(max(n, 1) * 16, dtype=torch.uint8, device=dev)
+        arena = torch.zeros(int(raw.size) + 48, dtype=torch.uint8, device=dev)
+        status = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+        spans = torch.zeros((max(n, 1), 6), dtype=torch.int64, device=dev)
+        _abi.check(_abi.lib().gofr_http_parse_device(self._e, d_raw.data_ptr(), d_off.data_ptr(), n, desc.data_ptr(),
+                                                     arena.data_ptr(), status.data_ptr(), spans.data_ptr(), st.cuda_stream),
+                   "gofr_http_parse_device")
+        return desc[:n * 16], arena, status[:n], spans[:n]
+
     # ---- RequestLog lines (middleware.Logging → logger.Log), device resident ----
     def request_log_device(self, batch: S.LogBatch, out_cap: Optional[int] = None, stream=None):
         """Uploads a LogBatch, runs gofr_requestlog_device, returns (out, out_off) torch tensors (uint8, int32 view)."""

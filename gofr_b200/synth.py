@@ -356,3 +356,31 @@ def reqlog_batch(n: int, start: int = 0, seed: int = SEED, n_routes: int = 16, h
     b = S.LogBatch.pack(recs)
     b.trace_ids[:] = trace_ids(seed, idx)
     return b
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# raw HTTP/1.1 request messages: the config-2 stream as a client would send it
+# ---------------------------------------------------------------------------------------------------------------
+def http_messages(n: int, start: int = 0, seed: int = SEED, n_routes: int = 16, seed_msgs=None):
+    """n request messages back to back: (raw uint8, raw_off uint32[n+1]).  seed_msgs (directed cases, valid or not) are
+    interleaved every 50 messages when given."""
+    idx = np.arange(start, start + n, dtype=np.uint64)
+    r = rand_u64(seed, idx, 21)
+    msgs = []
+    for k in range(n):
+        a = int(r[k])
+        if seed_msgs and k % 50 == 7:
+            msgs.append(seed_msgs[(k // 50) % len(seed_msgs)])
+            continue
+        route = a % n_routes
+        ua = _UAS[(a >> 8) % len(_UAS)]
+        head = b"GET /api/v1/r%02d HTTP/1.1\r\nHost: api.example.com:8000\r\n" % route
+        if ua:
+            head += b"User-Agent: " + ua + b"\r\n"
+        if (a >> 16) % 3 == 0:
+            head += b"X-Forwarded-For: 10.%d.%d.%d, 35.191.0.1\r\n" % ((a >> 20) % 256, (a >> 28) % 256, (a >> 36) % 256)
+        head += b"Accept: application/json\r\nAccept-Encoding: gzip\r\n\r\n"
+        msgs.append(head)
+    raw = np.frombuffer(b"".join(msgs), dtype=np.uint8).copy()
+    off = np.cumsum([0] + [len(m) for m in msgs]).astype(np.uint32)
+    return raw, off

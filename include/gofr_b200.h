@@ -22,6 +22,8 @@
  *                                 hello_grpc.pb.go:73-89           gofr_grpc_hello_device
  *   Router.Match + mux.Vars (routing only, closures on the host)
  *                                 pkg/gofr/http/router.go:14,30-33 gofr_route_device
+ *   net/http readRequest + url.ParseRequestURI (stdlib, reached from pkg/gofr/httpServer.go:29-33)
+ *                                                                  gofr_http_parse_device
  *   middleware.Logging's RequestLog line → logger.Log
  *                                 pkg/gofr/http/middleware/logger.go:24-33,41-84,
  *                                 pkg/gofr/logging/logger.go:37-74 gofr_requestlog_device
@@ -304,6 +306,31 @@ typedef struct gofr_log_desc { /* 48 bytes */
 } gofr_log_desc;
 int gofr_requestlog_device(gofr_engine*, const gofr_log_desc* d_desc, const uint8_t* d_trace_ids, const uint8_t* d_arena,
                            uint32_t n, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off, void* stream);
+
+/* HTTP/1.1 request heads: what net/http's readRequest + url.ParseRequestURI hand to
+ * Router.ServeHTTP, for a batch of raw request messages resident in HBM, in the layout the serve calls consume.
+ *   d_raw / d_raw_off: message i = d_raw[d_raw_off[i] .. d_raw_off[i+1]) — exactly one request (head + body) as framed
+ *                      by the connection reader; d_raw needs 16 readable bytes after the last message.
+ *   d_status[i]      : GOFR_HTTP_OK, or GOFR_HTTP_DEFER = "not in the subset below: parse it on the host" (nothing is
+ *                      claimed about such a message — it may be perfectly valid).  Never a different answer.
+ *   d_desc[i], d_arena: for OK messages the gofr_req_desc and its bytes (decoded URL.Path | URL.RawQuery | pad4 | body) at
+ *                      arena_off = d_raw_off[i] rounded up to 4 (the parsed form is never longer than the message, so
+ *                      d_arena is a buffer as large as d_raw + 16 and no offsets have to be computed across requests).
+ *   d_spans[i][k]    : offset into d_raw | length << 32 of METHOD, TARGET (= RequestURI), USER_AGENT, X_FORWARDED_FOR,
+ *                      HOST, BODY — the strings a gofr_log_desc needs come straight from here.
+ * The subset (anything else → DEFER): request line `METHOD SP target SP HTTP/1.1 CRLF`; METHOD one of GET HEAD POST PUT
+ * PATCH DELETE OPTIONS; target in origin form (`/…`, not `//…`), bytes 0x21–0x7E, no '#', every '%' in the path part
+ * followed by two hex digits; header lines `name: value CRLF` with RFC 7230 token names, no leading whitespace (no
+ * obs-fold), value bytes HTAB / 0x20–0x7E / ≥ 0x80, CRLF line ends only, head ≤ 16 KiB; exactly one Host header with a
+ * non-empty value of [A-Za-z0-9.:_-] and brackets; at most one Content-Length (1–9 digits) and then exactly that many body
+ * bytes, otherwise no bytes after the head; no Transfer-Encoding, Expect, Upgrade or Trailer header; a Connection header
+ * only with the value keep-alive.  For such a message URL.Path is the percent-decoded path, URL.RawQuery what follows
+ * the first '?', ForceQuery a trailing '?' with nothing after it, header values are trimmed of spaces and tabs. */
+enum { GOFR_HTTP_OK = 0, GOFR_HTTP_DEFER = 1 };
+enum { GOFR_HTTP_SPAN_METHOD = 0, GOFR_HTTP_SPAN_TARGET = 1, GOFR_HTTP_SPAN_USER_AGENT = 2, GOFR_HTTP_SPAN_XFF = 3,
+       GOFR_HTTP_SPAN_HOST = 4, GOFR_HTTP_SPAN_BODY = 5, GOFR_HTTP_SPANS = 6 };
+int gofr_http_parse_device(gofr_engine*, const uint8_t* d_raw, const uint32_t* d_raw_off, uint32_t n, gofr_req_desc* d_desc,
+                           uint8_t* d_arena, uint32_t* d_status, uint64_t* d_spans, void* stream);
 
 /* number of kernels launched by this engine so far (bench.py reports it as gpu_launches) */
 uint64_t gofr_engine_launch_count(const gofr_engine*);

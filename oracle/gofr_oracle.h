@@ -65,6 +65,9 @@ int orc_rpclog_string(const char* id, const char* start_time, int64_t response_t
 /* Router.Match + mux.Vars for a batch (the oracle of gofr_route_device); desc = gofr_req_desc[n]. */
 int orc_route_batch(const orc_table*, const void* desc, const uint8_t* arena, uint32_t n, uint32_t* meta, uint32_t* vars,
               int max_vars);
+/* HTTP/1.1 request heads (the oracle of gofr_http_parse_device, orc_http.c): status 0 = parsed, 1 = deferred. */
+int orc_http_parse(const uint8_t* raw, const uint32_t* raw_off, uint32_t n, void* desc, uint8_t* arena, uint32_t* status,
+                   uint64_t* spans);
 /* The JSON line middleware.Logging → logger.Log writes per request (orc_reqlog.c; logger.go:41-70, logging/logger.go:37-74).
  * desc: n records of 48 bytes in the layout of gofr_log_desc (include/gofr_b200.h); lines are packed back to back. */
 int orc_request_log(const void* desc, const uint8_t* ids, const uint8_t* arena, uint32_t n, uint8_t* out, uint64_t out_cap,

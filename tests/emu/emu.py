@@ -18,6 +18,7 @@ def _build():
             os.path.join(ROOT, "gofr_b200", "csrc", "bind_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "grpc_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "reqlog_device.cuh"),
+            os.path.join(ROOT, "gofr_b200", "csrc", "http_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "table_format.h")]
     srcs = [s for s in srcs if os.path.exists(s)]
     if os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
@@ -39,6 +40,7 @@ def lib():
         _lib.emu_serve_slots.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p,
                                          C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.emu_route.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        _lib.emu_http_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.emu_reqlog.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                     C.c_uint32]
     return _lib
@@ -67,6 +69,18 @@ def route(image: bytes, batch):
     lib().emu_route(img.ctypes.data, batch.desc.ctypes.data, batch.arena.ctypes.data, n, meta.ctypes.data,
                     vars_.ctypes.data)
     return meta, vars_
+
+
+def http_parse(raw: np.ndarray, raw_off: np.ndarray):
+    n = len(raw_off) - 1
+    desc = np.zeros(n * 16, dtype=np.uint8)
+    arena = np.zeros(int(raw.size) + 32, dtype=np.uint8)
+    status = np.zeros(n, dtype=np.uint32)
+    spans = np.zeros((n, 6), dtype=np.uint64)
+    rawp = np.concatenate([raw, np.zeros(16, dtype=np.uint8)])
+    lib().emu_http_parse(rawp.ctypes.data, raw_off.ctypes.data, n, desc.ctypes.data, arena.ctypes.data, status.ctypes.data,
+                         spans.ctypes.data)
+    return desc, arena, status, spans
 
 
 def request_log(batch, misalign: int = 0):

@@ -102,6 +102,24 @@ extern "C" int emu_route(const uint8_t* image, const uint8_t* desc, const uint8_
     return 0;
 }
 
+// ---- HTTP/1.1 request heads (gofr_http_parse_device): http_device.cuh on the CPU ----
+#include "../../gofr_b200/csrc/http_device.cuh"
+
+extern "C" int emu_http_parse(const uint8_t* raw, const uint32_t* raw_off, uint32_t n, uint8_t* desc, uint8_t* arena,
+                              uint32_t* status, uint64_t* spans) {
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t mo = raw_off[i], mn = raw_off[i + 1] - mo, a = (mo + 3u) & ~3u;
+        HttpOut o;
+        http_parse(raw + mo, mn, arena + a, &o);
+        status[i] = o.status;
+        uint32_t d[4] = {0, 0, 0, 0};
+        if (o.status == GOFR_HTTP_OK) { d[0] = a; d[1] = o.path_len | o.query_len << 16; d[2] = o.data_len; d[3] = o.method | o.flags << 8; }
+        memcpy(desc + (size_t)i * 16, d, 16);
+        for (int k = 0; k < GOFR_HTTP_SPANS; k++) spans[(size_t)i * GOFR_HTTP_SPANS + k] = o.status == GOFR_HTTP_OK ? o.spans[k] + mo : 0;
+    }
+    return 0;
+}
+
 // ---- RequestLog line: the same reqlog_device.cuh code the CUDA kernel runs ----
 #include "../../gofr_b200/csrc/reqlog_device.cuh"
 

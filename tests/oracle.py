@@ -44,6 +44,7 @@ def lib():
         L.orc_serve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p, C.c_void_p,
                                 C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_route_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_http_parse.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_request_log.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
         L.orc_grpc_hello.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                      C.c_int]
@@ -167,6 +168,19 @@ def route(table: "OracleTable", batch) -> Tuple[np.ndarray, np.ndarray]:
 def responses(out: np.ndarray, off: np.ndarray):
     b = out.tobytes()
     return [b[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)]
+
+
+def http_parse(raw: np.ndarray, raw_off: np.ndarray):
+    """orc_http_parse → (desc[n] in gofr_req_desc layout, arena, status[n], spans[n, 6])."""
+    n = len(raw_off) - 1
+    desc = np.zeros(n, dtype=S.DESC_DTYPE)
+    arena = np.zeros(int(raw.size) + 32, dtype=np.uint8)
+    status = np.zeros(n, dtype=np.uint32)
+    spans = np.zeros((n, 6), dtype=np.uint64)
+    rawp = np.concatenate([raw, np.zeros(16, dtype=np.uint8)])
+    lib().orc_http_parse(rawp.ctypes.data, raw_off.ctypes.data, n, desc.ctypes.data, arena.ctypes.data, status.ctypes.data,
+                         spans.ctypes.data)
+    return desc, arena, status, spans
 
 
 def request_log(batch):
