@@ -212,3 +212,12 @@ func (e *Engine) ServeDeviceSlots(dDesc, dTraceIDs, dArena unsafe.Pointer, n int
 		C.uint32_t(n), &date[0], (*C.uint8_t)(dOut), C.uint32_t(slotBytes), (*C.uint32_t)(dOutLen), (*C.uint32_t)(dMeta), stream),
 		"gofr_serve_device_slots")
 }
+
+// HTTPParseDevice turns raw HTTP/1.1 request messages (back to back in dRaw, message i = dRaw[off[i]:off[i+1]]) into
+// request descriptors + arena for the serve calls (gofr_http_parse_device).  status[i] != 0 (GOFR_HTTP_DEFER): hand
+// that connection's bytes to net/http as before.
+func (e *Engine) HTTPParseDevice(dRaw, dRawOff unsafe.Pointer, n int, dDesc, dArena, dStatus, dSpans unsafe.Pointer,
+	stream unsafe.Pointer) error {
+	return check(C.gofr_http_parse_device(e.e, (*C.uint8_t)(dRaw), (*C.uint32_t)(dRawOff), C.uint32_t(n), (*C.gofr_req_desc)(dDesc),
+		(*C.uint8_t)(dArena), (*C.uint32_t)(dStatus), (*C.uint64_t)(dSpans), stream), "gofr_http_parse_device")
+}

@@ -251,3 +251,32 @@ def test_gpu_matches_oracle():
     assert np.array_equal(sp1, spans.cpu().numpy().view(np.uint64))
     assert np.array_equal(a1[:raw.size], arena.cpu().numpy()[:raw.size])
     eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline_raw_bytes_to_wire_bytes():
+    """raw request messages → gofr_http_parse_device → gofr_serve_device_slots, all resident; compared with the oracle
+    serving the oracle-parsed batch."""
+    import torch
+    from gofr_b200.engine import DeviceBatch, Engine
+    spec = synth.config2_spec()
+    eng = Engine(Table(spec), 0)
+    n = 30000
+    raw, off = synth.http_messages(n)
+    desc, arena, status, spans = eng.http_parse_device(raw, off)
+    assert int((status != 0).sum().item()) == 0
+    ids_np = synth.trace_ids(synth.SEED, np.arange(n, dtype=np.uint64))
+    ids = torch.from_numpy(ids_np.reshape(-1).copy()).cuda()
+    db = DeviceBatch(desc, ids, arena, n, 0)
+    date = S.http_date(1_700_000_000)
+    out, out_len, meta = eng.serve_device_slots(db, date, 512)
+    d1, a1, s1, _ = O.http_parse(raw, off)
+    parsed = S.RequestBatch(d1, ids_np, a1)
+    o1, f1, m1 = O.OracleTable(spec).serve(parsed, date)
+    ln = out_len.cpu().numpy().view(np.uint32)
+    assert np.array_equal(ln, np.diff(f1.astype(np.int64)).astype(np.uint32)) and np.array_equal(meta.cpu().numpy().view(np.uint32), m1)
+    o = out.cpu().numpy().reshape(n, 512)
+    ob = o1.tobytes()
+    for i in range(0, n, 13):
+        assert o[i, :int(ln[i])].tobytes() == ob[int(f1[i]):int(f1[i + 1])]
+    eng.close()
