@@ -43,4 +43,7 @@ d_meta = torch.zeros(1000, dtype=torch.int32, device="cuda")
 _abi.check(_abi.lib().gofr_grpc_hello_device(eng._e, d_in.data_ptr(), d_off.data_ptr(), 1000, d_out.data_ptr(), cap,
                                              d_ooff.data_ptr(), d_meta.data_ptr(), torch.cuda.current_stream().cuda_stream), "grpc")
 torch.cuda.synchronize()
-print("reqlog + grpc ok")
+raw, roff = synth.http_messages(900, seed_msgs=[b"GET /a HTTP/1.0\r\nHost: h\r\n\r\n", b"", b"POST /e HTTP/1.1\r\nHost: h\r\nContent-Length: 3\r\n\r\nabc"])
+eng.http_parse_device(raw, roff)
+torch.cuda.synchronize()
+print("reqlog + grpc + http ok")
