@@ -17,10 +17,9 @@ struct HttpOut {
     uint64_t spans[GOFR_HTTP_SPANS];  // offset into the message | length << 32
 };
 
-GOFR_HD bool http_tchar(uint32_t c) {  // RFC 7230 token character
-    if (c - '0' < 10u || (c | 0x20u) - 'a' < 26u) return true;
-    return c == '!' || c == '#' || c == '$' || c == '%' || c == '&' || c == '\'' || c == '*' || c == '+' || c == '-' || c == '.' ||
-           c == '^' || c == '_' || c == '`' || c == '|' || c == '~';
+GOFR_HD bool http_tchar(uint32_t c) {  // RFC 7230 token character: digits, letters and !#$%&'*+-.^_`|~ (a 128-bit set)
+    const uint32_t w = c < 32 ? 0u : c < 64 ? 0x03FF6CFAu : c < 96 ? 0xC7FFFFFEu : c < 128 ? 0x57FFFFFFu : 0u;
+    return (w >> (c & 31u)) & 1u;
 }
 GOFR_HD int http_hex(uint32_t c) {
     if (c - '0' < 10u) return (int)(c - '0');
@@ -94,10 +93,12 @@ GOFR_HD_NOINLINE void http_parse(const uint8_t* m, uint32_t n, uint8_t* dst, Htt
         pos++;
         while (pos < n && (m[pos] == ' ' || m[pos] == '\t')) pos++;
         const uint32_t v0 = pos;
-        while (pos < n && m[pos] != '\r') {
+        for (; pos < n; pos++) {  // one compare per byte on the common path (printable or obs-text)
             const uint32_t c = m[pos];
-            if ((c < 0x20 && c != '\t') || c == 0x7F) return;
-            pos++;
+            if (c >= 0x20 && c != 0x7F) continue;
+            if (c == '\t') continue;
+            if (c == '\r') break;
+            return;
         }
         if (pos + 1 >= n || m[pos + 1] != '\n') return;
         uint32_t v1 = pos;
