@@ -63,7 +63,8 @@ def profiled_traffic(layout="packed"):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+    """Samples SM clocks and throttle reasons DURING the timed region.  NVML in-process (one query takes tens of
+    microseconds, so even a few-millisecond region gets many samples); `nvidia-smi -lms` as a fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -71,8 +72,48 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.idx = gpu_index
+        self.nvml = None
+        self.stop_flag = False
+        self.samples = []  # (sm_mhz, reasons bitmask)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; map through the UUID torch reports when possible
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                for cand in ("GPU-" + uuid, uuid):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        h = None
+            except Exception:
+                h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nvml, self.h = pynvml, h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv, h = self.nvml, self.h
+        while not self.stop_flag:
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+            except Exception:
+                break
+            time.sleep(0.0005)
 
     def start(self):
+        if self.nvml is not None:
+            self.stop_flag = False
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -87,6 +128,21 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+            nv = self.nvml
+            bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            sm = [s[0] for s in self.samples]
+            seen = 0
+            for s in self.samples:
+                seen |= s[1]
+            reasons = sorted(k for k, b in bits.items() if seen & b)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -107,7 +163,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def dist_env():
