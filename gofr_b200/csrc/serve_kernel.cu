@@ -79,6 +79,8 @@ __device__ __forceinline__ void serve_body(const ServeParams& p) {
         const bool valid = i < p.n;
         uint4 d = make_uint4(0, 0, 0, 0);
         if (valid) d = __ldg((const uint4*)p.desc + i);
+        // the trace ids are read only when the response is written: have the line in L1 by then (one lane per 128-byte line)
+        if (valid && (lane & 7u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"((const uint4*)p.ids + i));
         const uint32_t arena_off = d.x, path_len = d.y & 0xFFFFu, query_len = d.y >> 16, data_len = d.z;
         const uint32_t data_off = (arena_off + path_len + query_len + 3u) & ~3u;
         const uint32_t end = data_off + data_len;
