@@ -14,14 +14,14 @@
 namespace gofr {
 
 constexpr int HT = kServeThreads;
-constexpr uint32_t kHttpStage = 40 * 1024;  // bytes of raw messages staged per tile (128 messages × 320 B)
+constexpr uint32_t kHttpStage = 26 * 1024;  // bytes of raw messages staged per tile (128 messages × 208 B): 8 CTAs per SM
 
 struct HttpShared {
     uint64_t bar;
     __align__(16) uint8_t in[kHttpStage + 32];
 };
 
-__global__ void __launch_bounds__(HT, 4) http_parse_kernel(const HttpParams p) {
+__global__ void __launch_bounds__(HT, 8) http_parse_kernel(const HttpParams p) {
     __shared__ __align__(16) HttpShared sh;
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {

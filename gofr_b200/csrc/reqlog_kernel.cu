@@ -27,7 +27,7 @@ struct LogShared {
     __align__(16) uint8_t in[kLogStage + 32];
 };
 
-__global__ void __launch_bounds__(LT, 4) reqlog_kernel(const LogParams p) {
+__global__ void __launch_bounds__(LT, 5) reqlog_kernel(const LogParams p) {
     __shared__ __align__(16) LogShared sh;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {

@@ -242,7 +242,10 @@ def test_parse_then_serve_equals_packed_batch():
 def test_gpu_matches_oracle():
     from gofr_b200.engine import Engine
     eng = Engine(Table(synth.config1_spec()), 0)
-    msgs = [m for m, _ in GOOD] + DEFERRED
+    big = [b"GET /big HTTP/1.1\r\nHost: h\r\nX-Pad: " + b"p" * 9000 + b"\r\n\r\n",      # tiles beyond the staging budget
+           b"POST /big HTTP/1.1\r\nHost: h\r\nContent-Length: 30000\r\n\r\n" + b"b" * 30000,
+           b"GET /" + b"a" * 9000 + b" HTTP/1.1\r\nHost: h\r\n\r\n"]                        # target longer than 8192: deferred
+    msgs = [m for m, _ in GOOD] + DEFERRED + big
     raw, off = synth.http_messages(40000, seed_msgs=msgs)
     d1, a1, s1, sp1 = O.http_parse(raw, off)
     desc, arena, status, spans = eng.http_parse_device(raw, off)
