@@ -25,7 +25,7 @@ struct GrpcShared {
     __align__(16) uint8_t in[kGrpcStage + 32];
 };
 
-__global__ void __launch_bounds__(GT, 4) grpc_hello_kernel(const GrpcParams p) {
+__global__ void __launch_bounds__(GT, 12) grpc_hello_kernel(const GrpcParams p) {
     __shared__ __align__(16) GrpcShared sh;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
