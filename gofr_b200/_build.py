@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgofr_b200.so")
-SOURCES = ["serve_kernel.cu", "grpc_kernel.cu", "reqlog_kernel.cu", "route_kernel.cu", "http_kernel.cu", "egress_kernel.cu", "engine.cu", "table_build.cpp"]
+SOURCES = ["serve_kernel.cu", "grpc_kernel.cu", "reqlog_kernel.cu", "route_kernel.cu", "http_kernel.cu", "egress_kernel.cu", "engine.cu", "table_build.cpp", "frontend.cpp"]
 HEADERS = ["serve_device.cuh", "bind_device.cuh", "grpc_device.cuh", "reqlog_device.cuh", "http_device.cuh", "tile_common.cuh", "table_format.h", "engine_internal.h",
            "../../include/gofr_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -307,6 +307,24 @@ typedef struct gofr_log_desc { /* 48 bytes */
 int gofr_requestlog_device(gofr_engine*, const gofr_log_desc* d_desc, const uint8_t* d_trace_ids, const uint8_t* d_arena,
                            uint32_t n, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off, void* stream);
 
+/* Batching front-end: the reference serves one request per goroutine (net/http conn.serve →
+ * router.ServeHTTP, pkg/gofr/httpServer.go:29-33); the GPU wants batches.  Any number of threads call
+ * gofr_frontend_serve with ONE request each and block until its response is ready; a dispatcher thread closes a batch
+ * when it holds max_batch requests or its oldest request has waited max_wait_us, serves it through
+ * gofr_batch_submit_slots and wakes the callers.  Two pinned batches alternate (one fills while the other is in
+ * flight).  The Date header of a batch is the wall clock at dispatch (gofr_frontend_set_clock pins it for tests).
+ * serve returns GOFR_ERR_CAPACITY (with *resp_len set) when the response does not fit slot_bytes or resp_cap.
+ * destroy may only be called when no thread is inside gofr_frontend_serve. */
+typedef struct gofr_frontend gofr_frontend;
+int gofr_frontend_create(gofr_frontend** out, gofr_engine*, uint32_t max_batch, uint32_t max_wait_us, uint32_t slot_bytes,
+                         uint32_t max_request_bytes);
+void gofr_frontend_destroy(gofr_frontend*);
+int gofr_frontend_set_clock(gofr_frontend*, int64_t unix_seconds);
+int gofr_frontend_stats(gofr_frontend*, uint64_t* batches, uint64_t* requests);
+int gofr_frontend_serve(gofr_frontend*, uint8_t method, const uint8_t* path, uint16_t path_len, const uint8_t* query,
+                        uint16_t query_len, uint8_t flags, const uint8_t* data, uint32_t data_len, const uint8_t trace_id[16],
+                        uint8_t* resp, uint32_t resp_cap, uint32_t* resp_len, uint32_t* meta);
+
 /* HTTP/1.1 request heads: what net/http's readRequest + url.ParseRequestURI hand to
  * Router.ServeHTTP, for a batch of raw request messages resident in HBM, in the layout the serve calls consume.
  *   d_raw / d_raw_off: message i = d_raw[d_raw_off[i] .. d_raw_off[i+1]) — exactly one request (head + body) as framed
