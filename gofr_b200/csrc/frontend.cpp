@@ -7,18 +7,53 @@
 // ready; one dispatcher thread closes a batch when it is full or when its oldest request has waited max_wait_us, runs it
 // through the engine's slot-layout host path and wakes the producers, each of which copies its own slot out.
 // Two pinned batches alternate: while one is in flight the other fills.
+//
+// No lock on the request path (a mutex + condition variable version spent 5–10 µs per woken thread handing the mutex
+// around: 93 k req/s at 256 threads):
+//   claim     one CAS on the batch's claim word (closed bit | request count | arena bytes) reserves slot i and its arena
+//             range; the request bytes are copied in afterwards, outside any critical section (`filled` counts them in)
+//   close     the dispatcher sets the closed bit with fetch_or — the count is frozen at that instant
+//   complete  the dispatcher publishes the round number in one futex word per group of 32 slots and wakes group 0;
+//             the first thread of group g to notice wakes groups 2g+1 and 2g+2 (a wake tree: the dispatcher does not
+//             pay one wake per thread)
+//   recycle   the last producer to copy its response out reopens the batch
 #include <atomic>
 #include <chrono>
-#include <condition_variable>
+#include <climits>
 #include <cstring>
-#include <mutex>
 #include <thread>
 #include <time.h>
+
+#include <linux/futex.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "../../include/gofr_b200.h"
 #include "engine_internal.h"
 
-using namespace gofr;
+namespace {
+
+using Word = std::atomic<uint32_t>;
+static_assert(sizeof(Word) == 4, "futex words are 32-bit");
+
+void futex_wait(Word* w, uint32_t expect, const struct timespec* rel = nullptr) {
+    syscall(SYS_futex, reinterpret_cast<uint32_t*>(w), FUTEX_WAIT_PRIVATE, expect, rel, nullptr, 0);
+}
+void futex_wake_all(Word* w) { syscall(SYS_futex, reinterpret_cast<uint32_t*>(w), FUTEX_WAKE_PRIVATE, INT_MAX, nullptr, nullptr, 0); }
+void bump(Word* w) {
+    w->fetch_add(1, std::memory_order_release);
+    futex_wake_all(w);
+}
+int64_t mono_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+constexpr uint64_t kClosed = 1ull << 63;
+inline uint32_t claim_count(uint64_t w) { return (uint32_t)(w >> 32) & 0x7FFFFFFFu; }
+inline uint32_t claim_arena(uint64_t w) { return (uint32_t)w; }
+constexpr uint32_t kGroup = 32;  // slots per wake word
+
+}  // namespace
 
 struct gofr_frontend_batch {
     // pinned staging in the ABI layout (gofr_req_batch / gofr_slot_batch)
@@ -28,76 +63,102 @@ struct gofr_frontend_batch {
     uint8_t* out = nullptr;
     uint32_t* out_len = nullptr;
     uint32_t* meta = nullptr;
-    enum State { FILLING, IN_FLIGHT, DONE } state = FILLING;
-    uint32_t count = 0;      // requests appended
-    std::atomic<uint32_t> collected{0};  // producers that have copied their response out (DONE state)
-    std::condition_variable cv_ready;    // this batch's producers: "your round is DONE"
-    uint32_t arena_used = 0;
-    uint64_t generation = 0;  // bumped when the batch is recycled: producers wait for "their" generation to complete
+    std::atomic<uint64_t> claim{0};       // closed bit | count << 32 | arena bytes
+    std::atomic<uint32_t> filled{0};      // requests whose bytes are in place
+    std::atomic<uint32_t> collected{0};   // producers that have copied their response out
+    std::atomic<uint32_t> round{0};       // bumped at recycle; round r is complete when done[g] == r + 1
+    std::atomic<int64_t> first_ns{0};     // arrival of the round's first request (0: not stored yet)
+    uint32_t closed_count = 0;            // count at close (written by the dispatcher before done[] is published)
     int rc = GOFR_OK;
-    std::chrono::steady_clock::time_point first_arrival;
+    Word* done = nullptr;                 // per group of kGroup slots: last completed round + 1
+    Word* woke = nullptr;                 // per group: somebody already woke this group's children
 };
 using Batch = gofr_frontend_batch;
 
 struct gofr_frontend {
     gofr_engine* eng = nullptr;
-    uint32_t max_batch = 0, max_wait_us = 0, slot_bytes = 0, arena_cap = 0;
-    int64_t fixed_clock = 0;  // tests: the Date of every batch; 0 = wall clock
+    uint32_t max_batch = 0, max_wait_us = 0, slot_bytes = 0, per_request = 0, groups = 0;
+    std::atomic<int64_t> fixed_clock{0};  // tests: the Date of every batch; 0 = wall clock
     Batch b[2];
-    int filling = 0;          // index of the batch producers append to
-    bool stop = false;
-    std::mutex mu;
-    std::condition_variable cv_dispatch;  // dispatcher: "a batch may be ready"
-    std::condition_variable cv_room;      // producers without a place yet: "the filling batch changed / was recycled"
+    std::atomic<int> filling{0};          // the batch producers try first
+    std::atomic<bool> stop{false};
+    Word disp_seq{0};                     // dispatcher sleeps on this: first claim of a round, full batch, recycle, stop
+    Word room_seq{0};                     // producers without a slot sleep on this: batch closed (flip) or recycled
     std::thread worker;
-    // counters
-    uint64_t batches = 0, requests = 0;
+    std::atomic<uint64_t> batches{0}, requests{0};
 };
 
 static void free_batch(Batch& x) {
     gofr_free_pinned(x.desc); gofr_free_pinned(x.ids); gofr_free_pinned(x.arena);
     gofr_free_pinned(x.out); gofr_free_pinned(x.out_len); gofr_free_pinned(x.meta);
+    delete[] x.done;
+    delete[] x.woke;
 }
 
 static void dispatcher(gofr_frontend* f) {
-    std::unique_lock<std::mutex> lk(f->mu);
     for (;;) {
-        Batch& cur = f->b[f->filling];
-        if (cur.state != Batch::FILLING) { f->cv_dispatch.wait(lk); continue; }  // still being collected by its producers
-        if (cur.count == 0) {
-            if (f->stop) return;
-            f->cv_dispatch.wait(lk);
+        const uint32_t seq = f->disp_seq.load(std::memory_order_acquire);
+        int k = f->filling.load(std::memory_order_relaxed);
+        uint64_t w = f->b[k].claim.load(std::memory_order_acquire);
+        if (!(w & kClosed) && claim_count(w) == 0) {
+            // a producer that read `filling` just before the last flip may have claimed a slot in the other batch after
+            // that batch was recycled: serve it from there
+            const uint64_t wo = f->b[k ^ 1].claim.load(std::memory_order_acquire);
+            if (!(wo & kClosed) && claim_count(wo) > 0) {
+                k ^= 1;
+                f->filling.store(k, std::memory_order_release);
+                w = wo;
+            }
+        }
+        Batch& x = f->b[k];
+        const bool stopping = f->stop.load(std::memory_order_acquire);
+        if ((w & kClosed) || claim_count(w) == 0) {  // still being collected by its previous round / nothing to do
+            if (stopping && !(w & kClosed)) return;
+            futex_wait(&f->disp_seq, seq);
             continue;
         }
-        if (cur.count < f->max_batch && !f->stop) {
+        if (claim_count(w) < f->max_batch && !stopping) {
             // not full: wait until the oldest request has been here max_wait_us (or the batch fills up)
-            auto deadline = cur.first_arrival + std::chrono::microseconds(f->max_wait_us);
-            if (std::chrono::steady_clock::now() < deadline) { f->cv_dispatch.wait_until(lk, deadline); continue; }
+            const int64_t first = x.first_ns.load(std::memory_order_acquire), now = mono_ns();
+            const int64_t deadline = (first ? first : now) + (int64_t)f->max_wait_us * 1000;
+            if (now < deadline) {
+                struct timespec rel;
+                rel.tv_sec = (deadline - now) / 1000000000;
+                rel.tv_nsec = (deadline - now) % 1000000000;
+                futex_wait(&f->disp_seq, seq, &rel);
+                continue;
+            }
         }
-        // close the batch: producers now fill the other one (as soon as its previous occupants have left)
-        cur.state = Batch::IN_FLIGHT;
-        f->filling ^= 1;
-        f->cv_room.notify_all();
-        Batch& x = cur;
+        // close: the count is frozen by the fetch_or; producers move on to the other batch
+        w = x.claim.fetch_or(kClosed, std::memory_order_acq_rel);
+        const uint32_t n = claim_count(w);
+        x.closed_count = n;
+        f->filling.store(k ^ 1, std::memory_order_release);
+        bump(&f->room_seq);
+        while (x.filled.load(std::memory_order_acquire) != n) {  // the last claimants are still copying their bytes in
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
         gofr_req_batch in;
         memset(&in, 0, sizeof in);
-        in.desc = x.desc; in.trace_ids = x.ids; in.arena = x.arena; in.arena_bytes = (x.arena_used + 15u) & ~15u; in.n = x.count;
-        int64_t now = f->fixed_clock;
+        in.desc = x.desc; in.trace_ids = x.ids; in.arena = x.arena; in.arena_bytes = (claim_arena(w) + 15u) & ~15u; in.n = n;
+        int64_t now = f->fixed_clock.load(std::memory_order_relaxed);
         if (!now) { struct timespec ts; clock_gettime(CLOCK_REALTIME, &ts); now = (int64_t)ts.tv_sec; }
         gofr_format_http_date(now, in.date);
         gofr_slot_batch out;
         memset(&out, 0, sizeof out);
         out.out = x.out; out.slot_bytes = f->slot_bytes; out.out_len = x.out_len; out.meta = x.meta;
-        lk.unlock();
         gofr_ticket t = 0;
         int rc = gofr_batch_submit_slots(f->eng, &in, &out, &t);
         if (rc == GOFR_OK) rc = gofr_batch_wait(f->eng, t);
-        lk.lock();
         x.rc = rc;
-        x.state = Batch::DONE;
-        f->batches++;
-        f->requests += x.count;
-        x.cv_ready.notify_all();
+        f->batches.fetch_add(1, std::memory_order_relaxed);
+        f->requests.fetch_add(n, std::memory_order_relaxed);
+        // publish the round in every group's word, then start the wake tree at its root
+        const uint32_t r1 = x.round.load(std::memory_order_relaxed) + 1, g_used = (n + kGroup - 1) / kGroup;
+        for (uint32_t g = 0; g < g_used; g++) x.done[g].store(r1, std::memory_order_release);
+        futex_wake_all(&x.done[0]);
     }
 }
 
@@ -105,22 +166,27 @@ extern "C" {
 
 int gofr_frontend_create(gofr_frontend** out, gofr_engine* e, uint32_t max_batch, uint32_t max_wait_us, uint32_t slot_bytes,
                          uint32_t max_request_bytes) {
-    if (!out || !e || max_batch == 0 || slot_bytes == 0 || (slot_bytes & 15u)) return GOFR_ERR_INVALID;
+    if (!out || !e || max_batch == 0 || max_batch > 0x7FFFFFFFu || slot_bytes == 0 || (slot_bytes & 15u)) return GOFR_ERR_INVALID;
     gofr_frontend* f = new gofr_frontend();
     f->eng = e;
     f->max_batch = max_batch;
     f->max_wait_us = max_wait_us;
     f->slot_bytes = slot_bytes;
-    const uint64_t cap = (uint64_t)max_batch * (((uint64_t)max_request_bytes + 7u) & ~(uint64_t)3u) + 64;
+    f->groups = (max_batch + kGroup - 1) / kGroup;
+    const uint64_t per = ((uint64_t)max_request_bytes + 7u) & ~(uint64_t)3u;  // path|query and body are each padded to 4
+    const uint64_t cap = (uint64_t)max_batch * per + 64;
     if (cap > 0xFFFFFFF0ull) { delete f; return GOFR_ERR_CAPACITY; }
-    f->arena_cap = (uint32_t)cap;
+    f->per_request = (uint32_t)per;
     for (auto& x : f->b) {
         x.desc = (gofr_req_desc*)gofr_alloc_pinned((size_t)max_batch * sizeof(gofr_req_desc));
         x.ids = (uint8_t*)gofr_alloc_pinned((size_t)max_batch * 16);
-        x.arena = (uint8_t*)gofr_alloc_pinned(f->arena_cap);
+        x.arena = (uint8_t*)gofr_alloc_pinned((size_t)cap);
         x.out = (uint8_t*)gofr_alloc_pinned((size_t)max_batch * slot_bytes);
         x.out_len = (uint32_t*)gofr_alloc_pinned((size_t)max_batch * 4);
         x.meta = (uint32_t*)gofr_alloc_pinned((size_t)max_batch * 4);
+        x.done = new Word[f->groups];
+        x.woke = new Word[f->groups];
+        for (uint32_t g = 0; g < f->groups; g++) { x.done[g].store(0); x.woke[g].store(0); }
         if (!x.desc || !x.ids || !x.arena || !x.out || !x.out_len || !x.meta) {
             for (auto& y : f->b) free_batch(y);
             delete f;
@@ -134,11 +200,9 @@ int gofr_frontend_create(gofr_frontend** out, gofr_engine* e, uint32_t max_batch
 
 void gofr_frontend_destroy(gofr_frontend* f) {
     if (!f) return;
-    {
-        std::lock_guard<std::mutex> g(f->mu);
-        f->stop = true;
-    }
-    f->cv_dispatch.notify_all();
+    f->stop.store(true, std::memory_order_release);
+    bump(&f->disp_seq);
+    bump(&f->room_seq);
     if (f->worker.joinable()) f->worker.join();
     for (auto& x : f->b) free_batch(x);
     delete f;
@@ -146,16 +210,14 @@ void gofr_frontend_destroy(gofr_frontend* f) {
 
 int gofr_frontend_set_clock(gofr_frontend* f, int64_t unix_seconds) {
     if (!f) return GOFR_ERR_INVALID;
-    std::lock_guard<std::mutex> g(f->mu);
-    f->fixed_clock = unix_seconds;
+    f->fixed_clock.store(unix_seconds, std::memory_order_relaxed);
     return GOFR_OK;
 }
 
 int gofr_frontend_stats(gofr_frontend* f, uint64_t* batches, uint64_t* requests) {
     if (!f) return GOFR_ERR_INVALID;
-    std::lock_guard<std::mutex> g(f->mu);
-    if (batches) *batches = f->batches;
-    if (requests) *requests = f->requests;
+    if (batches) *batches = f->batches.load(std::memory_order_relaxed);
+    if (requests) *requests = f->requests.load(std::memory_order_relaxed);
     return GOFR_OK;
 }
 
@@ -163,38 +225,58 @@ int gofr_frontend_serve(gofr_frontend* f, uint8_t method, const uint8_t* path, u
                         uint16_t query_len, uint8_t flags, const uint8_t* data, uint32_t data_len, const uint8_t trace_id[16],
                         uint8_t* resp, uint32_t resp_cap, uint32_t* resp_len, uint32_t* meta) {
     if (!f || !resp_len || !trace_id || (path_len && !path) || (query_len && !query) || (data_len && !data)) return GOFR_ERR_INVALID;
-    const uint32_t need = (((uint32_t)path_len + query_len + 3u) & ~3u) + ((data_len + 3u) & ~3u);
-    if (need > f->arena_cap / f->max_batch) { set_last_error("request of %u bytes exceeds the front-end's max_request_bytes", need); return GOFR_ERR_CAPACITY; }
-    std::unique_lock<std::mutex> lk(f->mu);
-    // room in the filling batch?  (it can be full, or still be handing out the responses of its previous round)
-    for (;;) {
-        if (f->stop) return GOFR_ERR_INVALID;
-        Batch& cur = f->b[f->filling];
-        if (cur.state == Batch::FILLING && cur.count < f->max_batch && cur.arena_used + need <= f->arena_cap) break;
-        if (cur.state == Batch::FILLING) f->cv_dispatch.notify_one();  // full: the dispatcher should close it now
-        f->cv_room.wait(lk);
+    const uint64_t need64 = (((uint64_t)path_len + query_len + 3u) & ~(uint64_t)3u) + (((uint64_t)data_len + 3u) & ~(uint64_t)3u);
+    if (need64 > f->per_request) {
+        set_last_error("request of %llu bytes exceeds the front-end's max_request_bytes", (unsigned long long)need64);
+        return GOFR_ERR_CAPACITY;
     }
-    Batch& x = f->b[f->filling];
-    const uint32_t i = x.count++;
-    if (i == 0) x.first_arrival = std::chrono::steady_clock::now();
-    const uint64_t gen = x.generation;
-    uint32_t a = x.arena_used;
+    const uint32_t need = (uint32_t)need64;
+    // ---- claim slot i and `need` arena bytes in the filling batch ----
+    Batch* xp;
+    uint32_t i, a;
+    for (;;) {
+        if (f->stop.load(std::memory_order_acquire)) return GOFR_ERR_INVALID;
+        const uint32_t rs = f->room_seq.load(std::memory_order_acquire);
+        Batch& c = f->b[f->filling.load(std::memory_order_acquire)];
+        uint64_t w = c.claim.load(std::memory_order_acquire);
+        if (!(w & kClosed) && claim_count(w) < f->max_batch) {
+            // arena bytes never run out first: the arena holds max_batch requests of the largest admissible size
+            if (!c.claim.compare_exchange_weak(w, w + (1ull << 32) + need, std::memory_order_acq_rel)) continue;
+            xp = &c; i = claim_count(w); a = claim_arena(w);
+            break;
+        }
+        if (!(w & kClosed)) bump(&f->disp_seq);  // full: the dispatcher should close it now
+        futex_wait(&f->room_seq, rs);            // until a batch is closed (the other one becomes current) or recycled
+    }
+    Batch& x = *xp;
+    const uint32_t round = x.round.load(std::memory_order_acquire);  // stable until this producer has collected
+    if (i == 0) x.first_ns.store(mono_ns(), std::memory_order_release);
     gofr_req_desc d;
     memset(&d, 0, sizeof d);
     d.arena_off = a; d.path_len = path_len; d.query_len = query_len; d.data_len = data_len; d.method = method; d.flags = flags;
     if (path_len) memcpy(x.arena + a, path, path_len);
     if (query_len) memcpy(x.arena + a + path_len, query, query_len);
-    a = (a + path_len + query_len + 3u) & ~3u;
-    if (data_len) memcpy(x.arena + a, data, data_len);
-    x.arena_used = (a + data_len + 3u) & ~3u;
+    const uint32_t body_at = (a + path_len + query_len + 3u) & ~3u;
+    if (data_len) memcpy(x.arena + body_at, data, data_len);
     x.desc[i] = d;
     memcpy(x.ids + (size_t)i * 16, trace_id, 16);
-    if (i == 0 || x.count == f->max_batch) f->cv_dispatch.notify_one();  // start the batch's timer / close a full batch
-    // wait for this round of the batch to come back; the copy-out happens outside the lock
-    while (!(x.generation == gen && x.state == Batch::DONE)) x.cv_ready.wait(lk);
+    x.filled.fetch_add(1, std::memory_order_release);
+    if (i == 0 || i + 1 == f->max_batch) bump(&f->disp_seq);  // start the round's timer / close a full batch
+
+    // ---- wait for the round to come back ----
+    const uint32_t g = i / kGroup;
+    for (;;) {
+        const uint32_t v = x.done[g].load(std::memory_order_acquire);
+        if (v == round + 1) break;
+        futex_wait(&x.done[g], v);
+    }
+    const uint32_t n = x.closed_count;
+    const uint32_t g_used = (n + kGroup - 1) / kGroup;
+    if (2 * g + 1 < g_used && x.woke[g].exchange(1, std::memory_order_acq_rel) == 0) {
+        futex_wake_all(&x.done[2 * g + 1]);
+        if (2 * g + 2 < g_used) futex_wake_all(&x.done[2 * g + 2]);
+    }
     int rc = x.rc;
-    const uint32_t count = x.count;
-    lk.unlock();
     const uint32_t len = x.out_len[i];
     if (meta) *meta = x.meta[i];
     *resp_len = len;
@@ -202,16 +284,16 @@ int gofr_frontend_serve(gofr_frontend* f, uint8_t method, const uint8_t* path, u
         if (len > f->slot_bytes || len > resp_cap) rc = GOFR_ERR_CAPACITY;  // the caller serves it through the packed path
         else if (len) memcpy(resp, x.out + (size_t)i * f->slot_bytes, len);
     }
-    // the last producer to leave recycles the batch
-    if (x.collected.fetch_add(1, std::memory_order_acq_rel) + 1 == count) {
-        lk.lock();
-        x.state = Batch::FILLING;
-        x.count = 0;
+    // ---- the last producer to leave reopens the batch ----
+    if (x.collected.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
+        for (uint32_t k = 0; k < g_used; k++) x.woke[k].store(0, std::memory_order_relaxed);
+        x.filled.store(0, std::memory_order_relaxed);
         x.collected.store(0, std::memory_order_relaxed);
-        x.arena_used = 0;
-        x.generation++;
-        f->cv_room.notify_all();
-        f->cv_dispatch.notify_one();
+        x.first_ns.store(0, std::memory_order_relaxed);
+        x.round.store(round + 1, std::memory_order_release);
+        x.claim.store(0, std::memory_order_release);
+        bump(&f->room_seq);
+        bump(&f->disp_seq);
     }
     return rc;
 }
