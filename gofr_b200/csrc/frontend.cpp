@@ -6,7 +6,8 @@
 // goroutines through cgo, or the threads of the C++ stand-in) hand in single requests and block until their response is
 // ready; one dispatcher thread closes a batch when it is full or when its oldest request has waited max_wait_us, runs it
 // through the engine's slot-layout host path and wakes the producers, each of which copies its own slot out.
-// Two pinned batches alternate: while one is in flight the other fills.
+// A small ring of pinned batches rotates: while one is in flight the next fills, and a batch whose producers are slow to
+// pick their responses up (a descheduled thread) is skipped instead of stalling everybody.
 //
 // No lock on the request path (a mutex + condition variable version spent 5–10 µs per woken thread handing the mutex
 // around: 93 k req/s at 256 threads):
@@ -52,6 +53,7 @@ constexpr uint64_t kClosed = 1ull << 63;
 inline uint32_t claim_count(uint64_t w) { return (uint32_t)(w >> 32) & 0x7FFFFFFFu; }
 inline uint32_t claim_arena(uint64_t w) { return (uint32_t)w; }
 constexpr uint32_t kGroup = 32;  // slots per wake word
+constexpr int kBatches = 4;      // ring of batches
 
 }  // namespace
 
@@ -79,7 +81,7 @@ struct gofr_frontend {
     gofr_engine* eng = nullptr;
     uint32_t max_batch = 0, max_wait_us = 0, slot_bytes = 0, per_request = 0, groups = 0;
     std::atomic<int64_t> fixed_clock{0};  // tests: the Date of every batch; 0 = wall clock
-    Batch b[2];
+    Batch b[kBatches];
     std::atomic<int> filling{0};          // the batch producers try first
     std::atomic<bool> stop{false};
     Word disp_seq{0};                     // dispatcher sleeps on this: first claim of a round, full batch, recycle, stop
@@ -100,14 +102,22 @@ static void dispatcher(gofr_frontend* f) {
         const uint32_t seq = f->disp_seq.load(std::memory_order_acquire);
         int k = f->filling.load(std::memory_order_relaxed);
         uint64_t w = f->b[k].claim.load(std::memory_order_acquire);
-        if (!(w & kClosed) && claim_count(w) == 0) {
-            // a producer that read `filling` just before the last flip may have claimed a slot in the other batch after
-            // that batch was recycled: serve it from there
-            const uint64_t wo = f->b[k ^ 1].claim.load(std::memory_order_acquire);
-            if (!(wo & kClosed) && claim_count(wo) > 0) {
-                k ^= 1;
+        if ((w & kClosed) || claim_count(w) == 0) {
+            // Nothing to serve in the current batch.  Another one may hold requests (a producer that read `filling` just
+            // before a flip can claim a slot in a batch that was recycled in between); and if the current batch is still
+            // handing out its previous round, any open batch is a better place for producers to go.
+            int best = -1;
+            for (int j = 1; j < kBatches && best < 0; j++) {
+                const uint64_t wj = f->b[(k + j) % kBatches].claim.load(std::memory_order_acquire);
+                if (!(wj & kClosed) && claim_count(wj) > 0) best = (k + j) % kBatches;
+            }
+            for (int j = 1; j < kBatches && best < 0 && (w & kClosed); j++)
+                if (!(f->b[(k + j) % kBatches].claim.load(std::memory_order_acquire) & kClosed)) best = (k + j) % kBatches;
+            if (best >= 0) {
+                k = best;
                 f->filling.store(k, std::memory_order_release);
-                w = wo;
+                bump(&f->room_seq);
+                w = f->b[k].claim.load(std::memory_order_acquire);
             }
         }
         Batch& x = f->b[k];
@@ -129,11 +139,14 @@ static void dispatcher(gofr_frontend* f) {
                 continue;
             }
         }
-        // close: the count is frozen by the fetch_or; producers move on to the other batch
+        // close: the count is frozen by the fetch_or; producers move on to the next open batch of the ring
         w = x.claim.fetch_or(kClosed, std::memory_order_acq_rel);
         const uint32_t n = claim_count(w);
         x.closed_count = n;
-        f->filling.store(k ^ 1, std::memory_order_release);
+        int next = (k + 1) % kBatches;
+        for (int j = 1; j < kBatches; j++)
+            if (!(f->b[(k + j) % kBatches].claim.load(std::memory_order_acquire) & kClosed)) { next = (k + j) % kBatches; break; }
+        f->filling.store(next, std::memory_order_release);
         bump(&f->room_seq);
         while (x.filled.load(std::memory_order_acquire) != n) {  // the last claimants are still copying their bytes in
 #if defined(__x86_64__)

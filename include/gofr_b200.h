@@ -311,8 +311,9 @@ int gofr_requestlog_device(gofr_engine*, const gofr_log_desc* d_desc, const uint
  * router.ServeHTTP, pkg/gofr/httpServer.go:29-33); the GPU wants batches.  Any number of threads call
  * gofr_frontend_serve with ONE request each and block until its response is ready; a dispatcher thread closes a batch
  * when it holds max_batch requests or its oldest request has waited max_wait_us, serves it through
- * gofr_batch_submit_slots and wakes the callers.  Two pinned batches alternate (one fills while the other is in
- * flight).  The Date header of a batch is the wall clock at dispatch (gofr_frontend_set_clock pins it for tests).
+ * gofr_batch_submit_slots and wakes the callers.  A small ring of pinned batches rotates (one fills while another is in
+ * flight; a batch whose callers are slow to pick up their responses is skipped).  The Date header of a batch is the
+ * wall clock at dispatch (gofr_frontend_set_clock pins it for tests).
  * serve returns GOFR_ERR_CAPACITY (with *resp_len set) when the response does not fit slot_bytes or resp_cap.
  * destroy may only be called when no thread is inside gofr_frontend_serve. */
 typedef struct gofr_frontend gofr_frontend;
