@@ -221,3 +221,36 @@ func (e *Engine) HTTPParseDevice(dRaw, dRawOff unsafe.Pointer, n int, dDesc, dAr
 	return check(C.gofr_http_parse_device(e.e, (*C.uint8_t)(dRaw), (*C.uint32_t)(dRawOff), C.uint32_t(n), (*C.gofr_req_desc)(dDesc),
 		(*C.uint8_t)(dArena), (*C.uint32_t)(dStatus), (*C.uint64_t)(dSpans), stream), "gofr_http_parse_device")
 }
+
+// Frontend gathers single requests from many goroutines into batches (gofr_frontend_*): the per-request call that stands
+// where router.ServeHTTP stands in the reference (pkg/gofr/httpServer.go:29-33).
+type Frontend struct{ f *C.gofr_frontend }
+
+func NewFrontend(e *Engine, maxBatch, maxWaitMicros, slotBytes, maxRequestBytes int) (*Frontend, error) {
+	var f *C.gofr_frontend
+	if err := check(C.gofr_frontend_create(&f, e.e, C.uint32_t(maxBatch), C.uint32_t(maxWaitMicros), C.uint32_t(slotBytes),
+		C.uint32_t(maxRequestBytes)), "gofr_frontend_create"); err != nil {
+		return nil, err
+	}
+	return &Frontend{f}, nil
+}
+
+// Close must not run while a Serve call is in progress.
+func (f *Frontend) Close() { C.gofr_frontend_destroy(f.f); f.f = nil }
+
+// Serve blocks until the batch this request joined has been served; resp[:n] is the response (wire bytes in FRAME_WIRE
+// mode), meta = status | route id << 16.  A response that does not fit resp or the slot returns an error with n set.
+func (f *Frontend) Serve(method uint8, path, query []byte, flags uint8, body []byte, traceID *[16]byte, resp []byte) (n int, meta uint32, err error) {
+	var cn, cm C.uint32_t
+	rc := C.gofr_frontend_serve(f.f, C.uint8_t(method), bytesPtr(path), C.uint16_t(len(path)), bytesPtr(query), C.uint16_t(len(query)),
+		C.uint8_t(flags), bytesPtr(body), C.uint32_t(len(body)), (*C.uint8_t)(unsafe.Pointer(&traceID[0])), bytesPtr(resp),
+		C.uint32_t(len(resp)), &cn, &cm)
+	return int(cn), uint32(cm), check(rc, "gofr_frontend_serve")
+}
+
+func bytesPtr(b []byte) *C.uint8_t {
+	if len(b) == 0 {
+		return nil
+	}
+	return (*C.uint8_t)(unsafe.Pointer(&b[0]))
+}

@@ -21,6 +21,8 @@
 #include <atomic>
 #include <chrono>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <time.h>
@@ -88,6 +90,10 @@ struct gofr_frontend {
     Word room_seq{0};                     // producers without a slot sleep on this: batch closed (flip) or recycled
     std::thread worker;
     std::atomic<uint64_t> batches{0}, requests{0};
+    // GOFR_FRONTEND_DEBUG=1: where the dispatcher's time goes (printed at destroy)
+    bool debug = false;
+    int64_t dbg_spin_ns = 0, dbg_spin_max = 0, dbg_eng_ns = 0, dbg_eng_max = 0, dbg_wake_ns = 0, dbg_wake_max = 0, dbg_idle_ns = 0;
+    uint64_t dbg_eng_slow = 0;
 };
 
 static void free_batch(Batch& x) {
@@ -148,11 +154,13 @@ static void dispatcher(gofr_frontend* f) {
             if (!(f->b[(k + j) % kBatches].claim.load(std::memory_order_acquire) & kClosed)) { next = (k + j) % kBatches; break; }
         f->filling.store(next, std::memory_order_release);
         bump(&f->room_seq);
+        const int64_t t_close = f->debug ? mono_ns() : 0;
         while (x.filled.load(std::memory_order_acquire) != n) {  // the last claimants are still copying their bytes in
 #if defined(__x86_64__)
             __builtin_ia32_pause();
 #endif
         }
+        const int64_t t_filled = f->debug ? mono_ns() : 0;
         gofr_req_batch in;
         memset(&in, 0, sizeof in);
         in.desc = x.desc; in.trace_ids = x.ids; in.arena = x.arena; in.arena_bytes = (claim_arena(w) + 15u) & ~15u; in.n = n;
@@ -165,6 +173,7 @@ static void dispatcher(gofr_frontend* f) {
         gofr_ticket t = 0;
         int rc = gofr_batch_submit_slots(f->eng, &in, &out, &t);
         if (rc == GOFR_OK) rc = gofr_batch_wait(f->eng, t);
+        const int64_t t_eng = f->debug ? mono_ns() : 0;
         x.rc = rc;
         f->batches.fetch_add(1, std::memory_order_relaxed);
         f->requests.fetch_add(n, std::memory_order_relaxed);
@@ -172,6 +181,13 @@ static void dispatcher(gofr_frontend* f) {
         const uint32_t r1 = x.round.load(std::memory_order_relaxed) + 1, g_used = (n + kGroup - 1) / kGroup;
         for (uint32_t g = 0; g < g_used; g++) x.done[g].store(r1, std::memory_order_release);
         futex_wake_all(&x.done[0]);
+        if (f->debug) {
+            const int64_t t_end = mono_ns();
+            f->dbg_spin_ns += t_filled - t_close; if (t_filled - t_close > f->dbg_spin_max) f->dbg_spin_max = t_filled - t_close;
+            f->dbg_eng_ns += t_eng - t_filled; if (t_eng - t_filled > f->dbg_eng_max) f->dbg_eng_max = t_eng - t_filled;
+            if (t_eng - t_filled > 5000000) f->dbg_eng_slow++;
+            f->dbg_wake_ns += t_end - t_eng; if (t_end - t_eng > f->dbg_wake_max) f->dbg_wake_max = t_end - t_eng;
+        }
     }
 }
 
@@ -206,6 +222,7 @@ int gofr_frontend_create(gofr_frontend** out, gofr_engine* e, uint32_t max_batch
             return GOFR_ERR_NOMEM;
         }
     }
+    { const char* dbg = getenv("GOFR_FRONTEND_DEBUG"); f->debug = dbg && dbg[0] == '1'; }
     f->worker = std::thread(dispatcher, f);
     *out = f;
     return GOFR_OK;
@@ -217,6 +234,12 @@ void gofr_frontend_destroy(gofr_frontend* f) {
     bump(&f->disp_seq);
     bump(&f->room_seq);
     if (f->worker.joinable()) f->worker.join();
+    if (f->debug) {
+        const double nb = (double)(f->batches.load() ? f->batches.load() : 1);
+        fprintf(stderr, "[gofr frontend] batches %llu  fill-spin avg %.1f max %.1f us  engine avg %.1f max %.1f us (>5ms: %llu)  publish+wake avg %.1f max %.1f us\n",
+                (unsigned long long)f->batches.load(), f->dbg_spin_ns / nb / 1e3, f->dbg_spin_max / 1e3, f->dbg_eng_ns / nb / 1e3,
+                f->dbg_eng_max / 1e3, (unsigned long long)f->dbg_eng_slow, f->dbg_wake_ns / nb / 1e3, f->dbg_wake_max / 1e3);
+    }
     for (auto& x : f->b) free_batch(x);
     delete f;
 }

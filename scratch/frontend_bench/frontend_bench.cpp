@@ -41,6 +41,7 @@ int main(int argc, char** argv) {
     std::atomic<bool> stop{false};
     std::atomic<uint64_t> bad{0};
     std::vector<std::vector<float>> lat((size_t)T);
+    std::vector<std::vector<float>> slow_at((size_t)T);  // start offsets (ms) of requests slower than 20 ms
     std::vector<std::thread> th;
     auto t0 = std::chrono::steady_clock::now();
     for (int t = 0; t < T; t++)
@@ -58,6 +59,7 @@ int main(int argc, char** argv) {
                 auto e = std::chrono::steady_clock::now();
                 if (rc || len < 17 || resp[0] != 'H') bad++;
                 lat[(size_t)t].push_back(std::chrono::duration<float, std::micro>(e - s).count());
+                if (e - s > std::chrono::milliseconds(20)) slow_at[(size_t)t].push_back(std::chrono::duration<float, std::milli>(s - t0).count());
                 i = (i + (size_t)T) % n;
             }
         });
@@ -68,6 +70,14 @@ int main(int argc, char** argv) {
     std::vector<float> all;
     for (auto& v : lat) all.insert(all.end(), v.begin(), v.end());
     std::sort(all.begin(), all.end());
+    if (getenv("FRONTEND_BENCH_SLOW")) {
+        std::vector<float> sl;
+        for (auto& v : slow_at) sl.insert(sl.end(), v.begin(), v.end());
+        std::sort(sl.begin(), sl.end());
+        fprintf(stderr, "slow (>20 ms) requests: %zu; start offsets (ms), every %zu-th:", sl.size(), sl.size() / 40 + 1);
+        for (size_t k = 0; k < sl.size(); k += sl.size() / 40 + 1) fprintf(stderr, " %.0f", sl[k]);
+        fprintf(stderr, "\n");
+    }
     uint64_t batches = 0, reqs = 0;
     gofr_frontend_stats(fe, &batches, &reqs);
     auto pct = [&](double p) { return all.empty() ? 0.f : all[(size_t)(p * (all.size() - 1))]; };

@@ -11,7 +11,8 @@ b.desc.tofile("$D/desc.bin"); b.trace_ids.tofile("$D/ids.bin"); b.arena.tofile("
 PY
 LIB=$(python -c "from gofr_b200 import _build; print(_build.LIB)")
 g++ -O2 -std=c++17 -pthread scratch/frontend_bench/frontend_bench.cpp -o $D/frontend_bench "$LIB" -Wl,-rpath,$(dirname "$LIB")
-for cfg in "1 1 0" "64 64 50" "256 256 100" "1024 1024 200" "4096 4096 200" "4096 1024 200"; do
-  set -- $cfg
-  timeout 120 $D/frontend_bench $D/table.img $D/desc.bin $D/ids.bin $D/arena.bin $1 $2 $3 3 | tee -a $D/results.jsonl
+CFGS=${CFGS:-"1,1,0 64,64,50 256,256,100 512,512,100 1024,1024,200 4096,4096,200 4096,1024,200"}
+for cfg in $CFGS; do
+  IFS=, read -r T B W <<< "$cfg"
+  GOFR_FRONTEND_DEBUG=${DEBUG:-0} FRONTEND_BENCH_SLOW=${SLOW:-} timeout 120 $D/frontend_bench $D/table.img $D/desc.bin $D/ids.bin $D/arena.bin $T $B $W 3 | tee -a $D/results.jsonl
 done
