@@ -977,11 +977,13 @@ GOFR_HD void route_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) 
     } else if (R.hkind == GOFR_H_RESULT) {
         // the closure ran on the host; its outcome word selects what Responder.Respond does (responder.go:19-62)
         const uint32_t outcome = c.data_len >= 4 ? *(const uint32_t*)c.data() : 0xFFFFFFFFu;
-        if (outcome > GOFR_RESULT_BOTH) { c.prog = H.prog_panic; return; }  // malformed record from the host shim
+        if (outcome > GOFR_RESULT_STRING) { c.prog = H.prog_panic; return; }  // malformed record from the host shim
         c.data_off += 4;
         c.data_len -= 4;
         c.prog = outcome == GOFR_RESULT_DATA ? R.prog_ok : outcome == GOFR_RESULT_ERROR ? R.prog_err
-               : outcome == GOFR_RESULT_NIL ? R.key_len : outcome == GOFR_RESULT_MISSING ? R.def_len : R.key_off;
+               : outcome == GOFR_RESULT_NIL ? R.key_len : outcome == GOFR_RESULT_MISSING ? R.def_len
+               : outcome == GOFR_RESULT_BOTH ? (R.key_off & 0xFFFFu) : (R.key_off >> 16);
+        if (c.prog == 0xFFFFu) c.prog = H.prog_panic;  // DATA / BOTH on a route registered without a schema
     } else if (R.hkind == GOFR_H_BIND_ECHO) {
         // var v T; if err := c.Bind(&v); err != nil { return nil, err }; return v, nil
         uint32_t* brow = c.brow(br);

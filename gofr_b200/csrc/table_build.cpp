@@ -562,13 +562,15 @@ int seal_table(gofr_table* t) {
 
     // ---- per-route programs ----
     std::vector<int> prog_ok(t->routes.size(), 0xFFFF), prog_err(t->routes.size(), 0xFFFF);
-    std::vector<int> prog_err404(t->routes.size(), 0xFFFF), prog_nil(t->routes.size(), 0xFFFF), prog_both(t->routes.size(), 0xFFFF);
+    std::vector<int> prog_err404(t->routes.size(), 0xFFFF), prog_nil(t->routes.size(), 0xFFFF), prog_both(t->routes.size(), 0xFFFF),
+        prog_str(t->routes.size(), 0xFFFF);
     for (size_t ri = 0; ri < t->routes.size(); ri++) {
         RouteDef& r = t->routes[ri];
         const SchemaDef* sc = nullptr;
         if (r.hkind == GOFR_H_ROW || r.hkind == GOFR_H_BIND_ECHO || r.hkind == GOFR_H_RESULT) {
             for (auto& s : t->schemas) if (s.id == r.schema_id) sc = &s;
-            if (!sc) { set_last_error("route %s: unknown schema %u", r.pattern.c_str(), r.schema_id); return GOFR_ERR_INVALID; }
+            // a closure that only ever returns strings / errors / nil needs no struct schema
+            if (!sc && !(r.hkind == GOFR_H_RESULT && r.schema_id == 0)) { set_last_error("route %s: unknown schema %u", r.pattern.c_str(), r.schema_id); return GOFR_ERR_INVALID; }
         }
         switch (r.hkind) {
             case GOFR_H_HOST: break;
@@ -611,13 +613,27 @@ int seal_table(gofr_table* t) {
             }
             case GOFR_H_RESULT: {
                 // Responder.Respond on a (data, err) the host closure produced (responder.go:19-62)
-                Prog p;
-                p.status = 200;
-                build_header(p, fm, 200, true, BODY_JSON, false, "", "", false);
-                p.ops.push_back(lit("{\"data\":", true));
-                build_struct_ops(p, *sc, false);
-                p.ops.push_back(lit("}\n", true));
-                prog_ok[ri] = b.add(std::move(p));
+                if (sc) {
+                    Prog p;
+                    p.status = 200;
+                    build_header(p, fm, 200, true, BODY_JSON, false, "", "", false);
+                    p.ops.push_back(lit("{\"data\":", true));
+                    build_struct_ops(p, *sc, false);
+                    p.ops.push_back(lit("}\n", true));
+                    prog_ok[ri] = b.add(std::move(p));
+                }
+                {   // data is a string: {"data":"…"} (encoding/json string escaping, as for struct fields)
+                    Prog p;
+                    p.status = 200;
+                    build_header(p, fm, 200, true, BODY_JSON, false, "", "", false);
+                    p.ops.push_back(lit("{\"data\":\"", true));
+                    SOp m = op(OP_STR, true);
+                    m.off = 0;  // row word 0 = len, the bytes follow
+                    p.ops.push_back(m);
+                    p.ops.push_back(lit("\"}\n", true));
+                    p.row_words = 1;
+                    prog_str[ri] = b.add(std::move(p));
+                }
                 for (int which = 0; which < 2; which++) {  // 500, and 404 for errors.Is(err, http.ErrMissingFile)
                     Prog e;
                     e.status = which ? 404 : 500;
@@ -631,7 +647,7 @@ int seal_table(gofr_table* t) {
                     (which ? prog_err404 : prog_err)[ri] = b.add(std::move(e));
                 }
                 prog_nil[ri] = b.json_prog(200, {lit("{}\n", true)});
-                {   // (data, err) both non-nil: response{Error, Data} with both members (responder.go:59-62)
+                if (sc) {  // (data, err) both non-nil: response{Error, Data} with both members (responder.go:59-62)
                     Prog e;
                     e.status = 500;
                     build_header(e, fm, 500, true, BODY_JSON, false, "", "", false);
@@ -733,7 +749,7 @@ int seal_table(gofr_table* t) {
         if (r.hkind == GOFR_H_RESULT) {  // the two spare 16-bit fields carry the other outcomes' programs
             R.key_len = (uint16_t)prog_nil[ri];
             R.def_len = (uint16_t)prog_err404[ri];
-            R.key_off = (uint32_t)prog_both[ri];
+            R.key_off = (uint32_t)prog_both[ri] | (uint32_t)prog_str[ri] << 16;
         }
         if (r.hkind == GOFR_H_ROW || r.hkind == GOFR_H_BIND_ECHO || r.hkind == GOFR_H_RESULT)
             for (size_t si = 0; si < t->schemas.size(); si++)

@@ -12,7 +12,7 @@
 namespace gofr {
 
 constexpr uint32_t kMagic = 0x52464F47u;  // "GOFR"
-constexpr uint32_t kImageVersion = 11;
+constexpr uint32_t kImageVersion = 12;
 constexpr uint32_t kMaxHotBytes = 40 * 1024;  // shared-memory budget for the table
 constexpr int kMaxVars = 8;                   // variables per route template
 constexpr int kMaxFields = 32;                // struct fields per schema

@@ -24,12 +24,13 @@ FRAME_WIRE, FRAME_INTENDED, FRAME_BODY = 0, 1, 2
 # handler kinds
 (H_HOST, H_STATIC_STRING, H_STATIC_ERROR, H_NIL, H_PARAM_FORMAT, H_ROW, H_BIND_ECHO, H_HEALTH, H_MISSING_FILE, H_FILE,
  H_PANIC, H_PATHPARAM_FORMAT, H_RESULT) = range(13)
-RESULT_DATA, RESULT_ERROR, RESULT_NIL, RESULT_MISSING, RESULT_BOTH = range(5)
+RESULT_DATA, RESULT_ERROR, RESULT_NIL, RESULT_MISSING, RESULT_BOTH, RESULT_STRING = range(6)
 
 
 def result_record(outcome: int, payload: bytes = b"") -> bytes:
-    """Data section of a GOFR_H_RESULT request: outcome word, then a schema row (DATA) or len + message (ERROR/MISSING)."""
-    if outcome in (RESULT_ERROR, RESULT_MISSING):
+    """Data section of a GOFR_H_RESULT request: outcome word, then a schema row (DATA) or len + bytes (ERROR / MISSING: err.Error();
+    STRING: the string the handler returned)."""
+    if outcome in (RESULT_ERROR, RESULT_MISSING, RESULT_STRING):
         payload = len(payload).to_bytes(4, "little") + payload
     return outcome.to_bytes(4, "little") + payload
 

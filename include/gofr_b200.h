@@ -104,9 +104,13 @@ enum {
                                    GOFR_RESULT_MISSING  u32 length + message; errors.Is(err, http.ErrMissingFile) → 404
                                    GOFR_RESULT_BOTH     (data, err) both non-nil: one row whose first field is the message
                                                         string followed by the schema's fields (length word + fixed
-                                                        words, then message bytes + string bytes) → 500 {"error":…,"data":…} */
+                                                        words, then message bytes + string bytes) → 500 {"error":…,"data":…}
+                                   GOFR_RESULT_STRING   data is a Go string (what most of the reference's example handlers
+                                                        return, examples/http-server/main.go:29-41): u32 length + bytes
+                                                        → 200 {"data":"…"}  (the route needs no schema for this outcome) */
 };
-enum { GOFR_RESULT_DATA = 0, GOFR_RESULT_ERROR = 1, GOFR_RESULT_NIL = 2, GOFR_RESULT_MISSING = 3, GOFR_RESULT_BOTH = 4 };
+enum { GOFR_RESULT_DATA = 0, GOFR_RESULT_ERROR = 1, GOFR_RESULT_NIL = 2, GOFR_RESULT_MISSING = 3, GOFR_RESULT_BOTH = 4,
+       GOFR_RESULT_STRING = 5 };
 
 /* ---- struct field kinds for response / Bind schemas ---- */
 enum {

@@ -984,6 +984,12 @@ static void serve_one(const orc_table* t, const req_desc* d, const uint8_t* id16
                     decode_row(sc, tmp2.p, tmp2.n, vals); /* vals must point into memory that outlives this block */
                     hr.has_err = 1; hr.err_msg = rest + fixed; hr.err_len = mlen;
                     hr.data_kind = 2; hr.sc = sc; hr.vals = vals;
+                } else if (outcome == 5) {
+                    /* data is a Go string: Respond marshals response{Data: "…"} (responder.go:59-62) */
+                    uint32_t len = 0;
+                    if (rn >= 4) memcpy(&len, rest, 4);
+                    if (rn < 4 || (uint64_t)len + 4 > rn) { hr.data_kind = -1; break; }
+                    hr.data_kind = 1; hr.str = rest + 4; hr.str_len = len;
                 } else if (outcome != 2) hr.data_kind = -1;
                 break;
             }

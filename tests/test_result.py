@@ -117,3 +117,103 @@ def test_gpu_split_api_round_trip():
     assert o1[:f1[-1]].tobytes() == out.tobytes()
     assert (m1 & 0xFFFF == 500).sum() > 100 and (m1 & 0xFFFF == 404).sum() > 100 and (m1 & 0xFFFF == 200).sum() > 100
     eng.close()
+
+
+# ---- GOFR_RESULT_STRING: the closure returned a Go string (most handlers of the reference's examples do,
+#      examples/http-server/main.go:29-41; gofr_test.go:95-105 expects {"data":"Hello World!"} etc.) ----
+
+def _string_spec(frame=S.FRAME_WIRE) -> S.TableSpec:
+    return S.TableSpec(frame_mode=frame, schemas=[ITEM], routes=[
+        S.Route(S.M_GET, "/hello", S.H_RESULT),                    # no schema: strings, errors and nil only
+        S.Route(S.M_GET, "/items/{id}", S.H_RESULT, schema_id=7),  # the same outcome on a route that also has a schema
+    ])
+
+
+def _string_batch() -> S.RequestBatch:
+    R, rec = S.Req, S.result_record
+    reqs = [R(S.M_GET, b"/hello", data=rec(S.RESULT_STRING, b"Hello World!")),
+            R(S.M_GET, b"/hello", b"name=Vikash", data=rec(S.RESULT_STRING, b"Hello Vikash!")),
+            R(S.M_GET, b"/hello", data=rec(S.RESULT_STRING, b"")),
+            R(S.M_GET, b"/hello", data=rec(S.RESULT_STRING, b'<b>"q"</b> & \\ \x01\x7f \xe2\x80\xa8\xe2\x80\xa9 \xff\xfe caf\xc3\xa9\n')),
+            R(S.M_GET, b"/hello", data=rec(S.RESULT_STRING, b"x" * 3000)),
+            R(S.M_GET, b"/hello", data=rec(S.RESULT_ERROR, b"some error occurred")),
+            R(S.M_GET, b"/hello", data=rec(S.RESULT_NIL)),
+            R(S.M_GET, b"/hello", data=rec(S.RESULT_DATA, ITEM.encode_row(["A", 1, ""]))),   # no schema on this route → panic
+            R(S.M_GET, b"/hello", data=S.result_both(ITEM, ["A", 1, ""], b"m")),             # likewise
+            R(S.M_GET, b"/hello", data=b"\x05\x00\x00\x00\x09\x00\x00\x00abc"),              # string longer than the record
+            R(S.M_GET, b"/hello", data=b"\x05\x00\x00\x00"),                                 # no length word
+            R(S.M_HEAD, b"/hello", data=rec(S.RESULT_STRING, b"Hello")),                     # GET-only route, the catch-all answers
+            R(S.M_GET, b"/items/1", data=rec(S.RESULT_STRING, b"one")),
+            R(S.M_GET, b"/items/2", data=rec(S.RESULT_DATA, ITEM.encode_row(["A-2", 2, "n"]))),
+            R(S.M_GET, b"/hello", data=rec(S.RESULT_STRING, "Success ✓ – naïve".encode()))]
+    return S.RequestBatch.pack(reqs)
+
+
+def test_string_outcome_oracle_bodies():
+    out, off, meta = O.OracleTable(_string_spec(S.FRAME_BODY)).serve(_string_batch(), DATE)
+    r = O.responses(out, off)
+    st = [int(m) & 0xFFFF for m in meta]
+    assert r[0] == b'{"data":"Hello World!"}\n' and st[0] == 200          # gofr_test.go:95-105
+    assert r[1] == b'{"data":"Hello Vikash!"}\n' and st[1] == 200
+    assert r[2] == b'{"data":""}\n' and st[2] == 200
+    assert r[3] == (b'{"data":"\\u003cb\\u003e\\"q\\"\\u003c/b\\u003e \\u0026 \\\\ \\u0001\x7f \\u2028\\u2029 \\ufffd\\ufffd caf\xc3\xa9\\n"}\n')
+    assert r[4] == b'{"data":"' + b"x" * 3000 + b'"}\n'
+    assert r[5] == b'{"error":{"message":"some error occurred"}}\n' and st[5] == 500
+    assert r[6] == b"{}\n" and st[6] == 200
+    assert st[7] == st[8] == st[9] == st[10] == 500 and all(b"Some unexpected error" in r[k] for k in (7, 8, 9, 10))
+    assert st[11] == 404     # method mismatch on /hello, then the catch-all of App.Run matches (gofr.go:104)
+    assert r[12] == b'{"data":"one"}\n' and r[13] == b'{"data":{"sku":"A-2","qty":2,"note":"n"}}\n'
+    assert r[14] == b'{"data":"Success \xe2\x9c\x93 \xe2\x80\x93 na\xc3\xafve"}\n'
+    # the same strings through Python's json module (ensure_ascii off, HTML-safe escapes applied by hand)
+    import json
+    want = {0: "Hello World!", 1: "Hello Vikash!", 2: "", 4: "x" * 3000, 12: "one", 14: "Success ✓ – naïve"}
+    for k, v in want.items():
+        assert json.loads(r[k])["data"] == v
+    assert json.loads(r[3])["data"] == '<b>"q"</b> & \\ \x01\x7f \u2028\u2029 \ufffd\ufffd café\n'
+
+
+@pytest.mark.parametrize("frame", [S.FRAME_WIRE, S.FRAME_INTENDED, S.FRAME_BODY])
+@pytest.mark.parametrize("mis", [0, 3])
+def test_string_outcome_emu_matches_oracle(frame, mis):
+    spec, b = _string_spec(frame), _string_batch()
+    o1, f1, m1 = O.OracleTable(spec).serve(b, DATE)
+    o2, f2, m2 = emu.serve(Table(spec).serialize(), b, DATE, misalign=mis)
+    assert np.array_equal(m1, m2) and np.array_equal(f1 + mis, f2)
+    assert o1[:f1[-1]].tobytes() == o2[mis:f2[-1]].tobytes()
+
+
+def test_string_outcome_emu_slots():
+    spec, b = _string_spec(), _string_batch()
+    o1, f1, m1 = O.OracleTable(spec).serve(b, DATE)
+    out, ln, meta = emu.serve_slots(Table(spec).serialize(), b, DATE, 4096)
+    assert np.array_equal(meta, m1) and np.array_equal(ln, np.diff(f1.astype(np.int64)).astype(np.uint32))
+    ob = o1.tobytes()
+    for i in range(b.n):
+        assert out[i, :int(ln[i])].tobytes() == ob[int(f1[i]):int(f1[i + 1])], i
+
+
+@pytest.mark.gpu
+def test_gpu_string_outcome():
+    from gofr_b200.engine import Engine
+    spec = _string_spec()
+    eng = Engine(Table(spec), 0)
+    base = _string_batch()
+    rng = np.random.default_rng(11)
+    reqs = []
+    alphabet = np.frombuffer(b'abcXYZ019 <>&"\\\n\t\x01\x7f\xc3\xa9\xe2\x80\xa8\xff', dtype=np.uint8)
+    for k in range(20000):
+        ln = int(rng.integers(0, 120))
+        s = alphabet[rng.integers(0, len(alphabet), ln)].tobytes()
+        path = b"/hello" if k % 2 else b"/items/%d" % k
+        reqs.append(S.Req(S.M_GET, path, data=S.result_record(S.RESULT_STRING if k % 5 else S.RESULT_ERROR, s)))
+    for b in (base, S.RequestBatch.pack(reqs)):
+        o1, f1, m1 = O.OracleTable(spec).serve(b, DATE)
+        resp = eng.alloc_responses(b.n, int(f1[-1]) + 4096)
+        eng.serve_device(eng.upload(b), DATE, resp)
+        out, off, m2 = resp.to_host()
+        assert np.array_equal(m1, m2) and np.array_equal(f1, off)
+        assert o1[:f1[-1]].tobytes() == out.tobytes()
+        o_s, ln_s, m_s = eng.serve_device_slots(eng.upload(b), DATE, 4096)
+        assert np.array_equal(m_s.cpu().numpy().view(np.uint32), m1)
+        assert np.array_equal(ln_s.cpu().numpy().view(np.uint32), np.diff(f1.astype(np.int64)).astype(np.uint32))
+    eng.close()
