@@ -93,6 +93,9 @@ struct gofr_engine {
     uint32_t debug_flags = 0;  // GOFR_DEBUG_* environment switches, read once at creation
     double timed_ms = 0;
     uint64_t timed_launches = 0;
+    // gofr_batch_route scratch (host-buffer stage 1 of the split API)
+    uint8_t* d_rt_desc = nullptr; uint8_t* d_rt_arena = nullptr; uint8_t* d_rt_meta = nullptr; uint8_t* d_rt_vars = nullptr;
+    size_t rt_desc_cap = 0, rt_arena_cap = 0, rt_meta_cap = 0, rt_vars_cap = 0;
     // tickets
     // tickets of finished submits whose result has not been collected yet (submit completes the batch; wait reports)
     std::vector<std::pair<gofr_ticket, int>> done_tickets;
@@ -184,6 +187,7 @@ void gofr_engine_destroy(gofr_engine* e) {
     cudaFree(e->d_chain); cudaFree(e->d_info);
     if (e->h_status) cudaFreeHost(e->h_status);
     cudaFree(e->d_image); cudaFree(e->d_state); cudaFree(e->d_flag); cudaFree(e->d_bind);
+    cudaFree(e->d_rt_desc); cudaFree(e->d_rt_arena); cudaFree(e->d_rt_meta); cudaFree(e->d_rt_vars);
     delete e;
 }
 
@@ -737,6 +741,48 @@ int gofr_route_device(gofr_engine* e, const gofr_req_desc* d_desc, const uint8_t
     int rc = launch_route(p, e->sm_count, stream);
     if (rc != 0) { set_last_error("route kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
     e->launches++;
+    return GOFR_OK;
+}
+
+int gofr_batch_route(gofr_engine* e, const gofr_req_batch* in, uint32_t* meta, uint32_t* vars) {
+    if (!e || !in || (in->n && (!in->desc || !meta || !vars))) return GOFR_ERR_INVALID;
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    const uint32_t n = in->n;
+    for (uint32_t lo = 0; lo < n; lo += e->chunk) {
+        const uint32_t hi = std::min<uint32_t>(n, lo + e->chunk), cn = hi - lo;
+        uint32_t alo = 0xFFFFFFFFu, ahi = 0;
+        for (uint32_t i = lo; i < hi; i++) {  // routing reads the path only
+            const gofr_req_desc& d = in->desc[i];
+            alo = d.arena_off < alo ? d.arena_off : alo;
+            ahi = d.arena_off + d.path_len > ahi ? d.arena_off + d.path_len : ahi;
+        }
+        alo &= ~15u;
+        ahi = (ahi + 15u) & ~15u;
+        if ((uint64_t)ahi > ((in->arena_bytes + 15u) & ~(uint64_t)15u)) { set_last_error("descriptor %u..%u points outside the arena", lo, hi); return GOFR_ERR_INVALID; }
+        const size_t abytes = (size_t)ahi - alo;
+        int rc;
+        if ((rc = grow((void**)&e->d_rt_desc, &e->rt_desc_cap, (size_t)cn * 16, 256))) return rc;
+        if ((rc = grow((void**)&e->d_rt_arena, &e->rt_arena_cap, abytes + 16, 256))) return rc;
+        if ((rc = grow((void**)&e->d_rt_meta, &e->rt_meta_cap, (size_t)cn * 4, 256))) return rc;
+        if ((rc = grow((void**)&e->d_rt_vars, &e->rt_vars_cap, (size_t)cn * 4 * GOFR_MAX_PATH_VARS, 256))) return rc;
+        cudaStream_t st = e->st_compute;
+        CUDA_TRY(cudaMemcpyAsync(e->d_rt_desc, in->desc + lo, (size_t)cn * 16, cudaMemcpyHostToDevice, st));
+        if (abytes) {
+            const size_t avail = in->arena_bytes > alo ? (size_t)in->arena_bytes - alo : 0;
+            CUDA_TRY(cudaMemcpyAsync(e->d_rt_arena, in->arena + alo, std::min(abytes, avail), cudaMemcpyHostToDevice, st));
+        }
+        RouteParams p;
+        memset(&p, 0, sizeof p);
+        p.desc = (const gofr_req_desc*)e->d_rt_desc; p.arena = e->d_rt_arena - alo; p.n = cn; p.image = e->d_image;
+        p.hot_bytes = e->hdr.hot_bytes; p.meta = (uint32_t*)e->d_rt_meta; p.vars = (uint32_t*)e->d_rt_vars;
+        rc = launch_route(p, e->sm_count, st);
+        if (rc != 0) { set_last_error("route kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
+        e->launches++;
+        CUDA_TRY(cudaMemcpyAsync(meta + lo, e->d_rt_meta, (size_t)cn * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(vars + (size_t)lo * GOFR_MAX_PATH_VARS, e->d_rt_vars, (size_t)cn * 4 * GOFR_MAX_PATH_VARS, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
     return GOFR_OK;
 }
 

@@ -1116,6 +1116,16 @@ uint32_t gofr_table_max_response_bytes(const gofr_table* t, uint32_t max_data_le
     return H.max_fixed_len + 16 + 6 * max_data_len + 3 * 65535 + 65535 + 2;
 }
 
+uint32_t gofr_table_response_bound(const gofr_table* t, uint32_t path_len, uint32_t query_len, uint32_t data_len) {
+    if (!t || t->image.empty()) return 0;
+    ImageHeader H;
+    memcpy(&H, t->image.data(), sizeof H);
+    // fixed part + Content-Length digits + every request byte that can reach the response (a path variable, a query value,
+    // a data byte; the Location of a redirect is at most 3x path + query) escaped six-fold (\u00XX)
+    const uint64_t b = (uint64_t)H.max_fixed_len + 16 + 6ull * ((uint64_t)path_len + query_len + data_len) + 2;
+    return b > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)b;
+}
+
 }  // extern "C"
 
 const std::vector<uint8_t>& gofr_table_image(const gofr_table* t) { return t->image; }

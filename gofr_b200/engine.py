@@ -130,6 +130,15 @@ class Engine:
                                                 vars_.data_ptr(), st.cuda_stream), "gofr_route_device")
         return meta[:b.n], vars_[:b.n]
 
+    def route_host(self, batch: S.RequestBatch):
+        """gofr_batch_route: the same for a batch in host memory → (meta uint32[n], vars uint32[n, 8])."""
+        rb = _abi.ReqBatch(desc=batch.desc.ctypes.data, trace_ids=batch.trace_ids.ctypes.data, arena=batch.arena.ctypes.data,
+                           arena_bytes=batch.arena.size, n=batch.n, date=b"")
+        meta = np.zeros(max(batch.n, 1), dtype=np.uint32)
+        vars_ = np.zeros((max(batch.n, 1), 8), dtype=np.uint32)
+        _abi.check(_abi.lib().gofr_batch_route(self._e, C.byref(rb), meta.ctypes.data, vars_.ctypes.data), "gofr_batch_route")
+        return meta[:batch.n], vars_[:batch.n]
+
     # ---- HTTP/1.1 request heads → request descriptors (the step in front of the router) ----
     def http_parse_device(self, raw: np.ndarray, raw_off: np.ndarray, stream=None):
         """gofr_http_parse_device on host arrays (uploaded here).  Returns torch tensors (desc uint8[n*16], arena uint8,

@@ -188,6 +188,8 @@ int gofr_table_serialize(const gofr_table*, uint8_t* buf, uint64_t* len_inout);
 int gofr_table_deserialize(gofr_table** out, const uint8_t* buf, uint64_t len);
 uint32_t gofr_table_route_count(const gofr_table*);
 uint32_t gofr_table_max_response_bytes(const gofr_table*, uint32_t max_data_len);
+/* Upper bound of ONE response given that request's sizes (what a host batcher sums up to size its output buffer). */
+uint32_t gofr_table_response_bound(const gofr_table*, uint32_t path_len, uint32_t query_len, uint32_t data_len);
 
 /* ================= engine (one per GPU / process) ================= */
 int gofr_engine_create(gofr_engine** out, const gofr_table* sealed, int device);
@@ -283,6 +285,10 @@ int gofr_grpc_hello_device(gofr_engine*, const uint8_t* d_in, const uint32_t* d_
 #define GOFR_MAX_PATH_VARS 8
 int gofr_route_device(gofr_engine*, const gofr_req_desc* d_desc, const uint8_t* d_arena, uint32_t n, uint32_t* d_meta,
                       uint32_t* d_vars, void* stream);
+/* The same for a batch in host memory (synchronous: H2D of descriptors and paths, the route kernel, D2H of meta and vars
+ * — n and n * GOFR_MAX_PATH_VARS words).  What the C++ stand-in of the app API (include/gofr_b200.hpp) calls before it
+ * runs the closures. */
+int gofr_batch_route(gofr_engine*, const gofr_req_batch* in, uint32_t* meta, uint32_t* vars);
 
 /* The JSON line middleware.Logging hands to logger.Log after every request (non-terminal writer:
  * json.NewEncoder(out).Encode(logEntry{Level: INFO, Time: time.Now(), Message: RequestLog{...}})):

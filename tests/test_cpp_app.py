@@ -1,0 +1,106 @@
+"""The C++ stand-in of the reference's app API (include/gofr_b200.hpp): gofr.New / GET / PUT / POST / DELETE /
+Context.Param / Context.PathParam / Run / ServeHTTP (pkg/gofr/gofr.go:49-73,152-177; pkg/gofr/http/request.go:28-38).
+
+examples/cpp/server_routes.cpp is the reference's TestGofr_ServerRoutes (pkg/gofr/gofr_test.go:40-105) written against
+it, with closures as handlers; this file builds it, runs it on the GPU and compares every response byte with the oracle
+serving the same requests (the closures restated in Python below)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from gofr_b200 import _build
+from gofr_b200 import spec as S
+from tests import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATE = S.http_date(1_700_000_000)
+
+
+def _compile(src, exe, link=True):
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), src, "-o", exe]
+    if link:
+        cmd += [_build.LIB, "-Wl,-rpath," + os.path.dirname(_build.LIB)]
+    subprocess.check_call(cmd)
+
+
+def test_header_compiles_and_host_helpers_match_oracle(tmp_path):
+    """no GPU: the example builds against the library; Param's query parsing agrees with the oracle's url.ParseQuery
+    restatement on hostile queries; template variable names come out in mux's order"""
+    from gofr_b200 import _abi
+    _abi.lib()  # builds the .so if needed
+    _compile(os.path.join(ROOT, "examples", "cpp", "server_routes.cpp"), str(tmp_path / "server_routes"))
+    exe = str(tmp_path / "hpp_host_check")
+    _compile(os.path.join(ROOT, "tests", "emu", "hpp_host_check.cpp"), exe, link=False)
+    rng = np.random.default_rng(5)
+    alphabet = [b"a", b"b", b"name", b"=", b"&", b"&", b";", b"+", b"%41", b"%zz", b"%", b"%4", b"x", b"=", b"%26", b"%3D", b"\xff", b" "]
+    cases = [(b"name=Vikash", b"name"), (b"", b"name"), (b"name", b"name"), (b"a=1&name=&name=2", b"name"), (b"a=1;name=2&name=3", b"name"),
+             (b"name=%zz&name=ok", b"name"), (b"n%61me=v", b"name"), (b"name=a+b%20c", b"name"), (b"=v", b""), (b"&&name=x&&", b"name"),
+             (b"name=x=y", b"name"), (b"name=%", b"name"), (b"name=%4", b"name"), (b"name=a%", b"name")]
+    for _ in range(3000):
+        q = b"".join(alphabet[int(k)] for k in rng.integers(0, len(alphabet), int(rng.integers(0, 12))))
+        cases.append((q, [b"name", b"a", b"b", b"x", b""][int(rng.integers(0, 5))]))
+    lines = "".join("Q %s %s\n" % (q.hex() or "-", k.hex() or "-") for q, k in cases)
+    tmpl = ["/a/{id}/b/{name:[a-z]+}", "/{x:[0-9]{2}}/{y}", "/plain", "/{a}-{b}.{c}", "/{v:.*}"]
+    lines += "".join("T %s\n" % t.encode().hex() for t in tmpl)
+    out = subprocess.run([exe], input=lines, capture_output=True, text=True, check=True).stdout.splitlines()
+    for (q, k), got in zip(cases, out):
+        assert bytes.fromhex(got) == O.query_get(q, k), (q, k)
+    assert out[len(cases):] == ["id,name", "x,y", "", "a,b,c", "v"]
+
+
+def _records():
+    """the closures of examples/cpp/server_routes.cpp, restated: (method, target, body) → result record"""
+    hello = S.result_record(S.RESULT_STRING, b"Hello World!")
+    person = S.Schema(1, "main.Person", [S.Field("ID", S.F_INT, "id"), S.Field("Name", S.F_STRING, "name"),
+                                         S.Field("Admin", S.F_BOOL, "admin", omitempty=True)])
+    cases = [("GET", "/hello", b"", hello), ("GET", "/hello2", b"", hello), ("PUT", "/hello", b"", hello), ("POST", "/hello", b"", hello),
+             ("GET", "/params?name=Vikash", b"", S.result_record(S.RESULT_STRING, b"Hello Vikash!")),
+             ("DELETE", "/delete", b"", S.result_record(S.RESULT_STRING, b"Success")),
+             ("GET", "/greet", b"", hello),
+             ("GET", "/greet?name=a%26b+c&name=second", b"", S.result_record(S.RESULT_STRING, b"Hello a&b c!")),
+             ("GET", "/greet?name=%zz&x=1", b"", hello),
+             ("GET", "/error", b"", S.result_record(S.RESULT_ERROR, b"some error occurred")),
+             ("GET", "/users/42/posts/hello-world", b"", S.result_record(S.RESULT_STRING, b"user 42 post hello-world")),
+             ("GET", "/users/4x2/posts/p", b"", b""),
+             ("GET", "/person/root", b"", S.result_record(S.RESULT_DATA, person.encode_row([4, "root", True]))),
+             ("GET", "/person/al%20ice", b"", S.result_record(S.RESULT_DATA, person.encode_row([6, "al ice", False]))),
+             ("GET", "/person/nobody", b"", S.result_both(person, [0, "nobody", False], b"partial <result>")),
+             ("GET", "/nil", b"", S.result_record(S.RESULT_NIL)),
+             ("GET", "/file", b"", S.result_record(S.RESULT_MISSING, b"http: no such file")),
+             ("GET", "/panic", b"", (0xFFFFFFFF).to_bytes(4, "little")),
+             ("POST", "/echo", b'line1\n"quoted" <tag>', S.result_record(S.RESULT_STRING, b'line1\n"quoted" <tag>')),
+             ("GET", "/hello/", b"", b""), ("GET", "//hello", b"", b""), ("OPTIONS", "/hello", b"", b""), ("PATCH", "/hello", b"", b""),
+             ("GET", "/.well-known/health", b"", b"")]
+    routes = [("GET", "/hello", 0), ("GET", "/hello2", 0), ("PUT", "/hello", 0), ("POST", "/hello", 0), ("GET", "/params", 0),
+              ("DELETE", "/delete", 0), ("GET", "/greet", 0), ("GET", "/error", 0), ("GET", "/users/{id:[0-9]+}/posts/{slug}", 0),
+              ("GET", "/person/{name}", 1), ("GET", "/nil", 0), ("GET", "/file", 0), ("GET", "/panic", 0), ("POST", "/echo", 0)]
+    spec = S.TableSpec(schemas=[person], favicon=b"",
+                       routes=[S.Route(S.method_code(m), p, S.H_RESULT, schema_id=sid) for m, p, sid in routes])
+    return spec, cases
+
+
+@pytest.mark.gpu
+def test_reference_route_test_through_the_cpp_app(tmp_path):
+    import urllib.parse
+    from gofr_b200 import _abi
+    _abi.lib()
+    exe = str(tmp_path / "server_routes")
+    _compile(os.path.join(ROOT, "examples", "cpp", "server_routes.cpp"), exe)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr          # the C++ side checks status and body against the reference's expectations
+    got = [(int(l.split(" ")[0]), bytes.fromhex(l.split(" ")[1]) if len(l.split(" ")) > 1 else b"") for l in r.stdout.splitlines()]
+    spec, cases = _records()
+    reqs = []
+    for m, target, _body, rec in cases:
+        path, _, query = target.partition("?")
+        reqs.append(S.Req(S.method_code(m), urllib.parse.unquote_to_bytes(path), query.encode(), data=rec))
+    b = S.RequestBatch.pack(reqs)
+    for i in range(b.n):
+        b.trace_ids[i] = np.arange(i * 16, i * 16 + 16, dtype=np.uint8)
+    out, off, meta = O.OracleTable(spec).serve(b, DATE)
+    want = O.responses(out, off)
+    assert len(got) == len(want)
+    for i, ((st, by), w) in enumerate(zip(got, want)):
+        assert st == int(meta[i]) & 0xFFFF and by == w, (i, cases[i][:2])

@@ -135,6 +135,9 @@ def test_gpu_matches_oracle(which, n):
     meta, vars_ = eng.route_device(eng.upload(b))
     assert np.array_equal(m1, meta.cpu().numpy().view(np.uint32))
     assert np.array_equal(v1, vars_.cpu().numpy().view(np.uint32))
+    eng.set_chunk(30000)                     # several chunks through the host-buffer variant
+    m2, v2 = eng.route_host(b)
+    assert np.array_equal(m1, m2) and np.array_equal(v1, v2)
     eng.close()
 
 
