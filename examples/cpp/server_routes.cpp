@@ -68,7 +68,8 @@ int main() {
         {"GET", "/file", "", 404, "{\"error\":{\"message\":\"http: no such file\"}}\n"},
         {"GET", "/panic", "", 500, "{\"code\":500,\"message\":\"Some unexpected error has occurred\",\"status\":\"ERROR\"}\n"},
         {"POST", "/echo", "line1\n\"quoted\" <tag>", 200, "{\"data\":\"line1\\n\\\"quoted\\\" \\u003ctag\\u003e\"}\n"},
-        {"GET", "/hello/", "", 301, nullptr},
+        {"GET", "/hello/", "", 404, "{\"error\":{\"message\":\"http: no such file\"}}\n"},  // cleanPath keeps the slash; no StrictSlash
+        {"GET", "/a/../hello", "", 301, nullptr},
         {"GET", "//hello", "", 301, nullptr},
         {"OPTIONS", "/hello", "", 200, ""},
         {"PATCH", "/hello", "", 404, "{\"error\":{\"message\":\"http: no such file\"}}\n"},
