@@ -69,7 +69,7 @@ struct gofr_engine {
     uint32_t image_bytes = 0;
     // launch geometry
     uint32_t in_cap = 0, smem_bytes = 0;
-    int grid = 0, blocks_per_sm = 0, grpc_grid = 0, reqlog_grid = 0, http_grid = 0;
+    int grid = 0, blocks_per_sm = 0, grpc_grid = 0, reqlog_grid = 0, http_grid = 0, proto_grid = 0;
     uint32_t epoch = 0;
     // resident path scratch
     unsigned long long* d_state = nullptr;
@@ -723,6 +723,65 @@ int gofr_grpc_hello_device(gofr_engine* e, const uint8_t* d_in, const uint32_t* 
     }
     int rc = launch_grpc_hello(p, (int)std::min<size_t>((size_t)e->grpc_grid, tiles), st);
     if (rc != 0) { set_last_error("grpc kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
+    if (e->timing_on) { CUDA_TRY(cudaEventRecord(ev1, st)); e->timing.emplace_back(ev0, ev1); }
+    e->launches++;
+    return GOFR_OK;
+}
+
+int gofr_proto_encode_device(gofr_engine* e, const gofr_proto_field* fields, uint32_t n_fields, const uint8_t* d_rows,
+                             const uint32_t* d_row_off, uint32_t n, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off,
+                             uint32_t* d_meta, void* stream) {
+    if (!e || (n_fields && !fields) || (n && (!d_rows || !d_row_off || !d_out || !d_out_off || !d_meta))) return GOFR_ERR_INVALID;
+    if (n_fields > GOFR_PROTO_MAX_FIELDS) { set_last_error("a message type may have at most %d fields", GOFR_PROTO_MAX_FIELDS); return GOFR_ERR_CAPACITY; }
+    ProtoSchema S;
+    memset(&S, 0, sizeof S);
+    S.n_fields = n_fields;
+    for (uint32_t k = 0; k < n_fields; k++) {
+        const uint32_t num = fields[k].number, t = fields[k].type;
+        const bool known = (t >= GOFR_PB_DOUBLE && t <= GOFR_PB_STRING) || (t >= GOFR_PB_BYTES && t <= GOFR_PB_SINT64);
+        if (!known) { set_last_error("field %u: type %u is not a scalar proto3 type this encoder takes", num, t); return GOFR_ERR_UNSUPPORTED; }
+        if (num == 0 || num > 0x1FFFFFFFu || (num >= 19000 && num <= 19999)) { set_last_error("field number %u is not valid", num); return GOFR_ERR_INVALID; }
+        if (k && num <= fields[k - 1].number) { set_last_error("fields must be listed in ascending field-number order (%u after %u)", num, fields[k - 1].number); return GOFR_ERR_INVALID; }
+        const bool is64 = t == GOFR_PB_DOUBLE || t == GOFR_PB_INT64 || t == GOFR_PB_UINT64 || t == GOFR_PB_FIXED64 || t == GOFR_PB_SFIXED64 || t == GOFR_PB_SINT64;
+        const uint32_t wire = (t == GOFR_PB_STRING || t == GOFR_PB_BYTES) ? 2u : (t == GOFR_PB_DOUBLE || t == GOFR_PB_FIXED64 || t == GOFR_PB_SFIXED64) ? 1u
+                            : (t == GOFR_PB_FLOAT || t == GOFR_PB_FIXED32 || t == GOFR_PB_SFIXED32) ? 5u : 0u;
+        S.tag[k] = num << 3 | wire;
+        S.type[k] = (uint8_t)t;
+        S.fixed_bytes += is64 ? 8u : 4u;
+    }
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st)); return GOFR_OK; }
+    size_t tiles = (n + kServeThreads - 1) / kServeThreads;
+    if (tiles > e->state_tiles) {
+        cudaFree(e->d_state);
+        e->d_state = nullptr;
+        CUDA_TRY(cudaMalloc(&e->d_state, tiles * 8));
+        CUDA_TRY(cudaMemset(e->d_state, 0, tiles * 8));
+        e->state_tiles = tiles;
+    }
+    if (e->proto_grid <= 0) {
+        e->proto_grid = proto_max_grid(e->device);
+        if (e->proto_grid <= 0) { set_last_error("proto kernel cannot be resident"); return GOFR_ERR_CUDA; }
+    }
+    GrpcParams p;
+    memset(&p, 0, sizeof p);
+    p.in = d_rows; p.in_off = d_row_off; p.n = n; p.n_tiles = (uint32_t)tiles;
+    e->epoch = (e->epoch + 1) & 0xFFFFFu;
+    if (e->epoch == 0) e->epoch = 1;
+    p.epoch = e->epoch;
+    p.out = d_out; p.out_cap = out_cap; p.out_off = d_out_off; p.meta = d_meta;
+    p.tile_state = e->d_state; p.overflow = e->d_flag;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (e->timing_on) {
+        fold_timing(e);
+        CUDA_TRY(cudaEventCreate(&ev0));
+        CUDA_TRY(cudaEventCreate(&ev1));
+        CUDA_TRY(cudaEventRecord(ev0, st));
+    }
+    int rc = launch_proto_encode(p, S, (int)std::min<size_t>((size_t)e->proto_grid, tiles), st);
+    if (rc != 0) { set_last_error("proto kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
     if (e->timing_on) { CUDA_TRY(cudaEventRecord(ev1, st)); e->timing.emplace_back(ev0, ev1); }
     e->launches++;
     return GOFR_OK;

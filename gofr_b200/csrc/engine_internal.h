@@ -80,6 +80,15 @@ struct GrpcParams {
     uint32_t* overflow;
 };
 int launch_grpc_hello(const GrpcParams& p, int grid, void* stream);
+// message type of gofr_proto_encode_device (kernel parameter, by value); 32 = GOFR_PROTO_MAX_FIELDS
+struct ProtoSchema {
+    uint32_t n_fields;
+    uint32_t fixed_bytes;  // size of a row's fixed part
+    uint32_t tag[32];      // number << 3 | wire type
+    uint8_t type[32];      // GOFR_PB_*
+};
+int launch_proto_encode(const GrpcParams& p, const ProtoSchema& S, int grid, void* stream);
+int proto_max_grid(int device);
 
 struct RouteParams {
     const void* desc;

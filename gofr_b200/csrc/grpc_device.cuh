@@ -9,6 +9,7 @@
 // 1..2^29-1, unknown fields of every wire type skipped (groups balanced), the last occurrence of field 1 wins, proto3
 // strings must be valid UTF-8.  __host__ __device__ so tests/emu runs the same code on the CPU.
 #pragma once
+#include "engine_internal.h"
 #include "serve_device.cuh"
 
 namespace gofr {
@@ -124,6 +125,118 @@ GOFR_HD void hello_emit(const uint8_t* f, const HelloReq r, uint8_t* dst, uint32
     else { w.put4('W' | 'o' << 8 | 'r' << 16 | 'l' << 24); w.putc('d'); }
     w.reserve(2);
     w.putc('!');
+    w.finish();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// proto3 message encoder (gofr_proto_encode_device): proto.Marshal of the message a unary handler
+// returns (examples/grpc-server/grpc/hello_grpc.pb.go:73-89 → grpc-go's proto codec, protobuf-go v1.32.0) plus the
+// 5-byte length-prefixed-message header, for flat messages with scalar fields.  Fields are emitted in the order given
+// (= field-number order), a field holding its zero value is skipped (proto3 implicit presence), strings must be valid
+// UTF-8.  Rows use the GOFR_H_ROW layout (fixed words, then string bytes).
+// ---------------------------------------------------------------------------------------------------------------
+static_assert(GOFR_PROTO_MAX_FIELDS == 32, "ProtoSchema (engine_internal.h) is sized for 32 fields");
+
+struct ProtoMsg {
+    uint32_t status;   // GOFR_GRPC_OK / GOFR_GRPC_BAD_UTF8 / GOFR_GRPC_BAD_ROW
+    uint32_t out_len;  // 5 + message bytes (0 on error)
+};
+
+GOFR_HD bool proto_is64(uint32_t t) {
+    return t == GOFR_PB_DOUBLE || t == GOFR_PB_INT64 || t == GOFR_PB_UINT64 || t == GOFR_PB_FIXED64 || t == GOFR_PB_SFIXED64 ||
+           t == GOFR_PB_SINT64;
+}
+GOFR_HD uint32_t proto_wire(uint32_t t) {
+    if (t == GOFR_PB_STRING || t == GOFR_PB_BYTES) return 2;
+    if (t == GOFR_PB_DOUBLE || t == GOFR_PB_FIXED64 || t == GOFR_PB_SFIXED64) return 1;
+    if (t == GOFR_PB_FLOAT || t == GOFR_PB_FIXED32 || t == GOFR_PB_SFIXED32) return 5;
+    return 0;
+}
+GOFR_HD uint32_t varint_len64(uint64_t v) {
+    uint32_t n = 1;
+    while (v >= 0x80) { v >>= 7; n++; }
+    return n;
+}
+// the varint payload of a varint-typed field (what follows the tag), from the row's words
+GOFR_HD uint64_t proto_varint_value(uint32_t t, uint32_t w0, uint32_t w1) {
+    const uint64_t v64 = (uint64_t)w0 | (uint64_t)w1 << 32;
+    if (t == GOFR_PB_INT64 || t == GOFR_PB_UINT64) return v64;
+    if (t == GOFR_PB_SINT64) return (v64 << 1) ^ (uint64_t)((int64_t)v64 >> 63);
+    if (t == GOFR_PB_INT32 || t == GOFR_PB_ENUM) return (uint64_t)(int64_t)(int32_t)w0;  // negative: sign-extended, 10 bytes
+    if (t == GOFR_PB_SINT32) return (uint32_t)((w0 << 1) ^ (uint32_t)((int32_t)w0 >> 31));
+    if (t == GOFR_PB_BOOL) return w0 ? 1u : 0u;
+    return w0;  // uint32
+}
+
+// size pass: validates the row and returns the exact frame length
+GOFR_HD ProtoMsg proto_size(const ProtoSchema& S, const uint8_t* row, uint32_t rn, bool aligned) {
+    ProtoMsg m = {GOFR_GRPC_OK, 0};
+    if (!aligned || rn < S.fixed_bytes) { m.status = GOFR_GRPC_BAD_ROW; return m; }
+    const uint32_t* w = (const uint32_t*)row;
+    uint32_t wi = 0, spos = S.fixed_bytes, len = 0;
+    for (uint32_t k = 0; k < S.n_fields; k++) {
+        const uint32_t t = S.type[k], tl = varint_len(S.tag[k]);
+        const uint32_t w0 = w[wi], w1 = proto_is64(t) ? w[wi + 1] : 0u;
+        wi += proto_is64(t) ? 2u : 1u;
+        const uint32_t wire = S.tag[k] & 7u;
+        if (wire == 2) {
+            if (w0 > rn - spos) { m.status = GOFR_GRPC_BAD_ROW; return m; }
+            if (t == GOFR_PB_STRING && !grpc_utf8_ok(row + spos, w0)) { m.status = GOFR_GRPC_BAD_UTF8; return m; }
+            if (w0) len += tl + varint_len(w0) + w0;
+            spos += w0;
+        } else if (wire == 1) {
+            if (w0 | w1) len += tl + 8;
+        } else if (wire == 5) {
+            if (w0) len += tl + 4;
+        } else {
+            if (proto_is64(t) ? (w0 | w1) != 0 : w0 != 0) len += tl + varint_len64(proto_varint_value(t, w0, w1));
+        }
+    }
+    m.out_len = 5 + len;
+    return m;
+}
+
+GOFR_HD void proto_put_varint(Writer& w, uint64_t v) {
+    for (;;) {
+        const uint32_t b = (uint32_t)v & 0x7Fu;
+        v >>= 7;
+        w.putc(v ? b | 0x80u : b);
+        if (!v) break;
+    }
+}
+
+// emit pass: the frame at dst (arbitrary alignment inside the packed output)
+GOFR_HD void proto_emit(const ProtoSchema& S, const uint8_t* row, const ProtoMsg m, uint8_t* dst, uint32_t* stage_col) {
+    if (!m.out_len) return;
+    Writer w;
+    w.init(dst, stage_col);
+    const uint32_t plen = m.out_len - 5;
+    w.put4(0u | (plen >> 24) << 8 | ((plen >> 16) & 0xFF) << 16 | ((plen >> 8) & 0xFF) << 24);  // 00, be32[0..2]
+    w.putc(plen & 0xFF);
+    const uint32_t* rw = (const uint32_t*)row;
+    uint32_t wi = 0, spos = S.fixed_bytes;
+    for (uint32_t k = 0; k < S.n_fields; k++) {
+        const uint32_t t = S.type[k];
+        const uint32_t w0 = rw[wi], w1 = proto_is64(t) ? rw[wi + 1] : 0u;
+        wi += proto_is64(t) ? 2u : 1u;
+        const uint32_t wire = S.tag[k] & 7u;
+        w.reserve(6);  // tag (<= 5 bytes) + payload (<= 10) + carried bytes: at most 5 new words before the next check
+        if (wire == 2) {
+            if (w0) {
+                proto_put_varint(w, S.tag[k]);
+                proto_put_varint(w, w0);
+                w.copy<false>(row + spos, w0);
+            }
+            spos += w0;
+        } else if (wire == 1) {
+            if (w0 | w1) { proto_put_varint(w, S.tag[k]); w.put4(w0); w.put4(w1); }
+        } else if (wire == 5) {
+            if (w0) { proto_put_varint(w, S.tag[k]); w.put4(w0); }
+        } else if (proto_is64(t) ? (w0 | w1) != 0 : w0 != 0) {
+            proto_put_varint(w, S.tag[k]);
+            proto_put_varint(w, proto_varint_value(t, w0, w1));
+        }
+    }
     w.finish();
 }
 

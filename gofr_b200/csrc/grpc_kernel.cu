@@ -25,8 +25,9 @@ struct GrpcShared {
     __align__(16) uint8_t in[kGrpcStage + 32];
 };
 
-__global__ void __launch_bounds__(GT, 12) grpc_hello_kernel(const GrpcParams p) {
-    __shared__ __align__(16) GrpcShared sh;
+// The tile loop shared by the two frame codecs (Hello request → response, row → proto3 message).
+template <class Codec>
+__device__ __forceinline__ void frame_tiles(const GrpcParams& p, const Codec& cd, GrpcShared& sh) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         mbar_init(&sh.bar, 1);
@@ -53,8 +54,8 @@ __global__ void __launch_bounds__(GT, 12) grpc_hello_kernel(const GrpcParams p) 
             parity ^= 1;
             base = sh.in - lo;
         }
-        HelloReq r = {GOFR_GRPC_OK, 0, 0, 0};
-        if (valid) r = hello_parse(base + fo, fn);
+        typename Codec::R r = cd.none();
+        if (valid) r = cd.parse(base + fo, fn, fo);
 
         uint32_t incl = r.out_len;
 #pragma unroll
@@ -85,13 +86,52 @@ __global__ void __launch_bounds__(GT, 12) grpc_hello_kernel(const GrpcParams p) 
             p.meta[i] = r.status;
             if (i == p.n - 1) p.out_off[p.n] = (uint32_t)(tile_base + excl + r.out_len);
         }
-        if (fits && valid && r.out_len) hello_emit(base + fo, r, p.out + tile_base + excl, &sh.stage[tid]);
+        if (fits && valid && r.out_len) cd.emit(base + fo, r, p.out + tile_base + excl, &sh.stage[tid]);
     }
+}
+
+struct HelloCodec {
+    typedef HelloReq R;
+    __device__ R none() const { return HelloReq{GOFR_GRPC_OK, 0, 0, 0}; }
+    __device__ R parse(const uint8_t* f, uint32_t fn, uint32_t) const { return hello_parse(f, fn); }
+    __device__ void emit(const uint8_t* f, const R& r, uint8_t* dst, uint32_t* col) const { hello_emit(f, r, dst, col); }
+};
+
+struct ProtoCodec {
+    typedef ProtoMsg R;
+    const ProtoSchema& S;
+    __device__ R none() const { return ProtoMsg{GOFR_GRPC_OK, 0}; }
+    __device__ R parse(const uint8_t* row, uint32_t rn, uint32_t off) const { return proto_size(S, row, rn, (off & 3u) == 0); }
+    __device__ void emit(const uint8_t* row, const R& r, uint8_t* dst, uint32_t* col) const { proto_emit(S, row, r, dst, col); }
+};
+
+__global__ void __launch_bounds__(GT, 12) grpc_hello_kernel(const GrpcParams p) {
+    __shared__ __align__(16) GrpcShared sh;
+    frame_tiles(p, HelloCodec{}, sh);
+}
+
+// rows → proto3 messages (gofr_proto_encode_device): the same pipeline, the row in place of the request frame
+__global__ void __launch_bounds__(GT, 8) proto_encode_kernel(const GrpcParams p, const __grid_constant__ ProtoSchema S) {
+    __shared__ __align__(16) GrpcShared sh;
+    frame_tiles(p, ProtoCodec{S}, sh);
 }
 
 int launch_grpc_hello(const GrpcParams& p, int grid, void* stream) {
     grpc_hello_kernel<<<grid, GT, 0, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
+}
+
+int launch_proto_encode(const GrpcParams& p, const ProtoSchema& S, int grid, void* stream) {
+    proto_encode_kernel<<<grid, GT, 0, (cudaStream_t)stream>>>(p, S);
+    return (int)cudaGetLastError();
+}
+
+int proto_max_grid(int device) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, proto_encode_kernel, GT, 0) != cudaSuccess) return -1;
+    return nb * prop.multiProcessorCount;
 }
 
 int grpc_max_grid(int device) {

@@ -130,6 +130,25 @@ class Engine:
                                                 vars_.data_ptr(), st.cuda_stream), "gofr_route_device")
         return meta[:b.n], vars_[:b.n]
 
+    def proto_encode_device(self, fields, rows: np.ndarray, row_off: np.ndarray, out_cap: Optional[int] = None, stream=None):
+        """gofr_proto_encode_device: rows (spec.pack_proto_rows) → packed gRPC frames.  Returns (out uint8, out_off int32
+        view of uint32[n+1], meta int32 view of uint32[n]) on the device."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        n = len(row_off) - 1
+        ft = (_abi.ProtoField * max(len(fields), 1))(*[_abi.ProtoField(f.number, f.type) for f in fields])
+        d_rows = torch.from_numpy(np.ascontiguousarray(rows)).to(dev)
+        d_off = torch.from_numpy(row_off.view(np.int32)).to(dev)
+        cap = out_cap if out_cap is not None else int(rows.size) * 3 + 32 * n * max(len(fields), 1) + 64
+        out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        off = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        meta = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+        _abi.check(_abi.lib().gofr_proto_encode_device(self._e, ft, len(fields), d_rows.data_ptr(), d_off.data_ptr(), n,
+                                                       out.data_ptr(), cap, off.data_ptr(), meta.data_ptr(), st.cuda_stream),
+                   "gofr_proto_encode_device")
+        return out, off, meta[:n]
+
     def route_host(self, batch: S.RequestBatch):
         """gofr_batch_route: the same for a batch in host memory → (meta uint32[n], vars uint32[n, 8])."""
         rb = _abi.ReqBatch(desc=batch.desc.ctypes.data, trace_ids=batch.trace_ids.ctypes.data, arena=batch.arena.ctypes.data,

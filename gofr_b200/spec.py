@@ -250,6 +250,52 @@ class LogBatch:
         return LogBatch(desc, ids, np.frombuffer(bytes(arena), dtype=np.uint8).copy())
 
 
+# protobuf field types (google.protobuf.FieldDescriptorProto.Type numbers) the proto3 encoder takes
+(PB_DOUBLE, PB_FLOAT, PB_INT64, PB_UINT64, PB_INT32, PB_FIXED64, PB_FIXED32, PB_BOOL, PB_STRING) = range(1, 10)
+PB_BYTES, PB_UINT32, PB_ENUM, PB_SFIXED32, PB_SFIXED64, PB_SINT32, PB_SINT64 = 12, 13, 14, 15, 16, 17, 18
+PB_64BIT = (PB_DOUBLE, PB_INT64, PB_UINT64, PB_FIXED64, PB_SFIXED64, PB_SINT64)
+GRPC_OK, GRPC_COMPRESSED, GRPC_BAD_LENGTH, GRPC_BAD_PROTO, GRPC_BAD_UTF8, GRPC_BAD_ROW = range(6)
+
+
+@dataclass
+class ProtoField:
+    number: int
+    type: int
+
+
+def pack_proto_rows(fields: Sequence[ProtoField], messages: Sequence[Sequence]) -> "tuple[np.ndarray, np.ndarray]":
+    """Rows for gofr_proto_encode_device: per field (in the order given = field-number order) 64-bit kinds two LE words,
+    the others one (floats and doubles as their IEEE bits, strings / bytes as their length), then the string bytes.
+    Values: ints (any sign, taken modulo the width), bools, floats, bytes / str.  Returns (rows uint8, row_off uint32);
+    8 bytes of padding follow the last row (the device copies with aligned word loads)."""
+    import struct
+    blob = bytearray()
+    off = [0]
+    for msg in messages:
+        words = bytearray()
+        tail = bytearray()
+        for f, v in zip(fields, msg):
+            if f.type == PB_DOUBLE:
+                words += struct.pack("<d", v) if isinstance(v, float) else int(v).to_bytes(8, "little")
+            elif f.type == PB_FLOAT:
+                words += struct.pack("<f", v) if isinstance(v, float) else int(v).to_bytes(4, "little")
+            elif f.type in PB_64BIT:
+                words += (int(v) & 0xFFFFFFFFFFFFFFFF).to_bytes(8, "little")
+            elif f.type in (PB_STRING, PB_BYTES):
+                b = v.encode("utf-8", "surrogateescape") if isinstance(v, str) else bytes(v)
+                words += len(b).to_bytes(4, "little")
+                tail += b
+            elif f.type == PB_BOOL:
+                words += (1 if v else 0).to_bytes(4, "little")
+            else:
+                words += (int(v) & 0xFFFFFFFF).to_bytes(4, "little")
+        blob += words + tail
+        blob += b"\0" * ((-len(blob)) % 4)
+        off.append(len(blob))
+    blob += b"\0" * 8
+    return np.frombuffer(bytes(blob), dtype=np.uint8).copy(), np.array(off, dtype=np.uint32)
+
+
 def http_date(unix_seconds: int) -> bytes:
     """net/http appendTime: IMF-fixdate, always 29 bytes."""
     import time

@@ -268,9 +268,38 @@ void gofr_free_pinned(void*);
 
 /* gRPC unary Hello (config 5): length-prefixed HelloRequest frames in, length-prefixed HelloResponse frames out,
  * packed; frame i of the input starts at in_off[i].  meta[i] = 0 ok, else a GOFR_GRPC_* error (frame emitted empty). */
-enum { GOFR_GRPC_OK = 0, GOFR_GRPC_COMPRESSED = 1, GOFR_GRPC_BAD_LENGTH = 2, GOFR_GRPC_BAD_PROTO = 3, GOFR_GRPC_BAD_UTF8 = 4 };
+enum { GOFR_GRPC_OK = 0, GOFR_GRPC_COMPRESSED = 1, GOFR_GRPC_BAD_LENGTH = 2, GOFR_GRPC_BAD_PROTO = 3, GOFR_GRPC_BAD_UTF8 = 4,
+       GOFR_GRPC_BAD_ROW = 5 };
 int gofr_grpc_hello_device(gofr_engine*, const uint8_t* d_in, const uint32_t* d_in_off, uint32_t n, uint8_t* d_out,
                            uint64_t out_cap, uint32_t* d_out_off, uint32_t* d_meta, void* stream);
+
+/* proto3 message encoder: proto.Marshal of the message a unary gRPC handler returns + the
+ * 5-byte length-prefixed-message header grpc-go puts in front (examples/grpc-server/grpc/hello_grpc.pb.go:73-89 hands
+ * the response to grpc-go; protobuf-go v1.32.0, grpc-go v1.60.1), for a batch of flat messages with scalar fields.
+ *   fields     the message type: (number, GOFR_PB_* type) in ascending field-number order — the order proto.Marshal
+ *              emits them; at most GOFR_PROTO_MAX_FIELDS
+ *   d_rows     row i = d_rows[d_row_off[i] .. d_row_off[i+1]), offsets multiples of 4, GOFR_H_ROW layout: per field
+ *              (same order) 64-bit types two LE words (lo, hi), the others one (float / double: IEEE bits; string /
+ *              bytes: byte length), then the string bytes in field order.  The buffer must stay readable for 8 bytes
+ *              past the last row.
+ *   output     packed frames in row order, d_out_off[n+1]; d_meta[i] = GOFR_GRPC_OK, GOFR_GRPC_BAD_UTF8 (a string
+ *              field is not valid UTF-8: proto.Marshal fails, the RPC fails — no frame), GOFR_GRPC_BAD_ROW (malformed
+ *              row from the host shim — no frame).
+ * Zero values are not emitted (proto3 implicit presence; -0.0 is not a zero value); negative int32 / enum values take
+ * ten bytes; sint32 / sint64 are zigzag encoded. */
+enum {
+    GOFR_PB_DOUBLE = 1, GOFR_PB_FLOAT = 2, GOFR_PB_INT64 = 3, GOFR_PB_UINT64 = 4, GOFR_PB_INT32 = 5, GOFR_PB_FIXED64 = 6,
+    GOFR_PB_FIXED32 = 7, GOFR_PB_BOOL = 8, GOFR_PB_STRING = 9, GOFR_PB_BYTES = 12, GOFR_PB_UINT32 = 13, GOFR_PB_ENUM = 14,
+    GOFR_PB_SFIXED32 = 15, GOFR_PB_SFIXED64 = 16, GOFR_PB_SINT32 = 17, GOFR_PB_SINT64 = 18
+}; /* google.protobuf.FieldDescriptorProto.Type */
+#define GOFR_PROTO_MAX_FIELDS 32
+typedef struct gofr_proto_field {
+    uint32_t number; /* 1 .. 2^29-1 */
+    uint32_t type;   /* GOFR_PB_* */
+} gofr_proto_field;
+int gofr_proto_encode_device(gofr_engine*, const gofr_proto_field* fields, uint32_t n_fields, const uint8_t* d_rows,
+                             const uint32_t* d_row_off, uint32_t n, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off,
+                             uint32_t* d_meta, void* stream);
 
 /* Stage 1 of the split API for routes whose closure stays on the host (GOFR_H_HOST): everything mux.Router.ServeHTTP
  * and the middleware chain decide before handler.ServeHTTP runs (pkg/gofr/http/router.go:14,30-33;

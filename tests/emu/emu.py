@@ -37,6 +37,8 @@ def lib():
                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
         _lib.emu_grpc_hello.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                         C.c_void_p, C.c_uint32]
+        _lib.emu_proto_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
+                                          C.c_void_p, C.c_void_p, C.c_uint32]
         _lib.emu_serve_slots.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p,
                                          C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.emu_route.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -95,6 +97,22 @@ def request_log(batch, misalign: int = 0):
     if rc != 0:
         raise RuntimeError("emu output capacity too small")
     return out, off
+
+
+def proto_encode(fields, rows, row_off, misalign: int = 0):
+    """proto_size + proto_emit (grpc_device.cuh) on the CPU → (out, out_off, meta)"""
+    n = len(row_off) - 1
+    ft = np.array([[f.number, f.type] for f in fields], dtype=np.uint32).reshape(-1)
+    cap = int(rows.size) * 3 + 32 * n * max(len(fields), 1) + 64 + misalign
+    out = np.full(cap, 0xEE, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    meta = np.zeros(max(n, 1), dtype=np.uint32)
+    rows = np.ascontiguousarray(rows)
+    rc = lib().emu_proto_encode(ft.ctypes.data, len(fields), rows.ctypes.data, row_off.ctypes.data, n, out.ctypes.data, cap,
+                                off.ctypes.data, meta.ctypes.data, misalign)
+    if rc != 0:
+        raise RuntimeError("emu output capacity too small")
+    return out, off, meta[:n]
 
 
 def grpc_hello(frames, in_off, misalign: int = 0):

@@ -145,8 +145,37 @@ extern "C" int emu_reqlog(const uint8_t* desc, const uint8_t* ids, const uint8_t
     return 0;
 }
 
-// ---- gRPC Hello (config 5): the same grpc_device.cuh code the CUDA kernel runs ----
+// ---- proto3 encoder (gofr_proto_encode_device): proto_size / proto_emit as the CUDA kernel runs them; the schema is
+// built the way engine.cu builds it ----
 #include "../../gofr_b200/csrc/grpc_device.cuh"
+
+extern "C" int emu_proto_encode(const uint32_t* fields, uint32_t n_fields, const uint8_t* rows, const uint32_t* row_off, uint32_t n,
+                                uint8_t* out, uint64_t out_cap, uint32_t* out_off, uint32_t* meta, uint32_t start_misalign) {
+    ProtoSchema S;
+    memset(&S, 0, sizeof S);
+    S.n_fields = n_fields;
+    for (uint32_t k = 0; k < n_fields; k++) {
+        const uint32_t t = fields[2 * k + 1];
+        S.tag[k] = fields[2 * k] << 3 | proto_wire(t);
+        S.type[k] = (uint8_t)t;
+        S.fixed_bytes += proto_is64(t) ? 8u : 4u;
+    }
+    uint32_t stage[GOFR_STAGE_WORDS];
+    uint64_t pos = start_misalign;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint8_t* r = rows + row_off[i];
+        ProtoMsg m = proto_size(S, r, row_off[i + 1] - row_off[i], (row_off[i] & 3u) == 0);
+        out_off[i] = (uint32_t)pos;
+        meta[i] = m.status;
+        if (pos + m.out_len > out_cap) return -1;
+        proto_emit(S, r, m, out + pos, stage);
+        pos += m.out_len;
+    }
+    out_off[n] = (uint32_t)pos;
+    return 0;
+}
+
+// ---- gRPC Hello (config 5): the same grpc_device.cuh code the CUDA kernel runs ----
 
 extern "C" int emu_grpc_hello(const uint8_t* in, const uint32_t* in_off, uint32_t n, uint8_t* out, uint64_t out_cap,
                               uint32_t* out_off, uint32_t* meta, uint32_t start_misalign) {

@@ -19,7 +19,7 @@ _lib = None
 
 
 def build() -> None:
-    srcs = ["gofr_oracle.c", "orc_bind.c", "orc_grpc.c", "gofr_oracle.h", "orc_internal.h"]
+    srcs = ["gofr_oracle.c", "orc_bind.c", "orc_grpc.c", "orc_reqlog.c", "orc_http.c", "orc_proto.c", "gofr_oracle.h", "orc_internal.h", "Makefile"]
     odir = os.path.join(_ROOT, "oracle")
     if os.path.exists(_LIB_PATH):
         so_m = os.path.getmtime(_LIB_PATH)
@@ -48,6 +48,8 @@ def lib():
         L.orc_request_log.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
         L.orc_grpc_hello.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                      C.c_int]
+        L.orc_proto_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
+                                       C.c_void_p]
         for name in ("orc_json_string", "orc_clean_path", "orc_escape_path"):
             getattr(L, name).argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
         L.orc_json_int.argtypes = [C.c_int64, C.c_char_p, C.c_int]
@@ -208,3 +210,18 @@ def grpc_hello(frames: np.ndarray, in_off: np.ndarray, nthreads: int = 1):
     if rc != 0:
         raise RuntimeError("oracle output capacity too small")
     return out, off, meta
+
+
+def proto_encode(fields, rows: np.ndarray, row_off: np.ndarray):
+    """orc_proto_encode: proto.Marshal + gRPC length prefix per row → (out, out_off, meta)."""
+    n = len(row_off) - 1
+    ft = np.array([[f.number, f.type] for f in fields], dtype=np.uint32).reshape(-1)
+    cap = int(rows.size) * 3 + 32 * n * max(len(fields), 1) + 64
+    out = np.zeros(cap, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    meta = np.zeros(max(n, 1), dtype=np.uint32)
+    rows = np.ascontiguousarray(rows)
+    rc = lib().orc_proto_encode(ft.ctypes.data, len(fields), rows.ctypes.data, row_off.ctypes.data, n, out.ctypes.data, cap,
+                                off.ctypes.data, meta.ctypes.data)
+    assert rc == 0
+    return out, off, meta[:n]
