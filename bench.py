@@ -269,7 +269,7 @@ def run_secondary(args):
     from tests import oracle as O
     date = S.http_date(DATE_UNIX)
     w = args.workload
-    n = {"config3": 65536, "config4": 262144, "config5": 1 << 20, "reqlog": 1 << 18, "http": 1 << 20}[w] if args.requests == (1 << 20) and w != "config5" else args.requests
+    n = {"config3": 65536, "config4": 262144, "config5": 1 << 20, "proto": 1 << 20, "reqlog": 1 << 18, "http": 1 << 20}[w] if args.requests == (1 << 20) and w not in ("config5", "proto") else args.requests
     cpu = None
     if w == "reqlog":
         # the RequestLog line of middleware.Logging for the config-2 stream
@@ -320,6 +320,50 @@ def run_secondary(args):
         O.http_parse(raw, off)
         cpu = {"value": n / (time.perf_counter() - t0), "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"one pass over the same {n} messages, scalar C restatement (oracle/orc_http.c)"}
+    elif w == "proto":
+        # rows of a 9-field message (string, int64, sint32, bool, double, bytes, fixed32, int32, string) → gRPC frames
+        rng = np.random.default_rng(synth.SEED)
+        fields = [S.ProtoField(1, S.PB_STRING), S.ProtoField(2, S.PB_INT64), S.ProtoField(3, S.PB_SINT32), S.ProtoField(4, S.PB_BOOL),
+                  S.ProtoField(5, S.PB_DOUBLE), S.ProtoField(7, S.PB_BYTES), S.ProtoField(9, S.PB_FIXED32), S.ProtoField(300, S.PB_INT32),
+                  S.ProtoField(301, S.PB_STRING)]
+        # rows built vectorised: 12 fixed words + a 16-byte name + 8 bytes + a 12-byte tag = 84 bytes each
+        fixed = np.zeros((n, 12), dtype=np.uint32)
+        r = rng.integers(0, 1 << 62, (n, 4), dtype=np.int64)
+        fixed[:, 0] = 16
+        fixed[:, 1] = (r[:, 0] & 0xFFFFFFFF).astype(np.uint32); fixed[:, 2] = ((r[:, 0] >> 32) & 0x3FFFFF).astype(np.uint32)
+        fixed[:, 3] = (r[:, 1] % 2001 - 1000).astype(np.int32).view(np.uint32)
+        fixed[:, 4] = (r[:, 1] >> 20 & 1).astype(np.uint32)
+        dbl = ((r[:, 2] % 100000) / 8.0).astype(np.float64).view(np.uint64)
+        fixed[:, 5] = (dbl & 0xFFFFFFFF).astype(np.uint32); fixed[:, 6] = (dbl >> 32).astype(np.uint32)
+        fixed[:, 7] = 8
+        fixed[:, 8] = (r[:, 3] & 0xFFFFFFFF).astype(np.uint32)
+        fixed[:, 9] = (-(r[:, 3] >> 40) % 50000).astype(np.int32).view(np.uint32)
+        fixed[:, 10] = 12
+        tail = (rng.integers(0, 26, (n, 36), dtype=np.uint8) + 97).astype(np.uint8)
+        rows = np.concatenate([fixed.view(np.uint8).reshape(n, 48), tail], axis=1).reshape(-1)
+        rows = np.concatenate([rows, np.zeros(64, np.uint8)])
+        off = (np.arange(n + 1, dtype=np.uint64) * 84).astype(np.uint32)
+        eng = Engine(Table(synth.config1_spec()), 0)
+        eng.set_timing(True)
+        # parity of the bench's own input (first 4096 rows)
+        o_out, o_off, o_meta = O.proto_encode(fields, rows, off[:4097])
+        d_in = torch.from_numpy(rows).cuda()
+        d_off = torch.from_numpy(off.view(np.int32)).cuda()
+        cap = n * 128
+        d_out = torch.zeros(cap + 64, dtype=torch.uint8, device="cuda")
+        d_ooff = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+        d_meta = torch.zeros(n, dtype=torch.int32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        ft = (_abi.ProtoField * len(fields))(*[_abi.ProtoField(f.number, f.type) for f in fields])
+
+        def step():
+            _abi.check(_abi.lib().gofr_proto_encode_device(eng._e, ft, len(fields), d_in.data_ptr(), d_off.data_ptr(), n,
+                                                           d_out.data_ptr(), cap, d_ooff.data_ptr(), d_meta.data_ptr(), st), "proto")
+        step()
+        torch.cuda.synchronize()
+        assert d_out[:int(o_off[4096])].cpu().numpy().tobytes() == o_out[:int(o_off[4096])].tobytes(), "bench output differs from the oracle"
+        in_bytes = int(off[n]) + 4 * (n + 1)
+        get_out = lambda: int(d_ooff[n].item())
     elif w == "config5":
         frames, off = synth.config5_frames(n)
         eng = Engine(Table(synth.config1_spec()), 0)
@@ -403,7 +447,7 @@ def main():
     ap.add_argument("--layout", default="slots", choices=["packed", "slots"],
                     help="resident measurement: packed offsets (gofr_serve_device) or one 528-byte slot per response "
                          "(gofr_serve_device_slots)")
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5", "reqlog", "http"],
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5", "proto", "reqlog", "http"],
                     help="config2 is the BASELINE metric line; the others are secondary measurements (resident only)")
     args = ap.parse_args()
     if args.warmup < 3:

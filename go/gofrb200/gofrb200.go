@@ -254,3 +254,18 @@ func bytesPtr(b []byte) *C.uint8_t {
 	}
 	return (*C.uint8_t)(unsafe.Pointer(&b[0]))
 }
+
+// ProtoField is one field of a flat proto3 message type: (number, FieldDescriptorProto.Type).
+type ProtoField struct{ Number, Type uint32 }
+
+// ProtoEncodeDevice marshals n rows (GOFR_H_ROW layout, resident in HBM) as messages of the given type and frames them
+// for gRPC (gofr_proto_encode_device): what proto.Marshal + grpc-go's msgHeader do for a unary handler's response.
+func (e *Engine) ProtoEncodeDevice(fields []ProtoField, dRows, dRowOff unsafe.Pointer, n int, dOut unsafe.Pointer, outCap uint64,
+	dOutOff, dMeta unsafe.Pointer, stream unsafe.Pointer) error {
+	var fp *C.gofr_proto_field
+	if len(fields) > 0 {
+		fp = (*C.gofr_proto_field)(unsafe.Pointer(&fields[0]))
+	}
+	return check(C.gofr_proto_encode_device(e.e, fp, C.uint32_t(len(fields)), (*C.uint8_t)(dRows), (*C.uint32_t)(dRowOff), C.uint32_t(n),
+		(*C.uint8_t)(dOut), C.uint64_t(outCap), (*C.uint32_t)(dOutOff), (*C.uint32_t)(dMeta), stream), "gofr_proto_encode_device")
+}
