@@ -47,3 +47,29 @@ raw, roff = synth.http_messages(900, seed_msgs=[b"GET /a HTTP/1.0\r\nHost: h\r\n
 eng.http_parse_device(raw, roff)
 torch.cuda.synchronize()
 print("reqlog + grpc + http ok")
+# additions of the end of round 1: proto3 encoder, host-buffer routing, slot host path, string outcomes, front-end
+fields = [S.ProtoField(1, S.PB_STRING), S.ProtoField(2, S.PB_INT64), S.ProtoField(3, S.PB_SINT32), S.ProtoField(5, S.PB_DOUBLE),
+          S.ProtoField(7, S.PB_BYTES), S.ProtoField(300, S.PB_INT32)]
+msgs = [["n" * (k % 70), k * 977 - 5000, (k % 41) - 20, float(k % 7), bytes([k & 0xFF]) * (k % 9), -k if k % 3 else 0] for k in range(700)]
+msgs[13][0] = b"\xff"
+rows, roff2 = S.pack_proto_rows(fields, msgs)
+eng.proto_encode_device(fields, rows, roff2)
+torch.cuda.synchronize()
+spec = S.TableSpec(routes=[S.Route(S.M_GET, "/hello", S.H_RESULT), S.Route(S.M_GET, "/u/{id}", S.H_RESULT)])
+reqs = [S.Req(S.M_GET, b"/hello" if k % 2 else b"/u/%d" % k, data=S.result_record(S.RESULT_STRING if k % 3 else S.RESULT_ERROR, b"<v %d>" % k * (k % 30)))
+        for k in range(500)]
+b2 = S.RequestBatch.pack(reqs)
+e2 = Engine(Table(spec), 0)
+e2.set_chunk(128)
+e2.route_host(b2)
+so = np.zeros((b2.n, 1024), dtype=np.uint8); sl = np.zeros(b2.n, dtype=np.uint32); sm = np.zeros(b2.n, dtype=np.uint32)
+e2.serve_host_slots(b2, date, 1024, so.reshape(-1), sl, sm)
+from gofr_b200.frontend import Frontend
+fe = Frontend(e2, max_batch=16, max_wait_us=100, slot_bytes=1024, max_request_bytes=2048)
+for k in range(40):
+    r = reqs[k]
+    fe.serve(r.method, r.path, r.query, r.data)
+fe.close()
+e2.close()
+torch.cuda.synchronize()
+print("proto + route_host + slots host + front-end ok")
