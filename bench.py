@@ -198,14 +198,19 @@ def pick_cpu_threads(run_with):
     q = cpu_quota()
     if q and math.ceil(q) < ncpu:
         cands.append(max(1, math.ceil(q)))
-    best, best_dt = cands[0], None
+    best, best_rate = cands[0], None
     for c in cands:
         run_with(c)                       # touch the pages / spin the threads up
+        # at least half a second per candidate: a single pass can fit into what is left of one 100 ms quota period and
+        # look unthrottled
         t0 = time.perf_counter()
-        run_with(c)
-        dt = time.perf_counter() - t0
-        if best_dt is None or dt < best_dt:
-            best, best_dt = c, dt
+        passes = 0
+        while passes < 3 or time.perf_counter() - t0 < 0.5:
+            run_with(c)
+            passes += 1
+        rate = passes / (time.perf_counter() - t0)
+        if best_rate is None or rate > best_rate:
+            best, best_rate = c, rate
     return best, q
 
 
@@ -436,7 +441,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--requests", type=int, default=1 << 20, help="requests per GPU per step")
-    ap.add_argument("--ref-requests", type=int, default=1 << 18, help="requests per step of the CPU reference arm")
+    ap.add_argument("--ref-requests", type=int, default=1 << 20, help="requests per step of the CPU reference arm")
     ap.add_argument("--cpu-sample", type=int, default=1 << 19, help="requests in the cpu_baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer measurement (default: --steps)")
     ap.add_argument("--chunk", type=int, default=65536)

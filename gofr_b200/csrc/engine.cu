@@ -746,7 +746,7 @@ int gofr_proto_encode_device(gofr_engine* e, const gofr_proto_field* fields, uin
         const uint32_t wire = (t == GOFR_PB_STRING || t == GOFR_PB_BYTES) ? 2u : (t == GOFR_PB_DOUBLE || t == GOFR_PB_FIXED64 || t == GOFR_PB_SFIXED64) ? 1u
                             : (t == GOFR_PB_FLOAT || t == GOFR_PB_FIXED32 || t == GOFR_PB_SFIXED32) ? 5u : 0u;
         S.tag[k] = num << 3 | wire;
-        S.type[k] = (uint8_t)t;
+        S.cls[k] = (uint8_t)proto_class(t);
         S.fixed_bytes += is64 ? 8u : 4u;
     }
     std::lock_guard<std::mutex> g(e->mu);

@@ -85,8 +85,41 @@ struct ProtoSchema {
     uint32_t n_fields;
     uint32_t fixed_bytes;  // size of a row's fixed part
     uint32_t tag[32];      // number << 3 | wire type
-    uint8_t type[32];      // GOFR_PB_*
+    uint8_t cls[32];       // PC_* bits derived from the GOFR_PB_* type once, on the host (proto_class below)
 };
+#if defined(__CUDACC__)
+#define GOFR_INTERNAL_HD __host__ __device__ inline
+#else
+#define GOFR_INTERNAL_HD inline
+#endif
+GOFR_INTERNAL_HD bool proto_is64(uint32_t t) {  // GOFR_PB_DOUBLE, INT64, UINT64, FIXED64, SFIXED64, SINT64
+    return t == 1 || t == 3 || t == 4 || t == 6 || t == 16 || t == 18;
+}
+GOFR_INTERNAL_HD uint32_t proto_wire(uint32_t t) {
+    if (t == 9 || t == 12) return 2;             // STRING, BYTES
+    if (t == 1 || t == 6 || t == 16) return 1;   // DOUBLE, FIXED64, SFIXED64
+    if (t == 2 || t == 7 || t == 15) return 5;   // FLOAT, FIXED32, SFIXED32
+    return 0;
+}
+// What the per-message loops need to know about a field type, decided once per call on the host: the device tests bits
+// instead of walking compare chains per field per message.
+enum : uint32_t {
+    PC_WIRE = 7u,       // wire type (0 varint, 1 fixed64, 2 length-delimited, 5 fixed32)
+    PC_64 = 8u,         // two row words
+    PC_ZIGZAG = 16u,    // sint32 / sint64
+    PC_SIGNEXT = 32u,   // int32 / enum: negative values are sign-extended to 64 bits
+    PC_UTF8 = 64u,      // string: must be valid UTF-8
+    PC_BOOL = 128u,
+};
+GOFR_INTERNAL_HD uint32_t proto_class(uint32_t t) {
+    uint32_t c = proto_wire(t);
+    if (proto_is64(t)) c |= PC_64;
+    if (t == 17 || t == 18) c |= PC_ZIGZAG;   // SINT32, SINT64
+    if (t == 5 || t == 14) c |= PC_SIGNEXT;   // INT32, ENUM
+    if (t == 9) c |= PC_UTF8;                 // STRING
+    if (t == 8) c |= PC_BOOL;                 // BOOL
+    return c;
+}
 int launch_proto_encode(const GrpcParams& p, const ProtoSchema& S, int grid, void* stream);
 int proto_max_grid(int device);
 

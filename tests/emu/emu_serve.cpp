@@ -157,7 +157,7 @@ extern "C" int emu_proto_encode(const uint32_t* fields, uint32_t n_fields, const
     for (uint32_t k = 0; k < n_fields; k++) {
         const uint32_t t = fields[2 * k + 1];
         S.tag[k] = fields[2 * k] << 3 | proto_wire(t);
-        S.type[k] = (uint8_t)t;
+        S.cls[k] = (uint8_t)proto_class(t);
         S.fixed_bytes += proto_is64(t) ? 8u : 4u;
     }
     uint32_t stage[GOFR_STAGE_WORDS];
