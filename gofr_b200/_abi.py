@@ -71,7 +71,8 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    # GOFR_LIB_PATH: load a prebuilt variant of the library instead (A/B measurements of two builds in one GPU session)
+    path = os.environ.get("GOFR_LIB_PATH") or _build.build()
     L = C.CDLL(path)
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
     L.gofr_table_create.argtypes = [C.POINTER(vp), u32]
