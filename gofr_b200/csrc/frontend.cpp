@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <vector>
 #include <time.h>
 
 #include <linux/futex.h>
@@ -73,6 +74,7 @@ struct gofr_frontend_batch {
     std::atomic<uint32_t> round{0};       // bumped at recycle; round r is complete when done[g] == r + 1
     std::atomic<int64_t> first_ns{0};     // arrival of the round's first request (0: not stored yet)
     uint32_t closed_count = 0;            // count at close (written by the dispatcher before done[] is published)
+    char date[29] = {0};                  // the round's Date header (a response too long for its slot is served again, alone)
     int rc = GOFR_OK;
     Word* done = nullptr;                 // per group of kGroup slots: last completed round + 1
     Word* woke = nullptr;                 // per group: somebody already woke this group's children
@@ -167,6 +169,7 @@ static void dispatcher(gofr_frontend* f) {
         int64_t now = f->fixed_clock.load(std::memory_order_relaxed);
         if (!now) { struct timespec ts; clock_gettime(CLOCK_REALTIME, &ts); now = (int64_t)ts.tv_sec; }
         gofr_format_http_date(now, in.date);
+        memcpy(x.date, in.date, sizeof x.date);
         gofr_slot_batch out;
         memset(&out, 0, sizeof out);
         out.out = x.out; out.slot_bytes = f->slot_bytes; out.out_len = x.out_len; out.meta = x.meta;
@@ -316,8 +319,11 @@ int gofr_frontend_serve(gofr_frontend* f, uint8_t method, const uint8_t* path, u
     const uint32_t len = x.out_len[i];
     if (meta) *meta = x.meta[i];
     *resp_len = len;
+    bool alone = false;
+    char date[29];
     if (rc == GOFR_OK) {
-        if (len > f->slot_bytes || len > resp_cap) rc = GOFR_ERR_CAPACITY;  // the caller serves it through the packed path
+        if (len > resp_cap) rc = GOFR_ERR_CAPACITY;
+        else if (len > f->slot_bytes) { alone = true; memcpy(date, x.date, sizeof date); }  // did not fit its slot: see below
         else if (len) memcpy(resp, x.out + (size_t)i * f->slot_bytes, len);
     }
     // ---- the last producer to leave reopens the batch ----
@@ -330,6 +336,27 @@ int gofr_frontend_serve(gofr_frontend* f, uint8_t method, const uint8_t* path, u
         x.claim.store(0, std::memory_order_release);
         bump(&f->room_seq);
         bump(&f->disp_seq);
+    }
+    if (alone) {
+        // The slot layout reports the length of a response that does not fit but writes nothing: serve this one request
+        // again through the packed call, straight into the caller's buffer, with the Date of the batch it belonged to.
+        std::vector<uint8_t> arena((size_t)need + 64, 0);
+        if (path_len) memcpy(arena.data(), path, path_len);
+        if (query_len) memcpy(arena.data() + path_len, query, query_len);
+        if (data_len) memcpy(arena.data() + (((size_t)path_len + query_len + 3u) & ~(size_t)3u), data, data_len);
+        d.arena_off = 0;
+        gofr_req_batch in;
+        memset(&in, 0, sizeof in);
+        in.desc = &d; in.trace_ids = trace_id; in.arena = arena.data(); in.arena_bytes = arena.size(); in.n = 1;
+        memcpy(in.date, date, sizeof date);
+        uint32_t off2[2] = {0, 0}, meta1 = 0;
+        gofr_resp_batch out;
+        memset(&out, 0, sizeof out);
+        out.out = resp; out.out_cap = resp_cap; out.out_off = off2; out.meta = &meta1;
+        gofr_ticket t = 0;
+        rc = gofr_batch_submit(f->eng, &in, &out, &t);
+        if (rc == GOFR_OK) rc = gofr_batch_wait(f->eng, t);
+        if (rc == GOFR_OK) { *resp_len = off2[1]; if (meta) *meta = meta1; }
     }
     return rc;
 }

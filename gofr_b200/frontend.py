@@ -43,12 +43,14 @@ class Frontend:
         return int(b.value), int(r.value)
 
     def serve(self, method: int, path: bytes, query: bytes = b"", data: bytes = b"", trace_id: bytes = b"\0" * 16,
-              flags: int = 0) -> Tuple[bytes, int]:
-        """One request → (response bytes, meta).  Blocks until the batch it joined has been served."""
+              flags: int = 0, resp_cap: int = 0) -> Tuple[bytes, int]:
+        """One request → (response bytes, meta).  Blocks until the batch it joined has been served.  resp_cap: size of
+        the caller's buffer (default: one slot); a response longer than the slot but within resp_cap is served alone."""
         assert len(trace_id) == 16
-        buf = C.create_string_buffer(self.slot_bytes)
+        cap = resp_cap or self.slot_bytes
+        buf = C.create_string_buffer(cap)
         n, meta = C.c_uint32(), C.c_uint32()
         _abi.check(_abi.lib().gofr_frontend_serve(self._f, method, path, len(path), query, len(query), flags, data, len(data),
-                                                  trace_id, buf, self.slot_bytes, C.byref(n), C.byref(meta)),
+                                                  trace_id, buf, cap, C.byref(n), C.byref(meta)),
                    "gofr_frontend_serve")
         return buf.raw[:n.value], int(meta.value)

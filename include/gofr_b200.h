@@ -353,7 +353,8 @@ int gofr_requestlog_device(gofr_engine*, const gofr_log_desc* d_desc, const uint
  * gofr_batch_submit_slots and wakes the callers.  A small ring of pinned batches rotates (one fills while another is in
  * flight; a batch whose callers are slow to pick up their responses is skipped).  The Date header of a batch is the
  * wall clock at dispatch (gofr_frontend_set_clock pins it for tests).
- * serve returns GOFR_ERR_CAPACITY (with *resp_len set) when the response does not fit slot_bytes or resp_cap.
+ * A response longer than slot_bytes is served again on its own through the packed call (same Date), into resp; serve
+ * returns GOFR_ERR_CAPACITY (with *resp_len set) only when the response does not fit resp_cap.
  * destroy may only be called when no thread is inside gofr_frontend_serve. */
 typedef struct gofr_frontend gofr_frontend;
 int gofr_frontend_create(gofr_frontend** out, gofr_engine*, uint32_t max_batch, uint32_t max_wait_us, uint32_t slot_bytes,

@@ -17,25 +17,48 @@ extern "C" {
 void* gofr_alloc_pinned(size_t n) { return calloc(1, n ? n : 1); }
 void gofr_free_pinned(void* p) { free(p); }
 void gofr_format_http_date(int64_t t, char out[29]) { snprintf(out, 29, "%028lld", (long long)t); }
+static uint32_t stub_response(const gofr_req_batch* in, uint32_t i, uint8_t* o) {
+    const gofr_req_desc& d = in->desc[i];
+    const uint8_t* p = in->arena + d.arena_off;
+    const uint8_t* body = in->arena + ((d.arena_off + d.path_len + d.query_len + 3u) & ~3u);
+    uint32_t w = 0;
+    memcpy(o + w, in->date, 28); w += 28;
+    memcpy(o + w, in->trace_ids + (size_t)i * 16, 16); w += 16;
+    o[w++] = d.method; o[w++] = d.flags;
+    memcpy(o + w, p, (size_t)d.path_len + d.query_len); w += d.path_len + d.query_len;
+    memcpy(o + w, body, d.data_len); w += d.data_len;
+    return w;
+}
 int gofr_batch_submit_slots(gofr_engine*, const gofr_req_batch* in, gofr_slot_batch* out, gofr_ticket* t) {
     g_batches++;
     uint64_t l = g_largest.load();
     while (in->n > l && !g_largest.compare_exchange_weak(l, in->n)) {}
     for (uint32_t i = 0; i < in->n; i++) {
-        const gofr_req_desc& d = in->desc[i];
-        const uint8_t* p = in->arena + d.arena_off;
-        const uint8_t* body = in->arena + ((d.arena_off + d.path_len + d.query_len + 3u) & ~3u);
-        uint8_t* o = out->out + (size_t)i * out->slot_bytes;
-        uint32_t w = 0;
-        memcpy(o + w, in->date, 28); w += 28;
-        memcpy(o + w, in->trace_ids + (size_t)i * 16, 16); w += 16;
-        o[w++] = d.method; o[w++] = d.flags;
-        memcpy(o + w, p, (size_t)d.path_len + d.query_len); w += d.path_len + d.query_len;
-        memcpy(o + w, body, d.data_len); w += d.data_len;
+        uint8_t tmp[512];
+        const uint32_t w = stub_response(in, i, tmp);
         out->out_len[i] = w;
-        out->meta[i] = 200u | (uint32_t)d.path_len << 16;
+        if (w <= out->slot_bytes) memcpy(out->out + (size_t)i * out->slot_bytes, tmp, w);  // too long: length only, like the engine
+        out->meta[i] = 200u | (uint32_t)in->desc[i].path_len << 16;
     }
     *t = 1;
+    return 0;
+}
+static std::atomic<uint64_t> g_alone{0};
+int gofr_batch_submit(gofr_engine*, const gofr_req_batch* in, gofr_resp_batch* out, gofr_ticket* t) {
+    g_alone++;
+    uint64_t pos = 0;
+    for (uint32_t i = 0; i < in->n; i++) {
+        out->out_off[i] = (uint32_t)pos;
+        uint8_t tmp[512];
+        const uint32_t w = stub_response(in, i, tmp);
+        if (pos + w > out->out_cap) return GOFR_ERR_CAPACITY;
+        memcpy(out->out + pos, tmp, w);
+        out->meta[i] = 200u | (uint32_t)in->desc[i].path_len << 16;
+        pos += w;
+    }
+    out->out_off[in->n] = (uint32_t)pos;
+    out->out_bytes = pos;
+    *t = 2;
     return 0;
 }
 int gofr_batch_wait(gofr_engine*, gofr_ticket) { return 0; }
@@ -45,7 +68,9 @@ int main(int argc, char** argv) {
     const int T = argc > 1 ? atoi(argv[1]) : 16, R = argc > 2 ? atoi(argv[2]) : 200;
     const uint32_t max_batch = argc > 3 ? (uint32_t)atoi(argv[3]) : 8, wait_us = argc > 4 ? (uint32_t)atoi(argv[4]) : 100;
     gofr_frontend* fe = nullptr;
-    if (gofr_frontend_create(&fe, (gofr_engine*)0x1, max_batch, wait_us, 256, 128)) return 2;
+    // a fifth argument of 64 makes every response longer than its slot: each one is then served alone (packed stub)
+    const uint32_t slot = argc > 5 ? (uint32_t)atoi(argv[5]) : 256;
+    if (gofr_frontend_create(&fe, (gofr_engine*)0x1, max_batch, wait_us, slot, 128)) return 2;
     gofr_frontend_set_clock(fe, 1700000000);
     std::atomic<uint64_t> bad{0};
     std::vector<std::thread> th;
@@ -83,8 +108,8 @@ int main(int argc, char** argv) {
         if (rc != GOFR_ERR_CAPACITY) bad++;
     }
     gofr_frontend_destroy(fe);
-    printf("{\"requests\": %llu, \"batches\": %llu, \"stub_batches\": %llu, \"largest\": %llu, \"bad\": %llu}\n",
+    printf("{\"requests\": %llu, \"batches\": %llu, \"stub_batches\": %llu, \"largest\": %llu, \"alone\": %llu, \"bad\": %llu}\n",
            (unsigned long long)reqs, (unsigned long long)batches, (unsigned long long)g_batches.load(),
-           (unsigned long long)g_largest.load(), (unsigned long long)bad.load());
+           (unsigned long long)g_largest.load(), (unsigned long long)g_alone.load(), (unsigned long long)bad.load());
     return bad.load() || reqs != (uint64_t)T * R ? 1 : 0;
 }

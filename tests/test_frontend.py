@@ -84,8 +84,10 @@ def test_frontend_matches_oracle(which, max_batch, wait_us, threads):
 
 
 @pytest.mark.gpu
-def test_frontend_capacity_and_reuse():
-    """a response longer than the slot is reported (length set, GOFR_ERR_CAPACITY) and the front-end keeps serving"""
+def test_frontend_oversize_responses_and_reuse():
+    """a response longer than its slot is served again alone through the packed call (same bytes as the oracle); only a
+    response longer than the caller's buffer is an error; the front-end keeps serving afterwards"""
+    import ctypes as C
     import torch
     assert torch.cuda.is_available()
     from gofr_b200 import _abi
@@ -93,23 +95,56 @@ def test_frontend_capacity_and_reuse():
     from gofr_b200.frontend import Frontend
     spec, batch = synth.config2_spec(), synth.config2_batch(40)
     o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
+    ob = o1.tobytes()
     eng = Engine(Table(spec), 0)
     reqs = _requests(batch)
-    fe = Frontend(eng, max_batch=4, max_wait_us=50, slot_bytes=64, max_request_bytes=2048)   # every response is longer
+    fe = Frontend(eng, max_batch=4, max_wait_us=50, slot_bytes=64, max_request_bytes=2048)   # every response is longer than 64
     fe.set_clock(CLOCK)
+    # Frontend.serve hands in a buffer of slot_bytes: too small for the caller as well → CAPACITY with the length set
     with pytest.raises(_abi.GofrError):
         fe.serve(*reqs[0])
+    # with room on the caller's side the oversize response arrives through the packed path
+    got = _run_raw(fe, reqs[:12], 4, resp_cap=2048)
+    for i, (resp, meta) in enumerate(got):
+        assert resp == ob[int(f1[i]):int(f1[i + 1])] and meta == int(m1[i]), i
     with pytest.raises(_abi.GofrError):           # request larger than max_request_bytes: refused before it is queued
         Frontend(eng, max_batch=4, max_wait_us=50, slot_bytes=1024, max_request_bytes=16).serve(0, b"/" + b"a" * 200)
     fe.close()
     fe = Frontend(eng, max_batch=4, max_wait_us=50, slot_bytes=1024, max_request_bytes=2048)
     fe.set_clock(CLOCK)
-    ob = o1.tobytes()
     for i in (0, 1, 2):
         resp, meta = fe.serve(*reqs[i])
         assert resp == ob[int(f1[i]):int(f1[i + 1])] and meta == int(m1[i])
     fe.close()
     eng.close()
+
+
+def _run_raw(fe, reqs, n_threads, resp_cap):
+    """like _run, with a caller buffer larger than the slot (calls the C entry point directly)"""
+    import ctypes as C
+    from gofr_b200 import _abi
+    got = [None] * len(reqs)
+    errs = []
+
+    def work(t):
+        try:
+            for i in range(t, len(reqs), n_threads):
+                m, p, q, d, tid, fl = reqs[i]
+                buf = C.create_string_buffer(resp_cap)
+                n, meta = C.c_uint32(), C.c_uint32()
+                _abi.check(_abi.lib().gofr_frontend_serve(fe._f, m, p, len(p), q, len(q), fl, d, len(d), tid, buf, resp_cap,
+                                                          C.byref(n), C.byref(meta)), "gofr_frontend_serve")
+                got[i] = (buf.raw[:n.value], int(meta.value))
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in th) and not errs, errs
+    return got
 
 
 def test_frontend_argument_checks():
@@ -127,7 +162,7 @@ def test_frontend_argument_checks():
     L.gofr_frontend_destroy(None)
 
 
-@pytest.mark.parametrize("args", ["16 200 8 100", "32 100 64 50", "8 100 1 0", "64 50 16 100000", "4 50 1000 200"])
+@pytest.mark.parametrize("args", ["16 200 8 100", "32 100 64 50", "8 100 1 0", "64 50 16 100000", "4 50 1000 200", "16 100 8 100 64"])
 def test_frontend_fan_in_fan_out_tsan(args):
     """no GPU: the batching logic itself (frontend.cpp) against a stub engine, under ThreadSanitizer — every producer
     gets the response built from ITS request, batches never exceed max_batch, nothing races."""
@@ -146,5 +181,7 @@ def test_frontend_fan_in_fan_out_tsan(args):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ThreadSanitizer" not in r.stderr, r.stderr
     res = json.loads(r.stdout.strip().splitlines()[-1])
-    t, n, max_batch, _ = (int(v) for v in args.split())
+    t, n, max_batch = (int(v) for v in args.split()[:3])
     assert res["bad"] == 0 and res["requests"] == t * n and res["largest"] <= max_batch
+    if len(args.split()) > 4:                       # 64-byte slots: the responses that carry a body do not fit and went the packed way, alone
+        assert res["alone"] >= t * n // 3
