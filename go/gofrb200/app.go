@@ -1,0 +1,357 @@
+// UNVERIFIED SOURCE (see gofrb200.go: no Go toolchain exists where this repository is built and tested).
+//
+// The app-level shim: gofr.New / GET / PUT / POST / DELETE / Context.Param / PathParam / Bind / Run with the reference's
+// signatures (pkg/gofr/gofr.go:49-73,152-177; pkg/gofr/context.go:12-54; pkg/gofr/handler.go:12), handlers unchanged —
+// arbitrary closures — served through the split API:
+//
+//	Engine.RouteHost   gofr_batch_route   mux match + middleware decisions + mux.Vars spans      (GPU)
+//	the closures       Handler(c)         only for requests whose handler the reference would call (host, this file)
+//	Engine.Serve       gofr_batch_submit  Responder.Respond + net/http framing                    (GPU)
+//
+// include/gofr_b200.hpp is the same flow in C++, compiled and tested (examples/cpp/server_routes.cpp is the reference's
+// TestGofr_ServerRoutes written against it); keep the two in step.
+package gofrb200
+
+/*
+#include <stdlib.h>
+#include "gofr_b200.h"
+*/
+import "C"
+
+import (
+	"encoding/binary"
+	"encoding/json"
+	"errors"
+	"io"
+	"net/http"
+	"reflect"
+	"strings"
+	"time"
+	"unsafe"
+)
+
+const (
+	resultData    = 0
+	resultError   = 1
+	resultNil     = 2
+	resultMissing = 3
+	resultBoth    = 4
+	resultString  = 5
+	hResult       = 12 // GOFR_H_RESULT
+)
+
+// Context is what a handler sees (pkg/gofr/context.go:12-27): the request behind the reference's Request interface.
+type Context struct {
+	req        *http.Request
+	body       []byte
+	pathParams map[string]string
+}
+
+func (c *Context) Param(key string) string     { return c.req.URL.Query().Get(key) } // http/request.go:28-30
+func (c *Context) PathParam(key string) string { return c.pathParams[key] }          // http/request.go:36-38
+func (c *Context) Bind(i interface{}) error    { return json.Unmarshal(c.body, &i) } // http/request.go:40-47
+
+// HandlerFunc is the reference's gofr.Handler (pkg/gofr/handler.go:12); `Handler` in this package is the declarative
+// description of gofrb200.go.
+type HandlerFunc func(c *Context) (interface{}, error)
+
+type route struct {
+	method, pattern string
+	fn              HandlerFunc
+	schemaID        uint32
+	rtype           reflect.Type
+	vars            []string
+}
+
+// App mirrors gofr.App for the HTTP path.
+type App struct {
+	table   *Table
+	engine  *Engine
+	routes  []route
+	schemas map[reflect.Type]uint32
+}
+
+// New is gofr.New() (pkg/gofr/gofr.go:49-73) without config, container and servers other than the HTTP path.
+func New() (*App, error) {
+	t, err := NewTable(0) // GOFR_FRAME_WIRE
+	if err != nil {
+		return nil, err
+	}
+	return &App{table: t, schemas: map[reflect.Type]uint32{}}, nil
+}
+
+// GET / PUT / POST / DELETE (pkg/gofr/gofr.go:152-169).  returns: optionally one sample value of the struct type the
+// handler returns, so that its fields can be registered before the table is sealed (Go needs no such hint because
+// encoding/json reflects at run time; the GPU encoder wants the field list up front).
+func (a *App) GET(pattern string, h HandlerFunc, returns ...interface{})    { a.add("GET", pattern, h, returns...) }
+func (a *App) PUT(pattern string, h HandlerFunc, returns ...interface{})    { a.add("PUT", pattern, h, returns...) }
+func (a *App) POST(pattern string, h HandlerFunc, returns ...interface{})   { a.add("POST", pattern, h, returns...) }
+func (a *App) DELETE(pattern string, h HandlerFunc, returns ...interface{}) { a.add("DELETE", pattern, h, returns...) }
+
+// add is App.add (pkg/gofr/gofr.go:171-177): registration order is match priority.
+func (a *App) add(method, pattern string, h HandlerFunc, returns ...interface{}) {
+	r := route{method: method, pattern: pattern, fn: h, vars: templateVars(pattern)}
+	if len(returns) > 0 {
+		r.rtype = reflect.TypeOf(returns[0])
+		id, ok := a.schemas[r.rtype]
+		if !ok {
+			id = uint32(len(a.schemas) + 1)
+			a.schemas[r.rtype] = id
+		}
+		r.schemaID = id
+	}
+	a.routes = append(a.routes, r)
+}
+
+// templateVars lists the variable names of a mux template in order ("{name}" or "{name:pattern}", nested braces allowed).
+func templateVars(pattern string) []string {
+	var names []string
+	level, start := 0, 0
+	for i := 0; i < len(pattern); i++ {
+		switch pattern[i] {
+		case '{':
+			if level == 0 {
+				start = i + 1
+			}
+			level++
+		case '}':
+			if level > 0 {
+				level--
+				if level == 0 {
+					inner := pattern[start:i]
+					if k := strings.IndexByte(inner, ':'); k >= 0 {
+						inner = inner[:k]
+					}
+					names = append(names, inner)
+				}
+			}
+		}
+	}
+	return names
+}
+
+// fieldKind maps a Go field type to GOFR_F_*; 0 = not supported by the GPU encoder.
+func fieldKind(t reflect.Type) uint8 {
+	switch t.Kind() {
+	case reflect.Int64:
+		return 1
+	case reflect.Int32:
+		return 2
+	case reflect.Bool:
+		return 3
+	case reflect.String:
+		return 4
+	case reflect.Int:
+		return 5
+	}
+	return 0
+}
+
+// Run is App.Run (pkg/gofr/gofr.go:90-126) minus the listener: struct types, routes, default routes, seal, engine.
+func (a *App) Run(device int, favicon []byte) error {
+	for t, id := range a.schemas {
+		n := t.NumField()
+		fields := make([]C.gofr_field_desc, 0, n)
+		var keep []unsafe.Pointer
+		for i := 0; i < n; i++ {
+			f := t.Field(i)
+			kind := fieldKind(f.Type)
+			if kind == 0 || f.PkgPath != "" {
+				return errors.New("gofrb200: " + t.String() + "." + f.Name + ": field type not supported by the GPU encoder")
+			}
+			name, opts, _ := strings.Cut(f.Tag.Get("json"), ",")
+			var d C.gofr_field_desc
+			d.go_name = C.CString(f.Name)
+			d.json_name = C.CString(name)
+			keep = append(keep, unsafe.Pointer(d.go_name), unsafe.Pointer(d.json_name))
+			d.kind = C.uint8_t(kind)
+			if strings.Contains(","+opts+",", ",omitempty,") {
+				d.omitempty = 1
+			}
+			fields = append(fields, d)
+		}
+		tn := C.CString(t.String())
+		keep = append(keep, unsafe.Pointer(tn))
+		var fp *C.gofr_field_desc
+		if n > 0 {
+			fp = &fields[0]
+		}
+		err := check(C.gofr_table_add_schema(a.table.t, C.uint32_t(id), tn, fp, C.uint32_t(n)), "gofr_table_add_schema")
+		for _, p := range keep {
+			C.free(p)
+		}
+		if err != nil {
+			return err
+		}
+	}
+	for _, r := range a.routes {
+		if _, err := a.table.AddRoute(r.method, r.pattern, Handler{Kind: hResult, SchemaID: r.schemaID}); err != nil {
+			return err
+		}
+	}
+	if err := a.table.AddDefaultRoutes(favicon); err != nil {
+		return err
+	}
+	if err := a.table.Seal(); err != nil {
+		return err
+	}
+	e, err := NewEngine(a.table, device)
+	a.engine = e
+	return err
+}
+
+// RouteHost is gofr_batch_route: stage 1 for a batch in host memory.
+func (e *Engine) RouteHost(b *Batch, meta, vars []uint32) error {
+	var in C.gofr_req_batch
+	in.desc = &b.Desc[0]
+	in.trace_ids = (*C.uint8_t)(unsafe.Pointer(&b.TraceIDs[0]))
+	in.arena = (*C.uint8_t)(unsafe.Pointer(&b.Arena[0]))
+	in.arena_bytes = C.uint64_t(len(b.Arena))
+	in.n = C.uint32_t(len(b.Desc))
+	return check(C.gofr_batch_route(e.e, &in, (*C.uint32_t)(unsafe.Pointer(&meta[0])), (*C.uint32_t)(unsafe.Pointer(&vars[0]))),
+		"gofr_batch_route")
+}
+
+func pad4(b []byte) []byte {
+	for len(b)%4 != 0 {
+		b = append(b, 0)
+	}
+	return b
+}
+
+func u32(b []byte, v uint32) []byte { return binary.LittleEndian.AppendUint32(b, v) }
+
+// encodeRow lays a struct value out as a GOFR_H_ROW row: fixed words in field order, then the string bytes.
+func encodeRow(v reflect.Value) (fixed, strs []byte) {
+	for i := 0; i < v.NumField(); i++ {
+		f := v.Field(i)
+		switch f.Kind() {
+		case reflect.Int64, reflect.Int:
+			fixed = binary.LittleEndian.AppendUint64(fixed, uint64(f.Int()))
+		case reflect.Int32:
+			fixed = u32(fixed, uint32(int32(f.Int())))
+		case reflect.Bool:
+			if f.Bool() {
+				fixed = u32(fixed, 1)
+			} else {
+				fixed = u32(fixed, 0)
+			}
+		case reflect.String:
+			fixed = u32(fixed, uint32(f.Len()))
+			strs = append(strs, f.String()...)
+		}
+	}
+	return fixed, strs
+}
+
+// resultRecord describes (data, err) for Responder.Respond (pkg/gofr/http/responder.go:19-62) as a GOFR_H_RESULT record.
+func (a *App) resultRecord(r *route, data interface{}, err error) []byte {
+	var rec []byte
+	rv := reflect.ValueOf(data)
+	isStruct := data != nil && r.rtype != nil && rv.Type() == r.rtype
+	switch {
+	case isStruct && err != nil:
+		fixed, strs := encodeRow(rv)
+		msg := err.Error()
+		rec = u32(u32(rec, resultBoth), uint32(len(msg)))
+		rec = append(append(append(rec, fixed...), msg...), strs...)
+	case isStruct:
+		fixed, strs := encodeRow(rv)
+		rec = append(append(u32(rec, resultData), fixed...), strs...)
+	case err != nil:
+		kind := uint32(resultError)
+		if errors.Is(err, http.ErrMissingFile) {
+			kind = resultMissing
+		}
+		msg := err.Error()
+		rec = append(u32(u32(rec, kind), uint32(len(msg))), msg...)
+	case data == nil:
+		rec = u32(rec, resultNil)
+	default:
+		if s, ok := data.(string); ok {
+			rec = append(u32(u32(rec, resultString), uint32(len(s))), s...)
+		} else {
+			rec = u32(rec, 0xFFFFFFFF) // a type the GPU encoder was not told about: answered like a panic; serve it on the host instead
+		}
+	}
+	return rec
+}
+
+// ServeBatch is router.ServeHTTP (pkg/gofr/httpServer.go:29-33) for a batch of parsed requests; response i is the wire
+// bytes the reference's server would have written for reqs[i].  traceIDs: 16 bytes per request (the tracer's span ids).
+func (a *App) ServeBatch(reqs []*http.Request, traceIDs []byte, now time.Time) ([][]byte, error) {
+	n := len(reqs)
+	if n == 0 {
+		return nil, nil
+	}
+	b := &Batch{Desc: make([]C.gofr_req_desc, n), TraceIDs: traceIDs}
+	bodies := make([][]byte, n)
+	for i, r := range reqs {
+		d := &b.Desc[i]
+		d.arena_off = C.uint32_t(len(b.Arena))
+		d.path_len = C.uint16_t(len(r.URL.Path))
+		d.query_len = C.uint16_t(len(r.URL.RawQuery))
+		d.method = C.uint8_t(MethodCode(r.Method))
+		if r.URL.ForceQuery {
+			d.flags = 1 // GOFR_REQ_FORCE_QUERY
+		}
+		b.Arena = pad4(append(append(b.Arena, r.URL.Path...), r.URL.RawQuery...))
+		if r.Body != nil {
+			bodies[i], _ = io.ReadAll(r.Body)
+		}
+	}
+	b.Arena = append(b.Arena, make([]byte, 64)...)
+	meta := make([]uint32, n)
+	vars := make([]uint32, n*8) // GOFR_MAX_PATH_VARS
+	if err := a.engine.RouteHost(b, meta, vars); err != nil {
+		return nil, err
+	}
+	// the closures, only where the reference would have called one
+	arena := make([]byte, 0, len(b.Arena))
+	var bound uint64 = 4096
+	for i, r := range reqs {
+		var rec []byte
+		status, rid := meta[i]&0xFFFF, int(meta[i]>>16)
+		if status == 0 && rid < len(a.routes) {
+			rt := &a.routes[rid]
+			c := &Context{req: r, body: bodies[i], pathParams: map[string]string{}}
+			for k, name := range rt.vars {
+				if k >= 8 { // GOFR_MAX_PATH_VARS
+					break
+				}
+				if v := vars[i*8+k]; v != 0xFFFFFFFF {
+					c.pathParams[name] = r.URL.Path[(v & 0xFFFF) : (v&0xFFFF)+(v>>16)]
+				}
+			}
+			rec = a.call(rt, c)
+		}
+		d := &b.Desc[i]
+		d.arena_off = C.uint32_t(len(arena))
+		d.data_len = C.uint32_t(len(rec))
+		arena = pad4(append(append(arena, r.URL.Path...), r.URL.RawQuery...))
+		arena = pad4(append(arena, rec...))
+		bound += uint64(C.gofr_table_response_bound(a.table.t, C.uint32_t(d.path_len), C.uint32_t(d.query_len), d.data_len))
+	}
+	b.Arena = append(arena, make([]byte, 64)...)
+	out := make([]byte, bound)
+	off := make([]uint32, n+1)
+	if _, err := a.engine.Serve(b, now, out, off, meta); err != nil {
+		return nil, err
+	}
+	resp := make([][]byte, n)
+	for i := range resp {
+		resp[i] = out[off[i]:off[i+1]]
+	}
+	return resp, nil
+}
+
+// call runs one closure; a panic is answered like the reference's panicRecovery (middleware/logger.go:91-114).
+func (a *App) call(rt *route, c *Context) (rec []byte) {
+	defer func() {
+		if recover() != nil {
+			rec = u32(nil, 0xFFFFFFFF)
+		}
+	}()
+	data, err := rt.fn(c)
+	return a.resultRecord(rt, data, err)
+}
