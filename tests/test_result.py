@@ -217,3 +217,33 @@ def test_gpu_string_outcome():
         assert np.array_equal(m_s.cpu().numpy().view(np.uint32), m1)
         assert np.array_equal(ln_s.cpu().numpy().view(np.uint32), np.diff(f1.astype(np.int64)).astype(np.uint32))
     eng.close()
+
+
+# ---- property test: any byte string a closure may return, three ways (oracle, device code on the CPU, Python's json) ----
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+from tests.test_independent_checks import _go_json_string_from_python  # noqa: E402
+
+
+@settings(max_examples=120, deadline=None)
+@given(st.lists(st.one_of(st.binary(max_size=60),
+                          st.text(alphabet=st.characters(blacklist_categories=("Cs",)), max_size=40).map(lambda s: s.encode("utf-8")),
+                          st.sampled_from([b"<>&", b"\xe2\x80\xa8", b"\xff\xfe", b"\\\"", b"\x00\x1f\x7f", b"x" * 700])),
+                min_size=1, max_size=12), st.integers(0, 15))
+def test_string_outcome_property(strings, mis):
+    spec = _string_spec(S.FRAME_BODY)
+    b = S.RequestBatch.pack([S.Req(S.M_GET, b"/hello", data=S.result_record(S.RESULT_STRING if k % 4 else S.RESULT_ERROR, s))
+                             for k, s in enumerate(strings)])
+    o1, f1, m1 = O.OracleTable(spec).serve(b, DATE)
+    o2, f2, m2 = emu.serve(Table(spec).serialize(), b, DATE, misalign=mis)
+    assert np.array_equal(m1, m2) and np.array_equal(f1 + mis, f2)
+    assert o1[:f1[-1]].tobytes() == o2[mis:f2[-1]].tobytes()
+    for k, (s, r) in enumerate(zip(strings, O.responses(o1, f1))):
+        try:
+            text = s.decode("utf-8")
+        except UnicodeDecodeError:
+            continue                      # invalid UTF-8 becomes U+FFFD per byte sequence: covered by the oracle's own vectors
+        if "\\" in text:
+            continue                      # see test_independent_checks: the textual replacement trick needs no backslashes
+        want = _go_json_string_from_python(text)
+        assert r == (b'{"data":' if k % 4 else b'{"error":{"message":') + want + (b"}\n" if k % 4 else b"}}\n"), k
