@@ -69,7 +69,7 @@ struct gofr_engine {
     uint32_t image_bytes = 0;
     // launch geometry
     uint32_t in_cap = 0, smem_bytes = 0;
-    int grid = 0, blocks_per_sm = 0, grpc_grid = 0, reqlog_grid = 0, http_grid = 0, proto_grid = 0;
+    int grid = 0, blocks_per_sm = 0, grpc_grid = 0, reqlog_grid = 0, http_grid = 0, proto_grid = 0, proto_decode_grid = 0;
     uint32_t epoch = 0;
     // resident path scratch
     unsigned long long* d_state = nullptr;
@@ -728,9 +728,10 @@ int gofr_grpc_hello_device(gofr_engine* e, const uint8_t* d_in, const uint32_t* 
     return GOFR_OK;
 }
 
-int gofr_proto_encode_device(gofr_engine* e, const gofr_proto_field* fields, uint32_t n_fields, const uint8_t* d_rows,
-                             const uint32_t* d_row_off, uint32_t n, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off,
-                             uint32_t* d_meta, void* stream) {
+// rows → frames (decode == false) or frames → rows (decode == true): the same launch plumbing, two codecs
+static int proto_run(gofr_engine* e, const gofr_proto_field* fields, uint32_t n_fields, const uint8_t* d_rows,
+                     const uint32_t* d_row_off, uint32_t n, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off,
+                     uint32_t* d_meta, void* stream, bool decode) {
     if (!e || (n_fields && !fields) || (n && (!d_rows || !d_row_off || !d_out || !d_out_off || !d_meta))) return GOFR_ERR_INVALID;
     if (n_fields > GOFR_PROTO_MAX_FIELDS) { set_last_error("a message type may have at most %d fields", GOFR_PROTO_MAX_FIELDS); return GOFR_ERR_CAPACITY; }
     ProtoSchema S;
@@ -761,9 +762,10 @@ int gofr_proto_encode_device(gofr_engine* e, const gofr_proto_field* fields, uin
         CUDA_TRY(cudaMemset(e->d_state, 0, tiles * 8));
         e->state_tiles = tiles;
     }
-    if (e->proto_grid <= 0) {
-        e->proto_grid = proto_max_grid(e->device);
-        if (e->proto_grid <= 0) { set_last_error("proto kernel cannot be resident"); return GOFR_ERR_CUDA; }
+    int& grid = decode ? e->proto_decode_grid : e->proto_grid;
+    if (grid <= 0) {
+        grid = decode ? proto_decode_max_grid(e->device) : proto_max_grid(e->device);
+        if (grid <= 0) { set_last_error("proto kernel cannot be resident"); return GOFR_ERR_CUDA; }
     }
     GrpcParams p;
     memset(&p, 0, sizeof p);
@@ -780,11 +782,24 @@ int gofr_proto_encode_device(gofr_engine* e, const gofr_proto_field* fields, uin
         CUDA_TRY(cudaEventCreate(&ev1));
         CUDA_TRY(cudaEventRecord(ev0, st));
     }
-    int rc = launch_proto_encode(p, S, (int)std::min<size_t>((size_t)e->proto_grid, tiles), st);
+    const int g_ = (int)std::min<size_t>((size_t)grid, tiles);
+    int rc = decode ? launch_proto_decode(p, S, g_, st) : launch_proto_encode(p, S, g_, st);
     if (rc != 0) { set_last_error("proto kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
     if (e->timing_on) { CUDA_TRY(cudaEventRecord(ev1, st)); e->timing.emplace_back(ev0, ev1); }
     e->launches++;
     return GOFR_OK;
+}
+
+int gofr_proto_encode_device(gofr_engine* e, const gofr_proto_field* fields, uint32_t n_fields, const uint8_t* d_rows,
+                             const uint32_t* d_row_off, uint32_t n, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off,
+                             uint32_t* d_meta, void* stream) {
+    return proto_run(e, fields, n_fields, d_rows, d_row_off, n, d_out, out_cap, d_out_off, d_meta, stream, false);
+}
+
+int gofr_proto_decode_device(gofr_engine* e, const gofr_proto_field* fields, uint32_t n_fields, const uint8_t* d_in,
+                             const uint32_t* d_in_off, uint32_t n, uint8_t* d_rows, uint64_t rows_cap, uint32_t* d_row_off,
+                             uint32_t* d_meta, void* stream) {
+    return proto_run(e, fields, n_fields, d_in, d_in_off, n, d_rows, rows_cap, d_row_off, d_meta, stream, true);
 }
 
 int gofr_route_device(gofr_engine* e, const gofr_req_desc* d_desc, const uint8_t* d_arena, uint32_t n, uint32_t* d_meta,

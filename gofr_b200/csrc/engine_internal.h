@@ -122,6 +122,8 @@ GOFR_INTERNAL_HD uint32_t proto_class(uint32_t t) {
 }
 int launch_proto_encode(const GrpcParams& p, const ProtoSchema& S, int grid, void* stream);
 int proto_max_grid(int device);
+int launch_proto_decode(const GrpcParams& p, const ProtoSchema& S, int grid, void* stream);
+int proto_decode_max_grid(int device);
 
 struct RouteParams {
     const void* desc;

@@ -249,4 +249,125 @@ GOFR_HD void proto_emit(const ProtoSchema& S, const uint8_t* row, const ProtoMsg
     w.finish();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// proto3 message decoder (gofr_proto_decode_device): dec(in) of a unary handler (hello_grpc.pb.go:73-89) for any flat
+// message type — length-prefixed frame → proto.Unmarshal → the field values as a row (the layout the encoder reads).
+// Same wire rules as hello_parse (varints <= 10 bytes, numbers 1..2^29-1, unknown fields and balanced groups skipped);
+// a known field carrying a foreign wire type is an unknown field; scalars: last occurrence wins, 32-bit kinds keep the
+// low 32 bits of the varint, bool is v != 0, sint kinds are zigzag decoded; strings must be valid UTF-8.
+// ---------------------------------------------------------------------------------------------------------------
+struct ProtoRow {
+    uint32_t status;   // GOFR_GRPC_*
+    uint32_t out_len;  // bytes of the row (multiple of 4; 0 on error)
+    // per field: scalar words (lo, hi) — or, for string / bytes, the value's offset in the frame and its length
+    uint32_t a[GOFR_PROTO_MAX_FIELDS];
+    uint32_t b[GOFR_PROTO_MAX_FIELDS];
+};
+
+GOFR_HD void proto_decode_scan(const ProtoSchema& S, const uint8_t* f, uint32_t fn, ProtoRow& r) {
+    r.status = GOFR_GRPC_OK;
+    r.out_len = 0;
+    for (uint32_t k = 0; k < S.n_fields; k++) { r.a[k] = 0; r.b[k] = 0; }
+    if (fn < 5) { r.status = GOFR_GRPC_BAD_LENGTH; return; }
+    if (f[0] == 1) { r.status = GOFR_GRPC_COMPRESSED; return; }
+    if (f[0] != 0) { r.status = GOFR_GRPC_BAD_LENGTH; return; }
+    const uint32_t L = (uint32_t)f[1] << 24 | (uint32_t)f[2] << 16 | (uint32_t)f[3] << 8 | f[4];
+    if (L != fn - 5) { r.status = GOFR_GRPC_BAD_LENGTH; return; }
+    const uint8_t* p = f + 5;
+    uint32_t i = 0, depth = 0;
+    uint32_t stack[kMaxGroupDepth];
+    while (i < L) {
+        uint64_t tag, v = 0;
+        int k = grpc_varint(p + i, L - i, &tag);
+        if (k < 0) { r.status = GOFR_GRPC_BAD_PROTO; return; }
+        i += (uint32_t)k;
+        const uint64_t num = tag >> 3;
+        const uint32_t wt = (uint32_t)(tag & 7);
+        if (num == 0 || num > 0x1FFFFFFFull) { r.status = GOFR_GRPC_BAD_PROTO; return; }
+        // the schema field this tag addresses: same number AND same wire type, outside any unknown group
+        uint32_t fld = 0xFFFFFFFFu;
+        if (depth == 0) {
+            const uint32_t want = (uint32_t)tag;  // number << 3 | wire, exactly what S.tag holds
+            for (uint32_t q = 0; q < S.n_fields; q++)
+                if (S.tag[q] == want) fld = q;
+        }
+        uint32_t poff = 0, plen = 0;
+        if (wt == 0) {
+            k = grpc_varint(p + i, L - i, &v);
+            if (k < 0) { r.status = GOFR_GRPC_BAD_PROTO; return; }
+            i += (uint32_t)k;
+        } else if (wt == 1) {
+            if (L - i < 8) { r.status = GOFR_GRPC_BAD_PROTO; return; }
+            for (int q = 7; q >= 0; q--) v = v << 8 | p[i + (uint32_t)q];
+            i += 8;
+        } else if (wt == 5) {
+            if (L - i < 4) { r.status = GOFR_GRPC_BAD_PROTO; return; }
+            for (int q = 3; q >= 0; q--) v = v << 8 | p[i + (uint32_t)q];
+            i += 4;
+        } else if (wt == 2) {
+            k = grpc_varint(p + i, L - i, &v);
+            if (k < 0) { r.status = GOFR_GRPC_BAD_PROTO; return; }
+            i += (uint32_t)k;
+            if (v > L - i) { r.status = GOFR_GRPC_BAD_PROTO; return; }
+            poff = 5 + i;
+            plen = (uint32_t)v;
+            i += plen;
+        } else if (wt == 3) {
+            if (depth == kMaxGroupDepth) { r.status = GOFR_GRPC_BAD_PROTO; return; }
+            stack[depth++] = (uint32_t)num;
+            continue;
+        } else if (wt == 4) {
+            if (depth == 0 || stack[depth - 1] != (uint32_t)num) { r.status = GOFR_GRPC_BAD_PROTO; return; }
+            depth--;
+            continue;
+        } else { r.status = GOFR_GRPC_BAD_PROTO; return; }
+        if (fld == 0xFFFFFFFFu) continue;
+        const uint32_t cls = S.cls[fld];
+        if (wt == 2) {
+            if ((cls & PC_UTF8) && !proto_utf8_ok(f + poff, plen)) { r.status = GOFR_GRPC_BAD_UTF8; return; }
+            r.a[fld] = poff;
+            r.b[fld] = plen;
+        } else if (wt != 0 || ((cls & PC_64) && !(cls & PC_ZIGZAG))) {
+            r.a[fld] = (uint32_t)v;            // fixed32 / fixed64 / int64 / uint64: the bits
+            r.b[fld] = (uint32_t)(v >> 32);
+        } else if (cls & PC_ZIGZAG) {
+            if (cls & PC_64) {
+                const uint64_t z = (v >> 1) ^ (uint64_t)-(int64_t)(v & 1);
+                r.a[fld] = (uint32_t)z;
+                r.b[fld] = (uint32_t)(z >> 32);
+            } else {
+                const uint32_t x = (uint32_t)v;
+                r.a[fld] = (x >> 1) ^ (uint32_t)-(int32_t)(x & 1);
+            }
+        } else if (cls & PC_BOOL) {
+            r.a[fld] = v != 0 ? 1u : 0u;
+        } else {
+            r.a[fld] = (uint32_t)v;            // int32 / uint32 / enum: the low 32 bits
+        }
+    }
+    if (depth != 0) { r.status = GOFR_GRPC_BAD_PROTO; return; }
+    uint32_t need = S.fixed_bytes;
+    for (uint32_t k = 0; k < S.n_fields; k++)
+        if ((S.cls[k] & PC_WIRE) == 2) need += r.b[k];
+    r.out_len = (need + 3u) & ~3u;
+}
+
+GOFR_HD void proto_decode_emit(const ProtoSchema& S, const uint8_t* f, const ProtoRow& r, uint8_t* dst, uint32_t* stage_col) {
+    if (!r.out_len) return;
+    Writer w;
+    w.init(dst, stage_col);
+    uint32_t produced = S.fixed_bytes;
+    for (uint32_t k = 0; k < S.n_fields; k++) {
+        const uint32_t cls = S.cls[k];
+        w.reserve(3);
+        if ((cls & PC_WIRE) == 2) w.put4(r.b[k]);
+        else { w.put4(r.a[k]); if (cls & PC_64) w.put4(r.b[k]); }
+    }
+    for (uint32_t k = 0; k < S.n_fields; k++)
+        if ((S.cls[k] & PC_WIRE) == 2 && r.b[k]) { w.copy<false>(f + r.a[k], r.b[k]); produced += r.b[k]; }
+    w.reserve(2);
+    for (; produced & 3u; produced++) w.putc(0);
+    w.finish();
+}
+
 }  // namespace gofr

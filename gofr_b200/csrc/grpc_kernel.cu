@@ -105,6 +105,14 @@ struct ProtoCodec {
     __device__ void emit(const uint8_t* row, const R& r, uint8_t* dst, uint32_t* col) const { proto_emit(S, row, r, dst, col); }
 };
 
+struct ProtoDecodeCodec {
+    typedef ProtoRow R;
+    const ProtoSchema& S;
+    __device__ R none() const { ProtoRow r; r.status = GOFR_GRPC_OK; r.out_len = 0; return r; }
+    __device__ R parse(const uint8_t* f, uint32_t fn, uint32_t) const { ProtoRow r; proto_decode_scan(S, f, fn, r); return r; }
+    __device__ void emit(const uint8_t* f, const R& r, uint8_t* dst, uint32_t* col) const { proto_decode_emit(S, f, r, dst, col); }
+};
+
 __global__ void __launch_bounds__(GT, 12) grpc_hello_kernel(const GrpcParams p) {
     __shared__ __align__(16) GrpcShared sh;
     frame_tiles(p, HelloCodec{}, sh);
@@ -119,6 +127,25 @@ __global__ void __launch_bounds__(GT, 8) proto_encode_kernel(const GrpcParams p,
 int launch_grpc_hello(const GrpcParams& p, int grid, void* stream) {
     grpc_hello_kernel<<<grid, GT, 0, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
+}
+
+// frames → rows (gofr_proto_decode_device)
+__global__ void __launch_bounds__(GT, 8) proto_decode_kernel(const GrpcParams p, const __grid_constant__ ProtoSchema S) {
+    __shared__ __align__(16) GrpcShared sh;
+    frame_tiles(p, ProtoDecodeCodec{S}, sh);
+}
+
+int launch_proto_decode(const GrpcParams& p, const ProtoSchema& S, int grid, void* stream) {
+    proto_decode_kernel<<<grid, GT, 0, (cudaStream_t)stream>>>(p, S);
+    return (int)cudaGetLastError();
+}
+
+int proto_decode_max_grid(int device) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, proto_decode_kernel, GT, 0) != cudaSuccess) return -1;
+    return nb * prop.multiProcessorCount;
 }
 
 int launch_proto_encode(const GrpcParams& p, const ProtoSchema& S, int grid, void* stream) {

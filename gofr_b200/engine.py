@@ -149,6 +149,24 @@ class Engine:
                    "gofr_proto_encode_device")
         return out, off, meta[:n]
 
+    def proto_decode_device(self, fields, frames: np.ndarray, in_off: np.ndarray, rows_cap: Optional[int] = None, stream=None):
+        """gofr_proto_decode_device: packed gRPC frames → rows.  Returns (rows uint8, row_off, meta) on the device."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        n = len(in_off) - 1
+        ft = (_abi.ProtoField * max(len(fields), 1))(*[_abi.ProtoField(f.number, f.type) for f in fields])
+        d_in = torch.from_numpy(np.concatenate([np.ascontiguousarray(frames), np.zeros(16, np.uint8)])).to(dev)
+        d_off = torch.from_numpy(in_off.view(np.int32)).to(dev)
+        cap = rows_cap if rows_cap is not None else int(frames.size) + (8 * len(fields) + 8) * n + 64
+        rows = torch.empty(cap, dtype=torch.uint8, device=dev)
+        off = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        meta = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+        _abi.check(_abi.lib().gofr_proto_decode_device(self._e, ft, len(fields), d_in.data_ptr(), d_off.data_ptr(), n,
+                                                       rows.data_ptr(), cap, off.data_ptr(), meta.data_ptr(), st.cuda_stream),
+                   "gofr_proto_decode_device")
+        return rows, off, meta[:n]
+
     def route_host(self, batch: S.RequestBatch):
         """gofr_batch_route: the same for a batch in host memory → (meta uint32[n], vars uint32[n, 8])."""
         rb = _abi.ReqBatch(desc=batch.desc.ctypes.data, trace_ids=batch.trace_ids.ctypes.data, arena=batch.arena.ctypes.data,

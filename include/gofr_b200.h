@@ -300,6 +300,16 @@ typedef struct gofr_proto_field {
 int gofr_proto_encode_device(gofr_engine*, const gofr_proto_field* fields, uint32_t n_fields, const uint8_t* d_rows,
                              const uint32_t* d_row_off, uint32_t n, uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off,
                              uint32_t* d_meta, void* stream);
+/* The other direction — dec(in) of the same handler: length-prefixed frames in (frame i = d_in[d_in_off[i] ..
+ * d_in_off[i+1]), as for gofr_grpc_hello_device), proto.Unmarshal into the message type, the field values out as rows in
+ * the layout above (row sizes are multiples of 4; absent fields hold their zero value), packed, d_row_off[n+1].
+ * d_meta[i]: GOFR_GRPC_OK or COMPRESSED / BAD_LENGTH / BAD_PROTO / BAD_UTF8 as for the Hello call (a failed frame gives an
+ * empty row).  Unknown fields — and known fields arriving with a foreign wire type — are skipped; the last occurrence of
+ * a field wins; int32 / uint32 / enum keep the low 32 bits of the varint, bool is v != 0.  d_in must stay readable for 8
+ * bytes past the last frame. */
+int gofr_proto_decode_device(gofr_engine*, const gofr_proto_field* fields, uint32_t n_fields, const uint8_t* d_in,
+                             const uint32_t* d_in_off, uint32_t n, uint8_t* d_rows, uint64_t rows_cap, uint32_t* d_row_off,
+                             uint32_t* d_meta, void* stream);
 
 /* Stage 1 of the split API for routes whose closure stays on the host (GOFR_H_HOST): everything mux.Router.ServeHTTP
  * and the middleware chain decide before handler.ServeHTTP runs (pkg/gofr/http/router.go:14,30-33;

@@ -47,6 +47,9 @@ int orc_serve(const orc_table*, const void* desc, const uint8_t* ids, const uint
 /* proto.Marshal of flat proto3 messages + the gRPC length prefix (orc_proto.c); fields = n_fields pairs (number, type) */
 int orc_proto_encode(const uint32_t* fields, uint32_t n_fields, const uint8_t* rows, const uint32_t* row_off, uint32_t n,
                      uint8_t* out, uint64_t out_cap, uint32_t* out_off, uint32_t* meta);
+/* the other direction: length-prefixed frames → rows (proto.Unmarshal of a flat proto3 message type) */
+int orc_proto_decode(const uint32_t* fields, uint32_t n_fields, const uint8_t* in, const uint32_t* in_off, uint32_t n,
+                     uint8_t* rows, uint64_t rows_cap, uint32_t* row_off, uint32_t* meta);
 int orc_grpc_hello(const uint8_t* in, const uint32_t* in_off, uint32_t n, uint8_t* out, uint64_t out_cap,
                    uint32_t* out_off, uint32_t* meta, int nthreads);
 

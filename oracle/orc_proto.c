@@ -144,3 +144,156 @@ int orc_proto_encode(const uint32_t* fields, uint32_t n_fields, const uint8_t* r
     free(b.p);
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * The other direction: what dec(in) does for the request of a unary RPC (examples/grpc-server/grpc/
+ * hello_grpc.pb.go:73-89 calls dec, grpc-go has stripped nothing yet at the level modelled here): check the 5-byte
+ * length-prefixed-message header, proto.Unmarshal into a flat proto3 message type, hand the field values on — here as a
+ * row in the layout the encoder takes.  protobuf-go v1.32.0 rules restated:
+ *   - tags: field number 1 .. 2^29-1, wire types 0,1,2,5 and groups 3/4 (only ever unknown here, skipped balanced);
+ *   - a known field arriving with another wire type than its own is an unknown field (skipped);
+ *   - scalars: the last occurrence wins; int32 / uint32 / enum keep the low 32 bits of the varint, bool is v != 0,
+ *     sint32 zigzag-decodes the low 32 bits, sint64 all 64;
+ *   - proto3 strings must be valid UTF-8 (every occurrence, also one that is overwritten later);
+ *   - absent fields hold their zero value.
+ * meta: 0 ok, 1 compressed flag set (no decompressor registered, pkg/gofr/grpc.go:23-26), 2 bad length prefix,
+ * 3 malformed message, 4 invalid UTF-8.  A failed frame yields an empty row.
+ * Independent check: tests/test_proto.py parses the same frames with python google.protobuf and packs rows from the
+ * field values it reports.
+ * --------------------------------------------------------------------------------------------------------------- */
+enum { ST_COMPRESSED = 1, ST_BAD_LENGTH = 2, ST_BAD_PROTO = 3 };
+#define DEC_MAX_FIELDS 32
+#define DEC_MAX_GROUP_DEPTH 16
+
+typedef struct { uint64_t scalar; const uint8_t* str; size_t str_len; } dec_value;
+
+static int dec_varint(const uint8_t* p, size_t n, uint64_t* v) { /* protowire.ConsumeVarint */
+    uint64_t x = 0;
+    for (int i = 0; i < 10; i++) {
+        if ((size_t)i >= n) return -1;
+        uint8_t b = p[i];
+        if (i == 9 && b > 1) return -1;
+        x |= (uint64_t)(b & 0x7F) << (7 * i);
+        if (b < 0x80) { *v = x; return i + 1; }
+    }
+    return -1;
+}
+
+static int wire_of(uint32_t t) {
+    switch (t) {
+        case PB_STRING: case PB_BYTES: return 2;
+        case PB_DOUBLE: case PB_FIXED64: case PB_SFIXED64: return 1;
+        case PB_FLOAT: case PB_FIXED32: case PB_SFIXED32: return 5;
+        default: return 0;
+    }
+}
+
+static int unmarshal(const uint32_t* ftab, uint32_t nf, const uint8_t* p, size_t n, dec_value* val) {
+    size_t i = 0;
+    uint32_t group_stack[DEC_MAX_GROUP_DEPTH];
+    int depth = 0;
+    while (i < n) {
+        uint64_t tag, v = 0;
+        int k = dec_varint(p + i, n - i, &tag);
+        if (k < 0) return ST_BAD_PROTO;
+        i += (size_t)k;
+        const uint64_t num = tag >> 3;
+        const int wt = (int)(tag & 7);
+        if (num == 0 || num > 0x1FFFFFFF) return ST_BAD_PROTO;
+        int field = -1;
+        if (depth == 0)
+            for (uint32_t f = 0; f < nf; f++)
+                if (ftab[2 * f] == num && wire_of(ftab[2 * f + 1]) == wt) field = (int)f;
+        const uint8_t* payload = p + i;
+        size_t plen = 0;
+        switch (wt) {
+            case 0:
+                k = dec_varint(p + i, n - i, &v);
+                if (k < 0) return ST_BAD_PROTO;
+                i += (size_t)k;
+                break;
+            case 1:
+                if (n - i < 8) return ST_BAD_PROTO;
+                for (int b = 7; b >= 0; b--) v = v << 8 | p[i + (size_t)b];
+                i += 8;
+                break;
+            case 5:
+                if (n - i < 4) return ST_BAD_PROTO;
+                for (int b = 3; b >= 0; b--) v = v << 8 | p[i + (size_t)b];
+                i += 4;
+                break;
+            case 2:
+                k = dec_varint(p + i, n - i, &v);
+                if (k < 0) return ST_BAD_PROTO;
+                i += (size_t)k;
+                if (v > n - i) return ST_BAD_PROTO;
+                payload = p + i;
+                plen = (size_t)v;
+                i += plen;
+                break;
+            case 3:
+                if (depth == DEC_MAX_GROUP_DEPTH) return ST_BAD_PROTO;
+                group_stack[depth++] = (uint32_t)num;
+                continue;
+            case 4:
+                if (depth == 0 || group_stack[depth - 1] != (uint32_t)num) return ST_BAD_PROTO;
+                depth--;
+                continue;
+            default: return ST_BAD_PROTO;
+        }
+        if (field < 0) continue;
+        const uint32_t t = ftab[2 * field + 1];
+        switch (t) {
+            case PB_STRING:
+                if (!str_utf8_valid(payload, plen)) return ST_BAD_UTF8;
+                /* fall through */
+            case PB_BYTES: val[field].str = payload; val[field].str_len = plen; break;
+            case PB_INT32: case PB_UINT32: case PB_ENUM: val[field].scalar = (uint32_t)v; break;
+            case PB_SINT32: { uint32_t x = (uint32_t)v; val[field].scalar = (uint32_t)((x >> 1) ^ (uint32_t)-(int32_t)(x & 1)); break; }
+            case PB_SINT64: val[field].scalar = (v >> 1) ^ (uint64_t)-(int64_t)(v & 1); break;
+            case PB_BOOL: val[field].scalar = v != 0; break;
+            default: val[field].scalar = v; break; /* int64, uint64, fixed*, float, double: the bits */
+        }
+    }
+    return depth == 0 ? ST_OK : ST_BAD_PROTO;
+}
+
+int orc_proto_decode(const uint32_t* fields, uint32_t n_fields, const uint8_t* in, const uint32_t* in_off, uint32_t n,
+                     uint8_t* rows, uint64_t rows_cap, uint32_t* row_off, uint32_t* meta) {
+    if (n_fields > DEC_MAX_FIELDS) return -2;
+    uint64_t pos = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        row_off[i] = (uint32_t)pos;
+        const uint8_t* f = in + in_off[i];
+        const size_t fn = in_off[i + 1] - in_off[i];
+        dec_value val[DEC_MAX_FIELDS];
+        memset(val, 0, sizeof val);
+        int st;
+        if (fn < 5) st = ST_BAD_LENGTH;
+        else if (f[0] == 1) st = ST_COMPRESSED;
+        else if (f[0] != 0) st = ST_BAD_LENGTH;
+        else {
+            const uint32_t L = (uint32_t)f[1] << 24 | (uint32_t)f[2] << 16 | (uint32_t)f[3] << 8 | f[4];
+            st = (size_t)L != fn - 5 ? ST_BAD_LENGTH : unmarshal(fields, n_fields, f + 5, L, val);
+        }
+        meta[i] = (uint32_t)st;
+        if (st != ST_OK) continue;
+        size_t need = 0;
+        for (uint32_t k = 0; k < n_fields; k++) need += 4 * (size_t)kind_words(fields[2 * k + 1]) + val[k].str_len;
+        need = (need + 3) & ~(size_t)3;
+        if (pos + need > rows_cap) return -1;
+        uint8_t* o = rows + pos;
+        size_t w = 0;
+        for (uint32_t k = 0; k < n_fields; k++) {
+            const uint32_t t = fields[2 * k + 1];
+            const uint64_t s = (t == PB_STRING || t == PB_BYTES) ? (uint64_t)val[k].str_len : val[k].scalar;
+            for (int b = 0; b < 4 * kind_words(t); b++) o[w++] = (uint8_t)(s >> (8 * b));
+        }
+        for (uint32_t k = 0; k < n_fields; k++)
+            if (val[k].str_len) { memcpy(o + w, val[k].str, val[k].str_len); w += val[k].str_len; }
+        while (w < need) o[w++] = 0;
+        pos += need;
+    }
+    row_off[n] = (uint32_t)pos;
+    return 0;
+}

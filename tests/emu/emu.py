@@ -39,6 +39,7 @@ def lib():
                                         C.c_void_p, C.c_uint32]
         _lib.emu_proto_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
                                           C.c_void_p, C.c_void_p, C.c_uint32]
+        _lib.emu_proto_decode.argtypes = _lib.emu_proto_encode.argtypes
         _lib.emu_serve_slots.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p,
                                          C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.emu_route.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -113,6 +114,22 @@ def proto_encode(fields, rows, row_off, misalign: int = 0):
     if rc != 0:
         raise RuntimeError("emu output capacity too small")
     return out, off, meta[:n]
+
+
+def proto_decode(fields, frames, in_off, misalign: int = 0):
+    """proto_decode_scan + proto_decode_emit (grpc_device.cuh) on the CPU → (rows, row_off, meta)"""
+    n = len(in_off) - 1
+    ft = np.array([[f.number, f.type] for f in fields], dtype=np.uint32).reshape(-1)
+    cap = int(frames.size) + (8 * len(fields) + 8) * n + 64 + misalign
+    rows = np.full(cap, 0xEE, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    meta = np.zeros(max(n, 1), dtype=np.uint32)
+    frames = np.concatenate([np.ascontiguousarray(frames), np.zeros(16, np.uint8)])
+    rc = lib().emu_proto_decode(ft.ctypes.data, len(fields), frames.ctypes.data, in_off.ctypes.data, n, rows.ctypes.data, cap,
+                                off.ctypes.data, meta.ctypes.data, misalign)
+    if rc != 0:
+        raise RuntimeError("emu output capacity too small")
+    return rows, off, meta[:n]
 
 
 def grpc_hello(frames, in_off, misalign: int = 0):

@@ -175,6 +175,33 @@ extern "C" int emu_proto_encode(const uint32_t* fields, uint32_t n_fields, const
     return 0;
 }
 
+extern "C" int emu_proto_decode(const uint32_t* fields, uint32_t n_fields, const uint8_t* in, const uint32_t* in_off, uint32_t n,
+                                uint8_t* rows, uint64_t rows_cap, uint32_t* row_off, uint32_t* meta, uint32_t start_misalign) {
+    ProtoSchema S;
+    memset(&S, 0, sizeof S);
+    S.n_fields = n_fields;
+    for (uint32_t k = 0; k < n_fields; k++) {
+        const uint32_t t = fields[2 * k + 1];
+        S.tag[k] = fields[2 * k] << 3 | proto_wire(t);
+        S.cls[k] = (uint8_t)proto_class(t);
+        S.fixed_bytes += proto_is64(t) ? 8u : 4u;
+    }
+    uint32_t stage[GOFR_STAGE_WORDS];
+    uint64_t pos = start_misalign;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint8_t* f = in + in_off[i];
+        ProtoRow r;
+        proto_decode_scan(S, f, in_off[i + 1] - in_off[i], r);
+        row_off[i] = (uint32_t)pos;
+        meta[i] = r.status;
+        if (pos + r.out_len > rows_cap) return -1;
+        proto_decode_emit(S, f, r, rows + pos, stage);
+        pos += r.out_len;
+    }
+    row_off[n] = (uint32_t)pos;
+    return 0;
+}
+
 // ---- gRPC Hello (config 5): the same grpc_device.cuh code the CUDA kernel runs ----
 
 extern "C" int emu_grpc_hello(const uint8_t* in, const uint32_t* in_off, uint32_t n, uint8_t* out, uint64_t out_cap,

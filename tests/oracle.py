@@ -50,6 +50,8 @@ def lib():
                                      C.c_int]
         L.orc_proto_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                        C.c_void_p]
+        L.orc_proto_decode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
+                                       C.c_void_p]
         for name in ("orc_json_string", "orc_clean_path", "orc_escape_path"):
             getattr(L, name).argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
         L.orc_json_int.argtypes = [C.c_int64, C.c_char_p, C.c_int]
@@ -225,3 +227,18 @@ def proto_encode(fields, rows: np.ndarray, row_off: np.ndarray):
                                 off.ctypes.data, meta.ctypes.data)
     assert rc == 0
     return out, off, meta[:n]
+
+
+def proto_decode(fields, frames: np.ndarray, in_off: np.ndarray):
+    """orc_proto_decode: gRPC frames → rows (proto.Unmarshal) → (rows, row_off, meta)."""
+    n = len(in_off) - 1
+    ft = np.array([[f.number, f.type] for f in fields], dtype=np.uint32).reshape(-1)
+    cap = int(frames.size) + (8 * len(fields) + 8) * n + 64
+    rows = np.zeros(cap, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    meta = np.zeros(max(n, 1), dtype=np.uint32)
+    frames = np.ascontiguousarray(frames)
+    rc = lib().orc_proto_decode(ft.ctypes.data, len(fields), frames.ctypes.data, in_off.ctypes.data, n, rows.ctypes.data, cap,
+                                off.ctypes.data, meta.ctypes.data)
+    assert rc == 0
+    return rows, off, meta[:n]

@@ -201,3 +201,203 @@ def test_gpu_matches_oracle():
         with pytest.raises(_abi.GofrError):
             eng.proto_encode_device(bad, rows, off)
     eng.close()
+
+
+# =====================================================================================================================
+# the other direction: gofr_proto_decode_device — frames → rows (proto.Unmarshal of the request message)
+# =====================================================================================================================
+
+def _frame(body: bytes, flag: int = 0) -> bytes:
+    return bytes([flag]) + len(body).to_bytes(4, "big") + body
+
+
+def _pack_frames(frames):
+    off = np.zeros(len(frames) + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(f) for f in frames])
+    return np.frombuffer(b"".join(frames), dtype=np.uint8).copy(), off
+
+
+def _py_parse_rows(fields, frames):
+    """rows as python protobuf sees the messages: ParseFromString, then pack the reported field values (None on error)"""
+    from google.protobuf.message import DecodeError
+    cls = _py_class(fields)
+    out = []
+    for fr in frames:
+        m = cls()
+        try:
+            m.ParseFromString(fr[5:])
+        except DecodeError:
+            out.append(None)
+            continue
+        vals = [getattr(m, "f%d" % f.number) for f in fields]
+        rows, off = S.pack_proto_rows(fields, [vals])
+        out.append(rows[:int(off[1])].tobytes())
+    return out
+
+
+def _rows(rows, off):
+    return [rows[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(off) - 1)]
+
+
+def _has_overflowing_varint(b: bytes) -> bool:
+    """nine continuation bytes followed by a byte > 1: protobuf-go's protowire.ConsumeVarint rejects the overflow
+    (errCodeOverflow); python's upb parser drops the extra bits instead — the one place the two parsers disagree"""
+    run = 0
+    for c in b:
+        if run >= 9 and c > 1:
+            return True
+        run = run + 1 if c >= 0x80 else 0
+    return False
+
+
+def _varint(v):
+    out = bytearray()
+    while v >= 0x80:
+        out.append(v & 0x7F | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def test_decode_round_trip_and_python_protobuf():
+    fields, msgs = _bulk(1500)
+    rows, off = S.pack_proto_rows(fields, msgs)
+    out, o, meta = O.proto_encode(fields, rows, off)
+    ok = meta == 0
+    r2, o2, m2 = O.proto_decode(fields, out[:int(o[-1])], o)
+    want = _rows(rows, off)
+    got = _rows(r2, o2)
+    frames = _frames(out, o)
+    py = _py_parse_rows(fields, frames)
+    for i in range(len(msgs)):
+        if ok[i]:
+            assert m2[i] == 0 and got[i] == want[i] == py[i], i        # decode(encode(row)) == row == python's view
+        else:
+            assert m2[i] == S.GRPC_BAD_LENGTH and got[i] == b""          # encoder emitted no frame: an empty frame is too short
+    for mis in (0, 6):
+        e_rows, e_off, e_meta = emu.proto_decode(fields, out[:int(o[-1])], o, mis)
+        assert np.array_equal(e_meta, m2) and np.array_equal(e_off, o2 + mis)
+        assert e_rows[mis:int(e_off[-1])].tobytes() == r2[:int(o2[-1])].tobytes()
+
+
+def test_decode_hostile_frames():
+    f = [S.ProtoField(1, S.PB_STRING), S.ProtoField(2, S.PB_INT32), S.ProtoField(3, S.PB_SINT32), S.ProtoField(4, S.PB_BOOL),
+         S.ProtoField(5, S.PB_FIXED32), S.ProtoField(6, S.PB_UINT64), S.ProtoField(7, S.PB_BYTES), S.ProtoField(8, S.PB_SINT64),
+         S.ProtoField(9, S.PB_DOUBLE)]
+    T = lambda num, wt: _varint(num << 3 | wt)
+    bodies = [
+        b"",                                                                    # all defaults
+        T(1, 2) + b"\x02hi" + T(1, 2) + b"\x03bye",                              # last occurrence wins
+        T(2, 0) + _varint(2**64 - 1),                                           # int32 -1 as ten bytes
+        T(2, 0) + _varint(2**35 + 7),                                           # int32 keeps the low 32 bits
+        T(4, 0) + _varint(2**40),                                               # bool: any non-zero varint is true
+        T(3, 0) + _varint(2**33 + 3),                                           # sint32: zigzag of the low 32 bits
+        T(8, 0) + _varint(2**64 - 1) + T(6, 0) + _varint(2**64 - 1),
+        T(2, 2) + b"\x01\x07",                                                  # int32 with a length-delimited wire type: unknown, skipped
+        T(1, 0) + b"\x05",                                                      # string with a varint wire type: unknown, skipped
+        T(5, 5) + b"\x01\x02\x03\x04" + T(9, 1) + struct.pack("<d", -0.0),
+        T(99, 0) + b"\x01" + T(100, 2) + b"\x03abc" + T(101, 1) + b"\0" * 8 + T(102, 5) + b"\0" * 4 + T(1, 2) + b"\x01z",  # unknown fields
+        T(50, 3) + T(1, 2) + b"\x01q" + T(50, 4) + T(1, 2) + b"\x01r",           # field 1 inside an unknown group belongs to the group
+        T(50, 3) + T(51, 3) + T(51, 4) + T(50, 4),
+        T(50, 3),                                                               # unterminated group
+        T(50, 4),                                                               # end group without start
+        T(50, 3) + T(51, 4),                                                    # mismatched end group
+        T(1, 2) + b"\x05ab",                                                    # length runs past the message
+        T(1, 2) + b"\x01\xff",                                                  # invalid UTF-8 in a string
+        T(1, 2) + b"\x01\xff" + T(1, 2) + b"\x01a",                              # … even when overwritten later
+        T(7, 2) + b"\x02\xff\xfe",                                              # bytes may hold anything
+        b"\x00",                                                                # field number 0
+        _varint((2**29) << 3),                                                  # field number 2^29
+        T(1, 6), T(1, 7),                                                       # wire types 6 and 7
+        T(2, 0) + b"\x80" * 10 + b"\x01",                                       # varint longer than ten bytes
+        T(2, 0) + b"\xff" * 9 + b"\x02",                                        # tenth byte > 1
+        T(2, 0) + b"\x80",                                                      # truncated varint
+        T(5, 5) + b"\x01\x02",                                                  # truncated fixed32
+        T(9, 1) + b"\0" * 7,                                                    # truncated fixed64
+        b"".join(T(60 + d, 3) for d in range(17)),                              # groups nested deeper than 16
+    ]
+    frames = [_frame(b) for b in bodies]
+    frames += [_frame(T(2, 0) + b"\x01", flag=1), _frame(b"", flag=2), b"\x00\x00\x00", b"", b"\x00\x00\x00\x00\x05" + T(2, 0) + b"\x01",
+               _frame(T(2, 0) + b"\x01") + b"\x00"]
+    raw, off = _pack_frames(frames)
+    rows, roff, meta = O.proto_decode(f, raw, off)
+    py = _py_parse_rows(f, frames[:len(bodies)])
+    got = _rows(rows, roff)
+    for i in range(len(bodies)):
+        if i == len(bodies) - 1:
+            assert meta[i] == S.GRPC_BAD_PROTO       # our 16-level group limit; python accepts deeper nesting
+            continue
+        if py[i] is None or _has_overflowing_varint(bodies[i]):
+            assert meta[i] in (S.GRPC_BAD_PROTO, S.GRPC_BAD_UTF8) and got[i] == b"", (i, bodies[i])
+        else:
+            assert meta[i] == 0 and got[i] == py[i], (i, bodies[i])
+    assert list(meta[len(bodies):]) == [S.GRPC_COMPRESSED, S.GRPC_BAD_LENGTH, S.GRPC_BAD_LENGTH, S.GRPC_BAD_LENGTH, S.GRPC_BAD_LENGTH,
+                                        S.GRPC_BAD_LENGTH]
+    assert meta[17] == meta[18] == S.GRPC_BAD_UTF8
+    for mis in (0, 3):
+        e_rows, e_off, e_meta = emu.proto_decode(f, raw, off, mis)
+        assert np.array_equal(e_meta, meta) and np.array_equal(e_off, roff + mis)
+        assert e_rows[mis:int(e_off[-1])].tobytes() == rows[:int(roff[-1])].tobytes()
+
+
+@st.composite
+def _wire_soup(draw):
+    """a message type plus frames made of random well-formed and malformed wire fragments"""
+    nf = draw(st.integers(1, 8))
+    numbers = sorted(draw(st.sets(st.integers(1, 12), min_size=nf, max_size=nf)))
+    fields = [S.ProtoField(n, draw(st.sampled_from(ALL_TYPES))) for n in numbers]
+    frag = st.one_of(
+        st.tuples(st.integers(1, 14), st.just(0), st.integers(0, 2**64 - 1)).map(lambda t: _varint(t[0] << 3) + _varint(t[2])),
+        st.tuples(st.integers(1, 14), st.binary(min_size=8, max_size=8)).map(lambda t: _varint(t[0] << 3 | 1) + t[1]),
+        st.tuples(st.integers(1, 14), st.binary(min_size=4, max_size=4)).map(lambda t: _varint(t[0] << 3 | 5) + t[1]),
+        st.tuples(st.integers(1, 14), st.binary(max_size=12) | st.text(max_size=8).map(lambda s: s.encode("utf-8", "surrogatepass")))
+        .map(lambda t: _varint(t[0] << 3 | 2) + _varint(len(t[1])) + t[1]),
+        st.integers(1, 14).map(lambda n: _varint(n << 3 | 3) + _varint(n << 3 | 4)),
+        st.binary(min_size=1, max_size=3),                                        # junk
+    )
+    frames = [_frame(b"".join(draw(st.lists(frag, max_size=6)))) for _ in range(draw(st.integers(1, 5)))]
+    return fields, frames
+
+
+@settings(max_examples=200, deadline=None)
+@given(_wire_soup(), st.integers(0, 15))
+def test_decode_random_wire_three_way(soup, mis):
+    """python protobuf == oracle == device code (CPU emulation) on random wire fragments, accepted or rejected alike"""
+    fields, frames = soup
+    raw, off = _pack_frames(frames)
+    rows, roff, meta = O.proto_decode(fields, raw, off)
+    py = _py_parse_rows(fields, frames)
+    got = _rows(rows, roff)
+    for i in range(len(frames)):
+        if py[i] is None or (meta[i] == S.GRPC_BAD_PROTO and _has_overflowing_varint(frames[i][5:])):
+            assert meta[i] in (S.GRPC_BAD_PROTO, S.GRPC_BAD_UTF8) and got[i] == b"", frames[i]
+        else:
+            assert meta[i] == 0 and got[i] == py[i], frames[i]
+    e_rows, e_off, e_meta = emu.proto_decode(fields, raw, off, mis)
+    assert np.array_equal(e_meta, meta) and np.array_equal(e_off, roff + mis)
+    assert e_rows[mis:int(e_off[-1])].tobytes() == rows[:int(roff[-1])].tobytes()
+
+
+@pytest.mark.gpu
+def test_gpu_decode_matches_oracle():
+    from gofr_b200 import synth
+    from gofr_b200.engine import Engine
+    from gofr_b200.table import Table
+    eng = Engine(Table(synth.config1_spec()), 0)
+    fields, msgs = _bulk(40000, seed=11)
+    rows, off = S.pack_proto_rows(fields, msgs)
+    out, o, _ = O.proto_encode(fields, rows, off)
+    raw = out[:int(o[-1])]
+    r1, o1, m1 = O.proto_decode(fields, raw, o)
+    d_rows, d_off, d_meta = eng.proto_decode_device(fields, raw, o)
+    assert np.array_equal(d_off.cpu().numpy().view(np.uint32), o1)
+    assert np.array_equal(d_meta.cpu().numpy().view(np.uint32), m1)
+    assert d_rows[:int(o1[-1])].cpu().numpy().tobytes() == r1[:int(o1[-1])].tobytes()
+    # the Hello request type through the general decoder: the same names the Hello kernel extracts
+    frames, foff = synth.config5_frames(20000)
+    hf = [S.ProtoField(1, S.PB_STRING)]
+    r1, o1, m1 = O.proto_decode(hf, frames, foff)
+    d_rows, d_off, d_meta = eng.proto_decode_device(hf, frames, foff)
+    assert np.array_equal(d_off.cpu().numpy().view(np.uint32), o1) and np.array_equal(d_meta.cpu().numpy().view(np.uint32), m1)
+    assert d_rows[:int(o1[-1])].cpu().numpy().tobytes() == r1[:int(o1[-1])].tobytes()
+    eng.close()
