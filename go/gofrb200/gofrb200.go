@@ -269,3 +269,14 @@ func (e *Engine) ProtoEncodeDevice(fields []ProtoField, dRows, dRowOff unsafe.Po
 	return check(C.gofr_proto_encode_device(e.e, fp, C.uint32_t(len(fields)), (*C.uint8_t)(dRows), (*C.uint32_t)(dRowOff), C.uint32_t(n),
 		(*C.uint8_t)(dOut), C.uint64_t(outCap), (*C.uint32_t)(dOutOff), (*C.uint32_t)(dMeta), stream), "gofr_proto_encode_device")
 }
+
+// ProtoDecodeDevice is the other direction (gofr_proto_decode_device): length-prefixed request frames → rows.
+func (e *Engine) ProtoDecodeDevice(fields []ProtoField, dIn, dInOff unsafe.Pointer, n int, dRows unsafe.Pointer, rowsCap uint64,
+	dRowOff, dMeta unsafe.Pointer, stream unsafe.Pointer) error {
+	var fp *C.gofr_proto_field
+	if len(fields) > 0 {
+		fp = (*C.gofr_proto_field)(unsafe.Pointer(&fields[0]))
+	}
+	return check(C.gofr_proto_decode_device(e.e, fp, C.uint32_t(len(fields)), (*C.uint8_t)(dIn), (*C.uint32_t)(dInOff), C.uint32_t(n),
+		(*C.uint8_t)(dRows), C.uint64_t(rowsCap), (*C.uint32_t)(dRowOff), (*C.uint32_t)(dMeta), stream), "gofr_proto_decode_device")
+}

@@ -53,7 +53,9 @@ fields = [S.ProtoField(1, S.PB_STRING), S.ProtoField(2, S.PB_INT64), S.ProtoFiel
 msgs = [["n" * (k % 70), k * 977 - 5000, (k % 41) - 20, float(k % 7), bytes([k & 0xFF]) * (k % 9), -k if k % 3 else 0] for k in range(700)]
 msgs[13][0] = b"\xff"
 rows, roff2 = S.pack_proto_rows(fields, msgs)
-eng.proto_encode_device(fields, rows, roff2)
+d_o, d_oo, _ = eng.proto_encode_device(fields, rows, roff2)
+oo = d_oo.cpu().numpy().view(np.uint32)
+eng.proto_decode_device(fields, d_o[:int(oo[-1])].cpu().numpy(), oo)
 torch.cuda.synchronize()
 spec = S.TableSpec(routes=[S.Route(S.M_GET, "/hello", S.H_RESULT), S.Route(S.M_GET, "/u/{id}", S.H_RESULT)])
 reqs = [S.Req(S.M_GET, b"/hello" if k % 2 else b"/u/%d" % k, data=S.result_record(S.RESULT_STRING if k % 3 else S.RESULT_ERROR, b"<v %d>" % k * (k % 30)))
