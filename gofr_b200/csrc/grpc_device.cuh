@@ -1,4 +1,5 @@
-// grpc_device.cuh — per-frame device logic of the gRPC unary Hello path (BASELINE config 5).
+// grpc_device.cuh — per-frame device logic of the gRPC message path: the unary Hello of BASELINE config 5 (first part)
+// and the proto3 encoder / decoder for flat message types (second part).
 //
 // Replaces, for a batch of length-prefixed messages, what grpc-go + the generated code do per RPC in the reference:
 //   dec(in) in _Hello_SayHello_Handler (examples/grpc-server/grpc/hello_grpc.pb.go:73-89): strip the 5-byte gRPC

@@ -1,4 +1,5 @@
-// grpc_kernel.cu — gRPC unary Hello over a batch of length-prefixed frames (config 5), sm_100a.
+// grpc_kernel.cu — the gRPC message path over batches of length-prefixed frames, sm_100a: the unary Hello of config 5
+// (request frame → response frame) and the proto3 encoder / decoder for any flat message type (rows ↔ frames).
 //
 // Same execution model as serve_kernel.cu: persistent co-resident CTAs, one thread per frame, the tile's contiguous
 // input byte range pulled into shared memory with one TMA bulk copy, exact output sizes scanned in the CTA and chained

@@ -20,8 +20,12 @@
  *   Request.Param / Bind          pkg/gofr/http/request.go:28-47   (fused into the serve kernel per handler kind)
  *   _Hello_SayHello_Handler       examples/grpc-server/grpc/
  *                                 hello_grpc.pb.go:73-89           gofr_grpc_hello_device
+ *   dec(in) / proto.Marshal of any flat proto3 message type (the codec grpc-go calls around a unary handler)
+ *                                 hello_grpc.pb.go:73-89           gofr_proto_decode_device / gofr_proto_encode_device
  *   Router.Match + mux.Vars (routing only, closures on the host)
- *                                 pkg/gofr/http/router.go:14,30-33 gofr_route_device
+ *                                 pkg/gofr/http/router.go:14,30-33 gofr_route_device / gofr_batch_route
+ *   router.ServeHTTP per request under net/http's conn goroutine
+ *                                 pkg/gofr/httpServer.go:29-33     gofr_frontend_serve (batches the concurrent callers)
  *   net/http readRequest + url.ParseRequestURI (stdlib, reached from pkg/gofr/httpServer.go:29-33)
  *                                                                  gofr_http_parse_device
  *   middleware.Logging's RequestLog line → logger.Log
