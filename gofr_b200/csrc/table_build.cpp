@@ -18,6 +18,13 @@
 
 namespace gofr {
 
+// FNV-1a, 32 bit: integrity of a sealed image in transit (not a security feature)
+static uint32_t image_checksum(const uint8_t* p, size_t n) {
+    uint32_t h = 2166136261u;
+    for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 16777619u; }
+    return h;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------------------------
@@ -979,6 +986,9 @@ int seal_table(gofr_table* t) {
     H.cold_off = append(cold.data(), cold.size());
     align16();
     H.total_bytes = (uint32_t)img.size();
+    H.checksum = 0;
+    memcpy(img.data(), &H, sizeof H);
+    H.checksum = image_checksum(img.data(), img.size());
     memcpy(img.data(), &H, sizeof H);
     if (H.hot_bytes > kMaxHotBytes) {
         set_last_error("sealed table needs %u bytes of shared memory (limit %u)", H.hot_bytes, kMaxHotBytes);
@@ -1097,6 +1107,18 @@ int gofr_table_deserialize(gofr_table** out, const uint8_t* buf, uint64_t len) {
     t->frame_mode = H.frame_mode;
     t->has_catchall = H.has_catchall != 0;
     t->image.assign(buf, buf + len);
+    {   // the image crossed a process boundary: refuse anything that is not byte for byte what seal produced
+        ImageHeader Z = H;
+        Z.checksum = 0;
+        memcpy(t->image.data(), &Z, sizeof Z);
+        const uint32_t sum = gofr::image_checksum(t->image.data(), t->image.size());
+        memcpy(t->image.data(), &H, sizeof H);
+        if (sum != H.checksum) {
+            delete t;
+            set_last_error("sealed table image is corrupt (checksum %08x, expected %08x)", sum, H.checksum);
+            return GOFR_ERR_INVALID;
+        }
+    }
     t->sealed = true;
     *out = t;
     return GOFR_OK;

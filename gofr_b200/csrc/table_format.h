@@ -12,7 +12,7 @@
 namespace gofr {
 
 constexpr uint32_t kMagic = 0x52464F47u;  // "GOFR"
-constexpr uint32_t kImageVersion = 12;
+constexpr uint32_t kImageVersion = 13;
 constexpr uint32_t kMaxHotBytes = 40 * 1024;  // shared-memory budget for the table
 constexpr int kMaxVars = 8;                   // variables per route template
 constexpr int kMaxFields = 32;                // struct fields per schema
@@ -43,7 +43,9 @@ struct ImageHeader {  // 144 B
     // bytes (chained through RouteRec.next_lit in registration order); tmpl_off lists only the others
     uint32_t thash_off;      // uint16[1 << thash_bits], 0xFFFF = empty
     uint32_t thash_bits;
-    uint32_t reserved2[2];
+    uint32_t checksum;       // FNV-1a over the whole image with this field zero: set at seal, checked by deserialize (the
+                             // image travels between ranks); never read on the device
+    uint32_t reserved2;
 };
 static_assert(sizeof(ImageHeader) == 144, "ImageHeader layout");
 

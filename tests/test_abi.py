@@ -70,3 +70,31 @@ def test_engine_fails_loudly_without_a_gpu():
     rc = _abi.lib().gofr_engine_create(C.byref(e), t.handle, 0)
     assert rc == 8  # GOFR_ERR_NO_DEVICE
     assert b"no CPU path" in _abi.lib().gofr_last_error()
+
+
+def test_sealed_image_integrity():
+    """the sealed image travels between ranks (NCCL broadcast): deserialize refuses anything that is not byte for byte what
+    seal produced — flipped bits, truncation, trailing bytes, a foreign version"""
+    import ctypes as C
+    import numpy as np
+    from gofr_b200 import _abi, synth
+    from gofr_b200.table import Table
+    L = _abi.lib()
+    image = Table(synth.config4_spec()).serialize()
+    rng = np.random.default_rng(1)
+
+    def load(b: bytes) -> int:
+        t = C.c_void_p()
+        buf = np.frombuffer(b, dtype=np.uint8).copy()
+        rc = L.gofr_table_deserialize(C.byref(t), buf.ctypes.data, len(b))
+        if rc == 0:
+            L.gofr_table_destroy(t)
+        return rc
+
+    assert load(image) == 0
+    for _ in range(200):
+        b = bytearray(image)
+        pos = int(rng.integers(0, len(b)))
+        b[pos] ^= 1 << int(rng.integers(0, 8))
+        assert load(bytes(b)) != 0, pos
+    assert load(image[:-16]) != 0 and load(image + b"\0" * 16) != 0 and load(image[:100]) != 0
