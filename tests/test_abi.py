@@ -98,3 +98,34 @@ def test_sealed_image_integrity():
         b[pos] ^= 1 << int(rng.integers(0, 8))
         assert load(bytes(b)) != 0, pos
     assert load(image[:-16]) != 0 and load(image + b"\0" * 16) != 0 and load(image[:100]) != 0
+
+
+def test_response_bound_covers_every_response():
+    """gofr_table_response_bound is what a host batcher sums up to size its output buffer (include/gofr_b200.hpp does):
+    it must never be below the response the oracle produces for that request"""
+    import numpy as np
+    from gofr_b200 import _abi, spec as S, synth
+    from gofr_b200.table import Table
+    from tests import oracle as O
+    L = _abi.lib()
+    date = S.http_date(1_700_000_000)
+    hostile = S.TableSpec(routes=[S.Route(S.M_GET, "/hello", S.H_RESULT), S.Route(S.M_GET, "/p/{v}", S.H_PATHPARAM_FORMAT, s0=b"v", s2=b"<", s3=b">"),
+                                  S.Route(S.M_GET, "/q", S.H_PARAM_FORMAT, s0=b"k", s1=b"d", s2=b"[", s3=b"]")])
+    hb = S.RequestBatch.pack(
+        [S.Req(S.M_GET, b"/hello", data=S.result_record(S.RESULT_STRING, bytes([1]) * 300)),     # every byte grows six-fold
+         S.Req(S.M_GET, b"/hello", data=S.result_record(S.RESULT_ERROR, b"<&>" * 100)),
+         S.Req(S.M_GET, b"/p/" + bytes([2]) * 200), S.Req(S.M_GET, b"/q", b"k=" + b"%01" * 150),
+         S.Req(S.M_GET, b"//a/../" + b"x" * 500, b"y=" + b"z" * 400),                            # 301 with a long Location
+         S.Req(S.M_GET, b"/" + b"%".join([b"a"] * 200))])
+    cases = [(synth.config1_spec(), synth.config1_batch(300)), (synth.config2_spec(), synth.config2_batch(300, escape_every=3)),
+             (synth.config3_spec(), synth.config3_batch(300)), (synth.config4_spec(), synth.config4_batch(600)), (hostile, hb)]
+    for spec, batch in cases:
+        for frame in (S.FRAME_WIRE, S.FRAME_INTENDED, S.FRAME_BODY):
+            spec.frame_mode = frame
+            t = Table(spec)
+            out, off, meta = O.OracleTable(spec).serve(batch, date)
+            lens = np.diff(off.astype(np.int64))
+            for i in range(batch.n):
+                d = batch.desc[i]
+                bound = L.gofr_table_response_bound(t.handle, int(d["path_len"]), int(d["query_len"]), int(d["data_len"]))
+                assert bound >= lens[i], (frame, i, bound, int(lens[i]))
