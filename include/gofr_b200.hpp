@@ -311,6 +311,9 @@ public:
         return out;
     }
 
+    // the record Serve hands to stage 2 for this (data, err) when the route returns struct type `returns` (tests)
+    std::string ResultRecord(const Result& res, const StructType* returns = nullptr) const { return encode_result(returns ? returns->id_ : 0u, res); }
+
     gofr_engine* engine() const { return engine_; }
     gofr_table* table() const { return table_; }
 
@@ -365,18 +368,24 @@ private:
             if (vars[k] == 0xFFFFFFFFu) continue;
             c.path_params_.emplace_back(r.var_names[k], p.path.substr(vars[k] & 0xFFFFu, vars[k] >> 16));
         }
-        std::string rec;
         Result res;
         try {
             res = r.fn(c);
         } catch (...) {
+            std::string rec;
             detail::put_u32(&rec, 0xFFFFFFFFu);  // not an outcome: answered like a panicking handler
             return rec;
         }
+        return encode_result(r.type_id, res);
+    }
+
+    // (data, err) as the GOFR_H_RESULT record stage 2 reads (include/gofr_b200.h): what Responder.Respond will see
+    std::string encode_result(uint32_t route_type_id, const Result& res) const {
+        std::string rec;
         const bool has_err = res.err.has_value();
         if (auto* sv = std::get_if<StructValue>(&res.data)) {
             std::string fixed, strings;
-            if (sv->type_id != r.type_id || !encode_struct(*sv, &fixed, &strings)) { detail::put_u32(&rec, 0xFFFFFFFFu); return rec; }
+            if (sv->type_id != route_type_id || !encode_struct(*sv, &fixed, &strings)) { detail::put_u32(&rec, 0xFFFFFFFFu); return rec; }
             if (has_err) {  // (data, err): message length word + fixed words, then message bytes + string bytes
                 detail::put_u32(&rec, GOFR_RESULT_BOTH);
                 detail::put_u32(&rec, (uint32_t)res.err->message.size());

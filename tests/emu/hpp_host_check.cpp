@@ -26,6 +26,26 @@ int main() {
             const std::string v = gofr::detail::query_get(unhex(a), unhex(b));
             for (unsigned char c : v) printf("%02x", c);
             printf("\n");
+        } else if (kind == "R") {
+            // R <case>: result records of a fixed set of (data, err) values, hex
+            static gofr::App app;
+            static auto& item = app.Struct("main.Item").String("SKU", "sku").Int32("Qty", "qty").Int64("Big", "big").Bool("Ok", "ok").Int("N", "n").String("Note", "note", true);
+            const int c = atoi(a.c_str());
+            gofr::Result res;
+            const gofr::App::StructType* ty = &item;
+            if (c == 0) res = gofr::Result(std::string("Hello World!"));
+            else if (c == 1) res = gofr::Result(gofr::Error{"db: connection refused"});
+            else if (c == 2) res = gofr::Result();
+            else if (c == 3) res = gofr::Result(gofr::ErrMissingFile());
+            else if (c == 4) res = gofr::Result(gofr::Data(item({std::string("A-1"), int64_t(-3), int64_t(-5000000000LL), true, int64_t(1) << 40, std::string("fragile")})));
+            else if (c == 5) res = gofr::Result(gofr::Data(item({std::string(""), int64_t(0), int64_t(0), false, int64_t(0), std::string("")})), gofr::Error{"partial"});
+            else if (c == 6) { res = gofr::Result(gofr::Data(item({std::string("x"), int64_t(1)}))); }                         // wrong field count
+            else if (c == 7) { res = gofr::Result(gofr::Data(item({int64_t(1), int64_t(1), int64_t(1), true, int64_t(1), std::string("")}))); }  // wrong kind
+            else if (c == 8) { res = gofr::Result(gofr::Data(item({std::string("A"), int64_t(1), int64_t(1), true, int64_t(1), std::string("")}))); ty = nullptr; }  // route without a type
+            else if (c == 9) res = gofr::Result(gofr::Data(std::string("s")), gofr::Error{"e"});                                 // string next to an error
+            const std::string rec = app.ResultRecord(res, ty);
+            for (unsigned char ch : rec) printf("%02x", ch);
+            printf("\n");
         } else if (kind == "T") {
             const auto names = gofr::detail::template_vars(unhex(a));
             for (size_t i = 0; i < names.size(); i++) printf("%s%s", i ? "," : "", names[i].c_str());

@@ -32,7 +32,7 @@ def test_header_compiles_and_host_helpers_match_oracle(tmp_path):
     _abi.lib()  # builds the .so if needed
     _compile(os.path.join(ROOT, "examples", "cpp", "server_routes.cpp"), str(tmp_path / "server_routes"))
     exe = str(tmp_path / "hpp_host_check")
-    _compile(os.path.join(ROOT, "tests", "emu", "hpp_host_check.cpp"), exe, link=False)
+    _compile(os.path.join(ROOT, "tests", "emu", "hpp_host_check.cpp"), exe)
     rng = np.random.default_rng(5)
     alphabet = [b"a", b"b", b"name", b"=", b"&", b"&", b";", b"+", b"%41", b"%zz", b"%", b"%4", b"x", b"=", b"%26", b"%3D", b"\xff", b" "]
     cases = [(b"name=Vikash", b"name"), (b"", b"name"), (b"name", b"name"), (b"a=1&name=&name=2", b"name"), (b"a=1;name=2&name=3", b"name"),
@@ -44,10 +44,21 @@ def test_header_compiles_and_host_helpers_match_oracle(tmp_path):
     lines = "".join("Q %s %s\n" % (q.hex() or "-", k.hex() or "-") for q, k in cases)
     tmpl = ["/a/{id}/b/{name:[a-z]+}", "/{x:[0-9]{2}}/{y}", "/plain", "/{a}-{b}.{c}", "/{v:.*}"]
     lines += "".join("T %s\n" % t.encode().hex() for t in tmpl)
+    lines += "".join("R %d\n" % c for c in range(10))
     out = subprocess.run([exe], input=lines, capture_output=True, text=True, check=True).stdout.splitlines()
     for (q, k), got in zip(cases, out):
         assert bytes.fromhex(got) == O.query_get(q, k), (q, k)
-    assert out[len(cases):] == ["id,name", "x,y", "", "a,b,c", "v"]
+    assert out[len(cases):len(cases) + 5] == ["id,name", "x,y", "", "a,b,c", "v"]
+    # the (data, err) → GOFR_H_RESULT record encoding against the Python packer the oracle-side tests use
+    item = S.Schema(1, "main.Item", [S.Field("SKU", S.F_STRING, "sku"), S.Field("Qty", S.F_INT32, "qty"), S.Field("Big", S.F_INT64, "big"),
+                                     S.Field("Ok", S.F_BOOL, "ok"), S.Field("N", S.F_INT, "n"), S.Field("Note", S.F_STRING, "note", omitempty=True)])
+    bad = (0xFFFFFFFF).to_bytes(4, "little")
+    want = [S.result_record(S.RESULT_STRING, b"Hello World!"), S.result_record(S.RESULT_ERROR, b"db: connection refused"),
+            S.result_record(S.RESULT_NIL), S.result_record(S.RESULT_MISSING, b"http: no such file"),
+            S.result_record(S.RESULT_DATA, item.encode_row(["A-1", -3, -5000000000, True, 1 << 40, "fragile"])),
+            S.result_both(item, ["", 0, 0, False, 0, ""], b"partial"), bad, bad, bad, S.result_record(S.RESULT_ERROR, b"e")]
+    got = [bytes.fromhex(l) for l in out[len(cases) + 5:]]
+    assert got == want
 
 
 def _records():
