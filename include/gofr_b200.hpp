@@ -311,6 +311,17 @@ public:
         return out;
     }
 
+    // url.ParseRequestURI as Serve applies it to Request::target (tests): false for what httptest.NewRequest would refuse
+    static bool ParseTarget(const std::string& target, std::string* path, std::string* raw_query, bool* force_query) {
+        try {
+            Parsed p = parse_target(target);
+            *path = p.path; *raw_query = p.query; *force_query = p.force_query;
+            return true;
+        } catch (const std::invalid_argument&) {
+            return false;
+        }
+    }
+
     // the record Serve hands to stage 2 for this (data, err) when the route returns struct type `returns` (tests)
     std::string ResultRecord(const Result& res, const StructType* returns = nullptr) const { return encode_result(returns ? returns->id_ : 0u, res); }
 

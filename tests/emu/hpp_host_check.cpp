@@ -46,6 +46,15 @@ int main() {
             const std::string rec = app.ResultRecord(res, ty);
             for (unsigned char ch : rec) printf("%02x", ch);
             printf("\n");
+        } else if (kind == "P") {
+            std::string path, query;
+            bool force = false;
+            if (!gofr::App::ParseTarget(unhex(a), &path, &query, &force)) { printf("ERR\n"); continue; }
+            printf("-");
+            for (unsigned char ch : path) printf("%02x", ch);
+            printf(" -");
+            for (unsigned char ch : query) printf("%02x", ch);
+            printf(" %d\n", force ? 1 : 0);
         } else if (kind == "T") {
             const auto names = gofr::detail::template_vars(unhex(a));
             for (size_t i = 0; i < names.size(); i++) printf("%s%s", i ? "," : "", names[i].c_str());

@@ -45,6 +45,14 @@ def test_header_compiles_and_host_helpers_match_oracle(tmp_path):
     tmpl = ["/a/{id}/b/{name:[a-z]+}", "/{x:[0-9]{2}}/{y}", "/plain", "/{a}-{b}.{c}", "/{v:.*}"]
     lines += "".join("T %s\n" % t.encode().hex() for t in tmpl)
     lines += "".join("R %d\n" % c for c in range(10))
+    # request targets: path unescaping, the first '?' splits, a lone trailing '?' is ForceQuery, bad escapes are refused
+    import re
+    import urllib.parse
+    tparts = [b"/", b"a", b"b c", b"%41", b"%2F", b"%2f", b"%zz", b"%4", b"%", b"?", b"?", b"x=1", b"&", b"%3F", b"+", b"\xc3\xa9", b"//", b".."]
+    targets = [b"/", b"/a?", b"/a??", b"/a%3Fb?c", b"/%", b"/%4", b"/a%zzb", b"/x?y=%zz", b"a/b", b"", b"/p%41th/%2F?q=%41"]
+    for _ in range(1500):
+        targets.append(b"/" + b"".join(tparts[int(k)] for k in rng.integers(0, len(tparts), int(rng.integers(0, 8)))))
+    lines += "".join("P %s\n" % (t.hex() or "-") for t in targets)
     out = subprocess.run([exe], input=lines, capture_output=True, text=True, check=True).stdout.splitlines()
     for (q, k), got in zip(cases, out):
         assert bytes.fromhex(got) == O.query_get(q, k), (q, k)
@@ -57,8 +65,17 @@ def test_header_compiles_and_host_helpers_match_oracle(tmp_path):
             S.result_record(S.RESULT_NIL), S.result_record(S.RESULT_MISSING, b"http: no such file"),
             S.result_record(S.RESULT_DATA, item.encode_row(["A-1", -3, -5000000000, True, 1 << 40, "fragile"])),
             S.result_both(item, ["", 0, 0, False, 0, ""], b"partial"), bad, bad, bad, S.result_record(S.RESULT_ERROR, b"e")]
-    got = [bytes.fromhex(l) for l in out[len(cases) + 5:]]
+    got = [bytes.fromhex(l) for l in out[len(cases) + 5:len(cases) + 15]]
     assert got == want
+    for t, line in zip(targets, out[len(cases) + 15:]):
+        path, sep, query = t.partition(b"?")
+        bad = not t.startswith(b"/") or re.search(rb"%(?![0-9a-fA-F]{2})", path) is not None
+        if bad:
+            assert line == "ERR", t
+        else:
+            p_hex, q_hex, force = line.split(" ")
+            assert bytes.fromhex(p_hex[1:]) == urllib.parse.unquote_to_bytes(path) and bytes.fromhex(q_hex[1:]) == query, t
+            assert force == ("1" if sep and not query else "0"), t
 
 
 def _records():
