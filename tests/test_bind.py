@@ -114,3 +114,33 @@ def test_gpu_bind_edge_cases_and_host_path():
     batch = S.RequestBatch.pack([S.Req(S.M_POST, b"/echo", b"", b) for b in bodies])
     _check(KAT_SPEC, batch)
     _check(synth.config3_spec(), synth.config3_batch(20000, variant_every=5), host=True, chunk=3000)
+
+
+@settings(max_examples=400, deadline=None)
+@given(st.lists(st.lists(_json_atoms, min_size=0, max_size=14).map(b"".join), min_size=1, max_size=8))
+def test_syntax_verdict_agrees_with_python_json(bodies):
+    """Independent check of the scanner: a body Python's json module rejects as malformed must not bind (Go's decoder
+    checks the whole document before it stores anything), and a body that binds is something Python can load.  The
+    two parsers disagree only on things this generator avoids or that are filtered below: NaN / Infinity literals
+    (Python extension) and raw bytes that are not UTF-8 (Python refuses to decode the document, Go replaces them)."""
+    import json
+    spec = KAT_SPEC
+    spec.frame_mode = S.FRAME_BODY
+    batch = S.RequestBatch.pack([S.Req(S.M_POST, b"/echo", b"", b) for b in bodies])
+    out, off, meta = O.OracleTable(spec).serve(batch, DATE)
+    for b, r, m in zip(bodies, O.responses(out, off), meta):
+        try:
+            text = b.decode("utf-8")
+        except UnicodeDecodeError:
+            continue
+        try:
+            doc = json.loads(text, parse_constant=lambda c: (_ for _ in ()).throw(ValueError(c)))
+            py_ok = True
+        except ValueError:
+            py_ok = False
+        bound = (int(m) & 0xFFFF) == 200
+        if not py_ok:
+            assert not bound, (b, r)
+            assert b"invalid character" in r or b"unexpected end of JSON input" in r or b"invalid" in r or b"cannot unmarshal" in r, (b, r)
+        elif bound:
+            assert isinstance(doc, dict) or doc is None, (b, r)   # only an object (or null) binds into a struct
