@@ -150,7 +150,6 @@ def _llhttp_response(wire: bytes):
 def test_wire_responses_parse_as_http11():
     """every response of the mixed-traffic stream (200 / 301 / 404 / 405 / 500, HEAD and OPTIONS included) is one complete
     HTTP/1.1 message for h11 and for llhttp: status as reported in meta, Content-Length == body length, JSON bodies load"""
-    import numpy as np
     from gofr_b200 import spec as S, synth
     bare = S.TableSpec(default_routes=False, routes=[S.Route(S.M_GET, "/only-get", S.H_STATIC_STRING, s0=b"x"),
                                                     S.Route(S.M_POST, "/only-post", S.H_NIL)])
@@ -158,21 +157,21 @@ def test_wire_responses_parse_as_http11():
                                       S.Req(S.M_GET, b"/only-get"), S.Req(S.M_POST, b"/only-post"), S.Req(S.M_GET, b"//only-get")])
     seen = set()
     for spec, batch in ((synth.config4_spec(), synth.config4_batch(1500)), (bare, bare_batch)):
-      out, off, meta = O.OracleTable(spec).serve(batch, S.http_date(1_700_000_000))
-      for i, wire in enumerate(O.responses(out, off)):
-          status = int(meta[i]) & 0xFFFF
-          if status == 0:
-              continue                                  # host-only handler: no bytes
-          head = int(batch.desc[i]["method"]) == S.M_HEAD
-          st, hdr, body = _h11_response(wire, head)
-          assert st == status, (i, wire[:40])
-          if "content-length" in hdr and not head:
-              assert int(hdr["content-length"]) == len(body)
-          if hdr.get("content-type") == "application/json" and body:
-              json.loads(body)
-          assert hdr.get("date") == "Tue, 14 Nov 2023 22:13:20 GMT"
-          if not head:
-              st2, hdr2, body2, done = _llhttp_response(wire)
-              assert st2 == status and body2 == body and done and hdr2 == hdr, (i, wire[:60])
-          seen.add(status)
+        out, off, meta = O.OracleTable(spec).serve(batch, S.http_date(1_700_000_000))
+        for i, wire in enumerate(O.responses(out, off)):
+            status = int(meta[i]) & 0xFFFF
+            if status == 0:
+                continue                                  # host-only handler: no bytes
+            head = int(batch.desc[i]["method"]) == S.M_HEAD
+            st, hdr, body = _h11_response(wire, head)
+            assert st == status, (i, wire[:40])
+            if "content-length" in hdr and not head:
+                assert int(hdr["content-length"]) == len(body)
+            if hdr.get("content-type") == "application/json" and body:
+                json.loads(body)
+            assert hdr.get("date") == "Tue, 14 Nov 2023 22:13:20 GMT"
+            if not head:
+                st2, hdr2, body2, done = _llhttp_response(wire)
+                assert st2 == status and body2 == body and done and hdr2 == hdr, (i, wire[:60])
+            seen.add(status)
     assert {200, 301, 404, 405, 500} <= seen
