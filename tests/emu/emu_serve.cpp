@@ -145,6 +145,21 @@ extern "C" int emu_reqlog(const uint8_t* desc, const uint8_t* ids, const uint8_t
     return 0;
 }
 
+// ---- program inspection (scratch/prog_stats.py): the op list of program `prog` of a sealed image ----
+extern "C" int emu_prog_ops(const uint8_t* image, uint32_t prog, uint8_t* ops_out, uint32_t cap_ops, uint32_t* hdr_fixed,
+                            uint32_t* body_fixed, uint32_t* shape_class) {
+    TableView tv;
+    tv.bind(image, image);
+    if (prog >= tv.hdr()->n_progs) return -1;
+    const ProgRec P = tv.progs()[prog];
+    if (P.n_ops > cap_ops) return -2;
+    memcpy(ops_out, tv.ops() + P.first_op, (size_t)P.n_ops * sizeof(Op));
+    *hdr_fixed = P.hdr_fixed;
+    *body_fixed = P.body_fixed;
+    *shape_class = P.shape_class;
+    return (int)P.n_ops;
+}
+
 // ---- proto3 encoder (gofr_proto_encode_device): proto_size / proto_emit as the CUDA kernel runs them; the schema is
 // built the way engine.cu builds it ----
 #include "../../gofr_b200/csrc/grpc_device.cuh"
