@@ -401,3 +401,78 @@ def test_gpu_decode_matches_oracle():
     assert np.array_equal(d_off.cpu().numpy().view(np.uint32), o1) and np.array_equal(d_meta.cpu().numpy().view(np.uint32), m1)
     assert d_rows[:int(o1[-1])].cpu().numpy().tobytes() == r1[:int(o1[-1])].tobytes()
     eng.close()
+
+
+# =====================================================================================================================
+# a pin from the reference itself: the FileDescriptorProto protoc embedded in examples/grpc-server/grpc/hello.pb.go
+# (file_hello_proto_rawDesc; extracted by tests/golden/make_descriptor_pin.py) is the one byte string in the reference
+# that a real protobuf encoder wrote.  Its nested messages are flat at every level, so both directions can be pinned to it.
+# =====================================================================================================================
+
+def _rawdesc() -> bytes:
+    import os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hello_proto_rawdesc.hex")
+    return bytes.fromhex([l for l in open(p).read().splitlines() if not l.startswith("#")][0])
+
+
+def _decode_one(fields, body: bytes):
+    raw, off = _pack_frames([_frame(body)])
+    rows, roff, meta = O.proto_decode(fields, raw, off)
+    e_rows, e_off, e_meta = emu.proto_decode(fields, raw, off, 5)
+    assert np.array_equal(meta, e_meta) and rows[:int(roff[-1])].tobytes() == e_rows[5:int(e_off[-1])].tobytes()
+    assert meta[0] == 0
+    row = rows[:int(roff[1])].tobytes()
+    # unpack the row: fixed words, then the string bytes in field order
+    vals, pos, spos = [], 0, sum(8 if f.type in S.PB_64BIT else 4 for f in fields)
+    for f in fields:
+        if f.type in (S.PB_STRING, S.PB_BYTES):
+            ln = int.from_bytes(row[pos:pos + 4], "little")
+            vals.append(row[spos:spos + ln])
+            spos += ln
+            pos += 4
+        elif f.type in S.PB_64BIT:
+            vals.append(int.from_bytes(row[pos:pos + 8], "little"))
+            pos += 8
+        else:
+            vals.append(int.from_bytes(row[pos:pos + 4], "little"))
+            pos += 4
+    return vals
+
+
+def _encode_one(fields, values) -> bytes:
+    rows, off = S.pack_proto_rows(fields, [values])
+    out, o, meta = O.proto_encode(fields, rows, off)
+    e_out, e_off, e_meta = emu.proto_encode(fields, rows, off, 3)
+    assert meta[0] == 0 and e_meta[0] == 0 and out[:int(o[1])].tobytes() == e_out[3:int(e_off[1])].tobytes()
+    return out[5:int(o[1])].tobytes()
+
+
+def test_reference_descriptor_pin():
+    from google.protobuf import descriptor_pb2
+    raw = _rawdesc()
+    fd = descriptor_pb2.FileDescriptorProto.FromString(raw)
+    # ---- decoder: the top level of FileDescriptorProto (name=1, message_type=4, service=6, options=8, syntax=12); the
+    # repeated message_type keeps its LAST element when read as a singular field
+    FILE = [S.ProtoField(1, S.PB_STRING), S.ProtoField(4, S.PB_BYTES), S.ProtoField(6, S.PB_BYTES), S.ProtoField(8, S.PB_BYTES),
+            S.ProtoField(12, S.PB_STRING)]
+    name, last_msg, service, options, syntax = _decode_one(FILE, raw)
+    assert name == b"hello.proto" and syntax == b"proto3"                       # hello.proto:1
+    assert last_msg == fd.message_type[1].SerializeToString() and service == fd.service[0].SerializeToString()
+    assert options == fd.options.SerializeToString()
+    # one level down: DescriptorProto{name=1, field=2}, FieldDescriptorProto{name=1, number=3, label=4, type=5, json_name=10}
+    MSG = [S.ProtoField(1, S.PB_STRING), S.ProtoField(2, S.PB_BYTES)]
+    FIELD = [S.ProtoField(1, S.PB_STRING), S.ProtoField(3, S.PB_INT32), S.ProtoField(4, S.PB_ENUM), S.ProtoField(5, S.PB_ENUM),
+             S.ProtoField(10, S.PB_STRING)]
+    mname, mfield = _decode_one(MSG, last_msg)
+    assert mname == b"HelloResponse"                                            # hello.proto:8-10
+    assert _decode_one(FIELD, mfield) == [b"message", 1, 1, 9, b"message"]      # string message = 1 (LABEL_OPTIONAL, TYPE_STRING)
+    OPTS = [S.ProtoField(11, S.PB_STRING)]                                       # FileOptions.go_package
+    assert _decode_one(OPTS, options) == [fd.options.go_package.encode()]
+    # ---- encoder: rebuild the nested pieces bottom-up and find each of them, byte for byte, inside protoc's output
+    for msg_name, fld in (("HelloRequest", "name"), ("HelloResponse", "message")):
+        fbytes = _encode_one(FIELD, [fld, 1, 1, 9, fld])
+        mbytes = _encode_one(MSG, [msg_name, fbytes])
+        assert b"\x22" + bytes([len(mbytes)]) + mbytes in raw, msg_name           # field 4 (message_type), length, payload
+    obytes = _encode_one(OPTS, [fd.options.go_package])
+    assert raw.endswith(b"\x42" + bytes([len(obytes)]) + obytes + b"\x62\x06proto3")
+    assert raw.startswith(_encode_one([S.ProtoField(1, S.PB_STRING)], ["hello.proto"]))
