@@ -27,14 +27,38 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    srcs = [os.path.join(CSRC, f) for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
+    srcs = [f for f in SOURCES if os.path.exists(os.path.join(CSRC, f))]
     extra = os.environ.get("GOFR_EXTRA_NVCC", "").split()  # experiments only, e.g. -DGOFR_SERVE_T=96
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + srcs + ["-lcudart"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode != 0:
+    flags = NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else [])
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_m = max(os.path.getmtime(f) for f in [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)] if os.path.exists(f))
+    tag = os.path.join(objdir, ".flags")
+    flags_changed = not os.path.exists(tag) or open(tag).read() != " ".join(flags)
+
+    # one translation unit per nvcc process, in parallel; objects are reused when neither the source, a header nor the
+    # flags changed
+    def compile_one(f: str):
+        src, obj = os.path.join(CSRC, f), os.path.join(objdir, f + ".o")
+        if not force and not flags_changed and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_m):
+            return obj, 0, ""
+        r = subprocess.run([nvcc] + flags + ["-c", "-o", obj, src], capture_output=True, text=True)
+        return obj, r.returncode, r.stdout + r.stderr
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, srcs))
+    log = "".join(o for _, _, o in results)
+    if verbose or any(rc for _, rc, _ in results):
+        sys.stderr.write(log)
+    if any(rc for _, rc, _ in results):
         raise RuntimeError("nvcc failed building libgofr_b200.so")
+    open(tag, "w").write(" ".join(flags))
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + [o for o, _, _ in results] + ["-lcudart"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("linking libgofr_b200.so failed")
     return LIB
 
 

@@ -114,6 +114,8 @@ static int configure_geometry(gofr_engine* e, uint32_t in_per_req) {
 
 extern "C" {
 
+static int engine_init(gofr_engine* e, const std::vector<uint8_t>& img, int device);
+
 int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
     if (!out || !t) return GOFR_ERR_INVALID;
     const std::vector<uint8_t>& img = gofr_table_image(t);
@@ -126,6 +128,13 @@ int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
     if (device < 0 || device >= ndev) return GOFR_ERR_INVALID;
     CUDA_TRY(cudaSetDevice(device));
     gofr_engine* e = new gofr_engine();
+    const int rc_create = engine_init(e, img, device);
+    if (rc_create != GOFR_OK) { gofr_engine_destroy(e); return rc_create; }  // releases whatever the failed step left behind
+    *out = e;
+    return GOFR_OK;
+}
+
+static int engine_init(gofr_engine* e, const std::vector<uint8_t>& img, int device) {
     e->device = device;
     memcpy(&e->hdr, img.data(), sizeof(ImageHeader));
     cudaDeviceProp prop;
@@ -144,7 +153,7 @@ int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
     uint32_t in_per = per_cta > hot + 64u * kServeT ? ((per_cta - hot - 64u) / kServeT) & ~15u : 64u;
     if (in_per > 256u) in_per = 256u;
     int rc = configure_geometry(e, in_per);
-    if (rc != GOFR_OK) { delete e; return rc; }
+    if (rc != GOFR_OK) return rc;
     for (auto& s : e->slots) {
         CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -159,10 +168,10 @@ int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
     CUDA_TRY(cudaMalloc(&e->d_chain, 64));
     CUDA_TRY(cudaMalloc(&e->d_info, sizeof(ChunkInfo) * kSlots));
     CUDA_TRY(cudaMallocHost(&e->h_status, 64));
+    if (const char* w = getenv("GOFR_DEBUG_EPOCH_START")) e->epoch = (uint32_t)strtoul(w, nullptr, 0) & kEpochMask;  // tests: start next to the wrap
     if (getenv("GOFR_DEBUG_NO_LOOKBACK")) e->debug_flags |= 1u;  // diagnostic only: offsets are wrong unless every response has the same size
     e->egress_grid = e->sm_count / 4 > 0 ? e->sm_count / 4 : 1;
     if (const char* g = getenv("GOFR_EGRESS_GRID")) { int v = atoi(g); if (v > 0) e->egress_grid = v; }
-    *out = e;
     return GOFR_OK;
 }
 
@@ -222,6 +231,25 @@ static void fold_timing(gofr_engine* e) {
     cudaGetLastError();  // cudaEventQuery reports cudaErrorNotReady through the sticky-free last-error slot
 }
 
+
+// Look-back generation for the next launch.  State words written by older launches carry an older epoch and read as
+// "not ready"; the epoch field is kEpochBits wide, so it wraps.  Every state buffer the engine owns is cleared when it
+// does (after the device has drained), otherwise a word left by launch k would read as ready in launch k + 2^kEpochBits
+// for a tile index that no launch in between has overwritten.  Called with the engine lock held.
+static int next_epoch(gofr_engine* e, uint32_t* out) {
+    uint32_t ep = (e->epoch + 1) & gofr::kEpochMask;
+    if (ep == 0) {  // wrapped (epoch 0 is what zero-initialised words carry: never handed out)
+        if (cudaDeviceSynchronize() != cudaSuccess) { set_last_error("device synchronisation failed at the look-back epoch wrap"); return GOFR_ERR_CUDA; }
+        if (e->d_state && cudaMemset(e->d_state, 0, e->state_tiles * 8) != cudaSuccess) return GOFR_ERR_CUDA;
+        for (auto& s : e->slots)
+            if (s.d_state && cudaMemset(s.d_state, 0, ((s.cap_n + 63) / 64) * 8) != cudaSuccess) return GOFR_ERR_CUDA;
+        ep = 1;
+    }
+    e->epoch = ep;
+    *out = ep;
+    return GOFR_OK;
+}
+
 // one fused launch; `state`/`flag` are scratch owned by the caller of this helper
 static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, const uint8_t* d_arena, uint32_t n,
                       const char* date29, uint8_t* d_out, uint64_t out_cap, uint32_t* d_off, uint32_t* d_meta,
@@ -232,9 +260,7 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
     p.desc = d_desc; p.ids = d_ids; p.arena = d_arena; p.n = n;
     p.n_tiles = (n + kServeT - 1) / kServeT;
     p.image = e->d_image; p.hot_bytes = e->hdr.hot_bytes;
-    e->epoch = (e->epoch + 1) & 0xFFFFFu;
-    if (e->epoch == 0) e->epoch = 1;  // state words are zero-initialised: epoch 0 never matches
-    p.epoch = e->epoch;
+    { int erc = next_epoch(e, &p.epoch); if (erc) return erc; }
     p.out = d_out; p.out_cap = out_cap; p.out_off = d_off; p.meta = d_meta;
     p.tile_state = d_state; p.overflow = d_flag;
     p.in_cap = e->in_cap;
@@ -387,11 +413,58 @@ static int grow(void** p, size_t* cap, size_t need, size_t slack) {
 // A chunk = contiguous request range [lo, hi) and the arena byte range it covers.
 struct ChunkPlan { uint32_t lo, hi; uint32_t arena_lo, arena_hi; };
 
+// The arena byte range [*alo, *ahi) (16-byte granular) that requests [lo, hi) reference.  All arithmetic in 64 bits: a
+// descriptor with a huge arena_off or data_len (say a data_len taken from a Content-Length header) must be refused, not
+// wrap around and pass.
+static int chunk_arena_range(const gofr_req_batch* in, uint32_t lo, uint32_t hi, uint32_t* alo_out, uint32_t* ahi_out) {
+    uint64_t alo = ~0ull, ahi = 0;
+    const gofr_req_desc* dd = in->desc;
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint64_t a = dd[i].arena_off;
+        const uint64_t dend = ((a + dd[i].path_len + dd[i].query_len + 3u) & ~3ull) + dd[i].data_len;
+        alo = a < alo ? a : alo;
+        ahi = dend > ahi ? dend : ahi;
+    }
+    if (hi <= lo) alo = 0;
+    alo &= ~15ull;
+    ahi = (ahi + 15ull) & ~15ull;
+    if (ahi > (((uint64_t)in->arena_bytes + 15ull) & ~15ull) || ahi > 0xFFFFFFF0ull) {
+        set_last_error("a descriptor of requests %u..%u points outside the arena", lo, hi);
+        return GOFR_ERR_INVALID;
+    }
+    if (ahi > alo && !in->arena) { set_last_error("requests reference arena bytes but the batch has no arena"); return GOFR_ERR_INVALID; }
+    *alo_out = (uint32_t)alo;
+    *ahi_out = (uint32_t)(ahi > alo ? ahi : alo);
+    return GOFR_OK;
+}
+
+// Error exit of a host-batch call after work has been enqueued: earlier chunks' kernels and copies may still be
+// writing into the caller's buffers, which the caller is free to release once we return.
+static void drain_streams(gofr_engine* e) {
+    cudaStreamSynchronize(e->st_h2d);
+    cudaStreamSynchronize(e->st_compute);
+    cudaStreamSynchronize(e->st_egress);
+    for (auto& s : e->slots) { if (s.stream) cudaStreamSynchronize(s.stream); s.egress_pending = false; }
+    cudaGetLastError();
+}
+
+static int batch_submit_locked(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch* out, gofr_ticket* ticket);
+static int batch_submit_slots_locked(gofr_engine* e, const gofr_req_batch* in, gofr_slot_batch* out, gofr_ticket* ticket);
+
 int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch* out, gofr_ticket* ticket) {
     if (!e || !in || !out || !ticket) return GOFR_ERR_INVALID;
     if (in->n && (!in->desc || !in->trace_ids || !out->out || !out->out_off || !out->meta)) return GOFR_ERR_INVALID;
     std::lock_guard<std::mutex> g(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
+    // Descriptors are validated chunk by chunk as the batch is enqueued (an up-front scan of 1 Mi descriptors is
+    // milliseconds of pure latency), so an error can surface with earlier chunks in flight: nothing may still be
+    // writing into the caller's buffers when the error is returned.
+    const int rc = batch_submit_locked(e, in, out, ticket);
+    if (rc != GOFR_OK) drain_streams(e);
+    return rc;
+}
+
+static int batch_submit_locked(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch* out, gofr_ticket* ticket) {
     out->out_bytes = 0;
     const uint32_t n = in->n;
     int final_rc = GOFR_OK;
@@ -406,22 +479,13 @@ int gofr_batch_submit(gofr_engine* e, const gofr_req_batch* in, gofr_resp_batch*
     auto plan_chunk = [&](size_t ci) -> int {
         if (planned[ci]) return GOFR_OK;
         uint32_t lo = (uint32_t)(ci * e->chunk), hi = std::min<uint32_t>(n, lo + e->chunk);
-        uint32_t alo = 0xFFFFFFFFu, ahi = 0;
-        const gofr_req_desc* dd = in->desc;
-        for (uint32_t i = lo; i < hi; i++) {
-            uint32_t a = dd[i].arena_off;
-            uint32_t dend = ((a + dd[i].path_len + dd[i].query_len + 3u) & ~3u) + dd[i].data_len;
-            alo = a < alo ? a : alo;
-            ahi = dend > ahi ? dend : ahi;
-        }
-        alo &= ~15u;
-        ahi = (ahi + 15u) & ~15u;
-        if ((uint64_t)ahi > ((in->arena_bytes + 15u) & ~(uint64_t)15u)) { set_last_error("descriptor %u..%u points outside the arena", lo, hi); return GOFR_ERR_INVALID; }
+        uint32_t alo = 0, ahi = 0;
+        int prc = chunk_arena_range(in, lo, hi, &alo, &ahi);
+        if (prc) return prc;
         plan[ci] = {lo, hi, alo, ahi};
         planned[ci] = 1;
         return GOFR_OK;
     };
-
     // ---- streaming path: caller buffers are pinned → egress is device driven, the host never blocks mid-batch ----
     auto device_visible = [](const void* p) {
         cudaPointerAttributes a;
@@ -586,6 +650,12 @@ int gofr_batch_submit_slots(gofr_engine* e, const gofr_req_batch* in, gofr_slot_
     if (out->slot_bytes == 0 || (out->slot_bytes & 15u)) { set_last_error("slot_bytes must be a positive multiple of 16"); return GOFR_ERR_INVALID; }
     std::lock_guard<std::mutex> g(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
+    const int rc = batch_submit_slots_locked(e, in, out, ticket);
+    if (rc != GOFR_OK) drain_streams(e);  // see gofr_batch_submit
+    return rc;
+}
+
+static int batch_submit_slots_locked(gofr_engine* e, const gofr_req_batch* in, gofr_slot_batch* out, gofr_ticket* ticket) {
     const uint32_t n = in->n, slot = out->slot_bytes;
     int final_rc = GOFR_OK;
     const size_t nchunks = n ? (n + e->chunk - 1) / e->chunk : 0;
@@ -593,16 +663,8 @@ int gofr_batch_submit_slots(gofr_engine* e, const gofr_req_batch* in, gofr_slot_
         Slot& s = e->slots[ci % kSlots];
         // the chunk's request range and the arena bytes it covers (scanned right before the chunk is enqueued)
         const uint32_t lo = (uint32_t)(ci * e->chunk), hi = std::min<uint32_t>(n, lo + e->chunk), cn = hi - lo;
-        uint32_t alo = 0xFFFFFFFFu, ahi = 0;
-        for (uint32_t i = lo; i < hi; i++) {
-            const gofr_req_desc& d = in->desc[i];
-            const uint32_t dend = ((d.arena_off + d.path_len + d.query_len + 3u) & ~3u) + d.data_len;
-            alo = d.arena_off < alo ? d.arena_off : alo;
-            ahi = dend > ahi ? dend : ahi;
-        }
-        alo &= ~15u;
-        ahi = (ahi + 15u) & ~15u;
-        if ((uint64_t)ahi > ((in->arena_bytes + 15u) & ~(uint64_t)15u)) { set_last_error("descriptor %u..%u points outside the arena", lo, hi); return GOFR_ERR_INVALID; }
+        uint32_t alo = 0, ahi = 0;
+        { int prc = chunk_arena_range(in, lo, hi, &alo, &ahi); if (prc) return prc; }
         const size_t abytes = (size_t)ahi - alo, obytes = (size_t)cn * slot;
         if (s.egress_pending) {  // the slot's previous chunk must have left before its buffers are reused
             const bool grows = cn > s.cap_n || abytes > s.cap_arena || obytes > s.cap_out;
@@ -709,9 +771,7 @@ int gofr_grpc_hello_device(gofr_engine* e, const uint8_t* d_in, const uint32_t* 
     GrpcParams p;
     memset(&p, 0, sizeof p);
     p.in = d_in; p.in_off = d_in_off; p.n = n; p.n_tiles = (uint32_t)tiles;
-    e->epoch = (e->epoch + 1) & 0xFFFFFu;
-    if (e->epoch == 0) e->epoch = 1;
-    p.epoch = e->epoch;
+    { int erc = next_epoch(e, &p.epoch); if (erc) return erc; }
     p.out = d_out; p.out_cap = out_cap; p.out_off = d_out_off; p.meta = d_meta;
     p.tile_state = e->d_state; p.overflow = e->d_flag;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -770,9 +830,7 @@ static int proto_run(gofr_engine* e, const gofr_proto_field* fields, uint32_t n_
     GrpcParams p;
     memset(&p, 0, sizeof p);
     p.in = d_rows; p.in_off = d_row_off; p.n = n; p.n_tiles = (uint32_t)tiles;
-    e->epoch = (e->epoch + 1) & 0xFFFFFu;
-    if (e->epoch == 0) e->epoch = 1;
-    p.epoch = e->epoch;
+    { int erc = next_epoch(e, &p.epoch); if (erc) return erc; }
     p.out = d_out; p.out_cap = out_cap; p.out_off = d_out_off; p.meta = d_meta;
     p.tile_state = e->d_state; p.overflow = e->d_flag;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -825,15 +883,18 @@ int gofr_batch_route(gofr_engine* e, const gofr_req_batch* in, uint32_t* meta, u
     const uint32_t n = in->n;
     for (uint32_t lo = 0; lo < n; lo += e->chunk) {
         const uint32_t hi = std::min<uint32_t>(n, lo + e->chunk), cn = hi - lo;
-        uint32_t alo = 0xFFFFFFFFu, ahi = 0;
+        uint64_t alo64 = ~0ull, ahi64 = 0;
         for (uint32_t i = lo; i < hi; i++) {  // routing reads the path only
             const gofr_req_desc& d = in->desc[i];
-            alo = d.arena_off < alo ? d.arena_off : alo;
-            ahi = d.arena_off + d.path_len > ahi ? d.arena_off + d.path_len : ahi;
+            const uint64_t a = d.arena_off, b = a + d.path_len;
+            alo64 = a < alo64 ? a : alo64;
+            ahi64 = b > ahi64 ? b : ahi64;
         }
-        alo &= ~15u;
-        ahi = (ahi + 15u) & ~15u;
-        if ((uint64_t)ahi > ((in->arena_bytes + 15u) & ~(uint64_t)15u)) { set_last_error("descriptor %u..%u points outside the arena", lo, hi); return GOFR_ERR_INVALID; }
+        alo64 &= ~15ull;
+        ahi64 = (ahi64 + 15ull) & ~15ull;
+        if (ahi64 > (((uint64_t)in->arena_bytes + 15ull) & ~15ull) || ahi64 > 0xFFFFFFF0ull) { set_last_error("a descriptor of requests %u..%u points outside the arena", lo, hi); return GOFR_ERR_INVALID; }
+        if (ahi64 > alo64 && !in->arena) { set_last_error("requests reference arena bytes but the batch has no arena"); return GOFR_ERR_INVALID; }
+        const uint32_t alo = (uint32_t)alo64, ahi = (uint32_t)(ahi64 > alo64 ? ahi64 : alo64);
         const size_t abytes = (size_t)ahi - alo;
         int rc;
         if ((rc = grow((void**)&e->d_rt_desc, &e->rt_desc_cap, (size_t)cn * 16, 256))) return rc;
@@ -911,9 +972,7 @@ int gofr_requestlog_device(gofr_engine* e, const gofr_log_desc* d_desc, const ui
     LogParams p;
     memset(&p, 0, sizeof p);
     p.desc = d_desc; p.ids = d_trace_ids; p.arena = d_arena; p.n = n; p.n_tiles = (uint32_t)tiles;
-    e->epoch = (e->epoch + 1) & 0xFFFFFu;
-    if (e->epoch == 0) e->epoch = 1;
-    p.epoch = e->epoch;
+    { int erc = next_epoch(e, &p.epoch); if (erc) return erc; }
     p.out = d_out; p.out_cap = out_cap; p.out_off = d_out_off;
     p.tile_state = e->d_state; p.overflow = e->d_flag;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

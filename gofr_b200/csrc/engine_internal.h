@@ -37,6 +37,9 @@ struct ServeParams {
     uint32_t debug_flags;    // bit0: skip the look-back (tile_base = tile * tile_total; only valid for fixed-size responses)
 };
 
+constexpr int kEpochBits = 24;  // look-back generation field of a tile state word (tile_common.cuh)
+constexpr uint32_t kEpochMask = (1u << kEpochBits) - 1;
+
 constexpr int kServeThreads = 128;  // gRPC / request-log kernels: requests per tile = threads per CTA
 #ifndef GOFR_SERVE_T
 #define GOFR_SERVE_T 128

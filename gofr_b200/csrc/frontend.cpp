@@ -180,9 +180,13 @@ static void dispatcher(gofr_frontend* f) {
         x.rc = rc;
         f->batches.fetch_add(1, std::memory_order_relaxed);
         f->requests.fetch_add(n, std::memory_order_relaxed);
-        // publish the round in every group's word, then start the wake tree at its root
+        // publish the round in every group's word, then start the wake tree at its root.  DESCENDING group order: a
+        // caller of group g that is already awake may see done[g] == r1 at any moment and wake its children 2g+1 and
+        // 2g+2 exactly once (woke[g]); with release stores from the highest group down, seeing done[g] implies both
+        // children's words are already stored, so a child woken by that futex_wake cannot read the old value and go back
+        // to sleep with nobody left to wake it.
         const uint32_t r1 = x.round.load(std::memory_order_relaxed) + 1, g_used = (n + kGroup - 1) / kGroup;
-        for (uint32_t g = 0; g < g_used; g++) x.done[g].store(r1, std::memory_order_release);
+        for (uint32_t g = g_used; g-- > 0;) x.done[g].store(r1, std::memory_order_release);
         futex_wake_all(&x.done[0]);
         if (f->debug) {
             const int64_t t_end = mono_ns();

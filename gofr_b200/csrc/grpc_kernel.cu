@@ -53,7 +53,7 @@ __device__ __forceinline__ void frame_tiles(const GrpcParams& p, const Codec& cd
         if (staged) {
             mbar_wait(&sh.bar, parity);
             parity ^= 1;
-            base = sh.in - lo;
+            base = launder_after_sync((const uint8_t*)sh.in) - lo;
         }
         typename Codec::R r = cd.none();
         if (valid) r = cd.parse(base + fo, fn, fo);

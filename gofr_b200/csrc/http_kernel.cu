@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(HT, 8) http_parse_kernel(const HttpParams p) {
         if (staged) {
             mbar_wait(&sh.bar, parity);
             parity ^= 1;
-            base = sh.in - lo;
+            base = launder_after_sync((const uint8_t*)sh.in) - lo;
         }
         if (!valid) continue;
         const uint32_t a = (mo + 3u) & ~3u;

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(LT, 5) reqlog_kernel(const LogParams p) {
         if (staged) {
             mbar_wait(&sh.bar, parity);
             parity ^= 1;
-            abase = sh.in - in_lo;
+            abase = launder_after_sync((const uint8_t*)sh.in) - in_lo;
         }
         const uint8_t* rec = abase + d.arena_off;
 

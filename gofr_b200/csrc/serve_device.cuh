@@ -57,29 +57,45 @@ GOFR_HD int clz64(uint64_t v) {
 
 // true if the predicate holds for ANY currently active lane: used so that lanes whose phases differ still take
 // flush decisions together (flushing early is harmless, flushing at different times runs the flush code repeatedly)
+#if !defined(__CUDACC__)
+// host build (tests/emu): on the GPU a lane also flushes whenever ANOTHER lane of its warp needs room, i.e. at any of the
+// decision points and in any state; the emulation can replay that (mode 1: always, mode 2: pseudo-randomly)
+inline int& emu_any_mode() { static int m = 0; return m; }
+inline bool emu_any_extra() {
+    static uint32_t x = 0x9E3779B9u;
+    if (emu_any_mode() == 1) return true;
+    if (emu_any_mode() == 2) { x ^= x << 13; x ^= x >> 17; x ^= x << 5; return (x & 3u) == 0; }
+    return false;
+}
+#endif
 GOFR_HD bool warp_any(bool p) {
 #if defined(__CUDA_ARCH__)
     return __any_sync(__activemask(), p);
+#elif !defined(__CUDACC__)
+    return p || emu_any_extra();
 #else
     return p;
 #endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// output writer: appends bytes at an arbitrary byte address of the packed output; HBM only ever sees aligned 16-byte
-// st.global.cs.v4 stores (plus the few edge bytes a response shares with its neighbours in the packed stream).
+// output writer: appends bytes at an arbitrary byte address of the output; HBM only ever sees whole, aligned 32-byte
+// SECTORS written by one 256-bit st.global.cs.v8 (STG.E.256, new with sm_100) per lane — plus the few edge bytes a
+// response shares with its neighbours.  Measured on B200 (scratch/experiments/bulk_store/v8_bench.cu): one lane per
+// response writing its 528-byte slot with 16-byte stores takes 0.39 ms per 1 Mi responses (every store is a partial
+// sector for L2), with aligned 32-byte stores 0.14 ms — the same as fully coalesced warp-wide stores.
 //
-// Each thread owns a 32-word staging buffer in shared memory, laid out word-major (word k of thread t at
+// Each thread owns a 16-word staging buffer in shared memory, laid out word-major (word k of thread t at
 // [k * CTA + t]): whatever word index a lane is at, its bank is its lane id, so accesses never conflict.  The buffer is
-// DESTINATION-ALIGNED: word 0 is the first word of the 16-byte chunk at `chunk`.
+// DESTINATION-ALIGNED: word 0 is the first word of the 32-byte sector at `chunk`.
 //   produce: bytes are appended as whole words.  `pend` holds the nb (0..3) incomplete bytes in its TOP bytes, so
 //            appending a word is one funnel shift + one STS + a pointer bump — no branches, no per-word flush test,
 //            and the same code for every lane whatever its phase.  A memory source is streamed with the pending
 //            bytes treated as a prefix of the source ("virtual source"): one aligned load + one funnel shift per
 //            output word regardless of source and destination alignment.
-//   flush:   decoupled from producing — between ops, when at least 16 words wait, whole chunks leave as
-//            4 conflict-free LDS + one st.global.cs.v4; no shifting is needed because the buffer is already aligned.
-//   edges:   the first chunk's leading `lead` bytes and the last chunk's tail belong to neighbouring responses
+//   flush:   decoupled from producing — between ops, when at least 8 words wait, whole sectors leave as
+//            8 conflict-free LDS + one st.global.cs.v8; no shifting is needed because the buffer is already aligned.
+//   edges:   the first sector's leading `lead` bytes and the last sector's tail belong to neighbouring responses
 //            written by other threads; only this response's bytes are stored there.
 // ---------------------------------------------------------------------------------------------------------------
 #if defined(__CUDA_ARCH__)
@@ -156,17 +172,17 @@ GOFR_HD uint32_t load_bytes(const uint8_t* p, uint32_t k) {
 }
 
 struct Writer {
-    uint8_t* chunk;  // 16-byte aligned global address that staging word 0 maps to
+    uint8_t* chunk;  // 32-byte aligned global address that staging word 0 maps to
     saddr_t base;    // this thread's column of the staging buffer
     saddr_t wp;      // base + wl * stride: where the next complete word goes
     uint32_t wl;     // complete words staged (0 .. GOFR_STAGE_WORDS)
     uint32_t pend, nb;
-    uint32_t lead;   // bytes at the start of the first chunk owned by the previous response
+    uint32_t lead;   // bytes at the start of the first sector owned by the previous response(s)
 
     GOFR_HD void init(uint8_t* dst, uint32_t* col) {
         uintptr_t x = (uintptr_t)dst;
-        chunk = (uint8_t*)(x & ~(uintptr_t)15);
-        lead = (uint32_t)(x & 15);
+        chunk = (uint8_t*)(x & ~(uintptr_t)31);
+        lead = (uint32_t)(x & 31);
         wl = lead >> 2;  // phantom words of the neighbour: never stored
         nb = lead & 3;
         base = to_saddr(col);
@@ -177,50 +193,93 @@ struct Writer {
 
     GOFR_HD static void store16(uint8_t* addr, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
 #if defined(__CUDA_ARCH__)
+#if defined(GOFR_EXP_NO_STORE)  /* experiment: the kernel without its global stores (what is left is issue/latency bound) */
+        if (v0 == 0x12345678u && v1 == 0x9ABCDEF0u && v2 == 0x0F1E2D3Cu)
+#endif
         __stcs((uint4*)addr, make_uint4(v0, v1, v2, v3));
 #else
         uint32_t v[4] = {v0, v1, v2, v3};
         memcpy(addr, v, 16);
 #endif
     }
-    // Write bytes [lo, hi) of the 16-byte chunk at addr from the four staging words at rp: whole words where possible,
-    // else single bytes.  Runs twice per response at most (first and last chunk), so it is a loop, not unrolled code.
+    // One whole sector: addr is 32-byte aligned.  Two back-to-back 16-byte stores by default.  A single 256-bit store
+    // (st.global.v8.b32 -> STG.E.256, new with sm_100; -DGOFR_STORE256) is 7 % faster on the 1 Mi config-2 batch (0.318
+    // against 0.340 ms) but is NOT shipped: with it, and only with it — two `st.global.v4` in the same asm pass every
+    // test — responses of divergent warps in the packed layout come out with sectors whose first word is right and whose
+    // other seven are stale (memcheck / racecheck clean, deterministic, worse from a noinline
+    // wrapper; the store itself is correct in isolation, scratch/experiments/bulk_store/v8_check.cu).  Unexplained, so off.
+    template <int SITE = 0>
+    GOFR_HD static void store32(uint8_t* addr, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t v4, uint32_t v5,
+                                uint32_t v6, uint32_t v7) {
+#if defined(__CUDA_ARCH__)
+#if defined(GOFR_EXP_NO_STORE)
+        if (v0 == 0x12345678u && v1 == 0x9ABCDEF0u && v2 == 0x0F1E2D3Cu)
+#endif
+#if defined(GOFR_STORE256)
+        asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(addr), "r"(v0), "r"(v1), "r"(v2), "r"(v3),
+                     "r"(v4), "r"(v5), "r"(v6), "r"(v7)
+                     : "memory");
+#else
+        { __stcs((uint4*)addr, make_uint4(v0, v1, v2, v3)); __stcs((uint4*)(addr + 16), make_uint4(v4, v5, v6, v7)); }
+#endif
+#else
+        uint32_t v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
+        memcpy(addr, v, 32);
+#endif
+    }
+    // Write bytes [lo, hi) of the 32-byte sector at addr from the eight staging words at rp: a 16-byte half where one is
+    // whole, else words, else single bytes.  Runs twice per response at most (first and last sector), so it is a loop,
+    // not unrolled code.
     GOFR_HD static void store_partial(uint8_t* addr, saddr_t rp, uint32_t lo, uint32_t hi) {
         uint32_t b = lo;
 #pragma unroll 1
         for (; b < hi && (b & 3u); b++) addr[b] = (uint8_t)stg_ld8(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES + (b & 3u));
 #pragma unroll 1
+        for (; b + 4 <= hi && (b & 15u); b += 4) *(uint32_t*)(addr + b) = stg_ld(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES);
+#pragma unroll 1
+        for (; b + 16 <= hi; b += 16) {
+            const saddr_t q = rp + (b >> 2) * GOFR_RING_STRIDE_BYTES;
+            store16(addr + b, stg_ld(q), stg_ld(q + GOFR_RING_STRIDE_BYTES), stg_ld(q + 2 * GOFR_RING_STRIDE_BYTES),
+                    stg_ld(q + 3 * GOFR_RING_STRIDE_BYTES));
+        }
+#pragma unroll 1
         for (; b + 4 <= hi; b += 4) *(uint32_t*)(addr + b) = stg_ld(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES);
 #pragma unroll 1
         for (; b < hi; b++) addr[b] = (uint8_t)stg_ld8(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES + (b & 3u));
     }
-    // store every complete chunk, move the (< 4) left-over words to the front
+    GOFR_HD void store_sector(saddr_t rp) {
+        store32(chunk, stg_ld(rp), stg_ld(rp + GOFR_RING_STRIDE_BYTES), stg_ld(rp + 2 * GOFR_RING_STRIDE_BYTES),
+                stg_ld(rp + 3 * GOFR_RING_STRIDE_BYTES), stg_ld(rp + 4 * GOFR_RING_STRIDE_BYTES),
+                stg_ld(rp + 5 * GOFR_RING_STRIDE_BYTES), stg_ld(rp + 6 * GOFR_RING_STRIDE_BYTES),
+                stg_ld(rp + 7 * GOFR_RING_STRIDE_BYTES));
+    }
+    // store every complete sector, move the (< 8) left-over words to the front
     GOFR_HD void flush() {
-        uint32_t n = wl >> 2;
+        uint32_t n = wl >> 3;
         saddr_t rp = base;
-        if (n && lead) {  // first chunk of the response: skip the neighbour's bytes
-            store_partial(chunk, rp, lead, 16);
+        if (n && lead) {  // first sector of the response: skip the neighbour's bytes
+            store_partial(chunk, rp, lead, 32);
             lead = 0;
-            chunk += 16;
-            rp += 4 * GOFR_RING_STRIDE_BYTES;
+            chunk += 32;
+            rp += 8 * GOFR_RING_STRIDE_BYTES;
             n--;
         }
+#pragma unroll 1
         for (; n; n--) {
-            store16(chunk, stg_ld(rp), stg_ld(rp + GOFR_RING_STRIDE_BYTES), stg_ld(rp + 2 * GOFR_RING_STRIDE_BYTES),
-                    stg_ld(rp + 3 * GOFR_RING_STRIDE_BYTES));
-            chunk += 16;
-            rp += 4 * GOFR_RING_STRIDE_BYTES;
+            store_sector(rp);
+            chunk += 32;
+            rp += 8 * GOFR_RING_STRIDE_BYTES;
         }
-        uint32_t r = wl & 3;
-        if (wl >= 4) {
-            if (r > 0) stg_st(base, stg_ld(rp));
-            if (r > 1) stg_st(base + GOFR_RING_STRIDE_BYTES, stg_ld(rp + GOFR_RING_STRIDE_BYTES));
-            if (r > 2) stg_st(base + 2 * GOFR_RING_STRIDE_BYTES, stg_ld(rp + 2 * GOFR_RING_STRIDE_BYTES));
+        const uint32_t r = wl & 7;
+        if (wl >= 8 && r) {
+#pragma unroll
+            for (uint32_t j = 0; j < 7; j++)
+                if (r > j) stg_st(base + j * GOFR_RING_STRIDE_BYTES, stg_ld(rp + j * GOFR_RING_STRIDE_BYTES));
         }
         wl = r;
         wp = base + r * GOFR_RING_STRIDE_BYTES;
     }
-    // make room for n more words (n <= 28); the decision is taken together by all active lanes
+    // make room for n more words (n <= 8); the decision is taken together by all active lanes
     GOFR_HD void reserve(uint32_t n) {
         if (warp_any(wl + n > GOFR_STAGE_WORDS)) flush();
     }
@@ -280,31 +339,36 @@ struct Writer {
             nb = nn;
             return;
         }
-        reserve(8);  // at most 8 words staged from here on: the head below adds <= 4, a short copy <= 7
+        reserve(8);  // at most 8 words staged from here on: this word + (head <= 7 | a short copy <= 7)
         store_word(w0);
         cur = nxt;
         Y += 8;  // Y now points at the NEXT word to load
         nwords--;
         if (nwords >= 8) {
-            // Long copy.  Head: complete the chunk under construction (<= 3 more words), store it; from then on the
-            // staging buffer is empty and whole chunks go from registers straight to HBM.
-            while (wl & 3u) {
+            // Long copy.  Head: complete the sector under construction (<= 7 more words), store it; from then on the
+            // staging buffer is empty and whole sectors go from registers straight to HBM.
+#pragma unroll 1
+            while (wl & 7u) {
                 nxt = M::ld(Y);
                 Y += 4;
                 store_word(fsr(cur, nxt, sh));
                 cur = nxt;
                 nwords--;
             }
-            flush();  // wl is a multiple of 4: nothing is left behind
-            while (nwords >= 4) {
+            flush();  // wl is a multiple of 8: nothing is left behind
+#pragma unroll 1
+            while (nwords >= 8) {
                 const uint32_t n0 = M::ld(Y), n1 = M::ld(Y + 4), n2 = M::ld(Y + 8), n3 = M::ld(Y + 12);
-                store16(chunk, fsr(cur, n0, sh), fsr(n0, n1, sh), fsr(n1, n2, sh), fsr(n2, n3, sh));
-                chunk += 16;
-                cur = n3;
-                Y += 16;
-                nwords -= 4;
+                const uint32_t n4 = M::ld(Y + 16), n5 = M::ld(Y + 20), n6 = M::ld(Y + 24), n7 = M::ld(Y + 28);
+                store32<1>(chunk, fsr(cur, n0, sh), fsr(n0, n1, sh), fsr(n1, n2, sh), fsr(n2, n3, sh), fsr(n3, n4, sh),
+                           fsr(n4, n5, sh), fsr(n5, n6, sh), fsr(n6, n7, sh));
+                chunk += 32;
+                cur = n7;
+                Y += 32;
+                nwords -= 8;
             }
         }
+#pragma unroll 1
         for (; nwords; nwords--) {  // <= 7 words
             nxt = M::ld(Y);
             Y += 4;
@@ -318,21 +382,25 @@ struct Writer {
         }
         nb = nn;
     }
-    // Slot layout (gofr_serve_device_slots): the response owns its 16-byte aligned slot, so the last chunk is stored
-    // whole, zero padded — no byte stores, nothing of a neighbour to preserve.
+    // Slot layout (gofr_serve_device_slots): the response owns its 16-byte aligned slot, so the last 16-byte chunk is
+    // stored whole, zero padded — no byte stores, nothing of a neighbour to preserve.  A slot starts either on a sector
+    // boundary or in the middle of one (lead 0 or 16).
     GOFR_HD void finish_padded() {
         flush();
-        if (wl || nb) {
+        const uint32_t end = 4 * wl + nb;  // bytes of the last sector in use, phantom lead included
+        if (end > lead) {
             const uint32_t tail = nb ? pend >> (8 * (4 - nb)) : 0u;
-            uint32_t v[4];
+            uint32_t v[8];
 #pragma unroll
-            for (uint32_t j = 0; j < 4; j++) v[j] = j < wl ? word(j) : (j == wl ? tail : 0u);
-            store16(chunk, v[0], v[1], v[2], v[3]);
+            for (uint32_t j = 0; j < 8; j++) v[j] = j < wl ? word(j) : (j == wl ? tail : 0u);
+            if (lead) store16(chunk + 16, v[4], v[5], v[6], v[7]);              // upper half only: the lower one is the neighbour's
+            else if (end > 16) store32<2>(chunk, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+            else store16(chunk, v[0], v[1], v[2], v[3]);                          // the upper half may be the next slot's
         }
     }
     GOFR_HD void finish() {
         flush();
-        if (wl || nb) {  // the last, partial chunk; wl <= 3 after the flush
+        if (4 * wl + nb > lead) {  // the last, partial sector; wl <= 7 after the flush
             if (nb) stg_st(wp, pend >> (8 * (4 - nb)));
             store_partial(chunk, base, lead, 4 * wl + nb);
         }

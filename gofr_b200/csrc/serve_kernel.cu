@@ -63,6 +63,7 @@ __device__ __forceinline__ void serve_body(const ServeParams& p) {
     __syncthreads();
     patch_dates(tbl, (const uint8_t*)p.date, tid, T);
     __syncthreads();
+    tbl = launder_after_sync(tbl);
     TableView tv;
     tv.bind(tbl, p.image);
     BatchRefs br;
@@ -114,7 +115,7 @@ __device__ __forceinline__ void serve_body(const ServeParams& p) {
         if (in_staged) {
             mbar_wait(&sh.bar, parity);
             parity ^= 1;
-            abase = in_stage - in_lo;  // abase + arena_off lands in the staged copy
+            abase = launder_after_sync((const uint8_t*)in_stage) - in_lo;  // abase + arena_off lands in the staged copy
         }
 
         // ---- stage 1: route ----

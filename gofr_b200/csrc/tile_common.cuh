@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "engine_internal.h"
+
 namespace gofr {
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -35,6 +37,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_global,
                  "l"(src_global), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
+// The copy sources read staged bytes through NON-volatile `ld.shared` inline asm (the compiler may schedule them freely
+// among themselves).  Such an asm has no memory operand, so neither a barrier nor a "memory" clobber orders it: only a
+// data dependence does.  Every pointer to freshly staged shared memory (the TMA-filled tile after the mbarrier wait, the
+// table copy after its __syncthreads) is therefore passed through this empty asm right after the synchronisation: all
+// addresses derived from the result depend on it, so no load of the staged bytes can be hoisted above the wait.
+// (Round 2: a build with a different store instruction hoisted literal-pool loads above the table barrier in the first
+// tile of a CTA — zeros in the output, visible only on the GPU.)
+template <typename T>
+__device__ __forceinline__ T* launder_after_sync(T* p) {
+    asm volatile("" : "+l"(p) : : "memory");
+    return p;
+}
 __device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -45,12 +59,14 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// decoupled look-back over tile totals.  state = epoch(20) | flag(2) | value(42); flag 1 = tile total, 2 = inclusive
-// prefix.  Words written by earlier launches carry an older epoch and read as "not ready".
+// decoupled look-back over tile totals.  state = epoch(24) | flag(2) | value(38); flag 1 = tile total, 2 = inclusive
+// prefix.  Words written by earlier launches carry an older epoch and read as "not ready"; the host clears every state
+// buffer when the epoch wraps (engine.cu, next_epoch).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr unsigned long long kValMask = (1ull << 42) - 1;
+constexpr int kValBits = 38;
+constexpr unsigned long long kValMask = (1ull << kValBits) - 1;
 __device__ __forceinline__ unsigned long long pack_state(uint32_t epoch, uint32_t flag, unsigned long long v) {
-    return ((unsigned long long)(epoch & 0xFFFFFu) << 44) | ((unsigned long long)flag << 42) | (v & kValMask);
+    return ((unsigned long long)(epoch & kEpochMask) << (kValBits + 2)) | ((unsigned long long)flag << kValBits) | (v & kValMask);
 }
 
 // Called by warp 0.  Returns the exclusive prefix of `tile` (valid in every lane).
@@ -63,8 +79,8 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* state
         for (;;) {
             long long t = base - (long long)lane;
             unsigned long long s = t >= 0 ? ld_state(&state[t]) : pack_state(epoch, 2, 0);
-            uint32_t flag = (uint32_t)(s >> 42) & 3u;
-            bool ready = (uint32_t)(s >> 44) == (epoch & 0xFFFFFu) && flag != 0;
+            uint32_t flag = (uint32_t)(s >> kValBits) & 3u;
+            bool ready = (uint32_t)(s >> (kValBits + 2)) == (epoch & kEpochMask) && flag != 0;
             uint32_t not_ready = __ballot_sync(0xFFFFFFFFu, !ready);
             uint32_t is_p = __ballot_sync(0xFFFFFFFFu, ready && flag == 2);
             uint32_t upto = is_p ? (uint32_t)__ffs((int)is_p) - 1 : 31u;  // lanes 0..upto contribute

@@ -49,6 +49,12 @@ def lib():
     return _lib
 
 
+def set_flush_mode(mode: int):
+    """0: flush decisions per request; 1: flush at every decision point; 2: pseudo-random extra flushes (on the GPU the
+    other lanes of a warp impose theirs)."""
+    lib().emu_set_flush_mode(mode)
+
+
 def serve_slots(image: bytes, batch, date: bytes, slot_bytes: int):
     """Slot layout on the CPU: (out uint8[n, slot_bytes] pre-filled with 0xEE, out_len, meta)."""
     n = batch.n
@@ -158,6 +164,8 @@ def serve(image: bytes, batch, date: bytes, out_cap: int | None = None, misalign
                          misalign)
     if rc == -2:
         raise AssertionError("hashed and linear route matchers disagree")
+    if rc == -3:
+        raise AssertionError("a response wrote bytes outside its own range")
     if rc != 0:
         raise RuntimeError("emu output capacity too small")
     return out, off, meta

@@ -13,6 +13,10 @@
 
 using namespace gofr;
 
+// 0: a lane flushes only when it needs room itself; 1: at every decision point; 2: pseudo-randomly (what the other lanes
+// of a warp impose on it on the GPU)
+extern "C" void emu_set_flush_mode(int mode) { emu_any_mode() = mode; }
+
 extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t* desc, const uint8_t* ids,
                          const uint8_t* arena, uint32_t n, const char* date29, uint8_t* out, uint64_t out_cap,
                          uint32_t* out_off, uint32_t* meta, uint32_t start_misalign) {
@@ -45,8 +49,14 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
         }
         out_off[i] = (uint32_t)pos;
         meta[i] = request_status(tv, c) | (c.route << 16);
-        if (pos + c.total_len > out_cap) return -1;
+        if (pos + c.total_len + 32 > out_cap) return -1;
+        // a response may only touch its own bytes: on the GPU its neighbours are written concurrently by other threads
+        uint8_t before[32], after[32];
+        const uint64_t b0 = pos >= 32 ? pos - 32 : 0;
+        memcpy(before, out + b0, (size_t)(pos - b0));
+        memcpy(after, out + pos + c.total_len, 32);
         emit_request(tv, br, c, out + pos, ring);
+        if (memcmp(before, out + b0, (size_t)(pos - b0)) != 0 || memcmp(after, out + pos + c.total_len, 32) != 0) return -3;
         pos += c.total_len;
     }
     out_off[n] = (uint32_t)pos;
