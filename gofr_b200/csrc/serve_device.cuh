@@ -136,6 +136,12 @@ GOFR_HD uint32_t stg_ld8(saddr_t a) {
     return v;
 }
 GOFR_HD uint32_t salign(saddr_t a) { return a & 3u; }
+// 16 aligned source bytes (response templates)
+GOFR_HD uint4 src_ld128(saddr_t a) {
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 #else
 typedef const uint8_t* saddr_t;
 GOFR_HD saddr_t to_saddr(const void* p) { return (const uint8_t*)p; }
@@ -144,6 +150,7 @@ GOFR_HD uint32_t stg_ld(saddr_t a) { return *(const uint32_t*)a; }
 GOFR_HD uint32_t stg_ld8(saddr_t a) { return *a; }
 GOFR_HD uint32_t src_ld(saddr_t a) { return *(const uint32_t*)a; }
 GOFR_HD uint32_t salign(saddr_t a) { return (uint32_t)((uintptr_t)a & 3u); }
+GOFR_HD uint4 src_ld128(saddr_t a) { uint4 v; memcpy(&v, a, 16); return v; }
 #endif
 
 // memory policy of a copy source: SH = shared-memory address, otherwise a generic pointer
@@ -315,6 +322,20 @@ struct Writer {
     // one byte from the hot path, where the caller has already made room
     GOFR_HD void putc(uint32_t c) { putk(c, 1); }
 
+    // K consecutive words of a copy: output word i is the unaligned word at Y + 4i (cur holds the aligned word before Y)
+    template <typename M, int K>
+    GOFR_HD void stream_words(typename M::A& Y, uint32_t& cur, uint32_t sh) {
+        uint32_t n[K];
+#pragma unroll
+        for (int i = 0; i < K; i++) n[i] = M::ld(Y + 4 * i);
+#pragma unroll
+        for (int i = 0; i < K; i++) stg_st(wp + i * GOFR_RING_STRIDE_BYTES, fsr(i ? n[i - 1] : cur, n[i], sh));
+        cur = n[K - 1];
+        Y += 4 * K;
+        wp += K * GOFR_RING_STRIDE_BYTES;
+        wl += K;
+    }
+
     // Append len bytes from memory (any alignment).  With y = src - nb the stream "pending bytes ++ source" is
     // word-aligned with the destination, so output word k is the unaligned word at y + 4k: one aligned load (the
     // previous one is carried) and one funnel shift.  Only word 0 mixes in `pend`.
@@ -347,14 +368,11 @@ struct Writer {
         if (nwords >= 8) {
             // Long copy.  Head: complete the sector under construction (<= 7 more words), store it; from then on the
             // staging buffer is empty and whole sectors go from registers straight to HBM.
-#pragma unroll 1
-            while (wl & 7u) {
-                nxt = M::ld(Y);
-                Y += 4;
-                store_word(fsr(cur, nxt, sh));
-                cur = nxt;
-                nwords--;
-            }
+            const uint32_t h = (8u - (wl & 7u)) & 7u;
+            if (h & 4u) stream_words<M, 4>(Y, cur, sh);
+            if (h & 2u) stream_words<M, 2>(Y, cur, sh);
+            if (h & 1u) stream_words<M, 1>(Y, cur, sh);
+            nwords -= h;
             flush();  // wl is a multiple of 8: nothing is left behind
 #pragma unroll 1
             while (nwords >= 8) {
@@ -368,13 +386,11 @@ struct Writer {
                 nwords -= 8;
             }
         }
-#pragma unroll 1
-        for (; nwords; nwords--) {  // <= 7 words
-            nxt = M::ld(Y);
-            Y += 4;
-            store_word(fsr(cur, nxt, sh));
-            cur = nxt;
-        }
+        // <= 7 words left: 4 + 2 + 1, each group with its loads issued together and immediate offsets (a word-at-a-time
+        // loop spends more on its counters than on the words)
+        if (nwords & 4u) stream_words<M, 4>(Y, cur, sh);
+        if (nwords & 2u) stream_words<M, 2>(Y, cur, sh);
+        if (nwords & 1u) stream_words<M, 1>(Y, cur, sh);
         if (nn) {
             // the partial last word: its bytes may or may not spill into the next aligned word
             nxt = (yo + nn > 4) ? M::ld(Y) : 0u;
@@ -435,6 +451,18 @@ GOFR_HD uint32_t json_special_mask(uint32_t x) {
     uint32_t bs = (y ^ 0x5C5C5C5Cu) + 0x7F7F7F7Fu;                  // bit7 clear iff y == 0x5C
     return (~(ge20 & qa & lg & bs) | x) & 0x80808080u;
 }
+// the same test accumulated over many words: bit 7 of a byte lane of `acc` ends up set iff some word had a special byte
+// there (two three-input logic ops per word instead of four; the final `& 0x80808080` is the caller's)
+GOFR_HD uint32_t json_special_acc(uint32_t acc, uint32_t x) {
+    const uint32_t y = x & 0x7F7F7F7Fu;
+    const uint32_t ge20 = y + 0x60606060u;
+    const uint32_t qa = ((y | 0x04040404u) ^ 0x26262626u) + 0x7F7F7F7Fu;
+    const uint32_t lg = ((y | 0x02020202u) ^ 0x3E3E3E3Eu) + 0x7F7F7F7Fu;
+    const uint32_t bs = (y ^ 0x5C5C5C5Cu) + 0x7F7F7F7Fu;
+    const uint32_t t = ge20 & qa & lg;   // one LOP3
+    acc |= x;                            // bytes >= 0x80 (folds into the next LOP3 on the device)
+    return acc | ~(t & bs);              // one LOP3
+}
 
 // true if [p, p+len) contains a byte that encoding/json does not copy verbatim
 template <bool SH>
@@ -453,11 +481,18 @@ GOFR_HD bool json_needs_escape(typename SrcMem<SH>::A p, uint32_t len) {
         if (keep) x = (x & (0xFFFFFFFFu >> (8 * (4 - keep)))) | (0x61616161u << (8 * keep));
         return json_special_mask(x) != 0;
     }
-    uint32_t bad = json_special_mask(x);
-    for (uint32_t i = 1; i < last; i++) bad |= json_special_mask(M::ld(q + 4 * i));
+    uint32_t acc = json_special_acc(0u, x);
+    uint32_t i = 1;
+#pragma unroll 1
+    for (; i + 4 <= last; i += 4) {  // four words per trip: the loads go out together
+        const uint32_t a = M::ld(q + 4 * i), b = M::ld(q + 4 * i + 4), c = M::ld(q + 4 * i + 8), d = M::ld(q + 4 * i + 12);
+        acc = json_special_acc(json_special_acc(json_special_acc(json_special_acc(acc, a), b), c), d);
+    }
+#pragma unroll 1
+    for (; i < last; i++) acc = json_special_acc(acc, M::ld(q + 4 * i));
     x = M::ld(q + 4 * last);
     if (keep) x = (x & (0xFFFFFFFFu >> (8 * (4 - keep)))) | (0x61616161u << (8 * keep));
-    return (bad | json_special_mask(x)) != 0;
+    return (json_special_acc(acc, x) & 0x80808080u) != 0;
 }
 
 // Go utf8.DecodeRune acceptance on a plain byte range: length of the well-formed sequence at p (2..4) or 0.
@@ -538,6 +573,19 @@ GOFR_HD uint32_t ascii4(uint32_t q) {
     return (a | b << 8 | c << 16 | d << 24) + 0x30303030u;
 }
 
+// v < 10^8 with nd digits (nd = 1..8): at most two four-digit groups — what Content-Length, counters and most ids need
+GOFR_HD void emit_small_digits(Writer* w, uint32_t v, uint32_t nd) {
+    const uint32_t hi = v / 10000u, lo = v - hi * 10000u;
+    const uint32_t wlo = ascii4(lo);
+    if (nd <= 4) {
+        if (nd == 4) w->put4(wlo); else w->putk(wlo >> (8 * (4 - nd)), nd);
+        return;
+    }
+    const uint32_t whi = ascii4(hi), part = nd - 4;
+    if (part == 4) w->put4(whi); else w->putk(whi >> (8 * (4 - part)), part);
+    w->put4(wlo);
+}
+
 template <bool EMIT>
 GOFR_HD uint32_t emit_i64(Writer* w, int64_t sv) {
     uint64_t v = sv < 0 ? (uint64_t)0 - (uint64_t)sv : (uint64_t)sv;
@@ -545,6 +593,7 @@ GOFR_HD uint32_t emit_i64(Writer* w, int64_t sv) {
     uint32_t total = nd + (sv < 0 ? 1u : 0u);
     if (!EMIT) return total;
     if (sv < 0) w->putc('-');
+    if (v < 100000000ull) { emit_small_digits(w, (uint32_t)v, nd); return total; }
     // zero-padded 20 digits as five words W[0..4], W[0] most significant
     uint32_t W[5];
     uint64_t top = v / 10000000000000000ull;           // < 1845
@@ -568,6 +617,7 @@ GOFR_HD uint32_t emit_u32(Writer* w, uint32_t v) {
     uint32_t nd = v < 10 ? 1 : v < 100 ? 2 : v < 1000 ? 3 : v < 10000 ? 4 : v < 100000 ? 5 : v < 1000000 ? 6
                 : v < 10000000 ? 7 : v < 100000000 ? 8 : v < 1000000000 ? 9 : 10;
     if (!EMIT) return nd;
+    if (v < 100000000u) { emit_small_digits(w, v, nd); return nd; }
     uint32_t hi = v / 100000000u, rest = v - hi * 100000000u;
     uint32_t W[3] = {ascii4(hi), ascii4(rest / 10000), ascii4(rest % 10000)};
     uint32_t skip = 12 - nd, wi = skip >> 2, part = 4 - (skip & 3);
@@ -616,6 +666,7 @@ struct TableView {
     GOFR_HD const uint16_t* thash_tab() const { return (const uint16_t*)(base + hdr()->thash_off); }
     GOFR_HD const uint32_t* tmpl_keys() const { return (const uint32_t*)(base + hdr()->tmplkey_off); }
     GOFR_HD const uint16_t* last_method() const { return (const uint16_t*)(base + hdr()->last_method_off); }
+    GOFR_HD const FastRec* fast() const { return (const FastRec*)(base + hdr()->fast_off); }
     GOFR_HD const uint32_t* lit_words(uint32_t off) const { return (const uint32_t*)(lits() + off); }
     GOFR_HD const uint8_t* lit_bytes(uint32_t off) const { return lits() + off; }
 };
@@ -641,12 +692,14 @@ struct ReqCtx {
     uint32_t body_len, total_len;
     uint32_t slow_mask;    // bit k: k-th OP_STR of the program needs the slow escape path
     uint32_t def_off, def_len;  // OP_PARAM default (pre-escaped literal)
+    uint32_t str_base;     // fast path: byte offset of the row's string area inside the data section (size_fast)
 
     GOFR_HD const uint8_t* query() const { return path + path_len; }
     GOFR_HD const uint8_t* data() const { return path + data_off; }
     GOFR_HD uint32_t method() const { return mflags & 0xFFu; }
     GOFR_HD uint32_t flags() const { return (mflags >> 8) & 0xFFu; }
     GOFR_HD bool staged() const { return (mflags >> 16) & 1u; }
+    GOFR_HD bool fast() const { return (mflags >> 17) & 1u; }  // sized by size_fast: emit_fast may write it
     GOFR_HD void set(const uint8_t* arena_base, uint32_t arena_off, uint32_t pl, uint32_t ql, uint32_t dl, uint32_t method_,
                      uint32_t flags_, bool staged_, uint32_t idx) {
         path = arena_base + arena_off;
@@ -656,7 +709,7 @@ struct ReqCtx {
         index = idx;
         prog = 0xFFFF; route = GOFR_ROUTE_NONE;
         pv_off = pv_len = pv_flags = 0;
-        body_len = total_len = 0; slow_mask = 0; def_off = def_len = 0;
+        body_len = total_len = 0; slow_mask = 0; def_off = def_len = 0; str_base = 0;
     }
     GOFR_HD uint32_t* brow(const BatchRefs& br) const { return br.bind_scratch + (size_t)index * br.bind_row_words; }
 };
@@ -1260,6 +1313,220 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
     return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// slot-layout fast path (table_format.h FastRec): programs made of literals and plain values, requests whose values
+// need no escaping, tiles staged in shared memory.  Anything else takes run_prog — the general interpreter above.
+// ---------------------------------------------------------------------------------------------------------------
+
+// Row words of a staged request: the data section lives in shared memory, so it is read with ld.shared (a generic load
+// of the same address takes the slow LD.E path and showed up as the second largest long-scoreboard stall); Bind span rows
+// live in global scratch.
+struct RowReader {
+    saddr_t sh;           // data section in shared memory
+    const uint32_t* gl;   // Bind span row (global), or null
+    GOFR_HD uint32_t operator[](uint32_t k) const { return gl ? gl[k] : src_ld(sh + 4 * k); }
+};
+
+// Lean size pass of a PF_FAST program (every dynamic op is a plain value of the body).  Returns false when the request
+// needs something emit_fast does not do — a string encoding/json would escape, a query value that needs decoding, a
+// malformed row, a tile that is not staged, HEAD — and the caller runs the general size pass instead.
+GOFR_HD bool size_fast(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
+    const ProgRec P = tv.progs()[c.prog];
+    if (!(P.flags & PF_FAST) || !c.staged() || c.method() == GOFR_M_HEAD) return false;
+    const Op* ops = tv.ops() + P.first_dyn;
+    RowReader row;
+    row.sh = to_saddr(c.data());
+    row.gl = (P.flags & PF_BIND) ? c.brow(br) : nullptr;
+    uint32_t str_base = 0;
+    if ((P.flags & PF_NEEDS_ROW) && !(P.flags & PF_BIND)) {
+        str_base = P.row_words ? (uint32_t)P.row_words * 4 : (uint32_t)tv.schemas()[tv.routes()[c.route].schema].fixed_words * 4;
+        if (str_base > c.data_len) return false;
+    }
+    uint32_t cursor = 0, dyn = 0;
+    bool first = true, skip = false;  // struct keys with omitempty (OP_KEY) and the ops they govern
+#pragma unroll 1
+    for (uint32_t oi = 0; oi < P.n_dyn; oi++) {
+        const uint4 raw = *(const uint4*)(ops + oi);
+        const uint32_t code = raw.x & 0xFFu, oflags = (raw.x >> 16) & 0xFFu, ooff = raw.z;
+        if (code == OP_KEY) {
+            bool empty = false;
+            if (oflags & OPF_OMITEMPTY) {
+                const uint32_t okind = raw.x >> 24, wv = row[raw.w];
+                if (okind == GOFR_F_INT64 || okind == GOFR_F_INT) empty = (wv | row[raw.w + 1]) == 0;
+                else if (okind == GOFR_F_STRING && (P.flags & PF_BIND)) empty = (row[raw.w + 1] & 0x7FFFFFFFu) == 0;
+                else empty = wv == 0;
+            }
+            skip = empty;
+            if (!empty) { dyn += (first ? 0u : 1u) + raw.y; first = false; }
+            continue;
+        }
+        const bool skipped = (oflags & OPF_VALUE_OF_KEY) && skip;
+        if (code == OP_STR) {
+            const uint32_t len = row[ooff];
+            if (str_base + cursor + (uint64_t)len > c.data_len) return false;
+            const uint8_t* sp = c.data() + str_base + cursor;
+            cursor += len;
+            if (skipped) continue;
+            if (json_needs_escape<true>(SrcMem<true>::from(sp), len)) return false;
+            dyn += len;
+        } else if (skipped) {
+            continue;
+        } else if (code == OP_LIT) {  // a literal governed by a key (ungoverned ones are pre-summed)
+            dyn += raw.y;
+        } else if (code == OP_I64) {
+            dyn += emit_i64<false>(nullptr, (int64_t)((uint64_t)row[ooff] | (uint64_t)row[ooff + 1] << 32));
+        } else if (code == OP_I32) {
+            dyn += emit_i64<false>(nullptr, (int64_t)(int32_t)row[ooff]);
+        } else if (code == OP_BOOL) {
+            dyn += row[ooff] ? 4u : 5u;
+        } else if (code == OP_PARAM) {
+            if (c.pv_flags & 1) {
+                if (c.pv_flags & 2) return false;
+                dyn += c.pv_len;
+            } else dyn += c.def_len;
+        } else if (code == OP_BSTR) {
+            const uint32_t lenw = row[ooff + 1];
+            if (lenw >> 31) return false;
+            dyn += lenw;
+        } else return false;
+    }
+    c.str_base = str_base;
+    c.body_len = P.body_fixed + dyn;
+    uint32_t hl = P.hdr_fixed;
+    if (P.flags & PF_HAS_CLEN) hl += emit_u32<false>(nullptr, c.body_len);
+    c.total_len = hl + c.body_len;
+    c.mflags |= 1u << 17;
+    return true;
+}
+
+// Writes a response sized by size_fast into its 16-byte aligned slot: the template with aligned 16-byte loads and
+// stores, the trace id patched into the windows it touches, then the tail ops through the Writer.
+GOFR_HD void emit_fast(const TableView& tv, const BatchRefs& br, ReqCtx& c, uint8_t* dst, uint32_t* ring_col) {
+    const FastRec F = *(tv.fast() + c.prog);
+    const uint32_t nwin = F.tmpl_windows;
+    // the trace id is needed after the template copy: ask for it now
+    uint4 id = {0u, 0u, 0u, 0u};
+    if (F.hex_pos != 0xFFFFu) id = *(const uint4*)(br.ids + (size_t)c.index * 16);
+    if (nwin) {
+        const saddr_t tp = to_saddr(tv.lits() + F.tmpl_off);
+        uint32_t h0 = nwin, h1 = nwin;  // [h0, h1): windows the 32 hex characters touch
+        if (F.hex_pos != 0xFFFFu) { h0 = (uint32_t)F.hex_pos >> 4; h1 = (((uint32_t)F.hex_pos + 31u) >> 4) + 1u; }
+#pragma unroll 1
+        for (uint32_t k = 0; k < h0; k++) {
+            const uint4 v = src_ld128(tp + 16 * k);
+            Writer::store16(dst + 16 * k, v.x, v.y, v.z, v.w);
+        }
+#pragma unroll 1
+        for (uint32_t k = h1; k < nwin; k++) {
+            const uint4 v = src_ld128(tp + 16 * k);
+            Writer::store16(dst + 16 * k, v.x, v.y, v.z, v.w);
+        }
+        if (h0 < nwin) {
+            // the 2 or 3 windows around the trace id: template words into the (idle) staging column, the 8 hex words
+            // shifted to their byte offset on top, then whole windows out
+            const saddr_t col = to_saddr(ring_col);
+            const uint32_t nw = (h1 - h0) * 4;  // 8 or 12 words
+#pragma unroll 1
+            for (uint32_t k = 0; k < nw; k++) stg_st(col + k * GOFR_RING_STRIDE_BYTES, src_ld(tp + 16 * h0 + 4 * k));
+            uint32_t H[8];
+            hex8(id.x, H[0], H[1]); hex8(id.y, H[2], H[3]); hex8(id.z, H[4], H[5]); hex8(id.w, H[6], H[7]);
+            const uint32_t o = (uint32_t)F.hex_pos & 15u, q = o >> 2, sh = (o & 3u) * 8;
+            const saddr_t hp = col + q * GOFR_RING_STRIDE_BYTES;
+            if (sh == 0) {
+#pragma unroll
+                for (uint32_t j = 0; j < 8; j++) stg_st(hp + j * GOFR_RING_STRIDE_BYTES, H[j]);
+            } else {
+                const uint32_t lowmask = (1u << sh) - 1u;
+                stg_st(hp, (stg_ld(hp) & lowmask) | (H[0] << sh));
+#pragma unroll
+                for (uint32_t j = 1; j < 8; j++) stg_st(hp + j * GOFR_RING_STRIDE_BYTES, fsr(H[j - 1], H[j], 32 - sh));
+                stg_st(hp + 8 * GOFR_RING_STRIDE_BYTES, (H[7] >> (32 - sh)) | (stg_ld(hp + 8 * GOFR_RING_STRIDE_BYTES) & ~lowmask));
+            }
+#pragma unroll 1
+            for (uint32_t k = h0; k < h1; k++) {
+                const saddr_t rp = col + (k - h0) * 4 * GOFR_RING_STRIDE_BYTES;
+                Writer::store16(dst + 16 * k, stg_ld(rp), stg_ld(rp + GOFR_RING_STRIDE_BYTES), stg_ld(rp + 2 * GOFR_RING_STRIDE_BYTES),
+                                stg_ld(rp + 3 * GOFR_RING_STRIDE_BYTES));
+            }
+        }
+    }
+    if (F.flags & FR_COMPLETE) return;
+
+    Writer w;
+    w.init(dst + 16 * nwin, ring_col);
+    const Op* ops = tv.ops() + F.tail_op;
+    const uint8_t* const lits = tv.lits();
+    RowReader row;
+    row.sh = to_saddr(c.data());
+    row.gl = (F.flags & FR_BIND) ? c.brow(br) : nullptr;
+    uint32_t str_cursor = 0;
+    bool first = true, skip = false;
+#pragma unroll 1
+    for (uint32_t oi = 0; oi < F.n_tail_ops; oi++) {
+        const uint4 raw = *(const uint4*)(ops + oi);
+        const uint32_t code = raw.x & 0xFFu, oflags = (raw.x >> 16) & 0xFFu, ooff = raw.z;
+        if (code == OP_KEY) {
+            bool empty = false;
+            if (oflags & OPF_OMITEMPTY) {
+                const uint32_t okind = raw.x >> 24, wv = row[raw.w];
+                if (okind == GOFR_F_INT64 || okind == GOFR_F_INT) empty = (wv | row[raw.w + 1]) == 0;
+                else if (okind == GOFR_F_STRING && (F.flags & FR_BIND)) empty = (row[raw.w + 1] & 0x7FFFFFFFu) == 0;
+                else empty = wv == 0;
+            }
+            skip = empty;
+            if (empty) continue;
+            if (!first) {
+                if (warp_any(w.wl >= GOFR_STAGE_WORDS - 8)) w.flush();
+                w.putc(',');
+            }
+            first = false;
+        } else if ((oflags & OPF_VALUE_OF_KEY) && skip) {
+            if (code == OP_STR) str_cursor += row[ooff];
+            continue;
+        }
+        const bool lit_only = code == OP_LIT || code == OP_KEY;
+        // step 0: the op's literal bytes (OP_LIT / OP_KEY: the literal itself, else the folded prefix); step 1: its value
+        const uint8_t* csrc = lits + (lit_only ? raw.z : raw.w);
+        uint32_t clen = raw.y;
+#pragma unroll 1
+        for (uint32_t step = 0; step < 2; step++) {
+            if (step == 1) {
+                if (lit_only) break;
+                clen = 0;
+                if (warp_any(w.wl >= GOFR_STAGE_WORDS - 8)) w.flush();  // a generated value appends at most 8 words
+                if (code == OP_STR) {
+                    clen = row[ooff];
+                    csrc = c.data() + c.str_base + str_cursor;
+                    str_cursor += clen;
+                } else if (code == OP_I64) {
+                    emit_i64<true>(&w, (int64_t)((uint64_t)row[ooff] | (uint64_t)row[ooff + 1] << 32));
+                } else if (code == OP_I32) {
+                    emit_i64<true>(&w, (int64_t)(int32_t)row[ooff]);
+                } else if (code == OP_BOOL) {
+                    if (row[ooff]) w.put4('t' | 'r' << 8 | 'u' << 16 | 'e' << 24);
+                    else { w.put4('f' | 'a' << 8 | 'l' << 16 | 's' << 24); w.putc('e'); }
+                } else if (code == OP_CLEN) {
+                    emit_u32<true>(&w, c.body_len);
+                } else if (code == OP_HEXID) {
+                    const uint4 id = *(const uint4*)(br.ids + (size_t)c.index * 16);
+                    const uint32_t idw[4] = {id.x, id.y, id.z, id.w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { uint32_t a, b; hex8(idw[k], a, b); w.put4(a); w.put4(b); }
+                } else if (code == OP_PARAM) {
+                    if (c.pv_flags & 1) { csrc = ((c.pv_flags & 4) ? c.path : c.query()) + c.pv_off; clen = c.pv_len; }
+                    else { csrc = lits + c.def_off; clen = c.def_len; }
+                } else {  // OP_BSTR
+                    csrc = c.data() + row[ooff];
+                    clen = row[ooff + 1];
+                }
+            }
+            if (clen) w.copy<true>(SrcMem<true>::from(csrc), clen);
+        }
+    }
+    w.finish_padded();
+}
+
 // Full size stage for one request: route, size; a malformed handler-result row is answered like a handler panic.
 #if defined(GOFR_STATIC_PROG)
 #include GOFR_STATIC_PROG  /* experiment: one program of one table as compile-time constants */
@@ -1268,8 +1535,8 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
 #endif
 #endif
 
-// sizes a routed request (route_request has run)
-GOFR_HD void size_routed(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
+// sizes a routed request (route_request has run) with the general interpreter
+GOFR_HD void size_routed_general(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
     if (c.prog == 0xFFFF) {  // GOFR_H_HOST: nothing to emit, status 0 = pending on the host
         c.body_len = c.total_len = 0;
         return;
@@ -1286,6 +1553,22 @@ GOFR_HD void size_routed(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
         run_prog<false>(tv, br, c, nullptr);
     }
 }
+// The slot-layout kernel keeps the general interpreter OUT of line: its hot path is size_fast / emit_fast, and two more
+// inlined copies of run_prog cost it registers and instruction-cache room (measured: no gain from the fast path until the
+// general path became a call).
+GOFR_HD_NOINLINE void size_routed_call(const TableView tv, const BatchRefs br, ReqCtx* c) { size_routed_general(tv, br, *c); }
+
+// FAST: the slot-layout kernel — the lean size pass where it applies (the response is then written by emit_fast)
+template <bool FAST = false>
+GOFR_HD void size_routed(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
+    if (FAST) {
+        if (c.prog == 0xFFFF) { c.body_len = c.total_len = 0; return; }
+        if (size_fast(tv, br, c)) return;
+        size_routed_call(tv, br, &c);
+        return;
+    }
+    size_routed_general(tv, br, c);
+}
 
 GOFR_HD void size_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
     route_request(tv, br, c);
@@ -1295,9 +1578,8 @@ GOFR_HD void size_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
 // HTTP status of a sized request (0: GOFR_H_HOST, the closure runs on the host)
 GOFR_HD uint32_t request_status(const TableView& tv, const ReqCtx& c) { return c.prog == 0xFFFF ? 0u : tv.progs()[c.prog].status; }
 
-template <bool SLOTS = false>
-GOFR_HD void emit_request(const TableView& tv, const BatchRefs& br, ReqCtx& c, uint8_t* dst, uint32_t* ring_col) {
-    if (c.total_len == 0) return;
+template <bool SLOTS>
+GOFR_HD void emit_request_general(const TableView& tv, const BatchRefs& br, ReqCtx& c, uint8_t* dst, uint32_t* ring_col) {
     Writer w;
     w.init(dst, ring_col);
 #ifdef GOFR_IS_STATIC
@@ -1306,6 +1588,20 @@ GOFR_HD void emit_request(const TableView& tv, const BatchRefs& br, ReqCtx& c, u
 #endif
     run_prog<true>(tv, br, c, &w);
     if (SLOTS) w.finish_padded(); else w.finish();
+}
+GOFR_HD_NOINLINE void emit_request_slots_call(const TableView tv, const BatchRefs br, ReqCtx* c, uint8_t* dst, uint32_t* ring_col) {
+    emit_request_general<true>(tv, br, *c, dst, ring_col);
+}
+
+template <bool SLOTS = false>
+GOFR_HD void emit_request(const TableView& tv, const BatchRefs& br, ReqCtx& c, uint8_t* dst, uint32_t* ring_col) {
+    if (c.total_len == 0) return;
+    if (SLOTS) {
+        if (c.fast()) emit_fast(tv, br, c, dst, ring_col);
+        else emit_request_slots_call(tv, br, &c, dst, ring_col);
+        return;
+    }
+    emit_request_general<false>(tv, br, c, dst, ring_col);
 }
 
 // Patch the batch's Date into a private copy of the table's hot part (the kernel does this on its shared-memory

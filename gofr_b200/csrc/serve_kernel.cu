@@ -167,7 +167,7 @@ __device__ __forceinline__ void serve_body(const ServeParams& p) {
             }
             const uint32_t r = c.index;  // the request this thread serves now
             if (r != 0xFFFFFFFFu) {
-                size_routed(tv, br, c);
+                size_routed<true>(tv, br, c);
                 p.out_off[r] = c.total_len;  // the length column; > slot_bytes tells the host the slot was too small
                 p.meta[r] = request_status(tv, c) | (c.route << 16);
                 if (c.total_len <= p.slot_bytes && c.total_len)

@@ -494,6 +494,14 @@ struct Pool {
         seen[key] = off;
         return off;
     }
+    // 16-byte aligned, never shared (response templates: read with aligned 128-bit loads)
+    uint32_t put16(const std::string& s) {
+        while (img.size() % 16) img.push_back(0);
+        uint32_t off = (uint32_t)img.size();
+        img.insert(img.end(), s.begin(), s.end());
+        while (img.size() % 16) img.push_back(0);
+        return off;
+    }
 };
 
 static void merge_literals(std::vector<SOp>& ops) {
@@ -507,6 +515,19 @@ static void merge_literals(std::vector<SOp>& ops) {
         } else out.push_back(o);
     }
     ops.swap(out);
+}
+
+// A body made of literals only has a Content-Length known at seal time: the digits become part of the header literal, and
+// the whole response becomes position-fixed (one template for the slot-layout kernel, table_format.h FastRec).
+static void fold_static_clen(std::vector<SOp>& ops) {
+    size_t body = 0;
+    for (auto& o : ops) {
+        if (!o.body) continue;
+        if (o.code != OP_LIT || o.flags) return;  // a value, a blob or a governed literal: length not static
+        body += o.lit.size();
+    }
+    for (auto& o : ops)
+        if (o.code == OP_CLEN) { o.code = OP_LIT; o.lit = std::to_string(body); }
 }
 
 // LIT followed by a value op of the same part (header/body) → the literal becomes the value op's prefix
@@ -812,6 +833,7 @@ int seal_table(gofr_table* t) {
     uint32_t max_fixed = 0;
     for (size_t pi = 0; pi < b.progs.size(); pi++) {
         Prog& p = b.progs[pi];
+        fold_static_clen(p.ops);
         merge_literals(p.ops);
         fold_prefixes(p.ops);
         ProgRec& P = progs[pi];
@@ -899,6 +921,98 @@ int seal_table(gofr_table* t) {
         ops.insert(ops.end(), dyn.begin(), dyn.end());
     }
 
+    // ---- slot-layout fast path: templates and tail ops (table_format.h FastRec) ----
+    std::vector<FastRec> fast(progs.size());
+    for (size_t pi = 0; pi < progs.size(); pi++) {
+        ProgRec& P = progs[pi];
+        FastRec& F = fast[pi];
+        memset(&F, 0, sizeof F);
+        F.hex_pos = 0xFFFF;
+        F.tail_op = P.first_op;
+        F.n_tail_ops = P.n_ops;
+        if (P.flags & PF_BIND) F.flags |= FR_BIND;
+        bool simple_ops = true;
+        for (uint32_t k = 0; k < P.n_ops; k++) {
+            const Op& o = ops[P.first_op + k];
+            const bool ok = o.code == OP_LIT || o.code == OP_HEXID || o.code == OP_CLEN || o.code == OP_I64 || o.code == OP_I32 ||
+                            o.code == OP_BOOL || o.code == OP_STR || o.code == OP_BSTR || o.code == OP_PARAM || o.code == OP_KEY;
+            if (!ok) simple_ops = false;
+            // the lean size pass adds every dynamic length to the body
+            const bool dynamic = (o.code != OP_LIT || (o.flags & OPF_VALUE_OF_KEY)) && o.code != OP_HEXID && o.code != OP_CLEN;
+            if (ok && dynamic && !(o.flags & OPF_BODY)) simple_ops = false;
+        }
+        if (!simple_ops) continue;
+        P.flags |= PF_FAST;
+        // the position-fixed prefix: literal bytes (an op's own literal or its folded prefix) and the trace id placeholder,
+        // up to the first value whose length depends on the request
+        std::string tmpl;
+        std::vector<uint32_t> date_at;  // template offsets of Date placeholders
+        struct Span { uint32_t op, lit_start, lit_len; };  // where each op's literal bytes sit in the template
+        std::vector<Span> spans;
+        uint32_t stop_op = P.n_ops;  // first op with a variable-length value
+        for (uint32_t k = 0; k < P.n_ops; k++) {
+            const Op& o = ops[P.first_op + k];
+            if (o.code == OP_KEY || (o.flags & OPF_VALUE_OF_KEY)) { stop_op = k; break; }  // emitted or not: depends on the row
+            const uint32_t loff = o.code == OP_LIT ? o.off : o.aux;
+            spans.push_back({k, (uint32_t)tmpl.size(), o.len});
+            for (uint32_t fx : fixups)
+                if (o.len >= 29 && fx >= loff && fx + 29 <= loff + o.len) date_at.push_back((uint32_t)tmpl.size() + (fx - loff));
+            tmpl.append((const char*)lits.data() + loff, o.len);
+            if (o.code == OP_LIT) continue;
+            if (o.code == OP_HEXID && F.hex_pos == 0xFFFF) { F.hex_pos = (uint16_t)tmpl.size(); tmpl.append(32, '0'); continue; }
+            stop_op = k;
+            break;
+        }
+        const bool complete = stop_op == P.n_ops;
+        uint32_t covered = complete ? (uint32_t)tmpl.size() : ((uint32_t)tmpl.size() & ~15u);
+        if (F.hex_pos != 0xFFFF && covered < (uint32_t)F.hex_pos + 32u) {  // the cut would split the trace id: stop before it
+            covered = (uint32_t)F.hex_pos & ~15u;
+            F.hex_pos = 0xFFFF;
+        }
+        if (covered > 255u * 16u) covered = 255u * 16u;
+        if (!complete || covered != tmpl.size()) covered &= ~15u;
+        if (covered == 0) continue;  // nothing worth a template: the whole program is the tail
+        std::sort(date_at.begin(), date_at.end());
+        date_at.erase(std::unique(date_at.begin(), date_at.end()), date_at.end());
+        tmpl.resize(covered);
+        F.tmpl_off = pool.put16(tmpl);
+        F.tmpl_windows = (uint8_t)((covered + 15u) / 16u);
+        F.tmpl_bytes = covered;
+        for (uint32_t d : date_at)
+            if (d + 29 <= covered) fixups.push_back(F.tmpl_off + d);
+            else if (d < covered) { F.tmpl_off = 0; F.tmpl_windows = 0; F.tmpl_bytes = 0; F.hex_pos = 0xFFFF; break; }  // never: Date is followed by > 16 literal bytes
+        if (!F.tmpl_windows) continue;
+        if (complete && covered == (uint32_t)P.hdr_fixed + P.body_fixed) {
+            F.flags |= FR_COMPLETE;
+            F.tail_op = 0;
+            F.n_tail_ops = 0;
+            continue;
+        }
+        // tail ops: a private copy of the ops from the one that holds byte `covered` on, its literal cut
+        uint32_t first = P.n_ops, cut = 0;
+        for (auto& sp : spans) {
+            const Op& o = ops[P.first_op + sp.op];
+            const bool fixed_value = o.code == OP_LIT || (o.code == OP_HEXID && sp.op != stop_op);
+            const uint32_t ext = sp.lit_len + (o.code == OP_HEXID && sp.op != stop_op ? 32u : 0u);
+            if (fixed_value && sp.lit_start + ext <= covered) continue;  // literal and value both inside the template
+            first = sp.op;
+            cut = covered > sp.lit_start ? std::min(covered - sp.lit_start, sp.lit_len) : 0u;
+            break;
+        }
+        if (first == P.n_ops && stop_op < P.n_ops) first = stop_op;  // everything before the first variable op is covered
+        if (first == P.n_ops) { F.flags |= FR_COMPLETE; F.tail_op = 0; F.n_tail_ops = 0; continue; }
+        F.tail_op = (uint16_t)ops.size();
+        F.n_tail_ops = (uint16_t)(P.n_ops - first);
+        for (uint32_t k = first; k < P.n_ops; k++) {
+            Op o = ops[P.first_op + k];
+            if (k == first && cut) {  // cut <= o.len by construction (the cut never falls inside a value)
+                if (o.code == OP_LIT) o.off += cut; else o.aux += cut;
+                o.len -= cut;
+            }
+            ops.push_back(o);
+        }
+    }
+
     std::vector<uint8_t> schema_bytes;
     std::vector<SchemaRec> srecs(t->schemas.size());
     std::vector<std::vector<FieldRec>> frecs(t->schemas.size());
@@ -969,6 +1083,7 @@ int seal_table(gofr_table* t) {
         H.tmplkey_off = append(keys.data(), keys.size() * 4);
     }
     H.last_method_off = append(last_method.data(), last_method.size() * 2);
+    H.fast_off = append(fast.data(), fast.size() * sizeof(FastRec));
     H.fixups_off = append(fixups.data(), fixups.size() * 4);
     H.n_fixups = (uint32_t)fixups.size();
     // schemas: SchemaRec[n] then each field table

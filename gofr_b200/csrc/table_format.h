@@ -12,7 +12,7 @@
 namespace gofr {
 
 constexpr uint32_t kMagic = 0x52464F47u;  // "GOFR"
-constexpr uint32_t kImageVersion = 13;
+constexpr uint32_t kImageVersion = 14;
 constexpr uint32_t kMaxHotBytes = 40 * 1024;  // shared-memory budget for the table
 constexpr int kMaxVars = 8;                   // variables per route template
 constexpr int kMaxFields = 32;                // struct fields per schema
@@ -45,7 +45,7 @@ struct ImageHeader {  // 144 B
     uint32_t thash_bits;
     uint32_t checksum;       // FNV-1a over the whole image with this field zero: set at seal, checked by deserialize (the
                              // image travels between ranks); never read on the device
-    uint32_t reserved2;
+    uint32_t fast_off;       // FastRec[n_progs]: how the slot-layout kernel emits each program (templates + tail ops)
 };
 static_assert(sizeof(ImageHeader) == 144, "ImageHeader layout");
 
@@ -147,6 +147,33 @@ enum ProgFlags : uint16_t {
     PF_DYNAMIC = 2,   // has at least one variable-length op besides CLEN
     PF_NEEDS_ROW = 4,
     PF_BIND = 8,      // the row is the Bind span row in scratch (bind_device.cuh), not the request's data section
+    PF_FAST = 16,     // only literals, plain values and struct keys (LIT, HEXID, CLEN, I64, I32, BOOL, STR, BSTR, PARAM, KEY):
+                      // eligible for the slot-layout fast path (FastRec) when the request has no escapes
+};
+
+// Slot layout fast path (serve_device.cuh emit_fast).  A response owns a 16-byte aligned slot, so every byte of the
+// response whose POSITION does not depend on the request — the status line and the sorted header block up to the first
+// variable-length value, i.e. up to the Content-Length digits — can be prepared at seal time exactly as it will lie in the
+// slot: a dst-aligned TEMPLATE in the literal pool (Date patched at kernel start like every literal, 32 placeholder bytes
+// where the trace id goes).  The kernel copies it with aligned 16-byte loads and stores (no funnel shifts, no staging),
+// patches the hex characters in, and interprets only the ops after it ("tail").  Programs without any variable-length
+// value (static bodies, 404, OPTIONS ...) are template only: Content-Length is folded at seal time and the last window
+// is zero padded like the slot layout wants it.
+struct FastRec {  // 16 B
+    uint32_t tmpl_off;     // literal-pool offset of the template, 16-byte aligned
+    uint8_t tmpl_windows;  // template length in 16-byte windows; 0: no template (tail = whole program)
+    uint8_t flags;         // FR_*
+    uint16_t hex_pos;      // byte offset of the 32 hex characters inside the template; 0xFFFF: none
+    uint16_t tail_op;      // absolute index of the first tail op (a private copy of the program's remaining ops: the first
+                           // one has the bytes the template already covers cut off its literal)
+    uint16_t n_tail_ops;
+    uint32_t tmpl_bytes;   // response bytes the template covers (= 16 * tmpl_windows, less the zero padding of a
+                           // template-only program)
+};
+static_assert(sizeof(FastRec) == 16, "FastRec layout");
+enum FastFlags : uint8_t {
+    FR_BIND = 1,       // PF_BIND
+    FR_COMPLETE = 2,   // template only: nothing left to interpret
 };
 
 struct SchemaRec {  // 16 B + per-field table

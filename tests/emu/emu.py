@@ -49,6 +49,17 @@ def lib():
     return _lib
 
 
+def fast_taken(reset: bool = True) -> int:
+    """Requests the slot-layout emulation sized with size_fast (hence wrote with emit_fast) since the last reset."""
+    lib().emu_fast_taken.restype = C.c_uint64
+    return int(lib().emu_fast_taken(1 if reset else 0))
+
+
+def set_stage_mode(mode: int):
+    """Slot emulation: which requests count as staged in shared memory (0: every other one, 1: all, 2: none)."""
+    lib().emu_set_stage_mode(mode)
+
+
 def set_flush_mode(mode: int):
     """0: flush decisions per request; 1: flush at every decision point; 2: pseudo-random extra flushes (on the GPU the
     other lanes of a warp impose theirs)."""

@@ -64,6 +64,10 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
 }
 
 // ---- slot layout (gofr_serve_device_slots): same per-request code, emit_request<true> + finish_padded ----
+static int g_stage_mode = 0;  // which requests of the slot emulation count as staged: 0 every other one, 1 all, 2 none
+extern "C" void emu_set_stage_mode(int m) { g_stage_mode = m; }
+static uint64_t g_fast_taken = 0;  // requests sized by size_fast (and therefore written by emit_fast) since the last reset
+extern "C" uint64_t emu_fast_taken(int reset) { const uint64_t v = g_fast_taken; if (reset) g_fast_taken = 0; return v; }
 extern "C" int emu_serve_slots(const uint8_t* image, uint64_t image_len, const uint8_t* desc, const uint8_t* ids,
                                const uint8_t* arena, uint32_t n, const char* date29, uint8_t* out, uint32_t slot_bytes,
                                uint32_t* out_len, uint32_t* meta) {
@@ -83,11 +87,14 @@ extern "C" int emu_serve_slots(const uint8_t* image, uint64_t image_len, const u
         uint32_t d[4];
         memcpy(d, desc + (size_t)i * 16, 16);
         ReqCtx c;
-        c.set(arena, d[0], d[1] & 0xFFFF, d[1] >> 16, d[2], d[3] & 0xFF, (d[3] >> 8) & 0xFF, (i & 1) != 0, 0);
+        c.set(arena, d[0], d[1] & 0xFFFF, d[1] >> 16, d[2], d[3] & 0xFF, (d[3] >> 8) & 0xFF,
+              g_stage_mode == 1 || (g_stage_mode == 0 && (i & 1) != 0), 0);
         br.ids = ids + (size_t)i * 16;
-        size_request(tv, br, c);
+        route_request(tv, br, c);
+        size_routed<true>(tv, br, c);  // as serve_slots_kernel does: the lean size pass where it applies, then emit_fast
         out_len[i] = c.total_len;
         meta[i] = request_status(tv, c) | (c.route << 16);
+        if (c.fast()) g_fast_taken++;
         if (c.total_len && c.total_len <= slot_bytes) emit_request<true>(tv, br, c, out + (size_t)i * slot_bytes, ring);
     }
     return 0;

@@ -61,6 +61,31 @@ def test_emu_slots_match_oracle(which, slot):
     _check_slots(out, ln, meta, spec, batch, slot)
 
 
+@pytest.mark.parametrize("mode", [S.FRAME_WIRE, S.FRAME_INTENDED, S.FRAME_BODY])
+@pytest.mark.parametrize("flush_mode", [0, 1, 2])
+def test_emu_fast_path(mode, flush_mode):
+    """emit_fast (seal-time response templates + tail ops) against the oracle: every framing mode, the flush decisions
+    other lanes impose on the GPU replayed (emu.set_flush_mode), and a check that the fast path really ran"""
+    from tests.emu import emu
+    emu.set_flush_mode(flush_mode)
+    emu.set_stage_mode(1)
+    try:
+        for spec, batch, slot, min_fast in (
+                (synth.config1_spec(mode), synth.config1_batch(300), 320, 0.9),          # template-only programs
+                (synth.config2_spec(mode), synth.config2_batch(600), 528, 0.99),         # template + struct tail
+                (synth.config2_spec(mode), synth.config2_batch(600, escape_every=4), 640, 0.7),
+                (synth.config4_spec(mode), synth.config4_batch(2500), 704, 0.5),
+                (synth.config3_spec(mode), synth.config3_batch(400), 1024, 0.5)):
+            emu.fast_taken()
+            out, ln, meta = emu.serve_slots(Table(spec).serialize(), batch, DATE, slot)
+            taken = emu.fast_taken()
+            _check_slots(out, ln, meta, spec, batch, slot)
+            assert taken >= min_fast * batch.n, (taken, batch.n)
+    finally:
+        emu.set_flush_mode(0)
+        emu.set_stage_mode(0)
+
+
 @pytest.fixture(scope="module")
 def torch_cuda():
     import torch
