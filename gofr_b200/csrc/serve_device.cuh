@@ -203,7 +203,13 @@ struct Writer {
 #if defined(GOFR_EXP_NO_STORE)  /* experiment: the kernel without its global stores (what is left is issue/latency bound) */
         if (v0 == 0x12345678u && v1 == 0x9ABCDEF0u && v2 == 0x0F1E2D3Cu)
 #endif
+#if defined(GOFR_STORE256)
+        // not .cs: in a 256-bit build the ONLY evict-first stores are the sector stores, which is what the build-time SASS
+        // check relies on (gofr_b200/_build.py, check_sector_stores)
+        *(uint4*)addr = make_uint4(v0, v1, v2, v3);
+#else
         __stcs((uint4*)addr, make_uint4(v0, v1, v2, v3));
+#endif
 #else
         uint32_t v[4] = {v0, v1, v2, v3};
         memcpy(addr, v, 16);
@@ -222,7 +228,16 @@ struct Writer {
 #if defined(GOFR_EXP_NO_STORE)
         if (v0 == 0x12345678u && v1 == 0x9ABCDEF0u && v2 == 0x0F1E2D3Cu)
 #endif
-#if defined(GOFR_STORE256)
+#if defined(GOFR_STORE256) && defined(GOFR_EXP_V8_PLAIN)
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(addr), "r"(v0), "r"(v1), "r"(v2), "r"(v3),
+                     "r"(v4), "r"(v5), "r"(v6), "r"(v7)
+                     : "memory");
+#elif defined(GOFR_STORE256) && defined(GOFR_EXP_V4B64)
+        asm volatile("{\n\t.reg .b64 q0, q1, q2, q3;\n\tmov.b64 q0, {%1,%2};\n\tmov.b64 q1, {%3,%4};\n\tmov.b64 q2, {%5,%6};\n\tmov.b64 q3, {%7,%8};\n\t"
+                     "st.global.cs.v4.b64 [%0], {q0,q1,q2,q3};\n\t}" ::"l"(addr), "r"(v0), "r"(v1), "r"(v2), "r"(v3),
+                     "r"(v4), "r"(v5), "r"(v6), "r"(v7)
+                     : "memory");
+#elif defined(GOFR_STORE256)
         asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(addr), "r"(v0), "r"(v1), "r"(v2), "r"(v3),
                      "r"(v4), "r"(v5), "r"(v6), "r"(v7)
                      : "memory");
@@ -237,12 +252,19 @@ struct Writer {
     // Write bytes [lo, hi) of the 32-byte sector at addr from the eight staging words at rp: a 16-byte half where one is
     // whole, else words, else single bytes.  Runs twice per response at most (first and last sector), so it is a loop,
     // not unrolled code.
+#if defined(__CUDA_ARCH__) && defined(GOFR_EXP_STG_PARTIAL)
+    static __device__ __forceinline__ void st8(uint8_t* a, uint32_t v) { asm volatile("st.global.u8 [%0], %1;" ::"l"(a), "r"(v) : "memory"); }
+    static __device__ __forceinline__ void st32(uint8_t* a, uint32_t v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(a), "r"(v) : "memory"); }
+#else
+    GOFR_HD static void st8(uint8_t* a, uint32_t v) { *a = (uint8_t)v; }
+    GOFR_HD static void st32(uint8_t* a, uint32_t v) { *(uint32_t*)a = v; }
+#endif
     GOFR_HD static void store_partial(uint8_t* addr, saddr_t rp, uint32_t lo, uint32_t hi) {
         uint32_t b = lo;
 #pragma unroll 1
-        for (; b < hi && (b & 3u); b++) addr[b] = (uint8_t)stg_ld8(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES + (b & 3u));
+        for (; b < hi && (b & 3u); b++) st8(addr + b, stg_ld8(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES + (b & 3u)));
 #pragma unroll 1
-        for (; b + 4 <= hi && (b & 15u); b += 4) *(uint32_t*)(addr + b) = stg_ld(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES);
+        for (; b + 4 <= hi && (b & 15u); b += 4) st32(addr + b, stg_ld(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES));
 #pragma unroll 1
         for (; b + 16 <= hi; b += 16) {
             const saddr_t q = rp + (b >> 2) * GOFR_RING_STRIDE_BYTES;
@@ -250,9 +272,9 @@ struct Writer {
                     stg_ld(q + 3 * GOFR_RING_STRIDE_BYTES));
         }
 #pragma unroll 1
-        for (; b + 4 <= hi; b += 4) *(uint32_t*)(addr + b) = stg_ld(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES);
+        for (; b + 4 <= hi; b += 4) st32(addr + b, stg_ld(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES));
 #pragma unroll 1
-        for (; b < hi; b++) addr[b] = (uint8_t)stg_ld8(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES + (b & 3u));
+        for (; b < hi; b++) st8(addr + b, stg_ld8(rp + (b >> 2) * GOFR_RING_STRIDE_BYTES + (b & 3u)));
     }
     GOFR_HD void store_sector(saddr_t rp) {
         store32(chunk, stg_ld(rp), stg_ld(rp + GOFR_RING_STRIDE_BYTES), stg_ld(rp + 2 * GOFR_RING_STRIDE_BYTES),
@@ -1325,7 +1347,9 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
 struct RowReader {
     saddr_t sh;           // data section in shared memory
     const uint32_t* gl;   // Bind span row (global), or null
-    GOFR_HD uint32_t operator[](uint32_t k) const { return gl ? gl[k] : src_ld(sh + 4 * k); }
+    // stg_ld, not src_ld: a non-volatile asm is a pure function to the compiler, which hoisted these loads above the
+    // op-code tests that guard them — with a literal-pool offset as the "row index" (memcheck: invalid __shared__ read)
+    GOFR_HD uint32_t operator[](uint32_t k) const { return gl ? gl[k] : stg_ld(sh + 4 * k); }
 };
 
 // Lean size pass of a PF_FAST program (every dynamic op is a plain value of the body).  Returns false when the request
@@ -1564,7 +1588,11 @@ GOFR_HD void size_routed(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
     if (FAST) {
         if (c.prog == 0xFFFF) { c.body_len = c.total_len = 0; return; }
         if (size_fast(tv, br, c)) return;
-        size_routed_call(tv, br, &c);
+        // the call works on a copy: taking the address of `c` itself would move the whole request context to local
+        // memory for the hot path too (it did: 568 LDL/STL in the kernel, and no gain from the fast path)
+        ReqCtx t = c;
+        size_routed_call(tv, br, &t);
+        c.prog = t.prog; c.body_len = t.body_len; c.total_len = t.total_len; c.slow_mask = t.slow_mask;
         return;
     }
     size_routed_general(tv, br, c);
@@ -1598,7 +1626,7 @@ GOFR_HD void emit_request(const TableView& tv, const BatchRefs& br, ReqCtx& c, u
     if (c.total_len == 0) return;
     if (SLOTS) {
         if (c.fast()) emit_fast(tv, br, c, dst, ring_col);
-        else emit_request_slots_call(tv, br, &c, dst, ring_col);
+        else { ReqCtx t = c; emit_request_slots_call(tv, br, &t, dst, ring_col); }  // a copy: see size_routed
         return;
     }
     emit_request_general<false>(tv, br, c, dst, ring_col);
