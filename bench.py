@@ -46,18 +46,31 @@ def hbm_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
-def profiled_traffic(layout="packed"):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch on this exact workload (1 Mi requests), from the
-    committed `ncu --set full` captures (profiles/r01/serve_{slots_,}kernel_*1M_key_metrics.txt)."""
+KERNEL_SOURCES = ["gofr_b200/csrc/serve_body.cuh", "gofr_b200/csrc/serve_device.cuh", "gofr_b200/csrc/bind_device.cuh",
+                  "gofr_b200/csrc/serve_slots_kernel.cu", "gofr_b200/csrc/serve_kernel.cu", "gofr_b200/csrc/tile_common.cuh",
+                  "gofr_b200/csrc/table_format.h", "gofr_b200/_build.py"]
+
+
+def kernel_source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def profiled_traffic(layout="slots"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the headline kernel on this exact workload, from an
+    `ncu --set full` capture — reported only when the capture was taken from the kernel sources that are being run now
+    (profiles/r02/traffic.json records their SHA-256; a stale capture yields null, never an old number)."""
     try:
-        tot = 0.0
-        name = "serve_slots_kernel_1M_key_metrics.txt" if layout == "slots" else "serve_kernel_v11_1M_key_metrics.txt"
-        with open(os.path.join(ROOT, "profiles", "r01", name)) as f:
-            for ln in f:
-                p = ln.split()
-                if p and p[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                    tot += float(p[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[p[1]]
-        return tot or None
+        with open(os.path.join(ROOT, "profiles", "r02", "traffic.json")) as f:
+            t = json.load(f)
+        ent = t.get(layout)
+        if not ent or ent.get("source_sha256") != kernel_source_hash():
+            return None
+        return float(ent["dram_bytes_read"]) + float(ent["dram_bytes_write"])
     except Exception:
         return None
 
@@ -166,6 +179,40 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvidia-smi"}
 
 
+def bind_to_gpu_numa(device: int):
+    import ctypes as C
+    from gofr_b200 import _abi
+    node = C.c_int(-1)
+    rc = _abi.lib().gofr_bind_host_thread(device, C.byref(node))
+    d = {"bound": rc == 0, "node": node.value if node.value >= 0 else None, "cpus": len(os.sched_getaffinity(0))}
+    if rc != 0:
+        d["why"] = _abi.lib().gofr_last_error().decode(errors="replace")
+    return d
+
+
+def link_floor_ms(device, h2d_bytes: int, d2h_bytes: int, steps: int = 5):
+    """The platform floor of one end-to-end step: the step's H2D and D2H bytes moved concurrently between pinned host
+    buffers and HBM, no kernel (CUDA events on two streams; the caller takes the max over ranks)."""
+    import torch
+    h_in = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(h2d_bytes, dtype=torch.uint8, device=device)
+    d_out = torch.zeros(d2h_bytes, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device), torch.cuda.Stream(device)
+
+    def step():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+        s1.synchronize(); s2.synchronize()
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps * 1e3
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -249,7 +296,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(n, args.gpus, "cpu"),
+            "config": workload_config(n, args.gpus, args),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "cpu_quota": quota},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -257,12 +304,15 @@ def run_reference(args):
     return 0
 
 
-def workload_config(n, gpus, where):
-    return {"workload": "BASELINE config 2: 16-route GET table, 256B JSON struct body (521B full HTTP/1.1 response, "
-                        "wire framing), %d requests per %s" % (n, "GPU" if where == "gpu" else "step"),
-            "requests_per_gpu": n, "frame_mode": "wire", "routes": 16, "parallelism": f"dp{gpus} (requests sharded, no data-path collective)",
-            "l2": "inputs+outputs per step (~%.2f GB) %s the 126 MB L2" % (n * 793 / 1e9, "exceed" if n * 793 > 126e6 else "DO NOT exceed")
-                  if where == "gpu" else "n/a (CPU arm)"}
+def workload_config(n, gpus, args):
+    """The `config` object of both arms (this repo's and `--impl reference`): identical by construction."""
+    return {"workload": "BASELINE config 2: 16-route GET table, 256B JSON struct body (521B full HTTP/1.1 response, wire "
+                        "framing), %d requests per step per worker (GPU rank / CPU arm)" % n,
+            "requests_per_step_per_worker": n, "frame_mode": "wire", "routes": 16,
+            "parallelism": f"dp{gpus} (requests sharded, no data-path collective)",
+            "l2": "inputs+outputs per step (~%.2f GB) %s the 126 MB L2" % (n * 793 / 1e9, "exceed" if n * 793 > 126e6 else "DO NOT exceed"),
+            "resident_layout": ("slots: response i in its own 528-byte slot (gofr_serve_device_slots)" if args.layout == "slots" else "packed offsets (gofr_serve_device)"),
+            "e2e_layout": ("slots (gofr_batch_submit_slots)" if args.e2e_layout == "slots" else "packed offsets (gofr_batch_submit)")}
 
 
 def run_secondary(args):
@@ -276,6 +326,8 @@ def run_secondary(args):
     w = args.workload
     n = {"config3": 65536, "config4": 262144, "config5": 1 << 20, "proto": 1 << 20, "reqlog": 1 << 18, "http": 1 << 20}[w] if args.requests == (1 << 20) and w not in ("config5", "proto") else args.requests
     cpu = None
+    cpu_fn = cpu_what = e2e_step = None
+    xfer_in, xfer_out, e2e_bytes = [], [], None
     if w == "reqlog":
         # the RequestLog line of middleware.Logging for the config-2 stream
         lb = synth.reqlog_batch(n)
@@ -293,10 +345,8 @@ def run_secondary(args):
         in_bytes = lb.input_bytes() - 8 * n  # the generic "+ 8 * n" below counts offsets + meta; here only 4-byte offsets leave
         in_bytes += 4 * n
         get_out = lambda: int(d_ooff[n].item())
-        t0 = time.perf_counter()
-        O.request_log(lb)
-        cpu = {"value": n / (time.perf_counter() - t0), "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"one pass over the same {n} records, scalar C restatement (oracle/orc_reqlog.c)"}
+        cpu_fn, cpu_what = (lambda: (O.request_log(lb), n)[1]), "scalar C restatement (oracle/orc_reqlog.c), 1 thread"
+        xfer_in, xfer_out = [d_desc, d_ids, d_arena], [(d_out, lambda: int(d_ooff[n].item())), (d_ooff, None)]
     elif w == "http":
         # raw HTTP/1.1 request messages of the config-2 stream → descriptors + arena
         n = args.requests if args.requests != (1 << 20) else (1 << 20)
@@ -321,10 +371,8 @@ def run_secondary(args):
         written = int(((dd["path_len"].astype(np.int64) + dd["query_len"] + 3) & ~3).sum() + dd["data_len"].astype(np.int64).sum())
         in_bytes = int(raw.size) + 4 * (n + 1) + 16 * n + 4 * n + 48 * n - 8 * n  # the generic "+ 8 * n" is added below
         get_out = lambda: written
-        t0 = time.perf_counter()
-        O.http_parse(raw, off)
-        cpu = {"value": n / (time.perf_counter() - t0), "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"one pass over the same {n} messages, scalar C restatement (oracle/orc_http.c)"}
+        cpu_fn, cpu_what = (lambda: (O.http_parse(raw, off), n)[1]), "scalar C restatement (oracle/orc_http.c), 1 thread"
+        xfer_in, xfer_out = [d_raw, d_off], [(d_desc, None), (d_arena, lambda: int(raw.size)), (d_status, None)]
     elif w == "proto":
         # rows of a 9-field message (string, int64, sint32, bool, double, bytes, fixed32, int32, string) → gRPC frames
         rng = np.random.default_rng(synth.SEED)
@@ -369,6 +417,9 @@ def run_secondary(args):
         assert d_out[:int(o_off[4096])].cpu().numpy().tobytes() == o_out[:int(o_off[4096])].tobytes(), "bench output differs from the oracle"
         in_bytes = int(off[n]) + 4 * (n + 1)
         get_out = lambda: int(d_ooff[n].item())
+        m_cpu = min(n, 1 << 18)
+        cpu_fn, cpu_what = (lambda: (O.proto_encode(fields, rows, off[:m_cpu + 1]), m_cpu)[1]), "scalar C restatement (oracle/orc_proto.c), 1 thread"
+        xfer_in, xfer_out = [d_in, d_off], [(d_out, lambda: int(d_ooff[n].item())), (d_ooff, None), (d_meta, None)]
     elif w == "config5":
         frames, off = synth.config5_frames(n)
         eng = Engine(Table(synth.config1_spec()), 0)
@@ -386,6 +437,9 @@ def run_secondary(args):
                                                          d_ooff.data_ptr(), d_meta.data_ptr(), st), "grpc")
         in_bytes = int(off[n]) + 4 * (n + 1)
         get_out = lambda: int(d_ooff[n].item())
+        cpu_threads = max(1, int(cpu_quota() or os.cpu_count() or 1))
+        cpu_fn, cpu_what = (lambda: (O.grpc_hello(frames, off, cpu_threads), n)[1]), f"C restatement (oracle/orc_grpc.c), {cpu_threads} pthreads"
+        xfer_in, xfer_out = [d_in, d_off], [(d_out, lambda: int(d_ooff[n].item())), (d_ooff, None), (d_meta, None)]
     else:
         spec, batch = {"config3": (synth.config3_spec(), lambda: synth.config3_batch(n)),
                        "config4": (synth.config4_spec(), lambda: synth.config4_batch(n))}[w]
@@ -410,6 +464,17 @@ def run_secondary(args):
                 eng.serve_device(db, date, resp)
             get_out = lambda: int(resp.out_off[n].item())
         in_bytes = batch.input_bytes()
+        ot = O.OracleTable(spec)
+        cpu_threads = max(1, int(cpu_quota() or os.cpu_count() or 1))
+        m_cpu = min(n, 1 << 18)
+        sbatch = batch.slice(0, m_cpu)
+        cpu_fn, cpu_what = (lambda: (ot.serve(sbatch, date, nthreads=cpu_threads), m_cpu)[1]), f"C restatement (oracle/gofr_oracle.c), {cpu_threads} pthreads"
+        from gofr_b200.engine import pin_batch, pinned_array
+        hb = pin_batch(batch)
+        eslot = 1024
+        h_out, h_len, h_meta = pinned_array(n * eslot), pinned_array(4 * n, np.uint32), pinned_array(4 * n, np.uint32)
+        e2e_step = lambda: eng.serve_host_slots(hb, date, eslot, h_out, h_len, h_meta)
+        e2e_bytes = (n * 32 + int(batch.arena_span()), n * eslot + 8 * n)
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -425,13 +490,150 @@ def run_secondary(args):
     out_bytes = get_out()
     algo = in_bytes + out_bytes + 8 * n
     peak, src = hbm_peak()
-    print(json.dumps({"metric": "requests_per_sec", "workload": w, "layout": args.layout if w in ("config3", "config4") else None, "value": n / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+    # ---- end to end: pinned host buffers -> HBM -> kernel -> pinned host buffers, every step ----
+    if e2e_step is None:
+        h_in = [t.cpu().pin_memory() for t in xfer_in]
+        outs = [(d, (f() if f else d.numel() * d.element_size())) for d, f in xfer_out]
+        h_outs = [torch.empty(nb, dtype=torch.uint8).pin_memory() for _, nb in outs]
+
+        def e2e_step():
+            for h, d in zip(h_in, xfer_in):
+                d.copy_(h, non_blocking=True)
+            step()
+            for (d, nb), h in zip(outs, h_outs):
+                h.copy_(d.view(torch.uint8).reshape(-1)[:nb], non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_bytes = (sum(t.numel() * t.element_size() for t in xfer_in), sum(nb for _, nb in outs))
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_dt = (time.perf_counter() - t0) / args.steps
+    e2e = {"value": n / e2e_dt, "unit": UNIT, "ms_per_step": e2e_dt * 1e3, "h2d_bytes_per_step": int(e2e_bytes[0]), "d2h_bytes_per_step": int(e2e_bytes[1])}
+    # ---- CPU restatement beside it: bounded sample, at least ~1 s ----
+    if cpu_fn is not None:
+        cpu_fn()
+        t0 = time.perf_counter()
+        units = 0
+        while time.perf_counter() - t0 < 1.0:
+            units += cpu_fn()
+        cpu = {"value": units / (time.perf_counter() - t0), "unit": UNIT, "kind": "port", "sample": f"passes over (a prefix of) the same input for >= 1 s: {cpu_what}"}
+    print(json.dumps({"metric": "requests_per_sec", "workload": w, "e2e": e2e, "layout": args.layout if w in ("config3", "config4") else None, "value": n / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": ms, "requests": n, "out_bytes": out_bytes, "data": "synthetic",
                       "roofline": {"bound": "hbm", "achieved": algo / (kms / kl / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                    "frac": algo / (kms / kl / 1e3) / 1e9 / peak, "algorithmic_bytes_per_request": algo / n,
                                    "kernel_ms_per_launch": kms / kl},
                       **({"cpu_baseline": cpu} if cpu else {})}))
     return 0
+
+
+def sharded_config4(eng_factory, rank, world, dev, barrier, reduce_max, steps, per_gpu=1 << 18):
+    """BASELINE config 4 ("mixed 64-route GET/POST with the 3-deep middleware chain, 4xB200 shard"): the 64-route table is
+    sealed on rank 0 and broadcast (NCCL), every rank serves its contiguous shard of ONE request stream, resident and
+    through host buffers; parity of a sample of the rank's shard against the oracle run on exactly those requests."""
+    import torch
+    from gofr_b200.engine import pin_batch, pinned_array
+    from tests import oracle as O
+    date = S.http_date(DATE_UNIX)
+    spec = synth.config4_spec()
+    eng = eng_factory(spec)
+    eng.set_timing(True)
+    n = per_gpu
+    batch = synth.config4_batch(n, start=rank * n)
+    db = eng.upload(batch)
+    slot = 1024
+    s_out = torch.zeros(n * slot, dtype=torch.uint8, device=dev)
+    s_len = torch.zeros(n, dtype=torch.int32, device=dev)
+    s_meta = torch.zeros(n, dtype=torch.int32, device=dev)
+    step = lambda: eng.serve_device_slots(db, date, slot, out=s_out, out_len=s_len, meta=s_meta)
+    for _ in range(3):
+        step()
+    barrier()
+    eng.kernel_time_ms(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = reduce_max(e0.elapsed_time(e1)) / steps
+    kms, kl = eng.kernel_time_ms(reset=True)
+    # parity: the first 4096 requests of this rank's shard against the oracle on the same requests
+    m = 4096
+    o1, f1, m1 = O.OracleTable(spec).serve(batch.slice(0, m), date)
+    ln = s_len[:m].cpu().numpy().view(np.uint32)
+    assert np.array_equal(ln, np.diff(f1.astype(np.int64)).astype(np.uint32)) and np.array_equal(s_meta[:m].cpu().numpy().view(np.uint32), m1), "config 4 shard: columns differ from the oracle"
+    so = s_out[:m * slot].cpu().numpy().reshape(m, slot)
+    for i in range(m):
+        L = int(ln[i])
+        assert L > slot or so[i, :L].tobytes() == o1[int(f1[i]):int(f1[i]) + L].tobytes(), f"config 4 shard: response {i} of rank {rank} differs from the oracle"
+    out_bytes = int(s_len.sum().item())
+    # end to end through host buffers
+    hb = pin_batch(batch)
+    h_out, h_len, h_meta = pinned_array(n * slot), pinned_array(4 * n, np.uint32), pinned_array(4 * n, np.uint32)
+    for _ in range(2):
+        eng.serve_host_slots(hb, date, slot, h_out, h_len, h_meta)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.serve_host_slots(hb, date, slot, h_out, h_len, h_meta)
+    barrier()
+    dt = reduce_max(time.perf_counter() - t0) / steps
+    assert np.array_equal(h_len[:m], ln)
+    algo = batch.input_bytes() + out_bytes + 8 * n
+    peak, _ = hbm_peak()
+    eng.close()
+    return {"workload": "BASELINE config 4: 64 mixed routes (GET/POST, OPTIONS / 404 / 301 / HEAD traffic), %d requests per GPU, table broadcast from rank 0" % n,
+            "value": n * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "kernel_ms_per_launch": kms / max(kl, 1),
+            "roofline_frac": algo / (kms / max(kl, 1) / 1e3) / 1e9 / peak, "algorithmic_bytes_per_request": algo / n,
+            "e2e": {"value": n * world / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": n * 32 + int(batch.arena_span()), "d2h_bytes_per_step": n * slot + 8 * n},
+            "parity": f"first {m} responses of every rank's shard byte-identical to the oracle run on those requests"}
+
+
+def sharded_config5(eng, rank, world, dev, barrier, reduce_max, steps, per_gpu=1 << 20):
+    """BASELINE config 5 ("gRPC unary protobuf encode path, 1M req, 8xB200 with NCCL route-table broadcast"): every rank
+    decodes / answers / encodes its contiguous shard of one HelloRequest frame stream (the engine's table came from the
+    NCCL broadcast at start-up); parity of a sample against the oracle."""
+    import torch
+    from gofr_b200 import _abi
+    from tests import oracle as O
+    n = per_gpu
+    frames, off = synth.config5_frames(n, start=rank * n)
+    d_in = torch.from_numpy(np.concatenate([frames, np.zeros(64, np.uint8)])).to(dev)
+    d_off = torch.from_numpy(off.view(np.int32)).to(dev)
+    cap = int(frames.size) + 40 * n
+    d_out = torch.zeros(cap + 64, dtype=torch.uint8, device=dev)
+    d_ooff = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    d_meta = torch.zeros(n, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    step = lambda: _abi.check(_abi.lib().gofr_grpc_hello_device(eng._e, d_in.data_ptr(), d_off.data_ptr(), n, d_out.data_ptr(), cap,
+                                                                  d_ooff.data_ptr(), d_meta.data_ptr(), st), "grpc")
+    for _ in range(3):
+        step()
+    barrier()
+    eng.kernel_time_ms(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = reduce_max(e0.elapsed_time(e1)) / steps
+    kms, kl = eng.kernel_time_ms(reset=True)
+    m = 8192
+    o_out, o_off, o_meta = O.grpc_hello(frames, off[:m + 1])
+    g_off = d_ooff[:m + 1].cpu().numpy().view(np.uint32)
+    assert np.array_equal(g_off, o_off) and d_out[:int(o_off[m])].cpu().numpy().tobytes() == o_out[:int(o_off[m])].tobytes(), "config 5 shard differs from the oracle"
+    out_bytes = int(d_ooff[n].item())
+    algo = int(off[n]) + 4 * (n + 1) + out_bytes + 8 * n
+    peak, _ = hbm_peak()
+    return {"workload": "BASELINE config 5: gRPC unary SayHello, %d length-prefixed HelloRequest frames per GPU" % n,
+            "value": n * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "kernel_ms_per_launch": kms / max(kl, 1),
+            "roofline_frac": algo / (kms / max(kl, 1) / 1e3) / 1e9 / peak, "algorithmic_bytes_per_request": algo / n,
+            "parity": f"first {m} response frames of every rank's shard byte-identical to the oracle"}
 
 
 def main():
@@ -446,6 +648,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer measurement (default: --steps)")
     ap.add_argument("--chunk", type=int, default=65536)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="leave the rank's threads and pinned buffers wherever the OS puts them")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sharded config-4 (4 GPUs) / config-5 (8 GPUs) legs")
     ap.add_argument("--e2e-layout", default="slots", choices=["packed", "slots"],
                     help="end-to-end measurement: gofr_batch_submit (packed offsets, device-driven egress) or "
                          "gofr_batch_submit_slots (one slot per response, plain async copies)")
@@ -471,6 +675,10 @@ def main():
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device: gofr_b200 has no CPU path"}))
         return 2
+    # Before anything is pinned: this rank's threads and the pages they touch go to the NUMA node its GPU hangs off
+    # (GPU0-3 and GPU4-7 sit on different sockets on the 8-GPU boxes; unbound, every rank's pinned buffers can land on
+    # one socket and half of the PCIe traffic crosses the inter-socket link).
+    numa = bind_to_gpu_numa(local) if not args.no_numa_bind else {"bound": False, "node": None, "why": "--no-numa-bind"}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -615,9 +823,16 @@ def main():
             # the last host result must match the resident one byte for byte
             dev_out = resp.out[:out_bytes].cpu().numpy()
             assert np.array_equal(h_out[:out_bytes], dev_out), "host path and resident path disagree"
+        barrier()
+        floor = reduce_max(link_floor_ms(dev, int(h2d), int(d2h)))
+        barrier()
         e2e = {"value": n * world * ksteps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": dt / ksteps * 1e3, "steps": ksteps, "chunk_requests": args.chunk, "layout": args.e2e_layout,
-               "timing": "wall clock around the synchronous host-buffer calls, max over ranks"}
+               "timing": "wall clock around the synchronous host-buffer calls, max over ranks",
+               "link_floor_ms_per_step": floor,
+               "link_floor": "the same H2D + D2H bytes per rank moved concurrently on all ranks with no kernel (pinned buffers, "
+                             "max over ranks): what PCIe and host memory allow at this N",
+               "frac_of_link_floor": floor / (dt / ksteps * 1e3)}
 
     # ---- CPU baseline beside it (rank 0, bounded sample of the same stream) ----
     cpu = None
@@ -649,17 +864,27 @@ def main():
         g = resp.out[:4096 * synth.C2_WIRE_BYTES].cpu().numpy()
         assert np.array_equal(g, o1[:4096 * synth.C2_WIRE_BYTES]), "bench output differs from the oracle"
 
+    # ---- sharded legs of the other BASELINE configs (config 4 on 4 GPUs, config 5 on 8 GPUs) ----
+    extras = {}
+    if not args.no_extras:
+        if world == 4:
+            extras["config4_sharded"] = sharded_config4(eng_factory=lambda spec: Engine(Table(image=gd.broadcast_table_image(
+                Table(spec).serialize() if rank == 0 else None, rank, dev)), local), rank=rank, world=world, dev=dev,
+                barrier=barrier, reduce_max=reduce_max, steps=args.steps)
+        if world == 8:
+            extras["config5_sharded"] = sharded_config5(eng, rank, world, dev, barrier, reduce_max, args.steps)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8", "data": "synthetic", "config": dict(workload_config(n, world, "gpu"), resident_layout=("slots: response i in its own 528-byte slot (gofr_serve_device_slots)" if args.layout == "slots" else "packed offsets (gofr_serve_device)"), e2e_layout=("slots (gofr_batch_submit_slots)" if args.e2e_layout == "slots" else "packed offsets (gofr_batch_submit)")),
+                "dtype": "u8", "data": "synthetic", "config": workload_config(n, world, args),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": profiled_traffic(args.layout) if n == (1 << 20) else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                              "algorithmic_bytes_per_request": algo_bytes / n, "kernel_ms_per_launch": per_launch_ms,
                              "kernel": "gofr::serve_slots_kernel" if args.layout == "slots" else "gofr::serve_kernel"},
                 "other_layout": alt,
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "geometry": eng.geometry()}
+                "geometry": eng.geometry(), "numa": numa, **extras}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

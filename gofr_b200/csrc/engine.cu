@@ -13,8 +13,13 @@
 #include <string.h>
 #include <time.h>
 
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "../../include/gofr_b200.h"
@@ -80,6 +85,8 @@ struct gofr_engine {
     // host path
     Slot slots[kSlots];
     cudaStream_t st_h2d = nullptr, st_compute = nullptr, st_egress = nullptr;
+    cudaEvent_t ev_batch_done = nullptr;  // blocking-sync event: the caller's thread SLEEPS until its batch is back (a
+                                          // spinning cudaStreamSynchronize per rank burns the CPU quota eight ranks share)
     unsigned long long* d_chain = nullptr;  // packed position of the batch in flight
     ChunkInfo* d_info = nullptr;            // one per slot
     unsigned long long* h_status = nullptr; // pinned: [0] total bytes, [1] overflow
@@ -165,6 +172,7 @@ static int engine_init(gofr_engine* e, const std::vector<uint8_t>& img, int devi
     CUDA_TRY(cudaStreamCreateWithFlags(&e->st_h2d, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->st_compute, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->st_egress, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_batch_done, cudaEventBlockingSync | cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&e->d_chain, 64));
     CUDA_TRY(cudaMalloc(&e->d_info, sizeof(ChunkInfo) * kSlots));
     CUDA_TRY(cudaMallocHost(&e->h_status, 64));
@@ -193,6 +201,7 @@ void gofr_engine_destroy(gofr_engine* e) {
     if (e->st_h2d) cudaStreamDestroy(e->st_h2d);
     if (e->st_compute) cudaStreamDestroy(e->st_compute);
     if (e->st_egress) cudaStreamDestroy(e->st_egress);
+    if (e->ev_batch_done) cudaEventDestroy(e->ev_batch_done);
     cudaFree(e->d_chain); cudaFree(e->d_info);
     if (e->h_status) cudaFreeHost(e->h_status);
     cudaFree(e->d_image); cudaFree(e->d_state); cudaFree(e->d_flag); cudaFree(e->d_bind);
@@ -438,6 +447,15 @@ static int chunk_arena_range(const gofr_req_batch* in, uint32_t lo, uint32_t hi,
     return GOFR_OK;
 }
 
+// Waits for everything enqueued on the egress stream.  A large batch takes milliseconds: the thread sleeps on a
+// blocking-sync event.  A small one (the per-request front-end's batches) is back in tens of microseconds: spinning is
+// the faster wake-up there.
+static cudaError_t wait_batch(gofr_engine* e, uint32_t n) {
+    if (n < 16384u) return cudaStreamSynchronize(e->st_egress);
+    cudaError_t er = cudaEventRecord(e->ev_batch_done, e->st_egress);
+    return er != cudaSuccess ? er : cudaEventSynchronize(e->ev_batch_done);
+}
+
 // Error exit of a host-batch call after work has been enqueued: earlier chunks' kernels and copies may still be
 // writing into the caller's buffers, which the caller is free to release once we return.
 static void drain_streams(gofr_engine* e) {
@@ -557,7 +575,7 @@ static int batch_submit_locked(gofr_engine* e, const gofr_req_batch* in, gofr_re
             e->launches += 2;
         }
         CUDA_TRY(cudaMemcpyAsync((void*)&e->h_status[0], e->d_chain, 8, cudaMemcpyDeviceToHost, e->st_egress));
-        CUDA_TRY(cudaStreamSynchronize(e->st_egress));
+        CUDA_TRY(wait_batch(e, n));
         for (auto& s : e->slots) s.egress_pending = false;
         uint64_t total = e->h_status[0];
         if (e->h_status[1]) { final_rc = GOFR_ERR_CAPACITY; set_last_error("output capacity too small (device chunk buffer or caller buffer)"); }
@@ -707,7 +725,7 @@ static int batch_submit_slots_locked(gofr_engine* e, const gofr_req_batch* in, g
         s.egress_pending = true;
     }
     if (nchunks) {
-        CUDA_TRY(cudaStreamSynchronize(e->st_egress));
+        CUDA_TRY(wait_batch(e, n));
         for (auto& s : e->slots) s.egress_pending = false;
     }
     *ticket = e->next_ticket++;
@@ -725,6 +743,62 @@ int gofr_batch_wait(gofr_engine* e, gofr_ticket ticket) {
         return rc;
     }
     return GOFR_ERR_INVALID;  // unknown ticket, or already waited for
+}
+
+// Parses a sysfs cpu list ("0-31,64-95") into a cpu_set_t; returns the number of CPUs.
+static int parse_cpulist(const char* s, cpu_set_t* set) {
+    CPU_ZERO(set);
+    int count = 0;
+    while (*s) {
+        char* end = nullptr;
+        long a = strtol(s, &end, 10);
+        if (end == s) break;
+        long b = a;
+        if (*end == '-') { s = end + 1; b = strtol(s, &end, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET((int)c, set); count++; }
+        s = *end == ',' ? end + 1 : end;
+        if (*end != ',') break;
+    }
+    return count;
+}
+
+int gofr_bind_host_thread(int device, int* numa_node_out) {
+    if (numa_node_out) *numa_node_out = -1;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) { cudaGetLastError(); set_last_error("no PCI bus id for device %d", device); return GOFR_ERR_CUDA; }
+    for (char* c = bus; *c; c++) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c + 32);  // sysfs names are lower case
+    auto read_line = [](const std::string& path, char* buf, size_t cap) -> bool {
+        FILE* f = fopen(path.c_str(), "r");
+        if (!f) return false;
+        const bool ok = fgets(buf, (int)cap, f) != nullptr;
+        fclose(f);
+        return ok;
+    };
+    const std::string base = std::string("/sys/bus/pci/devices/") + bus + "/";
+    char line[4096];
+    int node = -1;
+    if (read_line(base + "numa_node", line, sizeof line)) node = atoi(line);
+    if (numa_node_out) *numa_node_out = node;
+    cpu_set_t set;
+    int ncpu = 0;
+    if (node >= 0 && read_line("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist", line, sizeof line)) ncpu = parse_cpulist(line, &set);
+    if (!ncpu && read_line(base + "local_cpulist", line, sizeof line)) ncpu = parse_cpulist(line, &set);
+    if (!ncpu) { set_last_error("no NUMA information for device %d (%s)", device, bus); return GOFR_ERR_UNSUPPORTED; }
+    // stay inside what the container allows
+    cpu_set_t cur;
+    if (sched_getaffinity(0, sizeof cur, &cur) == 0) {
+        cpu_set_t both;
+        CPU_AND(&both, &set, &cur);
+        if (CPU_COUNT(&both) > 0) set = both;
+    }
+    if (sched_setaffinity(0, sizeof set, &set) != 0) { set_last_error("sched_setaffinity failed for device %d", device); return GOFR_ERR_UNSUPPORTED; }
+#if defined(SYS_set_mempolicy)
+    if (node >= 0 && node < 64) {  // MPOL_PREFERRED: pages this thread touches (pinned allocations included) come from the GPU's node
+        unsigned long mask = 1ul << node;
+        syscall(SYS_set_mempolicy, 1 /*MPOL_PREFERRED*/, &mask, 65ul);
+    }
+#endif
+    return GOFR_OK;
 }
 
 void* gofr_alloc_pinned(size_t bytes) {

@@ -267,6 +267,13 @@ int gofr_engine_geometry(const gofr_engine*, uint32_t* grid, uint32_t* blocks_pe
 int gofr_engine_overflowed(gofr_engine*, int* flag_out, int reset);
 int gofr_engine_set_timing(gofr_engine*, int on);
 
+/* Binds the CALLING thread to the CPUs of the NUMA node the GPU hangs off (sysfs: /sys/bus/pci/devices/<bus id>/numa_node)
+ * and makes that node the preferred one for the pages the thread touches from now on — call it before gofr_alloc_pinned
+ * and before the threads that fill the batches are started.  With eight GPUs on two sockets, pinned buffers that all sit
+ * on one socket make half of the H2D/D2H traffic cross the inter-socket link: the reference has nothing like it (its
+ * goroutines are scheduled by the Go runtime, pkg/gofr/httpServer.go:29-33); a host that feeds GPUs needs it.
+ * numa_node_out (may be NULL) receives the node, -1 if unknown.  GOFR_ERR_UNSUPPORTED when the topology cannot be read. */
+int gofr_bind_host_thread(int device, int* numa_node_out);
 void* gofr_alloc_pinned(size_t bytes);
 void gofr_free_pinned(void*);
 
