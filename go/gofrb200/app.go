@@ -37,8 +37,21 @@ const (
 	resultMissing = 3
 	resultBoth    = 4
 	resultString  = 5
-	hResult       = 12 // GOFR_H_RESULT
+	// response.Raw outcomes; the error selector goes into bits 8..15 (include/gofr_b200.h)
+	resultRawData   = 6
+	resultRawString = 7
+	resultRawNil    = 8
+	rawOK           = 0
+	rawErr          = 1
+	rawMissing      = 2
+	hResult         = 12 // GOFR_H_RESULT
 )
+
+// Raw is the reference's response.Raw (pkg/gofr/http/response/raw.go:3-5): a handler that returns Raw{Data: v} gets v
+// encoded bare, without the {"error":…,"data":…} envelope (pkg/gofr/http/responder.go:24-26).
+type Raw struct {
+	Data interface{}
+}
 
 // Context is what a handler sees (pkg/gofr/context.go:12-27): the request behind the reference's Request interface.
 type Context struct {
@@ -247,6 +260,31 @@ func encodeRow(v reflect.Value) (fixed, strs []byte) {
 // resultRecord describes (data, err) for Responder.Respond (pkg/gofr/http/responder.go:19-62) as a GOFR_H_RESULT record.
 func (a *App) resultRecord(r *route, data interface{}, err error) []byte {
 	var rec []byte
+	if raw, ok := data.(Raw); ok {
+		// response.Raw (pkg/gofr/http/response/raw.go:3-5): Respond encodes raw.Data bare; the error only picks the status
+		es := uint32(rawOK)
+		if err != nil {
+			es = rawErr
+			if errors.Is(err, http.ErrMissingFile) {
+				es = rawMissing
+			}
+		}
+		rv := reflect.ValueOf(raw.Data)
+		switch {
+		case raw.Data == nil:
+			rec = u32(rec, resultRawNil|es<<8)
+		case r.rtype != nil && rv.Type() == r.rtype:
+			fixed, strs := encodeRow(rv)
+			rec = append(append(u32(rec, resultRawData|es<<8), fixed...), strs...)
+		default:
+			if s, ok := raw.Data.(string); ok {
+				rec = append(u32(u32(rec, resultRawString|es<<8), uint32(len(s))), s...)
+			} else {
+				rec = u32(rec, 0xFFFFFFFF)
+			}
+		}
+		return rec
+	}
 	rv := reflect.ValueOf(data)
 	isStruct := data != nil && r.rtype != nil && rv.Type() == r.rtype
 	switch {

@@ -689,6 +689,7 @@ struct TableView {
     GOFR_HD const uint32_t* tmpl_keys() const { return (const uint32_t*)(base + hdr()->tmplkey_off); }
     GOFR_HD const uint16_t* last_method() const { return (const uint16_t*)(base + hdr()->last_method_off); }
     GOFR_HD const FastRec* fast() const { return (const FastRec*)(base + hdr()->fast_off); }
+    GOFR_HD const uint16_t* rawprogs() const { return (const uint16_t*)(base + hdr()->rawprog_off); }
     GOFR_HD const uint32_t* lit_words(uint32_t off) const { return (const uint32_t*)(lits() + off); }
     GOFR_HD const uint8_t* lit_bytes(uint32_t off) const { return lits() + off; }
 };
@@ -1120,9 +1121,18 @@ GOFR_HD void route_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) 
     } else if (R.hkind == GOFR_H_RESULT) {
         // the closure ran on the host; its outcome word selects what Responder.Respond does (responder.go:19-62)
         const uint32_t outcome = c.data_len >= 4 ? *(const uint32_t*)c.data() : 0xFFFFFFFFu;
-        if (outcome > GOFR_RESULT_STRING) { c.prog = H.prog_panic; return; }  // malformed record from the host shim
+        const uint32_t okind = outcome & 0xFFu, oerr = outcome >> 8;
+        if (okind > GOFR_RESULT_RAW_NIL || (okind < GOFR_RESULT_RAW_DATA ? oerr != 0 : oerr > GOFR_RESULT_RAW_MISSING)) {
+            c.prog = H.prog_panic;  // malformed record from the host shim
+            return;
+        }
         c.data_off += 4;
         c.data_len -= 4;
+        if (okind >= GOFR_RESULT_RAW_DATA) {  // response.Raw: data encoded bare, the error picks the status (responder.go:21-26)
+            c.prog = tv.rawprogs()[(uint32_t)m * 9u + (okind - GOFR_RESULT_RAW_DATA) * 3u + oerr];
+            if (c.prog == 0xFFFFu) c.prog = H.prog_panic;  // RAW_DATA on a route registered without a schema
+            return;
+        }
         c.prog = outcome == GOFR_RESULT_DATA ? R.prog_ok : outcome == GOFR_RESULT_ERROR ? R.prog_err
                : outcome == GOFR_RESULT_NIL ? R.key_len : outcome == GOFR_RESULT_MISSING ? R.def_len
                : outcome == GOFR_RESULT_BOTH ? (R.key_off & 0xFFFFu) : (R.key_off >> 16);

@@ -592,6 +592,7 @@ int seal_table(gofr_table* t) {
     std::vector<int> prog_ok(t->routes.size(), 0xFFFF), prog_err(t->routes.size(), 0xFFFF);
     std::vector<int> prog_err404(t->routes.size(), 0xFFFF), prog_nil(t->routes.size(), 0xFFFF), prog_both(t->routes.size(), 0xFFFF),
         prog_str(t->routes.size(), 0xFFFF);
+    std::vector<uint16_t> rawprogs(t->routes.size() * 9, 0xFFFF);  // response.Raw outcomes of GOFR_H_RESULT routes
     for (size_t ri = 0; ri < t->routes.size(); ri++) {
         RouteDef& r = t->routes[ri];
         const SchemaDef* sc = nullptr;
@@ -675,6 +676,31 @@ int seal_table(gofr_table* t) {
                     (which ? prog_err404 : prog_err)[ri] = b.add(std::move(e));
                 }
                 prog_nil[ri] = b.json_prog(200, {lit("{}\n", true)});
+                // response.Raw{Data: …}: the data encoded bare (responder.go:24-26); the error only picks the status
+                for (int es = 0; es < 3; es++) {
+                    const int status = es == 0 ? 200 : es == 1 ? 500 : 404;
+                    if (sc) {
+                        Prog p;
+                        p.status = status;
+                        build_header(p, fm, status, true, BODY_JSON, false, "", "", false);
+                        build_struct_ops(p, *sc, false);
+                        p.ops.push_back(lit("\n", true));
+                        rawprogs[ri * 9 + 0 + es] = (uint16_t)b.add(std::move(p));
+                    }
+                    {
+                        Prog p;
+                        p.status = status;
+                        build_header(p, fm, status, true, BODY_JSON, false, "", "", false);
+                        p.ops.push_back(lit("\"", true));
+                        SOp m = op(OP_STR, true);
+                        m.off = 0;
+                        p.ops.push_back(m);
+                        p.ops.push_back(lit("\"\n", true));
+                        p.row_words = 1;
+                        rawprogs[ri * 9 + 3 + es] = (uint16_t)b.add(std::move(p));
+                    }
+                    rawprogs[ri * 9 + 6 + es] = (uint16_t)b.json_prog(status, {lit("null\n", true)});
+                }
                 if (sc) {  // (data, err) both non-nil: response{Error, Data} with both members (responder.go:59-62)
                     Prog e;
                     e.status = 500;
@@ -1084,6 +1110,8 @@ int seal_table(gofr_table* t) {
     }
     H.last_method_off = append(last_method.data(), last_method.size() * 2);
     H.fast_off = append(fast.data(), fast.size() * sizeof(FastRec));
+    if (rawprogs.empty()) rawprogs.resize(9, 0xFFFF);
+    H.rawprog_off = append(rawprogs.data(), rawprogs.size() * 2);
     H.fixups_off = append(fixups.data(), fixups.size() * 4);
     H.n_fixups = (uint32_t)fixups.size();
     // schemas: SchemaRec[n] then each field table

@@ -12,12 +12,12 @@
 namespace gofr {
 
 constexpr uint32_t kMagic = 0x52464F47u;  // "GOFR"
-constexpr uint32_t kImageVersion = 14;
+constexpr uint32_t kImageVersion = 15;
 constexpr uint32_t kMaxHotBytes = 40 * 1024;  // shared-memory budget for the table
 constexpr int kMaxVars = 8;                   // variables per route template
 constexpr int kMaxFields = 32;                // struct fields per schema
 
-struct ImageHeader {  // 144 B
+struct ImageHeader {  // 160 B
     uint32_t magic, version;
     uint32_t frame_mode;
     uint32_t n_routes, n_pieces, n_progs, n_ops, n_schemas;
@@ -46,8 +46,11 @@ struct ImageHeader {  // 144 B
     uint32_t checksum;       // FNV-1a over the whole image with this field zero: set at seal, checked by deserialize (the
                              // image travels between ranks); never read on the device
     uint32_t fast_off;       // FastRec[n_progs]: how the slot-layout kernel emits each program (templates + tail ops)
+    uint32_t rawprog_off;    // uint16[n_routes][9]: GOFR_H_RESULT routes, programs of the response.Raw outcomes
+                             // [(RAW_DATA, RAW_STRING, RAW_NIL) x (200, 500, 404)], 0xFFFF = none
+    uint32_t reserved3[3];
 };
-static_assert(sizeof(ImageHeader) == 144, "ImageHeader layout");
+static_assert(sizeof(ImageHeader) == 160, "ImageHeader layout");
 
 enum RouteFlags : uint8_t {
     RF_PREFIX = 1,   // PathPrefix: regexp has no trailing '$'

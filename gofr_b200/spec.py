@@ -24,15 +24,18 @@ FRAME_WIRE, FRAME_INTENDED, FRAME_BODY = 0, 1, 2
 # handler kinds
 (H_HOST, H_STATIC_STRING, H_STATIC_ERROR, H_NIL, H_PARAM_FORMAT, H_ROW, H_BIND_ECHO, H_HEALTH, H_MISSING_FILE, H_FILE,
  H_PANIC, H_PATHPARAM_FORMAT, H_RESULT) = range(13)
-RESULT_DATA, RESULT_ERROR, RESULT_NIL, RESULT_MISSING, RESULT_BOTH, RESULT_STRING = range(6)
+(RESULT_DATA, RESULT_ERROR, RESULT_NIL, RESULT_MISSING, RESULT_BOTH, RESULT_STRING, RESULT_RAW_DATA, RESULT_RAW_STRING,
+ RESULT_RAW_NIL) = range(9)
+RAW_OK, RAW_ERR, RAW_MISSING = 0, 1, 2   # bits 8..15 of a RAW outcome word: which status the (ignored) error picks
 
 
-def result_record(outcome: int, payload: bytes = b"") -> bytes:
-    """Data section of a GOFR_H_RESULT request: outcome word, then a schema row (DATA) or len + bytes (ERROR / MISSING: err.Error();
-    STRING: the string the handler returned)."""
-    if outcome in (RESULT_ERROR, RESULT_MISSING, RESULT_STRING):
+def result_record(outcome: int, payload: bytes = b"", raw_err: int = RAW_OK) -> bytes:
+    """Data section of a GOFR_H_RESULT request: outcome word, then a schema row (DATA / RAW_DATA) or len + bytes (ERROR / MISSING:
+    err.Error(); STRING / RAW_STRING: the string the handler returned).  raw_err: for the RAW outcomes, the error the closure
+    returned next to the response.Raw value (it only selects the status code)."""
+    if outcome in (RESULT_ERROR, RESULT_MISSING, RESULT_STRING, RESULT_RAW_STRING):
         payload = len(payload).to_bytes(4, "little") + payload
-    return outcome.to_bytes(4, "little") + payload
+    return (outcome | raw_err << 8).to_bytes(4, "little") + payload
 
 
 def result_both(schema: "Schema", values: Sequence, message: bytes) -> bytes:

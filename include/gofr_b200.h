@@ -111,10 +111,20 @@ enum {
                                                         words, then message bytes + string bytes) → 500 {"error":…,"data":…}
                                    GOFR_RESULT_STRING   data is a Go string (what most of the reference's example handlers
                                                         return, examples/http-server/main.go:29-41): u32 length + bytes
-                                                        → 200 {"data":"…"}  (the route needs no schema for this outcome) */
+                                                        → 200 {"data":"…"}  (the route needs no schema for this outcome)
+                                 The closure returned a response.Raw (pkg/gofr/http/response/raw.go:3-5): Respond encodes
+                                 Raw.Data bare, without the {"error":…,"data":…} envelope (responder.go:24-26); the error, if
+                                 any, only picks the status code (written at responder.go:21 before the type switch):
+                                   GOFR_RESULT_RAW_DATA    a row of the route's schema                      → {…}\n
+                                   GOFR_RESULT_RAW_STRING  u32 length + bytes                               → "…"\n
+                                   GOFR_RESULT_RAW_NIL     nothing (Raw{}: Data is a nil interface)         → null\n
+                                 with the error in bits 8..15 of the outcome word: GOFR_RESULT_RAW_OK (err == nil, 200),
+                                 GOFR_RESULT_RAW_ERR (500), GOFR_RESULT_RAW_MISSING (errors.Is(err, http.ErrMissingFile), 404);
+                                 e.g. GOFR_RESULT_RAW_STRING | GOFR_RESULT_RAW_ERR << 8. */
 };
 enum { GOFR_RESULT_DATA = 0, GOFR_RESULT_ERROR = 1, GOFR_RESULT_NIL = 2, GOFR_RESULT_MISSING = 3, GOFR_RESULT_BOTH = 4,
-       GOFR_RESULT_STRING = 5 };
+       GOFR_RESULT_STRING = 5, GOFR_RESULT_RAW_DATA = 6, GOFR_RESULT_RAW_STRING = 7, GOFR_RESULT_RAW_NIL = 8 };
+enum { GOFR_RESULT_RAW_OK = 0, GOFR_RESULT_RAW_ERR = 1, GOFR_RESULT_RAW_MISSING = 2 };
 
 /* ---- struct field kinds for response / Bind schemas ---- */
 enum {

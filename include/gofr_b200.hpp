@@ -51,11 +51,21 @@ struct StructValue {
 };
 // interface{} as handlers of this path return it: nil, a string, or a registered struct.
 using Data = std::variant<std::monostate, std::string, StructValue>;
+// response.Raw{Data: ...} (pkg/gofr/http/response/raw.go:3-5): Respond writes the data bare, without the envelope
+struct Raw {
+    Data data;
+    Raw() = default;
+    Raw(Data d) : data(std::move(d)) {}
+    Raw(const char* s) : data(std::string(s)) {}
+};
 // (interface{}, error)
 struct Result {
     Data data;
     std::optional<Error> err;
+    bool raw = false;  // data was returned wrapped in response.Raw
     Result() = default;
+    Result(Raw r) : data(std::move(r.data)), raw(true) {}                     // return response.Raw{...}, nil
+    Result(Raw r, Error e) : data(std::move(r.data)), err(std::move(e)), raw(true) {}
     Result(Data d) : data(std::move(d)) {}                                    // return data, nil
     Result(const char* s) : data(std::string(s)) {}
     Result(std::string s) : data(std::move(s)) {}
@@ -394,6 +404,21 @@ private:
     std::string encode_result(uint32_t route_type_id, const Result& res) const {
         std::string rec;
         const bool has_err = res.err.has_value();
+        if (res.raw) {  // the error only picks the status code (responder.go:20-26)
+            const uint32_t es = !has_err ? GOFR_RESULT_RAW_OK : res.err->missing_file ? GOFR_RESULT_RAW_MISSING : GOFR_RESULT_RAW_ERR;
+            if (auto* sv = std::get_if<StructValue>(&res.data)) {
+                std::string fixed, strings;
+                if (sv->type_id != route_type_id || !encode_struct(*sv, &fixed, &strings)) { detail::put_u32(&rec, 0xFFFFFFFFu); return rec; }
+                detail::put_u32(&rec, GOFR_RESULT_RAW_DATA | es << 8);
+                rec += fixed;
+                rec += strings;
+            } else if (auto* s = std::get_if<std::string>(&res.data)) {
+                detail::put_u32(&rec, GOFR_RESULT_RAW_STRING | es << 8);
+                detail::put_u32(&rec, (uint32_t)s->size());
+                rec += *s;
+            } else detail::put_u32(&rec, GOFR_RESULT_RAW_NIL | es << 8);
+            return rec;
+        }
         if (auto* sv = std::get_if<StructValue>(&res.data)) {
             std::string fixed, strings;
             if (sv->type_id != route_type_id || !encode_struct(*sv, &fixed, &strings)) { detail::put_u32(&rec, 0xFFFFFFFFu); return rec; }

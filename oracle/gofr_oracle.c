@@ -757,6 +757,7 @@ typedef struct {
     int err_is_missing_file; /* errors.Is(err, http.ErrMissingFile) */
     const uint8_t* err_msg;
     size_t err_len;
+    int raw; /* data is a response.Raw{Data: ...}: Respond encodes v.Data bare (pkg/gofr/http/responder.go:24-26, response/raw.go:3-5) */
 } handler_result;
 
 static void respond(rw_t* w, const handler_result* r) {
@@ -770,9 +771,19 @@ static void respond(rw_t* w, const handler_result* r) {
         return;
     }
     rw_set(w, "Content-Type", "application/json", 16); /* :39 "Content-type" canonicalises to Content-Type */
-    /* json.NewEncoder(w).Encode(response{Error, Data}) :40 ; struct order: error, data; both omitempty on interface */
     obuf* b = &w->body;
     if (!w->wrote_header) rw_write_header(w, 200);
+    if (r->raw) {
+        /* case resTypes.Raw: resp = v.Data (:25-26) — no envelope, and the error object computed at :20 is not part of
+         * the body (the status code it produced was already written at :21).  Raw{} holds a nil interface: "null". */
+        if (r->data_kind == 0) ob_puts(b, "null");
+        else if (r->data_kind == 1) orc_enc_string(b, r->str, r->str_len);
+        else if (r->data_kind == 2) orc_enc_struct(b, r->sc, r->vals);
+        else ob_puts(b, "{}");
+        ob_putc(b, '\n');
+        return;
+    }
+    /* json.NewEncoder(w).Encode(response{Error, Data}) :40 ; struct order: error, data; both omitempty on interface */
     ob_putc(b, '{');
     int first = 1;
     if (r->has_err) {
@@ -957,6 +968,23 @@ static void serve_one(const orc_table* t, const req_desc* d, const uint8_t* id16
                 if (dn >= 4) memcpy(&outcome, data, 4);
                 const uint8_t* rest = data + 4;
                 size_t rn = dn >= 4 ? dn - 4 : 0;
+                if ((outcome & 0xFFu) >= 6 && (outcome & 0xFFu) <= 8 && (outcome >> 8) <= 2) {
+                    /* response.Raw{Data: struct | string | nil}; bits 8..: 0 = err == nil, 1 = some error (500),
+                     * 2 = errors.Is(err, http.ErrMissingFile) (404).  The error only picks the status. */
+                    const uint32_t kind = outcome & 0xFFu, es = outcome >> 8;
+                    hr.raw = 1;
+                    if (es) { hr.has_err = 1; hr.err_is_missing_file = es == 2; hr.err_msg = (const uint8_t*)""; hr.err_len = 0; }
+                    if (kind == 6) {
+                        if (!sc || decode_row(sc, rest, rn, vals) != 0) hr.data_kind = -1;
+                        else { hr.data_kind = 2; hr.sc = sc; hr.vals = vals; }
+                    } else if (kind == 7) {
+                        uint32_t len = 0;
+                        if (rn >= 4) memcpy(&len, rest, 4);
+                        if (rn < 4 || (uint64_t)len + 4 > rn) { hr.data_kind = -1; break; }
+                        hr.data_kind = 1; hr.str = rest + 4; hr.str_len = len;
+                    }
+                    break;
+                }
                 if (outcome == 0) {
                     if (!sc || decode_row(sc, rest, rn, vals) != 0) hr.data_kind = -1;
                     else { hr.data_kind = 2; hr.sc = sc; hr.vals = vals; }

@@ -1,6 +1,8 @@
 """GOFR_H_RESULT — stage 2 of the split API: the closure ran on the host, Responder.Respond runs on its (data, err)
 (pkg/gofr/http/responder.go:19-62; handler.ServeHTTP pkg/gofr/handler.go:32-36).  Stage 1 is gofr_route_device
 (tests/test_route.py)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -247,3 +249,113 @@ def test_string_outcome_property(strings, mis):
             continue                      # see test_independent_checks: the textual replacement trick needs no backslashes
         want = _go_json_string_from_python(text)
         assert r == (b'{"data":' if k % 4 else b'{"error":{"message":') + want + (b"}\n" if k % 4 else b"}}\n"), k
+
+
+# ---- response.Raw (pkg/gofr/http/response/raw.go:3-5): Respond encodes Raw.Data bare — no envelope — and the error, if any,
+#      only picks the status code (responder.go:19-26).  responder_test.go:21 pins Raw{} -> Content-Type application/json ----
+
+def _raw_batch() -> S.RequestBatch:
+    R, rec = S.Req, S.result_record
+    row = ITEM.encode_row(["A-1", 3, "n<1>"])
+    reqs = [R(S.M_GET, b"/hello", data=rec(S.RESULT_RAW_NIL)),                                    # response.Raw{}
+            R(S.M_GET, b"/hello", data=rec(S.RESULT_RAW_STRING, b"plain text")),
+            R(S.M_GET, b"/hello", data=rec(S.RESULT_RAW_STRING, b'<b>"q"</b> & \\ \x01 \xe2\x80\xa8 \xff caf\xc3\xa9\n')),
+            R(S.M_GET, b"/hello", data=rec(S.RESULT_RAW_STRING, b"")),
+            R(S.M_GET, b"/items/1", data=rec(S.RESULT_RAW_DATA, row)),
+            R(S.M_GET, b"/items/1", data=rec(S.RESULT_RAW_DATA, row, S.RAW_ERR)),                  # (Raw{...}, err): 500, same body
+            R(S.M_GET, b"/items/1", data=rec(S.RESULT_RAW_NIL, b"", S.RAW_MISSING)),               # (Raw{}, ErrMissingFile): 404 null
+            R(S.M_GET, b"/hello", data=rec(S.RESULT_RAW_STRING, b"x", S.RAW_ERR)),
+            R(S.M_GET, b"/hello", data=rec(S.RESULT_RAW_DATA, row)),                               # no schema on this route: panic
+            R(S.M_GET, b"/hello", data=(S.RESULT_RAW_NIL | 3 << 8).to_bytes(4, "little")),         # unknown error selector: panic
+            R(S.M_GET, b"/hello", data=(S.RESULT_STRING | 1 << 8).to_bytes(4, "little") + b"\x01\0\0\0x"),  # selector on a non-Raw outcome
+            R(S.M_GET, b"/hello", data=(9).to_bytes(4, "little")),                                 # unknown outcome
+            R(S.M_GET, b"/items/2", data=rec(S.RESULT_RAW_DATA, row[:5])),                         # truncated row
+            R(S.M_GET, b"/hello", data=rec(S.RESULT_RAW_STRING, b"y" * 2000)),
+            R(S.M_HEAD, b"/hello", data=rec(S.RESULT_RAW_NIL)),
+            R(S.M_OPTIONS, b"/items/7", data=rec(S.RESULT_RAW_NIL))]
+    return S.RequestBatch.pack(reqs)
+
+
+def test_raw_oracle_bodies():
+    out, off, meta = O.OracleTable(_string_spec(S.FRAME_BODY)).serve(_raw_batch(), DATE)
+    r = O.responses(out, off)
+    st = [int(m) & 0xFFFF for m in meta]
+    assert r[0] == b"null\n" and st[0] == 200                      # json.Encoder.Encode(nil interface)
+    assert r[1] == b'"plain text"\n' and st[1] == 200
+    assert r[2] == b'"\\u003cb\\u003e\\"q\\"\\u003c/b\\u003e \\u0026 \\\\ \\u0001 \\u2028 \\ufffd caf\xc3\xa9\\n"\n'
+    assert r[3] == b'""\n'
+    assert r[4] == b'{"sku":"A-1","qty":3,"note":"n\\u003c1\\u003e"}\n' and st[4] == 200
+    assert r[5] == r[4] and st[5] == 500                             # the error object is computed and dropped
+    assert r[6] == b"null\n" and st[6] == 404
+    assert r[7] == b'"x"\n' and st[7] == 500
+    assert all(st[k] == 500 and b"Some unexpected error" in r[k] for k in (8, 9, 10, 11, 12))
+    assert r[13] == b'"' + b"y" * 2000 + b'"\n'
+    assert st[14] == 404 and st[15] == 200 and r[15] == b""         # HEAD: GET-only route -> catch-all; OPTIONS: CORS answers
+    import json
+    assert json.loads(r[0]) is None and json.loads(r[1]) == "plain text" and json.loads(r[4]) == {"sku": "A-1", "qty": 3, "note": "n<1>"}
+
+
+def test_raw_content_type_pin():
+    """pkg/gofr/http/responder_test.go:21 — `{"raw response type", resTypes.Raw{}, "application/json"}` read from the
+    live recorder map (GOFR_FRAME_INTENDED); on the wire net/http sniffs the body instead (WriteHeader came first)."""
+    import json as _json
+    pins = _json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_pins.json")))
+    pin = [c for c in pins["responder_content_type"]["cases"] if c["kind"] == "raw"][0]
+    b = S.RequestBatch.pack([S.Req(S.M_GET, b"/hello", data=S.result_record(S.RESULT_RAW_NIL))])
+    for frame, want in ((S.FRAME_INTENDED, pin["content_type"]), (S.FRAME_WIRE, "text/plain; charset=utf-8")):
+        out, off, _ = O.OracleTable(_string_spec(frame)).serve(b, DATE)
+        head = O.responses(out, off)[0].split(b"\r\n\r\n")[0].decode().lower()
+        assert "content-type: " + want in head, head
+
+
+@pytest.mark.parametrize("frame", [S.FRAME_WIRE, S.FRAME_INTENDED, S.FRAME_BODY])
+@pytest.mark.parametrize("mis", [0, 5])
+def test_raw_emu_matches_oracle(frame, mis):
+    spec, b = _string_spec(frame), _raw_batch()
+    o1, f1, m1 = O.OracleTable(spec).serve(b, DATE)
+    o2, f2, m2 = emu.serve(Table(spec).serialize(), b, DATE, misalign=mis)
+    assert np.array_equal(m1, m2) and np.array_equal(f1 + mis, f2)
+    assert o1[:f1[-1]].tobytes() == o2[mis:f2[-1]].tobytes()
+    for stage in (0, 1):            # slot layout: general interpreter and the fast path (all requests "staged")
+        emu.set_stage_mode(stage)
+        try:
+            out, ln, meta = emu.serve_slots(Table(spec).serialize(), b, DATE, 4096)
+        finally:
+            emu.set_stage_mode(0)
+        assert np.array_equal(meta, m1) and np.array_equal(ln, np.diff(f1.astype(np.int64)).astype(np.uint32))
+        ob = o1.tobytes()
+        for i in range(b.n):
+            assert out[i, :int(ln[i])].tobytes() == ob[int(f1[i]):int(f1[i + 1])], i
+
+
+@pytest.mark.gpu
+def test_gpu_raw_outcomes():
+    from gofr_b200.engine import Engine
+    spec = _string_spec()
+    eng = Engine(Table(spec), 0)
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b'abcXYZ019 <>&"\\\n\x01\xc3\xa9\xe2\x80\xa8\xff', dtype=np.uint8)
+    reqs = []
+    for k in range(20000):
+        s = alphabet[rng.integers(0, len(alphabet), int(rng.integers(0, 90)))].tobytes()
+        es = (S.RAW_OK, S.RAW_OK, S.RAW_ERR, S.RAW_MISSING)[k % 4]
+        if k % 3 == 0:
+            reqs.append(S.Req(S.M_GET, b"/items/%d" % k, data=S.result_record(S.RESULT_RAW_DATA, ITEM.encode_row([s[:20], k, s[20:]]), es)))
+        elif k % 3 == 1:
+            reqs.append(S.Req(S.M_GET, b"/hello", data=S.result_record(S.RESULT_RAW_STRING, s, es)))
+        else:
+            reqs.append(S.Req(S.M_GET, b"/hello", data=S.result_record(S.RESULT_RAW_NIL, b"", es)))
+    for b in (_raw_batch(), S.RequestBatch.pack(reqs)):
+        o1, f1, m1 = O.OracleTable(spec).serve(b, DATE)
+        resp = eng.alloc_responses(b.n, int(f1[-1]) + 4096)
+        eng.serve_device(eng.upload(b), DATE, resp)
+        out, off, m2 = resp.to_host()
+        assert np.array_equal(m1, m2) and np.array_equal(f1, off)
+        assert o1[:f1[-1]].tobytes() == out.tobytes()
+        o_s, ln_s, m_s = eng.serve_device_slots(eng.upload(b), DATE, 4096)
+        ln = ln_s.cpu().numpy().view(np.uint32)
+        assert np.array_equal(m_s.cpu().numpy().view(np.uint32), m1) and np.array_equal(ln, np.diff(f1.astype(np.int64)).astype(np.uint32))
+        so, ob = o_s.cpu().numpy().reshape(b.n, 4096), o1.tobytes()
+        for i in range(0, b.n, 3):
+            assert so[i, :int(ln[i])].tobytes() == ob[int(f1[i]):int(f1[i + 1])], i
+    eng.close()
