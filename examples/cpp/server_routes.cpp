@@ -44,6 +44,18 @@ int main() {
     g.GET("/file", [](gofr::Context&) -> gofr::Result { return gofr::ErrMissingFile(); });
     g.GET("/panic", [](gofr::Context&) -> gofr::Result { throw std::runtime_error("boom"); });
     g.POST("/echo", [](gofr::Context& c) -> gofr::Result { return c.Body(); });
+    // Context.Bind (pkg/gofr/context.go:52-54; the shape of pkg/gofr/context_test.go:23-49): bind the body, return the struct
+    g.POST("/people", [](gofr::Context& c) -> gofr::Result {
+        gofr::StructValue p;
+        if (auto err = c.Bind(&p)) return *err;
+        return gofr::Data(p);
+    }, &person);
+    g.Binds(person);
+    // response.Raw (pkg/gofr/http/response/raw.go:3-5): the data without the envelope; an error only picks the status
+    g.GET("/raw", [](gofr::Context&) -> gofr::Result { return gofr::Raw("just <text>"); });
+    g.GET("/rawnil", [](gofr::Context&) -> gofr::Result { return gofr::Raw(); });
+    g.GET("/rawperson", [&](gofr::Context&) -> gofr::Result { return gofr::Raw(gofr::Data(person({int64_t(9), std::string("raw"), true}))); }, &person);
+    g.GET("/rawerr", [](gofr::Context&) -> gofr::Result { return gofr::Result(gofr::Raw("x"), gofr::Error{"ignored"}); });
 
     g.Run(0);
 
@@ -74,6 +86,15 @@ int main() {
         {"OPTIONS", "/hello", "", 200, ""},
         {"PATCH", "/hello", "", 404, "{\"error\":{\"message\":\"http: no such file\"}}\n"},
         {"GET", "/.well-known/health", "", 200, "{\"data\":{}}\n"},
+        {"POST", "/people", "{\"id\":1,\"name\":\"Bob\"}", 200, "{\"data\":{\"id\":1,\"name\":\"Bob\"}}\n"},
+        {"POST", "/people", "{\"ID\":7,\"NAME\":\"caf\\u00e9 \\\"q\\\"\",\"admin\":true,\"extra\":[1,{\"a\":2}]}", 200, "{\"data\":{\"id\":7,\"name\":\"caf\xc3\xa9 \\\"q\\\"\",\"admin\":true}}\n"},
+        {"POST", "/people", "{\"id\":\"x\"}", 500, "{\"error\":{\"message\":\"json: cannot unmarshal string into Go struct field Person.id of type int\"}}\n"},
+        {"POST", "/people", "{bad", 500, "{\"error\":{\"message\":\"invalid character 'b' looking for beginning of object key string\"}}\n"},
+        {"POST", "/people", "", 500, "{\"error\":{\"message\":\"unexpected end of JSON input\"}}\n"},
+        {"GET", "/raw", "", 200, "\"just \\u003ctext\\u003e\"\n"},
+        {"GET", "/rawnil", "", 200, "null\n"},
+        {"GET", "/rawperson", "", 200, "{\"id\":9,\"name\":\"raw\",\"admin\":true}\n"},
+        {"GET", "/rawerr", "", 500, "\"x\"\n"},
     };
     std::vector<gofr::App::Request> reqs;
     for (auto& c : cases) {

@@ -202,6 +202,23 @@ func (e *Engine) RouteDevice(dDesc, dArena unsafe.Pointer, n int, dMeta, dVars u
 		(*C.uint32_t)(dVars), stream), "gofr_route_device")
 }
 
+// BindDevice is Context.Bind as a GPU stage for closures that stay in Go (gofr_bind_device): body i (the data section of
+// request i) is decoded with encoding/json's rules into a row of schema schemaID (status 0), or into err.Error() (status 1),
+// in slot i of dRows; status 2 = decide on the host.  pkg/gofr/context.go:52-54, pkg/gofr/http/request.go:40-47.
+func (e *Engine) BindDevice(schemaID uint32, dDesc, dArena unsafe.Pointer, n int, dRows unsafe.Pointer, slotBytes uint32,
+	dLen, dStatus unsafe.Pointer, stream unsafe.Pointer) error {
+	return check(C.gofr_bind_device(e.e, C.uint32_t(schemaID), (*C.gofr_req_desc)(dDesc), (*C.uint8_t)(dArena), C.uint32_t(n),
+		(*C.uint8_t)(dRows), C.uint32_t(slotBytes), (*C.uint32_t)(dLen), (*C.uint32_t)(dStatus), stream), "gofr_bind_device")
+}
+
+// BindHostThread pins the calling OS thread (runtime.LockOSThread first) to the CPUs and memory of the NUMA node the GPU
+// hangs off; call it before AllocPinned and before the goroutines that fill batches are started (gofr_bind_host_thread).
+func BindHostThread(device int) (numaNode int, err error) {
+	var node C.int
+	err = check(C.gofr_bind_host_thread(C.int(device), &node), "gofr_bind_host_thread")
+	return int(node), err
+}
+
 // ServeDeviceSlots writes response i into its own slotBytes-sized, 16-byte aligned slot of dOut and its length into
 // dOutLen[i] (gofr_serve_device_slots): the layout a ring of fixed-size response buffers maps onto directly.
 func (e *Engine) ServeDeviceSlots(dDesc, dTraceIDs, dArena unsafe.Pointer, n int, now time.Time, dOut unsafe.Pointer,

@@ -434,26 +434,45 @@ GOFR_HD_NOINLINE uint32_t bind_string_slow(Writer* w, const uint8_t* s, uint32_t
     return out;
 }
 
-// ---- err.Error() of a failed Bind, JSON-escaped (it is emitted inside {"error":{"message":"…"}}) ----
+// ---- string decoder for the Bind stage of the split API (gofr_bind_device): JSON-escaped input → the Go string's bytes
+//      (what json.Unmarshal stores: escapes resolved, invalid UTF-8 and lone surrogates replaced by U+FFFD) ----
 template <bool EMIT>
-GOFR_HD uint32_t be_put(Writer* w, const uint8_t* p, uint32_t n) {  // escape-and-append a short plain piece
-    return json_escape_slow<EMIT>(w, p, n);
+GOFR_HD_NOINLINE uint32_t bind_string_raw(Writer* w, const uint8_t* s, uint32_t len) {
+    uint32_t out = 0, i = 0;
+    while (i < len) {
+        const uint32_t r = bd_next_rune(s, len, &i);
+        if (EMIT) w->reserve_out(2);
+        if (r < 0x80) { if (EMIT) w->put1(r); out += 1; }
+        else if (r < 0x800) { if (EMIT) w->putk((0xC0 | r >> 6) | (0x80 | (r & 0x3F)) << 8, 2); out += 2; }
+        else if (r < 0x10000) { if (EMIT) w->putk((0xE0 | r >> 12) | (0x80 | ((r >> 6) & 0x3F)) << 8 | (0x80 | (r & 0x3F)) << 16, 3); out += 3; }
+        else { if (EMIT) w->put4((0xF0 | r >> 18) | (0x80 | ((r >> 12) & 0x3F)) << 8 | (0x80 | ((r >> 6) & 0x3F)) << 16 | (0x80 | (r & 0x3F)) << 24); out += 4; }
+    }
+    return out;
 }
-template <bool EMIT>
+
+// ---- err.Error() of a failed Bind; RAW == false: JSON-escaped (it is emitted inside {"error":{"message":"…"}}),
+//      RAW == true: the text itself (gofr_bind_device hands it to the host closure) ----
+template <bool EMIT, bool RAW = false>
+GOFR_HD uint32_t be_put(Writer* w, const uint8_t* p, uint32_t n) {  // append a short plain piece
+    if (!RAW) return json_escape_slow<EMIT>(w, p, n);
+    if (EMIT) for (uint32_t i = 0; i < n; i++) w->put1(p[i]);
+    return n;
+}
+template <bool EMIT, bool RAW = false>
 GOFR_HD uint32_t be_puts(Writer* w, const char* z) {
     uint32_t n = 0;
     while (z[n]) n++;
-    return be_put<EMIT>(w, (const uint8_t*)z, n);
+    return be_put<EMIT, RAW>(w, (const uint8_t*)z, n);
 }
 
-template <bool EMIT>
+template <bool EMIT, bool RAW>
 GOFR_HD_NOINLINE uint32_t emit_bind_error(Writer* w, const TableView tv, uint32_t schema_idx, const uint8_t* body, const uint32_t* row) {
     uint32_t out = 0;
     const uint32_t err = row[BR_ERR];
-    if (err == BE_EOF) return be_puts<EMIT>(w, "unexpected end of JSON input");
-    if (err == BE_DEPTH) return be_puts<EMIT>(w, "exceeded max depth");
+    if (err == BE_EOF) return be_puts<EMIT, RAW>(w, "unexpected end of JSON input");
+    if (err == BE_DEPTH) return be_puts<EMIT, RAW>(w, "exceeded max depth");
     if (err == BE_CHAR) {
-        out += be_puts<EMIT>(w, "invalid character ");
+        out += be_puts<EMIT, RAW>(w, "invalid character ");
         // json.quoteChar
         uint32_t c = row[BR_CHAR];
         uint8_t q[8];
@@ -471,36 +490,78 @@ GOFR_HD_NOINLINE uint32_t emit_bind_error(Writer* w, const TableView tv, uint32_
             else if (c < 0x80) { q[k++] = 'x'; q[k++] = (uint8_t)hex_lc(c >> 4); q[k++] = (uint8_t)hex_lc(c & 15); }
             else { q[k++] = 'u'; q[k++] = '0'; q[k++] = '0'; q[k++] = (uint8_t)hex_lc(c >> 4); q[k++] = (uint8_t)hex_lc(c & 15); }
         }
-        out += be_put<EMIT>(w, q, k);
-        out += be_puts<EMIT>(w, "' ");
-        out += be_puts<EMIT>(w, bind_ctx_text(row[BR_CTX]));
+        out += be_put<EMIT, RAW>(w, q, k);
+        out += be_puts<EMIT, RAW>(w, "' ");
+        out += be_puts<EMIT, RAW>(w, bind_ctx_text(row[BR_CTX]));
         return out;
     }
     // UnmarshalTypeError
     const SchemaRec S = tv.schemas()[schema_idx];
     const FieldRec* F = (const FieldRec*)(tv.base + S.fields_off);
-    out += be_puts<EMIT>(w, "json: cannot unmarshal ");
+    out += be_puts<EMIT, RAW>(w, "json: cannot unmarshal ");
     const uint32_t v = row[BR_VALUE];
-    out += be_puts<EMIT>(w, v == BV_STRING ? "string" : v == BV_BOOL ? "bool" : v == BV_OBJECT ? "object" : v == BV_ARRAY ? "array"
+    out += be_puts<EMIT, RAW>(w, v == BV_STRING ? "string" : v == BV_BOOL ? "bool" : v == BV_OBJECT ? "object" : v == BV_ARRAY ? "array"
                                                        : v == BV_NUMBER ? "number" : "number ");
-    if (v == BV_NUMBER_LIT) out += be_put<EMIT>(w, body + row[BR_LIT_OFF], row[BR_LIT_LEN]);
+    if (v == BV_NUMBER_LIT) out += be_put<EMIT, RAW>(w, body + row[BR_LIT_OFF], row[BR_LIT_LEN]);
     const uint8_t* ty = tv.lits() + S.type_off;  // NUL-terminated reflect.Type.String()
     uint32_t tl = 0, dot = 0xFFFFFFFFu;
     while (ty[tl]) { if (ty[tl] == '.') dot = tl; tl++; }
     const uint32_t fi = row[BR_FIELD];
     if (fi == 0xFFFFFFFFu) {
-        out += be_puts<EMIT>(w, " into Go value of type ");
-        out += be_put<EMIT>(w, ty, tl);
+        out += be_puts<EMIT, RAW>(w, " into Go value of type ");
+        out += be_put<EMIT, RAW>(w, ty, tl);
     } else {
-        out += be_puts<EMIT>(w, " into Go struct field ");
+        out += be_puts<EMIT, RAW>(w, " into Go struct field ");
         uint32_t ns = dot == 0xFFFFFFFFu ? 0 : dot + 1;  // reflect.Type.Name()
-        out += be_put<EMIT>(w, ty + ns, tl - ns);
-        out += be_puts<EMIT>(w, ".");
-        out += be_put<EMIT>(w, tv.lits() + F[fi].name_off, F[fi].name_len);
-        out += be_puts<EMIT>(w, " of type ");
-        out += be_put<EMIT>(w, tv.lits() + F[fi].type_off, F[fi].type_len);
+        out += be_put<EMIT, RAW>(w, ty + ns, tl - ns);
+        out += be_puts<EMIT, RAW>(w, ".");
+        out += be_put<EMIT, RAW>(w, tv.lits() + F[fi].name_off, F[fi].name_len);
+        out += be_puts<EMIT, RAW>(w, " of type ");
+        out += be_put<EMIT, RAW>(w, tv.lits() + F[fi].type_off, F[fi].type_len);
     }
     return out;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bind as a stage of the split API (gofr_bind_device): Context.Bind(&v) for closures that stay on the host
+// (pkg/gofr/context.go:52-54 -> pkg/gofr/http/request.go:40-47 -> json.Unmarshal).  One request: its body -> either the
+// typed row the closure reads its struct from (GOFR_H_ROW layout: one word per field — two for INT64/INT — then the
+// DECODED bytes of the string fields in schema order), or err.Error().  `row` is the span row bind_request filled.
+// EMIT == false: only the size.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool EMIT>
+GOFR_HD uint32_t bind_row_out(Writer* w, const TableView tv, uint32_t schema_idx, const uint8_t* body, const uint32_t* row) {
+    if (row[BR_ERR] != BE_OK) return emit_bind_error<EMIT, true>(w, tv, schema_idx, body, row);
+    const SchemaRec S = tv.schemas()[schema_idx];
+    const FieldRec* F = (const FieldRec*)(tv.base + S.fields_off);
+    uint32_t out = 0, wi = BR_FIELDS;
+    // fixed part
+    for (uint32_t f = 0; f < S.n_fields; f++) {
+        const uint32_t kind = F[f].kind;
+        if (EMIT) w->reserve_out(2);
+        if (kind == GOFR_F_INT64 || kind == GOFR_F_INT) { if (EMIT) { w->put4(row[wi]); w->put4(row[wi + 1]); } out += 8; wi += 2; }
+        else if (kind == GOFR_F_STRING) {
+            const uint32_t lenw = row[wi + 1], len = lenw & 0x7FFFFFFFu;
+            const uint32_t dl = (lenw >> 31) ? bind_string_raw<false>(nullptr, body + row[wi], len) : len;
+            if (EMIT) w->put4(dl);
+            out += 4; wi += 2;
+        } else { if (EMIT) w->put4(row[wi]); out += 4; wi += 1; }  // INT32, BOOL
+    }
+    // string bytes
+    wi = BR_FIELDS;
+    for (uint32_t f = 0; f < S.n_fields; f++) {
+        const uint32_t kind = F[f].kind;
+        if (kind == GOFR_F_STRING) {
+            const uint32_t lenw = row[wi + 1], len = lenw & 0x7FFFFFFFu;
+            if (lenw >> 31) out += bind_string_raw<EMIT>(w, body + row[wi], len);
+            else { if (EMIT && len) emit_bytes(*w, body + row[wi], len); out += len; }
+            wi += 2;
+        } else wi += (kind == GOFR_F_INT64 || kind == GOFR_F_INT) ? 2 : 1;
+    }
+    return out;
+}
+
+// status words of gofr_bind_device (include/gofr_b200.h GOFR_BIND_*)
+GOFR_HD uint32_t bind_row_status(const uint32_t* row) { return row[BR_ERR] == BE_OK ? 0u : row[BR_ERR] == BE_DEPTH ? 2u : 1u; }
 
 }  // namespace gofr

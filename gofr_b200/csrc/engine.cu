@@ -70,6 +70,7 @@ struct gofr_engine {
     int device = 0;
     int sm_count = 0;
     ImageHeader hdr;
+    std::vector<uint32_t> schema_ids;  // the table's schema ids in table order
     uint8_t* d_image = nullptr;
     uint32_t image_bytes = 0;
     // launch geometry
@@ -103,6 +104,8 @@ struct gofr_engine {
     // gofr_batch_route scratch (host-buffer stage 1 of the split API)
     uint8_t* d_rt_desc = nullptr; uint8_t* d_rt_arena = nullptr; uint8_t* d_rt_meta = nullptr; uint8_t* d_rt_vars = nullptr;
     size_t rt_desc_cap = 0, rt_arena_cap = 0, rt_meta_cap = 0, rt_vars_cap = 0;
+    uint8_t* d_rt_rows = nullptr;  // gofr_batch_bind: result slots
+    size_t rt_rows_cap = 0;
     // tickets
     // tickets of finished submits whose result has not been collected yet (submit completes the batch; wait reports)
     std::vector<std::pair<gofr_ticket, int>> done_tickets;
@@ -144,6 +147,8 @@ int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
 static int engine_init(gofr_engine* e, const std::vector<uint8_t>& img, int device) {
     e->device = device;
     memcpy(&e->hdr, img.data(), sizeof(ImageHeader));
+    e->schema_ids.resize(e->hdr.n_schemas);
+    if (e->hdr.n_schemas) memcpy(e->schema_ids.data(), img.data() + e->hdr.schema_ids_off, (size_t)e->hdr.n_schemas * 4);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     e->sm_count = prop.multiProcessorCount;
@@ -205,7 +210,7 @@ void gofr_engine_destroy(gofr_engine* e) {
     cudaFree(e->d_chain); cudaFree(e->d_info);
     if (e->h_status) cudaFreeHost(e->h_status);
     cudaFree(e->d_image); cudaFree(e->d_state); cudaFree(e->d_flag); cudaFree(e->d_bind);
-    cudaFree(e->d_rt_desc); cudaFree(e->d_rt_arena); cudaFree(e->d_rt_meta); cudaFree(e->d_rt_vars);
+    cudaFree(e->d_rt_desc); cudaFree(e->d_rt_arena); cudaFree(e->d_rt_meta); cudaFree(e->d_rt_vars); cudaFree(e->d_rt_rows);
     delete e;
 }
 
@@ -947,6 +952,68 @@ int gofr_route_device(gofr_engine* e, const gofr_req_desc* d_desc, const uint8_t
     int rc = launch_route(p, e->sm_count, stream);
     if (rc != 0) { set_last_error("route kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
     e->launches++;
+    return GOFR_OK;
+}
+
+int gofr_bind_device(gofr_engine* e, uint32_t schema_id, const gofr_req_desc* d_desc, const uint8_t* d_arena, uint32_t n,
+                     uint8_t* d_rows, uint32_t slot_bytes, uint32_t* d_len, uint32_t* d_status, void* stream) {
+    if (!e || (n && (!d_desc || !d_arena || !d_rows || !d_len || !d_status))) return GOFR_ERR_INVALID;
+    if (slot_bytes == 0 || (slot_bytes & 15u) || ((uintptr_t)d_rows & 15u)) { set_last_error("slot_bytes must be a positive multiple of 16 and d_rows 16-byte aligned"); return GOFR_ERR_INVALID; }
+    uint32_t sidx = 0xFFFFFFFFu;
+    for (size_t k = 0; k < e->schema_ids.size(); k++) if (e->schema_ids[k] == schema_id) sidx = (uint32_t)k;
+    if (sidx == 0xFFFFFFFFu) { set_last_error("schema %u is not part of the engine's table", schema_id); return GOFR_ERR_INVALID; }
+    if (n == 0) return GOFR_OK;
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    BindParams p;
+    memset(&p, 0, sizeof p);
+    p.desc = d_desc; p.arena = d_arena; p.n = n; p.image = e->d_image; p.hot_bytes = e->hdr.hot_bytes; p.schema_idx = sidx;
+    p.out = d_rows; p.slot_bytes = slot_bytes; p.len = d_len; p.status = d_status;
+    int rc = launch_bind(p, e->sm_count, stream);
+    if (rc != 0) { set_last_error("bind kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
+    e->launches++;
+    return GOFR_OK;
+}
+
+int gofr_batch_bind(gofr_engine* e, uint32_t schema_id, const gofr_req_batch* in, uint8_t* rows, uint32_t slot_bytes,
+                    uint32_t* len, uint32_t* status) {
+    if (!e || !in || (in->n && (!in->desc || !rows || !len || !status))) return GOFR_ERR_INVALID;
+    if (slot_bytes == 0 || (slot_bytes & 15u)) { set_last_error("slot_bytes must be a positive multiple of 16"); return GOFR_ERR_INVALID; }
+    uint32_t sidx = 0xFFFFFFFFu;
+    for (size_t k = 0; k < e->schema_ids.size(); k++) if (e->schema_ids[k] == schema_id) sidx = (uint32_t)k;
+    if (sidx == 0xFFFFFFFFu) { set_last_error("schema %u is not part of the engine's table", schema_id); return GOFR_ERR_INVALID; }
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    const uint32_t n = in->n;
+    for (uint32_t lo = 0; lo < n; lo += e->chunk) {
+        const uint32_t hi = std::min<uint32_t>(n, lo + e->chunk), cn = hi - lo;
+        uint32_t alo = 0, ahi = 0;
+        { int prc = chunk_arena_range(in, lo, hi, &alo, &ahi); if (prc) return prc; }
+        const size_t abytes = (size_t)ahi - alo;
+        int rc;
+        if ((rc = grow((void**)&e->d_rt_desc, &e->rt_desc_cap, (size_t)cn * 16, 256))) return rc;
+        if ((rc = grow((void**)&e->d_rt_arena, &e->rt_arena_cap, abytes + 16, 256))) return rc;
+        if ((rc = grow((void**)&e->d_rt_meta, &e->rt_meta_cap, (size_t)cn * 8, 256))) return rc;
+        if ((rc = grow((void**)&e->d_rt_rows, &e->rt_rows_cap, (size_t)cn * slot_bytes, 256))) return rc;
+        cudaStream_t st = e->st_compute;
+        CUDA_TRY(cudaMemcpyAsync(e->d_rt_desc, in->desc + lo, (size_t)cn * 16, cudaMemcpyHostToDevice, st));
+        if (abytes) {
+            const size_t avail = in->arena_bytes > alo ? (size_t)in->arena_bytes - alo : 0;
+            CUDA_TRY(cudaMemcpyAsync(e->d_rt_arena, in->arena + alo, std::min(abytes, avail), cudaMemcpyHostToDevice, st));
+        }
+        BindParams p;
+        memset(&p, 0, sizeof p);
+        p.desc = e->d_rt_desc; p.arena = e->d_rt_arena - alo; p.n = cn; p.image = e->d_image; p.hot_bytes = e->hdr.hot_bytes;
+        p.schema_idx = sidx; p.out = e->d_rt_rows; p.slot_bytes = slot_bytes;
+        p.len = (uint32_t*)e->d_rt_meta; p.status = (uint32_t*)e->d_rt_meta + cn;
+        rc = launch_bind(p, e->sm_count, st);
+        if (rc != 0) { set_last_error("bind kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
+        e->launches++;
+        CUDA_TRY(cudaMemcpyAsync(rows + (size_t)lo * slot_bytes, e->d_rt_rows, (size_t)cn * slot_bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(len + lo, p.len, (size_t)cn * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(status + lo, p.status, (size_t)cn * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
     return GOFR_OK;
 }
 

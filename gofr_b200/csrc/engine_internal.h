@@ -139,6 +139,20 @@ struct RouteParams {
 };
 int launch_route(const RouteParams& p, int sm_count, void* stream);
 
+struct BindParams {
+    const void* desc;
+    const uint8_t* arena;
+    uint32_t n;
+    const uint8_t* image;
+    uint32_t hot_bytes;
+    uint32_t schema_idx;
+    uint8_t* out;          // n * slot_bytes
+    uint32_t slot_bytes;
+    uint32_t* len;         // n
+    uint32_t* status;      // n
+};
+int launch_bind(const BindParams& p, int sm_count, void* stream);
+
 struct HttpParams {
     const uint8_t* raw;
     const uint32_t* raw_off;  // n + 1

@@ -1083,7 +1083,7 @@ GOFR_HD_NOINLINE uint32_t emit_param_slow(Writer* w, const uint8_t* v, uint32_t 
 // Bind (bind_device.cuh)
 GOFR_HD_NOINLINE bool bind_request(const TableView tv, uint32_t schema_idx, const uint8_t* body, uint32_t n, uint32_t* row);
 template <bool EMIT> GOFR_HD_NOINLINE uint32_t bind_string_slow(Writer* w, const uint8_t* s, uint32_t len);
-template <bool EMIT>
+template <bool EMIT, bool RAW>
 GOFR_HD_NOINLINE uint32_t emit_bind_error(Writer* w, const TableView tv, uint32_t schema_idx, const uint8_t* body, const uint32_t* row);
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1255,8 +1255,8 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
             }
         } else if (code == OP_ERRMSG) {
             const uint32_t sidx = tv.routes()[c.route].schema;
-            if (EMIT) GOFR_SLOW_CALL(w, emit_bind_error<true>(tw, tv, sidx, c.data(), c.brow(br)));
-            else produced = emit_bind_error<false>(nullptr, tv, sidx, c.data(), c.brow(br));
+            if (EMIT) GOFR_SLOW_CALL(w, (emit_bind_error<true, false>(tw, tv, sidx, c.data(), c.brow(br))));
+            else produced = emit_bind_error<false, false>(nullptr, tv, sidx, c.data(), c.brow(br));
         } else if (code == OP_I64 || code == OP_I32) {
             if (!(governed && skip)) {
                 const int64_t v = code == OP_I64 ? (int64_t)((uint64_t)row[ooff] | (uint64_t)row[ooff + 1] << 32)

@@ -1109,6 +1109,12 @@ int seal_table(gofr_table* t) {
         H.tmplkey_off = append(keys.data(), keys.size() * 4);
     }
     H.last_method_off = append(last_method.data(), last_method.size() * 2);
+    {
+        std::vector<uint32_t> ids;
+        for (auto& sdef : t->schemas) ids.push_back(sdef.id);
+        if (ids.empty()) ids.push_back(0xFFFFFFFFu);
+        H.schema_ids_off = append(ids.data(), ids.size() * 4);
+    }
     H.fast_off = append(fast.data(), fast.size() * sizeof(FastRec));
     if (rawprogs.empty()) rawprogs.resize(9, 0xFFFF);
     H.rawprog_off = append(rawprogs.data(), rawprogs.size() * 2);

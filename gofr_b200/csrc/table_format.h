@@ -48,7 +48,8 @@ struct ImageHeader {  // 160 B
     uint32_t fast_off;       // FastRec[n_progs]: how the slot-layout kernel emits each program (templates + tail ops)
     uint32_t rawprog_off;    // uint16[n_routes][9]: GOFR_H_RESULT routes, programs of the response.Raw outcomes
                              // [(RAW_DATA, RAW_STRING, RAW_NIL) x (200, 500, 404)], 0xFFFF = none
-    uint32_t reserved3[3];
+    uint32_t schema_ids_off; // uint32[n_schemas]: the caller's schema ids in table order (gofr_bind_device looks one up)
+    uint32_t reserved3[2];
 };
 static_assert(sizeof(ImageHeader) == 160, "ImageHeader layout");
 

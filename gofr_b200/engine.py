@@ -236,6 +236,18 @@ class Engine:
                                                       meta.data_ptr(), st.cuda_stream), "gofr_serve_device_slots")
         return out, out_len[:b.n], meta[:b.n]
 
+    def bind_device(self, b: DeviceBatch, schema_id: int, slot_bytes: int, stream=None):
+        """gofr_bind_device: Context.Bind for host closures.  Returns (rows uint8[n * slot_bytes], len int32[n], status int32[n])."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        rows = torch.zeros(max(b.n, 1) * slot_bytes, dtype=torch.uint8, device=dev)
+        ln = torch.zeros(max(b.n, 1), dtype=torch.int32, device=dev)
+        status = torch.zeros(max(b.n, 1), dtype=torch.int32, device=dev)
+        _abi.check(_abi.lib().gofr_bind_device(self._e, schema_id, b.desc.data_ptr(), b.arena.data_ptr(), b.n, rows.data_ptr(),
+                                               slot_bytes, ln.data_ptr(), status.data_ptr(), st.cuda_stream), "gofr_bind_device")
+        return rows, ln[:b.n], status[:b.n]
+
     # ---- host path (the call a user makes): host buffers in, host buffers out ----
     def serve_host(self, batch: S.RequestBatch, date: bytes, out: np.ndarray, out_off: np.ndarray, meta: np.ndarray) -> int:
         L = _abi.lib()

@@ -332,6 +332,29 @@ int gofr_proto_decode_device(gofr_engine*, const gofr_proto_field* fields, uint3
                              const uint32_t* d_in_off, uint32_t n, uint8_t* d_rows, uint64_t rows_cap, uint32_t* d_row_off,
                              uint32_t* d_meta, void* stream);
 
+/* Bind as a stage of the split API: Context.Bind(&v) for closures that stay on the host (pkg/gofr/context.go:52-54 ->
+ * pkg/gofr/http/request.go:40-47 -> json.Unmarshal(body, &v), v a struct of a registered schema).  Body i is the data
+ * section of request i (same descriptors / arena as the serve calls); result i lies in its own slot d_rows + i * slot_bytes
+ * (slot_bytes a multiple of 16, d_rows 16-byte aligned), zero padded to the next 16-byte boundary:
+ *   d_status[i] = GOFR_BIND_OK     the struct as a row in the GOFR_H_ROW layout (one LE u32 word per field in schema order,
+ *                                  two for INT64 / INT, STRING = byte length; then the DECODED string bytes in schema order:
+ *                                  escapes resolved, invalid UTF-8 replaced by U+FFFD, as json.Unmarshal stores them).
+ *                                  Keys are matched exactly, then case-insensitively; unknown keys are skipped; later
+ *                                  duplicates win; null leaves the zero value.
+ *   d_status[i] = GOFR_BIND_ERROR  err.Error() of json.Unmarshal: a syntax error ("invalid character 'x' after object key",
+ *                                  "unexpected end of JSON input"), or the FIRST UnmarshalTypeError ("json: cannot unmarshal
+ *                                  string into Go struct field T.f of type int64"); the partially filled struct Go also
+ *                                  leaves behind in that case is not reported
+ *   d_status[i] = GOFR_BIND_HOST   not decided on the device (nesting deeper than 64): run encoding/json on the host
+ * d_len[i] = bytes of the result; a value above slot_bytes means it did not fit and nothing was written.
+ * Pins: pkg/gofr/http/request_test.go:17-30, pkg/gofr/context_test.go:23-49. */
+enum { GOFR_BIND_OK = 0, GOFR_BIND_ERROR = 1, GOFR_BIND_HOST = 2 };
+int gofr_bind_device(gofr_engine* e, uint32_t schema_id, const gofr_req_desc* d_desc, const uint8_t* d_arena, uint32_t n,
+                     uint8_t* d_rows, uint32_t slot_bytes, uint32_t* d_len, uint32_t* d_status, void* stream);
+/* The same stage with host buffers (what a host shim calls between gofr_batch_route and its closures); synchronous. */
+int gofr_batch_bind(gofr_engine* e, uint32_t schema_id, const gofr_req_batch* in, uint8_t* rows, uint32_t slot_bytes,
+                    uint32_t* len, uint32_t* status);
+
 /* Stage 1 of the split API for routes whose closure stays on the host (GOFR_H_HOST): everything mux.Router.ServeHTTP
  * and the middleware chain decide before handler.ServeHTTP runs (pkg/gofr/http/router.go:14,30-33;
  * middleware/cors.go:10-13; pkg/gofr/handler.go:32-36), for a whole batch resident in HBM.

@@ -15,8 +15,10 @@
 //   (closures run here, only for requests whose handler the reference would have called)
 //   gofr_batch_submit     → Responder.Respond on every (data, err) + net/http framing: the response bytes
 // A handler that throws is answered like a Go handler that panics (middleware.panicRecovery, middleware/logger.go:91-114).
-// Not mirrored: c.Bind (json.Unmarshal with Go's rules lives in the fused GOFR_H_BIND_ECHO path; a closure can read
-// c.Body() itself), datasources, logging, CLI.
+//   c.Bind(&v)                                   pkg/gofr/context.go:52-54     c.Bind(&v) for a struct type the route declared
+//                                                                               with Binds(): json.Unmarshal with Go's rules runs
+//                                                                               on the GPU (gofr_batch_bind) before the closures
+// Not mirrored: datasources, logging, CLI.
 #pragma once
 #include <array>
 #include <cstdint>
@@ -149,11 +151,34 @@ public:
     const std::string& Method() const { return method_; }
     const std::string& Path() const { return path_; }
     const std::string& Body() const { return body_; }
+    // Context.Bind (pkg/gofr/context.go:52-54 -> http/request.go:40-47): json.Unmarshal(body, &v) with v of the struct type
+    // the route was registered to bind.  The decoding already happened on the GPU (gofr_batch_bind, Go's rules: exact then
+    // case-insensitive keys, unknown keys skipped, null a no-op, the first UnmarshalTypeError reported); this copies the
+    // fields out of the request's row, or returns json.Unmarshal's error.  A route without Binds() gets an error saying so.
+    std::optional<Error> Bind(StructValue* v) const {
+        if (bind_status_ == 0xFFFFFFFFu) return Error{"gofr::Context::Bind: the route was registered without a struct type to bind", false};
+        if (bind_status_ != GOFR_BIND_OK) return Error{bind_row_, false};
+        v->type_id = bind_type_;
+        v->fields.clear();
+        size_t w = 0, sp = 0;
+        for (uint32_t kind : bind_kinds_) sp += (kind == GOFR_F_INT64 || kind == GOFR_F_INT) ? 8 : 4;
+        auto word = [&](size_t at) { uint32_t x; memcpy(&x, bind_row_.data() + at, 4); return x; };
+        for (uint32_t kind : bind_kinds_) {
+            if (kind == GOFR_F_INT64 || kind == GOFR_F_INT) { v->fields.emplace_back((int64_t)((uint64_t)word(w) | (uint64_t)word(w + 4) << 32)); w += 8; }
+            else if (kind == GOFR_F_INT32) { v->fields.emplace_back((int64_t)(int32_t)word(w)); w += 4; }
+            else if (kind == GOFR_F_BOOL) { v->fields.emplace_back(word(w) != 0); w += 4; }
+            else { const uint32_t n = word(w); v->fields.emplace_back(bind_row_.substr(sp, n)); sp += n; w += 4; }
+        }
+        return std::nullopt;
+    }
 
 private:
     friend class App;
     std::string method_, path_, query_, body_;
     std::vector<std::pair<std::string, std::string>> path_params_;
+    uint32_t bind_status_ = 0xFFFFFFFFu, bind_type_ = 0;  // GOFR_BIND_* of this request's body, 0xFFFFFFFF: nothing was bound
+    std::string bind_row_;                                // the row (GOFR_BIND_OK) or err.Error() (GOFR_BIND_ERROR)
+    std::vector<uint32_t> bind_kinds_;
 };
 
 using Handler = std::function<Result(Context&)>;
@@ -217,7 +242,12 @@ public:
     // App.add (gofr.go:171-177): registration order is match priority, as in mux
     void add(const std::string& method, const std::string& pattern, Handler h, const StructType* returns = nullptr) {
         if (engine_) throw std::logic_error("gofr::App: routes are frozen once Run has been called");
-        routes_.push_back(RouteInfo{method, pattern, std::move(h), returns ? returns->id_ : 0u, detail::template_vars(pattern)});
+        routes_.push_back(RouteInfo{method, pattern, std::move(h), returns ? returns->id_ : 0u, detail::template_vars(pattern), 0u});
+    }
+    // the struct type the handler of the route registered LAST passes to c.Bind: app.POST(...); app.Binds(person);
+    void Binds(const StructType& t) {
+        if (routes_.empty() || engine_) throw std::logic_error("gofr::App::Binds: register the route first, before Run");
+        routes_.back().bind_type = t.id_;
     }
 
     // App.Run (gofr.go:90-126) minus the listener: registers the struct types and routes, appends the default routes
@@ -286,12 +316,47 @@ public:
         // ---- stage 1 (GPU): mux match, middleware decisions, path variables ----
         std::vector<uint32_t> meta(n), vars((size_t)n * GOFR_MAX_PATH_VARS);
         check(gofr_batch_route(engine_, &in, meta.data(), vars.data()), "gofr_batch_route");
+        // ---- stage 1b (GPU): Context.Bind — json.Unmarshal of the bodies of the routes that declared a struct type ----
+        std::vector<Bound> bound(n);
+        for (auto& t : types_) {
+            std::vector<uint32_t> who;
+            for (uint32_t i = 0; i < n; i++) {
+                const uint32_t status = meta[i] & 0xFFFFu, route = meta[i] >> 16;
+                if (status == 0 && route < routes_.size() && routes_[route].bind_type == t->id_) who.push_back(i);
+            }
+            if (who.empty()) continue;
+            std::vector<gofr_req_desc> bd(who.size());
+            std::string ba;
+            size_t longest = 0;
+            for (size_t k = 0; k < who.size(); k++) {
+                const std::string& body = reqs[who[k]].body;
+                memset(&bd[k], 0, sizeof bd[k]);
+                bd[k].arena_off = (uint32_t)ba.size();
+                bd[k].data_len = (uint32_t)body.size();
+                ba += body;
+                ba.append((4 - ba.size() % 4) % 4, '\0');
+                longest = std::max(longest, body.size());
+            }
+            ba.append(64, '\0');
+            gofr_req_batch bin;
+            memset(&bin, 0, sizeof bin);
+            bin.desc = bd.data(); bin.arena = (const uint8_t*)ba.data(); bin.arena_bytes = ba.size(); bin.n = (uint32_t)who.size();
+            // a row is never longer than its fixed words plus the body; an error text is short
+            const uint32_t slot = (uint32_t)((8 * t->fields_.size() + longest + 256 + 15) & ~(size_t)15);
+            std::vector<uint8_t> rows((size_t)who.size() * slot);
+            std::vector<uint32_t> blen(who.size()), bstat(who.size());
+            check(gofr_batch_bind(engine_, t->id_, &bin, rows.data(), slot, blen.data(), bstat.data()), "gofr_batch_bind");
+            for (size_t k = 0; k < who.size(); k++) {
+                bound[who[k]].status = blen[k] > slot ? (uint32_t)GOFR_BIND_HOST : bstat[k];
+                bound[who[k]].row.assign((const char*)rows.data() + k * slot, std::min<uint32_t>(blen[k], slot));
+            }
+        }
         // ---- the closures (host), only where the reference would have called one ----
         std::string arena2;
         for (uint32_t i = 0; i < n; i++) {
             std::string record;
             const uint32_t status = meta[i] & 0xFFFFu, route = meta[i] >> 16;
-            if (status == 0 && route < routes_.size()) record = run_handler(routes_[route], reqs[i], ps[i], &vars[(size_t)i * GOFR_MAX_PATH_VARS]);
+            if (status == 0 && route < routes_.size()) record = run_handler(routes_[route], reqs[i], ps[i], &vars[(size_t)i * GOFR_MAX_PATH_VARS], bound[i]);
             desc[i].arena_off = (uint32_t)arena2.size();
             desc[i].data_len = (uint32_t)record.size();
             arena2 += ps[i].path;
@@ -344,7 +409,9 @@ private:
         Handler fn;
         uint32_t type_id;
         std::vector<std::string> var_names;
+        uint32_t bind_type;  // struct type of c.Bind, 0: the handler does not bind
     };
+    struct Bound { uint32_t status = 0xFFFFFFFFu; std::string row; };
     struct Parsed { std::string path, query; bool force_query = false; };
 
     static void check(int rc, const char* where) {
@@ -379,8 +446,15 @@ private:
     }
 
     // handler.ServeHTTP (pkg/gofr/handler.go:32-36): build the Context, call the closure, describe (data, err) for Respond
-    std::string run_handler(const RouteInfo& r, const Request& rq, const Parsed& p, const uint32_t* vars) const {
+    std::string run_handler(const RouteInfo& r, const Request& rq, const Parsed& p, const uint32_t* vars, const Bound& bound) const {
         Context c;
+        if (r.bind_type) {
+            c.bind_status_ = bound.status;
+            c.bind_type_ = r.bind_type;
+            c.bind_row_ = bound.status == GOFR_BIND_HOST ? std::string("gofr::Context::Bind: body not decided on the device (nesting deeper than 64)") : bound.row;
+            if (bound.status == GOFR_BIND_HOST) c.bind_status_ = GOFR_BIND_ERROR;
+            for (auto& ty : types_) if (ty->id_ == r.bind_type) for (auto& f : ty->fields_) c.bind_kinds_.push_back(f.kind);
+        }
         c.method_ = rq.method;
         c.path_ = p.path;
         c.query_ = p.query;

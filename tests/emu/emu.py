@@ -81,6 +81,22 @@ def serve_slots(image: bytes, batch, date: bytes, slot_bytes: int):
     return out.reshape(n, slot_bytes), ln, meta
 
 
+def bind_rows(image: bytes, schema_idx: int, batch, slot_bytes: int):
+    """gofr_bind_device on the CPU: (out uint8[n, slot_bytes] pre-filled with 0xEE, len, status)."""
+    n = batch.n
+    img = np.frombuffer(image, dtype=np.uint8).copy()
+    base = np.full(n * slot_bytes + 64, 0xEE, dtype=np.uint8)
+    shift = (-base.ctypes.data) % 16
+    out = base[shift:shift + n * slot_bytes]
+    ln = np.zeros(n, dtype=np.uint32)
+    st = np.zeros(n, dtype=np.uint32)
+    arena = np.concatenate([batch.arena, np.zeros(32, dtype=np.uint8)])
+    lib().emu_bind_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib().emu_bind_rows(img.ctypes.data, schema_idx, batch.desc.ctypes.data, arena.ctypes.data, n, out.ctypes.data, slot_bytes,
+                        ln.ctypes.data, st.ctypes.data)
+    return out.reshape(n, slot_bytes), ln, st
+
+
 def route(image: bytes, batch):
     n = batch.n
     img = np.frombuffer(image, dtype=np.uint8).copy()

@@ -100,6 +100,40 @@ extern "C" int emu_serve_slots(const uint8_t* image, uint64_t image_len, const u
     return 0;
 }
 
+// ---- Bind as a split-API stage (gofr_bind_device): bind_device.cuh's bind_request + bind_row_out on the CPU ----
+extern "C" int emu_bind_rows(const uint8_t* image, uint32_t schema_idx, const uint8_t* desc, const uint8_t* arena, uint32_t n,
+                             uint8_t* out, uint32_t slot_bytes, uint32_t* len, uint32_t* status) {
+    ImageHeader H;
+    memcpy(&H, image, sizeof H);
+    std::vector<uint32_t> hot((H.hot_bytes + 3) / 4 + 4);
+    memcpy(hot.data(), image, H.hot_bytes);
+    TableView tv;
+    tv.bind((const uint8_t*)hot.data(), image);
+    uint32_t ring[GOFR_STAGE_WORDS];
+    std::vector<uint32_t> row(BR_FIELDS + 2 * kMaxFields);
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t d[4];
+        memcpy(d, desc + (size_t)i * 16, 16);
+        const uint32_t data_off = (d[0] + (d[1] & 0xFFFF) + (d[1] >> 16) + 3u) & ~3u;
+        const uint8_t* body = arena + data_off;
+        bind_request(tv, schema_idx, body, d[2], row.data());
+        const uint32_t st = bind_row_status(row.data());
+        uint32_t L = 0;
+        if (st != 2u) {
+            L = bind_row_out<false>(nullptr, tv, schema_idx, body, row.data());
+            if (L && L <= slot_bytes) {
+                Writer w;
+                w.init(out + (size_t)i * slot_bytes, ring);
+                bind_row_out<true>(&w, tv, schema_idx, body, row.data());
+                w.finish_padded();
+            }
+        }
+        len[i] = L;
+        status[i] = st;
+    }
+    return 0;
+}
+
 // ---- routing only (gofr_route_device): serve_device.cuh's route_only on the CPU ----
 extern "C" int emu_route(const uint8_t* image, const uint8_t* desc, const uint8_t* arena, uint32_t n, uint32_t* meta,
                          uint32_t* vars) {

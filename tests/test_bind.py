@@ -144,3 +144,82 @@ def test_syntax_verdict_agrees_with_python_json(bodies):
             assert b"invalid character" in r or b"unexpected end of JSON input" in r or b"invalid" in r or b"cannot unmarshal" in r, (b, r)
         elif bound:
             assert isinstance(doc, dict) or doc is None, (b, r)   # only an object (or null) binds into a struct
+
+
+# ---- Bind as a stage of the split API (gofr_bind_device): body -> typed row | err.Error(), for closures on the host ----
+
+def _bind_stage_bodies():
+    bodies = [b for b, _ in BIND_ERR_KAT] + [b for b, _ in BIND_OK_KAT]
+    bodies += [b'{"id":1,"name":"caf\\u00e9 \\ud83d\\ude00 \\ud800 x","email":"a\\"b\\\\c\\/d\\n","active":true,"count":-7}',
+               b'{"name":"\xff\xfe raw bytes \xc3\xa9"}', b'{"NAME":"folded key","Id":12}', b'{"id":null,"name":null}',
+               b'{"name":"' + b"x" * 900 + b'"}', b"{}", b"null", b"[1,2]", b'"str"', b"12", b"",
+               b'{"x":' + b"[" * 70 + b"]" * 70 + b"}"]
+    return bodies
+
+
+def _check_bind_stage(rows, ln, status, bodies, slot, ot, schema_id):
+    for i, body in enumerate(bodies):
+        ok, want = ot.bind(schema_id, body)
+        deep = body.count(b"[") > 64
+        if deep:
+            assert status[i] == 2 and ln[i] == 0, i          # the device does not decide; Go (the oracle) does
+            continue
+        assert status[i] == (0 if ok else 1), (i, body, status[i])
+        assert ln[i] == len(want), (i, body, ln[i], len(want))
+        if ln[i] <= slot:
+            assert rows[i, :ln[i]].tobytes() == want, (i, body, rows[i, :ln[i]].tobytes(), want)
+            pad = (-int(ln[i])) % 16
+            assert (rows[i, ln[i]:ln[i] + pad] == 0).all()
+
+
+def test_emu_bind_stage_known_answers():
+    """the device code of gofr_bind_device on the CPU against the oracle's json.Unmarshal restatement (orc_bind): the
+    reference's pins (request_test.go:17-30, context_test.go:23-49 are in BIND_OK_KAT), every error text, escapes,
+    invalid UTF-8, case-folded keys, oversize strings, non-object documents, deep nesting"""
+    bodies = _bind_stage_bodies()
+    batch = S.RequestBatch.pack([S.Req(S.M_POST, b"/echo", b"", b) for b in bodies])
+    slot = 512
+    rows, ln, status = emu.bind_rows(Table(KAT_SPEC).serialize(), 0, batch, slot)
+    _check_bind_stage(rows, ln, status, bodies, slot, O.OracleTable(KAT_SPEC), 7)
+    assert any(l > slot for l in ln)                         # the 900-byte string did not fit: reported, not written
+
+
+def test_emu_bind_stage_config3_stream():
+    batch = synth.config3_batch(3000, variant_every=5)
+    spec = synth.config3_spec()
+    bodies = []
+    ar = batch.arena.tobytes()
+    for d in batch.desc:
+        a = (int(d["arena_off"]) + int(d["path_len"]) + int(d["query_len"]) + 3) & ~3
+        bodies.append(ar[a:a + int(d["data_len"])])
+    rows, ln, status = emu.bind_rows(Table(spec).serialize(), 0, batch, 1024)
+    _check_bind_stage(rows, ln, status, bodies, 1024, O.OracleTable(spec), spec.schemas[0].id)
+    assert set(int(s) for s in status) == {0, 1}
+
+
+@pytest.mark.gpu
+def test_gpu_bind_stage():
+    import torch
+    from gofr_b200.engine import Engine
+    bodies = _bind_stage_bodies()
+    eng = Engine(Table(KAT_SPEC), 0)
+    batch = S.RequestBatch.pack([S.Req(S.M_POST, b"/echo", b"", b) for b in bodies])
+    rows, ln, status = eng.bind_device(eng.upload(batch), 7, 512)
+    torch.cuda.synchronize()
+    _check_bind_stage(rows.cpu().numpy().reshape(batch.n, 512), ln.cpu().numpy().view(np.uint32), status.cpu().numpy().view(np.uint32),
+                      bodies, 512, O.OracleTable(KAT_SPEC), 7)
+    eng.close()
+    spec = synth.config3_spec()
+    eng = Engine(Table(spec), 0)
+    batch = synth.config3_batch(65536, variant_every=9)
+    ar = batch.arena.tobytes()
+    bodies = []
+    for d in batch.desc:
+        a = (int(d["arena_off"]) + int(d["path_len"]) + int(d["query_len"]) + 3) & ~3
+        bodies.append(ar[a:a + int(d["data_len"])])
+    rows, ln, status = eng.bind_device(eng.upload(batch), spec.schemas[0].id, 1024)
+    torch.cuda.synchronize()
+    r, l, s = rows.cpu().numpy().reshape(batch.n, 1024), ln.cpu().numpy().view(np.uint32), status.cpu().numpy().view(np.uint32)
+    idx = list(range(0, batch.n, 13))
+    _check_bind_stage(r[idx], l[idx], s[idx], [bodies[i] for i in idx], 1024, O.OracleTable(spec), spec.schemas[0].id)
+    eng.close()

@@ -101,9 +101,20 @@ def _records():
              ("POST", "/echo", b'line1\n"quoted" <tag>', S.result_record(S.RESULT_STRING, b'line1\n"quoted" <tag>')),
              ("GET", "/hello/", b"", b""), ("GET", "/a/../hello", b"", b""), ("GET", "//hello", b"", b""), ("OPTIONS", "/hello", b"", b""), ("PATCH", "/hello", b"", b""),
              ("GET", "/.well-known/health", b"", b"")]
+    # Context.Bind: the closure binds the body and returns the struct (or json.Unmarshal's error): the records the C++ side
+    # builds from the GPU's rows must be the ones Go's json.Unmarshal (the oracle's restatement) leads to
+    ot = O.OracleTable(S.TableSpec(schemas=[person], routes=[]))
+    for body in (b'{"id":1,"name":"Bob"}', b'{"ID":7,"NAME":"caf\\u00e9 \\"q\\"","admin":true,"extra":[1,{"a":2}]}', b'{"id":"x"}', b"{bad", b""):
+        ok, res = ot.bind(1, body)
+        cases.append(("POST", "/people", body, S.result_record(S.RESULT_DATA if ok else S.RESULT_ERROR, res)))
+    cases += [("GET", "/raw", b"", S.result_record(S.RESULT_RAW_STRING, b"just <text>")),
+              ("GET", "/rawnil", b"", S.result_record(S.RESULT_RAW_NIL)),
+              ("GET", "/rawperson", b"", S.result_record(S.RESULT_RAW_DATA, person.encode_row([9, "raw", True]))),
+              ("GET", "/rawerr", b"", S.result_record(S.RESULT_RAW_STRING, b"x", S.RAW_ERR))]
     routes = [("GET", "/hello", 0), ("GET", "/hello2", 0), ("PUT", "/hello", 0), ("POST", "/hello", 0), ("GET", "/params", 0),
               ("DELETE", "/delete", 0), ("GET", "/greet", 0), ("GET", "/error", 0), ("GET", "/users/{id:[0-9]+}/posts/{slug}", 0),
-              ("GET", "/person/{name}", 1), ("GET", "/nil", 0), ("GET", "/file", 0), ("GET", "/panic", 0), ("POST", "/echo", 0)]
+              ("GET", "/person/{name}", 1), ("GET", "/nil", 0), ("GET", "/file", 0), ("GET", "/panic", 0), ("POST", "/echo", 0),
+              ("POST", "/people", 1), ("GET", "/raw", 0), ("GET", "/rawnil", 0), ("GET", "/rawperson", 1), ("GET", "/rawerr", 0)]
     spec = S.TableSpec(schemas=[person], favicon=b"",
                        routes=[S.Route(S.method_code(m), p, S.H_RESULT, schema_id=sid) for m, p, sid in routes])
     return spec, cases
