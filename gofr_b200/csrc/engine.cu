@@ -112,6 +112,23 @@ struct gofr_engine {
     gofr_ticket next_ticket = 1;
 };
 
+// Engines alive per device in this process.  The packed-layout kernels chain their tiles with a look-back that is only
+// deadlock free when every CTA of the grid is resident at once (tile t waits for tiles < t, all owned by resident CTAs).
+// A grid sized for the whole GPU is not co-resident with a second engine's grid on the same device, so every engine
+// launches its look-back kernels with the device's capacity divided by the number of live engines on it.  Other processes
+// on the same GPU (MPS) are not visible from here: INTEGRATION.md says one serving process per GPU.
+static std::mutex g_reg_mu;
+static int g_live_engines[64];
+static int engines_on_device(int device) {
+    std::lock_guard<std::mutex> g(g_reg_mu);
+    const int k = device >= 0 && device < 64 ? g_live_engines[device] : 1;
+    return k > 0 ? k : 1;
+}
+static void register_engine(int device, int delta) {
+    std::lock_guard<std::mutex> g(g_reg_mu);
+    if (device >= 0 && device < 64) g_live_engines[device] += delta;
+}
+
 static int configure_geometry(gofr_engine* e, uint32_t in_per_req) {
     e->in_cap = (kServeT * in_per_req + 127u) & ~127u;
     e->smem_bytes = serve_smem_bytes(e->hdr.hot_bytes, e->in_cap);
@@ -138,6 +155,8 @@ int gofr_engine_create(gofr_engine** out, const gofr_table* t, int device) {
     if (device < 0 || device >= ndev) return GOFR_ERR_INVALID;
     CUDA_TRY(cudaSetDevice(device));
     gofr_engine* e = new gofr_engine();
+    register_engine(device, +1);
+    e->device = device;
     const int rc_create = engine_init(e, img, device);
     if (rc_create != GOFR_OK) { gofr_engine_destroy(e); return rc_create; }  // releases whatever the failed step left behind
     *out = e;
@@ -190,6 +209,7 @@ static int engine_init(gofr_engine* e, const std::vector<uint8_t>& img, int devi
 
 void gofr_engine_destroy(gofr_engine* e) {
     if (!e) return;
+    register_engine(e->device, -1);
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto& s : e->slots) {
@@ -284,6 +304,7 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
     p.debug_flags = e->debug_flags;
     memcpy(p.date, date29, 29);
     int grid = (int)std::min<uint32_t>((uint32_t)e->grid, p.n_tiles);
+    if (!slot_bytes) grid = std::max(1, std::min(grid, e->grid / engines_on_device(e->device)));  // look-back: see engines_on_device
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (e->timing_on) {
         fold_timing(e);
@@ -860,7 +881,7 @@ int gofr_grpc_hello_device(gofr_engine* e, const uint8_t* d_in, const uint32_t* 
         CUDA_TRY(cudaEventCreate(&ev1));
         CUDA_TRY(cudaEventRecord(ev0, st));
     }
-    int rc = launch_grpc_hello(p, (int)std::min<size_t>((size_t)e->grpc_grid, tiles), st);
+    int rc = launch_grpc_hello(p, (int)std::min<size_t>((size_t)std::max(1, e->grpc_grid / engines_on_device(e->device)), tiles), st);
     if (rc != 0) { set_last_error("grpc kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
     if (e->timing_on) { CUDA_TRY(cudaEventRecord(ev1, st)); e->timing.emplace_back(ev0, ev1); }
     e->launches++;
@@ -919,7 +940,7 @@ static int proto_run(gofr_engine* e, const gofr_proto_field* fields, uint32_t n_
         CUDA_TRY(cudaEventCreate(&ev1));
         CUDA_TRY(cudaEventRecord(ev0, st));
     }
-    const int g_ = (int)std::min<size_t>((size_t)grid, tiles);
+    const int g_ = (int)std::min<size_t>((size_t)std::max(1, grid / engines_on_device(e->device)), tiles);
     int rc = decode ? launch_proto_decode(p, S, g_, st) : launch_proto_encode(p, S, g_, st);
     if (rc != 0) { set_last_error("proto kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
     if (e->timing_on) { CUDA_TRY(cudaEventRecord(ev1, st)); e->timing.emplace_back(ev0, ev1); }
@@ -1123,7 +1144,7 @@ int gofr_requestlog_device(gofr_engine* e, const gofr_log_desc* d_desc, const ui
         CUDA_TRY(cudaEventCreate(&ev1));
         CUDA_TRY(cudaEventRecord(ev0, st));
     }
-    int rc = launch_reqlog(p, (int)std::min<size_t>((size_t)e->reqlog_grid, tiles), st);
+    int rc = launch_reqlog(p, (int)std::min<size_t>((size_t)std::max(1, e->reqlog_grid / engines_on_device(e->device)), tiles), st);
     if (rc != 0) { set_last_error("request-log kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
     if (e->timing_on) { CUDA_TRY(cudaEventRecord(ev1, st)); e->timing.emplace_back(ev0, ev1); }
     e->launches++;

@@ -143,3 +143,21 @@ def test_reference_route_test_through_the_cpp_app(tmp_path):
     assert len(got) == len(want)
     for i, ((st, by), w) in enumerate(zip(got, want)):
         assert st == int(meta[i]) & 0xFFFF and by == w, (i, cases[i][:2])
+
+
+@pytest.mark.gpu
+def test_one_process_several_engines(tmp_path):
+    """The non-Python multi-GPU story: one sealed table, one engine per device, one host thread per
+    engine serving its contiguous shard; the concatenated shards equal the single-engine result.  Uses every visible GPU
+    (two engines share the device when there is only one)."""
+    import torch
+    from gofr_b200 import _abi
+    _abi.lib()
+    exe = str(tmp_path / "two_engines")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "cpp", "two_engines.cpp"), _build.LIB, "-Wl,-rpath," + os.path.dirname(_build.LIB),
+                    "-lpthread", "-o", exe], check=True)
+    ndev = max(1, torch.cuda.device_count())
+    r = subprocess.run([exe, str(max(2, ndev)), str(ndev)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert " 0 responses differ" in r.stdout, r.stdout
