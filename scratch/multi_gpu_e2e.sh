@@ -4,11 +4,13 @@
 N=${1:-8}
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+# never rebuild on the GPU box: a stale library must fail the run at once, not N processes racing nvcc
+python -c "from gofr_b200 import _build, _abi; import sys; sys.exit(1 if _build._stale() else 0)" || { echo "library is stale: build it before gpurun"; exit 1; }
 nvidia-smi topo -m > gpurun_out/mg_${N}_topo.txt 2>&1
 cat /sys/fs/cgroup/cpu.max > gpurun_out/mg_${N}_cpumax.txt 2>&1
-python scratch/pcie_probe.py --gpus $N --bind 1 --steps 10 | tee gpurun_out/mg_${N}_probe_bound.json
-python scratch/pcie_probe.py --gpus $N --bind 0 --steps 10 | tee gpurun_out/mg_${N}_probe_unbound.json
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 "$@"; }
+timeout 120 python scratch/pcie_probe.py --gpus $N --bind 1 --steps 10 | tee gpurun_out/mg_${N}_probe_bound.json
+timeout 120 python scratch/pcie_probe.py --gpus $N --bind 0 --steps 10 | tee gpurun_out/mg_${N}_probe_unbound.json
+run() { timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 "$@"; }
 run 2>gpurun_out/mg_${N}_bench_bound.err | tail -1 > gpurun_out/mg_${N}_bench_bound.json
 run --no-numa-bind --no-extras 2>gpurun_out/mg_${N}_bench_unbound.err | tail -1 > gpurun_out/mg_${N}_bench_unbound.json
 python - <<PY

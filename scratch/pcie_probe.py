@@ -33,12 +33,12 @@ def worker(rank, n, bind, steps, h2d_bytes, d2h_bytes, barrier, out):
         s1.synchronize(); s2.synchronize()
     for _ in range(3):
         step()
-    barrier.wait()
+    barrier.wait(timeout=120)   # a worker that died must not leave the others (and the GPU box) waiting
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    barrier.wait()
+    barrier.wait(timeout=120)
     out.put((rank, dt / steps * 1e3, node, sorted(os.sched_getaffinity(0))[:2]))
 
 
@@ -55,8 +55,8 @@ def main():
     barrier, out = ctx.Barrier(a.gpus), ctx.Queue()
     ps = [ctx.Process(target=worker, args=(r, a.gpus, a.bind, a.steps, a.h2d, a.d2h, barrier, out)) for r in range(a.gpus)]
     [p.start() for p in ps]
-    res = sorted(out.get() for _ in ps)
-    [p.join() for p in ps]
+    res = sorted(out.get(timeout=300) for _ in ps)
+    [p.join(timeout=30) for p in ps]
     ms = max(r[1] for r in res)
     print(json.dumps({"probe": "concurrent H2D + D2H, pinned, no kernel", "gpus": a.gpus, "numa_bound": bool(a.bind), "ms_per_step_max": round(ms, 3),
                       "ms_per_step_per_gpu": [round(r[1], 3) for r in res], "numa_node_per_gpu": [r[2] for r in res],
