@@ -141,7 +141,29 @@ __device__ __forceinline__ void serve_body(const ServeParams& p) {
                 mbar_expect_tx(&sh.bar, h - l);
                 bulk_g2s(in_stage, p.arena + l, h - l, &sh.bar);
             }
+#if defined(GOFR_PREFETCH_NEXT)
+            // the tile this CTA takes next: ask for its bytes in L2 now (a hint — the range is guessed from its first and
+            // last descriptor, which is exact whenever requests lie in the arena in index order)
+            const uint32_t nt = tile + gridDim.x;
+            if (nt < p.n_tiles) {
+                const uint32_t i0 = nt * T, i1 = min(p.n, i0 + T) - 1;
+                const uint4 d0 = __ldg((const uint4*)p.desc + i0), d1 = __ldg((const uint4*)p.desc + i1);
+                const uint32_t plo = d0.x & ~15u;
+                const uint32_t phi = (((d1.x + (d1.y & 0xFFFFu) + (d1.y >> 16) + 3u) & ~3u) + d1.z + 15u) & ~15u;
+                if (phi > plo && phi - plo <= 2u * p.in_cap)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.arena + plo), "r"(phi - plo) : "memory");
+            }
+#endif
         }
+#if defined(GOFR_PREFETCH_NEXT)
+        {   // next tile's descriptors and trace ids: one lane per 128-byte line
+            const uint32_t ni = (tile + gridDim.x) * T + tid;
+            if (ni < p.n && (lane & 7u) == 0) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"((const uint4*)p.desc + ni));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"((const uint4*)p.ids + ni));
+            }
+        }
+#endif
         __syncthreads();
         const uint32_t in_lo = sh.in_lo, in_hi = sh.in_hi;
         const bool in_staged = in_hi > in_lo && in_hi - in_lo <= p.in_cap;

@@ -1434,6 +1434,26 @@ GOFR_HD bool size_fast(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
     return true;
 }
 
+// Template windows [k0, k1) of a response into its slot: whole 32-byte sectors wherever the destination allows (a slot
+// starts on a sector boundary or in the middle of one), single 16-byte windows at the ends.
+GOFR_HD void copy_template_windows(uint8_t* dst, saddr_t tp, uint32_t k0, uint32_t k1) {
+    uint32_t k = k0;
+    if (k < k1 && (((uintptr_t)dst + 16 * k) & 16u)) {
+        const uint4 v = src_ld128(tp + 16 * k);
+        Writer::store16(dst + 16 * k, v.x, v.y, v.z, v.w);
+        k++;
+    }
+#pragma unroll 1
+    for (; k + 2 <= k1; k += 2) {
+        const uint4 a = src_ld128(tp + 16 * k), b = src_ld128(tp + 16 * k + 16);
+        Writer::store32<3>(dst + 16 * k, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w);
+    }
+    if (k < k1) {
+        const uint4 v = src_ld128(tp + 16 * k);
+        Writer::store16(dst + 16 * k, v.x, v.y, v.z, v.w);
+    }
+}
+
 // Writes a response sized by size_fast into its 16-byte aligned slot: the template with aligned 16-byte loads and
 // stores, the trace id patched into the windows it touches, then the tail ops through the Writer.
 GOFR_HD void emit_fast(const TableView& tv, const BatchRefs& br, ReqCtx& c, uint8_t* dst, uint32_t* ring_col) {
@@ -1446,16 +1466,8 @@ GOFR_HD void emit_fast(const TableView& tv, const BatchRefs& br, ReqCtx& c, uint
         const saddr_t tp = to_saddr(tv.lits() + F.tmpl_off);
         uint32_t h0 = nwin, h1 = nwin;  // [h0, h1): windows the 32 hex characters touch
         if (F.hex_pos != 0xFFFFu) { h0 = (uint32_t)F.hex_pos >> 4; h1 = (((uint32_t)F.hex_pos + 31u) >> 4) + 1u; }
-#pragma unroll 1
-        for (uint32_t k = 0; k < h0; k++) {
-            const uint4 v = src_ld128(tp + 16 * k);
-            Writer::store16(dst + 16 * k, v.x, v.y, v.z, v.w);
-        }
-#pragma unroll 1
-        for (uint32_t k = h1; k < nwin; k++) {
-            const uint4 v = src_ld128(tp + 16 * k);
-            Writer::store16(dst + 16 * k, v.x, v.y, v.z, v.w);
-        }
+        copy_template_windows(dst, tp, 0, h0);
+        copy_template_windows(dst, tp, h1, nwin);
         if (h0 < nwin) {
             // the 2 or 3 windows around the trace id: template words into the (idle) staging column, the 8 hex words
             // shifted to their byte offset on top, then whole windows out
