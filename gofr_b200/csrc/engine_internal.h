@@ -49,12 +49,14 @@ constexpr int kServeThreads = 128;  // gRPC / request-log kernels: requests per 
 #endif
 constexpr int kServeT = GOFR_SERVE_T;        // serve kernel: requests per tile = threads per CTA
 constexpr int kServeCtas = GOFR_SERVE_CTAS;  // serve kernel: CTAs per SM the register and shared-memory budgets aim at
+constexpr int kServeCtasWide = 4;  // slot layout, "wide" instance: 128 registers per thread (serve_slots_kernel.cu)
 
 // Returns dynamic shared memory bytes needed for the table's hot part plus the request-byte staging area.
 uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap);
 // cudaError_t as int
-int launch_serve(const ServeParams& p, int grid, uint32_t smem_bytes, void* stream);
-int serve_max_grid(uint32_t smem_bytes, int device, int* blocks_per_sm);
+int launch_serve(const ServeParams& p, int grid, uint32_t smem_bytes, void* stream, bool wide_slots = false);
+// grid of the persistent kernels (both layouts share it); *wide_grid: grid of the wide slot-layout instance
+int serve_max_grid(uint32_t smem_bytes, int device, int* blocks_per_sm, int* wide_grid);
 
 // egress of the host-batch path (egress_kernel.cu)
 struct ChunkInfo {

@@ -1,18 +1,30 @@
 // serve_slots_kernel.cu — slot-layout instance of the serve kernel (serve_body.cuh): the resident headline kernel.
+//
+// Two register budgets of the same body exist: this one (5 CTAs/SM, 96 registers) and serve_slots_wide_kernel.cu (4 CTAs/SM,
+// 128 registers).  The kernel is issue/latency bound, and which residency wins depends on the table
+// (profiles/r02/variants_ctas_prefetch.jsonl): when every route answers through the template fast path with one program
+// shape, the wide one is 4 % faster; with mixed tables the per-CTA general pass wants the fifth CTA.  The engine picks per
+// table (engine.cu choose_slot_residency).  They are separate translation units because whether CUDA 12.9's ptxas
+// scalarises the 256-bit sector store (serve_device.cuh Writer::store32, _build.py) changes with what else is in the unit.
 #include "serve_body.cuh"
 
 namespace gofr {
 
 __global__ void __launch_bounds__(T, kServeCtas) serve_slots_kernel(const __grid_constant__ ServeParams p) { serve_body<true>(p); }
 
-int serve_slots_blocks_per_sm(uint32_t smem_bytes) {
+int serve_slots_wide_blocks_per_sm(uint32_t smem_bytes);
+int launch_serve_slots_wide(const ServeParams& p, int grid, uint32_t smem_bytes, void* stream);
+
+int serve_slots_blocks_per_sm(uint32_t smem_bytes, bool wide) {
+    if (wide) return serve_slots_wide_blocks_per_sm(smem_bytes);
     if (cudaFuncSetAttribute(serve_slots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, serve_slots_kernel, T, smem_bytes) != cudaSuccess) return -1;
     return nb;
 }
 
-int launch_serve_slots(const ServeParams& p, int grid, uint32_t smem_bytes, void* stream) {
+int launch_serve_slots(const ServeParams& p, int grid, uint32_t smem_bytes, void* stream, bool wide) {
+    if (wide) return launch_serve_slots_wide(p, grid, smem_bytes, stream);
     serve_slots_kernel<<<grid, T, smem_bytes, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }

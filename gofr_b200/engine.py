@@ -70,6 +70,12 @@ class Engine:
     def set_timing(self, on: bool):
         _abi.check(_abi.lib().gofr_engine_set_timing(self._e, 1 if on else 0), "gofr_engine_set_timing")
 
+    def slot_ctas(self, force: int = 0) -> int:
+        """CTAs/SM of the slot-layout serve kernel in effect (4: wide instance, 5); force=4/5 overrides the engine's choice."""
+        v = C.c_int(0)
+        _abi.check(_abi.lib().gofr_engine_slot_ctas(self._e, int(force), C.byref(v)), "gofr_engine_slot_ctas")
+        return v.value
+
     def geometry(self):
         g, b, s, m = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
         _abi.check(_abi.lib().gofr_engine_geometry(self._e, C.byref(g), C.byref(b), C.byref(s), C.byref(m)),

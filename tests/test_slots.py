@@ -115,6 +115,22 @@ def test_mixed_traffic_and_short_slots(torch_cuda):
 
 
 @pytest.mark.gpu
+def test_both_slot_residencies(torch_cuda):
+    """The engine picks the 4-CTA (128-register) instance for one-shape tables and the 5-CTA one otherwise; either
+    instance forced on either table gives the same bytes."""
+    from gofr_b200.engine import Engine
+    for spec, batch, slot, auto in ((synth.config2_spec(), synth.config2_batch(40000, escape_every=11), 544, 4),
+                                    (synth.config4_spec(), synth.config4_batch(20000), 1024, 5),
+                                    (synth.config3_spec(), synth.config3_batch(4096), 1024, 5)):
+        eng = Engine(Table(spec), 0)
+        assert eng.slot_ctas() == auto
+        for force in (4, 5):
+            assert eng.slot_ctas(force) == force
+            _check(eng, spec, batch, slot)
+        eng.close()
+
+
+@pytest.mark.gpu
 def test_bind_and_results_in_slots(torch_cuda):
     from gofr_b200.engine import Engine
     spec = synth.config3_spec()
