@@ -14,7 +14,7 @@ _lib = None
 
 class FieldDesc(C.Structure):
     _fields_ = [("go_name", C.c_char_p), ("json_name", C.c_char_p), ("kind", C.c_uint8), ("omitempty", C.c_uint8),
-                ("reserved", C.c_uint8 * 6)]
+                ("container", C.c_uint8), ("flags", C.c_uint8), ("elem_schema", C.c_uint16), ("reserved", C.c_uint8 * 2)]
 
 
 class HandlerDesc(C.Structure):

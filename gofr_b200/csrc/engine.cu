@@ -71,6 +71,7 @@ struct gofr_engine {
     int sm_count = 0;
     ImageHeader hdr;
     std::vector<uint32_t> schema_ids;  // the table's schema ids in table order
+    std::vector<uint16_t> schema_flags;  // SchemaRec::flags, same order
     uint8_t* d_image = nullptr;
     uint32_t image_bytes = 0;
     // launch geometry
@@ -190,6 +191,9 @@ static int engine_init(gofr_engine* e, const std::vector<uint8_t>& img, int devi
     memcpy(&e->hdr, img.data(), sizeof(ImageHeader));
     e->schema_ids.resize(e->hdr.n_schemas);
     if (e->hdr.n_schemas) memcpy(e->schema_ids.data(), img.data() + e->hdr.schema_ids_off, (size_t)e->hdr.n_schemas * 4);
+    e->schema_flags.resize(e->hdr.n_schemas);
+    for (uint32_t k = 0; k < e->hdr.n_schemas; k++)
+        e->schema_flags[k] = reinterpret_cast<const SchemaRec*>(img.data() + e->hdr.schemas_off)[k].flags;
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     e->sm_count = prop.multiProcessorCount;
@@ -1017,6 +1021,7 @@ int gofr_bind_device(gofr_engine* e, uint32_t schema_id, const gofr_req_desc* d_
     uint32_t sidx = 0xFFFFFFFFu;
     for (size_t k = 0; k < e->schema_ids.size(); k++) if (e->schema_ids[k] == schema_id) sidx = (uint32_t)k;
     if (sidx == 0xFFFFFFFFu) { set_last_error("schema %u is not part of the engine's table", schema_id); return GOFR_ERR_INVALID; }
+    if (!(e->schema_flags[sidx] & SF_FLAT)) { set_last_error("schema %u: Bind takes flat structs of int / bool / string fields only", schema_id); return GOFR_ERR_UNSUPPORTED; }
     if (n == 0) return GOFR_OK;
     std::lock_guard<std::mutex> g(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
@@ -1037,6 +1042,7 @@ int gofr_batch_bind(gofr_engine* e, uint32_t schema_id, const gofr_req_batch* in
     uint32_t sidx = 0xFFFFFFFFu;
     for (size_t k = 0; k < e->schema_ids.size(); k++) if (e->schema_ids[k] == schema_id) sidx = (uint32_t)k;
     if (sidx == 0xFFFFFFFFu) { set_last_error("schema %u is not part of the engine's table", schema_id); return GOFR_ERR_INVALID; }
+    if (!(e->schema_flags[sidx] & SF_FLAT)) { set_last_error("schema %u: Bind takes flat structs of int / bool / string fields only", schema_id); return GOFR_ERR_UNSUPPORTED; }
     std::lock_guard<std::mutex> g(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
     const uint32_t n = in->n;

@@ -12,7 +12,7 @@
 #pragma once
 #include <stdint.h>
 
-#include "serve_device.cuh"
+// included by value_device.cuh, inside serve_device.cuh (GOFR_HD comes from there)
 
 namespace gofr {
 
@@ -224,16 +224,6 @@ GOFR_HD uint32_t json_float64_text(uint64_t bits, uint8_t* buf) {
         buf[n++] = '.';
         for (uint32_t k = nd - 1 - (uint32_t)(sci + 1) + 1; k-- > 0;) buf[n++] = d[k];
     }
-    return n;
-}
-
-// the field as the Writer sees it: EMIT == false only returns the length (0: the value is not encodable)
-template <bool EMIT>
-GOFR_HD uint32_t emit_f64(Writer* w, uint64_t bits) {
-    uint8_t buf[32];
-    const uint32_t n = json_float64_text(bits, buf);
-    if (EMIT)
-        for (uint32_t k = 0; k < n; k++) w->put1(buf[k]);
     return n;
 }
 

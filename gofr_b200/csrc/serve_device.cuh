@@ -1178,6 +1178,10 @@ GOFR_HD uint32_t route_only(const TableView& tv, uint32_t method, const uint8_t*
 // registers); the copy lives in local memory only while the rare path runs.
 #define GOFR_SLOW_CALL(w, expr) do { Writer t_ = *(w); Writer* tw = &t_; (void)tw; expr; *(w) = t_; } while (0)
 
+}  // namespace gofr
+#include "value_device.cuh"  // float64 text and the generic encoder behind OP_F64 / OP_VALUE
+namespace gofr {
+
 // STATIC_N > 0: the program's ops are compile-time constants (static_ops, STATIC_N of them): the op loop is unrolled
 // and every decision that depends only on the program folds away — what a table-specific build of the kernel runs for
 // its hot programs.  STATIC_N == 0: the interpreter, ops fetched from the table in shared memory.
@@ -1269,6 +1273,31 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
                 if (EMIT) { if (t) w->put4('t' | 'r' << 8 | 'u' << 16 | 'e' << 24); else { w->put4('f' | 'a' << 8 | 'l' << 16 | 's' << 24); w->putc('e'); } }
                 produced = t ? 4 : 5;
             }
+        } else if (code == OP_F64) {
+            if (!(governed && skip)) {
+                const uint64_t bits = (uint64_t)row[ooff] | (uint64_t)row[ooff + 1] << 32;
+                if (EMIT) GOFR_SLOW_CALL(w, emit_f64<true>(tw, bits));
+                else {
+                    produced = emit_f64<false>(nullptr, bits);
+                    if (!produced) { c.prog = P.encfail; return false; }  // NaN / Inf: the caller sizes the encfail program
+                }
+            }
+        } else if (code == OP_VALUE) {
+            // an omitted field (OP_KEY found it empty) owns no bytes of the variable part: nothing to walk
+            if (!(governed && skip)) {
+                const uint8_t* fx = (const uint8_t*)(row + ooff);
+                const uint8_t* vp = c.data() + str_base + str_cursor;
+                const uint32_t used = str_base + str_cursor;
+                uint32_t consumed = 0, vstatus = 0;
+                if (EMIT) GOFR_SLOW_CALL(w, (value_encode<true>(tw, tv, oaux, raw.x >> 8 & 0xFFu, fx, vp, c.data_len - used, &consumed, &vstatus)));
+                else {
+                    if (used > c.data_len) return false;
+                    produced = value_encode<false>(nullptr, tv, oaux, raw.x >> 8 & 0xFFu, fx, vp, c.data_len - used, &consumed, &vstatus);
+                    if (vstatus == VAL_UNENCODABLE) { c.prog = P.encfail; return false; }
+                    if (vstatus != VAL_OK) return false;
+                }
+                str_cursor += consumed;
+            }
         } else if (code == OP_HEXID) {
             if (EMIT) {
                 const uint4 id = *(const uint4*)(br.ids + (size_t)c.index * 16);  // loaded here, not carried
@@ -1282,7 +1311,10 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
             bool empty = false;
             if (oflags & OPF_OMITEMPTY) {
                 const uint32_t wv = row[oaux];
-                if (okind == GOFR_F_INT64 || okind == GOFR_F_INT) empty = (wv | row[oaux + 1]) == 0;
+                if (okind >> 4) empty = value_field_empty(okind & 15u, okind >> 4, (const uint8_t*)(row + oaux));  // *T, []T, map
+                else if (okind == GOFR_F_INT64 || okind == GOFR_F_INT) empty = (wv | row[oaux + 1]) == 0;
+                else if (okind == GOFR_F_FLOAT64) empty = (wv | row[oaux + 1] << 1) == 0;  // 0.0 of either sign
+                else if (okind == GOFR_F_STRUCT) empty = false;
                 else if (okind == GOFR_F_STRING && (P.flags & PF_BIND)) empty = (row[oaux + 1] & 0x7FFFFFFFu) == 0;
                 else empty = wv == 0;
             }
@@ -1592,9 +1624,12 @@ GOFR_HD void size_routed_general(const TableView& tv, const BatchRefs& br, ReqCt
     if (GOFR_IS_STATIC(c)) ok = run_prog<false, GOFR_STATIC_N_DYN>(tv, br, c, nullptr, kStaticDyn);
     else
 #endif
+    const uint32_t asked = c.prog;
     ok = run_prog<false>(tv, br, c, nullptr);
     if (!ok) {
-        c.prog = tv.hdr()->prog_panic;
+        // a malformed row is answered like a handler panic; a float that encoding/json cannot write (run_prog switched
+        // c.prog to the program's encfail companion) keeps its status and headers and loses its body
+        if (c.prog == asked || c.prog == 0xFFFF) c.prog = tv.hdr()->prog_panic;
         c.slow_mask = 0;
         run_prog<false>(tv, br, c, nullptr);
     }

@@ -175,12 +175,25 @@ struct FieldDef {
     std::string go_name, json_name;
     uint8_t kind;
     bool omitempty;
+    uint8_t container = GOFR_C_VALUE, flags = 0;
+    int elem = -1;  // GOFR_F_STRUCT: index of the struct's schema in gofr_table::schemas (always smaller than this one's)
 };
 struct SchemaDef {
     uint32_t id;
     std::string go_type;
     std::vector<FieldDef> fields;
+    uint32_t fixed_words = 0;  // words of the fixed part of a row (include/gofr_b200.h "Row format")
+    int depth = 1;             // struct nesting below this type, this one included
+    bool flat = true;          // scalars and strings by value only: what Bind schemas and the op programs of round 1 take
+    bool bare() const { return fields.size() == 1 && (fields[0].flags & GOFR_FIELD_BARE); }
 };
+static uint32_t kind_words(uint8_t kind) { return (kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_FLOAT64) ? 2u : 1u; }
+// words a field owns in the fixed part of its struct
+static uint32_t field_words(const std::vector<SchemaDef>& all, const FieldDef& f) {
+    if (f.container == GOFR_C_SLICE || f.container == GOFR_C_MAP) return 1;
+    const uint32_t w = f.kind == GOFR_F_STRUCT ? all[(size_t)f.elem].fixed_words : kind_words(f.kind);
+    return w + (f.container == GOFR_C_PTR ? 1u : 0u);
+}
 
 // symbolic op before literal-pool assignment
 struct SOp {
@@ -196,6 +209,7 @@ struct Prog {
     int status = 200;
     bool bind = false;
     int row_words = 0;  // see ProgRec::row_words
+    int encfail = -1;   // see ProgRec::encfail
     std::vector<SOp> ops;
 };
 
@@ -317,7 +331,8 @@ static int parse_template(const std::string& tpl, std::vector<Piece>& out) {
 
 struct HeaderKV { std::string k, v; bool hexid = false; };
 
-enum BodyKind { BODY_NONE, BODY_JSON, BODY_FILE, BODY_PLAIN404, BODY_PANIC };
+enum BodyKind { BODY_NONE, BODY_JSON, BODY_FILE, BODY_PLAIN404, BODY_PANIC,
+                BODY_JSON_FAILED };  // Respond set its Content-Type, then json.Encoder.Encode failed: no body bytes
 
 static SOp lit(const std::string& s, bool body) { SOp o; o.code = OP_LIT; o.lit = s; o.body = body; return o; }
 static SOp op(uint8_t code, bool body) { SOp o; o.code = code; o.body = body; return o; }
@@ -343,7 +358,7 @@ static void build_header(Prog& p, uint32_t frame_mode, int status, bool with_mw,
     }
     if (frame_mode == GOFR_FRAME_INTENDED) {
         // what the tests read from the live recorder map: the late Header().Set is visible
-        if (bk == BODY_JSON) { h.push_back({"Content-Type", "application/json"}); have_type = true; }
+        if (bk == BODY_JSON || bk == BODY_JSON_FAILED) { h.push_back({"Content-Type", "application/json"}); have_type = true; }
         if (bk == BODY_FILE) { h.push_back({"Content-Type", file_ct_given}); have_type = true; }
     }
     std::sort(h.begin(), h.end(), [](const HeaderKV& a, const HeaderKV& b) { return a.k < b.k; });
@@ -372,7 +387,7 @@ static void build_header(Prog& p, uint32_t frame_mode, int status, bool with_mw,
         p.ops.push_back(d);
     }
     acc = "\r\n";
-    bool body_nonempty = bk != BODY_NONE;
+    bool body_nonempty = bk != BODY_NONE && bk != BODY_JSON_FAILED;
     if (!head_no_body) {
         acc += "Content-Length: ";
         if (body_nonempty) {
@@ -390,50 +405,92 @@ static void build_header(Prog& p, uint32_t frame_mode, int status, bool with_mw,
     p.ops.push_back(lit(acc, false));
 }
 
-// struct → JSON object ops.  Schemas without omitempty collapse to literals around value ops.
-static void build_struct_ops(Prog& p, const SchemaDef& sc, bool bind_layout = false, uint16_t word_base = 0) {
+// struct → JSON object ops.  Levels without omitempty collapse to literals around value ops; plain nested structs of
+// such levels are flattened into the same op list (their words are inline in the parent's fixed part and their strings
+// follow in field order, so nothing distinguishes them from the parent's own fields).  Everything whose shape depends on
+// the row — pointers, slices, maps, nested structs with omitempty members — is ONE OP_VALUE op: the device walks it with the
+// generic encoder (serve_device.cuh value_encode).
+static bool flattenable(const std::vector<SchemaDef>& all, const SchemaDef& sc) {
+    if (sc.bare()) return false;
+    for (auto& f : sc.fields) {
+        if (f.container != GOFR_C_VALUE || f.omitempty) return false;
+        if (f.kind == GOFR_F_STRUCT && !flattenable(all, all[(size_t)f.elem])) return false;
+    }
+    return true;
+}
+static SOp value_op(int schema_idx, size_t field_idx, uint16_t word) {
+    SOp v;
+    v.code = OP_VALUE; v.body = true; v.off = word; v.aux = (uint32_t)schema_idx; v.arg = (uint8_t)field_idx;
+    return v;
+}
+static void struct_level_ops(Prog& p, const std::vector<SchemaDef>& all, int sidx, bool bind_layout, uint16_t& word,
+                             uint16_t& str_ord, std::string& acc) {
+    const SchemaDef& sc = all[(size_t)sidx];
+    if (sc.bare()) {  // the schema IS its one field's type: no braces, no key
+        if (!acc.empty()) { p.ops.push_back(lit(acc, true)); acc.clear(); }
+        p.ops.push_back(value_op(sidx, 0, word));
+        word = (uint16_t)(word + field_words(all, sc.fields[0]));
+        return;
+    }
     bool dynamic = false;
     for (auto& f : sc.fields) dynamic |= f.omitempty;
-    std::string acc = "{";
-    uint16_t word = word_base, str_ord = word_base ? 1 : 0;
+    acc += "{";
     bool first = true;
-    for (auto& f : sc.fields) {
+    for (size_t fi = 0; fi < sc.fields.size(); fi++) {
+        const FieldDef& f = sc.fields[fi];
         std::string key = "\"" + json_escape_go(f.json_name) + "\":";
         uint16_t w = word;
         if (bind_layout) {  // span row (bind_device.cuh): 8 header words, strings are (offset, length) pairs
             w = (uint16_t)(8 + word);
             word += (f.kind == GOFR_F_INT32 || f.kind == GOFR_F_BOOL) ? 1 : 2;
-        } else word += (f.kind == GOFR_F_INT64 || f.kind == 5) ? 2 : 1;
+        } else word = (uint16_t)(word + field_words(all, f));
+        const bool plain = f.container == GOFR_C_VALUE;
+        const bool is_str = plain && f.kind == GOFR_F_STRING;
         SOp v;
         v.body = true;
         v.off = w;
-        switch (f.kind) {
-            case GOFR_F_INT64: case 5: v.code = OP_I64; break;
+        bool generic = !plain;
+        if (plain) switch (f.kind) {
+            case GOFR_F_INT64: case GOFR_F_INT: v.code = OP_I64; break;
             case GOFR_F_INT32: v.code = OP_I32; break;
             case GOFR_F_BOOL: v.code = OP_BOOL; break;
-            default: v.code = bind_layout ? OP_BSTR : OP_STR; v.arg = (uint8_t)str_ord++; break;
+            case GOFR_F_FLOAT64: v.code = OP_F64; break;
+            case GOFR_F_STRING: v.code = bind_layout ? OP_BSTR : OP_STR; v.arg = (uint8_t)str_ord++; break;
+            default: generic = true; break;  // GOFR_F_STRUCT
         }
         if (!dynamic) {
             if (!first) acc += ",";
             acc += key;
-            if (f.kind == GOFR_F_STRING) acc += "\"";
-            p.ops.push_back(lit(acc, true));
-            p.ops.push_back(v);
-            acc = f.kind == GOFR_F_STRING ? "\"" : "";
+            if (plain && f.kind == GOFR_F_STRUCT && flattenable(all, all[(size_t)f.elem])) {
+                uint16_t sub_word = w;
+                struct_level_ops(p, all, f.elem, false, sub_word, str_ord, acc);
+            } else {
+                if (is_str) acc += "\"";
+                p.ops.push_back(lit(acc, true));
+                p.ops.push_back(generic ? value_op(sidx, fi, w) : v);
+                acc = is_str ? "\"" : "";
+            }
         } else {
             if (!acc.empty()) { p.ops.push_back(lit(acc, true)); acc.clear(); }
             SOp k;
-            k.code = OP_KEY; k.body = true; k.kind = f.kind; k.off = w; k.lit = key;
+            k.code = OP_KEY; k.body = true; k.kind = (uint8_t)(f.kind | f.container << 4); k.off = w; k.lit = key;
             k.flags = f.omitempty ? OPF_OMITEMPTY : 0;
-            if (f.kind == GOFR_F_STRING) k.lit += "\"";
+            if (is_str) k.lit += "\"";
             p.ops.push_back(k);
+            if (generic) v = value_op(sidx, fi, w);
             v.flags |= OPF_VALUE_OF_KEY;
             p.ops.push_back(v);
-            if (f.kind == GOFR_F_STRING) { SOp q = lit("\"", true); q.flags |= OPF_VALUE_OF_KEY; p.ops.push_back(q); }
+            if (is_str) { SOp q = lit("\"", true); q.flags |= OPF_VALUE_OF_KEY; p.ops.push_back(q); }
         }
         first = false;
     }
     acc += "}";
+}
+static void build_struct_ops(Prog& p, const std::vector<SchemaDef>& all, const SchemaDef& sc, bool bind_layout = false,
+                             uint16_t word_base = 0) {
+    uint16_t word = word_base, str_ord = word_base ? 1 : 0;
+    std::string acc;
+    struct_level_ops(p, all, (int)(&sc - all.data()), bind_layout, word, str_ord, acc);
     p.ops.push_back(lit(acc, true));
 }
 
@@ -445,6 +502,16 @@ struct Builder {
     std::map<std::string, int> prog_ids;
     // identical programs (e.g. sixteen routes returning the same struct type) are stored once
     int add(Prog p) {
+        // a program that can meet a NaN / Inf float gets a companion for "json.Encoder.Encode failed": same status and
+        // headers, no body bytes (ProgRec::encfail)
+        bool may_fail = false;
+        for (auto& o : p.ops) may_fail |= o.code == OP_F64 || o.code == OP_VALUE;
+        if (may_fail && p.encfail < 0) {
+            Prog q;
+            q.status = p.status;
+            build_header(q, t->frame_mode, p.status, true, BODY_JSON_FAILED, false, "", "", false);
+            p.encfail = add(std::move(q));
+        }
         std::string sig = std::to_string(p.status) + (p.bind ? "B" : "R") + std::to_string(p.row_words);
         for (auto& o : p.ops) {
             sig += "|" + std::to_string(o.code) + "," + std::to_string(o.arg) + "," + std::to_string(o.flags) + "," +
@@ -533,7 +600,7 @@ static void fold_static_clen(std::vector<SOp>& ops) {
 // LIT followed by a value op of the same part (header/body) → the literal becomes the value op's prefix
 static bool op_takes_prefix(uint8_t code) {
     return code == OP_HEXID || code == OP_CLEN || code == OP_I64 || code == OP_I32 || code == OP_BOOL || code == OP_STR ||
-           code == OP_BSTR || code == OP_PARAM || code == OP_LOCATION || code == OP_ERRMSG;
+           code == OP_BSTR || code == OP_PARAM || code == OP_LOCATION || code == OP_ERRMSG || code == OP_F64;
 }
 static void fold_prefixes(std::vector<SOp>& ops) {
     std::vector<SOp> out;
@@ -557,6 +624,8 @@ static const char* go_kind_name(uint8_t k) {
         case GOFR_F_BOOL: return "bool";
         case GOFR_F_STRING: return "string";
         case 5: return "int";
+        case GOFR_F_FLOAT64: return "float64";
+        case GOFR_F_STRUCT: return "struct";
     }
     return "?";
 }
@@ -600,6 +669,10 @@ int seal_table(gofr_table* t) {
             for (auto& s : t->schemas) if (s.id == r.schema_id) sc = &s;
             // a closure that only ever returns strings / errors / nil needs no struct schema
             if (!sc && !(r.hkind == GOFR_H_RESULT && r.schema_id == 0)) { set_last_error("route %s: unknown schema %u", r.pattern.c_str(), r.schema_id); return GOFR_ERR_INVALID; }
+            if (sc && r.hkind == GOFR_H_BIND_ECHO && !sc->flat) {
+                set_last_error("route %s: Bind takes flat structs of int / bool / string fields only (schema %u)", r.pattern.c_str(), r.schema_id);
+                return GOFR_ERR_UNSUPPORTED;
+            }
         }
         switch (r.hkind) {
             case GOFR_H_HOST: break;
@@ -631,7 +704,7 @@ int seal_table(gofr_table* t) {
                 p.status = 200;
                 build_header(p, fm, 200, true, BODY_JSON, false, "", "", false);
                 p.ops.push_back(lit("{\"data\":", true));
-                build_struct_ops(p, *sc, r.hkind == GOFR_H_BIND_ECHO);
+                build_struct_ops(p, t->schemas, *sc, r.hkind == GOFR_H_BIND_ECHO);
                 p.ops.push_back(lit("}\n", true));
                 p.bind = r.hkind == GOFR_H_BIND_ECHO;
                 prog_ok[ri] = b.add(std::move(p));
@@ -647,7 +720,7 @@ int seal_table(gofr_table* t) {
                     p.status = 200;
                     build_header(p, fm, 200, true, BODY_JSON, false, "", "", false);
                     p.ops.push_back(lit("{\"data\":", true));
-                    build_struct_ops(p, *sc, false);
+                    build_struct_ops(p, t->schemas, *sc, false);
                     p.ops.push_back(lit("}\n", true));
                     prog_ok[ri] = b.add(std::move(p));
                 }
@@ -683,7 +756,7 @@ int seal_table(gofr_table* t) {
                         Prog p;
                         p.status = status;
                         build_header(p, fm, status, true, BODY_JSON, false, "", "", false);
-                        build_struct_ops(p, *sc, false);
+                        build_struct_ops(p, t->schemas, *sc, false);
                         p.ops.push_back(lit("\n", true));
                         rawprogs[ri * 9 + 0 + es] = (uint16_t)b.add(std::move(p));
                     }
@@ -710,11 +783,9 @@ int seal_table(gofr_table* t) {
                     m.off = 0;
                     e.ops.push_back(m);
                     e.ops.push_back(lit("\"},\"data\":", true));
-                    build_struct_ops(e, *sc, false, 1);
+                    build_struct_ops(e, t->schemas, *sc, false, 1);
                     e.ops.push_back(lit("}\n", true));
-                    uint32_t fw = 1;
-                    for (auto& f : sc->fields) fw += (f.kind == GOFR_F_INT64 || f.kind == 5) ? 2 : 1;
-                    e.row_words = (int)fw;
+                    e.row_words = (int)(1 + sc->fixed_words);
                     prog_both[ri] = b.add(std::move(e));
                 }
                 break;
@@ -868,6 +939,7 @@ int seal_table(gofr_table* t) {
         P.n_ops = (uint16_t)p.ops.size();
         P.status = (uint16_t)p.status;
         P.row_words = (uint16_t)p.row_words;
+        P.encfail = p.encfail >= 0 ? (uint16_t)p.encfail : (uint16_t)0xFFFF;
         if (p.bind) P.flags |= PF_BIND;
         for (auto& so : p.ops) {
             Op o;
@@ -891,7 +963,9 @@ int seal_table(gofr_table* t) {
                     break;
                 case OP_HEXID: fixed = 32; break;
                 case OP_CLEN: P.flags |= PF_HAS_CLEN; break;
-                case OP_I64: case OP_I32: case OP_BOOL: case OP_STR: case OP_BSTR: P.flags |= PF_DYNAMIC | PF_NEEDS_ROW; break;
+                case OP_I64: case OP_I32: case OP_BOOL: case OP_STR: case OP_BSTR: case OP_F64: case OP_VALUE:
+                    P.flags |= PF_DYNAMIC | PF_NEEDS_ROW;
+                    break;
                 case OP_BLOB:
                     while (cold.size() % 16) cold.push_back(0);
                     o.off = (uint32_t)cold.size();
@@ -1053,16 +1127,23 @@ int seal_table(gofr_table* t) {
             FieldRec F;
             memset(&F, 0, sizeof F);
             F.kind = f.kind; F.omitempty = f.omitempty; F.word = word;
-            word += (f.kind == GOFR_F_INT64 || f.kind == 5) ? 2 : 1;
+            F.container = f.container;
+            F.n_words = (uint8_t)field_words(t->schemas, f);
+            F.elem = f.elem >= 0 ? (uint16_t)f.elem : (uint16_t)0xFFFF;
+            word = (uint16_t)(word + F.n_words);
             F.name_len = (uint16_t)f.json_name.size();
             F.name_off = pool.put(f.json_name);
             F.fold_off = pool.put(fold_lower(f.json_name));
-            if (f.kind == GOFR_F_STRING) F.str_ord = so++;
+            const std::string key = "\"" + json_escape_go(f.json_name) + "\":";
+            F.key_off = pool.put(key);
+            F.key_len = (uint16_t)key.size();
+            if (f.kind == GOFR_F_STRING && f.container == GOFR_C_VALUE) F.str_ord = so++;
             std::string tn = go_kind_name(f.kind);
             F.type_off = pool.put(tn);
             F.type_len = (uint16_t)tn.size();
             frecs[si].push_back(F);
         }
+        S.flags = (uint16_t)((s.flat ? SF_FLAT : 0) | (s.bare() ? SF_BARE : 0));
         S.fixed_words = word;
         S.n_strings = so;
     }
@@ -1074,7 +1155,7 @@ int seal_table(gofr_table* t) {
     for (size_t ri = 0; ri < t->routes.size(); ri++) {
         if (t->routes[ri].hkind != GOFR_H_BIND_ECHO) continue;
         uint32_t words = 8;
-        for (auto& f : t->schemas[routes[ri].schema].fields) words += (f.kind == GOFR_F_INT32 || f.kind == GOFR_F_BOOL) ? 1 : 2;
+        for (auto& f : t->schemas[routes[ri].schema].fields) words += (f.kind == GOFR_F_INT32 || f.kind == GOFR_F_BOOL) ? 1 : 2;  // flat: checked at seal
         H.bind_row_words = std::max(H.bind_row_words, words);
     }
     H.max_fixed_len = max_fixed;
@@ -1171,15 +1252,37 @@ int gofr_table_add_schema(gofr_table* t, uint32_t schema_id, const char* go_type
     SchemaDef s;
     s.id = schema_id;
     s.go_type = go_type_name ? go_type_name : "";
+    for (auto& o : t->schemas)
+        if (o.id == schema_id) { set_last_error("schema %u added twice", schema_id); return GOFR_ERR_INVALID; }
     for (uint32_t i = 0; i < n_fields; i++) {
         FieldDef f;
         f.go_name = fields[i].go_name ? fields[i].go_name : "";
         f.json_name = fields[i].json_name && fields[i].json_name[0] ? fields[i].json_name : f.go_name;
         f.kind = fields[i].kind;
         f.omitempty = fields[i].omitempty != 0;
-        if (f.kind < GOFR_F_INT64 || f.kind > 5) { set_last_error("schema %u: unsupported field kind %u", schema_id, f.kind); return GOFR_ERR_UNSUPPORTED; }
+        f.container = fields[i].container;
+        f.flags = fields[i].flags;
+        if (f.kind < GOFR_F_INT64 || f.kind > GOFR_F_STRUCT || f.container > GOFR_C_MAP || (f.flags & ~GOFR_FIELD_BARE)) {
+            set_last_error("schema %u: unsupported field kind %u / container %u", schema_id, f.kind, f.container);
+            return GOFR_ERR_UNSUPPORTED;
+        }
+        if ((f.flags & GOFR_FIELD_BARE) && n_fields != 1) { set_last_error("schema %u: a bare schema has exactly one field", schema_id); return GOFR_ERR_INVALID; }
+        if (f.kind == GOFR_F_STRUCT) {
+            for (size_t k = 0; k < t->schemas.size(); k++) if (t->schemas[k].id == fields[i].elem_schema) f.elem = (int)k;
+            // the struct type must exist already: a type cannot contain itself by value, and recursive pointer / slice
+            // types (trees) have no bound on the nesting the device walker would have to keep
+            if (f.elem < 0) { set_last_error("schema %u: field %s refers to schema %u, which has not been added", schema_id, f.go_name.c_str(), fields[i].elem_schema); return GOFR_ERR_INVALID; }
+            if (f.container == GOFR_C_MAP) { set_last_error("schema %u: maps of structs are not supported", schema_id); return GOFR_ERR_UNSUPPORTED; }
+            if (t->schemas[(size_t)f.elem].bare()) { set_last_error("schema %u: a bare schema cannot be a struct member", schema_id); return GOFR_ERR_INVALID; }
+            s.depth = std::max(s.depth, 1 + t->schemas[(size_t)f.elem].depth);
+        }
+        if (f.container != GOFR_C_VALUE || f.kind > GOFR_F_INT || f.flags) s.flat = false;
+        const uint32_t fw = field_words(t->schemas, f);
+        if (fw > 255u || s.fixed_words + fw > 4096u) { set_last_error("schema %u: fixed part too wide", schema_id); return GOFR_ERR_UNSUPPORTED; }
+        s.fixed_words += fw;
         s.fields.push_back(f);
     }
+    if (s.depth > kMaxValueDepth) { set_last_error("schema %u: structs nest deeper than %d levels", schema_id, kMaxValueDepth); return GOFR_ERR_UNSUPPORTED; }
     t->schemas.push_back(s);
     return GOFR_OK;
 }

@@ -12,9 +12,10 @@
 namespace gofr {
 
 constexpr uint32_t kMagic = 0x52464F47u;  // "GOFR"
-constexpr uint32_t kImageVersion = 15;
+constexpr uint32_t kImageVersion = 16;
 constexpr uint32_t kMaxHotBytes = 40 * 1024;  // shared-memory budget for the table
 constexpr int kMaxVars = 8;                   // variables per route template
+constexpr int kMaxValueDepth = 8;            // struct nesting the generic value encoder walks (its frame stack)
 constexpr int kMaxFields = 32;                // struct fields per schema
 
 struct ImageHeader {  // 160 B
@@ -104,6 +105,10 @@ enum OpCode : uint8_t {
     OP_ERRMSG = 10,   // escaped err.Error() of a failed Bind                   (responder.go:43-57)
     OP_BLOB = 11,     // raw bytes from the cold section                        (response.File)
     OP_BSTR = 13,     // string field of a Bind span row: off = word index of (offset into the body, length | escaped<<31)
+    OP_F64 = 14,      // float64 struct field: encoding/json floatEncoder text (float_device.cuh); off = word index of the bits
+    OP_VALUE = 15,    // a field the generic encoder walks (pointer, slice, map, nested struct with omitempty members, bare
+                      // schema): aux = schema index, arg = field index, off = word index of the field's fixed words;
+                      // consumes the field's share of the row's variable part (serve_device.cuh value_encode)
     OP_KEY = 12,      // struct member key with dynamic comma / omitempty: emits [","] + lits[off..off+len) unless the
                       // field (arg) is empty and flagged; used only for schemas that have an omitempty field
 };
@@ -121,7 +126,7 @@ struct Op {  // 16 B (one LDS.128)
     uint8_t code;
     uint8_t arg;
     uint8_t flags;
-    uint8_t kind;  // field kind for OP_KEY emptiness test
+    uint8_t kind;  // OP_KEY: field kind (low 4 bits) and GOFR_C_* container (high 4) for the emptiness test
     uint32_t len;
     uint32_t off;
     uint32_t aux;
@@ -142,7 +147,9 @@ struct ProgRec {  // 32 B
     uint8_t shape_class;  // 1..30: programs with the same op-code sequence (same control flow in run_prog) share a class;
                           // the kernel groups a tile's requests by class so that warps run few distinct programs
     uint8_t pad1[3];
-    uint32_t pad[1];
+    uint16_t encfail;     // program that answers when a float of this one turns out to be NaN / ±Inf (json.Encoder.Encode
+                          // fails after Respond wrote the status: same headers, no body); 0xFFFF: cannot happen
+    uint16_t pad2;
 };
 static_assert(sizeof(ProgRec) == 32, "ProgRec layout");
 
@@ -180,28 +187,36 @@ enum FastFlags : uint8_t {
     FR_COMPLETE = 2,   // template only: nothing left to interpret
 };
 
+enum SchemaFlags : uint16_t {
+    SF_FLAT = 1,  // scalars and strings by value only (Bind takes nothing else)
+    SF_BARE = 2,  // one field standing for its own type (GOFR_FIELD_BARE)
+};
 struct SchemaRec {  // 16 B + per-field table
     uint16_t n_fields;
     uint16_t n_strings;
     uint16_t fixed_words;  // words in the fixed part of a row
-    uint16_t pad;
+    uint16_t flags;        // SF_*
     uint32_t fields_off;  // FieldRec[n_fields]
     uint32_t type_off;    // reflect.Type.String(), for Bind error text
 };
 
-struct FieldRec {  // 24 B
+struct FieldRec {  // 32 B
     uint8_t kind;  // GOFR_F_*
     uint8_t omitempty;
-    uint16_t word;      // word index in the row
+    uint16_t word;      // word index in the fixed part of its struct
     uint16_t name_len;  // JSON key name (for Bind)
     uint16_t str_ord;   // ordinal among string fields
     uint32_t name_off;
     uint32_t fold_off;  // simple-folded (lower-cased) name
     uint16_t type_len;  // Go type name for error text ("int64", "string", ...)
-    uint16_t pad;
+    uint8_t container;  // GOFR_C_*
+    uint8_t n_words;    // words the field owns in the fixed part (nested structs inline, pointers + 1)
     uint32_t type_off;
+    uint32_t key_off;   // `"name":` as encoding/json writes it (escaped), for the generic encoder
+    uint16_t key_len;
+    uint16_t elem;      // GOFR_F_STRUCT: schema index of the struct type
 };
-static_assert(sizeof(FieldRec) == 24, "FieldRec layout");
+static_assert(sizeof(FieldRec) == 32, "FieldRec layout");
 
 // Hash of a path for the literal-route table: word-wise FNV-style over the 4-byte aligned, zero-padded path.
 // The device computes it from the request bytes, the builder from the pattern; both use this function.

@@ -38,15 +38,19 @@ def result_record(outcome: int, payload: bytes = b"", raw_err: int = RAW_OK) -> 
     return (outcome | raw_err << 8).to_bytes(4, "little") + payload
 
 
-def result_both(schema: "Schema", values: Sequence, message: bytes) -> bytes:
+def result_both(schema: "Schema", values: Sequence, message: bytes, lookup=None) -> bytes:
     """RESULT_BOTH record: (data, err) both non-nil — message length word + the row's fixed words, then the message
     bytes + the row's string bytes."""
-    row = schema.encode_row(values)
-    fixed = schema.fixed_bytes()
+    row = schema.encode_row(values, lookup)
+    fixed = schema.fixed_bytes(lookup)
     return (RESULT_BOTH.to_bytes(4, "little") + len(message).to_bytes(4, "little") + row[:fixed] + message + row[fixed:])
 
 # field kinds
-F_INT64, F_INT32, F_BOOL, F_STRING, F_INT = 1, 2, 3, 4, 5
+F_INT64, F_INT32, F_BOOL, F_STRING, F_INT, F_FLOAT64, F_STRUCT = 1, 2, 3, 4, 5, 6, 7
+# what a field holds of its kind T: T, *T, []T, map[string]T (include/gofr_b200.h GOFR_C_*)
+C_VALUE, C_PTR, C_SLICE, C_MAP = 0, 1, 2, 3
+FIELD_BARE = 1   # one-field schema standing for the field's own type (a handler returning []T, map[string]T, ...)
+NIL_COUNT = 0xFFFFFFFF
 
 REQ_FORCE_QUERY = 1
 ROUTE_NONE = 0xFFFF
@@ -67,10 +71,17 @@ class Field:
     kind: int
     json_name: str = ""
     omitempty: bool = False
+    container: int = C_VALUE
+    elem_schema: int = 0      # F_STRUCT: id of the struct's schema
+    flags: int = 0
 
     @property
     def name(self) -> str:
         return self.json_name or self.go_name
+
+
+def _str_bytes(v) -> bytes:
+    return v.encode("utf-8", "surrogateescape") if isinstance(v, str) else bytes(v)
 
 
 @dataclass
@@ -79,26 +90,85 @@ class Schema:
     go_type: str  # reflect.Type.String(), e.g. "main.Person"
     fields: List[Field]
 
-    def fixed_bytes(self) -> int:
-        return sum(8 if f.kind in (F_INT64, F_INT) else 4 for f in self.fields)
+    def is_flat(self) -> bool:
+        return all(f.container == C_VALUE and f.kind <= F_INT and not f.flags for f in self.fields)
 
-    def encode_row(self, values: Sequence) -> bytes:
-        """Handler-result row: one LE u32 word per field (INT64/INT two), then the string bytes in order."""
+    def fixed_bytes(self, lookup=None) -> int:
+        return sum(self._field_fixed(f, lookup) for f in self.fields)
+
+    @staticmethod
+    def _scalar_bytes(kind: int) -> int:
+        return 8 if kind in (F_INT64, F_INT, F_FLOAT64) else 4
+
+    def _field_fixed(self, f: Field, lookup) -> int:
+        if f.container in (C_SLICE, C_MAP):
+            return 4
+        n = lookup(f.elem_schema).fixed_bytes(lookup) if f.kind == F_STRUCT else self._scalar_bytes(f.kind)
+        return n + (4 if f.container == C_PTR else 0)
+
+    @staticmethod
+    def _scalar(kind: int, v) -> bytes:
+        if kind in (F_INT64, F_INT):
+            return int(v).to_bytes(8, "little", signed=True)
+        if kind == F_INT32:
+            return int(v).to_bytes(4, "little", signed=True)
+        if kind == F_BOOL:
+            return (1 if v else 0).to_bytes(4, "little")
+        if kind == F_FLOAT64:
+            import struct
+            return v if isinstance(v, (bytes, bytearray)) else struct.pack("<d", float(v))   # bytes: raw IEEE bits (NaN payloads)
+        raise ValueError(f"bad field kind {kind}")
+
+    def _plain(self, f: Field, v, lookup):
+        """(fixed, variable) of a T"""
+        if f.kind == F_STRING:
+            b = _str_bytes(v)
+            return len(b).to_bytes(4, "little"), b
+        if f.kind == F_STRUCT:
+            sub = lookup(f.elem_schema)
+            row = sub.encode_row(v, lookup)
+            fb = sub.fixed_bytes(lookup)
+            return row[:fb], row[fb:]
+        return self._scalar(f.kind, v), b""
+
+    def _element(self, f: Field, v, lookup) -> bytes:
+        if f.kind == F_STRING:
+            b = _str_bytes(v)
+            return len(b).to_bytes(4, "little") + b
+        if f.kind == F_STRUCT:
+            return lookup(f.elem_schema).encode_row(v, lookup)
+        return self._scalar(f.kind, v)
+
+    def encode_row(self, values: Sequence, lookup=None) -> bytes:
+        """Handler-result row (include/gofr_b200.h "Row format"): the fixed part — one LE u32 word per field (INT64 / INT /
+        FLOAT64 two, nested structs inline, pointers a presence word first, slices and maps their count) — then the
+        variable part.  values: one per field; a nested struct is a sequence, *T is None or the value, []T None or a list,
+        map[string]T None or a dict (row order = dict order; the encoder sorts).  lookup(schema_id) resolves F_STRUCT."""
         words = bytearray()
         tail = bytearray()
         for f, v in zip(self.fields, values):
-            if f.kind in (F_INT64, F_INT):
-                words += int(v).to_bytes(8, "little", signed=True)
-            elif f.kind == F_INT32:
-                words += int(v).to_bytes(4, "little", signed=True)
-            elif f.kind == F_BOOL:
-                words += (1 if v else 0).to_bytes(4, "little")
-            elif f.kind == F_STRING:
-                b = v.encode("utf-8", "surrogateescape") if isinstance(v, str) else bytes(v)
-                words += len(b).to_bytes(4, "little")
-                tail += b
+            if f.container == C_VALUE:
+                fx, var = self._plain(f, v, lookup)
+                words += fx
+                tail += var
+            elif f.container == C_PTR:
+                if v is None:
+                    words += bytes(self._field_fixed(f, lookup))
+                else:
+                    fx, var = self._plain(f, v, lookup)
+                    words += (1).to_bytes(4, "little") + fx
+                    tail += var
+            elif f.container == C_SLICE:
+                words += (NIL_COUNT if v is None else len(v)).to_bytes(4, "little")
+                for e in (v or ()):
+                    tail += self._element(f, e, lookup)
+            elif f.container == C_MAP:
+                words += (NIL_COUNT if v is None else len(v)).to_bytes(4, "little")
+                for k, e in (v or {}).items():
+                    kb = _str_bytes(k)
+                    tail += len(kb).to_bytes(4, "little") + kb + self._element(f, e, lookup)
             else:
-                raise ValueError(f"bad field kind {f.kind}")
+                raise ValueError(f"bad container {f.container}")
         return bytes(words + tail)
 
 

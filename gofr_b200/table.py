@@ -28,6 +28,7 @@ class Table:
                 g, j = f.go_name.encode(), f.json_name.encode()
                 keep += [g, j]
                 arr[i].go_name, arr[i].json_name, arr[i].kind, arr[i].omitempty = g, j, f.kind, 1 if f.omitempty else 0
+                arr[i].container, arr[i].flags, arr[i].elem_schema = f.container, f.flags, f.elem_schema
             _abi.check(L.gofr_table_add_schema(self._t, sc.id, sc.go_type.encode(), arr, len(sc.fields)),
                        "gofr_table_add_schema")
         for r in spec.routes:

@@ -124,11 +124,24 @@ int orc_add_schema(orc_table* t, int schema_id, const char* go_type_name, int n_
     return 0;
 }
 
-static const orc_schema* find_schema(const orc_table* t, int id) {
+/* the wider data model (include/gofr_b200.h gofr_field_desc: container, flags, elem_schema) for the last schema added */
+int orc_schema_extend(orc_table* t, const int* containers, const int* flags, const int* elem_schemas) {
+    if (!t->n_schemas) return -1;
+    orc_schema* s = &t->schemas[t->n_schemas - 1];
+    for (int i = 0; i < s->n_fields; i++) {
+        s->f[i].container = containers ? containers[i] : 0;
+        s->f[i].flags = flags ? flags[i] : 0;
+        s->f[i].elem_schema = elem_schemas ? elem_schemas[i] : 0;
+    }
+    return 0;
+}
+
+const orc_schema* orc_find_schema(const orc_table* t, int id) {
     for (int i = 0; i < t->n_schemas; i++)
         if (t->schemas[i].id == id) return &t->schemas[i];
     return NULL;
 }
+static const orc_schema* find_schema(const orc_table* t, int id) { return orc_find_schema(t, id); }
 
 static void cls_set(uint8_t* cls, int c) { cls[c >> 3] |= (uint8_t)(1u << (c & 7)); }
 static int cls_has(const uint8_t* cls, int c) { return (cls[c >> 3] >> (c & 7)) & 1; }
@@ -744,7 +757,10 @@ static void rw_finish(rw_t* w, int is_head, const char* date29, obuf* out) {
 /* ------------------------------------------------------------------------------------------------------------ */
 
 typedef struct {
-    int data_kind; /* 0 nil, 1 string, 2 struct, 3 empty map (health), 4 File */
+    int data_kind; /* 0 nil, 1 string, 2 struct, 3 empty map (health), 4 File, 5 a value already encoded (orc_value.c) */
+    const uint8_t* json; /* data_kind 5 */
+    size_t json_len;
+    int enc_failed;      /* data_kind 5: json.Encoder.Encode returned an UnsupportedValueError (NaN / Inf) */
     const uint8_t* str;
     size_t str_len;
     const orc_schema* sc;
@@ -773,12 +789,16 @@ static void respond(rw_t* w, const handler_result* r) {
     rw_set(w, "Content-Type", "application/json", 16); /* :39 "Content-type" canonicalises to Content-Type */
     obuf* b = &w->body;
     if (!w->wrote_header) rw_write_header(w, 200);
+    /* Encode marshals the whole value into its own buffer first and returns the error before touching w: nothing of the
+     * body is written, and Respond drops the error (:40 `_ =`) */
+    if (r->data_kind == 5 && r->enc_failed) return;
     if (r->raw) {
         /* case resTypes.Raw: resp = v.Data (:25-26) — no envelope, and the error object computed at :20 is not part of
          * the body (the status code it produced was already written at :21).  Raw{} holds a nil interface: "null". */
         if (r->data_kind == 0) ob_puts(b, "null");
         else if (r->data_kind == 1) orc_enc_string(b, r->str, r->str_len);
         else if (r->data_kind == 2) orc_enc_struct(b, r->sc, r->vals);
+        else if (r->data_kind == 5) ob_put(b, r->json, r->json_len);
         else ob_puts(b, "{}");
         ob_putc(b, '\n');
         return;
@@ -797,6 +817,7 @@ static void respond(rw_t* w, const handler_result* r) {
         ob_puts(b, "\"data\":");
         if (r->data_kind == 1) orc_enc_string(b, r->str, r->str_len);
         else if (r->data_kind == 2) orc_enc_struct(b, r->sc, r->vals);
+        else if (r->data_kind == 5) ob_put(b, r->json, r->json_len);
         else ob_puts(b, "{}");
     }
     ob_putc(b, '}');
@@ -844,6 +865,18 @@ static int decode_row(const orc_schema* sc, const uint8_t* row, size_t n, orc_va
         }
     }
     return 0;
+}
+
+/* a row of any schema: flat ones go through decode_row + orc_enc_struct (the path the reference pins cover), the wider
+ * data model through the row walker of orc_value.c.  fixed / var given separately (RESULT_BOTH interleaves a message). */
+static void row_to_result(const orc_table* t, const orc_schema* sc, const uint8_t* fixed, size_t fixed_avail,
+                          const uint8_t* var, const uint8_t* end, obuf* json, handler_result* hr) {
+    int rc = orc_enc_row(json, t, sc, fixed, fixed_avail, var, end);
+    if (rc == -1) { hr->data_kind = -1; return; }
+    hr->data_kind = 5;
+    hr->enc_failed = rc == -2;
+    hr->json = json->p;
+    hr->json_len = json->n;
 }
 
 static const char HTTP_ERR_MISSING_FILE[] = "http: no such file"; /* net/http.ErrMissingFile.Error() */
@@ -913,9 +946,10 @@ static void serve_one(const orc_table* t, const req_desc* d, const uint8_t* id16
         /* ---- handler.ServeHTTP (handler.go:32-36): run the closure, Respond(data, err) ---- */
         handler_result hr;
         memset(&hr, 0, sizeof hr);
-        obuf tmp, tmp2;
+        obuf tmp, tmp2, json;
         ob_init(&tmp);
         ob_init(&tmp2);
+        ob_init(&json);
         orc_value vals[64];
         memset(vals, 0, sizeof vals);
         int n_owned = 0;
@@ -954,7 +988,10 @@ static void serve_one(const orc_table* t, const req_desc* d, const uint8_t* id16
             }
             case H_ROW: {
                 const orc_schema* sc = find_schema(t, r->schema_id);
-                if (!sc || decode_row(sc, data, dn, vals) != 0) {
+                if (sc && !orc_schema_is_flat(sc)) {
+                    size_t fb = (size_t)orc_schema_fixed_words(t, sc) * 4;
+                    row_to_result(t, sc, data, dn, data + (fb < dn ? fb : dn), data + dn, &json, &hr);
+                } else if (!sc || decode_row(sc, data, dn, vals) != 0) {
                     /* malformed row from the host shim: not a reference behaviour; both sides answer as a panic */
                     hr.data_kind = -1;
                 } else { hr.data_kind = 2; hr.sc = sc; hr.vals = vals; }
@@ -974,7 +1011,10 @@ static void serve_one(const orc_table* t, const req_desc* d, const uint8_t* id16
                     const uint32_t kind = outcome & 0xFFu, es = outcome >> 8;
                     hr.raw = 1;
                     if (es) { hr.has_err = 1; hr.err_is_missing_file = es == 2; hr.err_msg = (const uint8_t*)""; hr.err_len = 0; }
-                    if (kind == 6) {
+                    if (kind == 6 && sc && !orc_schema_is_flat(sc)) {
+                        size_t fb = (size_t)orc_schema_fixed_words(t, sc) * 4;
+                        row_to_result(t, sc, rest, rn, rest + (fb < rn ? fb : rn), rest + rn, &json, &hr);
+                    } else if (kind == 6) {
                         if (!sc || decode_row(sc, rest, rn, vals) != 0) hr.data_kind = -1;
                         else { hr.data_kind = 2; hr.sc = sc; hr.vals = vals; }
                     } else if (kind == 7) {
@@ -985,7 +1025,10 @@ static void serve_one(const orc_table* t, const req_desc* d, const uint8_t* id16
                     }
                     break;
                 }
-                if (outcome == 0) {
+                if (outcome == 0 && sc && !orc_schema_is_flat(sc)) {
+                    size_t fb = (size_t)orc_schema_fixed_words(t, sc) * 4;
+                    row_to_result(t, sc, rest, rn, rest + (fb < rn ? fb : rn), rest + rn, &json, &hr);
+                } else if (outcome == 0) {
                     if (!sc || decode_row(sc, rest, rn, vals) != 0) hr.data_kind = -1;
                     else { hr.data_kind = 2; hr.sc = sc; hr.vals = vals; }
                 } else if (outcome == 1 || outcome == 3) {
@@ -997,10 +1040,15 @@ static void serve_one(const orc_table* t, const req_desc* d, const uint8_t* id16
                 } else if (outcome == 4) {
                     /* (data, err): one row = [message length word][schema fixed words][message bytes][string bytes] */
                     size_t fixed = 4;
-                    if (sc) for (int i = 0; i < sc->n_fields; i++) fixed += (sc->f[i].kind == F_INT64 || sc->f[i].kind == F_INT) ? 8 : 4;
+                    if (sc) fixed += (size_t)orc_schema_fixed_words(t, sc) * 4;
                     uint32_t mlen = 0;
                     if (rn >= 4) memcpy(&mlen, rest, 4);
                     if (!sc || rn < fixed || fixed + (uint64_t)mlen > rn) { hr.data_kind = -1; break; }
+                    if (!orc_schema_is_flat(sc)) {
+                        row_to_result(t, sc, rest + 4, fixed - 4, rest + fixed + mlen, rest + rn, &json, &hr);
+                        if (hr.data_kind == 5) { hr.has_err = 1; hr.err_msg = rest + fixed; hr.err_len = mlen; }
+                        break;
+                    }
                     /* the struct's words follow the length word, its strings follow the message bytes: present them to
                      * decode_row as an ordinary row */
                     uint8_t* tmp_row = (uint8_t*)malloc(rn);
@@ -1051,6 +1099,7 @@ static void serve_one(const orc_table* t, const req_desc* d, const uint8_t* id16
         for (int i = 0; i < n_owned; i++) free(vals[i].owned);
         ob_free(&tmp);
         ob_free(&tmp2);
+        ob_free(&json);
     }
 
 finish:
@@ -1214,6 +1263,31 @@ const char* orc_go_kind_name(int kind) {
         case F_BOOL: return "bool";
         case F_STRING: return "string";
         case F_INT: return "int";
+        case F_FLOAT64: return "float64";
     }
     return "?";
+}
+
+/* ---- unit-level entry points for the wider data model (orc_value.c) ---- */
+int orc_json_float64(double x, uint8_t* out, int cap) {
+    char tmp[40];
+    int n = orc_float_text(x, tmp);
+    if (n > cap) return -1;
+    memcpy(out, tmp, (size_t)n);
+    return n;
+}
+
+/* the JSON text of one row: bytes written, -1 malformed / too small, -2 not encodable (NaN, Inf) */
+int orc_encode_row_json(const orc_table* t, int schema_id, const uint8_t* row, int n, uint8_t* out, int cap) {
+    const orc_schema* sc = orc_find_schema(t, schema_id);
+    if (!sc) return -1;
+    size_t fb = (size_t)orc_schema_fixed_words(t, sc) * 4;
+    if (fb > (size_t)n) return -1;
+    obuf b;
+    ob_init(&b);
+    int rc = orc_enc_row(&b, t, sc, row, (size_t)n, row + fb, row + n);
+    int ret = rc < 0 ? rc : (b.n > (size_t)cap ? -1 : (int)b.n);
+    if (ret > 0) memcpy(out, b.p, b.n);
+    ob_free(&b);
+    return ret;
 }

@@ -30,6 +30,8 @@ orc_table* orc_table_new(int frame_mode);
 void orc_table_free(orc_table*);
 int orc_add_schema(orc_table*, int schema_id, const char* go_type_name, int n_fields, const char* const* go_names,
                    const char* const* json_names, const int* kinds, const int* omitempty);
+/* the wider data model of the schema added last: per field GOFR_C_* container, GOFR_FIELD_* flags, element schema id */
+int orc_schema_extend(orc_table*, const int* containers, const int* flags, const int* elem_schemas);
 /* method: 0..15 or 255 (= PathPrefix, no method matcher).  Returns route id (>=0) or <0 on error. */
 int orc_add_route(orc_table*, int method, const char* pattern, int pattern_len, int hkind, int schema_id,
                   const char* s0, int s0_len, const char* s1, int s1_len, const char* s2, int s2_len, const char* s3,
@@ -56,7 +58,9 @@ int orc_grpc_hello(const uint8_t* in, const uint32_t* in_off, uint32_t n, uint8_
 /* ---- unit-level entry points for the golden-vector tests; each returns the number of bytes written to out
  *      (or a negative error) ---- */
 int orc_json_string(const uint8_t* s, int n, uint8_t* out, int cap);      /* encoding/json string, HTML-safe */
-int orc_json_int(int64_t v, uint8_t* out, int cap);                        /* strconv.AppendInt base 10 */
+int orc_json_int(int64_t v, uint8_t* out, int cap);
+int orc_json_float64(double x, uint8_t* out, int cap);                     /* encoding/json floatEncoder; 0 = not encodable */
+int orc_encode_row_json(const orc_table*, int schema_id, const uint8_t* row, int n, uint8_t* out, int cap);                        /* strconv.AppendInt base 10 */
 int orc_clean_path(const uint8_t* p, int n, uint8_t* out, int cap);        /* mux cleanPath */
 int orc_query_get(const uint8_t* q, int qn, const uint8_t* key, int kn, uint8_t* out, int cap); /* URL.Query().Get */
 int orc_escape_path(const uint8_t* p, int n, uint8_t* out, int cap);       /* url.escape(p, encodePath) */

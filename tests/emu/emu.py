@@ -16,6 +16,8 @@ _lib = None
 def _build():
     srcs = [os.path.join(HERE, "emu_serve.cpp"), os.path.join(ROOT, "gofr_b200", "csrc", "serve_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "bind_device.cuh"),
+            os.path.join(ROOT, "gofr_b200", "csrc", "value_device.cuh"),
+            os.path.join(ROOT, "gofr_b200", "csrc", "float_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "grpc_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "reqlog_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "http_device.cuh"),
@@ -47,6 +49,24 @@ def lib():
         _lib.emu_reqlog.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
                                     C.c_uint32]
     return _lib
+
+
+def float_text(bits: int) -> bytes:
+    """json_float64_text of the device code (float_device.cuh): b"" for NaN / Inf."""
+    out = C.create_string_buffer(40)
+    lib().emu_float_text.argtypes = [C.c_uint64, C.c_char_p]
+    n = lib().emu_float_text(bits, out)
+    return out.raw[:n]
+
+
+def float_text_many(bits: np.ndarray):
+    """the texts of many float64 bit patterns: (bytes, offsets[n + 1])"""
+    bits = np.ascontiguousarray(bits, dtype=np.uint64)
+    out = np.zeros(len(bits) * 32, dtype=np.uint8)
+    off = np.zeros(len(bits) + 1, dtype=np.uint32)
+    lib().emu_float_text_many.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib().emu_float_text_many(bits.ctypes.data, len(bits), out.ctypes.data, off.ctypes.data)
+    return out, off
 
 
 def fast_taken(reset: bool = True) -> int:

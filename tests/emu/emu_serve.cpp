@@ -65,6 +65,12 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
 
 // ---- slot layout (gofr_serve_device_slots): same per-request code, emit_request<true> + finish_padded ----
 static int g_stage_mode = 0;  // which requests of the slot emulation count as staged: 0 every other one, 1 all, 2 none
+extern "C" int emu_float_text(uint64_t bits, uint8_t* out) { return (int)json_float64_text(bits, out); }
+extern "C" void emu_float_text_many(const uint64_t* bits, uint32_t n, uint8_t* out, uint32_t* off) {
+    uint32_t o = 0;
+    for (uint32_t i = 0; i < n; i++) { off[i] = o; o += json_float64_text(bits[i], out + o); }
+    off[n] = o;
+}
 extern "C" void emu_set_stage_mode(int m) { g_stage_mode = m; }
 static uint64_t g_fast_taken = 0;  // requests sized by size_fast (and therefore written by emit_fast) since the last reset
 extern "C" uint64_t emu_fast_taken(int reset) { const uint64_t v = g_fast_taken; if (reset) g_fast_taken = 0; return v; }

@@ -19,7 +19,7 @@ _lib = None
 
 
 def build() -> None:
-    srcs = ["gofr_oracle.c", "orc_bind.c", "orc_grpc.c", "orc_reqlog.c", "orc_http.c", "orc_proto.c", "gofr_oracle.h", "orc_internal.h", "Makefile"]
+    srcs = ["gofr_oracle.c", "orc_bind.c", "orc_grpc.c", "orc_reqlog.c", "orc_http.c", "orc_proto.c", "orc_value.c", "gofr_oracle.h", "orc_internal.h", "Makefile"]
     odir = os.path.join(_ROOT, "oracle")
     if os.path.exists(_LIB_PATH):
         so_m = os.path.getmtime(_LIB_PATH)
@@ -38,6 +38,9 @@ def lib():
         L.orc_table_free.argtypes = [C.c_void_p]
         L.orc_add_schema.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_char_p),
                                      C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_schema_extend.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_json_float64.argtypes = [C.c_double, C.c_char_p, C.c_int]
+        L.orc_encode_row_json.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
         L.orc_add_route.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int] + \
             [C.c_char_p, C.c_int] * 4 + [C.c_char_p, C.c_int]
         L.orc_add_default_routes.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
@@ -114,6 +117,8 @@ class OracleTable:
             kinds = (C.c_int * n)(*[f.kind for f in sc.fields])
             oe = (C.c_int * n)(*[1 if f.omitempty else 0 for f in sc.fields])
             L.orc_add_schema(self._t, sc.id, sc.go_type.encode(), n, go, js, kinds, oe)
+            L.orc_schema_extend(self._t, (C.c_int * n)(*[f.container for f in sc.fields]), (C.c_int * n)(*[f.flags for f in sc.fields]),
+                                (C.c_int * n)(*[f.elem_schema for f in sc.fields]))
         self.route_ids = []
         for r in spec.routes:
             p = r.pattern.encode()
@@ -133,6 +138,12 @@ class OracleTable:
 
     def match(self, method: int, path: bytes) -> int:
         return lib().orc_match(self._t, method, path, len(path))
+
+    def encode_row_json(self, schema_id: int, row: bytes):
+        """JSON text of one handler-result row; None: malformed, b"": not encodable (NaN / Inf)"""
+        out = C.create_string_buffer(64 + 8 * len(row))
+        n = lib().orc_encode_row_json(self._t, schema_id, row, len(row), out, len(out))
+        return None if n == -1 else b"" if n == -2 else out.raw[:n]
 
     def bind(self, schema_id: int, body: bytes):
         out = C.create_string_buffer(len(body) * 4 + 4096)

@@ -1,0 +1,478 @@
+"""Respond's wider data model: float64, nested structs, pointers, slices, map[string]T and bare
+(non-struct) values, encoded as encoding/json does (pkg/gofr/http/responder.go:32-40).
+
+Three independent statements of the same rules are compared:
+  * `go_json` below — Python: dict / list walking, sorted(keys), float text derived from repr() (shortest round-trip
+    digits, like strconv's) re-formatted the way encoding/json's floatEncoder does;
+  * the oracle (oracle/orc_value.c) — C, walks the row, finds shortest digits by printf / strtod search;
+  * the device code (value_device.cuh, float_device.cuh: Ryu) — on the CPU through tests/emu, on the GPU with -m gpu."""
+import math
+import random
+import struct
+from decimal import Decimal
+
+import numpy as np
+import pytest
+
+from gofr_b200 import spec as S
+from gofr_b200.table import Table
+from tests import oracle as O
+from tests.emu import emu as E
+
+DATE = S.http_date(1_700_000_000)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Python model
+# ---------------------------------------------------------------------------------------------------------------
+def go_json_float(x: float) -> str:
+    """encoding/json floatEncoder: strconv.AppendFloat(b, f, 'f' or 'e', -1, 64), 'e' when abs < 1e-6 or abs >= 1e21, and
+    "e-0X" cleaned to "e-X".  "" for NaN / Inf (UnsupportedValueError)."""
+    if x != x or x in (math.inf, -math.inf):
+        return ""
+    if x == 0:
+        return "-0" if math.copysign(1, x) < 0 else "0"
+    sign = "-" if x < 0 else ""
+    t = Decimal(repr(abs(x))).as_tuple()
+    raw = "".join(map(str, t.digits))
+    digs = raw.lstrip("0")
+    exp = t.exponent + len(raw) - 1 - (len(raw) - len(digs))   # decimal exponent of the first significant digit
+    digs = digs.rstrip("0") or "0"
+    if abs(x) < 1e-6 or abs(x) >= 1e21:
+        s = digs[0] + ("." + digs[1:] if len(digs) > 1 else "") + "e" + ("-" if exp < 0 else "+") + "%02d" % abs(exp)
+        if s[-4:-1] == "e-0":
+            s = s[:-2] + s[-1]
+        return sign + s
+    if exp < 0:
+        return sign + "0." + "0" * (-exp - 1) + digs
+    ip = (digs + "0" * (exp + 1))[:exp + 1]
+    fp = digs[exp + 1:]
+    return sign + ip + ("." + fp if fp else "")
+
+
+HTML = {"<": "\\u003c", ">": "\\u003e", "&": "\\u0026", " ": "\\u2028", " ": "\\u2029"}
+
+
+def go_json_string(v) -> str:
+    """encoding/json string with escapeHTML (only for valid UTF-8 input, which is all these tests generate)"""
+    s = v if isinstance(v, str) else bytes(v).decode("utf-8")
+    out = ['"']
+    for ch in s:
+        if ch in HTML:
+            out.append(HTML[ch])
+        elif ch == '"' or ch == "\\":
+            out.append("\\" + ch)
+        elif ch == "\n":
+            out.append("\\n")
+        elif ch == "\r":
+            out.append("\\r")
+        elif ch == "\t":
+            out.append("\\t")
+        elif ord(ch) < 0x20:
+            out.append("\\u%04x" % ord(ch))
+        else:
+            out.append(ch)
+    out.append('"')
+    return "".join(out)
+
+
+class Unencodable(Exception):
+    pass
+
+
+def go_json(spec: S.TableSpec, schema: S.Schema, values) -> str:
+    def scalar(kind, v):
+        if kind in (S.F_INT64, S.F_INT, S.F_INT32):
+            return str(int(v))
+        if kind == S.F_BOOL:
+            return "true" if v else "false"
+        if kind == S.F_FLOAT64:
+            t = go_json_float(v)
+            if not t:
+                raise Unencodable()
+            return t
+        if kind == S.F_STRING:
+            return go_json_string(v)
+        raise AssertionError(kind)
+
+    def t_value(f, v):
+        return go_json(spec, spec.schema(f.elem_schema), v) if f.kind == S.F_STRUCT else scalar(f.kind, v)
+
+    def empty(f, v):
+        if f.container == S.C_PTR:
+            return v is None
+        if f.container in (S.C_SLICE, S.C_MAP):
+            return v is None or len(v) == 0
+        if f.kind == S.F_STRUCT:
+            return False
+        if f.kind == S.F_STRING:
+            return len(v) == 0
+        return v == 0   # False == 0, -0.0 == 0
+
+    def field_value(f, v):
+        if f.container == S.C_VALUE:
+            return t_value(f, v)
+        if v is None:
+            return "null"
+        if f.container == S.C_PTR:
+            return t_value(f, v)
+        if f.container == S.C_SLICE:
+            return "[" + ",".join(t_value(f, e) for e in v) + "]"
+        keys = sorted(v, key=lambda k: k.encode("utf-8") if isinstance(k, str) else bytes(k))
+        return "{" + ",".join(go_json_string(k) + ":" + t_value(f, v[k]) for k in keys) + "}"
+
+    if len(schema.fields) == 1 and schema.fields[0].flags & S.FIELD_BARE:
+        return field_value(schema.fields[0], values[0])
+    parts = []
+    for f, v in zip(schema.fields, values):
+        if f.omitempty and empty(f, v):
+            continue
+        parts.append(go_json_string(f.name) + ":" + field_value(f, v))
+    return "{" + ",".join(parts) + "}"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# floats
+# ---------------------------------------------------------------------------------------------------------------
+def _float_corpus(n, seed):
+    rnd = random.Random(seed)
+    vals = [0.0, -0.0, 1.0, -1.0, 0.1, 0.5, 1e21, 1e20, 9.999999999999999e20, 1e-6, 9.999999999999999e-7, 1e-7, 123456789.125,
+            5e-324, 1.7976931348623157e308, 2.2250738585072014e-308, 2.225073858507201e-308, 100.0, 1e22, 1e23, 3.0e-5,
+            9.5367431640625e-07, float(2 ** 53), float(2 ** 53 + 2), 0.3, 2 / 3, 1 / 3, 4.35, 0.000001, 1234567.0, 1e15, 1e16, 1e17,
+            123456789012345680000.0, 5e-7, 1.5e300, -2.5e-300, 8.41e21, 4.9406564584124654e-324]
+    vals += [2.0 ** k for k in range(-1074, 1024)]
+    vals += [10.0 ** k for k in range(-323, 309)]
+    for _ in range(n):
+        vals.append(struct.unpack("<d", struct.pack("<Q", rnd.getrandbits(64)))[0])
+        vals.append(rnd.uniform(-1e6, 1e6))
+        vals.append(round(rnd.uniform(0, 1000), rnd.randint(0, 6)))
+        vals.append(rnd.uniform(0, 1) * 10.0 ** rnd.randint(-30, 30))
+        vals.append(float(rnd.randint(-10 ** 6, 10 ** 6)))
+    return vals
+
+
+def test_float_text_three_ways():
+    """oracle (printf/strtod search), device code (Ryu) and the Python model (repr digits) write the same text"""
+    vals = _float_corpus(40000, 11)
+    bits = np.array([struct.unpack("<Q", struct.pack("<d", v))[0] for v in vals], dtype=np.uint64)
+    out, off = E.float_text_many(bits)
+    L = O.lib()
+    import ctypes as C
+    buf = C.create_string_buffer(64)
+    for i, v in enumerate(vals):
+        want = go_json_float(v).encode()
+        dev = out[off[i]:off[i + 1]].tobytes()
+        n = L.orc_json_float64(v, buf, 64)
+        assert dev == want, (v, dev, want)
+        assert buf.raw[:n] == want, (v, buf.raw[:n], want)
+
+
+def test_float_text_known_answers():
+    """strconv / encoding/json documented behaviour: the format switch at 1e-6 and 1e21, the e-0X clean-up, shortest digits"""
+    known = {1e21: "1e+21", 1e20: "100000000000000000000", 1e-6: "0.000001", 1e-7: "1e-7", 1.5e-10: "1.5e-10", 0.1: "0.1",
+             100.0: "100", -0.0: "-0", 3.14: "3.14", 1e100: "1e+100", 5e-324: "5e-324", 123456789.0: "123456789",
+             1.7976931348623157e308: "1.7976931348623157e+308", 0.000001234: "0.000001234", 2.5e-7: "2.5e-7"}
+    for v, want in known.items():
+        assert go_json_float(v) == want
+        assert E.float_text(struct.unpack("<Q", struct.pack("<d", v))[0]) == want.encode()
+    for v in (math.nan, math.inf, -math.inf):
+        assert E.float_text(struct.unpack("<Q", struct.pack("<d", v))[0]) == b""
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# schemas and values
+# ---------------------------------------------------------------------------------------------------------------
+ADDR = S.Schema(10, "main.Addr", [S.Field("City", S.F_STRING, "city"), S.Field("Zip", S.F_INT32, "zip", True),
+                                  S.Field("Geo", S.F_FLOAT64, "geo", container=S.C_SLICE)])
+POINT = S.Schema(13, "main.Point", [S.Field("X", S.F_FLOAT64, "x"), S.Field("Y", S.F_FLOAT64, "y"), S.Field("Label", S.F_STRING, "label")])
+USER = S.Schema(11, "main.User", [
+    S.Field("Name", S.F_STRING, "name"), S.Field("Score", S.F_FLOAT64, "score"), S.Field("Home", S.F_STRUCT, "home", elem_schema=10),
+    S.Field("Work", S.F_STRUCT, "work", True, S.C_PTR, 10), S.Field("Tags", S.F_STRING, "tags", False, S.C_SLICE),
+    S.Field("Attrs", S.F_STRING, "attrs", True, S.C_MAP), S.Field("Hist", S.F_STRUCT, "hist", False, S.C_SLICE, 10),
+    S.Field("N", S.F_INT64, "n", True, S.C_PTR), S.Field("Counts", S.F_INT64, "counts", False, S.C_MAP),
+    S.Field("At", S.F_STRUCT, "at", elem_schema=13), S.Field("Ok", S.F_BOOL, "ok")])
+# no omitempty anywhere, plain nested structs only: flattened into one straight-line program at seal time
+SHAPE = S.Schema(14, "main.Shape", [S.Field("ID", S.F_INT64, "id"), S.Field("Centre", S.F_STRUCT, "centre", elem_schema=13),
+                                    S.Field("Area", S.F_FLOAT64, "area"), S.Field("Name", S.F_STRING, "name<>"),
+                                    S.Field("Corner", S.F_STRUCT, "corner", elem_schema=13), S.Field("Closed", S.F_BOOL, "closed")])
+BARE_LIST = S.Schema(12, "[]main.Addr", [S.Field("", S.F_STRUCT, "", container=S.C_SLICE, elem_schema=10, flags=S.FIELD_BARE)])
+BARE_MAP = S.Schema(15, "map[string]string", [S.Field("", S.F_STRING, "", container=S.C_MAP, flags=S.FIELD_BARE)])
+BARE_FLOATS = S.Schema(16, "[]float64", [S.Field("", S.F_FLOAT64, "", container=S.C_SLICE, flags=S.FIELD_BARE)])
+BARE_PTR = S.Schema(17, "*main.Point", [S.Field("", S.F_STRUCT, "", container=S.C_PTR, elem_schema=13, flags=S.FIELD_BARE)])
+DEEP1 = S.Schema(20, "main.D1", [S.Field("V", S.F_FLOAT64, "v", True), S.Field("S", S.F_STRING, "s", True, S.C_SLICE)])
+DEEP2 = S.Schema(21, "main.D2", [S.Field("In", S.F_STRUCT, "in", container=S.C_SLICE, elem_schema=20), S.Field("P", S.F_STRUCT, "p", True, S.C_PTR, 20)])
+DEEP3 = S.Schema(22, "main.D3", [S.Field("A", S.F_STRUCT, "a", elem_schema=21), S.Field("B", S.F_STRUCT, "b", container=S.C_SLICE, elem_schema=21),
+                                  S.Field("M", S.F_FLOAT64, "m", True, S.C_MAP), S.Field("F", S.F_BOOL, "f", True, S.C_PTR),
+                                  S.Field("I32", S.F_INT32, "i32s", False, S.C_SLICE), S.Field("BM", S.F_BOOL, "bm", False, S.C_MAP)])
+SCHEMAS = [ADDR, POINT, USER, SHAPE, BARE_LIST, BARE_MAP, BARE_FLOATS, BARE_PTR, DEEP1, DEEP2, DEEP3]
+ROUTED = [USER, SHAPE, BARE_LIST, BARE_MAP, BARE_FLOATS, BARE_PTR, DEEP3, ADDR]
+
+
+def _spec(mode=S.FRAME_WIRE, kind=S.H_ROW):
+    routes = [S.Route(S.M_GET, "/v/%d" % sc.id, kind, schema_id=sc.id) for sc in ROUTED]
+    return S.TableSpec(frame_mode=mode, schemas=list(SCHEMAS), routes=routes)
+
+
+WORDS = ["", "a", "Paris", "x<y>&z", "tab\there", 'q"uote', "naïve", "日本語", " sep", "long" * 23, "back\\slash", "\x01ctl", "ok"]
+
+
+def _rand_value(rnd, spec, schema, nan_rate=0.0):
+    def fl():
+        if nan_rate and rnd.random() < nan_rate:
+            return rnd.choice([math.nan, math.inf, -math.inf])
+        r = rnd.random()
+        if r < 0.2:
+            return float(rnd.randint(-1000, 1000))
+        if r < 0.4:
+            return round(rnd.uniform(-500, 500), rnd.randint(0, 4))
+        if r < 0.5:
+            return rnd.choice([0.0, -0.0, 1e21, 1e-7, 5e-324, 1e-6])
+        return rnd.uniform(-1, 1) * 10.0 ** rnd.randint(-25, 25)
+
+    def t(f):
+        if f.kind == S.F_STRUCT:
+            return _rand_value(rnd, spec, spec.schema(f.elem_schema), nan_rate)
+        if f.kind == S.F_STRING:
+            return rnd.choice(WORDS)
+        if f.kind == S.F_BOOL:
+            return rnd.random() < 0.5
+        if f.kind == S.F_FLOAT64:
+            return fl()
+        if f.kind == S.F_INT32:
+            return rnd.choice([0, 1, -1, 2 ** 31 - 1, -2 ** 31, rnd.randint(-10 ** 6, 10 ** 6)])
+        return rnd.choice([0, 7, -7, 2 ** 63 - 1, -2 ** 63, rnd.randint(-10 ** 12, 10 ** 12)])
+
+    vals = []
+    for f in schema.fields:
+        if f.container == S.C_VALUE:
+            vals.append(t(f))
+        elif f.container == S.C_PTR:
+            vals.append(None if rnd.random() < 0.35 else t(f))
+        elif f.container == S.C_SLICE:
+            r = rnd.random()
+            vals.append(None if r < 0.2 else [t(f) for _ in range(0 if r < 0.35 else rnd.randint(1, 5))])
+        else:
+            r = rnd.random()
+            if r < 0.2:
+                vals.append(None)
+            else:
+                keys = rnd.sample(["z", "a", "aa", "b<", "é", "Z", "", "a\x00", "k1", "k10", "k2", "日"], 0 if r < 0.35 else rnd.randint(1, 7))
+                vals.append({k: t(f) for k in keys})
+    return vals
+
+
+def _batch(spec, n, seed, nan_rate=0.0, result=False):
+    rnd = random.Random(seed)
+    reqs, want = [], []
+    for i in range(n):
+        sc = ROUTED[rnd.randrange(len(ROUTED))]
+        vals = _rand_value(rnd, spec, sc, nan_rate)
+        row = sc.encode_row(vals, spec.schema)
+        try:
+            body = go_json(spec, sc, vals)
+        except Unencodable:
+            body = None
+        if result:
+            which = rnd.randrange(3)
+            if which == 0:
+                data, body = S.result_record(S.RESULT_DATA, row), None if body is None else '{"data":%s}\n' % body
+            elif which == 1:
+                es = rnd.randrange(3)
+                data, body = S.result_record(S.RESULT_RAW_DATA, row, es), None if body is None else body + "\n"
+            else:
+                msg = rnd.choice(["boom", "bad <thing>", ""])
+                data = S.result_both(sc, vals, msg.encode(), spec.schema)
+                body = None if body is None else '{"error":{"message":%s},"data":%s}\n' % (go_json_string(msg), body)
+        else:
+            data, body = row, None if body is None else '{"data":%s}\n' % body
+        reqs.append(S.Req(S.M_GET, b"/v/%d" % sc.id, b"", data))
+        want.append(body)
+    return S.RequestBatch.pack(reqs, seed=seed), want
+
+
+def _bodies(out, off):
+    ob = out.tobytes()
+    res = []
+    for i in range(len(off) - 1):
+        r = ob[int(off[i]):int(off[i + 1])]
+        head, _, body = r.partition(b"\r\n\r\n")
+        res.append((head, body))
+    return res
+
+
+@pytest.mark.parametrize("mode", [S.FRAME_WIRE, S.FRAME_INTENDED, S.FRAME_BODY])
+@pytest.mark.parametrize("result", [False, True])
+def test_emu_values_match_oracle_and_model(mode, result):
+    spec = _spec(mode, S.H_RESULT if result else S.H_ROW)
+    batch, want = _batch(spec, 700, 5 + mode, nan_rate=0.01, result=result)
+    o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
+    image = Table(spec).serialize()
+    for flush in (0, 2):
+        E.set_flush_mode(flush)
+        try:
+            o2, f2, m2 = E.serve(image, batch, DATE)
+        finally:
+            E.set_flush_mode(0)
+        assert np.array_equal(m1, m2)
+        assert np.array_equal(f1, f2)
+        assert o1[:int(f1[-1])].tobytes() == o2[:int(f1[-1])].tobytes()
+    # the Python model: bodies of the oracle's responses
+    failed = 0
+    for i, (head, body) in enumerate(_bodies(o1, f1)) if mode != S.FRAME_BODY else []:
+        is_head = batch.desc["method"][i] == S.M_HEAD
+        if want[i] is None:      # NaN / Inf: Encode failed — status and headers stand, the body is empty
+            failed += 1
+            assert body == b"" and b"Content-Length: 0" in head, (i, head, body)
+            assert (b"Content-Type: application/json" in head) == (mode == S.FRAME_INTENDED)
+        elif not is_head:
+            assert body.decode("utf-8") == want[i], (i, body, want[i])
+            assert b"Content-Length: %d\r\n" % len(body) in head + b"\r\n"
+    if mode == S.FRAME_BODY:
+        ob = o1.tobytes()
+        for i in range(batch.n):
+            got = ob[int(f1[i]):int(f1[i + 1])]
+            if batch.desc["method"][i] != S.M_HEAD:
+                assert got.decode("utf-8") == (want[i] or ""), i
+    else:
+        assert failed > 0
+
+
+@pytest.mark.parametrize("slot", [512, 4096])
+def test_emu_values_in_slots(slot):
+    spec = _spec()
+    batch, _ = _batch(spec, 500, 77, nan_rate=0.01)
+    o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
+    out, ln, meta = E.serve_slots(Table(spec).serialize(), batch, DATE, slot)
+    assert np.array_equal(meta, m1)
+    want_len = np.diff(f1.astype(np.int64)).astype(np.uint32)
+    assert np.array_equal(ln, want_len)
+    ob = o1.tobytes()
+    for i in range(batch.n):
+        L = int(ln[i])
+        if L <= slot:
+            assert out[i, :L].tobytes() == ob[int(f1[i]):int(f1[i]) + L], i
+    assert (ln > slot).any() == (slot == 512)
+
+
+def test_reference_pin_map_response():
+    """pkg/gofr/http/responder_test.go:23 "map response type": Respond(map[string]string{}, nil) → Content-Type
+    application/json; the body encoding/json writes for an empty map inside the envelope is {"data":{}}"""
+    spec = S.TableSpec(frame_mode=S.FRAME_INTENDED, schemas=[BARE_MAP], routes=[S.Route(S.M_GET, "/m", S.H_ROW, schema_id=15)])
+    rows = [{}, None, {"b": "2", "a": "1"}]
+    batch = S.RequestBatch.pack([S.Req(S.M_GET, b"/m", b"", BARE_MAP.encode_row([r])) for r in rows], seed=1)
+    o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
+    o2, f2, m2 = E.serve(Table(spec).serialize(), batch, DATE)
+    assert np.array_equal(f1, f2) and o1[:int(f1[-1])].tobytes() == o2[:int(f1[-1])].tobytes()
+    got = _bodies(o1, f1)
+    assert [b for _, b in got] == [b'{"data":{}}\n', b'{"data":null}\n', b'{"data":{"a":"1","b":"2"}}\n']
+    assert all(b"Content-Type: application/json\r\n" in h + b"\r\n" for h, _ in got)
+
+
+def test_malformed_rows_answer_like_a_panic():
+    """rows that end before the walk does (a truncated slice, a map entry running off the data section) are not a
+    reference behaviour: both sides answer 500 like middleware.panicRecovery, as for flat rows"""
+    spec = _spec()
+    rnd = random.Random(3)
+    reqs = []
+    for i in range(300):
+        sc = ROUTED[i % len(ROUTED)]
+        row = sc.encode_row(_rand_value(rnd, spec, sc), spec.schema)
+        cut = rnd.randrange(0, len(row) + 1)
+        reqs.append(S.Req(S.M_GET, b"/v/%d" % sc.id, b"", row[:cut]))
+    # counts that promise more than the row holds
+    reqs.append(S.Req(S.M_GET, b"/v/16", b"", (1 << 30).to_bytes(4, "little") + b"\0" * 64))
+    reqs.append(S.Req(S.M_GET, b"/v/15", b"", (0xFFFFFFFE).to_bytes(4, "little") + b"\0" * 64))
+    reqs.append(S.Req(S.M_GET, b"/v/12", b"", (5).to_bytes(4, "little") + b"\0" * 10))
+    batch = S.RequestBatch.pack(reqs, seed=9)
+    o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
+    o2, f2, m2 = E.serve(Table(spec).serialize(), batch, DATE)
+    assert np.array_equal(m1, m2) and np.array_equal(f1, f2) and o1[:int(f1[-1])].tobytes() == o2[:int(f1[-1])].tobytes()
+    assert ((m1 & 0xFFFF) == 500).sum() > 50 and ((m1 & 0xFFFF) == 200).sum() > 5
+
+
+def test_flat_schemas_agree_between_the_two_oracle_encoders():
+    """the row walker (orc_value.c) and the pinned flat-struct encoder (orc_enc_struct) are two code paths of the oracle"""
+    from gofr_b200 import synth
+    spec = synth.config2_spec()
+    t = O.OracleTable(spec)
+    batch = synth.config2_batch(300, escape_every=5)
+    o1, f1, _ = t.serve(batch, DATE)
+    for i, (_, body) in enumerate(_bodies(o1, f1)):
+        off, dl = int(batch.desc["arena_off"][i]), int(batch.desc["data_len"][i])
+        pl, ql = int(batch.desc["path_len"][i]), int(batch.desc["query_len"][i])
+        start = (off + pl + ql + 3) & ~3
+        row = batch.arena[start:start + dl].tobytes()
+        assert body == b'{"data":' + t.encode_row_json(1, row) + b"}\n"
+
+
+def test_schema_validation():
+    def seal(schemas, routes=()):
+        return Table(S.TableSpec(schemas=schemas, routes=list(routes)))
+    with pytest.raises(Exception):   # struct type not added yet (also what a recursive type would need)
+        seal([S.Schema(1, "T", [S.Field("A", S.F_STRUCT, "a", elem_schema=2)])])
+    with pytest.raises(Exception):   # maps of structs
+        seal([POINT, S.Schema(1, "T", [S.Field("A", S.F_STRUCT, "a", container=S.C_MAP, elem_schema=13)])])
+    with pytest.raises(Exception):   # a bare field must be alone
+        seal([S.Schema(1, "T", [S.Field("A", S.F_INT64, "a", flags=S.FIELD_BARE), S.Field("B", S.F_INT64, "b")])])
+    with pytest.raises(Exception):   # Bind takes flat structs only
+        seal([POINT], [S.Route(S.M_POST, "/p", S.H_BIND_ECHO, schema_id=13)])
+    chain = [S.Schema(100, "L0", [S.Field("V", S.F_INT64, "v")])]
+    for k in range(1, 9):
+        chain.append(S.Schema(100 + k, "L%d" % k, [S.Field("C", S.F_STRUCT, "c", container=S.C_PTR, elem_schema=99 + k)]))
+    seal(chain[:8])                  # 8 levels: the walker's frame stack
+    with pytest.raises(Exception):
+        seal(chain)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("result", [False, True])
+def test_gpu_values_match_oracle(result):
+    import torch
+    from gofr_b200.engine import Engine
+    assert torch.cuda.is_available()
+    spec = _spec(S.FRAME_WIRE, S.H_RESULT if result else S.H_ROW)
+    batch, _ = _batch(spec, 6000, 21, nan_rate=0.01, result=result)
+    o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
+    eng = Engine(Table(spec), 0)
+    out, off, meta = eng.serve_device(eng.upload(batch), DATE)
+    assert np.array_equal(meta.cpu().numpy().view(np.uint32), m1)
+    assert np.array_equal(off.cpu().numpy().view(np.uint32), f1)
+    assert out.cpu().numpy()[:int(f1[-1])].tobytes() == o1[:int(f1[-1])].tobytes()
+    slot = 2048
+    canary = torch.full((batch.n * slot,), 0xEE, dtype=torch.uint8, device="cuda")
+    so, sl, sm = eng.serve_device_slots(eng.upload(batch), DATE, slot, out=canary)
+    so = so.cpu().numpy().reshape(batch.n, slot)
+    ln = sl.cpu().numpy().view(np.uint32)
+    assert np.array_equal(ln, np.diff(f1.astype(np.int64)).astype(np.uint32))
+    ob = o1.tobytes()
+    for i in range(batch.n):
+        L = int(ln[i])
+        if L <= slot:
+            assert so[i, :L].tobytes() == ob[int(f1[i]):int(f1[i]) + L], i
+            assert (so[i, L + (-L) % 16:] == 0xEE).all(), i
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_float_text_matches_python_repr():
+    """the Ryu digits as the GPU computes them (__umul64hi, device tables): a bare []float64 route carries the corpus"""
+    import torch
+    from gofr_b200.engine import Engine
+    spec = S.TableSpec(frame_mode=S.FRAME_BODY, schemas=[BARE_FLOATS], routes=[S.Route(S.M_GET, "/f", S.H_ROW, schema_id=16)])
+    vals = [v for v in _float_corpus(20000, 23)]
+    per = 50
+    reqs, want = [], []
+    for k in range(0, len(vals), per):
+        chunk = vals[k:k + per]
+        reqs.append(S.Req(S.M_GET, b"/f", b"", BARE_FLOATS.encode_row([chunk])))
+        want.append(('{"data":[' + ",".join(go_json_float(v) for v in chunk) + "]}\n").encode())
+    batch = S.RequestBatch.pack(reqs, seed=4)
+    eng = Engine(Table(spec), 0)
+    out, off, meta = eng.serve_device(eng.upload(batch), DATE)
+    ob, f = out.cpu().numpy().tobytes(), off.cpu().numpy().view(np.uint32)
+    for i, w in enumerate(want):
+        assert ob[int(f[i]):int(f[i + 1])] == w, i
+    eng.close()
