@@ -3,6 +3,7 @@
 // Prints one line per case — "<status>\t<body>" — which tests/test_cpp_app.py compares with the oracle; exits non-zero
 // when a response is not what the reference's test expects.
 //   g++ -std=c++17 -Iinclude examples/cpp/server_routes.cpp gofr_b200/libgofr_b200.so -o server_routes
+#include <cmath>
 #include <cstdio>
 #include <string>
 
@@ -56,6 +57,22 @@ int main() {
     g.GET("/rawnil", [](gofr::Context&) -> gofr::Result { return gofr::Raw(); });
     g.GET("/rawperson", [&](gofr::Context&) -> gofr::Result { return gofr::Raw(gofr::Data(person({int64_t(9), std::string("raw"), true}))); }, &person);
     g.GET("/rawerr", [](gofr::Context&) -> gofr::Result { return gofr::Result(gofr::Raw("x"), gofr::Error{"ignored"}); });
+    // what encoding/json does with the rest of Go's data model (responder.go:32-40): float64, nested structs, pointers,
+    // slices, map[string]T, a handler returning a slice rather than a struct; NaN makes Encode fail (no body)
+    auto& addr = g.Struct("main.Addr").String("City", "city").Int32("Zip", "zip", true).Float64("Geo", "geo").Slice();
+    auto& user = g.Struct("main.User").String("Name", "name").Float64("Score", "score").Struct("Home", addr, "home")
+                     .Struct("Work", addr, "work", true).Ptr().String("Tags", "tags").Slice().String("Attrs", "attrs", true).MapOf();
+    auto& addrs = g.Bare("[]main.Addr").Struct("", addr).Slice();
+    g.GET("/user/{name}", [&](gofr::Context& c) -> gofr::Result {
+        const std::string n = c.PathParam("name");
+        if (n == "nan") return gofr::Data(user({n, std::nan(""), addr({"", 0, gofr::Nil{}}), gofr::Nil{}, gofr::Nil{}, gofr::Nil{}}));
+        return gofr::Data(user({n, 1.5e-7, addr({"Paris", 75001, gofr::List{48.8566, 2.3522}}), addr({"Lyon", 0, gofr::List{}}),
+                                gofr::List{"a", "b<c>"}, gofr::Map{{{"z", "1"}, {"a", "2"}}}}));
+    }, &user);
+    g.GET("/addrs", [&](gofr::Context& c) -> gofr::Result {
+        if (c.Param("none") == "1") return gofr::Data(addrs({gofr::Nil{}}));
+        return gofr::Data(addrs({gofr::List{addr({"X", 7, gofr::Nil{}}), addr({"Y", 0, gofr::List{1e21, -0.0}})}}));
+    }, &addrs);
 
     g.Run(0);
 
@@ -95,6 +112,11 @@ int main() {
         {"GET", "/rawnil", "", 200, "null\n"},
         {"GET", "/rawperson", "", 200, "{\"id\":9,\"name\":\"raw\",\"admin\":true}\n"},
         {"GET", "/rawerr", "", 500, "\"x\"\n"},
+        {"GET", "/user/bob", "", 200, "{\"data\":{\"name\":\"bob\",\"score\":1.5e-7,\"home\":{\"city\":\"Paris\",\"zip\":75001,\"geo\":[48.8566,2.3522]},"
+                                      "\"work\":{\"city\":\"Lyon\",\"geo\":[]},\"tags\":[\"a\",\"b\\u003cc\\u003e\"],\"attrs\":{\"a\":\"2\",\"z\":\"1\"}}}\n"},
+        {"GET", "/user/nan", "", 200, ""},
+        {"GET", "/addrs", "", 200, "{\"data\":[{\"city\":\"X\",\"zip\":7,\"geo\":null},{\"city\":\"Y\",\"geo\":[1e+21,-0]}]}\n"},
+        {"GET", "/addrs?none=1", "", 200, "{\"data\":null}\n"},
     };
     std::vector<gofr::App::Request> reqs;
     for (auto& c : cases) {

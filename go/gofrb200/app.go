@@ -23,6 +23,7 @@ import (
 	"encoding/json"
 	"errors"
 	"io"
+	"math"
 	"net/http"
 	"reflect"
 	"strings"
@@ -82,6 +83,8 @@ type App struct {
 	engine  *Engine
 	routes  []route
 	schemas map[reflect.Type]uint32
+	order   []reflect.Type // registration order: a struct type comes after the struct types its fields use
+	regErr  error          // first type the GPU encoder does not model (reported by Run)
 }
 
 // New is gofr.New() (pkg/gofr/gofr.go:49-73) without config, container and servers other than the HTTP path.
@@ -106,12 +109,7 @@ func (a *App) add(method, pattern string, h HandlerFunc, returns ...interface{})
 	r := route{method: method, pattern: pattern, fn: h, vars: templateVars(pattern)}
 	if len(returns) > 0 {
 		r.rtype = reflect.TypeOf(returns[0])
-		id, ok := a.schemas[r.rtype]
-		if !ok {
-			id = uint32(len(a.schemas) + 1)
-			a.schemas[r.rtype] = id
-		}
-		r.schemaID = id
+		r.schemaID = a.register(r.rtype, map[reflect.Type]bool{})
 	}
 	a.routes = append(a.routes, r)
 }
@@ -143,53 +141,153 @@ func templateVars(pattern string) []string {
 	return names
 }
 
-// fieldKind maps a Go field type to GOFR_F_*; 0 = not supported by the GPU encoder.
-func fieldKind(t reflect.Type) uint8 {
+const (
+	cValue = 0 // GOFR_C_*: T, *T, []T, map[string]T
+	cPtr   = 1
+	cSlice = 2
+	cMap   = 3
+	fStruct   = 7
+	fieldBare = 1
+	nilCount  = 0xFFFFFFFF
+)
+
+// typeDesc resolves a Go type to (GOFR_F_* kind, GOFR_C_* container, struct type of a GOFR_F_STRUCT).  ok = false: a type the
+// GPU encoder does not model ([]byte, interface{}, [][]T, maps of structs or with non-string keys, unsigned and 8/16-bit
+// integers, float32, arrays, channels ...): such a route stays on the host path.
+func typeDesc(t reflect.Type) (kind, container uint8, elem reflect.Type, ok bool) {
+	switch t.Kind() {
+	case reflect.Ptr:
+		container, t = cPtr, t.Elem()
+	case reflect.Slice:
+		if t.Elem().Kind() == reflect.Uint8 {
+			return 0, 0, nil, false // []byte is base64 in encoding/json
+		}
+		container, t = cSlice, t.Elem()
+	case reflect.Map:
+		if t.Key().Kind() != reflect.String {
+			return 0, 0, nil, false
+		}
+		container, t = cMap, t.Elem()
+	}
 	switch t.Kind() {
 	case reflect.Int64:
-		return 1
+		kind = 1
 	case reflect.Int32:
-		return 2
+		kind = 2
 	case reflect.Bool:
-		return 3
+		kind = 3
 	case reflect.String:
-		return 4
+		kind = 4
 	case reflect.Int:
-		return 5
+		kind = 5
+	case reflect.Float64:
+		kind = 6
+	case reflect.Struct:
+		if container == cMap {
+			return 0, 0, nil, false
+		}
+		kind, elem = fStruct, t
+	default:
+		return 0, 0, nil, false
 	}
-	return 0
+	return kind, container, elem, true
+}
+
+// register gives t (a struct type, or a non-struct type a handler returns: a "bare" schema) a schema id, registering the
+// struct types below it first.  Recursive types (a struct reaching itself through a pointer or a slice) are refused: the
+// device walker has a fixed frame stack.
+func (a *App) register(t reflect.Type, visiting map[reflect.Type]bool) uint32 {
+	if id, ok := a.schemas[t]; ok {
+		return id
+	}
+	fail := func(msg string) uint32 {
+		if a.regErr == nil {
+			a.regErr = errors.New("gofrb200: " + t.String() + ": " + msg)
+		}
+		return 0
+	}
+	if visiting[t] {
+		return fail("recursive type")
+	}
+	visiting[t] = true
+	defer delete(visiting, t)
+	if t.Kind() == reflect.Struct {
+		for i := 0; i < t.NumField(); i++ {
+			f := t.Field(i)
+			if name, _, _ := strings.Cut(f.Tag.Get("json"), ","); name == "-" {
+				continue
+			}
+			if f.PkgPath != "" || f.Anonymous {
+				return fail("field " + f.Name + ": unexported and embedded fields are not modelled")
+			}
+			_, _, elem, ok := typeDesc(f.Type)
+			if !ok {
+				return fail("field " + f.Name + ": type not supported by the GPU encoder")
+			}
+			if elem != nil && a.register(elem, visiting) == 0 {
+				return 0
+			}
+		}
+	} else {
+		_, _, elem, ok := typeDesc(t)
+		if !ok {
+			return fail("type not supported by the GPU encoder")
+		}
+		if elem != nil && a.register(elem, visiting) == 0 {
+			return 0
+		}
+	}
+	id := uint32(len(a.schemas) + 1)
+	a.schemas[t] = id
+	a.order = append(a.order, t)
+	return id
 }
 
 // Run is App.Run (pkg/gofr/gofr.go:90-126) minus the listener: struct types, routes, default routes, seal, engine.
 func (a *App) Run(device int, favicon []byte) error {
-	for t, id := range a.schemas {
-		n := t.NumField()
-		fields := make([]C.gofr_field_desc, 0, n)
+	if a.regErr != nil {
+		return a.regErr
+	}
+	for _, t := range a.order {
+		id := a.schemas[t]
+		var fields []C.gofr_field_desc
 		var keep []unsafe.Pointer
-		for i := 0; i < n; i++ {
-			f := t.Field(i)
-			kind := fieldKind(f.Type)
-			if kind == 0 || f.PkgPath != "" {
-				return errors.New("gofrb200: " + t.String() + "." + f.Name + ": field type not supported by the GPU encoder")
-			}
-			name, opts, _ := strings.Cut(f.Tag.Get("json"), ",")
+		desc := func(goName, jsonName string, ft reflect.Type, omitempty bool, flags uint8) {
+			kind, container, elem, _ := typeDesc(ft)
 			var d C.gofr_field_desc
-			d.go_name = C.CString(f.Name)
-			d.json_name = C.CString(name)
+			d.go_name = C.CString(goName)
+			d.json_name = C.CString(jsonName)
 			keep = append(keep, unsafe.Pointer(d.go_name), unsafe.Pointer(d.json_name))
 			d.kind = C.uint8_t(kind)
-			if strings.Contains(","+opts+",", ",omitempty,") {
+			d.container = C.uint8_t(container)
+			d.flags = C.uint8_t(flags)
+			if elem != nil {
+				d.elem_schema = C.uint16_t(a.schemas[elem])
+			}
+			if omitempty {
 				d.omitempty = 1
 			}
 			fields = append(fields, d)
 		}
+		if t.Kind() == reflect.Struct {
+			for i := 0; i < t.NumField(); i++ {
+				f := t.Field(i)
+				name, opts, _ := strings.Cut(f.Tag.Get("json"), ",")
+				if name == "-" {
+					continue
+				}
+				desc(f.Name, name, f.Type, strings.Contains(","+opts+",", ",omitempty,"), 0)
+			}
+		} else {
+			desc("", "", t, false, fieldBare)
+		}
 		tn := C.CString(t.String())
 		keep = append(keep, unsafe.Pointer(tn))
 		var fp *C.gofr_field_desc
-		if n > 0 {
+		if len(fields) > 0 {
 			fp = &fields[0]
 		}
-		err := check(C.gofr_table_add_schema(a.table.t, C.uint32_t(id), tn, fp, C.uint32_t(n)), "gofr_table_add_schema")
+		err := check(C.gofr_table_add_schema(a.table.t, C.uint32_t(id), tn, fp, C.uint32_t(len(fields))), "gofr_table_add_schema")
 		for _, p := range keep {
 			C.free(p)
 		}
@@ -234,27 +332,118 @@ func pad4(b []byte) []byte {
 
 func u32(b []byte, v uint32) []byte { return binary.LittleEndian.AppendUint32(b, v) }
 
-// encodeRow lays a struct value out as a GOFR_H_ROW row: fixed words in field order, then the string bytes.
-func encodeRow(v reflect.Value) (fixed, strs []byte) {
-	for i := 0; i < v.NumField(); i++ {
-		f := v.Field(i)
-		switch f.Kind() {
-		case reflect.Int64, reflect.Int:
-			fixed = binary.LittleEndian.AppendUint64(fixed, uint64(f.Int()))
-		case reflect.Int32:
-			fixed = u32(fixed, uint32(int32(f.Int())))
-		case reflect.Bool:
-			if f.Bool() {
-				fixed = u32(fixed, 1)
-			} else {
-				fixed = u32(fixed, 0)
-			}
-		case reflect.String:
-			fixed = u32(fixed, uint32(f.Len()))
-			strs = append(strs, f.String()...)
+// scalarWords appends the fixed words of a scalar (include/gofr_b200.h "Row format").
+func scalarWords(b []byte, v reflect.Value) []byte {
+	switch v.Kind() {
+	case reflect.Int64, reflect.Int:
+		return binary.LittleEndian.AppendUint64(b, uint64(v.Int()))
+	case reflect.Int32:
+		return u32(b, uint32(int32(v.Int())))
+	case reflect.Bool:
+		if v.Bool() {
+			return u32(b, 1)
 		}
+		return u32(b, 0)
+	case reflect.Float64:
+		return binary.LittleEndian.AppendUint64(b, math.Float64bits(v.Float()))
 	}
-	return fixed, strs
+	return b
+}
+
+// fixedBytes is the size of the fixed words a field of type t owns.
+func fixedBytes(t reflect.Type) int {
+	switch t.Kind() {
+	case reflect.Slice, reflect.Map:
+		return 4
+	case reflect.Ptr:
+		return 4 + fixedBytes(t.Elem())
+	case reflect.Struct:
+		n := 0
+		for i := 0; i < t.NumField(); i++ {
+			if name, _, _ := strings.Cut(t.Field(i).Tag.Get("json"), ","); name != "-" {
+				n += fixedBytes(t.Field(i).Type)
+			}
+		}
+		return n
+	case reflect.Int64, reflect.Int, reflect.Float64:
+		return 8
+	}
+	return 4
+}
+
+// encodePlain: a T by value — its fixed words to fixed, its variable part to vars.
+func encodePlain(v reflect.Value, fixed, vars []byte) ([]byte, []byte) {
+	switch v.Kind() {
+	case reflect.String:
+		return u32(fixed, uint32(v.Len())), append(vars, v.String()...)
+	case reflect.Struct:
+		return encodeRow(v, fixed, vars)
+	}
+	return scalarWords(fixed, v), vars
+}
+
+// encodeElement: E(T), an element of a slice or map, entirely in the variable part.
+func encodeElement(v reflect.Value, vars []byte) []byte {
+	switch v.Kind() {
+	case reflect.String:
+		return append(u32(vars, uint32(v.Len())), v.String()...)
+	case reflect.Struct:
+		fx, vr := encodeRow(v, nil, nil)
+		return append(append(vars, fx...), vr...)
+	}
+	return scalarWords(vars, v)
+}
+
+// encodeField: one field (or the bare value of a non-struct type).
+func encodeField(f reflect.Value, fixed, vars []byte) ([]byte, []byte) {
+	switch f.Kind() {
+	case reflect.Ptr:
+		if f.IsNil() {
+			return append(fixed, make([]byte, fixedBytes(f.Type()))...), vars
+		}
+		return encodePlain(f.Elem(), u32(fixed, 1), vars)
+	case reflect.Slice:
+		if f.IsNil() {
+			return u32(fixed, nilCount), vars
+		}
+		fixed = u32(fixed, uint32(f.Len()))
+		for i := 0; i < f.Len(); i++ {
+			vars = encodeElement(f.Index(i), vars)
+		}
+		return fixed, vars
+	case reflect.Map:
+		if f.IsNil() {
+			return u32(fixed, nilCount), vars
+		}
+		fixed = u32(fixed, uint32(f.Len()))
+		it := f.MapRange() // any order: the device sorts the keys like encoding/json does
+		for it.Next() {
+			k := it.Key().String()
+			vars = encodeElement(it.Value(), append(u32(vars, uint32(len(k))), k...))
+		}
+		return fixed, vars
+	}
+	return encodePlain(f, fixed, vars)
+}
+
+// encodeRow lays a struct value out as a handler-result row: fixed words in field order, then the variable part.
+func encodeRow(v reflect.Value, fixed, vars []byte) ([]byte, []byte) {
+	t := v.Type()
+	for i := 0; i < v.NumField(); i++ {
+		if name, _, _ := strings.Cut(t.Field(i).Tag.Get("json"), ","); name == "-" {
+			continue
+		}
+		fixed, vars = encodeField(v.Field(i), fixed, vars)
+	}
+	return fixed, vars
+}
+
+// encodeValue: a value of a registered type — a struct, or the bare value of a non-struct type.
+func encodeValue(v reflect.Value) (fixed, vars []byte) {
+	if v.Kind() == reflect.Struct {
+		return encodeRow(v, nil, nil)
+	}
+	return encodeField(v, nil, nil)
 }
 
 // resultRecord describes (data, err) for Responder.Respond (pkg/gofr/http/responder.go:19-62) as a GOFR_H_RESULT record.
@@ -274,7 +463,7 @@ func (a *App) resultRecord(r *route, data interface{}, err error) []byte {
 		case raw.Data == nil:
 			rec = u32(rec, resultRawNil|es<<8)
 		case r.rtype != nil && rv.Type() == r.rtype:
-			fixed, strs := encodeRow(rv)
+			fixed, strs := encodeValue(rv)
 			rec = append(append(u32(rec, resultRawData|es<<8), fixed...), strs...)
 		default:
 			if s, ok := raw.Data.(string); ok {
@@ -289,12 +478,12 @@ func (a *App) resultRecord(r *route, data interface{}, err error) []byte {
 	isStruct := data != nil && r.rtype != nil && rv.Type() == r.rtype
 	switch {
 	case isStruct && err != nil:
-		fixed, strs := encodeRow(rv)
+		fixed, strs := encodeValue(rv)
 		msg := err.Error()
 		rec = u32(u32(rec, resultBoth), uint32(len(msg)))
 		rec = append(append(append(rec, fixed...), msg...), strs...)
 	case isStruct:
-		fixed, strs := encodeRow(rv)
+		fixed, strs := encodeValue(rv)
 		rec = append(append(u32(rec, resultData), fixed...), strs...)
 	case err != nil:
 		kind := uint32(resultError)

@@ -45,11 +45,32 @@ struct Error {
 };
 inline Error ErrMissingFile() { return Error{"http: no such file", true}; }
 
-// A value of a struct type registered with App::Struct (fields in declaration order).
-using Value = std::variant<int64_t, bool, std::string>;
+// A value of a struct type registered with App::Struct (fields in declaration order).  A field holds what its type says:
+// int64_t / bool / std::string / double for the scalar kinds, a StructValue for a nested struct, Nil for a nil pointer,
+// slice or map, a List for []T and a Map for map[string]T (a *T that is not nil is just the T).
+struct Value;
+struct Nil {};
+using List = std::vector<Value>;
 struct StructValue {
     uint32_t type_id = 0;
     std::vector<Value> fields;
+};
+struct Map {
+    std::vector<std::pair<std::string, Value>> entries;  // any order: the encoder sorts like encoding/json does
+};
+struct Value {
+    std::variant<int64_t, bool, std::string, double, Nil, StructValue, List, Map> v;
+    Value() : v(int64_t(0)) {}
+    Value(int64_t x) : v(x) {}
+    Value(int x) : v(int64_t(x)) {}
+    Value(bool x) : v(x) {}
+    Value(double x) : v(x) {}
+    Value(std::string x) : v(std::move(x)) {}
+    Value(const char* x) : v(std::string(x)) {}
+    Value(Nil x) : v(x) {}
+    Value(StructValue x) : v(std::move(x)) {}
+    Value(List x) : v(std::move(x)) {}
+    Value(Map x) : v(std::move(x)) {}
 };
 // interface{} as handlers of this path return it: nil, a string, or a registered struct.
 using Data = std::variant<std::monostate, std::string, StructValue>;
@@ -203,16 +224,28 @@ public:
         StructType& Int32(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_INT32, json, omitempty); }
         StructType& Bool(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_BOOL, json, omitempty); }
         StructType& String(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_STRING, json, omitempty); }
+        StructType& Float64(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_FLOAT64, json, omitempty); }
+        // a field of a struct type registered BEFORE this one
+        StructType& Struct(const char* go, const StructType& of, const char* json = "", bool omitempty = false) {
+            add(go, GOFR_F_STRUCT, json, omitempty);
+            fields_.back().elem = of.id_;
+            return *this;
+        }
+        // the field added last is a *T / []T / map[string]T of the kind it was added with
+        StructType& Ptr() { fields_.back().container = GOFR_C_PTR; return *this; }
+        StructType& Slice() { fields_.back().container = GOFR_C_SLICE; return *this; }
+        StructType& MapOf() { fields_.back().container = GOFR_C_MAP; return *this; }
         uint32_t id() const { return id_; }
         StructValue operator()(std::vector<Value> fields) const { return StructValue{id_, std::move(fields)}; }
 
     private:
         friend class App;
-        struct F { std::string go, json; uint32_t kind; bool omitempty; };
+        struct F { std::string go, json; uint32_t kind; bool omitempty; uint32_t container = GOFR_C_VALUE, elem = 0; };
         StructType& add(const char* go, uint32_t kind, const char* json, bool omitempty) {
             fields_.push_back(F{go, json, kind, omitempty});
             return *this;
         }
+        bool bare_ = false;  // App::Bare: the one field stands for the type itself
         uint32_t id_ = 0;
         std::string go_type_;
         std::vector<F> fields_;
@@ -232,6 +265,14 @@ public:
         types_.back()->id_ = (uint32_t)types_.size();  // ids start at 1: 0 means "no struct type"
         types_.back()->go_type_ = go_type;
         return *types_.back();
+    }
+
+    // a non-struct type some handler returns: app.Bare("[]main.Addr").Struct("", addr).Slice(), app.Bare("map[string]string")
+    // .String("").MapOf(), app.Bare("[]float64").Float64("").Slice().  Its values are StructValues with that one field.
+    StructType& Bare(const std::string& go_type) {
+        StructType& t = Struct(go_type);
+        t.bare_ = true;
+        return t;
     }
 
     void GET(const std::string& pattern, Handler h, const StructType* returns = nullptr) { add("GET", pattern, std::move(h), returns); }
@@ -262,6 +303,9 @@ public:
                 fd[i].json_name = t->fields_[i].json.c_str();
                 fd[i].kind = t->fields_[i].kind;
                 fd[i].omitempty = t->fields_[i].omitempty ? 1 : 0;
+                fd[i].container = (uint8_t)t->fields_[i].container;
+                fd[i].elem_schema = (uint16_t)t->fields_[i].elem;
+                fd[i].flags = t->bare_ ? GOFR_FIELD_BARE : 0;
             }
             check(gofr_table_add_schema(table_, t->id_, t->go_type_.c_str(), fd.data(), (uint32_t)fd.size()), "gofr_table_add_schema");
         }
@@ -522,27 +566,101 @@ private:
         return rec;
     }
 
-    bool encode_struct(const StructValue& sv, std::string* fixed, std::string* strings) const {
-        const StructType* t = nullptr;
-        for (auto& ty : types_) if (ty->id_ == sv.type_id) t = ty.get();
+    const StructType* type_of(uint32_t id) const {
+        for (auto& ty : types_) if (ty->id_ == id) return ty.get();
+        return nullptr;
+    }
+    static bool scalar_words(uint32_t kind, const Value& v, std::string* out) {
+        if (kind == GOFR_F_BOOL) {
+            auto* b = std::get_if<bool>(&v.v);
+            if (!b) return false;
+            detail::put_u32(out, *b ? 1u : 0u);
+        } else if (kind == GOFR_F_FLOAT64) {
+            double d;
+            if (auto* x = std::get_if<double>(&v.v)) d = *x;
+            else if (auto* i = std::get_if<int64_t>(&v.v)) d = (double)*i;
+            else return false;
+            uint64_t bits;
+            memcpy(&bits, &d, 8);
+            detail::put_u32(out, (uint32_t)bits);
+            detail::put_u32(out, (uint32_t)(bits >> 32));
+        } else {
+            auto* x = std::get_if<int64_t>(&v.v);
+            if (!x) return false;
+            if (kind == GOFR_F_INT32) detail::put_u32(out, (uint32_t)(int32_t)*x);
+            else { detail::put_u32(out, (uint32_t)(uint64_t)*x); detail::put_u32(out, (uint32_t)((uint64_t)*x >> 32)); }
+        }
+        return true;
+    }
+    // T by value: its fixed words to `fixed`, its variable part to `var` (include/gofr_b200.h "Row format")
+    bool encode_plain(const StructType::F& f, const Value& v, std::string* fixed, std::string* var) const {
+        if (f.kind == GOFR_F_STRING) {
+            auto* s = std::get_if<std::string>(&v.v);
+            if (!s) return false;
+            detail::put_u32(fixed, (uint32_t)s->size());
+            *var += *s;
+            return true;
+        }
+        if (f.kind == GOFR_F_STRUCT) {
+            auto* sv = std::get_if<StructValue>(&v.v);
+            return sv && sv->type_id == f.elem && encode_struct(*sv, fixed, var);
+        }
+        return scalar_words(f.kind, v, fixed);
+    }
+    // E(T): an element of a slice / map, entirely in the variable part
+    bool encode_element(const StructType::F& f, const Value& v, std::string* var) const {
+        if (f.kind == GOFR_F_STRING) {
+            auto* s = std::get_if<std::string>(&v.v);
+            if (!s) return false;
+            detail::put_u32(var, (uint32_t)s->size());
+            *var += *s;
+            return true;
+        }
+        if (f.kind == GOFR_F_STRUCT) {
+            auto* sv = std::get_if<StructValue>(&v.v);
+            std::string fx, vr;
+            if (!sv || sv->type_id != f.elem || !encode_struct(*sv, &fx, &vr)) return false;
+            *var += fx;
+            *var += vr;
+            return true;
+        }
+        return scalar_words(f.kind, v, var);
+    }
+    size_t fixed_bytes(const StructType::F& f) const {
+        if (f.container == GOFR_C_SLICE || f.container == GOFR_C_MAP) return 4;
+        size_t n = (f.kind == GOFR_F_INT64 || f.kind == GOFR_F_INT || f.kind == GOFR_F_FLOAT64) ? 8 : 4;
+        if (f.kind == GOFR_F_STRUCT) {
+            n = 0;
+            if (const StructType* t = type_of(f.elem)) for (auto& g : t->fields_) n += fixed_bytes(g);
+        }
+        return n + (f.container == GOFR_C_PTR ? 4 : 0);
+    }
+    bool encode_struct(const StructValue& sv, std::string* fixed, std::string* var) const {
+        const StructType* t = type_of(sv.type_id);
         if (!t || t->fields_.size() != sv.fields.size()) return false;
         for (size_t i = 0; i < sv.fields.size(); i++) {
-            const uint32_t kind = t->fields_[i].kind;
+            const StructType::F& f = t->fields_[i];
             const Value& v = sv.fields[i];
-            if (kind == GOFR_F_STRING) {
-                auto* s = std::get_if<std::string>(&v);
-                if (!s) return false;
-                detail::put_u32(fixed, (uint32_t)s->size());
-                *strings += *s;
-            } else if (kind == GOFR_F_BOOL) {
-                auto* b = std::get_if<bool>(&v);
-                if (!b) return false;
-                detail::put_u32(fixed, *b ? 1u : 0u);
+            const bool nil = std::holds_alternative<Nil>(v.v);
+            if (f.container == GOFR_C_VALUE) {
+                if (!encode_plain(f, v, fixed, var)) return false;
+            } else if (f.container == GOFR_C_PTR) {
+                if (nil) fixed->append(fixed_bytes(f), '\0');
+                else { detail::put_u32(fixed, 1); if (!encode_plain(f, v, fixed, var)) return false; }
+            } else if (f.container == GOFR_C_SLICE) {
+                auto* l = std::get_if<List>(&v.v);
+                if (!nil && !l) return false;
+                detail::put_u32(fixed, nil ? GOFR_NIL_COUNT : (uint32_t)l->size());
+                if (l) for (auto& e : *l) if (!encode_element(f, e, var)) return false;
             } else {
-                auto* x = std::get_if<int64_t>(&v);
-                if (!x) return false;
-                if (kind == GOFR_F_INT32) detail::put_u32(fixed, (uint32_t)(int32_t)*x);
-                else { detail::put_u32(fixed, (uint32_t)(uint64_t)*x); detail::put_u32(fixed, (uint32_t)((uint64_t)*x >> 32)); }
+                auto* m = std::get_if<Map>(&v.v);
+                if (!nil && !m) return false;
+                detail::put_u32(fixed, nil ? GOFR_NIL_COUNT : (uint32_t)m->entries.size());
+                if (m) for (auto& kv : m->entries) {
+                    detail::put_u32(var, (uint32_t)kv.first.size());
+                    *var += kv.first;
+                    if (!encode_element(f, kv.second, var)) return false;
+                }
             }
         }
         return true;

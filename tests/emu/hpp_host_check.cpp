@@ -46,6 +46,29 @@ int main() {
             const std::string rec = app.ResultRecord(res, ty);
             for (unsigned char ch : rec) printf("%02x", ch);
             printf("\n");
+        } else if (kind == "V") {
+            // V <case>: rows of the wider data model (nested struct, pointer, slice, map, float64, bare slice), hex
+            using gofr::List; using gofr::Map; using gofr::Nil; using gofr::Value;
+            static gofr::App app;
+            static auto& addr = app.Struct("main.Addr").String("City", "city").Int32("Zip", "zip", true).Float64("Geo", "geo").Slice();
+            static auto& user = app.Struct("main.User").String("Name", "name").Float64("Score", "score").Struct("Home", addr, "home")
+                                    .Struct("Work", addr, "work", true).Ptr().String("Tags", "tags").Slice().String("Attrs", "attrs", true).MapOf()
+                                    .Struct("Hist", addr, "hist").Slice().Int64("N", "n", true).Ptr().Int64("Counts", "counts").MapOf();
+            static auto& addrs = app.Bare("[]main.Addr").Struct("", addr).Slice();
+            const int c = atoi(a.c_str());
+            gofr::Result res;
+            const gofr::App::StructType* ty = &user;
+            if (c == 0) res = gofr::Result(gofr::Data(user({"bo<b>", 1.5e-7, addr({"Paris", 0, List{1.0, 2.5}}), Nil{}, List{"a", "b\n"},
+                                                            Map{{{"z", "1"}, {"a", "2"}, {"aa", "3"}}}, List{addr({"X", 7, Nil{}}), addr({"Y", 0, List{}})},
+                                                            int64_t(5), Nil{}})));
+            else if (c == 1) res = gofr::Result(gofr::Data(user({"", 0.0, addr({"", 0, Nil{}}), addr({"W", 1, List{-0.5}}), Nil{}, Nil{}, Nil{}, Nil{},
+                                                                 Map{{{"k", int64_t(-1)}}}})));
+            else if (c == 2) { ty = &addrs; res = gofr::Result(gofr::Data(addrs({List{addr({"X", 7, Nil{}}), addr({"Y", 2, List{3.25}})}}))); }
+            else if (c == 3) { ty = &addrs; res = gofr::Result(gofr::Data(addrs({Nil{}}))); }
+            else if (c == 4) res = gofr::Result(gofr::Data(user({"n", 1.0, addr({"P", 0, Nil{}}), "not a struct", Nil{}, Nil{}, Nil{}, Nil{}, Nil{}})));  // wrong kind
+            const std::string rec = app.ResultRecord(res, ty);
+            for (unsigned char ch : rec) printf("%02x", ch);
+            printf("\n");
         } else if (kind == "P") {
             std::string path, query;
             bool force = false;

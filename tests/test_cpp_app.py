@@ -45,6 +45,7 @@ def test_header_compiles_and_host_helpers_match_oracle(tmp_path):
     tmpl = ["/a/{id}/b/{name:[a-z]+}", "/{x:[0-9]{2}}/{y}", "/plain", "/{a}-{b}.{c}", "/{v:.*}"]
     lines += "".join("T %s\n" % t.encode().hex() for t in tmpl)
     lines += "".join("R %d\n" % c for c in range(10))
+    lines += "".join("V %d\n" % c for c in range(5))
     # request targets: path unescaping, the first '?' splits, a lone trailing '?' is ForceQuery, bad escapes are refused
     import re
     import urllib.parse
@@ -67,7 +68,22 @@ def test_header_compiles_and_host_helpers_match_oracle(tmp_path):
             S.result_both(item, ["", 0, 0, False, 0, ""], b"partial"), bad, bad, bad, S.result_record(S.RESULT_ERROR, b"e")]
     got = [bytes.fromhex(l) for l in out[len(cases) + 5:len(cases) + 15]]
     assert got == want
-    for t, line in zip(targets, out[len(cases) + 15:]):
+    # rows of the wider data model (include/gofr_b200.h "Row format") against the Python packer
+    addr = S.Schema(1, "main.Addr", [S.Field("City", S.F_STRING, "city"), S.Field("Zip", S.F_INT32, "zip", True),
+                                     S.Field("Geo", S.F_FLOAT64, "geo", container=S.C_SLICE)])
+    user = S.Schema(2, "main.User", [S.Field("Name", S.F_STRING, "name"), S.Field("Score", S.F_FLOAT64, "score"), S.Field("Home", S.F_STRUCT, "home", elem_schema=1),
+                                     S.Field("Work", S.F_STRUCT, "work", True, S.C_PTR, 1), S.Field("Tags", S.F_STRING, "tags", False, S.C_SLICE),
+                                     S.Field("Attrs", S.F_STRING, "attrs", True, S.C_MAP), S.Field("Hist", S.F_STRUCT, "hist", False, S.C_SLICE, 1),
+                                     S.Field("N", S.F_INT64, "n", True, S.C_PTR), S.Field("Counts", S.F_INT64, "counts", False, S.C_MAP)])
+    addrs = S.Schema(3, "[]main.Addr", [S.Field("", S.F_STRUCT, "", container=S.C_SLICE, elem_schema=1, flags=S.FIELD_BARE)])
+    look = {1: addr, 2: user, 3: addrs}.__getitem__
+    wantv = [S.result_record(S.RESULT_DATA, user.encode_row(["bo<b>", 1.5e-7, ["Paris", 0, [1.0, 2.5]], None, ["a", "b\n"], {"z": "1", "a": "2", "aa": "3"},
+                                                             [["X", 7, None], ["Y", 0, []]], 5, None], look)),
+             S.result_record(S.RESULT_DATA, user.encode_row(["", 0.0, ["", 0, None], ["W", 1, [-0.5]], None, None, None, None, {"k": -1}], look)),
+             S.result_record(S.RESULT_DATA, addrs.encode_row([[["X", 7, None], ["Y", 2, [3.25]]]], look)),
+             S.result_record(S.RESULT_DATA, addrs.encode_row([None], look)), bad]
+    assert [bytes.fromhex(l) for l in out[len(cases) + 15:len(cases) + 20]] == wantv
+    for t, line in zip(targets, out[len(cases) + 20:]):
         path, sep, query = t.partition(b"?")
         bad = not t.startswith(b"/") or re.search(rb"%(?![0-9a-fA-F]{2})", path) is not None
         if bad:
@@ -111,11 +127,24 @@ def _records():
               ("GET", "/rawnil", b"", S.result_record(S.RESULT_RAW_NIL)),
               ("GET", "/rawperson", b"", S.result_record(S.RESULT_RAW_DATA, person.encode_row([9, "raw", True]))),
               ("GET", "/rawerr", b"", S.result_record(S.RESULT_RAW_STRING, b"x", S.RAW_ERR))]
+    addr = S.Schema(2, "main.Addr", [S.Field("City", S.F_STRING, "city"), S.Field("Zip", S.F_INT32, "zip", True),
+                                     S.Field("Geo", S.F_FLOAT64, "geo", container=S.C_SLICE)])
+    user = S.Schema(3, "main.User", [S.Field("Name", S.F_STRING, "name"), S.Field("Score", S.F_FLOAT64, "score"), S.Field("Home", S.F_STRUCT, "home", elem_schema=2),
+                                     S.Field("Work", S.F_STRUCT, "work", True, S.C_PTR, 2), S.Field("Tags", S.F_STRING, "tags", False, S.C_SLICE),
+                                     S.Field("Attrs", S.F_STRING, "attrs", True, S.C_MAP)])
+    addrs = S.Schema(4, "[]main.Addr", [S.Field("", S.F_STRUCT, "", container=S.C_SLICE, elem_schema=2, flags=S.FIELD_BARE)])
+    look = {2: addr, 3: user, 4: addrs}.__getitem__
+    cases += [("GET", "/user/bob", b"", S.result_record(S.RESULT_DATA, user.encode_row(["bob", 1.5e-7, ["Paris", 75001, [48.8566, 2.3522]], ["Lyon", 0, []],
+                                                                                       ["a", "b<c>"], {"z": "1", "a": "2"}], look))),
+              ("GET", "/user/nan", b"", S.result_record(S.RESULT_DATA, user.encode_row(["nan", float("nan"), ["", 0, None], None, None, None], look))),
+              ("GET", "/addrs", b"", S.result_record(S.RESULT_DATA, addrs.encode_row([[["X", 7, None], ["Y", 0, [1e21, -0.0]]]], look))),
+              ("GET", "/addrs?none=1", b"", S.result_record(S.RESULT_DATA, addrs.encode_row([None], look)))]
     routes = [("GET", "/hello", 0), ("GET", "/hello2", 0), ("PUT", "/hello", 0), ("POST", "/hello", 0), ("GET", "/params", 0),
               ("DELETE", "/delete", 0), ("GET", "/greet", 0), ("GET", "/error", 0), ("GET", "/users/{id:[0-9]+}/posts/{slug}", 0),
               ("GET", "/person/{name}", 1), ("GET", "/nil", 0), ("GET", "/file", 0), ("GET", "/panic", 0), ("POST", "/echo", 0),
-              ("POST", "/people", 1), ("GET", "/raw", 0), ("GET", "/rawnil", 0), ("GET", "/rawperson", 1), ("GET", "/rawerr", 0)]
-    spec = S.TableSpec(schemas=[person], favicon=b"",
+              ("POST", "/people", 1), ("GET", "/raw", 0), ("GET", "/rawnil", 0), ("GET", "/rawperson", 1), ("GET", "/rawerr", 0),
+              ("GET", "/user/{name}", 3), ("GET", "/addrs", 4)]
+    spec = S.TableSpec(schemas=[person, addr, user, addrs], favicon=b"",
                        routes=[S.Route(S.method_code(m), p, S.H_RESULT, schema_id=sid) for m, p, sid in routes])
     return spec, cases
 
