@@ -49,7 +49,10 @@ constexpr int kServeThreads = 128;  // gRPC / request-log kernels: requests per 
 #endif
 constexpr int kServeT = GOFR_SERVE_T;        // serve kernel: requests per tile = threads per CTA
 constexpr int kServeCtas = GOFR_SERVE_CTAS;  // serve kernel: CTAs per SM the register and shared-memory budgets aim at
-constexpr int kServeCtasWide = 4;  // slot layout, "wide" instance: 128 registers per thread (serve_slots_kernel.cu)
+#ifndef GOFR_SERVE_CTAS_WIDE
+#define GOFR_SERVE_CTAS_WIDE 4
+#endif
+constexpr int kServeCtasWide = GOFR_SERVE_CTAS_WIDE;  // slot layout, "wide" instance: 128 registers per thread (serve_slots_kernel.cu)
 
 // Returns dynamic shared memory bytes needed for the table's hot part plus the request-byte staging area.
 uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap);
