@@ -47,7 +47,7 @@ def hbm_peak():
 
 
 KERNEL_SOURCES = ["gofr_b200/csrc/serve_body.cuh", "gofr_b200/csrc/serve_device.cuh", "gofr_b200/csrc/bind_device.cuh",
-                  "gofr_b200/csrc/serve_slots_kernel.cu", "gofr_b200/csrc/serve_slots_wide_kernel.cu", "gofr_b200/csrc/serve_kernel.cu", "gofr_b200/csrc/tile_common.cuh",
+                  "gofr_b200/csrc/serve_slots_kernel.cu", "gofr_b200/csrc/serve_slots_wide_kernel.cu", "gofr_b200/csrc/serve_values_kernel.cu", "gofr_b200/csrc/serve_slots_values_kernel.cu", "gofr_b200/csrc/value_device.cuh", "gofr_b200/csrc/float_device.cuh", "gofr_b200/csrc/serve_kernel.cu", "gofr_b200/csrc/tile_common.cuh",
                   "gofr_b200/csrc/table_format.h", "gofr_b200/_build.py"]
 
 

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgofr_b200.so")
-SOURCES = ["serve_kernel.cu", "serve_slots_kernel.cu", "serve_slots_wide_kernel.cu", "grpc_kernel.cu", "reqlog_kernel.cu", "route_kernel.cu", "bind_kernel.cu", "http_kernel.cu", "egress_kernel.cu", "engine.cu", "table_build.cpp", "frontend.cpp"]
+SOURCES = ["serve_kernel.cu", "serve_values_kernel.cu", "serve_slots_kernel.cu", "serve_slots_wide_kernel.cu", "serve_slots_values_kernel.cu", "grpc_kernel.cu", "reqlog_kernel.cu", "route_kernel.cu", "bind_kernel.cu", "http_kernel.cu", "egress_kernel.cu", "engine.cu", "table_build.cpp", "frontend.cpp"]
 HEADERS = ["serve_body.cuh", "serve_device.cuh", "value_device.cuh", "float_device.cuh", "ryu_tables.inc", "bind_device.cuh", "grpc_device.cuh", "reqlog_device.cuh", "http_device.cuh", "tile_common.cuh", "table_format.h", "engine_internal.h",
            "../../include/gofr_b200.h"]
 # Translation units whose Writer stores whole 32-byte sectors with ONE 256-bit store (st.global.cs.v8.b32 -> STG.E.EF.256,
@@ -16,7 +16,7 @@ HEADERS = ["serve_body.cuh", "serve_device.cuh", "value_device.cuh", "float_devi
 # store of its first word in SOME kernels (the packed serve kernel, never the slot one so far), so every such object is
 # disassembled after compilation and rebuilt with two 16-byte stores if a narrow evict-first store shows up
 # (profiles/check_sector_stores.py has the story; serve_device.cuh Writer::store32).
-SECTOR256 = ["serve_slots_kernel.cu", "serve_slots_wide_kernel.cu", "serve_kernel.cu", "grpc_kernel.cu", "reqlog_kernel.cu"]
+SECTOR256 = ["serve_values_kernel.cu", "serve_slots_values_kernel.cu", "serve_slots_kernel.cu", "serve_slots_wide_kernel.cu", "serve_kernel.cu", "grpc_kernel.cu", "reqlog_kernel.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
 

@@ -78,6 +78,7 @@ struct gofr_engine {
     uint32_t in_cap = 0, smem_bytes = 0;
     int wide_grid = 0;        // slot layout, wide instance (serve_slots_kernel.cu)
     bool slots_wide = false;  // choose_slot_residency
+    bool has_values = false;  // some program has PF_VALUES: the packed layout runs serve_kernel_values (serve_values_kernel.cu)
     int grid = 0, blocks_per_sm = 0, grpc_grid = 0, reqlog_grid = 0, http_grid = 0, proto_grid = 0, proto_decode_grid = 0;
     uint32_t epoch = 0;
     // resident path scratch
@@ -132,24 +133,9 @@ static void register_engine(int device, int delta) {
     if (device >= 0 && device < 64) g_live_engines[device] += delta;
 }
 
-// Which slot-layout instance serves this table (serve_slots_kernel.cu): the wide one (4 CTAs/SM, 128 registers) when every
-// live route answers through the template fast path with ONE program shape and no Bind — then warps never diverge between
-// programs and the general pass after the tile loop only sees the odd escaped string; otherwise the 5-CTA instance.
-static bool choose_slot_residency(const std::vector<uint8_t>& img, const ImageHeader& H) {
+static bool choose_slot_residency(const std::vector<uint8_t>& img, const ImageHeader&) {
     if (const char* v = getenv("GOFR_SLOT_CTAS")) return atoi(v) == kServeCtasWide;
-    const RouteRec* routes = reinterpret_cast<const RouteRec*>(img.data() + H.routes_off);
-    const ProgRec* progs = reinterpret_cast<const ProgRec*>(img.data() + H.progs_off);
-    int shape = -1;
-    for (uint32_t r = 0; r < H.n_routes; r++) {
-        const RouteRec& R = routes[r];
-        if (R.flags & RF_DEAD) continue;
-        if (R.prog_ok == 0xFFFF) return false;  // host handlers: the kernel only routes
-        const ProgRec& P = progs[R.prog_ok];
-        if (!(P.flags & PF_FAST) || (P.flags & PF_BIND)) return false;
-        if (shape >= 0 && shape != P.shape_class) return false;
-        shape = P.shape_class;
-    }
-    return shape >= 0;
+    return image_wants_wide_slots(img.data());
 }
 
 static int configure_geometry(gofr_engine* e, uint32_t in_per_req) {
@@ -212,6 +198,8 @@ static int engine_init(gofr_engine* e, const std::vector<uint8_t>& img, int devi
     int rc = configure_geometry(e, in_per);
     if (rc != GOFR_OK) return rc;
     e->slots_wide = choose_slot_residency(img, e->hdr);
+    for (uint32_t k = 0; k < e->hdr.n_progs; k++)
+        e->has_values |= (reinterpret_cast<const ProgRec*>(img.data() + e->hdr.progs_off)[k].flags & PF_VALUES) != 0;
     for (auto& s : e->slots) {
         CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -330,7 +318,7 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
     p.slot_bytes = slot_bytes;
     p.debug_flags = e->debug_flags;
     memcpy(p.date, date29, 29);
-    const bool wide = slot_bytes && e->slots_wide && e->wide_grid > 0;
+    const bool wide = slot_bytes && e->slots_wide && !e->has_values && e->wide_grid > 0;
     int grid = (int)std::min<uint32_t>((uint32_t)(wide ? e->wide_grid : e->grid), p.n_tiles);
     if (!slot_bytes) grid = std::max(1, std::min(grid, e->grid / engines_on_device(e->device)));  // look-back: see engines_on_device
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -340,7 +328,7 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
         CUDA_TRY(cudaEventCreate(&ev1));
         CUDA_TRY(cudaEventRecord(ev0, stream));
     }
-    int rc = launch_serve(p, grid, e->smem_bytes, stream, wide);
+    int rc = launch_serve(p, grid, e->smem_bytes, stream, wide, e->has_values);
     if (rc != 0) { set_last_error("serve kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
     if (e->timing_on) {
         CUDA_TRY(cudaEventRecord(ev1, stream));
@@ -464,7 +452,7 @@ int gofr_engine_slot_ctas(gofr_engine* e, int ctas_per_sm, int* in_effect) {
     if (ctas_per_sm == kServeCtasWide) e->slots_wide = true;
     else if (ctas_per_sm == kServeCtas) e->slots_wide = false;
     else if (ctas_per_sm != 0) return GOFR_ERR_INVALID;
-    if (in_effect) *in_effect = e->slots_wide && e->wide_grid > 0 ? kServeCtasWide : kServeCtas;
+    if (in_effect) *in_effect = e->slots_wide && !e->has_values && e->wide_grid > 0 ? kServeCtasWide : kServeCtas;
     return GOFR_OK;
 }
 

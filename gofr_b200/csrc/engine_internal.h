@@ -54,10 +54,13 @@ constexpr int kServeCtas = GOFR_SERVE_CTAS;  // serve kernel: CTAs per SM the re
 #endif
 constexpr int kServeCtasWide = GOFR_SERVE_CTAS_WIDE;  // slot layout, "wide" instance: 128 registers per thread (serve_slots_kernel.cu)
 
+// table_build.cpp: which slot-layout instance suits the sealed table (engine.cu choose_slot_residency)
+bool image_wants_wide_slots(const uint8_t* image);
+
 // Returns dynamic shared memory bytes needed for the table's hot part plus the request-byte staging area.
 uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap);
 // cudaError_t as int
-int launch_serve(const ServeParams& p, int grid, uint32_t smem_bytes, void* stream, bool wide_slots = false);
+int launch_serve(const ServeParams& p, int grid, uint32_t smem_bytes, void* stream, bool wide_slots = false, bool values = false);
 // grid of the persistent kernels (both layouts share it); *wide_grid: grid of the wide slot-layout instance
 int serve_max_grid(uint32_t smem_bytes, int device, int* blocks_per_sm, int* wide_grid);
 

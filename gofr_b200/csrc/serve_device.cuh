@@ -1185,7 +1185,12 @@ namespace gofr {
 // STATIC_N > 0: the program's ops are compile-time constants (static_ops, STATIC_N of them): the op loop is unrolled
 // and every decision that depends only on the program folds away — what a table-specific build of the kernel runs for
 // its hot programs.  STATIC_N == 0: the interpreter, ops fetched from the table in shared memory.
-template <bool EMIT, int STATIC_N = 0>
+// VALUES: the instance that also knows OP_F64 / OP_VALUE and the emptiness test of their kinds (the wider data model,
+// value_device.cuh).  Programs that contain such ops (PF_VALUES) run through out-of-line wrappers of that instance
+// (size_values_call / emit_values_call); the inlined hot instance is compiled without them — one more call site inside
+// its op loop cost the packed kernel 38 % (0.40 -> 0.555 ms per 1 Mi config-2 requests: registers live across the loop
+// spilled, 176 -> 600 bytes of spill stores) although no config-2 program has such an op.
+template <bool EMIT, int STATIC_N = 0, bool VALUES = false>
 GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Writer* w, const uint4* static_ops = nullptr) {
     const ProgRec P = tv.progs()[c.prog];  // by value: the staging stores below must not force re-reads of the table
     // the size pass visits only the ops whose length depends on the request
@@ -1273,28 +1278,19 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
                 if (EMIT) { if (t) w->put4('t' | 'r' << 8 | 'u' << 16 | 'e' << 24); else { w->put4('f' | 'a' << 8 | 'l' << 16 | 's' << 24); w->putc('e'); } }
                 produced = t ? 4 : 5;
             }
-        } else if (code == OP_F64) {
-            if (!(governed && skip)) {
-                const uint64_t bits = (uint64_t)row[ooff] | (uint64_t)row[ooff + 1] << 32;
-                if (EMIT) GOFR_SLOW_CALL(w, emit_f64<true>(tw, bits));
-                else {
-                    produced = emit_f64<false>(nullptr, bits);
-                    if (!produced) { c.prog = P.encfail; return false; }  // NaN / Inf: the caller sizes the encfail program
-                }
-            }
-        } else if (code == OP_VALUE) {
+        } else if (VALUES && code >= OP_F64) {  // OP_F64, OP_VALUE: one out-of-line call (value_device.cuh value_op)
             // an omitted field (OP_KEY found it empty) owns no bytes of the variable part: nothing to walk
             if (!(governed && skip)) {
-                const uint8_t* fx = (const uint8_t*)(row + ooff);
-                const uint8_t* vp = c.data() + str_base + str_cursor;
                 const uint32_t used = str_base + str_cursor;
                 uint32_t consumed = 0, vstatus = 0;
-                if (EMIT) GOFR_SLOW_CALL(w, (value_encode<true>(tw, tv, oaux, raw.x >> 8 & 0xFFu, fx, vp, c.data_len - used, &consumed, &vstatus)));
+                if (EMIT) GOFR_SLOW_CALL(w, (value_op<true>(tw, tv, raw, row, c.data(), c.data_len, used, &consumed, &vstatus)));
                 else {
-                    if (used > c.data_len) return false;
-                    produced = value_encode<false>(nullptr, tv, oaux, raw.x >> 8 & 0xFFu, fx, vp, c.data_len - used, &consumed, &vstatus);
-                    if (vstatus == VAL_UNENCODABLE) { c.prog = P.encfail; return false; }
-                    if (vstatus != VAL_OK) return false;
+                    produced = value_op<false>(nullptr, tv, raw, row, c.data(), c.data_len, used, &consumed, &vstatus);
+                    if (vstatus != VAL_OK) {
+                        // NaN / Inf: the caller sizes the program's encfail companion instead; anything else: malformed row
+                        if (vstatus == VAL_UNENCODABLE) c.prog = P.encfail;
+                        return false;
+                    }
                 }
                 str_cursor += consumed;
             }
@@ -1311,10 +1307,8 @@ GOFR_HD bool run_prog(const TableView& tv, const BatchRefs& br, ReqCtx& c, Write
             bool empty = false;
             if (oflags & OPF_OMITEMPTY) {
                 const uint32_t wv = row[oaux];
-                if (okind >> 4) empty = value_field_empty(okind & 15u, okind >> 4, (const uint8_t*)(row + oaux));  // *T, []T, map
-                else if (okind == GOFR_F_INT64 || okind == GOFR_F_INT) empty = (wv | row[oaux + 1]) == 0;
-                else if (okind == GOFR_F_FLOAT64) empty = (wv | row[oaux + 1] << 1) == 0;  // 0.0 of either sign
-                else if (okind == GOFR_F_STRUCT) empty = false;
+                if (okind == GOFR_F_INT64 || okind == GOFR_F_INT) empty = (wv | row[oaux + 1]) == 0;
+                else if (VALUES && okind > GOFR_F_INT) empty = value_key_empty(okind, (const uint8_t*)(row + oaux));  // float64, struct, *T, []T, map
                 else if (okind == GOFR_F_STRING && (P.flags & PF_BIND)) empty = (row[oaux + 1] & 0x7FFFFFFFu) == 0;
                 else empty = wv == 0;
             }
@@ -1613,18 +1607,42 @@ GOFR_HD void emit_fast(const TableView& tv, const BatchRefs& br, ReqCtx& c, uint
 #endif
 #endif
 
+// GOFR_TU_VALUES: whether this translation unit's inlined size / emit functions know about PF_VALUES programs at all.  The
+// packed kernel exists twice (serve_kernel.cu without, serve_values_kernel.cu with): the engine launches the second one
+// only for tables that contain such a program, so tables without them run exactly the code they ran before the wider
+// data model existed.  It is a template argument (VO), not an #if, so that the two variants are different functions.
+#ifndef GOFR_TU_VALUES
+#define GOFR_TU_VALUES 1
+#endif
+
+// programs with OP_F64 / OP_VALUE ops: the VALUES instance of the interpreter, out of line (see run_prog)
+GOFR_HD_NOINLINE bool size_values_call(const TableView tv, const BatchRefs br, ReqCtx* c) { return run_prog<false, 0, true>(tv, br, *c, nullptr); }
+template <bool SLOTS>
+GOFR_HD_NOINLINE void emit_values_call(const TableView tv, const BatchRefs br, ReqCtx* c, uint8_t* dst, uint32_t* ring_col) {
+    Writer w;
+    w.init(dst, ring_col);
+    run_prog<true, 0, true>(tv, br, *c, &w);
+    if (SLOTS) w.finish_padded(); else w.finish();
+}
+
 // sizes a routed request (route_request has run) with the general interpreter
+template <bool VO = (GOFR_TU_VALUES != 0)>
 GOFR_HD void size_routed_general(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
     if (c.prog == 0xFFFF) {  // GOFR_H_HOST: nothing to emit, status 0 = pending on the host
         c.body_len = c.total_len = 0;
         return;
     }
     bool ok;
+    const uint32_t asked = c.prog;
 #ifdef GOFR_IS_STATIC
     if (GOFR_IS_STATIC(c)) ok = run_prog<false, GOFR_STATIC_N_DYN>(tv, br, c, nullptr, kStaticDyn);
     else
 #endif
-    const uint32_t asked = c.prog;
+    if (VO && (tv.progs()[c.prog].flags & PF_VALUES)) {
+        ReqCtx t = c;  // a copy: taking the address of `c` itself would move the request context to local memory (size_routed)
+        ok = size_values_call(tv, br, &t);
+        c.prog = t.prog; c.body_len = t.body_len; c.total_len = t.total_len; c.slow_mask = t.slow_mask;
+    } else
     ok = run_prog<false>(tv, br, c, nullptr);
     if (!ok) {
         // a malformed row is answered like a handler panic; a float that encoding/json cannot write (run_prog switched
@@ -1637,10 +1655,11 @@ GOFR_HD void size_routed_general(const TableView& tv, const BatchRefs& br, ReqCt
 // The slot-layout kernel keeps the general interpreter OUT of line: its hot path is size_fast / emit_fast, and two more
 // inlined copies of run_prog cost it registers and instruction-cache room (measured: no gain from the fast path until the
 // general path became a call).
-GOFR_HD_NOINLINE void size_routed_call(const TableView tv, const BatchRefs br, ReqCtx* c) { size_routed_general(tv, br, *c); }
+template <bool VO = (GOFR_TU_VALUES != 0)>
+GOFR_HD_NOINLINE void size_routed_call(const TableView tv, const BatchRefs br, ReqCtx* c) { size_routed_general<VO>(tv, br, *c); }
 
 // FAST: the slot-layout kernel — the lean size pass where it applies (the response is then written by emit_fast)
-template <bool FAST = false>
+template <bool FAST = false, bool VO = (GOFR_TU_VALUES != 0)>
 GOFR_HD void size_routed(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
     if (FAST) {
         if (c.prog == 0xFFFF) { c.body_len = c.total_len = 0; return; }
@@ -1648,23 +1667,29 @@ GOFR_HD void size_routed(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
         // the call works on a copy: taking the address of `c` itself would move the whole request context to local
         // memory for the hot path too (it did: 568 LDL/STL in the kernel, and no gain from the fast path)
         ReqCtx t = c;
-        size_routed_call(tv, br, &t);
+        size_routed_call<VO>(tv, br, &t);
         c.prog = t.prog; c.body_len = t.body_len; c.total_len = t.total_len; c.slow_mask = t.slow_mask;
         return;
     }
-    size_routed_general(tv, br, c);
+    size_routed_general<VO>(tv, br, c);
 }
 
+template <bool VO = (GOFR_TU_VALUES != 0)>
 GOFR_HD void size_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) {
     route_request(tv, br, c);
-    size_routed(tv, br, c);
+    size_routed<false, VO>(tv, br, c);
 }
 
 // HTTP status of a sized request (0: GOFR_H_HOST, the closure runs on the host)
 GOFR_HD uint32_t request_status(const TableView& tv, const ReqCtx& c) { return c.prog == 0xFFFF ? 0u : tv.progs()[c.prog].status; }
 
-template <bool SLOTS>
+template <bool SLOTS, bool VO = (GOFR_TU_VALUES != 0)>
 GOFR_HD void emit_request_general(const TableView& tv, const BatchRefs& br, ReqCtx& c, uint8_t* dst, uint32_t* ring_col) {
+    if (VO && (tv.progs()[c.prog].flags & PF_VALUES)) {
+        ReqCtx t = c;
+        emit_values_call<SLOTS>(tv, br, &t, dst, ring_col);
+        return;
+    }
     Writer w;
     w.init(dst, ring_col);
 #ifdef GOFR_IS_STATIC
@@ -1674,19 +1699,20 @@ GOFR_HD void emit_request_general(const TableView& tv, const BatchRefs& br, ReqC
     run_prog<true>(tv, br, c, &w);
     if (SLOTS) w.finish_padded(); else w.finish();
 }
+template <bool VO = (GOFR_TU_VALUES != 0)>
 GOFR_HD_NOINLINE void emit_request_slots_call(const TableView tv, const BatchRefs br, ReqCtx* c, uint8_t* dst, uint32_t* ring_col) {
-    emit_request_general<true>(tv, br, *c, dst, ring_col);
+    emit_request_general<true, VO>(tv, br, *c, dst, ring_col);
 }
 
-template <bool SLOTS = false>
+template <bool SLOTS = false, bool VO = (GOFR_TU_VALUES != 0)>
 GOFR_HD void emit_request(const TableView& tv, const BatchRefs& br, ReqCtx& c, uint8_t* dst, uint32_t* ring_col) {
     if (c.total_len == 0) return;
     if (SLOTS) {
         if (c.fast()) emit_fast(tv, br, c, dst, ring_col);
-        else { ReqCtx t = c; emit_request_slots_call(tv, br, &t, dst, ring_col); }  // a copy: see size_routed
+        else { ReqCtx t = c; emit_request_slots_call<VO>(tv, br, &t, dst, ring_col); }  // a copy: see size_routed
         return;
     }
-    emit_request_general<false>(tv, br, c, dst, ring_col);
+    emit_request_general<false, VO>(tv, br, c, dst, ring_col);
 }
 
 // Patch the batch's Date into a private copy of the table's hot part (the kernel does this on its shared-memory

@@ -1,5 +1,6 @@
 // serve_slots_wide_kernel.cu — slot-layout instance of the serve kernel with the 128-register budget (4 CTAs/SM); see
 // serve_slots_kernel.cu for when the engine uses it.
+#define GOFR_TU_VALUES 0
 #include "serve_body.cuh"
 
 namespace gofr {

@@ -164,7 +164,7 @@ struct Piece {
 struct RouteDef {
     uint32_t method;
     std::string pattern;
-    bool prefix = false, dead = false;
+    bool prefix = false, dead = false, is_default = false;  // is_default: appended by gofr_table_add_default_routes
     std::vector<Piece> pieces;
     uint32_t hkind = 0, schema_id = 0;
     std::string s[4];
@@ -545,6 +545,30 @@ struct Builder {
 
 namespace gofr {
 
+// Which slot-layout instance serves this table (serve_slots_kernel.cu): the wide one (4 CTAs/SM, 128 registers) when every
+// live route answers through the template fast path with ONE program shape and no Bind — then warps never diverge between
+// programs and the general pass after the tile loop only sees the odd escaped string; otherwise the 5-CTA instance.
+bool image_wants_wide_slots(const uint8_t* img) {
+    const ImageHeader& H = *reinterpret_cast<const ImageHeader*>(img);
+    const RouteRec* routes = reinterpret_cast<const RouteRec*>(img + H.routes_off);
+    const ProgRec* progs = reinterpret_cast<const ProgRec*>(img + H.progs_off);
+    const FastRec* fast = reinterpret_cast<const FastRec*>(img + H.fast_off);
+    int shape = -1;
+    for (uint32_t r = 0; r < H.n_routes; r++) {
+        const RouteRec& R = routes[r];
+        // the routes App.Run appends (health, favicon, catch-all) are not what an application's traffic looks like
+        if (R.flags & (RF_DEAD | RF_DEFAULT)) continue;
+        if (R.prog_ok == 0xFFFF) return false;  // host handlers: the kernel only routes
+        const ProgRec& P = progs[R.prog_ok];
+        if (!(P.flags & PF_FAST) || (P.flags & PF_BIND)) return false;
+        if (fast[R.prog_ok].flags & FR_COMPLETE) continue;  // template only: nothing is interpreted
+        if (shape >= 0 && shape != P.shape_class) return false;
+        shape = P.shape_class;
+    }
+    return shape >= 0;
+}
+
+
 struct Pool {
     std::vector<uint8_t>& img;
     std::map<std::string, uint32_t> seen;
@@ -835,7 +859,7 @@ int seal_table(gofr_table* t) {
         RouteRec& R = routes[ri];
         memset(&R, 0, sizeof R);
         R.method = (uint8_t)r.method;
-        R.flags = (r.prefix ? RF_PREFIX : 0) | (r.dead ? RF_DEAD : 0);
+        R.flags = (r.prefix ? RF_PREFIX : 0) | (r.dead ? RF_DEAD : 0) | (r.is_default ? RF_DEFAULT : 0);
         R.hkind = (uint8_t)r.hkind;
         R.first_piece = (uint16_t)pieces.size();
         R.n_pieces = (uint8_t)r.pieces.size();
@@ -960,10 +984,12 @@ int seal_table(gofr_table* t) {
                     o.off = pool.put(so.lit);
                     o.len = (uint32_t)so.lit.size();
                     P.flags |= PF_DYNAMIC | PF_NEEDS_ROW;
+                    if (so.kind > GOFR_F_INT) P.flags |= PF_VALUES;  // emptiness test of the wider kinds
                     break;
                 case OP_HEXID: fixed = 32; break;
                 case OP_CLEN: P.flags |= PF_HAS_CLEN; break;
-                case OP_I64: case OP_I32: case OP_BOOL: case OP_STR: case OP_BSTR: case OP_F64: case OP_VALUE:
+                case OP_F64: case OP_VALUE: P.flags |= PF_VALUES;  // fall through
+                case OP_I64: case OP_I32: case OP_BOOL: case OP_STR: case OP_BSTR:
                     P.flags |= PF_DYNAMIC | PF_NEEDS_ROW;
                     break;
                 case OP_BLOB:
@@ -1311,6 +1337,13 @@ int gofr_table_add_route(gofr_table* t, uint32_t method, const char* pattern, ui
     return GOFR_OK;
 }
 
+int gofr_table_slot_ctas(const gofr_table* t, int* ctas_per_sm) {
+    if (!t || !ctas_per_sm) return GOFR_ERR_INVALID;
+    if (!t->sealed) return GOFR_ERR_NOT_SEALED;
+    *ctas_per_sm = gofr::image_wants_wide_slots(t->image.data()) ? gofr::kServeCtasWide : gofr::kServeCtas;
+    return GOFR_OK;
+}
+
 int gofr_table_add_default_routes(gofr_table* t, const uint8_t* favicon, uint32_t favicon_len) {
     if (!t) return GOFR_ERR_INVALID;
     if (t->sealed) return GOFR_ERR_SEALED;
@@ -1325,6 +1358,7 @@ int gofr_table_add_default_routes(gofr_table* t, const uint8_t* favicon, uint32_
     memset(&h, 0, sizeof h);
     h.kind = GOFR_H_MISSING_FILE;
     rc = gofr_table_add_route(t, GOFR_M_ANY, "/", 1, &h, nullptr);
+    for (size_t k = t->routes.size() >= 3 ? t->routes.size() - 3 : 0; k < t->routes.size(); k++) t->routes[k].is_default = true;
     if (rc) return rc;
     t->has_catchall = true;
     return GOFR_OK;

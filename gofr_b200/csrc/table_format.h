@@ -58,6 +58,7 @@ enum RouteFlags : uint8_t {
     RF_PREFIX = 1,   // PathPrefix: regexp has no trailing '$'
     RF_DEAD = 2,     // mux route.err != nil: never matches
     RF_LITERAL = 4,  // no variables: one word-wise compare
+    RF_DEFAULT = 8,  // appended by gofr_table_add_default_routes (health, favicon, catch-all): not the application's traffic
 };
 
 struct RouteRec {  // 32 B
@@ -160,6 +161,7 @@ enum ProgFlags : uint16_t {
     PF_BIND = 8,      // the row is the Bind span row in scratch (bind_device.cuh), not the request's data section
     PF_FAST = 16,     // only literals, plain values and struct keys (LIT, HEXID, CLEN, I64, I32, BOOL, STR, BSTR, PARAM, KEY):
                       // eligible for the slot-layout fast path (FastRec) when the request has no escapes
+    PF_VALUES = 32,   // has OP_F64 / OP_VALUE ops: runs through the VALUES instance of the interpreter (serve_device.cuh run_prog)
 };
 
 // Slot layout fast path (serve_device.cuh emit_fast).  A response owns a 16-byte aligned slot, so every byte of the

@@ -265,4 +265,25 @@ GOFR_HD_NOINLINE uint32_t value_encode(Writer* w, const TableView tv, uint32_t s
     return out;
 }
 
+// OP_KEY's emptiness test for the kinds of the wider data model (kind | container << 4), out of line: the interpreter's
+// own code stays what it was for flat structs
+GOFR_HD_NOINLINE bool value_key_empty(uint32_t okind, const uint8_t* p) { return value_field_empty(okind & 15u, okind >> 4, p); }
+
+// OP_F64 / OP_VALUE of the interpreter (serve_device.cuh run_prog) behind ONE out-of-line call.  raw = the op; row = the
+// row's fixed part; [data, data + data_len) the data section, `used` bytes of it consumed so far (fixed part + variable
+// cursor).  Returns the bytes produced; *consumed = bytes of the variable part walked; *status = ValueStatus.
+template <bool EMIT>
+GOFR_HD_NOINLINE uint32_t value_op(Writer* w, const TableView tv, const uint4 raw, const uint32_t* row, const uint8_t* data,
+                                   uint32_t data_len, uint32_t used, uint32_t* consumed, uint32_t* status) {
+    *consumed = 0;
+    *status = VAL_OK;
+    if ((raw.x & 0xFFu) == OP_F64) {
+        const uint32_t n = emit_f64<EMIT>(w, (uint64_t)row[raw.z] | (uint64_t)row[raw.z + 1] << 32);
+        if (!n) *status = VAL_UNENCODABLE;
+        return n;
+    }
+    if (used > data_len) { *status = VAL_MALFORMED; return 0; }
+    return value_encode<EMIT>(w, tv, raw.w, (raw.x >> 8) & 0xFFu, (const uint8_t*)(row + raw.z), data + used, data_len - used, consumed, status);
+}
+
 }  // namespace gofr

@@ -56,6 +56,12 @@ class Table:
         _abi.check(L.gofr_table_serialize(self._t, buf.ctypes.data, C.byref(n)), "gofr_table_serialize")
         return buf.tobytes()
 
+    def slot_ctas(self) -> int:
+        """CTAs/SM of the slot-layout serve kernel an engine will pick for this table (4: the 128-register instance)"""
+        v = C.c_int(0)
+        _abi.check(_abi.lib().gofr_table_slot_ctas(self._t, C.byref(v)), "gofr_table_slot_ctas")
+        return v.value
+
     def route_count(self) -> int:
         return _abi.lib().gofr_table_route_count(self._t)
 

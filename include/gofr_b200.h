@@ -303,6 +303,8 @@ int gofr_engine_geometry(const gofr_engine*, uint32_t* grid, uint32_t* blocks_pe
  * registers when every route takes the template fast path with one program shape, else 5 CTAs/SM).  ctas_per_sm 0 = query,
  * 4 or 5 = force; *in_effect (may be NULL) receives the value in effect.  Tuning knob, no effect on results. */
 int gofr_engine_slot_ctas(gofr_engine*, int ctas_per_sm, int* in_effect);
+/* the engine's choice for a sealed table, computable without a GPU */
+int gofr_table_slot_ctas(const gofr_table*, int* ctas_per_sm);
 /* gofr_serve_device reports an undersized d_out through this flag (the launch itself is asynchronous). */
 int gofr_engine_overflowed(gofr_engine*, int* flag_out, int reset);
 int gofr_engine_set_timing(gofr_engine*, int on);

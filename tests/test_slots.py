@@ -114,6 +114,18 @@ def test_mixed_traffic_and_short_slots(torch_cuda):
     eng.close()
 
 
+def test_slot_residency_choice():
+    """one-shape fast-path tables get the 128-register instance (the routes App.Run appends do not count), mixed tables and
+    Bind routes the 5-CTA one"""
+    from tests.test_result import _spec
+    assert Table(synth.config2_spec()).slot_ctas() == 4
+    assert Table(synth.config2_spec(S.FRAME_BODY, n_routes=64)).slot_ctas() == 4
+    assert Table(synth.config4_spec()).slot_ctas() == 5
+    assert Table(synth.config3_spec()).slot_ctas() == 5
+    assert Table(synth.config1_spec()).slot_ctas() == 5
+    assert Table(_spec()).slot_ctas() == 5
+
+
 @pytest.mark.gpu
 def test_both_slot_residencies(torch_cuda):
     """The engine picks the 4-CTA (128-register) instance for one-shape tables and the 5-CTA one otherwise; either

@@ -437,10 +437,13 @@ def test_gpu_values_match_oracle(result):
     batch, _ = _batch(spec, 6000, 21, nan_rate=0.01, result=result)
     o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
     eng = Engine(Table(spec), 0)
-    out, off, meta = eng.serve_device(eng.upload(batch), DATE)
-    assert np.array_equal(meta.cpu().numpy().view(np.uint32), m1)
-    assert np.array_equal(off.cpu().numpy().view(np.uint32), f1)
-    assert out.cpu().numpy()[:int(f1[-1])].tobytes() == o1[:int(f1[-1])].tobytes()
+    resp = eng.alloc_responses(batch.n, int(f1[-1]) + 4096)
+    eng.serve_device(eng.upload(batch), DATE, resp)
+    torch.cuda.synchronize()
+    out, off, meta = resp.to_host()
+    assert np.array_equal(meta, m1)
+    assert np.array_equal(off, f1)
+    assert out[:int(f1[-1])].tobytes() == o1[:int(f1[-1])].tobytes()
     slot = 2048
     canary = torch.full((batch.n * slot,), 0xEE, dtype=torch.uint8, device="cuda")
     so, sl, sm = eng.serve_device_slots(eng.upload(batch), DATE, slot, out=canary)
@@ -471,8 +474,11 @@ def test_gpu_float_text_matches_python_repr():
         want.append(('{"data":[' + ",".join(go_json_float(v) for v in chunk) + "]}\n").encode())
     batch = S.RequestBatch.pack(reqs, seed=4)
     eng = Engine(Table(spec), 0)
-    out, off, meta = eng.serve_device(eng.upload(batch), DATE)
-    ob, f = out.cpu().numpy().tobytes(), off.cpu().numpy().view(np.uint32)
+    resp = eng.alloc_responses(batch.n, sum(len(w) for w in want) + 4096)
+    eng.serve_device(eng.upload(batch), DATE, resp)
+    torch.cuda.synchronize()
+    out, f, meta = resp.to_host()
+    ob = out.tobytes()
     for i, w in enumerate(want):
         assert ob[int(f[i]):int(f[i + 1])] == w, i
     eng.close()
