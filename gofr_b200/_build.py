@@ -54,7 +54,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     hdr_m = max(os.path.getmtime(f) for f in [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)] if os.path.exists(f))
     tag = os.path.join(objdir, ".flags")
-    flags_changed = not os.path.exists(tag) or open(tag).read() != " ".join(flags)
+    tag_text = " ".join(flags) + (" [no STORE256]" if os.environ.get("GOFR_NO_STORE256") else "")
+    flags_changed = not os.path.exists(tag) or open(tag).read() != tag_text
 
     # one translation unit per nvcc process, in parallel; objects are reused when neither the source, a header nor the
     # flags changed
@@ -82,7 +83,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(log)
     if any(rc for _, rc, _ in results):
         raise RuntimeError("nvcc failed building libgofr_b200.so")
-    open(tag, "w").write(" ".join(flags))
+    open(tag, "w").write(tag_text)
     r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + [o for o, _, _ in results] + ["-lcudart"],
                        capture_output=True, text=True)
     if r.returncode != 0:
