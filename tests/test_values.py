@@ -471,7 +471,9 @@ def test_gpu_float_text_matches_python_repr():
     for k in range(0, len(vals), per):
         chunk = vals[k:k + per]
         reqs.append(S.Req(S.M_GET, b"/f", b"", BARE_FLOATS.encode_row([chunk])))
-        want.append(('{"data":[' + ",".join(go_json_float(v) for v in chunk) + "]}\n").encode())
+        texts = [go_json_float(v) for v in chunk]
+        # a NaN / Inf among the random bit patterns makes Encode fail for the whole value: no body at all
+        want.append(('{"data":[' + ",".join(texts) + "]}\n").encode() if all(texts) else b"")
     batch = S.RequestBatch.pack(reqs, seed=4)
     eng = Engine(Table(spec), 0)
     resp = eng.alloc_responses(batch.n, sum(len(w) for w in want) + 4096)
