@@ -838,16 +838,18 @@ GOFR_HD bool words_equal(const uint32_t* a, const uint32_t* b, uint32_t n) {
     return diff == 0;
 }
 
-// Anchored leftmost-first match of lit0 var0 lit1 var1 ... litN [$]: greedy variables with backtracking — what Go's
-// regexp reports for the regexp mux builds from a path template.
-// want_var >= 0: also report the span captured by that piece's variable (mux.Vars) in span_out[0..1] = (offset, length);
-// want_var == -2: report every variable, span_out[2k], span_out[2k+1] for the k-th one (template order)
+// Anchored leftmost-first match of lit0 atom0 lit1 atom1 ... litN [$]: greedy atoms (a character class repeated
+// min_rep..max_rep times) with backtracking — what Go's regexp reports for the regexp mux builds from a path template
+// whose variables are concatenations of quantified classes (table_build.cpp parse_var_regexp).  A variable is one atom
+// or several consecutive ones (PieceRec::var_idx / var_flags); its span runs from its first atom to its last.
+// want_var >= 0: also report the span captured by that VARIABLE (mux.Vars, template order) in span_out[0..1] = (offset,
+// length); want_var == -2: report every variable, span_out[2v], span_out[2v + 1] for variable v (other entries untouched)
 GOFR_HD_NOINLINE bool template_match(const TableView tv, const RouteRec R, const uint8_t* p, uint32_t n, int want_var = -1,
                                      uint32_t* span_out = nullptr) {
     const PieceRec* pc = tv.pieces() + R.first_piece;
     uint32_t np = R.n_pieces;
     bool prefix = R.flags & RF_PREFIX;
-    uint32_t start[kMaxVars + 1], take[kMaxVars + 1];
+    uint32_t start[kMaxPieces + 1], take[kMaxPieces + 1];
     uint32_t k = 0, pos = 0;
     for (;;) {
         // literal k at pos
@@ -856,15 +858,23 @@ GOFR_HD_NOINLINE bool template_match(const TableView tv, const RouteRec R, const
             pos += pc[k].lit_len;
             if (!pc[k].has_var) {
                 if (prefix || pos == n) {
-                    if (want_var >= 0) { span_out[0] = start[want_var]; span_out[1] = take[want_var]; }
-                    if (want_var == -2)
-                        for (uint32_t j = 0; j < k; j++) { span_out[2 * j] = start[j]; span_out[2 * j + 1] = take[j]; }
+                    if (want_var != -1) {
+                        uint32_t vs = 0;
+                        for (uint32_t j = 0; j < k; j++) {
+                            if (pc[j].var_flags & PV_FIRST) vs = start[j];
+                            if (!(pc[j].var_flags & PV_LAST)) continue;
+                            const uint32_t v = pc[j].var_idx, len = start[j] + take[j] - vs;
+                            if (want_var == (int)v) { span_out[0] = vs; span_out[1] = len; }
+                            if (want_var == -2 && v < (uint32_t)kMaxVars) { span_out[2 * v] = vs; span_out[2 * v + 1] = len; }
+                        }
+                    }
                     return true;
                 }
                 ok = false;
             } else {
+                const uint32_t cap = pc[k].max_rep ? pc[k].max_rep : 0xFFFFFFFFu;
                 uint32_t run = 0;
-                while (pos + run < n && cls_has(pc[k].cls, p[pos + run])) run++;
+                while (pos + run < n && run < cap && cls_has(pc[k].cls, p[pos + run])) run++;
                 if (run >= pc[k].min_rep) {
                     start[k] = pos;
                     take[k] = run;
@@ -876,7 +886,7 @@ GOFR_HD_NOINLINE bool template_match(const TableView tv, const RouteRec R, const
                 ok = false;
             }
         }
-        // backtrack: shorten the most recent variable that can still give a byte back
+        // backtrack: shorten the most recent atom that can still give a byte back
         for (;;) {
             if (k == 0) return false;
             k--;
@@ -1163,9 +1173,11 @@ GOFR_HD uint32_t route_only(const TableView& tv, uint32_t method, const uint8_t*
     *route = (uint32_t)m;
     const RouteRec R = tv.routes()[m];
     if (!(R.flags & RF_LITERAL) && R.n_pieces > 1) {
-        uint32_t sp[2 * kMaxVars + 2];
+        uint32_t sp[2 * kMaxVars];
+        for (int k = 0; k < 2 * kMaxVars; k++) sp[k] = 0xFFFFFFFFu;
         template_match(tv, R, path, n, -2, sp);
-        for (uint32_t k = 0; k + 1 < R.n_pieces && k < (uint32_t)kMaxVars; k++) vars[k] = sp[2 * k] | sp[2 * k + 1] << 16;
+        for (int k = 0; k < kMaxVars; k++)
+            if (sp[2 * k] != 0xFFFFFFFFu) vars[k] = sp[2 * k] | sp[2 * k + 1] << 16;
     }
     return method == GOFR_M_OPTIONS ? 200u : 0u;
 }

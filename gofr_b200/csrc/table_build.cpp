@@ -159,6 +159,9 @@ struct Piece {
     bool has_var = false;
     uint32_t cls[8] = {0};
     int min_rep = 1;
+    int max_rep = 0;       // 0 = unbounded
+    int var_idx = 0;       // which variable of the template this atom belongs to
+    bool var_first = true, var_last = true;  // first / last atom of its variable (a {name:regexp} may be several atoms)
 };
 
 struct RouteDef {
@@ -231,62 +234,117 @@ namespace gofr {
 static void cls_set(uint32_t* c, int b) { c[b >> 5] |= 1u << (b & 31); }
 static void cls_range(uint32_t* c, int a, int b) { for (int x = a; x <= b; x++) cls_set(c, x); }
 
-// {name:regexp}: accept  X+ / X*  with X a bracket class, \d, \w or '.'
-static int parse_var_regexp(const std::string& re, Piece& pc) {
-    memset(pc.cls, 0, sizeof pc.cls);
-    size_t n = re.size(), i = 0;
-    if (n < 2) return GOFR_ERR_UNSUPPORTED;
-    auto add_esc = [&](int e) {
-        if (e == 'd') cls_range(pc.cls, '0', '9');
-        else if (e == 'w') { cls_range(pc.cls, '0', '9'); cls_range(pc.cls, 'a', 'z'); cls_range(pc.cls, 'A', 'Z'); cls_set(pc.cls, '_'); }
-        else cls_set(pc.cls, e);
+// {name:regexp}: a CONCATENATION of quantified units — no alternation, no groups, no anchors, no lazy quantifiers:
+//   unit   a bracket class, \d, \w, '.', an escaped metacharacter (\. \- ...) or a plain literal character
+//   quant  none, + * ? {n} {n,} {n,m}  (n, m <= 250)
+// e.g. [0-9]+   \d{4}-\d{2}   v[0-9]+   [a-z]+\.[a-z]{2,4}   .*
+// Each unit becomes one atom (class, min, max) matched greedily with backtracking: what Go's regexp (leftmost-first)
+// reports for such a pattern.  Classes are sets of BYTES while Go counts runes: a counted quantifier ({n}, {n,m}, ?) on a
+// class that contains non-ASCII bytes ('.', negated classes) would count differently for multi-byte characters and is
+// refused; + and * do not care.
+struct Atom {
+    uint32_t cls[8] = {0};
+    int min_rep = 1, max_rep = 0;  // max 0 = unbounded
+};
+static int parse_var_regexp(const std::string& re, std::vector<Atom>& out) {
+    const size_t n = re.size();
+    size_t i = 0;
+    auto add_esc = [&](uint32_t* c, int e) {
+        if (e == 'd') cls_range(c, '0', '9');
+        else if (e == 'w') { cls_range(c, '0', '9'); cls_range(c, 'a', 'z'); cls_range(c, 'A', 'Z'); cls_set(c, '_'); }
+        else cls_set(c, e);
     };
-    if (re[0] == '[') {
-        bool neg = false, first = true;
-        i = 1;
-        if (i < n && re[i] == '^') { neg = true; i++; }
-        while (i < n && (re[i] != ']' || first)) {
-            int a = (uint8_t)re[i];
-            if (a == '\\') {
-                if (i + 1 >= n) return GOFR_ERR_UNSUPPORTED;
-                int e = (uint8_t)re[i + 1];
-                if (e == 'd' || e == 'w') { add_esc(e); i += 2; first = false; continue; }
-                a = e;
-                i++;
+    while (i < n) {
+        Atom at;
+        bool ascii_only = true;
+        const int ch = (uint8_t)re[i];
+        if (ch == '[') {
+            bool neg = false, first = true;
+            i++;
+            if (i < n && re[i] == '^') { neg = true; i++; }
+            while (i < n && (re[i] != ']' || first)) {
+                int a = (uint8_t)re[i];
+                if (a == '[' && i + 1 < n && re[i + 1] == ':') return GOFR_ERR_UNSUPPORTED;  // [[:alpha:]]
+                if (a == '\\') {
+                    if (i + 1 >= n) return GOFR_ERR_UNSUPPORTED;
+                    int e = (uint8_t)re[i + 1];
+                    if (e == 'd' || e == 'w') { add_esc(at.cls, e); i += 2; first = false; continue; }
+                    if ((e >= '0' && e <= '9') || (e >= 'a' && e <= 'z') || (e >= 'A' && e <= 'Z')) return GOFR_ERR_UNSUPPORTED;  // \s \pL \x41 ...
+                    a = e;
+                    i++;
+                }
+                if (a >= 0x80) return GOFR_ERR_UNSUPPORTED;
+                if (i + 2 < n && re[i + 1] == '-' && re[i + 2] != ']') {
+                    int b2 = (uint8_t)re[i + 2];
+                    if (b2 == '\\') { if (i + 3 >= n) return GOFR_ERR_UNSUPPORTED; b2 = (uint8_t)re[i + 3]; i++; }
+                    if (b2 >= 0x80 || b2 < a) return GOFR_ERR_UNSUPPORTED;
+                    cls_range(at.cls, a, b2);
+                    i += 3;
+                } else { cls_set(at.cls, a); i++; }
+                first = false;
             }
-            if (a >= 0x80) return GOFR_ERR_UNSUPPORTED;
-            if (i + 2 < n && re[i + 1] == '-' && re[i + 2] != ']') {
-                int b = (uint8_t)re[i + 2];
-                if (b == '\\') { if (i + 3 >= n) return GOFR_ERR_UNSUPPORTED; b = (uint8_t)re[i + 3]; i++; }
-                if (b >= 0x80 || b < a) return GOFR_ERR_UNSUPPORTED;
-                cls_range(pc.cls, a, b);
-                i += 3;
-            } else { cls_set(pc.cls, a); i++; }
-            first = false;
+            if (i >= n) return GOFR_ERR_UNSUPPORTED;
+            i++;  // ']'
+            if (neg) { for (auto& w : at.cls) w = ~w; ascii_only = false; }
+        } else if (ch == '\\') {
+            if (i + 1 >= n) return GOFR_ERR_UNSUPPORTED;
+            const int e = (uint8_t)re[i + 1];
+            if (e == 'd' || e == 'w') add_esc(at.cls, e);
+            else if ((e >= '0' && e <= '9') || (e >= 'a' && e <= 'z') || (e >= 'A' && e <= 'Z') || e >= 0x80) return GOFR_ERR_UNSUPPORTED;
+            else cls_set(at.cls, e);  // an escaped punctuation character stands for itself
+            i += 2;
+        } else if (ch == '.') {
+            for (auto& w : at.cls) w = 0xFFFFFFFFu;
+            at.cls[0] &= ~(1u << '\n');
+            ascii_only = false;
+            i++;
+        } else if (ch == '(' || ch == ')' || ch == '|' || ch == '^' || ch == '$' || ch == '+' || ch == '*' || ch == '?' || ch == '{' || ch == '}' ||
+                   ch == ']') {
+            return GOFR_ERR_UNSUPPORTED;  // groups, alternation, anchors; a quantifier without a unit
+        } else {
+            cls_set(at.cls, ch);  // a literal byte (the bytes of a multi-byte character are consecutive atoms)
+            if (ch >= 0x80) ascii_only = false;
+            i++;
         }
-        if (i >= n) return GOFR_ERR_UNSUPPORTED;
-        i++;
-        if (neg) for (auto& w : pc.cls) w = ~w;
-    } else if (re[0] == '\\') {
-        if (re[1] != 'd' && re[1] != 'w') return GOFR_ERR_UNSUPPORTED;
-        add_esc(re[1]);
-        i = 2;
-    } else if (re[0] == '.') {
-        for (auto& w : pc.cls) w = 0xFFFFFFFFu;
-        pc.cls[0] &= ~(1u << '\n');
-        i = 1;
-    } else return GOFR_ERR_UNSUPPORTED;
-    if (i != n - 1) return GOFR_ERR_UNSUPPORTED;
-    if (re[i] == '+') pc.min_rep = 1;
-    else if (re[i] == '*') pc.min_rep = 0;
-    else return GOFR_ERR_UNSUPPORTED;
-    return GOFR_OK;
+        // quantifier
+        bool counted = false;
+        if (i < n && re[i] == '+') { at.min_rep = 1; at.max_rep = 0; i++; }
+        else if (i < n && re[i] == '*') { at.min_rep = 0; at.max_rep = 0; i++; }
+        else if (i < n && re[i] == '?') { at.min_rep = 0; at.max_rep = 1; i++; counted = true; }
+        else if (i < n && re[i] == '{') {
+            size_t j = i + 1;
+            auto num = [&](int& v) { if (j >= n || re[j] < '0' || re[j] > '9') return false; v = 0; while (j < n && re[j] >= '0' && re[j] <= '9') { v = v * 10 + (re[j] - '0'); if (v > 250) return false; j++; } return true; };
+            int lo = 0, hi = 0;
+            if (!num(lo)) return GOFR_ERR_UNSUPPORTED;
+            if (j < n && re[j] == '}') hi = lo;
+            else if (j < n && re[j] == ',') {
+                j++;
+                if (j < n && re[j] == '}') hi = 0;  // {n,}
+                else { if (!num(hi) || hi < lo) return GOFR_ERR_UNSUPPORTED; if (hi == 0) return GOFR_ERR_UNSUPPORTED; }
+            } else return GOFR_ERR_UNSUPPORTED;
+            if (j >= n || re[j] != '}') return GOFR_ERR_UNSUPPORTED;
+            if (hi == 0 && lo == 0 && re[j - 1] != ',') return GOFR_ERR_UNSUPPORTED;  // {0}: matches nothing but the empty string
+            at.min_rep = lo; at.max_rep = hi;
+            counted = !(hi == 0);  // {n,} only needs "at least n" — still a count of runes when n > 1
+            if (hi == 0 && lo > 1) counted = true;
+            i = j + 1;
+        } else { at.min_rep = 1; at.max_rep = 1; counted = false; }  // exactly one: one rune; for non-ASCII classes see below
+        if (i < n && (re[i] == '?' || re[i] == '+' || re[i] == '*' || re[i] == '{')) return GOFR_ERR_UNSUPPORTED;  // lazy / possessive / stacked
+        // a byte of a multi-byte literal character: a quantifier after it would apply to the whole character in Go
+        if (ch >= 0x80 && !(at.min_rep == 1 && at.max_rep == 1)) return GOFR_ERR_UNSUPPORTED;
+        // exactly-one of a class with non-ASCII members matches one RUNE in Go, one byte here
+        if (!ascii_only && (counted || (at.min_rep == 1 && at.max_rep == 1 && ch != '\\' && (ch == '.' || ch == '[')))) return GOFR_ERR_UNSUPPORTED;
+        out.push_back(at);
+        if (out.size() > 12) return GOFR_ERR_UNSUPPORTED;
+    }
+    return out.empty() ? GOFR_ERR_UNSUPPORTED : GOFR_OK;
 }
 
 // mux newRouteRegexp: literal text between top-level {...}; returns GOFR_OK, GOFR_ERR_UNSUPPORTED, or -1 for a
 // template mux itself rejects (the route then exists but never matches).
 static int parse_template(const std::string& tpl, std::vector<Piece>& out) {
     size_t n = tpl.size(), i = 0;
+    int n_vars = 0;
     for (;;) {
         size_t j = i;
         while (j < n && tpl[j] != '{' && tpl[j] != '}') j++;
@@ -315,12 +373,31 @@ static int parse_template(const std::string& tpl, std::vector<Piece>& out) {
         } else {
             std::string re = body.substr(colon + 1);
             if (re.empty()) return -1;
-            int rc = parse_var_regexp(re, pc);
+            std::vector<Atom> atoms;
+            int rc = parse_var_regexp(re, atoms);
             if (rc != GOFR_OK) return rc;
+            // the first atom follows the piece's literal; the others are pieces with an empty literal
+            for (size_t ai = 0; ai < atoms.size(); ai++) {
+                Piece ap = ai == 0 ? pc : Piece();
+                ap.has_var = true;
+                ap.name = name;
+                memcpy(ap.cls, atoms[ai].cls, sizeof ap.cls);
+                ap.min_rep = atoms[ai].min_rep;
+                ap.max_rep = atoms[ai].max_rep;
+                ap.var_idx = n_vars;
+                ap.var_first = ai == 0;
+                ap.var_last = ai + 1 == atoms.size();
+                out.push_back(ap);
+            }
+            n_vars++;
+            i = k + 1;
+            if (n_vars > kMaxVars || (int)out.size() > kMaxPieces) return GOFR_ERR_UNSUPPORTED;
+            continue;
         }
+        pc.var_idx = n_vars++;
         out.push_back(pc);
         i = k + 1;
-        if ((int)out.size() > kMaxVars) return GOFR_ERR_UNSUPPORTED;
+        if (n_vars > kMaxVars || (int)out.size() > kMaxPieces) return GOFR_ERR_UNSUPPORTED;
     }
     return GOFR_OK;
 }
@@ -877,14 +954,17 @@ int seal_table(gofr_table* t) {
             P.lit_len = (uint16_t)pc.lit.size();
             P.has_var = pc.has_var;
             P.min_rep = (uint8_t)pc.min_rep;
+            P.max_rep = (uint8_t)pc.max_rep;
+            P.var_idx = (uint8_t)pc.var_idx;
+            P.var_flags = (uint8_t)((pc.var_first ? PV_FIRST : 0) | (pc.var_last ? PV_LAST : 0));
             memcpy(P.cls, pc.cls, sizeof P.cls);
             pieces.push_back(P);
         }
         if (r.hkind == GOFR_H_PATHPARAM_FORMAT) {
-            // mux.Vars(r)[s0]: resolved to the piece index of the variable; an unknown name always yields ""
+            // mux.Vars(r)[s0]: resolved to the index of the variable; an unknown name always yields ""
             R.key_len = 0xFFFF;
             for (size_t k = 0; k < r.pieces.size(); k++)
-                if (r.pieces[k].has_var && r.pieces[k].name == r.s[0]) R.key_len = (uint16_t)k;
+                if (r.pieces[k].has_var && r.pieces[k].name == r.s[0]) R.key_len = (uint16_t)r.pieces[k].var_idx;
             R.def_off = pool.put("");
             R.def_len = 0;
         }

@@ -12,9 +12,10 @@
 namespace gofr {
 
 constexpr uint32_t kMagic = 0x52464F47u;  // "GOFR"
-constexpr uint32_t kImageVersion = 16;
+constexpr uint32_t kImageVersion = 17;
 constexpr uint32_t kMaxHotBytes = 40 * 1024;  // shared-memory budget for the table
 constexpr int kMaxVars = 8;                   // variables per route template
+constexpr int kMaxPieces = 16;                // literal + atom pieces per route template
 constexpr int kMaxValueDepth = 8;            // struct nesting the generic value encoder walks (its frame stack)
 constexpr int kMaxFields = 32;                // struct fields per schema
 
@@ -81,13 +82,19 @@ struct RouteRec {  // 32 B
 };
 static_assert(sizeof(RouteRec) == 32, "RouteRec layout");
 
-struct PieceRec {  // 48 B: literal, then (optionally) a variable = class repeated >= min_rep times, greedy
+enum PieceVarFlags : uint8_t { PV_FIRST = 1, PV_LAST = 2 };  // first / last atom of its variable
+struct PieceRec {  // 48 B: literal, then (optionally) an atom of a variable = class repeated min_rep..max_rep times, greedy
     uint32_t lit_off;
     uint16_t lit_len;
     uint8_t has_var;
     uint8_t min_rep;
     uint32_t cls[8];  // 256-bit membership
-    uint32_t pad[2];
+    uint8_t max_rep;    // 0 = unbounded
+    uint8_t var_idx;    // the variable (mux.Vars, template order) this atom is part of; a {name:regexp} may be several
+                        // consecutive atoms ([a-z]+\.[a-z]{2,4}), all but the first with an empty literal
+    uint8_t var_flags;  // PV_*
+    uint8_t pad0;
+    uint32_t pad;
 };
 static_assert(sizeof(PieceRec) == 48, "PieceRec layout");
 

@@ -214,7 +214,10 @@ void gofr_table_destroy(gofr_table*);
 int gofr_table_add_schema(gofr_table*, uint32_t schema_id, const char* go_type_name, const gofr_field_desc* fields,
                           uint32_t n_fields);
 /* Call order is match priority (mux scans routes in registration order).  Patterns: literals, {name} (= [^/]+) and
- * {name:[class]+} / {name:[class]*} with a bracket class or \d / \w / .   Other regexps → GOFR_ERR_UNSUPPORTED. */
+ * {name:regexp} where the regexp is a concatenation of quantified units: a unit is a bracket class, \d, \w, '.', an escaped
+ * punctuation character or a literal character; a quantifier is + * ? {n} {n,} {n,m} (n, m <= 250) — e.g. [0-9]+,
+ * \d{4}-\d{2}, v[0-9]+, [a-z]+\.[a-z]{2,4}.  Alternation, groups, anchors, lazy quantifiers, \s / \p{..} / POSIX classes and
+ * counted repetition of classes with non-ASCII members ('.', negated classes: Go counts runes) → GOFR_ERR_UNSUPPORTED. */
 int gofr_table_add_route(gofr_table*, uint32_t method, const char* pattern, uint32_t pattern_len,
                          const gofr_handler_desc* handler, uint32_t* route_id_out);
 /* GET /.well-known/health, GET /favicon.ico, PathPrefix("/") catch-all — appended after the user routes, as

@@ -41,8 +41,13 @@ typedef struct {
     int lit_len;
     int has_var;
     char* name;      /* variable name (mux.Vars key) */
-    uint8_t cls[32]; /* 256-bit membership of the variable's character class */
-    int min_rep;     /* 1 for '+', 0 for '*' */
+    /* the variable's regexp as a concatenation of quantified character classes (mux default [^/]+ = one atom) */
+    int n_atoms;
+    struct tpl_atom {
+        uint8_t cls[32]; /* 256-bit membership */
+        int min_rep;     /* {min,max}; max < 0 = unbounded */
+        int max_rep;
+    } atoms[12];
 } tpl_piece;
 
 typedef struct {
@@ -153,23 +158,32 @@ static void cls_add_escape(uint8_t* cls, int e) {
     else cls_set(cls, e);
 }
 
-/* Parse a variable's regexp into (class, min repetitions).  Supported subset of RE2 syntax: X+ or X* where X is a
- * bracket class, \d, \w or '.'; mux's default is [^/]+ .  Returns 0 ok, -1 unsupported. */
-static int parse_var_pattern(const char* p, int n, uint8_t* cls, int* min_rep) {
+/* Parse a variable's regexp into atoms.  Supported subset of RE2 syntax (regexp/syntax): a concatenation of units, each
+ * optionally quantified —
+ *     unit:   [...] bracket class (ranges, \d \w and escaped punctuation inside) | \d | \w | \<punct> | . | a literal char
+ *     quant:  + * ? {n} {n,} {n,m}
+ * without alternation, groups, anchors or lazy quantifiers.  Matching is done on bytes; Go matches runes, so whatever
+ * would count non-ASCII runes ({n}, ?, a bare '.' or negated class) is outside the subset.  Returns 0 ok, -1 unsupported. */
+static int is_alnum_c(int c) { return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); }
+static int parse_unit(const char* p, int n, int* ip, uint8_t* cls, int* has_high, int* is_set) {
+    int i = *ip;
     memset(cls, 0, 32);
-    int i = 0;
-    if (n < 2) return -1;
-    if (p[0] == '[') {
-        int neg = 0;
-        i = 1;
+    *has_high = 0;
+    *is_set = 0;
+    int c = (uint8_t)p[i];
+    if (c == '[') {
+        *is_set = 1;
+        int neg = 0, first = 1;
+        i++;
         if (i < n && p[i] == '^') { neg = 1; i++; }
-        int first = 1;
-        while (i < n && (p[i] != ']' || first)) {
+        for (; i < n && (p[i] != ']' || first); first = 0) {
             int a = (uint8_t)p[i];
+            if (a == '[' && i + 1 < n && p[i + 1] == ':') return -1; /* POSIX classes */
             if (a == '\\') {
                 if (i + 1 >= n) return -1;
                 int e = (uint8_t)p[i + 1];
-                if (e == 'd' || e == 'w') { cls_add_escape(cls, e); i += 2; first = 0; continue; }
+                if (e == 'd' || e == 'w') { cls_add_escape(cls, e); i += 2; continue; }
+                if (is_alnum_c(e)) return -1; /* \s \p{..} \x.. \b ... */
                 a = e;
                 i++;
             }
@@ -184,27 +198,77 @@ static int parse_var_pattern(const char* p, int n, uint8_t* cls, int* min_rep) {
                 cls_set(cls, a);
                 i++;
             }
-            first = 0;
         }
         if (i >= n) return -1;
         i++; /* ']' */
-        if (neg) cls_invert(cls); /* negated class also matches every non-ASCII rune (and U+FFFD for bad bytes) */
-    } else if (p[0] == '\\') {
-        if (p[1] != 'd' && p[1] != 'w') return -1;
-        cls_add_escape(cls, p[1]);
-        i = 2;
-    } else if (p[0] == '.') {
+        if (neg) { cls_invert(cls); *has_high = 1; } /* a negated class also matches every non-ASCII rune */
+    } else if (c == '\\') {
+        if (i + 1 >= n) return -1;
+        int e = (uint8_t)p[i + 1];
+        if (e == 'd' || e == 'w') cls_add_escape(cls, e);
+        else if (is_alnum_c(e) || e >= 0x80) return -1;
+        else cls_set(cls, e);
+        i += 2;
+    } else if (c == '.') {
+        *is_set = 1;
         memset(cls, 0xFF, 32);
         cls[1] &= (uint8_t)~(1u << ('\n' & 7)); /* '.' does not match \n without (?s) */
-        i = 1;
-    } else {
+        *has_high = 1;
+        i++;
+    } else if (strchr("()|^$+*?{}]", c)) {
         return -1;
+    } else {
+        cls_set(cls, c);
+        if (c >= 0x80) *has_high = 1;
+        i++;
     }
-    if (i != n - 1) return -1;
-    if (p[i] == '+') *min_rep = 1;
-    else if (p[i] == '*') *min_rep = 0;
-    else return -1;
+    *ip = i;
     return 0;
+}
+
+static int parse_var_pattern(const char* p, int n, tpl_piece* pc) {
+    pc->n_atoms = 0;
+    int i = 0;
+    while (i < n) {
+        if (pc->n_atoms == 12) return -1;
+        struct tpl_atom* at = &pc->atoms[pc->n_atoms];
+        int high = 0, is_set = 0, lead = (uint8_t)p[i];
+        if (parse_unit(p, n, &i, at->cls, &high, &is_set) != 0) return -1;
+        int lo = 1, hi = 1, quantified = 0;
+        if (i < n && (p[i] == '+' || p[i] == '*' || p[i] == '?')) {
+            lo = p[i] == '+';
+            hi = p[i] == '?' ? 1 : -1;
+            quantified = 1;
+            i++;
+        } else if (i < n && p[i] == '{') {
+            int j = i + 1, d = 0;
+            lo = 0;
+            while (j < n && p[j] >= '0' && p[j] <= '9' && d < 4) { lo = lo * 10 + (p[j] - '0'); j++; d++; }
+            if (d == 0 || lo > 250) return -1;
+            if (j < n && p[j] == '}') hi = lo;
+            else if (j + 1 < n && p[j] == ',' && p[j + 1] == '}') { hi = -1; j++; }
+            else if (j < n && p[j] == ',') {
+                j++;
+                d = 0; hi = 0;
+                while (j < n && p[j] >= '0' && p[j] <= '9' && d < 4) { hi = hi * 10 + (p[j] - '0'); j++; d++; }
+                if (d == 0 || hi > 250 || hi < lo || hi == 0) return -1;
+            } else return -1;
+            if (j >= n || p[j] != '}') return -1;
+            if (hi == 0) return -1; /* {0} */
+            quantified = 1;
+            i = j + 1;
+        }
+        if (i < n && (p[i] == '+' || p[i] == '*' || p[i] == '?' || p[i] == '{')) return -1; /* lazy, stacked */
+        /* rune vs byte: only X+ / X* are the same thing on bytes when X can match non-ASCII */
+        int open_ended = hi < 0 && lo <= 1;
+        if (high && is_set && !open_ended) return -1;
+        if (high && !is_set && quantified) return -1; /* a byte of a multi-byte literal cannot carry the quantifier */
+        at->min_rep = lo;
+        at->max_rep = hi;
+        (void)lead;
+        pc->n_atoms++;
+    }
+    return pc->n_atoms ? 0 : -1;
 }
 
 /* mux newRouteRegexp: split the template at top-level braces; {name} → [^/]+, {name:pattern} → pattern. */
@@ -243,12 +307,14 @@ static int parse_template(orc_route* r, const char* tpl, int n) {
         for (int q = 0; q + 1 < r->n_pieces; q++) /* mux: "duplicated route variable" → route error */
             if (r->pieces[q].has_var && strcmp(r->pieces[q].name, pc->name) == 0) return -2;
         if (colon < 0) {
-            memset(pc->cls, 0xFF, 32);
-            pc->cls['/' >> 3] &= (uint8_t)~(1u << ('/' & 7));
-            pc->min_rep = 1;
+            pc->n_atoms = 1;
+            memset(pc->atoms[0].cls, 0xFF, 32);
+            pc->atoms[0].cls['/' >> 3] &= (uint8_t)~(1u << ('/' & 7));
+            pc->atoms[0].min_rep = 1;
+            pc->atoms[0].max_rep = -1;
         } else {
             if (bl - colon - 1 == 0) return -2; /* mux: missing pattern */
-            if (parse_var_pattern(body + colon + 1, bl - colon - 1, pc->cls, &pc->min_rep) != 0) return -1;
+            if (parse_var_pattern(body + colon + 1, bl - colon - 1, pc) != 0) return -1;
         }
         i = k + 1;
         lit_start = i;
@@ -503,23 +569,30 @@ static void query_get(const uint8_t* q, size_t qn, const uint8_t* key, size_t kn
 /* Anchored leftmost-first match of lit0 (var0 lit1 (var1 ...)) [$]: greedy variables with backtracking, which is
  * what Go's regexp reports for this shape. */
 typedef struct { size_t off, len; } var_span;
+static int tpl_match_from(const orc_route* r, int k, const uint8_t* p, size_t n, size_t pos, var_span* spans);
+/* atoms a.. of piece k's variable, the variable having started at var_start */
+static int tpl_match_atoms(const orc_route* r, int k, int a, const uint8_t* p, size_t n, size_t pos, size_t var_start, var_span* spans) {
+    const tpl_piece* pc = &r->pieces[k];
+    if (a == pc->n_atoms) {
+        int ok = k + 1 < r->n_pieces ? tpl_match_from(r, k + 1, p, n, pos, spans) : (r->prefix || pos == n);
+        if (ok && spans) { spans[k].off = var_start; spans[k].len = pos - var_start; }
+        return ok;
+    }
+    const struct tpl_atom* at = &pc->atoms[a];
+    size_t run = 0;
+    while (pos + run < n && (at->max_rep < 0 || run < (size_t)at->max_rep) && cls_has(at->cls, p[pos + run])) run++;
+    for (size_t take = run;; take--) { /* greedy, giving back one byte at a time */
+        if (take >= (size_t)at->min_rep && tpl_match_atoms(r, k, a + 1, p, n, pos + take, var_start, spans)) return 1;
+        if (take == 0) break;
+    }
+    return 0;
+}
 static int tpl_match_from(const orc_route* r, int k, const uint8_t* p, size_t n, size_t pos, var_span* spans) {
     const tpl_piece* pc = &r->pieces[k];
     if (n - pos < (size_t)pc->lit_len || memcmp(p + pos, pc->lit, (size_t)pc->lit_len) != 0) return 0;
     pos += (size_t)pc->lit_len;
     if (!pc->has_var) return r->prefix ? 1 : pos == n;
-    size_t run = 0;
-    while (pos + run < n && cls_has(pc->cls, p[pos + run])) run++;
-    for (size_t take = run;; take--) {
-        if (take >= (size_t)pc->min_rep) {
-            int ok = 0;
-            if (k + 1 < r->n_pieces) ok = tpl_match_from(r, k + 1, p, n, pos + take, spans);
-            else ok = r->prefix || pos + take == n;
-            if (ok) { if (spans) { spans[k].off = pos; spans[k].len = take; } return 1; }
-        }
-        if (take == 0) break;
-    }
-    return 0;
+    return tpl_match_atoms(r, k, 0, p, n, pos, pos, spans);
 }
 
 static int path_matches(const orc_route* r, const uint8_t* p, size_t n) {

@@ -147,7 +147,9 @@ from hypothesis import given, settings, strategies as st  # noqa: E402
 
 _seg = st.sampled_from(["a", "b", "ab", "users", "v1", "x.y", "1", "22", "a-b", "_", "apiservice", "apiserver", "api"])  # the long ones
 # give templates a leading literal of >= 8 bytes (keyed dispatch), two of them with the same first 8 bytes
-_var = st.sampled_from(["{id}", "{n:[0-9]+}", "{w:[a-z]+}", "{s:[a-z0-9.]*}", "{id}.{ext}", "{a}{b:[0-9]+}", "p{q}", "{d:\\d+}x"])
+_var = st.sampled_from(["{id}", "{n:[0-9]+}", "{w:[a-z]+}", "{s:[a-z0-9.]*}", "{id}.{ext}", "{a}{b:[0-9]+}", "p{q}", "{d:\\d+}x",
+                        "{y:[0-9]{2}}", "{v:v[0-9]+}", "{f:[a-z]+\\.[a-z]{1,3}}", "{o:[a-z]?[0-9]{1,2}}", "{r:\\d{1,}-?\\w*}", "{m:a{2,}b?}",
+                        "{h:[a-z]+-[a-z0-9]+}", "{t:.*x}"])
 _piece = st.one_of(_seg, _var)
 _pattern = st.lists(_piece, min_size=0, max_size=4).map(lambda ps: "/" + "/".join(ps))
 _method = st.sampled_from([S.M_GET, S.M_GET, S.M_POST, S.M_DELETE, S.M_ANY])
@@ -187,3 +189,100 @@ def test_random_tables_property(routes, defaults, reqs):
     # and the full serve path reports the same route ids (H_HOST routes come back with status 0)
     _, _, m3 = emu.serve(Table(spec).serialize(), batch, S.http_date(1_700_000_000))
     assert np.array_equal(m1 >> 16, m3 >> 16)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# variable regexps beyond one class: concatenations of quantified classes, cross-checked with Python's re
+# ---------------------------------------------------------------------------------------------------------------
+QUANT_ROUTES = ["/d/{date:[0-9]{4}-[0-9]{2}-[0-9]{2}}", "/api/{ver:v[0-9]+}/items/{id:[0-9]{1,3}}", "/f/{name:[a-z]+\\.[a-z]{2,4}}",
+                "/o/{x:[a-z]?[0-9]{2,}}/{y:\\w+-\\w+}", "/m/{a:a{2,}b?}c", "/t/{pre:.*}-{n:\\d+}", "/z/{k:[a-c]*}{l:[b-d]{2}}e",
+                "/s/{slug:[a-z0-9]+(?:-[a-z0-9]+)*}", "/q/{e:x{0,2}}y", "/u/{w:[^/]+}.{ext:[a-z]{3}}", "/c/{n:\\d\\d:\\d\\d}"]
+
+
+def _mux_regex(pattern: str):
+    """the regexp mux builds from a template (newRouteRegexp): ^ + QuoteMeta(literal) + (?P<v0>pattern) ... + $"""
+    import re
+    out, i, names = "^", 0, []
+    while i < len(pattern):
+        if pattern[i] == "{":
+            depth, j = 0, i
+            while True:
+                depth += pattern[j] == "{"
+                depth -= pattern[j] == "}"
+                if depth == 0:
+                    break
+                j += 1
+            name, _, pat = pattern[i + 1:j].partition(":")
+            out += "(%s)" % (pat or "[^/]+")
+            names.append(name)
+            i = j + 1
+        else:
+            j = pattern.find("{", i)
+            j = len(pattern) if j < 0 else j
+            out += re.escape(pattern[i:j])
+            i = j
+    return re.compile((out + "$").encode()), names
+
+
+def test_quantified_variable_patterns_against_python_re():
+    """oracle == device code == Python's re (leftmost-first backtracking, like RE2 reports for these patterns) on which
+    route matches and what every variable captures; patterns outside the subset are refused when the route is added"""
+    import random
+    ok_routes = []
+    for r in QUANT_ROUTES:
+        try:
+            Table(S.TableSpec(default_routes=False, routes=[S.Route(S.M_GET, r, S.H_HOST)]))
+            ok_routes.append(r)
+        except Exception:
+            assert "(?:" in r, r          # the only pattern of the list outside the subset: a group
+    assert len(ok_routes) == len(QUANT_ROUTES) - 1
+    spec = S.TableSpec(default_routes=False, routes=[S.Route(S.M_GET, r, S.H_HOST) for r in ok_routes])
+    rnd = random.Random(11)
+    frag = ["2024", "-", "01", "1", "v", "12", "abc", ".", "tar", "gz", "a", "aa", "aaa", "b", "c", "x", "y", "_", "ab-cd", "7", "e", "bb", "cd", "12:30", ":", "0"]
+    heads = ["/d/", "/api/", "/f/", "/o/", "/m/", "/t/", "/z/", "/q/", "/u/", "/c/", "/items/", "/"]
+    paths = [b"/d/2024-01-31", b"/d/2024-1-31", b"/api/v12/items/7", b"/api/v12/items/1234", b"/api/v/items/1", b"/f/archive.tar", b"/f/a.b",
+             b"/f/x.abcde", b"/o/a12/b-c", b"/o/123/x_1-y", b"/o/ab12/b-c", b"/m/aac", b"/m/aabc", b"/m/abc", b"/m/aaabbc", b"/t/a-b-12",
+             b"/t/-1", b"/t/x-", b"/z/abcbce", b"/z/bce", b"/z/ce", b"/q/y", b"/q/xxy", b"/q/xxxy", b"/u/a.b.txt", b"/u/.txt", b"/c/12:30", b"/c/1:30"]
+    for _ in range(1500):
+        paths.append((rnd.choice(heads) + "".join(rnd.choice(frag) + rnd.choice(["", "", "/"]) for _ in range(rnd.randint(1, 5)))).encode())
+    # near misses and hits built from each template: every variable filled from a pool of plausible values
+    pool = ["2024", "01", "31", "1", "12", "123", "1234", "v1", "v12", "v", "abc", "a", "aa", "aaa", "aab", "b", "tar", "gz", "abcde", "x", "xx", "xxx",
+            "", "a1", "ab12", "12a", "b-c", "x_1-y", "1-", "7-ab", "-", "a-b", "ab", "bc", "cd", "abcbc", "12:30", "1:30", "a.b", ".", "é", "2024-01-31", "ab.txt"]
+    import re
+    for r in ok_routes:
+        parts = re.split(r"\{(?:[^{}]|\{[^{}]*\})*\}", r)
+        for _ in range(250):
+            paths.append("".join(part + (rnd.choice(pool) if k + 1 < len(parts) else "") for k, part in enumerate(parts)).encode())
+    paths = [p for p in paths if b"//" not in p and not p.endswith(b"/.")]
+    batch = S.RequestBatch.pack([S.Req(S.M_GET, p) for p in paths])
+    m1, v1 = O.route(O.OracleTable(spec), batch)
+    m2, v2 = emu.route(Table(spec).serialize(), batch)
+    assert np.array_equal(m1, m2) and np.array_equal(v1, v2)
+    regs = [_mux_regex(r) for r in ok_routes]
+    hits = 0
+    for i, p in enumerate(paths):
+        want = None
+        for ri, (rx, names) in enumerate(regs):
+            m = rx.match(p)
+            if m:
+                want = (ri, [m.span(k + 1) for k in range(len(names))])
+                break
+        if (int(m1[i]) & 0xFFFF) == 301:
+            continue                       # cleanPath redirect decided before matching
+        if want is None:
+            assert int(m1[i]) & 0xFFFF == 404, (p, hex(int(m1[i])))
+            continue
+        hits += 1
+        assert int(m1[i]) >> 16 == want[0] and int(m1[i]) & 0xFFFF == 0, (p, want, hex(int(m1[i])))
+        for k, (a, b) in enumerate(want[1]):
+            assert (int(v1[i, k]) & 0xFFFF, int(v1[i, k]) >> 16) == (a, b - a), (p, k, want)
+    assert hits > 100
+
+
+def test_patterns_outside_the_subset_are_refused():
+    for pat in ["{a:(x|y)}", "{a:x|y}", "{a:[a-z]+?}", "{a:.{3}}", "{a:[^/]{2}}", "{a:\\s+}", "{a:[[:alpha:]]+}", "{a:^x}", "{a:x$}", "{a:é+}", "{a:.}",
+                "{a:[a-z]{0}}", "{a:[a-z]{3,2}}", "{a:[a-z]{300}}", "{a:\\pL+}", "{a:*}", "{a:a**}"]:
+        with pytest.raises(Exception):
+            Table(S.TableSpec(default_routes=False, routes=[S.Route(S.M_GET, "/p/" + pat, S.H_HOST)]))
+    for pat in ["{a:é}", "{a:[a-z]{0,}}", "{a:\\.}", "{a:.+}", "{a:[^/]*}", "{a:a{1}}"]:
+        Table(S.TableSpec(default_routes=False, routes=[S.Route(S.M_GET, "/p/" + pat, S.H_HOST)]))
