@@ -76,7 +76,8 @@ struct gofr_engine {
     uint32_t image_bytes = 0;
     // launch geometry
     uint32_t in_cap = 0, smem_bytes = 0;
-    int wide_grid = 0;        // slot layout, wide instance (serve_slots_kernel.cu)
+    uint32_t w_in_cap = 0, w_smem_bytes = 0;  // the same for the wide slot-layout instance (4 CTAs/SM: a larger staging area fits)
+    int wide_grid = 0, wide_blocks_per_sm = 0;
     bool slots_wide = false;  // choose_slot_residency
     bool has_values = false;  // some program has PF_VALUES: the packed layout runs serve_kernel_values (serve_values_kernel.cu)
     int grid = 0, blocks_per_sm = 0, grpc_grid = 0, reqlog_grid = 0, http_grid = 0, proto_grid = 0, proto_decode_grid = 0;
@@ -138,13 +139,21 @@ static bool choose_slot_residency(const std::vector<uint8_t>& img, const ImageHe
     return image_wants_wide_slots(img.data());
 }
 
-static int configure_geometry(gofr_engine* e, uint32_t in_per_req) {
+// in_per_req / w_in_per_req: bytes of request staging per request for the 5-CTA instances / the wide slot-layout instance
+static int configure_geometry(gofr_engine* e, uint32_t in_per_req, uint32_t w_in_per_req) {
+    // the slot layout keeps its deferred-request list (2 T words) in the staging area
+    if (in_per_req < 16u) in_per_req = 16u;
+    if (w_in_per_req < 16u) w_in_per_req = 16u;
     e->in_cap = (kServeT * in_per_req + 127u) & ~127u;
     e->smem_bytes = serve_smem_bytes(e->hdr.hot_bytes, e->in_cap);
-    if (e->smem_bytes > 227 * 1024) { set_last_error("tile geometry needs %u bytes of shared memory", e->smem_bytes); return GOFR_ERR_CAPACITY; }
-    int g = serve_max_grid(e->smem_bytes, e->device, &e->blocks_per_sm, &e->wide_grid);
+    e->w_in_cap = (kServeT * w_in_per_req + 127u) & ~127u;
+    e->w_smem_bytes = serve_smem_bytes(e->hdr.hot_bytes, e->w_in_cap);
+    if (e->smem_bytes > 227 * 1024 || e->w_smem_bytes > 227 * 1024) { set_last_error("tile geometry needs %u bytes of shared memory", std::max(e->smem_bytes, e->w_smem_bytes)); return GOFR_ERR_CAPACITY; }
+    int g = serve_max_grid(e->smem_bytes, e->device, &e->blocks_per_sm, false);
     if (g <= 0) { set_last_error("serve kernel cannot be resident with %u bytes of shared memory", e->smem_bytes); return GOFR_ERR_CUDA; }
     e->grid = g;
+    e->wide_grid = serve_max_grid(e->w_smem_bytes, e->device, &e->wide_blocks_per_sm, true);
+    if (e->wide_grid < 0) e->wide_grid = 0;  // the wide instance is optional: the engine falls back to the others
     return GOFR_OK;
 }
 
@@ -188,14 +197,15 @@ static int engine_init(gofr_engine* e, const std::vector<uint8_t>& img, int devi
     CUDA_TRY(cudaMemcpy(e->d_image, img.data(), img.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&e->d_flag, 64));
     CUDA_TRY(cudaMemset(e->d_flag, 0, 64));
-    // default tile geometry: stage as many request bytes per request in shared memory as still lets 5 CTAs share an
-    // SM (the kernel is latency bound: residency matters more than staging every tile); larger tiles are read from
-    // HBM directly.
-    uint32_t per_cta = 227u * 1024u / (uint32_t)kServeCtas - 1024u /*reserved*/ - (64u * kServeT + 256u) /*static: staging buffer + tile state*/;
-    uint32_t hot = (e->hdr.hot_bytes + 127u) & ~127u;
-    uint32_t in_per = per_cta > hot + 64u * kServeT ? ((per_cta - hot - 64u) / kServeT) & ~15u : 64u;
-    if (in_per > 256u) in_per = 256u;
-    int rc = configure_geometry(e, in_per);
+    // default tile geometry: as many request bytes per request staged in shared memory as still lets the instance keep
+    // its CTAs per SM (5, or 4 for the wide slot-layout instance — the kernel is latency bound: residency matters more than
+    // staging every tile; larger tiles are read from HBM directly).  The budget is found by asking the runtime's occupancy
+    // calculator, not by a formula.
+    uint32_t in_per = serve_fit_in_per(e->hdr.hot_bytes, kServeCtas, false);
+    uint32_t w_in_per = serve_fit_in_per(e->hdr.hot_bytes, kServeCtasWide, true);
+    if (in_per < 64u) in_per = 64u;    // a table this large: stage at least short requests, whatever residency is left
+    if (w_in_per < in_per) w_in_per = in_per;
+    int rc = configure_geometry(e, in_per, w_in_per);
     if (rc != GOFR_OK) return rc;
     e->slots_wide = choose_slot_residency(img, e->hdr);
     for (uint32_t k = 0; k < e->hdr.n_progs; k++)
@@ -252,7 +262,7 @@ void gofr_engine_destroy(gofr_engine* e) {
 int gofr_engine_set_tile(gofr_engine* e, uint32_t in_bytes_per_req) {
     if (!e || !in_bytes_per_req) return GOFR_ERR_INVALID;
     std::lock_guard<std::mutex> g(e->mu);
-    return configure_geometry(e, in_bytes_per_req);
+    return configure_geometry(e, in_bytes_per_req, in_bytes_per_req);
 }
 
 int gofr_engine_set_chunk(gofr_engine* e, uint32_t requests_per_chunk) {
@@ -312,13 +322,13 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
     { int erc = next_epoch(e, &p.epoch); if (erc) return erc; }
     p.out = d_out; p.out_cap = out_cap; p.out_off = d_off; p.meta = d_meta;
     p.tile_state = d_state; p.overflow = d_flag;
-    p.in_cap = e->in_cap;
+    const bool wide = slot_bytes && e->slots_wide && !e->has_values && e->wide_grid > 0;
+    p.in_cap = wide ? e->w_in_cap : e->in_cap;
     p.bind_scratch = d_bind; p.bind_row_words = e->hdr.bind_row_words;
     p.chain_pos = chain_pos;
     p.slot_bytes = slot_bytes;
     p.debug_flags = e->debug_flags;
     memcpy(p.date, date29, 29);
-    const bool wide = slot_bytes && e->slots_wide && !e->has_values && e->wide_grid > 0;
     int grid = (int)std::min<uint32_t>((uint32_t)(wide ? e->wide_grid : e->grid), p.n_tiles);
     if (!slot_bytes) grid = std::max(1, std::min(grid, e->grid / engines_on_device(e->device)));  // look-back: see engines_on_device
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -328,7 +338,7 @@ static int launch_one(gofr_engine* e, const void* d_desc, const void* d_ids, con
         CUDA_TRY(cudaEventCreate(&ev1));
         CUDA_TRY(cudaEventRecord(ev0, stream));
     }
-    int rc = launch_serve(p, grid, e->smem_bytes, stream, wide, e->has_values);
+    int rc = launch_serve(p, grid, wide ? e->w_smem_bytes : e->smem_bytes, stream, wide, e->has_values);
     if (rc != 0) { set_last_error("serve kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
     if (e->timing_on) {
         CUDA_TRY(cudaEventRecord(ev1, stream));

@@ -61,8 +61,10 @@ bool image_wants_wide_slots(const uint8_t* image);
 uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap);
 // cudaError_t as int
 int launch_serve(const ServeParams& p, int grid, uint32_t smem_bytes, void* stream, bool wide_slots = false, bool values = false);
-// grid of the persistent kernels (both layouts share it); *wide_grid: grid of the wide slot-layout instance
-int serve_max_grid(uint32_t smem_bytes, int device, int* blocks_per_sm, int* wide_grid);
+// grid of the persistent kernels of a group (wide: the 4-CTA slot-layout instance; else all the others) for that much
+// dynamic shared memory, and the largest per-request staging budget that keeps `ctas` CTAs of the group resident
+int serve_max_grid(uint32_t smem_bytes, int device, int* blocks_per_sm, bool wide);
+uint32_t serve_fit_in_per(uint32_t hot_bytes, int ctas, bool wide);
 
 // egress of the host-batch path (egress_kernel.cu)
 struct ChunkInfo {

@@ -43,8 +43,9 @@ struct TileShared {
     uint32_t warp_cls[NW];  // slot layout: program shape class of each warp's lane 0
     unsigned long long tile_base;
     uint32_t in_lo, in_hi;
-    uint32_t defer_n;         // slot layout: requests waiting for the general pass
-    uint32_t defer[2 * T];    // their indices (at most one tile's worth is added between two checks)
+    uint32_t defer_n;         // slot layout: requests waiting for the general pass; their indices (at most 2 T: one tile's
+                              // worth is added between two checks) live in the request staging area, which is idle once
+                              // the tile loop is over — as static shared memory the list cost every instance its fifth CTA
     uint32_t ring[GOFR_STAGE_WORDS * T];  // word-major staging buffer of the Writer (serve_device.cuh)
 };
 
@@ -57,11 +58,11 @@ struct TileShared {
 // request bytes are read from HBM here (the tile that staged them is gone); the code is out of line so that the tile loop
 // keeps its registers and its instruction-cache footprint.
 static __device__ __noinline__ void general_pass(const ServeParams* pp, const TableView tv, const BatchRefs br, TileShared* sh,
-                                          uint32_t first, uint32_t count) {
+                                          const uint32_t* defer, uint32_t first, uint32_t count) {
     const ServeParams& p = *pp;
     const uint32_t tid = threadIdx.x;
     if (tid >= count) return;
-    const uint32_t r = sh->defer[first + tid];
+    const uint32_t r = defer[first + tid];
     const uint4 d = __ldg((const uint4*)p.desc + r);
     ReqCtx c;
     c.set(p.arena, d.x, d.y & 0xFFFFu, d.y >> 16, d.z, d.w & 0xFFu, (d.w >> 8) & 0xFFu, false, r);
@@ -292,15 +293,16 @@ __device__ __forceinline__ void serve_body(const ServeParams& p) {
         // visible — read past L1, which may hold nothing newer than the launch), gathers the marked indices and serves
         // them 128 at a time.  Nothing of this is in the tile loop: no list, no atomics, no call site.
         __syncthreads();
+        uint32_t* const defer = (uint32_t*)in_stage;  // >= 2 T words: the engine never stages less than 16 bytes per request
         for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const uint32_t i = tile * T + tid;
             const bool marked = i < p.n && __ldcg(p.out_off + i) == kDeferred;
             if (__syncthreads_or(marked)) {
-                if (marked) sh.defer[atomicAdd(&sh.defer_n, 1u)] = i;
+                if (marked) defer[atomicAdd(&sh.defer_n, 1u)] = i;
                 __syncthreads();
                 const uint32_t dn = sh.defer_n;
                 if (dn >= (uint32_t)T) {
-                    general_pass(&p, tv, br, &sh, dn - T, T);
+                    general_pass(&p, tv, br, &sh, defer, dn - T, T);
                     __syncthreads();
                     if (tid == 0) sh.defer_n = dn - T;
                     __syncthreads();
@@ -308,7 +310,7 @@ __device__ __forceinline__ void serve_body(const ServeParams& p) {
             }
         }
         const uint32_t dn = sh.defer_n;
-        if (dn) general_pass(&p, tv, br, &sh, 0, dn);
+        if (dn) general_pass(&p, tv, br, &sh, defer, 0, dn);
     }
 }
 

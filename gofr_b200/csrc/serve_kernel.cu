@@ -21,19 +21,39 @@ uint32_t serve_smem_bytes(uint32_t hot_bytes, uint32_t in_cap) {
     return ((hot_bytes + 127u) & ~127u) + in_cap + 64;
 }
 
-int serve_max_grid(uint32_t smem_bytes, int device, int* blocks_per_sm, int* wide_grid) {
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+// CTAs per SM with which every instance of a group is resident for `smem_bytes` of dynamic shared memory: the wide
+// slot-layout instance alone, or all the others (packed / slots, with and without the wider data model).  Asked from
+// the runtime (static shared memory, registers and the per-CTA reservation included) — a hand-kept formula fell behind
+// the kernel once and the "5-CTA" instances silently ran 4 per SM.
+int serve_blocks_per_sm(uint32_t smem_bytes, bool wide) {
+    if (wide) return serve_slots_blocks_per_sm(smem_bytes, true);
     if (cudaFuncSetAttribute(serve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, serve_kernel, T, smem_bytes) != cudaSuccess) return -1;
     const int nb2 = serve_slots_blocks_per_sm(smem_bytes, false);
-    const int nbw = serve_slots_blocks_per_sm(smem_bytes, true);
     const int nbv = serve_values_blocks_per_sm(smem_bytes);
-    if (nb2 < 0 || nbw < 0 || nbv < 0) return -1;
+    if (nb2 < 0 || nbv < 0) return -1;
     if (nb2 < nb) nb = nb2;
     if (nbv < nb) nb = nbv;
-    if (wide_grid) *wide_grid = nbw * prop.multiProcessorCount;
+    return nb;
+}
+
+// The largest request staging budget (bytes per request: a multiple of 16 from 16 to 256) with which `ctas` CTAs of the
+// group stay resident per SM next to a table of hot_bytes; 0 when not even the smallest one fits.
+uint32_t serve_fit_in_per(uint32_t hot_bytes, int ctas, bool wide) {
+    for (uint32_t in_per = 256; in_per >= 16; in_per -= 16) {
+        const uint32_t smem = serve_smem_bytes(hot_bytes, ((uint32_t)T * in_per + 127u) & ~127u);
+        if (smem > 227u * 1024u) continue;
+        if (serve_blocks_per_sm(smem, wide) >= ctas) return in_per;
+    }
+    return 0;
+}
+
+int serve_max_grid(uint32_t smem_bytes, int device, int* blocks_per_sm, bool wide) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    const int nb = serve_blocks_per_sm(smem_bytes, wide);
+    if (nb < 0) return -1;
     if (blocks_per_sm) *blocks_per_sm = nb;
     return nb * prop.multiProcessorCount;
 }
