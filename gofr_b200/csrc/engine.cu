@@ -134,9 +134,15 @@ static void register_engine(int device, int delta) {
     if (device >= 0 && device < 64) g_live_engines[device] += delta;
 }
 
-static bool choose_slot_residency(const std::vector<uint8_t>& img, const ImageHeader&) {
+// Which slot-layout instance serves this table (serve_slots_kernel.cu): the 5-CTA one unless the wide one (4 CTAs/SM, 128
+// registers) is asked for (GOFR_SLOT_CTAS=4, gofr_engine_slot_ctas).  For a short while the wide instance was the default
+// for one-shape fast-path tables — it measured 4 % faster than the "5-CTA" instance on config 2 — until it turned out that
+// the 5-CTA instances had been resident 4 per SM: with the fifth CTA back they are 7.5 % faster than
+// the wide one on the same table (0.2737 against 0.2959 ms).  image_wants_wide_slots (table_build.cpp) still tells which
+// tables the wide instance was meant for.
+static bool choose_slot_residency(const std::vector<uint8_t>&, const ImageHeader&) {
     if (const char* v = getenv("GOFR_SLOT_CTAS")) return atoi(v) == kServeCtasWide;
-    return image_wants_wide_slots(img.data());
+    return false;
 }
 
 // in_per_req / w_in_per_req: bytes of request staging per request for the 5-CTA instances / the wide slot-layout instance
