@@ -78,7 +78,7 @@ GOFR_HD_NOINLINE void http_parse(const uint8_t* m, uint32_t n, uint8_t* dst, Htt
         if (m[k] == '%' && (k + 2 >= path_end || http_hex(m[k + 1]) < 0 || http_hex(m[k + 2]) < 0)) return;
 
     // ---- header lines ----
-    uint32_t pos = t1 + 11, hosts = 0, cls = 0;
+    uint32_t pos = t1 + 11, hosts = 0, cls = 0, chunked = 0;
     uint64_t content_length = 0;
     uint64_t sp_ua = 0, sp_xff = 0, sp_host = 0;
     bool have_ua = false, have_xff = false;
@@ -119,10 +119,14 @@ GOFR_HD_NOINLINE void http_parse(const uint8_t* m, uint32_t n, uint8_t* dst, Htt
             }
         } else if (http_name_is(nm, nl, "connection", 10)) {
             if (!http_name_is(m + v0, v1 - v0, "keep-alive", 10)) return;
-        } else if (http_name_is(nm, nl, "transfer-encoding", 17) || http_name_is(nm, nl, "expect", 6) ||
-                   http_name_is(nm, nl, "upgrade", 7) || http_name_is(nm, nl, "trailer", 7)) return;
+        } else if (http_name_is(nm, nl, "transfer-encoding", 17)) {
+            // exactly one coding, "chunked" (net/http readTransfer: any other coding is "unsupported transfer encoding")
+            if (chunked || !http_name_is(m + v0, v1 - v0, "chunked", 7)) return;
+            chunked = 1;
+        } else if (http_name_is(nm, nl, "expect", 6) || http_name_is(nm, nl, "upgrade", 7) || http_name_is(nm, nl, "trailer", 7)) return;
     }
     if (hosts != 1 || cls > 1) return;
+    if (chunked && cls) return;  // both: net/http drops the Content-Length of a chunked request — left to it
     {
         const uint32_t h0 = (uint32_t)sp_host, hl = (uint32_t)(sp_host >> 32);
         if (hl == 0) return;
@@ -131,8 +135,27 @@ GOFR_HD_NOINLINE void http_parse(const uint8_t* m, uint32_t n, uint8_t* dst, Htt
             if (!(c - '0' < 10u || (c | 0x20u) - 'a' < 26u || c == '.' || c == ':' || c == '-' || c == '_' || c == '[' || c == ']')) return;
         }
     }
-    const uint32_t body_len = n - pos;
-    if (cls ? (uint64_t)body_len != content_length : body_len != 0) return;
+    // ---- body: Content-Length bytes, or a chunk stream (net/http internal chunkedReader: `hex-size CRLF data CRLF` ... `0 CRLF
+    //      CRLF`); the subset has no chunk extensions, no whitespace in the size line, no trailer fields, sizes of at most
+    //      8 hex digits, and nothing after the last chunk.  Validated as a whole before a byte is written ----
+    uint32_t body_len = n - pos;
+    if (chunked) {
+        uint32_t q = pos, total = 0;
+        for (;;) {
+            uint32_t size = 0, nd = 0;
+            while (q < n && nd < 9 && http_hex(m[q]) >= 0) { size = size << 4 | (uint32_t)http_hex(m[q]); q++; nd++; }
+            if (nd == 0 || nd > 8 || q + 2 > n || m[q] != '\r' || m[q + 1] != '\n') return;
+            q += 2;
+            if (size == 0) {
+                if (q + 2 != n || m[q] != '\r' || m[q + 1] != '\n') return;  // trailer fields or bytes after the message
+                break;
+            }
+            if (size > n - q || n - q - size < 2 || m[q + size] != '\r' || m[q + size + 1] != '\n') return;
+            q += size + 2;
+            total += size;
+        }
+        body_len = total;
+    } else if (cls ? (uint64_t)body_len != content_length : body_len != 0) return;
 
     // ---- URL.Path | URL.RawQuery | pad4 | body ----
     uint32_t w = 0;
@@ -148,6 +171,18 @@ GOFR_HD_NOINLINE void http_parse(const uint8_t* m, uint32_t n, uint8_t* dst, Htt
         if (o.query_len == 0) o.flags |= GOFR_REQ_FORCE_QUERY;
     }
     while (w & 3u) dst[w++] = 0;
+    if (chunked) {
+        uint32_t q = pos, at = w;
+        for (;;) {
+            uint32_t size = 0;
+            while (m[q] != '\r') { size = size << 4 | (uint32_t)http_hex(m[q]); q++; }
+            q += 2;
+            if (size == 0) break;
+            for (uint32_t k = 0; k < size; k++) dst[at + k] = m[q + k];
+            at += size;
+            q += size + 2;
+        }
+    } else
     for (uint32_t k = 0; k < body_len; k++) dst[w + k] = m[pos + k];
     o.data_len = body_len;
     o.method = method;
@@ -156,7 +191,8 @@ GOFR_HD_NOINLINE void http_parse(const uint8_t* m, uint32_t n, uint8_t* dst, Htt
     o.spans[GOFR_HTTP_SPAN_USER_AGENT] = sp_ua;
     o.spans[GOFR_HTTP_SPAN_XFF] = sp_xff;
     o.spans[GOFR_HTTP_SPAN_HOST] = sp_host;
-    o.spans[GOFR_HTTP_SPAN_BODY] = (uint64_t)pos | (uint64_t)body_len << 32;
+    // a chunked body has no contiguous image in the message: the span covers the chunk stream as received
+    o.spans[GOFR_HTTP_SPAN_BODY] = (uint64_t)pos | (uint64_t)(chunked ? n - pos : body_len) << 32;
     o.status = GOFR_HTTP_OK;
     *out = o;
 }

@@ -471,8 +471,10 @@ int gofr_frontend_serve(gofr_frontend*, uint8_t method, const uint8_t* path, uin
  * followed by two hex digits; header lines `name: value CRLF` with RFC 7230 token names, no leading whitespace (no
  * obs-fold), value bytes HTAB / 0x20–0x7E / ≥ 0x80, CRLF line ends only, head ≤ 16 KiB; exactly one Host header with a
  * non-empty value of [A-Za-z0-9.:_-] and brackets; at most one Content-Length (1–9 digits) and then exactly that many body
- * bytes, otherwise no bytes after the head; no Transfer-Encoding, Expect, Upgrade or Trailer header; a Connection header
- * only with the value keep-alive.  For such a message URL.Path is the percent-decoded path, URL.RawQuery what follows
+ * bytes; or one `Transfer-Encoding: chunked` (no Content-Length beside it) and a chunk stream `hex-size CRLF data CRLF …
+ * 0 CRLF CRLF` with sizes of 1–8 hex digits, no chunk extensions, no trailer fields and nothing after it — the arena then
+ * holds the de-chunked body, as the handler's io.ReadAll(r.Body) would (BODY span: the chunk stream as received); otherwise
+ * no bytes after the head; no Expect, Upgrade or Trailer header; a Connection header only with the value keep-alive.  For such a message URL.Path is the percent-decoded path, URL.RawQuery what follows
  * the first '?', ForceQuery a trailing '?' with nothing after it, header values are trimmed of spaces and tabs. */
 enum { GOFR_HTTP_OK = 0, GOFR_HTTP_DEFER = 1 };
 enum { GOFR_HTTP_SPAN_METHOD = 0, GOFR_HTTP_SPAN_TARGET = 1, GOFR_HTTP_SPAN_USER_AGENT = 2, GOFR_HTTP_SPAN_XFF = 3,

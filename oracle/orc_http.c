@@ -6,7 +6,8 @@
  *   url.ParseRequestURI       origin form: Path = unescape(before '?', encodePath), RawQuery = after the first '?',
  *                             ForceQuery for a lone trailing '?'
  *   textproto.ReadMIMEHeader  one header per CRLF line, "name: value", value trimmed of spaces and tabs
- *   http.readTransfer         Content-Length delimits the body
+ *   http.readTransfer         Content-Length delimits the body, or Transfer-Encoding: chunked does
+ *   internal.chunkedReader    chunk = hex size line, data, CRLF; a zero-size chunk and a blank line end the body
  * for the conservative subset documented with gofr_http_parse_device (include/gofr_b200.h); every message outside the
  * subset is reported as DEFER.  Written line-first (split the head into lines, then classify) on purpose: the device
  * code walks the bytes once, so the two restatements do not share their structure. */
@@ -85,7 +86,7 @@ static int parse_one(const uint8_t* m, size_t n, uint8_t* dst, uint32_t* path_le
     for (size_t k = 0; k < plen; k++)
         if (rest[k] == '%' && (k + 2 >= plen || hexv(rest[k + 1]) < 0 || hexv(rest[k + 2]) < 0)) return 1;
     /* ---- headers ---- */
-    int n_host = 0, n_cl = 0, have_ua = 0, have_xff = 0;
+    int n_host = 0, n_cl = 0, n_te = 0, have_ua = 0, have_xff = 0;
     uint64_t cl = 0;
     for (int li = 1; li < nl; li++) {
         const uint8_t* L = m + lines[li].off;
@@ -113,15 +114,44 @@ static int parse_one(const uint8_t* m, size_t n, uint8_t* dst, uint32_t* path_le
             }
         } else if (ieq(L, c, "connection")) {
             if (!ieq(m + val.off, val.len, "keep-alive")) return 1;
-        } else if (ieq(L, c, "transfer-encoding") || ieq(L, c, "expect") || ieq(L, c, "upgrade") || ieq(L, c, "trailer")) return 1;
+        } else if (ieq(L, c, "transfer-encoding")) {
+            if (!ieq(m + val.off, val.len, "chunked")) return 1; /* other codings: readTransfer refuses them */
+            n_te++;
+        } else if (ieq(L, c, "expect") || ieq(L, c, "upgrade") || ieq(L, c, "trailer")) return 1;
     }
     if (n_host != 1 || n_cl > 1 || sp[SPAN_HOST].len == 0) return 1;
+    if (n_te > 1 || (n_te && n_cl)) return 1;
     for (size_t k = 0; k < sp[SPAN_HOST].len; k++) {
         uint8_t c = m[sp[SPAN_HOST].off + k];
         if (!((c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || strchr(".:-_[]", c))) return 1;
     }
     size_t body = n - head_end;
-    if (n_cl ? (uint64_t)body != cl : body != 0) return 1;
+    /* a chunked body is decoded into a scratch buffer first (chunk lines split off one by one) */
+    uint8_t* dechunked = NULL;
+    size_t raw_body = body;
+    if (n_te) {
+        dechunked = (uint8_t*)malloc(body + 1);
+        size_t at = head_end, out = 0;
+        int ok = 0;
+        for (;;) {
+            /* the size line: up to the next CRLF, hex digits only (no extension, no padding), 1..8 of them */
+            size_t e = at;
+            while (e < n && m[e] != '\r') e++;
+            if (e + 1 >= n || m[e + 1] != '\n' || e == at || e - at > 8) break;
+            uint64_t size = 0;
+            int bad = 0;
+            for (size_t k = at; k < e; k++) { int h = hexv(m[k]); if (h < 0) bad = 1; size = size * 16 + (uint64_t)(h < 0 ? 0 : h); }
+            if (bad) break;
+            at = e + 2;
+            if (size == 0) { ok = at + 2 == n && m[at] == '\r' && m[at + 1] == '\n'; break; } /* no trailers, nothing after */
+            if (size + 2 > n - at || m[at + size] != '\r' || m[at + size + 1] != '\n') break;
+            memcpy(dechunked + out, m + at, (size_t)size);
+            out += (size_t)size;
+            at += (size_t)size + 2;
+        }
+        if (!ok) { free(dechunked); return 1; }
+        body = out;
+    } else if (n_cl ? (uint64_t)body != cl : body != 0) return 1;
     /* ---- URL.Path | URL.RawQuery | pad4 | body ---- */
     size_t w = 0;
     for (size_t k = 0; k < plen; k++) {
@@ -140,12 +170,13 @@ static int parse_one(const uint8_t* m, size_t n, uint8_t* dst, uint32_t* path_le
         if (qn == 0) *flags = 1; /* ForceQuery */
     }
     while (w % 4) dst[w++] = 0;
-    memcpy(dst + w, m + head_end, body);
+    memcpy(dst + w, dechunked ? dechunked : m + head_end, body);
+    free(dechunked);
     *data_len = (uint32_t)body;
     *method = (uint32_t)mcode;
     sp[SPAN_METHOD].off = 0; sp[SPAN_METHOD].len = mlen;
     sp[SPAN_TARGET].off = (size_t)(rest - m); sp[SPAN_TARGET].len = tlen;
-    sp[SPAN_BODY].off = head_end; sp[SPAN_BODY].len = body;
+    sp[SPAN_BODY].off = head_end; sp[SPAN_BODY].len = raw_body; /* chunked: the chunk stream as received */
     return 0;
 }
 

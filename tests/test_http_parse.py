@@ -48,6 +48,11 @@ GOOD = [
     (b"PUT /p HTTP/1.1\r\nHost: h\r\nContent-Length: 0\r\n\r\n", (b"/p", b"", b"", S.M_PUT, 0)),
     (b"PATCH /p/%7Bid%7D;v=1 HTTP/1.1\r\nHost: h\r\nContent-Length: 2\r\n\r\nab", (b"/p/{id};v=1", b"", b"ab", S.M_PATCH, 0)),
     (b"HEAD / HTTP/1.1\r\nHost: h\r\n\r\n", (b"/", b"", b"", S.M_HEAD, 0)),
+    # Transfer-Encoding: chunked (net/http readTransfer + chunkedReader): the handler reads the de-chunked bytes
+    (b"GET /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n0\r\n\r\n", (b"/a", b"", b"", S.M_GET, 0)),
+    (b"POST /echo HTTP/1.1\r\nHost: h\r\ntransfer-encoding: Chunked\r\n\r\n5\r\n{\"id\"\r\n9\r\n:12,\"n\":\"\r\n4\r\n\r\n\"}\r\n0\r\n\r\n",
+     (b"/echo", b"", b'{"id":12,"n":"\r\n"}', S.M_POST, 0)),
+    (b"PUT /p?x HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n0000001f\r\n" + b"z" * 31 + b"\r\n00\r\n\r\n", (b"/p", b"x", b"z" * 31, S.M_PUT, 0)),
 ]
 
 DEFERRED = [
@@ -61,7 +66,25 @@ DEFERRED = [
     b"GET /a HTTP/1.1\r\nHost: h/evil\r\n\r\n", b"GET /a HTTP/1.1\r\nHost : h\r\n\r\n", b"GET /a HTTP/1.1\r\n Host: h\r\n\r\n",
     b"GET /a HTTP/1.1\r\nHost: h\r\n folded\r\n\r\n", b"GET /a HTTP/1.1\r\nHost: h\r\nX: a\x01b\r\n\r\n",
     b"GET /a HTTP/1.1\nHost: h\n\n", b"GET /a HTTP/1.1\r\nHost: h\r\nX: y\n\r\n", b"GET /a HTTP/1.1\r\nHost: h\r\n",
-    b"GET /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n0\r\n\r\n", b"GET /a HTTP/1.1\r\nHost: h\r\nExpect: 100-continue\r\n\r\n",
+    b"GET /a HTTP/1.1\r\nHost: h\r\nExpect: 100-continue\r\n\r\n",
+    # chunked bodies outside the subset: extensions, trailers, other codings, both framings, bad sizes, short data, leftovers
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n1;ext=1\r\na\r\n0\r\n\r\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n1\r\na\r\n0\r\nX-Trailer: v\r\n\r\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: gzip, chunked\r\n\r\n0\r\n\r\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: identity\r\n\r\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\nTransfer-Encoding: chunked\r\n\r\n0\r\n\r\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\nContent-Length: 1\r\n\r\n1\r\na\r\n0\r\n\r\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n\r\na\r\n0\r\n\r\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n1 \r\na\r\n0\r\n\r\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n0x1\r\na\r\n0\r\n\r\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n123456789\r\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n5\r\nab\r\n0\r\n\r\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n2\r\nabc\r\n0\r\n\r\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n1\r\na\r\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n1\r\na\r\n0\r\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n1\r\na\r\n0\r\n\r\nGET",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\n1\na\n0\n\n",
+    b"POST /a HTTP/1.1\r\nHost: h\r\nTransfer-Encoding: chunked\r\n\r\nffffffff\r\na\r\n0\r\n\r\n",
     b"GET /a HTTP/1.1\r\nHost: h\r\nConnection: close\r\n\r\n", b"GET /a HTTP/1.1\r\nHost: h\r\nUpgrade: websocket\r\n\r\n",
     b"POST /a HTTP/1.1\r\nHost: h\r\nContent-Length: 5\r\n\r\nab", b"POST /a HTTP/1.1\r\nHost: h\r\nContent-Length: 1\r\n\r\nab",
     b"POST /a HTTP/1.1\r\nHost: h\r\nContent-Length: +1\r\n\r\na", b"POST /a HTTP/1.1\r\nHost: h\r\nContent-Length: 1\r\nContent-Length: 1\r\n\r\na",
@@ -155,12 +178,21 @@ def _request(draw):
         headers.append(("X-Forwarded-For", draw(_hval)))
     for k in range(draw(st.integers(0, 2))):
         headers.append(("X-Extra-%d" % k, draw(_hval)))
-    if body or method in ("POST", "PUT", "PATCH"):
+    chunked = bool(body) and draw(st.booleans())
+    if chunked:
+        headers.append(("Transfer-Encoding", draw(st.sampled_from(["chunked", "Chunked", "CHUNKED"]))))
+    elif body or method in ("POST", "PUT", "PATCH"):
         headers.append(("Content-Length", str(len(body))))
     order = draw(st.permutations(headers))
     pad = draw(st.sampled_from(["", " ", "  "]))  # tabs around values: Go and h11 trim them, llhttp rejects them around
     # Content-Length — covered by a directed case instead
     head = "%s %s HTTP/1.1\r\n" % (method, target) + "".join("%s:%s%s%s\r\n" % (k, pad, v, pad) for k, v in order) + "\r\n"
+    if chunked:   # the body cut into 1..3 chunks, sizes written in hex with optional leading zeros / upper case
+        cuts = sorted(draw(st.lists(st.integers(1, max(1, len(body) - 1)), max_size=2, unique=True))) if len(body) > 1 else []
+        parts = [body[a:b] for a, b in zip([0] + cuts, cuts + [len(body)])]
+        fmt = draw(st.sampled_from(["%x", "%X", "%03x", "%08X"]))
+        wire = b"".join((fmt % len(p)).encode() + b"\r\n" + p + b"\r\n" for p in parts if p) + b"0\r\n\r\n"
+        return head.encode("latin-1") + wire
     return head.encode("latin-1") + body
 
 
