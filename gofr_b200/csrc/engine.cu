@@ -607,7 +607,7 @@ static int batch_submit_locked(gofr_engine* e, const gofr_req_batch* in, gofr_re
             const ChunkPlan& c = plan[ci];
             uint32_t cn = c.hi - c.lo;
             size_t abytes = (size_t)c.arena_hi - c.arena_lo;
-            size_t ocap = std::min<size_t>((size_t)cn * (e->hdr.max_fixed_len + 64) + 6 * abytes + 4096, 0xFFFFFFF0ull);
+            size_t ocap = std::min<size_t>((size_t)cn * (e->hdr.max_fixed_len + 64) + (size_t)image_data_expand(e->hdr) * abytes + 4096, 0xFFFFFFF0ull);
             if (s.egress_pending) {
                 // the slot's previous chunk must have left before its buffers are overwritten: a stream-side wait,
                 // unless the buffers have to grow (cudaFree needs the host to be sure)
@@ -688,7 +688,7 @@ static int batch_submit_locked(gofr_engine* e, const gofr_req_batch* in, gofr_re
             const ChunkPlan& c = plan[issued];
             uint32_t cn = c.hi - c.lo;
             size_t abytes = (size_t)c.arena_hi - c.arena_lo;
-            size_t ocap = std::min<size_t>((size_t)cn * (e->hdr.max_fixed_len + 64) + 6 * abytes + 4096, 0xFFFFFFF0ull);
+            size_t ocap = std::min<size_t>((size_t)cn * (e->hdr.max_fixed_len + 64) + (size_t)image_data_expand(e->hdr) * abytes + 4096, 0xFFFFFFF0ull);
             int rc = ensure(s, cn, abytes, ocap);
             if (rc) return rc;
             CUDA_TRY(cudaMemcpyAsync(s.d_desc, in->desc + c.lo, (size_t)cn * 16, cudaMemcpyHostToDevice, s.stream));

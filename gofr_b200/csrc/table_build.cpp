@@ -1266,6 +1266,17 @@ int seal_table(gofr_table* t) {
         H.bind_row_words = std::max(H.bind_row_words, words);
     }
     H.max_fixed_len = max_fixed;
+    {   // image_data_expand (engine_internal.h): the smallest thing that owns data bytes is a 4-byte word; it can drag along
+        // one key literal, a comma and a pair of braces per nesting level, and the longest scalar text (a float64: 25 bytes)
+        bool any_values = false;
+        for (auto& P : progs) any_values |= (P.flags & PF_VALUES) != 0;
+        size_t max_key = 0, depth = 1;
+        for (auto& sc : t->schemas) {
+            depth = std::max(depth, (size_t)sc.depth);
+            for (auto& f : sc.fields) max_key = std::max(max_key, json_escape_go(f.json_name).size() + 3);
+        }
+        H.reserved3[0] = any_values ? (uint32_t)std::max<size_t>(6, (depth * (max_key + 3) + 28 + 3) / 4) : 6u;
+    }
 
     auto append = [&](const void* p, size_t n) {
         align16();
@@ -1502,7 +1513,7 @@ uint32_t gofr_table_max_response_bytes(const gofr_table* t, uint32_t max_data_le
     ImageHeader H;
     memcpy(&H, t->image.data(), sizeof H);
     // fixed part + Content-Length digits + every data byte escaped six-fold (\u00XX) + Location (3x path + query)
-    return H.max_fixed_len + 16 + 6 * max_data_len + 3 * 65535 + 65535 + 2;
+    return H.max_fixed_len + 16 + gofr::image_data_expand(H) * max_data_len + 3 * 65535 + 65535 + 2;
 }
 
 uint32_t gofr_table_response_bound(const gofr_table* t, uint32_t path_len, uint32_t query_len, uint32_t data_len) {
@@ -1511,7 +1522,7 @@ uint32_t gofr_table_response_bound(const gofr_table* t, uint32_t path_len, uint3
     memcpy(&H, t->image.data(), sizeof H);
     // fixed part + Content-Length digits + every request byte that can reach the response (a path variable, a query value,
     // a data byte; the Location of a redirect is at most 3x path + query) escaped six-fold (\u00XX)
-    const uint64_t b = (uint64_t)H.max_fixed_len + 16 + 6ull * ((uint64_t)path_len + query_len + data_len) + 2;
+    const uint64_t b = (uint64_t)H.max_fixed_len + 16 + 6ull * ((uint64_t)path_len + query_len) + (uint64_t)gofr::image_data_expand(H) * data_len + 2;
     return b > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)b;
 }
 

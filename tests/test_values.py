@@ -484,3 +484,35 @@ def test_gpu_float_text_matches_python_repr():
     for i, w in enumerate(want):
         assert ob[int(f[i]):int(f[i + 1])] == w, i
     eng.close()
+
+
+def test_response_bound_holds_for_the_wider_data_model():
+    """gofr_table_response_bound sizes the host path's output buffers.  Six response bytes per data byte is the worst case of
+    flat rows (a control character becomes \\u00XX); an element of a slice of structs drags its key literals along, so tables
+    with such programs carry their own factor (engine_internal.h image_data_expand)."""
+    from gofr_b200 import _abi
+    L = _abi.lib()
+    inner = S.Schema(1, "main.I", [S.Field("F", S.F_BOOL, "a_rather_long_key_name_for_one_bit_of_information")])
+    mid = S.Schema(2, "main.M", [S.Field("In", S.F_STRUCT, "another_quite_long_key_name", elem_schema=1)])
+    outer = S.Schema(3, "[]main.M", [S.Field("", S.F_STRUCT, "", container=S.C_SLICE, elem_schema=2, flags=S.FIELD_BARE)])
+    spec = S.TableSpec(schemas=[inner, mid, outer], routes=[S.Route(S.M_GET, "/p", S.H_ROW, schema_id=3)])
+    t = Table(spec)
+    row = outer.encode_row([[[[True]]] * 200], spec.schema)
+    b = S.RequestBatch.pack([S.Req(S.M_GET, b"/p", b"", row)])
+    o, f, m = O.OracleTable(spec).serve(b, DATE, out_cap=1 << 20)
+    o2, f2, m2 = E.serve(t.serialize(), b, DATE, out_cap=1 << 20)
+    assert np.array_equal(f, f2) and o[:int(f[1])].tobytes() == o2[:int(f[1])].tobytes()
+    assert int(f[1]) > 6 * len(row)                                   # the old bound would have been too small
+    assert L.gofr_table_response_bound(t.handle, 2, 0, len(row)) >= int(f[1])
+    spec = _spec()
+    t = Table(spec)
+    batch, _ = _batch(spec, 2000, 5)
+    o, f, m = O.OracleTable(spec).serve(batch, DATE)
+    ln = np.diff(f.astype(np.int64))
+    for i in range(batch.n):
+        d = batch.desc[i]
+        assert L.gofr_table_response_bound(t.handle, int(d["path_len"]), int(d["query_len"]), int(d["data_len"])) >= ln[i], i
+    # tables without such programs keep the six-fold bound
+    from gofr_b200 import synth
+    t2 = Table(synth.config2_spec())
+    assert L.gofr_table_response_bound(t2.handle, 0, 0, 1000) - L.gofr_table_response_bound(t2.handle, 0, 0, 0) == 6000
