@@ -516,3 +516,89 @@ def test_response_bound_holds_for_the_wider_data_model():
     from gofr_b200 import synth
     t2 = Table(synth.config2_spec())
     assert L.gofr_table_response_bound(t2.handle, 0, 0, 1000) - L.gofr_table_response_bound(t2.handle, 0, 0, 0) == 6000
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# random SCHEMAS (not only random values): struct trees with every kind, container and omitempty combination
+# ---------------------------------------------------------------------------------------------------------------
+def _rand_schemas(rnd, n_types):
+    """n_types struct types, each free to use the ones before it, plus bare types on top of them"""
+    schemas = []
+    names = ["a", "id", "Name", "x<y", "long_key_name_%d", "k", "é", "v1", "data", "0"]
+    for t in range(n_types):
+        fields = []
+        for k in range(rnd.randint(1, 5)):
+            kind = rnd.choice([S.F_INT64, S.F_INT32, S.F_BOOL, S.F_STRING, S.F_INT, S.F_FLOAT64] + ([S.F_STRUCT] * 2 if schemas else []))
+            cont = rnd.choice([S.C_VALUE, S.C_VALUE, S.C_PTR, S.C_SLICE, S.C_MAP])
+            elem = 0
+            if kind == S.F_STRUCT:
+                elem = rnd.choice(schemas).id
+                if cont == S.C_MAP:
+                    cont = S.C_SLICE
+            jn = rnd.choice(names)
+            jn = (jn % k if "%" in jn else jn) + str(k)
+            fields.append(S.Field("F%d" % k, kind, jn, rnd.random() < 0.4, cont, elem))
+        schemas.append(S.Schema(100 + t, "main.T%d" % t, fields))
+    bare = []
+    for t in range(3):
+        kind = rnd.choice([S.F_INT64, S.F_BOOL, S.F_STRING, S.F_FLOAT64, S.F_STRUCT])
+        cont = rnd.choice([S.C_PTR, S.C_SLICE, S.C_MAP]) if kind != S.F_FLOAT64 else rnd.choice([S.C_VALUE, S.C_SLICE])
+        elem = rnd.choice(schemas).id if kind == S.F_STRUCT else 0
+        if kind == S.F_STRUCT and cont == S.C_MAP:
+            cont = S.C_SLICE
+        bare.append(S.Schema(200 + t, "bare%d" % t, [S.Field("", kind, "", container=cont, elem_schema=elem, flags=S.FIELD_BARE)]))
+    return schemas, bare
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_schemas_three_ways(seed):
+    rnd = random.Random(1000 + seed)
+    structs, bare = _rand_schemas(rnd, rnd.randint(2, 5))
+    routed = structs + bare
+    mode = [S.FRAME_WIRE, S.FRAME_BODY, S.FRAME_INTENDED][seed % 3]
+    spec = S.TableSpec(frame_mode=mode, schemas=structs + bare,
+                       routes=[S.Route(S.M_GET, "/t/%d" % sc.id, S.H_RESULT if seed % 2 else S.H_ROW, schema_id=sc.id) for sc in routed])
+    try:
+        table = Table(spec)
+    except Exception as e:      # deeper than 8 levels cannot happen with <= 5 types; anything else is a bug
+        raise AssertionError((e, structs, bare))
+    reqs, want = [], []
+    for i in range(400):
+        sc = routed[rnd.randrange(len(routed))]
+        vals = _rand_value(rnd, spec, sc, nan_rate=0.005)
+        row = sc.encode_row(vals, spec.schema)
+        try:
+            body = go_json(spec, sc, vals)
+        except Unencodable:
+            body = None
+        if seed % 2:
+            raw = rnd.random() < 0.5
+            data = S.result_record(S.RESULT_RAW_DATA if raw else S.RESULT_DATA, row)
+            body = None if body is None else (body + "\n" if raw else '{"data":%s}\n' % body)
+        else:
+            data = row
+            body = None if body is None else '{"data":%s}\n' % body
+        reqs.append(S.Req(S.M_GET, b"/t/%d" % sc.id, b"", data))
+        want.append(body)
+    batch = S.RequestBatch.pack(reqs, seed=seed)
+    o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE, out_cap=1 << 22)
+    image = table.serialize()
+    E.set_flush_mode(seed % 3)
+    try:
+        o2, f2, m2 = E.serve(image, batch, DATE, out_cap=1 << 22)
+    finally:
+        E.set_flush_mode(0)
+    assert np.array_equal(m1, m2) and np.array_equal(f1, f2)
+    assert o1[:int(f1[-1])].tobytes() == o2[:int(f1[-1])].tobytes()
+    ob = o1.tobytes()
+    for i in range(batch.n):
+        r = ob[int(f1[i]):int(f1[i + 1])]
+        body = r if mode == S.FRAME_BODY else r.partition(b"\r\n\r\n")[2]
+        assert body.decode("utf-8") == (want[i] or ""), (i, routed, want[i])
+    # the same batch through the slot layout of the device code
+    out, ln, meta = E.serve_slots(image, batch, DATE, 8192)
+    assert np.array_equal(ln, np.diff(f1.astype(np.int64)).astype(np.uint32))
+    for i in range(0, batch.n, 3):
+        L = int(ln[i])
+        if L <= 8192:
+            assert out[i, :L].tobytes() == ob[int(f1[i]):int(f1[i]) + L], i
