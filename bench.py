@@ -565,11 +565,16 @@ def sharded_config4(eng_factory, rank, world, dev, barrier, reduce_max, steps, p
     m = 4096
     o1, f1, m1 = O.OracleTable(spec).serve(batch.slice(0, m), date)
     ln = s_len[:m].cpu().numpy().view(np.uint32)
-    assert np.array_equal(ln, np.diff(f1.astype(np.int64)).astype(np.uint32)) and np.array_equal(s_meta[:m].cpu().numpy().view(np.uint32), m1), "config 4 shard: columns differ from the oracle"
+    # (recorded, not asserted: an assertion on one rank would leave the others waiting at the next barrier)
+    bad = 0 if (np.array_equal(ln, np.diff(f1.astype(np.int64)).astype(np.uint32)) and
+                np.array_equal(s_meta[:m].cpu().numpy().view(np.uint32), m1)) else 1
     so = s_out[:m * slot].cpu().numpy().reshape(m, slot)
-    for i in range(m):
-        L = int(ln[i])
-        assert L > slot or so[i, :L].tobytes() == o1[int(f1[i]):int(f1[i]) + L].tobytes(), f"config 4 shard: response {i} of rank {rank} differs from the oracle"
+    if not bad:
+        for i in range(m):
+            L = int(ln[i])
+            if L <= slot and so[i, :L].tobytes() != o1[int(f1[i]):int(f1[i]) + L].tobytes():
+                bad = 1
+                break
     out_bytes = int(s_len.sum().item())
     # end to end through host buffers
     hb = pin_batch(batch)
@@ -582,7 +587,9 @@ def sharded_config4(eng_factory, rank, world, dev, barrier, reduce_max, steps, p
         eng.serve_host_slots(hb, date, slot, h_out, h_len, h_meta)
     barrier()
     dt = reduce_max(time.perf_counter() - t0) / steps
-    assert np.array_equal(h_len[:m], ln)
+    if not np.array_equal(h_len[:m], ln):
+        bad = 1
+    bad = int(reduce_max(float(bad)))
     algo = batch.input_bytes() + out_bytes + 8 * n
     peak, _ = hbm_peak()
     eng.close()
@@ -590,7 +597,8 @@ def sharded_config4(eng_factory, rank, world, dev, barrier, reduce_max, steps, p
             "value": n * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "kernel_ms_per_launch": kms / max(kl, 1),
             "roofline_frac": algo / (kms / max(kl, 1) / 1e3) / 1e9 / peak, "algorithmic_bytes_per_request": algo / n,
             "e2e": {"value": n * world / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": n * 32 + int(batch.arena_span()), "d2h_bytes_per_step": n * slot + 8 * n},
-            "parity": f"first {m} responses of every rank's shard byte-identical to the oracle run on those requests"}
+            "parity": (f"first {m} responses of every rank's shard byte-identical to the oracle run on those requests" if not bad else
+                       "FAILED: some rank's shard differs from the oracle")}
 
 
 def sharded_config5(eng, rank, world, dev, barrier, reduce_max, steps, per_gpu=1 << 20):
@@ -626,14 +634,16 @@ def sharded_config5(eng, rank, world, dev, barrier, reduce_max, steps, per_gpu=1
     m = 8192
     o_out, o_off, o_meta = O.grpc_hello(frames, off[:m + 1])
     g_off = d_ooff[:m + 1].cpu().numpy().view(np.uint32)
-    assert np.array_equal(g_off, o_off) and d_out[:int(o_off[m])].cpu().numpy().tobytes() == o_out[:int(o_off[m])].tobytes(), "config 5 shard differs from the oracle"
+    bad = 0 if (np.array_equal(g_off, o_off) and d_out[:int(o_off[m])].cpu().numpy().tobytes() == o_out[:int(o_off[m])].tobytes()) else 1
+    bad = int(reduce_max(float(bad)))
     out_bytes = int(d_ooff[n].item())
     algo = int(off[n]) + 4 * (n + 1) + out_bytes + 8 * n
     peak, _ = hbm_peak()
     return {"workload": "BASELINE config 5: gRPC unary SayHello, %d length-prefixed HelloRequest frames per GPU" % n,
             "value": n * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "kernel_ms_per_launch": kms / max(kl, 1),
             "roofline_frac": algo / (kms / max(kl, 1) / 1e3) / 1e9 / peak, "algorithmic_bytes_per_request": algo / n,
-            "parity": f"first {m} response frames of every rank's shard byte-identical to the oracle"}
+            "parity": (f"first {m} response frames of every rank's shard byte-identical to the oracle" if not bad else
+                       "FAILED: some rank's shard differs from the oracle")}
 
 
 def main():
@@ -867,12 +877,16 @@ def main():
     # ---- sharded legs of the other BASELINE configs (config 4 on 4 GPUs, config 5 on 8 GPUs) ----
     extras = {}
     if not args.no_extras:
-        if world == 4:
-            extras["config4_sharded"] = sharded_config4(eng_factory=lambda spec: Engine(Table(image=gd.broadcast_table_image(
-                Table(spec).serialize() if rank == 0 else None, rank, dev)), local), rank=rank, world=world, dev=dev,
-                barrier=barrier, reduce_max=reduce_max, steps=args.steps)
-        if world == 8:
-            extras["config5_sharded"] = sharded_config5(eng, rank, world, dev, barrier, reduce_max, args.steps)
+        # a leg that raises the same way on every rank (a programming error) must not take the headline line with it
+        try:
+            if world == 4:
+                extras["config4_sharded"] = sharded_config4(eng_factory=lambda spec: Engine(Table(image=gd.broadcast_table_image(
+                    Table(spec).serialize() if rank == 0 else None, rank, dev)), local), rank=rank, world=world, dev=dev,
+                    barrier=barrier, reduce_max=reduce_max, steps=args.steps)
+            if world == 8:
+                extras["config5_sharded"] = sharded_config5(eng, rank, world, dev, barrier, reduce_max, args.steps)
+        except Exception as ex:  # noqa: BLE001
+            extras["sharded_leg_error"] = repr(ex)[:300]
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
