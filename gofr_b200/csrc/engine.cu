@@ -18,6 +18,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -80,7 +81,7 @@ struct gofr_engine {
     int wide_grid = 0, wide_blocks_per_sm = 0;
     bool slots_wide = false;  // choose_slot_residency
     bool has_values = false;  // some program has PF_VALUES: the packed layout runs serve_kernel_values (serve_values_kernel.cu)
-    int grid = 0, blocks_per_sm = 0, grpc_grid = 0, reqlog_grid = 0, http_grid = 0, proto_grid = 0, proto_decode_grid = 0;
+    int grid = 0, blocks_per_sm = 0, grpc_grid = 0, reqlog_grid = 0, http_grid = 0, proto_grid = 0, proto_decode_grid = 0, proto_nested_grid = 0;
     uint32_t epoch = 0;
     // resident path scratch
     unsigned long long* d_state = nullptr;
@@ -987,6 +988,115 @@ static int proto_run(gofr_engine* e, const gofr_proto_field* fields, uint32_t n_
     if (rc != 0) { set_last_error("proto kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
     if (e->timing_on) { CUDA_TRY(cudaEventRecord(ev1, st)); e->timing.emplace_back(ev0, ev1); }
     e->launches++;
+    return GOFR_OK;
+}
+
+// message types with nested / repeated fields -> the kernel's descriptor: validation, words of every fixed part, nesting depth
+static int pbn_build(const gofr_proto_nmsg* msgs, uint32_t n_msgs, const gofr_proto_nfield* fields, uint32_t n_fields, uint32_t root,
+                     PbnDesc* D) {
+    if (!msgs || !fields || n_msgs == 0 || n_msgs > (uint32_t)kPbnMaxMsgs || n_fields > (uint32_t)kPbnMaxFields || root >= n_msgs) {
+        set_last_error("at most %d message types with %d fields in all", kPbnMaxMsgs, kPbnMaxFields);
+        return GOFR_ERR_CAPACITY;
+    }
+    memset(D, 0, sizeof *D);
+    D->n_msgs = n_msgs;
+    D->root = root;
+    for (uint32_t m = 0; m < n_msgs; m++) {
+        if (msgs[m].n_fields == 0 || (uint32_t)msgs[m].first_field + msgs[m].n_fields > n_fields) { set_last_error("message type %u: bad field range", m); return GOFR_ERR_INVALID; }
+        D->first[m] = msgs[m].first_field;
+        D->count[m] = msgs[m].n_fields;
+        for (uint32_t k = 0; k < msgs[m].n_fields; k++) {
+            const gofr_proto_nfield& f = fields[msgs[m].first_field + k];
+            const uint32_t num = f.number, t = f.type;
+            const bool scalar = (t >= GOFR_PB_DOUBLE && t <= GOFR_PB_STRING) || (t >= GOFR_PB_BYTES && t <= GOFR_PB_SINT64);
+            if (!scalar && t != GOFR_PB_MESSAGE) { set_last_error("message type %u field %u: type %u is not taken", m, num, t); return GOFR_ERR_UNSUPPORTED; }
+            if (t == GOFR_PB_MESSAGE && f.msg >= n_msgs) { set_last_error("message type %u field %u: unknown message type %u", m, num, f.msg); return GOFR_ERR_INVALID; }
+            if (num == 0 || num > 0x1FFFFFFFu || (num >= 19000 && num <= 19999)) { set_last_error("field number %u is not valid", num); return GOFR_ERR_INVALID; }
+            if (k && num <= fields[msgs[m].first_field + k - 1].number) { set_last_error("message type %u: fields must be in ascending field-number order", m); return GOFR_ERR_INVALID; }
+            PbnField& F = D->f[msgs[m].first_field + k];
+            F.repeated = f.repeated ? 1 : 0;
+            F.msg = t == GOFR_PB_MESSAGE ? (uint8_t)f.msg : (uint8_t)0xFF;
+            F.cls = t == GOFR_PB_MESSAGE ? 0 : (uint8_t)proto_class(t);
+            // messages, strings, bytes and PACKED repeated scalars are length-delimited
+            const uint32_t wire = (t == GOFR_PB_MESSAGE || (f.repeated && proto_wire(t) != 2)) ? 2u : proto_wire(t);
+            F.tag = num << 3 | wire;
+        }
+    }
+    // fixed words and depth, depth first; a message type that reaches itself has no bound on its nesting
+    int state[kPbnMaxMsgs] = {0}, depth[kPbnMaxMsgs] = {0};
+    std::function<int(uint32_t)> visit = [&](uint32_t m) -> int {
+        if (state[m] == 2) return GOFR_OK;
+        if (state[m] == 1) { set_last_error("message type %u is recursive", m); return GOFR_ERR_UNSUPPORTED; }
+        state[m] = 1;
+        uint32_t words = 0;
+        int d = 1;
+        for (uint32_t k = 0; k < D->count[m]; k++) {
+            PbnField& F = D->f[D->first[m] + k];
+            uint32_t w = F.repeated ? 1u : (F.cls & PC_64) ? 2u : 1u;
+            if (F.msg != 0xFF) {
+                int rc = visit(F.msg);
+                if (rc) return rc;
+                d = std::max(d, 1 + depth[F.msg]);
+                if (!F.repeated) w = 1u + D->fixed_words[F.msg];
+            }
+            if (w > 255u) { set_last_error("message type %u: fixed part too wide", m); return GOFR_ERR_UNSUPPORTED; }
+            F.fixed_words = (uint8_t)w;
+            words += w;
+        }
+        if (words > 16383u) { set_last_error("message type %u: fixed part too wide", m); return GOFR_ERR_UNSUPPORTED; }
+        D->fixed_words[m] = (uint16_t)words;
+        depth[m] = d;
+        state[m] = 2;
+        return GOFR_OK;
+    };
+    for (uint32_t m = 0; m < n_msgs; m++) { int rc = visit(m); if (rc) return rc; }
+    if (depth[root] > kPbnMaxDepth) { set_last_error("messages nest deeper than %d levels", kPbnMaxDepth); return GOFR_ERR_UNSUPPORTED; }
+    return GOFR_OK;
+}
+
+int gofr_proto_encode_nested_device(gofr_engine* e, const gofr_proto_nmsg* msgs, uint32_t n_msgs, const gofr_proto_nfield* fields,
+                                    uint32_t n_fields, uint32_t root, const uint8_t* d_rows, const uint32_t* d_row_off, uint32_t n,
+                                    uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off, uint32_t* d_meta, void* stream) {
+    if (!e || (n && (!d_rows || !d_row_off || !d_out || !d_out_off || !d_meta))) return GOFR_ERR_INVALID;
+    PbnDesc D;
+    { int rc = pbn_build(msgs, n_msgs, fields, n_fields, root, &D); if (rc) return rc; }
+    std::lock_guard<std::mutex> g(e->mu);
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st)); return GOFR_OK; }
+    size_t tiles = (n + kServeThreads - 1) / kServeThreads;
+    if (tiles > e->state_tiles) {
+        cudaFree(e->d_state);
+        e->d_state = nullptr;
+        CUDA_TRY(cudaMalloc(&e->d_state, tiles * 8));
+        CUDA_TRY(cudaMemset(e->d_state, 0, tiles * 8));
+        e->state_tiles = tiles;
+    }
+    if (e->proto_nested_grid <= 0) {
+        e->proto_nested_grid = proto_nested_max_grid(e->device);
+        if (e->proto_nested_grid <= 0) { set_last_error("proto kernel cannot be resident"); return GOFR_ERR_CUDA; }
+    }
+    GrpcParams p;
+    memset(&p, 0, sizeof p);
+    p.in = d_rows; p.in_off = d_row_off; p.n = n; p.n_tiles = (uint32_t)tiles;
+    { int erc = next_epoch(e, &p.epoch); if (erc) return erc; }
+    p.out = d_out; p.out_cap = out_cap; p.out_off = d_out_off; p.meta = d_meta;
+    p.tile_state = e->d_state; p.overflow = e->d_flag;
+    const int g_ = (int)std::min<size_t>((size_t)std::max(1, e->proto_nested_grid / engines_on_device(e->device)), tiles);
+    int rc = launch_proto_encode_nested(p, D, g_, st);
+    if (rc != 0) { set_last_error("proto kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
+    e->launches++;
+    return GOFR_OK;
+}
+
+// the descriptor gofr_proto_encode_nested_device would hand to its kernel (tests/emu drives the device code with it)
+int gofr_proto_nested_describe(const gofr_proto_nmsg* msgs, uint32_t n_msgs, const gofr_proto_nfield* fields, uint32_t n_fields,
+                               uint32_t root, void* desc_out, uint32_t desc_cap) {
+    PbnDesc D;
+    int rc = pbn_build(msgs, n_msgs, fields, n_fields, root, &D);
+    if (rc) return rc;
+    if (!desc_out || desc_cap < sizeof D) return GOFR_ERR_CAPACITY;
+    memcpy(desc_out, &D, sizeof D);
     return GOFR_OK;
 }
 

@@ -99,6 +99,26 @@ struct GrpcParams {
     uint32_t* overflow;
 };
 int launch_grpc_hello(const GrpcParams& p, int grid, void* stream);
+// message types of gofr_proto_encode_nested_device (kernel parameter, by value): up to 8 message types with 48 fields in
+// all; fields of a type are consecutive, in ascending field-number order.  Rows use the layout of the wider data model
+// (include/gofr_b200.h "Row format"): a singular message field is a presence word + the message's fixed part inline, a
+// repeated field a count word with its elements in the variable part.
+constexpr int kPbnMaxMsgs = 8, kPbnMaxFields = 48, kPbnMaxDepth = 4;
+struct PbnField {
+    uint32_t tag;        // number << 3 | wire type (2 for messages and for packed repeated scalars)
+    uint8_t cls;         // PC_* bits of the scalar type; 0 for a message
+    uint8_t repeated;
+    uint8_t msg;         // message type index (type GOFR_PB_MESSAGE), else 0xFF
+    uint8_t fixed_words; // words the field owns in the fixed part of its message
+};
+struct PbnDesc {
+    uint32_t n_msgs, root;
+    uint16_t first[kPbnMaxMsgs], count[kPbnMaxMsgs], fixed_words[kPbnMaxMsgs];
+    PbnField f[kPbnMaxFields];
+};
+int launch_proto_encode_nested(const GrpcParams& p, const PbnDesc& D, int grid, void* stream);
+int proto_nested_max_grid(int device);
+
 // message type of gofr_proto_encode_device (kernel parameter, by value); 32 = GOFR_PROTO_MAX_FIELDS
 struct ProtoSchema {
     uint32_t n_fields;

@@ -369,6 +369,102 @@ def pack_proto_rows(fields: Sequence[ProtoField], messages: Sequence[Sequence]) 
     return np.frombuffer(bytes(blob), dtype=np.uint8).copy(), np.array(off, dtype=np.uint32)
 
 
+PB_MESSAGE = 11
+
+
+@dataclass
+class ProtoNField:
+    """one field of a message type with nested / repeated fields (gofr_proto_nfield)"""
+    number: int
+    type: int            # PB_* or PB_MESSAGE
+    repeated: bool = False
+    msg: int = 0         # PB_MESSAGE: index of the message type
+
+
+def proto_nested_tables(msgs: Sequence[Sequence[ProtoNField]]):
+    """(gofr_proto_nmsg[n_msgs] as uint16 pairs, gofr_proto_nfield[n_fields] as 8-byte records, n_fields)"""
+    nm = np.zeros((len(msgs), 2), dtype=np.uint16)
+    recs = bytearray()
+    k = 0
+    for m, fields in enumerate(msgs):
+        nm[m] = (k, len(fields))
+        for f in fields:
+            recs += int(f.number).to_bytes(4, "little") + bytes([f.type, 1 if f.repeated else 0]) + int(f.msg).to_bytes(2, "little")
+            k += 1
+    return nm, np.frombuffer(bytes(recs), dtype=np.uint8).copy(), k
+
+
+def _pb_scalar_words(t: int, v) -> bytes:
+    import struct
+    if t == PB_DOUBLE:
+        return struct.pack("<d", v) if isinstance(v, float) else int(v).to_bytes(8, "little")
+    if t == PB_FLOAT:
+        return struct.pack("<f", v) if isinstance(v, float) else int(v).to_bytes(4, "little")
+    if t in PB_64BIT:
+        return (int(v) & 0xFFFFFFFFFFFFFFFF).to_bytes(8, "little")
+    if t == PB_BOOL:
+        return (1 if v else 0).to_bytes(4, "little")
+    return (int(v) & 0xFFFFFFFF).to_bytes(4, "little")
+
+
+def _pb_fixed_bytes(msgs, m: int) -> int:
+    n = 0
+    for f in msgs[m]:
+        if f.repeated:
+            n += 4
+        elif f.type == PB_MESSAGE:
+            n += 4 + _pb_fixed_bytes(msgs, f.msg)
+        else:
+            n += 8 if f.type in PB_64BIT or f.type == PB_DOUBLE else 4
+    return n
+
+
+def pack_proto_nested_message(msgs, m: int, value) -> "tuple[bytes, bytes]":
+    """(fixed part, variable part) of one message of type m.  value: one entry per field — scalars as for pack_proto_rows, a
+    singular message None (not set) or its own value list, a repeated field a list."""
+    def element(f, v) -> bytes:
+        if f.type in (PB_STRING, PB_BYTES):
+            b = v.encode("utf-8", "surrogateescape") if isinstance(v, str) else bytes(v)
+            return len(b).to_bytes(4, "little") + b
+        if f.type == PB_MESSAGE:
+            fx, vr = pack_proto_nested_message(msgs, f.msg, v)
+            return fx + vr
+        return _pb_scalar_words(f.type, v)
+    fixed, var = bytearray(), bytearray()
+    for f, v in zip(msgs[m], value):
+        if f.repeated:
+            fixed += len(v).to_bytes(4, "little")
+            for e in v:
+                var += element(f, e)
+        elif f.type == PB_MESSAGE:
+            if v is None:
+                fixed += bytes(4 + _pb_fixed_bytes(msgs, f.msg))
+            else:
+                fx, vr = pack_proto_nested_message(msgs, f.msg, v)
+                fixed += (1).to_bytes(4, "little") + fx
+                var += vr
+        elif f.type in (PB_STRING, PB_BYTES):
+            b = v.encode("utf-8", "surrogateescape") if isinstance(v, str) else bytes(v)
+            fixed += len(b).to_bytes(4, "little")
+            var += b
+        else:
+            fixed += _pb_scalar_words(f.type, v)
+    return bytes(fixed), bytes(var)
+
+
+def pack_proto_nested_rows(msgs, root: int, messages) -> "tuple[np.ndarray, np.ndarray]":
+    """Rows for gofr_proto_encode_nested_device (4-byte aligned, 8 bytes of padding behind the last)."""
+    blob = bytearray()
+    off = [0]
+    for v in messages:
+        fx, vr = pack_proto_nested_message(msgs, root, v)
+        blob += fx + vr
+        blob += b"\0" * ((-len(blob)) % 4)
+        off.append(len(blob))
+    blob += b"\0" * 8
+    return np.frombuffer(bytes(blob), dtype=np.uint8).copy(), np.array(off, dtype=np.uint32)
+
+
 def http_date(unix_seconds: int) -> bytes:
     """net/http appendTime: IMF-fixdate, always 29 bytes."""
     import time

@@ -367,6 +367,35 @@ int gofr_proto_decode_device(gofr_engine*, const gofr_proto_field* fields, uint3
                              const uint32_t* d_in_off, uint32_t n, uint8_t* d_rows, uint64_t rows_cap, uint32_t* d_row_off,
                              uint32_t* d_meta, void* stream);
 
+/* The same encoder for message types with NESTED and REPEATED fields (proto.Marshal as protobuf-go v1.32.0 does it: fields
+ * in field-number order, singular zero values skipped, a set message field written even when empty, repeated numeric
+ * scalars packed, repeated strings / bytes / messages one tag per element).  msgs[m] names fields[first_field ..
+ * first_field + n_fields) (ascending numbers); a field of type GOFR_PB_MESSAGE names its message type in `msg`; `root` is the
+ * type of the rows.  At most 8 message types with 48 fields in all, nested at most 4 levels deep, no recursive types;
+ * map fields are not taken (protobuf-go writes them in random order: there is no byte sequence to match).
+ * Rows: the layout of "Row format" above — fixed words of a message in field order (64-bit kinds two words, string /
+ * bytes their length, a singular message a presence word 0 / 1 followed by its own fixed part, a repeated field its
+ * element count), then the variable part in field order (string bytes; a set message's variable part; the elements of a
+ * repeated field: scalars as their words, strings as u32 length + bytes, messages as fixed part + variable part).
+ * Output and d_meta as for gofr_proto_encode_device. */
+#define GOFR_PB_MESSAGE 11u
+typedef struct gofr_proto_nfield {
+    uint32_t number;
+    uint8_t type;     /* GOFR_PB_* or GOFR_PB_MESSAGE */
+    uint8_t repeated; /* 0 / 1 */
+    uint16_t msg;     /* GOFR_PB_MESSAGE: index into msgs */
+} gofr_proto_nfield;
+typedef struct gofr_proto_nmsg {
+    uint16_t first_field, n_fields;
+} gofr_proto_nmsg;
+int gofr_proto_encode_nested_device(gofr_engine*, const gofr_proto_nmsg* msgs, uint32_t n_msgs, const gofr_proto_nfield* fields,
+                                    uint32_t n_fields, uint32_t root, const uint8_t* d_rows, const uint32_t* d_row_off, uint32_t n,
+                                    uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off, uint32_t* d_meta, void* stream);
+/* validation of such a description without a GPU; desc_out (>= 512 bytes, may be NULL with desc_cap 0 to validate only...
+ * then GOFR_ERR_CAPACITY means "valid") receives the kernel's internal descriptor (test infrastructure reads it) */
+int gofr_proto_nested_describe(const gofr_proto_nmsg* msgs, uint32_t n_msgs, const gofr_proto_nfield* fields, uint32_t n_fields,
+                               uint32_t root, void* desc_out, uint32_t desc_cap);
+
 /* Bind as a stage of the split API: Context.Bind(&v) for closures that stay on the host (pkg/gofr/context.go:52-54 ->
  * pkg/gofr/http/request.go:40-47 -> json.Unmarshal(body, &v), v a struct of a registered schema).  Body i is the data
  * section of request i (same descriptors / arena as the serve calls); result i lies in its own slot d_rows + i * slot_bytes

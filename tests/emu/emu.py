@@ -7,6 +7,8 @@ import subprocess
 
 import numpy as np
 
+from gofr_b200 import spec as S
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "libgofr_emu.so")
@@ -19,6 +21,8 @@ def _build():
             os.path.join(ROOT, "gofr_b200", "csrc", "value_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "float_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "grpc_device.cuh"),
+            os.path.join(ROOT, "gofr_b200", "csrc", "proto_nested_device.cuh"),
+            os.path.join(ROOT, "gofr_b200", "csrc", "engine_internal.h"),
             os.path.join(ROOT, "gofr_b200", "csrc", "reqlog_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "http_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "table_format.h")]
@@ -164,6 +168,29 @@ def proto_encode(fields, rows, row_off, misalign: int = 0):
     rows = np.ascontiguousarray(rows)
     rc = lib().emu_proto_encode(ft.ctypes.data, len(fields), rows.ctypes.data, row_off.ctypes.data, n, out.ctypes.data, cap,
                                 off.ctypes.data, meta.ctypes.data, misalign)
+    if rc != 0:
+        raise RuntimeError("emu output capacity too small")
+    return out, off, meta[:n]
+
+
+def proto_encode_nested(msgs, root, rows, row_off, misalign: int = 0):
+    """pbn_size + pbn_emit (proto_nested_device.cuh) on the CPU → (out, out_off, meta).  The descriptor comes from the
+    product's own validation (gofr_proto_nested_describe: host code, no GPU)."""
+    from gofr_b200 import _abi
+    n = len(row_off) - 1
+    nm, nf, n_fields = S.proto_nested_tables(msgs)
+    lib().emu_pbn_desc_bytes.restype = C.c_uint32
+    desc = np.zeros(int(lib().emu_pbn_desc_bytes()), dtype=np.uint8)
+    _abi.check(_abi.lib().gofr_proto_nested_describe(nm.ctypes.data, len(msgs), nf.ctypes.data, n_fields, root, desc.ctypes.data, desc.size),
+               "gofr_proto_nested_describe")
+    cap = int(rows.size) * 4 + 64 * n + 64 + misalign
+    out = np.full(cap, 0xEE, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    meta = np.zeros(max(n, 1), dtype=np.uint32)
+    rows = np.concatenate([np.ascontiguousarray(rows), np.zeros(16, np.uint8)])
+    lib().emu_proto_encode_nested.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
+    rc = lib().emu_proto_encode_nested(desc.ctypes.data, rows.ctypes.data, row_off.ctypes.data, n, out.ctypes.data, cap, off.ctypes.data,
+                                       meta.ctypes.data, misalign)
     if rc != 0:
         raise RuntimeError("emu output capacity too small")
     return out, off, meta[:n]

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../gofr_b200/csrc/serve_device.cuh"
+#include "../../gofr_b200/csrc/proto_nested_device.cuh"
 
 using namespace gofr;
 
@@ -246,6 +247,29 @@ extern "C" int emu_proto_encode(const uint32_t* fields, uint32_t n_fields, const
     out_off[n] = (uint32_t)pos;
     return 0;
 }
+
+// rows -> frames for message types with nested / repeated fields (proto_nested_device.cuh); desc = the PbnDesc the product's
+// gofr_proto_nested_describe built
+extern "C" int emu_proto_encode_nested(const void* desc, const uint8_t* rows, const uint32_t* row_off, uint32_t n, uint8_t* out,
+                                       uint64_t out_cap, uint32_t* out_off, uint32_t* meta, uint32_t start_misalign) {
+    PbnDesc D;
+    memcpy(&D, desc, sizeof D);
+    uint32_t stage[GOFR_STAGE_WORDS];
+    uint64_t pos = start_misalign;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint8_t* r = rows + row_off[i];
+        const uint32_t rn = row_off[i + 1] - row_off[i];
+        PbnMsg m = pbn_size(D, r, rn);
+        out_off[i] = (uint32_t)pos;
+        meta[i] = m.status;
+        if (pos + m.out_len > out_cap) return -1;
+        pbn_emit(D, r, rn, m, out + pos, stage);
+        pos += m.out_len;
+    }
+    out_off[n] = (uint32_t)pos;
+    return 0;
+}
+extern "C" uint32_t emu_pbn_desc_bytes() { return (uint32_t)sizeof(PbnDesc); }
 
 extern "C" int emu_proto_decode(const uint32_t* fields, uint32_t n_fields, const uint8_t* in, const uint32_t* in_off, uint32_t n,
                                 uint8_t* rows, uint64_t rows_cap, uint32_t* row_off, uint32_t* meta, uint32_t start_misalign) {

@@ -19,7 +19,7 @@ _lib = None
 
 
 def build() -> None:
-    srcs = ["gofr_oracle.c", "orc_bind.c", "orc_grpc.c", "orc_reqlog.c", "orc_http.c", "orc_proto.c", "orc_value.c", "gofr_oracle.h", "orc_internal.h", "Makefile"]
+    srcs = ["gofr_oracle.c", "orc_bind.c", "orc_grpc.c", "orc_reqlog.c", "orc_http.c", "orc_proto.c", "orc_proto_nested.c", "orc_value.c", "gofr_oracle.h", "orc_internal.h", "Makefile"]
     odir = os.path.join(_ROOT, "oracle")
     if os.path.exists(_LIB_PATH):
         so_m = os.path.getmtime(_LIB_PATH)
@@ -236,6 +236,29 @@ def proto_encode(fields, rows: np.ndarray, row_off: np.ndarray):
     rows = np.ascontiguousarray(rows)
     rc = lib().orc_proto_encode(ft.ctypes.data, len(fields), rows.ctypes.data, row_off.ctypes.data, n, out.ctypes.data, cap,
                                 off.ctypes.data, meta.ctypes.data)
+    assert rc == 0
+    return out, off, meta[:n]
+
+
+def proto_encode_nested(msgs, root: int, rows: np.ndarray, row_off: np.ndarray):
+    """orc_proto_encode_nested: message types with nested / repeated fields → (out, out_off, meta)."""
+    n = len(row_off) - 1
+    mt, ft, k = [], [], 0
+    for fields in msgs:
+        mt += [k, len(fields)]
+        for f in fields:
+            ft += [f.number, f.type, 1 if f.repeated else 0, f.msg]
+            k += 1
+    mt, ft = np.array(mt, dtype=np.uint32), np.array(ft, dtype=np.uint32)
+    cap = int(rows.size) * 4 + 64 * n + 64
+    out = np.zeros(cap, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    meta = np.zeros(max(n, 1), dtype=np.uint32)
+    rows = np.ascontiguousarray(rows)
+    lib().orc_proto_encode_nested.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                              C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    rc = lib().orc_proto_encode_nested(mt.ctypes.data, len(msgs), ft.ctypes.data, k, root, rows.ctypes.data, row_off.ctypes.data, n,
+                                       out.ctypes.data, cap, off.ctypes.data, meta.ctypes.data)
     assert rc == 0
     return out, off, meta[:n]
 
