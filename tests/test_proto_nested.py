@@ -230,7 +230,7 @@ def test_gpu_matches_oracle():
     rnd = random.Random(77)
     eng = Engine(Table(synth.config1_spec()), 0)
     for msgs in (MSGS, _rand_types(rnd), _rand_types(rnd)):
-        values = [_rand_value(rnd, msgs, 0) for _ in range(20000)]
+        values = [_rand_value(rnd, msgs, 0) for _ in range(5000)]
         rows, off = S.pack_proto_nested_rows(msgs, 0, values)
         o_out, o_off, o_meta = O.proto_encode_nested(msgs, 0, rows, off)
         d_out, d_off, d_meta = eng.proto_encode_nested_device(msgs, 0, rows, off)
