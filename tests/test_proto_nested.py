@@ -143,7 +143,7 @@ def _rand_scalar(rnd, t):
         return rnd.choice([0, 1, -1, 2 ** 63 - 1, -2 ** 63, rnd.randint(-10 ** 6, 10 ** 6)])
     if t in (S.PB_UINT64, S.PB_FIXED64):
         return rnd.choice([0, 1, 2 ** 64 - 1, 127, 128, rnd.randint(0, 10 ** 12)])
-    if t in (S.PB_INT32, S.PB_SINT32, S.PB_SFIXED32):
+    if t in (S.PB_INT32, S.PB_SINT32, S.PB_SFIXED32, S.PB_ENUM):
         return rnd.choice([0, 1, -1, 2 ** 31 - 1, -2 ** 31, rnd.randint(-1000, 1000)])
     if t in (S.PB_UINT32, S.PB_FIXED32):
         return rnd.choice([0, 1, 2 ** 32 - 1, 16383, 16384])
