@@ -297,3 +297,36 @@ func (e *Engine) ProtoDecodeDevice(fields []ProtoField, dIn, dInOff unsafe.Point
 	return check(C.gofr_proto_decode_device(e.e, fp, C.uint32_t(len(fields)), (*C.uint8_t)(dIn), (*C.uint32_t)(dInOff), C.uint32_t(n),
 		(*C.uint8_t)(dRows), C.uint64_t(rowsCap), (*C.uint32_t)(dRowOff), (*C.uint32_t)(dMeta), stream), "gofr_proto_decode_device")
 }
+
+// ProtoNField / ProtoNMsg describe message types with nested and repeated fields (gofr_proto_nfield / gofr_proto_nmsg):
+// Msgs[m] owns Fields[FirstField : FirstField+NFields] in ascending field-number order; a field of Type 11
+// (TYPE_MESSAGE) names its message type in Msg.  protoreflect gives all of it: for a generated message,
+// walk md.Fields() (fd.Number(), fd.Kind(), fd.IsList(), fd.Message()).
+type ProtoNField struct {
+	Number   uint32
+	Type     uint8
+	Repeated uint8
+	Msg      uint16
+}
+type ProtoNMsg struct{ FirstField, NFields uint16 }
+
+// ProtoEncodeNestedDevice marshals n rows as messages of type msgs[root] and frames them for gRPC
+// (gofr_proto_encode_nested_device): proto.Marshal for responses that are not flat — nested messages (a presence word
+// and the message's fixed part inline in the row), repeated fields (a count, the elements in the row's variable part).
+func (e *Engine) ProtoEncodeNestedDevice(msgs []ProtoNMsg, fields []ProtoNField, root uint32, dRows, dRowOff unsafe.Pointer, n int,
+	dOut unsafe.Pointer, outCap uint64, dOutOff, dMeta unsafe.Pointer, stream unsafe.Pointer) error {
+	if len(msgs) == 0 || len(fields) == 0 {
+		return errors.New("gofrb200: empty message description")
+	}
+	return check(C.gofr_proto_encode_nested_device(e.e, (*C.gofr_proto_nmsg)(unsafe.Pointer(&msgs[0])), C.uint32_t(len(msgs)),
+		(*C.gofr_proto_nfield)(unsafe.Pointer(&fields[0])), C.uint32_t(len(fields)), C.uint32_t(root), (*C.uint8_t)(dRows),
+		(*C.uint32_t)(dRowOff), C.uint32_t(n), (*C.uint8_t)(dOut), C.uint64_t(outCap), (*C.uint32_t)(dOutOff), (*C.uint32_t)(dMeta), stream),
+		"gofr_proto_encode_nested_device")
+}
+
+// SlotCTAs queries (ctas == 0) or forces (4 / 5) the instance of the slot-layout serve kernel (gofr_engine_slot_ctas).
+func (e *Engine) SlotCTAs(ctas int) (int, error) {
+	var v C.int
+	err := check(C.gofr_engine_slot_ctas(e.e, C.int(ctas), &v), "gofr_engine_slot_ctas")
+	return int(v), err
+}
