@@ -286,3 +286,48 @@ def test_patterns_outside_the_subset_are_refused():
             Table(S.TableSpec(default_routes=False, routes=[S.Route(S.M_GET, "/p/" + pat, S.H_HOST)]))
     for pat in ["{a:é}", "{a:[a-z]{0,}}", "{a:\\.}", "{a:.+}", "{a:[^/]*}", "{a:a{1}}"]:
         Table(S.TableSpec(default_routes=False, routes=[S.Route(S.M_GET, "/p/" + pat, S.H_HOST)]))
+
+
+def test_fuzzed_variable_regexps_three_ways():
+    """random variable regexps: the product and the oracle accept exactly the same ones, and on the accepted ones the
+    oracle, the device code and Python's re agree on the match and on every capture"""
+    import random
+    import re
+    rnd = random.Random(7)
+    units = ["[0-9]", "[a-z]", "[a-c0-2_]", "\\d", "\\w", ".", "[^/]", "[^a-c]", "a", "b", "-", "\\.", "\\-", "x", "é", "(", ")", "|", "^", "$",
+             "[", "]", "\\s", "[[:alpha:]]"]
+    quants = ["", "", "+", "*", "?", "{2}", "{1,3}", "{2,}", "{0,1}", "{0}", "+?", "**", "{3,2}", "{300}"]
+    pool = ["a", "b", "ab", "abc", "12", "1", "a1", "a-b", "x.y", "aa", "aab", "bbb", "012", "_", "ab-12", "a.b", "", "aaa", "0", "a/b"]
+    accepted = 0
+    for k in range(700):
+        body = "".join(rnd.choice(units) + rnd.choice(quants) for _ in range(rnd.randint(1, 4)))
+        pat = "/r/{v:%s}%s" % (body, rnd.choice(["", "/t", "-{w}", ".{e:[a-z]+}"]))
+        spec = S.TableSpec(default_routes=False, routes=[S.Route(S.M_GET, pat, S.H_HOST), S.Route(S.M_GET, "/r/{any}", S.H_HOST)])
+        try:
+            t, okp = Table(spec), True
+        except Exception:
+            t, okp = None, False
+        ot = O.OracleTable(spec)
+        assert okp == all(r >= 0 for r in ot.route_ids), pat
+        if not okp:
+            continue
+        accepted += 1
+        reqs = [S.Req(S.M_GET, ("/r/" + rnd.choice(pool) + rnd.choice(["", "", "/t", "-q", ".txt", rnd.choice(pool)])).encode()) for _ in range(30)]
+        b = S.RequestBatch.pack(reqs)
+        m1, v1 = O.route(ot, b)
+        m2, v2 = emu.route(t.serialize(), b)
+        assert np.array_equal(m1, m2) and np.array_equal(v1, v2), pat
+        try:
+            rx, names = _mux_regex(pat)
+        except re.error:
+            continue
+        for i, rq in enumerate(reqs):
+            if (int(m1[i]) & 0xFFFF) == 301:
+                continue
+            mm = rx.match(rq.path)
+            assert bool(mm) == ((int(m1[i]) >> 16) == 0 and (int(m1[i]) & 0xFFFF) == 0), (pat, rq.path)
+            if mm:
+                for kk in range(len(names)):
+                    a, e = mm.span(kk + 1)
+                    assert (int(v1[i, kk]) & 0xFFFF, int(v1[i, kk]) >> 16) == (a, e - a), (pat, rq.path, kk)
+    assert accepted > 50
