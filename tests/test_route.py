@@ -307,8 +307,11 @@ def test_fuzzed_variable_regexps_three_ways():
             t, okp = Table(spec), True
         except Exception:
             t, okp = None, False
-        ot = O.OracleTable(spec)
-        assert okp == all(r >= 0 for r in ot.route_ids), pat
+        try:
+            ot, oko = O.OracleTable(spec), True
+        except ValueError:          # "oracle refused route": outside the subset
+            ot, oko = None, False
+        assert okp == oko, pat
         if not okp:
             continue
         accepted += 1
