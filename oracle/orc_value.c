@@ -114,6 +114,11 @@ typedef struct {
     int failed;         /* UnsupportedValueError somewhere: Encode writes nothing */
     int malformed;
 } walk;
+/* The walk stops at the FIRST thing that ends it — a value encoding/json cannot write, or a row that ends too early.  (Go
+ * stops at the first UnsupportedValueError as well; for malformed rows there is no reference behaviour, and what matters
+ * is that the product and this file answer alike: what comes first in field order wins.  Inside ONE map the entries'
+ * framing is checked as a whole before any value is looked at, because that is how the device code has to do it.) */
+#define WALK_OVER(w) ((w)->malformed || (w)->failed)
 
 static uint32_t rd32u(const uint8_t* p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
 static uint64_t rd64u(const uint8_t* p) { return (uint64_t)rd32u(p) | (uint64_t)rd32u(p + 4) << 32; }
@@ -217,8 +222,11 @@ static void enc_field_value(obuf* b, walk* w, const orc_field* f, const uint8_t*
         case C_SLICE: {
             uint32_t n = rd32u(p);
             if (n == 0xFFFFFFFFu) { ob_puts(b, "null"); break; }
+            /* a count that cannot fit (every scalar or string element owns at least a word) is malformed before any element
+             * is looked at; slices of structs are simply walked */
+            if (f->kind != F_STRUCT && (size_t)(w->end - w->var) / 4 < n) { w->malformed = 1; break; }
             ob_putc(b, '[');
-            for (uint32_t i = 0; i < n && !w->malformed; i++) {
+            for (uint32_t i = 0; i < n && !WALK_OVER(w); i++) {
                 if (i) ob_putc(b, ',');
                 enc_element(b, w, f);
             }
@@ -282,7 +290,7 @@ static void enc_struct(obuf* b, walk* w, const orc_schema* sc, const uint8_t* fi
     if (sc->n_fields == 1 && (sc->f[0].flags & FIELD_BARE)) { enc_field_value(b, w, &sc->f[0], fixed); return; }
     ob_putc(b, '{');
     int first = 1;
-    for (int i = 0; i < sc->n_fields && !w->malformed; i++) {
+    for (int i = 0; i < sc->n_fields && !WALK_OVER(w); i++) {
         const orc_field* f = &sc->f[i];
         const uint8_t* p = fixed;
         fixed += (size_t)field_fixed_words(w->t, f) * 4;

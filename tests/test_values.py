@@ -602,3 +602,40 @@ def test_random_schemas_three_ways(seed):
         L = int(ln[i])
         if L <= 8192:
             assert out[i, :L].tobytes() == ob[int(f1[i]):int(f1[i]) + L], i
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_mutated_rows_device_code_equals_oracle(seed):
+    """rows of random schemas with bytes flipped, count words overwritten, tails cut off or garbage appended: whatever the
+    walk meets first — a float encoding/json cannot write, or the end of the row — decides, on both sides alike"""
+    rnd = random.Random(4000 + seed)
+    for _ in range(3):
+        structs, bare = _rand_schemas(rnd, rnd.randint(2, 5))
+        routed = structs + bare
+        kind = S.H_RESULT if seed % 2 else S.H_ROW
+        spec = S.TableSpec(schemas=routed, routes=[S.Route(S.M_GET, "/t/%d" % sc.id, kind, schema_id=sc.id) for sc in routed])
+        reqs = []
+        for i in range(250):
+            sc = routed[rnd.randrange(len(routed))]
+            row = sc.encode_row(_rand_value(rnd, spec, sc), spec.schema)
+            data = bytearray(S.result_record(rnd.choice([S.RESULT_DATA, S.RESULT_RAW_DATA]), row) if kind == S.H_RESULT else row)
+            for _k in range(rnd.randint(0, 3)):
+                if not data:
+                    break
+                r, p = rnd.random(), rnd.randrange(len(data))
+                if r < 0.4:
+                    data[p] ^= 1 << rnd.randrange(8)
+                elif r < 0.6:
+                    data[p & ~3:(p & ~3) + 4] = rnd.choice([0xFFFFFFFF, 0xFFFFFFFE, 0x7FFFFFFF, 1 << 20, 3]).to_bytes(4, "little")
+                elif r < 0.8:
+                    del data[p:]
+                else:
+                    data += bytes(rnd.randrange(256) for _ in range(rnd.randint(1, 9)))
+            reqs.append(S.Req(S.M_GET, b"/t/%d" % sc.id, b"", bytes(data)))
+        b = S.RequestBatch.pack(reqs, seed=seed)
+        o1, f1, m1 = O.OracleTable(spec).serve(b, DATE, out_cap=1 << 24)
+        o2, f2, m2 = E.serve(Table(spec).serialize(), b, DATE, out_cap=1 << 24)
+        assert np.array_equal(m1, m2) and np.array_equal(f1, f2)
+        assert o1[:int(f1[-1])].tobytes() == o2[:int(f1[-1])].tobytes()
+        st = m1 & 0xFFFF
+        assert (st == 500).any() and (st == 200).any()
