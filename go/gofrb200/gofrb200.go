@@ -330,3 +330,16 @@ func (e *Engine) SlotCTAs(ctas int) (int, error) {
 	err := check(C.gofr_engine_slot_ctas(e.e, C.int(ctas), &v), "gofr_engine_slot_ctas")
 	return int(v), err
 }
+
+// ProtoDecodeNestedDevice is the other direction (gofr_proto_decode_nested_device): length-prefixed request frames → rows of
+// msgs[root].  dMeta[i] == 6 (GOFR_GRPC_DEFER): a valid frame this decoder leaves to proto.Unmarshal on the host.
+func (e *Engine) ProtoDecodeNestedDevice(msgs []ProtoNMsg, fields []ProtoNField, root uint32, dIn, dInOff unsafe.Pointer, n int,
+	dRows unsafe.Pointer, rowsCap uint64, dRowOff, dMeta unsafe.Pointer, stream unsafe.Pointer) error {
+	if len(msgs) == 0 || len(fields) == 0 {
+		return errors.New("gofrb200: empty message description")
+	}
+	return check(C.gofr_proto_decode_nested_device(e.e, (*C.gofr_proto_nmsg)(unsafe.Pointer(&msgs[0])), C.uint32_t(len(msgs)),
+		(*C.gofr_proto_nfield)(unsafe.Pointer(&fields[0])), C.uint32_t(len(fields)), C.uint32_t(root), (*C.uint8_t)(dIn),
+		(*C.uint32_t)(dInOff), C.uint32_t(n), (*C.uint8_t)(dRows), C.uint64_t(rowsCap), (*C.uint32_t)(dRowOff), (*C.uint32_t)(dMeta), stream),
+		"gofr_proto_decode_nested_device")
+}

@@ -101,6 +101,7 @@ def lib():
     L.gofr_engine_set_timing.argtypes = [vp, i32]
     L.gofr_engine_overflowed.argtypes = [vp, C.POINTER(i32), i32]
     L.gofr_proto_nested_describe.argtypes = [vp, u32, vp, u32, u32, vp, u32]
+    L.gofr_proto_decode_nested_device.argtypes = [vp, vp, u32, vp, u32, u32, vp, vp, u32, vp, u64, vp, vp, vp]
     L.gofr_proto_encode_nested_device.argtypes = [vp, vp, u32, vp, u32, u32, vp, vp, u32, vp, u64, vp, vp, vp]
     L.gofr_table_slot_ctas.argtypes = [vp, C.POINTER(C.c_int)]
     L.gofr_engine_slot_ctas.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
@@ -147,7 +148,7 @@ DECLARED_SYMBOLS = [
     "gofr_table_route_count", "gofr_table_max_response_bytes", "gofr_engine_create", "gofr_engine_destroy",
     "gofr_serve_device", "gofr_serve_device_slots", "gofr_batch_submit", "gofr_batch_wait", "gofr_batch_submit_slots", "gofr_engine_set_chunk", "gofr_engine_set_tile",
     "gofr_engine_set_timing", "gofr_engine_overflowed", "gofr_engine_geometry", "gofr_engine_slot_ctas", "gofr_table_slot_ctas", "gofr_alloc_pinned", "gofr_free_pinned", "gofr_bind_host_thread", "gofr_bind_device", "gofr_batch_bind",
-    "gofr_grpc_hello_device", "gofr_requestlog_device", "gofr_http_parse_device", "gofr_batch_route", "gofr_proto_encode_device", "gofr_proto_decode_device", "gofr_proto_encode_nested_device", "gofr_proto_nested_describe", "gofr_table_response_bound", "gofr_frontend_create", "gofr_frontend_destroy", "gofr_frontend_set_clock",
+    "gofr_grpc_hello_device", "gofr_requestlog_device", "gofr_http_parse_device", "gofr_batch_route", "gofr_proto_encode_device", "gofr_proto_decode_device", "gofr_proto_encode_nested_device", "gofr_proto_decode_nested_device", "gofr_proto_nested_describe", "gofr_table_response_bound", "gofr_frontend_create", "gofr_frontend_destroy", "gofr_frontend_set_clock",
     "gofr_frontend_stats", "gofr_frontend_serve", "gofr_route_device", "gofr_engine_launch_count", "gofr_engine_kernel_time_ms", "gofr_last_error",
     "gofr_abi_version", "gofr_format_http_date",
 ]

@@ -81,7 +81,7 @@ struct gofr_engine {
     int wide_grid = 0, wide_blocks_per_sm = 0;
     bool slots_wide = false;  // choose_slot_residency
     bool has_values = false;  // some program has PF_VALUES: the packed layout runs serve_kernel_values (serve_values_kernel.cu)
-    int grid = 0, blocks_per_sm = 0, grpc_grid = 0, reqlog_grid = 0, http_grid = 0, proto_grid = 0, proto_decode_grid = 0, proto_nested_grid = 0;
+    int grid = 0, blocks_per_sm = 0, grpc_grid = 0, reqlog_grid = 0, http_grid = 0, proto_grid = 0, proto_decode_grid = 0, proto_nested_grid = 0, proto_nested_decode_grid = 0;
     uint32_t epoch = 0;
     // resident path scratch
     unsigned long long* d_state = nullptr;
@@ -1054,10 +1054,10 @@ static int pbn_build(const gofr_proto_nmsg* msgs, uint32_t n_msgs, const gofr_pr
     return GOFR_OK;
 }
 
-int gofr_proto_encode_nested_device(gofr_engine* e, const gofr_proto_nmsg* msgs, uint32_t n_msgs, const gofr_proto_nfield* fields,
-                                    uint32_t n_fields, uint32_t root, const uint8_t* d_rows, const uint32_t* d_row_off, uint32_t n,
-                                    uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off, uint32_t* d_meta, void* stream) {
-    if (!e || (n && (!d_rows || !d_row_off || !d_out || !d_out_off || !d_meta))) return GOFR_ERR_INVALID;
+static int proto_nested_run(gofr_engine* e, const gofr_proto_nmsg* msgs, uint32_t n_msgs, const gofr_proto_nfield* fields, uint32_t n_fields,
+                            uint32_t root, const uint8_t* d_in, const uint32_t* d_in_off, uint32_t n, uint8_t* d_out, uint64_t out_cap,
+                            uint32_t* d_out_off, uint32_t* d_meta, void* stream, bool decode) {
+    if (!e || (n && (!d_in || !d_in_off || !d_out || !d_out_off || !d_meta))) return GOFR_ERR_INVALID;
     PbnDesc D;
     { int rc = pbn_build(msgs, n_msgs, fields, n_fields, root, &D); if (rc) return rc; }
     std::lock_guard<std::mutex> g(e->mu);
@@ -1072,21 +1072,34 @@ int gofr_proto_encode_nested_device(gofr_engine* e, const gofr_proto_nmsg* msgs,
         CUDA_TRY(cudaMemset(e->d_state, 0, tiles * 8));
         e->state_tiles = tiles;
     }
-    if (e->proto_nested_grid <= 0) {
-        e->proto_nested_grid = proto_nested_max_grid(e->device);
-        if (e->proto_nested_grid <= 0) { set_last_error("proto kernel cannot be resident"); return GOFR_ERR_CUDA; }
+    int& grid = decode ? e->proto_nested_decode_grid : e->proto_nested_grid;
+    if (grid <= 0) {
+        grid = decode ? proto_nested_decode_max_grid(e->device) : proto_nested_max_grid(e->device);
+        if (grid <= 0) { set_last_error("proto kernel cannot be resident"); return GOFR_ERR_CUDA; }
     }
     GrpcParams p;
     memset(&p, 0, sizeof p);
-    p.in = d_rows; p.in_off = d_row_off; p.n = n; p.n_tiles = (uint32_t)tiles;
+    p.in = d_in; p.in_off = d_in_off; p.n = n; p.n_tiles = (uint32_t)tiles;
     { int erc = next_epoch(e, &p.epoch); if (erc) return erc; }
     p.out = d_out; p.out_cap = out_cap; p.out_off = d_out_off; p.meta = d_meta;
     p.tile_state = e->d_state; p.overflow = e->d_flag;
-    const int g_ = (int)std::min<size_t>((size_t)std::max(1, e->proto_nested_grid / engines_on_device(e->device)), tiles);
-    int rc = launch_proto_encode_nested(p, D, g_, st);
+    const int g_ = (int)std::min<size_t>((size_t)std::max(1, grid / engines_on_device(e->device)), tiles);
+    int rc = decode ? launch_proto_decode_nested(p, D, g_, st) : launch_proto_encode_nested(p, D, g_, st);
     if (rc != 0) { set_last_error("proto kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); return GOFR_ERR_CUDA; }
     e->launches++;
     return GOFR_OK;
+}
+
+int gofr_proto_encode_nested_device(gofr_engine* e, const gofr_proto_nmsg* msgs, uint32_t n_msgs, const gofr_proto_nfield* fields,
+                                    uint32_t n_fields, uint32_t root, const uint8_t* d_rows, const uint32_t* d_row_off, uint32_t n,
+                                    uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off, uint32_t* d_meta, void* stream) {
+    return proto_nested_run(e, msgs, n_msgs, fields, n_fields, root, d_rows, d_row_off, n, d_out, out_cap, d_out_off, d_meta, stream, false);
+}
+
+int gofr_proto_decode_nested_device(gofr_engine* e, const gofr_proto_nmsg* msgs, uint32_t n_msgs, const gofr_proto_nfield* fields,
+                                    uint32_t n_fields, uint32_t root, const uint8_t* d_in, const uint32_t* d_in_off, uint32_t n,
+                                    uint8_t* d_rows, uint64_t rows_cap, uint32_t* d_row_off, uint32_t* d_meta, void* stream) {
+    return proto_nested_run(e, msgs, n_msgs, fields, n_fields, root, d_in, d_in_off, n, d_rows, rows_cap, d_row_off, d_meta, stream, true);
 }
 
 // the descriptor gofr_proto_encode_nested_device would hand to its kernel (tests/emu drives the device code with it)

@@ -118,6 +118,8 @@ struct PbnDesc {
 };
 int launch_proto_encode_nested(const GrpcParams& p, const PbnDesc& D, int grid, void* stream);
 int proto_nested_max_grid(int device);
+int launch_proto_decode_nested(const GrpcParams& p, const PbnDesc& D, int grid, void* stream);
+int proto_nested_decode_max_grid(int device);
 
 // message type of gofr_proto_encode_device (kernel parameter, by value); 32 = GOFR_PROTO_MAX_FIELDS
 struct ProtoSchema {

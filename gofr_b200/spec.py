@@ -327,7 +327,7 @@ class LogBatch:
 (PB_DOUBLE, PB_FLOAT, PB_INT64, PB_UINT64, PB_INT32, PB_FIXED64, PB_FIXED32, PB_BOOL, PB_STRING) = range(1, 10)
 PB_BYTES, PB_UINT32, PB_ENUM, PB_SFIXED32, PB_SFIXED64, PB_SINT32, PB_SINT64 = 12, 13, 14, 15, 16, 17, 18
 PB_64BIT = (PB_DOUBLE, PB_INT64, PB_UINT64, PB_FIXED64, PB_SFIXED64, PB_SINT64)
-GRPC_OK, GRPC_COMPRESSED, GRPC_BAD_LENGTH, GRPC_BAD_PROTO, GRPC_BAD_UTF8, GRPC_BAD_ROW = range(6)
+GRPC_OK, GRPC_COMPRESSED, GRPC_BAD_LENGTH, GRPC_BAD_PROTO, GRPC_BAD_UTF8, GRPC_BAD_ROW, GRPC_DEFER = range(7)
 
 
 @dataclass

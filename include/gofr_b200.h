@@ -325,7 +325,9 @@ void gofr_free_pinned(void*);
 /* gRPC unary Hello (config 5): length-prefixed HelloRequest frames in, length-prefixed HelloResponse frames out,
  * packed; frame i of the input starts at in_off[i].  meta[i] = 0 ok, else a GOFR_GRPC_* error (frame emitted empty). */
 enum { GOFR_GRPC_OK = 0, GOFR_GRPC_COMPRESSED = 1, GOFR_GRPC_BAD_LENGTH = 2, GOFR_GRPC_BAD_PROTO = 3, GOFR_GRPC_BAD_UTF8 = 4,
-       GOFR_GRPC_BAD_ROW = 5 };
+       GOFR_GRPC_BAD_ROW = 5,
+       GOFR_GRPC_DEFER = 6 /* gofr_proto_decode_nested_device: a valid frame outside its subset (a singular message field sent
+                              more than once, which protobuf-go merges): decode it on the host */ };
 int gofr_grpc_hello_device(gofr_engine*, const uint8_t* d_in, const uint32_t* d_in_off, uint32_t n, uint8_t* d_out,
                            uint64_t out_cap, uint32_t* d_out_off, uint32_t* d_meta, void* stream);
 
@@ -391,6 +393,15 @@ typedef struct gofr_proto_nmsg {
 int gofr_proto_encode_nested_device(gofr_engine*, const gofr_proto_nmsg* msgs, uint32_t n_msgs, const gofr_proto_nfield* fields,
                                     uint32_t n_fields, uint32_t root, const uint8_t* d_rows, const uint32_t* d_row_off, uint32_t n,
                                     uint8_t* d_out, uint64_t out_cap, uint32_t* d_out_off, uint32_t* d_meta, void* stream);
+/* The other direction for the same message types: length-prefixed frames -> rows (proto.Unmarshal as protobuf-go does it:
+ * unknown fields and balanced groups skipped at every level; a known number with a foreign wire type is unknown, except that
+ * repeated numeric scalars are accepted packed and unpacked; singular scalars and strings: the last occurrence wins;
+ * repeated strings / bytes / messages: one element per occurrence in wire order; strings must be valid UTF-8).  d_meta[i]:
+ * GOFR_GRPC_OK or COMPRESSED / BAD_LENGTH / BAD_PROTO / BAD_UTF8 / DEFER (a failed frame gives an empty row); rows are
+ * packed, 4-byte aligned, zero padded to a multiple of 4, d_row_off[n + 1]. */
+int gofr_proto_decode_nested_device(gofr_engine*, const gofr_proto_nmsg* msgs, uint32_t n_msgs, const gofr_proto_nfield* fields,
+                                    uint32_t n_fields, uint32_t root, const uint8_t* d_in, const uint32_t* d_in_off, uint32_t n,
+                                    uint8_t* d_rows, uint64_t rows_cap, uint32_t* d_row_off, uint32_t* d_meta, void* stream);
 /* validation of such a description without a GPU; desc_out (>= 512 bytes, may be NULL with desc_cap 0 to validate only...
  * then GOFR_ERR_CAPACITY means "valid") receives the kernel's internal descriptor (test infrastructure reads it) */
 int gofr_proto_nested_describe(const gofr_proto_nmsg* msgs, uint32_t n_msgs, const gofr_proto_nfield* fields, uint32_t n_fields,

@@ -57,6 +57,9 @@ int orc_proto_decode(const uint32_t* fields, uint32_t n_fields, const uint8_t* i
 int orc_proto_encode_nested(const uint32_t* msgs, uint32_t n_msgs, const uint32_t* fields, uint32_t n_fields, uint32_t root,
                             const uint8_t* rows, const uint32_t* row_off, uint32_t n, uint8_t* out, uint64_t out_cap,
                             uint32_t* out_off, uint32_t* meta);
+int orc_proto_decode_nested(const uint32_t* msgs, uint32_t n_msgs, const uint32_t* fields, uint32_t n_fields, uint32_t root,
+                            const uint8_t* in, const uint32_t* in_off, uint32_t n, uint8_t* rows, uint64_t rows_cap,
+                            uint32_t* row_off, uint32_t* meta);
 int orc_grpc_hello(const uint8_t* in, const uint32_t* in_off, uint32_t n, uint8_t* out, uint64_t out_cap,
                    uint32_t* out_off, uint32_t* meta, int nthreads);
 

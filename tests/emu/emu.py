@@ -22,6 +22,7 @@ def _build():
             os.path.join(ROOT, "gofr_b200", "csrc", "float_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "grpc_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "proto_nested_device.cuh"),
+            os.path.join(ROOT, "gofr_b200", "csrc", "proto_nested_decode_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "engine_internal.h"),
             os.path.join(ROOT, "gofr_b200", "csrc", "reqlog_device.cuh"),
             os.path.join(ROOT, "gofr_b200", "csrc", "http_device.cuh"),
@@ -194,6 +195,33 @@ def proto_encode_nested(msgs, root, rows, row_off, misalign: int = 0):
     if rc != 0:
         raise RuntimeError("emu output capacity too small")
     return out, off, meta[:n]
+
+
+def _pbn_desc(msgs, root):
+    from gofr_b200 import _abi
+    nm, nf, n_fields = S.proto_nested_tables(msgs)
+    lib().emu_pbn_desc_bytes.restype = C.c_uint32
+    desc = np.zeros(int(lib().emu_pbn_desc_bytes()), dtype=np.uint8)
+    _abi.check(_abi.lib().gofr_proto_nested_describe(nm.ctypes.data, len(msgs), nf.ctypes.data, n_fields, root, desc.ctypes.data, desc.size),
+               "gofr_proto_nested_describe")
+    return desc
+
+
+def proto_decode_nested(msgs, root, frames, in_off):
+    """pdn_decode_size + pdn_decode_emit (proto_nested_decode_device.cuh) on the CPU → (rows, row_off, meta)"""
+    n = len(in_off) - 1
+    desc = _pbn_desc(msgs, root)
+    cap = int(frames.size) * 10 + 4096 * max(n, 1)
+    rows = np.full(cap, 0xEE, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    meta = np.zeros(max(n, 1), dtype=np.uint32)
+    frames = np.concatenate([np.ascontiguousarray(frames), np.zeros(16, np.uint8)])
+    lib().emu_proto_decode_nested.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    rc = lib().emu_proto_decode_nested(desc.ctypes.data, frames.ctypes.data, in_off.ctypes.data, n, rows.ctypes.data, cap, off.ctypes.data,
+                                       meta.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("emu output capacity too small")
+    return rows, off, meta[:n]
 
 
 def proto_decode(fields, frames, in_off, misalign: int = 0):

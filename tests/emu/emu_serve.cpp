@@ -11,6 +11,7 @@
 
 #include "../../gofr_b200/csrc/serve_device.cuh"
 #include "../../gofr_b200/csrc/proto_nested_device.cuh"
+#include "../../gofr_b200/csrc/proto_nested_decode_device.cuh"
 
 using namespace gofr;
 
@@ -267,6 +268,25 @@ extern "C" int emu_proto_encode_nested(const void* desc, const uint8_t* rows, co
         pos += m.out_len;
     }
     out_off[n] = (uint32_t)pos;
+    return 0;
+}
+// frames -> rows for the same message types (proto_nested_decode_device.cuh)
+extern "C" int emu_proto_decode_nested(const void* desc, const uint8_t* in, const uint32_t* in_off, uint32_t n, uint8_t* rows,
+                                       uint64_t rows_cap, uint32_t* row_off, uint32_t* meta) {
+    PbnDesc D;
+    memcpy(&D, desc, sizeof D);
+    uint64_t pos = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint8_t* f = in + in_off[i];
+        const uint32_t fn = in_off[i + 1] - in_off[i];
+        PdnRow r = pdn_decode_size(D, f, fn);
+        row_off[i] = (uint32_t)pos;
+        meta[i] = r.status;
+        if (pos + r.out_len > rows_cap) return -1;
+        pdn_decode_emit(D, f, fn, r, rows + pos);
+        pos += r.out_len;
+    }
+    row_off[n] = (uint32_t)pos;
     return 0;
 }
 extern "C" uint32_t emu_pbn_desc_bytes() { return (uint32_t)sizeof(PbnDesc); }

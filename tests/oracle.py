@@ -263,6 +263,29 @@ def proto_encode_nested(msgs, root: int, rows: np.ndarray, row_off: np.ndarray):
     return out, off, meta[:n]
 
 
+def proto_decode_nested(msgs, root: int, frames: np.ndarray, in_off: np.ndarray):
+    """orc_proto_decode_nested: frames → rows of message types with nested / repeated fields → (rows, row_off, meta)."""
+    n = len(in_off) - 1
+    mt, ft, k = [], [], 0
+    for fields in msgs:
+        mt += [k, len(fields)]
+        for f in fields:
+            ft += [f.number, f.type, 1 if f.repeated else 0, f.msg]
+            k += 1
+    mt, ft = np.array(mt, dtype=np.uint32), np.array(ft, dtype=np.uint32)
+    cap = int(frames.size) * 10 + 4096 * max(n, 1)
+    rows = np.zeros(cap, dtype=np.uint8)
+    off = np.zeros(n + 1, dtype=np.uint32)
+    meta = np.zeros(max(n, 1), dtype=np.uint32)
+    frames = np.ascontiguousarray(frames)
+    lib().orc_proto_decode_nested.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                              C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    rc = lib().orc_proto_decode_nested(mt.ctypes.data, len(msgs), ft.ctypes.data, k, root, frames.ctypes.data, in_off.ctypes.data, n,
+                                       rows.ctypes.data, cap, off.ctypes.data, meta.ctypes.data)
+    assert rc == 0
+    return rows, off, meta[:n]
+
+
 def proto_decode(fields, frames: np.ndarray, in_off: np.ndarray):
     """orc_proto_decode: gRPC frames → rows (proto.Unmarshal) → (rows, row_off, meta)."""
     n = len(in_off) - 1
