@@ -48,15 +48,20 @@ def hbm_peak():
 
 KERNEL_SOURCES = ["gofr_b200/csrc/serve_body.cuh", "gofr_b200/csrc/serve_device.cuh", "gofr_b200/csrc/bind_device.cuh",
                   "gofr_b200/csrc/serve_slots_kernel.cu", "gofr_b200/csrc/serve_slots_wide_kernel.cu", "gofr_b200/csrc/serve_values_kernel.cu", "gofr_b200/csrc/serve_slots_values_kernel.cu", "gofr_b200/csrc/value_device.cuh", "gofr_b200/csrc/float_device.cuh", "gofr_b200/csrc/serve_kernel.cu", "gofr_b200/csrc/tile_common.cuh",
-                  "gofr_b200/csrc/table_format.h", "gofr_b200/_build.py"]
+                  "gofr_b200/csrc/table_format.h"]
 
 
 def kernel_source_hash():
+    """SHA-256 over what decides the serve kernels' binaries: their sources and headers, the compiler flags and the list of
+    translation units built with the 256-bit sector store (not the whole build script: adding an unrelated kernel to the
+    build must not invalidate a capture of this one)."""
     import hashlib
+    from gofr_b200 import _build
     h = hashlib.sha256()
     for f in KERNEL_SOURCES:
         with open(os.path.join(ROOT, f), "rb") as fh:
             h.update(fh.read())
+    h.update(repr((_build.NVCC_FLAGS, sorted(x for x in _build.SECTOR256 if x.startswith("serve")))).encode())
     return h.hexdigest()
 
 
