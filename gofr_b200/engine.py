@@ -174,6 +174,25 @@ class Engine:
                                                               st.cuda_stream), "gofr_proto_encode_nested_device")
         return out, off, meta[:n]
 
+    def proto_decode_nested_device(self, msgs, root: int, frames: np.ndarray, in_off: np.ndarray, rows_cap: Optional[int] = None, stream=None):
+        """gofr_proto_decode_nested_device: packed gRPC frames of message types with nested / repeated fields → rows.
+        Returns (rows uint8, row_off, meta) on the device."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        n = len(in_off) - 1
+        nm, nf, k = S.proto_nested_tables(msgs)
+        d_in = torch.from_numpy(np.concatenate([np.ascontiguousarray(frames), np.zeros(16, np.uint8)])).to(dev)
+        d_off = torch.from_numpy(in_off.view(np.int32)).to(dev)
+        cap = rows_cap if rows_cap is not None else int(frames.size) * 10 + 4096 * max(n, 1)
+        rows = torch.empty(cap, dtype=torch.uint8, device=dev)
+        off = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        meta = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+        _abi.check(_abi.lib().gofr_proto_decode_nested_device(self._e, nm.ctypes.data, len(msgs), nf.ctypes.data, k, root, d_in.data_ptr(),
+                                                              d_off.data_ptr(), n, rows.data_ptr(), cap, off.data_ptr(), meta.data_ptr(),
+                                                              st.cuda_stream), "gofr_proto_decode_nested_device")
+        return rows, off, meta[:n]
+
     def proto_decode_device(self, fields, frames: np.ndarray, in_off: np.ndarray, rows_cap: Optional[int] = None, stream=None):
         """gofr_proto_decode_device: packed gRPC frames → rows.  Returns (rows uint8, row_off, meta) on the device."""
         import torch

@@ -405,3 +405,51 @@ def test_decode_mutated_frames_device_code_equals_oracle(seed):
                 body = body[p:] + body[:p]
         frames.append(_frame(bytes(body)))
     _decode_three_ways(msgs, 0, frames)
+
+
+def _gpu_decode_check():
+    """the body of test_gpu_decode_matches_oracle (run in a process of its own)"""
+    import torch
+    from gofr_b200 import synth
+    from gofr_b200.engine import Engine
+    from gofr_b200.table import Table
+    assert torch.cuda.is_available()
+    rnd = random.Random(78)
+    eng = Engine(Table(synth.config1_spec()), 0)
+    for msgs in (MSGS, _rand_types(rnd), _rand_types(rnd)):
+        values = [_rand_value(rnd, msgs, 0) for _ in range(4000)]
+        rows, off = S.pack_proto_nested_rows(msgs, 0, values)
+        out, o, _ = O.proto_encode_nested(msgs, 0, rows, off)
+        frames = _frames(out, o)
+        for i in range(0, len(frames), 7):          # every seventh frame damaged: statuses and empty rows must agree too
+            body = bytearray(frames[i][5:])
+            if body:
+                body[rnd.randrange(len(body))] ^= 1 << rnd.randrange(8)
+            frames[i] = _frame(bytes(body))
+        raw, in_off = _pack_frames(frames)
+        o_rows, o_off, o_meta = O.proto_decode_nested(msgs, 0, raw, in_off)
+        d_rows, d_off, d_meta = eng.proto_decode_nested_device(msgs, 0, raw, in_off)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_meta.cpu().numpy().view(np.uint32), o_meta)
+        assert np.array_equal(d_off.cpu().numpy().view(np.uint32), o_off)
+        assert d_rows[:int(o_off[-1])].cpu().numpy().tobytes() == o_rows[:int(o_off[-1])].tobytes()
+        good = ~o_meta.astype(bool)                  # undamaged frames decode back to the rows they were encoded from
+        for i in np.flatnonzero(good)[:500]:
+            if i % 7:
+                assert o_rows[int(o_off[i]):int(o_off[i + 1])].tobytes() == rows[int(off[i]):int(off[i + 1])].tobytes()
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="the nested decoder's kernel was finished after this round's GPU minutes were spent: its device "
+                   "code is checked on the CPU three ways (above), its first launch on a GPU is this test — XPASS means it matched")
+def test_gpu_decode_matches_oracle():
+    """gofr_proto_decode_nested_device on the GPU == oracle (statuses, offsets, rows) — in a child process, so that a fault
+    in a kernel that has never run cannot leave a sticky CUDA error in the process the other GPU tests run in"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", "import tests.test_proto_nested as t; t._gpu_decode_check()"], cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
