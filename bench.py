@@ -693,6 +693,7 @@ def main():
     # Before anything is pinned: this rank's threads and the pages they touch go to the NUMA node its GPU hangs off
     # (GPU0-3 and GPU4-7 sit on different sockets on the 8-GPU boxes; unbound, every rank's pinned buffers can land on
     # one socket and half of the PCIe traffic crosses the inter-socket link).
+    cpus_before_bind = os.sched_getaffinity(0)
     numa = bind_to_gpu_numa(local) if not args.no_numa_bind else {"bound": False, "node": None, "why": "--no-numa-bind"}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -862,6 +863,10 @@ def main():
         mt = np.zeros(m, dtype=np.uint32)
         if world == 1:   # timed at N=1 only: at N>1 the other ranks' barrier spin shares the host's CPU quota
             reps = 4
+            # the CPU arm gets every CPU the process started with, not just the GPU's NUMA node (the pthreads it starts
+            # inherit this thread's affinity): the same footing as `--impl reference`
+            cpus_bound = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, cpus_before_bind)
             cores, quota = pick_cpu_threads(lambda c: O.lib().orc_serve(
                 ot._t, sb.desc.ctypes.data, sb.trace_ids.ctypes.data, sb.arena.ctypes.data, m, date, o.ctypes.data, cap,
                 f.ctypes.data, mt.ctypes.data, c))
@@ -873,7 +878,9 @@ def main():
             cpu = {"value": m * reps / dtc, "unit": UNIT, "cores": cores, "kind": "port",
                    "cpu_quota": quota,
                    "sample": f"{reps} passes over the first {m} requests of the same stream, {cores} pthreads of "
-                             f"{os.cpu_count()} logical CPUs (cgroup CPU quota: {quota if quota else 'none'}), in-memory"}
+                             f"{os.cpu_count()} logical CPUs (cgroup CPU quota: {quota if quota else 'none'}), in-memory, "
+                             f"affinity: {len(cpus_before_bind)} CPUs"}
+            os.sched_setaffinity(0, cpus_bound)
         # the sample doubles as a parity check of the bench's own output
         o1, f1, _ = ot.serve(sb.slice(0, 4096), date)
         g = resp.out[:4096 * synth.C2_WIRE_BYTES].cpu().numpy()
