@@ -38,8 +38,10 @@ def _build():
 def lib():
     global _lib
     if _lib is None:
-        _build()
-        _lib = C.CDLL(LIB)
+        alt = os.environ.get("GOFR_EMU_LIB")   # a differently instrumented build of the same source (scratch/fuzz_long.py --asan)
+        if not alt:
+            _build()
+        _lib = C.CDLL(alt or LIB)
         _lib.emu_serve.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p,
                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
         _lib.emu_grpc_hello.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p,
