@@ -488,6 +488,10 @@ static int grow(void** p, size_t* cap, size_t need, size_t slack) {
     return GOFR_OK;
 }
 
+// The copy loops read their source in whole aligned words: up to 16 bytes past the last byte a request names may be touched
+// (include/gofr_b200.h states the same for device-resident callers), so a staging arena is never sized to the byte.
+static constexpr size_t kArenaSlack = 16;
+
 // A chunk = contiguous request range [lo, hi) and the arena byte range it covers.
 struct ChunkPlan { uint32_t lo, hi; uint32_t arena_lo, arena_hi; };
 
@@ -595,7 +599,7 @@ static int batch_submit_locked(gofr_engine* e, const gofr_req_batch* in, gofr_re
             }
             if (!s.d_flag) { if (cudaMalloc(&s.d_flag, 64) != cudaSuccess || cudaMemset(s.d_flag, 0, 64) != cudaSuccess) return GOFR_ERR_NOMEM; }
             int rc;
-            if ((rc = grow((void**)&s.d_arena, &s.cap_arena, abytes, 256))) return rc;
+            if ((rc = grow((void**)&s.d_arena, &s.cap_arena, abytes + kArenaSlack, 256))) return rc;
             if ((rc = grow((void**)&s.d_out, &s.cap_out, ocap, 256))) return rc;
             return GOFR_OK;
         };
@@ -612,7 +616,7 @@ static int batch_submit_locked(gofr_engine* e, const gofr_req_batch* in, gofr_re
             if (s.egress_pending) {
                 // the slot's previous chunk must have left before its buffers are overwritten: a stream-side wait,
                 // unless the buffers have to grow (cudaFree needs the host to be sure)
-                const bool grows = cn > s.cap_n || abytes > s.cap_arena || ocap > s.cap_out;
+                const bool grows = cn > s.cap_n || abytes + kArenaSlack > s.cap_arena || ocap > s.cap_out;
                 if (grows) CUDA_TRY(cudaEventSynchronize(s.ev_egress));
                 else CUDA_TRY(cudaStreamWaitEvent(e->st_h2d, s.ev_egress, 0));
                 s.egress_pending = false;
@@ -671,7 +675,7 @@ static int batch_submit_locked(gofr_engine* e, const gofr_req_batch* in, gofr_re
             s.cap_n = c;
         }
         if (!s.d_flag) { if (cudaMalloc(&s.d_flag, 64) != cudaSuccess || cudaMemset(s.d_flag, 0, 64) != cudaSuccess) return GOFR_ERR_NOMEM; }
-        if ((rc = grow((void**)&s.d_arena, &s.cap_arena, abytes, 256))) return rc;
+        if ((rc = grow((void**)&s.d_arena, &s.cap_arena, abytes + kArenaSlack, 256))) return rc;
         if ((rc = grow((void**)&s.d_out, &s.cap_out, ocap, 256))) return rc;
         return GOFR_OK;
     };
@@ -754,7 +758,7 @@ static int batch_submit_slots_locked(gofr_engine* e, const gofr_req_batch* in, g
         { int prc = chunk_arena_range(in, lo, hi, &alo, &ahi); if (prc) return prc; }
         const size_t abytes = (size_t)ahi - alo, obytes = (size_t)cn * slot;
         if (s.egress_pending) {  // the slot's previous chunk must have left before its buffers are reused
-            const bool grows = cn > s.cap_n || abytes > s.cap_arena || obytes > s.cap_out;
+            const bool grows = cn > s.cap_n || abytes + kArenaSlack > s.cap_arena || obytes > s.cap_out;
             if (grows) CUDA_TRY(cudaEventSynchronize(s.ev_egress));
             else CUDA_TRY(cudaStreamWaitEvent(e->st_h2d, s.ev_egress, 0));
             s.egress_pending = false;
@@ -772,7 +776,7 @@ static int batch_submit_slots_locked(gofr_engine* e, const gofr_req_batch* in, g
         }
         if (!s.d_flag) { if (cudaMalloc(&s.d_flag, 64) != cudaSuccess || cudaMemset(s.d_flag, 0, 64) != cudaSuccess) return GOFR_ERR_NOMEM; }
         int rc;
-        if ((rc = grow((void**)&s.d_arena, &s.cap_arena, abytes, 256))) return rc;
+        if ((rc = grow((void**)&s.d_arena, &s.cap_arena, abytes + kArenaSlack, 256))) return rc;
         if ((rc = grow((void**)&s.d_out, &s.cap_out, obytes, 256))) return rc;
         CUDA_TRY(cudaMemcpyAsync(s.d_desc, in->desc + lo, (size_t)cn * 16, cudaMemcpyHostToDevice, e->st_h2d));
         CUDA_TRY(cudaMemcpyAsync(s.d_ids, in->trace_ids + (size_t)lo * 16, (size_t)cn * 16, cudaMemcpyHostToDevice, e->st_h2d));

@@ -59,6 +59,8 @@ def worker(job, jobs, deadline, only, counts):
             m = importlib.import_module(mod)
             fn = getattr(m, name)
             base = 1_000_003 * (rnd + 1) + 7919 * job + k
+            with open(f"/tmp/fuzz_job{job}.now", "w") as nf:   # what was running, should a sanitizer abort the process
+                nf.write(f"{mod}.{name} base={base}\n")
             try:
                 if kind == "h":
                     inner = fn

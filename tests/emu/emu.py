@@ -35,6 +35,12 @@ def _build():
                            "-o", LIB, os.path.join(HERE, "emu_serve.cpp")])
 
 
+def _padded(arena: np.ndarray) -> np.ndarray:
+    """the arena as the ABI promises it to the device code (include/gofr_b200.h: the allocation extends 16 bytes past the last
+    request byte — copies read whole words) and not one byte more: under ASan this checks the promise is enough"""
+    return np.concatenate([arena, np.zeros(16, dtype=np.uint8)])
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -102,7 +108,7 @@ def serve_slots(image: bytes, batch, date: bytes, slot_bytes: int):
     out = base[shift:shift + n * slot_bytes]
     ln = np.zeros(n, dtype=np.uint32)
     meta = np.zeros(n, dtype=np.uint32)
-    arena = np.concatenate([batch.arena, np.zeros(32, dtype=np.uint8)])
+    arena = _padded(batch.arena)
     lib().emu_serve_slots(img.ctypes.data, len(image), batch.desc.ctypes.data, batch.trace_ids.ctypes.data, arena.ctypes.data,
                           n, date, out.ctypes.data, slot_bytes, ln.ctypes.data, meta.ctypes.data)
     return out.reshape(n, slot_bytes), ln, meta
@@ -117,7 +123,7 @@ def bind_rows(image: bytes, schema_idx: int, batch, slot_bytes: int):
     out = base[shift:shift + n * slot_bytes]
     ln = np.zeros(n, dtype=np.uint32)
     st = np.zeros(n, dtype=np.uint32)
-    arena = np.concatenate([batch.arena, np.zeros(32, dtype=np.uint8)])
+    arena = _padded(batch.arena)
     lib().emu_bind_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     lib().emu_bind_rows(img.ctypes.data, schema_idx, batch.desc.ctypes.data, arena.ctypes.data, n, out.ctypes.data, slot_bytes,
                         ln.ctypes.data, st.ctypes.data)
@@ -129,7 +135,8 @@ def route(image: bytes, batch):
     img = np.frombuffer(image, dtype=np.uint8).copy()
     meta = np.zeros(n, dtype=np.uint32)
     vars_ = np.zeros((n, 8), dtype=np.uint32)
-    lib().emu_route(img.ctypes.data, batch.desc.ctypes.data, batch.arena.ctypes.data, n, meta.ctypes.data,
+    arena = _padded(batch.arena)
+    lib().emu_route(img.ctypes.data, batch.desc.ctypes.data, arena.ctypes.data, n, meta.ctypes.data,
                     vars_.ctypes.data)
     return meta, vars_
 
@@ -152,7 +159,7 @@ def request_log(batch, misalign: int = 0):
     cap = 400 * n + 6 * int(batch.arena.size) + 64
     out = np.full(cap, 0xEE, dtype=np.uint8)
     off = np.zeros(n + 1, dtype=np.uint32)
-    arena = np.concatenate([batch.arena, np.zeros(32, dtype=np.uint8)])
+    arena = _padded(batch.arena)
     rc = lib().emu_reqlog(batch.desc.ctypes.data, batch.trace_ids.ctypes.data, arena.ctypes.data, n, out.ctypes.data,
                           cap, off.ctypes.data, misalign)
     if rc != 0:
@@ -263,8 +270,9 @@ def serve(image: bytes, batch, date: bytes, out_cap: int | None = None, misalign
     out = np.full(out_cap, 0xEE, dtype=np.uint8)
     off = np.zeros(n + 1, dtype=np.uint32)
     meta = np.zeros(n, dtype=np.uint32)
+    arena = _padded(batch.arena)
     rc = lib().emu_serve(img.ctypes.data, len(image), batch.desc.ctypes.data, batch.trace_ids.ctypes.data,
-                         batch.arena.ctypes.data, n, date, out.ctypes.data, out_cap, off.ctypes.data, meta.ctypes.data,
+                         arena.ctypes.data, n, date, out.ctypes.data, out_cap, off.ctypes.data, meta.ctypes.data,
                          misalign)
     if rc == -2:
         raise AssertionError("hashed and linear route matchers disagree")
