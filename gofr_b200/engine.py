@@ -144,7 +144,7 @@ class Engine:
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
         n = len(row_off) - 1
         ft = (_abi.ProtoField * max(len(fields), 1))(*[_abi.ProtoField(f.number, f.type) for f in fields])
-        d_rows = torch.from_numpy(np.ascontiguousarray(rows)).to(dev)
+        d_rows = torch.from_numpy(np.concatenate([np.ascontiguousarray(rows), np.zeros(16, np.uint8)])).to(dev)
         d_off = torch.from_numpy(row_off.view(np.int32)).to(dev)
         cap = out_cap if out_cap is not None else int(rows.size) * 3 + 32 * n * max(len(fields), 1) + 64
         out = torch.empty(cap, dtype=torch.uint8, device=dev)

@@ -37,6 +37,10 @@
  * seal (the reference never mutates routes after Run()); no callbacks into the caller from CUDA threads (cgo-safe).
  * Values that are non-deterministic in the reference are INPUTS here: the 16-byte OTel trace id per request
  * (middleware/logger.go:46-47) and the IMF-fixdate `Date` string per batch (net/http).
+ * Device-resident INPUT buffers of variable-length bytes (d_arena, d_in of frames, d_rows, d_raw, the strings of log
+ * records): 16-byte aligned, and the allocation extends at least 16 bytes past the last byte an offset names — tiles are
+ * staged in 16-byte units and the copy loops read whole aligned words; the bytes there are never looked at.  The host-buffer
+ * entry points (gofr_batch_*) stage their inputs themselves and ask nothing of the kind.
  */
 #ifndef GOFR_B200_H
 #define GOFR_B200_H
