@@ -274,6 +274,7 @@ int gofr_engine_set_tile(gofr_engine* e, uint32_t in_bytes_per_req) {
 
 int gofr_engine_set_chunk(gofr_engine* e, uint32_t requests_per_chunk) {
     if (!e || requests_per_chunk == 0) return GOFR_ERR_INVALID;
+    std::lock_guard<std::mutex> g(e->mu);  // a batch in flight keeps the chunk size it started with
     e->chunk = requests_per_chunk;
     return GOFR_OK;
 }
@@ -365,7 +366,7 @@ int gofr_serve_device(gofr_engine* e, const gofr_req_desc* d_desc, const uint8_t
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) {
-        CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st));
+        if (d_out_off) CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st));
         return GOFR_OK;
     }
     size_t tiles = (n + 63) / 64;  // enough for any tile size in use (serve: kServeT, gRPC / log: 128)
@@ -449,6 +450,7 @@ int gofr_engine_kernel_time_ms(gofr_engine* e, double* total_ms, uint64_t* launc
 
 int gofr_engine_set_timing(gofr_engine* e, int on) {
     if (!e) return GOFR_ERR_INVALID;
+    std::lock_guard<std::mutex> g(e->mu);
     e->timing_on = on != 0;
     return GOFR_OK;
 }
@@ -559,7 +561,12 @@ static int batch_submit_locked(gofr_engine* e, const gofr_req_batch* in, gofr_re
     out->out_bytes = 0;
     const uint32_t n = in->n;
     int final_rc = GOFR_OK;
-    if (n == 0) { out->out_off[0] = 0; }
+    if (n == 0) {  // nothing to do; the caller may have passed no buffers at all
+        if (out->out_off) out->out_off[0] = 0;
+        *ticket = e->next_ticket++;
+        e->done_tickets.emplace_back(*ticket, GOFR_OK);
+        return GOFR_OK;
+    }
 
     // Chunks are contiguous request ranges; a chunk's arena range is the min/max over its descriptors.  The scan is done
     // lazily, right before a chunk is enqueued, so it overlaps with the GPU work of the chunks already in flight
@@ -902,7 +909,7 @@ int gofr_grpc_hello_device(gofr_engine* e, const uint8_t* d_in, const uint32_t* 
     std::lock_guard<std::mutex> g(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (n == 0) { CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st)); return GOFR_OK; }
+    if (n == 0) { if (d_out_off) CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st)); return GOFR_OK; }
     size_t tiles = (n + kServeThreads - 1) / kServeThreads;
     if (tiles > e->state_tiles) {
         cudaFree(e->d_state);
@@ -960,7 +967,7 @@ static int proto_run(gofr_engine* e, const gofr_proto_field* fields, uint32_t n_
     std::lock_guard<std::mutex> g(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (n == 0) { CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st)); return GOFR_OK; }
+    if (n == 0) { if (d_out_off) CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st)); return GOFR_OK; }
     size_t tiles = (n + kServeThreads - 1) / kServeThreads;
     if (tiles > e->state_tiles) {
         cudaFree(e->d_state);
@@ -1067,7 +1074,7 @@ static int proto_nested_run(gofr_engine* e, const gofr_proto_nmsg* msgs, uint32_
     std::lock_guard<std::mutex> g(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (n == 0) { CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st)); return GOFR_OK; }
+    if (n == 0) { if (d_out_off) CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st)); return GOFR_OK; }
     size_t tiles = (n + kServeThreads - 1) / kServeThreads;
     if (tiles > e->state_tiles) {
         cudaFree(e->d_state);
@@ -1289,7 +1296,7 @@ int gofr_requestlog_device(gofr_engine* e, const gofr_log_desc* d_desc, const ui
     std::lock_guard<std::mutex> g(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (n == 0) { CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st)); return GOFR_OK; }
+    if (n == 0) { if (d_out_off) CUDA_TRY(cudaMemsetAsync(d_out_off, 0, 4, st)); return GOFR_OK; }
     size_t tiles = (n + kServeThreads - 1) / kServeThreads;
     if (tiles > e->state_tiles) {
         cudaFree(e->d_state);
