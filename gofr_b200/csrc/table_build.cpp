@@ -1513,7 +1513,8 @@ uint32_t gofr_table_max_response_bytes(const gofr_table* t, uint32_t max_data_le
     ImageHeader H;
     memcpy(&H, t->image.data(), sizeof H);
     // fixed part + Content-Length digits + every data byte escaped six-fold (\u00XX) + Location (3x path + query)
-    return H.max_fixed_len + 16 + gofr::image_data_expand(H) * max_data_len + 3 * 65535 + 65535 + 2;
+    const uint64_t b = (uint64_t)H.max_fixed_len + 16 + (uint64_t)gofr::image_data_expand(H) * max_data_len + 3 * 65535 + 65535 + 2;
+    return b > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)b;  // saturates like gofr_table_response_bound
 }
 
 uint32_t gofr_table_response_bound(const gofr_table* t, uint32_t path_len, uint32_t query_len, uint32_t data_len) {
