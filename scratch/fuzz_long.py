@@ -31,6 +31,9 @@ HYP = [  # (module, test, examples per round)
     ("tests.test_reqlog", "test_emu_random_records_property", 1500),
     ("tests.test_result", "test_string_outcome_property", 1000),
     ("tests.test_grpc", "test_emu_random_messages", 1500),
+    ("tests.test_slots", "test_emu_slots_random_rows_property", 1500),
+    ("tests.test_slots", "test_emu_slots_random_requests_property", 1500),
+    ("tests.test_slots", "test_emu_slots_mixed_stream_property", 400),
 ]
 SEEDED = [  # (module, test, seeds per round)
     ("tests.test_proto_nested", "test_random_types_three_ways", 6),

@@ -199,3 +199,48 @@ def test_slot_argument_checks(torch_cuda):
     with pytest.raises(_abi.GofrError):
         eng.serve_device_slots(b, DATE, 500)            # not a multiple of 16
     eng.close()
+
+
+# ---- the slot-layout emit path on arbitrary inputs (CPU): every response equals the oracle's, is zero padded to the next
+#      16-byte boundary and leaves the rest of its slot alone; a response longer than its slot writes nothing ----
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_bytes40 = st.binary(min_size=0, max_size=40)
+
+
+@settings(max_examples=120, deadline=None)
+@given(st.lists(st.tuples(_bytes40, _bytes40, st.integers(-2 ** 63, 2 ** 63 - 1), st.booleans()), min_size=1, max_size=10),
+       st.sampled_from([16, 208, 528, 1024]), st.sampled_from([S.FRAME_WIRE, S.FRAME_INTENDED, S.FRAME_BODY]))
+def test_emu_slots_random_rows_property(rows, slot, mode):
+    from tests.emu import emu
+    sc = synth.C2_SCHEMA
+    spec = S.TableSpec(schemas=[sc], routes=[S.Route(S.M_GET, "/p", S.H_ROW, schema_id=1)], frame_mode=mode)
+    batch = S.RequestBatch.pack([S.Req(S.M_GET, b"/p", b"", sc.encode_row([i, a, b, f, i % 2 ** 31])) for a, b, i, f in rows])
+    out, ln, meta = emu.serve_slots(Table(spec).serialize(), batch, DATE, slot)
+    _check_slots(out, ln, meta, spec, batch, slot)
+
+
+@settings(max_examples=120, deadline=None)
+@given(st.lists(st.tuples(st.sampled_from([S.M_GET, S.M_POST, S.M_HEAD, S.M_OPTIONS, S.M_PUT]),
+                          st.text(alphabet="/.abx%? ", min_size=0, max_size=14).map(lambda s: ("/" + s).encode()),
+                          st.binary(min_size=0, max_size=24)), min_size=1, max_size=12),
+       st.sampled_from([16, 176, 352, 1024]))
+def test_emu_slots_random_requests_property(reqs, slot):
+    """mixed dispositions (200 / 301 / 404 / 405 / OPTIONS / HEAD) of the 64-route table through the slot layout"""
+    from tests.emu import emu
+    spec = synth.config4_spec()
+    batch = S.RequestBatch.pack([S.Req(m, p.split(b"?", 1)[0], (p.split(b"?", 1) + [b""])[1] + q if b"?" in p else q) for m, p, q in reqs])
+    out, ln, meta = emu.serve_slots(Table(spec).serialize(), batch, DATE, slot)
+    _check_slots(out, ln, meta, spec, batch, slot)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(1, 150), st.sampled_from([16, 176, 352, 1024]))
+def test_emu_slots_mixed_stream_property(seed, n, slot):
+    """any window of the seeded mixed-traffic stream (matching routes with rows, path variables, redirects, OPTIONS, HEAD,
+    panics) through the slot layout, short slots included"""
+    from tests.emu import emu
+    spec = synth.config4_spec()
+    batch = synth.config4_batch(n, seed=seed)
+    out, ln, meta = emu.serve_slots(Table(spec).serialize(), batch, DATE, slot)
+    _check_slots(out, ln, meta, spec, batch, slot)
