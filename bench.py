@@ -665,6 +665,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="leave the rank's threads and pinned buffers wherever the OS puts them")
     ap.add_argument("--no-extras", action="store_true", help="skip the sharded config-4 (4 GPUs) / config-5 (8 GPUs) legs")
+    ap.add_argument("--extras-timeout", type=int, default=240, help="seconds the sharded legs may take before the headline line is printed without them")
     ap.add_argument("--e2e-layout", default="slots", choices=["packed", "slots"],
                     help="end-to-end measurement: gofr_batch_submit (packed offsets, device-driven egress) or "
                          "gofr_batch_submit_slots (one slot per response, plain async copies)")
@@ -886,8 +887,42 @@ def main():
         g = resp.out[:4096 * synth.C2_WIRE_BYTES].cpu().numpy()
         assert np.array_equal(g, o1[:4096 * synth.C2_WIRE_BYTES]), "bench output differs from the oracle"
 
+    # ---- the headline line is complete here; the sharded legs below can only add keys to it ----
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic", "config": workload_config(n, world, args),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": profiled_traffic(args.layout) if n == (1 << 20) else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                             "algorithmic_bytes_per_request": algo_bytes / n, "kernel_ms_per_launch": per_launch_ms,
+                             "kernel": ("gofr::serve_slots_kernel_wide (4 CTAs/SM, 128 registers)" if eng.slot_ctas() == 4 else
+                                        "gofr::serve_slots_kernel (5 CTAs/SM)") if args.layout == "slots" else "gofr::serve_kernel"},
+                "other_layout": alt,
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "geometry": eng.geometry(), "numa": numa}
+    printed = threading.Lock()
+
+    def emit(extra):
+        """Exactly one JSON line per job, whoever gets here first (the normal exit or the watchdog below)."""
+        if not printed.acquire(blocking=False):
+            return
+        if rank == 0:
+            print(json.dumps({**line, **extra}), flush=True)
+
     # ---- sharded legs of the other BASELINE configs (config 4 on 4 GPUs, config 5 on 8 GPUs) ----
     extras = {}
+    watchdog = None
+    if not args.no_extras and world in (4, 8):
+        # A leg that stalls (one rank raising inside it leaves the others at a barrier) must not take the measured headline
+        # with it: after --extras-timeout seconds every rank's watchdog ends the process, rank 0 printing the line first.
+        def give_up():
+            emit({"sharded_leg_error": "timed out after %d s; headline unaffected" % args.extras_timeout})
+            sys.stdout.flush()
+            os._exit(0)
+        watchdog = threading.Timer(args.extras_timeout, give_up)
+        watchdog.daemon = True
+        watchdog.start()
     if not args.no_extras:
         # a leg that raises the same way on every rank (a programming error) must not take the headline line with it
         try:
@@ -900,20 +935,14 @@ def main():
         except Exception as ex:  # noqa: BLE001
             extras["sharded_leg_error"] = repr(ex)[:300]
 
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8", "data": "synthetic", "config": workload_config(n, world, args),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": profiled_traffic(args.layout) if n == (1 << 20) else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
-                             "algorithmic_bytes_per_request": algo_bytes / n, "kernel_ms_per_launch": per_launch_ms,
-                             "kernel": ("gofr::serve_slots_kernel_wide (4 CTAs/SM, 128 registers)" if eng.slot_ctas() == 4 else
-                                        "gofr::serve_slots_kernel (5 CTAs/SM)") if args.layout == "slots" else "gofr::serve_kernel"},
-                "other_layout": alt,
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "geometry": eng.geometry(), "numa": numa, **extras}
-        print(json.dumps(line))
+    if watchdog is not None:
+        watchdog.cancel()
+    emit(extras)
     if world > 1:
+        # the line is out; a rank that left a leg early (its own exception) must not wait forever for the others here
+        bye = threading.Timer(60, lambda: os._exit(0))
+        bye.daemon = True
+        bye.start()
         dist.barrier()
         dist.destroy_process_group()
     return 0
