@@ -19,7 +19,7 @@
 
 namespace gofr {
 
-enum BindErr : uint32_t { BE_OK = 0, BE_EOF = 1, BE_CHAR = 2, BE_TYPE = 3, BE_DEPTH = 4 };
+enum BindErr : uint32_t { BE_OK = 0, BE_EOF = 1, BE_CHAR = 2, BE_TYPE = 3, BE_DEPTH = 4, BE_DEFER = 5 };  // 4, 5: not decided here
 enum BindCtx : uint32_t {
     BC_BEGIN_VALUE, BC_BEGIN_KEY, BC_AFTER_KEY, BC_AFTER_PAIR, BC_AFTER_ELEM, BC_AFTER_TOP, BC_IN_STRING, BC_IN_ESC,
     BC_IN_U, BC_IN_NUM, BC_AFTER_DOT, BC_IN_EXP, BC_TRUE_R, BC_TRUE_U, BC_TRUE_E, BC_FALSE_A, BC_FALSE_L, BC_FALSE_S,
@@ -323,7 +323,80 @@ GOFR_HD bool bd_parse_int(const uint8_t* s, uint32_t n, int64_t* out) {
     return true;
 }
 
+// strconv.ParseFloat(lit, 64) on a valid JSON number literal, for float64 targets (literalStore, reflect.Float64).
+// ParseFloat rounds correctly; what is decided here is the part of the input space where one IEEE operation does too
+// (Clinger's exact cases, the same ones strconv's atof64exact takes first): at most 19 significant digits that fit 53
+// bits, times or divided by an exactly representable power of ten (|exponent| <= 22, or up to 37 when the digits leave
+// room).  Sure overflows (>= 1e310: UnmarshalTypeError "number <literal>", ErrRange) and sure underflows (< 1e-329:
+// ±0, not an error in Go) are decided as well.  Everything else — long mantissas, large exponents, subnormals — is
+// PF_DEFER: the request goes to the host like a body nested deeper than 64 levels, never to a differently rounded value.
+enum : uint32_t { PF_OK = 0, PF_OVERFLOW = 1, PF_DEFER = 2 };
+GOFR_HD uint32_t bd_parse_float(const uint8_t* s, uint32_t n, uint64_t* bits) {
+    uint32_t i = 0;
+    const bool neg = n && s[0] == '-';
+    if (neg) i = 1;
+    uint64_t mant = 0;
+    int32_t nd = 0;      // significant digits held in mant (<= 19)
+    int64_t exp10 = 0;   // value = mant [+ dropped digits] x 10^exp10
+    bool nonzero = false, trunc = false;
+    for (; i < n && js_digit(s[i]); i++) {
+        const uint32_t d = s[i] - '0';
+        if (!nonzero && d == 0) continue;
+        nonzero = true;
+        if (nd < 19) { mant = mant * 10 + d; nd++; }
+        else { trunc |= d != 0; exp10++; }
+    }
+    if (i < n && s[i] == '.') {
+        for (i++; i < n && js_digit(s[i]); i++) {
+            const uint32_t d = s[i] - '0';
+            if (!nonzero && d == 0) { exp10--; continue; }
+            nonzero = true;
+            if (nd < 19) { mant = mant * 10 + d; nd++; exp10--; }
+            else trunc |= d != 0;
+        }
+    }
+    if (i < n && (s[i] | 0x20u) == 'e') {
+        i++;
+        bool eneg = false;
+        if (i < n && (s[i] == '+' || s[i] == '-')) { eneg = s[i] == '-'; i++; }
+        int64_t e = 0;
+        for (; i < n && js_digit(s[i]); i++) if (e < 1000000) e = e * 10 + (s[i] - '0');
+        exp10 += eneg ? -e : e;
+    }
+    const uint64_t sign = neg ? 0x8000000000000000ull : 0ull;
+    if (mant == 0) { *bits = sign; return PF_OK; }
+    while (mant % 10 == 0) { mant /= 10; exp10++; nd--; }
+    const int64_t lead = exp10 + nd - 1;  // 10^lead <= |value| < 10^(lead + 1), dropped digits included
+    if (lead >= 310) return PF_OVERFLOW;
+    if (lead <= -330) { *bits = sign; return PF_OK; }
+    if (trunc || (mant >> 53) != 0) return PF_DEFER;
+    double x = (double)(int64_t)mant;
+    if (exp10 > 22) {
+        if (exp10 > 22 + 15) return PF_DEFER;
+        uint64_t p = 1;
+        for (int64_t k = 22; k < exp10; k++) p *= 10;
+        if (mant > ((1ull << 53) - 1) / p) return PF_DEFER;
+        x = (double)(int64_t)(mant * p);
+        exp10 = 22;
+    } else if (exp10 < -22) return PF_DEFER;
+    double p10 = 1.0;  // 10^k is a double for k <= 22, so every partial product is exact
+    for (int64_t k = exp10 < 0 ? -exp10 : exp10; k > 0; k--) p10 *= 10.0;
+    x = exp10 < 0 ? x / p10 : x * p10;
+#if defined(__CUDA_ARCH__)
+    const uint64_t b = (uint64_t)__double_as_longlong(x);
+#else
+    uint64_t b;
+    memcpy(&b, &x, 8);
+#endif
+    *bits = b | sign;
+    return PF_OK;
+}
+
 // d.object / d.literalStore into the span row.  `row` has BR_FIELDS + bind-layout words, zero-initialised here.
+// VO: whether this instance knows float64 members.  A Bind schema with one makes its echo program PF_VALUES (OP_F64), so
+// such tables only ever run the VALUES instances of the serve kernels (serve_device.cuh GOFR_TU_VALUES) — the default
+// instances keep exactly the code, registers and spills they had before float64 targets existed.
+template <bool VO = (GOFR_TU_VALUES != 0)>
 GOFR_HD_NOINLINE void bind_decode(const TableView tv, uint32_t schema_idx, const uint8_t* s, uint32_t n, uint32_t* row) {
     const SchemaRec S = tv.schemas()[schema_idx];
     const FieldRec* F = (const FieldRec*)(tv.base + S.fields_off);
@@ -331,7 +404,7 @@ GOFR_HD_NOINLINE void bind_decode(const TableView tv, uint32_t schema_idx, const
     uint32_t nwords = 0;
     for (uint32_t k = 0; k < S.n_fields; k++) nwords += (F[k].kind == GOFR_F_INT32 || F[k].kind == GOFR_F_BOOL) ? 1 : 2;
     for (uint32_t k = 0; k < BR_FIELDS + nwords; k++) row[k] = 0;
-    bool saved = false;
+    bool saved = false, deferred = false;
     auto type_error = [&](uint32_t value, uint32_t field, uint32_t lo, uint32_t ll) {
         if (saved) return;
         saved = true;
@@ -387,7 +460,13 @@ GOFR_HD_NOINLINE void bind_decode(const TableView tv, uint32_t schema_idx, const
                 }
             } else {  // number
                 if (kind == GOFR_F_STRING || kind == GOFR_F_BOOL) type_error(BV_NUMBER, fi, 0, 0);
-                else {
+                else if (VO && kind == GOFR_F_FLOAT64) {
+                    uint64_t fb = 0;
+                    const uint32_t pf = bd_parse_float(s + vs, ve - vs, &fb);
+                    if (pf == PF_DEFER) deferred = true;
+                    else if (pf == PF_OVERFLOW) type_error(BV_NUMBER_LIT, fi, vs, ve - vs);
+                    else { row[w] = (uint32_t)fb; row[w + 1] = (uint32_t)(fb >> 32); }
+                } else {
                     int64_t x;
                     bool ok = bd_parse_int(s + vs, ve - vs, &x);
                     if (ok && kind == GOFR_F_INT32 && (x < -2147483648ll || x > 2147483647ll)) ok = false;
@@ -401,9 +480,13 @@ GOFR_HD_NOINLINE void bind_decode(const TableView tv, uint32_t schema_idx, const
         uint32_t d = s[i++];
         if (d == '}') break;
     }
+    // a literal this code cannot round with certainty decides the whole request: whatever else was stored or recorded,
+    // encoding/json on the host has the last word
+    if (VO && deferred) row[BR_ERR] = BE_DEFER;
 }
 
 // Full Bind of one request body into `row`.  Returns true when the struct can be echoed.
+template <bool VO>
 GOFR_HD_NOINLINE bool bind_request(const TableView tv, uint32_t schema_idx, const uint8_t* body, uint32_t n, uint32_t* row) {
     uint32_t ech = 0, ectx = 0;
     uint32_t e = bind_scan(body, n, &ech, &ectx);
@@ -411,7 +494,7 @@ GOFR_HD_NOINLINE bool bind_request(const TableView tv, uint32_t schema_idx, cons
         row[BR_ERR] = e; row[BR_CHAR] = ech; row[BR_CTX] = ectx;
         return false;
     }
-    bind_decode(tv, schema_idx, body, n, row);
+    bind_decode<VO>(tv, schema_idx, body, n, row);
     return row[BR_ERR] == BE_OK;
 }
 
@@ -539,7 +622,7 @@ GOFR_HD uint32_t bind_row_out(Writer* w, const TableView tv, uint32_t schema_idx
     for (uint32_t f = 0; f < S.n_fields; f++) {
         const uint32_t kind = F[f].kind;
         if (EMIT) w->reserve_out(2);
-        if (kind == GOFR_F_INT64 || kind == GOFR_F_INT) { if (EMIT) { w->put4(row[wi]); w->put4(row[wi + 1]); } out += 8; wi += 2; }
+        if (kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_FLOAT64) { if (EMIT) { w->put4(row[wi]); w->put4(row[wi + 1]); } out += 8; wi += 2; }
         else if (kind == GOFR_F_STRING) {
             const uint32_t lenw = row[wi + 1], len = lenw & 0x7FFFFFFFu;
             const uint32_t dl = (lenw >> 31) ? bind_string_raw<false>(nullptr, body + row[wi], len) : len;
@@ -556,12 +639,12 @@ GOFR_HD uint32_t bind_row_out(Writer* w, const TableView tv, uint32_t schema_idx
             if (lenw >> 31) out += bind_string_raw<EMIT>(w, body + row[wi], len);
             else { if (EMIT && len) emit_bytes(*w, body + row[wi], len); out += len; }
             wi += 2;
-        } else wi += (kind == GOFR_F_INT64 || kind == GOFR_F_INT) ? 2 : 1;
+        } else wi += (kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_FLOAT64) ? 2 : 1;
     }
     return out;
 }
 
 // status words of gofr_bind_device (include/gofr_b200.h GOFR_BIND_*)
-GOFR_HD uint32_t bind_row_status(const uint32_t* row) { return row[BR_ERR] == BE_OK ? 0u : row[BR_ERR] == BE_DEPTH ? 2u : 1u; }
+GOFR_HD uint32_t bind_row_status(const uint32_t* row) { return row[BR_ERR] == BE_OK ? 0u : (row[BR_ERR] == BE_DEPTH || row[BR_ERR] == BE_DEFER) ? 2u : 1u; }
 
 }  // namespace gofr

@@ -1159,7 +1159,7 @@ int gofr_bind_device(gofr_engine* e, uint32_t schema_id, const gofr_req_desc* d_
     uint32_t sidx = 0xFFFFFFFFu;
     for (size_t k = 0; k < e->schema_ids.size(); k++) if (e->schema_ids[k] == schema_id) sidx = (uint32_t)k;
     if (sidx == 0xFFFFFFFFu) { set_last_error("schema %u is not part of the engine's table", schema_id); return GOFR_ERR_INVALID; }
-    if (!(e->schema_flags[sidx] & SF_FLAT)) { set_last_error("schema %u: Bind takes flat structs of int / bool / string fields only", schema_id); return GOFR_ERR_UNSUPPORTED; }
+    if (!(e->schema_flags[sidx] & SF_BINDABLE)) { set_last_error("schema %u: Bind takes flat structs of int / float64 / bool / string fields only", schema_id); return GOFR_ERR_UNSUPPORTED; }
     if (n == 0) return GOFR_OK;
     std::lock_guard<std::mutex> g(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
@@ -1180,7 +1180,7 @@ int gofr_batch_bind(gofr_engine* e, uint32_t schema_id, const gofr_req_batch* in
     uint32_t sidx = 0xFFFFFFFFu;
     for (size_t k = 0; k < e->schema_ids.size(); k++) if (e->schema_ids[k] == schema_id) sidx = (uint32_t)k;
     if (sidx == 0xFFFFFFFFu) { set_last_error("schema %u is not part of the engine's table", schema_id); return GOFR_ERR_INVALID; }
-    if (!(e->schema_flags[sidx] & SF_FLAT)) { set_last_error("schema %u: Bind takes flat structs of int / bool / string fields only", schema_id); return GOFR_ERR_UNSUPPORTED; }
+    if (!(e->schema_flags[sidx] & SF_BINDABLE)) { set_last_error("schema %u: Bind takes flat structs of int / float64 / bool / string fields only", schema_id); return GOFR_ERR_UNSUPPORTED; }
     std::lock_guard<std::mutex> g(e->mu);
     CUDA_TRY(cudaSetDevice(e->device));
     const uint32_t n = in->n;

@@ -16,6 +16,11 @@
 #include "../../include/gofr_b200.h"
 #include "table_format.h"
 
+// (defaulted here, documented below at size_routed: 1 unless the translation unit says otherwise before including this)
+#ifndef GOFR_TU_VALUES
+#define GOFR_TU_VALUES 1
+#endif
+
 #if defined(__CUDACC__)
 #define GOFR_HD __host__ __device__ __forceinline__
 #define GOFR_HD_NOINLINE inline __host__ __device__ __noinline__
@@ -1091,6 +1096,7 @@ GOFR_HD_NOINLINE uint32_t emit_param_slow(Writer* w, const uint8_t* v, uint32_t 
 }
 
 // Bind (bind_device.cuh)
+template <bool VO = (GOFR_TU_VALUES != 0)>
 GOFR_HD_NOINLINE bool bind_request(const TableView tv, uint32_t schema_idx, const uint8_t* body, uint32_t n, uint32_t* row);
 template <bool EMIT> GOFR_HD_NOINLINE uint32_t bind_string_slow(Writer* w, const uint8_t* s, uint32_t len);
 template <bool EMIT, bool RAW>
@@ -1153,7 +1159,10 @@ GOFR_HD void route_request(const TableView& tv, const BatchRefs& br, ReqCtx& c) 
         if (!bind_request(tv, R.schema, c.data(), c.data_len, brow)) {
             // bodies nested deeper than the device scanner's 64-level stack are handed to the host like a
             // GOFR_H_HOST route (status 0) rather than answered differently from encoding/json (limit 10000)
-            c.prog = brow[0] == 4u /* BE_DEPTH */ ? 0xFFFFu : R.prog_err;
+            // (BE_DEFER = 5 exists only where float64 members do, i.e. in the VALUES instances: the others keep the very
+            // compare they were validated with, so their binaries stay byte-identical)
+            const bool to_host = (GOFR_TU_VALUES != 0) ? brow[0] >= 4u /* BE_DEPTH, BE_DEFER */ : brow[0] == 4u /* BE_DEPTH */;
+            c.prog = to_host ? 0xFFFFu : R.prog_err;
         }
     }
 }
@@ -1623,9 +1632,6 @@ GOFR_HD void emit_fast(const TableView& tv, const BatchRefs& br, ReqCtx& c, uint
 // packed kernel exists twice (serve_kernel.cu without, serve_values_kernel.cu with): the engine launches the second one
 // only for tables that contain such a program, so tables without them run exactly the code they ran before the wider
 // data model existed.  It is a template argument (VO), not an #if, so that the two variants are different functions.
-#ifndef GOFR_TU_VALUES
-#define GOFR_TU_VALUES 1
-#endif
 
 // programs with OP_F64 / OP_VALUE ops: the VALUES instance of the interpreter, out of line (see run_prog)
 GOFR_HD_NOINLINE bool size_values_call(const TableView tv, const BatchRefs br, ReqCtx* c) { return run_prog<false, 0, true>(tv, br, *c, nullptr); }

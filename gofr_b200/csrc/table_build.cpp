@@ -187,7 +187,8 @@ struct SchemaDef {
     std::vector<FieldDef> fields;
     uint32_t fixed_words = 0;  // words of the fixed part of a row (include/gofr_b200.h "Row format")
     int depth = 1;             // struct nesting below this type, this one included
-    bool flat = true;          // scalars and strings by value only: what Bind schemas and the op programs of round 1 take
+    bool flat = true;          // int / bool / string fields by value only: what the op programs of round 1 take
+    bool bindable = true;      // the same plus float64: what Bind takes
     bool bare() const { return fields.size() == 1 && (fields[0].flags & GOFR_FIELD_BARE); }
 };
 static uint32_t kind_words(uint8_t kind) { return (kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_FLOAT64) ? 2u : 1u; }
@@ -771,8 +772,8 @@ int seal_table(gofr_table* t) {
             for (auto& s : t->schemas) if (s.id == r.schema_id) sc = &s;
             // a closure that only ever returns strings / errors / nil needs no struct schema
             if (!sc && !(r.hkind == GOFR_H_RESULT && r.schema_id == 0)) { set_last_error("route %s: unknown schema %u", r.pattern.c_str(), r.schema_id); return GOFR_ERR_INVALID; }
-            if (sc && r.hkind == GOFR_H_BIND_ECHO && !sc->flat) {
-                set_last_error("route %s: Bind takes flat structs of int / bool / string fields only (schema %u)", r.pattern.c_str(), r.schema_id);
+            if (sc && r.hkind == GOFR_H_BIND_ECHO && !sc->bindable) {
+                set_last_error("route %s: Bind takes flat structs of int / float64 / bool / string fields only (schema %u)", r.pattern.c_str(), r.schema_id);
                 return GOFR_ERR_UNSUPPORTED;
             }
         }
@@ -1250,7 +1251,7 @@ int seal_table(gofr_table* t) {
             F.type_len = (uint16_t)tn.size();
             frecs[si].push_back(F);
         }
-        S.flags = (uint16_t)((s.flat ? SF_FLAT : 0) | (s.bare() ? SF_BARE : 0));
+        S.flags = (uint16_t)((s.flat ? SF_FLAT : 0) | (s.bare() ? SF_BARE : 0) | (s.bindable ? SF_BINDABLE : 0));
         S.fixed_words = word;
         S.n_strings = so;
     }
@@ -1262,7 +1263,7 @@ int seal_table(gofr_table* t) {
     for (size_t ri = 0; ri < t->routes.size(); ri++) {
         if (t->routes[ri].hkind != GOFR_H_BIND_ECHO) continue;
         uint32_t words = 8;
-        for (auto& f : t->schemas[routes[ri].schema].fields) words += (f.kind == GOFR_F_INT32 || f.kind == GOFR_F_BOOL) ? 1 : 2;  // flat: checked at seal
+        for (auto& f : t->schemas[routes[ri].schema].fields) words += (f.kind == GOFR_F_INT32 || f.kind == GOFR_F_BOOL) ? 1 : 2;  // bindable: checked at seal
         H.bind_row_words = std::max(H.bind_row_words, words);
     }
     H.max_fixed_len = max_fixed;
@@ -1395,6 +1396,7 @@ int gofr_table_add_schema(gofr_table* t, uint32_t schema_id, const char* go_type
             s.depth = std::max(s.depth, 1 + t->schemas[(size_t)f.elem].depth);
         }
         if (f.container != GOFR_C_VALUE || f.kind > GOFR_F_INT || f.flags) s.flat = false;
+        if (f.container != GOFR_C_VALUE || f.kind > GOFR_F_FLOAT64 || f.flags) s.bindable = false;
         const uint32_t fw = field_words(t->schemas, f);
         if (fw > 255u || s.fixed_words + fw > 4096u) { set_last_error("schema %u: fixed part too wide", schema_id); return GOFR_ERR_UNSUPPORTED; }
         s.fixed_words += fw;

@@ -197,8 +197,9 @@ enum FastFlags : uint8_t {
 };
 
 enum SchemaFlags : uint16_t {
-    SF_FLAT = 1,  // scalars and strings by value only (Bind takes nothing else)
+    SF_FLAT = 1,  // int / bool / string fields by value only (what the op programs of round 1 take)
     SF_BARE = 2,  // one field standing for its own type (GOFR_FIELD_BARE)
+    SF_BINDABLE = 4,  // scalar and string fields by value only, float64 included: what Bind takes (bind_device.cuh)
 };
 struct SchemaRec {  // 16 B + per-field table
     uint16_t n_fields;

@@ -97,7 +97,13 @@ enum {
     GOFR_H_PARAM_FORMAT = 4,  /* v := c.Param(s0); if v == "" { v = s1 }; return s2 + v + s3, nil
                                  examples/http-server/main.go:31-39, gofr_test.go:80-82 */
     GOFR_H_ROW = 5,           /* return <struct of schema>, nil; field values arrive in the request's data section */
-    GOFR_H_BIND_ECHO = 6,     /* var v T; if err := c.Bind(&v); err != nil { return nil, err }; return v, nil */
+    GOFR_H_BIND_ECHO = 6,     /* var v T; if err := c.Bind(&v); err != nil { return nil, err }; return v, nil
+                                 T: a flat struct of int / int32 / int64 / float64 / bool / string fields.  A float64 member
+                                 gets strconv.ParseFloat's correctly rounded value when one IEEE operation yields it (at most
+                                 15-16 significant digits that fit 53 bits and a power of ten up to 1e22 — 1e37 when the
+                                 digits leave room —, sure overflows → the UnmarshalTypeError Go reports, sure underflows →
+                                 0); a request with any other literal for such a member comes back with status 0 ("run on
+                                 the host"), like a body nested deeper than 64 levels */
     GOFR_H_HEALTH = 7,        /* healthHandler with no datasources: map{} handler.go:38-40, container.go:26-38 */
     GOFR_H_MISSING_FILE = 8,  /* catchAllHandler: return nil, http.ErrMissingFile      handler.go:51-53 */
     GOFR_H_FILE = 9,          /* return response.File{Content: blob, ContentType: s0}   handler.go:42-49 */
@@ -416,7 +422,7 @@ int gofr_proto_nested_describe(const gofr_proto_nmsg* msgs, uint32_t n_msgs, con
  * section of request i (same descriptors / arena as the serve calls); result i lies in its own slot d_rows + i * slot_bytes
  * (slot_bytes a multiple of 16, d_rows 16-byte aligned), zero padded to the next 16-byte boundary:
  *   d_status[i] = GOFR_BIND_OK     the struct as a row in the GOFR_H_ROW layout (one LE u32 word per field in schema order,
- *                                  two for INT64 / INT, STRING = byte length; then the DECODED string bytes in schema order:
+ *                                  two for INT64 / INT / FLOAT64, STRING = byte length; then the DECODED string bytes in schema order:
  *                                  escapes resolved, invalid UTF-8 replaced by U+FFFD, as json.Unmarshal stores them).
  *                                  Keys are matched exactly, then case-insensitively; unknown keys are skipped; later
  *                                  duplicates win; null leaves the zero value.
@@ -424,7 +430,8 @@ int gofr_proto_nested_describe(const gofr_proto_nmsg* msgs, uint32_t n_msgs, con
  *                                  "unexpected end of JSON input"), or the FIRST UnmarshalTypeError ("json: cannot unmarshal
  *                                  string into Go struct field T.f of type int64"); the partially filled struct Go also
  *                                  leaves behind in that case is not reported
- *   d_status[i] = GOFR_BIND_HOST   not decided on the device (nesting deeper than 64): run encoding/json on the host
+ *   d_status[i] = GOFR_BIND_HOST   not decided on the device (nesting deeper than 64, or a number for a float64 member that
+ *                                  needs more than one IEEE operation to round — see GOFR_H_BIND_ECHO): run encoding/json on the host
  * d_len[i] = bytes of the result; a value above slot_bytes means it did not fit and nothing was written.
  * Pins: pkg/gofr/http/request_test.go:17-30, pkg/gofr/context_test.go:23-49. */
 enum { GOFR_BIND_OK = 0, GOFR_BIND_ERROR = 1, GOFR_BIND_HOST = 2 };

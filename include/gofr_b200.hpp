@@ -182,10 +182,11 @@ public:
         v->type_id = bind_type_;
         v->fields.clear();
         size_t w = 0, sp = 0;
-        for (uint32_t kind : bind_kinds_) sp += (kind == GOFR_F_INT64 || kind == GOFR_F_INT) ? 8 : 4;
+        for (uint32_t kind : bind_kinds_) sp += (kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_FLOAT64) ? 8 : 4;
         auto word = [&](size_t at) { uint32_t x; memcpy(&x, bind_row_.data() + at, 4); return x; };
         for (uint32_t kind : bind_kinds_) {
             if (kind == GOFR_F_INT64 || kind == GOFR_F_INT) { v->fields.emplace_back((int64_t)((uint64_t)word(w) | (uint64_t)word(w + 4) << 32)); w += 8; }
+            else if (kind == GOFR_F_FLOAT64) { const uint64_t b = (uint64_t)word(w) | (uint64_t)word(w + 4) << 32; double x; memcpy(&x, &b, 8); v->fields.emplace_back(x); w += 8; }
             else if (kind == GOFR_F_INT32) { v->fields.emplace_back((int64_t)(int32_t)word(w)); w += 4; }
             else if (kind == GOFR_F_BOOL) { v->fields.emplace_back(word(w) != 0); w += 4; }
             else { const uint32_t n = word(w); v->fields.emplace_back(bind_row_.substr(sp, n)); sp += n; w += 4; }
@@ -495,7 +496,7 @@ private:
         if (r.bind_type) {
             c.bind_status_ = bound.status;
             c.bind_type_ = r.bind_type;
-            c.bind_row_ = bound.status == GOFR_BIND_HOST ? std::string("gofr::Context::Bind: body not decided on the device (nesting deeper than 64)") : bound.row;
+            c.bind_row_ = bound.status == GOFR_BIND_HOST ? std::string("gofr::Context::Bind: body not decided on the device (nesting deeper than 64, or a float64 literal it does not round itself)") : bound.row;
             if (bound.status == GOFR_BIND_HOST) c.bind_status_ = GOFR_BIND_ERROR;
             for (auto& ty : types_) if (ty->id_ == r.bind_type) for (auto& f : ty->fields_) c.bind_kinds_.push_back(f.kind);
         }

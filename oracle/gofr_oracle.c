@@ -436,7 +436,7 @@ void orc_enc_struct(obuf* b, const orc_schema* sc, const orc_value* v) {
     for (int i = 0; i < sc->n_fields; i++) {
         const orc_field* f = &sc->f[i];
         if (f->omitempty) {
-            if (f->kind == F_STRING ? v[i].sn == 0 : v[i].i == 0) continue;
+            if (f->kind == F_STRING ? v[i].sn == 0 : f->kind == F_FLOAT64 ? ((uint64_t)v[i].i << 1) == 0 : v[i].i == 0) continue;
         }
         if (!first) ob_putc(b, ',');
         first = 0;
@@ -446,6 +446,13 @@ void orc_enc_struct(obuf* b, const orc_schema* sc, const orc_value* v) {
         switch (f->kind) {
             case F_STRING: orc_enc_string(b, v[i].s, (size_t)v[i].sn); break;
             case F_BOOL: ob_puts(b, v[i].i ? "true" : "false"); break;
+            case F_FLOAT64: { /* Bind stores only finite values: the text always exists */
+                double x;
+                char tmp[40];
+                memcpy(&x, &v[i].i, 8);
+                ob_put(b, tmp, (size_t)orc_float_text(x, tmp));
+                break;
+            }
             default: orc_enc_int(b, v[i].i); break;
         }
     }
@@ -1286,7 +1293,7 @@ int orc_bind(const orc_table* t, int schema_id, const uint8_t* body, int n, uint
             uint64_t u = (uint64_t)vals[i].i;
             if (sc->f[i].kind == F_STRING) u = (uint64_t)vals[i].sn;
             for (int k = 0; k < 8; k++) w[k] = (uint8_t)(u >> (8 * k));
-            ob_put(&row, w, (sc->f[i].kind == F_INT64 || sc->f[i].kind == F_INT) ? 8 : 4);
+            ob_put(&row, w, (sc->f[i].kind == F_INT64 || sc->f[i].kind == F_INT || sc->f[i].kind == F_FLOAT64) ? 8 : 4);
         }
         for (int i = 0; i < sc->n_fields; i++)
             if (sc->f[i].kind == F_STRING) ob_put(&row, vals[i].s, (size_t)vals[i].sn);

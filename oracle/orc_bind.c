@@ -11,6 +11,7 @@
  */
 #include "orc_internal.h"
 
+#include <math.h>
 #include <stdio.h>
 
 /* ------------------------------------------------------------------------------------------------------------ */
@@ -460,6 +461,19 @@ static void store_value(dec* d, const orc_field* f, orc_value* v) {
     }
     /* number */
     if (f->kind == F_STRING || f->kind == F_BOOL) { type_error(d, "number", 0, NULL, f); return; }
+    if (f->kind == F_FLOAT64) {
+        /* literalStore, reflect.Float64: strconv.ParseFloat(item, 64); err (only ErrRange is possible on a literal the
+         * scanner accepted, and only overflow raises it: underflow yields 0, nil) or OverflowFloat → UnmarshalTypeError
+         * "number <literal>".  ParseFloat rounds correctly (to nearest, ties to even) — so does glibc's strtod. */
+        char tmp[64], *z = ln < sizeof tmp ? tmp : (char*)malloc(ln + 1);
+        memcpy(z, lit, ln);
+        z[ln] = 0;
+        double x = strtod(z, NULL);
+        if (z != tmp) free(z);
+        if (isinf(x)) { type_error(d, "number ", ln, lit, f); return; }
+        memcpy(&v->i, &x, 8); /* the value's bits */
+        return;
+    }
     int64_t x;
     int bad = parse_int64(lit, ln, &x) != 0;
     if (!bad && f->kind == F_INT32 && (x < INT32_MIN || x > INT32_MAX)) bad = 1; /* v.OverflowInt */

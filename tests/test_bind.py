@@ -223,3 +223,168 @@ def test_gpu_bind_stage():
     idx = list(range(0, batch.n, 13))
     _check_bind_stage(r[idx], l[idx], s[idx], [bodies[i] for i in idx], 1024, O.OracleTable(spec), spec.schemas[0].id)
     eng.close()
+
+
+# ---- float64 targets (round 2): strconv.ParseFloat's correctly rounded value where ONE IEEE operation gives it, the
+#      host otherwise — checked against Python's float(), which rounds correctly too ----
+FL_SCHEMA = S.Schema(9, "pkg.Reading", [S.Field("Name", S.F_STRING, "name"), S.Field("Value", S.F_FLOAT64, "value"),
+                                        S.Field("Delta", S.F_FLOAT64, "delta", True), S.Field("N", S.F_INT, "n")])
+FL_SPEC = S.TableSpec(schemas=[FL_SCHEMA], routes=[S.Route(S.M_POST, "/echo", S.H_BIND_ECHO, schema_id=9)])
+
+
+def _float_cmp(bodies, mis=1):
+    """device code vs oracle on every body the device decides; returns the indices it left to the host"""
+    FL_SPEC.frame_mode = S.FRAME_BODY
+    batch = S.RequestBatch.pack([S.Req(S.M_POST, b"/echo", b"", b) for b in bodies])
+    o1, f1, m1 = O.OracleTable(FL_SPEC).serve(batch, DATE)
+    o2, f2, m2 = emu.serve(Table(FL_SPEC).serialize(), batch, DATE, misalign=mis)
+    r1, r2 = O.responses(o1, f1), O.responses(o2, f2)
+    deferred = []
+    for i, b in enumerate(bodies):
+        if (m2[i] & 0xFFFF) == 0:
+            assert r2[i] == b"", b
+            deferred.append(i)
+        else:
+            assert r1[i] == r2[i] and m1[i] == m2[i], (b, r1[i], r2[i])
+    return r1, deferred
+
+
+def test_emu_bind_float_known_answers():
+    import json
+    lits = [b"0", b"-0", b"0.0", b"-0.0e5", b"1", b"-1", b"1.5", b"3.14159", b"1e2", b"1E+2", b"1e-2", b"100", b"1e21", b"1e20", b"1e-6", b"1e-7",
+            b"123456789012345", b"9007199254740991", b"0.1", b"0.2", b"0.30000000000000004", b"2.5e-5", b"1e22", b"1e23", b"123e35", b"1.7976931348623157e308",
+            b"1e400", b"-1e400", b"1e-400", b"-1e-400", b"1e309", b"1e310", b"4.9e-324", b"2.2250738585072014e-308", b"9007199254740993",
+            b"0.000000000000000000000000000001", b"1" + b"0" * 30, b"1" + b"0" * 400, b"0." + b"0" * 400 + b"1", b"12345678901234567890123",
+            b"1.00000000000000000000000000000000001", b"1e0000000000000000000002", b"1e-0000000000000000000002", b"5e-1", b"625e-4"]
+    bodies = [b'{"name":"s","value":' + x + b',"n":3}' for x in lits]
+    r1, deferred = _float_cmp(bodies)
+    decided = 0
+    for i, x in enumerate(lits):
+        v = float(x)
+        if v in (float("inf"), float("-inf")):  # ErrRange -> UnmarshalTypeError naming the literal
+            assert json.loads(r1[i])["error"]["message"] == "json: cannot unmarshal number " + x.decode() + " into Go struct field Reading.value of type float64"
+        else:
+            assert json.loads(r1[i])["data"]["value"] == v, x  # the oracle's strtod against Python's float()
+        decided += i not in deferred
+    # the plain cases are decided on the device; the hard ones (17+ digits, subnormals, exponents near the ends) are not
+    for x in (b"0", b"-0", b"1.5", b"3.14159", b"1e22", b"1e23", b"123e35", b"0.1", b"1e400", b"-1e400", b"1e-400", b"1e310", b"9007199254740991",
+              b"1" + b"0" * 30, b"1" + b"0" * 400, b"0." + b"0" * 400 + b"1", b"625e-4", b"1e0000000000000000000002"):
+        assert lits.index(x) not in deferred, x
+    for x in (b"9007199254740993", b"4.9e-324", b"1.7976931348623157e308", b"1e309", b"12345678901234567890123", b"1.00000000000000000000000000000000001"):
+        assert lits.index(x) in deferred, x
+    assert decided >= 30
+
+
+def test_emu_bind_float_type_errors_and_omitempty():
+    bodies = [b'{"value":"1.5"}', b'{"value":true}', b'{"value":[1]}', b'{"value":{}}', b'{"value":null,"n":2}', b'{"n":1.5}', b'{"n":1e2}',
+              b'{"value":1,"delta":0}', b'{"value":1,"delta":-0.0}', b'{"value":1,"delta":0.5}', b'{"VALUE":2.5,"Delta":1e-7}',
+              b'{"value":1e400,"n":"x"}', b'{"n":"x","value":1e400}', b'{"value":1e400,"value":2}', b'{"name":3.5}', b'3.5', b'{"value":1.5,"value":"s"}',
+              # a literal the device cannot round decides the whole request, whatever else is wrong with it
+              b'{"n":"x","value":9007199254740993}']
+    for mis in range(4):
+        r1, deferred = _float_cmp(bodies, mis)
+        assert deferred == [len(bodies) - 1]
+    assert r1[7] == b'{"data":{"name":"","value":1,"n":0}}\n' and r1[8] == r1[7] and r1[9] == b'{"data":{"name":"","value":1,"delta":0.5,"n":0}}\n'
+    assert r1[10] == b'{"data":{"name":"","value":2.5,"delta":1e-7,"n":0}}\n'
+    assert b"cannot unmarshal number 1e400 into Go struct field Reading.value of type float64" in r1[11]
+    assert b"cannot unmarshal string into Go struct field Reading.n of type int" in r1[12]
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.one_of(
+    st.floats(allow_nan=False, allow_infinity=False).map(lambda v: repr(v).encode()),
+    st.tuples(st.integers(0, 10 ** 17), st.integers(-30, 30)).map(lambda t: b"%de%d" % t),
+    st.tuples(st.integers(0, 10 ** 9), st.integers(0, 10 ** 9), st.integers(-12, 12)).map(lambda t: b"-%d.%09dE%+d" % t),
+    st.decimals(allow_nan=False, allow_infinity=False, places=6, min_value=-10 ** 8, max_value=10 ** 8).map(lambda d: format(d, "f").encode())),
+    min_size=1, max_size=12), st.integers(0, 3))
+def test_emu_bind_float_against_python_float(lits, mis):
+    """every literal the device decides carries exactly the double Python's float() — correctly rounded, like
+    strconv.ParseFloat — gives; literals with at most 15 digits and a small exponent are always decided"""
+    import json, struct
+    lits = [x if x[:1] != b"-" or x[1:2].isdigit() else x[1:] for x in lits]
+    bodies = [b'{"value":' + x + b"}" for x in lits]
+    r1, deferred = _float_cmp(bodies, mis)
+    for i, x in enumerate(lits):
+        if i in deferred:
+            digits = x.split(b"e")[0].split(b"E")[0].replace(b"-", b"").replace(b".", b"").lstrip(b"0").rstrip(b"0")
+            assert len(digits) > 15 or abs(float(x)) > 1e22 or (float(x) != 0 and abs(float(x)) < 1e-7), x
+        else:
+            got = json.loads(r1[i])["data"]["value"]
+            assert struct.pack("<d", got) == struct.pack("<d", float(x)) or (got == 0 and float(x) == 0), (x, got)
+
+
+def test_emu_bind_stage_float_fields():
+    """gofr_bind_device with float64 members: the value's bits as two row words (like INT64), ErrRange as the error text,
+    GOFR_BIND_HOST for literals the device does not round itself"""
+    import struct
+    bodies = [b'{"name":"a","value":1.5,"delta":-2.5e-3,"n":7}', b'{"value":1e400}', b'{"value":0.1,"delta":1e23}', b'{"value":"x"}',
+              b'{"value":9007199254740993}', b'{"value":-0}', b'{"value":123456789.125,"name":"caf\\u00e9"}']
+    batch = S.RequestBatch.pack([S.Req(S.M_POST, b"/echo", b"", b) for b in bodies])
+    rows, ln, status = emu.bind_rows(Table(FL_SPEC).serialize(), 0, batch, 256)
+    ot = O.OracleTable(FL_SPEC)
+    for i, body in enumerate(bodies):
+        ok, want = ot.bind(9, body)
+        if i == 4:
+            assert status[i] == 2 and ln[i] == 0
+            continue
+        assert status[i] == (0 if ok else 1) and rows[i, :ln[i]].tobytes() == want, (body, rows[i, :ln[i]].tobytes(), want)
+    # layout: name length, value bits, delta bits, n (two words), then the string bytes
+    assert rows[0, :ln[0]].tobytes() == struct.pack("<IddqB", 1, 1.5, -2.5e-3, 7, ord("a"))
+    assert rows[5, 4:12].tobytes() == struct.pack("<d", -0.0)
+
+
+def _gpu_float_check():
+    import torch
+    from gofr_b200.engine import Engine
+    from tests.test_gpu_parity import _check
+    rng = np.random.default_rng(5)
+    bodies = []
+    for i in range(20000):
+        v = float(rng.integers(-10 ** 9, 10 ** 9)) / 10 ** int(rng.integers(0, 9))
+        d = [b"0", b"1e-7", b"2.5e21", b"-0.0", b"1e400", b'"s"', b"12345678901234567890"][i % 7]
+        bodies.append(b'{"name":"r%d","value":%s,"delta":%s,"n":%d}' % (i, repr(v).encode(), d, i))
+    FL_SPEC.frame_mode = S.FRAME_WIRE
+    batch = S.RequestBatch.pack([S.Req(S.M_POST, b"/echo", b"", b) for b in bodies])
+    # packed and slot layouts against the oracle; requests the device leaves to the host (status 0) are skipped there
+    eng = Engine(Table(FL_SPEC), 0)
+    o1, f1, m1 = O.OracleTable(FL_SPEC).serve(batch, DATE)
+    s_out, s_len, s_meta = eng.serve_device_slots(eng.upload(batch), DATE, 1024)
+    torch.cuda.synchronize()
+    s_out = s_out.cpu().numpy().reshape(batch.n, 1024)
+    s_len, s_meta = s_len.cpu().numpy().view(np.uint32), s_meta.cpu().numpy().view(np.uint32)
+    host = 0
+    for i in range(batch.n):
+        if (s_meta[i] & 0xFFFF) == 0:
+            assert s_len[i] == 0 and i % 7 == 6, i
+            host += 1
+            continue
+        L = int(f1[i + 1]) - int(f1[i])
+        assert s_meta[i] == m1[i] and s_len[i] == L and s_out[i, :L].tobytes() == o1[int(f1[i]):int(f1[i + 1])].tobytes(), (i, bodies[i])
+    assert host == len(range(6, batch.n, 7))
+    rows, ln, status = eng.bind_device(eng.upload(batch), 9, 256)
+    torch.cuda.synchronize()
+    rows, ln, status = rows.cpu().numpy().reshape(batch.n, 256), ln.cpu().numpy().view(np.uint32), status.cpu().numpy().view(np.uint32)
+    ot = O.OracleTable(FL_SPEC)
+    for i in range(0, batch.n, 3):
+        ok, want = ot.bind(9, bodies[i])
+        if i % 7 == 6:
+            assert status[i] == 2
+        else:
+            assert status[i] == (0 if ok else 1) and rows[i, :ln[i]].tobytes() == want, (i, bodies[i])
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="float64 Bind targets were added after this round's GPU minutes were spent: the device code is "
+                   "checked on the CPU against the oracle and Python's float() (above); its first launch on a GPU is this test — "
+                   "XPASS means it matched")
+def test_gpu_bind_float_fields():
+    """the serve kernels (VALUES instance, PF_BIND program with OP_F64) and gofr_bind_device on 20 000 bodies with float64
+    members — in a child process, so that a fault cannot leave a sticky CUDA error behind for the other GPU tests"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", "import tests.test_bind as t; t._gpu_float_check()"], cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
