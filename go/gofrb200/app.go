@@ -151,29 +151,38 @@ const (
 	nilCount  = 0xFFFFFFFF
 )
 
+// isBytes: []byte (any []T with T of kind uint8 without its own marshaller): base64 in encoding/json, kind GOFR_F_BYTES here.
+func isBytes(t reflect.Type) bool { return t.Kind() == reflect.Slice && t.Elem().Kind() == reflect.Uint8 }
+
 // typeDesc resolves a Go type to (GOFR_F_* kind, GOFR_C_* container, struct type of a GOFR_F_STRUCT).  ok = false: a type the
-// GPU encoder does not model ([]byte, interface{}, [][]T, maps of structs or with non-string keys, unsigned and 8/16-bit
-// integers, float32, arrays, channels ...): such a route stays on the host path.
+// GPU encoder does not model (interface{}, [][]T other than [][]byte, maps of structs or with non-string keys, arrays,
+// channels ...): such a route stays on the host path.  Integers narrower than the row's words are widened (int8 / int16 →
+// INT32, uint8 / uint16 / uint32 → INT64): the JSON text is the same.
 func typeDesc(t reflect.Type) (kind, container uint8, elem reflect.Type, ok bool) {
-	switch t.Kind() {
-	case reflect.Ptr:
+	switch {
+	case isBytes(t): // a []byte by value: kind 9 below
+	case t.Kind() == reflect.Ptr:
 		container, t = cPtr, t.Elem()
-	case reflect.Slice:
-		if t.Elem().Kind() == reflect.Uint8 {
-			return 0, 0, nil, false // []byte is base64 in encoding/json
-		}
+	case t.Kind() == reflect.Slice:
 		container, t = cSlice, t.Elem()
-	case reflect.Map:
+	case t.Kind() == reflect.Map:
 		if t.Key().Kind() != reflect.String {
 			return 0, 0, nil, false
 		}
 		container, t = cMap, t.Elem()
 	}
+	if isBytes(t) {
+		return 9, container, nil, true
+	}
 	switch t.Kind() {
-	case reflect.Int64:
+	case reflect.Int64, reflect.Uint8, reflect.Uint16, reflect.Uint32:
 		kind = 1
-	case reflect.Int32:
+	case reflect.Int32, reflect.Int8, reflect.Int16:
 		kind = 2
+	case reflect.Uint64, reflect.Uint, reflect.Uintptr:
+		kind = 8
+	case reflect.Float32:
+		kind = 10
 	case reflect.Bool:
 		kind = 3
 	case reflect.String:
@@ -337,8 +346,12 @@ func scalarWords(b []byte, v reflect.Value) []byte {
 	switch v.Kind() {
 	case reflect.Int64, reflect.Int:
 		return binary.LittleEndian.AppendUint64(b, uint64(v.Int()))
-	case reflect.Int32:
+	case reflect.Uint64, reflect.Uint, reflect.Uintptr, reflect.Uint8, reflect.Uint16, reflect.Uint32: // the narrow ones ride as INT64
+		return binary.LittleEndian.AppendUint64(b, v.Uint())
+	case reflect.Int32, reflect.Int8, reflect.Int16:
 		return u32(b, uint32(int32(v.Int())))
+	case reflect.Float32:
+		return u32(b, math.Float32bits(float32(v.Float())))
 	case reflect.Bool:
 		if v.Bool() {
 			return u32(b, 1)
@@ -365,7 +378,7 @@ func fixedBytes(t reflect.Type) int {
 			}
 		}
 		return n
-	case reflect.Int64, reflect.Int, reflect.Float64:
+	case reflect.Int64, reflect.Int, reflect.Float64, reflect.Uint64, reflect.Uint, reflect.Uintptr, reflect.Uint8, reflect.Uint16, reflect.Uint32:
 		return 8
 	}
 	return 4
@@ -373,6 +386,12 @@ func fixedBytes(t reflect.Type) int {
 
 // encodePlain: a T by value — its fixed words to fixed, its variable part to vars.
 func encodePlain(v reflect.Value, fixed, vars []byte) ([]byte, []byte) {
+	if isBytes(v.Type()) { // length word (nilCount: the nil slice), the bytes in the variable part
+		if v.IsNil() {
+			return u32(fixed, nilCount), vars
+		}
+		return u32(fixed, uint32(v.Len())), append(vars, v.Bytes()...)
+	}
 	switch v.Kind() {
 	case reflect.String:
 		return u32(fixed, uint32(v.Len())), append(vars, v.String()...)
@@ -384,6 +403,12 @@ func encodePlain(v reflect.Value, fixed, vars []byte) ([]byte, []byte) {
 
 // encodeElement: E(T), an element of a slice or map, entirely in the variable part.
 func encodeElement(v reflect.Value, vars []byte) []byte {
+	if isBytes(v.Type()) {
+		if v.IsNil() {
+			return u32(vars, nilCount)
+		}
+		return append(u32(vars, uint32(v.Len())), v.Bytes()...)
+	}
 	switch v.Kind() {
 	case reflect.String:
 		return append(u32(vars, uint32(v.Len())), v.String()...)
@@ -396,6 +421,9 @@ func encodeElement(v reflect.Value, vars []byte) []byte {
 
 // encodeField: one field (or the bare value of a non-struct type).
 func encodeField(f reflect.Value, fixed, vars []byte) ([]byte, []byte) {
+	if isBytes(f.Type()) {
+		return encodePlain(f, fixed, vars)
+	}
 	switch f.Kind() {
 	case reflect.Ptr:
 		if f.IsNil() {

@@ -77,12 +77,17 @@ GOFR_HD int32_t ryu_pow5bits(int32_t e) { return (int32_t)(((uint32_t)e * 121735
 GOFR_HD uint32_t ryu_log10_pow2(int32_t e) { return ((uint32_t)e * 78913u) >> 18; }
 GOFR_HD uint32_t ryu_log10_pow5(int32_t e) { return ((uint32_t)e * 732923u) >> 20; }
 
-// Shortest decimal of a finite non-zero float64 (sign stripped): value = digits * 10^exp10.
+// Shortest decimal of a finite non-zero binary floating-point number (sign stripped): value = digits * 10^exp10.
+// MBITS / BIAS: 52 / 1023 for a float64, 23 / 127 for a float32 (strconv.AppendFloat(…, -1, 32): the shortest digits that
+// identify the FLOAT32).  The core is the same for both — the interval around 4·m2 scaled by a power of five with the
+// 125-bit tables, whose precision covers any m2 < 2^53 and every exponent of either format; the published float32 variant
+// differs only in using narrower tables.
+template <int MBITS = 52, int BIAS = 1023>
 GOFR_HD void ryu_shortest(uint64_t ieee_mantissa, uint32_t ieee_exponent, uint64_t* digits, int32_t* exp10) {
     int32_t e2;
     uint64_t m2;
-    if (ieee_exponent == 0) { e2 = 1 - 1023 - 52 - 2; m2 = ieee_mantissa; }
-    else { e2 = (int32_t)ieee_exponent - 1023 - 52 - 2; m2 = (1ull << 52) | ieee_mantissa; }
+    if (ieee_exponent == 0) { e2 = 1 - BIAS - MBITS - 2; m2 = ieee_mantissa; }
+    else { e2 = (int32_t)ieee_exponent - BIAS - MBITS - 2; m2 = (1ull << MBITS) | ieee_mantissa; }
     const bool accept = (m2 & 1) == 0;  // round-to-even: the interval's bounds are themselves valid
     const uint64_t mv = 4 * m2;
     const uint32_t mm_shift = ieee_mantissa != 0 || ieee_exponent <= 1;
@@ -178,18 +183,22 @@ GOFR_HD void ryu_shortest(uint64_t ieee_mantissa, uint32_t ieee_exponent, uint64
     *exp10 = e10 + removed;
 }
 
-// The text encoding/json writes for a float64 with the given bits: fills buf (<= 32 bytes), returns the length;
-// 0 for NaN / ±Inf (UnsupportedValueError).
-GOFR_HD uint32_t json_float64_text(uint64_t bits, uint8_t* buf) {
-    const uint32_t ieee_exponent = (uint32_t)(bits >> 52) & 0x7FFu;
-    const uint64_t ieee_mantissa = bits & ((1ull << 52) - 1);
-    if (ieee_exponent == 0x7FFu) return 0;
+// The text encoding/json writes for a float64 (F32 == false) or a float32 (F32 == true: its bits in the low word) with
+// the given bits: fills buf (<= 32 bytes), returns the length; 0 for NaN / ±Inf (UnsupportedValueError).
+// float32 (floatEncoder with bits == 32): the format switch compares float32(abs) with float32(1e-6) and float32(1e21) —
+// both of which have the shortest digits "1e-06" / "1e+21", so the decade of the shortest digits decides as for float64.
+template <bool F32 = false>
+GOFR_HD uint32_t json_float_text(uint64_t bits, uint8_t* buf) {
+    const uint32_t ieee_exponent = F32 ? ((uint32_t)bits >> 23) & 0xFFu : (uint32_t)(bits >> 52) & 0x7FFu;
+    const uint64_t ieee_mantissa = F32 ? (bits & 0x7FFFFFu) : (bits & ((1ull << 52) - 1));
+    if (ieee_exponent == (F32 ? 0xFFu : 0x7FFu)) return 0;
     uint32_t n = 0;
-    if (bits >> 63) buf[n++] = '-';
+    if (F32 ? (bits >> 31) & 1 : bits >> 63) buf[n++] = '-';
     if (ieee_exponent == 0 && ieee_mantissa == 0) { buf[n++] = '0'; return n; }
     uint64_t dig;
     int32_t e10;
-    ryu_shortest(ieee_mantissa, ieee_exponent, &dig, &e10);
+    if (F32) ryu_shortest<23, 127>(ieee_mantissa, ieee_exponent, &dig, &e10);
+    else ryu_shortest<52, 1023>(ieee_mantissa, ieee_exponent, &dig, &e10);
     uint8_t d[20];
     uint32_t nd = 0;
     while (dig) { d[nd++] = (uint8_t)('0' + (uint32_t)(dig % 10)); dig /= 10; }  // least significant first
@@ -226,5 +235,7 @@ GOFR_HD uint32_t json_float64_text(uint64_t bits, uint8_t* buf) {
     }
     return n;
 }
+GOFR_HD uint32_t json_float64_text(uint64_t bits, uint8_t* buf) { return json_float_text<false>(bits, buf); }
+GOFR_HD uint32_t json_float32_text(uint32_t bits, uint8_t* buf) { return json_float_text<true>(bits, buf); }
 
 }  // namespace gofr

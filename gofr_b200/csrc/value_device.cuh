@@ -34,13 +34,59 @@ GOFR_HD_NOINLINE uint32_t emit_f64(Writer* w, uint64_t bits) {
     return n;
 }
 
+// float32 → text (floatEncoder with bits == 32: the shortest digits that identify the float32); 0 for NaN / ±Inf
+template <bool EMIT>
+GOFR_HD_NOINLINE uint32_t emit_f32(Writer* w, uint32_t bits) {
+    uint8_t buf[32];
+    const uint32_t n = json_float32_text(bits, buf);
+    if (EMIT)
+        for (uint32_t k = 0; k < n; k++) w->put1(buf[k]);
+    return n;
+}
+// uint64 → decimal (uintEncoder: strconv.AppendUint)
+template <bool EMIT>
+GOFR_HD uint32_t emit_u64_slow(Writer* w, uint64_t v) {
+    uint8_t d[20];
+    uint32_t n = 0;
+    do { d[n++] = (uint8_t)('0' + (uint32_t)(v % 10)); v /= 10; } while (v);
+    if (EMIT)
+        for (uint32_t k = n; k-- > 0;) w->put1(d[k]);
+    return n;
+}
+// []byte → base64.StdEncoding with padding (encodeByteSlice), without the quotes
+template <bool EMIT>
+GOFR_HD uint32_t emit_base64(Writer* w, const uint8_t* p, uint32_t n) {
+    if (EMIT) {
+        auto ch = [](uint32_t x) -> uint32_t { return x < 26 ? 'A' + x : x < 52 ? 'a' + (x - 26) : x < 62 ? '0' + (x - 52) : x == 62 ? '+' : '/'; };
+        uint32_t i = 0;
+        for (; i + 3 <= n; i += 3) {
+            const uint32_t t = (uint32_t)p[i] << 16 | (uint32_t)p[i + 1] << 8 | p[i + 2];
+            w->put1(ch(t >> 18)); w->put1(ch((t >> 12) & 63)); w->put1(ch((t >> 6) & 63)); w->put1(ch(t & 63));
+        }
+        if (n - i == 1) {
+            const uint32_t t = (uint32_t)p[i] << 16;
+            w->put1(ch(t >> 18)); w->put1(ch((t >> 12) & 63)); w->put1('='); w->put1('=');
+        } else if (n - i == 2) {
+            const uint32_t t = (uint32_t)p[i] << 16 | (uint32_t)p[i + 1] << 8;
+            w->put1(ch(t >> 18)); w->put1(ch((t >> 12) & 63)); w->put1(ch((t >> 6) & 63)); w->put1('=');
+        }
+    }
+    return (n + 2) / 3 * 4;
+}
+// bytes a scalar kind owns (fixed words, or as an element of a slice / map)
+GOFR_HD uint32_t value_scalar_bytes(uint32_t kind) {
+    return (kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_FLOAT64 || kind == GOFR_F_UINT64) ? 8u : 4u;
+}
+
 // isEmptyValue (encode.go) of a field whose fixed words are at p: false, 0, 0.0 of either sign, "", nil pointer, nil or
 // empty slice / map; a struct value is never empty
 GOFR_HD bool value_field_empty(uint32_t kind, uint32_t container, const uint8_t* p) {
     if (container == GOFR_C_PTR) return ld32u(p) == 0;
     if (container == GOFR_C_SLICE || container == GOFR_C_MAP) { const uint32_t n = ld32u(p); return n == 0 || n == GOFR_NIL_COUNT; }
-    if (kind == GOFR_F_INT64 || kind == GOFR_F_INT) return ld64u(p) == 0;
+    if (kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_UINT64) return ld64u(p) == 0;
     if (kind == GOFR_F_FLOAT64) return (ld64u(p) << 1) == 0;
+    if (kind == GOFR_F_FLOAT32) return (ld32u(p) << 1) == 0;
+    if (kind == GOFR_F_BYTES) { const uint32_t n = ld32u(p); return n == 0 || n == GOFR_NIL_COUNT; }  // len(v) == 0: nil or empty
     if (kind == GOFR_F_STRUCT) return false;
     return ld32u(p) == 0;  // INT32, BOOL, STRING (its length)
 }
@@ -100,7 +146,22 @@ GOFR_HD_NOINLINE uint32_t value_encode(Writer* w, const TableView tv, uint32_t s
             const uint32_t n = emit_f64<EMIT>(w, ld64u(p));
             if (!n) err = VAL_UNENCODABLE;
             out += n;
+        } else if (kind == GOFR_F_FLOAT32) {
+            const uint32_t n = emit_f32<EMIT>(w, ld32u(p));
+            if (!n) err = VAL_UNENCODABLE;
+            out += n;
+        } else if (kind == GOFR_F_UINT64) {
+            out += emit_u64_slow<EMIT>(w, ld64u(p));
         } else err = VAL_MALFORMED;
+    };
+    // a []byte whose length word (GOFR_NIL_COUNT: nil) has been read: null, or the base64 text in quotes
+    auto bytes_val = [&](uint32_t len) {
+        if (len == GOFR_NIL_COUNT) { put_null(); return; }
+        const uint8_t* s = take(len);
+        if (!s) return;
+        put_c('"');
+        out += emit_base64<EMIT>(w, s, len);
+        put_c('"');
     };
     auto push_struct = [&](uint32_t schema, const uint8_t* fx) {
         if (depth > kMaxValueDepth) { err = VAL_MALFORMED; return; }
@@ -117,8 +178,11 @@ GOFR_HD_NOINLINE uint32_t value_encode(Writer* w, const TableView tv, uint32_t s
             const uint32_t len = ld32u(lp);
             const uint8_t* s = take(len);
             if (s) string_val(s, len);
+        } else if (kind == GOFR_F_BYTES) {
+            const uint8_t* lp = take(4);
+            if (lp) bytes_val(ld32u(lp));
         } else {
-            const uint8_t* p = take((kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_FLOAT64) ? 8u : 4u);
+            const uint8_t* p = take(value_scalar_bytes(kind));
             if (p) scalar(kind, p);
         }
     };
@@ -128,7 +192,8 @@ GOFR_HD_NOINLINE uint32_t value_encode(Writer* w, const TableView tv, uint32_t s
             const uint32_t len = ld32u(p);
             const uint8_t* s = take(len);
             if (s) string_val(s, len);
-        } else if (F.kind == GOFR_F_STRUCT) push_struct(F.elem, p);
+        } else if (F.kind == GOFR_F_BYTES) bytes_val(ld32u(p));
+        else if (F.kind == GOFR_F_STRUCT) push_struct(F.elem, p);
         else scalar(F.kind, p);
     };
     // map[string]T, T a string or a scalar: entries (u32 key length, key, E(T)) in the row's order; encoding/json sorts
@@ -142,13 +207,14 @@ GOFR_HD_NOINLINE uint32_t value_encode(Writer* w, const TableView tv, uint32_t s
             if ((uint32_t)(end - q) < klen) return false;
             key = q; q += klen;
             val = q;
-            if (kind == GOFR_F_STRING) {
+            if (kind == GOFR_F_STRING || kind == GOFR_F_BYTES) {
                 if ((uint32_t)(end - q) < 4u) return false;
-                const uint32_t vlen = ld32u(q); q += 4;
+                uint32_t vlen = ld32u(q); q += 4;
+                if (kind == GOFR_F_BYTES && vlen == GOFR_NIL_COUNT) vlen = 0;  // a nil []byte owns no bytes
                 if ((uint32_t)(end - q) < vlen) return false;
                 q += vlen;
             } else {
-                const uint32_t vb = (kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_FLOAT64) ? 8u : 4u;
+                const uint32_t vb = value_scalar_bytes(kind);
                 if ((uint32_t)(end - q) < vb) return false;
                 q += vb;
             }

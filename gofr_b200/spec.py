@@ -47,6 +47,7 @@ def result_both(schema: "Schema", values: Sequence, message: bytes, lookup=None)
 
 # field kinds
 F_INT64, F_INT32, F_BOOL, F_STRING, F_INT, F_FLOAT64, F_STRUCT = 1, 2, 3, 4, 5, 6, 7
+F_UINT64, F_BYTES, F_FLOAT32 = 8, 9, 10   # uint64 / uint, []byte (base64, nil -> null), float32
 # what a field holds of its kind T: T, *T, []T, map[string]T (include/gofr_b200.h GOFR_C_*)
 C_VALUE, C_PTR, C_SLICE, C_MAP = 0, 1, 2, 3
 FIELD_BARE = 1   # one-field schema standing for the field's own type (a handler returning []T, map[string]T, ...)
@@ -98,7 +99,7 @@ class Schema:
 
     @staticmethod
     def _scalar_bytes(kind: int) -> int:
-        return 8 if kind in (F_INT64, F_INT, F_FLOAT64) else 4
+        return 8 if kind in (F_INT64, F_INT, F_FLOAT64, F_UINT64) else 4
 
     def _field_fixed(self, f: Field, lookup) -> int:
         if f.container in (C_SLICE, C_MAP):
@@ -117,6 +118,11 @@ class Schema:
         if kind == F_FLOAT64:
             import struct
             return v if isinstance(v, (bytes, bytearray)) else struct.pack("<d", float(v))   # bytes: raw IEEE bits (NaN payloads)
+        if kind == F_FLOAT32:
+            import struct
+            return v if isinstance(v, (bytes, bytearray)) else struct.pack("<f", float(v))
+        if kind == F_UINT64:
+            return int(v).to_bytes(8, "little", signed=False)
         raise ValueError(f"bad field kind {kind}")
 
     def _plain(self, f: Field, v, lookup):
@@ -124,6 +130,8 @@ class Schema:
         if f.kind == F_STRING:
             b = _str_bytes(v)
             return len(b).to_bytes(4, "little"), b
+        if f.kind == F_BYTES:   # []byte: None is the nil slice
+            return (NIL_COUNT.to_bytes(4, "little"), b"") if v is None else (len(v).to_bytes(4, "little"), bytes(v))
         if f.kind == F_STRUCT:
             sub = lookup(f.elem_schema)
             row = sub.encode_row(v, lookup)
@@ -135,6 +143,8 @@ class Schema:
         if f.kind == F_STRING:
             b = _str_bytes(v)
             return len(b).to_bytes(4, "little") + b
+        if f.kind == F_BYTES:
+            return NIL_COUNT.to_bytes(4, "little") if v is None else len(v).to_bytes(4, "little") + bytes(v)
         if f.kind == F_STRUCT:
             return lookup(f.elem_schema).encode_row(v, lookup)
         return self._scalar(f.kind, v)

@@ -145,14 +145,22 @@ enum {
     GOFR_F_INT = 5,    /* Go int (64-bit); only the type name in Bind error text differs from INT64 */
     GOFR_F_FLOAT64 = 6, /* encoding/json floatEncoder: shortest digits that round-trip, 'e' form below 1e-6 and from 1e21,
                            "e-0X" written "e-X"; NaN / ±Inf make Encode fail: the response keeps its status and headers
-                           and has no body (responder.go:40 drops the error)                    response schemas only */
-    GOFR_F_STRUCT = 7   /* a struct value of the schema `elem_schema`                            response schemas only */
+                           and has no body (responder.go:40 drops the error).  Bind schemas: see GOFR_H_BIND_ECHO */
+    GOFR_F_STRUCT = 7,  /* a struct value of the schema `elem_schema`                            response schemas only */
+    GOFR_F_UINT64 = 8,  /* uint64 / uint / uintptr: two words, unsigned decimal (narrower unsigned types fit INT64, int8 /
+                           int16 fit INT32: the text is the same)                               response schemas only */
+    GOFR_F_BYTES = 9,   /* []byte: encoding/json writes base64.StdEncoding with padding in quotes, null when nil.  Row:
+                           one fixed word = the byte length (GOFR_NIL_COUNT: nil), the bytes in the variable part;
+                           as an element E([]byte) = u32 length (GOFR_NIL_COUNT: nil) + bytes     response schemas only */
+    GOFR_F_FLOAT32 = 10 /* float32: one word (IEEE-754 bits), the shortest digits that identify the FLOAT32
+                           (strconv.AppendFloat(…, -1, 32)), same format rules and NaN / Inf behaviour as FLOAT64
+                                                                                                response schemas only */
 };
-/* What the field holds of its kind T (response schemas only; Bind schemas take GOFR_C_VALUE of kinds 1..5):
+/* What the field holds of its kind T (response schemas only; Bind schemas take GOFR_C_VALUE of kinds 1..6):
  *   GOFR_C_VALUE  T          GOFR_C_PTR  *T (nil → null)      GOFR_C_SLICE  []T (nil → null, empty → [])
  *   GOFR_C_MAP    map[string]T, T not a struct (nil → null; keys sorted bytewise like encoding/json does)
  * One container level per field; deeper types nest through GOFR_F_STRUCT (a struct field may again be a pointer, slice
- * or map).  []byte (base64), interface{} values, [][]T and maps of structs are not modelled: GOFR_ERR_UNSUPPORTED. */
+ * or map).  interface{} values, [][]T (other than [][]byte) and maps of structs are not modelled: GOFR_ERR_UNSUPPORTED. */
 enum { GOFR_C_VALUE = 0, GOFR_C_PTR = 1, GOFR_C_SLICE = 2, GOFR_C_MAP = 3 };
 #define GOFR_FIELD_BARE 0x01u /* the schema has this ONE field and stands for the field's own type: the handler returns a
                                  []T, map[string]T, *T or float64 rather than a struct; no {"name":…} around the value */
@@ -186,14 +194,15 @@ typedef struct gofr_handler_desc {
  * arena_off must be a multiple of 4.  The data section is the request body for GOFR_H_BIND_ECHO routes and the
  * handler-result row for GOFR_H_ROW routes.  Row format of a struct S: its FIXED part, then its VARIABLE part.
  *   fixed part, little-endian 32-bit words, fields in schema order:
- *     INT64 / INT / FLOAT64  two words (lo, hi; FLOAT64: the IEEE-754 bits)      INT32  one      BOOL  one, 0/1
+ *     INT64 / INT / UINT64 / FLOAT64  two words (lo, hi; FLOAT64: the IEEE-754 bits)   INT32 / FLOAT32  one   BOOL  one, 0/1
+ *     BYTES                  one word, the byte length, GOFR_NIL_COUNT when nil
  *     STRING                 one word, the byte length                            STRUCT  the struct's fixed part, inline
  *     *T                     one word 0 (nil) / 1, then T's fixed words (ignored, and T's variable part ABSENT, when nil)
  *     []T, map[string]T      one word, the element count, GOFR_NIL_COUNT when nil
  *   variable part, bytes, fields in schema order, nothing aligned:
- *     STRING  its bytes       STRUCT / *STRUCT  the struct's variable part       other scalars  nothing
+ *     STRING / BYTES  the bytes   STRUCT / *STRUCT  the struct's variable part   other scalars  nothing
  *     []T            count elements E(T)            map[string]T   count entries: u32 key length, key bytes, E(T)
- *     E(T): scalars — their fixed words; STRING — u32 length + bytes; STRUCT — its fixed part + its variable part
+ *     E(T): scalars — their fixed words; STRING / BYTES — u32 length + bytes; STRUCT — its fixed part + its variable part
  * A flat struct of scalars and strings therefore is: one word per field (INT64: two) followed by the string bytes of all
  * STRING fields concatenated in schema order. */
 typedef struct gofr_req_desc {

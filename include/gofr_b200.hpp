@@ -46,8 +46,9 @@ struct Error {
 inline Error ErrMissingFile() { return Error{"http: no such file", true}; }
 
 // A value of a struct type registered with App::Struct (fields in declaration order).  A field holds what its type says:
-// int64_t / bool / std::string / double for the scalar kinds, a StructValue for a nested struct, Nil for a nil pointer,
-// slice or map, a List for []T and a Map for map[string]T (a *T that is not nil is just the T).
+// int64_t / bool / std::string / double for the scalar kinds (uint64_t for a Uint64 member, a double for a Float32 one, a
+// std::string or Nil for a []byte), a StructValue for a nested struct, Nil for a nil pointer, slice or map, a List for
+// []T and a Map for map[string]T (a *T that is not nil is just the T).
 struct Value;
 struct Nil {};
 using List = std::vector<Value>;
@@ -59,9 +60,10 @@ struct Map {
     std::vector<std::pair<std::string, Value>> entries;  // any order: the encoder sorts like encoding/json does
 };
 struct Value {
-    std::variant<int64_t, bool, std::string, double, Nil, StructValue, List, Map> v;
+    std::variant<int64_t, bool, std::string, double, Nil, StructValue, List, Map, uint64_t> v;
     Value() : v(int64_t(0)) {}
     Value(int64_t x) : v(x) {}
+    Value(uint64_t x) : v(x) {}
     Value(int x) : v(int64_t(x)) {}
     Value(bool x) : v(x) {}
     Value(double x) : v(x) {}
@@ -226,6 +228,10 @@ public:
         StructType& Bool(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_BOOL, json, omitempty); }
         StructType& String(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_STRING, json, omitempty); }
         StructType& Float64(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_FLOAT64, json, omitempty); }
+        StructType& Float32(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_FLOAT32, json, omitempty); }
+        StructType& Uint64(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_UINT64, json, omitempty); }
+        // []byte: encoding/json writes it as base64; the value is a std::string of the bytes, or Nil for the nil slice
+        StructType& Bytes(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_BYTES, json, omitempty); }
         // a field of a struct type registered BEFORE this one
         StructType& Struct(const char* go, const StructType& of, const char* json = "", bool omitempty = false) {
             add(go, GOFR_F_STRUCT, json, omitempty);
@@ -585,6 +591,21 @@ private:
             memcpy(&bits, &d, 8);
             detail::put_u32(out, (uint32_t)bits);
             detail::put_u32(out, (uint32_t)(bits >> 32));
+        } else if (kind == GOFR_F_FLOAT32) {
+            float d;
+            if (auto* x = std::get_if<double>(&v.v)) d = (float)*x;
+            else if (auto* i = std::get_if<int64_t>(&v.v)) d = (float)*i;
+            else return false;
+            uint32_t bits;
+            memcpy(&bits, &d, 4);
+            detail::put_u32(out, bits);
+        } else if (kind == GOFR_F_UINT64) {
+            uint64_t u;
+            if (auto* x = std::get_if<uint64_t>(&v.v)) u = *x;
+            else if (auto* i = std::get_if<int64_t>(&v.v); i && *i >= 0) u = (uint64_t)*i;
+            else return false;
+            detail::put_u32(out, (uint32_t)u);
+            detail::put_u32(out, (uint32_t)(u >> 32));
         } else {
             auto* x = std::get_if<int64_t>(&v.v);
             if (!x) return false;
@@ -596,6 +617,14 @@ private:
     // T by value: its fixed words to `fixed`, its variable part to `var` (include/gofr_b200.h "Row format")
     bool encode_plain(const StructType::F& f, const Value& v, std::string* fixed, std::string* var) const {
         if (f.kind == GOFR_F_STRING) {
+            auto* s = std::get_if<std::string>(&v.v);
+            if (!s) return false;
+            detail::put_u32(fixed, (uint32_t)s->size());
+            *var += *s;
+            return true;
+        }
+        if (f.kind == GOFR_F_BYTES) {  // length word (GOFR_NIL_COUNT: the nil slice), bytes in the variable part
+            if (std::holds_alternative<Nil>(v.v)) { detail::put_u32(fixed, GOFR_NIL_COUNT); return true; }
             auto* s = std::get_if<std::string>(&v.v);
             if (!s) return false;
             detail::put_u32(fixed, (uint32_t)s->size());
@@ -617,6 +646,14 @@ private:
             *var += *s;
             return true;
         }
+        if (f.kind == GOFR_F_BYTES) {
+            if (std::holds_alternative<Nil>(v.v)) { detail::put_u32(var, GOFR_NIL_COUNT); return true; }
+            auto* s = std::get_if<std::string>(&v.v);
+            if (!s) return false;
+            detail::put_u32(var, (uint32_t)s->size());
+            *var += *s;
+            return true;
+        }
         if (f.kind == GOFR_F_STRUCT) {
             auto* sv = std::get_if<StructValue>(&v.v);
             std::string fx, vr;
@@ -629,7 +666,7 @@ private:
     }
     size_t fixed_bytes(const StructType::F& f) const {
         if (f.container == GOFR_C_SLICE || f.container == GOFR_C_MAP) return 4;
-        size_t n = (f.kind == GOFR_F_INT64 || f.kind == GOFR_F_INT || f.kind == GOFR_F_FLOAT64) ? 8 : 4;
+        size_t n = (f.kind == GOFR_F_INT64 || f.kind == GOFR_F_INT || f.kind == GOFR_F_FLOAT64 || f.kind == GOFR_F_UINT64) ? 8 : 4;
         if (f.kind == GOFR_F_STRUCT) {
             n = 0;
             if (const StructType* t = type_of(f.elem)) for (auto& g : t->fields_) n += fixed_bytes(g);

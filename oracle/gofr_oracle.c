@@ -1357,6 +1357,14 @@ int orc_json_float64(double x, uint8_t* out, int cap) {
     return n;
 }
 
+int orc_json_float32(float x, uint8_t* out, int cap) {
+    char tmp[40];
+    int n = orc_float32_text(x, tmp);
+    if (n > cap) return -1;
+    memcpy(out, tmp, (size_t)n);
+    return n;
+}
+
 /* the JSON text of one row: bytes written, -1 malformed / too small, -2 not encodable (NaN, Inf) */
 int orc_encode_row_json(const orc_table* t, int schema_id, const uint8_t* row, int n, uint8_t* out, int cap) {
     const orc_schema* sc = orc_find_schema(t, schema_id);

@@ -30,7 +30,7 @@ static inline void ob_putc(obuf* b, uint8_t c) { ob_reserve(b, 1); b->p[b->n++] 
 static inline void ob_puts(obuf* b, const char* s) { ob_put(b, s, strlen(s)); }
 
 /* field kinds (numeric values match include/gofr_b200.h) */
-enum { F_INT64 = 1, F_INT32 = 2, F_BOOL = 3, F_STRING = 4, F_INT = 5, F_FLOAT64 = 6, F_STRUCT = 7 };
+enum { F_INT64 = 1, F_INT32 = 2, F_BOOL = 3, F_STRING = 4, F_INT = 5, F_FLOAT64 = 6, F_STRUCT = 7, F_UINT64 = 8, F_BYTES = 9, F_FLOAT32 = 10 };
 enum { C_VALUE = 0, C_PTR = 1, C_SLICE = 2, C_MAP = 3 }; /* T, *T, []T, map[string]T */
 enum { FIELD_BARE = 1 };                                 /* one-field schema standing for the field's own type */
 
@@ -73,6 +73,7 @@ const char* orc_go_kind_name(int kind);
 struct orc_table;
 const orc_schema* orc_find_schema(const struct orc_table* t, int id);
 int orc_float_text(double x, char* out); /* encoding/json float64 text; 0 = NaN / Inf (not encodable) */
+int orc_float32_text(float x, char* out); /* the same for a float32 (shortest digits that identify the float32) */
 int orc_schema_is_flat(const orc_schema* sc);
 int orc_schema_fixed_words(const struct orc_table* t, const orc_schema* sc);
 int orc_enc_row(obuf* b, const struct orc_table* t, const orc_schema* sc, const uint8_t* fixed, size_t fixed_avail,

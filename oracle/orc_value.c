@@ -21,15 +21,18 @@ typedef struct orc_table orc_table;
  *   fmt = 'f'; if abs != 0 && (abs < 1e-6 || abs >= 1e21) fmt = 'e'; AppendFloat(b, f, fmt, -1, 64);
  *   then for 'e': "e-0X" → "e-X" (n >= 4 && b[n-4]=='e' && b[n-3]=='-' && b[n-2]=='0').
  * Returns the length, 0 for NaN / ±Inf (UnsupportedValueError). */
-static int round_trips(const char* s, double x) { return strtod(s, NULL) == x; }
+/* f32: ax holds a float32 value exactly and "the same float" means the same float32 (bitSize 32 of AppendFloat) */
+static int round_trips_w(const char* s, double x, int f32) { return f32 ? strtof(s, NULL) == (float)x : strtod(s, NULL) == x; }
+#define round_trips(s, x) round_trips_w(s, x, f32)
 
 /* shortest decimal digits (no dot, no leading zeros beyond a single 0) and the decimal exponent of the first digit */
-static void shortest_digits(double ax, char* digits, int* nd, int* exp10) {
+static void shortest_digits(double ax, char* digits, int* nd, int* exp10, int f32) {
     char buf[64];
-    for (int p = 1; p <= 17; p++) {
+    const int maxp = f32 ? 9 : 17;
+    for (int p = 1; p <= maxp; p++) {
         snprintf(buf, sizeof buf, "%.*e", p - 1, ax);
         int ok = round_trips(buf, ax);
-        if (!ok && p < 17) {
+        if (!ok && p < maxp) {
             /* the interval of decimals that parse back to ax is not symmetric around it at a power of two: a
              * p-digit decimal other than the correctly rounded one may still lie inside.  Try its two neighbours. */
             char m[32];
@@ -67,7 +70,12 @@ static void shortest_digits(double ax, char* digits, int* nd, int* exp10) {
     *exp10 = e;
 }
 
-int orc_float_text(double x, char* out) {
+static int float_text_w(double x, char* out, int f32);
+int orc_float_text(double x, char* out) { return float_text_w(x, out, 0); }
+/* floatEncoder with bits == 32: the cutoffs are compared as float32 ("Must use float32 comparisons for underlying float32
+ * value to get precise cutoffs right") */
+int orc_float32_text(float x, char* out) { return float_text_w((double)x, out, 1); }
+static int float_text_w(double x, char* out, int f32) {
     if (isnan(x) || isinf(x)) return 0;
     int n = 0;
     if (signbit(x)) out[n++] = '-';
@@ -75,8 +83,8 @@ int orc_float_text(double x, char* out) {
     if (ax == 0) { out[n++] = '0'; return n; }
     char d[32];
     int nd, e;
-    shortest_digits(ax, d, &nd, &e);
-    if (ax < 1e-6 || ax >= 1e21) {
+    shortest_digits(ax, d, &nd, &e, f32);
+    if (f32 ? ((float)ax < 1e-6f || (float)ax >= 1e21f) : (ax < 1e-6 || ax >= 1e21)) {
         /* %e: d.ddde±XX, at least two exponent digits */
         out[n++] = d[0];
         if (nd > 1) { out[n++] = '.'; memcpy(out + n, d + 1, (size_t)nd - 1); n += nd - 1; }
@@ -123,7 +131,29 @@ typedef struct {
 static uint32_t rd32u(const uint8_t* p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
 static uint64_t rd64u(const uint8_t* p) { return (uint64_t)rd32u(p) | (uint64_t)rd32u(p + 4) << 32; }
 
-static int kind_words(int kind) { return (kind == F_INT64 || kind == F_INT || kind == F_FLOAT64) ? 2 : 1; }
+static int kind_words(int kind) { return (kind == F_INT64 || kind == F_INT || kind == F_FLOAT64 || kind == F_UINT64) ? 2 : 1; }
+
+/* encodeByteSlice: base64.StdEncoding (padding) in quotes; a nil slice is null */
+static void enc_bytes(obuf* b, walk* w, uint32_t len) {
+    static const char A[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+    if (len == 0xFFFFFFFFu) { ob_puts(b, "null"); return; }
+    if ((size_t)(w->end - w->var) < len) { w->malformed = 1; return; }
+    const uint8_t* s = w->var;
+    w->var += len;
+    ob_putc(b, '"');
+    uint32_t i = 0;
+    for (; i + 3 <= len; i += 3) {
+        uint32_t t = (uint32_t)s[i] << 16 | (uint32_t)s[i + 1] << 8 | s[i + 2];
+        ob_putc(b, (uint8_t)A[t >> 18]); ob_putc(b, (uint8_t)A[(t >> 12) & 63]); ob_putc(b, (uint8_t)A[(t >> 6) & 63]); ob_putc(b, (uint8_t)A[t & 63]);
+    }
+    if (len - i) {
+        uint32_t t = (uint32_t)s[i] << 16 | (len - i == 2 ? (uint32_t)s[i + 1] << 8 : 0u);
+        ob_putc(b, (uint8_t)A[t >> 18]); ob_putc(b, (uint8_t)A[(t >> 12) & 63]);
+        ob_putc(b, len - i == 2 ? (uint8_t)A[(t >> 6) & 63] : (uint8_t)'=');
+        ob_putc(b, '=');
+    }
+    ob_putc(b, '"');
+}
 
 /* words of the fixed part of a struct / of one field */
 int orc_schema_fixed_words(const orc_table* t, const orc_schema* sc);
@@ -168,6 +198,22 @@ static void enc_scalar(obuf* b, walk* w, int kind, const uint8_t* p) {
             ob_put(b, tmp, (size_t)n);
             break;
         }
+        case F_FLOAT32: {
+            uint32_t bits = rd32u(p);
+            float x;
+            memcpy(&x, &bits, 4);
+            char tmp[40];
+            int n = orc_float32_text(x, tmp);
+            if (!n) w->failed = 1;
+            ob_put(b, tmp, (size_t)n);
+            break;
+        }
+        case F_UINT64: { /* uintEncoder: strconv.AppendUint(b, v.Uint(), 10) */
+            char tmp[24];
+            int n = snprintf(tmp, sizeof tmp, "%llu", (unsigned long long)rd64u(p));
+            ob_put(b, tmp, (size_t)n);
+            break;
+        }
         default: w->malformed = 1;
     }
 }
@@ -181,6 +227,9 @@ static void enc_element(obuf* b, walk* w, const orc_field* f) {
         const uint8_t* s = take(w, len);
         if (!s) return;
         orc_enc_string(b, s, len);
+    } else if (f->kind == F_BYTES) {
+        const uint8_t* lp = take(w, 4);
+        if (lp) enc_bytes(b, w, rd32u(lp));
     } else if (f->kind == F_STRUCT) {
         const orc_schema* es = orc_find_schema(w->t, f->elem_schema);
         if (!es) { w->malformed = 1; return; }
@@ -199,6 +248,8 @@ static void enc_plain(obuf* b, walk* w, const orc_field* f, const uint8_t* p) {
         uint32_t len = rd32u(p);
         const uint8_t* s = take(w, len);
         if (s) orc_enc_string(b, s, len);
+    } else if (f->kind == F_BYTES) {
+        enc_bytes(b, w, rd32u(p));
     } else if (f->kind == F_STRUCT) {
         const orc_schema* es = orc_find_schema(w->t, f->elem_schema);
         if (!es) { w->malformed = 1; return; }
@@ -279,8 +330,10 @@ static int field_empty(const orc_field* f, const uint8_t* p) {
     if (f->container == C_PTR) return rd32u(p) == 0;
     if (f->container == C_SLICE || f->container == C_MAP) { uint32_t n = rd32u(p); return n == 0 || n == 0xFFFFFFFFu; }
     switch (f->kind) {
-        case F_INT64: case F_INT: return rd64u(p) == 0;
+        case F_INT64: case F_INT: case F_UINT64: return rd64u(p) == 0;
         case F_FLOAT64: return (rd64u(p) << 1) == 0; /* +0 and -0 */
+        case F_FLOAT32: return (uint32_t)(rd32u(p) << 1) == 0;
+        case F_BYTES: { uint32_t n = rd32u(p); return n == 0 || n == 0xFFFFFFFFu; } /* len(v) == 0 */
         case F_STRUCT: return 0;
         default: return rd32u(p) == 0; /* INT32, BOOL, STRING (length) */
     }

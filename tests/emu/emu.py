@@ -72,6 +72,22 @@ def float_text(bits: int) -> bytes:
     return out.raw[:n]
 
 
+def float32_text(bits: int) -> bytes:
+    """json_float32_text of the device code: the text encoding/json writes for a float32 member; b"" for NaN / Inf."""
+    out = C.create_string_buffer(40)
+    lib().emu_float32_text.argtypes = [C.c_uint32, C.c_char_p]
+    n = lib().emu_float32_text(bits, out)
+    return out.raw[:n]
+
+
+def float32_check(first: int, step: int, count: int):
+    """float32 bit patterns first, first + step, ... against the C library (round trip, shortest, nearest): (failures, first bad)"""
+    lib().emu_float32_check.restype = C.c_uint64
+    lib().emu_float32_check.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32)]
+    bad = C.c_uint32(0)
+    return int(lib().emu_float32_check(first, step, count, C.byref(bad))), int(bad.value)
+
+
 def float_text_many(bits: np.ndarray):
     """the texts of many float64 bit patterns: (bytes, offsets[n + 1])"""
     bits = np.ascontiguousarray(bits, dtype=np.uint64)

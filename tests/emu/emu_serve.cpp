@@ -6,6 +6,8 @@
 // here against the oracle; tile staging, the block scan and the look-back only exist in serve_kernel.cu and are
 // covered by the `-m gpu` tests.  Nothing in the product links or loads this file.
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -68,6 +70,52 @@ extern "C" int emu_serve(const uint8_t* image, uint64_t image_len, const uint8_t
 // ---- slot layout (gofr_serve_device_slots): same per-request code, emit_request<true> + finish_padded ----
 static int g_stage_mode = 0;  // which requests of the slot emulation count as staged: 0 every other one, 1 all, 2 none
 extern "C" int emu_float_text(uint64_t bits, uint8_t* out) { return (int)json_float64_text(bits, out); }
+extern "C" int emu_float32_text(uint32_t bits, uint8_t* out) { return (int)json_float32_text(bits, out); }
+// float32 text of the bit patterns first, first + step, … (count of them) checked against the C library, which rounds
+// correctly: the text parses back to the same float32 (strtof), one digit fewer does not (shortest), and the digits are the
+// correctly rounded ones of that length (printf on the exact value: closest, ties to even) — unless those do not parse back
+// (at a power of two the interval below the value is half as wide as the one above: three float32 values have a shortest
+// decimal that is not the nearest one of its length).  Returns the number of bit
+// patterns that fail, the first one in *bad.  Exhaustive with first = 0, step = 1, count = 2^31 (sign bit aside).
+extern "C" uint64_t emu_float32_check(uint32_t first, uint32_t step, uint64_t count, uint32_t* bad) {
+    uint64_t fails = 0;
+    uint32_t b = first;
+    for (uint64_t k = 0; k < count; k++, b += step) {
+        if (((b >> 23) & 0xFFu) == 0xFFu || (b & 0x7FFFFFFFu) == 0) continue;
+        float x;
+        memcpy(&x, &b, 4);
+        uint8_t t[40];
+        const uint32_t n = json_float32_text(b, t);
+        t[n] = 0;
+        bool ok = n > 0 && strtof((const char*)t, nullptr) == x;
+        // digits of the text
+        char dg[24];
+        int nd = 0;
+        bool lead = true;
+        for (uint32_t i = 0; i < n && t[i] != 'e'; i++) {
+            if (t[i] < '0' || t[i] > '9') continue;
+            if (lead && t[i] == '0') continue;
+            lead = false;
+            dg[nd++] = (char)t[i];
+        }
+        while (nd > 1 && dg[nd - 1] == '0') nd--;  // 'f' format pads integers with zeros
+        dg[nd] = 0;
+        char ref[48];
+        snprintf(ref, sizeof ref, "%.*e", nd - 1, (double)x);  // float -> double is exact
+        char rd[24];
+        int rn = 0;
+        for (const char* p = ref; *p && *p != 'e'; p++) if (*p >= '0' && *p <= '9') rd[rn++] = *p;
+        while (rn > 1 && rd[rn - 1] == '0') rn--;
+        rd[rn] = 0;
+        ok = ok && (strcmp(rd, dg) == 0 || strtof(ref, nullptr) != x);
+        if (ok && nd > 1) {
+            snprintf(ref, sizeof ref, "%.*e", nd - 2, (double)x);
+            ok = strtof(ref, nullptr) != x;
+        }
+        if (!ok) { if (!fails && bad) *bad = b; fails++; }
+    }
+    return fails;
+}
 extern "C" void emu_float_text_many(const uint64_t* bits, uint32_t n, uint8_t* out, uint32_t* off) {
     uint32_t o = 0;
     for (uint32_t i = 0; i < n; i++) { off[i] = o; o += json_float64_text(bits[i], out + o); }

@@ -40,6 +40,7 @@ def lib():
                                      C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_schema_extend.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_json_float64.argtypes = [C.c_double, C.c_char_p, C.c_int]
+        L.orc_json_float32.argtypes = [C.c_float, C.c_char_p, C.c_int]
         L.orc_encode_row_json.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int]
         L.orc_add_route.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int] + \
             [C.c_char_p, C.c_int] * 4 + [C.c_char_p, C.c_int]

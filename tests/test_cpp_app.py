@@ -45,7 +45,7 @@ def test_header_compiles_and_host_helpers_match_oracle(tmp_path):
     tmpl = ["/a/{id}/b/{name:[a-z]+}", "/{x:[0-9]{2}}/{y}", "/plain", "/{a}-{b}.{c}", "/{v:.*}"]
     lines += "".join("T %s\n" % t.encode().hex() for t in tmpl)
     lines += "".join("R %d\n" % c for c in range(10))
-    lines += "".join("V %d\n" % c for c in range(5))
+    lines += "".join("V %d\n" % c for c in range(6))
     # request targets: path unescaping, the first '?' splits, a lone trailing '?' is ForceQuery, bad escapes are refused
     import re
     import urllib.parse
@@ -76,14 +76,19 @@ def test_header_compiles_and_host_helpers_match_oracle(tmp_path):
                                      S.Field("Attrs", S.F_STRING, "attrs", True, S.C_MAP), S.Field("Hist", S.F_STRUCT, "hist", False, S.C_SLICE, 1),
                                      S.Field("N", S.F_INT64, "n", True, S.C_PTR), S.Field("Counts", S.F_INT64, "counts", False, S.C_MAP)])
     addrs = S.Schema(3, "[]main.Addr", [S.Field("", S.F_STRUCT, "", container=S.C_SLICE, elem_schema=1, flags=S.FIELD_BARE)])
-    look = {1: addr, 2: user, 3: addrs}.__getitem__
+    blob = S.Schema(4, "main.Blob", [S.Field("ID", S.F_UINT64, "id"), S.Field("Data", S.F_BYTES, "data"), S.Field("Sum", S.F_BYTES, "sum", True),
+                                     S.Field("Ratio", S.F_FLOAT32, "ratio"), S.Field("Parts", S.F_BYTES, "parts", False, S.C_SLICE),
+                                     S.Field("UM", S.F_UINT64, "um", False, S.C_MAP), S.Field("PF", S.F_FLOAT32, "pf", False, S.C_PTR)])
+    look = {1: addr, 2: user, 3: addrs, 4: blob}.__getitem__
     wantv = [S.result_record(S.RESULT_DATA, user.encode_row(["bo<b>", 1.5e-7, ["Paris", 0, [1.0, 2.5]], None, ["a", "b\n"], {"z": "1", "a": "2", "aa": "3"},
                                                              [["X", 7, None], ["Y", 0, []]], 5, None], look)),
              S.result_record(S.RESULT_DATA, user.encode_row(["", 0.0, ["", 0, None], ["W", 1, [-0.5]], None, None, None, None, {"k": -1}], look)),
              S.result_record(S.RESULT_DATA, addrs.encode_row([[["X", 7, None], ["Y", 2, [3.25]]]], look)),
-             S.result_record(S.RESULT_DATA, addrs.encode_row([None], look)), bad]
-    assert [bytes.fromhex(l) for l in out[len(cases) + 15:len(cases) + 20]] == wantv
-    for t, line in zip(targets, out[len(cases) + 20:]):
+             S.result_record(S.RESULT_DATA, addrs.encode_row([None], look)), bad,
+             # uint64 / []byte (nil and not) / float32 members, by value, in a slice, a map and behind a pointer
+             S.result_record(S.RESULT_DATA, blob.encode_row([2 ** 64 - 1, b"\x00\xff\x10", None, 0.1, [b"ab", None, b""], {"k": 2 ** 63, "j": 7}, 2.5], look))]
+    assert [bytes.fromhex(l) for l in out[len(cases) + 15:len(cases) + 21]] == wantv
+    for t, line in zip(targets, out[len(cases) + 21:]):
         path, sep, query = t.partition(b"?")
         bad = not t.startswith(b"/") or re.search(rb"%(?![0-9a-fA-F]{2})", path) is not None
         if bad:
