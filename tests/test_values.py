@@ -642,14 +642,16 @@ def test_response_bound_holds_for_the_wider_data_model():
 # ---------------------------------------------------------------------------------------------------------------
 # random SCHEMAS (not only random values): struct trees with every kind, container and omitempty combination
 # ---------------------------------------------------------------------------------------------------------------
-def _rand_schemas(rnd, n_types):
-    """n_types struct types, each free to use the ones before it, plus bare types on top of them"""
+def _rand_schemas(rnd, n_types, late=False):
+    """n_types struct types, each free to use the ones before it, plus bare types on top of them (late: uint64, []byte and
+    float32 members as well)"""
+    extra = [S.F_UINT64, S.F_BYTES, S.F_FLOAT32] * 2 if late else []
     schemas = []
     names = ["a", "id", "Name", "x<y", "long_key_name_%d", "k", "é", "v1", "data", "0"]
     for t in range(n_types):
         fields = []
         for k in range(rnd.randint(1, 5)):
-            kind = rnd.choice([S.F_INT64, S.F_INT32, S.F_BOOL, S.F_STRING, S.F_INT, S.F_FLOAT64] + ([S.F_STRUCT] * 2 if schemas else []))
+            kind = rnd.choice([S.F_INT64, S.F_INT32, S.F_BOOL, S.F_STRING, S.F_INT, S.F_FLOAT64] + extra + ([S.F_STRUCT] * 2 if schemas else []))
             cont = rnd.choice([S.C_VALUE, S.C_VALUE, S.C_PTR, S.C_SLICE, S.C_MAP])
             elem = 0
             if kind == S.F_STRUCT:
@@ -662,8 +664,8 @@ def _rand_schemas(rnd, n_types):
         schemas.append(S.Schema(100 + t, "main.T%d" % t, fields))
     bare = []
     for t in range(3):
-        kind = rnd.choice([S.F_INT64, S.F_BOOL, S.F_STRING, S.F_FLOAT64, S.F_STRUCT])
-        cont = rnd.choice([S.C_PTR, S.C_SLICE, S.C_MAP]) if kind != S.F_FLOAT64 else rnd.choice([S.C_VALUE, S.C_SLICE])
+        kind = rnd.choice([S.F_INT64, S.F_BOOL, S.F_STRING, S.F_FLOAT64, S.F_STRUCT] + extra)
+        cont = rnd.choice([S.C_PTR, S.C_SLICE, S.C_MAP]) if kind not in (S.F_FLOAT64, S.F_BYTES, S.F_FLOAT32) else rnd.choice([S.C_VALUE, S.C_SLICE])
         elem = rnd.choice(schemas).id if kind == S.F_STRUCT else 0
         if kind == S.F_STRUCT and cont == S.C_MAP:
             cont = S.C_SLICE
@@ -671,10 +673,10 @@ def _rand_schemas(rnd, n_types):
     return schemas, bare
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(24))
 def test_random_schemas_three_ways(seed):
     rnd = random.Random(1000 + seed)
-    structs, bare = _rand_schemas(rnd, rnd.randint(2, 5))
+    structs, bare = _rand_schemas(rnd, rnd.randint(2, 5), late=seed >= 12)
     routed = structs + bare
     mode = [S.FRAME_WIRE, S.FRAME_BODY, S.FRAME_INTENDED][seed % 3]
     spec = S.TableSpec(frame_mode=mode, schemas=structs + bare,
