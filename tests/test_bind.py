@@ -239,13 +239,17 @@ def _float_cmp(bodies, mis=1):
     o1, f1, m1 = O.OracleTable(FL_SPEC).serve(batch, DATE)
     o2, f2, m2 = emu.serve(Table(FL_SPEC).serialize(), batch, DATE, misalign=mis)
     r1, r2 = O.responses(o1, f1), O.responses(o2, f2)
+    # the same requests through the slot layout of the device code (what gofr_serve_device_slots runs)
+    s_out, s_len, s_meta = emu.serve_slots(Table(FL_SPEC).serialize(), batch, DATE, 1024)
+    s_out = np.asarray(s_out).reshape(batch.n, 1024)
     deferred = []
     for i, b in enumerate(bodies):
         if (m2[i] & 0xFFFF) == 0:
-            assert r2[i] == b"", b
+            assert r2[i] == b"" and s_len[i] == 0 and (s_meta[i] & 0xFFFF) == 0, b
             deferred.append(i)
         else:
             assert r1[i] == r2[i] and m1[i] == m2[i], (b, r1[i], r2[i])
+            assert s_meta[i] == m1[i] and s_out[i, :int(s_len[i])].tobytes() == r1[i], b
     return r1, deferred
 
 
@@ -336,7 +340,6 @@ def test_emu_bind_stage_float_fields():
 def _gpu_float_check():
     import torch
     from gofr_b200.engine import Engine
-    from tests.test_gpu_parity import _check
     rng = np.random.default_rng(5)
     bodies = []
     for i in range(20000):
