@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgofr_b200.so")
 SOURCES = ["serve_kernel.cu", "serve_values_kernel.cu", "serve_slots_kernel.cu", "serve_slots_wide_kernel.cu", "serve_slots_values_kernel.cu", "grpc_kernel.cu", "proto_nested_kernel.cu", "proto_nested_decode_kernel.cu", "reqlog_kernel.cu", "route_kernel.cu", "bind_kernel.cu", "http_kernel.cu", "egress_kernel.cu", "engine.cu", "table_build.cpp", "frontend.cpp"]
-HEADERS = ["frame_tiles.cuh", "proto_nested_device.cuh", "proto_nested_decode_device.cuh", "serve_body.cuh", "serve_device.cuh", "value_device.cuh", "float_device.cuh", "ryu_tables.inc", "bind_device.cuh", "grpc_device.cuh", "reqlog_device.cuh", "http_device.cuh", "tile_common.cuh", "table_format.h", "engine_internal.h",
+HEADERS = ["frame_tiles.cuh", "proto_nested_device.cuh", "proto_nested_decode_device.cuh", "serve_body.cuh", "serve_device.cuh", "value_device.cuh", "float_device.cuh", "ryu_tables.inc", "el_tables.inc", "bind_device.cuh", "grpc_device.cuh", "reqlog_device.cuh", "http_device.cuh", "tile_common.cuh", "table_format.h", "engine_internal.h",
            "../../include/gofr_b200.h"]
 # Translation units whose Writer stores whole 32-byte sectors with ONE 256-bit store (st.global.cs.v8.b32 -> STG.E.EF.256,
 # new with sm_100: 0.311 against 0.354 ms on the 1 Mi config-2 batch).  CUDA 12.9's ptxas lowers that store to a scalar

@@ -330,7 +330,62 @@ GOFR_HD bool bd_parse_int(const uint8_t* s, uint32_t n, int64_t* out) {
 // room).  Sure overflows (>= 1e310: UnmarshalTypeError "number <literal>", ErrRange) and sure underflows (< 1e-329:
 // ±0, not an error in Go) are decided as well.  Everything else — long mantissas, large exponents, subnormals — is
 // PF_DEFER: the request goes to the host like a body nested deeper than 64 levels, never to a differently rounded value.
+// Between the two sits the Eisel-Lemire step (below), which settles nearly everything else: what is left for the host are
+// exact half-way literals, subnormals, values within a decade of the overflow threshold, and literals with more than 19
+// digits whose cut-off matters.
 enum : uint32_t { PF_OK = 0, PF_OVERFLOW = 1, PF_DEFER = 2 };
+GOFR_HD uint32_t bd_parse_float(const uint8_t* s, uint32_t n, uint64_t* bits);
+#if GOFR_TU_VALUES  // defined (tables included) only where float64 members exist: the other translation units' modules keep their layout
+
+// ---- the Eisel-Lemire step (strconv/eisel_lemire.go eiselLemire64; D. Lemire, "Number Parsing at a Gigabyte per
+// Second"): what ParseFloat tries when the exact cases above do not apply.  man x 10^exp10 with a 128-bit (if need be 192-bit)
+// product against a table of normalised powers of ten (el_tables.inc, generated with exact integers by
+// scratch/gen/el_tables.py); it either yields the correctly rounded float64 or says it cannot tell (half-way cases, the
+// subnormal and overflow ranges) — then Go falls back to its big-decimal slow path, and this code to the host. ----
+#define EL_TABLE(name, n) static const uint64_t name##_host[n][2]
+#include "el_tables.inc"
+#undef EL_TABLE
+#if defined(__CUDACC__)
+#define EL_TABLE(name, n) static __device__ const uint64_t name##_dev[n][2]
+#include "el_tables.inc"
+#undef EL_TABLE
+#endif
+GOFR_HD const uint64_t* el_pow10(int32_t exp10) {  // -348 <= exp10 <= 347
+#if defined(__CUDA_ARCH__)
+    return EL_POW10_dev[exp10 + 348];
+#else
+    return EL_POW10_host[exp10 + 348];
+#endif
+}
+GOFR_HD bool bd_eisel_lemire(uint64_t man, int64_t exp10, uint64_t* bits) {
+    if (man == 0) { *bits = 0; return true; }
+    if (exp10 < -348 || exp10 > 347) return false;
+    const int clz = clz64(man);
+    man <<= clz;
+    uint64_t ret_exp2 = (uint64_t)(((217706 * exp10) >> 16) + 64 + 1023) - (uint64_t)clz;
+    const uint64_t* pw = el_pow10((int32_t)exp10);
+    uint64_t x_hi, x_lo = umul128(man, pw[1], &x_hi);
+    if ((x_hi & 0x1FFu) == 0x1FFu && x_lo + man < man) {  // the 128-bit product may be one too low: add the next 64 bits
+        uint64_t y_hi;
+        const uint64_t y_lo = umul128(man, pw[0], &y_hi);
+        uint64_t m_hi = x_hi;
+        const uint64_t m_lo = x_lo + y_hi;
+        if (m_lo < x_lo) m_hi++;
+        if ((m_hi & 0x1FFu) == 0x1FFu && m_lo + 1 == 0 && y_lo + man < man) return false;
+        x_hi = m_hi; x_lo = m_lo;
+    }
+    const uint64_t msb = x_hi >> 63;
+    uint64_t ret_man = x_hi >> (msb + 9);  // 54 bits
+    ret_exp2 -= 1 ^ msb;
+    if (x_lo == 0 && (x_hi & 0x1FFu) == 0 && (ret_man & 3u) == 1) return false;  // exactly half-way: cannot tell
+    ret_man += ret_man & 1;
+    ret_man >>= 1;
+    if (ret_man >> 53) { ret_man >>= 1; ret_exp2 += 1; }
+    if (ret_exp2 - 1 >= 0x7FFull - 1) return false;  // subnormal or overflow: not decided here
+    *bits = ret_exp2 << 52 | (ret_man & 0x000FFFFFFFFFFFFFull);
+    return true;
+}
+
 GOFR_HD uint32_t bd_parse_float(const uint8_t* s, uint32_t n, uint64_t* bits) {
     uint32_t i = 0;
     const bool neg = n && s[0] == '-';
@@ -365,20 +420,30 @@ GOFR_HD uint32_t bd_parse_float(const uint8_t* s, uint32_t n, uint64_t* bits) {
     }
     const uint64_t sign = neg ? 0x8000000000000000ull : 0ull;
     if (mant == 0) { *bits = sign; return PF_OK; }
-    while (mant % 10 == 0) { mant /= 10; exp10++; nd--; }
+    // (with dropped digits the value lies in (mant, mant + 1) x 10^exp10 of the 19-digit mantissa: keep that scale)
+    while (!trunc && mant % 10 == 0) { mant /= 10; exp10++; nd--; }
     const int64_t lead = exp10 + nd - 1;  // 10^lead <= |value| < 10^(lead + 1), dropped digits included
     if (lead >= 310) return PF_OVERFLOW;
     if (lead <= -330) { *bits = sign; return PF_OK; }
-    if (trunc || (mant >> 53) != 0) return PF_DEFER;
+    // everything the exact cases below do not take: Eisel-Lemire; with dropped digits the value lies between mant and
+    // mant + 1 — if both round to the same float64, that is the answer (strconv.atof64 does exactly this)
+    auto approx = [&]() -> uint32_t {
+        uint64_t f = 0, f_up = 0;
+        if (!bd_eisel_lemire(mant, exp10, &f)) return PF_DEFER;
+        if (trunc && (!bd_eisel_lemire(mant + 1, exp10, &f_up) || f_up != f)) return PF_DEFER;
+        *bits = f | sign;
+        return PF_OK;
+    };
+    if (trunc || (mant >> 53) != 0) return approx();
     double x = (double)(int64_t)mant;
     if (exp10 > 22) {
-        if (exp10 > 22 + 15) return PF_DEFER;
+        if (exp10 > 22 + 15) return approx();
         uint64_t p = 1;
         for (int64_t k = 22; k < exp10; k++) p *= 10;
-        if (mant > ((1ull << 53) - 1) / p) return PF_DEFER;
+        if (mant > ((1ull << 53) - 1) / p) return approx();
         x = (double)(int64_t)(mant * p);
         exp10 = 22;
-    } else if (exp10 < -22) return PF_DEFER;
+    } else if (exp10 < -22) return approx();
     double p10 = 1.0;  // 10^k is a double for k <= 22, so every partial product is exact
     for (int64_t k = exp10 < 0 ? -exp10 : exp10; k > 0; k--) p10 *= 10.0;
     x = exp10 < 0 ? x / p10 : x * p10;
@@ -391,6 +456,8 @@ GOFR_HD uint32_t bd_parse_float(const uint8_t* s, uint32_t n, uint64_t* bits) {
     *bits = b | sign;
     return PF_OK;
 }
+
+#endif  // GOFR_TU_VALUES
 
 // d.object / d.literalStore into the span row.  `row` has BR_FIELDS + bind-layout words, zero-initialised here.
 // VO: whether this instance knows float64 members.  A Bind schema with one makes its echo program PF_VALUES (OP_F64), so
@@ -459,13 +526,17 @@ GOFR_HD_NOINLINE void bind_decode(const TableView tv, uint32_t schema_idx, const
                     row[w + 1] = len | (esc ? 0x80000000u : 0u);
                 }
             } else {  // number
+                bool is_float = false;
+                if constexpr (VO) is_float = kind == GOFR_F_FLOAT64;
                 if (kind == GOFR_F_STRING || kind == GOFR_F_BOOL) type_error(BV_NUMBER, fi, 0, 0);
-                else if (VO && kind == GOFR_F_FLOAT64) {
-                    uint64_t fb = 0;
-                    const uint32_t pf = bd_parse_float(s + vs, ve - vs, &fb);
-                    if (pf == PF_DEFER) deferred = true;
-                    else if (pf == PF_OVERFLOW) type_error(BV_NUMBER_LIT, fi, vs, ve - vs);
-                    else { row[w] = (uint32_t)fb; row[w + 1] = (uint32_t)(fb >> 32); }
+                else if (is_float) {
+                    if constexpr (VO) {
+                        uint64_t fb = 0;
+                        const uint32_t pf = bd_parse_float(s + vs, ve - vs, &fb);
+                        if (pf == PF_DEFER) deferred = true;
+                        else if (pf == PF_OVERFLOW) type_error(BV_NUMBER_LIT, fi, vs, ve - vs);
+                        else { row[w] = (uint32_t)fb; row[w + 1] = (uint32_t)(fb >> 32); }
+                    }
                 } else {
                     int64_t x;
                     bool ok = bd_parse_int(s + vs, ve - vs, &x);

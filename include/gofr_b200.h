@@ -99,11 +99,11 @@ enum {
     GOFR_H_ROW = 5,           /* return <struct of schema>, nil; field values arrive in the request's data section */
     GOFR_H_BIND_ECHO = 6,     /* var v T; if err := c.Bind(&v); err != nil { return nil, err }; return v, nil
                                  T: a flat struct of int / int32 / int64 / float64 / bool / string fields.  A float64 member
-                                 gets strconv.ParseFloat's correctly rounded value when one IEEE operation yields it (at most
-                                 15-16 significant digits that fit 53 bits and a power of ten up to 1e22 — 1e37 when the
-                                 digits leave room —, sure overflows → the UnmarshalTypeError Go reports, sure underflows →
-                                 0); a request with any other literal for such a member comes back with status 0 ("run on
-                                 the host"), like a body nested deeper than 64 levels */
+                                 gets strconv.ParseFloat's correctly rounded value through ParseFloat's own fast steps (the
+                                 exact cases, then Eisel-Lemire; sure overflows → the UnmarshalTypeError Go reports, sure
+                                 underflows → 0); a request with a literal Go needs its big-decimal slow path for (an exact
+                                 half-way case, a subnormal, 1e308-ish) comes back with status 0 ("run on the host"), like a
+                                 body nested deeper than 64 levels */
     GOFR_H_HEALTH = 7,        /* healthHandler with no datasources: map{} handler.go:38-40, container.go:26-38 */
     GOFR_H_MISSING_FILE = 8,  /* catchAllHandler: return nil, http.ErrMissingFile      handler.go:51-53 */
     GOFR_H_FILE = 9,          /* return response.File{Content: blob, ContentType: s0}   handler.go:42-49 */
@@ -440,7 +440,7 @@ int gofr_proto_nested_describe(const gofr_proto_nmsg* msgs, uint32_t n_msgs, con
  *                                  string into Go struct field T.f of type int64"); the partially filled struct Go also
  *                                  leaves behind in that case is not reported
  *   d_status[i] = GOFR_BIND_HOST   not decided on the device (nesting deeper than 64, or a number for a float64 member that
- *                                  needs more than one IEEE operation to round — see GOFR_H_BIND_ECHO): run encoding/json on the host
+ *                                  is one of the rare literals left to Go's slow path — see GOFR_H_BIND_ECHO): run encoding/json on the host
  * d_len[i] = bytes of the result; a value above slot_bytes means it did not fit and nothing was written.
  * Pins: pkg/gofr/http/request_test.go:17-30, pkg/gofr/context_test.go:23-49. */
 enum { GOFR_BIND_OK = 0, GOFR_BIND_ERROR = 1, GOFR_BIND_HOST = 2 };

@@ -6,6 +6,7 @@
 // here against the oracle; tile staging, the block scan and the look-back only exist in serve_kernel.cu and are
 // covered by the `-m gpu` tests.  Nothing in the product links or loads this file.
 #include <cstdint>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -115,6 +116,72 @@ extern "C" uint64_t emu_float32_check(uint32_t first, uint32_t step, uint64_t co
         if (!ok) { if (!fails && bad) *bad = b; fails++; }
     }
     return fails;
+}
+// bd_parse_float (Bind into float64 members) against the C library's correctly rounded strtod on `count` generated
+// literals.  mode 0: random 1..19-digit mantissas with exponents over the whole range; 1: the 17-digit text of random
+// doubles (what encoders emit) and its 16 / 18 / 19 / 25-digit variants; 2: integers around 2^53 .. 2^64 incl. the exact
+// half-way points between doubles, with small exponents; 3: random doubles' neighbourhood written with 19 digits plus a
+// tail of more digits (the truncated-mantissa path).  out[0] decided, out[1] deferred, out[2] mismatches (must be 0),
+// out[3] overflow verdicts; *bad_len / bad = the first mismatching literal.
+extern "C" void emu_parse_float_check(uint64_t seed, uint64_t count, int mode, uint64_t* out, char* bad, uint32_t bad_cap) {
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+    out[0] = out[1] = out[2] = out[3] = 0;
+    char lit[512];
+    for (uint64_t k = 0; k < count; k++) {
+        int n = 0;
+        if (mode == 0) {
+            const int nd = 1 + (int)(rnd() % 19);
+            uint64_t m = rnd();
+            uint64_t lim = 1;
+            for (int i = 0; i < nd; i++) lim *= 10;
+            m %= lim;
+            const int e = (int)(rnd() % 700) - 350;
+            n = snprintf(lit, sizeof lit, "%s%llue%d", (rnd() & 1) ? "-" : "", (unsigned long long)m, e);
+        } else if (mode == 1) {
+            uint64_t b = rnd();
+            if (((b >> 52) & 0x7FF) == 0x7FF) b &= ~(1ull << 62);
+            double d;
+            memcpy(&d, &b, 8);
+            static const int prec[] = {17, 16, 18, 19, 25, 17, 17, 15};
+            n = snprintf(lit, sizeof lit, "%.*e", prec[rnd() % 8] - 1, d);
+        } else if (mode == 2) {
+            const int sh = (int)(rnd() % 11);                       // doubles in [2^(53+sh), 2^(54+sh)) are 2^(sh+1) apart
+            uint64_t base = ((1ull << 53) | (rnd() & ((1ull << 53) - 1))) << sh;
+            const uint64_t half = 1ull << sh;                       // base + half: exactly between two doubles
+            const int64_t delta[] = {0, 1, -1, 2, -2};
+            uint64_t v = base + half + (uint64_t)delta[rnd() % 5] * (rnd() % 3 == 0 ? 0 : 1);
+            const int e = (int)(rnd() % 5);
+            if (e == 0) n = snprintf(lit, sizeof lit, "%llu", (unsigned long long)v);
+            else if (e == 1) n = snprintf(lit, sizeof lit, "%llu.0", (unsigned long long)v);
+            else if (e == 2) n = snprintf(lit, sizeof lit, "%llu000e-3", (unsigned long long)v);
+            else if (e == 3) n = snprintf(lit, sizeof lit, "%llu.%03llue0", (unsigned long long)(v / 1000), (unsigned long long)(v % 1000));
+            else n = snprintf(lit, sizeof lit, "%llue%d", (unsigned long long)v, (int)(rnd() % 40) - 20);
+        } else {
+            uint64_t b = rnd();
+            if (((b >> 52) & 0x7FF) == 0x7FF) b &= ~(1ull << 62);
+            double d;
+            memcpy(&d, &b, 8);
+            n = snprintf(lit, sizeof lit, "%.18e", d);               // 19 digits d.dddddddddddddddddde+XX
+            char* e = strchr(lit, 'e');
+            char tail[64];
+            snprintf(tail, sizeof tail, "%s", e);
+            int extra = (int)(rnd() % 12);
+            char* p = e;
+            for (int i = 0; i < extra; i++) *p++ = (char)('0' + (rnd() % 4 == 0 ? rnd() % 10 : (rnd() & 1 ? 0 : 9)));
+            n = (int)(p - lit) + snprintf(p, sizeof lit - (size_t)(p - lit), "%s", tail);
+        }
+        // JSON number grammar: no '+' after the mantissa sign position, exponent sign allowed
+        uint64_t bits = 0;
+        const uint32_t pf = bd_parse_float((const uint8_t*)lit, (uint32_t)n, &bits);
+        const double want = strtod(lit, nullptr);
+        if (pf == PF_DEFER) { out[1]++; continue; }
+        bool ok;
+        if (pf == PF_OVERFLOW) { out[3]++; ok = want == HUGE_VAL || want == -HUGE_VAL; }
+        else { uint64_t wb; memcpy(&wb, &want, 8); ok = wb == bits; }
+        out[0]++;
+        if (!ok) { if (!out[2] && bad) snprintf(bad, bad_cap, "%s", lit); out[2]++; }
+    }
 }
 extern "C" void emu_float_text_many(const uint64_t* bits, uint32_t n, uint8_t* out, uint32_t* off) {
     uint32_t o = 0;

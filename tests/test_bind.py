@@ -259,7 +259,9 @@ def test_emu_bind_float_known_answers():
             b"123456789012345", b"9007199254740991", b"0.1", b"0.2", b"0.30000000000000004", b"2.5e-5", b"1e22", b"1e23", b"123e35", b"1.7976931348623157e308",
             b"1e400", b"-1e400", b"1e-400", b"-1e-400", b"1e309", b"1e310", b"4.9e-324", b"2.2250738585072014e-308", b"9007199254740993",
             b"0.000000000000000000000000000001", b"1" + b"0" * 30, b"1" + b"0" * 400, b"0." + b"0" * 400 + b"1", b"12345678901234567890123",
-            b"1.00000000000000000000000000000000001", b"1e0000000000000000000002", b"1e-0000000000000000000002", b"5e-1", b"625e-4"]
+            b"1.00000000000000000000000000000000001", b"1e0000000000000000000002", b"1e-0000000000000000000002", b"5e-1", b"625e-4",
+            b"123456789012345678", b"8.5e-310", b"1.7976931348623158e308", b"1.7976931348623159e308", b"9007199254740992.5",
+            b"9007199254740993.0000000000000000000001", b"0.1234567890123456789012345", b"7.2057594037927933e16", b"1e-320"]
     bodies = [b'{"name":"s","value":' + x + b',"n":3}' for x in lits]
     r1, deferred = _float_cmp(bodies)
     decided = 0
@@ -268,15 +270,19 @@ def test_emu_bind_float_known_answers():
         if v in (float("inf"), float("-inf")):  # ErrRange -> UnmarshalTypeError naming the literal
             assert json.loads(r1[i])["error"]["message"] == "json: cannot unmarshal number " + x.decode() + " into Go struct field Reading.value of type float64"
         else:
-            assert json.loads(r1[i])["data"]["value"] == v, x  # the oracle's strtod against Python's float()
+            assert float(json.loads(r1[i])["data"]["value"]) == v, x  # the oracle's strtod against Python's float() (an integral
+            # float is written without a point: json.loads makes it an int)
         decided += i not in deferred
-    # the plain cases are decided on the device; the hard ones (17+ digits, subnormals, exponents near the ends) are not
+    # nearly everything is decided on the device (exact cases, then Eisel-Lemire); what is left for the host: exact half-way
+    # literals, subnormals, the last decade before the overflow threshold
     for x in (b"0", b"-0", b"1.5", b"3.14159", b"1e22", b"1e23", b"123e35", b"0.1", b"1e400", b"-1e400", b"1e-400", b"1e310", b"9007199254740991",
-              b"1" + b"0" * 30, b"1" + b"0" * 400, b"0." + b"0" * 400 + b"1", b"625e-4", b"1e0000000000000000000002"):
+              b"1" + b"0" * 30, b"1" + b"0" * 400, b"0." + b"0" * 400 + b"1", b"625e-4", b"1e0000000000000000000002",
+              b"1.7976931348623157e308", b"12345678901234567890123", b"1.00000000000000000000000000000000001", b"0.30000000000000004",
+              b"2.2250738585072014e-308"):
         assert lits.index(x) not in deferred, x
-    for x in (b"9007199254740993", b"4.9e-324", b"1.7976931348623157e308", b"1e309", b"12345678901234567890123", b"1.00000000000000000000000000000000001"):
+    for x in (b"9007199254740993", b"4.9e-324", b"1e309"):
         assert lits.index(x) in deferred, x
-    assert decided >= 30
+    assert decided >= 40
 
 
 def test_emu_bind_float_type_errors_and_omitempty():
@@ -294,6 +300,25 @@ def test_emu_bind_float_type_errors_and_omitempty():
     assert b"cannot unmarshal string into Go struct field Reading.n of type int" in r1[12]
 
 
+def test_emu_bind_float_bulk_against_strtod():
+    """bd_parse_float on 2 million generated literals against glibc's correctly rounded strtod (scratch/parse_float_campaign.py
+    runs 420 million: profiles/r02/parse_float_campaign.txt): no decided literal may differ; encoder output (the 15 .. 17 digit
+    texts of random doubles) is decided on the device practically always"""
+    import ctypes as C
+    L = emu.lib()
+    L.emu_parse_float_check.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.c_char_p, C.c_uint32]
+    for mode in range(4):
+        out = (C.c_uint64 * 4)()
+        bad = C.create_string_buffer(600)
+        L.emu_parse_float_check(99 + mode, 500_000, mode, out, bad, 600)
+        assert out[2] == 0, (mode, bad.value)
+        assert out[0] + out[1] == 500_000
+        if mode == 1:
+            assert out[1] < 2000   # ~0.1 %: subnormals and the like
+        if mode == 2:
+            assert out[1] > 10000  # the exact half-way integers must NOT be decided
+
+
 @settings(max_examples=200, deadline=None)
 @given(st.lists(st.one_of(
     st.floats(allow_nan=False, allow_infinity=False).map(lambda v: repr(v).encode()),
@@ -309,11 +334,11 @@ def test_emu_bind_float_against_python_float(lits, mis):
     bodies = [b'{"value":' + x + b"}" for x in lits]
     r1, deferred = _float_cmp(bodies, mis)
     for i, x in enumerate(lits):
-        if i in deferred:
+        if i in deferred:   # only what Eisel-Lemire cannot settle: half-way literals (17+ digits), subnormals, the top decade
             digits = x.split(b"e")[0].split(b"E")[0].replace(b"-", b"").replace(b".", b"").lstrip(b"0").rstrip(b"0")
-            assert len(digits) > 15 or abs(float(x)) > 1e22 or (float(x) != 0 and abs(float(x)) < 1e-7), x
+            assert len(digits) > 15 or abs(float(x)) > 1e307 or (float(x) != 0 and abs(float(x)) < 2.3e-308), x
         else:
-            got = json.loads(r1[i])["data"]["value"]
+            got = float(json.loads(r1[i])["data"]["value"])
             assert struct.pack("<d", got) == struct.pack("<d", float(x)) or (got == 0 and float(x) == 0), (x, got)
 
 
@@ -344,7 +369,7 @@ def _gpu_float_check():
     bodies = []
     for i in range(20000):
         v = float(rng.integers(-10 ** 9, 10 ** 9)) / 10 ** int(rng.integers(0, 9))
-        d = [b"0", b"1e-7", b"2.5e21", b"-0.0", b"1e400", b'"s"', b"12345678901234567890"][i % 7]
+        d = [b"0", b"1e-7", b"2.5e21", b"-0.0", b"1e400", b'"s"', b"9007199254740993"][i % 7]   # the last one: exactly half-way, left to the host
         bodies.append(b'{"name":"r%d","value":%s,"delta":%s,"n":%d}' % (i, repr(v).encode(), d, i))
     FL_SPEC.frame_mode = S.FRAME_WIRE
     batch = S.RequestBatch.pack([S.Req(S.M_POST, b"/echo", b"", b) for b in bodies])
