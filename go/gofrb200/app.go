@@ -151,6 +151,15 @@ const (
 	nilCount  = 0xFFFFFFFF
 )
 
+var timeType = reflect.TypeOf(time.Time{})
+
+// timeWords: Unix seconds, nanoseconds, zone offset — what Time.MarshalJSON's text is made of.
+func timeWords(b []byte, t time.Time) []byte {
+	_, off := t.Zone()
+	b = binary.LittleEndian.AppendUint64(b, uint64(t.Unix()))
+	return u32(u32(b, uint32(t.Nanosecond())), uint32(int32(off)))
+}
+
 // isBytes: []byte (any []T with T of kind uint8 without its own marshaller): base64 in encoding/json, kind GOFR_F_BYTES here.
 func isBytes(t reflect.Type) bool { return t.Kind() == reflect.Slice && t.Elem().Kind() == reflect.Uint8 }
 
@@ -173,6 +182,9 @@ func typeDesc(t reflect.Type) (kind, container uint8, elem reflect.Type, ok bool
 	}
 	if isBytes(t) {
 		return 9, container, nil, true
+	}
+	if t == timeType { // time.Time: Time.MarshalJSON's RFC 3339 text (kind GOFR_F_TIME), not its unexported fields
+		return 11, container, nil, true
 	}
 	switch t.Kind() {
 	case reflect.Int64, reflect.Uint8, reflect.Uint16, reflect.Uint32:
@@ -220,7 +232,7 @@ func (a *App) register(t reflect.Type, visiting map[reflect.Type]bool) uint32 {
 	}
 	visiting[t] = true
 	defer delete(visiting, t)
-	if t.Kind() == reflect.Struct {
+	if t.Kind() == reflect.Struct && t != timeType { // a bare time.Time is a value, not a struct to walk
 		for i := 0; i < t.NumField(); i++ {
 			f := t.Field(i)
 			if name, _, _ := strings.Cut(f.Tag.Get("json"), ","); name == "-" {
@@ -278,7 +290,7 @@ func (a *App) Run(device int, favicon []byte) error {
 			}
 			fields = append(fields, d)
 		}
-		if t.Kind() == reflect.Struct {
+		if t.Kind() == reflect.Struct && t != timeType {
 			for i := 0; i < t.NumField(); i++ {
 				f := t.Field(i)
 				name, opts, _ := strings.Cut(f.Tag.Get("json"), ",")
@@ -343,6 +355,9 @@ func u32(b []byte, v uint32) []byte { return binary.LittleEndian.AppendUint32(b,
 
 // scalarWords appends the fixed words of a scalar (include/gofr_b200.h "Row format").
 func scalarWords(b []byte, v reflect.Value) []byte {
+	if v.Type() == timeType {
+		return timeWords(b, v.Interface().(time.Time))
+	}
 	switch v.Kind() {
 	case reflect.Int64, reflect.Int:
 		return binary.LittleEndian.AppendUint64(b, uint64(v.Int()))
@@ -371,6 +386,9 @@ func fixedBytes(t reflect.Type) int {
 	case reflect.Ptr:
 		return 4 + fixedBytes(t.Elem())
 	case reflect.Struct:
+		if t == timeType {
+			return 16
+		}
 		n := 0
 		for i := 0; i < t.NumField(); i++ {
 			if name, _, _ := strings.Cut(t.Field(i).Tag.Get("json"), ","); name != "-" {
@@ -392,6 +410,9 @@ func encodePlain(v reflect.Value, fixed, vars []byte) ([]byte, []byte) {
 		}
 		return u32(fixed, uint32(v.Len())), append(vars, v.Bytes()...)
 	}
+	if v.Type() == timeType {
+		return scalarWords(fixed, v), vars
+	}
 	switch v.Kind() {
 	case reflect.String:
 		return u32(fixed, uint32(v.Len())), append(vars, v.String()...)
@@ -408,6 +429,9 @@ func encodeElement(v reflect.Value, vars []byte) []byte {
 			return u32(vars, nilCount)
 		}
 		return append(u32(vars, uint32(v.Len())), v.Bytes()...)
+	}
+	if v.Type() == timeType {
+		return scalarWords(vars, v)
 	}
 	switch v.Kind() {
 	case reflect.String:
@@ -468,7 +492,7 @@ func encodeRow(v reflect.Value, fixed, vars []byte) ([]byte, []byte) {
 
 // encodeValue: a value of a registered type — a struct, or the bare value of a non-struct type.
 func encodeValue(v reflect.Value) (fixed, vars []byte) {
-	if v.Kind() == reflect.Struct {
+	if v.Kind() == reflect.Struct && v.Type() != timeType {
 		return encodeRow(v, nil, nil)
 	}
 	return encodeField(v, nil, nil)

@@ -191,7 +191,7 @@ struct SchemaDef {
     bool bindable = true;      // the same plus float64: what Bind takes
     bool bare() const { return fields.size() == 1 && (fields[0].flags & GOFR_FIELD_BARE); }
 };
-static uint32_t kind_words(uint8_t kind) { return (kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_FLOAT64 || kind == GOFR_F_UINT64) ? 2u : 1u; }
+static uint32_t kind_words(uint8_t kind) { return kind == GOFR_F_TIME ? 4u : (kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_FLOAT64 || kind == GOFR_F_UINT64) ? 2u : 1u; }
 // words a field owns in the fixed part of its struct
 static uint32_t field_words(const std::vector<SchemaDef>& all, const FieldDef& f) {
     if (f.container == GOFR_C_SLICE || f.container == GOFR_C_MAP) return 1;
@@ -732,6 +732,7 @@ static const char* go_kind_name(uint8_t k) {
         case GOFR_F_UINT64: return "uint64";
         case GOFR_F_BYTES: return "[]uint8";
         case GOFR_F_FLOAT32: return "float32";
+        case GOFR_F_TIME: return "time.Time";
     }
     return "?";
 }
@@ -1384,7 +1385,7 @@ int gofr_table_add_schema(gofr_table* t, uint32_t schema_id, const char* go_type
         f.omitempty = fields[i].omitempty != 0;
         f.container = fields[i].container;
         f.flags = fields[i].flags;
-        if (f.kind < GOFR_F_INT64 || f.kind > GOFR_F_FLOAT32 || f.container > GOFR_C_MAP || (f.flags & ~GOFR_FIELD_BARE)) {
+        if (f.kind < GOFR_F_INT64 || f.kind > GOFR_F_TIME || f.container > GOFR_C_MAP || (f.flags & ~GOFR_FIELD_BARE)) {
             set_last_error("schema %u: unsupported field kind %u / container %u", schema_id, f.kind, f.container);
             return GOFR_ERR_UNSUPPORTED;
         }

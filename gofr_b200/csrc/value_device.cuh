@@ -73,9 +73,54 @@ GOFR_HD uint32_t emit_base64(Writer* w, const uint8_t* p, uint32_t n) {
     }
     return (n + 2) / 3 * 4;
 }
+// time.Time → Time.MarshalJSON's text, quotes included (time/format_rfc3339.go appendFormatRFC3339 + appendStrictRFC3339,
+// Go 1.21): "2006-01-02T15:04:05[.fraction]" + "Z" | ±hh:mm.  sec = Unix seconds, off = zone offset in seconds.
+// Returns the length; 0 when MarshalJSON fails (year outside [0, 9999], zone hour outside [0, 23]); *bad = a row that
+// cannot be a Time (nanoseconds >= 1e9).
+template <bool EMIT>
+GOFR_HD_NOINLINE uint32_t emit_time_json(Writer* w, int64_t sec, uint32_t nsec, int32_t off, bool* bad) {
+    *bad = nsec >= 1000000000u;
+    if (*bad) return 0;
+    const int64_t local = sec + off;
+    // 0000-01-01T00:00:00 .. 9999-12-31T23:59:59 in the zone's wall clock; the zone itself: |offset| < 24 h
+    if (local < -62167219200ll || local >= 253402300800ll) return 0;
+    int32_t zone = off / 60;  // minutes, truncated toward zero like Go
+    const bool zneg = zone < 0;
+    if (zneg) zone = -zone;
+    if (zone / 60 >= 24) return 0;
+    int64_t days = local / 86400;
+    int32_t sod = (int32_t)(local - days * 86400);
+    if (sod < 0) { sod += 86400; days -= 1; }
+    // days since 1970-01-01 → proleptic Gregorian date (the usual era / day-of-era arithmetic)
+    const int32_t z = (int32_t)days + 719468;
+    const int32_t era = (z >= 0 ? z : z - 146096) / 146097;
+    const uint32_t doe = (uint32_t)(z - era * 146097);
+    const uint32_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    const uint32_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const uint32_t mp = (5 * doy + 2) / 153;
+    const uint32_t day = doy - (153 * mp + 2) / 5 + 1, month = mp < 10 ? mp + 3 : mp - 9;
+    const uint32_t year = (uint32_t)((int32_t)yoe + era * 400) + (month <= 2 ? 1u : 0u);
+    uint32_t fd = 0;  // digits of the fraction that survive the trailing-zero trim
+    if (nsec) { fd = 9; for (uint32_t t = nsec; t % 10 == 0; t /= 10) fd--; }
+    const uint32_t total = 2 + 19 + (fd ? 1 + fd : 0) + (off == 0 ? 1 : 6);
+    if (!EMIT) return total;
+    auto two = [&](uint32_t x) { w->put1('0' + x / 10); w->put1('0' + x % 10); };
+    w->put1('"');
+    two(year / 100); two(year % 100); w->put1('-'); two(month); w->put1('-'); two(day); w->put1('T');
+    two((uint32_t)sod / 3600); w->put1(':'); two((uint32_t)sod / 60 % 60); w->put1(':'); two((uint32_t)sod % 60);
+    if (fd) {
+        w->put1('.');
+        uint32_t div = 100000000u;
+        for (uint32_t k = 0; k < fd; k++, div /= 10) w->put1('0' + nsec / div % 10);
+    }
+    if (off == 0) w->put1('Z');
+    else { w->put1(zneg ? '-' : '+'); two((uint32_t)zone / 60); w->put1(':'); two((uint32_t)zone % 60); }
+    w->put1('"');
+    return total;
+}
 // bytes a scalar kind owns (fixed words, or as an element of a slice / map)
 GOFR_HD uint32_t value_scalar_bytes(uint32_t kind) {
-    return (kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_FLOAT64 || kind == GOFR_F_UINT64) ? 8u : 4u;
+    return kind == GOFR_F_TIME ? 16u : (kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_FLOAT64 || kind == GOFR_F_UINT64) ? 8u : 4u;
 }
 
 // isEmptyValue (encode.go) of a field whose fixed words are at p: false, 0, 0.0 of either sign, "", nil pointer, nil or
@@ -87,7 +132,7 @@ GOFR_HD bool value_field_empty(uint32_t kind, uint32_t container, const uint8_t*
     if (kind == GOFR_F_FLOAT64) return (ld64u(p) << 1) == 0;
     if (kind == GOFR_F_FLOAT32) return (ld32u(p) << 1) == 0;
     if (kind == GOFR_F_BYTES) { const uint32_t n = ld32u(p); return n == 0 || n == GOFR_NIL_COUNT; }  // len(v) == 0: nil or empty
-    if (kind == GOFR_F_STRUCT) return false;
+    if (kind == GOFR_F_STRUCT || kind == GOFR_F_TIME) return false;  // isEmptyValue knows no empty struct (time.Time is one)
     return ld32u(p) == 0;  // INT32, BOOL, STRING (its length)
 }
 
@@ -152,6 +197,12 @@ GOFR_HD_NOINLINE uint32_t value_encode(Writer* w, const TableView tv, uint32_t s
             out += n;
         } else if (kind == GOFR_F_UINT64) {
             out += emit_u64_slow<EMIT>(w, ld64u(p));
+        } else if (kind == GOFR_F_TIME) {
+            bool bad = false;
+            const uint32_t n = emit_time_json<EMIT>(w, (int64_t)ld64u(p), ld32u(p + 8), (int32_t)ld32u(p + 12), &bad);
+            if (bad) err = VAL_MALFORMED;
+            else if (!n) err = VAL_UNENCODABLE;
+            out += n;
         } else err = VAL_MALFORMED;
     };
     // a []byte whose length word (GOFR_NIL_COUNT: nil) has been read: null, or the base64 text in quotes

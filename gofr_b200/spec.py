@@ -48,6 +48,7 @@ def result_both(schema: "Schema", values: Sequence, message: bytes, lookup=None)
 # field kinds
 F_INT64, F_INT32, F_BOOL, F_STRING, F_INT, F_FLOAT64, F_STRUCT = 1, 2, 3, 4, 5, 6, 7
 F_UINT64, F_BYTES, F_FLOAT32 = 8, 9, 10   # uint64 / uint, []byte (base64, nil -> null), float32
+F_TIME = 11   # time.Time: (unix seconds, nanoseconds, zone offset seconds)
 # what a field holds of its kind T: T, *T, []T, map[string]T (include/gofr_b200.h GOFR_C_*)
 C_VALUE, C_PTR, C_SLICE, C_MAP = 0, 1, 2, 3
 FIELD_BARE = 1   # one-field schema standing for the field's own type (a handler returning []T, map[string]T, ...)
@@ -99,7 +100,7 @@ class Schema:
 
     @staticmethod
     def _scalar_bytes(kind: int) -> int:
-        return 8 if kind in (F_INT64, F_INT, F_FLOAT64, F_UINT64) else 4
+        return 16 if kind == F_TIME else 8 if kind in (F_INT64, F_INT, F_FLOAT64, F_UINT64) else 4
 
     def _field_fixed(self, f: Field, lookup) -> int:
         if f.container in (C_SLICE, C_MAP):
@@ -123,6 +124,8 @@ class Schema:
             return v if isinstance(v, (bytes, bytearray)) else struct.pack("<f", float(v))
         if kind == F_UINT64:
             return int(v).to_bytes(8, "little", signed=False)
+        if kind == F_TIME:   # (unix seconds, nanoseconds, zone offset in seconds)
+            return int(v[0]).to_bytes(8, "little", signed=True) + int(v[1]).to_bytes(4, "little") + int(v[2]).to_bytes(4, "little", signed=True)
         raise ValueError(f"bad field kind {kind}")
 
     def _plain(self, f: Field, v, lookup):

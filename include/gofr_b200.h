@@ -152,9 +152,15 @@ enum {
     GOFR_F_BYTES = 9,   /* []byte: encoding/json writes base64.StdEncoding with padding in quotes, null when nil.  Row:
                            one fixed word = the byte length (GOFR_NIL_COUNT: nil), the bytes in the variable part;
                            as an element E([]byte) = u32 length (GOFR_NIL_COUNT: nil) + bytes     response schemas only */
-    GOFR_F_FLOAT32 = 10 /* float32: one word (IEEE-754 bits), the shortest digits that identify the FLOAT32
+    GOFR_F_FLOAT32 = 10, /* float32: one word (IEEE-754 bits), the shortest digits that identify the FLOAT32
                            (strconv.AppendFloat(…, -1, 32)), same format rules and NaN / Inf behaviour as FLOAT64
                                                                                                 response schemas only */
+    GOFR_F_TIME = 11    /* time.Time: Time.MarshalJSON = the quoted RFC 3339 text with nanoseconds, trailing zeros of the
+                           fraction trimmed, "Z" for offset 0 else ±hh:mm ("2006-01-02T15:04:05.999999999Z07:00").  Four
+                           words: Unix seconds (lo, hi; the zero Time is -62135596800), nanoseconds (0 .. 999999999), zone
+                           offset in seconds east of UTC (int32).  A year outside [0, 9999] or a zone hour outside [0, 23]
+                           makes MarshalJSON — and with it Encode — fail: the response keeps its status and headers and
+                           has no body, as for NaN.  Never "empty" for omitempty (a struct).     response schemas only */
 };
 /* What the field holds of its kind T (response schemas only; Bind schemas take GOFR_C_VALUE of kinds 1..6):
  *   GOFR_C_VALUE  T          GOFR_C_PTR  *T (nil → null)      GOFR_C_SLICE  []T (nil → null, empty → [])
@@ -196,6 +202,7 @@ typedef struct gofr_handler_desc {
  *   fixed part, little-endian 32-bit words, fields in schema order:
  *     INT64 / INT / UINT64 / FLOAT64  two words (lo, hi; FLOAT64: the IEEE-754 bits)   INT32 / FLOAT32  one   BOOL  one, 0/1
  *     BYTES                  one word, the byte length, GOFR_NIL_COUNT when nil
+ *     TIME                   four words: seconds lo, hi, nanoseconds, zone offset
  *     STRING                 one word, the byte length                            STRUCT  the struct's fixed part, inline
  *     *T                     one word 0 (nil) / 1, then T's fixed words (ignored, and T's variable part ABSENT, when nil)
  *     []T, map[string]T      one word, the element count, GOFR_NIL_COUNT when nil

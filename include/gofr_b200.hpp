@@ -51,6 +51,12 @@ inline Error ErrMissingFile() { return Error{"http: no such file", true}; }
 // []T and a Map for map[string]T (a *T that is not nil is just the T).
 struct Value;
 struct Nil {};
+// time.Time as Time.MarshalJSON sees it: Unix seconds, nanoseconds, zone offset in seconds east of UTC (Time{} = the zero Time)
+struct Time {
+    int64_t unix_seconds = -62135596800ll;
+    uint32_t nanoseconds = 0;
+    int32_t zone_offset_seconds = 0;
+};
 using List = std::vector<Value>;
 struct StructValue {
     uint32_t type_id = 0;
@@ -60,10 +66,11 @@ struct Map {
     std::vector<std::pair<std::string, Value>> entries;  // any order: the encoder sorts like encoding/json does
 };
 struct Value {
-    std::variant<int64_t, bool, std::string, double, Nil, StructValue, List, Map, uint64_t> v;
+    std::variant<int64_t, bool, std::string, double, Nil, StructValue, List, Map, uint64_t, Time> v;
     Value() : v(int64_t(0)) {}
     Value(int64_t x) : v(x) {}
     Value(uint64_t x) : v(x) {}
+    Value(Time x) : v(x) {}
     Value(int x) : v(int64_t(x)) {}
     Value(bool x) : v(x) {}
     Value(double x) : v(x) {}
@@ -230,6 +237,7 @@ public:
         StructType& Float64(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_FLOAT64, json, omitempty); }
         StructType& Float32(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_FLOAT32, json, omitempty); }
         StructType& Uint64(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_UINT64, json, omitempty); }
+        StructType& TimeField(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_TIME, json, omitempty); }
         // []byte: encoding/json writes it as base64; the value is a std::string of the bytes, or Nil for the nil slice
         StructType& Bytes(const char* go, const char* json = "", bool omitempty = false) { return add(go, GOFR_F_BYTES, json, omitempty); }
         // a field of a struct type registered BEFORE this one
@@ -599,6 +607,13 @@ private:
             uint32_t bits;
             memcpy(&bits, &d, 4);
             detail::put_u32(out, bits);
+        } else if (kind == GOFR_F_TIME) {
+            auto* t = std::get_if<Time>(&v.v);
+            if (!t) return false;
+            detail::put_u32(out, (uint32_t)(uint64_t)t->unix_seconds);
+            detail::put_u32(out, (uint32_t)((uint64_t)t->unix_seconds >> 32));
+            detail::put_u32(out, t->nanoseconds);
+            detail::put_u32(out, (uint32_t)t->zone_offset_seconds);
         } else if (kind == GOFR_F_UINT64) {
             uint64_t u;
             if (auto* x = std::get_if<uint64_t>(&v.v)) u = *x;
@@ -666,7 +681,7 @@ private:
     }
     size_t fixed_bytes(const StructType::F& f) const {
         if (f.container == GOFR_C_SLICE || f.container == GOFR_C_MAP) return 4;
-        size_t n = (f.kind == GOFR_F_INT64 || f.kind == GOFR_F_INT || f.kind == GOFR_F_FLOAT64 || f.kind == GOFR_F_UINT64) ? 8 : 4;
+        size_t n = f.kind == GOFR_F_TIME ? 16 : (f.kind == GOFR_F_INT64 || f.kind == GOFR_F_INT || f.kind == GOFR_F_FLOAT64 || f.kind == GOFR_F_UINT64) ? 8 : 4;
         if (f.kind == GOFR_F_STRUCT) {
             n = 0;
             if (const StructType* t = type_of(f.elem)) for (auto& g : t->fields_) n += fixed_bytes(g);

@@ -12,6 +12,7 @@
  */
 #include <math.h>
 #include <stdio.h>
+#include <time.h>
 
 #include "orc_internal.h"
 
@@ -131,7 +132,7 @@ typedef struct {
 static uint32_t rd32u(const uint8_t* p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
 static uint64_t rd64u(const uint8_t* p) { return (uint64_t)rd32u(p) | (uint64_t)rd32u(p + 4) << 32; }
 
-static int kind_words(int kind) { return (kind == F_INT64 || kind == F_INT || kind == F_FLOAT64 || kind == F_UINT64) ? 2 : 1; }
+static int kind_words(int kind) { return kind == F_TIME ? 4 : (kind == F_INT64 || kind == F_INT || kind == F_FLOAT64 || kind == F_UINT64) ? 2 : 1; }
 
 /* encodeByteSlice: base64.StdEncoding (padding) in quotes; a nil slice is null */
 static void enc_bytes(obuf* b, walk* w, uint32_t len) {
@@ -205,6 +206,37 @@ static void enc_scalar(obuf* b, walk* w, int kind, const uint8_t* p) {
             char tmp[40];
             int n = orc_float32_text(x, tmp);
             if (!n) w->failed = 1;
+            ob_put(b, tmp, (size_t)n);
+            break;
+        }
+        case F_TIME: { /* Time.MarshalJSON (time/time.go, format_rfc3339.go; Go 1.21): appendFormatRFC3339(b, true) between
+                        * quotes, then appendStrictRFC3339's checks: year exactly four digits wide, zone hour < 24.  The civil
+                        * fields come from the C library's gmtime_r of the zone's wall clock. */
+            int64_t sec = (int64_t)rd64u(p);
+            uint32_t nsec = rd32u(p + 8);
+            int32_t off = (int32_t)rd32u(p + 12);
+            if (nsec >= 1000000000u) { w->malformed = 1; break; }
+            time_t local = (time_t)(sec + off);
+            struct tm g;
+            if (!gmtime_r(&local, &g)) { w->failed = 1; break; }
+            long year = (long)g.tm_year + 1900;
+            int zone = off / 60, zneg = zone < 0;
+            if (zneg) zone = -zone;
+            if (year < 0 || year > 9999 || zone / 60 >= 24) { w->failed = 1; break; }
+            char tmp[64];
+            int n = snprintf(tmp, sizeof tmp, "\"%04ld-%02d-%02dT%02d:%02d:%02d", year, g.tm_mon + 1, g.tm_mday, g.tm_hour, g.tm_min, g.tm_sec);
+            if (nsec) {
+                char fr[16];
+                snprintf(fr, sizeof fr, "%09u", nsec);
+                int k = 9;
+                while (fr[k - 1] == '0') k--;
+                tmp[n++] = '.';
+                memcpy(tmp + n, fr, (size_t)k);
+                n += k;
+            }
+            if (off == 0) tmp[n++] = 'Z';
+            else n += snprintf(tmp + n, sizeof tmp - (size_t)n, "%c%02d:%02d", zneg ? '-' : '+', zone / 60, zone % 60);
+            tmp[n++] = '"';
             ob_put(b, tmp, (size_t)n);
             break;
         }
@@ -334,7 +366,7 @@ static int field_empty(const orc_field* f, const uint8_t* p) {
         case F_FLOAT64: return (rd64u(p) << 1) == 0; /* +0 and -0 */
         case F_FLOAT32: return (uint32_t)(rd32u(p) << 1) == 0;
         case F_BYTES: { uint32_t n = rd32u(p); return n == 0 || n == 0xFFFFFFFFu; } /* len(v) == 0 */
-        case F_STRUCT: return 0;
+        case F_STRUCT: case F_TIME: return 0; /* a struct is never empty */
         default: return rd32u(p) == 0; /* INT32, BOOL, STRING (length) */
     }
 }

@@ -75,6 +75,31 @@ def go_json_float32(x) -> str:
     return sign + ip + ("." + fp if fp else "")
 
 
+def go_json_time(v) -> str:
+    """Time.MarshalJSON (Go 1.21) of (unix seconds, nanoseconds, zone offset seconds): quoted RFC 3339 with nanoseconds, trailing
+    zeros trimmed, Z for offset 0; "" when it fails (year outside [0, 9999], zone hour >= 24).  Python's datetime does the calendar."""
+    import datetime
+    sec, nsec, off = v
+    local = sec + off
+    zone = abs(off) // 60 if off >= 0 else (-off) // 60
+    if zone // 60 >= 24:
+        return ""
+    if -62167219200 <= local < -62135596800:      # year 0 (datetime starts at year 1): 0000 is a leap year of 366 days
+        d = datetime.datetime(4, 1, 1) + datetime.timedelta(seconds=local + 62167219200)   # year 4 has the same calendar
+        ymd = "0000-%02d-%02d" % (d.month, d.day)
+    elif -62135596800 <= local < 253402300800:
+        d = datetime.datetime(1970, 1, 1) + datetime.timedelta(seconds=local)
+        ymd = "%04d-%02d-%02d" % (d.year, d.month, d.day)
+    else:
+        return ""
+    s = ymd + "T%02d:%02d:%02d" % (d.hour, d.minute, d.second)
+    if nsec:
+        s += "." + ("%09d" % nsec).rstrip("0")
+    # zone := offset / 60 (truncated); the sign is the sign of THAT: an offset of -30 s prints as +00:00
+    s += "Z" if off == 0 else "%s%02d:%02d" % ("-" if off < 0 and zone else "+", zone // 60, zone % 60)
+    return '"' + s + '"'
+
+
 def go_json_string(v) -> str:
     """encoding/json string with escapeHTML (only for valid UTF-8 input, which is all these tests generate)"""
     s = v if isinstance(v, str) else bytes(v).decode("utf-8")
@@ -125,6 +150,11 @@ def go_json(spec: S.TableSpec, schema: S.Schema, values) -> str:
         if kind == S.F_BYTES:
             import base64
             return "null" if v is None else '"' + base64.b64encode(bytes(v)).decode() + '"'
+        if kind == S.F_TIME:
+            t = go_json_time(v)
+            if not t:
+                raise Unencodable()
+            return t
         raise AssertionError(kind)
 
     def t_value(f, v):
@@ -141,6 +171,8 @@ def go_json(spec: S.TableSpec, schema: S.Schema, values) -> str:
             return len(v) == 0
         if f.kind == S.F_BYTES:
             return v is None or len(v) == 0
+        if f.kind == S.F_TIME:
+            return False
         return v == 0   # False == 0, -0.0 == 0
 
     def field_value(f, v):
@@ -282,12 +314,15 @@ MIXED = S.Schema(24, "main.Mixed", [S.Field("Parts", S.F_BYTES, "parts", False, 
                                     S.Field("PF", S.F_FLOAT32, "pf", False, S.C_PTR), S.Field("Blobs", S.F_STRUCT, "blobs", False, S.C_SLICE, 23),
                                     S.Field("Tail", S.F_STRING, "tail")])
 BARE_BYTES = S.Schema(25, "[]uint8", [S.Field("", S.F_BYTES, "", flags=S.FIELD_BARE)])
-SCHEMAS = [ADDR, POINT, USER, SHAPE, BARE_LIST, BARE_MAP, BARE_FLOATS, BARE_PTR, DEEP1, DEEP2, DEEP3, BLOB, MIXED, BARE_BYTES]
-ROUTED = [USER, SHAPE, BARE_LIST, BARE_MAP, BARE_FLOATS, BARE_PTR, DEEP3, ADDR, BLOB, MIXED, BARE_BYTES]
+EVENT = S.Schema(26, "main.Event", [S.Field("ID", S.F_INT64, "id"), S.Field("CreatedAt", S.F_TIME, "created_at"), S.Field("UpdatedAt", S.F_TIME, "updated_at", True),
+                                    S.Field("DeletedAt", S.F_TIME, "deleted_at", False, S.C_PTR), S.Field("Seen", S.F_TIME, "seen", True, S.C_SLICE),
+                                    S.Field("Marks", S.F_TIME, "marks", False, S.C_MAP), S.Field("Note", S.F_STRING, "note")])
+SCHEMAS = [ADDR, POINT, USER, SHAPE, BARE_LIST, BARE_MAP, BARE_FLOATS, BARE_PTR, DEEP1, DEEP2, DEEP3, BLOB, MIXED, BARE_BYTES, EVENT]
+ROUTED = [USER, SHAPE, BARE_LIST, BARE_MAP, BARE_FLOATS, BARE_PTR, DEEP3, ADDR, BLOB, MIXED, BARE_BYTES]   # (one table: the shared-memory budget of the hot part)
 # the schema set the GPU ran (and matched) in this round's last GPU test run; the kinds added afterwards have their own,
 # separately reported GPU test (test_gpu_late_kinds)
 ROUTED_GPU_VALIDATED = ROUTED[:8]
-LATE = [BLOB, MIXED, BARE_BYTES]
+LATE = [BLOB, MIXED, BARE_BYTES, EVENT]
 
 
 def _spec(mode=S.FRAME_WIRE, kind=S.H_ROW, routed=None):
@@ -324,6 +359,17 @@ def _rand_value(rnd, spec, schema, nan_rate=0.0):
             return fl()
         if f.kind == S.F_INT32:
             return rnd.choice([0, 1, -1, 2 ** 31 - 1, -2 ** 31, rnd.randint(-10 ** 6, 10 ** 6)])
+        if f.kind == S.F_TIME:
+            r = rnd.random()
+            if r < 0.1:
+                sec = rnd.choice([-62135596800, 0, -62167219200, -62167219201, 253402300799, 253402300800, -62135596801, 951782400, 1709164800])
+            elif r < 0.2 and nan_rate:
+                sec = rnd.choice([-10 ** 12, 10 ** 12, 2 ** 62, -2 ** 62])   # far outside [0, 9999]: MarshalJSON fails
+            else:
+                sec = rnd.randint(-62135596800, 253402300799) if r < 0.5 else rnd.randint(0, 2 * 10 ** 9)
+            nsec = rnd.choice([0, 0, 1, 10, 500000000, 999999999, 123456000, rnd.randint(0, 999999999)])
+            off = rnd.choice([0, 0, 3600, -3600, 19800, -34200, 30, -30, 86399, -86399, 50400, 86400 if nan_rate else 0, rnd.randint(-50000, 50000)])
+            return (sec, nsec, off)
         if f.kind == S.F_UINT64:
             return rnd.choice([0, 1, 2 ** 64 - 1, 2 ** 63, 10 ** 19, rnd.randint(0, 10 ** 15), rnd.getrandbits(64)])
         if f.kind == S.F_BYTES:
@@ -401,9 +447,11 @@ def _bodies(out, off):
 
 @pytest.mark.parametrize("mode", [S.FRAME_WIRE, S.FRAME_INTENDED, S.FRAME_BODY])
 @pytest.mark.parametrize("result", [False, True])
-def test_emu_values_match_oracle_and_model(mode, result):
-    spec = _spec(mode, S.H_RESULT if result else S.H_ROW)
-    batch, want = _batch(spec, 700, 5 + mode, nan_rate=0.01, result=result)
+@pytest.mark.parametrize("late", [False, True])
+def test_emu_values_match_oracle_and_model(mode, result, late):
+    routed = LATE + [USER] if late else None   # late: the kinds added last (uint64, []byte, float32, time.Time) in a table of their own
+    spec = _spec(mode, S.H_RESULT if result else S.H_ROW, routed)
+    batch, want = _batch(spec, 700, 5 + mode, nan_rate=0.01, result=result, routed=routed)
     o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
     image = Table(spec).serialize()
     for flush in (0, 2):
@@ -522,6 +570,35 @@ def test_schema_validation():
     seal(chain[:8])                  # 8 levels: the walker's frame stack
     with pytest.raises(Exception):
         seal(chain)
+
+
+def test_time_known_answers():
+    """Time.MarshalJSON as documented (time.RFC3339Nano with strict checks): known texts, three ways"""
+    bare = S.Schema(30, "time.Time", [S.Field("", S.F_TIME, "", flags=S.FIELD_BARE)])
+    spec = S.TableSpec(frame_mode=S.FRAME_BODY, schemas=[bare], routes=[S.Route(S.M_GET, "/t", S.H_ROW, schema_id=30)])
+    known = [((-62135596800, 0, 0), '"0001-01-01T00:00:00Z"'),                       # the zero Time
+             ((0, 0, 0), '"1970-01-01T00:00:00Z"'),
+             ((1709210096, 123456789, 19800), '"2024-02-29T18:04:56.123456789+05:30"'),
+             ((1709210096, 500000000, -28800), '"2024-02-29T04:34:56.5-08:00"'),
+             ((1709210096, 120000, 0), '"2024-02-29T12:34:56.00012Z"'),
+             ((951782400, 0, 0), '"2000-02-29T00:00:00Z"'),
+             ((4107542400, 1, 3600), '"2100-03-01T01:00:00.000000001+01:00"'),       # 2100 is not a leap year
+             ((253402300799, 999999999, 0), '"9999-12-31T23:59:59.999999999Z"'),
+             ((-62167219200, 0, 0), '"0000-01-01T00:00:00Z"'),
+             ((0, 0, -30), '"1969-12-31T23:59:30+00:00"'),                            # zone minutes truncate to 0: "+00:00", not "Z"
+             ((0, 0, 86340), '"1970-01-01T23:59:00+23:59"'),
+             ((253402300800, 0, 0), None), ((-62167219201, 0, 0), None),              # years 10000 and -1: MarshalJSON fails
+             ((0, 0, 86400), None), ((0, 0, -90000), None),                           # zone hour outside [0, 23]
+             ((253402300799, 0, 1), None)]                                            # the wall clock is what counts
+    reqs = [S.Req(S.M_GET, b"/t", b"", bare.encode_row([v])) for v, _ in known]
+    batch = S.RequestBatch.pack(reqs)
+    o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
+    o2, f2, m2 = E.serve(Table(spec).serialize(), batch, DATE)
+    r1, r2 = O.responses(o1, f1), O.responses(o2, f2)
+    for (v, want), a, b in zip(known, r1, r2):
+        w = b"" if want is None else ('{"data":%s}\n' % want).encode()
+        assert a == b == w, (v, a, b, w)
+        assert go_json_time(v) == (want or ""), v
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -645,7 +722,7 @@ def test_response_bound_holds_for_the_wider_data_model():
 def _rand_schemas(rnd, n_types, late=False):
     """n_types struct types, each free to use the ones before it, plus bare types on top of them (late: uint64, []byte and
     float32 members as well)"""
-    extra = [S.F_UINT64, S.F_BYTES, S.F_FLOAT32] * 2 if late else []
+    extra = [S.F_UINT64, S.F_BYTES, S.F_FLOAT32, S.F_TIME] * 2 if late else []
     schemas = []
     names = ["a", "id", "Name", "x<y", "long_key_name_%d", "k", "é", "v1", "data", "0"]
     for t in range(n_types):
@@ -665,7 +742,7 @@ def _rand_schemas(rnd, n_types, late=False):
     bare = []
     for t in range(3):
         kind = rnd.choice([S.F_INT64, S.F_BOOL, S.F_STRING, S.F_FLOAT64, S.F_STRUCT] + extra)
-        cont = rnd.choice([S.C_PTR, S.C_SLICE, S.C_MAP]) if kind not in (S.F_FLOAT64, S.F_BYTES, S.F_FLOAT32) else rnd.choice([S.C_VALUE, S.C_SLICE])
+        cont = rnd.choice([S.C_PTR, S.C_SLICE, S.C_MAP]) if kind not in (S.F_FLOAT64, S.F_BYTES, S.F_FLOAT32, S.F_TIME) else rnd.choice([S.C_VALUE, S.C_SLICE])
         elem = rnd.choice(schemas).id if kind == S.F_STRUCT else 0
         if kind == S.F_STRUCT and cont == S.C_MAP:
             cont = S.C_SLICE
