@@ -110,42 +110,93 @@ static const char* status_text(int code) {
     return "";
 }
 
-// http.DetectContentType for static file blobs (seal time).  Signature list restated from net/http's sniffing
-// algorithm; covers the formats a static asset route serves.
+// http.DetectContentType for static file blobs (seal time): net/http's sniffing algorithm (sniff.go, the WHATWG MIME
+// Sniffing tables) restated in the order of its sniffSignatures — the first signature that matches the first 512 bytes wins.
 static std::string sniff_content_type(const std::string& blob) {
-    std::string d = blob.substr(0, 512);
-    auto starts = [&](const char* sig, size_t n) { return d.size() >= n && memcmp(d.data(), sig, n) == 0; };
-    size_t ws = 0;
-    while (ws < d.size() && strchr("\t\n\x0c\r ", d[ws]) && d[ws]) ws++;
-    static const char* html[] = {"<!DOCTYPE HTML", "<HTML", "<HEAD", "<SCRIPT", "<IFRAME", "<H1", "<DIV", "<FONT", "<TABLE",
-                                 "<A", "<STYLE", "<TITLE", "<B", "<BODY", "<BR", "<P", "<!--"};
+    const std::string d = blob.substr(0, 512);
+    const size_t n = d.size();
+    const uint8_t* p = (const uint8_t*)d.data();
+    size_t ws = 0;  // firstNonWS
+    while (ws < n && (p[ws] == '\t' || p[ws] == '\n' || p[ws] == '\x0c' || p[ws] == '\r' || p[ws] == ' ')) ws++;
+    // htmlSig: case-insensitive tag name after leading whitespace, followed by a space or '>'
+    static const char* const html[] = {"<!DOCTYPE HTML", "<HTML", "<HEAD", "<SCRIPT", "<IFRAME", "<H1", "<DIV", "<FONT", "<TABLE",
+                                       "<A", "<STYLE", "<TITLE", "<B", "<BODY", "<BR", "<P", "<!--"};
     for (const char* sig : html) {
-        size_t L = strlen(sig);
-        if (d.size() - ws < L + 1) continue;
+        const size_t L = strlen(sig);
+        if (n - ws < L + 1) continue;
         bool ok = true;
         for (size_t q = 0; q < L && ok; q++) {
-            uint8_t c = (uint8_t)d[ws + q], s = (uint8_t)sig[q];
-            if (s >= 'A' && s <= 'Z') c &= 0xDF;
-            ok = c == s;
+            uint8_t c = p[ws + q];
+            const uint8_t t = (uint8_t)sig[q];
+            if (t >= 'A' && t <= 'Z') c &= 0xDF;
+            ok = c == t;
         }
-        if (ok && (d[ws + L] == ' ' || d[ws + L] == '>')) return "text/html; charset=utf-8";
+        if (ok && (p[ws + L] == ' ' || p[ws + L] == '>')) return "text/html; charset=utf-8";
     }
-    if (d.size() - ws >= 5 && memcmp(d.data() + ws, "<?xml", 5) == 0) return "text/xml; charset=utf-8";
-    if (starts("%PDF-", 5)) return "application/pdf";
-    if (starts("%!PS-Adobe-", 11)) return "application/postscript";
-    if (d.size() >= 4 && (uint8_t)d[0] == 0xFE && (uint8_t)d[1] == 0xFF) return "text/plain; charset=utf-16be";
-    if (d.size() >= 4 && (uint8_t)d[0] == 0xFF && (uint8_t)d[1] == 0xFE) return "text/plain; charset=utf-16le";
-    if (d.size() >= 4 && (uint8_t)d[0] == 0xEF && (uint8_t)d[1] == 0xBB && (uint8_t)d[2] == 0xBF) return "text/plain; charset=utf-8";
-    if (starts("\x00\x00\x01\x00", 4) || starts("\x00\x00\x02\x00", 4)) return "image/x-icon";
-    if (starts("BM", 2)) return "image/bmp";
-    if (starts("GIF87a", 6) || starts("GIF89a", 6)) return "image/gif";
-    if (d.size() >= 14 && starts("RIFF", 4) && memcmp(d.data() + 8, "WEBPVP", 6) == 0) return "image/webp";
-    if (starts("\x89PNG\x0D\x0A\x1A\x0A", 8)) return "image/png";
-    if (starts("\xFF\xD8\xFF", 3)) return "image/jpeg";
-    if (starts("\x1F\x8B\x08", 3)) return "application/x-gzip";
-    if (starts("PK\x03\x04", 4)) return "application/zip";
-    for (unsigned char c : d)
+    // exactSig / maskedSig entries: pattern, mask (nullptr = all ones), length, skip leading whitespace, type
+    struct Sig { const char* pat; const char* mask; size_t len; bool skip_ws; const char* ct; };
+    static const char kLP[37] = "\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0LP";
+    static const char kLPm[37] = "\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\0\xFF\xFF";
+    static const Sig before_mp4[] = {
+        {"<?xml", nullptr, 5, true, "text/xml; charset=utf-8"},
+        {"%PDF-", nullptr, 5, false, "application/pdf"},
+        {"%!PS-Adobe-", nullptr, 11, false, "application/postscript"},
+        {"\xFE\xFF\0\0", "\xFF\xFF\0\0", 4, false, "text/plain; charset=utf-16be"},
+        {"\xFF\xFE\0\0", "\xFF\xFF\0\0", 4, false, "text/plain; charset=utf-16le"},
+        {"\xEF\xBB\xBF\0", "\xFF\xFF\xFF\0", 4, false, "text/plain; charset=utf-8"},
+        {"\0\0\x01\0", nullptr, 4, false, "image/x-icon"},
+        {"\0\0\x02\0", nullptr, 4, false, "image/x-icon"},
+        {"BM", nullptr, 2, false, "image/bmp"},
+        {"GIF87a", nullptr, 6, false, "image/gif"},
+        {"GIF89a", nullptr, 6, false, "image/gif"},
+        {"RIFF\0\0\0\0WEBPVP", "\xFF\xFF\xFF\xFF\0\0\0\0\xFF\xFF\xFF\xFF\xFF\xFF", 14, false, "image/webp"},
+        {"\x89PNG\x0D\x0A\x1A\x0A", nullptr, 8, false, "image/png"},
+        {"\xFF\xD8\xFF", nullptr, 3, false, "image/jpeg"},
+        {"FORM\0\0\0\0AIFF", "\xFF\xFF\xFF\xFF\0\0\0\0\xFF\xFF\xFF\xFF", 12, false, "audio/aiff"},
+        {"ID3", nullptr, 3, false, "audio/mpeg"},
+        {"OggS\0", nullptr, 5, false, "application/ogg"},
+        {"MThd\0\0\0\x06", nullptr, 8, false, "audio/midi"},
+        {"RIFF\0\0\0\0AVI ", "\xFF\xFF\xFF\xFF\0\0\0\0\xFF\xFF\xFF\xFF", 12, false, "video/avi"},
+        {"RIFF\0\0\0\0WAVE", "\xFF\xFF\xFF\xFF\0\0\0\0\xFF\xFF\xFF\xFF", 12, false, "audio/wave"},
+    };
+    static const Sig after_mp4[] = {
+        {"\x1A\x45\xDF\xA3", nullptr, 4, false, "video/webm"},
+        {kLP, kLPm, 36, false, "application/vnd.ms-fontobject"},
+        {"\0\x01\0\0", nullptr, 4, false, "font/ttf"},
+        {"OTTO", nullptr, 4, false, "font/otf"},
+        {"ttcf", nullptr, 4, false, "font/collection"},
+        {"wOFF", nullptr, 4, false, "font/woff"},
+        {"wOF2", nullptr, 4, false, "font/woff2"},
+        {"\x1F\x8B\x08", nullptr, 3, false, "application/x-gzip"},
+        {"PK\x03\x04", nullptr, 4, false, "application/zip"},
+        {"Rar!\x1A\x07\0", nullptr, 7, false, "application/x-rar-compressed"},
+        {"Rar!\x1A\x07\x01\0", nullptr, 8, false, "application/x-rar-compressed"},
+        {"\0\x61\x73\x6D", nullptr, 4, false, "application/wasm"},
+    };
+    auto match = [&](const Sig& g) {
+        const uint8_t* q = p + (g.skip_ws ? ws : 0);
+        const size_t avail = n - (g.skip_ws ? ws : 0);
+        if (avail < g.len) return false;
+        for (size_t k = 0; k < g.len; k++) {
+            const uint8_t m = g.mask ? (uint8_t)g.mask[k] : 0xFF;
+            if ((q[k] & m) != (uint8_t)g.pat[k]) return false;
+        }
+        return true;
+    };
+    for (const Sig& g : before_mp4) if (match(g)) return g.ct;
+    // mp4Sig: an "ftyp" box whose size covers it, with a compatible brand starting "mp4" (the major brand's version is skipped)
+    if (n >= 12) {
+        const size_t box = (size_t)p[0] << 24 | (size_t)p[1] << 16 | (size_t)p[2] << 8 | p[3];
+        if (n >= box && box % 4 == 0 && memcmp(p + 4, "ftyp", 4) == 0)
+            for (size_t st = 8; st < box; st += 4)
+                if (st != 12 && memcmp(p + st, "mp4", 3) == 0) return "video/mp4";
+    }
+    for (const Sig& g : after_mp4) if (match(g)) return g.ct;
+    // textSig: no binary byte from the first non-whitespace byte on
+    for (size_t k = ws; k < n; k++) {
+        const uint8_t c = p[k];
         if (c <= 0x08 || c == 0x0B || (c >= 0x0E && c <= 0x1A) || (c >= 0x1C && c <= 0x1F)) return "application/octet-stream";
+    }
     return "text/plain; charset=utf-8";
 }
 

@@ -743,9 +743,13 @@ static const char* status_text(int code) {
     }
 }
 
-/* http.DetectContentType, restricted to what this path can produce: JSON text never contains a "binary" byte
- * (all < 0x20 are \u-escaped) and never starts with a sniffed signature → text/plain; charset=utf-8.  File blobs
- * are checked against the image/archive signatures the favicon route needs. */
+/* http.DetectContentType (net/http sniff.go; the WHATWG MIME Sniffing tables), signatures in sniffSignatures' order: html
+ * tags, xml, pdf / postscript, BOMs, images, audio / video incl. the mp4 box walk, fonts, archives, wasm, then text vs
+ * binary.  (JSON text never contains a "binary" byte — all < 0x20 are \u-escaped — and never starts with a signature →
+ * text/plain; charset=utf-8.) */
+static int sig_at(const uint8_t* p, size_t n, size_t off, const char* pat, size_t len) {
+    return n >= off + len && memcmp(p + off, pat, len) == 0;
+}
 static const char* detect_content_type(const uint8_t* p, size_t n) {
     if (n > 512) n = 512;
     size_t ws = 0;
@@ -777,9 +781,37 @@ static const char* detect_content_type(const uint8_t* p, size_t n) {
     if (n >= 14 && memcmp(p, "RIFF", 4) == 0 && memcmp(p + 8, "WEBPVP", 6) == 0) return "image/webp";
     if (n >= 8 && memcmp(p, "\x89PNG\x0D\x0A\x1A\x0A", 8) == 0) return "image/png";
     if (n >= 3 && memcmp(p, "\xFF\xD8\xFF", 3) == 0) return "image/jpeg";
+    /* audio and video */
+    if (sig_at(p, n, 0, "FORM", 4) && sig_at(p, n, 8, "AIFF", 4)) return "audio/aiff";
+    if (sig_at(p, n, 0, "ID3", 3)) return "audio/mpeg";
+    if (sig_at(p, n, 0, "OggS\0", 5)) return "application/ogg";
+    if (sig_at(p, n, 0, "MThd\0\0\0\x06", 8)) return "audio/midi";
+    if (sig_at(p, n, 0, "RIFF", 4) && sig_at(p, n, 8, "AVI ", 4)) return "video/avi";
+    if (sig_at(p, n, 0, "RIFF", 4) && sig_at(p, n, 8, "WAVE", 4)) return "audio/wave";
+    if (n >= 12) { /* mp4Sig.match */
+        size_t box = (size_t)p[0] << 24 | (size_t)p[1] << 16 | (size_t)p[2] << 8 | (size_t)p[3];
+        if (n >= box && box % 4 == 0 && memcmp(p + 4, "ftyp", 4) == 0) {
+            for (size_t st = 8; st < box; st += 4) {
+                if (st == 12) continue; /* the version number of the major brand */
+                if (memcmp(p + st, "mp4", 3) == 0) return "video/mp4";
+            }
+        }
+    }
+    if (sig_at(p, n, 0, "\x1A\x45\xDF\xA3", 4)) return "video/webm";
+    /* fonts: 34 NUL bytes then "LP"; TrueType, OpenType, collections, WOFF */
+    if (n >= 36 && p[34] == 'L' && p[35] == 'P') return "application/vnd.ms-fontobject"; /* the mask ignores bytes 0..33 */
+    if (sig_at(p, n, 0, "\0\x01\0\0", 4)) return "font/ttf";
+    if (sig_at(p, n, 0, "OTTO", 4)) return "font/otf";
+    if (sig_at(p, n, 0, "ttcf", 4)) return "font/collection";
+    if (sig_at(p, n, 0, "wOFF", 4)) return "font/woff";
+    if (sig_at(p, n, 0, "wOF2", 4)) return "font/woff2";
+    /* archives */
     if (n >= 3 && memcmp(p, "\x1F\x8B\x08", 3) == 0) return "application/x-gzip";
     if (n >= 4 && memcmp(p, "PK\x03\x04", 4) == 0) return "application/zip";
-    for (size_t i = 0; i < n; i++) {
+    if (sig_at(p, n, 0, "Rar!\x1A\x07\0", 7)) return "application/x-rar-compressed";
+    if (sig_at(p, n, 0, "Rar!\x1A\x07\x01\0", 8)) return "application/x-rar-compressed";
+    if (sig_at(p, n, 0, "\0\x61\x73\x6D", 4)) return "application/wasm";
+    for (size_t i = ws; i < n; i++) { /* textSig: from the first non-whitespace byte */
         uint8_t c = p[i];
         if (c <= 0x08 || c == 0x0B || (c >= 0x0E && c <= 0x1A) || (c >= 0x1C && c <= 0x1F)) return "application/octet-stream";
     }

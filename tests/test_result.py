@@ -359,3 +359,44 @@ def test_gpu_raw_outcomes():
         for i in range(0, b.n, 3):
             assert so[i, :int(ln[i])].tobytes() == ob[int(f1[i]):int(f1[i + 1])], i
     eng.close()
+
+
+def test_file_responses_are_sniffed_like_detect_content_type():
+    """response.File on the wire: the handler's Content-Type is set after WriteHeader and never leaves, net/http sniffs the
+    first 512 bytes (http.DetectContentType, the WHATWG MIME Sniffing tables).  Known answers for every signature family, the
+    product's seal-time sniffer (table_build.cpp) and the oracle's agreeing byte for byte on the whole response."""
+    kat = [(b"", "text/plain; charset=utf-8"), (b"hello", "text/plain; charset=utf-8"), (b"  \n<html><body>", "text/html; charset=utf-8"),
+           (b"<HTML lang=en>", "text/html; charset=utf-8"), (b"<htmlx>", "text/plain; charset=utf-8"), (b"<!-- c -->", "text/html; charset=utf-8"),
+           (b"<!DOCTYPE html>", "text/html; charset=utf-8"), (b"<p>x", "text/html; charset=utf-8"), (b"<p", "text/plain; charset=utf-8"),
+           (b"\t<?xml version='1.0'?>", "text/xml; charset=utf-8"), (b"%PDF-1.7", "application/pdf"), (b"%!PS-Adobe-3.0", "application/postscript"),
+           (b"\xfe\xff\x00h", "text/plain; charset=utf-16be"), (b"\xff\xfeh\x00", "text/plain; charset=utf-16le"), (b"\xef\xbb\xbfhi", "text/plain; charset=utf-8"),
+           (b"\xfe\xff", "text/plain; charset=utf-8"),                                 # a BOM signature needs four bytes; 0xFE 0xFF are not "binary" bytes
+           (b"\x00\x00\x01\x00\x01", "image/x-icon"), (b"\x00\x00\x02\x00", "image/x-icon"), (b"BM6\x00", "image/bmp"),
+           (b"GIF87a..", "image/gif"), (b"GIF89a..", "image/gif"), (b"RIFF\x24\x00\x00\x00WEBPVP8 ", "image/webp"),
+           (b"\x89PNG\r\n\x1a\n\x00\x00", "image/png"), (b"\xff\xd8\xff\xe0", "image/jpeg"),
+           (b"FORM\x00\x00\x10\x00AIFFCOMM", "audio/aiff"), (b"ID3\x03\x00", "audio/mpeg"), (b"OggS\x00\x02", "application/ogg"),
+           (b"MThd\x00\x00\x00\x06\x00\x01", "audio/midi"), (b"RIFF\x10\x00\x00\x00AVI LIST", "video/avi"), (b"RIFF\x10\x00\x00\x00WAVEfmt ", "audio/wave"),
+           (b"\x00\x00\x00\x18ftypmp42\x00\x00\x00\x00mp42isom", "video/mp4"), (b"\x00\x00\x00\x18ftypisom\x00\x00\x02\x00isomiso2", "application/octet-stream"),
+           (b"\x00\x00\x00\x14ftypisom\x00\x00\x02\x00mp41", "video/mp4"), (b"\x00\x00\x00\x10ftypqt  mp4 ", "application/octet-stream"),  # the version word is skipped
+           (b"\x1a\x45\xdf\xa3\x9f", "video/webm"), (b"\x01" * 34 + b"LP", "application/vnd.ms-fontobject"), (b"\x00\x01\x00\x00\x00\x0c", "font/ttf"),
+           (b"OTTO\x00", "font/otf"), (b"ttcf\x00", "font/collection"), (b"wOFF\x00", "font/woff"), (b"wOF2\x00", "font/woff2"),
+           (b"\x1f\x8b\x08\x00", "application/x-gzip"), (b"PK\x03\x04\x14", "application/zip"), (b"Rar!\x1a\x07\x00\xcf", "application/x-rar-compressed"),
+           (b"Rar!\x1a\x07\x01\x00", "application/x-rar-compressed"), (b"\x00asm\x01\x00\x00\x00", "application/wasm"),
+           (b"text with \x1b escape", "text/plain; charset=utf-8"), (b"bin\x00ary", "application/octet-stream"), (b"\x7f\x80\xff", "text/plain; charset=utf-8"),
+           (b"x" * 600 + b"\x00", "text/plain; charset=utf-8"), (b"x" * 511 + b"\x00", "application/octet-stream")]   # only the first 512 bytes are looked at
+    for k0 in range(0, len(kat), 10):
+        part = kat[k0:k0 + 10]
+        spec = S.TableSpec(frame_mode=S.FRAME_WIRE, routes=[S.Route(S.M_GET, "/f%d" % k, S.H_FILE, s0=b"application/json", blob=blob)
+                                                           for k, (blob, _) in enumerate(part)])
+        b = S.RequestBatch.pack([S.Req(S.M_GET, b"/f%d" % k) for k in range(len(part))])
+        o1, f1, m1 = O.OracleTable(spec).serve(b, DATE)
+        o2, f2, m2 = emu.serve(Table(spec).serialize(), b, DATE)
+        r1, r2 = O.responses(o1, f1), O.responses(o2, f2)
+        for (blob, want), a, c in zip(part, r1, r2):
+            assert a == c, (blob[:40], a[:300], c[:300])
+            head, _, body = a.partition(b"\r\n\r\n")
+            assert body == blob
+            if blob:
+                assert ("Content-Type: " + want).encode() in head, (blob[:40], want, head)
+            else:   # an empty file: Content-Length: 0 and nothing to sniff
+                assert b"Content-Type" not in head and b"Content-Length: 0" in head
