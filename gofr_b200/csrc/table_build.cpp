@@ -469,8 +469,11 @@ static SOp op(uint8_t code, bool body) { SOp o; o.code = code; o.body = body; re
 // The header block net/http 1.21 writes (chunkWriter.writeHeader + Header.WriteSubset + extraHeader.Write).
 //   handler headers sorted by key; then Date, Content-Length, Content-Type (sniffed only if the handler's snapshot has
 //   none and the body is non-empty).  `with_mw`: the Tracer/Logging/CORS chain ran (a route matched).
+// `chunked`: the body is ONE Write of more than 2048 bytes — it bypasses response.w (a 2 KiB bufio.Writer) and reaches
+// chunkWriter.Write while the handler is still running, so writeHeader knows no Content-Length and an HTTP/1.1 response
+// becomes "Transfer-Encoding: chunked" (extraHeader order: Date, Content-Length, Content-Type, Connection, Transfer-Encoding).
 static void build_header(Prog& p, uint32_t frame_mode, int status, bool with_mw, BodyKind bk, bool head_no_body,
-                         const std::string& file_ct_given, const std::string& file_ct_sniffed, bool location) {
+                         const std::string& file_ct_given, const std::string& file_ct_sniffed, bool location, bool chunked = false) {
     if (frame_mode == GOFR_FRAME_BODY) return;
     std::vector<HeaderKV> h;
     if (with_mw) {
@@ -517,7 +520,7 @@ static void build_header(Prog& p, uint32_t frame_mode, int status, bool with_mw,
     }
     acc = "\r\n";
     bool body_nonempty = bk != BODY_NONE && bk != BODY_JSON_FAILED;
-    if (!head_no_body) {
+    if (!head_no_body && !chunked) {
         acc += "Content-Length: ";
         if (body_nonempty) {
             p.ops.push_back(lit(acc, false));
@@ -530,6 +533,7 @@ static void build_header(Prog& p, uint32_t frame_mode, int status, bool with_mw,
         acc += bk == BODY_FILE ? file_ct_sniffed : "text/plain; charset=utf-8";  // JSON text never sniffs as anything else
         acc += "\r\n";
     }
+    if (chunked) acc += "Transfer-Encoding: chunked\r\n";
     acc += "\r\n";
     p.ops.push_back(lit(acc, false));
 }
@@ -956,10 +960,21 @@ int seal_table(gofr_table* t) {
                     // recorder's live map (INTENDED) still shows the type the handler set.
                     build_header(p, fm, 200, true, fm == GOFR_FRAME_INTENDED ? BODY_FILE : BODY_NONE, false, r.s[0], "", false);
                 } else {
-                    build_header(p, fm, 200, true, BODY_FILE, false, r.s[0], sniff_content_type(r.blob), false);
+                    // w.Write(v.Content) is one Write: beyond net/http's 2 KiB buffer the response is chunked on the wire
+                    // (the reference's own favicon, 13 149 bytes, is) — one chunk, then chunkWriter.close's terminator.
+                    // (A HEAD request would get neither Content-Length nor Transfer-Encoding there; GoFr registers
+                    // GET / PUT / POST / DELETE only, so no File route ever sees one.)
+                    const bool chunked = fm == GOFR_FRAME_WIRE && r.blob.size() > 2048;
+                    build_header(p, fm, 200, true, BODY_FILE, false, r.s[0], sniff_content_type(r.blob), false, chunked);
+                    if (chunked) {
+                        char hx[32];
+                        snprintf(hx, sizeof hx, "%zx\r\n", r.blob.size());
+                        p.ops.push_back(lit(hx, true));
+                    }
                     SOp bo = op(OP_BLOB, true);
                     bo.lit = r.blob;
                     p.ops.push_back(bo);
+                    if (chunked) p.ops.push_back(lit("\r\n0\r\n\r\n", true));
                 }
                 prog_ok[ri] = b.add(std::move(p));
                 break;

@@ -693,7 +693,19 @@ typedef struct {
     int status;
     obuf body;
     int frame_mode;
+    int chunked; /* a Write larger than the 2 KiB bufio.Writer reached chunkWriter before the handler returned */
+    int is_file; /* the body comes from resTypes.File */
 } rw_t;
+
+/* response.w is bufio.NewWriterSize(&w.cw, 2048): a Write of more than 2048 bytes into the empty buffer goes straight to
+ * chunkWriter.Write, which writes the header block THEN — the handler has not returned, so no Content-Length is known and an
+ * HTTP/1.1 response switches to "Transfer-Encoding: chunked" (server.go chunkWriter.writeHeader); the one Write becomes one
+ * chunk.  Every body of this path is a single Write (json.Encoder.Encode, File).
+ * For File bodies the product frames exactly like this.  For JSON bodies beyond 2 KiB it sends Content-Length instead — a
+ * DEVIATION stated in DESIGN.md §8 — and the oracle follows the product unless orc_set_strict_chunking(1) is in effect, which
+ * tests/test_result.py uses to pin what the difference is. */
+static int g_strict_chunking = 0;
+void orc_set_strict_chunking(int on) { g_strict_chunking = on; }
 
 static void rw_init(rw_t* w, int frame_mode) { memset(w, 0, sizeof *w); w->frame_mode = frame_mode; ob_init(&w->body); }
 static void rw_free(rw_t* w) {
@@ -729,7 +741,13 @@ static void rw_write_header(rw_t* w, int code) {
 }
 static void rw_write(rw_t* w, const void* p, size_t n) {
     if (!w->wrote_header) rw_write_header(w, 200);
+    if (n > 2048 && w->body.n == 0 && w->frame_mode == FRAME_WIRE && (w->is_file || g_strict_chunking)) w->chunked = 1;
     ob_put(&w->body, p, n);
+}
+
+/* Encoder.Encode: enc.w.Write(e.Bytes()) — the body assembled in w->body above arrives as ONE Write (see rw_write) */
+static void rw_encoded_in_one_write(rw_t* w) {
+    if (w->body.n > 2048 && w->frame_mode == FRAME_WIRE && g_strict_chunking) w->chunked = 1;
 }
 
 static const char* status_text(int code) {
@@ -851,7 +869,7 @@ static void rw_finish(rw_t* w, int is_head, const char* date29, obuf* out) {
     ob_put(out, date29, 29);
     ob_put(out, "\r\n", 2);
     size_t plen = w->body.n;
-    if (!is_head || plen > 0) { /* handlerDone && bodyAllowedForStatus && no Content-Length && (!isHEAD || len(p)>0) */
+    if (!w->chunked && (!is_head || plen > 0)) { /* handlerDone && bodyAllowedForStatus && no Content-Length && (!isHEAD || len(p)>0) */
         L = snprintf(line, sizeof line, "Content-Length: %zu\r\n", plen);
         ob_put(out, line, (size_t)L);
     }
@@ -860,8 +878,17 @@ static void rw_finish(rw_t* w, int is_head, const char* date29, obuf* out) {
         ob_puts(out, detect_content_type(w->body.p, w->body.n));
         ob_put(out, "\r\n", 2);
     }
+    if (w->chunked && !is_head) ob_puts(out, "Transfer-Encoding: chunked\r\n"); /* HEAD: "do nothing" — neither length nor encoding */
     ob_put(out, "\r\n", 2);
-    if (!is_head) ob_put(out, w->body.p, w->body.n); /* chunkWriter.Write eats the body of a HEAD response */
+    if (is_head) return; /* chunkWriter.Write eats the body of a HEAD response */
+    if (w->chunked) { /* one chunk, then chunkWriter.close's terminator */
+        L = snprintf(line, sizeof line, "%zx\r\n", plen);
+        ob_put(out, line, (size_t)L);
+        ob_put(out, w->body.p, w->body.n);
+        ob_puts(out, "\r\n0\r\n\r\n");
+        return;
+    }
+    ob_put(out, w->body.p, w->body.n);
 }
 
 /* ------------------------------------------------------------------------------------------------------------ */
@@ -894,6 +921,7 @@ static void respond(rw_t* w, const handler_result* r) {
     if (r->has_err) status = r->err_is_missing_file ? 404 : 500;
     rw_write_header(w, status); /* :21 — BEFORE the Content-type Set below */
     if (r->data_kind == 4) {    /* resTypes.File :27-31 */
+        w->is_file = 1;
         rw_set(w, "Content-Type", r->file_ct, r->file_ct_len);
         rw_write(w, r->file, r->file_len);
         return;
@@ -913,6 +941,7 @@ static void respond(rw_t* w, const handler_result* r) {
         else if (r->data_kind == 5) ob_put(b, r->json, r->json_len);
         else ob_puts(b, "{}");
         ob_putc(b, '\n');
+        rw_encoded_in_one_write(w);
         return;
     }
     /* json.NewEncoder(w).Encode(response{Error, Data}) :40 ; struct order: error, data; both omitempty on interface */
@@ -934,6 +963,7 @@ static void respond(rw_t* w, const handler_result* r) {
     }
     ob_putc(b, '}');
     ob_putc(b, '\n'); /* Encoder.Encode appends a newline */
+    rw_encoded_in_one_write(w);
 }
 
 /* ------------------------------------------------------------------------------------------------------------ */

@@ -68,7 +68,8 @@ int orc_grpc_hello(const uint8_t* in, const uint32_t* in_off, uint32_t n, uint8_
 int orc_json_string(const uint8_t* s, int n, uint8_t* out, int cap);      /* encoding/json string, HTML-safe */
 int orc_json_int(int64_t v, uint8_t* out, int cap);
 int orc_json_float64(double x, uint8_t* out, int cap);                     /* encoding/json floatEncoder; 0 = not encodable */
-int orc_json_float32(float x, uint8_t* out, int cap);                      /* the same for a float32 */
+int orc_json_float32(float x, uint8_t* out, int cap);
+void orc_set_strict_chunking(int on); /* JSON bodies > 2048 B framed as the reference does (chunked); default: as the product does */                      /* the same for a float32 */
 int orc_encode_row_json(const orc_table*, int schema_id, const uint8_t* row, int n, uint8_t* out, int cap);                        /* strconv.AppendInt base 10 */
 int orc_clean_path(const uint8_t* p, int n, uint8_t* out, int cap);        /* mux cleanPath */
 int orc_query_get(const uint8_t* q, int qn, const uint8_t* key, int kn, uint8_t* out, int cap); /* URL.Query().Get */

@@ -68,6 +68,12 @@ def lib():
     return _lib
 
 
+def set_strict_chunking(on: bool) -> None:
+    """oracle only: frame JSON bodies beyond 2 KiB as the reference does (Transfer-Encoding: chunked) instead of as the product
+    does (Content-Length) — see oracle/gofr_oracle.c rw_write and DESIGN.md §8"""
+    lib().orc_set_strict_chunking(1 if on else 0)
+
+
 def _buf_call(fn, *args, cap=1 << 16) -> bytes:
     out = C.create_string_buffer(cap)
     n = fn(*args, out, cap)

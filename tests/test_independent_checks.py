@@ -175,3 +175,59 @@ def test_wire_responses_parse_as_http11():
                 assert st2 == status and body2 == body and done and hdr2 == hdr, (i, wire[:60])
             seen.add(status)
     assert {200, 301, 404, 405, 500} <= seen
+
+
+def test_large_file_response_is_chunked_and_parses():
+    """a File body of more than 2048 bytes is ONE Write past net/http's 2 KiB bufio.Writer: the reference answers with
+    Transfer-Encoding: chunked (its own 13 149-byte favicon does).  Product (device code on the CPU) == oracle, and two
+    independent HTTP parsers (h11, llhttp) read the chunked message back to exactly the blob."""
+    from gofr_b200 import spec as S
+    from gofr_b200.table import Table
+    from tests.emu import emu
+    date = S.http_date(1_700_000_000)
+    for size in (1, 2048, 2049, 13149, 70000):
+        blob = b"\x00\x00\x01\x00" + bytes((i * 131 + 7) & 0xFF for i in range(size - 4)) if size > 4 else b"x" * size
+        spec = S.TableSpec(frame_mode=S.FRAME_WIRE, routes=[S.Route(S.M_GET, "/favicon.ico", S.H_FILE, s0=b"image/x-icon", blob=blob)])
+        batch = S.RequestBatch.pack([S.Req(S.M_GET, b"/favicon.ico")])
+        o1, f1, m1 = O.OracleTable(spec).serve(batch, date, out_cap=1 << 18)
+        o2, f2, m2 = emu.serve(Table(spec).serialize(), batch, date, out_cap=1 << 18)
+        wire = O.responses(o1, f1)[0]
+        assert wire == O.responses(o2, f2)[0] and int(m1[0]) == int(m2[0])
+        st, hdr, body = _h11_response(wire, False)
+        st2, hdr2, body2, done = _llhttp_response(wire)
+        assert st == st2 == 200 and body == body2 == blob and done
+        if size > 2048:
+            assert hdr.get("transfer-encoding") == "chunked" and "content-length" not in hdr
+            assert wire.endswith(b"\r\n0\r\n\r\n") and (b"\r\n\r\n%x\r\n" % size) in wire
+        else:
+            assert int(hdr["content-length"]) == size and "transfer-encoding" not in hdr
+        if size > 4:
+            assert hdr["content-type"] == "image/x-icon"          # sniffed from the first 512 bytes, not the handler's value
+
+
+def test_known_deviation_json_bodies_beyond_2k_are_chunked_by_the_reference():
+    """json.Encoder.Encode hands the whole body to ONE Write; beyond 2048 bytes that Write bypasses response.w's buffer and the
+    reference's response is chunked.  The product sends the same bytes with Content-Length (a stated deviation:
+    the framing decision depends on the body length, which the kernels' header programs do not branch on).  This pins exactly
+    what differs: the Content-Length line against a Transfer-Encoding line after Content-Type, and the chunk framing."""
+    from gofr_b200 import spec as S
+    date = S.http_date(1_700_000_000)
+    spec = S.TableSpec(frame_mode=S.FRAME_WIRE, routes=[S.Route(S.M_GET, "/big", S.H_RESULT), S.Route(S.M_GET, "/small", S.H_RESULT)])
+    big, small = b"y" * 2037, b"y" * 2036   # {"data":"…"}\n adds 12 bytes: 2049 (one past the buffer) and 2048 (fits exactly)
+    batch = S.RequestBatch.pack([S.Req(S.M_GET, b"/big", data=S.result_record(S.RESULT_STRING, big)),
+                                 S.Req(S.M_GET, b"/small", data=S.result_record(S.RESULT_STRING, small))])
+    plain = O.responses(*O.OracleTable(spec).serve(batch, date)[:2])
+    O.set_strict_chunking(True)
+    try:
+        strict = O.responses(*O.OracleTable(spec).serve(batch, date)[:2])
+    finally:
+        O.set_strict_chunking(False)
+    assert plain[1] == strict[1]                                   # 2048 bytes: buffered, Content-Length either way
+    hp, _, bp = plain[0].partition(b"\r\n\r\n")
+    hs, _, bs = strict[0].partition(b"\r\n\r\n")
+    assert len(bp) == 2049 and bs == b"%x\r\n" % len(bp) + bp + b"\r\n0\r\n\r\n"
+    lp, ls = hp.split(b"\r\n"), hs.split(b"\r\n")
+    assert [l for l in lp if l not in ls] == [b"Content-Length: 2049"] and [l for l in ls if l not in lp] == [b"Transfer-Encoding: chunked"]
+    assert ls[-1] == b"Transfer-Encoding: chunked" and ls[-2].startswith(b"Content-Type: ")
+    st, hdr, body = _h11_response(strict[0], False)
+    assert st == 200 and body == bp and hdr.get("transfer-encoding") == "chunked"
