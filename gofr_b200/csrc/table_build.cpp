@@ -664,8 +664,21 @@ struct Builder {
         Prog p;
         p.status = status;
         p.bind = bind;
-        build_header(p, t->frame_mode, status, true, BODY_JSON, false, "", "", false);
+        // a body that is all literals has its length now: beyond net/http's 2 KiB buffer the one Write of Encoder.Encode makes the
+        // response chunked (see build_header) — decided here for static bodies; bodies whose length depends on the request keep
+        // Content-Length whatever their size (a stated deviation)
+        size_t static_len = 0;
+        bool all_static = true;
+        for (auto& o : body_ops) { all_static &= o.code == OP_LIT && !(o.flags & OPF_VALUE_OF_KEY); static_len += o.lit.size(); }
+        const bool chunked = all_static && t->frame_mode == GOFR_FRAME_WIRE && static_len > 2048;
+        build_header(p, t->frame_mode, status, true, BODY_JSON, false, "", "", false, chunked);
+        if (chunked) {
+            char hx[32];
+            snprintf(hx, sizeof hx, "%zx\r\n", static_len);
+            p.ops.push_back(lit(hx, true));
+        }
         for (auto o : body_ops) { o.body = true; p.ops.push_back(o); }
+        if (chunked) p.ops.push_back(lit("\r\n0\r\n\r\n", true));
         return add(std::move(p));
     }
 };

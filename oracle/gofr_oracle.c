@@ -694,6 +694,7 @@ typedef struct {
     obuf body;
     int frame_mode;
     int chunked; /* a Write larger than the 2 KiB bufio.Writer reached chunkWriter before the handler returned */
+    int static_body; /* handler_result.static_body */
     int is_file; /* the body comes from resTypes.File */
 } rw_t;
 
@@ -747,7 +748,7 @@ static void rw_write(rw_t* w, const void* p, size_t n) {
 
 /* Encoder.Encode: enc.w.Write(e.Bytes()) — the body assembled in w->body above arrives as ONE Write (see rw_write) */
 static void rw_encoded_in_one_write(rw_t* w) {
-    if (w->body.n > 2048 && w->frame_mode == FRAME_WIRE && g_strict_chunking) w->chunked = 1;
+    if (w->body.n > 2048 && w->frame_mode == FRAME_WIRE && (g_strict_chunking || w->static_body)) w->chunked = 1;
 }
 
 static const char* status_text(int code) {
@@ -912,6 +913,8 @@ typedef struct {
     int err_is_missing_file; /* errors.Is(err, http.ErrMissingFile) */
     const uint8_t* err_msg;
     size_t err_len;
+    int static_body; /* the handler returns a constant (GOFR_H_STATIC_*): the product knows the body length when the table is
+                        sealed and frames bodies beyond 2 KiB as the reference does — see rw_write */
     int raw; /* data is a response.Raw{Data: ...}: Respond encodes v.Data bare (pkg/gofr/http/responder.go:24-26, response/raw.go:3-5) */
 } handler_result;
 
@@ -920,6 +923,7 @@ static void respond(rw_t* w, const handler_result* r) {
     int status = 200;
     if (r->has_err) status = r->err_is_missing_file ? 404 : 500;
     rw_write_header(w, status); /* :21 — BEFORE the Content-type Set below */
+    w->static_body = r->static_body;
     if (r->data_kind == 4) {    /* resTypes.File :27-31 */
         w->is_file = 1;
         rw_set(w, "Content-Type", r->file_ct, r->file_ct_len);
@@ -1102,8 +1106,8 @@ static void serve_one(const orc_table* t, const req_desc* d, const uint8_t* id16
                 rw_free(&w);
                 *meta = 0u | (uint32_t)route_id << 16;
                 return;
-            case H_STATIC_STRING: hr.data_kind = 1; hr.str = r->s[0]; hr.str_len = (size_t)r->sl[0]; break;
-            case H_STATIC_ERROR: hr.has_err = 1; hr.err_msg = r->s[0]; hr.err_len = (size_t)r->sl[0]; break;
+            case H_STATIC_STRING: hr.data_kind = 1; hr.str = r->s[0]; hr.str_len = (size_t)r->sl[0]; hr.static_body = 1; break;
+            case H_STATIC_ERROR: hr.has_err = 1; hr.err_msg = r->s[0]; hr.err_len = (size_t)r->sl[0]; hr.static_body = 1; break;
             case H_NIL: break;
             case H_PARAM_FORMAT: {
                 query_get(query, qn, r->s[0], (size_t)r->sl[0], &tmp);

@@ -231,3 +231,22 @@ def test_known_deviation_json_bodies_beyond_2k_are_chunked_by_the_reference():
     assert ls[-1] == b"Transfer-Encoding: chunked" and ls[-2].startswith(b"Content-Type: ")
     st, hdr, body = _h11_response(strict[0], False)
     assert st == 200 and body == bp and hdr.get("transfer-encoding") == "chunked"
+
+
+def test_static_bodies_beyond_2k_are_chunked_like_the_reference():
+    """handlers that return a constant: the body length is known when the table is sealed, so the product frames bodies of more
+    than 2048 bytes the way net/http does (one chunk); 2048 bytes exactly still fit the buffer.  Product == oracle, h11 agrees."""
+    from gofr_b200 import spec as S
+    from gofr_b200.table import Table
+    from tests.emu import emu
+    date = S.http_date(1_700_000_000)
+    for n, chunked in ((2036, False), (2037, True), (9000, True)):      # {"data":"…"}\n adds 12 bytes
+        spec = S.TableSpec(frame_mode=S.FRAME_WIRE, routes=[S.Route(S.M_GET, "/s", S.H_STATIC_STRING, s0=b"q" * n)])
+        b = S.RequestBatch.pack([S.Req(S.M_GET, b"/s")])
+        o1, f1, m1 = O.OracleTable(spec).serve(b, date, out_cap=1 << 16)
+        o2, f2, m2 = emu.serve(Table(spec).serialize(), b, date, out_cap=1 << 16)
+        wire = O.responses(o1, f1)[0]
+        assert wire == O.responses(o2, f2)[0]
+        st, hdr, body = _h11_response(wire, False)
+        assert st == 200 and body == b'{"data":"' + b"q" * n + b'"}\n'
+        assert (hdr.get("transfer-encoding") == "chunked") == chunked and ("content-length" in hdr) == (not chunked)
