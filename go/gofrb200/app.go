@@ -146,6 +146,7 @@ const (
 	cPtr   = 1
 	cSlice = 2
 	cMap   = 3
+	cSlicePtr = 4 // []*T
 	fStruct   = 7
 	fieldBare = 1
 	nilCount  = 0xFFFFFFFF
@@ -172,6 +173,8 @@ func typeDesc(t reflect.Type) (kind, container uint8, elem reflect.Type, ok bool
 	case isBytes(t): // a []byte by value: kind 9 below
 	case t.Kind() == reflect.Ptr:
 		container, t = cPtr, t.Elem()
+	case t.Kind() == reflect.Slice && t.Elem().Kind() == reflect.Ptr: // []*T: what ORMs hand back
+		container, t = cSlicePtr, t.Elem().Elem()
 	case t.Kind() == reflect.Slice:
 		container, t = cSlice, t.Elem()
 	case t.Kind() == reflect.Map:
@@ -460,7 +463,15 @@ func encodeField(f reflect.Value, fixed, vars []byte) ([]byte, []byte) {
 		}
 		fixed = u32(fixed, uint32(f.Len()))
 		for i := 0; i < f.Len(); i++ {
-			vars = encodeElement(f.Index(i), vars)
+			e := f.Index(i)
+			if e.Kind() == reflect.Ptr { // []*T: a presence word, then the pointee
+				if e.IsNil() {
+					vars = u32(vars, 0)
+					continue
+				}
+				vars, e = u32(vars, 1), e.Elem()
+			}
+			vars = encodeElement(e, vars)
 		}
 		return fixed, vars
 	case reflect.Map:

@@ -245,7 +245,7 @@ struct SchemaDef {
 static uint32_t kind_words(uint8_t kind) { return kind == GOFR_F_TIME ? 4u : (kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_FLOAT64 || kind == GOFR_F_UINT64) ? 2u : 1u; }
 // words a field owns in the fixed part of its struct
 static uint32_t field_words(const std::vector<SchemaDef>& all, const FieldDef& f) {
-    if (f.container == GOFR_C_SLICE || f.container == GOFR_C_MAP) return 1;
+    if (f.container == GOFR_C_SLICE || f.container == GOFR_C_MAP || f.container == GOFR_C_SLICE_PTR) return 1;
     const uint32_t w = f.kind == GOFR_F_STRUCT ? all[(size_t)f.elem].fixed_words : kind_words(f.kind);
     return w + (f.container == GOFR_C_PTR ? 1u : 0u);
 }
@@ -1464,7 +1464,7 @@ int gofr_table_add_schema(gofr_table* t, uint32_t schema_id, const char* go_type
         f.omitempty = fields[i].omitempty != 0;
         f.container = fields[i].container;
         f.flags = fields[i].flags;
-        if (f.kind < GOFR_F_INT64 || f.kind > GOFR_F_TIME || f.container > GOFR_C_MAP || (f.flags & ~GOFR_FIELD_BARE)) {
+        if (f.kind < GOFR_F_INT64 || f.kind > GOFR_F_TIME || f.container > GOFR_C_SLICE_PTR || (f.flags & ~GOFR_FIELD_BARE)) {
             set_last_error("schema %u: unsupported field kind %u / container %u", schema_id, f.kind, f.container);
             return GOFR_ERR_UNSUPPORTED;
         }

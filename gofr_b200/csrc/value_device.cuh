@@ -127,7 +127,7 @@ GOFR_HD uint32_t value_scalar_bytes(uint32_t kind) {
 // empty slice / map; a struct value is never empty
 GOFR_HD bool value_field_empty(uint32_t kind, uint32_t container, const uint8_t* p) {
     if (container == GOFR_C_PTR) return ld32u(p) == 0;
-    if (container == GOFR_C_SLICE || container == GOFR_C_MAP) { const uint32_t n = ld32u(p); return n == 0 || n == GOFR_NIL_COUNT; }
+    if (container == GOFR_C_SLICE || container == GOFR_C_MAP || container == GOFR_C_SLICE_PTR) { const uint32_t n = ld32u(p); return n == 0 || n == GOFR_NIL_COUNT; }
     if (kind == GOFR_F_INT64 || kind == GOFR_F_INT || kind == GOFR_F_UINT64) return ld64u(p) == 0;
     if (kind == GOFR_F_FLOAT64) return (ld64u(p) << 1) == 0;
     if (kind == GOFR_F_FLOAT32) return (ld32u(p) << 1) == 0;
@@ -145,6 +145,7 @@ struct ValueFrame {
     uint8_t first;         // no member written yet (comma logic)
     uint8_t in_slice;      // 1: first element pending, 2: later elements
     uint8_t single;        // root frame: exactly one field, no braces, no key (the OP_VALUE field itself)
+    uint8_t slice_ptr;     // the slice is a []*T: a presence word before every element
 };
 
 // Encodes field `fidx` of schema `sidx` whose fixed words are at `fixed`; its variable bytes start at `var` (avail bytes
@@ -218,7 +219,7 @@ GOFR_HD_NOINLINE uint32_t value_encode(Writer* w, const TableView tv, uint32_t s
         if (depth > kMaxValueDepth) { err = VAL_MALFORMED; return; }
         ValueFrame& f = st[depth++];
         f.fixed = fx; f.slice_left = 0; f.schema = (uint16_t)schema; f.slice_elem = 0;
-        f.next_field = 0; f.first = 1; f.in_slice = 0; f.single = 0;
+        f.next_field = 0; f.first = 1; f.in_slice = 0; f.single = 0; f.slice_ptr = 0;
         put_c('{');
     };
     // E(T) of a STRING / scalar element, taken from the variable part (struct elements go through push_struct)
@@ -326,15 +327,21 @@ GOFR_HD_NOINLINE uint32_t value_encode(Writer* w, const TableView tv, uint32_t s
             map_value(F.kind, n);
             return;
         }
+        const bool eptr = F.container == GOFR_C_SLICE_PTR;
         put_c('[');
         if (F.kind == GOFR_F_STRUCT) {
             if (n == 0) { put_c(']'); return; }
-            st[fi].slice_left = n; st[fi].slice_elem = F.elem; st[fi].in_slice = 1;
+            st[fi].slice_left = n; st[fi].slice_elem = F.elem; st[fi].in_slice = 1; st[fi].slice_ptr = eptr;
             return;
         }
         if ((uint32_t)(end - var) / 4u < n) { err = VAL_MALFORMED; return; }  // every element owns at least a word
         for (uint32_t i = 0; i < n && err == VAL_OK; i++) {
             if (i) put_c(',');
+            if (eptr) {  // []*T: nil elements are null
+                const uint8_t* pw = take(4);
+                if (!pw) break;
+                if (!ld32u(pw)) { put_null(); continue; }
+            }
             leaf_element(F.kind);
         }
         put_c(']');
@@ -344,7 +351,7 @@ GOFR_HD_NOINLINE uint32_t value_encode(Writer* w, const TableView tv, uint32_t s
         const FieldRec& F = fields_of(sidx)[fidx];
         ValueFrame& r = st[depth++];
         r.fixed = fixed - (size_t)F.word * 4; r.slice_left = 0; r.schema = (uint16_t)sidx; r.slice_elem = 0;
-        r.next_field = (uint8_t)fidx; r.first = 1; r.in_slice = 0; r.single = 1;
+        r.next_field = (uint8_t)fidx; r.first = 1; r.in_slice = 0; r.single = 1; r.slice_ptr = 0;
     }
     while (depth > 0 && err == VAL_OK) {
         const int fi = depth - 1;
@@ -352,6 +359,11 @@ GOFR_HD_NOINLINE uint32_t value_encode(Writer* w, const TableView tv, uint32_t s
             if (st[fi].in_slice == 2) put_c(',');
             st[fi].in_slice = 2;
             st[fi].slice_left--;
+            if (st[fi].slice_ptr) {  // []*T: a nil element is null and owns nothing else
+                const uint8_t* pw = take(4);
+                if (!pw) continue;
+                if (!ld32u(pw)) { put_null(); continue; }
+            }
             const uint32_t es = st[fi].slice_elem;
             const uint8_t* fx = take((uint32_t)schemas[es].fixed_words * 4u);
             if (fx) push_struct(es, fx);

@@ -51,6 +51,7 @@ F_UINT64, F_BYTES, F_FLOAT32 = 8, 9, 10   # uint64 / uint, []byte (base64, nil -
 F_TIME = 11   # time.Time: (unix seconds, nanoseconds, zone offset seconds)
 # what a field holds of its kind T: T, *T, []T, map[string]T (include/gofr_b200.h GOFR_C_*)
 C_VALUE, C_PTR, C_SLICE, C_MAP = 0, 1, 2, 3
+C_SLICE_PTR = 4   # []*T: a presence word before every element (None elements are nil pointers)
 FIELD_BARE = 1   # one-field schema standing for the field's own type (a handler returning []T, map[string]T, ...)
 NIL_COUNT = 0xFFFFFFFF
 
@@ -103,7 +104,7 @@ class Schema:
         return 16 if kind == F_TIME else 8 if kind in (F_INT64, F_INT, F_FLOAT64, F_UINT64) else 4
 
     def _field_fixed(self, f: Field, lookup) -> int:
-        if f.container in (C_SLICE, C_MAP):
+        if f.container in (C_SLICE, C_MAP, C_SLICE_PTR):
             return 4
         n = lookup(f.elem_schema).fixed_bytes(lookup) if f.kind == F_STRUCT else self._scalar_bytes(f.kind)
         return n + (4 if f.container == C_PTR else 0)
@@ -175,6 +176,10 @@ class Schema:
                 words += (NIL_COUNT if v is None else len(v)).to_bytes(4, "little")
                 for e in (v or ()):
                     tail += self._element(f, e, lookup)
+            elif f.container == C_SLICE_PTR:
+                words += (NIL_COUNT if v is None else len(v)).to_bytes(4, "little")
+                for e in (v or ()):
+                    tail += (0).to_bytes(4, "little") if e is None else (1).to_bytes(4, "little") + self._element(f, e, lookup)
             elif f.container == C_MAP:
                 words += (NIL_COUNT if v is None else len(v)).to_bytes(4, "little")
                 for k, e in (v or {}).items():

@@ -167,7 +167,8 @@ enum {
  *   GOFR_C_MAP    map[string]T, T not a struct (nil → null; keys sorted bytewise like encoding/json does)
  * One container level per field; deeper types nest through GOFR_F_STRUCT (a struct field may again be a pointer, slice
  * or map).  interface{} values, [][]T (other than [][]byte) and maps of structs are not modelled: GOFR_ERR_UNSUPPORTED. */
-enum { GOFR_C_VALUE = 0, GOFR_C_PTR = 1, GOFR_C_SLICE = 2, GOFR_C_MAP = 3 };
+enum { GOFR_C_VALUE = 0, GOFR_C_PTR = 1, GOFR_C_SLICE = 2, GOFR_C_MAP = 3,
+       GOFR_C_SLICE_PTR = 4 /* []*T (what ORMs hand back): like []T, each element preceded by a presence word (0: nil → null) */ };
 #define GOFR_FIELD_BARE 0x01u /* the schema has this ONE field and stands for the field's own type: the handler returns a
                                  []T, map[string]T, *T or float64 rather than a struct; no {"name":…} around the value */
 #define GOFR_NIL_COUNT 0xFFFFFFFFu /* count word of a nil slice / map */
@@ -205,10 +206,11 @@ typedef struct gofr_handler_desc {
  *     TIME                   four words: seconds lo, hi, nanoseconds, zone offset
  *     STRING                 one word, the byte length                            STRUCT  the struct's fixed part, inline
  *     *T                     one word 0 (nil) / 1, then T's fixed words (ignored, and T's variable part ABSENT, when nil)
- *     []T, map[string]T      one word, the element count, GOFR_NIL_COUNT when nil
+ *     []T, []*T, map[string]T  one word, the element count, GOFR_NIL_COUNT when nil
  *   variable part, bytes, fields in schema order, nothing aligned:
  *     STRING / BYTES  the bytes   STRUCT / *STRUCT  the struct's variable part   other scalars  nothing
  *     []T            count elements E(T)            map[string]T   count entries: u32 key length, key bytes, E(T)
+ *     []*T           count elements: u32 presence (0 = nil, nothing follows; else 1), E(T)
  *     E(T): scalars — their fixed words; STRING / BYTES — u32 length + bytes; STRUCT — its fixed part + its variable part
  * A flat struct of scalars and strings therefore is: one word per field (INT64: two) followed by the string bytes of all
  * STRING fields concatenated in schema order. */

@@ -249,6 +249,7 @@ public:
         // the field added last is a *T / []T / map[string]T of the kind it was added with
         StructType& Ptr() { fields_.back().container = GOFR_C_PTR; return *this; }
         StructType& Slice() { fields_.back().container = GOFR_C_SLICE; return *this; }
+        StructType& SliceOfPtr() { fields_.back().container = GOFR_C_SLICE_PTR; return *this; }  // []*T: Nil elements are nil pointers
         StructType& MapOf() { fields_.back().container = GOFR_C_MAP; return *this; }
         uint32_t id() const { return id_; }
         StructValue operator()(std::vector<Value> fields) const { return StructValue{id_, std::move(fields)}; }
@@ -680,7 +681,7 @@ private:
         return scalar_words(f.kind, v, var);
     }
     size_t fixed_bytes(const StructType::F& f) const {
-        if (f.container == GOFR_C_SLICE || f.container == GOFR_C_MAP) return 4;
+        if (f.container == GOFR_C_SLICE || f.container == GOFR_C_MAP || f.container == GOFR_C_SLICE_PTR) return 4;
         size_t n = f.kind == GOFR_F_TIME ? 16 : (f.kind == GOFR_F_INT64 || f.kind == GOFR_F_INT || f.kind == GOFR_F_FLOAT64 || f.kind == GOFR_F_UINT64) ? 8 : 4;
         if (f.kind == GOFR_F_STRUCT) {
             n = 0;
@@ -700,11 +701,18 @@ private:
             } else if (f.container == GOFR_C_PTR) {
                 if (nil) fixed->append(fixed_bytes(f), '\0');
                 else { detail::put_u32(fixed, 1); if (!encode_plain(f, v, fixed, var)) return false; }
-            } else if (f.container == GOFR_C_SLICE) {
+            } else if (f.container == GOFR_C_SLICE || f.container == GOFR_C_SLICE_PTR) {
                 auto* l = std::get_if<List>(&v.v);
                 if (!nil && !l) return false;
                 detail::put_u32(fixed, nil ? GOFR_NIL_COUNT : (uint32_t)l->size());
-                if (l) for (auto& e : *l) if (!encode_element(f, e, var)) return false;
+                if (l) for (auto& e : *l) {
+                    if (f.container == GOFR_C_SLICE_PTR) {  // presence word; a nil element owns nothing else
+                        const bool enil = std::holds_alternative<Nil>(e.v);
+                        detail::put_u32(var, enil ? 0u : 1u);
+                        if (enil) continue;
+                    }
+                    if (!encode_element(f, e, var)) return false;
+                }
             } else {
                 auto* m = std::get_if<Map>(&v.v);
                 if (!nil && !m) return false;

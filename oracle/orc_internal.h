@@ -31,7 +31,7 @@ static inline void ob_puts(obuf* b, const char* s) { ob_put(b, s, strlen(s)); }
 
 /* field kinds (numeric values match include/gofr_b200.h) */
 enum { F_INT64 = 1, F_INT32 = 2, F_BOOL = 3, F_STRING = 4, F_INT = 5, F_FLOAT64 = 6, F_STRUCT = 7, F_UINT64 = 8, F_BYTES = 9, F_FLOAT32 = 10, F_TIME = 11 };
-enum { C_VALUE = 0, C_PTR = 1, C_SLICE = 2, C_MAP = 3 }; /* T, *T, []T, map[string]T */
+enum { C_VALUE = 0, C_PTR = 1, C_SLICE = 2, C_MAP = 3, C_SLICE_PTR = 4 }; /* T, *T, []T, map[string]T, []*T */
 enum { FIELD_BARE = 1 };                                 /* one-field schema standing for the field's own type */
 
 typedef struct {

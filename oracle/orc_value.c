@@ -159,7 +159,7 @@ static void enc_bytes(obuf* b, walk* w, uint32_t len) {
 /* words of the fixed part of a struct / of one field */
 int orc_schema_fixed_words(const orc_table* t, const orc_schema* sc);
 static int field_fixed_words(const orc_table* t, const orc_field* f) {
-    if (f->container == C_SLICE || f->container == C_MAP) return 1;
+    if (f->container == C_SLICE || f->container == C_MAP || f->container == C_SLICE_PTR) return 1;
     int w = 0;
     if (f->kind == F_STRUCT) {
         const orc_schema* es = orc_find_schema(t, f->elem_schema);
@@ -302,6 +302,7 @@ static void enc_field_value(obuf* b, walk* w, const orc_field* f, const uint8_t*
         case C_PTR:
             if (!rd32u(p)) ob_puts(b, "null"); else enc_plain(b, w, f, p + 4);
             break;
+        case C_SLICE_PTR: /* []*T: ptrEncoder per element — nil → null */
         case C_SLICE: {
             uint32_t n = rd32u(p);
             if (n == 0xFFFFFFFFu) { ob_puts(b, "null"); break; }
@@ -311,6 +312,11 @@ static void enc_field_value(obuf* b, walk* w, const orc_field* f, const uint8_t*
             ob_putc(b, '[');
             for (uint32_t i = 0; i < n && !WALK_OVER(w); i++) {
                 if (i) ob_putc(b, ',');
+                if (f->container == C_SLICE_PTR) {
+                    const uint8_t* pw = take(w, 4);
+                    if (!pw) break;
+                    if (!rd32u(pw)) { ob_puts(b, "null"); continue; }
+                }
                 enc_element(b, w, f);
             }
             ob_putc(b, ']');
@@ -360,7 +366,7 @@ static void enc_field_value(obuf* b, walk* w, const orc_field* f, const uint8_t*
 /* isEmptyValue (encode.go): false, 0, 0.0, "", nil pointer, len 0 slice / map; structs never */
 static int field_empty(const orc_field* f, const uint8_t* p) {
     if (f->container == C_PTR) return rd32u(p) == 0;
-    if (f->container == C_SLICE || f->container == C_MAP) { uint32_t n = rd32u(p); return n == 0 || n == 0xFFFFFFFFu; }
+    if (f->container == C_SLICE || f->container == C_MAP || f->container == C_SLICE_PTR) { uint32_t n = rd32u(p); return n == 0 || n == 0xFFFFFFFFu; }
     switch (f->kind) {
         case F_INT64: case F_INT: case F_UINT64: return rd64u(p) == 0;
         case F_FLOAT64: return (rd64u(p) << 1) == 0; /* +0 and -0 */

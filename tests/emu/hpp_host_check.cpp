@@ -56,7 +56,8 @@ int main() {
                                     .Struct("Hist", addr, "hist").Slice().Int64("N", "n", true).Ptr().Int64("Counts", "counts").MapOf();
             static auto& addrs = app.Bare("[]main.Addr").Struct("", addr).Slice();
             static auto& blob = app.Struct("main.Blob").Uint64("ID", "id").Bytes("Data", "data").Bytes("Sum", "sum", true).Float32("Ratio", "ratio")
-                                    .Bytes("Parts", "parts").Slice().Uint64("UM", "um").MapOf().Float32("PF", "pf").Ptr().TimeField("At", "at").TimeField("Seen", "seen").Slice();
+                                    .Bytes("Parts", "parts").Slice().Uint64("UM", "um").MapOf().Float32("PF", "pf").Ptr().TimeField("At", "at").TimeField("Seen", "seen").Slice()
+                                    .Struct("Kids", addr, "kids").SliceOfPtr().Int64("PI", "pi").SliceOfPtr();
             const int c = atoi(a.c_str());
             gofr::Result res;
             const gofr::App::StructType* ty = &user;
@@ -70,7 +71,8 @@ int main() {
             else if (c == 4) res = gofr::Result(gofr::Data(user({"n", 1.0, addr({"P", 0, Nil{}}), "not a struct", Nil{}, Nil{}, Nil{}, Nil{}, Nil{}})));  // wrong kind
             else if (c == 5) { ty = &blob; res = gofr::Result(gofr::Data(blob({uint64_t(18446744073709551615ull), std::string("\x00\xff\x10", 3), Nil{}, 0.1,
                                                                                List{std::string("ab"), Nil{}, std::string("")}, Map{{{"k", uint64_t(1) << 63}, {"j", int64_t(7)}}}, 2.5,
-                                                                               gofr::Time{1709210096, 123456789, 19800}, List{gofr::Time{}, gofr::Time{0, 5, -3600}}}))); }
+                                                                               gofr::Time{1709210096, 123456789, 19800}, List{gofr::Time{}, gofr::Time{0, 5, -3600}},
+                                                                               List{Nil{}, addr({"K", 9, List{0.5}}), Nil{}}, List{int64_t(4), Nil{}}}))); }
             const std::string rec = app.ResultRecord(res, ty);
             for (unsigned char ch : rec) printf("%02x", ch);
             printf("\n");

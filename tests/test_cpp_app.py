@@ -79,7 +79,8 @@ def test_header_compiles_and_host_helpers_match_oracle(tmp_path):
     blob = S.Schema(4, "main.Blob", [S.Field("ID", S.F_UINT64, "id"), S.Field("Data", S.F_BYTES, "data"), S.Field("Sum", S.F_BYTES, "sum", True),
                                      S.Field("Ratio", S.F_FLOAT32, "ratio"), S.Field("Parts", S.F_BYTES, "parts", False, S.C_SLICE),
                                      S.Field("UM", S.F_UINT64, "um", False, S.C_MAP), S.Field("PF", S.F_FLOAT32, "pf", False, S.C_PTR),
-                                     S.Field("At", S.F_TIME, "at"), S.Field("Seen", S.F_TIME, "seen", False, S.C_SLICE)])
+                                     S.Field("At", S.F_TIME, "at"), S.Field("Seen", S.F_TIME, "seen", False, S.C_SLICE),
+                                     S.Field("Kids", S.F_STRUCT, "kids", False, S.C_SLICE_PTR, 1), S.Field("PI", S.F_INT64, "pi", False, S.C_SLICE_PTR)])
     look = {1: addr, 2: user, 3: addrs, 4: blob}.__getitem__
     wantv = [S.result_record(S.RESULT_DATA, user.encode_row(["bo<b>", 1.5e-7, ["Paris", 0, [1.0, 2.5]], None, ["a", "b\n"], {"z": "1", "a": "2", "aa": "3"},
                                                              [["X", 7, None], ["Y", 0, []]], 5, None], look)),
@@ -88,7 +89,8 @@ def test_header_compiles_and_host_helpers_match_oracle(tmp_path):
              S.result_record(S.RESULT_DATA, addrs.encode_row([None], look)), bad,
              # uint64 / []byte (nil and not) / float32 members, by value, in a slice, a map and behind a pointer
              S.result_record(S.RESULT_DATA, blob.encode_row([2 ** 64 - 1, b"\x00\xff\x10", None, 0.1, [b"ab", None, b""], {"k": 2 ** 63, "j": 7}, 2.5,
-                                                             (1709210096, 123456789, 19800), [(-62135596800, 0, 0), (0, 5, -3600)]], look))]
+                                                             (1709210096, 123456789, 19800), [(-62135596800, 0, 0), (0, 5, -3600)],
+                                                             [None, ["K", 9, [0.5]], None], [4, None]], look))]
     assert [bytes.fromhex(l) for l in out[len(cases) + 15:len(cases) + 21]] == wantv
     for t, line in zip(targets, out[len(cases) + 21:]):
         path, sep, query = t.partition(b"?")

@@ -163,7 +163,7 @@ def go_json(spec: S.TableSpec, schema: S.Schema, values) -> str:
     def empty(f, v):
         if f.container == S.C_PTR:
             return v is None
-        if f.container in (S.C_SLICE, S.C_MAP):
+        if f.container in (S.C_SLICE, S.C_MAP, S.C_SLICE_PTR):
             return v is None or len(v) == 0
         if f.kind == S.F_STRUCT:
             return False
@@ -184,6 +184,8 @@ def go_json(spec: S.TableSpec, schema: S.Schema, values) -> str:
             return t_value(f, v)
         if f.container == S.C_SLICE:
             return "[" + ",".join(t_value(f, e) for e in v) + "]"
+        if f.container == S.C_SLICE_PTR:   # []*T: ptrEncoder per element
+            return "[" + ",".join("null" if e is None else t_value(f, e) for e in v) + "]"
         keys = sorted(v, key=lambda k: k.encode("utf-8") if isinstance(k, str) else bytes(k))
         return "{" + ",".join(go_json_string(k) + ":" + t_value(f, v[k]) for k in keys) + "}"
 
@@ -312,7 +314,8 @@ MIXED = S.Schema(24, "main.Mixed", [S.Field("Parts", S.F_BYTES, "parts", False, 
                                     S.Field("F", S.F_FLOAT32, "f", False, S.C_SLICE), S.Field("FM", S.F_FLOAT32, "fm", True, S.C_MAP),
                                     S.Field("PB", S.F_BYTES, "pb", False, S.C_PTR), S.Field("PU", S.F_UINT64, "pu", True, S.C_PTR),
                                     S.Field("PF", S.F_FLOAT32, "pf", False, S.C_PTR), S.Field("Blobs", S.F_STRUCT, "blobs", False, S.C_SLICE, 23),
-                                    S.Field("Tail", S.F_STRING, "tail")])
+                                    S.Field("Kids", S.F_STRUCT, "kids", False, S.C_SLICE_PTR, 23), S.Field("PS", S.F_STRING, "ps", True, S.C_SLICE_PTR),
+                                    S.Field("PI", S.F_INT64, "pi", False, S.C_SLICE_PTR), S.Field("Tail", S.F_STRING, "tail")])
 BARE_BYTES = S.Schema(25, "[]uint8", [S.Field("", S.F_BYTES, "", flags=S.FIELD_BARE)])
 EVENT = S.Schema(26, "main.Event", [S.Field("ID", S.F_INT64, "id"), S.Field("CreatedAt", S.F_TIME, "created_at"), S.Field("UpdatedAt", S.F_TIME, "updated_at", True),
                                     S.Field("DeletedAt", S.F_TIME, "deleted_at", False, S.C_PTR), S.Field("Seen", S.F_TIME, "seen", True, S.C_SLICE),
@@ -395,6 +398,9 @@ def _rand_value(rnd, spec, schema, nan_rate=0.0):
         elif f.container == S.C_SLICE:
             r = rnd.random()
             vals.append(None if r < 0.2 else [t(f) for _ in range(0 if r < 0.35 else rnd.randint(1, 5))])
+        elif f.container == S.C_SLICE_PTR:
+            r = rnd.random()
+            vals.append(None if r < 0.2 else [None if rnd.random() < 0.3 else t(f) for _ in range(0 if r < 0.35 else rnd.randint(1, 5))])
         else:
             r = rnd.random()
             if r < 0.2:
@@ -729,7 +735,7 @@ def _rand_schemas(rnd, n_types, late=False):
         fields = []
         for k in range(rnd.randint(1, 5)):
             kind = rnd.choice([S.F_INT64, S.F_INT32, S.F_BOOL, S.F_STRING, S.F_INT, S.F_FLOAT64] + extra + ([S.F_STRUCT] * 2 if schemas else []))
-            cont = rnd.choice([S.C_VALUE, S.C_VALUE, S.C_PTR, S.C_SLICE, S.C_MAP])
+            cont = rnd.choice([S.C_VALUE, S.C_VALUE, S.C_PTR, S.C_SLICE, S.C_MAP] + ([S.C_SLICE_PTR] if late else []))
             elem = 0
             if kind == S.F_STRUCT:
                 elem = rnd.choice(schemas).id
