@@ -81,6 +81,7 @@ template <bool EMIT>
 GOFR_HD_NOINLINE uint32_t emit_time_json(Writer* w, int64_t sec, uint32_t nsec, int32_t off, bool* bad) {
     *bad = nsec >= 1000000000u;
     if (*bad) return 0;
+    if (sec < -70000000000ll || sec > 300000000000ll) return 0;  // far outside years [0, 9999] (and sec + off cannot overflow)
     const int64_t local = sec + off;
     // 0000-01-01T00:00:00 .. 9999-12-31T23:59:59 in the zone's wall clock; the zone itself: |offset| < 24 h
     if (local < -62167219200ll || local >= 253402300800ll) return 0;

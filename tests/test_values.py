@@ -595,7 +595,8 @@ def test_time_known_answers():
              ((0, 0, 86340), '"1970-01-01T23:59:00+23:59"'),
              ((253402300800, 0, 0), None), ((-62167219201, 0, 0), None),              # years 10000 and -1: MarshalJSON fails
              ((0, 0, 86400), None), ((0, 0, -90000), None),                           # zone hour outside [0, 23]
-             ((253402300799, 0, 1), None)]                                            # the wall clock is what counts
+             ((253402300799, 0, 1), None),                                            # the wall clock is what counts
+             ((2 ** 63 - 1, 0, 86399), None), ((-2 ** 63, 0, -86399), None), ((2 ** 63 - 1, 999999999, 0), None)]   # no overflow on the way
     reqs = [S.Req(S.M_GET, b"/t", b"", bare.encode_row([v])) for v, _ in known]
     batch = S.RequestBatch.pack(reqs)
     o1, f1, m1 = O.OracleTable(spec).serve(batch, DATE)
