@@ -24,6 +24,7 @@ HYP = [  # (module, test, examples per round)
     ("tests.test_bind", "test_emu_random_bodies", 2000),
     ("tests.test_bind", "test_emu_valid_json_roundtrip", 1000),
     ("tests.test_bind", "test_syntax_verdict_agrees_with_python_json", 2000),
+    ("tests.test_bind", "test_emu_bind_float_against_python_float", 1500),
     ("tests.test_http_parse", "test_accepted_messages_against_h11_and_llhttp", 1000),
     ("tests.test_http_parse", "test_mutated_messages_device_code_equals_oracle", 2000),
     ("tests.test_proto", "test_random_message_types_three_way", 1000),
