@@ -75,12 +75,12 @@ GOFR_HD uint32_t emit_base64(Writer* w, const uint8_t* p, uint32_t n) {
 }
 // time.Time → Time.MarshalJSON's text, quotes included (time/format_rfc3339.go appendFormatRFC3339 + appendStrictRFC3339,
 // Go 1.21): "2006-01-02T15:04:05[.fraction]" + "Z" | ±hh:mm.  sec = Unix seconds, off = zone offset in seconds.
-// Returns the length; 0 when MarshalJSON fails (year outside [0, 9999], zone hour outside [0, 23]); *bad = a row that
-// cannot be a Time (nanoseconds >= 1e9).
+// Returns the length; 0 when MarshalJSON fails (year outside [0, 9999], zone hour outside [0, 23]) — and for words no Time
+// can hold (nanoseconds >= 1e9): the CONTENT of a scalar never makes a row "malformed", only its framing does, so that
+// "what ends the walk first" does not depend on the order values are looked at (map values are written in key order).
 template <bool EMIT>
-GOFR_HD_NOINLINE uint32_t emit_time_json(Writer* w, int64_t sec, uint32_t nsec, int32_t off, bool* bad) {
-    *bad = nsec >= 1000000000u;
-    if (*bad) return 0;
+GOFR_HD_NOINLINE uint32_t emit_time_json(Writer* w, int64_t sec, uint32_t nsec, int32_t off) {
+    if (nsec >= 1000000000u) return 0;
     if (sec < -70000000000ll || sec > 300000000000ll) return 0;  // far outside years [0, 9999] (and sec + off cannot overflow)
     const int64_t local = sec + off;
     // 0000-01-01T00:00:00 .. 9999-12-31T23:59:59 in the zone's wall clock; the zone itself: |offset| < 24 h
@@ -200,10 +200,8 @@ GOFR_HD_NOINLINE uint32_t value_encode(Writer* w, const TableView tv, uint32_t s
         } else if (kind == GOFR_F_UINT64) {
             out += emit_u64_slow<EMIT>(w, ld64u(p));
         } else if (kind == GOFR_F_TIME) {
-            bool bad = false;
-            const uint32_t n = emit_time_json<EMIT>(w, (int64_t)ld64u(p), ld32u(p + 8), (int32_t)ld32u(p + 12), &bad);
-            if (bad) err = VAL_MALFORMED;
-            else if (!n) err = VAL_UNENCODABLE;
+            const uint32_t n = emit_time_json<EMIT>(w, (int64_t)ld64u(p), ld32u(p + 8), (int32_t)ld32u(p + 12));
+            if (!n) err = VAL_UNENCODABLE;
             out += n;
         } else err = VAL_MALFORMED;
     };

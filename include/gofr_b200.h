@@ -160,7 +160,7 @@ enum {
                            words: Unix seconds (lo, hi; the zero Time is -62135596800), nanoseconds (0 .. 999999999), zone
                            offset in seconds east of UTC (int32).  A year outside [0, 9999] or a zone hour outside [0, 23]
                            makes MarshalJSON — and with it Encode — fail: the response keeps its status and headers and
-                           has no body, as for NaN.  Never "empty" for omitempty (a struct).     response schemas only */
+                           has no body, as for NaN (a nanoseconds word >= 1e9, which no Time holds, is answered the same way).  Never "empty" for omitempty (a struct).     response schemas only */
 };
 /* What the field holds of its kind T (response schemas only; Bind schemas take GOFR_C_VALUE of kinds 1..6):
  *   GOFR_C_VALUE  T          GOFR_C_PTR  *T (nil → null)      GOFR_C_SLICE  []T (nil → null, empty → [])

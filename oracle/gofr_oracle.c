@@ -769,7 +769,12 @@ static const char* status_text(int code) {
 static int sig_at(const uint8_t* p, size_t n, size_t off, const char* pat, size_t len) {
     return n >= off + len && memcmp(p + off, pat, len) == 0;
 }
-static const char* detect_content_type(const uint8_t* p, size_t n) {
+/* allow_masked_font: the embedded-OpenType signature is 34 DON'T-CARE bytes followed by "LP" — the only signature JSON text
+ * can hit (any body with "LP" at offset 34, e.g. inside a string, is sniffed as application/vnd.ms-fontobject by the
+ * reference).  The product's programs assume JSON never sniffs as anything but text/plain — a DEVIATION stated in DESIGN.md
+ * §8; the oracle follows the product for JSON bodies unless orc_set_strict_chunking(1) is in effect, and always applies the
+ * signature to File bodies (as the product's seal-time sniffer does). */
+static const char* detect_content_type(const uint8_t* p, size_t n, int allow_masked_font) {
     if (n > 512) n = 512;
     size_t ws = 0;
     while (ws < n && (p[ws] == '\t' || p[ws] == '\n' || p[ws] == '\x0c' || p[ws] == '\r' || p[ws] == ' ')) ws++;
@@ -818,7 +823,7 @@ static const char* detect_content_type(const uint8_t* p, size_t n) {
     }
     if (sig_at(p, n, 0, "\x1A\x45\xDF\xA3", 4)) return "video/webm";
     /* fonts: 34 NUL bytes then "LP"; TrueType, OpenType, collections, WOFF */
-    if (n >= 36 && p[34] == 'L' && p[35] == 'P') return "application/vnd.ms-fontobject"; /* the mask ignores bytes 0..33 */
+    if (allow_masked_font && n >= 36 && p[34] == 'L' && p[35] == 'P') return "application/vnd.ms-fontobject"; /* the mask ignores bytes 0..33 */
     if (sig_at(p, n, 0, "\0\x01\0\0", 4)) return "font/ttf";
     if (sig_at(p, n, 0, "OTTO", 4)) return "font/otf";
     if (sig_at(p, n, 0, "ttcf", 4)) return "font/collection";
@@ -876,7 +881,7 @@ static void rw_finish(rw_t* w, int is_head, const char* date29, obuf* out) {
     }
     if (!have_type && plen > 0) {
         ob_puts(out, "Content-Type: ");
-        ob_puts(out, detect_content_type(w->body.p, w->body.n));
+        ob_puts(out, detect_content_type(w->body.p, w->body.n, w->is_file || g_strict_chunking));
         ob_put(out, "\r\n", 2);
     }
     if (w->chunked && !is_head) ob_puts(out, "Transfer-Encoding: chunked\r\n"); /* HEAD: "do nothing" — neither length nor encoding */

@@ -215,7 +215,8 @@ static void enc_scalar(obuf* b, walk* w, int kind, const uint8_t* p) {
             int64_t sec = (int64_t)rd64u(p);
             uint32_t nsec = rd32u(p + 8);
             int32_t off = (int32_t)rd32u(p + 12);
-            if (nsec >= 1000000000u) { w->malformed = 1; break; }
+            if (nsec >= 1000000000u) { w->failed = 1; break; } /* no Time holds this: answered like a Time that cannot be marshalled
+                                                                 * (a scalar's content never makes the ROW malformed: see WALK_OVER) */
             if (sec < -70000000000ll || sec > 300000000000ll) { w->failed = 1; break; } /* far outside [0, 9999]; no overflow below */
             time_t local = (time_t)(sec + off);
             struct tm g;

@@ -250,3 +250,26 @@ def test_static_bodies_beyond_2k_are_chunked_like_the_reference():
         st, hdr, body = _h11_response(wire, False)
         assert st == 200 and body == b'{"data":"' + b"q" * n + b'"}\n'
         assert (hdr.get("transfer-encoding") == "chunked") == chunked and ("content-length" in hdr) == (not chunked)
+
+
+def test_known_deviation_json_with_LP_at_offset_34_sniffs_as_a_font_in_the_reference():
+    """http.DetectContentType's embedded-OpenType signature is 34 don't-care bytes followed by "LP": a JSON body that happens to
+    carry "LP" at offset 34 leaves the reference with Content-Type: application/vnd.ms-fontobject.  The product's programs
+    assume JSON text only ever sniffs as text/plain (a stated deviation); the oracle follows the product unless
+    strict mode is on.  This pins the difference to that one header value."""
+    from gofr_b200 import spec as S
+    date = S.http_date(1_700_000_000)
+    spec = S.TableSpec(frame_mode=S.FRAME_WIRE, routes=[S.Route(S.M_GET, "/s", S.H_RESULT)])
+    text = b"x" * (34 - len(b'{"data":"')) + b"LP and so on"          # {"data":"xxxxxxxxxxxxxxxxxxxxxxxxxLP and so on"}
+    batch = S.RequestBatch.pack([S.Req(S.M_GET, b"/s", data=S.result_record(S.RESULT_STRING, text)),
+                                 S.Req(S.M_GET, b"/s", data=S.result_record(S.RESULT_STRING, b"y" + text))])
+    plain = O.responses(*O.OracleTable(spec).serve(batch, date)[:2])
+    O.set_strict_chunking(True)
+    try:
+        strict = O.responses(*O.OracleTable(spec).serve(batch, date)[:2])
+    finally:
+        O.set_strict_chunking(False)
+    assert plain[0][34 + plain[0].index(b"\r\n\r\n") + 4:][:2] == b"LP"
+    assert plain[1] == strict[1]                                   # one byte further along: nothing special
+    assert plain[0].replace(b"Content-Type: text/plain; charset=utf-8", b"Content-Type: application/vnd.ms-fontobject") == strict[0]
+    assert plain[0] != strict[0]

@@ -80,6 +80,8 @@ def go_json_time(v) -> str:
     zeros trimmed, Z for offset 0; "" when it fails (year outside [0, 9999], zone hour >= 24).  Python's datetime does the calendar."""
     import datetime
     sec, nsec, off = v
+    if nsec >= 10 ** 9:     # not a Time: answered like one that cannot be marshalled
+        return ""
     local = sec + off
     zone = abs(off) // 60 if off >= 0 else (-off) // 60
     if zone // 60 >= 24:
@@ -596,6 +598,7 @@ def test_time_known_answers():
              ((253402300800, 0, 0), None), ((-62167219201, 0, 0), None),              # years 10000 and -1: MarshalJSON fails
              ((0, 0, 86400), None), ((0, 0, -90000), None),                           # zone hour outside [0, 23]
              ((253402300799, 0, 1), None),                                            # the wall clock is what counts
+             ((0, 10 ** 9, 0), None), ((0, 2 ** 32 - 1, 0), None),                    # nanoseconds no Time holds
              ((2 ** 63 - 1, 0, 86399), None), ((-2 ** 63, 0, -86399), None), ((2 ** 63 - 1, 999999999, 0), None)]   # no overflow on the way
     reqs = [S.Req(S.M_GET, b"/t", b"", bare.encode_row([v])) for v, _ in known]
     batch = S.RequestBatch.pack(reqs)
